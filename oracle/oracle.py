@@ -1,0 +1,240 @@
+"""ctypes binding of the CPU oracle (oracle/libsavont_oracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs.  Nothing under savont_b200/ imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libsavont_oracle.so")
+
+STATUS_ASSIGNED, STATUS_NO_CANDIDATE, STATUS_RATIO_FILTERED, STATUS_NO_ALIGNMENT, STATUS_TOO_SHORT = 0, 1, 2, 3, 4
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("k", C.c_int32), ("c", C.c_int32), ("l", C.c_int32), ("min_bq", C.c_int32),
+        ("band", C.c_int32), ("strand_mode", C.c_int32),
+        ("ratio_thresh", C.c_double), ("min_mini_frac_base", C.c_double),
+    ]
+
+
+def default_params(**kw) -> Params:
+    p = Params(17, 11, 3, 25, 64, 0, 0.005, 0.95)
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "savont_oracle.c")
+    hdr = os.path.join(_HERE, "savont_oracle.h")
+    if os.path.exists(src) and (force or not os.path.exists(_LIB_PATH)
+                                or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(src), os.path.getmtime(hdr))):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def _p(arr, typ):
+    if arr is None:
+        return None
+    return arr.ctypes.data_as(C.POINTER(typ))
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        L.so_encode_base.restype = C.c_uint8
+        L.so_encode_base.argtypes = [C.c_uint8]
+        L.so_mm_hash64.restype = C.c_uint64
+        L.so_mm_hash64.argtypes = [C.c_uint64]
+        L.so_kmer_from_ascii.restype = C.c_uint64
+        L.so_kmer_from_ascii.argtypes = [C.c_char_p, C.c_int]
+        L.so_kmer_revcomp.restype = C.c_uint64
+        L.so_kmer_revcomp.argtypes = [C.c_uint64, C.c_int]
+        L.so_kmer48_from_u64.restype = None
+        L.so_kmer48_from_u64.argtypes = [C.c_uint64, C.POINTER(C.c_uint8)]
+        L.so_kmer48_to_u64.restype = C.c_uint64
+        L.so_kmer48_to_u64.argtypes = [C.POINTER(C.c_uint8)]
+        L.so_powi.restype = C.c_double
+        L.so_powi.argtypes = [C.c_double, C.c_int]
+        L.so_split_mask.restype = C.c_uint64
+        L.so_split_mask.argtypes = [C.c_int]
+        L.so_create.restype = C.c_void_p
+        L.so_create.argtypes = [C.POINTER(Params), C.POINTER(C.c_uint64), C.c_size_t]
+        L.so_destroy.restype = None
+        L.so_destroy.argtypes = [C.c_void_p]
+        L.so_load_asvs.restype = C.c_int
+        L.so_load_asvs.argtypes = [C.c_void_p, C.POINTER(C.c_uint8), C.POINTER(C.c_uint64), C.c_size_t]
+        L.so_num_asvs.restype = C.c_size_t
+        L.so_num_asvs.argtypes = [C.c_void_p]
+        L.so_sketch_batch.restype = C.c_int
+        L.so_find_candidates.restype = C.c_int
+        L.so_align_pairs.restype = C.c_int
+        L.so_map_reads.restype = C.c_int
+        L.so_em.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def as_u8(x) -> np.ndarray:
+    if isinstance(x, (bytes, bytearray)):
+        return np.frombuffer(bytes(x), dtype=np.uint8).copy()
+    return np.ascontiguousarray(x, dtype=np.uint8)
+
+
+def concat(seqs):
+    """list of bytes -> (uint8 concatenation, uint64 offsets[n+1])"""
+    offs = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    if len(seqs):
+        offs[1:] = np.cumsum([len(s) for s in seqs], dtype=np.uint64)
+    buf = np.frombuffer(b"".join(bytes(s) for s in seqs), dtype=np.uint8).copy() if len(seqs) else np.zeros(0, np.uint8)
+    return buf, offs
+
+
+def mm_hash64(x: int) -> int:
+    return int(lib().so_mm_hash64(C.c_uint64(x)))
+
+
+def sketch_batch(params: Params, snpmers, bases, quals, offsets):
+    L = lib()
+    snp = np.ascontiguousarray(snpmers, dtype=np.uint64)
+    bases = as_u8(bases)
+    quals = None if quals is None else as_u8(quals)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    n = len(offsets) - 1
+    total = int(offsets[-1]) if n >= 0 else 0
+    cap = max(total, 1)
+    status = np.zeros(max(n, 1), np.uint8)
+    est = np.zeros(max(n, 1), np.float64)
+    mo = np.zeros(n + 1, np.uint64)
+    so = np.zeros(n + 1, np.uint64)
+    mpos = np.zeros(cap, np.uint32); mk = np.zeros(cap, np.uint64); mf = np.zeros(cap, np.uint8)
+    spos = np.zeros(cap, np.uint32); sk = np.zeros(cap, np.uint64)
+    codes = np.zeros(cap, np.uint8)
+    rc = L.so_sketch_batch(C.byref(params), _p(snp, C.c_uint64), C.c_size_t(len(snp)),
+                           _p(bases, C.c_uint8), _p(quals, C.c_uint8), _p(offsets, C.c_uint64), C.c_size_t(n),
+                           _p(status, C.c_uint8), _p(est, C.c_double),
+                           _p(mo, C.c_uint64), _p(mpos, C.c_uint32), _p(mk, C.c_uint64), _p(mf, C.c_uint8), C.c_size_t(cap),
+                           _p(so, C.c_uint64), _p(spos, C.c_uint32), _p(sk, C.c_uint64), C.c_size_t(cap),
+                           _p(codes, C.c_uint8))
+    assert rc == 0, rc
+    nm, ns = int(mo[-1]), int(so[-1])
+    return dict(status=status[:n], est_id=est[:n], mini_offsets=mo, mini_pos=mpos[:nm], mini_kmer=mk[:nm],
+                mini_fwd=mf[:nm], snp_offsets=so, snp_pos=spos[:ns], snp_kmer=sk[:ns], codes=codes[:total])
+
+
+class Oracle:
+    def __init__(self, params: Params, snpmers):
+        self.L = lib()
+        self.params = params
+        self.snpmers = np.ascontiguousarray(snpmers, dtype=np.uint64)
+        self.h = self.L.so_create(C.byref(params), _p(self.snpmers, C.c_uint64), C.c_size_t(len(self.snpmers)))
+        self.n_asv = 0
+
+    def close(self):
+        if self.h:
+            self.L.so_destroy(C.c_void_p(self.h))
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def load_asvs(self, bases, offsets):
+        bases = as_u8(bases)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        rc = self.L.so_load_asvs(C.c_void_p(self.h), _p(bases, C.c_uint8), _p(offsets, C.c_uint64), C.c_size_t(len(offsets) - 1))
+        if rc != 0:
+            raise RuntimeError(f"so_load_asvs failed: {rc}")
+        self.n_asv = int(self.L.so_num_asvs(C.c_void_p(self.h)))
+
+    def find_candidates(self, bases, quals, offsets):
+        bases = as_u8(bases)
+        quals = None if quals is None else as_u8(quals)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1
+        cap = max(n * max(self.n_asv, 1), 1)
+        st = np.zeros(max(n, 1), np.uint8)
+        co = np.zeros(n + 1, np.uint64)
+        ca = np.zeros(cap, np.uint32); cm = np.zeros(cap, np.uint32); ci = np.zeros(cap, np.uint32); cs = np.zeros(cap, np.uint8)
+        rc = self.L.so_find_candidates(C.c_void_p(self.h), _p(bases, C.c_uint8), _p(quals, C.c_uint8), _p(offsets, C.c_uint64),
+                                       C.c_size_t(n), _p(st, C.c_uint8), _p(co, C.c_uint64), _p(ca, C.c_uint32),
+                                       _p(cm, C.c_uint32), _p(ci, C.c_uint32), _p(cs, C.c_uint8), C.c_size_t(cap))
+        assert rc == 0, rc
+        t = int(co[-1])
+        return dict(status=st[:n], offsets=co, asv=ca[:t], mm=cm[:t], mini=ci[:t], strand=cs[:t])
+
+    def align_pairs(self, bases, offsets, pair_read, pair_asv, pair_strand, want_cigar=False):
+        bases = as_u8(bases)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        pr = np.ascontiguousarray(pair_read, dtype=np.uint32)
+        pa = np.ascontiguousarray(pair_asv, dtype=np.uint32)
+        ps = np.ascontiguousarray(pair_strand, dtype=np.uint8)
+        n = len(pr)
+        nm = np.zeros(max(n, 1), np.int32); ae = np.zeros(max(n, 1), np.int32); re = np.zeros(max(n, 1), np.int32)
+        as_ = np.zeros(max(n, 1), np.int32); rs = np.zeros(max(n, 1), np.int32)
+        cap = 1
+        if want_cigar:
+            lens = (offsets[1:] - offsets[:-1]).astype(np.int64)
+            cap = int(sum(int(lens[r]) for r in pr) * 2 + 16 * n + 16)
+        co = np.zeros(n + 1, np.uint64)
+        cg = np.zeros(cap, np.uint32)
+        rc = self.L.so_align_pairs(C.c_void_p(self.h), _p(bases, C.c_uint8), _p(offsets, C.c_uint64), C.c_size_t(len(offsets) - 1),
+                                   _p(pr, C.c_uint32), _p(pa, C.c_uint32), _p(ps, C.c_uint8), C.c_size_t(n),
+                                   _p(nm, C.c_int32), _p(ae, C.c_int32), _p(re, C.c_int32),
+                                   C.c_int(1 if want_cigar else 0), _p(as_, C.c_int32), _p(rs, C.c_int32),
+                                   _p(co, C.c_uint64), _p(cg, C.c_uint32), C.c_size_t(cap))
+        assert rc == 0, rc
+        out = dict(nm=nm[:n], asv_end=ae[:n], read_end=re[:n])
+        if want_cigar:
+            out.update(asv_start=as_[:n], read_start=rs[:n], cigar_offsets=co, cigar=cg[:int(co[-1])])
+        return out
+
+    def map_reads(self, bases, quals, offsets, file_idx=None, n_samples=1, n_threads=0):
+        bases = as_u8(bases)
+        quals = None if quals is None else as_u8(quals)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1
+        A = self.n_asv
+        fi = None if file_idx is None else np.ascontiguousarray(file_idx, dtype=np.uint32)
+        cap = max(n * max(min(A, 64), 1), 1)
+        st = np.zeros(max(n, 1), np.uint8); bn = np.zeros(max(n, 1), np.int32)
+        co = np.zeros(n + 1, np.uint64); ca = np.zeros(cap, np.uint32)
+        un = np.zeros(max(A, 1), np.uint64); am = np.zeros(max(A, 1), np.uint64); le = np.zeros(max(A, 1), np.uint64)
+        tot = np.zeros(2, np.uint64)
+        ss = np.zeros(max(A * n_samples, 1), np.uint64)
+        cells = C.c_uint64(0)
+        rc = self.L.so_map_reads(C.c_void_p(self.h), _p(bases, C.c_uint8), _p(quals, C.c_uint8), _p(offsets, C.c_uint64),
+                                 _p(fi, C.c_uint32), C.c_size_t(n), C.c_int(n_samples),
+                                 _p(st, C.c_uint8), _p(bn, C.c_int32), _p(co, C.c_uint64), _p(ca, C.c_uint32), C.c_size_t(cap),
+                                 _p(un, C.c_uint64), _p(am, C.c_uint64), _p(le, C.c_uint64), _p(tot, C.c_uint64),
+                                 _p(ss, C.c_uint64), C.byref(cells), C.c_int(n_threads))
+        assert rc == 0, rc
+        t = int(co[-1])
+        return dict(status=st[:n], best_nm=bn[:n], class_offsets=co, class_asv=ca[:t], unambig=un[:A], ambig=am[:A],
+                    leq10=le[:A], totals=tot, sample_singleton=ss[:A * n_samples].reshape(n_samples, A), dp_cells=int(cells.value))
+
+
+def em(n_asv, cls_offsets, cls_asv, counts, total_assigned):
+    L = lib()
+    co = np.ascontiguousarray(cls_offsets, dtype=np.uint64)
+    ca = np.ascontiguousarray(cls_asv, dtype=np.uint32)
+    cn = np.ascontiguousarray(counts, dtype=np.uint64)
+    ab = np.zeros(max(n_asv, 1), np.float64); dp = np.zeros(max(n_asv, 1), np.uint64)
+    it = L.so_em(C.c_size_t(n_asv), _p(co, C.c_uint64), _p(ca, C.c_uint32), _p(cn, C.c_uint64), C.c_size_t(len(cn)),
+                 C.c_uint64(int(total_assigned)), _p(ab, C.c_double), _p(dp, C.c_uint64))
+    return ab[:n_asv], dp[:n_asv], it

@@ -1,0 +1,773 @@
+/*
+ * savont_oracle.c -- CPU oracle (TEST INFRASTRUCTURE, see savont_oracle.h).
+ *
+ * Scalar restatement of savont v0.6.4's read-vs-ASV assignment path.  Written to be
+ * obviously equivalent to the Rust source (rolling registers, a deque of s-mer hashes,
+ * per-pair set intersections, a cell-by-cell banded DP), NOT to be fast, and NOT sharing
+ * any code or data structure with the CUDA product path.
+ *
+ * NM parity with the reference (minimap2 lr:hq) is UNPINNED -- see the header.
+ */
+#include "savont_oracle.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ------------------------------------------------------------------------------------ */
+/* primitives                                                                           */
+/* ------------------------------------------------------------------------------------ */
+
+/* src/types.rs:92-101 BYTE_TO_SEQ: A/a=0 C/c=1 G/g=2 T/t/U/u=3, everything else 0 */
+uint8_t so_encode_base(uint8_t b) {
+    switch (b) {
+        case 'A': case 'a': return 0;
+        case 'C': case 'c': return 1;
+        case 'G': case 'g': return 2;
+        case 'T': case 't': case 'U': case 'u': return 3;
+        /* the table also maps raw bytes 0,1,2,3 to themselves */
+        case 1: return 1;
+        case 2: return 2;
+        case 3: return 3;
+        default: return 0;
+    }
+}
+
+/* src/seeding.rs:18-28 */
+uint64_t so_mm_hash64(uint64_t key) {
+    key = (~key) + (key << 21);
+    key = key ^ (key >> 24);
+    key = (key + (key << 3)) + (key << 8);
+    key = key ^ (key >> 14);
+    key = (key + (key << 2)) + (key << 4);
+    key = key ^ (key >> 28);
+    key = key + (key << 31);
+    return key;
+}
+
+/* first base in the highest used bit pair (src/types.rs:1118-1128: ACGTG -> 0b00_01_10_11_10) */
+uint64_t so_kmer_from_ascii(const char *s, int k) {
+    uint64_t v = 0;
+    for (int i = 0; i < k; i++) v = (v << 2) | so_encode_base((uint8_t)s[i]);
+    return v;
+}
+
+/* src/types.rs:559-568 reverse_bit_pairs */
+static uint64_t reverse_bits64(uint64_t n) {
+    uint64_t r = 0;
+    for (int i = 0; i < 64; i++) { r = (r << 1) | (n & 1); n >>= 1; }
+    return r;
+}
+static uint64_t reverse_bit_pairs(uint64_t n, int k) {
+    const uint64_t even_mask = 0xAAAAAAAAAAAAAAAAull, odd_mask = 0x5555555555555555ull;
+    uint64_t odd_bits_rev = reverse_bits64(n & odd_mask) >> (64 - 2 * k);
+    uint64_t even_bits_rev = reverse_bits64(n & even_mask) >> (64 - 2 * k);
+    return (odd_bits_rev >> 1) | (even_bits_rev << 1);
+}
+/* src/types.rs:654 reverse_kmer = reverse_bit_pairs(kmer ^ u64::MAX, k) */
+uint64_t so_kmer_revcomp(uint64_t kmer, int k) { return reverse_bit_pairs(kmer ^ UINT64_MAX, k); }
+
+/* src/types.rs:112-127 */
+void so_kmer48_from_u64(uint64_t v, uint8_t out[6]) {
+    for (int i = 0; i < 6; i++) out[i] = (uint8_t)(v >> (8 * i));
+}
+uint64_t so_kmer48_to_u64(const uint8_t in[6]) {
+    uint64_t v = 0;
+    for (int i = 0; i < 6; i++) v |= (uint64_t)in[i] << (8 * i);
+    return v;
+}
+
+/* f64::powi lowers to llvm.powi -> compiler-rt __powidf2 (repeated squaring) */
+double so_powi(double a, int b) {
+    const int recip = b < 0;
+    double r = 1;
+    while (1) {
+        if (b & 1) r *= a;
+        b /= 2;
+        if (b == 0) break;
+        a *= a;
+    }
+    return recip ? 1 / r : r;
+}
+
+/* src/seeding.rs:353  split_mask = !(3 << (k-1)) */
+uint64_t so_split_mask(int k) { return ~((uint64_t)3 << (k - 1)); }
+
+/* ------------------------------------------------------------------------------------ */
+/* small containers                                                                     */
+/* ------------------------------------------------------------------------------------ */
+typedef struct { uint64_t *keys; uint32_t *vals; size_t cap; size_t n; } u64map; /* key -> u32, EMPTY = UINT64_MAX */
+
+static void u64map_init(u64map *m, size_t expect) {
+    size_t cap = 16;
+    while (cap < expect * 2 + 2) cap <<= 1;
+    m->cap = cap; m->n = 0;
+    m->keys = (uint64_t *)malloc(cap * sizeof(uint64_t));
+    m->vals = (uint32_t *)calloc(cap, sizeof(uint32_t));
+    for (size_t i = 0; i < cap; i++) m->keys[i] = UINT64_MAX;
+}
+static void u64map_free(u64map *m) { free(m->keys); free(m->vals); m->keys = NULL; m->vals = NULL; }
+static uint32_t *u64map_slot(u64map *m, uint64_t key, int insert) {
+    size_t i = (size_t)so_mm_hash64(key) & (m->cap - 1);
+    while (1) {
+        if (m->keys[i] == key) return &m->vals[i];
+        if (m->keys[i] == UINT64_MAX) {
+            if (!insert) return NULL;
+            m->keys[i] = key; m->vals[i] = 0; m->n++;
+            return &m->vals[i];
+        }
+        i = (i + 1) & (m->cap - 1);
+    }
+}
+
+typedef struct {
+    uint32_t *mini_pos; uint64_t *mini_kmer; uint8_t *mini_fwd; size_t n_mini, cap_mini;
+    uint32_t *snp_pos; uint64_t *snp_kmer; size_t n_snp, cap_snp;
+    uint8_t *codes; size_t len;
+    double est_id; /* NaN = None */
+    int ok;
+} sketch_t;
+
+static void sketch_free(sketch_t *s) {
+    free(s->mini_pos); free(s->mini_kmer); free(s->mini_fwd); free(s->snp_pos); free(s->snp_kmer); free(s->codes);
+    memset(s, 0, sizeof(*s));
+}
+static void push_mini(sketch_t *s, uint32_t pos, uint64_t kmer, uint8_t fwd) {
+    if (s->n_mini == s->cap_mini) {
+        s->cap_mini = s->cap_mini ? s->cap_mini * 2 : 64;
+        s->mini_pos = (uint32_t *)realloc(s->mini_pos, s->cap_mini * sizeof(uint32_t));
+        s->mini_kmer = (uint64_t *)realloc(s->mini_kmer, s->cap_mini * sizeof(uint64_t));
+        s->mini_fwd = (uint8_t *)realloc(s->mini_fwd, s->cap_mini);
+    }
+    s->mini_pos[s->n_mini] = pos; s->mini_kmer[s->n_mini] = kmer; s->mini_fwd[s->n_mini] = fwd; s->n_mini++;
+}
+static void push_snp(sketch_t *s, uint32_t pos, uint64_t kmer) {
+    if (s->n_snp == s->cap_snp) {
+        s->cap_snp = s->cap_snp ? s->cap_snp * 2 : 64;
+        s->snp_pos = (uint32_t *)realloc(s->snp_pos, s->cap_snp * sizeof(uint32_t));
+        s->snp_kmer = (uint64_t *)realloc(s->snp_kmer, s->cap_snp * sizeof(uint64_t));
+    }
+    s->snp_pos[s->n_snp] = pos; s->snp_kmer[s->n_snp] = kmer; s->n_snp++;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* a3: get_twin_read_syncmer  (src/seeding.rs:317-658)                                  */
+/* ------------------------------------------------------------------------------------ */
+static void sketch_one(const so_params *p, const u64map *snpmer_set, const uint8_t *string, const uint8_t *qualities,
+                       size_t len, sketch_t *out) {
+    memset(out, 0, sizeof(*out));
+    const int k = p->k;
+    out->est_id = NAN;
+    if (len < (size_t)k) { out->ok = 0; return; }           /* :339-341 */
+    out->ok = 1;
+    out->len = len;
+
+    uint64_t rolling_kmer_f = 0, rolling_kmer_r = 0;
+    const int marker_reverse_shift_dist = 2 * (k - 1);
+    const uint64_t split_mask = so_split_mask(k);                          /* :353 */
+    const uint64_t marker_mask = UINT64_MAX >> (64 - 2 * k);               /* :354 */
+    const uint64_t marker_rev_mask = ~((uint64_t)3 << (2 * k - 2));        /* :355 */
+    const int mid_k = k / 2;
+
+    const int s = k - p->c + 1;                                            /* :363 */
+    const uint64_t s_mask = UINT64_MAX >> (64 - 2 * s);
+    const uint64_t s_rev_mask = ~((uint64_t)3 << (2 * s - 2));
+    const int s_reverse_shift_dist = 2 * (s - 1);
+    const int win = k - s + 1;                                             /* :368 */
+
+    uint64_t *window = (uint64_t *)malloc((size_t)(win + 1) * sizeof(uint64_t)); /* the VecDeque */
+    int wlen = 0;
+    uint64_t rolling_s_f = 0, rolling_s_r = 0;
+
+    int all_equal_q = 0;                                                   /* :372-380 */
+    if (qualities) {
+        all_equal_q = 1;
+        for (size_t i = 1; i < len; i++) if (qualities[i] != qualities[0]) { all_equal_q = 0; break; }
+    }
+
+    for (int i = 0; i < k - 1; i++) {                                      /* :383-398 */
+        uint64_t nuc_f = so_encode_base(string[i]);
+        uint64_t nuc_r = 3 - nuc_f;
+        rolling_kmer_f <<= 2; rolling_kmer_f |= nuc_f;
+        rolling_kmer_r >>= 2; rolling_kmer_r |= nuc_r << marker_reverse_shift_dist;
+        if (i < s - 1) {
+            rolling_s_f <<= 2; rolling_s_f |= nuc_f;
+            rolling_s_r >>= 2; rolling_s_r |= nuc_r << s_reverse_shift_dist;
+        }
+    }
+
+    /* all SNPmer hits (pre-dedup) + splitmer multiplicities */
+    u64map dedup; u64map_init(&dedup, 64);
+    sketch_t hits; memset(&hits, 0, sizeof(hits));
+
+    for (size_t i = (size_t)k - 1; i < len; i++) {                         /* :413 */
+        uint64_t nuc_f = so_encode_base(string[i]);
+        uint64_t nuc_r = 3 - nuc_f;
+        rolling_kmer_f <<= 2; rolling_kmer_f |= nuc_f; rolling_kmer_f &= marker_mask;
+        rolling_kmer_r >>= 2; rolling_kmer_r &= marker_rev_mask; rolling_kmer_r |= nuc_r << marker_reverse_shift_dist;
+
+        uint64_t split_f = rolling_kmer_f & split_mask, split_r = rolling_kmer_r & split_mask;
+        int canonical_marker = split_f < split_r;                          /* :429 tie -> reverse */
+        uint64_t canonical_kmer = canonical_marker ? rolling_kmer_f : rolling_kmer_r;
+
+        rolling_s_f <<= 2; rolling_s_f |= nuc_f; rolling_s_f &= s_mask;   /* :437-443 */
+        rolling_s_r >>= 2; rolling_s_r &= s_rev_mask; rolling_s_r |= nuc_r << s_reverse_shift_dist;
+        uint64_t canonical_s = rolling_s_f < rolling_s_r ? rolling_s_f : rolling_s_r;
+        uint64_t hash = so_mm_hash64(canonical_s);
+
+        window[wlen++] = hash;                                             /* :455-458 */
+        if (wlen > win) { memmove(window, window + 1, (size_t)(wlen - 1) * sizeof(uint64_t)); wlen--; }
+
+        /* blockmers (:461-505) are skipped: the blockmer set is empty on this path
+         * (src/kmer_comp.rs:59; --use-blockmers is a hidden flag, src/cli.rs:160-162). */
+
+        if (snpmer_set && u64map_slot((u64map *)snpmer_set, canonical_kmer, 0)) {   /* :509 */
+            int mid_base_qval = 60;
+            if (qualities) mid_base_qval = (int)qualities[i + 1 + mid_k - k] - 33;  /* :510-515 */
+            if (mid_base_qval > p->min_bq || all_equal_q)                            /* :517 strict > */
+                push_snp(&hits, (uint32_t)(i + 1 - k), canonical_kmer);
+            if (dedup.n * 2 + 2 >= dedup.cap) {                                     /* grow */
+                u64map bigger; u64map_init(&bigger, dedup.cap);
+                for (size_t t = 0; t < dedup.cap; t++)
+                    if (dedup.keys[t] != UINT64_MAX) *u64map_slot(&bigger, dedup.keys[t], 1) = dedup.vals[t];
+                u64map_free(&dedup); dedup = bigger;
+            }
+            *u64map_slot(&dedup, canonical_kmer & split_mask, 1) += 1;             /* :522-524 */
+        }
+
+        if (wlen == win) {                                                 /* :527-543 */
+            int middle_idx = (k - s) / 2;
+            uint64_t middle_hash = window[middle_idx];
+            int syncmer = 1;
+            for (int j = 0; j < wlen; j++)
+                if (j != middle_idx && window[j] <= middle_hash) { syncmer = 0; break; }
+            if (syncmer) push_mini(out, (uint32_t)(i + 1 - k), canonical_kmer, (uint8_t)canonical_marker);
+        }
+    }
+
+    for (size_t t = 0; t < hits.n_snp; t++) {                              /* :550-568 DEDUP_SNPMERS */
+        uint32_t *cnt = u64map_slot(&dedup, hits.snp_kmer[t] & split_mask, 0);
+        if (cnt && *cnt == 1) push_snp(out, hits.snp_pos[t], hits.snp_kmer[t]);
+    }
+    sketch_free(&hits);
+    u64map_free(&dedup);
+    free(window);
+
+    if (qualities && !all_equal_q) {                                       /* :570-576, :801-817 */
+        double sum = 0.0; size_t count = 0;
+        for (size_t i = 0; i < len; i++) {
+            double q = (double)((int)qualities[i] - 33);
+            double pr = pow(10.0, -q / 10.0);
+            sum += pr; count++;
+        }
+        out->est_id = 100. - (sum / (double)count * 100.);
+    }
+
+    out->codes = (uint8_t *)malloc(len);                                   /* :604-626 non-ACGT -> A */
+    for (size_t i = 0; i < len; i++) out->codes[i] = so_encode_base(string[i]);
+}
+
+int so_sketch_batch(const so_params *p, const uint64_t *snpmers, size_t n_snpmers,
+                    const uint8_t *bases, const uint8_t *quals, const uint64_t *offsets, size_t n_seqs,
+                    uint8_t *status, double *est_id,
+                    uint64_t *mini_offsets, uint32_t *mini_pos, uint64_t *mini_kmer, uint8_t *mini_fwd, size_t mini_cap,
+                    uint64_t *snp_offsets, uint32_t *snp_pos, uint64_t *snp_kmer, size_t snp_cap,
+                    uint8_t *codes) {
+    u64map set; u64map_init(&set, n_snpmers);
+    for (size_t i = 0; i < n_snpmers; i++) u64map_slot(&set, snpmers[i], 1);
+    size_t nm = 0, ns = 0; int rc = 0;
+    mini_offsets[0] = 0; snp_offsets[0] = 0;
+    for (size_t r = 0; r < n_seqs; r++) {
+        size_t off = offsets[r], len = offsets[r + 1] - off;
+        sketch_t sk; sketch_one(p, &set, bases + off, quals ? quals + off : NULL, len, &sk);
+        status[r] = sk.ok ? 0 : SO_TOO_SHORT;
+        if (est_id) est_id[r] = sk.est_id;
+        if (sk.ok) {
+            if (nm + sk.n_mini > mini_cap || ns + sk.n_snp > snp_cap) { rc = -1; sketch_free(&sk); break; }
+            for (size_t t = 0; t < sk.n_mini; t++) {
+                mini_pos[nm + t] = sk.mini_pos[t]; mini_kmer[nm + t] = sk.mini_kmer[t];
+                if (mini_fwd) mini_fwd[nm + t] = sk.mini_fwd[t];
+            }
+            for (size_t t = 0; t < sk.n_snp; t++) { snp_pos[ns + t] = sk.snp_pos[t]; snp_kmer[ns + t] = sk.snp_kmer[t]; }
+            nm += sk.n_mini; ns += sk.n_snp;
+            if (codes) memcpy(codes + off, sk.codes, len);
+        } else if (codes) {
+            for (size_t t = 0; t < len; t++) codes[off + t] = so_encode_base(bases[off + t]);
+        }
+        mini_offsets[r + 1] = nm; snp_offsets[r + 1] = ns;
+        sketch_free(&sk);
+    }
+    u64map_free(&set);
+    return rc;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* context: ASV sketches + SNPmer inverted index                                        */
+/* ------------------------------------------------------------------------------------ */
+typedef struct { uint64_t splitmer; uint32_t asv; uint64_t kmer; } idx_entry;
+
+typedef struct {
+    uint8_t *codes; size_t len;
+    uint64_t *mset; uint8_t *mset_fwd; size_t n_mset;   /* distinct minimizer k-mers, sorted; fwd-any flag */
+} asv_t;
+
+struct so_ctx {
+    so_params p;
+    u64map snpmer_set;
+    asv_t *asvs; size_t n_asv;
+    idx_entry *index; size_t n_index;                   /* sorted by splitmer */
+};
+
+so_ctx *so_create(const so_params *p, const uint64_t *snpmers, size_t n_snpmers) {
+    so_ctx *c = (so_ctx *)calloc(1, sizeof(so_ctx));
+    c->p = *p;
+    u64map_init(&c->snpmer_set, n_snpmers);
+    for (size_t i = 0; i < n_snpmers; i++) u64map_slot(&c->snpmer_set, snpmers[i], 1);
+    return c;
+}
+
+static void free_asvs(so_ctx *c) {
+    for (size_t i = 0; i < c->n_asv; i++) { free(c->asvs[i].codes); free(c->asvs[i].mset); free(c->asvs[i].mset_fwd); }
+    free(c->asvs); free(c->index);
+    c->asvs = NULL; c->index = NULL; c->n_asv = 0; c->n_index = 0;
+}
+void so_destroy(so_ctx *c) {
+    if (!c) return;
+    free_asvs(c); u64map_free(&c->snpmer_set); free(c);
+}
+size_t so_num_asvs(const so_ctx *c) { return c->n_asv; }
+
+static int cmp_u64(const void *a, const void *b) {
+    uint64_t x = *(const uint64_t *)a, y = *(const uint64_t *)b;
+    return x < y ? -1 : x > y;
+}
+static int cmp_idx(const void *a, const void *b) {
+    const idx_entry *x = (const idx_entry *)a, *y = (const idx_entry *)b;
+    if (x->splitmer != y->splitmer) return x->splitmer < y->splitmer ? -1 : 1;
+    return x->asv < y->asv ? -1 : x->asv > y->asv;
+}
+
+/* distinct k-mers of a sketch, sorted; flag = OR of the forward flags of all occurrences */
+static void build_mset(const sketch_t *sk, uint64_t **mset, uint8_t **fwd, size_t *n) {
+    size_t cnt = sk->n_mini;
+    uint64_t *tmp = (uint64_t *)malloc((cnt + 1) * sizeof(uint64_t));
+    for (size_t i = 0; i < cnt; i++) tmp[i] = (sk->mini_kmer[i] << 1) | (uint64_t)(sk->mini_fwd[i] & 1);
+    qsort(tmp, cnt, sizeof(uint64_t), cmp_u64);
+    uint64_t *keys = (uint64_t *)malloc((cnt + 1) * sizeof(uint64_t));
+    uint8_t *flags = (uint8_t *)malloc(cnt + 1);
+    size_t m = 0;
+    for (size_t i = 0; i < cnt; i++) {
+        uint64_t key = tmp[i] >> 1; uint8_t f = (uint8_t)(tmp[i] & 1);
+        if (m > 0 && keys[m - 1] == key) flags[m - 1] |= f;
+        else { keys[m] = key; flags[m] = f; m++; }
+    }
+    free(tmp);
+    *mset = keys; *fwd = flags; *n = m;
+}
+
+/* src/types.rs:622-663 kmer_from_position: canonical by splitmer, tie -> forward */
+static uint64_t kmer_from_position(const uint8_t *codes, uint32_t pos, int k) {
+    uint64_t kmer = 0;
+    for (int t = 0; t < k; t++) kmer = (kmer << 2) | codes[pos + t];
+    uint64_t reverse_kmer = so_kmer_revcomp(kmer, k);
+    uint64_t mid_mask = so_split_mask(k);
+    if ((reverse_kmer & mid_mask) < (kmer & mid_mask)) return reverse_kmer;
+    return kmer;
+}
+
+/* src/kmer_comp.rs:39-66 (twin_reads_from_fasta) + src/alignment.rs:1754-1765 (index) */
+int so_load_asvs(so_ctx *c, const uint8_t *bases, const uint64_t *offsets, size_t n_asv) {
+    free_asvs(c);
+    c->asvs = (asv_t *)calloc(n_asv ? n_asv : 1, sizeof(asv_t));
+    size_t cap = 1024; c->index = (idx_entry *)malloc(cap * sizeof(idx_entry)); c->n_index = 0;
+    const uint64_t mask = so_split_mask(c->p.k);
+    size_t kept = 0;
+    for (size_t a = 0; a < n_asv; a++) {
+        size_t off = offsets[a], len = offsets[a + 1] - off;
+        sketch_t sk; sketch_one(&c->p, &c->snpmer_set, bases + off, NULL, len, &sk);
+        if (!sk.ok) { sketch_free(&sk); return -2; }   /* reference would silently drop it; the ABI rejects */
+        asv_t *A = &c->asvs[kept];
+        A->codes = sk.codes; sk.codes = NULL; A->len = len;
+        build_mset(&sk, &A->mset, &A->mset_fwd, &A->n_mset);
+        for (size_t t = 0; t < sk.n_snp; t++) {        /* asv_read.snpmers_vec(): re-extracted from positions */
+            uint64_t kmer = kmer_from_position(A->codes, sk.snp_pos[t], c->p.k);
+            if (c->n_index == cap) { cap *= 2; c->index = (idx_entry *)realloc(c->index, cap * sizeof(idx_entry)); }
+            c->index[c->n_index].splitmer = kmer & mask;
+            c->index[c->n_index].asv = (uint32_t)kept;
+            c->index[c->n_index].kmer = kmer;
+            c->n_index++;
+        }
+        sketch_free(&sk);
+        kept++;
+    }
+    c->n_asv = kept;
+    qsort(c->index, c->n_index, sizeof(idx_entry), cmp_idx);
+    return 0;
+}
+
+static void index_range(const so_ctx *c, uint64_t splitmer, size_t *lo_out, size_t *hi_out) {
+    size_t lo = 0, hi = c->n_index;
+    while (lo < hi) { size_t mid = (lo + hi) / 2; if (c->index[mid].splitmer < splitmer) lo = mid + 1; else hi = mid; }
+    size_t start = lo; hi = c->n_index;
+    while (lo < hi) { size_t mid = (lo + hi) / 2; if (c->index[mid].splitmer <= splitmer) lo = mid + 1; else hi = mid; }
+    *lo_out = start; *hi_out = lo;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* a8-a10: candidates for one sketched read                                             */
+/* ------------------------------------------------------------------------------------ */
+typedef struct { uint32_t asv, mm, mini; uint8_t strand; } cand_t;
+typedef struct { cand_t *v; size_t n, cap; } cand_vec;
+static void cand_push(cand_vec *cv, cand_t x) {
+    if (cv->n == cv->cap) { cv->cap = cv->cap ? cv->cap * 2 : 8; cv->v = (cand_t *)realloc(cv->v, cv->cap * sizeof(cand_t)); }
+    cv->v[cv->n++] = x;
+}
+static int cmp_cand_asv(const void *a, const void *b) {
+    const cand_t *x = (const cand_t *)a, *y = (const cand_t *)b;
+    return x->asv < y->asv ? -1 : x->asv > y->asv;
+}
+
+/* scratch: hits[A], mism[A] zeroed on entry and exit */
+static int candidates_one(const so_ctx *c, const sketch_t *rd, uint32_t *hits, uint32_t *mism, cand_vec *kept) {
+    const int k = c->p.k;
+    const uint64_t mask = so_split_mask(k);
+    kept->n = 0;
+
+    /* find_compatible_candidates, src/asv_cluster.rs:356-383 (matches are unused downstream) */
+    uint32_t *touched = (uint32_t *)malloc((c->n_asv + 1) * sizeof(uint32_t)); size_t n_touched = 0;
+    for (size_t t = 0; t < rd->n_snp; t++) {
+        uint64_t q = rd->snp_kmer[t];
+        size_t lo, hi; index_range(c, q & mask, &lo, &hi);
+        for (size_t e = lo; e < hi; e++) {
+            uint32_t a = c->index[e].asv;
+            if (hits[a] == 0) touched[n_touched++] = a;
+            hits[a]++;
+            if (q != c->index[e].kmer) mism[a]++;
+        }
+    }
+
+    /* read_minimizers: FxHashSet<Kmer48> of the UNPRUNED minimizer_kmers, src/alignment.rs:1788 */
+    uint64_t *rset; uint8_t *rfwd; size_t n_rset;
+    build_mset(rd, &rset, &rfwd, &n_rset);
+
+    const double min_frac = so_powi(c->p.min_mini_frac_base, k);          /* (0.950f64).powi(k) :1806 */
+    cand_vec scores = {0, 0, 0};
+    for (size_t ti = 0; ti < n_touched; ti++) {                            /* :1796-1814 */
+        uint32_t a = touched[ti];
+        const asv_t *A = &c->asvs[a];
+        size_t m = 0, same = 0, opp = 0;
+        for (size_t x = 0; x < n_rset; x++) {
+            size_t lo = 0, hi = A->n_mset;
+            while (lo < hi) { size_t mid = (lo + hi) / 2; if (A->mset[mid] < rset[x]) lo = mid + 1; else hi = mid; }
+            if (lo < A->n_mset && A->mset[lo] == rset[x]) {
+                m++;
+                if (rfwd[x] == A->mset_fwd[lo]) same++; else opp++;
+            }
+        }
+        if (m == 0) continue;
+        size_t mn = n_rset < A->n_mset ? n_rset : A->n_mset;
+        if ((double)m / (double)mn < min_frac) continue;
+        cand_t cd; cd.asv = a; cd.mm = mism[a]; cd.mini = (uint32_t)m; cd.strand = (uint8_t)(opp > same);
+        cand_push(&scores, cd);
+    }
+    for (size_t ti = 0; ti < n_touched; ti++) { hits[touched[ti]] = 0; mism[touched[ti]] = 0; }
+    free(touched); free(rset); free(rfwd);
+
+    if (scores.n == 0) { free(scores.v); return SO_NO_CANDIDATE; }        /* :1817-1820 */
+
+    uint32_t lowest = UINT32_MAX; size_t n_ok = 0;                         /* :1829-1843 */
+    for (size_t i = 0; i < scores.n; i++) {
+        double ratio = (double)scores.v[i].mm / (double)scores.v[i].mini / (double)c->p.c;   /* :1811 */
+        if (ratio <= c->p.ratio_thresh) { n_ok++; if (scores.v[i].mm < lowest) lowest = scores.v[i].mm; }
+        else scores.v[i].asv = UINT32_MAX;
+    }
+    if (n_ok == 0) { free(scores.v); return SO_RATIO_FILTERED; }
+    for (size_t i = 0; i < scores.n; i++)
+        if (scores.v[i].asv != UINT32_MAX && scores.v[i].mm == lowest) cand_push(kept, scores.v[i]);
+    free(scores.v);
+    qsort(kept->v, kept->n, sizeof(cand_t), cmp_cand_asv);
+    return 0;
+}
+
+int so_find_candidates(so_ctx *c, const uint8_t *bases, const uint8_t *quals, const uint64_t *offsets, size_t n_reads,
+                       uint8_t *cand_status, uint64_t *cand_offsets,
+                       uint32_t *cand_asv, uint32_t *cand_mm, uint32_t *cand_mini, uint8_t *cand_strand, size_t cand_cap) {
+    uint32_t *hits = (uint32_t *)calloc(c->n_asv + 1, sizeof(uint32_t));
+    uint32_t *mism = (uint32_t *)calloc(c->n_asv + 1, sizeof(uint32_t));
+    cand_vec kept = {0, 0, 0};
+    size_t n = 0; int rc = 0;
+    cand_offsets[0] = 0;
+    for (size_t r = 0; r < n_reads; r++) {
+        size_t off = offsets[r], len = offsets[r + 1] - off;
+        sketch_t sk; sketch_one(&c->p, &c->snpmer_set, bases + off, quals ? quals + off : NULL, len, &sk);
+        if (!sk.ok) { cand_status[r] = SO_TOO_SHORT; cand_offsets[r + 1] = n; sketch_free(&sk); continue; }
+        int st = candidates_one(c, &sk, hits, mism, &kept);
+        cand_status[r] = (uint8_t)st;
+        if (st == 0) {
+            if (n + kept.n > cand_cap) { rc = -1; sketch_free(&sk); break; }
+            for (size_t i = 0; i < kept.n; i++) {
+                cand_asv[n + i] = kept.v[i].asv; cand_mm[n + i] = kept.v[i].mm;
+                cand_mini[n + i] = kept.v[i].mini; cand_strand[n + i] = kept.v[i].strand;
+            }
+            n += kept.n;
+        }
+        cand_offsets[r + 1] = n;
+        sketch_free(&sk);
+    }
+    free(hits); free(mism); free(kept.v);
+    return rc;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* a11: banded, both-ends-free unit-cost edit distance (SURVEY.md 8c "S2")              */
+/*                                                                                      */
+/*   rows i = 0..n over the ASV a[1..n], columns j = 0..m over the read r[1..m]         */
+/*   (reverse-complemented when strand==1); cell (i,j) exists iff |i-j| <= B.           */
+/*   D[0][j] = 0, D[i][0] = 0 (in band); D[i][j] = min(D[i-1][j-1] + (a_i != r_j),      */
+/*   D[i-1][j] + 1, D[i][j-1] + 1) over existing cells.                                 */
+/*   NM = min over end cells {(n,j)} U {(i,m)}; tie -> largest i+j, then the last-row   */
+/*   cell.  Traceback preference: diagonal, then D (consume ASV), then I (consume read);*/
+/*   stops at the first cell with i==0 or j==0.                                         */
+/* ------------------------------------------------------------------------------------ */
+#define SO_INF (1 << 29)
+
+typedef struct {
+    int32_t nm, asv_end, read_end, asv_start, read_start;
+    uint32_t *cigar; size_t n_cigar, cap_cigar;
+} aln_t;
+
+static void cigar_push(aln_t *al, int op) {
+    if (al->n_cigar > 0 && (int)(al->cigar[al->n_cigar - 1] & 15u) == op) { al->cigar[al->n_cigar - 1] += 16u; return; }
+    if (al->n_cigar == al->cap_cigar) {
+        al->cap_cigar = al->cap_cigar ? al->cap_cigar * 2 : 16;
+        al->cigar = (uint32_t *)realloc(al->cigar, al->cap_cigar * sizeof(uint32_t));
+    }
+    al->cigar[al->n_cigar++] = (1u << 4) | (uint32_t)op;
+}
+
+static void banded_align(const uint8_t *a, int n, const uint8_t *r, int m, int B, int want_cigar, aln_t *out) {
+    const int W = 2 * B + 1;
+    int32_t *D = (int32_t *)malloc((size_t)(n + 1) * (size_t)W * sizeof(int32_t));
+#define CELL(i, j) D[(size_t)(i) * (size_t)W + (size_t)((j) - (i) + B)]
+#define INBAND(i, j) ((i) >= 0 && (j) >= 0 && (i) <= n && (j) <= m && (j) - (i) <= B && (i) - (j) <= B)
+    for (int i = 0; i <= n; i++) {
+        int jlo = i - B < 0 ? 0 : i - B, jhi = i + B > m ? m : i + B;
+        for (int j = jlo; j <= jhi; j++) {
+            if (i == 0 || j == 0) { CELL(i, j) = 0; continue; }
+            int32_t best = CELL(i - 1, j - 1) + (a[i - 1] != r[j - 1]);
+            if (INBAND(i - 1, j)) { int32_t v = CELL(i - 1, j) + 1; if (v < best) best = v; }
+            if (INBAND(i, j - 1)) { int32_t v = CELL(i, j - 1) + 1; if (v < best) best = v; }
+            CELL(i, j) = best;
+        }
+    }
+    int32_t bd = SO_INF; int bi = -1, bj = -1;
+    {
+        int jlo = n - B < 0 ? 0 : n - B, jhi = n + B > m ? m : n + B;
+        for (int j = jlo; j <= jhi; j++) {           /* last-row cells */
+            int32_t d = CELL(n, j);
+            if (d < bd || (d == bd && n + j > bi + bj)) { bd = d; bi = n; bj = j; }
+        }
+        int ilo = m - B < 0 ? 0 : m - B, ihi = m + B > n ? n : m + B;
+        for (int i = ilo; i <= ihi; i++) {           /* last-column cells; a last-row cell wins an i+j tie */
+            int32_t d = CELL(i, m);
+            if (d < bd || (d == bd && i + m > bi + bj)) { bd = d; bi = i; bj = m; }
+        }
+    }
+    out->nm = bd; out->asv_end = bi; out->read_end = bj;
+    out->asv_start = -1; out->read_start = -1; out->n_cigar = 0;
+    if (want_cigar) {
+        int i = bi, j = bj;
+        aln_t rev; memset(&rev, 0, sizeof(rev));
+        while (i > 0 && j > 0) {
+            int32_t d = CELL(i, j);
+            if (d == CELL(i - 1, j - 1) + (a[i - 1] != r[j - 1])) { cigar_push(&rev, 0); i--; j--; }
+            else if (INBAND(i - 1, j) && d == CELL(i - 1, j) + 1) { cigar_push(&rev, 2); i--; }
+            else { cigar_push(&rev, 1); j--; }
+        }
+        out->asv_start = i; out->read_start = j;
+        for (size_t t = rev.n_cigar; t > 0; t--) {
+            uint32_t e = rev.cigar[t - 1];
+            if (out->n_cigar == out->cap_cigar) {
+                out->cap_cigar = out->cap_cigar ? out->cap_cigar * 2 : 16;
+                out->cigar = (uint32_t *)realloc(out->cigar, out->cap_cigar * sizeof(uint32_t));
+            }
+            out->cigar[out->n_cigar++] = e;
+        }
+        free(rev.cigar);
+    }
+    free(D);
+#undef CELL
+#undef INBAND
+}
+
+static uint8_t *oriented_codes(const uint8_t *codes, size_t len, int strand) {
+    uint8_t *o = (uint8_t *)malloc(len ? len : 1);
+    if (!strand) memcpy(o, codes, len);
+    else for (size_t i = 0; i < len; i++) o[i] = (uint8_t)(3 - codes[len - 1 - i]);
+    return o;
+}
+
+int so_align_pairs(so_ctx *c, const uint8_t *bases, const uint64_t *offsets, size_t n_reads,
+                   const uint32_t *pair_read, const uint32_t *pair_asv, const uint8_t *pair_strand, size_t n_pairs,
+                   int32_t *nm, int32_t *asv_end, int32_t *read_end,
+                   int want_cigar, int32_t *asv_start, int32_t *read_start,
+                   uint64_t *cigar_offsets, uint32_t *cigar, size_t cigar_cap) {
+    size_t nc = 0; int rc = 0;
+    if (want_cigar) cigar_offsets[0] = 0;
+    for (size_t pi = 0; pi < n_pairs; pi++) {
+        uint32_t r = pair_read[pi], a = pair_asv[pi];
+        if (r >= n_reads || a >= c->n_asv) return -3;
+        size_t off = offsets[r], len = offsets[r + 1] - off;
+        uint8_t *codes = (uint8_t *)malloc(len ? len : 1);
+        for (size_t t = 0; t < len; t++) codes[t] = so_encode_base(bases[off + t]);
+        uint8_t *rd = oriented_codes(codes, len, pair_strand[pi]);
+        aln_t al; memset(&al, 0, sizeof(al));
+        banded_align(c->asvs[a].codes, (int)c->asvs[a].len, rd, (int)len, c->p.band, want_cigar, &al);
+        nm[pi] = al.nm; asv_end[pi] = al.asv_end; read_end[pi] = al.read_end;
+        if (want_cigar) {
+            asv_start[pi] = al.asv_start; read_start[pi] = al.read_start;
+            if (nc + al.n_cigar > cigar_cap) rc = -1;
+            else { memcpy(cigar + nc, al.cigar, al.n_cigar * sizeof(uint32_t)); nc += al.n_cigar; }
+            cigar_offsets[pi + 1] = nc;
+        }
+        free(al.cigar); free(rd); free(codes);
+        if (rc) break;
+    }
+    return rc;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* whole path, src/alignment.rs:1786-1925 (Stage 7b duplicate :2095-2171)               */
+/* ------------------------------------------------------------------------------------ */
+int so_map_reads(so_ctx *c, const uint8_t *bases, const uint8_t *quals, const uint64_t *offsets,
+                 const uint32_t *file_idx, size_t n_reads, int n_samples,
+                 uint8_t *status, int32_t *best_nm_out, uint64_t *class_offsets, uint32_t *class_asv, size_t class_cap,
+                 uint64_t *unambig, uint64_t *ambig, uint64_t *leq10, uint64_t *totals, uint64_t *sample_singleton,
+                 uint64_t *dp_cells, int n_threads) {
+    const size_t A = c->n_asv;
+    uint32_t **cls = (uint32_t **)calloc(n_reads ? n_reads : 1, sizeof(uint32_t *));
+    uint32_t *cls_n = (uint32_t *)calloc(n_reads ? n_reads : 1, sizeof(uint32_t));
+    uint64_t cells_total = 0;
+#ifdef _OPENMP
+    if (n_threads > 0) omp_set_num_threads(n_threads);
+#else
+    (void)n_threads;
+#endif
+#pragma omp parallel reduction(+ : cells_total)
+    {
+        uint32_t *hits = (uint32_t *)calloc(A + 1, sizeof(uint32_t));
+        uint32_t *mism = (uint32_t *)calloc(A + 1, sizeof(uint32_t));
+        cand_vec kept = {0, 0, 0};
+#pragma omp for schedule(dynamic, 16)
+        for (long long rr = 0; rr < (long long)n_reads; rr++) {
+            size_t r = (size_t)rr;
+            size_t off = offsets[r], len = offsets[r + 1] - off;
+            best_nm_out[r] = INT32_MAX;
+            sketch_t sk; sketch_one(&c->p, &c->snpmer_set, bases + off, quals ? quals + off : NULL, len, &sk);
+            if (!sk.ok) { status[r] = SO_TOO_SHORT; sketch_free(&sk); continue; }
+            int st = candidates_one(c, &sk, hits, mism, &kept);
+            if (st != 0) { status[r] = (uint8_t)st; sketch_free(&sk); continue; }
+
+            /* :1846-1863 -- NM per kept candidate (north-star DP instead of minimap2) */
+            int32_t *nms = (int32_t *)malloc(kept.n * sizeof(int32_t));
+            uint8_t *fw = oriented_codes(sk.codes, len, 0), *rv = oriented_codes(sk.codes, len, 1);
+            for (size_t i = 0; i < kept.n; i++) {
+                const asv_t *Av = &c->asvs[kept.v[i].asv];
+                aln_t al; memset(&al, 0, sizeof(al));
+                if (c->p.strand_mode == 1) {
+                    aln_t al2; memset(&al2, 0, sizeof(al2));
+                    banded_align(Av->codes, (int)Av->len, fw, (int)len, c->p.band, 0, &al);
+                    banded_align(Av->codes, (int)Av->len, rv, (int)len, c->p.band, 0, &al2);
+                    nms[i] = al2.nm < al.nm ? al2.nm : al.nm;
+                    cells_total += 2ull * Av->len * (uint64_t)(2 * c->p.band + 1);
+                } else {
+                    banded_align(Av->codes, (int)Av->len, kept.v[i].strand ? rv : fw, (int)len, c->p.band, 0, &al);
+                    nms[i] = al.nm;
+                    cells_total += (uint64_t)Av->len * (uint64_t)(2 * c->p.band + 1);
+                }
+            }
+            free(fw); free(rv);
+            /* :1865-1873 best_nm and its ties; kept is sorted by asv id so the class is sorted (:1893) */
+            int32_t best = INT32_MAX;
+            for (size_t i = 0; i < kept.n; i++) if (nms[i] < best) best = nms[i];
+            size_t cn = 0;
+            cls[r] = (uint32_t *)malloc((kept.n + 1) * sizeof(uint32_t));
+            for (size_t i = 0; i < kept.n; i++) if (nms[i] == best) cls[r][cn++] = kept.v[i].asv;
+            cls_n[r] = (uint32_t)cn;
+            free(nms);
+            if (cn == 0) { status[r] = SO_NO_ALIGNMENT; free(cls[r]); cls[r] = NULL; }
+            else { status[r] = SO_ASSIGNED; best_nm_out[r] = best; }
+            sketch_free(&sk);
+        }
+        free(hits); free(mism); free(kept.v);
+    }
+    /* :1890-1920 counters, serial so the output is deterministic */
+    size_t n = 0; int rc = 0;
+    class_offsets[0] = 0;
+    for (size_t r = 0; r < n_reads; r++) {
+        if (status[r] == SO_ASSIGNED) {
+            uint32_t cn = cls_n[r];
+            if (n + cn > class_cap) { rc = -1; }
+            else {
+                memcpy(class_asv + n, cls[r], cn * sizeof(uint32_t)); n += cn;
+                if (cn == 1) {
+                    unambig[cls[r][0]]++;
+                    if (sample_singleton) {
+                        uint32_t s = file_idx ? file_idx[r] : 0;
+                        if ((int)s < n_samples) sample_singleton[(size_t)s * A + cls[r][0]]++;
+                    }
+                } else for (uint32_t t = 0; t < cn; t++) ambig[cls[r][t]]++;
+                if (best_nm_out[r] <= 10) for (uint32_t t = 0; t < cn; t++) leq10[cls[r][t]]++;
+                totals[0]++;
+            }
+        } else if (status[r] != SO_TOO_SHORT) {
+            totals[1]++;
+        }
+        class_offsets[r + 1] = n;
+        free(cls[r]);
+    }
+    free(cls); free(cls_n);
+    if (dp_cells) *dp_cells += cells_total;
+    return rc;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* a13-a14: EM, src/alignment.rs:1957-2038                                              */
+/* ------------------------------------------------------------------------------------ */
+int so_em(size_t n_asv, const uint64_t *cls_offsets, const uint32_t *cls_asv, const uint64_t *counts, size_t n_cls,
+          uint64_t total_assigned, double *abundances, uint64_t *depths) {
+    double *ab = (double *)malloc((n_asv + 1) * sizeof(double));
+    double *nw = (double *)malloc((n_asv + 1) * sizeof(double));
+    for (size_t a = 0; a < n_asv; a++) ab[a] = 1.0 / (double)n_asv;
+    const double convergence_threshold = 0.01 / (double)total_assigned;
+    int iteration = 0;
+    const int MAX_ITERATIONS = 10000;
+    while (1) {
+        iteration++;
+        for (size_t a = 0; a < n_asv; a++) nw[a] = 0.0;
+        for (size_t q = 0; q < n_cls; q++) {
+            double denominator = 0.0;
+            for (uint64_t e = cls_offsets[q]; e < cls_offsets[q + 1]; e++) denominator += ab[cls_asv[e]];
+            if (denominator > 0.0)
+                for (uint64_t e = cls_offsets[q]; e < cls_offsets[q + 1]; e++)
+                    nw[cls_asv[e]] += (double)counts[q] * ab[cls_asv[e]] / denominator;
+        }
+        double total_counts = 0.0;
+        for (size_t a = 0; a < n_asv; a++) total_counts += nw[a];
+        if (total_counts > 0.0) for (size_t a = 0; a < n_asv; a++) nw[a] /= (double)total_assigned;
+        double max_change = 0.0;
+        for (size_t a = 0; a < n_asv; a++) { double d = fabs(ab[a] - nw[a]); if (d > max_change) max_change = d; }
+        memcpy(ab, nw, n_asv * sizeof(double));
+        if (max_change < convergence_threshold || iteration >= MAX_ITERATIONS) break;
+    }
+    for (size_t a = 0; a < n_asv; a++) {
+        if (abundances) abundances[a] = ab[a];
+        if (depths) depths[a] = (uint64_t)round(ab[a] * (double)total_assigned);   /* f64::round: half away from zero */
+    }
+    free(ab); free(nw);
+    return iteration;
+}

@@ -1,0 +1,133 @@
+/*
+ * savont_oracle.h -- CPU oracle for the read-vs-ASV assignment path of savont v0.6.4.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This is a scalar, sequential C restatement of the
+ * reference's Rust logic (Stage 7 / 7b of `savont asv`).  Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load it; the product (libsavont_b200.so) never links or calls it.
+ *
+ * PARITY STATUS
+ *   - sketch (a1-a3), ASV index (a5-a7), candidate filter (a8-a10), tie/eq-class
+ *     counters (a12), EM + depths (a13-a14): restated line by line from the Rust
+ *     source; pinned by the reference's own known-answer tests (src/types.rs:1108-1140)
+ *     and by mm_hash64 / powi constants derived from the formulas.
+ *   - alignment NM (a11): the reference calls minimap2 2.30 (`lr:hq`) through the
+ *     minimap2 crate 0.1.31; that C library is NOT in /root/reference and no Rust or
+ *     minimap2 toolchain exists in this image, so its per-read NM cannot be
+ *     reproduced or checked.  The oracle implements the north-star definition instead
+ *     (banded, both-ends-free unit-cost edit distance, SURVEY.md 8c "S2").
+ *     ==> NM / CIGAR parity against the reference is UNPINNED ("parity unpinned").
+ *         GPU-vs-oracle parity is bit-exact.
+ *
+ * Every function cites the reference file:line it follows (paths relative to
+ * /root/reference/).
+ */
+#ifndef SAVONT_ORACLE_H
+#define SAVONT_ORACLE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct so_params {
+    int32_t k;            /* src/cli.rs:153-154  default 17 (odd) */
+    int32_t c;            /* src/cli.rs:83-84    default 11 */
+    int32_t l;            /* src/cli.rs:157-158  default 3 (blockmers: unused on this path) */
+    int32_t min_bq;       /* src/cli.rs:99-100   default 25 */
+    int32_t band;         /* DP half band B (|i-j| <= B) */
+    int32_t strand_mode;  /* 0 = orientation by minimizer seed vote, 1 = both strands, min NM */
+    double  ratio_thresh;        /* src/alignment.rs:1829 0.0050 */
+    double  min_mini_frac_base;  /* src/alignment.rs:1806 0.950 (raised to k) */
+} so_params;
+
+/* status codes of per-read assignment (shared with the product ABI) */
+enum {
+    SO_ASSIGNED = 0,   /* eq-class emitted                      src/alignment.rs:1890-1920 */
+    SO_NO_CANDIDATE = 1, /* asv_scores empty                    src/alignment.rs:1817-1820 */
+    SO_RATIO_FILTERED = 2, /* no candidate with ratio <= thresh src/alignment.rs:1835-1838 */
+    SO_NO_ALIGNMENT = 3, /* best_alns empty                     src/alignment.rs:1921-1924 */
+    SO_TOO_SHORT = 4   /* get_twin_read_syncmer returned None   src/seeding.rs:339-341 */
+};
+
+/* ---- primitives with known answers ------------------------------------------------ */
+uint8_t  so_encode_base(uint8_t b);                 /* src/types.rs:92-101 */
+uint64_t so_mm_hash64(uint64_t key);                /* src/seeding.rs:18-28 */
+uint64_t so_kmer_from_ascii(const char *s, int k);  /* src/types.rs:1118-1128 convention */
+uint64_t so_kmer_revcomp(uint64_t kmer, int k);     /* src/types.rs:559-568, 654 */
+void     so_kmer48_from_u64(uint64_t v, uint8_t out[6]); /* src/types.rs:112-127 */
+uint64_t so_kmer48_to_u64(const uint8_t in[6]);
+double   so_powi(double a, int b);                  /* compiler-rt __powidf2, used by f64::powi */
+uint64_t so_split_mask(int k);                      /* src/seeding.rs:353 */
+
+/* ---- a3: sketch a batch of sequences (src/seeding.rs:317-658) ------------------------
+ * bases/quals: concatenated ASCII; offsets[n+1].  quals may be NULL (FASTA / ASV side).
+ * Outputs are CSR; *_cap are capacities of the flat arrays.  mini_fwd[i]=1 iff the
+ * canonical k-mer equals the forward-strand k-mer at that position (b200 extension used
+ * for the strand vote).  codes: one 2-bit code per base (N->0).  est_id = NaN when None.
+ * Returns 0, or -1 if a capacity was too small.
+ */
+int so_sketch_batch(const so_params *p, const uint64_t *snpmers, size_t n_snpmers,
+                    const uint8_t *bases, const uint8_t *quals, const uint64_t *offsets, size_t n_seqs,
+                    uint8_t *status, double *est_id,
+                    uint64_t *mini_offsets, uint32_t *mini_pos, uint64_t *mini_kmer, uint8_t *mini_fwd, size_t mini_cap,
+                    uint64_t *snp_offsets, uint32_t *snp_pos, uint64_t *snp_kmer, size_t snp_cap,
+                    uint8_t *codes);
+
+/* ---- context: params + SNPmer set + ASV sketches/index (a5-a7) ---------------------- */
+typedef struct so_ctx so_ctx;
+so_ctx *so_create(const so_params *p, const uint64_t *snpmers, size_t n_snpmers);
+void    so_destroy(so_ctx *ctx);
+/* src/kmer_comp.rs:39-66 + src/alignment.rs:1754-1765 */
+int     so_load_asvs(so_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, size_t n_asv);
+size_t  so_num_asvs(const so_ctx *ctx);
+
+/* ---- a8-a10: candidate filter (src/asv_cluster.rs:356-383, src/alignment.rs:1786-1843)
+ * Per read: cand_status in {0 kept>0, SO_NO_CANDIDATE, SO_RATIO_FILTERED, SO_TOO_SHORT};
+ * kept candidates (minimum SNPmer mismatches among ratio<=thresh) sorted by asv id:
+ * cand_asv, cand_mm (snpmer mismatches), cand_mini (shared distinct minimizers),
+ * cand_strand (0 fwd / 1 rev, by seed vote).
+ */
+int so_find_candidates(so_ctx *ctx, const uint8_t *bases, const uint8_t *quals, const uint64_t *offsets, size_t n_reads,
+                       uint8_t *cand_status, uint64_t *cand_offsets,
+                       uint32_t *cand_asv, uint32_t *cand_mm, uint32_t *cand_mini, uint8_t *cand_strand, size_t cand_cap);
+
+/* ---- a11: banded both-ends-free edit distance (north-star definition) --
+ * pair i aligns read pair_read[i] (strand pair_strand[i]) against ASV pair_asv[i].
+ * nm, end cell (asv_end, read_end) always; with want_cigar also start cell and CIGAR
+ * (BAM encoding len<<4|op, op 0=M 1=I(read only) 2=D(ASV only)), CSR via cigar_offsets.
+ * Coordinates are in DP orientation (read reverse-complemented when strand==1).
+ */
+int so_align_pairs(so_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, size_t n_reads,
+                   const uint32_t *pair_read, const uint32_t *pair_asv, const uint8_t *pair_strand, size_t n_pairs,
+                   int32_t *nm, int32_t *asv_end, int32_t *read_end,
+                   int want_cigar, int32_t *asv_start, int32_t *read_start,
+                   uint64_t *cigar_offsets, uint32_t *cigar, size_t cigar_cap);
+
+/* ---- whole path: a3 + a8-a12 (src/alignment.rs:1786-1925; Stage 7b :2095-2171) ------
+ * file_idx may be NULL (single sample).  n_samples>=1.  Counters are ADDED to (caller zeroes).
+ * unambig/ambig/leq10: [A]; totals[0]=assigned, totals[1]=filtered;
+ * sample_singleton: [n_samples*A] counts of singleton classes per (sample, asv) (may be NULL).
+ * n_threads: OpenMP threads (<=0: all).
+ */
+int so_map_reads(so_ctx *ctx, const uint8_t *bases, const uint8_t *quals, const uint64_t *offsets,
+                 const uint32_t *file_idx, size_t n_reads, int n_samples,
+                 uint8_t *status, int32_t *best_nm, uint64_t *class_offsets, uint32_t *class_asv, size_t class_cap,
+                 uint64_t *unambig, uint64_t *ambig, uint64_t *leq10, uint64_t *totals, uint64_t *sample_singleton,
+                 uint64_t *dp_cells, int n_threads);
+
+/* ---- a13-a14: EM over equivalence classes (src/alignment.rs:1957-2038) ---------------
+ * classes in CSR (cls_offsets[n_cls+1], cls_asv), counts[n_cls]; total_assigned;
+ * out: abundances[A] (f64), depths[A] = round(ab*total).  Classes are iterated in the
+ * given order (the reference iterates a randomly seeded std::HashMap; parity target is
+ * the integer depths).  Returns the number of EM iterations.
+ */
+int so_em(size_t n_asv, const uint64_t *cls_offsets, const uint32_t *cls_asv, const uint64_t *counts, size_t n_cls,
+          uint64_t total_assigned, double *abundances, uint64_t *depths);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,102 @@
+"""Pure-Python second restatement of the sketch and of the banded
+both-ends-free edit distance, written independently of oracle/savont_oracle.c and used only
+to cross-check the C oracle on small inputs (tests/test_oracle.py)."""
+import math
+
+M64 = (1 << 64) - 1
+ENC = {ord('A'): 0, ord('a'): 0, ord('C'): 1, ord('c'): 1, ord('G'): 2, ord('g'): 2,
+       ord('T'): 3, ord('t'): 3, ord('U'): 3, ord('u'): 3, 1: 1, 2: 2, 3: 3}
+
+
+def enc(b):
+    return ENC.get(b, 0)
+
+
+def mm_hash64(key):
+    key = (~key + (key << 21)) & M64
+    key ^= key >> 24
+    key = (key + (key << 3) + (key << 8)) & M64
+    key ^= key >> 14
+    key = (key + (key << 2) + (key << 4)) & M64
+    key ^= key >> 28
+    key = (key + (key << 31)) & M64
+    return key
+
+
+def revcomp_kmer(x, k):
+    out = 0
+    for _ in range(k):
+        out = (out << 2) | (3 - (x & 3))
+        x >>= 2
+    return out
+
+
+def sketch(seq: bytes, qual, k, c, min_bq, snpmer_set):
+    L = len(seq)
+    if L < k:
+        return None
+    s = k - c + 1
+    W = k - s + 1
+    mid = (k - s) // 2
+    split_mask = M64 ^ (3 << (k - 1))
+    mask2k = (1 << (2 * k)) - 1
+    mask2s = (1 << (2 * s)) - 1
+    flat = qual is not None and all(q == qual[0] for q in qual)
+    F = R = f7 = r7 = 0
+    for i in range(k - 1):
+        e = enc(seq[i])
+        F = (F << 2) | e
+        R = (R >> 2) | ((3 - e) << (2 * (k - 1)))
+        if i < s - 1:
+            f7 = (f7 << 2) | e
+            r7 = (r7 >> 2) | ((3 - e) << (2 * (s - 1)))
+    window = []
+    mini, snp, dup = [], [], {}
+    for i in range(k - 1, L):
+        e = enc(seq[i])
+        F = ((F << 2) | e) & mask2k
+        R = ((R >> 2) & ~(3 << (2 * k - 2))) | ((3 - e) << (2 * (k - 1)))
+        fwd = (F & split_mask) < (R & split_mask)
+        canon = F if fwd else R
+        f7 = ((f7 << 2) | e) & mask2s
+        r7 = ((r7 >> 2) & ~(3 << (2 * s - 2))) | ((3 - e) << (2 * (s - 1)))
+        window.append(mm_hash64(min(f7, r7)))
+        if len(window) > W:
+            window.pop(0)
+        if canon in snpmer_set:
+            q = (qual[i + 1 + k // 2 - k] - 33) if qual is not None else 60
+            if q > min_bq or flat:
+                snp.append((i + 1 - k, canon))
+            dup[canon & split_mask] = dup.get(canon & split_mask, 0) + 1
+        if len(window) == W and all(window[j] > window[mid] for j in range(W) if j != mid):
+            mini.append((i + 1 - k, canon, int(fwd)))
+    snp = [x for x in snp if dup[x[1] & split_mask] == 1]
+    est = None
+    if qual is not None and not flat:
+        sm = 0.0
+        for q in qual:
+            sm += math.pow(10.0, -float(q - 33) / 10.0)
+        est = 100. - (sm / len(qual) * 100.)
+    return dict(mini=mini, snp=snp, est_id=est, codes=[enc(b) for b in seq])
+
+
+def banded_nm(a, r, B):
+    """Full (n+1)x(m+1) matrix with out-of-band cells = inf; returns (nm, i_end, j_end)."""
+    n, m = len(a), len(r)
+    INF = 10 ** 9
+    D = [[INF] * (m + 1) for _ in range(n + 1)]
+    for i in range(n + 1):
+        for j in range(m + 1):
+            if abs(i - j) > B:
+                continue
+            if i == 0 or j == 0:
+                D[i][j] = 0
+                continue
+            D[i][j] = min(D[i - 1][j - 1] + (a[i - 1] != r[j - 1]), D[i - 1][j] + 1, D[i][j - 1] + 1)
+    best = (INF, -1, -1)
+    cells = [(n, j) for j in range(m + 1) if abs(n - j) <= B] + [(i, m) for i in range(n + 1) if abs(i - m) <= B]
+    for (i, j) in cells:
+        d = D[i][j]
+        if d < best[0] or (d == best[0] and i + j > best[1] + best[2]):
+            best = (d, i, j)
+    return best

@@ -1,0 +1,198 @@
+"""Oracle pinning: the reference's own known-answer tests plus an independent pure-Python
+restatement.  CPU only."""
+import random
+import struct
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests import pyref
+
+
+def test_kmer48_from_u64_layout():
+    # src/types.rs:1112-1116  Kmer48::from_u64(1).data == [1,0,0,0,0,0]
+    import ctypes as C
+    out = (C.c_uint8 * 6)()
+    O.lib().so_kmer48_from_u64(C.c_uint64(1), out)
+    assert list(out) == [1, 0, 0, 0, 0, 0]
+    O.lib().so_kmer48_from_u64(C.c_uint64(0x0000a1b2c3d4e5f6), out)
+    assert list(out) == [0xf6, 0xe5, 0xd4, 0xc3, 0xb2, 0xa1]
+    assert O.lib().so_kmer48_to_u64(out) == 0x0000a1b2c3d4e5f6
+
+
+def test_two_bit_encoding_acgtg():
+    # src/types.rs:1118-1128  "ACGTG" -> 0b00_01_10_11_10
+    assert O.lib().so_kmer_from_ascii(b"ACGTG", 5) == 0b0001101110
+
+
+def test_kmer_reverse_complement():
+    # src/types.rs:1130-1139  revcomp(ACGTG) = CACGT -> 0b01_00_01_10_11
+    x = O.lib().so_kmer_from_ascii(b"ACGTG", 5)
+    assert O.lib().so_kmer_revcomp(x, 5) == 0b0100011011
+    assert O.lib().so_kmer_revcomp(x, 5) == O.lib().so_kmer_from_ascii(b"CACGT", 5)
+
+
+def test_byte_to_seq_table():
+    # src/types.rs:92-101
+    L = O.lib()
+    for ch, v in [("A", 0), ("a", 0), ("C", 1), ("c", 1), ("G", 2), ("g", 2), ("T", 3), ("t", 3), ("U", 3), ("u", 3),
+                  ("N", 0), ("n", 0), ("R", 0), ("-", 0)]:
+        assert L.so_encode_base(ord(ch)) == v
+    table = [L.so_encode_base(b) for b in range(256)]
+    assert table[:4] == [0, 1, 2, 3]
+    assert sum(1 for t in table if t) == 8 + 3  # C c G g T t U u + raw bytes 1,2,3
+
+
+@pytest.mark.parametrize("x,h", [
+    (0x0, 0x77cfa1eef01bca90), (0x1, 0x5bca7c69b794f8ce), (0x2, 0xb795033f6f2a0674),
+    (0x3fff, 0xfd1fa399fa3deb64), (0x123456789, 0xfd3d49f2cb78951a), (0x3ffffffff, 0xb0cddf11a4f33e9c)])
+def test_mm_hash64_kats(x, h):
+    # values computed from the formula at src/seeding.rs:18-28
+    assert O.mm_hash64(x) == h
+    assert pyref.mm_hash64(x) == h
+
+
+def test_powi_and_ratio_constants():
+    # 0.95f64.powi(17) by repeated squaring, bits 0x3fdac27bcb63c568
+    v = O.lib().so_powi(0.95, 17)
+    assert struct.unpack("<Q", struct.pack("<d", v))[0] == 0x3fdac27bcb63c568
+    assert v == 0.41812033521917735
+    assert (11.0 / 200.0) / 11.0 == 0.005
+    assert O.lib().so_split_mask(17) == (~(3 << 16)) & ((1 << 64) - 1)
+
+
+def _rand_seq(rng, n, alphabet=b"ACGT"):
+    return bytes(rng.choice(alphabet) for _ in range(n))
+
+
+def _snpmer_set_from(seqs, k, every=7):
+    """take some canonical k-mers (both alleles of their middle base) as a SNPmer set"""
+    s = set()
+    mask = ((1 << 64) - 1) ^ (3 << (k - 1))
+    for sq in seqs:
+        for p in range(0, len(sq) - k + 1, every):
+            f = 0
+            for b in sq[p:p + k]:
+                f = (f << 2) | pyref.enc(b)
+            r = pyref.revcomp_kmer(f, k)
+            canon = f if (f & mask) < (r & mask) else r
+            s.add(canon)
+            s.add((canon & mask) | (((canon >> (k - 1)) + 1) & 3) << (k - 1))
+    return s
+
+
+@pytest.mark.parametrize("k,c", [(17, 11), (15, 9), (21, 11), (13, 7)])
+def test_sketch_matches_python_restatement(k, c):
+    rng = random.Random(1234 + k)
+    seqs, quals = [], []
+    for t in range(24):
+        L = rng.choice([k - 1, k, k + 1, 30, 64, 200, 333, 800])
+        alpha = b"ACGT" if t % 3 else b"ACGTNacgtRY"
+        sq = _rand_seq(rng, L, alpha)
+        if t % 5 == 0 and L > 60:   # low-complexity stretch -> duplicate k-mers / splitmers
+            sq = sq[:20] + b"ACACACACACACACACACACACACACACAC" + sq[50:]
+        if t % 7 == 0 and L > 100:  # exact repeat -> duplicated SNPmers
+            sq = sq[:50] + sq[:50] + sq[100:]
+        seqs.append(sq)
+        if t % 4 == 3:
+            quals.append(bytes([40 + 33] * L))            # flat qualities
+        else:
+            quals.append(bytes(33 + rng.choice([5, 12, 25, 26, 30, 40, 50]) for _ in range(L)))
+    snp = _snpmer_set_from(seqs, k)
+    p = O.default_params(k=k, c=c)
+    bases, offs = O.concat(seqs)
+    qcat, _ = O.concat(quals)
+    for use_q in (True, False):
+        got = O.sketch_batch(p, sorted(snp), bases, qcat if use_q else None, offs)
+        for i, sq in enumerate(seqs):
+            ref = pyref.sketch(sq, quals[i] if use_q else None, k, c, 25, snp)
+            if ref is None:
+                assert got["status"][i] == O.STATUS_TOO_SHORT
+                continue
+            assert got["status"][i] == 0
+            a, b = int(got["mini_offsets"][i]), int(got["mini_offsets"][i + 1])
+            assert [(int(x), int(y), int(z)) for x, y, z in
+                    zip(got["mini_pos"][a:b], got["mini_kmer"][a:b], got["mini_fwd"][a:b])] == ref["mini"]
+            a, b = int(got["snp_offsets"][i]), int(got["snp_offsets"][i + 1])
+            assert [(int(x), int(y)) for x, y in zip(got["snp_pos"][a:b], got["snp_kmer"][a:b])] == ref["snp"]
+            o0, o1 = int(offs[i]), int(offs[i + 1])
+            assert list(got["codes"][o0:o1]) == ref["codes"]
+            if ref["est_id"] is None:
+                assert np.isnan(got["est_id"][i])
+            else:
+                assert got["est_id"][i] == ref["est_id"]
+
+
+def test_sketch_warmup_quirk_positions():
+    # k-mer start positions 0..9 are never syncmer-tested (k=17,c=11)
+    rng = random.Random(7)
+    seqs = [_rand_seq(rng, 400) for _ in range(20)]
+    bases, offs = O.concat(seqs)
+    got = O.sketch_batch(O.default_params(), [], bases, None, offs)
+    assert got["mini_pos"].min() >= 10
+    dens = len(got["mini_pos"]) / sum(len(s) for s in seqs)
+    assert 0.06 < dens < 0.12     # open-syncmer density ~ 1/11
+
+
+def _mutate(rng, s, nsub, nins, ndel):
+    s = bytearray(s)
+    for _ in range(nsub):
+        i = rng.randrange(len(s)); s[i] = rng.choice(b"ACGT")
+    for _ in range(nins):
+        i = rng.randrange(len(s)); s.insert(i, rng.choice(b"ACGT"))
+    for _ in range(ndel):
+        i = rng.randrange(len(s)); del s[i]
+    return bytes(s)
+
+
+@pytest.mark.parametrize("band", [0, 1, 3, 8, 33])
+def test_banded_dp_matches_full_matrix(band):
+    rng = random.Random(99 + band)
+    asvs = [_rand_seq(rng, rng.choice([20, 37, 64, 90])) for _ in range(6)]
+    reads, pr, pa, ps = [], [], [], []
+    for a, s in enumerate(asvs):
+        for t in range(6):
+            rd = _mutate(rng, s, rng.randrange(4), rng.randrange(3), rng.randrange(3))
+            if t == 4:
+                rd = rd[rng.randrange(1, 6):]
+            if t == 5:
+                rd = rd[:-rng.randrange(1, 6)] + _rand_seq(rng, 3)
+            reads.append(rd); pr.append(len(reads) - 1); pa.append(a); ps.append(t % 2)
+    p = O.default_params(band=band)
+    orc = O.Oracle(p, [])
+    ab, ao = O.concat(asvs)
+    orc.load_asvs(ab, ao)
+    rb, ro = O.concat(reads)
+    got = orc.align_pairs(rb, ro, pr, pa, ps, want_cigar=True)
+    comp = {0: 3, 1: 2, 2: 1, 3: 0}
+    for i in range(len(pr)):
+        a = [pyref.enc(b) for b in asvs[pa[i]]]
+        r = [pyref.enc(b) for b in reads[pr[i]]]
+        if ps[i]:
+            r = [comp[x] for x in reversed(r)]
+        nm, ie, je = pyref.banded_nm(a, r, band)
+        assert (int(got["nm"][i]), int(got["asv_end"][i]), int(got["read_end"][i])) == (nm, ie, je)
+        # CIGAR consistency: spans and edit count
+        c0, c1 = int(got["cigar_offsets"][i]), int(got["cigar_offsets"][i + 1])
+        ai, rj, edits = int(got["asv_start"][i]), int(got["read_start"][i]), 0
+        assert ai == 0 or rj == 0
+        for e in got["cigar"][c0:c1]:
+            ln, op = int(e) >> 4, int(e) & 15
+            if op == 0:
+                edits += sum(1 for t in range(ln) if a[ai + t] != r[rj + t]); ai += ln; rj += ln
+            elif op == 1:
+                edits += ln; rj += ln
+            else:
+                edits += ln; ai += ln
+        assert (ai, rj) == (ie, je)
+        assert edits == nm
+
+
+def test_em_simple():
+    # two ASVs; 10 reads unambiguous to 0, 10 ambiguous {0,1}: EM pushes everything to ASV 0
+    ab, depths, it = O.em(2, [0, 1, 3], [0, 0, 1], [10, 10], 20)
+    assert depths.tolist() == [20, 0]
+    assert abs(ab.sum() - 1.0) < 1e-9 and it > 1
+    ab, depths, it = O.em(3, [0, 1, 2, 3], [0, 1, 2], [5, 3, 2], 10)
+    assert depths.tolist() == [5, 3, 2]
