@@ -1,0 +1,169 @@
+/*
+ * savont_b200.h -- C ABI of libsavont_b200.so: the B200 (sm_100a) implementation of savont's
+ * read-vs-ASV assignment path (Stage 7 / 7b of `savont asv`, reference v0.6.4).
+ *
+ * The reference (a pure-Rust crate) has no FFI for this path; this header IS the seam a Rust
+ * `extern "C"` shim binds.  Each entry point names the reference
+ * interface it stands in for (paths relative to the reference repository root).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all buffers are caller-owned HOST memory unless the name
+ *     says `_dev`; the library owns all GPU memory and copies in/out itself.
+ *   - every function returns 0 (SAVONT_B200_OK) or a negative error code; the message is in
+ *     savont_b200_last_error() (thread-local).  No exceptions or panics cross the ABI.
+ *   - there is NO CPU fallback: without a usable CUDA device every call fails with
+ *     SAVONT_B200_ERR_CUDA.
+ *   - one context = one GPU; use one context per device (one process per GPU under
+ *     torch.distributed / NCCL, or one thread per context).
+ *   - sequences are concatenated ASCII (`bases`, and Phred+33 `quals` or NULL) with
+ *     `offsets[n+1]`; k-mers are u64 in the reference's encoding (A=0 C=1 G=2 T=3, first base
+ *     in the highest used bit pair, canonical-by-splitmer; low 48 bits == Kmer48).
+ */
+#ifndef SAVONT_B200_H
+#define SAVONT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SAVONT_B200_ABI_VERSION 1
+
+typedef struct savont_b200_ctx savont_b200_ctx;
+
+/* Parameters the path reads from the reference's Cli (src/cli.rs:83-84,99-100,153-158) plus
+ * the two constants hard-coded in src/alignment.rs:1806,1829 and the DP band. */
+typedef struct savont_b200_params {
+    int32_t k;                  /* --kmer-size, odd, 13..23 (src/types.rs:580-609); default 17 */
+    int32_t c;                  /* -c, open-syncmer window; default 11; s = k-c+1 */
+    int32_t l;                  /* --blockmer-length; accepted and ignored (blockmers are off this path) */
+    int32_t min_bq;             /* --minimum-base-quality; default 25 */
+    int32_t band;               /* half band B of the DP: cells |i-j| <= B; default 64 */
+    int32_t strand_mode;        /* 0: strand by minimizer seed vote; 1: align both strands, keep min NM */
+    double  ratio_thresh;       /* 0.0050  (src/alignment.rs:1829) */
+    double  min_mini_frac_base; /* 0.950, raised to the k-th power (src/alignment.rs:1806) */
+} savont_b200_params;
+
+/* per-read status, shared by find_candidates and map_reads */
+enum {
+    SAVONT_B200_READ_ASSIGNED = 0,       /* eq-class emitted            src/alignment.rs:1890-1920 */
+    SAVONT_B200_READ_NO_CANDIDATE = 1,   /* asv_scores empty            src/alignment.rs:1817-1820 */
+    SAVONT_B200_READ_RATIO_FILTERED = 2, /* nothing with ratio<=thresh  src/alignment.rs:1835-1838 */
+    SAVONT_B200_READ_NO_ALIGNMENT = 3,   /* best_alns empty             src/alignment.rs:1921-1924 */
+    SAVONT_B200_READ_TOO_SHORT = 4       /* len < k: no TwinRead        src/seeding.rs:339-341 */
+};
+
+enum {
+    SAVONT_B200_OK = 0,
+    SAVONT_B200_ERR_INVALID = -1,    /* bad argument / params / call order */
+    SAVONT_B200_ERR_CUDA = -2,       /* CUDA runtime error or no device */
+    SAVONT_B200_ERR_CAPACITY = -3,   /* a caller-provided output buffer is too small */
+    SAVONT_B200_ERR_OVERFLOW = -4,   /* an internal per-read limit was exceeded (message says which) */
+    SAVONT_B200_ERR_NOMEM = -5
+};
+
+/* timing / work counters of the last map_reads / map_resident call (CUDA events on the
+ * context's stream; see DESIGN.md "Measurement") */
+typedef struct savont_b200_stats {
+    double   sketch_ms, filter_ms, align_ms, assign_ms; /* per-kernel-group device time, summed over batches */
+    double   h2d_ms, d2h_ms, total_ms;                  /* total_ms: first enqueue to last completion (device) */
+    uint64_t n_reads, n_bases, n_pairs, dp_cells;       /* dp_cells = sum over aligned pairs of L_asv*(2B+1) */
+    uint64_t h2d_bytes, d2h_bytes;
+    uint64_t kernel_launches;
+    uint64_t n_batches;
+} savont_b200_stats;
+
+int         savont_b200_abi_version(void);
+const char *savont_b200_last_error(void);
+void        savont_b200_default_params(savont_b200_params *p);
+
+/* Context lifetime.  device_id is a CUDA ordinal. */
+int savont_b200_create(int device_id, savont_b200_ctx **out);
+int savont_b200_destroy(savont_b200_ctx *ctx);
+/* Run all work of this context on an existing cudaStream_t (e.g. torch's current stream);
+ * NULL restores the context's own stream. */
+int savont_b200_set_stream(savont_b200_ctx *ctx, void *cuda_stream);
+int savont_b200_set_params(savont_b200_ctx *ctx, const savont_b200_params *p);
+/* Upper bound on reads per internal batch (0 = default). */
+int savont_b200_set_batch_reads(savont_b200_ctx *ctx, size_t max_reads_per_batch);
+
+/* The SNPmer set: both alleles of every SNPmer, exactly the u64 values the reference inserts
+ * at src/kmer_comp.rs:41-48 (`split_kmer | mid_base << (k-1)`). */
+int savont_b200_load_snpmers(savont_b200_ctx *ctx, const uint64_t *kmers, size_t n);
+
+/* Replaces kmer_comp::twin_reads_from_fasta (src/kmer_comp.rs:39-66) + the SNPmer inverted
+ * index build (src/alignment.rs:1754-1765): sketches the ASVs on the GPU (no qualities) and
+ * builds the replicated device index.  ASV index = order given. */
+int savont_b200_load_asvs(savont_b200_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, size_t n_asv);
+int savont_b200_num_asvs(savont_b200_ctx *ctx, size_t *n_asv);
+
+/* Replaces seeding::get_twin_read_syncmer (src/seeding.rs:317-327) for a batch: per sequence
+ * the open-syncmer minimizers (position, canonical k-mer, forward flag), the quality-gated,
+ * deduplicated SNPmers, est_id (NaN = None) and optionally one 2-bit code per base.
+ * CSR outputs; mini_cap / snp_cap are the capacities of the flat arrays (total #bases is
+ * always enough).  status[i] is 0 or SAVONT_B200_READ_TOO_SHORT. */
+int savont_b200_sketch(savont_b200_ctx *ctx, const uint8_t *bases, const uint8_t *quals, const uint64_t *offsets,
+                       size_t n_seqs, uint8_t *status, double *est_id,
+                       uint64_t *mini_offsets, uint32_t *mini_pos, uint64_t *mini_kmer, uint8_t *mini_fwd, size_t mini_cap,
+                       uint64_t *snp_offsets, uint32_t *snp_pos, uint64_t *snp_kmer, size_t snp_cap,
+                       uint8_t *codes /* may be NULL */);
+
+/* Replaces asv_cluster::find_compatible_candidates (src/asv_cluster.rs:356-383) plus the
+ * minimizer-overlap / ratio / min-mismatch selection of src/alignment.rs:1796-1843.  Kept
+ * candidates per read, sorted by ASV index. */
+int savont_b200_find_candidates(savont_b200_ctx *ctx, const uint8_t *bases, const uint8_t *quals,
+                                const uint64_t *offsets, size_t n_reads,
+                                uint8_t *cand_status, uint64_t *cand_offsets,
+                                uint32_t *cand_asv, uint32_t *cand_mm, uint32_t *cand_mini, uint8_t *cand_strand,
+                                size_t cand_cap);
+
+/* Replaces the minimap2 call of src/alignment.rs:1848-1863 (Aligner::with_seq(read) +
+ * map(asv) -> alignment.nm / cigar) for explicit (read, ASV, strand) pairs, with the
+ * north-star NM definition (banded, both-ends-free unit-cost edit distance).
+ * Coordinates are in DP orientation (read reverse-complemented when strand==1);
+ * CIGAR is BAM-encoded (len<<4|op; 0=M, 1=I read-only, 2=D ASV-only), CSR. */
+int savont_b200_align_pairs(savont_b200_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, size_t n_reads,
+                            const uint32_t *pair_read, const uint32_t *pair_asv, const uint8_t *pair_strand,
+                            size_t n_pairs, int32_t *nm, int32_t *asv_end, int32_t *read_end,
+                            int want_cigar, int32_t *asv_start, int32_t *read_start,
+                            uint64_t *cigar_offsets, uint32_t *cigar, size_t cigar_cap);
+
+/* The whole per-read closure of refine_asv_depths_with_em / compute_per_sample_depths
+ * (src/alignment.rs:1786-1925, :2095-2171): sketch -> candidates -> NM -> best-NM ties ->
+ * equivalence class and counters.  file_idx may be NULL (n_samples = 1).
+ * Counter arrays are ADDED to: unambig/ambig/leq10 [n_asv], totals[2] = {assigned, filtered},
+ * sample_singleton [n_samples*n_asv] (may be NULL).  class_* is the per-read sorted
+ * equivalence class in CSR (empty for unassigned reads).  stats may be NULL. */
+int savont_b200_map_reads(savont_b200_ctx *ctx, const uint8_t *bases, const uint8_t *quals, const uint64_t *offsets,
+                          const uint32_t *file_idx, size_t n_reads, int n_samples,
+                          uint8_t *status, int32_t *best_nm, uint64_t *class_offsets, uint32_t *class_asv,
+                          size_t class_cap,
+                          uint64_t *unambig, uint64_t *ambig, uint64_t *leq10, uint64_t *totals,
+                          uint64_t *sample_singleton, savont_b200_stats *stats);
+
+/* Device-resident variant used for kernel-only measurement and by the multi-GPU host layer:
+ * upload once, then map repeatedly without host<->device traffic of the inputs.
+ * map_resident leaves the counters in the context's device counter vector
+ *   [unambig(A) | ambig(A) | leq10(A) | assigned | filtered | sample_singleton(S*A)]  (u64)
+ * which savont_b200_counts_dev exposes (for an in-place ncclAllReduce by the host layer) and
+ * savont_b200_read_counts copies out.  Per-read outputs stay on the device until
+ * savont_b200_fetch_resident. */
+int savont_b200_upload_reads(savont_b200_ctx *ctx, const uint8_t *bases, const uint8_t *quals, const uint64_t *offsets,
+                             const uint32_t *file_idx, size_t n_reads, int n_samples);
+int savont_b200_map_resident(savont_b200_ctx *ctx, int zero_counters, savont_b200_stats *stats);
+int savont_b200_fetch_resident(savont_b200_ctx *ctx, uint8_t *status, int32_t *best_nm, uint64_t *class_offsets,
+                               uint32_t *class_asv, size_t class_cap);
+int savont_b200_counts_dev(savont_b200_ctx *ctx, void **dev_ptr, size_t *n_u64);
+int savont_b200_read_counts(savont_b200_ctx *ctx, uint64_t *unambig, uint64_t *ambig, uint64_t *leq10, uint64_t *totals,
+                            uint64_t *sample_singleton);
+
+/* Pinned host memory helpers (inputs placed here are copied without a staging pass). */
+int savont_b200_host_alloc(size_t bytes, void **out);
+int savont_b200_host_free(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,283 @@
+"""ctypes binding of libsavont_b200.so (include/savont_b200.h).
+
+The library is the product; this module is only the Python doorway used by the tests, the bench
+and the multi-GPU host layer.  It never falls back to a CPU implementation: if the shared library
+or a CUDA device is missing the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libsavont_b200.so")
+HEADER_PATH = os.path.join(_HERE, "..", "include", "savont_b200.h")
+
+READ_ASSIGNED, READ_NO_CANDIDATE, READ_RATIO_FILTERED, READ_NO_ALIGNMENT, READ_TOO_SHORT = 0, 1, 2, 3, 4
+OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_OVERFLOW, ERR_NOMEM = 0, -1, -2, -3, -4, -5
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("k", C.c_int32), ("c", C.c_int32), ("l", C.c_int32), ("min_bq", C.c_int32),
+        ("band", C.c_int32), ("strand_mode", C.c_int32),
+        ("ratio_thresh", C.c_double), ("min_mini_frac_base", C.c_double),
+    ]
+
+
+class Stats(C.Structure):
+    _fields_ = [
+        ("sketch_ms", C.c_double), ("filter_ms", C.c_double), ("align_ms", C.c_double), ("assign_ms", C.c_double),
+        ("h2d_ms", C.c_double), ("d2h_ms", C.c_double), ("total_ms", C.c_double),
+        ("n_reads", C.c_uint64), ("n_bases", C.c_uint64), ("n_pairs", C.c_uint64), ("dp_cells", C.c_uint64),
+        ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("kernel_launches", C.c_uint64), ("n_batches", C.c_uint64),
+    ]
+
+    def as_dict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+class SavontB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libsavont_b200 error {code}: {msg}")
+        self.code = code
+
+
+def declared_symbols():
+    """every function declared in include/savont_b200.h"""
+    txt = open(HEADER_PATH).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(savont_b200_[a-z_0-9]+)\s*\(", txt)))
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SavontB200Error(ERR_CUDA, f"{LIB_PATH} is missing: run `python -m savont_b200.build` (nvcc, sm_100a); "
+                                            "there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        L.savont_b200_last_error.restype = C.c_char_p
+        L.savont_b200_abi_version.restype = C.c_int
+        for name in declared_symbols():
+            fn = getattr(L, name)
+            if name not in ("savont_b200_last_error", "savont_b200_default_params"):
+                fn.restype = C.c_int
+        L.savont_b200_default_params.restype = None
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise SavontB200Error(rc, lib().savont_b200_last_error().decode())
+
+
+def _p(arr, typ):
+    if arr is None:
+        return None
+    return arr.ctypes.data_as(C.POINTER(typ))
+
+
+def _u8(x):
+    if x is None:
+        return None
+    if isinstance(x, (bytes, bytearray)):
+        return np.frombuffer(bytes(x), dtype=np.uint8)
+    return np.ascontiguousarray(x, dtype=np.uint8)
+
+
+def default_params(**kw) -> Params:
+    p = Params()
+    lib().savont_b200_default_params(C.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def pinned_array(nbytes: int) -> np.ndarray:
+    """uint8 numpy array backed by cudaMallocHost memory (never freed explicitly: process lifetime)"""
+    ptr = C.c_void_p()
+    _check(lib().savont_b200_host_alloc(C.c_size_t(max(nbytes, 1)), C.byref(ptr)))
+    buf = (C.c_uint8 * max(nbytes, 1)).from_address(ptr.value)
+    return np.frombuffer(buf, dtype=np.uint8, count=nbytes)
+
+
+class Context:
+    """One GPU.  Mirrors the order of calls in refine_asv_depths_with_em (reference
+    src/alignment.rs:1723-1765): params -> SNPmer set -> ASVs -> reads."""
+
+    def __init__(self, device: int = 0, params: Params | None = None):
+        self.L = lib()
+        h = C.c_void_p()
+        _check(self.L.savont_b200_create(C.c_int(device), C.byref(h)))
+        self.h = h
+        self.device = device
+        self.n_asv = 0
+        self.params = default_params()
+        if params is not None:
+            self.set_params(params)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.savont_b200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_params(self, p: Params):
+        _check(self.L.savont_b200_set_params(self.h, C.byref(p)))
+        self.params = p
+
+    def set_stream(self, cuda_stream_ptr: int | None):
+        _check(self.L.savont_b200_set_stream(self.h, C.c_void_p(cuda_stream_ptr or 0)))
+
+    def set_batch_reads(self, n: int):
+        _check(self.L.savont_b200_set_batch_reads(self.h, C.c_size_t(n)))
+
+    def load_snpmers(self, kmers):
+        k = np.ascontiguousarray(kmers, dtype=np.uint64)
+        _check(self.L.savont_b200_load_snpmers(self.h, _p(k, C.c_uint64), C.c_size_t(len(k))))
+
+    def load_asvs(self, bases, offsets):
+        b = _u8(bases)
+        o = np.ascontiguousarray(offsets, dtype=np.uint64)
+        _check(self.L.savont_b200_load_asvs(self.h, _p(b, C.c_uint8), _p(o, C.c_uint64), C.c_size_t(len(o) - 1)))
+        n = C.c_size_t()
+        _check(self.L.savont_b200_num_asvs(self.h, C.byref(n)))
+        self.n_asv = int(n.value)
+
+    # ---- a3 ----
+    def sketch(self, bases, quals, offsets, want_codes=True):
+        b = _u8(bases); q = _u8(quals)
+        o = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(o) - 1
+        total = int(o[-1] - o[0]) if n > 0 else 0
+        spacing = (self.params.c - 1) // 2 + 1
+        mcap = max(total // spacing + 2 * n + 16, 16)
+        scap = max(total, 16)
+        st = np.zeros(max(n, 1), np.uint8); est = np.zeros(max(n, 1), np.float64)
+        mo = np.zeros(n + 1, np.uint64); so = np.zeros(n + 1, np.uint64)
+        mpos = np.zeros(mcap, np.uint32); mk = np.zeros(mcap, np.uint64); mf = np.zeros(mcap, np.uint8)
+        spos = np.zeros(scap, np.uint32); sk = np.zeros(scap, np.uint64)
+        codes = np.zeros(max(int(o[-1]) if n > 0 else 0, 1), np.uint8) if want_codes else None
+        _check(self.L.savont_b200_sketch(self.h, _p(b, C.c_uint8), _p(q, C.c_uint8), _p(o, C.c_uint64), C.c_size_t(n),
+                                         _p(st, C.c_uint8), _p(est, C.c_double),
+                                         _p(mo, C.c_uint64), _p(mpos, C.c_uint32), _p(mk, C.c_uint64), _p(mf, C.c_uint8), C.c_size_t(mcap),
+                                         _p(so, C.c_uint64), _p(spos, C.c_uint32), _p(sk, C.c_uint64), C.c_size_t(scap),
+                                         _p(codes, C.c_uint8)))
+        nm, ns = int(mo[-1]), int(so[-1])
+        out = dict(status=st[:n], est_id=est[:n], mini_offsets=mo, mini_pos=mpos[:nm], mini_kmer=mk[:nm], mini_fwd=mf[:nm],
+                   snp_offsets=so, snp_pos=spos[:ns], snp_kmer=sk[:ns])
+        if want_codes:
+            out["codes"] = codes[:int(o[-1]) if n > 0 else 0]
+        return out
+
+    # ---- a8-a10 ----
+    def find_candidates(self, bases, quals, offsets, cap=None):
+        b = _u8(bases); q = _u8(quals)
+        o = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(o) - 1
+        cap = cap or max(n * max(min(self.n_asv, 64), 1), 16)
+        st = np.zeros(max(n, 1), np.uint8); co = np.zeros(n + 1, np.uint64)
+        ca = np.zeros(cap, np.uint32); cm = np.zeros(cap, np.uint32); ci = np.zeros(cap, np.uint32); cs = np.zeros(cap, np.uint8)
+        _check(self.L.savont_b200_find_candidates(self.h, _p(b, C.c_uint8), _p(q, C.c_uint8), _p(o, C.c_uint64), C.c_size_t(n),
+                                                  _p(st, C.c_uint8), _p(co, C.c_uint64), _p(ca, C.c_uint32), _p(cm, C.c_uint32),
+                                                  _p(ci, C.c_uint32), _p(cs, C.c_uint8), C.c_size_t(cap)))
+        t = int(co[-1])
+        return dict(status=st[:n], offsets=co, asv=ca[:t], mm=cm[:t], mini=ci[:t], strand=cs[:t])
+
+    # ---- a11 ----
+    def align_pairs(self, bases, offsets, pair_read, pair_asv, pair_strand, want_cigar=False, cigar_cap=None):
+        b = _u8(bases)
+        o = np.ascontiguousarray(offsets, dtype=np.uint64)
+        pr = np.ascontiguousarray(pair_read, dtype=np.uint32)
+        pa = np.ascontiguousarray(pair_asv, dtype=np.uint32)
+        ps = np.ascontiguousarray(pair_strand, dtype=np.uint8)
+        n = len(pr)
+        nm = np.zeros(max(n, 1), np.int32); ae = np.zeros(max(n, 1), np.int32); re_ = np.zeros(max(n, 1), np.int32)
+        as_ = np.zeros(max(n, 1), np.int32); rs = np.zeros(max(n, 1), np.int32)
+        co = np.zeros(n + 1, np.uint64)
+        if want_cigar and cigar_cap is None:
+            lens = (o[1:] - o[:-1]).astype(np.int64)
+            cigar_cap = int(lens[pr].sum() * 2 + 16 * n + 16) if n else 16
+        cg = np.zeros(cigar_cap or 1, np.uint32)
+        _check(self.L.savont_b200_align_pairs(self.h, _p(b, C.c_uint8), _p(o, C.c_uint64), C.c_size_t(len(o) - 1),
+                                              _p(pr, C.c_uint32), _p(pa, C.c_uint32), _p(ps, C.c_uint8), C.c_size_t(n),
+                                              _p(nm, C.c_int32), _p(ae, C.c_int32), _p(re_, C.c_int32),
+                                              C.c_int(1 if want_cigar else 0), _p(as_, C.c_int32), _p(rs, C.c_int32),
+                                              _p(co, C.c_uint64), _p(cg, C.c_uint32), C.c_size_t(len(cg))))
+        out = dict(nm=nm[:n], asv_end=ae[:n], read_end=re_[:n])
+        if want_cigar:
+            out.update(asv_start=as_[:n], read_start=rs[:n], cigar_offsets=co, cigar=cg[:int(co[-1])])
+        return out
+
+    # ---- whole path ----
+    def _out_buffers(self, n, n_samples, class_cap):
+        A = self.n_asv
+        return dict(status=np.zeros(max(n, 1), np.uint8), best_nm=np.zeros(max(n, 1), np.int32),
+                    class_offsets=np.zeros(n + 1, np.uint64), class_asv=np.zeros(max(class_cap, 1), np.uint32),
+                    unambig=np.zeros(max(A, 1), np.uint64), ambig=np.zeros(max(A, 1), np.uint64), leq10=np.zeros(max(A, 1), np.uint64),
+                    totals=np.zeros(2, np.uint64), sample_singleton=np.zeros(max(A * n_samples, 1), np.uint64))
+
+    def map_reads(self, bases, quals, offsets, file_idx=None, n_samples=1, class_cap=None):
+        b = _u8(bases); q = _u8(quals)
+        o = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(o) - 1
+        fi = None if file_idx is None else np.ascontiguousarray(file_idx, dtype=np.uint32)
+        class_cap = class_cap or max(8 * n + 1024, 16)
+        B = self._out_buffers(n, n_samples, class_cap)
+        st = Stats()
+        _check(self.L.savont_b200_map_reads(self.h, _p(b, C.c_uint8), _p(q, C.c_uint8), _p(o, C.c_uint64), _p(fi, C.c_uint32),
+                                            C.c_size_t(n), C.c_int(n_samples), _p(B["status"], C.c_uint8), _p(B["best_nm"], C.c_int32),
+                                            _p(B["class_offsets"], C.c_uint64), _p(B["class_asv"], C.c_uint32), C.c_size_t(class_cap),
+                                            _p(B["unambig"], C.c_uint64), _p(B["ambig"], C.c_uint64), _p(B["leq10"], C.c_uint64),
+                                            _p(B["totals"], C.c_uint64), _p(B["sample_singleton"], C.c_uint64), C.byref(st)))
+        return self._finish(B, n, n_samples, st)
+
+    def _finish(self, B, n, n_samples, st):
+        A = self.n_asv
+        t = int(B["class_offsets"][-1])
+        return dict(status=B["status"][:n], best_nm=B["best_nm"][:n], class_offsets=B["class_offsets"], class_asv=B["class_asv"][:t],
+                    unambig=B["unambig"][:A], ambig=B["ambig"][:A], leq10=B["leq10"][:A], totals=B["totals"],
+                    sample_singleton=B["sample_singleton"][:A * n_samples].reshape(n_samples, A), stats=st.as_dict())
+
+    # ---- device-resident variant ----
+    def upload_reads(self, bases, quals, offsets, file_idx=None, n_samples=1):
+        b = _u8(bases); q = _u8(quals)
+        o = np.ascontiguousarray(offsets, dtype=np.uint64)
+        fi = None if file_idx is None else np.ascontiguousarray(file_idx, dtype=np.uint32)
+        _check(self.L.savont_b200_upload_reads(self.h, _p(b, C.c_uint8), _p(q, C.c_uint8), _p(o, C.c_uint64), _p(fi, C.c_uint32),
+                                               C.c_size_t(len(o) - 1), C.c_int(n_samples)))
+        self._resident = (len(o) - 1, n_samples)
+
+    def map_resident(self, zero_counters=True):
+        st = Stats()
+        _check(self.L.savont_b200_map_resident(self.h, C.c_int(1 if zero_counters else 0), C.byref(st)))
+        return st.as_dict()
+
+    def fetch_resident(self, class_cap=None):
+        n, n_samples = self._resident
+        class_cap = class_cap or max(8 * n + 1024, 16)
+        B = self._out_buffers(n, n_samples, class_cap)
+        _check(self.L.savont_b200_fetch_resident(self.h, _p(B["status"], C.c_uint8), _p(B["best_nm"], C.c_int32),
+                                                 _p(B["class_offsets"], C.c_uint64), _p(B["class_asv"], C.c_uint32), C.c_size_t(class_cap)))
+        _check(self.L.savont_b200_read_counts(self.h, _p(B["unambig"], C.c_uint64), _p(B["ambig"], C.c_uint64), _p(B["leq10"], C.c_uint64),
+                                              _p(B["totals"], C.c_uint64), _p(B["sample_singleton"], C.c_uint64)))
+        return self._finish(B, n, n_samples, Stats())
+
+    def counts_dev(self):
+        """(device pointer, length in u64) of [unambig|ambig|leq10|assigned|filtered|singleton S*A]"""
+        ptr = C.c_void_p(); n = C.c_size_t()
+        _check(self.L.savont_b200_counts_dev(self.h, C.byref(ptr), C.byref(n)))
+        return int(ptr.value), int(n.value)

@@ -1,0 +1,421 @@
+// align.cu -- K3: banded, both-ends-free unit-cost edit distance (NM), bit-parallel.
+//
+// Stands in for the minimap2 call of reference src/alignment.rs:1848-1863 (NM of read vs ASV) with
+// the north-star definition (SURVEY.md 8c "S2", restated in oracle/savont_oracle.c banded_align):
+//   rows i = 0..n (ASV), columns j = 0..m (oriented read), cells |i-j| <= B,
+//   D[0][j] = D[i][0] = 0, unit costs, NM = min over last-row / last-column cells,
+//   tie -> largest i+j, then the last-row cell.
+//
+// One THREAD per (read, ASV, strand) pair; the W = 2B+1 band cells of a column live in NW 32-bit
+// registers as Myers/Hyyro delta vectors (Pv, Mv) aligned to the diagonal band: bit b of column j is
+// row j-B+b.  Per column: Eq from the two bit-planes of the ASV window (funnel shifts) and the
+// read base (broadcast masks), D0 = (((X&Pv)+Pv)^Pv)|X with one IADD3.X carry chain,
+// Ph/Mh, then the diagonal re-alignment X = D0>>1.  Rows <= 0 are virtual cells with D = 0
+// (forced matches, only while j <= B); rows > n and bits >= W are garbage below the band that never
+// feeds back (the only back-edge, bit W -> W-1 through D0>>1, is masked in Mv).
+// The score of the band's top cell is tracked from bit 0 of D0; last-row cells are read with
+// popcounts of the vertical deltas, last-column cells by a walk over the final column.
+// No tensor cores: this is integer DP, ~14 INT32 ops per 32 cells.
+#include "common.cuh"
+
+namespace sb {
+
+struct AlignArgs {
+    const uint64_t *read_offsets;
+    const uint2 *read_planes;
+    const uint2 *asv_planes;
+    const uint32_t *asv_plane_off;
+    const uint32_t *asv_len;
+    const uint32_t *pair_read;
+    const uint32_t *pair_asv;
+    const uint8_t *pair_strand;
+    const uint32_t *n_pairs_dev;   // device-side pair count (may be null -> n_pairs_max)
+    uint32_t n_pairs_max;
+    int32_t *nm, *asv_end, *read_end;
+    // traceback mode
+    uint32_t *hist;                // [(col*2*NW + w) * hist_stride + t]
+    uint32_t hist_stride;
+    int32_t *asv_start, *read_start;
+    uint32_t *cigar;               // [pair * cigar_stride + ...] filled from the back
+    uint32_t cigar_stride;
+    uint32_t *cigar_cnt;
+    int band, padl;
+};
+
+// s = a + b (+ carry chain across NW words) in ONE asm statement so nothing can clobber CC.
+template <int NW>
+__device__ __forceinline__ void add_chain(const uint32_t (&a)[NW], const uint32_t (&b)[NW], uint32_t (&s)[NW]);
+
+template <>
+__device__ __forceinline__ void add_chain<1>(const uint32_t (&a)[1], const uint32_t (&b)[1], uint32_t (&s)[1]) { s[0] = a[0] + b[0]; }
+template <>
+__device__ __forceinline__ void add_chain<2>(const uint32_t (&a)[2], const uint32_t (&b)[2], uint32_t (&s)[2]) {
+    asm("add.cc.u32 %0, %2, %4;\n\taddc.u32 %1, %3, %5;" : "=r"(s[0]), "=r"(s[1]) : "r"(a[0]), "r"(a[1]), "r"(b[0]), "r"(b[1]));
+}
+template <>
+__device__ __forceinline__ void add_chain<3>(const uint32_t (&a)[3], const uint32_t (&b)[3], uint32_t (&s)[3]) {
+    asm("add.cc.u32 %0, %3, %6;\n\taddc.cc.u32 %1, %4, %7;\n\taddc.u32 %2, %5, %8;"
+        : "=r"(s[0]), "=r"(s[1]), "=r"(s[2])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(b[0]), "r"(b[1]), "r"(b[2]));
+}
+template <>
+__device__ __forceinline__ void add_chain<5>(const uint32_t (&a)[5], const uint32_t (&b)[5], uint32_t (&s)[5]) {
+    asm("add.cc.u32 %0, %5, %10;\n\taddc.cc.u32 %1, %6, %11;\n\taddc.cc.u32 %2, %7, %12;\n\taddc.cc.u32 %3, %8, %13;\n\t"
+        "addc.u32 %4, %9, %14;"
+        : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]));
+}
+template <>
+__device__ __forceinline__ void add_chain<7>(const uint32_t (&a)[7], const uint32_t (&b)[7], uint32_t (&s)[7]) {
+    asm("add.cc.u32 %0, %7, %14;\n\taddc.cc.u32 %1, %8, %15;\n\taddc.cc.u32 %2, %9, %16;\n\taddc.cc.u32 %3, %10, %17;\n\t"
+        "addc.cc.u32 %4, %11, %18;\n\taddc.cc.u32 %5, %12, %19;\n\taddc.u32 %6, %13, %20;"
+        : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(s[5]), "=r"(s[6])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]),
+          "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]));
+}
+template <>
+__device__ __forceinline__ void add_chain<9>(const uint32_t (&a)[9], const uint32_t (&b)[9], uint32_t (&s)[9]) {
+    asm("add.cc.u32 %0, %9, %18;\n\taddc.cc.u32 %1, %10, %19;\n\taddc.cc.u32 %2, %11, %20;\n\taddc.cc.u32 %3, %12, %21;\n\t"
+        "addc.cc.u32 %4, %13, %22;\n\taddc.cc.u32 %5, %14, %23;\n\taddc.cc.u32 %6, %15, %24;\n\taddc.cc.u32 %7, %16, %25;\n\t"
+        "addc.u32 %8, %17, %26;"
+        : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(s[5]), "=r"(s[6]), "=r"(s[7]), "=r"(s[8])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(a[8]),
+          "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]), "r"(b[8]));
+}
+template <>
+__device__ __forceinline__ void add_chain<13>(const uint32_t (&a)[13], const uint32_t (&b)[13], uint32_t (&s)[13]) {
+    asm("add.cc.u32 %0, %13, %26;\n\taddc.cc.u32 %1, %14, %27;\n\taddc.cc.u32 %2, %15, %28;\n\taddc.cc.u32 %3, %16, %29;\n\t"
+        "addc.cc.u32 %4, %17, %30;\n\taddc.cc.u32 %5, %18, %31;\n\taddc.cc.u32 %6, %19, %32;\n\taddc.cc.u32 %7, %20, %33;\n\t"
+        "addc.cc.u32 %8, %21, %34;\n\taddc.cc.u32 %9, %22, %35;\n\taddc.cc.u32 %10, %23, %36;\n\taddc.cc.u32 %11, %24, %37;\n\t"
+        "addc.u32 %12, %25, %38;"
+        : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(s[5]), "=r"(s[6]), "=r"(s[7]), "=r"(s[8]),
+          "=r"(s[9]), "=r"(s[10]), "=r"(s[11]), "=r"(s[12])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(a[8]), "r"(a[9]),
+          "r"(a[10]), "r"(a[11]), "r"(a[12]),
+          "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]), "r"(b[8]), "r"(b[9]),
+          "r"(b[10]), "r"(b[11]), "r"(b[12]));
+}
+
+// 32 bases [32t, 32t+32) of the oriented read as (low plane, high plane)
+__device__ __forceinline__ uint2 read_word(const uint2 *rp, uint32_t m, uint32_t t, bool rev) {
+    if (!rev) return rp[t];
+    const int s0 = (int)m - 32 * (int)t - 32;          // forward index of the LAST base of this word
+    uint32_t lo, hi;
+    if (s0 >= 0) {
+        const uint32_t ws = (uint32_t)s0 >> 5, sh = (uint32_t)s0 & 31u;
+        const uint2 a = rp[ws], b = rp[ws + 1];
+        lo = __funnelshift_r(a.x, b.x, sh);
+        hi = __funnelshift_r(a.y, b.y, sh);
+    } else {
+        const uint2 a = rp[0];
+        lo = a.x << (uint32_t)(-s0);
+        hi = a.y << (uint32_t)(-s0);
+    }
+    return make_uint2(~__brev(lo), ~__brev(hi));        // reverse + complement (3 - code)
+}
+
+template <int NW, bool TB>
+struct Band {
+    uint32_t Pv[NW], Mv[NW];
+    uint32_t Alo[NW + 1], Ahi[NW + 1];   // ASV window planes, word aligned; view = funnel shift by sh
+    uint32_t vm2[NW];                    // bits < W-1 (mask for Mv after the diagonal shift)
+    uint32_t sh;                         // bit offset of the window inside Alo/Ahi
+    uint32_t aw;                         // next ASV plane word to load
+    const uint2 *ap;
+    int T;                               // D at the band's top cell
+    int bd, bi, bj;                      // best end cell so far
+};
+
+// one DP column.  TOP: rows <= 0 may be inside the window (j <= B).  LAST: j may be >= n-B.
+template <int NW, bool TB, bool TOP, bool LAST>
+__device__ __forceinline__ void dp_column(Band<NW, TB> &s, uint32_t (&TM)[NW], uint32_t clo, uint32_t chi, int j, int n, int B,
+                                          uint32_t *hist_col, uint32_t hist_stride) {
+    uint32_t Eq[NW], X[NW], t[NW], sum[NW], D0[NW], Ph[NW], Mh[NW];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        const uint32_t lo = __funnelshift_r(s.Alo[w], s.Alo[w + 1], s.sh);
+        const uint32_t hi = __funnelshift_r(s.Ahi[w], s.Ahi[w + 1], s.sh);
+        Eq[w] = ~((lo ^ clo) | (hi ^ chi));
+        if (TOP) Eq[w] |= TM[w];
+        X[w] = Eq[w] | s.Mv[w];
+        t[w] = X[w] & s.Pv[w];
+    }
+    add_chain<NW>(t, s.Pv, sum);
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        D0[w] = (sum[w] ^ s.Pv[w]) | X[w];
+        Ph[w] = s.Mv[w] | ~(D0[w] | s.Pv[w]);
+        Mh[w] = s.Pv[w] & D0[w];
+    }
+    s.T += (int)((~D0[0]) & 1u);
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        const uint32_t Xs = (w + 1 < NW) ? __funnelshift_r(D0[w], D0[w + 1], 1) : (D0[w] >> 1);
+        s.Pv[w] = Mh[w] | ~(Xs | Ph[w]);
+        s.Mv[w] = Ph[w] & Xs & s.vm2[w];
+    }
+    if (TB) {
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            hist_col[(size_t)w * hist_stride] = D0[w];
+            hist_col[(size_t)(NW + w) * hist_stride] = s.Pv[w];
+        }
+    }
+    if (TOP) {
+#pragma unroll
+        for (int w = 0; w < NW; ++w) TM[w] = (w + 1 < NW) ? __funnelshift_r(TM[w], TM[w + 1], 1) : (TM[w] >> 1);
+    }
+    if (LAST) {
+        if (j + B >= n) {                                   // row n is inside the window: bit b = n - j + B
+            const int b = n - j + B;
+            int d = s.T;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                const int rem = b - 32 * w;                 // number of delta bits of this word below b
+                const uint32_t msk = rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
+                d += __popc(s.Pv[w] & msk) - __popc(s.Mv[w] & msk);
+            }
+            if (d < s.bd || (d == s.bd && n + j > s.bi + s.bj)) { s.bd = d; s.bi = n; s.bj = j; }
+        }
+    }
+    // slide the ASV window by one base
+    s.sh += 1u;
+    if (s.sh == 32u) {
+        s.sh = 0u;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) { s.Alo[w] = s.Alo[w + 1]; s.Ahi[w] = s.Ahi[w + 1]; }
+        const uint2 v = s.ap[s.aw++];
+        s.Alo[NW] = v.x; s.Ahi[NW] = v.y;
+    }
+}
+
+template <int NW, bool TB>
+__device__ __forceinline__ void align_pair(const AlignArgs &a, uint32_t pi, uint32_t tslot) {
+    const uint32_t r = a.pair_read[pi], asv = a.pair_asv[pi];
+    const bool rev = a.pair_strand[pi] != 0;
+    const uint64_t roff = a.read_offsets[r];
+    const int m = (int)(a.read_offsets[r + 1] - roff);
+    const int n = (int)a.asv_len[asv];
+    const int B = a.band, W = 2 * B + 1;
+    const uint2 *rp = a.read_planes + plane_word_off(roff, r);
+    const int jmax = m < n + B ? m : n + B;
+
+    Band<NW, TB> s;
+    s.ap = a.asv_planes + a.asv_plane_off[asv];
+    s.T = 0; s.bd = 1 << 29; s.bi = -1; s.bj = -1;
+    uint32_t TM[NW];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        s.Pv[w] = 0u; s.Mv[w] = 0u;
+        const int remW = (W - 1) - 32 * w;                  // bits of this word below W-1
+        s.vm2[w] = remW >= 32 ? 0xffffffffu : (remW <= 0 ? 0u : ((1u << remW) - 1u));
+        const int remT = B - 32 * w;                        // column 1: rows <= 0 are bits 0..B-1
+        TM[w] = remT >= 32 ? 0xffffffffu : (remT <= 0 ? 0u : ((1u << remT) - 1u));
+    }
+    {   // ASV window of column 1 starts at bit (1 - B - 1) + padl of the padded planes
+        const uint32_t ws = (uint32_t)(a.padl - B);
+        const uint32_t w0 = ws >> 5;
+        s.sh = ws & 31u;
+#pragma unroll
+        for (int w = 0; w <= NW; ++w) { const uint2 v = s.ap[w0 + w]; s.Alo[w] = v.x; s.Ahi[w] = v.y; }
+        s.aw = w0 + NW + 1;
+    }
+    // degenerate: no columns
+    if (jmax <= 0) {
+        if (TB) { a.asv_start[pi] = 0; a.read_start[pi] = 0; a.cigar_cnt[pi] = 0; }
+        // empty read: D[i][0] = 0 for i <= B; the tie rule picks the largest i
+        a.nm[pi] = 0;
+        if (a.asv_end) { a.asv_end[pi] = n <= B ? n : B; a.read_end[pi] = 0; }
+        return;
+    }
+
+    uint32_t cw_lo = 0, cw_hi = 0;
+    int j = 1;
+    uint32_t *hist = TB ? (a.hist + tslot) : nullptr;
+    const size_t hist_col_stride = (size_t)2 * NW * a.hist_stride;
+
+    auto next_masks = [&](int jj, uint32_t &clo, uint32_t &chi) {
+        const uint32_t bit = (uint32_t)(jj - 1) & 31u;
+        if (bit == 0u) { const uint2 v = read_word(rp, (uint32_t)m, (uint32_t)(jj - 1) >> 5, rev); cw_lo = v.x; cw_hi = v.y; }
+        clo = 0u - ((cw_lo >> bit) & 1u);
+        chi = 0u - ((cw_hi >> bit) & 1u);
+    };
+
+    // phase 1: virtual rows (<= 0) inside the window
+    const int j1 = B < jmax ? B : jmax;
+    for (; j <= j1; ++j) {
+        uint32_t clo, chi; next_masks(j, clo, chi);
+        dp_column<NW, TB, true, true>(s, TM, clo, chi, j, n, B, TB ? hist + (size_t)(j - 1) * hist_col_stride : nullptr, a.hist_stride);
+    }
+    // phase 2: interior
+    const int j2 = (n - B - 1) < jmax ? (n - B - 1) : jmax;
+    for (; j <= j2; ++j) {
+        uint32_t clo, chi; next_masks(j, clo, chi);
+        dp_column<NW, TB, false, false>(s, TM, clo, chi, j, n, B, TB ? hist + (size_t)(j - 1) * hist_col_stride : nullptr, a.hist_stride);
+    }
+    // phase 3: last row inside the window
+    for (; j <= jmax; ++j) {
+        uint32_t clo, chi; next_masks(j, clo, chi);
+        dp_column<NW, TB, false, true>(s, TM, clo, chi, j, n, B, TB ? hist + (size_t)(j - 1) * hist_col_stride : nullptr, a.hist_stride);
+    }
+
+    // row n may already be inside the window of column 0 (n <= B): cell (n, 0) = 0 is a last-row cell
+    // (handled below together with the last column when m == 0; for m > 0 the oracle also considers it)
+    if (n <= B) {
+        const int d = 0;
+        if (d < s.bd || (d == s.bd && n + 0 > s.bi + s.bj)) { s.bd = d; s.bi = n; s.bj = 0; }
+    }
+    // last-column cells (only if column m was reached)
+    if (jmax == m) {
+        int d = s.T;                                        // b = 0: row m - B
+        const int bmin = B - m > 0 ? B - m : 0;
+        const int bmax = (n - m + B) < 2 * B ? (n - m + B) : 2 * B;
+        if (bmin == 0 && bmax >= 0) {
+            const int i = m - B;
+            if (d < s.bd || (d == s.bd && i + m > s.bi + s.bj)) { s.bd = d; s.bi = i; s.bj = m; }
+        }
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            uint32_t pv = s.Pv[w], mv = s.Mv[w];
+            for (int q = 0; q < 32; ++q) {
+                const int b = 32 * w + q + 1;               // delta bit (b-1) leads to band bit b
+                if (b > bmax) break;
+                d += (int)(pv & 1u) - (int)(mv & 1u);
+                pv >>= 1; mv >>= 1;
+                if (b >= bmin) {
+                    const int i = m - B + b;
+                    if (d < s.bd || (d == s.bd && i + m > s.bi + s.bj)) { s.bd = d; s.bi = i; s.bj = m; }
+                }
+            }
+        }
+    }
+    a.nm[pi] = s.bd;
+    if (a.asv_end) { a.asv_end[pi] = s.bi; a.read_end[pi] = s.bj; }
+
+    if (TB) {
+        // ---- traceback over the stored D0 / Pv' vectors; preference diagonal > D (ASV) > I (read) ----
+        const uint2 *app = a.asv_planes + a.asv_plane_off[asv];
+        int i = s.bi, jj = s.bj;
+        uint32_t *cg = a.cigar + (size_t)tslot * a.cigar_stride;
+        uint32_t pos = a.cigar_stride;           // fill from the back
+        uint32_t cur_op = 3u, cur_len = 0u;
+        while (i > 0 && jj > 0) {
+            const int b = i - jj + B;
+            const uint32_t *hc = hist + (size_t)(jj - 1) * hist_col_stride;
+            const uint32_t d0 = (hc[(size_t)(b >> 5) * a.hist_stride] >> (b & 31)) & 1u;
+            // bases: ASV row i -> base i-1 at padded bit i-1+padl; read column jj -> oriented base jj-1
+            const uint32_t abit = (uint32_t)(i - 1 + a.padl);
+            const uint2 av = app[abit >> 5];
+            const uint32_t ac = ((av.x >> (abit & 31u)) & 1u) | (((av.y >> (abit & 31u)) & 1u) << 1);
+            uint32_t rc;
+            if (!rev) {
+                const uint32_t rb = (uint32_t)(jj - 1);
+                const uint2 rv = rp[rb >> 5];
+                rc = ((rv.x >> (rb & 31u)) & 1u) | (((rv.y >> (rb & 31u)) & 1u) << 1);
+            } else {
+                const uint32_t rb = (uint32_t)(m - jj);
+                const uint2 rv = rp[rb >> 5];
+                rc = 3u - (((rv.x >> (rb & 31u)) & 1u) | (((rv.y >> (rb & 31u)) & 1u) << 1));
+            }
+            uint32_t op;
+            if (ac == rc || d0 == 0u) { op = 0u; --i; --jj; }
+            else {
+                uint32_t pvb = 0u;
+                if (b >= 1) pvb = (hc[(size_t)(NW + ((b - 1) >> 5)) * a.hist_stride] >> ((b - 1) & 31)) & 1u;
+                if (pvb) { op = 2u; --i; } else { op = 1u; --jj; }
+            }
+            if (op == cur_op) ++cur_len;
+            else {
+                if (cur_len && pos > 0) cg[--pos] = (cur_len << 4) | cur_op;
+                cur_op = op; cur_len = 1u;
+            }
+        }
+        if (cur_len && pos > 0) cg[--pos] = (cur_len << 4) | cur_op;
+        a.asv_start[pi] = i; a.read_start[pi] = jj;
+        a.cigar_cnt[pi] = a.cigar_stride - pos;
+    }
+}
+
+template <int NW>
+__global__ void __launch_bounds__(128) align_nm_kernel(AlignArgs a) {
+    const uint32_t n_pairs = a.n_pairs_dev ? min(*a.n_pairs_dev, a.n_pairs_max) : a.n_pairs_max;
+    for (uint32_t pi = blockIdx.x * blockDim.x + threadIdx.x; pi < n_pairs; pi += gridDim.x * blockDim.x)
+        align_pair<NW, false>(a, pi, 0);
+}
+template <int NW>
+__global__ void __launch_bounds__(128) align_tb_kernel(AlignArgs a) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.n_pairs_max) return;
+    align_pair<NW, true>(a, t, t);
+}
+
+static int pick_nw(int band) {
+    const int need = (2 * band + 1 + 31) / 32;
+    const int avail[] = {1, 2, 3, 5, 7, 9, 13};
+    for (int v : avail) if (v >= need) return v;
+    return -1;
+}
+int align_supported_band_max() { return (13 * 32 - 1) / 2; }
+int align_words_for_band(int band) { return pick_nw(band); }
+
+static AlignArgs make_args(const SeqBatch &in, const uint2 *read_planes, const AsvIndex &ix, const uint32_t *pair_read,
+                           const uint32_t *pair_asv, const uint8_t *pair_strand, const AlignOut &out, const DeviceParams &p) {
+    AlignArgs a{};
+    a.read_offsets = in.offsets; a.read_planes = read_planes;
+    a.asv_planes = ix.planes; a.asv_plane_off = ix.plane_off; a.asv_len = ix.len;
+    a.pair_read = pair_read; a.pair_asv = pair_asv; a.pair_strand = pair_strand;
+    a.nm = out.nm; a.asv_end = out.asv_end; a.read_end = out.read_end;
+    a.band = p.band; a.padl = p.asv_padl;
+    return a;
+}
+
+void launch_align_nm(const SeqBatch &in, const uint2 *read_planes, const AsvIndex &ix, const uint32_t *pair_read,
+                     const uint32_t *pair_asv, const uint8_t *pair_strand, const uint32_t *n_pairs_dev, uint32_t n_pairs_max,
+                     const AlignOut &out, const DeviceParams &p, int sm_count, cudaStream_t st) {
+    if (n_pairs_max == 0) return;
+    AlignArgs a = make_args(in, read_planes, ix, pair_read, pair_asv, pair_strand, out, p);
+    a.n_pairs_dev = n_pairs_dev; a.n_pairs_max = n_pairs_max;
+    uint32_t grid = (n_pairs_max + 127u) / 128u;
+    const uint32_t cap = (uint32_t)sm_count * 16u;       // 16 CTAs x 128 threads = full occupancy per SM
+    if (grid > cap) grid = cap;
+    switch (pick_nw(p.band)) {
+        case 1: align_nm_kernel<1><<<grid, 128, 0, st>>>(a); break;
+        case 2: align_nm_kernel<2><<<grid, 128, 0, st>>>(a); break;
+        case 3: align_nm_kernel<3><<<grid, 128, 0, st>>>(a); break;
+        case 5: align_nm_kernel<5><<<grid, 128, 0, st>>>(a); break;
+        case 7: align_nm_kernel<7><<<grid, 128, 0, st>>>(a); break;
+        case 9: align_nm_kernel<9><<<grid, 128, 0, st>>>(a); break;
+        case 13: align_nm_kernel<13><<<grid, 128, 0, st>>>(a); break;
+        default: break;
+    }
+}
+
+size_t align_tb_hist_words(uint32_t n_pairs, uint32_t hist_cols, const DeviceParams &p) {
+    const int nw = pick_nw(p.band);
+    return (size_t)n_pairs * hist_cols * 2u * (size_t)(nw > 0 ? nw : 1);
+}
+
+void launch_align_tb(const SeqBatch &in, const uint2 *read_planes, const AsvIndex &ix, const uint32_t *pair_read,
+                     const uint32_t *pair_asv, const uint8_t *pair_strand, uint32_t n_pairs,
+                     uint32_t *hist, const AlignOut &out, int32_t *asv_start, int32_t *read_start,
+                     uint32_t *cigar, uint32_t cigar_stride, uint32_t *cigar_cnt, const DeviceParams &p, cudaStream_t st) {
+    if (n_pairs == 0) return;
+    AlignArgs a = make_args(in, read_planes, ix, pair_read, pair_asv, pair_strand, out, p);
+    a.n_pairs_dev = nullptr; a.n_pairs_max = n_pairs;
+    a.hist = hist; a.hist_stride = n_pairs;
+    a.asv_start = asv_start; a.read_start = read_start;
+    a.cigar = cigar; a.cigar_stride = cigar_stride; a.cigar_cnt = cigar_cnt;
+    const uint32_t grid = (n_pairs + 127u) / 128u;
+    switch (pick_nw(p.band)) {
+        case 1: align_tb_kernel<1><<<grid, 128, 0, st>>>(a); break;
+        case 2: align_tb_kernel<2><<<grid, 128, 0, st>>>(a); break;
+        case 3: align_tb_kernel<3><<<grid, 128, 0, st>>>(a); break;
+        case 5: align_tb_kernel<5><<<grid, 128, 0, st>>>(a); break;
+        case 7: align_tb_kernel<7><<<grid, 128, 0, st>>>(a); break;
+        case 9: align_tb_kernel<9><<<grid, 128, 0, st>>>(a); break;
+        case 13: align_tb_kernel<13><<<grid, 128, 0, st>>>(a); break;
+        default: break;
+    }
+}
+
+}  // namespace sb

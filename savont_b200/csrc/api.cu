@@ -1,0 +1,1055 @@
+// api.cu -- host side of libsavont_b200.so: context, replicated ASV index, batch pipeline and the
+// extern "C" entry points declared in include/savont_b200.h.
+//
+// Everything that computes on reads runs in the CUDA kernels (sketch.cu, filter.cu, align.cu,
+// assign.cu).  The host only orchestrates: stages buffers, builds the (small, once per call)
+// replicated ASV index from the GPU-produced ASV sketches, and sums counters.  There is no CPU
+// fallback: without a device every entry point fails with SAVONT_B200_ERR_CUDA.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/savont_b200.h"
+#include "common.cuh"
+
+namespace sb {
+
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CK(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e__ = (call);                                                                             \
+        if (e__ != cudaSuccess)                                                                               \
+            return fail(SAVONT_B200_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,            \
+                        cudaGetErrorString(e__));                                                             \
+    } while (0)
+#define TRY(call)                    \
+    do {                             \
+        int rc__ = (call);           \
+        if (rc__ != 0) return rc__;  \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            return fail(SAVONT_B200_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e != cudaSuccess) { p = nullptr; return fail(SAVONT_B200_ERR_NOMEM, "cudaMallocHost(%zu) failed", want); }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+// device-resident inputs, intermediates and outputs of one batch of sequences
+struct Batch {
+    DevBuf bases, quals, offsets, file_idx;
+    bool has_quals = false, has_file_idx = false;
+    uint32_t n = 0, max_len = 0;
+    uint64_t total_bases = 0;
+    // sketch
+    DevBuf planes, sk_status, flatq, mini_cnt, mini_kmer, mini_pos, snp_start, snp_cnt, snp_kmer, snp_pos, est_id;
+    uint32_t snp_cap = 0;
+    DevBuf ctrs;   // u32[4]: snp pool counter, pair counter, error bits, spare
+    // filter
+    DevBuf cand_status, pair_start, pair_cnt, low_mm, p_read, p_asv, p_mini, p_strand;
+    uint32_t pair_cap = 0;
+    // align
+    DevBuf nm, asv_end, read_end;
+    // assign
+    DevBuf rstatus, best_nm, class_cnt, class_slot, class_off, class_out, scan_tmp;
+    bool mapped = false;
+    void release() {
+        DevBuf *all[] = {&bases, &quals, &offsets, &file_idx, &planes, &sk_status, &flatq, &mini_cnt, &mini_kmer, &mini_pos,
+                         &snp_start, &snp_cnt, &snp_kmer, &snp_pos, &est_id, &ctrs, &cand_status, &pair_start, &pair_cnt,
+                         &low_mm, &p_read, &p_asv, &p_mini, &p_strand, &nm, &asv_end, &read_end, &rstatus, &best_nm,
+                         &class_cnt, &class_slot, &class_off, &class_out, &scan_tmp};
+        for (DevBuf *b : all) b->release();
+    }
+};
+
+struct Context {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    savont_b200_params params;
+    DeviceParams dp;
+    size_t batch_reads = 262144;
+
+    // tables
+    DevBuf d_rank_table; bool use_rank_table = false;
+    DevBuf d_snp_keys; uint32_t snp_mask = 0; std::vector<uint64_t> h_snpmers;
+    DevBuf d_phred;
+
+    // ASVs (replicated index)
+    std::vector<uint8_t> asv_bases_h; std::vector<uint64_t> asv_offsets_h;
+    size_t n_asv = 0; bool index_dirty = true; uint32_t max_asv_len = 0;
+    DevBuf d_idx_keys, d_idx_vals, d_idx_entries, d_mset, d_mset_off, d_asv_planes, d_asv_plane_off, d_asv_len;
+    uint32_t idx_mask = 0;
+    std::vector<uint32_t> asv_len_h;
+
+    // counters [unambig A | ambig A | leq10 A | assigned | filtered | singleton S*A]
+    DevBuf d_counters; size_t counters_len = 0; int counters_samples = 0;
+
+    Batch work, resident, asvb;
+    int resident_samples = 1;
+    PinBuf pin_offsets, pin_small, pin_out;
+    cudaEvent_t ev[8] = {nullptr};
+    savont_b200_stats last_stats;
+};
+
+// ------------------------------------------------------------------------------------------------
+static uint32_t next_pow2_u32(uint64_t x) { uint32_t p = 1; while ((uint64_t)p < x) p <<= 1; return p; }
+
+static int validate_params(const savont_b200_params &p) {
+    if (p.k < 13 || p.k > 23 || (p.k % 2) == 0)
+        return fail(SAVONT_B200_ERR_INVALID, "k=%d unsupported: must be odd, 13..23 (reference src/types.rs:580-609)", p.k);
+    if (p.c < 1 || p.c > p.k) return fail(SAVONT_B200_ERR_INVALID, "c=%d must be in 1..k", p.c);
+    const int s = p.k - p.c + 1;
+    if (s < 1 || s > 16) return fail(SAVONT_B200_ERR_INVALID, "s=k-c+1=%d must be in 1..16", s);
+    if (p.band < 0 || p.band > align_supported_band_max())
+        return fail(SAVONT_B200_ERR_INVALID, "band=%d unsupported (0..%d)", p.band, align_supported_band_max());
+    if (p.min_bq < 0 || p.min_bq > 93) return fail(SAVONT_B200_ERR_INVALID, "min_bq=%d out of range", p.min_bq);
+    if (p.strand_mode != 0 && p.strand_mode != 1) return fail(SAVONT_B200_ERR_INVALID, "strand_mode must be 0 or 1");
+    if (!(p.ratio_thresh >= 0.0) || !(p.min_mini_frac_base > 0.0)) return fail(SAVONT_B200_ERR_INVALID, "bad thresholds");
+    return 0;
+}
+
+// compiler-rt __powidf2: what Rust's f64::powi lowers to
+static double powi_rt(double a, int b) {
+    const bool recip = b < 0;
+    double r = 1;
+    while (true) {
+        if (b & 1) r *= a;
+        b /= 2;
+        if (b == 0) break;
+        a *= a;
+    }
+    return recip ? 1 / r : r;
+}
+
+static DeviceParams make_device_params(const savont_b200_params &p) {
+    DeviceParams d{};
+    d.k = p.k; d.c = p.c; d.s = p.k - p.c + 1;
+    d.min_bq = p.min_bq; d.band = p.band; d.strand_mode = p.strand_mode;
+    d.asv_padl = ((p.band + 1 + 31) / 32) * 32;
+    d.mini_spacing = (p.c - 1) / 2 + 1;
+    d.split_mask = ~(3ull << (p.k - 1));
+    d.kmer_mask = (p.k == 32) ? ~0ull : ((1ull << (2 * p.k)) - 1ull);
+    d.ratio_thresh = p.ratio_thresh;
+    d.min_frac = powi_rt(p.min_mini_frac_base, p.k);
+    return d;
+}
+
+static uint64_t revcomp_kmer_host(uint64_t x, int k) {
+    uint64_t out = 0;
+    for (int i = 0; i < k; ++i) { out = (out << 2) | (3 - (x & 3)); x >>= 2; }
+    return out;
+}
+static uint8_t enc_host(uint8_t b) {
+    switch (b) {
+        case 'C': case 'c': case 1: return 1;
+        case 'G': case 'g': case 2: return 2;
+        case 'T': case 't': case 'U': case 'u': case 3: return 3;
+        default: return 0;
+    }
+}
+
+static int build_tables(Context *c) {
+    const int s = c->dp.s;
+    c->use_rank_table = s <= 7;
+    if (c->use_rank_table) {
+        // rank of mm_hash64(canonical s-mer) among all s-mers; indexed by the FORWARD s-mer
+        const uint32_t n = 1u << (2 * s);
+        std::vector<std::pair<uint64_t, uint32_t>> hs;
+        hs.reserve(n);
+        std::vector<uint32_t> canon(n);
+        for (uint32_t f = 0; f < n; ++f) {
+            const uint32_t r = (uint32_t)revcomp_kmer_host(f, s);
+            canon[f] = f < r ? f : r;
+            if (canon[f] == f) hs.emplace_back(mm_hash64((uint64_t)f), f);
+        }
+        std::sort(hs.begin(), hs.end());
+        std::vector<uint16_t> rank_of(n, 0);
+        for (size_t i = 0; i < hs.size(); ++i) rank_of[hs[i].second] = (uint16_t)i;
+        std::vector<uint16_t> table(n);
+        for (uint32_t f = 0; f < n; ++f) table[f] = rank_of[canon[f]];
+        TRY(c->d_rank_table.ensure(n * sizeof(uint16_t)));
+        CK(cudaMemcpyAsync(c->d_rank_table.p, table.data(), n * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    // est_id table: 10^(-(b-33)/10) with the host libm (reference src/seeding.rs:812-813)
+    std::vector<double> ph(256);
+    for (int b = 0; b < 256; ++b) { const double q = (double)(b - 33); ph[b] = pow(10.0, -q / 10.0); }
+    TRY(c->d_phred.ensure(256 * sizeof(double)));
+    CK(cudaMemcpyAsync(c->d_phred.p, ph.data(), 256 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+static int upload_snp_set(Context *c) {
+    const size_t n = c->h_snpmers.size();
+    if (n == 0) { c->snp_mask = 0; return 0; }
+    const uint32_t cap = next_pow2_u32(2 * n + 2);
+    std::vector<uint64_t> keys(cap, kEmpty64);
+    for (uint64_t key : c->h_snpmers) {
+        uint32_t slot = (uint32_t)mix64(key) & (cap - 1);
+        while (keys[slot] != kEmpty64 && keys[slot] != key) slot = (slot + 1) & (cap - 1);
+        keys[slot] = key;
+    }
+    TRY(c->d_snp_keys.ensure(cap * sizeof(uint64_t)));
+    CK(cudaMemcpyAsync(c->d_snp_keys.p, keys.data(), cap * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->snp_mask = cap - 1;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// batch staging
+// ------------------------------------------------------------------------------------------------
+static int batch_upload(Context *c, Batch &b, const uint8_t *bases, const uint8_t *quals, const uint64_t *offsets,
+                        const uint32_t *file_idx, size_t n, uint64_t *h2d_bytes) {
+    const uint64_t base0 = offsets[0];
+    const uint64_t total = offsets[n] - base0;
+    if (total >= (1ull << 32) - 64) return fail(SAVONT_B200_ERR_INVALID, "batch of %llu bases exceeds 4 Gi", (unsigned long long)total);
+    TRY(c->pin_offsets.ensure((n + 1) * sizeof(uint64_t)));
+    uint64_t *rel = c->pin_offsets.as<uint64_t>();
+    uint32_t max_len = 0;
+    for (size_t i = 0; i <= n; ++i) {
+        if (i > 0 && offsets[i] < offsets[i - 1]) return fail(SAVONT_B200_ERR_INVALID, "offsets not monotonic at %zu", i);
+        rel[i] = offsets[i] - base0;
+        if (i > 0) { const uint64_t len = offsets[i] - offsets[i - 1]; if (len > max_len) max_len = (uint32_t)std::min<uint64_t>(len, 0xffffffffu); }
+    }
+    b.n = (uint32_t)n; b.total_bases = total; b.max_len = max_len; b.mapped = false;
+    b.has_quals = quals != nullptr; b.has_file_idx = file_idx != nullptr;
+    TRY(b.bases.ensure(total + 64));
+    TRY(b.offsets.ensure((n + 1) * sizeof(uint64_t)));
+    CK(cudaMemcpyAsync(b.offsets.p, rel, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+    if (total) CK(cudaMemcpyAsync(b.bases.p, bases + base0, total, cudaMemcpyHostToDevice, c->stream));
+    uint64_t bytes = (n + 1) * sizeof(uint64_t) + total;
+    if (quals) {
+        TRY(b.quals.ensure(total + 64));
+        if (total) CK(cudaMemcpyAsync(b.quals.p, quals + base0, total, cudaMemcpyHostToDevice, c->stream));
+        bytes += total;
+    }
+    if (file_idx) {
+        TRY(b.file_idx.ensure(n * sizeof(uint32_t) + 4));
+        if (n) CK(cudaMemcpyAsync(b.file_idx.p, file_idx, n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        bytes += n * sizeof(uint32_t);
+    }
+    if (h2d_bytes) *h2d_bytes += bytes;
+    return 0;
+}
+
+static SeqBatch seq_view(const Batch &b) {
+    SeqBatch v{};
+    v.bases = b.bases.as<uint8_t>();
+    v.quals = b.has_quals ? b.quals.as<uint8_t>() : nullptr;
+    v.offsets = b.offsets.as<uint64_t>();
+    v.n = b.n; v.max_len = b.max_len;
+    return v;
+}
+
+static SketchOut sketch_view(const Batch &b, bool with_pos) {
+    SketchOut o{};
+    o.status = b.sk_status.as<uint8_t>(); o.flatq = b.flatq.as<uint8_t>();
+    o.planes = b.planes.as<uint2>();
+    o.mini_cnt = b.mini_cnt.as<uint32_t>(); o.mini_kmer = b.mini_kmer.as<uint64_t>();
+    o.mini_pos = with_pos ? b.mini_pos.as<uint32_t>() : nullptr;
+    o.snp_start = b.snp_start.as<uint32_t>(); o.snp_cnt = b.snp_cnt.as<uint32_t>();
+    o.snp_kmer = b.snp_kmer.as<uint64_t>(); o.snp_pos = b.snp_pos.as<uint32_t>();
+    o.snp_pool_ctr = b.ctrs.as<uint32_t>(); o.snp_pool_cap = b.snp_cap;
+    o.err = b.ctrs.as<uint32_t>() + 2;
+    return o;
+}
+
+static int stage_sketch(Context *c, Batch &b, bool with_pos) {
+    const size_t n = b.n;
+    const uint64_t total = b.total_bases;
+    const size_t plane_words = (size_t)plane_word_off(total, n) + 4;
+    const size_t mini_slots = (size_t)mini_slot_off(total, n, (uint32_t)c->dp.mini_spacing) + 4;
+    TRY(b.planes.ensure(plane_words * sizeof(uint2)));
+    TRY(b.sk_status.ensure(n + 4)); TRY(b.flatq.ensure(n + 4));
+    TRY(b.mini_cnt.ensure((n + 1) * 4)); TRY(b.mini_kmer.ensure(mini_slots * 8));
+    if (with_pos) TRY(b.mini_pos.ensure(mini_slots * 4));
+    TRY(b.snp_start.ensure((n + 1) * 4)); TRY(b.snp_cnt.ensure((n + 1) * 4));
+    if (b.snp_cap == 0 || b.snp_cap < total / 8 + 4096) b.snp_cap = (uint32_t)std::min<uint64_t>(total / 8 + 4096, 0xfffffff0u);
+    TRY(b.ctrs.ensure(4 * sizeof(uint32_t)));
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        TRY(b.snp_kmer.ensure((size_t)b.snp_cap * 8)); TRY(b.snp_pos.ensure((size_t)b.snp_cap * 4));
+        CK(cudaMemsetAsync(b.ctrs.p, 0, 4 * sizeof(uint32_t), c->stream));
+        SnpSet set{c->snp_mask ? c->d_snp_keys.as<uint64_t>() : nullptr, c->snp_mask};
+        launch_sketch(seq_view(b), sketch_view(b, with_pos), set, c->use_rank_table ? c->d_rank_table.as<uint16_t>() : nullptr,
+                      c->dp, c->sm_count, c->stream);
+        CK(cudaGetLastError());
+        c->last_stats.kernel_launches += 1;
+        // the SNPmer pool is sized generously (1 entry per 8 bases); verify lazily with the pair pool check
+        uint32_t h[4];
+        CK(cudaMemcpyAsync(h, b.ctrs.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        if (h[2] & kErrSnpHits)
+            return fail(SAVONT_B200_ERR_OVERFLOW, "a sequence has more than %d SNPmer hits (limit of the shared-memory hit list)",
+                        kSnpHitCap);
+        if (h[2] & kErrSnpPool) {
+            if (attempt == 2) return fail(SAVONT_B200_ERR_OVERFLOW, "SNPmer pool overflow (%u needed)", h[0]);
+            b.snp_cap = h[0] + 1024;
+            continue;
+        }
+        break;
+    }
+    return 0;
+}
+
+static AsvIndex index_view(const Context *c) {
+    AsvIndex ix{};
+    ix.idx_keys = c->idx_mask ? c->d_idx_keys.as<uint64_t>() : nullptr;
+    ix.idx_vals = c->d_idx_vals.as<uint2>(); ix.idx_mask = c->idx_mask; ix.idx_entries = c->d_idx_entries.as<uint32_t>();
+    ix.mset = c->d_mset.as<uint64_t>(); ix.mset_off = c->d_mset_off.as<uint32_t>();
+    ix.planes = c->d_asv_planes.as<uint2>(); ix.plane_off = c->d_asv_plane_off.as<uint32_t>(); ix.len = c->d_asv_len.as<uint32_t>();
+    ix.n_asv = (uint32_t)c->n_asv;
+    return ix;
+}
+
+static PairPool pool_view(const Batch &b) {
+    PairPool p{};
+    p.read = b.p_read.as<uint32_t>(); p.asv = b.p_asv.as<uint32_t>(); p.mini = b.p_mini.as<uint32_t>();
+    p.strand = b.p_strand.as<uint8_t>(); p.counter = b.ctrs.as<uint32_t>() + 1; p.cap = b.pair_cap;
+    return p;
+}
+static FilterOut filter_view(const Batch &b) {
+    FilterOut f{};
+    f.cand_status = b.cand_status.as<uint8_t>(); f.pair_start = b.pair_start.as<uint32_t>(); f.pair_cnt = b.pair_cnt.as<uint32_t>();
+    f.low_mm = b.low_mm.as<uint32_t>(); f.err = b.ctrs.as<uint32_t>() + 2;
+    return f;
+}
+
+static int ensure_pair_pool(Batch &b) {
+    TRY(b.p_read.ensure((size_t)b.pair_cap * 4)); TRY(b.p_asv.ensure((size_t)b.pair_cap * 4));
+    TRY(b.p_mini.ensure((size_t)b.pair_cap * 4)); TRY(b.p_strand.ensure((size_t)b.pair_cap + 4));
+    TRY(b.nm.ensure((size_t)b.pair_cap * 4)); TRY(b.asv_end.ensure((size_t)b.pair_cap * 4)); TRY(b.read_end.ensure((size_t)b.pair_cap * 4));
+    TRY(b.class_slot.ensure((size_t)b.pair_cap * 4));
+    return 0;
+}
+
+// filter with pool-overflow retry; leaves the pair count in *n_pairs
+static int stage_filter(Context *c, Batch &b, int strand_mode, uint32_t *n_pairs) {
+    const size_t n = b.n;
+    if (n > 0 && (uint64_t)b.max_len / (uint64_t)c->dp.mini_spacing + 2 >= 32768u)
+        return fail(SAVONT_B200_ERR_OVERFLOW, "read of %u bases is too long for the candidate filter", b.max_len);
+    TRY(b.cand_status.ensure(n + 4)); TRY(b.pair_start.ensure((n + 1) * 4)); TRY(b.pair_cnt.ensure((n + 1) * 4));
+    TRY(b.low_mm.ensure((n + 1) * 4));
+    const uint32_t per = strand_mode == 1 ? 2u : 1u;
+    if (b.pair_cap < 4u * per * (uint32_t)n + 1024u) b.pair_cap = 4u * per * (uint32_t)n + 1024u;
+    DeviceParams dp = c->dp; dp.strand_mode = strand_mode;
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        TRY(ensure_pair_pool(b));
+        CK(cudaMemsetAsync(b.ctrs.as<uint32_t>() + 1, 0, 2 * sizeof(uint32_t), c->stream));
+        launch_filter(seq_view(b), sketch_view(b, false), index_view(c), pool_view(b), filter_view(b), dp, c->sm_count, c->stream);
+        CK(cudaGetLastError());
+        c->last_stats.kernel_launches += 1;
+        uint32_t h[4];
+        CK(cudaMemcpyAsync(h, b.ctrs.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        if (h[2] & kErrPairPool) {
+            if (attempt == 2) return fail(SAVONT_B200_ERR_OVERFLOW, "candidate pair pool overflow (%u needed)", h[1]);
+            b.pair_cap = h[1] + 1024;
+            continue;
+        }
+        *n_pairs = h[1];
+        break;
+    }
+    return 0;
+}
+
+static int stage_align(Context *c, Batch &b, uint32_t n_pairs) {
+    AlignOut ao{b.nm.as<int32_t>(), b.asv_end.as<int32_t>(), b.read_end.as<int32_t>()};
+    launch_align_nm(seq_view(b), b.planes.as<uint2>(), index_view(c), b.p_read.as<uint32_t>(), b.p_asv.as<uint32_t>(),
+                    b.p_strand.as<uint8_t>(), nullptr, n_pairs, ao, c->dp, c->sm_count, c->stream);
+    CK(cudaGetLastError());
+    if (n_pairs) c->last_stats.kernel_launches += 1;
+    return 0;
+}
+
+static int ensure_counters(Context *c, int n_samples, bool zero) {
+    const size_t len = 3 * c->n_asv + 2 + (size_t)n_samples * c->n_asv;
+    if (len != c->counters_len || n_samples != c->counters_samples) {
+        TRY(c->d_counters.ensure(len * sizeof(uint64_t)));
+        c->counters_len = len; c->counters_samples = n_samples;
+        zero = true;
+    }
+    if (zero) CK(cudaMemsetAsync(c->d_counters.p, 0, len * sizeof(uint64_t), c->stream));
+    return 0;
+}
+
+static int stage_assign(Context *c, Batch &b, int n_samples, int strand_mode) {
+    const size_t n = b.n;
+    TRY(b.rstatus.ensure(n + 4)); TRY(b.best_nm.ensure((n + 1) * 4)); TRY(b.class_cnt.ensure((n + 1) * 4));
+    TRY(b.class_off.ensure((n + 2) * 4)); TRY(b.class_out.ensure((size_t)b.pair_cap * 4 + 4));
+    TRY(b.scan_tmp.ensure((n / 2048 + 4) * 4));
+    launch_assign(filter_view(b), pool_view(b), b.nm.as<int32_t>(), b.has_file_idx ? b.file_idx.as<uint32_t>() : nullptr, (uint32_t)n,
+                  (uint32_t)c->n_asv, n_samples, strand_mode, b.rstatus.as<uint8_t>(), b.best_nm.as<int32_t>(),
+                  b.class_cnt.as<uint32_t>(), b.class_slot.as<uint32_t>(), c->d_counters.as<unsigned long long>(), c->stream);
+    launch_scan_u32(b.class_cnt.as<uint32_t>(), b.class_off.as<uint32_t>(), (uint32_t)n, b.scan_tmp.as<uint32_t>(), c->stream);
+    launch_gather_u32(b.class_slot.as<uint32_t>(), b.pair_start.as<uint32_t>(), b.class_cnt.as<uint32_t>(), b.class_off.as<uint32_t>(),
+                      b.class_out.as<uint32_t>(), (uint32_t)n, c->stream);
+    CK(cudaGetLastError());
+    if (n) c->last_stats.kernel_launches += 5;
+    b.mapped = true;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ASV index (reference src/kmer_comp.rs:39-66 + src/alignment.rs:1754-1765)
+// ------------------------------------------------------------------------------------------------
+static int build_asv_index(Context *c) {
+    const size_t A = c->asv_offsets_h.empty() ? 0 : c->asv_offsets_h.size() - 1;
+    c->n_asv = A;
+    c->index_dirty = false;
+    c->counters_len = 0;
+    if (A == 0) { c->idx_mask = 0; return 0; }
+    const int k = c->dp.k;
+    Batch &b = c->asvb;
+    TRY(batch_upload(c, b, c->asv_bases_h.data(), nullptr, c->asv_offsets_h.data(), nullptr, A, nullptr));
+    TRY(stage_sketch(c, b, true));
+    // download the sketches
+    const size_t mini_slots = (size_t)mini_slot_off(b.total_bases, A, (uint32_t)c->dp.mini_spacing) + 4;
+    std::vector<uint8_t> st(A);
+    std::vector<uint32_t> mini_cnt(A), snp_start(A), snp_cnt(A);
+    std::vector<uint64_t> mini_kmer(mini_slots);
+    uint32_t ctr[4];
+    CK(cudaMemcpyAsync(ctr, b.ctrs.p, sizeof(ctr), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(st.data(), b.sk_status.p, A, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(mini_cnt.data(), b.mini_cnt.p, A * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(snp_start.data(), b.snp_start.p, A * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(snp_cnt.data(), b.snp_cnt.p, A * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(mini_kmer.data(), b.mini_kmer.p, mini_slots * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    std::vector<uint32_t> snp_pos(ctr[0] + 1);
+    if (ctr[0]) CK(cudaMemcpy(snp_pos.data(), b.snp_pos.p, (size_t)ctr[0] * 4, cudaMemcpyDeviceToHost));
+    for (size_t a = 0; a < A; ++a)
+        if (st[a] != 0) return fail(SAVONT_B200_ERR_INVALID, "ASV %zu is shorter than k=%d", a, k);
+
+    // (1) distinct minimizer sets, sorted, forward-any flag in bit 63
+    std::vector<uint64_t> mset; std::vector<uint32_t> mset_off(A + 1, 0);
+    std::vector<uint64_t> tmp;
+    for (size_t a = 0; a < A; ++a) {
+        const uint64_t mo = mini_slot_off(c->asv_offsets_h[a] - c->asv_offsets_h[0], a, (uint32_t)c->dp.mini_spacing);
+        tmp.assign(mini_kmer.begin() + mo, mini_kmer.begin() + mo + mini_cnt[a]);
+        for (uint64_t &v : tmp) v = (v << 1) | (v >> 63);            // key in the high bits, flag in bit 0
+        std::sort(tmp.begin(), tmp.end());
+        size_t first = mset.size();
+        for (uint64_t v : tmp) {
+            const uint64_t key = v >> 1, f = v & 1;
+            if (mset.size() > first && (mset.back() & ~kFwdBit) == key) { if (f) mset.back() |= kFwdBit; }
+            else mset.push_back(key | (f ? kFwdBit : 0));
+        }
+        mset_off[a + 1] = (uint32_t)mset.size();
+    }
+    // (2) SNPmer inverted index from asv.snpmers_vec(): k-mers re-extracted from positions with
+    //     kmer_from_position's canonical rule (tie -> forward), src/types.rs:622-663
+    struct Ent { uint64_t sp; uint32_t asv; uint32_t mid; };
+    std::vector<Ent> ents;
+    const uint64_t split_mask = c->dp.split_mask;
+    for (size_t a = 0; a < A; ++a) {
+        const uint8_t *sq = c->asv_bases_h.data() + c->asv_offsets_h[a];
+        for (uint32_t t = 0; t < snp_cnt[a]; ++t) {
+            const uint32_t pos = snp_pos[snp_start[a] + t];
+            uint64_t kmer = 0;
+            for (int q = 0; q < k; ++q) kmer = (kmer << 2) | enc_host(sq[pos + q]);
+            const uint64_t rc = revcomp_kmer_host(kmer, k);
+            const uint64_t canon = ((rc & split_mask) < (kmer & split_mask)) ? rc : kmer;
+            ents.push_back({canon & split_mask, (uint32_t)a, (uint32_t)((canon >> (k - 1)) & 3)});
+        }
+    }
+    std::sort(ents.begin(), ents.end(), [](const Ent &x, const Ent &y) { return x.sp != y.sp ? x.sp < y.sp : x.asv < y.asv; });
+    size_t n_keys = 0;
+    for (size_t i = 0; i < ents.size(); ++i) if (i == 0 || ents[i].sp != ents[i - 1].sp) ++n_keys;
+    std::vector<uint32_t> entries(ents.size() + 1);
+    const uint32_t cap = n_keys ? next_pow2_u32(2 * n_keys + 2) : 0;
+    std::vector<uint64_t> keys(cap ? cap : 1, kEmpty64);
+    std::vector<uint2> vals(cap ? cap : 1, make_uint2(0, 0));
+    for (size_t i = 0; i < ents.size();) {
+        size_t j = i;
+        while (j < ents.size() && ents[j].sp == ents[i].sp) { entries[j] = (ents[j].asv << 2) | ents[j].mid; ++j; }
+        uint32_t slot = (uint32_t)mix64(ents[i].sp) & (cap - 1);
+        while (keys[slot] != kEmpty64) slot = (slot + 1) & (cap - 1);
+        keys[slot] = ents[i].sp; vals[slot] = make_uint2((uint32_t)i, (uint32_t)(j - i));
+        i = j;
+    }
+    c->idx_mask = cap ? cap - 1 : 0;
+    // (3) DP planes: padl zero bits, then the bases, then >= 32*(NW+4) zero bits
+    const int nw = align_words_for_band(c->dp.band);
+    const uint32_t padl = (uint32_t)c->dp.asv_padl;
+    std::vector<uint32_t> plane_off(A), lens(A);
+    size_t words = 0;
+    c->max_asv_len = 0;
+    for (size_t a = 0; a < A; ++a) {
+        const uint32_t len = (uint32_t)(c->asv_offsets_h[a + 1] - c->asv_offsets_h[a]);
+        lens[a] = len; plane_off[a] = (uint32_t)words;
+        words += (padl + len) / 32 + (size_t)nw + 6;
+        if (len > c->max_asv_len) c->max_asv_len = len;
+    }
+    std::vector<uint2> planes(words + 8, make_uint2(0, 0));
+    for (size_t a = 0; a < A; ++a) {
+        const uint8_t *sq = c->asv_bases_h.data() + c->asv_offsets_h[a];
+        uint2 *pw = planes.data() + plane_off[a];
+        for (uint32_t i = 0; i < lens[a]; ++i) {
+            const uint32_t code = enc_host(sq[i]), bit = i + padl;
+            if (code & 1) pw[bit >> 5].x |= 1u << (bit & 31);
+            if (code & 2) pw[bit >> 5].y |= 1u << (bit & 31);
+        }
+    }
+    c->asv_len_h = lens;
+    // upload
+    TRY(c->d_mset.ensure((mset.size() + 1) * 8)); TRY(c->d_mset_off.ensure((A + 1) * 4));
+    TRY(c->d_idx_keys.ensure(keys.size() * 8)); TRY(c->d_idx_vals.ensure(vals.size() * 8)); TRY(c->d_idx_entries.ensure(entries.size() * 4));
+    TRY(c->d_asv_planes.ensure(planes.size() * 8)); TRY(c->d_asv_plane_off.ensure(A * 4)); TRY(c->d_asv_len.ensure(A * 4));
+    if (!mset.empty()) CK(cudaMemcpy(c->d_mset.p, mset.data(), mset.size() * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_mset_off.p, mset_off.data(), (A + 1) * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_idx_keys.p, keys.data(), keys.size() * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_idx_vals.p, vals.data(), vals.size() * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_idx_entries.p, entries.data(), entries.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_asv_planes.p, planes.data(), planes.size() * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_asv_plane_off.p, plane_off.data(), A * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_asv_len.p, lens.data(), A * 4, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static int ensure_index(Context *c) {
+    if (c->index_dirty) TRY(build_asv_index(c));
+    if (c->n_asv == 0) return fail(SAVONT_B200_ERR_INVALID, "no ASVs loaded (call savont_b200_load_asvs first)");
+    return 0;
+}
+
+static int use_device(Context *c) {
+    if (!c) return fail(SAVONT_B200_ERR_INVALID, "null context");
+    CK(cudaSetDevice(c->device));
+    return 0;
+}
+
+static float ev_ms(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
+
+// sketch -> filter -> align -> assign on a device-resident batch, timed with events on the stream
+static int run_path(Context *c, Batch &b, int n_samples, savont_b200_stats &st) {
+    uint32_t n_pairs = 0;
+    CK(cudaEventRecord(c->ev[0], c->stream));
+    TRY(stage_sketch(c, b, false));
+    CK(cudaEventRecord(c->ev[1], c->stream));
+    TRY(stage_filter(c, b, c->dp.strand_mode, &n_pairs));
+    CK(cudaEventRecord(c->ev[2], c->stream));
+    TRY(stage_align(c, b, n_pairs));
+    CK(cudaEventRecord(c->ev[3], c->stream));
+    TRY(stage_assign(c, b, n_samples, c->dp.strand_mode));
+    CK(cudaEventRecord(c->ev[4], c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    st.sketch_ms += ev_ms(c->ev[0], c->ev[1]);
+    st.filter_ms += ev_ms(c->ev[1], c->ev[2]);
+    st.align_ms += ev_ms(c->ev[2], c->ev[3]);
+    st.assign_ms += ev_ms(c->ev[3], c->ev[4]);
+    st.n_pairs += n_pairs;
+    st.n_reads += b.n; st.n_bases += b.total_bases;
+    // dp_cells = sum over pairs of L_asv * (2B+1): needs the pair ASVs; computed from a device-side copy of p_asv
+    if (n_pairs) {
+        std::vector<uint32_t> pa(n_pairs);
+        CK(cudaMemcpy(pa.data(), b.p_asv.p, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost));
+        uint64_t cells = 0;
+        for (uint32_t a : pa) cells += (uint64_t)c->asv_len_h[a] * (uint64_t)(2 * c->dp.band + 1);
+        st.dp_cells += cells;
+    }
+    return 0;
+}
+
+static int fetch_batch(Context *c, Batch &b, uint8_t *status, int32_t *best_nm, uint64_t *class_offsets, uint64_t class_base,
+                       uint32_t *class_asv, size_t class_cap, uint64_t *n_class_out, uint64_t *d2h_bytes) {
+    const size_t n = b.n;
+    TRY(c->pin_small.ensure((n + 2) * 4));
+    uint32_t *off = c->pin_small.as<uint32_t>();
+    CK(cudaMemcpyAsync(off, b.class_off.p, (n + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (n) CK(cudaMemcpyAsync(status, b.rstatus.p, n, cudaMemcpyDeviceToHost, c->stream));
+    if (n) CK(cudaMemcpyAsync(best_nm, b.best_nm.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    const uint32_t total = off[n];
+    if (class_base + total > class_cap)
+        return fail(SAVONT_B200_ERR_CAPACITY, "class_asv capacity %zu too small (need >= %llu)", class_cap,
+                    (unsigned long long)(class_base + total));
+    if (total) CK(cudaMemcpyAsync(class_asv + class_base, b.class_out.p, (size_t)total * 4, cudaMemcpyDeviceToHost, c->stream));
+    for (size_t i = 0; i <= n; ++i) class_offsets[i] = class_base + off[i];
+    CK(cudaStreamSynchronize(c->stream));
+    *n_class_out = total;
+    if (d2h_bytes) *d2h_bytes += (n + 1) * 4 + n * 5 + (uint64_t)total * 4;
+    return 0;
+}
+
+static int read_counters(Context *c, uint64_t *unambig, uint64_t *ambig, uint64_t *leq10, uint64_t *totals, uint64_t *single,
+                         bool add) {
+    if (c->counters_len == 0) return fail(SAVONT_B200_ERR_INVALID, "no counters: nothing was mapped yet");
+    std::vector<uint64_t> h(c->counters_len);
+    CK(cudaMemcpyAsync(h.data(), c->d_counters.p, c->counters_len * 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    const size_t A = c->n_asv;
+    auto put = [&](uint64_t *dst, const uint64_t *src, size_t n) {
+        if (!dst) return;
+        for (size_t i = 0; i < n; ++i) dst[i] = (add ? dst[i] : 0) + src[i];
+    };
+    put(unambig, h.data(), A); put(ambig, h.data() + A, A); put(leq10, h.data() + 2 * A, A);
+    put(totals, h.data() + 3 * A, 2);
+    put(single, h.data() + 3 * A + 2, (size_t)c->counters_samples * A);
+    return 0;
+}
+
+}  // namespace sb
+
+// ================================================================================================
+// extern "C"
+// ================================================================================================
+using namespace sb;
+
+struct savont_b200_ctx { Context c; };
+
+extern "C" {
+
+int savont_b200_abi_version(void) { return SAVONT_B200_ABI_VERSION; }
+const char *savont_b200_last_error(void) { return g_last_error.c_str(); }
+
+void savont_b200_default_params(savont_b200_params *p) {
+    if (!p) return;
+    p->k = 17; p->c = 11; p->l = 3; p->min_bq = 25; p->band = 64; p->strand_mode = 0;
+    p->ratio_thresh = 0.0050; p->min_mini_frac_base = 0.950;
+}
+
+int savont_b200_create(int device_id, savont_b200_ctx **out) {
+    if (!out) return fail(SAVONT_B200_ERR_INVALID, "out is null");
+    *out = nullptr;
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+        return fail(SAVONT_B200_ERR_CUDA, "no CUDA device available (%s); libsavont_b200 has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device_id < 0 || device_id >= n_dev) return fail(SAVONT_B200_ERR_INVALID, "device %d out of range (0..%d)", device_id, n_dev - 1);
+    CK(cudaSetDevice(device_id));
+    savont_b200_ctx *h = new savont_b200_ctx();
+    Context *c = &h->c;
+    c->device = device_id;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device_id));
+    c->sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    for (auto &ev : c->ev) CK(cudaEventCreate(&ev));
+    savont_b200_default_params(&c->params);
+    c->dp = make_device_params(c->params);
+    memset(&c->last_stats, 0, sizeof(c->last_stats));
+    int rc = build_tables(c);
+    if (rc != 0) { delete h; return rc; }
+    *out = h;
+    return 0;
+}
+
+int savont_b200_destroy(savont_b200_ctx *h) {
+    if (!h) return 0;
+    Context *c = &h->c;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->work.release(); c->resident.release(); c->asvb.release();
+    DevBuf *bufs[] = {&c->d_rank_table, &c->d_snp_keys, &c->d_phred, &c->d_idx_keys, &c->d_idx_vals, &c->d_idx_entries, &c->d_mset,
+                      &c->d_mset_off, &c->d_asv_planes, &c->d_asv_plane_off, &c->d_asv_len, &c->d_counters};
+    for (DevBuf *b : bufs) b->release();
+    c->pin_offsets.release(); c->pin_small.release(); c->pin_out.release();
+    for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete h;
+    return 0;
+}
+
+int savont_b200_set_stream(savont_b200_ctx *h, void *cuda_stream) {
+    TRY(use_device(h ? &h->c : nullptr));
+    h->c.stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : h->c.own_stream;
+    return 0;
+}
+
+int savont_b200_set_params(savont_b200_ctx *h, const savont_b200_params *p) {
+    TRY(use_device(h ? &h->c : nullptr));
+    if (!p) return fail(SAVONT_B200_ERR_INVALID, "params is null");
+    TRY(validate_params(*p));
+    Context *c = &h->c;
+    c->params = *p;
+    c->dp = make_device_params(*p);
+    c->index_dirty = true;
+    return build_tables(c);
+}
+
+int savont_b200_set_batch_reads(savont_b200_ctx *h, size_t n) {
+    if (!h) return fail(SAVONT_B200_ERR_INVALID, "null context");
+    h->c.batch_reads = n ? n : 262144;
+    return 0;
+}
+
+int savont_b200_load_snpmers(savont_b200_ctx *h, const uint64_t *kmers, size_t n) {
+    TRY(use_device(h ? &h->c : nullptr));
+    if (n && !kmers) return fail(SAVONT_B200_ERR_INVALID, "kmers is null");
+    Context *c = &h->c;
+    c->h_snpmers.assign(kmers, kmers + n);
+    std::sort(c->h_snpmers.begin(), c->h_snpmers.end());
+    c->h_snpmers.erase(std::unique(c->h_snpmers.begin(), c->h_snpmers.end()), c->h_snpmers.end());
+    for (uint64_t v : c->h_snpmers)
+        if (v == kEmpty64) return fail(SAVONT_B200_ERR_INVALID, "0xffffffffffffffff is not a valid k-mer");
+    c->index_dirty = true;
+    return upload_snp_set(c);
+}
+
+int savont_b200_load_asvs(savont_b200_ctx *h, const uint8_t *bases, const uint64_t *offsets, size_t n_asv) {
+    TRY(use_device(h ? &h->c : nullptr));
+    if (n_asv && (!bases || !offsets)) return fail(SAVONT_B200_ERR_INVALID, "null ASV input");
+    Context *c = &h->c;
+    if (n_asv >= (1u << 30)) return fail(SAVONT_B200_ERR_INVALID, "too many ASVs");
+    c->asv_offsets_h.assign(n_asv + 1, 0);
+    const uint64_t base0 = n_asv ? offsets[0] : 0;
+    for (size_t i = 0; i <= n_asv && n_asv; ++i) c->asv_offsets_h[i] = offsets[i] - base0;
+    c->asv_bases_h.assign(bases + base0, bases + base0 + (n_asv ? offsets[n_asv] - base0 : 0));
+    c->index_dirty = true;
+    return build_asv_index(c);
+}
+
+int savont_b200_num_asvs(savont_b200_ctx *h, size_t *n_asv) {
+    if (!h || !n_asv) return fail(SAVONT_B200_ERR_INVALID, "null argument");
+    *n_asv = h->c.n_asv;
+    return 0;
+}
+
+int savont_b200_sketch(savont_b200_ctx *h, const uint8_t *bases, const uint8_t *quals, const uint64_t *offsets, size_t n_seqs,
+                       uint8_t *status, double *est_id, uint64_t *mini_offsets, uint32_t *mini_pos, uint64_t *mini_kmer,
+                       uint8_t *mini_fwd, size_t mini_cap, uint64_t *snp_offsets, uint32_t *snp_pos, uint64_t *snp_kmer,
+                       size_t snp_cap, uint8_t *codes) {
+    TRY(use_device(h ? &h->c : nullptr));
+    Context *c = &h->c;
+    if (!offsets || !status || !mini_offsets || !snp_offsets) return fail(SAVONT_B200_ERR_INVALID, "null argument");
+    mini_offsets[0] = 0; snp_offsets[0] = 0;
+    size_t mini_base = 0, snp_base = 0;
+    for (size_t r0 = 0; r0 < n_seqs;) {
+        size_t r1 = std::min(n_seqs, r0 + c->batch_reads);
+        while (r1 > r0 + 1 && offsets[r1] - offsets[r0] > (3ull << 30)) r1 = r0 + (r1 - r0) / 2;
+        const size_t n = r1 - r0;
+        Batch &b = c->work;
+        TRY(batch_upload(c, b, bases, quals, offsets + r0, nullptr, n, nullptr));
+        TRY(stage_sketch(c, b, true));
+        // compact CSR on the device
+        TRY(b.class_off.ensure((n + 2) * 4)); TRY(b.pair_start.ensure((n + 2) * 4)); TRY(b.scan_tmp.ensure((n / 2048 + 4) * 4));
+        uint32_t *d_moff = b.class_off.as<uint32_t>(), *d_soff = b.pair_start.as<uint32_t>();
+        launch_scan_u32(b.mini_cnt.as<uint32_t>(), d_moff, (uint32_t)n, b.scan_tmp.as<uint32_t>(), c->stream);
+        launch_scan_u32(b.snp_cnt.as<uint32_t>(), d_soff, (uint32_t)n, b.scan_tmp.as<uint32_t>(), c->stream);
+        std::vector<uint32_t> moff(n + 1), soff(n + 1);
+        CK(cudaMemcpyAsync(moff.data(), d_moff, (n + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(soff.data(), d_soff, (n + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        const size_t nm = moff[n], ns = soff[n];
+        if (mini_base + nm > mini_cap || snp_base + ns > snp_cap)
+            return fail(SAVONT_B200_ERR_CAPACITY, "sketch output capacity too small (need mini>=%zu snp>=%zu)", mini_base + nm, snp_base + ns);
+        DevBuf &o_mk = b.p_read, &o_mp = b.p_asv, &o_mf = b.p_strand, &o_sk = b.p_mini, &o_sp = b.nm;   // reuse as scratch
+        TRY(o_mk.ensure((nm + 1) * 8)); TRY(o_mp.ensure((nm + 1) * 4)); TRY(o_mf.ensure(nm + 4));
+        TRY(o_sk.ensure((ns + 1) * 8)); TRY(o_sp.ensure((ns + 1) * 4));
+        launch_gather_sketch(seq_view(b), sketch_view(b, true), d_moff, d_soff, o_mp.as<uint32_t>(), o_mk.as<uint64_t>(),
+                             o_mf.as<uint8_t>(), o_sp.as<uint32_t>(), o_sk.as<uint64_t>(), c->dp, c->stream);
+        if (est_id) {
+            TRY(b.est_id.ensure((n + 1) * 8));
+            launch_est_id(seq_view(b), b.sk_status.as<uint8_t>(), b.flatq.as<uint8_t>(), c->d_phred.as<double>(), b.est_id.as<double>(), c->stream);
+            CK(cudaMemcpyAsync(est_id + r0, b.est_id.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
+        }
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(status + r0, b.sk_status.p, n, cudaMemcpyDeviceToHost, c->stream));
+        if (nm) {
+            CK(cudaMemcpyAsync(mini_pos + mini_base, o_mp.p, nm * 4, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaMemcpyAsync(mini_kmer + mini_base, o_mk.p, nm * 8, cudaMemcpyDeviceToHost, c->stream));
+            if (mini_fwd) CK(cudaMemcpyAsync(mini_fwd + mini_base, o_mf.p, nm, cudaMemcpyDeviceToHost, c->stream));
+        }
+        if (ns) {
+            CK(cudaMemcpyAsync(snp_pos + snp_base, o_sp.p, ns * 4, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaMemcpyAsync(snp_kmer + snp_base, o_sk.p, ns * 8, cudaMemcpyDeviceToHost, c->stream));
+        }
+        if (codes && b.total_bases) {
+            TRY(b.class_out.ensure(b.total_bases + 16));
+            launch_codes(b.bases.as<uint8_t>(), b.class_out.as<uint8_t>(), b.total_bases, c->stream);
+            CK(cudaMemcpyAsync(codes + offsets[r0], b.class_out.p, b.total_bases, cudaMemcpyDeviceToHost, c->stream));
+        }
+        CK(cudaStreamSynchronize(c->stream));
+        for (size_t i = 0; i < n; ++i) { mini_offsets[r0 + i + 1] = mini_base + moff[i + 1]; snp_offsets[r0 + i + 1] = snp_base + soff[i + 1]; }
+        mini_base += nm; snp_base += ns;
+        r0 = r1;
+    }
+    return 0;
+}
+
+int savont_b200_find_candidates(savont_b200_ctx *h, const uint8_t *bases, const uint8_t *quals, const uint64_t *offsets,
+                                size_t n_reads, uint8_t *cand_status, uint64_t *cand_offsets, uint32_t *cand_asv,
+                                uint32_t *cand_mm, uint32_t *cand_mini, uint8_t *cand_strand, size_t cand_cap) {
+    TRY(use_device(h ? &h->c : nullptr));
+    Context *c = &h->c;
+    TRY(ensure_index(c));
+    if (!offsets || !cand_status || !cand_offsets) return fail(SAVONT_B200_ERR_INVALID, "null argument");
+    cand_offsets[0] = 0;
+    size_t base = 0;
+    for (size_t r0 = 0; r0 < n_reads;) {
+        size_t r1 = std::min(n_reads, r0 + c->batch_reads);
+        while (r1 > r0 + 1 && offsets[r1] - offsets[r0] > (3ull << 30)) r1 = r0 + (r1 - r0) / 2;
+        const size_t n = r1 - r0;
+        Batch &b = c->work;
+        uint32_t n_pairs = 0;
+        TRY(batch_upload(c, b, bases, quals, offsets + r0, nullptr, n, nullptr));
+        TRY(stage_sketch(c, b, false));
+        TRY(stage_filter(c, b, 0, &n_pairs));
+        if (base + n_pairs > cand_cap) return fail(SAVONT_B200_ERR_CAPACITY, "candidate capacity too small (need >= %zu)", base + n_pairs);
+        TRY(b.class_off.ensure((n + 2) * 4)); TRY(b.scan_tmp.ensure((n / 2048 + 4) * 4));
+        TRY(b.class_out.ensure(((size_t)n_pairs + 1) * 4)); TRY(b.class_slot.ensure(((size_t)n_pairs + 1) * 4));
+        TRY(b.nm.ensure(((size_t)n_pairs + 1) * 4)); TRY(b.asv_end.ensure((size_t)n_pairs + 4));
+        launch_scan_u32(b.pair_cnt.as<uint32_t>(), b.class_off.as<uint32_t>(), (uint32_t)n, b.scan_tmp.as<uint32_t>(), c->stream);
+        launch_gather_cand(pool_view(b), b.pair_start.as<uint32_t>(), b.pair_cnt.as<uint32_t>(), b.low_mm.as<uint32_t>(),
+                           b.class_off.as<uint32_t>(), b.class_out.as<uint32_t>(), b.class_slot.as<uint32_t>(), b.nm.as<uint32_t>(),
+                           b.asv_end.as<uint8_t>(), (uint32_t)n, c->stream);
+        CK(cudaGetLastError());
+        std::vector<uint32_t> off(n + 1);
+        CK(cudaMemcpyAsync(off.data(), b.class_off.p, (n + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(cand_status + r0, b.cand_status.p, n, cudaMemcpyDeviceToHost, c->stream));
+        if (n_pairs) {
+            CK(cudaMemcpyAsync(cand_asv + base, b.class_out.p, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaMemcpyAsync(cand_mm + base, b.class_slot.p, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaMemcpyAsync(cand_mini + base, b.nm.p, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaMemcpyAsync(cand_strand + base, b.asv_end.p, (size_t)n_pairs, cudaMemcpyDeviceToHost, c->stream));
+        }
+        CK(cudaStreamSynchronize(c->stream));
+        for (size_t i = 0; i < n; ++i) cand_offsets[r0 + i + 1] = base + off[i + 1];
+        base += n_pairs;
+        r0 = r1;
+    }
+    return 0;
+}
+
+int savont_b200_align_pairs(savont_b200_ctx *h, const uint8_t *bases, const uint64_t *offsets, size_t n_reads,
+                            const uint32_t *pair_read, const uint32_t *pair_asv, const uint8_t *pair_strand, size_t n_pairs,
+                            int32_t *nm, int32_t *asv_end, int32_t *read_end, int want_cigar, int32_t *asv_start,
+                            int32_t *read_start, uint64_t *cigar_offsets, uint32_t *cigar, size_t cigar_cap) {
+    TRY(use_device(h ? &h->c : nullptr));
+    Context *c = &h->c;
+    TRY(ensure_index(c));
+    if (!offsets || (n_pairs && (!pair_read || !pair_asv || !pair_strand || !nm || !asv_end || !read_end)))
+        return fail(SAVONT_B200_ERR_INVALID, "null argument");
+    if (want_cigar && (!asv_start || !read_start || !cigar_offsets)) return fail(SAVONT_B200_ERR_INVALID, "null cigar argument");
+    for (size_t i = 0; i < n_pairs; ++i)
+        if (pair_read[i] >= n_reads || pair_asv[i] >= c->n_asv) return fail(SAVONT_B200_ERR_INVALID, "pair %zu out of range", i);
+    if (n_pairs >= (1ull << 31)) return fail(SAVONT_B200_ERR_INVALID, "too many pairs");
+    Batch &b = c->work;
+    TRY(batch_upload(c, b, bases, nullptr, offsets, nullptr, n_reads, nullptr));
+    TRY(b.planes.ensure(((size_t)plane_word_off(b.total_bases, n_reads) + 4) * sizeof(uint2)));
+    launch_pack_planes(seq_view(b), b.planes.as<uint2>(), c->stream);
+    b.pair_cap = std::max<uint32_t>(b.pair_cap, (uint32_t)n_pairs + 16);
+    TRY(ensure_pair_pool(b));
+    if (n_pairs) {
+        CK(cudaMemcpyAsync(b.p_read.p, pair_read, n_pairs * 4, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(b.p_asv.p, pair_asv, n_pairs * 4, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(b.p_strand.p, pair_strand, n_pairs, cudaMemcpyHostToDevice, c->stream));
+    }
+    if (cigar_offsets) cigar_offsets[0] = 0;
+    if (!want_cigar) {
+        TRY(stage_align(c, b, (uint32_t)n_pairs));
+        if (n_pairs) {
+            CK(cudaMemcpyAsync(nm, b.nm.p, n_pairs * 4, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaMemcpyAsync(asv_end, b.asv_end.p, n_pairs * 4, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaMemcpyAsync(read_end, b.read_end.p, n_pairs * 4, cudaMemcpyDeviceToHost, c->stream));
+        }
+        CK(cudaStreamSynchronize(c->stream));
+        return 0;
+    }
+    // traceback path, in sub-batches bounded by a 1 GiB history workspace
+    const uint32_t hist_cols = std::max<uint32_t>(b.max_len, 1u);
+    const uint32_t cigar_stride = b.max_len + c->max_asv_len + 2;
+    const size_t per_pair_words = align_tb_hist_words(1, hist_cols, c->dp);
+    size_t sub = std::max<size_t>(128, ((size_t)1 << 28) / std::max<size_t>(per_pair_words, 1));
+    sub = std::min<size_t>(sub, 1u << 16);
+    DevBuf d_hist, d_cigar, d_cnt, d_as, d_rs;
+    auto cleanup = [&]() { d_hist.release(); d_cigar.release(); d_cnt.release(); d_as.release(); d_rs.release(); };
+    size_t cig_base = 0;
+    std::vector<uint32_t> h_cnt, h_cig;
+    int rc = 0;
+    for (size_t p0 = 0; p0 < n_pairs && rc == 0; p0 += sub) {
+        const uint32_t np = (uint32_t)std::min(sub, n_pairs - p0);
+        if ((rc = d_hist.ensure(align_tb_hist_words(np, hist_cols, c->dp) * 4)) != 0) break;
+        if ((rc = d_cigar.ensure((size_t)np * cigar_stride * 4)) != 0) break;
+        if ((rc = d_cnt.ensure((size_t)np * 4)) != 0) break;
+        if ((rc = d_as.ensure((size_t)np * 4)) != 0) break;
+        if ((rc = d_rs.ensure((size_t)np * 4)) != 0) break;
+        AlignOut ao{b.nm.as<int32_t>() + p0, b.asv_end.as<int32_t>() + p0, b.read_end.as<int32_t>() + p0};
+        launch_align_tb(seq_view(b), b.planes.as<uint2>(), index_view(c), b.p_read.as<uint32_t>() + p0, b.p_asv.as<uint32_t>() + p0,
+                        b.p_strand.as<uint8_t>() + p0, np, d_hist.as<uint32_t>(), ao, d_as.as<int32_t>(), d_rs.as<int32_t>(),
+                        d_cigar.as<uint32_t>(), cigar_stride, d_cnt.as<uint32_t>(), c->dp, c->stream);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { rc = fail(SAVONT_B200_ERR_CUDA, "align_tb launch: %s", cudaGetErrorString(e)); break; }
+        h_cnt.resize(np); h_cig.resize((size_t)np * cigar_stride);
+        cudaMemcpyAsync(h_cnt.data(), d_cnt.p, (size_t)np * 4, cudaMemcpyDeviceToHost, c->stream);
+        cudaMemcpyAsync(h_cig.data(), d_cigar.p, (size_t)np * cigar_stride * 4, cudaMemcpyDeviceToHost, c->stream);
+        cudaMemcpyAsync(nm + p0, ao.nm, (size_t)np * 4, cudaMemcpyDeviceToHost, c->stream);
+        cudaMemcpyAsync(asv_end + p0, ao.asv_end, (size_t)np * 4, cudaMemcpyDeviceToHost, c->stream);
+        cudaMemcpyAsync(read_end + p0, ao.read_end, (size_t)np * 4, cudaMemcpyDeviceToHost, c->stream);
+        cudaMemcpyAsync(asv_start + p0, d_as.p, (size_t)np * 4, cudaMemcpyDeviceToHost, c->stream);
+        cudaMemcpyAsync(read_start + p0, d_rs.p, (size_t)np * 4, cudaMemcpyDeviceToHost, c->stream);
+        e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) { rc = fail(SAVONT_B200_ERR_CUDA, "align_tb: %s", cudaGetErrorString(e)); break; }
+        for (uint32_t t = 0; t < np; ++t) {
+            const uint32_t cnt = h_cnt[t];
+            if (cig_base + cnt > cigar_cap) { rc = fail(SAVONT_B200_ERR_CAPACITY, "cigar capacity too small"); break; }
+            if (cnt) memcpy(cigar + cig_base, h_cig.data() + (size_t)t * cigar_stride + (cigar_stride - cnt), (size_t)cnt * 4);
+            cig_base += cnt;
+            cigar_offsets[p0 + t + 1] = cig_base;
+        }
+    }
+    cleanup();
+    return rc;
+}
+
+int savont_b200_map_reads(savont_b200_ctx *h, const uint8_t *bases, const uint8_t *quals, const uint64_t *offsets,
+                          const uint32_t *file_idx, size_t n_reads, int n_samples, uint8_t *status, int32_t *best_nm,
+                          uint64_t *class_offsets, uint32_t *class_asv, size_t class_cap, uint64_t *unambig, uint64_t *ambig,
+                          uint64_t *leq10, uint64_t *totals, uint64_t *sample_singleton, savont_b200_stats *stats) {
+    TRY(use_device(h ? &h->c : nullptr));
+    Context *c = &h->c;
+    TRY(ensure_index(c));
+    if (!offsets || !status || !best_nm || !class_offsets) return fail(SAVONT_B200_ERR_INVALID, "null argument");
+    if (n_samples < 1) return fail(SAVONT_B200_ERR_INVALID, "n_samples must be >= 1");
+    savont_b200_stats st; memset(&st, 0, sizeof(st));
+    memset(&c->last_stats, 0, sizeof(c->last_stats));
+    TRY(ensure_counters(c, n_samples, true));
+    CK(cudaEventRecord(c->ev[6], c->stream));
+    class_offsets[0] = 0;
+    uint64_t class_base = 0;
+    for (size_t r0 = 0; r0 < n_reads;) {
+        size_t r1 = std::min(n_reads, r0 + c->batch_reads);
+        while (r1 > r0 + 1 && offsets[r1] - offsets[r0] > (3ull << 30)) r1 = r0 + (r1 - r0) / 2;
+        const size_t n = r1 - r0;
+        Batch &b = c->work;
+        CK(cudaEventRecord(c->ev[5], c->stream));
+        TRY(batch_upload(c, b, bases, quals, offsets + r0, file_idx ? file_idx + r0 : nullptr, n, &st.h2d_bytes));
+        CK(cudaEventRecord(c->ev[0], c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        st.h2d_ms += ev_ms(c->ev[5], c->ev[0]);
+        TRY(run_path(c, b, n_samples, st));
+        CK(cudaEventRecord(c->ev[5], c->stream));
+        uint64_t n_cls = 0;
+        TRY(fetch_batch(c, b, status + r0, best_nm + r0, class_offsets + r0, class_base, class_asv, class_cap, &n_cls, &st.d2h_bytes));
+        CK(cudaEventRecord(c->ev[0], c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        st.d2h_ms += ev_ms(c->ev[5], c->ev[0]);
+        class_base += n_cls;
+        st.n_batches += 1;
+        r0 = r1;
+    }
+    TRY(read_counters(c, unambig, ambig, leq10, totals, sample_singleton, true));
+    st.d2h_bytes += c->counters_len * 8;
+    CK(cudaEventRecord(c->ev[7], c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    st.total_ms = ev_ms(c->ev[6], c->ev[7]);
+    st.kernel_launches = c->last_stats.kernel_launches;
+    c->last_stats = st;
+    if (stats) *stats = st;
+    return 0;
+}
+
+int savont_b200_upload_reads(savont_b200_ctx *h, const uint8_t *bases, const uint8_t *quals, const uint64_t *offsets,
+                             const uint32_t *file_idx, size_t n_reads, int n_samples) {
+    TRY(use_device(h ? &h->c : nullptr));
+    Context *c = &h->c;
+    if (!offsets || (n_reads && !bases)) return fail(SAVONT_B200_ERR_INVALID, "null argument");
+    if (n_samples < 1) return fail(SAVONT_B200_ERR_INVALID, "n_samples must be >= 1");
+    TRY(batch_upload(c, c->resident, bases, quals, offsets, file_idx, n_reads, nullptr));
+    CK(cudaStreamSynchronize(c->stream));
+    c->resident_samples = n_samples;
+    return 0;
+}
+
+int savont_b200_map_resident(savont_b200_ctx *h, int zero_counters, savont_b200_stats *stats) {
+    TRY(use_device(h ? &h->c : nullptr));
+    Context *c = &h->c;
+    TRY(ensure_index(c));
+    savont_b200_stats st; memset(&st, 0, sizeof(st));
+    memset(&c->last_stats, 0, sizeof(c->last_stats));
+    TRY(ensure_counters(c, c->resident_samples, zero_counters != 0));
+    CK(cudaEventRecord(c->ev[6], c->stream));
+    TRY(run_path(c, c->resident, c->resident_samples, st));
+    CK(cudaEventRecord(c->ev[7], c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    st.total_ms = ev_ms(c->ev[6], c->ev[7]);
+    st.n_batches = 1;
+    st.kernel_launches = c->last_stats.kernel_launches;
+    c->last_stats = st;
+    if (stats) *stats = st;
+    return 0;
+}
+
+int savont_b200_fetch_resident(savont_b200_ctx *h, uint8_t *status, int32_t *best_nm, uint64_t *class_offsets,
+                               uint32_t *class_asv, size_t class_cap) {
+    TRY(use_device(h ? &h->c : nullptr));
+    Context *c = &h->c;
+    if (!c->resident.mapped) return fail(SAVONT_B200_ERR_INVALID, "map_resident has not run");
+    if (!status || !best_nm || !class_offsets) return fail(SAVONT_B200_ERR_INVALID, "null argument");
+    uint64_t n_cls = 0;
+    return fetch_batch(c, c->resident, status, best_nm, class_offsets, 0, class_asv, class_cap, &n_cls, nullptr);
+}
+
+int savont_b200_counts_dev(savont_b200_ctx *h, void **dev_ptr, size_t *n_u64) {
+    if (!h || !dev_ptr || !n_u64) return fail(SAVONT_B200_ERR_INVALID, "null argument");
+    if (h->c.counters_len == 0) return fail(SAVONT_B200_ERR_INVALID, "no counters: nothing was mapped yet");
+    *dev_ptr = h->c.d_counters.p;
+    *n_u64 = h->c.counters_len;
+    return 0;
+}
+
+int savont_b200_read_counts(savont_b200_ctx *h, uint64_t *unambig, uint64_t *ambig, uint64_t *leq10, uint64_t *totals,
+                            uint64_t *sample_singleton) {
+    TRY(use_device(h ? &h->c : nullptr));
+    return read_counters(&h->c, unambig, ambig, leq10, totals, sample_singleton, false);
+}
+
+int savont_b200_host_alloc(size_t bytes, void **out) {
+    if (!out) return fail(SAVONT_B200_ERR_INVALID, "null argument");
+    CK(cudaMallocHost(out, bytes ? bytes : 1));
+    return 0;
+}
+int savont_b200_host_free(void *p) {
+    if (p) CK(cudaFreeHost(p));
+    return 0;
+}
+
+}  // extern "C"

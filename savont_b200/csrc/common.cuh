@@ -1,0 +1,172 @@
+// common.cuh -- shared device/host definitions for libsavont_b200 (sm_100a).
+//
+// Data layout in HBM (per batch of sequences; all offsets derive from the byte offsets of the
+// concatenated input so no prefix sums are needed):
+//   bases/quals  u8[total]                 raw ASCII / Phred+33 as handed over by the caller
+//   planes       uint2[(off + 63*r) >> 5 ..] bit-planes of the 2-bit codes, bit i of word w = base
+//                                           32*w+i; .x = low code bit, .y = high code bit
+//   mini slots   u64[(off / 6) + 2*r ..]    minimizer k-mers (bit 63 = forward flag), <= len/6+1 each
+//   snp pool     u64/u32 chunks            SNPmer k-mers+positions, chunk per read (atomic bump)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sb {
+
+constexpr uint64_t kEmpty64 = ~0ull;
+constexpr uint64_t kFwdBit = 1ull << 63;
+constexpr int kSnpHitCap = 256;        // per-sequence SNPmer hits held in shared memory
+constexpr int kSketchWarps = 8;        // warps per CTA in the sketch kernel
+constexpr int kFilterWarps = 4;        // warps per CTA in the filter kernel
+
+// error flag bits written by kernels into Context::d_err
+enum : uint32_t {
+    kErrSnpPool = 1u,      // SNPmer pool exhausted
+    kErrSnpHits = 2u,      // > kSnpHitCap SNPmer hits in one sequence
+    kErrPairPool = 4u,     // candidate pair pool exhausted
+    kErrMiniSet = 8u,      // read minimizer set overflow (should be impossible)
+};
+
+struct DeviceParams {
+    int k, c, s;            // s = k - c + 1
+    int min_bq, band, strand_mode;
+    int asv_padl;           // left padding (bits) of the ASV DP planes
+    int mini_spacing;       // minimum distance between two open syncmers = (c-1)/2 + 1
+    uint64_t split_mask;    // ~(3 << (k-1))
+    uint64_t kmer_mask;     // low 2k bits
+    double ratio_thresh, min_frac;
+};
+
+// multiplicative mixer shared by host-built and device-probed tables
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
+    x ^= x >> 31;
+    x *= 0x9E3779B97F4A7C15ull;
+    x ^= x >> 29;
+    return x;
+}
+
+// src/seeding.rs:18-28
+__host__ __device__ __forceinline__ uint64_t mm_hash64(uint64_t key) {
+    key = (~key) + (key << 21);
+    key = key ^ (key >> 24);
+    key = (key + (key << 3)) + (key << 8);
+    key = key ^ (key >> 14);
+    key = (key + (key << 2)) + (key << 4);
+    key = key ^ (key >> 28);
+    key = key + (key << 31);
+    return key;
+}
+
+// plane word offset of sequence r starting at byte offset `off` (>= ceil(len/32)+1 words each)
+__host__ __device__ __forceinline__ uint64_t plane_word_off(uint64_t off, uint64_t r) { return (off + 63ull * r) >> 5; }
+// minimizer slot offset (>= len/spacing + 2 slots each; two open syncmers are >= spacing apart)
+__host__ __device__ __forceinline__ uint64_t mini_slot_off(uint64_t off, uint64_t r, uint32_t spacing) {
+    return off / spacing + 2ull * r;
+}
+
+struct SeqBatch {            // device view of a batch of sequences
+    const uint8_t *bases;
+    const uint8_t *quals;    // may be null
+    const uint64_t *offsets; // [n+1]
+    uint32_t n;
+    uint32_t max_len;
+};
+
+struct SketchOut {
+    uint8_t *status;         // [n] 0 / 4
+    uint8_t *flatq;          // [n] 1 if all qualities equal
+    uint2 *planes;           // bit planes
+    uint32_t *mini_cnt;      // [n]
+    uint64_t *mini_kmer;     // slots
+    uint32_t *mini_pos;      // slots or null
+    uint32_t *snp_start;     // [n]
+    uint32_t *snp_cnt;       // [n]
+    uint64_t *snp_kmer;      // pool
+    uint32_t *snp_pos;       // pool
+    uint32_t *snp_pool_ctr;  // [1]
+    uint32_t snp_pool_cap;
+    uint32_t *err;           // [1] error bits
+};
+
+struct SnpSet {              // open addressing, kEmpty64 = empty
+    const uint64_t *keys;
+    uint32_t mask;           // cap-1, 0 when the set is empty (keys == null)
+};
+
+struct AsvIndex {
+    // SNPmer inverted index: splitmer -> bucket of (asv << 2 | mid base)
+    const uint64_t *idx_keys;
+    const uint2 *idx_vals;       // (start, len)
+    uint32_t idx_mask;
+    const uint32_t *idx_entries;
+    // distinct minimizer sets per ASV (sorted; bit 63 = forward-any flag)
+    const uint64_t *mset;
+    const uint32_t *mset_off;    // [A+1]
+    // DP planes (left-padded by asv_padl zero bits)
+    const uint2 *planes;
+    const uint32_t *plane_off;   // [A] word offsets
+    const uint32_t *len;         // [A]
+    uint32_t n_asv;
+};
+
+struct PairPool {
+    uint32_t *read;      // [cap]
+    uint32_t *asv;       // [cap]
+    uint32_t *mini;      // [cap]
+    uint8_t *strand;     // [cap]
+    uint32_t *counter;   // [1]
+    uint32_t cap;
+};
+
+struct FilterOut {
+    uint8_t *cand_status;  // [n]
+    uint32_t *pair_start;  // [n]
+    uint32_t *pair_cnt;    // [n]
+    uint32_t *low_mm;      // [n] SNPmer mismatches of the kept candidates
+    uint32_t *err;
+};
+
+struct AlignOut {
+    int32_t *nm;        // [pairs]
+    int32_t *asv_end;   // [pairs] or null
+    int32_t *read_end;  // [pairs] or null
+};
+
+// launchers (defined in the .cu files)
+void launch_sketch(const SeqBatch &in, const SketchOut &out, const SnpSet &set, const uint16_t *rank_table,
+                   const DeviceParams &p, int sm_count, cudaStream_t st);
+void launch_est_id(const SeqBatch &in, const uint8_t *status, const uint8_t *flatq, const double *phred_table,
+                   double *est_id, cudaStream_t st);
+void launch_codes(const uint8_t *bases, uint8_t *codes, uint64_t total, cudaStream_t st);
+void launch_filter(const SeqBatch &in, const SketchOut &sk, const AsvIndex &ix, const PairPool &pool, const FilterOut &out,
+                   const DeviceParams &p, int sm_count, cudaStream_t st);
+void launch_align_nm(const SeqBatch &in, const uint2 *read_planes, const AsvIndex &ix, const uint32_t *pair_read,
+                     const uint32_t *pair_asv, const uint8_t *pair_strand, const uint32_t *n_pairs_dev, uint32_t n_pairs_max,
+                     const AlignOut &out, const DeviceParams &p, int sm_count, cudaStream_t st);
+// traceback variant for a sub-batch of n_pairs (all pointers pre-offset to the sub-batch): history workspace
+// hist[(col * 2*NW + w) * n_pairs + t]; cigar slots of `cigar_stride` ops per pair filled from the back
+// (the last cigar_cnt[t] entries of slot t are the ops in forward order).
+void launch_align_tb(const SeqBatch &in, const uint2 *read_planes, const AsvIndex &ix, const uint32_t *pair_read,
+                     const uint32_t *pair_asv, const uint8_t *pair_strand, uint32_t n_pairs,
+                     uint32_t *hist, const AlignOut &out, int32_t *asv_start, int32_t *read_start,
+                     uint32_t *cigar, uint32_t cigar_stride, uint32_t *cigar_cnt, const DeviceParams &p, cudaStream_t st);
+int align_supported_band_max();
+int align_words_for_band(int band);
+size_t align_tb_hist_words(uint32_t n_pairs, uint32_t hist_cols, const DeviceParams &p);
+void launch_assign(const FilterOut &fo, const PairPool &pool, const int32_t *nm,
+                   const uint32_t *file_idx, uint32_t n_reads, uint32_t n_asv, int n_samples, int strand_mode,
+                   uint8_t *status, int32_t *best_nm, uint32_t *class_cnt, uint32_t *class_slot,
+                   unsigned long long *counters, cudaStream_t st);
+void launch_gather_cand(const PairPool &pool, const uint32_t *pair_start, const uint32_t *pair_cnt, const uint32_t *low_mm,
+                        const uint32_t *dst_off, uint32_t *asv, uint32_t *mm, uint32_t *mini, uint8_t *strand, uint32_t n,
+                        cudaStream_t st);
+// exclusive scan of counts[n] -> offsets[n+1] (u32), then gather variable-length runs
+void launch_scan_u32(const uint32_t *counts, uint32_t *offsets, uint32_t n, uint32_t *tmp, cudaStream_t st);
+void launch_gather_u32(const uint32_t *src, const uint32_t *src_start, const uint32_t *cnt, const uint32_t *dst_off,
+                       uint32_t *dst, uint32_t n, cudaStream_t st);
+void launch_gather_sketch(const SeqBatch &in, const SketchOut &sk, const uint32_t *mini_off, const uint32_t *snp_off,
+                          uint32_t *mini_pos, uint64_t *mini_kmer, uint8_t *mini_fwd, uint32_t *snp_pos, uint64_t *snp_kmer,
+                          const DeviceParams &p, cudaStream_t st);
+void launch_pack_planes(const SeqBatch &in, uint2 *planes, cudaStream_t st);
+
+}  // namespace sb

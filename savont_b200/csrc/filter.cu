@@ -1,0 +1,261 @@
+// filter.cu -- K2: candidate-ASV filter, one warp per read.
+//
+// Stands in for asv_cluster::find_compatible_candidates (reference src/asv_cluster.rs:356-383) and
+// the minimizer-overlap / ratio / minimum-mismatch selection of src/alignment.rs:1786-1843:
+//   1. the read's minimizer k-mers go into a shared-memory open-addressing set (set semantics of
+//      the reference's FxHashSet<Kmer48>, src/alignment.rs:1788); the forward flags of duplicate
+//      k-mers are OR-ed so the result does not depend on insertion order;
+//   2. every read SNPmer probes the replicated splitmer -> bucket index; the warp walks each bucket
+//      cooperatively (coalesced) and bumps a packed u16 mismatch counter per ASV in shared memory
+//      plus a two-level candidate bitmap (the reference's FxHashMap<asv,(matches,mismatches)>;
+//      `matches` is never used downstream);
+//   3. candidates are visited in ascending ASV order; the warp streams the ASV's distinct
+//      minimizers (coalesced 64-bit loads, L2 resident) through the read's set: m = |R n A| and the
+//      same/opposite-orientation vote; the f64 tests use the reference's operation order
+//      (src/alignment.rs:1805-1811, :1829);
+//   4. candidates with ratio <= threshold and the minimum SNPmer mismatch count are emitted, in
+//      ASV order, into a chunk of the pair pool (one atomic bump per read).
+#include "common.cuh"
+
+namespace sb {
+
+struct FilterSmem {
+    uint32_t rcap;      // read set capacity (power of two)
+    uint32_t acc_words; // ceil(A/2)
+    uint32_t bm_words;  // ceil(A/32)
+    uint32_t sum_words; // ceil(bm_words/32)
+    __host__ __device__ size_t per_warp() const {
+        size_t b = (size_t)rcap * 8u + ((size_t)acc_words + 2u * bm_words + sum_words) * 4u;
+        return (b + 15u) & ~(size_t)15u;
+    }
+};
+
+__global__ void __launch_bounds__(kFilterWarps * 32)
+filter_kernel(SeqBatch in, SketchOut sk, AsvIndex ix, PairPool pool, FilterOut out, DeviceParams p, FilterSmem lay) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint8_t *wbase = smem + (size_t)warp * lay.per_warp();
+    unsigned long long *rset = reinterpret_cast<unsigned long long *>(wbase);
+    uint32_t *acc = reinterpret_cast<uint32_t *>(wbase + (size_t)lay.rcap * 8u);
+    uint32_t *bm1 = acc + lay.acc_words;
+    uint32_t *bm2 = bm1 + lay.bm_words;
+    uint32_t *sum1 = bm2 + lay.bm_words;
+    const uint32_t rmask = lay.rcap - 1u;
+    const uint32_t clear_words = lay.acc_words + 2u * lay.bm_words + lay.sum_words;
+    const int mid_shift = p.k - 1;
+
+    for (uint32_t seq = blockIdx.x * kFilterWarps + warp; seq < in.n; seq += gridDim.x * kFilterWarps) {
+        if (sk.status[seq] != 0) {
+            if (lane == 0) { out.cand_status[seq] = sk.status[seq]; out.pair_start[seq] = 0; out.pair_cnt[seq] = 0; out.low_mm[seq] = 0; }
+            continue;
+        }
+        // ---- clear per-read state ----
+        for (uint32_t i = lane; i < lay.rcap; i += 32u) rset[i] = kEmpty64;
+        for (uint32_t i = lane; i < clear_words; i += 32u) acc[i] = 0u;
+        __syncwarp();
+
+        // ---- 1. read minimizer set ----
+        const uint64_t off = in.offsets[seq];
+        const uint64_t mo = mini_slot_off(off, seq, (uint32_t)p.mini_spacing);
+        const uint32_t nmini = sk.mini_cnt[seq];
+        uint32_t nR = 0;
+        for (uint32_t t0 = 0; t0 < nmini; t0 += 32u) {
+            const uint32_t t = t0 + lane;
+            bool inserted = false;
+            if (t < nmini) {
+                const unsigned long long v = sk.mini_kmer[mo + t];
+                const unsigned long long key = v & ~kFwdBit;
+                uint32_t slot = (uint32_t)mix64(key) & rmask;
+                while (true) {
+                    const unsigned long long old = atomicCAS(&rset[slot], (unsigned long long)kEmpty64, v);
+                    if (old == kEmpty64) { inserted = true; break; }
+                    if ((old & ~kFwdBit) == key) {
+                        if (v & kFwdBit) atomicOr(&rset[slot], (unsigned long long)kFwdBit);
+                        break;
+                    }
+                    slot = (slot + 1u) & rmask;
+                }
+            }
+            nR += __popc(__ballot_sync(0xffffffffu, inserted));
+        }
+        __syncwarp();
+
+        // ---- 2. SNPmer buckets -> per-ASV mismatch counters + candidate bitmap ----
+        const uint32_t ns = sk.snp_cnt[seq], s0 = sk.snp_start[seq];
+        for (uint32_t t0 = 0; t0 < ns; t0 += 32u) {
+            const uint32_t t = t0 + lane;
+            uint32_t bstart = 0, blen = 0, mid = 0;
+            if (t < ns && ix.idx_keys != nullptr) {
+                const uint64_t q = sk.snp_kmer[s0 + t];
+                const uint64_t sp = q & p.split_mask;
+                mid = (uint32_t)(q >> mid_shift) & 3u;
+                uint32_t slot = (uint32_t)mix64(sp) & ix.idx_mask;
+                while (true) {
+                    const uint64_t key = __ldg(ix.idx_keys + slot);
+                    if (key == sp) { const uint2 v = __ldg(ix.idx_vals + slot); bstart = v.x; blen = v.y; break; }
+                    if (key == kEmpty64) break;
+                    slot = (slot + 1u) & ix.idx_mask;
+                }
+            }
+            uint32_t active = __ballot_sync(0xffffffffu, blen > 0u);
+            while (active) {
+                const int src = __ffs(active) - 1;
+                active &= active - 1u;
+                const uint32_t bs = __shfl_sync(0xffffffffu, bstart, src);
+                const uint32_t bl = __shfl_sync(0xffffffffu, blen, src);
+                const uint32_t md = __shfl_sync(0xffffffffu, mid, src);
+                for (uint32_t e = lane; e < bl; e += 32u) {
+                    const uint32_t ent = __ldg(ix.idx_entries + bs + e);
+                    const uint32_t a = ent >> 2;
+                    if ((ent & 3u) != md) atomicAdd(&acc[a >> 1], 1u << (16u * (a & 1u)));
+                    const uint32_t w = a >> 5;
+                    const uint32_t old = atomicOr(&bm1[w], 1u << (a & 31u));
+                    if (old == 0u) atomicOr(&sum1[w >> 5], 1u << (w & 31u));
+                }
+            }
+        }
+        __syncwarp();
+
+        // ---- 3. evaluate candidates in ascending ASV order ----
+        uint32_t lowest = 0xffffffffu, n_low = 0;
+        bool any_scored = false;
+        for (uint32_t sw = 0; sw < lay.sum_words; ++sw) {
+            uint32_t sbits = sum1[sw];
+            while (sbits) {
+                const uint32_t w = sw * 32u + (uint32_t)(__ffs(sbits) - 1);
+                sbits &= sbits - 1u;
+                uint32_t bits = bm1[w];
+                while (bits) {
+                    const uint32_t bit = (uint32_t)(__ffs(bits) - 1);
+                    bits &= bits - 1u;
+                    const uint32_t a = w * 32u + bit;
+                    const uint32_t m0 = __ldg(ix.mset_off + a);
+                    const uint32_t nA = __ldg(ix.mset_off + a + 1) - m0;
+                    uint32_t m = 0, same = 0;
+                    for (uint32_t t0 = 0; t0 < nA; t0 += 32u) {
+                        const uint32_t t = t0 + lane;
+                        bool found = false, sm = false;
+                        if (t < nA) {
+                            const uint64_t v = __ldg(ix.mset + m0 + t);
+                            const uint64_t key = v & ~kFwdBit;
+                            uint32_t slot = (uint32_t)mix64(key) & rmask;
+                            while (true) {
+                                const uint64_t r = rset[slot];
+                                if (r == kEmpty64) break;
+                                if ((r & ~kFwdBit) == key) { found = true; sm = ((r ^ v) >> 63) == 0ull; break; }
+                                slot = (slot + 1u) & rmask;
+                            }
+                        }
+                        m += __popc(__ballot_sync(0xffffffffu, found));
+                        same += __popc(__ballot_sync(0xffffffffu, found && sm));
+                    }
+                    if (m == 0u) continue;                                        // src/alignment.rs:1801-1803
+                    const uint32_t mn = nR < nA ? nR : nA;
+                    if ((double)m / (double)mn < p.min_frac) continue;            // :1805-1808
+                    any_scored = true;
+                    const uint32_t mm = (acc[a >> 1] >> (16u * (a & 1u))) & 0xffffu;
+                    const double ratio = (double)mm / (double)m / (double)p.c;    // :1811
+                    if (ratio <= p.ratio_thresh) {                                // :1829-1833
+                        if (mm < lowest) {
+                            lowest = mm; n_low = 0;
+                            __syncwarp();
+                            for (uint32_t i = lane; i < lay.bm_words; i += 32u) bm2[i] = 0u;
+                            __syncwarp();
+                        }
+                        if (mm == lowest) {
+                            ++n_low;
+                            if (lane == 0) {
+                                bm2[w] |= 1u << bit;
+                                // mm is no longer needed for this ASV: stash (m | strand<<15) in its counter
+                                const uint32_t opp = m - same;
+                                const uint32_t stash = (m & 0x7fffu) | ((opp > same) ? 0x8000u : 0u);
+                                const uint32_t sh = 16u * (a & 1u);
+                                acc[a >> 1] = (acc[a >> 1] & ~(0xffffu << sh)) | (stash << sh);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+
+        // ---- 4. emit the kept candidates ----
+        uint8_t status = 0;
+        uint32_t total = 0, start = 0;
+        if (!any_scored) status = 1;            // SAVONT_B200_READ_NO_CANDIDATE
+        else if (n_low == 0u) status = 2;       // SAVONT_B200_READ_RATIO_FILTERED
+        else {
+            const uint32_t per = (p.strand_mode == 1) ? 2u : 1u;
+            total = n_low * per;
+            if (lane == 0) start = atomicAdd(pool.counter, total);
+            start = __shfl_sync(0xffffffffu, start, 0);
+            if ((uint64_t)start + total > pool.cap) {
+                if (lane == 0) atomicOr(out.err, kErrPairPool);
+                total = 0;
+            } else {
+                uint32_t running = 0;
+                for (uint32_t w0 = 0; w0 < lay.bm_words; w0 += 32u) {
+                    const uint32_t w = w0 + lane;
+                    uint32_t bits = (w < lay.bm_words) ? bm2[w] : 0u;
+                    const uint32_t pc = __popc(bits);
+                    uint32_t incl = pc;                               // inclusive warp scan
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+                        if (lane >= d) incl += y;
+                    }
+                    uint32_t o = start + (running + incl - pc) * per;
+                    while (bits) {
+                        const uint32_t bit = (uint32_t)(__ffs(bits) - 1);
+                        bits &= bits - 1u;
+                        const uint32_t a = w * 32u + bit;
+                        const uint32_t stash = (acc[a >> 1] >> (16u * (a & 1u))) & 0xffffu;
+                        if (per == 1u) {
+                            pool.read[o] = seq; pool.asv[o] = a; pool.mini[o] = stash & 0x7fffu; pool.strand[o] = (uint8_t)(stash >> 15);
+                            o += 1u;
+                        } else {
+                            pool.read[o] = seq; pool.asv[o] = a; pool.mini[o] = stash & 0x7fffu; pool.strand[o] = 0;
+                            pool.read[o + 1] = seq; pool.asv[o + 1] = a; pool.mini[o + 1] = stash & 0x7fffu; pool.strand[o + 1] = 1;
+                            o += 2u;
+                        }
+                    }
+                    running += __shfl_sync(0xffffffffu, incl, 31);
+                }
+            }
+        }
+        if (lane == 0) {
+            out.cand_status[seq] = status;
+            out.pair_start[seq] = start;
+            out.pair_cnt[seq] = total;
+            out.low_mm[seq] = (status == 0) ? lowest : 0u;
+        }
+        __syncwarp();
+    }
+}
+
+static uint32_t next_pow2(uint32_t x) { uint32_t p = 1; while (p < x) p <<= 1; return p; }
+
+void launch_filter(const SeqBatch &in, const SketchOut &sk, const AsvIndex &ix, const PairPool &pool, const FilterOut &out,
+                   const DeviceParams &p, int sm_count, cudaStream_t st) {
+    if (in.n == 0) return;
+    FilterSmem lay;
+    const uint32_t max_mini = in.max_len / (uint32_t)p.mini_spacing + 2u;
+    lay.rcap = next_pow2(2u * max_mini + 2u);
+    if (lay.rcap < 64u) lay.rcap = 64u;
+    lay.acc_words = (ix.n_asv + 1u) / 2u + 1u;
+    lay.bm_words = (ix.n_asv + 31u) / 32u;
+    if (lay.bm_words == 0u) lay.bm_words = 1u;
+    lay.sum_words = (lay.bm_words + 31u) / 32u;
+    const size_t smem = lay.per_warp() * kFilterWarps;
+    cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int ctas_per_sm = (int)(220u * 1024u / (smem + 1024u));
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    if (ctas_per_sm > 12) ctas_per_sm = 12;
+    uint32_t grid = (uint32_t)(sm_count * ctas_per_sm);
+    const uint32_t need = (in.n + kFilterWarps - 1) / kFilterWarps;
+    if (grid > need) grid = need;
+    filter_kernel<<<grid, kFilterWarps * 32, smem, st>>>(in, sk, ix, pool, out, p, lay);
+}
+
+}  // namespace sb

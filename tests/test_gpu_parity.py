@@ -1,0 +1,253 @@
+"""GPU parity: libsavont_b200.so (through the C ABI) vs the CPU oracle, bit-exact.
+Run on the B200 box: python -m pytest tests -m gpu"""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests.util import assert_same, mutate, rand_seq, snpmer_set_from, weird_sequences
+
+pytestmark = pytest.mark.gpu
+
+SKETCH_KEYS = ["status", "est_id", "mini_offsets", "mini_pos", "mini_kmer", "mini_fwd", "snp_offsets", "snp_pos", "snp_kmer", "codes"]
+CAND_KEYS = ["status", "offsets", "asv", "mm", "mini", "strand"]
+MAP_KEYS = ["status", "best_nm", "class_offsets", "class_asv", "unambig", "ambig", "leq10", "totals", "sample_singleton"]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from savont_b200 import _lib
+    c = _lib.Context(0)
+    yield c
+    c.close()
+
+
+def _params(lib_mod, **kw):
+    return lib_mod.default_params(**kw), O.default_params(**kw)
+
+
+@pytest.mark.parametrize("k,c", [(17, 11), (15, 9), (21, 11), (13, 7), (23, 5), (19, 19), (17, 1)])
+def test_sketch_ragged_inputs(ctx, k, c):
+    from savont_b200 import _lib
+    seqs, quals = weird_sequences(100 + k, k)
+    snp = sorted(snpmer_set_from(seqs, k))
+    gp, op = _params(_lib, k=k, c=c)
+    ctx.set_params(gp)
+    ctx.load_snpmers(snp)
+    bases, offs = O.concat(seqs)
+    qcat, _ = O.concat(quals)
+    for q in (qcat, None):
+        want = O.sketch_batch(op, snp, bases, q, offs)
+        got = ctx.sketch(bases, q, offs)
+        assert_same(got, want, SKETCH_KEYS, f"sketch k={k} c={c} quals={'y' if q is not None else 'n'}")
+
+
+def test_sketch_empty_and_no_snpmers(ctx):
+    from savont_b200 import _lib
+    gp, op = _params(_lib)
+    ctx.set_params(gp)
+    ctx.load_snpmers([])
+    rng = random.Random(5)
+    seqs = [rand_seq(rng, 300) for _ in range(5)]
+    bases, offs = O.concat(seqs)
+    assert_same(ctx.sketch(bases, None, offs), O.sketch_batch(op, [], bases, None, offs), SKETCH_KEYS, "no snpmers")
+    empty = ctx.sketch(np.zeros(0, np.uint8), None, np.zeros(1, np.uint64))
+    assert len(empty["status"]) == 0 and len(empty["mini_pos"]) == 0
+
+
+def test_sketch_synthetic_reads_small_batches(ctx):
+    from savont_b200 import _lib, synth
+    w = synth.Workload("ont16s", n_roots=6)
+    r = w.reads(3000)
+    gp, op = _params(_lib, band=w.band)
+    ctx.set_params(gp)
+    ctx.load_snpmers(w.snpmers)
+    ctx.set_batch_reads(700)          # several internal batches
+    try:
+        got = ctx.sketch(r["bases"], r["quals"], r["offsets"])
+    finally:
+        ctx.set_batch_reads(0)
+    want = O.sketch_batch(op, w.snpmers, r["bases"], r["quals"], r["offsets"])
+    assert_same(got, want, SKETCH_KEYS, "synthetic sketch")
+    assert np.all(want["est_id"] > 98.0)
+
+
+def _dp_cases(seed, band):
+    rng = random.Random(seed)
+    lens = [1, 5, 20, 37, 64, 90, 150, 300] if band < 40 else [40, 90, 300, 700, 1500]
+    asvs = [rand_seq(rng, max(L, 17)) for L in lens]
+    reads, pr, pa, ps = [], [], [], []
+    for a, s in enumerate(asvs):
+        for t in range(8):
+            rd = mutate(rng, s, rng.randrange(6), rng.randrange(4), rng.randrange(4))
+            if t == 4:
+                rd = rd[rng.randrange(1, 8):]
+            if t == 5:
+                rd = rd[:max(1, len(rd) - rng.randrange(1, 8))] + rand_seq(rng, 3)
+            if t == 6:
+                rd = rand_seq(rng, rng.randrange(1, 2 * band + 40))    # unrelated, odd length
+            if t == 7:
+                rd = rand_seq(rng, 30) + rd                            # offset beyond small bands
+            reads.append(rd); pr.append(len(reads) - 1); pa.append(a); ps.append(t % 2)
+    return asvs, reads, pr, pa, ps
+
+
+@pytest.mark.parametrize("band", [0, 1, 3, 8, 15, 16, 31, 33, 47, 64, 79, 100, 143, 192, 207])
+def test_align_pairs_nm_and_cigar(ctx, band):
+    from savont_b200 import _lib
+    asvs, reads, pr, pa, ps = _dp_cases(900 + band, band)
+    gp, op = _params(_lib, band=band)
+    ctx.set_params(gp)
+    ctx.load_snpmers([])
+    ab, ao = O.concat(asvs)
+    ctx.load_asvs(ab, ao)
+    orc = O.Oracle(op, [])
+    orc.load_asvs(ab, ao)
+    rb, ro = O.concat(reads)
+    want = orc.align_pairs(rb, ro, pr, pa, ps, want_cigar=True)
+    got_nm = ctx.align_pairs(rb, ro, pr, pa, ps, want_cigar=False)
+    assert_same(got_nm, want, ["nm", "asv_end", "read_end"], f"align nm band={band}")
+    got = ctx.align_pairs(rb, ro, pr, pa, ps, want_cigar=True)
+    assert_same(got, want, ["nm", "asv_end", "read_end", "asv_start", "read_start", "cigar_offsets", "cigar"], f"align cigar band={band}")
+
+
+def test_align_pairs_full_length_reads(ctx):
+    """config-2 shaped pairs: 1500 bp, 2% errors, band 64, both strands"""
+    from savont_b200 import _lib, synth
+    w = synth.Workload("ont16s", n_roots=4)
+    r = w.reads(400)
+    gp, op = _params(_lib, band=64)
+    ctx.set_params(gp); ctx.load_snpmers(w.snpmers); ctx.load_asvs(w.asv_bases, w.asv_offsets)
+    orc = O.Oracle(op, w.snpmers); orc.load_asvs(w.asv_bases, w.asv_offsets)
+    rng = np.random.default_rng(1)
+    pr = np.arange(400, dtype=np.uint32)
+    pa = r["truth_asv"].copy()
+    pa[::3] = rng.integers(0, w.n_asv, size=len(pa[::3]))        # some wrong ASVs
+    ps = r["truth_strand"].copy(); ps[::5] ^= 1                  # some wrong strands
+    want = orc.align_pairs(r["bases"], r["offsets"], pr, pa, ps, want_cigar=True)
+    got = ctx.align_pairs(r["bases"], r["offsets"], pr, pa, ps, want_cigar=True)
+    assert_same(got, want, ["nm", "asv_end", "read_end", "asv_start", "read_start", "cigar_offsets", "cigar"], "full length")
+
+
+def _make_workload(name, **kw):
+    from savont_b200 import synth
+    return synth.Workload(name, **kw)
+
+
+@pytest.mark.parametrize("name,kw,n", [
+    ("ont16s", dict(n_roots=8), 4000),
+    ("ont16s", dict(n_roots=5, sites_per_genus=3), 3000),     # near-identical variants -> ambiguous classes
+    ("hifi16s", dict(n_roots=8), 3000),
+    ("operon", dict(n_roots=4), 600),
+])
+def test_candidates_and_map_reads(ctx, name, kw, n):
+    from savont_b200 import _lib
+    w = _make_workload(name, **kw)
+    r = w.reads(n)
+    # degrade a few reads: truncate below k, wipe SNPmers with N, flat qualities
+    gp, op = _params(_lib, band=w.band)
+    ctx.set_params(gp); ctx.load_snpmers(w.snpmers); ctx.load_asvs(w.asv_bases, w.asv_offsets)
+    orc = O.Oracle(op, w.snpmers); orc.load_asvs(w.asv_bases, w.asv_offsets)
+    assert_same(ctx.find_candidates(r["bases"], r["quals"], r["offsets"]),
+                orc.find_candidates(r["bases"], r["quals"], r["offsets"]), CAND_KEYS, f"candidates {name}")
+    want = orc.map_reads(r["bases"], r["quals"], r["offsets"])
+    ctx.set_batch_reads(1000)
+    try:
+        got = ctx.map_reads(r["bases"], r["quals"], r["offsets"])
+    finally:
+        ctx.set_batch_reads(0)
+    assert_same(got, want, MAP_KEYS, f"map_reads {name}")
+    assert got["stats"]["dp_cells"] == want["dp_cells"]
+    assert int(want["totals"][0]) > 0.9 * n
+    # device-resident variant gives the same answer
+    ctx.upload_reads(r["bases"], r["quals"], r["offsets"])
+    ctx.map_resident()
+    assert_same(ctx.fetch_resident(), want, MAP_KEYS, f"map_resident {name}")
+
+
+def test_map_reads_both_strands_mode(ctx):
+    from savont_b200 import _lib
+    w = _make_workload("ont16s", n_roots=5)
+    r = w.reads(1500)
+    gp, op = _params(_lib, band=w.band, strand_mode=1)
+    ctx.set_params(gp); ctx.load_snpmers(w.snpmers); ctx.load_asvs(w.asv_bases, w.asv_offsets)
+    orc = O.Oracle(op, w.snpmers); orc.load_asvs(w.asv_bases, w.asv_offsets)
+    want = orc.map_reads(r["bases"], r["quals"], r["offsets"])
+    got = ctx.map_reads(r["bases"], r["quals"], r["offsets"])
+    assert_same(got, want, MAP_KEYS, "strand_mode=1")
+    assert got["stats"]["dp_cells"] == want["dp_cells"]
+
+
+def test_map_reads_pooled_samples_and_degenerate_reads(ctx):
+    from savont_b200 import _lib
+    w = _make_workload("pooled", n_roots=6, n_samples=5)
+    r = w.reads(3000)
+    bases = r["bases"].copy(); quals = r["quals"].copy(); offs = r["offsets"]
+    # read 0: all N; read 1: flat qualities; read 2: low quality everywhere (SNPmers gated out)
+    bases[int(offs[0]):int(offs[1])] = ord("N")
+    quals[int(offs[1]):int(offs[2])] = 33 + 40
+    quals[int(offs[2]):int(offs[3])] = 33 + 10
+    # append reads that are too short / exactly k
+    extra = [b"ACGT", b"ACGTACGTACGTACGTA", b""]
+    eb, eo = O.concat(extra)
+    bases = np.concatenate([bases, eb]); quals = np.concatenate([quals, np.full(len(eb), 33 + 30, np.uint8)])
+    offs = np.concatenate([offs, offs[-1] + eo[1:]])
+    fidx = np.concatenate([r["file_idx"], np.array([0, 1, 2], np.uint32)])
+    gp, op = _params(_lib, band=w.band)
+    ctx.set_params(gp); ctx.load_snpmers(w.snpmers); ctx.load_asvs(w.asv_bases, w.asv_offsets)
+    orc = O.Oracle(op, w.snpmers); orc.load_asvs(w.asv_bases, w.asv_offsets)
+    want = orc.map_reads(bases, quals, offs, file_idx=fidx, n_samples=5)
+    got = ctx.map_reads(bases, quals, offs, file_idx=fidx, n_samples=5)
+    assert_same(got, want, MAP_KEYS, "pooled")
+    assert want["status"][-3] == O.STATUS_TOO_SHORT and want["status"][-1] == O.STATUS_TOO_SHORT
+    assert want["sample_singleton"].sum() == want["unambig"].sum()
+    assert len(set(fidx.tolist())) == 5
+
+
+def test_map_reads_properties_at_scale(ctx):
+    """size-independent properties on a larger sample than the oracle comfortably checks:
+    counters add up, classes are sorted and within range, reruns are identical."""
+    from savont_b200 import _lib
+    w = _make_workload("ont16s")
+    r = w.reads(60000)
+    gp, _ = _params(_lib, band=w.band)
+    ctx.set_params(gp); ctx.load_snpmers(w.snpmers); ctx.load_asvs(w.asv_bases, w.asv_offsets)
+    a = ctx.map_reads(r["bases"], r["quals"], r["offsets"])
+    b = ctx.map_reads(r["bases"], r["quals"], r["offsets"])
+    assert_same(a, b, MAP_KEYS, "rerun")
+    co = a["class_offsets"].astype(np.int64); sizes = co[1:] - co[:-1]
+    assert np.all((sizes > 0) == (a["status"] == 0))
+    assert int(a["totals"][0]) == int((a["status"] == 0).sum())
+    assert int(a["totals"][1]) == int(((a["status"] > 0) & (a["status"] < 4)).sum())
+    assert int(a["unambig"].sum()) == int((sizes == 1).sum())
+    assert int(a["ambig"].sum()) == int(sizes[sizes > 1].sum())
+    cls = a["class_asv"]
+    assert cls.max() < w.n_asv
+    inner = np.ones(len(cls), bool); inner[co[:-1][sizes > 0]] = False
+    assert np.all(cls[1:][inner[1:]] > cls[:-1][inner[1:]])        # sorted inside every class
+    single = a["status"] == 0
+    hit = cls[co[:-1][single & (sizes == 1)]] == r["truth_asv"][single & (sizes == 1)]
+    assert hit.mean() > 0.99
+
+
+def test_errors_are_loud(ctx):
+    from savont_b200 import _lib
+    with pytest.raises(_lib.SavontB200Error):
+        ctx.set_params(_lib.default_params(k=16))
+    with pytest.raises(_lib.SavontB200Error):
+        ctx.set_params(_lib.default_params(band=500))
+    gp = _lib.default_params()
+    ctx.set_params(gp); ctx.load_snpmers([])
+    rng = random.Random(3)
+    asvs = [rand_seq(rng, 200), rand_seq(rng, 10)]
+    ab, ao = O.concat(asvs)
+    with pytest.raises(_lib.SavontB200Error):
+        ctx.load_asvs(ab, ao)                   # ASV shorter than k
+    ab, ao = O.concat(asvs[:1])
+    ctx.load_asvs(ab, ao)
+    rb, ro = O.concat([rand_seq(rng, 100)])
+    with pytest.raises(_lib.SavontB200Error):
+        ctx.align_pairs(rb, ro, [0], [5], [0])  # ASV index out of range
+    with pytest.raises(_lib.SavontB200Error):
+        ctx.map_reads(rb, None, ro, class_cap=None, n_samples=0)

@@ -1,0 +1,76 @@
+"""helpers shared by the parity tests"""
+import random
+
+import numpy as np
+
+from tests import pyref
+
+
+def rand_seq(rng, n, alphabet=b"ACGT"):
+    return bytes(rng.choice(alphabet) for _ in range(n))
+
+
+def snpmer_set_from(seqs, k, every=7):
+    """some canonical k-mers of the sequences, both alleles of the middle base"""
+    s = set()
+    mask = ((1 << 64) - 1) ^ (3 << (k - 1))
+    for sq in seqs:
+        for p in range(0, len(sq) - k + 1, every):
+            f = 0
+            for b in sq[p:p + k]:
+                f = (f << 2) | pyref.enc(b)
+            r = pyref.revcomp_kmer(f, k)
+            canon = f if (f & mask) < (r & mask) else r
+            s.add(canon)
+            s.add((canon & mask) | (((canon >> (k - 1)) + 1) & 3) << (k - 1))
+    return s
+
+
+def mutate(rng, s, nsub, nins, ndel):
+    s = bytearray(s)
+    for _ in range(nsub):
+        i = rng.randrange(len(s)); s[i] = rng.choice(b"ACGT")
+    for _ in range(nins):
+        i = rng.randrange(len(s)); s.insert(i, rng.choice(b"ACGT"))
+    for _ in range(ndel):
+        if len(s) > 1:
+            i = rng.randrange(len(s)); del s[i]
+    return bytes(s)
+
+
+def weird_sequences(seed, k, n=40, lengths=(0, 1, 16, 17, 18, 26, 27, 31, 32, 33, 63, 64, 65, 100, 257, 800, 1500, 2100)):
+    """ragged / degenerate inputs: too short, exactly k, non-ACGT, low complexity, repeats"""
+    rng = random.Random(seed)
+    seqs, quals = [], []
+    for t in range(n):
+        L = lengths[t % len(lengths)] if t < len(lengths) else rng.choice([k - 1, k, k + 1, 30, 64, 200, 333, 800])
+        alpha = b"ACGT" if t % 3 else b"ACGTNacgtRYu"
+        sq = rand_seq(rng, L, alpha)
+        if t % 5 == 0 and L > 60:
+            sq = sq[:20] + b"ACACACACACACACACACACACACACACAC" + sq[50:]
+        if t % 7 == 0 and L > 100:
+            sq = sq[:50] + sq[:50] + sq[100:]
+        if t % 11 == 0 and L > 40:
+            sq = b"A" * 25 + sq[25:]
+        seqs.append(sq)
+        if t % 4 == 3:
+            quals.append(bytes([40 + 33] * L))
+        else:
+            quals.append(bytes(33 + rng.choice([5, 12, 25, 26, 30, 40, 50]) for _ in range(L)))
+    return seqs, quals
+
+
+def assert_same(a, b, keys, ctx=""):
+    for key in keys:
+        x, y = np.asarray(a[key]), np.asarray(b[key])
+        if x.dtype.kind == "f":
+            ok = x.shape == y.shape and np.array_equal(x.view(np.uint64), y.view(np.uint64)) or \
+                (x.shape == y.shape and np.all((x == y) | (np.isnan(x) & np.isnan(y))))
+        else:
+            ok = x.shape == y.shape and np.array_equal(x, y)
+        if not ok:
+            bad = None
+            if x.shape == y.shape and x.size:
+                idx = np.flatnonzero(x != y)
+                bad = (idx[:8], x[idx[:8]], y[idx[:8]])
+            raise AssertionError(f"{ctx}: mismatch in '{key}': shapes {x.shape} vs {y.shape}; first diffs {bad}")
