@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py -- reads aligned/s (and GCUPS of the banded DP) of the read-vs-ASV assignment path.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload ont16s] [--reads R]
+
+A "step" = one pass of the hot path (sketch -> candidate filter -> banded DP -> tie/eq-class
+counters) over one batch of synthetic reads (BASELINE.json configs[1]: 1M ONT 16S reads vs 500
+ASVs by default).  N>1 (under torchrun): reads are sharded, R reads per rank (weak scaling), ASV
+index replicated, one all-reduce of the per-ASV count vector per step (NCCL, in place on the
+library's device counter vector).
+
+  value     whole-job reads/s with the reads already resident in HBM (kernel pipeline only)
+  e2e       the same metric through savont_b200_map_reads with pinned HOST buffers
+            (H2D of bases+quals+offsets and D2H of per-read results inside the timed region)
+  roofline  the dominant kernel (banded DP): achieved GCUPS vs the INT32 ALU-pipe peak
+  cpu_baseline / --impl reference: the CPU oracle (C port of the reference path; the Rust
+            reference itself cannot be built here) on all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm_gbs=float(d.get("hbm_gbs", 6650.0)), source="measured (MEASURED_PEAKS.json)",
+                    sm_max_mhz=float(d.get("sm_max_mhz", 1965.0)))
+    return dict(hbm_gbs=6650.0, source="fallback (B200_PROFILING.md)", sm_max_mhz=1965.0)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = max(mx, float(r[2]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        busy = [x for x in sm if x > 0.5 * mx] or sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def _workload(args):
+    from savont_b200 import synth
+    w = synth.Workload(args.workload)
+    return w
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle port of the reference path on all host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    w = _workload(args)
+    cores = os.cpu_count() or 1
+    sample = args.cpu_reads
+    r = w.reads(sample)
+    orc = O.Oracle(O.default_params(band=w.band), w.snpmers)
+    orc.load_asvs(w.asv_bases, w.asv_offsets)
+    times, cells = [], 0
+    for it in range(args.warmup + args.steps):
+        if it >= args.warmup and it > args.warmup and sum(times) > 150:
+            break
+        t0 = time.perf_counter()
+        res = orc.map_reads(r["bases"], r["quals"], r["offsets"], n_threads=cores)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt); cells = res["dp_cells"]
+    steps = len(times)
+    tot = sum(times)
+    value = sample * steps / tot
+    line = {
+        "impl": "reference", "metric": "reads aligned/sec (read-vs-ASV assignment path)", "value": value, "unit": "reads/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32 (bit-parallel INT32 DP) / f64 thresholds", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {w.cfg['desc']}", "n_asv": w.n_asv, "band": w.band, "reads_per_step": sample},
+        "gcups": cells * steps / tot / 1e9,
+        "cpu_baseline": {"value": value, "unit": "reads/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} reads of the workload per step, OpenMP over reads, scalar banded DP "
+                                   "(oracle/savont_oracle.c; the Rust reference + minimap2 cannot be built in this image)"},
+        "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from savont_b200 import _lib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the b200 arm has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=dev)
+
+    w = _workload(args)
+    n_reads = args.reads
+    ctx = _lib.Context(local_rank, _lib.default_params(band=w.band))
+    stream = torch.cuda.current_stream(dev)
+    ctx.set_stream(stream.cuda_stream)
+    ctx.load_snpmers(w.snpmers)
+    ctx.load_asvs(w.asv_bases, w.asv_offsets)
+    ctx.set_batch_reads(args.batch_reads)
+
+    # this rank's shard: reads [rank*R, (rank+1)*R) of the deterministic stream, generated into pinned memory
+    t_gen = time.perf_counter()
+    r = w.reads(n_reads, first=rank * n_reads, alloc=_lib.pinned_array)
+    t_gen = time.perf_counter() - t_gen
+    fidx = r["file_idx"] if w.n_samples > 1 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    class CountsView:                      # the library's device counter vector as a torch tensor (no copy)
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 2}
+
+    def allreduce_counts():
+        if world > 1:
+            ptr, n = ctx.counts_dev()
+            t = torch.as_tensor(CountsView(ptr, n), device=dev)
+            dist.all_reduce(t)             # one NCCL all-reduce of [unambig|ambig|leq10|totals|singleton]
+
+    # ---------------- kernel-only arm: reads resident in HBM ----------------
+    ctx.upload_reads(r["bases"], r["quals"], r["offsets"], file_idx=fidx, n_samples=w.n_samples)
+    for _ in range(args.warmup):
+        ctx.map_resident(); allreduce_counts()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    step_ms, stats = [], []
+    for _ in range(args.steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        st = ctx.map_resident()
+        allreduce_counts()
+        e1.record(stream)
+        barrier()
+        step_ms.append(e0.elapsed_time(e1)); stats.append(st)
+    clocks = sampler.stop()
+    dev_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dev_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(dev_ms.item())
+    got = ctx.fetch_resident()
+
+    # ---------------- e2e arm: host buffers through the C ABI ----------------
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    ctx.map_reads(r["bases"], r["quals"], r["offsets"], file_idx=fidx, n_samples=w.n_samples)   # warm-up (allocations)
+    e2e_ms, e2e_stats = [], None
+    for _ in range(e2e_steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        res = ctx.map_reads(r["bases"], r["quals"], r["offsets"], file_idx=fidx, n_samples=w.n_samples)
+        allreduce_counts()
+        e1.record(stream)
+        barrier()
+        e2e_ms.append(e0.elapsed_time(e1))
+        e2e_stats = res["stats"]
+    e2e_t = torch.tensor([sum(e2e_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_total_ms = float(e2e_t.item())
+
+    if rank != 0:
+        return
+    peaks = _peaks()
+    K = args.steps
+    value = world * n_reads * K / (total_ms / 1e3)
+    e2e_value = world * n_reads * e2e_steps / (e2e_total_ms / 1e3)
+    align_ms = float(np.mean([s["align_ms"] for s in stats]))
+    sketch_ms = float(np.mean([s["sketch_ms"] for s in stats]))
+    filter_ms = float(np.mean([s["filter_ms"] for s in stats]))
+    assign_ms = float(np.mean([s["assign_ms"] for s in stats]))
+    cells = stats[-1]["dp_cells"]; pairs = stats[-1]["n_pairs"]; bases = stats[-1]["n_bases"]
+    gcups = cells / (align_ms / 1e3) / 1e9 if align_ms > 0 else 0.0
+    # INT32 roofline of the DP kernel: ALU pipe = 16 lanes/clk/SMSP x 4 SMSP x SMs; OPS_PER_WORD INT32 ALU
+    # instructions per 32-cell word-column counted from the kernel's SASS (DESIGN.md "K3")
+    sm_mhz = clocks.get("sm_mhz") or peaks["sm_max_mhz"]
+    nw = {64: 5, 32: 3, 192: 13}.get(w.band, (2 * w.band + 1 + 31) // 32)
+    used_frac = (2 * w.band + 1) / (32.0 * nw)
+    alu_ops = 148 * 4 * 16 * sm_mhz * 1e6
+    peak_gcups = alu_ops * 32.0 * used_frac / OPS_PER_WORD / 1e9
+    # HBM view of the sketch kernel (algorithmic bytes: bases + quals in, planes + sketch out)
+    sk_bytes = bases * 2 + bases / 4 + 12.0 * (stats[-1]["n_reads"] * (bases / max(stats[-1]["n_reads"], 1) / 11.0 + 25))
+    line = {
+        "metric": "reads aligned/sec (read-vs-ASV assignment path)", "value": value, "unit": "reads/s",
+        "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": total_ms / K, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32 (bit-parallel INT32 DP) / f64 thresholds", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {w.cfg['desc']}", "n_asv": w.n_asv, "band": w.band,
+                   "reads_per_gpu_per_step": n_reads, "parallelism": f"reads sharded x{world}, ASV index replicated",
+                   "l2": "inputs (~%.1f GB per step) larger than L2" % (2 * bases / 1e9)},
+        "gcups": gcups,
+        "kernel_ms": {"sketch": sketch_ms, "filter": filter_ms, "align": align_ms, "assign": assign_ms},
+        "pairs_per_step": pairs, "dp_cells_per_step": cells,
+        "roofline": {"bound": "int32", "kernel": "align_nm_kernel", "achieved": gcups, "peak": peak_gcups, "unit": "GCUPS",
+                     "frac": gcups / peak_gcups if peak_gcups else None, "traffic": None,
+                     "peak_how": f"148 SM x 64 INT32 ALU lanes x {sm_mhz:.0f} MHz (sampled) x 32 cells / {OPS_PER_WORD} ALU ops per "
+                                 f"32-cell word, x {used_frac:.3f} (band {2 * w.band + 1} of {32 * nw} vector bits)"},
+        "roofline_hbm": {"bound": "hbm", "kernel": "sketch_kernel", "achieved": sk_bytes / (sketch_ms / 1e3) / 1e9 if sketch_ms else None,
+                         "peak": peaks["hbm_gbs"], "unit": "GB/s", "peak_source": peaks["source"],
+                         "frac": (sk_bytes / (sketch_ms / 1e3) / 1e9) / peaks["hbm_gbs"] if sketch_ms else None, "traffic": None},
+        "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(e2e_stats["h2d_bytes"]),
+                "d2h_bytes_per_step": int(e2e_stats["d2h_bytes"]), "steps": e2e_steps, "ms_per_step": e2e_total_ms / e2e_steps,
+                "h2d_ms": e2e_stats["h2d_ms"], "d2h_ms": e2e_stats["d2h_ms"]},
+        "gpu_launches": int(sum(s["kernel_launches"] for s in stats)),
+        "clocks": clocks,
+        "assigned_frac": float(got["totals"][0]) / max(n_reads * (world if world > 1 else 1), 1),
+        "gen_s": t_gen,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        from oracle import oracle as O
+        cores = os.cpu_count() or 1
+        ns = min(args.cpu_reads, n_reads)
+        sub = {k: r[k] for k in ("bases", "quals")}
+        offs = r["offsets"][: ns + 1]
+        orc = O.Oracle(O.default_params(band=w.band), w.snpmers)
+        orc.load_asvs(w.asv_bases, w.asv_offsets)
+        t0 = time.perf_counter()
+        want = orc.map_reads(sub["bases"], sub["quals"], offs, file_idx=None if fidx is None else fidx[:ns], n_samples=w.n_samples,
+                             n_threads=cores)
+        dt = time.perf_counter() - t0
+        same = bool(np.array_equal(want["status"], got["status"][:ns]) and np.array_equal(want["best_nm"], got["best_nm"][:ns]))
+        line["cpu_baseline"] = {"value": ns / dt, "unit": "reads/s", "cores": cores, "kind": "port",
+                                "sample": f"first {ns} reads of the same workload, OpenMP over reads (oracle/savont_oracle.c)",
+                                "gpu_matches_oracle_on_sample": same}
+    print(json.dumps(line), flush=True)
+
+
+# INT32 ALU-pipe instructions per 32-cell word-column of align_nm_kernel<5> (counted in DESIGN.md from cuobjdump -sass)
+OPS_PER_WORD = 15.0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="ont16s")
+    ap.add_argument("--reads", type=int, default=1_000_000, help="reads per GPU per step")
+    ap.add_argument("--batch-reads", type=int, default=262144)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-reads", type=int, default=100_000, help="sample size of the CPU baseline / reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        print(f"bench.py: WORLD_SIZE={world} != --gpus {args.gpus}", file=sys.stderr)
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, world, local_rank)
+        try:
+            import torch.distributed as dist
+            if dist.is_initialized():
+                dist.destroy_process_group()
+        except Exception:
+            pass
+
+
+if __name__ == "__main__":
+    main()

@@ -86,6 +86,7 @@ struct Batch {
     uint64_t total_bases = 0;
     // sketch
     DevBuf planes, sk_status, flatq, mini_cnt, mini_kmer, mini_pos, snp_start, snp_cnt, snp_kmer, snp_pos, est_id;
+    DevBuf spill_k, spill_p; uint32_t spill_stride = 0;
     uint32_t snp_cap = 0;
     DevBuf ctrs;   // u32[4]: snp pool counter, pair counter, error bits, spare
     // filter
@@ -98,7 +99,7 @@ struct Batch {
     bool mapped = false;
     void release() {
         DevBuf *all[] = {&bases, &quals, &offsets, &file_idx, &planes, &sk_status, &flatq, &mini_cnt, &mini_kmer, &mini_pos,
-                         &snp_start, &snp_cnt, &snp_kmer, &snp_pos, &est_id, &ctrs, &cand_status, &pair_start, &pair_cnt,
+                         &snp_start, &snp_cnt, &snp_kmer, &snp_pos, &est_id, &spill_k, &spill_p, &ctrs, &cand_status, &pair_start, &pair_cnt,
                          &low_mm, &p_read, &p_asv, &p_mini, &p_strand, &nm, &asv_end, &read_end, &rstatus, &best_nm,
                          &class_cnt, &class_slot, &class_off, &class_out, &scan_tmp};
         for (DevBuf *b : all) b->release();
@@ -296,6 +297,7 @@ static SketchOut sketch_view(const Batch &b, bool with_pos) {
     o.snp_start = b.snp_start.as<uint32_t>(); o.snp_cnt = b.snp_cnt.as<uint32_t>();
     o.snp_kmer = b.snp_kmer.as<uint64_t>(); o.snp_pos = b.snp_pos.as<uint32_t>();
     o.snp_pool_ctr = b.ctrs.as<uint32_t>(); o.snp_pool_cap = b.snp_cap;
+    o.spill_kmer = b.spill_k.as<uint64_t>(); o.spill_pos = b.spill_p.as<uint32_t>(); o.spill_stride = b.spill_stride;
     o.err = b.ctrs.as<uint32_t>() + 2;
     return o;
 }
@@ -312,6 +314,12 @@ static int stage_sketch(Context *c, Batch &b, bool with_pos) {
     TRY(b.snp_start.ensure((n + 1) * 4)); TRY(b.snp_cnt.ensure((n + 1) * 4));
     if (b.snp_cap == 0 || b.snp_cap < total / 8 + 4096) b.snp_cap = (uint32_t)std::min<uint64_t>(total / 8 + 4096, 0xfffffff0u);
     TRY(b.ctrs.ensure(4 * sizeof(uint32_t)));
+    {   // per-warp spill region for sequences with more than kSnpHitCap SNPmer hits
+        const uint32_t grid = sketch_grid(b.n, b.max_len, c->use_rank_table, c->dp.s, c->sm_count);
+        b.spill_stride = b.max_len + 1;
+        const size_t entries = (size_t)grid * kSketchWarps * b.spill_stride;
+        TRY(b.spill_k.ensure(entries * 8)); TRY(b.spill_p.ensure(entries * 4));
+    }
     for (int attempt = 0; attempt < 3; ++attempt) {
         TRY(b.snp_kmer.ensure((size_t)b.snp_cap * 8)); TRY(b.snp_pos.ensure((size_t)b.snp_cap * 4));
         CK(cudaMemsetAsync(b.ctrs.p, 0, 4 * sizeof(uint32_t), c->stream));
@@ -324,9 +332,6 @@ static int stage_sketch(Context *c, Batch &b, bool with_pos) {
         uint32_t h[4];
         CK(cudaMemcpyAsync(h, b.ctrs.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
-        if (h[2] & kErrSnpHits)
-            return fail(SAVONT_B200_ERR_OVERFLOW, "a sequence has more than %d SNPmer hits (limit of the shared-memory hit list)",
-                        kSnpHitCap);
         if (h[2] & kErrSnpPool) {
             if (attempt == 2) return fail(SAVONT_B200_ERR_OVERFLOW, "SNPmer pool overflow (%u needed)", h[0]);
             b.snp_cap = h[0] + 1024;

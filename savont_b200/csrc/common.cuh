@@ -85,6 +85,9 @@ struct SketchOut {
     uint32_t *snp_pos;       // pool
     uint32_t *snp_pool_ctr;  // [1]
     uint32_t snp_pool_cap;
+    uint64_t *spill_kmer;    // per-warp overflow of the shared-memory SNPmer hit list
+    uint32_t *spill_pos;
+    uint32_t spill_stride;   // entries per warp (>= max_len)
     uint32_t *err;           // [1] error bits
 };
 
@@ -135,6 +138,7 @@ struct AlignOut {
 // launchers (defined in the .cu files)
 void launch_sketch(const SeqBatch &in, const SketchOut &out, const SnpSet &set, const uint16_t *rank_table,
                    const DeviceParams &p, int sm_count, cudaStream_t st);
+uint32_t sketch_grid(uint32_t n, uint32_t max_len, bool use_table, int s, int sm_count);
 void launch_est_id(const SeqBatch &in, const uint8_t *status, const uint8_t *flatq, const double *phred_table,
                    double *est_id, cudaStream_t st);
 void launch_codes(const uint8_t *bases, uint8_t *codes, uint64_t total, cudaStream_t st);

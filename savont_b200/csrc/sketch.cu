@@ -132,6 +132,12 @@ sketch_kernel(SeqBatch in, SketchOut out, SnpSet set, const uint16_t *__restrict
 
     const uint32_t mid_idx = (c - 1u) >> 1;      // (k - s) / 2, src/seeding.rs:528
     const uint32_t half_k = k >> 1;
+    // SNPmer hits beyond the shared-memory list spill to a per-warp global region (rare)
+    uint64_t *spill_k = out.spill_kmer + (size_t)(blockIdx.x * kSketchWarps + warp) * out.spill_stride;
+    uint32_t *spill_p = out.spill_pos + (size_t)(blockIdx.x * kSketchWarps + warp) * out.spill_stride;
+    auto hit_k = [&](uint32_t h) -> uint64_t { return h < (uint32_t)kSnpHitCap ? hits_k[h] : spill_k[h - kSnpHitCap]; };
+    auto hit_p = [&](uint32_t h) -> uint32_t { return h < (uint32_t)kSnpHitCap ? hits_p[h] : spill_p[h - kSnpHitCap]; };
+    auto set_hit_p = [&](uint32_t h, uint32_t v) { if (h < (uint32_t)kSnpHitCap) hits_p[h] = v; else spill_p[h - kSnpHitCap] = v; };
 
     for (uint32_t seq = blockIdx.x * kSketchWarps + warp; seq < in.n; seq += gridDim.x * kSketchWarps) {
         const uint64_t off = in.offsets[seq];
@@ -218,30 +224,27 @@ sketch_kernel(SeqBatch in, SketchOut out, SnpSet set, const uint16_t *__restrict
             if (is_snp) {
                 const uint32_t o = n_hits + __popc(hb & lt_mask);
                 if (o < (uint32_t)kSnpHitCap) { hits_k[o] = canon; hits_p[o] = pos | (gate ? 0x80000000u : 0u); }
+                else { spill_k[o - kSnpHitCap] = canon; spill_p[o - kSnpHitCap] = pos | (gate ? 0x80000000u : 0u); }
             }
             n_hits += __popc(hb);
             __syncwarp();
         }
 
         // ---- SNPmer dedup: keep gated hits whose splitmer occurs exactly once among ALL hits ----
-        uint32_t nh = n_hits;
-        if (nh > (uint32_t)kSnpHitCap) {
-            if (lane == 0) atomicOr(out.err, kErrSnpHits);
-            nh = kSnpHitCap;
-        }
+        const uint32_t nh = n_hits;
         uint32_t kept_total = 0;
         for (uint32_t base = 0; base < nh; base += 32u) {
             const uint32_t h = base + lane;
             bool keep = false;
             if (h < nh) {
-                const uint64_t sp = hits_k[h] & p.split_mask;
+                const uint64_t sp = hit_k(h) & p.split_mask;
                 uint32_t cnt = 0;
-                for (uint32_t j = 0; j < nh; ++j) cnt += ((hits_k[j] & p.split_mask) == sp) ? 1u : 0u;
-                keep = (hits_p[h] >> 31) && cnt == 1u;
+                for (uint32_t j = 0; j < nh; ++j) cnt += ((hit_k(j) & p.split_mask) == sp) ? 1u : 0u;
+                keep = (hit_p(h) >> 31) && cnt == 1u;
             }
             const uint32_t b = __ballot_sync(0xffffffffu, keep);
             __syncwarp();
-            if (h < nh) hits_p[h] = (hits_p[h] & 0x7fffffffu) | (keep ? 0x80000000u : 0u);
+            if (h < nh) set_hit_p(h, (hit_p(h) & 0x7fffffffu) | (keep ? 0x80000000u : 0u));
             kept_total += __popc(b);
         }
         __syncwarp();
@@ -256,12 +259,12 @@ sketch_kernel(SeqBatch in, SketchOut out, SnpSet set, const uint16_t *__restrict
             uint32_t idx = 0;
             for (uint32_t base = 0; base < nh; base += 32u) {
                 const uint32_t h = base + lane;
-                const bool keep = (h < nh) && (hits_p[h] >> 31);
+                const bool keep = (h < nh) && (hit_p(h) >> 31);
                 const uint32_t b = __ballot_sync(0xffffffffu, keep);
                 if (keep) {
                     const uint32_t o = start + idx + __popc(b & lt_mask);
-                    out.snp_kmer[o] = hits_k[h];
-                    out.snp_pos[o] = hits_p[h] & 0x7fffffffu;
+                    out.snp_kmer[o] = hit_k(h);
+                    out.snp_pos[o] = hit_p(h) & 0x7fffffffu;
                 }
                 idx += __popc(b);
             }
@@ -284,19 +287,27 @@ size_t sketch_smem_bytes(bool use_table, int s, uint32_t packed_words) {
     return table + per_warp * kSketchWarps;
 }
 
+// grid used by launch_sketch (the host sizes the per-warp spill region with it)
+uint32_t sketch_grid(uint32_t n, uint32_t max_len, bool use_table, int s, int sm_count) {
+    const uint32_t packed_words = (max_len >> 4) + 6u;
+    const size_t smem = sketch_smem_bytes(use_table, s, packed_words);
+    // persistent-style grid: a multiple of the SM count, capped by the work available
+    int ctas_per_sm = (int)(200u * 1024u / (smem + 1024u));
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    if (ctas_per_sm > 8) ctas_per_sm = 8;
+    uint32_t grid = (uint32_t)(sm_count * ctas_per_sm);
+    const uint32_t need = (n + kSketchWarps - 1) / kSketchWarps;
+    if (grid > need) grid = need;
+    return grid ? grid : 1u;
+}
+
 void launch_sketch(const SeqBatch &in, const SketchOut &out, const SnpSet &set, const uint16_t *rank_table,
                    const DeviceParams &p, int sm_count, cudaStream_t st) {
     if (in.n == 0) return;
     const uint32_t packed_words = (in.max_len >> 4) + 6u;
     const bool use_table = rank_table != nullptr;
     const size_t smem = sketch_smem_bytes(use_table, p.s, packed_words);
-    // persistent-style grid: a multiple of the SM count, capped by the work available
-    int ctas_per_sm = (int)(200u * 1024u / (smem + 1024u));
-    if (ctas_per_sm < 1) ctas_per_sm = 1;
-    if (ctas_per_sm > 8) ctas_per_sm = 8;
-    uint32_t grid = (uint32_t)(sm_count * ctas_per_sm);
-    const uint32_t need = (in.n + kSketchWarps - 1) / kSketchWarps;
-    if (grid > need) grid = need;
+    const uint32_t grid = sketch_grid(in.n, in.max_len, use_table, p.s, sm_count);
     if (use_table) {
         cudaFuncSetAttribute(sketch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         sketch_kernel<true><<<grid, kSketchWarps * 32, smem, st>>>(in, out, set, rank_table, p, packed_words);

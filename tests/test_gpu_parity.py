@@ -27,7 +27,7 @@ def _params(lib_mod, **kw):
     return lib_mod.default_params(**kw), O.default_params(**kw)
 
 
-@pytest.mark.parametrize("k,c", [(17, 11), (15, 9), (21, 11), (13, 7), (23, 5), (19, 19), (17, 1)])
+@pytest.mark.parametrize("k,c", [(17, 11), (15, 9), (21, 11), (13, 7), (23, 8), (19, 19), (17, 2), (19, 6)])
 def test_sketch_ragged_inputs(ctx, k, c):
     from savont_b200 import _lib
     seqs, quals = weird_sequences(100 + k, k)
@@ -135,13 +135,13 @@ def _make_workload(name, **kw):
     return synth.Workload(name, **kw)
 
 
-@pytest.mark.parametrize("name,kw,n", [
-    ("ont16s", dict(n_roots=8), 4000),
-    ("ont16s", dict(n_roots=5, sites_per_genus=3), 3000),     # near-identical variants -> ambiguous classes
-    ("hifi16s", dict(n_roots=8), 3000),
-    ("operon", dict(n_roots=4), 600),
+@pytest.mark.parametrize("name,kw,n,min_assigned", [
+    ("ont16s", dict(n_roots=8), 4000, 0.9),
+    ("ont16s", dict(n_roots=5, sites_per_genus=3), 3000, 0.5),     # near-identical variants -> ambiguous classes
+    ("hifi16s", dict(n_roots=8), 3000, 0.9),
+    ("operon", dict(n_roots=4), 600, 0.9),
 ])
-def test_candidates_and_map_reads(ctx, name, kw, n):
+def test_candidates_and_map_reads(ctx, name, kw, n, min_assigned):
     from savont_b200 import _lib
     w = _make_workload(name, **kw)
     r = w.reads(n)
@@ -159,7 +159,7 @@ def test_candidates_and_map_reads(ctx, name, kw, n):
         ctx.set_batch_reads(0)
     assert_same(got, want, MAP_KEYS, f"map_reads {name}")
     assert got["stats"]["dp_cells"] == want["dp_cells"]
-    assert int(want["totals"][0]) > 0.9 * n
+    assert int(want["totals"][0]) > min_assigned * n
     # device-resident variant gives the same answer
     ctx.upload_reads(r["bases"], r["quals"], r["offsets"])
     ctx.map_resident()
