@@ -116,14 +116,15 @@ struct Context {
 
     // tables
     DevBuf d_rank_table; bool use_rank_table = false;
-    DevBuf d_snp_keys; uint32_t snp_mask = 0; std::vector<uint64_t> h_snpmers;
+    DevBuf d_snp_keys, d_snp_bloom; uint32_t snp_mask = 0, snp_shift = 0, bloom_shift = 0, bloom_words = 0;
+    std::vector<uint64_t> h_snpmers;
     DevBuf d_phred;
 
     // ASVs (replicated index)
     std::vector<uint8_t> asv_bases_h; std::vector<uint64_t> asv_offsets_h;
     size_t n_asv = 0; bool index_dirty = true; uint32_t max_asv_len = 0;
     DevBuf d_idx_keys, d_idx_vals, d_idx_entries, d_mset, d_mset_off, d_asv_planes, d_asv_plane_off, d_asv_len;
-    uint32_t idx_mask = 0;
+    uint32_t idx_mask = 0, idx_shift = 0;
     std::vector<uint32_t> asv_len_h;
 
     // counters [unambig A | ambig A | leq10 A | assigned | filtered | singleton S*A]
@@ -137,7 +138,8 @@ struct Context {
 };
 
 // ------------------------------------------------------------------------------------------------
-static uint32_t next_pow2_u32(uint64_t x) { uint32_t p = 1; while ((uint64_t)p < x) p <<= 1; return p; }
+static uint32_t next_pow2_u32(uint64_t x) { uint32_t p = 2; while ((uint64_t)p < x) p <<= 1; return p; }
+static uint32_t shift_for_cap(uint32_t cap) { uint32_t b = 0; while ((1u << b) < cap) ++b; return 64u - b; }
 
 static int validate_params(const savont_b200_params &p) {
     if (p.k < 13 || p.k > 23 || (p.k % 2) == 0)
@@ -228,17 +230,29 @@ static int build_tables(Context *c) {
 static int upload_snp_set(Context *c) {
     const size_t n = c->h_snpmers.size();
     if (n == 0) { c->snp_mask = 0; return 0; }
-    const uint32_t cap = next_pow2_u32(2 * n + 2);
+    const uint32_t cap = next_pow2_u32(4 * n + 2);           // load factor <= 0.25: ~1.2 probes per lookup
+    const uint32_t shift = shift_for_cap(cap);
     std::vector<uint64_t> keys(cap, kEmpty64);
+    // one-hash Bloom filter over the same Fibonacci product, staged in shared memory by the sketch kernel:
+    // >= 32 bits per key, between 8 KiB and 32 KiB
+    uint32_t bloom_bits = next_pow2_u32(32 * n);
+    if (bloom_bits < (1u << 16)) bloom_bits = 1u << 16;
+    if (bloom_bits > (1u << 18)) bloom_bits = 1u << 18;
+    const uint32_t bshift = shift_for_cap(bloom_bits);
+    std::vector<uint32_t> bloom(bloom_bits / 32, 0u);
     for (uint64_t key : c->h_snpmers) {
-        uint32_t slot = (uint32_t)mix64(key) & (cap - 1);
+        uint32_t slot = hash_slot(key, shift);
         while (keys[slot] != kEmpty64 && keys[slot] != key) slot = (slot + 1) & (cap - 1);
         keys[slot] = key;
+        const uint32_t bi = (uint32_t)((key * kFibMul) >> bshift);
+        bloom[bi >> 5] |= 1u << (bi & 31);
     }
     TRY(c->d_snp_keys.ensure(cap * sizeof(uint64_t)));
+    TRY(c->d_snp_bloom.ensure(bloom.size() * 4));
     CK(cudaMemcpyAsync(c->d_snp_keys.p, keys.data(), cap * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_snp_bloom.p, bloom.data(), bloom.size() * 4, cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    c->snp_mask = cap - 1;
+    c->snp_mask = cap - 1; c->snp_shift = shift; c->bloom_shift = bshift; c->bloom_words = (uint32_t)bloom.size();
     return 0;
 }
 
@@ -279,6 +293,15 @@ static int batch_upload(Context *c, Batch &b, const uint8_t *bases, const uint8_
     return 0;
 }
 
+static SnpSet snp_view(const Context *c) {
+    SnpSet set{};
+    if (c->snp_mask) {
+        set.keys = c->d_snp_keys.as<uint64_t>(); set.mask = c->snp_mask; set.shift = c->snp_shift;
+        set.bloom = c->d_snp_bloom.as<uint32_t>(); set.bloom_shift = c->bloom_shift; set.bloom_words = c->bloom_words;
+    }
+    return set;
+}
+
 static SeqBatch seq_view(const Batch &b) {
     SeqBatch v{};
     v.bases = b.bases.as<uint8_t>();
@@ -315,7 +338,7 @@ static int stage_sketch(Context *c, Batch &b, bool with_pos) {
     if (b.snp_cap == 0 || b.snp_cap < total / 8 + 4096) b.snp_cap = (uint32_t)std::min<uint64_t>(total / 8 + 4096, 0xfffffff0u);
     TRY(b.ctrs.ensure(4 * sizeof(uint32_t)));
     {   // per-warp spill region for sequences with more than kSnpHitCap SNPmer hits
-        const uint32_t grid = sketch_grid(b.n, b.max_len, c->use_rank_table, c->dp.s, c->sm_count);
+        const uint32_t grid = sketch_grid(b.n, b.max_len, c->use_rank_table, c->dp, snp_view(c), c->sm_count);
         b.spill_stride = b.max_len + 1;
         const size_t entries = (size_t)grid * kSketchWarps * b.spill_stride;
         TRY(b.spill_k.ensure(entries * 8)); TRY(b.spill_p.ensure(entries * 4));
@@ -323,8 +346,7 @@ static int stage_sketch(Context *c, Batch &b, bool with_pos) {
     for (int attempt = 0; attempt < 3; ++attempt) {
         TRY(b.snp_kmer.ensure((size_t)b.snp_cap * 8)); TRY(b.snp_pos.ensure((size_t)b.snp_cap * 4));
         CK(cudaMemsetAsync(b.ctrs.p, 0, 4 * sizeof(uint32_t), c->stream));
-        SnpSet set{c->snp_mask ? c->d_snp_keys.as<uint64_t>() : nullptr, c->snp_mask};
-        launch_sketch(seq_view(b), sketch_view(b, with_pos), set, c->use_rank_table ? c->d_rank_table.as<uint16_t>() : nullptr,
+        launch_sketch(seq_view(b), sketch_view(b, with_pos), snp_view(c), c->use_rank_table ? c->d_rank_table.as<uint16_t>() : nullptr,
                       c->dp, c->sm_count, c->stream);
         CK(cudaGetLastError());
         c->last_stats.kernel_launches += 1;
@@ -345,7 +367,7 @@ static int stage_sketch(Context *c, Batch &b, bool with_pos) {
 static AsvIndex index_view(const Context *c) {
     AsvIndex ix{};
     ix.idx_keys = c->idx_mask ? c->d_idx_keys.as<uint64_t>() : nullptr;
-    ix.idx_vals = c->d_idx_vals.as<uint2>(); ix.idx_mask = c->idx_mask; ix.idx_entries = c->d_idx_entries.as<uint32_t>();
+    ix.idx_vals = c->d_idx_vals.as<uint2>(); ix.idx_mask = c->idx_mask; ix.idx_shift = c->idx_shift; ix.idx_entries = c->d_idx_entries.as<uint32_t>();
     ix.mset = c->d_mset.as<uint64_t>(); ix.mset_off = c->d_mset_off.as<uint32_t>();
     ix.planes = c->d_asv_planes.as<uint2>(); ix.plane_off = c->d_asv_plane_off.as<uint32_t>(); ix.len = c->d_asv_len.as<uint32_t>();
     ix.n_asv = (uint32_t)c->n_asv;
@@ -507,18 +529,19 @@ static int build_asv_index(Context *c) {
     size_t n_keys = 0;
     for (size_t i = 0; i < ents.size(); ++i) if (i == 0 || ents[i].sp != ents[i - 1].sp) ++n_keys;
     std::vector<uint32_t> entries(ents.size() + 1);
-    const uint32_t cap = n_keys ? next_pow2_u32(2 * n_keys + 2) : 0;
+    const uint32_t cap = n_keys ? next_pow2_u32(4 * n_keys + 2) : 0;
+    const uint32_t ishift = cap ? shift_for_cap(cap) : 0;
     std::vector<uint64_t> keys(cap ? cap : 1, kEmpty64);
     std::vector<uint2> vals(cap ? cap : 1, make_uint2(0, 0));
     for (size_t i = 0; i < ents.size();) {
         size_t j = i;
         while (j < ents.size() && ents[j].sp == ents[i].sp) { entries[j] = (ents[j].asv << 2) | ents[j].mid; ++j; }
-        uint32_t slot = (uint32_t)mix64(ents[i].sp) & (cap - 1);
+        uint32_t slot = hash_slot(ents[i].sp, ishift);
         while (keys[slot] != kEmpty64) slot = (slot + 1) & (cap - 1);
         keys[slot] = ents[i].sp; vals[slot] = make_uint2((uint32_t)i, (uint32_t)(j - i));
         i = j;
     }
-    c->idx_mask = cap ? cap - 1 : 0;
+    c->idx_mask = cap ? cap - 1 : 0; c->idx_shift = ishift;
     // (3) DP planes: padl zero bits, then the bases, then >= 32*(NW+4) zero bits
     const int nw = align_words_for_band(c->dp.band);
     const uint32_t padl = (uint32_t)c->dp.asv_padl;
@@ -693,7 +716,7 @@ int savont_b200_destroy(savont_b200_ctx *h) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     c->work.release(); c->resident.release(); c->asvb.release();
-    DevBuf *bufs[] = {&c->d_rank_table, &c->d_snp_keys, &c->d_phred, &c->d_idx_keys, &c->d_idx_vals, &c->d_idx_entries, &c->d_mset,
+    DevBuf *bufs[] = {&c->d_rank_table, &c->d_snp_keys, &c->d_snp_bloom, &c->d_phred, &c->d_idx_keys, &c->d_idx_vals, &c->d_idx_entries, &c->d_mset,
                       &c->d_mset_off, &c->d_asv_planes, &c->d_asv_plane_off, &c->d_asv_len, &c->d_counters};
     for (DevBuf *b : bufs) b->release();
     c->pin_offsets.release(); c->pin_small.release(); c->pin_out.release();

@@ -15,8 +15,8 @@ namespace sb {
 
 constexpr uint64_t kEmpty64 = ~0ull;
 constexpr uint64_t kFwdBit = 1ull << 63;
-constexpr int kSnpHitCap = 256;        // per-sequence SNPmer hits held in shared memory
-constexpr int kSketchWarps = 8;        // warps per CTA in the sketch kernel
+constexpr int kSnpHitCap = 128;        // per-sequence SNPmer hits held in shared memory (more spill to global)
+constexpr int kSketchWarps = 16;       // warps per CTA in the sketch kernel
 constexpr int kFilterWarps = 4;        // warps per CTA in the filter kernel
 
 // error flag bits written by kernels into Context::d_err
@@ -37,13 +37,10 @@ struct DeviceParams {
     double ratio_thresh, min_frac;
 };
 
-// multiplicative mixer shared by host-built and device-probed tables
-__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
-    x ^= x >> 31;
-    x *= 0x9E3779B97F4A7C15ull;
-    x ^= x >> 29;
-    return x;
-}
+// Fibonacci hashing shared by host-built and device-probed open-addressing tables: the slot is the
+// TOP log2(cap) bits of key * 2^64/phi (shift = 64 - log2(cap), cap >= 2).
+constexpr uint64_t kFibMul = 0x9E3779B97F4A7C15ull;
+__host__ __device__ __forceinline__ uint32_t hash_slot(uint64_t key, uint32_t shift) { return (uint32_t)((key * kFibMul) >> shift); }
 
 // src/seeding.rs:18-28
 __host__ __device__ __forceinline__ uint64_t mm_hash64(uint64_t key) {
@@ -92,8 +89,12 @@ struct SketchOut {
 };
 
 struct SnpSet {              // open addressing, kEmpty64 = empty
-    const uint64_t *keys;
-    uint32_t mask;           // cap-1, 0 when the set is empty (keys == null)
+    const uint64_t *keys;    // null when the set is empty
+    uint32_t mask;           // cap-1
+    uint32_t shift;          // 64 - log2(cap)
+    const uint32_t *bloom;   // one-hash Bloom filter over the same Fibonacci product (staged in shared memory)
+    uint32_t bloom_shift;    // 64 - log2(bloom bits)
+    uint32_t bloom_words;
 };
 
 struct AsvIndex {
@@ -101,6 +102,7 @@ struct AsvIndex {
     const uint64_t *idx_keys;
     const uint2 *idx_vals;       // (start, len)
     uint32_t idx_mask;
+    uint32_t idx_shift;
     const uint32_t *idx_entries;
     // distinct minimizer sets per ASV (sorted; bit 63 = forward-any flag)
     const uint64_t *mset;
@@ -138,7 +140,7 @@ struct AlignOut {
 // launchers (defined in the .cu files)
 void launch_sketch(const SeqBatch &in, const SketchOut &out, const SnpSet &set, const uint16_t *rank_table,
                    const DeviceParams &p, int sm_count, cudaStream_t st);
-uint32_t sketch_grid(uint32_t n, uint32_t max_len, bool use_table, int s, int sm_count);
+uint32_t sketch_grid(uint32_t n, uint32_t max_len, bool use_table, const DeviceParams &p, const SnpSet &set, int sm_count);
 void launch_est_id(const SeqBatch &in, const uint8_t *status, const uint8_t *flatq, const double *phred_table,
                    double *est_id, cudaStream_t st);
 void launch_codes(const uint8_t *bases, uint8_t *codes, uint64_t total, cudaStream_t st);

@@ -42,6 +42,7 @@ filter_kernel(SeqBatch in, SketchOut sk, AsvIndex ix, PairPool pool, FilterOut o
     uint32_t *bm2 = bm1 + lay.bm_words;
     uint32_t *sum1 = bm2 + lay.bm_words;
     const uint32_t rmask = lay.rcap - 1u;
+    const uint32_t rshift = 64u - (uint32_t)__popc(rmask);
     const uint32_t clear_words = lay.acc_words + 2u * lay.bm_words + lay.sum_words;
     const int mid_shift = p.k - 1;
 
@@ -66,7 +67,7 @@ filter_kernel(SeqBatch in, SketchOut sk, AsvIndex ix, PairPool pool, FilterOut o
             if (t < nmini) {
                 const unsigned long long v = sk.mini_kmer[mo + t];
                 const unsigned long long key = v & ~kFwdBit;
-                uint32_t slot = (uint32_t)mix64(key) & rmask;
+                uint32_t slot = hash_slot(key, rshift);
                 while (true) {
                     const unsigned long long old = atomicCAS(&rset[slot], (unsigned long long)kEmpty64, v);
                     if (old == kEmpty64) { inserted = true; break; }
@@ -90,7 +91,7 @@ filter_kernel(SeqBatch in, SketchOut sk, AsvIndex ix, PairPool pool, FilterOut o
                 const uint64_t q = sk.snp_kmer[s0 + t];
                 const uint64_t sp = q & p.split_mask;
                 mid = (uint32_t)(q >> mid_shift) & 3u;
-                uint32_t slot = (uint32_t)mix64(sp) & ix.idx_mask;
+                uint32_t slot = hash_slot(sp, ix.idx_shift);
                 while (true) {
                     const uint64_t key = __ldg(ix.idx_keys + slot);
                     if (key == sp) { const uint2 v = __ldg(ix.idx_vals + slot); bstart = v.x; blen = v.y; break; }
@@ -117,57 +118,75 @@ filter_kernel(SeqBatch in, SketchOut sk, AsvIndex ix, PairPool pool, FilterOut o
         }
         __syncwarp();
 
-        // ---- 3. evaluate candidates in ascending ASV order ----
+        // ---- 3. evaluate candidates, lowest SNPmer mismatch count first ----
+        // Only candidates with the MINIMUM mismatch count among those that pass the minimizer / ratio
+        // tests are kept (src/alignment.rs:1829-1843), so the groups are visited in ascending
+        // mismatch order and the walk stops at the first group with a passing candidate; every
+        // group is visited (and any_scored is exact) only when nothing passes.
         uint32_t lowest = 0xffffffffu, n_low = 0;
         bool any_scored = false;
-        for (uint32_t sw = 0; sw < lay.sum_words; ++sw) {
-            uint32_t sbits = sum1[sw];
-            while (sbits) {
-                const uint32_t w = sw * 32u + (uint32_t)(__ffs(sbits) - 1);
-                sbits &= sbits - 1u;
+        uint32_t cur = 0;
+        while (true) {
+            // smallest mismatch count >= cur over all candidates (lanes stride over bitmap words)
+            uint32_t round_min = 0xffffffffu;
+            for (uint32_t w = lane; w < lay.bm_words; w += 32u) {
                 uint32_t bits = bm1[w];
                 while (bits) {
-                    const uint32_t bit = (uint32_t)(__ffs(bits) - 1);
+                    const uint32_t a = w * 32u + (uint32_t)(__ffs(bits) - 1);
                     bits &= bits - 1u;
-                    const uint32_t a = w * 32u + bit;
-                    const uint32_t m0 = __ldg(ix.mset_off + a);
-                    const uint32_t nA = __ldg(ix.mset_off + a + 1) - m0;
-                    uint32_t m = 0, same = 0;
-                    for (uint32_t t0 = 0; t0 < nA; t0 += 32u) {
-                        const uint32_t t = t0 + lane;
-                        bool found = false, sm = false;
-                        if (t < nA) {
-                            const uint64_t v = __ldg(ix.mset + m0 + t);
-                            const uint64_t key = v & ~kFwdBit;
-                            uint32_t slot = (uint32_t)mix64(key) & rmask;
-                            while (true) {
-                                const uint64_t r = rset[slot];
-                                if (r == kEmpty64) break;
-                                if ((r & ~kFwdBit) == key) { found = true; sm = ((r ^ v) >> 63) == 0ull; break; }
-                                slot = (slot + 1u) & rmask;
-                            }
-                        }
-                        m += __popc(__ballot_sync(0xffffffffu, found));
-                        same += __popc(__ballot_sync(0xffffffffu, found && sm));
-                    }
-                    if (m == 0u) continue;                                        // src/alignment.rs:1801-1803
-                    const uint32_t mn = nR < nA ? nR : nA;
-                    if ((double)m / (double)mn < p.min_frac) continue;            // :1805-1808
-                    any_scored = true;
                     const uint32_t mm = (acc[a >> 1] >> (16u * (a & 1u))) & 0xffffu;
-                    const double ratio = (double)mm / (double)m / (double)p.c;    // :1811
-                    if (ratio <= p.ratio_thresh) {                                // :1829-1833
-                        if (mm < lowest) {
-                            lowest = mm; n_low = 0;
-                            __syncwarp();
-                            for (uint32_t i = lane; i < lay.bm_words; i += 32u) bm2[i] = 0u;
-                            __syncwarp();
+                    if (mm >= cur && mm < round_min) round_min = mm;
+                }
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                const uint32_t y = __shfl_xor_sync(0xffffffffu, round_min, d);
+                round_min = y < round_min ? y : round_min;
+            }
+            if (round_min == 0xffffffffu) break;
+            // visit the candidates of this group in ascending ASV order
+            for (uint32_t sw = 0; sw < lay.sum_words; ++sw) {
+                uint32_t sbits = sum1[sw];
+                while (sbits) {
+                    const uint32_t w = sw * 32u + (uint32_t)(__ffs(sbits) - 1);
+                    sbits &= sbits - 1u;
+                    uint32_t bits = bm1[w];
+                    while (bits) {
+                        const uint32_t bit = (uint32_t)(__ffs(bits) - 1);
+                        bits &= bits - 1u;
+                        const uint32_t a = w * 32u + bit;
+                        const uint32_t mm = (acc[a >> 1] >> (16u * (a & 1u))) & 0xffffu;
+                        if (mm != round_min) continue;
+                        const uint32_t m0 = __ldg(ix.mset_off + a);
+                        const uint32_t nA = __ldg(ix.mset_off + a + 1) - m0;
+                        uint32_t m = 0, same = 0;
+                        for (uint32_t t0 = 0; t0 < nA; t0 += 32u) {
+                            const uint32_t t = t0 + lane;
+                            bool found = false, sm = false;
+                            if (t < nA) {
+                                const uint64_t v = __ldg(ix.mset + m0 + t);
+                                const uint64_t key = v & ~kFwdBit;
+                                uint32_t slot = hash_slot(key, rshift);
+                                while (true) {
+                                    const uint64_t r = rset[slot];
+                                    if (r == kEmpty64) break;
+                                    if ((r & ~kFwdBit) == key) { found = true; sm = ((r ^ v) >> 63) == 0ull; break; }
+                                    slot = (slot + 1u) & rmask;
+                                }
+                            }
+                            m += __popc(__ballot_sync(0xffffffffu, found));
+                            same += __popc(__ballot_sync(0xffffffffu, found && sm));
                         }
-                        if (mm == lowest) {
+                        if (m == 0u) continue;                                        // src/alignment.rs:1801-1803
+                        const uint32_t mn = nR < nA ? nR : nA;
+                        if ((double)m / (double)mn < p.min_frac) continue;            // :1805-1808
+                        any_scored = true;
+                        const double ratio = (double)mm / (double)m / (double)p.c;    // :1811
+                        if (ratio <= p.ratio_thresh) {                                // :1829-1833
                             ++n_low;
                             if (lane == 0) {
                                 bm2[w] |= 1u << bit;
-                                // mm is no longer needed for this ASV: stash (m | strand<<15) in its counter
+                                // the mismatch count of a kept ASV is `lowest`: reuse its counter for (m | strand<<15)
                                 const uint32_t opp = m - same;
                                 const uint32_t stash = (m & 0x7fffu) | ((opp > same) ? 0x8000u : 0u);
                                 const uint32_t sh = 16u * (a & 1u);
@@ -177,6 +196,8 @@ filter_kernel(SeqBatch in, SketchOut sk, AsvIndex ix, PairPool pool, FilterOut o
                     }
                 }
             }
+            if (n_low) { lowest = round_min; break; }
+            cur = round_min + 1u;
         }
         __syncwarp();
 

@@ -57,22 +57,6 @@ __device__ __forceinline__ uint32_t revcomp_smer(uint32_t f, uint32_t s) {
     return (s == 16u) ? sw : (sw & ((1u << (2u * s)) - 1u));
 }
 
-__device__ __forceinline__ bool snp_set_contains(const SnpSet &set, uint64_t key) {
-    if (set.keys == nullptr) return false;
-    uint32_t slot = (uint32_t)mix64(key) & set.mask;
-    while (true) {
-        const uint64_t v = __ldg(set.keys + slot);
-        if (v == key) return true;
-        if (v == kEmpty64) return false;
-        slot = (slot + 1u) & set.mask;
-    }
-}
-
-template <bool USE_TABLE>
-struct RankT { using type = uint64_t; };
-template <>
-struct RankT<true> { using type = uint32_t; };
-
 // phase A shared by the sketch kernel and pack_planes_kernel
 __device__ __forceinline__ bool pack_sequence(const SeqBatch &in, uint64_t off, uint32_t L, uint2 *planes, uint32_t *packed,
                                               int lane) {
@@ -103,31 +87,52 @@ __device__ __forceinline__ bool pack_sequence(const SeqBatch &in, uint64_t off, 
     return flat && in.quals != nullptr;
 }
 
-template <bool USE_TABLE>
+// shared memory layout of the sketch kernel
+struct SketchSmem {
+    uint32_t table_bytes;    // s-mer rank table (0 when hashes are computed directly)
+    uint32_t bloom_bytes;    // SNPmer Bloom filter (0 when the set is empty)
+    uint32_t packed_words;   // per warp
+    uint32_t rank_bytes;     // per warp: (32 + c) ranks, u32 or u64
+    __host__ __device__ size_t per_warp() const {
+        const size_t b = (size_t)kSnpHitCap * 12u + rank_bytes + (size_t)packed_words * 4u;
+        return (b + 15u) & ~(size_t)15u;
+    }
+    __host__ __device__ size_t total() const { return (size_t)table_bytes + bloom_bytes + per_warp() * kSketchWarps; }
+};
+
+template <bool B> struct RankT { using type = uint64_t; };
+template <> struct RankT<true> { using type = uint32_t; };
+
+// K, C > 0: compile-time k-mer / window sizes (the default 17/11 path); K == 0: runtime parameters.
+// USE_TABLE: s-mer hash ranks from the 4^s-entry shared-memory table instead of mm_hash64.
+template <int K, int C, bool USE_TABLE>
 __global__ void __launch_bounds__(kSketchWarps * 32)
-sketch_kernel(SeqBatch in, SketchOut out, SnpSet set, const uint16_t *__restrict__ rank_table_g, DeviceParams p,
-              uint32_t packed_words) {
+sketch_kernel(SeqBatch in, SketchOut out, SnpSet set, const uint16_t *__restrict__ rank_table_g, DeviceParams p, SketchSmem lay) {
     using rank_t = typename RankT<USE_TABLE>::type;
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    const uint32_t k = p.k, c = p.c, s = p.s;
+    const uint32_t k = K ? (uint32_t)K : (uint32_t)p.k;
+    const uint32_t c = K ? (uint32_t)C : (uint32_t)p.c;
+    const uint32_t s = k - c + 1u;
+    const uint64_t kmer_mask = (1ull << (2u * k)) - 1ull;
+    const uint64_t split_mask = ~(3ull << (k - 1u));
+    const uint32_t smask = (s >= 16u) ? 0xffffffffu : ((1u << (2u * s)) - 1u);
 
-    size_t sm_off = 0;
     const uint16_t *s_rank = reinterpret_cast<const uint16_t *>(smem);
-    if (USE_TABLE) {
-        const uint32_t n_words = (1u << (2u * s)) / 2u;
+    const uint32_t *s_bloom = reinterpret_cast<const uint32_t *>(smem + lay.table_bytes);
+    {
         uint32_t *dst = reinterpret_cast<uint32_t *>(smem);
         const uint32_t *src = reinterpret_cast<const uint32_t *>(rank_table_g);
-        for (uint32_t i = threadIdx.x; i < n_words; i += blockDim.x) dst[i] = __ldg(src + i);
-        sm_off = ((size_t)n_words * 4u + 15u) & ~(size_t)15u;
+        const uint32_t nt = lay.table_bytes / 4u, nb = lay.bloom_bytes / 4u;
+        for (uint32_t i = threadIdx.x; i < nt; i += blockDim.x) dst[i] = __ldg(src + i);
+        for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) dst[nt + i] = __ldg(set.bloom + i);
         __syncthreads();
     }
-    const size_t per_warp = (size_t)kSnpHitCap * 8u + 64u * 8u + (size_t)kSnpHitCap * 4u + (size_t)packed_words * 4u;
-    uint8_t *wbase = smem + sm_off + (size_t)warp * ((per_warp + 15u) & ~(size_t)15u);
+    uint8_t *wbase = smem + lay.table_bytes + lay.bloom_bytes + (size_t)warp * lay.per_warp();
     uint64_t *hits_k = reinterpret_cast<uint64_t *>(wbase);
-    rank_t *ring = reinterpret_cast<rank_t *>(wbase + (size_t)kSnpHitCap * 8u);
-    uint32_t *hits_p = reinterpret_cast<uint32_t *>(wbase + (size_t)kSnpHitCap * 8u + 64u * 8u);
+    rank_t *rbuf = reinterpret_cast<rank_t *>(wbase + (size_t)kSnpHitCap * 8u);
+    uint32_t *hits_p = reinterpret_cast<uint32_t *>(wbase + (size_t)kSnpHitCap * 8u + lay.rank_bytes);
     uint32_t *packed = hits_p + kSnpHitCap;
 
     const uint32_t mid_idx = (c - 1u) >> 1;      // (k - s) / 2, src/seeding.rs:528
@@ -144,8 +149,7 @@ sketch_kernel(SeqBatch in, SketchOut out, SnpSet set, const uint16_t *__restrict
         const uint32_t L = (uint32_t)(in.offsets[seq + 1] - off);
         uint2 *planes = out.planes + plane_word_off(off, seq);
         if (L < k) {                              // src/seeding.rs:339-341 -> None
-            // still emit planes so that align_pairs can use short reads
-            pack_sequence(in, off, L, planes, nullptr, lane);
+            pack_sequence(in, off, L, planes, nullptr, lane);   // planes still serve align_pairs
             if (lane == 0) {
                 out.status[seq] = 4; out.flatq[seq] = 0; out.mini_cnt[seq] = 0;
                 out.snp_start[seq] = 0; out.snp_cnt[seq] = 0;
@@ -157,67 +161,85 @@ sketch_kernel(SeqBatch in, SketchOut out, SnpSet set, const uint16_t *__restrict
         __syncwarp();
 
         const uint32_t n_pos = L - k + 1u;
-        const uint64_t mo = mini_slot_off(off, seq, (uint32_t)p.mini_spacing);
+        uint64_t *mini_out = out.mini_kmer + mini_slot_off(off, seq, (uint32_t)p.mini_spacing);
+        uint32_t *mini_pos_out = out.mini_pos ? out.mini_pos + mini_slot_off(off, seq, (uint32_t)p.mini_spacing) : nullptr;
         uint32_t n_mini = 0, n_hits = 0;
 
+        // rbuf[e] holds the s-mer hash rank of base index  base_p + (k - c) + e,  e in [0, 31 + c)
         for (uint32_t base_p = 0; base_p < n_pos; base_p += 32u) {
-            // ---- s-mer hash rank at base index i = base_p + k-1 + lane ----
-            {
-                const uint32_t i = base_p + k - 1u + lane;
-                if (i < L) {
-                    uint32_t f;
-                    if (i + 2u >= k + s) {                      // contiguous s-mer ending at i
-                        f = extract32(packed, i + 1u - s, s);
-                    } else {                                    // warm-up quirk, src/seeding.rs:392-397,413
-                        const uint32_t nt = i + 2u - k;         // bases taken from k-1..i
-                        const uint32_t head = extract32(packed, nt - 1u, s - nt);
-                        const uint32_t tail = extract32(packed, k - 1u, nt);
-                        f = (head << (2u * nt)) | tail;
-                    }
-                    rank_t rk;
-                    if (USE_TABLE) {
-                        rk = (rank_t)s_rank[f];
-                    } else {
-                        const uint32_t r = revcomp_smer(f, s);
-                        rk = (rank_t)mm_hash64((uint64_t)(f < r ? f : r));
-                    }
-                    ring[i & 63u] = rk;
-                }
-            }
-            __syncwarp();
-
             const uint32_t pos = base_p + lane;
             const bool valid = pos < n_pos;
+            // carry the c-1 trailing ranks of the previous tile to the front
+            rank_t carry = 0;
+            if ((uint32_t)lane < c - 1u) carry = rbuf[32u + lane];
+            __syncwarp();
+            if ((uint32_t)lane < c - 1u) rbuf[lane] = carry;
+
             uint64_t canon = 0; bool fwd = false;
-            bool is_snp = false, gate = false, is_mini = false;
+            bool is_snp = false, gate = false;
             if (valid) {
                 const uint64_t x = window64(packed, pos);
                 const uint64_t kf = x >> (64u - 2u * k);
-                const uint64_t kr = revcomp_top(x, p.kmer_mask);
-                fwd = (kf & p.split_mask) < (kr & p.split_mask);       // tie -> reverse
+                const uint64_t kr = revcomp_top(x, kmer_mask);
+                fwd = (kf & split_mask) < (kr & split_mask);       // tie -> reverse (src/seeding.rs:429)
                 canon = fwd ? kf : kr;
-                if (snp_set_contains(set, canon)) {
-                    is_snp = true;
-                    int q = 60;
-                    if (in.quals) q = (int)in.quals[off + pos + half_k] - 33;
-                    gate = (q > p.min_bq) || flat;                     // strict >
+                // the s-mer ending at base pos+k-1 is the tail of this k-mer ...
+                uint32_t f = (uint32_t)kf & smask;
+                if (pos + 1u < s) {
+                    // ... except for the reference's warm-up quirk (src/seeding.rs:392-397,413): the s-mer
+                    // register was primed with bases 0..s-2 only, so the first s-1 s-mers are
+                    // bases pos..s-2 (head of this k-mer) followed by bases k-1..k-1+pos (its tail)
+                    const uint32_t nt = pos + 1u;
+                    const uint32_t head = (uint32_t)(kf >> (2u * (k - (s - nt))));
+                    f = (head << (2u * nt)) | ((uint32_t)kf & ((1u << (2u * nt)) - 1u));
                 }
-                if (pos + 1u >= c) {                                   // window of c hashes is full
-                    const uint32_t i0 = pos + k - c;
-                    const rank_t mid = ring[(i0 + mid_idx) & 63u];
-                    bool ok = true;
-                    for (uint32_t j = 0; j < c; ++j) {
-                        const rank_t v = ring[(i0 + j) & 63u];
-                        ok = ok && (j == mid_idx || v > mid);
+                rank_t rk;
+                if (USE_TABLE) {
+                    rk = (rank_t)s_rank[f];
+                } else {
+                    const uint32_t r = revcomp_smer(f, s);
+                    rk = (rank_t)mm_hash64((uint64_t)(f < r ? f : r));
+                }
+                rbuf[c - 1u + lane] = rk;
+                if (set.keys != nullptr) {
+                    const uint64_t prod = canon * kFibMul;
+                    const uint32_t bi = (uint32_t)(prod >> set.bloom_shift);
+                    if ((s_bloom[bi >> 5] >> (bi & 31u)) & 1u) {
+                        uint32_t slot = (uint32_t)(prod >> set.shift);
+                        while (true) {
+                            const uint64_t v = __ldg(set.keys + slot);
+                            if (v == canon) { is_snp = true; break; }
+                            if (v == kEmpty64) break;
+                            slot = (slot + 1u) & set.mask;
+                        }
+                        if (is_snp) {
+                            int q = 60;
+                            if (in.quals) q = (int)in.quals[off + pos + half_k] - 33;
+                            gate = (q > p.min_bq) || flat;             // strict > (src/seeding.rs:517)
+                        }
                     }
-                    is_mini = ok;
                 }
+            }
+            __syncwarp();
+            bool is_mini = false;
+            if (valid && pos + 1u >= c) {                              // the window of c hashes is full
+                const rank_t mid = rbuf[lane + mid_idx];
+                rank_t others = ~(rank_t)0;
+                if (K) {
+#pragma unroll
+                    for (uint32_t j = 0; j < (uint32_t)(C ? C : 1); ++j)
+                        if (j != mid_idx) { const rank_t v = rbuf[lane + j]; others = v < others ? v : others; }
+                } else {
+                    for (uint32_t j = 0; j < c; ++j)
+                        if (j != mid_idx) { const rank_t v = rbuf[lane + j]; others = v < others ? v : others; }
+                }
+                is_mini = mid < others || (c == 1u);                   // strict minimum at the middle offset
             }
             const uint32_t mb = __ballot_sync(0xffffffffu, is_mini);
             if (is_mini) {
-                const uint64_t o = mo + n_mini + __popc(mb & lt_mask);
-                out.mini_kmer[o] = canon | (fwd ? kFwdBit : 0ull);
-                if (out.mini_pos) out.mini_pos[o] = pos;
+                const uint32_t o = n_mini + __popc(mb & lt_mask);
+                mini_out[o] = canon | (fwd ? kFwdBit : 0ull);
+                if (mini_pos_out) mini_pos_out[o] = pos;
             }
             n_mini += __popc(mb);
             const uint32_t hb = __ballot_sync(0xffffffffu, is_snp);
@@ -227,8 +249,8 @@ sketch_kernel(SeqBatch in, SketchOut out, SnpSet set, const uint16_t *__restrict
                 else { spill_k[o - kSnpHitCap] = canon; spill_p[o - kSnpHitCap] = pos | (gate ? 0x80000000u : 0u); }
             }
             n_hits += __popc(hb);
-            __syncwarp();
         }
+        __syncwarp();
 
         // ---- SNPmer dedup: keep gated hits whose splitmer occurs exactly once among ALL hits ----
         const uint32_t nh = n_hits;
@@ -237,9 +259,9 @@ sketch_kernel(SeqBatch in, SketchOut out, SnpSet set, const uint16_t *__restrict
             const uint32_t h = base + lane;
             bool keep = false;
             if (h < nh) {
-                const uint64_t sp = hit_k(h) & p.split_mask;
+                const uint64_t sp = hit_k(h) & split_mask;
                 uint32_t cnt = 0;
-                for (uint32_t j = 0; j < nh; ++j) cnt += ((hit_k(j) & p.split_mask) == sp) ? 1u : 0u;
+                for (uint32_t j = 0; j < nh; ++j) cnt += ((hit_k(j) & split_mask) == sp) ? 1u : 0u;
                 keep = (hit_p(h) >> 31) && cnt == 1u;
             }
             const uint32_t b = __ballot_sync(0xffffffffu, keep);
@@ -280,21 +302,21 @@ sketch_kernel(SeqBatch in, SketchOut out, SnpSet set, const uint16_t *__restrict
     }
 }
 
-size_t sketch_smem_bytes(bool use_table, int s, uint32_t packed_words) {
-    size_t table = use_table ? ((((size_t)1 << (2 * s)) * 2u + 15u) & ~(size_t)15u) : 0;
-    size_t per_warp = (size_t)kSnpHitCap * 8u + 64u * 8u + (size_t)kSnpHitCap * 4u + (size_t)packed_words * 4u;
-    per_warp = (per_warp + 15u) & ~(size_t)15u;
-    return table + per_warp * kSketchWarps;
+static SketchSmem sketch_layout(uint32_t max_len, bool use_table, const DeviceParams &p, const SnpSet &set) {
+    SketchSmem lay{};
+    lay.table_bytes = use_table ? (uint32_t)((((size_t)1 << (2 * p.s)) * 2u + 15u) & ~(size_t)15u) : 0u;
+    lay.bloom_bytes = set.keys ? set.bloom_words * 4u : 0u;
+    lay.packed_words = (max_len >> 4) + 6u;
+    lay.rank_bytes = (uint32_t)(((32u + (uint32_t)p.c) * (use_table ? 4u : 8u) + 15u) & ~15u);
+    return lay;
 }
 
 // grid used by launch_sketch (the host sizes the per-warp spill region with it)
-uint32_t sketch_grid(uint32_t n, uint32_t max_len, bool use_table, int s, int sm_count) {
-    const uint32_t packed_words = (max_len >> 4) + 6u;
-    const size_t smem = sketch_smem_bytes(use_table, s, packed_words);
-    // persistent-style grid: a multiple of the SM count, capped by the work available
-    int ctas_per_sm = (int)(200u * 1024u / (smem + 1024u));
+uint32_t sketch_grid(uint32_t n, uint32_t max_len, bool use_table, const DeviceParams &p, const SnpSet &set, int sm_count) {
+    const SketchSmem lay = sketch_layout(max_len, use_table, p, set);
+    int ctas_per_sm = (int)(220u * 1024u / (lay.total() + 1024u));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
-    if (ctas_per_sm > 8) ctas_per_sm = 8;
+    if (ctas_per_sm > 4) ctas_per_sm = 4;          // 4 x 16 warps = 64 resident warps
     uint32_t grid = (uint32_t)(sm_count * ctas_per_sm);
     const uint32_t need = (n + kSketchWarps - 1) / kSketchWarps;
     if (grid > need) grid = need;
@@ -304,16 +326,19 @@ uint32_t sketch_grid(uint32_t n, uint32_t max_len, bool use_table, int s, int sm
 void launch_sketch(const SeqBatch &in, const SketchOut &out, const SnpSet &set, const uint16_t *rank_table,
                    const DeviceParams &p, int sm_count, cudaStream_t st) {
     if (in.n == 0) return;
-    const uint32_t packed_words = (in.max_len >> 4) + 6u;
     const bool use_table = rank_table != nullptr;
-    const size_t smem = sketch_smem_bytes(use_table, p.s, packed_words);
-    const uint32_t grid = sketch_grid(in.n, in.max_len, use_table, p.s, sm_count);
-    if (use_table) {
-        cudaFuncSetAttribute(sketch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        sketch_kernel<true><<<grid, kSketchWarps * 32, smem, st>>>(in, out, set, rank_table, p, packed_words);
+    const SketchSmem lay = sketch_layout(in.max_len, use_table, p, set);
+    const size_t smem = lay.total();
+    const uint32_t grid = sketch_grid(in.n, in.max_len, use_table, p, set, sm_count);
+    if (p.k == 17 && p.c == 11 && use_table) {
+        cudaFuncSetAttribute(sketch_kernel<17, 11, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        sketch_kernel<17, 11, true><<<grid, kSketchWarps * 32, smem, st>>>(in, out, set, rank_table, p, lay);
+    } else if (use_table) {
+        cudaFuncSetAttribute(sketch_kernel<0, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        sketch_kernel<0, 0, true><<<grid, kSketchWarps * 32, smem, st>>>(in, out, set, rank_table, p, lay);
     } else {
-        cudaFuncSetAttribute(sketch_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        sketch_kernel<false><<<grid, kSketchWarps * 32, smem, st>>>(in, out, set, rank_table, p, packed_words);
+        cudaFuncSetAttribute(sketch_kernel<0, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        sketch_kernel<0, 0, false><<<grid, kSketchWarps * 32, smem, st>>>(in, out, set, rank_table, p, lay);
     }
 }
 
