@@ -233,10 +233,10 @@ static int upload_snp_set(Context *c) {
     const uint32_t cap = next_pow2_u32(4 * n + 2);           // load factor <= 0.25: ~1.2 probes per lookup
     const uint32_t shift = shift_for_cap(cap);
     std::vector<uint64_t> keys(cap, kEmpty64);
-    // one-hash Bloom filter over the same Fibonacci product, staged in shared memory by the sketch kernel:
-    // >= 32 bits per key, between 8 KiB and 32 KiB
-    uint32_t bloom_bits = next_pow2_u32(32 * n);
-    if (bloom_bits < (1u << 16)) bloom_bits = 1u << 16;
+    // blocked two-bit Bloom filter over the same Fibonacci product, staged in shared memory by the sketch
+    // kernel: >= 16 bits per key, between 4 KiB and 32 KiB
+    uint32_t bloom_bits = next_pow2_u32(16 * n);
+    if (bloom_bits < (1u << 15)) bloom_bits = 1u << 15;
     if (bloom_bits > (1u << 18)) bloom_bits = 1u << 18;
     const uint32_t bshift = shift_for_cap(bloom_bits);
     std::vector<uint32_t> bloom(bloom_bits / 32, 0u);
@@ -244,8 +244,9 @@ static int upload_snp_set(Context *c) {
         uint32_t slot = hash_slot(key, shift);
         while (keys[slot] != kEmpty64 && keys[slot] != key) slot = (slot + 1) & (cap - 1);
         keys[slot] = key;
-        const uint32_t bi = (uint32_t)((key * kFibMul) >> bshift);
-        bloom[bi >> 5] |= 1u << (bi & 31);
+        const uint64_t prod = key * kFibMul;
+        const uint32_t b1 = (uint32_t)(prod >> bshift);           // blocked: both bits in word b1 >> 5
+        bloom[b1 >> 5] |= (1u << (b1 & 31)) | (1u << ((uint32_t)(prod >> 20) & 31));
     }
     TRY(c->d_snp_keys.ensure(cap * sizeof(uint64_t)));
     TRY(c->d_snp_bloom.ensure(bloom.size() * 4));

@@ -15,7 +15,7 @@ namespace sb {
 
 constexpr uint64_t kEmpty64 = ~0ull;
 constexpr uint64_t kFwdBit = 1ull << 63;
-constexpr int kSnpHitCap = 128;        // per-sequence SNPmer hits held in shared memory (more spill to global)
+constexpr int kSnpHitCap = 64;         // per-sequence SNPmer hits held in shared memory (more spill to global)
 constexpr int kSketchWarps = 16;       // warps per CTA in the sketch kernel
 constexpr int kFilterWarps = 4;        // warps per CTA in the filter kernel
 
@@ -92,7 +92,7 @@ struct SnpSet {              // open addressing, kEmpty64 = empty
     const uint64_t *keys;    // null when the set is empty
     uint32_t mask;           // cap-1
     uint32_t shift;          // 64 - log2(cap)
-    const uint32_t *bloom;   // one-hash Bloom filter over the same Fibonacci product (staged in shared memory)
+    const uint32_t *bloom;   // two-hash Bloom filter over the same Fibonacci product (staged in shared memory)
     uint32_t bloom_shift;    // 64 - log2(bloom bits)
     uint32_t bloom_words;
 };

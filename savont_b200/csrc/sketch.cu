@@ -1,20 +1,27 @@
 // sketch.cu -- K1: 2-bit packing + open-syncmer / SNPmer sketch of a batch of sequences.
 //
 // Stands in for seeding::get_twin_read_syncmer (reference src/seeding.rs:317-658), one warp per
-// sequence, position-parallel (lane = k-mer start position inside a 32-position tile) instead of
-// the reference's rolling registers:
+// sequence:
 //   phase A  coalesced byte loads -> BYTE_TO_SEQ codes (src/types.rs:92-101) -> warp ballots give
 //            the two bit planes (stored for the DP) and a 16-bases-per-word packed copy in shared
 //            memory; all-equal-quality check (src/seeding.rs:372-380).
-//   phase B  per tile: s-mer hash rank at every base index (a 4^s-entry rank table of
-//            mm_hash64(canonical s-mer) staged in shared memory replaces the 64-bit hash: only the
-//            ORDER of the hashes is ever used, src/seeding.rs:526-543), forward/reverse k-mer
-//            extraction, splitmer-canonical choice (:426-434, tie -> reverse), SNPmer set probe +
-//            mid-base quality gate (:508-521), open-syncmer test (:527-543); ordered compaction by
-//            ballot/popc.
-//   phase C  SNPmer de-duplication by splitmer multiplicity (:550-568) and pool allocation.
-// The reference's s-mer warm-up quirk (SURVEY.md 8a note 1) is reproduced: the s-mers ending at
-// base indices k-1 .. k+s-3 are formed from bases 0..s-2 followed by bases k-1.. .
+//   phase B  the k-mer start positions are split into 32 contiguous chunks, one per lane, and every
+//            lane ROLLS its forward / reverse-complement k-mer registers over its chunk exactly as
+//            the reference does (:419-443), after a (c-1)-position warm-up that refills the
+//            open-syncmer window.  Per position: splitmer-canonical choice (:426-434, tie ->
+//            reverse); the s-mer hash is replaced by its RANK among all 4^s s-mers, looked up in a
+//            shared-memory table indexed by the k-mer's last s bases (only the ORDER of the hashes is
+//            ever used, :526-543); the window of c ranks lives in registers (loop unrolled by c) and
+//            the strict-minimum-at-the-middle test is a min tree; SNPmer membership (:508-521) goes
+//            through a two-hash Bloom filter in shared memory before the exact global table.
+//            Minimizers are buffered per lane in shared memory and written out lane-major, which is
+//            position order.
+//   phase C  SNPmer de-duplication by splitmer multiplicity (:550-568), position sort by rank
+//            counting, and pool allocation.
+// The reference's s-mer warm-up quirk (SURVEY.md 8a note 1) is reproduced: for k-mer start
+// positions q < s-1 the "s-mer" is bases q..s-2 followed by bases k-1..k-1+q.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace sb {
@@ -36,19 +43,14 @@ __device__ __forceinline__ uint64_t window64(const uint32_t *packed, uint32_t a)
     const uint32_t lo = __funnelshift_l(w2, w1, sh);
     return ((uint64_t)hi << 32) | lo;
 }
-// len (1..16) bases starting at base a, right-aligned
-__device__ __forceinline__ uint32_t extract32(const uint32_t *packed, uint32_t a, uint32_t len) {
-    const uint32_t w = a >> 4, sh = (a & 15u) * 2u;
-    return __funnelshift_l(packed[w + 1], packed[w], sh) >> (32u - 2u * len);
-}
 __device__ __forceinline__ uint64_t swap_pairs64(uint64_t r) {
     return ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1);
 }
-// reverse complement of the k-mer held in the TOP 2k bits of x; result right-aligned
-__device__ __forceinline__ uint64_t revcomp_top(uint64_t x, uint64_t kmer_mask) {
+// reverse complement of the n-mer held in the TOP 2n bits of x; result right-aligned (mask = low 2n bits)
+__device__ __forceinline__ uint64_t revcomp_top(uint64_t x, uint64_t mask) {
     const uint64_t z = ~x;
     const uint64_t r = ((uint64_t)__brev((uint32_t)z) << 32) | (uint64_t)__brev((uint32_t)(z >> 32));
-    return swap_pairs64(r) & kmer_mask;
+    return swap_pairs64(r) & mask;
 }
 __device__ __forceinline__ uint32_t revcomp_smer(uint32_t f, uint32_t s) {
     const uint32_t z = ~(f << (32u - 2u * s));
@@ -57,34 +59,60 @@ __device__ __forceinline__ uint32_t revcomp_smer(uint32_t f, uint32_t s) {
     return (s == 16u) ? sw : (sw & ((1u << (2u * s)) - 1u));
 }
 
-// phase A shared by the sketch kernel and pack_planes_kernel
+// phase A shared by the sketch kernel and pack_planes_kernel: 128 bases per warp iteration.
+// Every lane loads one aligned 32-bit word of bases (and of qualities), the neighbour's word comes by
+// shuffle and a funnel shift removes the misalignment of the sequence start; the four bytes go through
+// the BYTE_TO_SEQ table in shared memory (src/types.rs:92-101).  The 4-bit plane nibbles of 8 lanes are
+// OR-reduced into one 32-bit plane word, the 8-bit packed codes of 4 lanes into one 16-base word.
+// Returns true iff qualities are present and all equal (src/seeding.rs:372-380).
 __device__ __forceinline__ bool pack_sequence(const SeqBatch &in, uint64_t off, uint32_t L, uint2 *planes, uint32_t *packed,
-                                              int lane) {
-    const uint32_t nblk = (L + 31u) >> 5;
-    bool flat = true;
-    const uint32_t q0 = in.quals ? in.quals[off] : 0u;
+                                              const uint8_t *lut, int lane) {
+    const uint32_t nblk = (L + 127u) >> 7;
+    const uint32_t nw = (L + 31u) >> 5;             // plane words; word nw is the zero guard word of the DP look-ahead
+    const uint8_t *bp = in.bases + off;
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(bp) & 3u);
+    const uint32_t *bw = reinterpret_cast<const uint32_t *>(bp - mis);
+    const uint8_t *qp = in.quals ? in.quals + off : nullptr;
+    const uint32_t qmis = qp ? (uint32_t)(reinterpret_cast<uintptr_t>(qp) & 3u) : 0u;
+    const uint32_t *qw = qp ? reinterpret_cast<const uint32_t *>(qp - qmis) : nullptr;
+    const uint32_t q0x4 = qp ? (uint32_t)qp[0] * 0x01010101u : 0u;
+    uint32_t qdiff = 0;
     for (uint32_t blk = 0; blk < nblk; ++blk) {
-        const uint32_t i = blk * 32u + lane;
-        const uint32_t code = (i < L) ? enc_base(in.bases[off + i]) : 0u;
-        const uint32_t lo = __ballot_sync(0xffffffffu, code & 1u);
-        const uint32_t hi = __ballot_sync(0xffffffffu, code & 2u);
-        if (lane == 0) planes[blk] = make_uint2(lo, hi);
+        const uint32_t w = blk * 32u + lane;
+        const uint32_t g = w * 4u;                         // first base handled by this lane
+        uint32_t x0 = (g < L + 4u) ? __ldg(bw + w) : 0u;
+        uint32_t x1 = __shfl_down_sync(0xffffffffu, x0, 1);
+        if (lane == 31) x1 = (mis && g + 4u < L + 4u) ? __ldg(bw + w + 1) : 0u;
+        const uint32_t x = __funnelshift_r(x0, x1, 8u * mis);
+        const uint32_t nvalid = (g < L) ? min(4u, L - g) : 0u;
+        uint32_t c0 = lut[x & 0xffu], c1 = lut[(x >> 8) & 0xffu], c2 = lut[(x >> 16) & 0xffu], c3 = lut[x >> 24];
+        c0 = nvalid > 0u ? c0 : 0u; c1 = nvalid > 1u ? c1 : 0u; c2 = nvalid > 2u ? c2 : 0u; c3 = nvalid > 3u ? c3 : 0u;
+        uint32_t lo = (c0 & 1u) | ((c1 & 1u) << 1) | ((c2 & 1u) << 2) | ((c3 & 1u) << 3);
+        uint32_t hi = (c0 >> 1) | ((c1 >> 1) << 1) | ((c2 >> 1) << 2) | ((c3 >> 1) << 3);
+        lo <<= 4u * (lane & 7u); hi <<= 4u * (lane & 7u);
+        lo |= __shfl_xor_sync(0xffffffffu, lo, 1); hi |= __shfl_xor_sync(0xffffffffu, hi, 1);
+        lo |= __shfl_xor_sync(0xffffffffu, lo, 2); hi |= __shfl_xor_sync(0xffffffffu, hi, 2);
+        lo |= __shfl_xor_sync(0xffffffffu, lo, 4); hi |= __shfl_xor_sync(0xffffffffu, hi, 4);
+        if ((lane & 7) == 0 && blk * 4u + (lane >> 3) <= nw) planes[blk * 4u + (lane >> 3)] = make_uint2(lo, hi);
         if (packed) {
-            uint32_t v = code << (30u - 2u * (lane & 15u));
+            uint32_t v = ((c0 << 6) | (c1 << 4) | (c2 << 2) | c3) << (24u - 8u * (lane & 3u));
             v |= __shfl_xor_sync(0xffffffffu, v, 1);
             v |= __shfl_xor_sync(0xffffffffu, v, 2);
-            v |= __shfl_xor_sync(0xffffffffu, v, 4);
-            v |= __shfl_xor_sync(0xffffffffu, v, 8);
-            if ((lane & 15) == 0) packed[blk * 2u + (lane >> 4)] = v;
+            if ((lane & 3) == 0) packed[blk * 8u + (lane >> 2)] = v;
         }
-        if (in.quals) {
-            const uint32_t q = (i < L) ? in.quals[off + i] : q0;
-            flat = flat && __all_sync(0xffffffffu, q == q0);
+        if (qw) {
+            uint32_t y0 = (g < L + 4u) ? __ldg(qw + w) : 0u;
+            uint32_t y1 = __shfl_down_sync(0xffffffffu, y0, 1);
+            if (lane == 31) y1 = (qmis && g + 4u < L + 4u) ? __ldg(qw + w + 1) : 0u;
+            const uint32_t y = __funnelshift_r(y0, y1, 8u * qmis);
+            const uint32_t vm = nvalid >= 4u ? 0xffffffffu : ((1u << (8u * nvalid)) - 1u);
+            qdiff |= (y ^ q0x4) & vm;
         }
     }
-    if (lane == 0) planes[nblk] = make_uint2(0u, 0u);   // guard word read by the DP look-ahead
-    if (packed && lane < 4) packed[nblk * 2u + lane] = 0u;
-    return flat && in.quals != nullptr;
+    // guard words: one plane word read by the DP look-ahead, packed words read by window64
+    if (lane == 0 && (nw & 3u) == 0u) planes[nw] = make_uint2(0u, 0u);
+    if (packed && lane < 8) packed[nblk * 8u + lane] = 0u;
+    return qp != nullptr && !__any_sync(0xffffffffu, qdiff != 0u);
 }
 
 // shared memory layout of the sketch kernel
@@ -92,48 +120,57 @@ struct SketchSmem {
     uint32_t table_bytes;    // s-mer rank table (0 when hashes are computed directly)
     uint32_t bloom_bytes;    // SNPmer Bloom filter (0 when the set is empty)
     uint32_t packed_words;   // per warp
-    uint32_t rank_bytes;     // per warp: (32 + c) ranks, u32 or u64
+    uint32_t ring_bytes;     // per warp: lane-private rank ring (runtime-c path only)
+    uint32_t max_t;          // chunk length per lane (positions)
+    uint32_t mini_cap;       // minimizers a lane can emit per chunk: max_t / spacing + 2
     __host__ __device__ size_t per_warp() const {
-        const size_t b = (size_t)kSnpHitCap * 12u + rank_bytes + (size_t)packed_words * 4u;
+        const size_t b = (size_t)kSnpHitCap * 12u + 16u + ring_bytes + (size_t)mini_cap * 32u * 8u + (size_t)packed_words * 4u;
         return (b + 15u) & ~(size_t)15u;
     }
-    __host__ __device__ size_t total() const { return (size_t)table_bytes + bloom_bytes + per_warp() * kSketchWarps; }
+    __host__ __device__ size_t total() const { return 256u + (size_t)table_bytes + bloom_bytes + per_warp() * kSketchWarps; }
 };
 
 template <bool B> struct RankT { using type = uint64_t; };
 template <> struct RankT<true> { using type = uint32_t; };
 
-// K, C > 0: compile-time k-mer / window sizes (the default 17/11 path); K == 0: runtime parameters.
+// K, C > 0: compile-time k-mer / window sizes (the default 17/11 path, window in registers);
+// K == 0: runtime parameters (window in a lane-private shared-memory ring).
 // USE_TABLE: s-mer hash ranks from the 4^s-entry shared-memory table instead of mm_hash64.
 template <int K, int C, bool USE_TABLE>
 __global__ void __launch_bounds__(kSketchWarps * 32)
 sketch_kernel(SeqBatch in, SketchOut out, SnpSet set, const uint16_t *__restrict__ rank_table_g, DeviceParams p, SketchSmem lay) {
     using rank_t = typename RankT<USE_TABLE>::type;
+    constexpr int CC = C > 0 ? C : 1;
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t k = K ? (uint32_t)K : (uint32_t)p.k;
     const uint32_t c = K ? (uint32_t)C : (uint32_t)p.c;
     const uint32_t s = k - c + 1u;
     const uint64_t kmer_mask = (1ull << (2u * k)) - 1ull;
+    const uint64_t km1_mask = (1ull << (2u * (k - 1u))) - 1ull;
     const uint64_t split_mask = ~(3ull << (k - 1u));
     const uint32_t smask = (s >= 16u) ? 0xffffffffu : ((1u << (2u * s)) - 1u);
+    const uint32_t rc_shift = 2u * (k - 1u);
 
-    const uint16_t *s_rank = reinterpret_cast<const uint16_t *>(smem);
-    const uint32_t *s_bloom = reinterpret_cast<const uint32_t *>(smem + lay.table_bytes);
+    uint8_t *s_lut = smem;                        // BYTE_TO_SEQ
+    const uint16_t *s_rank = reinterpret_cast<const uint16_t *>(smem + 256);
+    const uint32_t *s_bloom = reinterpret_cast<const uint32_t *>(smem + 256 + lay.table_bytes);
     {
-        uint32_t *dst = reinterpret_cast<uint32_t *>(smem);
+        if (threadIdx.x < 256) s_lut[threadIdx.x] = (uint8_t)enc_base(threadIdx.x);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(smem + 256);
         const uint32_t *src = reinterpret_cast<const uint32_t *>(rank_table_g);
         const uint32_t nt = lay.table_bytes / 4u, nb = lay.bloom_bytes / 4u;
         for (uint32_t i = threadIdx.x; i < nt; i += blockDim.x) dst[i] = __ldg(src + i);
         for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) dst[nt + i] = __ldg(set.bloom + i);
         __syncthreads();
     }
-    uint8_t *wbase = smem + lay.table_bytes + lay.bloom_bytes + (size_t)warp * lay.per_warp();
+    uint8_t *wbase = smem + 256 + lay.table_bytes + lay.bloom_bytes + (size_t)warp * lay.per_warp();
     uint64_t *hits_k = reinterpret_cast<uint64_t *>(wbase);
-    rank_t *rbuf = reinterpret_cast<rank_t *>(wbase + (size_t)kSnpHitCap * 8u);
-    uint32_t *hits_p = reinterpret_cast<uint32_t *>(wbase + (size_t)kSnpHitCap * 8u + lay.rank_bytes);
-    uint32_t *packed = hits_p + kSnpHitCap;
+    uint64_t *mbuf = hits_k + kSnpHitCap;                                           // [mini_cap][32]
+    rank_t *ring = reinterpret_cast<rank_t *>(mbuf + (size_t)lay.mini_cap * 32u);   // [c][32] (runtime-c path)
+    uint32_t *hits_p = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(ring) + lay.ring_bytes);
+    uint32_t *hcnt = hits_p + kSnpHitCap;                                           // [4]
+    uint32_t *packed = hcnt + 4;
 
     const uint32_t mid_idx = (c - 1u) >> 1;      // (k - s) / 2, src/seeding.rs:528
     const uint32_t half_k = k >> 1;
@@ -149,7 +186,7 @@ sketch_kernel(SeqBatch in, SketchOut out, SnpSet set, const uint16_t *__restrict
         const uint32_t L = (uint32_t)(in.offsets[seq + 1] - off);
         uint2 *planes = out.planes + plane_word_off(off, seq);
         if (L < k) {                              // src/seeding.rs:339-341 -> None
-            pack_sequence(in, off, L, planes, nullptr, lane);   // planes still serve align_pairs
+            pack_sequence(in, off, L, planes, nullptr, s_lut, lane);   // planes still serve align_pairs
             if (lane == 0) {
                 out.status[seq] = 4; out.flatq[seq] = 0; out.mini_cnt[seq] = 0;
                 out.snp_start[seq] = 0; out.snp_cnt[seq] = 0;
@@ -157,41 +194,61 @@ sketch_kernel(SeqBatch in, SketchOut out, SnpSet set, const uint16_t *__restrict
             continue;
         }
         __syncwarp();
-        const bool flat = pack_sequence(in, off, L, planes, packed, lane);
+        const bool flat = pack_sequence(in, off, L, planes, packed, s_lut, lane);
+        if (lane == 0) hcnt[0] = 0u;
         __syncwarp();
 
         const uint32_t n_pos = L - k + 1u;
         uint64_t *mini_out = out.mini_kmer + mini_slot_off(off, seq, (uint32_t)p.mini_spacing);
         uint32_t *mini_pos_out = out.mini_pos ? out.mini_pos + mini_slot_off(off, seq, (uint32_t)p.mini_spacing) : nullptr;
-        uint32_t n_mini = 0, n_hits = 0;
+        uint32_t n_mini = 0;
 
-        // rbuf[e] holds the s-mer hash rank of base index  base_p + (k - c) + e,  e in [0, 31 + c)
-        for (uint32_t base_p = 0; base_p < n_pos; base_p += 32u) {
-            const uint32_t pos = base_p + lane;
-            const bool valid = pos < n_pos;
-            // carry the c-1 trailing ranks of the previous tile to the front
-            rank_t carry = 0;
-            if ((uint32_t)lane < c - 1u) carry = rbuf[32u + lane];
-            __syncwarp();
-            if ((uint32_t)lane < c - 1u) rbuf[lane] = carry;
+        // positions are processed in segments of at most 32 * max_t; inside a segment lane l owns
+        // positions [p0, p1) and starts rolling c-1 positions earlier to refill the window
+        const uint32_t seg_span = 32u * lay.max_t;
+        const uint32_t n_seg = (n_pos + seg_span - 1u) / seg_span;
+        const uint32_t seg_len = (n_pos + n_seg - 1u) / n_seg;
+        for (uint32_t seg = 0; seg < n_seg; ++seg) {
+            const uint32_t pstart = seg * seg_len;
+            const uint32_t pend = min(n_pos, pstart + seg_len);
+            const uint32_t T = (pend - pstart + 31u) >> 5;
+            const uint32_t p0 = min(pstart + lane * T, pend);
+            const uint32_t p1 = min(p0 + T, pend);
+            const uint32_t qs = (p0 >= c - 1u) ? p0 - (c - 1u) : 0u;       // first position rolled by this lane
+            const uint32_t ns = p1 - qs;                                    // steps of this lane
+            const uint32_t NS = T + c - 1u;                                 // uniform loop bound
+            // prime the registers with the k-1 bases before the first pushed base
+            uint64_t F, Rv;
+            {
+                const uint64_t x = window64(packed, qs);
+                F = x >> (64u - 2u * (k - 1u));
+                Rv = revcomp_top(x, km1_mask) << 2;
+            }
+            uint32_t bidx = qs + k - 1u;                                    // next base to push
+            uint32_t pw = packed[bidx >> 4] << (2u * (bidx & 15u));
+            uint32_t cnt = 0;                                               // minimizers buffered by this lane
+            rank_t win[CC];
+#pragma unroll
+            for (int t = 0; t < CC; ++t) win[t] = 0;
 
-            uint64_t canon = 0; bool fwd = false;
-            bool is_snp = false, gate = false;
-            if (valid) {
-                const uint64_t x = window64(packed, pos);
-                const uint64_t kf = x >> (64u - 2u * k);
-                const uint64_t kr = revcomp_top(x, kmer_mask);
-                fwd = (kf & split_mask) < (kr & split_mask);       // tie -> reverse (src/seeding.rs:429)
-                canon = fwd ? kf : kr;
-                // the s-mer ending at base pos+k-1 is the tail of this k-mer ...
-                uint32_t f = (uint32_t)kf & smask;
-                if (pos + 1u < s) {
-                    // ... except for the reference's warm-up quirk (src/seeding.rs:392-397,413): the s-mer
-                    // register was primed with bases 0..s-2 only, so the first s-1 s-mers are
-                    // bases pos..s-2 (head of this k-mer) followed by bases k-1..k-1+pos (its tail)
-                    const uint32_t nt = pos + 1u;
-                    const uint32_t head = (uint32_t)(kf >> (2u * (k - (s - nt))));
-                    f = (head << (2u * nt)) | ((uint32_t)kf & ((1u << (2u * nt)) - 1u));
+            auto step = [&](auto quirk_tag, const uint32_t j, const int jj) {
+                constexpr bool QUIRK = decltype(quirk_tag)::value;
+                const uint32_t q = qs + j;
+                const uint32_t e = pw >> 30;
+                pw <<= 2;
+                ++bidx;
+                if ((bidx & 15u) == 0u) pw = packed[bidx >> 4];
+                F = ((F << 2) | (uint64_t)e) & kmer_mask;
+                Rv = (Rv >> 2) | ((uint64_t)(3u - e) << rc_shift);
+                const bool fwd = (F & split_mask) < (Rv & split_mask);      // tie -> reverse (src/seeding.rs:429)
+                const uint64_t canon = fwd ? F : Rv;
+                // the s-mer ending at base q+k-1 is the tail of this k-mer ...
+                uint32_t f = (uint32_t)F & smask;
+                if (QUIRK && q + 1u < s) {
+                    // ... except for the reference's warm-up quirk (src/seeding.rs:392-397,413)
+                    const uint32_t nt = q + 1u;
+                    const uint32_t head = (uint32_t)(F >> (2u * (k - (s - nt))));
+                    f = (head << (2u * nt)) | ((uint32_t)F & ((1u << (2u * nt)) - 1u));
                 }
                 rank_t rk;
                 if (USE_TABLE) {
@@ -200,12 +257,16 @@ sketch_kernel(SeqBatch in, SketchOut out, SnpSet set, const uint16_t *__restrict
                     const uint32_t r = revcomp_smer(f, s);
                     rk = (rank_t)mm_hash64((uint64_t)(f < r ? f : r));
                 }
-                rbuf[c - 1u + lane] = rk;
+                if (K) win[jj] = rk; else ring[(j % c) * 32u + lane] = rk;
+                if (q < p0) return;
+                // ---- SNPmer membership ----
                 if (set.keys != nullptr) {
                     const uint64_t prod = canon * kFibMul;
-                    const uint32_t bi = (uint32_t)(prod >> set.bloom_shift);
-                    if ((s_bloom[bi >> 5] >> (bi & 31u)) & 1u) {
+                    const uint32_t b1 = (uint32_t)(prod >> set.bloom_shift);          // word = b1 >> 5, first bit = b1 & 31
+                    const uint32_t bmask = (1u << (b1 & 31u)) | (1u << ((uint32_t)(prod >> 20) & 31u));
+                    if ((s_bloom[b1 >> 5] & bmask) == bmask) {
                         uint32_t slot = (uint32_t)(prod >> set.shift);
+                        bool is_snp = false;
                         while (true) {
                             const uint64_t v = __ldg(set.keys + slot);
                             if (v == canon) { is_snp = true; break; }
@@ -213,56 +274,90 @@ sketch_kernel(SeqBatch in, SketchOut out, SnpSet set, const uint16_t *__restrict
                             slot = (slot + 1u) & set.mask;
                         }
                         if (is_snp) {
-                            int q = 60;
-                            if (in.quals) q = (int)in.quals[off + pos + half_k] - 33;
-                            gate = (q > p.min_bq) || flat;             // strict > (src/seeding.rs:517)
+                            int qv = 60;
+                            if (in.quals) qv = (int)in.quals[off + q + half_k] - 33;
+                            const bool gate = (qv > p.min_bq) || flat;      // strict > (src/seeding.rs:517)
+                            const uint32_t o = atomicAdd(hcnt, 1u);
+                            const uint32_t pv = q | (gate ? 0x80000000u : 0u);
+                            if (o < (uint32_t)kSnpHitCap) { hits_k[o] = canon; hits_p[o] = pv; }
+                            else if (o - kSnpHitCap < out.spill_stride) { spill_k[o - kSnpHitCap] = canon; spill_p[o - kSnpHitCap] = pv; }
                         }
                     }
                 }
-            }
-            __syncwarp();
-            bool is_mini = false;
-            if (valid && pos + 1u >= c) {                              // the window of c hashes is full
-                const rank_t mid = rbuf[lane + mid_idx];
-                rank_t others = ~(rank_t)0;
-                if (K) {
+                // ---- open syncmer: strict minimum at the middle of the last c ranks ----
+                if (j + 1u >= c) {
+                    bool is_mini;
+                    if (K) {
+                        const int mslot = (jj + 1 + ((CC - 1) >> 1)) % CC;
+                        rank_t others = ~(rank_t)0;
 #pragma unroll
-                    for (uint32_t j = 0; j < (uint32_t)(C ? C : 1); ++j)
-                        if (j != mid_idx) { const rank_t v = rbuf[lane + j]; others = v < others ? v : others; }
-                } else {
-                    for (uint32_t j = 0; j < c; ++j)
-                        if (j != mid_idx) { const rank_t v = rbuf[lane + j]; others = v < others ? v : others; }
+                        for (int t = 0; t < CC; ++t) if (t != mslot) others = min(others, win[t]);
+                        is_mini = win[mslot] < others || CC == 1;
+                    } else {
+                        const uint32_t mslot = (j + 1u + mid_idx) % c;
+                        const rank_t mid = ring[mslot * 32u + lane];
+                        rank_t others = ~(rank_t)0;
+                        for (uint32_t t = 0; t < c; ++t) {
+                            const rank_t v = ring[t * 32u + lane];
+                            if (t != mslot) others = min(others, v);
+                        }
+                        is_mini = mid < others || c == 1u;
+                    }
+                    if (is_mini) {
+                        mbuf[cnt * 32u + lane] = canon | (fwd ? kFwdBit : 0ull) | ((uint64_t)(q - p0) << 48);
+                        ++cnt;
+                    }
                 }
-                is_mini = mid < others || (c == 1u);                   // strict minimum at the middle offset
+            };
+
+            // the warm-up quirk only concerns positions q < s-1, i.e. the first steps of the first segment
+            const bool quirk_seg = (seg == 0u);
+            if (K) {
+                uint32_t jb = 0;
+                if (quirk_seg) {
+#pragma unroll
+                    for (int jj = 0; jj < CC; ++jj)
+                        if ((uint32_t)jj < ns) step(std::true_type{}, (uint32_t)jj, jj);
+                    jb = (uint32_t)CC;
+                }
+                for (; jb < NS; jb += (uint32_t)CC) {
+#pragma unroll
+                    for (int jj = 0; jj < CC; ++jj) {
+                        const uint32_t j = jb + (uint32_t)jj;
+                        if (j < ns) step(std::false_type{}, j, jj);
+                    }
+                }
+            } else {
+                for (uint32_t j = 0; j < NS; ++j)
+                    if (j < ns) step(std::true_type{}, j, 0);
             }
-            const uint32_t mb = __ballot_sync(0xffffffffu, is_mini);
-            if (is_mini) {
-                const uint32_t o = n_mini + __popc(mb & lt_mask);
-                mini_out[o] = canon | (fwd ? kFwdBit : 0ull);
-                if (mini_pos_out) mini_pos_out[o] = pos;
+            // ---- write the buffered minimizers lane-major (= position order) ----
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += y; }
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            const uint32_t o0 = n_mini + incl - cnt;
+            for (uint32_t i = 0; i < cnt; ++i) {
+                const uint64_t v = mbuf[i * 32u + lane];
+                mini_out[o0 + i] = v & ~(0x3full << 48);
+                if (mini_pos_out) mini_pos_out[o0 + i] = p0 + (uint32_t)((v >> 48) & 0x3fu);
             }
-            n_mini += __popc(mb);
-            const uint32_t hb = __ballot_sync(0xffffffffu, is_snp);
-            if (is_snp) {
-                const uint32_t o = n_hits + __popc(hb & lt_mask);
-                if (o < (uint32_t)kSnpHitCap) { hits_k[o] = canon; hits_p[o] = pos | (gate ? 0x80000000u : 0u); }
-                else { spill_k[o - kSnpHitCap] = canon; spill_p[o - kSnpHitCap] = pos | (gate ? 0x80000000u : 0u); }
-            }
-            n_hits += __popc(hb);
+            n_mini += total;
+            __syncwarp();
         }
-        __syncwarp();
 
         // ---- SNPmer dedup: keep gated hits whose splitmer occurs exactly once among ALL hits ----
-        const uint32_t nh = n_hits;
+        uint32_t nh = hcnt[0];
+        if (nh > (uint32_t)kSnpHitCap + out.spill_stride) nh = kSnpHitCap + out.spill_stride;   // cannot happen: stride > max_len
         uint32_t kept_total = 0;
         for (uint32_t base = 0; base < nh; base += 32u) {
             const uint32_t h = base + lane;
             bool keep = false;
             if (h < nh) {
                 const uint64_t sp = hit_k(h) & split_mask;
-                uint32_t cnt = 0;
-                for (uint32_t j = 0; j < nh; ++j) cnt += ((hit_k(j) & split_mask) == sp) ? 1u : 0u;
-                keep = (hit_p(h) >> 31) && cnt == 1u;
+                uint32_t dup = 0;
+                for (uint32_t j = 0; j < nh; ++j) dup += ((hit_k(j) & split_mask) == sp) ? 1u : 0u;
+                keep = (hit_p(h) >> 31) && dup == 1u;
             }
             const uint32_t b = __ballot_sync(0xffffffffu, keep);
             __syncwarp();
@@ -278,17 +373,19 @@ sketch_kernel(SeqBatch in, SketchOut out, SnpSet set, const uint16_t *__restrict
             kept_total = 0;
         }
         if (kept_total) {
-            uint32_t idx = 0;
+            // hits were appended in arbitrary order: the output slot of a kept hit is its position rank
             for (uint32_t base = 0; base < nh; base += 32u) {
                 const uint32_t h = base + lane;
-                const bool keep = (h < nh) && (hit_p(h) >> 31);
-                const uint32_t b = __ballot_sync(0xffffffffu, keep);
-                if (keep) {
-                    const uint32_t o = start + idx + __popc(b & lt_mask);
-                    out.snp_kmer[o] = hit_k(h);
-                    out.snp_pos[o] = hit_p(h) & 0x7fffffffu;
+                if (h < nh && (hit_p(h) >> 31)) {
+                    const uint32_t ph = hit_p(h) & 0x7fffffffu;
+                    uint32_t rank = 0;
+                    for (uint32_t j = 0; j < nh; ++j) {
+                        const uint32_t pj = hit_p(j);
+                        rank += ((pj >> 31) && (pj & 0x7fffffffu) < ph) ? 1u : 0u;
+                    }
+                    out.snp_kmer[start + rank] = hit_k(h);
+                    out.snp_pos[start + rank] = ph;
                 }
-                idx += __popc(b);
             }
         }
         if (lane == 0) {
@@ -304,10 +401,21 @@ sketch_kernel(SeqBatch in, SketchOut out, SnpSet set, const uint16_t *__restrict
 
 static SketchSmem sketch_layout(uint32_t max_len, bool use_table, const DeviceParams &p, const SnpSet &set) {
     SketchSmem lay{};
+    const bool fixed = (p.k == 17 && p.c == 11 && use_table);
     lay.table_bytes = use_table ? (uint32_t)((((size_t)1 << (2 * p.s)) * 2u + 15u) & ~(size_t)15u) : 0u;
     lay.bloom_bytes = set.keys ? set.bloom_words * 4u : 0u;
-    lay.packed_words = (max_len >> 4) + 6u;
-    lay.rank_bytes = (uint32_t)(((32u + (uint32_t)p.c) * (use_table ? 4u : 8u) + 15u) & ~15u);
+    lay.packed_words = (max_len >> 4) + 20u;
+    lay.ring_bytes = fixed ? 0u : (uint32_t)((size_t)p.c * 32u * (use_table ? 4u : 8u));
+    // chunk length: at most 64 positions per lane, and small enough that a lane emits <= 12 minimizers
+    uint32_t max_t = 10u * (uint32_t)p.mini_spacing;
+    if (max_t > 64u) max_t = 64u;
+    lay.max_t = max_t;
+    // the longest chunk any lane can get for this batch
+    const uint32_t n_pos = max_len >= (uint32_t)p.k ? max_len - (uint32_t)p.k + 1u : 1u;
+    const uint32_t n_seg = (n_pos + 32u * max_t - 1u) / (32u * max_t);
+    const uint32_t seg_len = (n_pos + n_seg - 1u) / n_seg;
+    const uint32_t t_eff = (seg_len + 31u) / 32u;
+    lay.mini_cap = t_eff / (uint32_t)p.mini_spacing + 2u;
     return lay;
 }
 
@@ -344,13 +452,16 @@ void launch_sketch(const SeqBatch &in, const SketchOut &out, const SnpSet &set, 
 
 // planes only (align_pairs entry point: reads that were never sketched)
 __global__ void pack_planes_kernel(SeqBatch in, uint2 *planes_all) {
+    __shared__ uint8_t s_lut[256];
+    if (threadIdx.x < 256) s_lut[threadIdx.x] = (uint8_t)enc_base(threadIdx.x);
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t seq = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; seq < in.n; seq += warps) {
         const uint64_t off = in.offsets[seq];
         const uint32_t L = (uint32_t)(in.offsets[seq + 1] - off);
         SeqBatch nq = in; nq.quals = nullptr;
-        pack_sequence(nq, off, L, planes_all + plane_word_off(off, seq), nullptr, lane);
+        pack_sequence(nq, off, L, planes_all + plane_word_off(off, seq), nullptr, s_lut, lane);
     }
 }
 void launch_pack_planes(const SeqBatch &in, uint2 *planes, cudaStream_t st) {
