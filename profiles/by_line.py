@@ -7,7 +7,7 @@ rep, cubin, kname, units = sys.argv[1], sys.argv[2], sys.argv[3], float(sys.argv
 thr = float(sys.argv[5]) if len(sys.argv) > 5 else 20
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out))); hdr = rows[1]
-iS, iI = hdr.index("Source"), hdr.index("Instructions Executed")
+iS, iI = hdr.index("Source"), hdr.index(sys.argv[6] if len(sys.argv) > 6 else "Instructions Executed")
 counts = [(r[iS].strip(), float(r[iI])) for r in rows[2:]]
 dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout.splitlines()
 # locate the kernel's section

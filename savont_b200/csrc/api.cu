@@ -238,15 +238,14 @@ static int upload_snp_set(Context *c) {
     uint32_t bloom_bits = next_pow2_u32(16 * n);
     if (bloom_bits < (1u << 15)) bloom_bits = 1u << 15;
     if (bloom_bits > (1u << 18)) bloom_bits = 1u << 18;
-    const uint32_t bshift = shift_for_cap(bloom_bits);
+    const uint32_t bshift = shift_for_cap(bloom_bits / 32) - 32u;     // 32 - log2(words)
     std::vector<uint32_t> bloom(bloom_bits / 32, 0u);
     for (uint64_t key : c->h_snpmers) {
         uint32_t slot = hash_slot(key, shift);
         while (keys[slot] != kEmpty64 && keys[slot] != key) slot = (slot + 1) & (cap - 1);
         keys[slot] = key;
-        const uint64_t prod = key * kFibMul;
-        const uint32_t b1 = (uint32_t)(prod >> bshift);           // blocked: both bits in word b1 >> 5
-        bloom[b1 >> 5] |= (1u << (b1 & 31)) | (1u << ((uint32_t)(prod >> 20) & 31));
+        const uint32_t h = bloom_hash32(key);                     // blocked: both bits in one word
+        bloom[h >> bshift] |= (1u << (h & 31)) | (1u << ((h >> 5) & 31));
     }
     TRY(c->d_snp_keys.ensure(cap * sizeof(uint64_t)));
     TRY(c->d_snp_bloom.ensure(bloom.size() * 4));

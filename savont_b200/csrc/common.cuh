@@ -16,6 +16,7 @@ namespace sb {
 constexpr uint64_t kEmpty64 = ~0ull;
 constexpr uint64_t kFwdBit = 1ull << 63;
 constexpr int kSnpHitCap = 64;         // per-sequence SNPmer hits held in shared memory (more spill to global)
+constexpr int kSnpCandCap = 128;       // Bloom-positive k-mers per sequence awaiting the exact probe (more resolve inline)
 constexpr int kSketchWarps = 16;       // warps per CTA in the sketch kernel
 constexpr int kFilterWarps = 4;        // warps per CTA in the filter kernel
 
@@ -41,6 +42,10 @@ struct DeviceParams {
 // TOP log2(cap) bits of key * 2^64/phi (shift = 64 - log2(cap), cap >= 2).
 constexpr uint64_t kFibMul = 0x9E3779B97F4A7C15ull;
 __host__ __device__ __forceinline__ uint32_t hash_slot(uint64_t key, uint32_t shift) { return (uint32_t)((key * kFibMul) >> shift); }
+// 32-bit hash for the SNPmer Bloom filter: word = h >> (32 - log2(words)), bits h & 31 and (h >> 5) & 31
+__host__ __device__ __forceinline__ uint32_t bloom_hash32(uint64_t key) {
+    return ((uint32_t)key ^ ((uint32_t)(key >> 32) * 0x85EBCA6Bu)) * 0x9E3779B1u;
+}
 
 // src/seeding.rs:18-28
 __host__ __device__ __forceinline__ uint64_t mm_hash64(uint64_t key) {
@@ -92,8 +97,8 @@ struct SnpSet {              // open addressing, kEmpty64 = empty
     const uint64_t *keys;    // null when the set is empty
     uint32_t mask;           // cap-1
     uint32_t shift;          // 64 - log2(cap)
-    const uint32_t *bloom;   // two-hash Bloom filter over the same Fibonacci product (staged in shared memory)
-    uint32_t bloom_shift;    // 64 - log2(bloom bits)
+    const uint32_t *bloom;   // blocked two-bit Bloom filter keyed by bloom_hash32 (staged in shared memory)
+    uint32_t bloom_shift;    // 32 - log2(bloom words)
     uint32_t bloom_words;
 };
 

@@ -77,12 +77,21 @@ __device__ __forceinline__ bool pack_sequence(const SeqBatch &in, uint64_t off, 
     const uint32_t *qw = qp ? reinterpret_cast<const uint32_t *>(qp - qmis) : nullptr;
     const uint32_t q0x4 = qp ? (uint32_t)qp[0] * 0x01010101u : 0u;
     uint32_t qdiff = 0;
+    // software pipeline: the words of block blk+1 are requested before block blk is processed
+    auto load_b = [&](uint32_t w) -> uint32_t { return (w * 4u < L + 4u) ? __ldg(bw + w) : 0u; };
+    auto load_q = [&](uint32_t w) -> uint32_t { return (qw && w * 4u < L + 4u) ? __ldg(qw + w) : 0u; };
+    uint32_t xn = load_b(lane), yn = load_q(lane);
+    uint32_t xe = (lane == 31 && mis) ? load_b(32u) : 0u, ye = (lane == 31 && qmis) ? load_q(32u) : 0u;
     for (uint32_t blk = 0; blk < nblk; ++blk) {
         const uint32_t w = blk * 32u + lane;
         const uint32_t g = w * 4u;                         // first base handled by this lane
-        uint32_t x0 = (g < L + 4u) ? __ldg(bw + w) : 0u;
+        const uint32_t x0 = xn, y0 = yn, xe0 = xe, ye0 = ye;
+        if (blk + 1u < nblk) {
+            xn = load_b(w + 32u); yn = load_q(w + 32u);
+            if (lane == 31) { xe = mis ? load_b(w + 33u) : 0u; ye = qmis ? load_q(w + 33u) : 0u; }
+        }
         uint32_t x1 = __shfl_down_sync(0xffffffffu, x0, 1);
-        if (lane == 31) x1 = (mis && g + 4u < L + 4u) ? __ldg(bw + w + 1) : 0u;
+        if (lane == 31) x1 = xe0;
         const uint32_t x = __funnelshift_r(x0, x1, 8u * mis);
         const uint32_t nvalid = (g < L) ? min(4u, L - g) : 0u;
         uint32_t c0 = lut[x & 0xffu], c1 = lut[(x >> 8) & 0xffu], c2 = lut[(x >> 16) & 0xffu], c3 = lut[x >> 24];
@@ -101,9 +110,8 @@ __device__ __forceinline__ bool pack_sequence(const SeqBatch &in, uint64_t off, 
             if ((lane & 3) == 0) packed[blk * 8u + (lane >> 2)] = v;
         }
         if (qw) {
-            uint32_t y0 = (g < L + 4u) ? __ldg(qw + w) : 0u;
             uint32_t y1 = __shfl_down_sync(0xffffffffu, y0, 1);
-            if (lane == 31) y1 = (qmis && g + 4u < L + 4u) ? __ldg(qw + w + 1) : 0u;
+            if (lane == 31) y1 = ye0;
             const uint32_t y = __funnelshift_r(y0, y1, 8u * qmis);
             const uint32_t vm = nvalid >= 4u ? 0xffffffffu : ((1u << (8u * nvalid)) - 1u);
             qdiff |= (y ^ q0x4) & vm;
@@ -124,7 +132,8 @@ struct SketchSmem {
     uint32_t max_t;          // chunk length per lane (positions)
     uint32_t mini_cap;       // minimizers a lane can emit per chunk: max_t / spacing + 2
     __host__ __device__ size_t per_warp() const {
-        const size_t b = (size_t)kSnpHitCap * 12u + 16u + ring_bytes + (size_t)mini_cap * 32u * 8u + (size_t)packed_words * 4u;
+        const size_t b = (size_t)(kSnpHitCap + kSnpCandCap) * 12u + 16u + ring_bytes + (size_t)mini_cap * 32u * 8u +
+                         (size_t)packed_words * 4u;
         return (b + 15u) & ~(size_t)15u;
     }
     __host__ __device__ size_t total() const { return 256u + (size_t)table_bytes + bloom_bytes + per_warp() * kSketchWarps; }
@@ -166,10 +175,12 @@ sketch_kernel(SeqBatch in, SketchOut out, SnpSet set, const uint16_t *__restrict
     }
     uint8_t *wbase = smem + 256 + lay.table_bytes + lay.bloom_bytes + (size_t)warp * lay.per_warp();
     uint64_t *hits_k = reinterpret_cast<uint64_t *>(wbase);
-    uint64_t *mbuf = hits_k + kSnpHitCap;                                           // [mini_cap][32]
+    uint64_t *cand_k = hits_k + kSnpHitCap;                                         // Bloom-positive k-mers awaiting the exact probe
+    uint64_t *mbuf = cand_k + kSnpCandCap;                                          // [mini_cap][32]
     rank_t *ring = reinterpret_cast<rank_t *>(mbuf + (size_t)lay.mini_cap * 32u);   // [c][32] (runtime-c path)
     uint32_t *hits_p = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(ring) + lay.ring_bytes);
-    uint32_t *hcnt = hits_p + kSnpHitCap;                                           // [4]
+    uint32_t *cand_p = hits_p + kSnpHitCap;
+    uint32_t *hcnt = cand_p + kSnpCandCap;                                          // [0] hits, [1] candidates
     uint32_t *packed = hcnt + 4;
 
     const uint32_t mid_idx = (c - 1u) >> 1;      // (k - s) / 2, src/seeding.rs:528
@@ -195,8 +206,26 @@ sketch_kernel(SeqBatch in, SketchOut out, SnpSet set, const uint16_t *__restrict
         }
         __syncwarp();
         const bool flat = pack_sequence(in, off, L, planes, packed, s_lut, lane);
-        if (lane == 0) hcnt[0] = 0u;
+        if (lane == 0) { hcnt[0] = 0u; hcnt[1] = 0u; }
         __syncwarp();
+
+        // exact SNPmer set probe + mid-base quality gate (src/seeding.rs:509-521) -> hit list
+        auto resolve_snp = [&](const uint64_t canon, const uint32_t q) {
+            uint32_t slot = hash_slot(canon, set.shift);
+            while (true) {
+                const uint64_t v = __ldg(set.keys + slot);
+                if (v == canon) break;
+                if (v == kEmpty64) return;
+                slot = (slot + 1u) & set.mask;
+            }
+            int qv = 60;
+            if (in.quals) qv = (int)in.quals[off + q + half_k] - 33;
+            const bool gate = (qv > p.min_bq) || flat;                      // strict > (src/seeding.rs:517)
+            const uint32_t o = atomicAdd(hcnt, 1u);
+            const uint32_t pv = q | (gate ? 0x80000000u : 0u);
+            if (o < (uint32_t)kSnpHitCap) { hits_k[o] = canon; hits_p[o] = pv; }
+            else if (o - kSnpHitCap < out.spill_stride) { spill_k[o - kSnpHitCap] = canon; spill_p[o - kSnpHitCap] = pv; }
+        };
 
         const uint32_t n_pos = L - k + 1u;
         uint64_t *mini_out = out.mini_kmer + mini_slot_off(off, seq, (uint32_t)p.mini_spacing);
@@ -231,8 +260,11 @@ sketch_kernel(SeqBatch in, SketchOut out, SnpSet set, const uint16_t *__restrict
 #pragma unroll
             for (int t = 0; t < CC; ++t) win[t] = 0;
 
-            auto step = [&](auto quirk_tag, const uint32_t j, const int jj) {
+            // QUIRK: positions q < s-1 may occur (first block of the first segment).  CHECKS: the step may
+            // still be a warm-up step (q < p0) or the window may not be full yet (first block of a segment).
+            auto step = [&](auto quirk_tag, auto checks_tag, const uint32_t j, const int jj) {
                 constexpr bool QUIRK = decltype(quirk_tag)::value;
+                constexpr bool CHECKS = decltype(checks_tag)::value;
                 const uint32_t q = qs + j;
                 const uint32_t e = pw >> 30;
                 pw <<= 2;
@@ -258,34 +290,19 @@ sketch_kernel(SeqBatch in, SketchOut out, SnpSet set, const uint16_t *__restrict
                     rk = (rank_t)mm_hash64((uint64_t)(f < r ? f : r));
                 }
                 if (K) win[jj] = rk; else ring[(j % c) * 32u + lane] = rk;
-                if (q < p0) return;
-                // ---- SNPmer membership ----
+                if (CHECKS && q < p0) return;
+                // ---- SNPmer membership: Bloom filter now, exact probe after the loop ----
                 if (set.keys != nullptr) {
-                    const uint64_t prod = canon * kFibMul;
-                    const uint32_t b1 = (uint32_t)(prod >> set.bloom_shift);          // word = b1 >> 5, first bit = b1 & 31
-                    const uint32_t bmask = (1u << (b1 & 31u)) | (1u << ((uint32_t)(prod >> 20) & 31u));
-                    if ((s_bloom[b1 >> 5] & bmask) == bmask) {
-                        uint32_t slot = (uint32_t)(prod >> set.shift);
-                        bool is_snp = false;
-                        while (true) {
-                            const uint64_t v = __ldg(set.keys + slot);
-                            if (v == canon) { is_snp = true; break; }
-                            if (v == kEmpty64) break;
-                            slot = (slot + 1u) & set.mask;
-                        }
-                        if (is_snp) {
-                            int qv = 60;
-                            if (in.quals) qv = (int)in.quals[off + q + half_k] - 33;
-                            const bool gate = (qv > p.min_bq) || flat;      // strict > (src/seeding.rs:517)
-                            const uint32_t o = atomicAdd(hcnt, 1u);
-                            const uint32_t pv = q | (gate ? 0x80000000u : 0u);
-                            if (o < (uint32_t)kSnpHitCap) { hits_k[o] = canon; hits_p[o] = pv; }
-                            else if (o - kSnpHitCap < out.spill_stride) { spill_k[o - kSnpHitCap] = canon; spill_p[o - kSnpHitCap] = pv; }
-                        }
+                    const uint32_t h = bloom_hash32(canon);
+                    const uint32_t bmask = (1u << (h & 31u)) | (1u << ((h >> 5) & 31u));
+                    if ((s_bloom[h >> set.bloom_shift] & bmask) == bmask) {
+                        const uint32_t o = atomicAdd(hcnt + 1, 1u);
+                        if (o < (uint32_t)kSnpCandCap) { cand_k[o] = canon; cand_p[o] = q; }
+                        else resolve_snp(canon, q);
                     }
                 }
                 // ---- open syncmer: strict minimum at the middle of the last c ranks ----
-                if (j + 1u >= c) {
+                if (!CHECKS || j + 1u >= c) {
                     bool is_mini;
                     if (K) {
                         const int mslot = (jj + 1 + ((CC - 1) >> 1)) % CC;
@@ -310,26 +327,27 @@ sketch_kernel(SeqBatch in, SketchOut out, SnpSet set, const uint16_t *__restrict
                 }
             };
 
-            // the warm-up quirk only concerns positions q < s-1, i.e. the first steps of the first segment
-            const bool quirk_seg = (seg == 0u);
             if (K) {
-                uint32_t jb = 0;
-                if (quirk_seg) {
+                // first block of CC steps: warm-up and window-fill checks (and the quirk in segment 0)
+                if (seg == 0u) {
 #pragma unroll
                     for (int jj = 0; jj < CC; ++jj)
-                        if ((uint32_t)jj < ns) step(std::true_type{}, (uint32_t)jj, jj);
-                    jb = (uint32_t)CC;
+                        if ((uint32_t)jj < ns) step(std::true_type{}, std::true_type{}, (uint32_t)jj, jj);
+                } else {
+#pragma unroll
+                    for (int jj = 0; jj < CC; ++jj)
+                        if ((uint32_t)jj < ns) step(std::false_type{}, std::true_type{}, (uint32_t)jj, jj);
                 }
-                for (; jb < NS; jb += (uint32_t)CC) {
+                for (uint32_t jb = (uint32_t)CC; jb < NS; jb += (uint32_t)CC) {
 #pragma unroll
                     for (int jj = 0; jj < CC; ++jj) {
                         const uint32_t j = jb + (uint32_t)jj;
-                        if (j < ns) step(std::false_type{}, j, jj);
+                        if (j < ns) step(std::false_type{}, std::false_type{}, j, jj);
                     }
                 }
             } else {
                 for (uint32_t j = 0; j < NS; ++j)
-                    if (j < ns) step(std::true_type{}, j, 0);
+                    if (j < ns) step(std::true_type{}, std::true_type{}, j, 0);
             }
             // ---- write the buffered minimizers lane-major (= position order) ----
             uint32_t incl = cnt;
@@ -346,6 +364,15 @@ sketch_kernel(SeqBatch in, SketchOut out, SnpSet set, const uint16_t *__restrict
             __syncwarp();
         }
 
+        // ---- exact probe of the Bloom-positive k-mers, one candidate per lane ----
+        {
+            const uint32_t nc = min(hcnt[1], (uint32_t)kSnpCandCap);
+            for (uint32_t base = 0; base < nc; base += 32u) {
+                const uint32_t t = base + lane;
+                if (t < nc) resolve_snp(cand_k[t], cand_p[t]);
+            }
+            __syncwarp();
+        }
         // ---- SNPmer dedup: keep gated hits whose splitmer occurs exactly once among ALL hits ----
         uint32_t nh = hcnt[0];
         if (nh > (uint32_t)kSnpHitCap + out.spill_stride) nh = kSnpHitCap + out.spill_stride;   // cannot happen: stride > max_len
