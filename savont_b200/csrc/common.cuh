@@ -15,8 +15,9 @@ namespace sb {
 
 constexpr uint64_t kEmpty64 = ~0ull;
 constexpr uint64_t kFwdBit = 1ull << 63;
-constexpr int kSnpHitCap = 64;         // per-sequence SNPmer hits held in shared memory (more spill to global)
-constexpr int kSnpCandCap = 128;       // Bloom-positive k-mers per sequence awaiting the exact probe (more resolve inline)
+constexpr int kSnpHitCap = 32;         // per-sequence SNPmer hits held in shared memory (more spill to global)
+constexpr int kSnpCandPerLane = 3;     // Bloom-positive k-mers a lane buffers per chunk for the exact probe (more resolve inline)
+constexpr int kSnpCandCap = 32 * kSnpCandPerLane;
 constexpr int kSketchWarps = 16;       // warps per CTA in the sketch kernel
 constexpr int kFilterWarps = 4;        // warps per CTA in the filter kernel
 

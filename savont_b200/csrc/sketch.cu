@@ -180,7 +180,7 @@ sketch_kernel(SeqBatch in, SketchOut out, SnpSet set, const uint16_t *__restrict
     rank_t *ring = reinterpret_cast<rank_t *>(mbuf + (size_t)lay.mini_cap * 32u);   // [c][32] (runtime-c path)
     uint32_t *hits_p = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(ring) + lay.ring_bytes);
     uint32_t *cand_p = hits_p + kSnpHitCap;
-    uint32_t *hcnt = cand_p + kSnpCandCap;                                          // [0] hits, [1] candidates
+    uint32_t *hcnt = cand_p + kSnpCandCap;                                          // [0] hits
     uint32_t *packed = hcnt + 4;
 
     const uint32_t mid_idx = (c - 1u) >> 1;      // (k - s) / 2, src/seeding.rs:528
@@ -206,7 +206,8 @@ sketch_kernel(SeqBatch in, SketchOut out, SnpSet set, const uint16_t *__restrict
         }
         __syncwarp();
         const bool flat = pack_sequence(in, off, L, planes, packed, s_lut, lane);
-        if (lane == 0) { hcnt[0] = 0u; hcnt[1] = 0u; }
+        if (lane == 0) hcnt[0] = 0u;
+        uint32_t ccnt = 0;                      // Bloom-positive k-mers buffered by this lane
         __syncwarp();
 
         // exact SNPmer set probe + mid-base quality gate (src/seeding.rs:509-521) -> hit list
@@ -296,8 +297,7 @@ sketch_kernel(SeqBatch in, SketchOut out, SnpSet set, const uint16_t *__restrict
                     const uint32_t h = bloom_hash32(canon);
                     const uint32_t bmask = (1u << (h & 31u)) | (1u << ((h >> 5) & 31u));
                     if ((s_bloom[h >> set.bloom_shift] & bmask) == bmask) {
-                        const uint32_t o = atomicAdd(hcnt + 1, 1u);
-                        if (o < (uint32_t)kSnpCandCap) { cand_k[o] = canon; cand_p[o] = q; }
+                        if (ccnt < (uint32_t)kSnpCandPerLane) { cand_k[ccnt * 32u + lane] = canon; cand_p[ccnt * 32u + lane] = q; ++ccnt; }
                         else resolve_snp(canon, q);
                     }
                 }
@@ -361,18 +361,13 @@ sketch_kernel(SeqBatch in, SketchOut out, SnpSet set, const uint16_t *__restrict
                 if (mini_pos_out) mini_pos_out[o0 + i] = p0 + (uint32_t)((v >> 48) & 0x3fu);
             }
             n_mini += total;
+            // ---- exact probe of the Bloom-positive k-mers this lane buffered in the segment ----
+            for (uint32_t t = 0; t < ccnt; ++t) resolve_snp(cand_k[t * 32u + lane], cand_p[t * 32u + lane]);
+            ccnt = 0;
             __syncwarp();
         }
 
-        // ---- exact probe of the Bloom-positive k-mers, one candidate per lane ----
-        {
-            const uint32_t nc = min(hcnt[1], (uint32_t)kSnpCandCap);
-            for (uint32_t base = 0; base < nc; base += 32u) {
-                const uint32_t t = base + lane;
-                if (t < nc) resolve_snp(cand_k[t], cand_p[t]);
-            }
-            __syncwarp();
-        }
+
         // ---- SNPmer dedup: keep gated hits whose splitmer occurs exactly once among ALL hits ----
         uint32_t nh = hcnt[0];
         if (nh > (uint32_t)kSnpHitCap + out.spill_stride) nh = kSnpHitCap + out.spill_stride;   // cannot happen: stride > max_len
