@@ -16,6 +16,8 @@
 // The score of the band's top cell is tracked from bit 0 of D0; last-row cells are read with
 // popcounts of the vertical deltas, last-column cells by a walk over the final column.
 // No tensor cores: this is integer DP, ~14 INT32 ops per 32 cells.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace sb {
@@ -119,7 +121,6 @@ struct Band {
     uint32_t Pv[NW], Mv[NW];
     uint32_t Alo[NW + 1], Ahi[NW + 1];   // ASV window planes, word aligned; view = funnel shift by sh
     uint32_t vm2[NW];                    // bits < W-1 (mask for Mv after the diagonal shift)
-    uint32_t sh;                         // bit offset of the window inside Alo/Ahi
     uint32_t aw;                         // next ASV plane word to load
     const uint2 *ap;
     int T;                               // D at the band's top cell
@@ -128,13 +129,13 @@ struct Band {
 
 // one DP column.  TOP: rows <= 0 may be inside the window (j <= B).  LAST: j may be >= n-B.
 template <int NW, bool TB, bool TOP, bool LAST>
-__device__ __forceinline__ void dp_column(Band<NW, TB> &s, uint32_t (&TM)[NW], uint32_t clo, uint32_t chi, int j, int n, int B,
-                                          uint32_t *hist_col, uint32_t hist_stride) {
+__device__ __forceinline__ void dp_column(Band<NW, TB> &s, uint32_t (&TM)[NW], uint32_t clo, uint32_t chi, uint32_t sh, int j, int n,
+                                          int B, uint32_t *hist_col, uint32_t hist_stride) {
     uint32_t Eq[NW], X[NW], t[NW], sum[NW], D0[NW], Ph[NW], Mh[NW];
 #pragma unroll
     for (int w = 0; w < NW; ++w) {
-        const uint32_t lo = __funnelshift_r(s.Alo[w], s.Alo[w + 1], s.sh);
-        const uint32_t hi = __funnelshift_r(s.Ahi[w], s.Ahi[w + 1], s.sh);
+        const uint32_t lo = __funnelshift_r(s.Alo[w], s.Alo[w + 1], sh);
+        const uint32_t hi = __funnelshift_r(s.Ahi[w], s.Ahi[w + 1], sh);
         Eq[w] = ~((lo ^ clo) | (hi ^ chi));
         if (TOP) Eq[w] |= TM[w];
         X[w] = Eq[w] | s.Mv[w];
@@ -178,15 +179,6 @@ __device__ __forceinline__ void dp_column(Band<NW, TB> &s, uint32_t (&TM)[NW], u
             if (d < s.bd || (d == s.bd && n + j > s.bi + s.bj)) { s.bd = d; s.bi = n; s.bj = j; }
         }
     }
-    // slide the ASV window by one base
-    s.sh += 1u;
-    if (s.sh == 32u) {
-        s.sh = 0u;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) { s.Alo[w] = s.Alo[w + 1]; s.Ahi[w] = s.Ahi[w + 1]; }
-        const uint2 v = s.ap[s.aw++];
-        s.Alo[NW] = v.x; s.Ahi[NW] = v.y;
-    }
 }
 
 template <int NW, bool TB>
@@ -212,13 +204,13 @@ __device__ __forceinline__ void align_pair(const AlignArgs &a, uint32_t pi, uint
         const int remT = B - 32 * w;                        // column 1: rows <= 0 are bits 0..B-1
         TM[w] = remT >= 32 ? 0xffffffffu : (remT <= 0 ? 0u : ((1u << remT) - 1u));
     }
-    {   // ASV window of column 1 starts at bit (1 - B - 1) + padl of the padded planes
-        const uint32_t ws = (uint32_t)(a.padl - B);
-        const uint32_t w0 = ws >> 5;
-        s.sh = ws & 31u;
+    // The planes are left-padded by padl = B + 32 zero bits, so the window of column j starts at padded
+    // bit 32 + (j - 1): its offset inside the register window equals the read's bit index (j-1) & 31,
+    // and both the ASV window and the read word advance at the same 32-column boundaries.
+    {
 #pragma unroll
-        for (int w = 0; w <= NW; ++w) { const uint2 v = s.ap[w0 + w]; s.Alo[w] = v.x; s.Ahi[w] = v.y; }
-        s.aw = w0 + NW + 1;
+        for (int w = 0; w <= NW; ++w) { const uint2 v = s.ap[1 + w]; s.Alo[w] = v.x; s.Ahi[w] = v.y; }
+        s.aw = NW + 2;
     }
     // degenerate: no columns
     if (jmax <= 0) {
@@ -234,30 +226,36 @@ __device__ __forceinline__ void align_pair(const AlignArgs &a, uint32_t pi, uint
     uint32_t *hist = TB ? (a.hist + tslot) : nullptr;
     const size_t hist_col_stride = (size_t)2 * NW * a.hist_stride;
 
-    auto next_masks = [&](int jj, uint32_t &clo, uint32_t &chi) {
-        const uint32_t bit = (uint32_t)(jj - 1) & 31u;
-        if (bit == 0u) { const uint2 v = read_word(rp, (uint32_t)m, (uint32_t)(jj - 1) >> 5, rev); cw_lo = v.x; cw_hi = v.y; }
-        clo = 0u - ((cw_lo >> bit) & 1u);
-        chi = 0u - ((cw_hi >> bit) & 1u);
+    // runs columns j..jend of one phase; inner runs never cross a 32-column boundary, so the word
+    // reload / register rotation is a real (rare) branch and the column body stays straight-line
+    auto run_phase = [&](auto top_tag, auto last_tag, const int jend) {
+        constexpr bool TOP = decltype(top_tag)::value;
+        constexpr bool LAST = decltype(last_tag)::value;
+        while (j <= jend) {
+            uint32_t bit = (uint32_t)(j - 1) & 31u;
+            if (bit == 0u) {
+                const uint2 v = read_word(rp, (uint32_t)m, (uint32_t)(j - 1) >> 5, rev);
+                cw_lo = v.x; cw_hi = v.y;
+                if (j > 1) {
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) { s.Alo[w] = s.Alo[w + 1]; s.Ahi[w] = s.Ahi[w + 1]; }
+                    const uint2 nv = s.ap[s.aw++];
+                    s.Alo[NW] = nv.x; s.Ahi[NW] = nv.y;
+                }
+            }
+            const int stop = min(jend, j + 31 - (int)bit);
+            for (; j <= stop; ++j, ++bit) {
+                const uint32_t clo = (uint32_t)((int32_t)(cw_lo << (31u - bit)) >> 31);
+                const uint32_t chi = (uint32_t)((int32_t)(cw_hi << (31u - bit)) >> 31);
+                dp_column<NW, TB, TOP, LAST>(s, TM, clo, chi, bit, j, n, B,
+                                             TB ? hist + (size_t)(j - 1) * hist_col_stride : nullptr, a.hist_stride);
+            }
+        }
     };
-
-    // phase 1: virtual rows (<= 0) inside the window
-    const int j1 = B < jmax ? B : jmax;
-    for (; j <= j1; ++j) {
-        uint32_t clo, chi; next_masks(j, clo, chi);
-        dp_column<NW, TB, true, true>(s, TM, clo, chi, j, n, B, TB ? hist + (size_t)(j - 1) * hist_col_stride : nullptr, a.hist_stride);
-    }
-    // phase 2: interior
-    const int j2 = (n - B - 1) < jmax ? (n - B - 1) : jmax;
-    for (; j <= j2; ++j) {
-        uint32_t clo, chi; next_masks(j, clo, chi);
-        dp_column<NW, TB, false, false>(s, TM, clo, chi, j, n, B, TB ? hist + (size_t)(j - 1) * hist_col_stride : nullptr, a.hist_stride);
-    }
-    // phase 3: last row inside the window
-    for (; j <= jmax; ++j) {
-        uint32_t clo, chi; next_masks(j, clo, chi);
-        dp_column<NW, TB, false, true>(s, TM, clo, chi, j, n, B, TB ? hist + (size_t)(j - 1) * hist_col_stride : nullptr, a.hist_stride);
-    }
+    // phase 1: virtual rows (<= 0) inside the window; phase 2: interior; phase 3: last row inside the window
+    run_phase(std::true_type{}, std::true_type{}, B < jmax ? B : jmax);
+    run_phase(std::false_type{}, std::false_type{}, (n - B - 1) < jmax ? (n - B - 1) : jmax);
+    run_phase(std::false_type{}, std::true_type{}, jmax);
 
     // row n may already be inside the window of column 0 (n <= B): cell (n, 0) = 0 is a last-row cell
     // (handled below together with the last column when m == 0; for m > 0 the oracle also considers it)

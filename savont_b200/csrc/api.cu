@@ -172,7 +172,7 @@ static DeviceParams make_device_params(const savont_b200_params &p) {
     DeviceParams d{};
     d.k = p.k; d.c = p.c; d.s = p.k - p.c + 1;
     d.min_bq = p.min_bq; d.band = p.band; d.strand_mode = p.strand_mode;
-    d.asv_padl = ((p.band + 1 + 31) / 32) * 32;
+    d.asv_padl = p.band + 32;      // window of DP column j starts at padded bit 32 + (j-1), see align.cu
     d.mini_spacing = (p.c - 1) / 2 + 1;
     d.split_mask = ~(3ull << (p.k - 1));
     d.kmer_mask = (p.k == 32) ? ~0ull : ((1ull << (2 * p.k)) - 1ull);
