@@ -1,0 +1,204 @@
+"""Python mirror of the reference's Rust interface for the read-vs-ASV path (same function names and
+argument meaning as savont v0.6.4), implemented over libsavont_b200.so (C ABI) and libsavont_host.so (the
+C++ host layer: equivalence classes, EM, writers).  No CPU fallback: without the CUDA library every
+function raises.
+
+  get_twin_read_syncmer      src/seeding.rs:317-327
+  twin_reads_from_fasta      src/kmer_comp.rs:39-66
+  find_compatible_candidates src/asv_cluster.rs:356-360 (+ the selection of src/alignment.rs:1796-1843)
+  refine_asv_depths_with_em  src/alignment.rs:1723-1729
+  compute_per_sample_depths  src/alignment.rs:2044-2051
+  write_consensus_fasta      src/alignment.rs:830-860
+  write_feature_table        src/main.rs:381-400
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+
+_HOST_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libsavont_host.so")
+_host = None
+
+
+def host():
+    global _host
+    if _host is None:
+        _lib.lib()                      # libsavont_b200.so first (rpath $ORIGIN also finds it)
+        H = C.CDLL(_HOST_PATH)
+        H.savont_host_last_error.restype = C.c_char_p
+        H.savont_host_em.restype = C.c_int
+        H.savont_host_refine.restype = C.c_longlong
+        H.savont_host_per_sample.restype = C.c_int
+        H.savont_host_write_outputs.restype = C.c_int
+        _host = H
+    return _host
+
+
+def _p(a, t):
+    return None if a is None else a.ctypes.data_as(C.POINTER(t))
+
+
+def _fail(what):
+    raise RuntimeError(f"{what}: {host().savont_host_last_error().decode()}")
+
+
+@dataclass
+class Cli:
+    """the Cli fields the path reads (src/cli.rs)"""
+    kmer_size: int = 17
+    c: int = 11
+    blockmer_length: int = 3
+    minimum_base_quality: int = 25
+    band: int = 64
+    strand_mode: int = 0
+
+    def params(self) -> _lib.Params:
+        return _lib.default_params(k=self.kmer_size, c=self.c, l=self.blockmer_length, min_bq=self.minimum_base_quality,
+                                   band=self.band, strand_mode=self.strand_mode)
+
+
+@dataclass
+class ConsensusSequence:
+    """src/types.rs:162-190, the fields Stage 7 / 7b and the writers touch"""
+    sequence: bytes
+    depth: int = 0
+    id: int = 0
+    unambig_best_read_map_count: int = 0
+    ambig_read_map_count: int = 0
+    num_map_leq_10nm: int = 0
+    per_sample_depths: list = field(default_factory=list)
+
+
+def _concat(seqs):
+    offs = np.zeros(len(seqs) + 1, np.uint64)
+    if len(seqs):
+        offs[1:] = np.cumsum([len(s) for s in seqs], dtype=np.uint64)
+    buf = np.frombuffer(b"".join(bytes(s) for s in seqs), dtype=np.uint8).copy() if len(seqs) else np.zeros(0, np.uint8)
+    return buf, offs
+
+
+def get_twin_read_syncmer(ctx: _lib.Context, string: bytes, qualities, id: str = ""):
+    """one sequence -> dict(minimizer_positions, minimizer_kmers, snpmer_positions, snpmer_kmers, est_id) or None"""
+    b, o = _concat([string])
+    q = None if qualities is None else np.frombuffer(bytes(qualities), np.uint8)
+    r = ctx.sketch(b, q, o, want_codes=False)
+    if r["status"][0] != 0:
+        return None
+    est = float(r["est_id"][0])
+    return dict(id=id, minimizer_positions=r["mini_pos"], minimizer_kmers=r["mini_kmer"], snpmer_positions=r["snp_pos"],
+                snpmer_kmers=r["snp_kmer"], est_id=None if np.isnan(est) else est, base_length=len(string))
+
+
+def twin_reads_from_fasta(ctx: _lib.Context, seqs):
+    """ASV sequences -> sketches (qualities None, no high-frequency pruning)"""
+    b, o = _concat(seqs)
+    return ctx.sketch(b, None, o, want_codes=False)
+
+
+def find_compatible_candidates(ctx: _lib.Context, bases, quals, offsets):
+    return ctx.find_candidates(bases, quals, offsets)
+
+
+def em(n_asv, cls_offsets, cls_asv, counts, total_assigned):
+    H = host()
+    co = np.ascontiguousarray(cls_offsets, np.uint64); ca = np.ascontiguousarray(cls_asv, np.uint32); cn = np.ascontiguousarray(counts, np.uint64)
+    ab = np.zeros(max(n_asv, 1), np.float64); dp = np.zeros(max(n_asv, 1), np.uint64)
+    it = H.savont_host_em(C.c_size_t(n_asv), _p(co, C.c_uint64), _p(ca, C.c_uint32), _p(cn, C.c_uint64), C.c_size_t(len(cn)),
+                          C.c_uint64(int(total_assigned)), _p(ab, C.c_double), _p(dp, C.c_uint64))
+    if it < 0:
+        _fail("savont_host_em")
+    return ab[:n_asv], dp[:n_asv], it
+
+
+def eq_classes(status, class_offsets, class_asv, file_idx=None, sample=None):
+    """sorted equivalence classes (CSR) with counts from per-read classes"""
+    hist = {}
+    co = np.asarray(class_offsets, np.int64)
+    sel = np.flatnonzero(np.asarray(status) == 0)
+    if sample is not None and file_idx is not None:
+        sel = sel[np.asarray(file_idx)[sel] == sample]
+    for i in sel:
+        key = tuple(int(x) for x in class_asv[co[i]:co[i + 1]])
+        hist[key] = hist.get(key, 0) + 1
+    keys = sorted(hist)
+    offs = np.zeros(len(keys) + 1, np.uint64)
+    if keys:
+        offs[1:] = np.cumsum([len(k) for k in keys])
+    flat = np.array([a for k in keys for a in k], np.uint32)
+    return offs, flat, np.array([hist[k] for k in keys], np.uint64), int(len(sel))
+
+
+def refine_asv_depths_with_em(twin_reads, consensuses, kmer_info, args: Cli, temp_dir=None, device=0):
+    """Stage 7.  twin_reads: dict(bases, quals, offsets); kmer_info: u64 SNPmer k-mers (both alleles);
+    consensuses: list[ConsensusSequence], updated and filtered in place like the reference."""
+    H = host()
+    ab, ao = _concat([c.sequence for c in consensuses])
+    b = np.ascontiguousarray(twin_reads["bases"], np.uint8)
+    q = None if twin_reads.get("quals") is None else np.ascontiguousarray(twin_reads["quals"], np.uint8)
+    o = np.ascontiguousarray(twin_reads["offsets"], np.uint64)
+    snp = np.ascontiguousarray(kmer_info, np.uint64)
+    A = len(consensuses)
+    out = [np.zeros(max(A, 1), np.uint64) for _ in range(5)]
+    p = args.params()
+    n = H.savont_host_refine(C.c_int(device), C.byref(p), _p(snp, C.c_uint64), C.c_size_t(len(snp)), _p(ab, C.c_uint8), _p(ao, C.c_uint64),
+                             C.c_size_t(A), _p(b, C.c_uint8), _p(q, C.c_uint8), _p(o, C.c_uint64), C.c_size_t(len(o) - 1),
+                             None if temp_dir is None else str(temp_dir).encode(), *[_p(x, C.c_uint64) for x in out])
+    if n < 0:
+        _fail("refine_asv_depths_with_em")
+    kept = []
+    for i in range(int(n)):
+        c = consensuses[int(out[4][i])]
+        c.depth = int(out[0][i]); c.unambig_best_read_map_count = int(out[1][i])
+        c.ambig_read_map_count = int(out[2][i]); c.num_map_leq_10nm = int(out[3][i])
+        kept.append(c)
+    consensuses[:] = kept
+
+
+def compute_per_sample_depths(twin_reads, n_samples, consensuses, kmer_info, args: Cli, device=0):
+    """Stage 7b -> list[asv][sample]"""
+    H = host()
+    ab, ao = _concat([c.sequence for c in consensuses])
+    b = np.ascontiguousarray(twin_reads["bases"], np.uint8)
+    q = None if twin_reads.get("quals") is None else np.ascontiguousarray(twin_reads["quals"], np.uint8)
+    o = np.ascontiguousarray(twin_reads["offsets"], np.uint64)
+    fi = np.ascontiguousarray(twin_reads["file_idx"], np.uint32)
+    snp = np.ascontiguousarray(kmer_info, np.uint64)
+    A = len(consensuses)
+    out = np.zeros(max(A * n_samples, 1), np.uint64)
+    p = args.params()
+    rc = H.savont_host_per_sample(C.c_int(device), C.byref(p), _p(snp, C.c_uint64), C.c_size_t(len(snp)), _p(ab, C.c_uint8), _p(ao, C.c_uint64),
+                                  C.c_size_t(A), _p(b, C.c_uint8), _p(q, C.c_uint8), _p(o, C.c_uint64), _p(fi, C.c_uint32),
+                                  C.c_size_t(len(o) - 1), C.c_size_t(n_samples), _p(out, C.c_uint64))
+    if rc != 0:
+        _fail("compute_per_sample_depths")
+    return out[:A * n_samples].reshape(A, n_samples).astype(np.int64).tolist()
+
+
+def _write(consensuses, fasta_path, prefix, table_path, sample_names):
+    H = host()
+    ab, ao = _concat([c.sequence for c in consensuses])
+    A = len(consensuses)
+    arr = lambda f: np.array([f(c) for c in consensuses] or [0], np.uint64)
+    ns = len(consensuses[0].per_sample_depths) if A and consensuses[0].per_sample_depths else 0
+    ps = np.array([d for c in consensuses for d in c.per_sample_depths] or [0], np.uint64) if ns else None
+    rc = H.savont_host_write_outputs(_p(ab, C.c_uint8), _p(ao, C.c_uint64), C.c_size_t(A), _p(arr(lambda c: c.depth), C.c_uint64),
+                                     _p(arr(lambda c: c.id), C.c_uint64), _p(arr(lambda c: c.unambig_best_read_map_count), C.c_uint64),
+                                     _p(arr(lambda c: c.ambig_read_map_count), C.c_uint64), _p(arr(lambda c: c.num_map_leq_10nm), C.c_uint64),
+                                     _p(ps, C.c_uint64), C.c_size_t(ns), None if fasta_path is None else str(fasta_path).encode(),
+                                     prefix.encode(), None if table_path is None else str(table_path).encode(),
+                                     "\t".join(sample_names or ["sample"]).encode())
+    if rc != 0:
+        _fail("write outputs")
+
+
+def write_consensus_fasta(consensuses, output_path, prefix):
+    _write(consensuses, output_path, prefix, None, None)
+
+
+def write_feature_table(consensuses, path, sample_names):
+    _write(consensuses, None, "final", path, sample_names)

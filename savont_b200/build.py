@@ -66,5 +66,25 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+HOST_LIB = os.path.join(LIB_DIR, "libsavont_host.so")
+
+
+def build_host(force: bool = False) -> str:
+    """the C++ host layer above the C ABI (savont_b200/host); links against libsavont_b200.so"""
+    src = os.path.join(HERE, "host", "savont_host.cpp")
+    hdr = os.path.join(HERE, "host", "savont_host.hpp")
+    if not os.path.exists(src):
+        return HOST_LIB
+    if force or _stale(HOST_LIB, [src, hdr, LIB_PATH]):
+        cxx = shutil.which("g++") or "/usr/bin/g++"
+        cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", HOST_LIB, src, "-L" + LIB_DIR, "-lsavont_b200",
+               "-Wl,-rpath,$ORIGIN"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"host build failed:\n{r.stdout}\n{r.stderr}")
+    return HOST_LIB
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_host(force="--force" in sys.argv))

@@ -1,0 +1,127 @@
+"""Multi-GPU plumbing for the read-vs-ASV path: one process per GPU under torch.distributed.
+
+Reads shard into contiguous ranges (order preserving, reference src/main.rs:538); the SNPmer set, the ASVs
+and their index are replicated; there is no data-path exchange.  The only collective is ONE all-reduce (sum)
+of the u64 counter vector [unambig | ambig | leq10 | assigned | filtered | singleton S*A]; the sparse
+multi-ASV equivalence classes are gathered to rank 0 for the EM.
+
+`mapper` is anything with `map_shard(bases, quals, offsets, file_idx, n_samples) -> dict` returning the
+per-read results and the counter arrays: the CUDA context in production (GpuMapper), a stub in the
+CPU-only gloo tests."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_reads: int, world: int, rank: int):
+    """contiguous, order-preserving ranges; the first n % world ranks get one extra read"""
+    base, rem = divmod(n_reads, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def slice_reads(reads: dict, lo: int, hi: int) -> dict:
+    offs = np.asarray(reads["offsets"], np.uint64)
+    b0, b1 = int(offs[lo]), int(offs[hi])
+    out = dict(bases=np.asarray(reads["bases"])[b0:b1], offsets=offs[lo:hi + 1] - offs[lo],
+               quals=None if reads.get("quals") is None else np.asarray(reads["quals"])[b0:b1],
+               file_idx=None if reads.get("file_idx") is None else np.asarray(reads["file_idx"])[lo:hi])
+    return out
+
+
+class GpuMapper:
+    """libsavont_b200 context on this rank's device; counters are all-reduced in place on the device"""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+
+    def map_shard(self, bases, quals, offsets, file_idx, n_samples):
+        self.ctx.upload_reads(bases, quals, offsets, file_idx=file_idx, n_samples=n_samples)
+        self.ctx.map_resident()
+        return None   # results fetched after the all-reduce
+
+    def allreduce_counts(self, group=None):
+        ptr, n = self.ctx.counts_dev()
+
+        class _View:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 2}
+        t = torch.as_tensor(_View(), device=torch.device("cuda", self.ctx.device))
+        dist.all_reduce(t, group=group)          # NCCL, one launch, in place
+
+    def fetch(self):
+        return self.ctx.fetch_resident()
+
+
+def _counter_vector(res, n_asv, n_samples):
+    return np.concatenate([res["unambig"], res["ambig"], res["leq10"], res["totals"], res["sample_singleton"].reshape(-1)]).astype(np.int64)
+
+
+def map_reads_sharded(mapper, reads: dict, n_asv: int, n_samples: int = 1, group=None):
+    """Every rank maps its shard; returns on every rank the globally reduced counters and, on rank 0, the
+    merged multi-ASV class histogram {(sample, asv tuple): count}; per-read outputs stay local."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    n = len(reads["offsets"]) - 1
+    lo, hi = shard_bounds(n, world, rank)
+    sh = slice_reads(reads, lo, hi)
+    res = mapper.map_shard(sh["bases"], sh["quals"], sh["offsets"], sh["file_idx"], n_samples)
+    if res is None:                       # GPU path: counters live on the device
+        if world > 1:
+            mapper.allreduce_counts(group)
+        res = mapper.fetch()
+        vec = _counter_vector(res, n_asv, n_samples)
+    else:                                 # host path (tests): reduce a CPU tensor (gloo)
+        vec = _counter_vector(res, n_asv, n_samples)
+        if world > 1:
+            t = torch.from_numpy(vec.copy())
+            dist.all_reduce(t, group=group)
+            vec = t.numpy()
+    A = n_asv
+    counters = dict(unambig=vec[:A], ambig=vec[A:2 * A], leq10=vec[2 * A:3 * A], totals=vec[3 * A:3 * A + 2],
+                    sample_singleton=vec[3 * A + 2:].reshape(n_samples, A))
+    # sparse part: classes with more than one ASV, keyed by (sample, ids)
+    co = res["class_offsets"].astype(np.int64)
+    sizes = co[1:] - co[:-1]
+    fi = sh["file_idx"] if sh["file_idx"] is not None else np.zeros(hi - lo, np.uint32)
+    local = {}
+    for i in np.flatnonzero(sizes > 1):
+        key = (int(fi[i]), tuple(int(x) for x in res["class_asv"][co[i]:co[i + 1]]))
+        local[key] = local.get(key, 0) + 1
+    merged = None
+    if world > 1:
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object(local, gathered, dst=0, group=group)
+        if rank == 0:
+            merged = {}
+            for d in gathered:
+                for k, v in d.items():
+                    merged[k] = merged.get(k, 0) + v
+    else:
+        merged = local
+    return dict(counters=counters, multi_classes=merged, local=res, shard=(lo, hi))
+
+
+def depths_from_counts(counters, multi_classes, n_asv, sample=None):
+    """EM depths from the reduced singleton counts + merged multi-ASV classes (rank 0)"""
+    from . import api
+    if sample is None:
+        single = counters["unambig"]
+        multi = {}
+        for (s, ids), c in multi_classes.items():
+            multi[ids] = multi.get(ids, 0) + c
+    else:
+        single = counters["sample_singleton"][sample]
+        multi = {ids: c for (s, ids), c in multi_classes.items() if s == sample}
+    classes = {(a,): int(single[a]) for a in range(n_asv) if single[a] > 0}
+    classes.update({k: int(v) for k, v in multi.items()})
+    keys = sorted(classes)
+    if not keys:
+        return np.zeros(n_asv, np.uint64)
+    offs = np.zeros(len(keys) + 1, np.uint64)
+    offs[1:] = np.cumsum([len(k) for k in keys])
+    flat = np.array([a for k in keys for a in k], np.uint32)
+    counts = np.array([classes[k] for k in keys], np.uint64)
+    _, depths, _ = api.em(n_asv, offs, flat, counts, int(counts.sum()))
+    return depths

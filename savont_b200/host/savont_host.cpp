@@ -1,0 +1,289 @@
+// savont_host.cpp -- see savont_host.hpp
+#include "savont_host.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <sstream>
+
+namespace savont_host {
+
+[[noreturn]] static void die(const std::string &what) {
+    // the reference panics (expect/unwrap) on this path: src/alignment.rs:1853,1858
+    throw std::runtime_error(what + ": " + savont_b200_last_error());
+}
+static void ck(int rc, const char *what) { if (rc != 0) die(what); }
+
+Mapper::Mapper(int device, const Cli &args, const KmerGlobalInfo &kmer_info) {
+    if (args.low_polymorphism)
+        throw std::runtime_error("low-polymorphism mode (refine_asv_depths_with_minimap2, src/alignment.rs:1527) is not part of this path");
+    ck(savont_b200_create(device, &ctx_), "savont_b200_create");
+    savont_b200_params p;
+    savont_b200_default_params(&p);
+    p.k = args.kmer_size; p.c = args.c; p.l = args.blockmer_length; p.min_bq = args.minimum_base_quality;
+    p.band = args.band; p.strand_mode = args.strand_mode;
+    ck(savont_b200_set_params(ctx_, &p), "savont_b200_set_params");
+    ck(savont_b200_load_snpmers(ctx_, kmer_info.snpmers.data(), kmer_info.snpmers.size()), "savont_b200_load_snpmers");
+}
+Mapper::~Mapper() { if (ctx_) savont_b200_destroy(ctx_); }
+
+void Mapper::load_asvs(const std::vector<ConsensusSequence> &consensuses) {
+    std::vector<uint8_t> bases; std::vector<uint64_t> off{0};
+    for (const auto &c : consensuses) { bases.insert(bases.end(), c.sequence.begin(), c.sequence.end()); off.push_back(bases.size()); }
+    ck(savont_b200_load_asvs(ctx_, bases.data(), off.data(), consensuses.size()), "savont_b200_load_asvs");
+    n_asv_ = consensuses.size();
+}
+
+Assignments Mapper::map_reads(const ReadSet &r, int n_samples) {
+    Assignments a;
+    const size_t n = r.n, A = n_asv_;
+    a.status.assign(n ? n : 1, 0); a.best_nm.assign(n ? n : 1, 0); a.class_offsets.assign(n + 1, 0);
+    a.unambig.assign(A ? A : 1, 0); a.ambig.assign(A ? A : 1, 0); a.leq10.assign(A ? A : 1, 0);
+    a.sample_singleton.assign(A * (size_t)n_samples + 1, 0);
+    size_t cap = 4 * n + 1024;
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        a.class_asv.assign(cap, 0);
+        std::fill(a.unambig.begin(), a.unambig.end(), 0); std::fill(a.ambig.begin(), a.ambig.end(), 0);
+        std::fill(a.leq10.begin(), a.leq10.end(), 0); std::fill(a.sample_singleton.begin(), a.sample_singleton.end(), 0);
+        a.totals[0] = a.totals[1] = 0;
+        const int rc = savont_b200_map_reads(ctx_, r.bases, r.quals, r.offsets, r.file_idx, n, n_samples, a.status.data(), a.best_nm.data(),
+                                             a.class_offsets.data(), a.class_asv.data(), cap, a.unambig.data(), a.ambig.data(), a.leq10.data(),
+                                             a.totals, a.sample_singleton.data(), &a.stats);
+        if (rc == SAVONT_B200_ERR_CAPACITY) { cap *= 4; continue; }
+        ck(rc, "savont_b200_map_reads");
+        break;
+    }
+    a.status.resize(n); a.best_nm.resize(n);
+    a.class_asv.resize(a.class_offsets[n]);
+    a.unambig.resize(A); a.ambig.resize(A); a.leq10.resize(A); a.sample_singleton.resize(A * (size_t)n_samples);
+    return a;
+}
+
+EqClasses build_eq_classes(const Assignments &a, const uint32_t *file_idx, int sample) {
+    std::map<std::vector<uint32_t>, uint64_t> hist;
+    uint64_t total = 0;
+    const size_t n = a.status.size();
+    for (size_t i = 0; i < n; ++i) {
+        if (a.status[i] != SAVONT_B200_READ_ASSIGNED) continue;
+        if (sample >= 0 && (file_idx ? file_idx[i] : 0u) != (uint32_t)sample) continue;
+        std::vector<uint32_t> cls(a.class_asv.begin() + a.class_offsets[i], a.class_asv.begin() + a.class_offsets[i + 1]);
+        ++hist[cls];
+        ++total;
+    }
+    EqClasses e;
+    e.total_assigned = total;
+    for (const auto &kv : hist) {
+        e.asv.insert(e.asv.end(), kv.first.begin(), kv.first.end());
+        e.offsets.push_back(e.asv.size());
+        e.counts.push_back(kv.second);
+    }
+    return e;
+}
+
+int run_em(size_t n_asv, const EqClasses &cls, std::vector<double> &ab, std::vector<uint64_t> &depths) {
+    ab.assign(n_asv, n_asv ? 1.0 / (double)n_asv : 0.0);                    // :1959
+    depths.assign(n_asv, 0);
+    if (cls.size() == 0 || cls.total_assigned == 0) return 0;
+    const double total_assigned = (double)cls.total_assigned;
+    const double convergence_threshold = 0.01 / total_assigned;           // :1960
+    std::vector<double> nw(n_asv);
+    int iteration = 0;
+    const int MAX_ITERATIONS = 10000;
+    while (true) {
+        ++iteration;
+        std::fill(nw.begin(), nw.end(), 0.0);
+        for (size_t q = 0; q < cls.size(); ++q) {                           // :1972-1983
+            double denominator = 0.0;
+            for (uint64_t e = cls.offsets[q]; e < cls.offsets[q + 1]; ++e) denominator += ab[cls.asv[e]];
+            if (denominator > 0.0)
+                for (uint64_t e = cls.offsets[q]; e < cls.offsets[q + 1]; ++e)
+                    nw[cls.asv[e]] += (double)cls.counts[q] * ab[cls.asv[e]] / denominator;
+        }
+        double total_counts = 0.0;
+        for (double v : nw) total_counts += v;
+        if (total_counts > 0.0) for (double &v : nw) v /= total_assigned;    // :1986-1991
+        double max_change = 0.0;
+        for (size_t a = 0; a < n_asv; ++a) max_change = std::max(max_change, std::fabs(ab[a] - nw[a]));
+        ab = nw;
+        if (max_change < convergence_threshold || iteration >= MAX_ITERATIONS) break;   // :2001
+    }
+    for (size_t a = 0; a < n_asv; ++a) depths[a] = (uint64_t)std::llround(ab[a] * total_assigned);   // f64::round, :2015
+    return iteration;
+}
+
+void write_consensus_fasta(const std::vector<ConsensusSequence> &cons, const std::string &path, const std::string &prefix) {
+    std::ofstream f(path);
+    if (!f) throw std::runtime_error("cannot create " + path);
+    for (size_t i = 0; i < cons.size(); ++i) {
+        const ConsensusSequence &c = cons[i];
+        std::string depth_field;
+        if (c.per_sample_depths.empty()) depth_field = std::to_string(c.depth + c.appended_depth);
+        else for (size_t s = 0; s < c.per_sample_depths.size(); ++s) depth_field += (s ? "-" : "") + std::to_string(c.per_sample_depths[s]);
+        // src/alignment.rs:848-850
+        f << ">" << prefix << "_consensus_" << i << "_depth_" << depth_field << " debug_id:" << c.id << " chimera_score:" << c.chimera_score
+          << " unambiguous_read_assignments:" << c.unambig_best_read_map_count << " ambig_read_assignments:" << c.ambig_read_map_count
+          << " num_align_leq_10_mismatches:" << c.num_map_leq_10nm << "\n";
+        size_t b = 0, e = c.sequence.size();                                // trim leading / trailing N (:842-843)
+        while (b < e && c.sequence[b] == 'N') ++b;
+        while (e > b && c.sequence[e - 1] == 'N') --e;
+        f.write(reinterpret_cast<const char *>(c.sequence.data()) + b, (std::streamsize)(e - b));
+        f << "\n";
+    }
+}
+
+void write_feature_table(const std::vector<ConsensusSequence> &cons, const std::string &path, const std::vector<std::string> &sample_names) {
+    std::ofstream f(path);
+    if (!f) throw std::runtime_error("cannot create " + path);
+    f << "#OTU ID";
+    for (size_t s = 0; s < sample_names.size(); ++s) f << "\t" << sample_names[s];   // "#OTU ID\t" + join("\t"), src/main.rs:388
+    if (sample_names.empty()) f << "\t";
+    f << "\n";
+    for (size_t i = 0; i < cons.size(); ++i) {
+        const ConsensusSequence &c = cons[i];
+        if (c.per_sample_depths.empty()) {
+            const size_t d = c.depth + c.appended_depth;
+            f << "final_consensus_" << i << "_depth_" << d << "\t" << d << "\n";
+        } else {
+            std::string dash, tab;
+            for (size_t s = 0; s < c.per_sample_depths.size(); ++s) {
+                dash += (s ? "-" : "") + std::to_string(c.per_sample_depths[s]);
+                tab += (s ? "\t" : "") + std::to_string(c.per_sample_depths[s]);
+            }
+            f << "final_consensus_" << i << "_depth_" << dash << "\t" << tab << "\n";
+        }
+    }
+}
+
+void refine_asv_depths_with_em(const ReadSet &twin_reads, std::vector<ConsensusSequence> &consensuses,
+                               const KmerGlobalInfo &kmer_info, const Cli &args, const std::string &temp_dir, int device) {
+    if (consensuses.empty()) return;                                        // :1734-1737
+    if (!temp_dir.empty()) write_consensus_fasta(consensuses, temp_dir + "/final_asvs_for_em.fasta", "em_refinement");   // :1747-1749
+    Mapper mapper(device, args, kmer_info);
+    mapper.load_asvs(consensuses);
+    const Assignments a = mapper.map_reads(twin_reads, 1);
+    for (size_t i = 0; i < consensuses.size(); ++i) {                       // :1941-1945
+        consensuses[i].unambig_best_read_map_count = (size_t)a.unambig[i];
+        consensuses[i].ambig_read_map_count = (size_t)a.ambig[i];
+        consensuses[i].num_map_leq_10nm = (size_t)a.leq10[i];
+    }
+    const EqClasses cls = build_eq_classes(a, nullptr, -1);
+    if (cls.size() == 0) return;                                            // "Keeping original depths", :1953-1956
+    std::vector<double> ab; std::vector<uint64_t> depths;
+    run_em(consensuses.size(), cls, ab, depths);
+    for (size_t i = 0; i < consensuses.size(); ++i) consensuses[i].depth = (size_t)depths[i];   // :2013-2027
+    consensuses.erase(std::remove_if(consensuses.begin(), consensuses.end(), [](const ConsensusSequence &c) { return c.depth == 0; }),
+                      consensuses.end());                                  // :2031
+}
+
+std::vector<std::vector<size_t>> compute_per_sample_depths(const ReadSet &twin_reads, size_t n_samples,
+                                                           const std::vector<ConsensusSequence> &consensuses,
+                                                           const KmerGlobalInfo &kmer_info, const Cli &args, int device) {
+    const size_t n_asvs = consensuses.size();
+    std::vector<std::vector<size_t>> result(n_asvs, std::vector<size_t>(n_samples, 0));
+    if (n_asvs == 0 || n_samples == 0) return result;                       // :2055-2057
+    Mapper mapper(device, args, kmer_info);
+    mapper.load_asvs(consensuses);
+    const Assignments a = mapper.map_reads(twin_reads, (int)n_samples);    // one pass for all samples
+    for (size_t s = 0; s < n_samples; ++s) {                                // :2080-2211
+        const EqClasses cls = build_eq_classes(a, twin_reads.file_idx, (int)s);
+        if (cls.size() == 0 || cls.total_assigned == 0) continue;
+        std::vector<double> ab; std::vector<uint64_t> depths;
+        run_em(n_asvs, cls, ab, depths);
+        for (size_t i = 0; i < n_asvs; ++i) result[i][s] = (size_t)depths[i];
+    }
+    return result;
+}
+
+}  // namespace savont_host
+
+// ---- flat C wrappers so that the Python tests / host layer can drive this library with ctypes ----
+extern "C" {
+
+static thread_local std::string g_host_error;
+const char *savont_host_last_error(void) { return g_host_error.c_str(); }
+
+// EM over CSR classes; returns iterations, or -1 on error
+int savont_host_em(size_t n_asv, const uint64_t *cls_offsets, const uint32_t *cls_asv, const uint64_t *counts, size_t n_cls,
+                   uint64_t total_assigned, double *abundances, uint64_t *depths) {
+    try {
+        savont_host::EqClasses c;
+        c.offsets.assign(cls_offsets, cls_offsets + n_cls + 1);
+        c.asv.assign(cls_asv, cls_asv + cls_offsets[n_cls]);
+        c.counts.assign(counts, counts + n_cls);
+        c.total_assigned = total_assigned;
+        std::vector<double> ab; std::vector<uint64_t> dp;
+        const int it = savont_host::run_em(n_asv, c, ab, dp);
+        for (size_t a = 0; a < n_asv; ++a) { if (abundances) abundances[a] = ab[a]; if (depths) depths[a] = dp[a]; }
+        return it;
+    } catch (const std::exception &e) { g_host_error = e.what(); return -1; }
+}
+
+// Stage 7 on flat arrays: ASVs (bases/offsets) with initial depths; returns the number of ASVs kept and
+// writes depth / counters / original index of every kept ASV.  Returns -1 on error.
+long long savont_host_refine(int device, const savont_b200_params *p, const uint64_t *snpmers, size_t n_snpmers,
+                             const uint8_t *asv_bases, const uint64_t *asv_offsets, size_t n_asv,
+                             const uint8_t *bases, const uint8_t *quals, const uint64_t *offsets, size_t n_reads,
+                             const char *temp_dir, uint64_t *depth, uint64_t *unambig, uint64_t *ambig, uint64_t *leq10, uint64_t *orig_idx) {
+    try {
+        savont_host::Cli args;
+        args.kmer_size = p->k; args.c = p->c; args.blockmer_length = p->l; args.minimum_base_quality = p->min_bq;
+        args.band = p->band; args.strand_mode = p->strand_mode;
+        savont_host::KmerGlobalInfo ki; ki.snpmers.assign(snpmers, snpmers + n_snpmers);
+        std::vector<savont_host::ConsensusSequence> cons(n_asv);
+        for (size_t a = 0; a < n_asv; ++a) { cons[a].sequence.assign(asv_bases + asv_offsets[a], asv_bases + asv_offsets[a + 1]); cons[a].id = a; cons[a].depth = 1; }
+        savont_host::ReadSet rs; rs.bases = bases; rs.quals = quals; rs.offsets = offsets; rs.n = n_reads;
+        savont_host::refine_asv_depths_with_em(rs, cons, ki, args, temp_dir ? temp_dir : "", device);
+        for (size_t i = 0; i < cons.size(); ++i) {
+            depth[i] = cons[i].depth; unambig[i] = cons[i].unambig_best_read_map_count; ambig[i] = cons[i].ambig_read_map_count;
+            leq10[i] = cons[i].num_map_leq_10nm; orig_idx[i] = cons[i].id;
+        }
+        return (long long)cons.size();
+    } catch (const std::exception &e) { g_host_error = e.what(); return -1; }
+}
+
+// Stage 7b on flat arrays: out[asv * n_samples + sample]
+int savont_host_per_sample(int device, const savont_b200_params *p, const uint64_t *snpmers, size_t n_snpmers,
+                           const uint8_t *asv_bases, const uint64_t *asv_offsets, size_t n_asv,
+                           const uint8_t *bases, const uint8_t *quals, const uint64_t *offsets, const uint32_t *file_idx, size_t n_reads,
+                           size_t n_samples, uint64_t *out) {
+    try {
+        savont_host::Cli args;
+        args.kmer_size = p->k; args.c = p->c; args.blockmer_length = p->l; args.minimum_base_quality = p->min_bq;
+        args.band = p->band; args.strand_mode = p->strand_mode;
+        savont_host::KmerGlobalInfo ki; ki.snpmers.assign(snpmers, snpmers + n_snpmers);
+        std::vector<savont_host::ConsensusSequence> cons(n_asv);
+        for (size_t a = 0; a < n_asv; ++a) { cons[a].sequence.assign(asv_bases + asv_offsets[a], asv_bases + asv_offsets[a + 1]); cons[a].id = a; }
+        savont_host::ReadSet rs; rs.bases = bases; rs.quals = quals; rs.offsets = offsets; rs.file_idx = file_idx; rs.n = n_reads;
+        const auto res = savont_host::compute_per_sample_depths(rs, n_samples, cons, ki, args, device);
+        for (size_t a = 0; a < n_asv; ++a) for (size_t s = 0; s < n_samples; ++s) out[a * n_samples + s] = res[a][s];
+        return 0;
+    } catch (const std::exception &e) { g_host_error = e.what(); return -1; }
+}
+
+// writers on flat arrays (format checks in tests/test_host_api.py)
+int savont_host_write_outputs(const uint8_t *asv_bases, const uint64_t *asv_offsets, size_t n_asv, const uint64_t *depth,
+                              const uint64_t *ids, const uint64_t *unambig, const uint64_t *ambig, const uint64_t *leq10,
+                              const uint64_t *per_sample, size_t n_samples, const char *fasta_path, const char *prefix,
+                              const char *table_path, const char *sample_names_tab) {
+    try {
+        std::vector<savont_host::ConsensusSequence> cons(n_asv);
+        for (size_t a = 0; a < n_asv; ++a) {
+            cons[a].sequence.assign(asv_bases + asv_offsets[a], asv_bases + asv_offsets[a + 1]);
+            cons[a].depth = depth[a]; cons[a].id = ids[a];
+            cons[a].unambig_best_read_map_count = unambig[a]; cons[a].ambig_read_map_count = ambig[a]; cons[a].num_map_leq_10nm = leq10[a];
+            if (per_sample) for (size_t s = 0; s < n_samples; ++s) cons[a].per_sample_depths.push_back(per_sample[a * n_samples + s]);
+        }
+        if (fasta_path) savont_host::write_consensus_fasta(cons, fasta_path, prefix ? prefix : "final");
+        if (table_path) {
+            std::vector<std::string> names; std::stringstream ss(sample_names_tab ? sample_names_tab : "sample"); std::string t;
+            while (std::getline(ss, t, '\t')) names.push_back(t);
+            savont_host::write_feature_table(cons, table_path, names);
+        }
+        return 0;
+    } catch (const std::exception &e) { g_host_error = e.what(); return -1; }
+}
+
+}  // extern "C"

@@ -1,0 +1,115 @@
+// savont_host.hpp -- host layer above the C ABI that mirrors the reference's Rust interface for the
+// read-vs-ASV path (same names, argument meaning and error behaviour: errors are fatal, like the
+// reference's expect()/unwrap()).  The reference is compiled Rust; Rust is absent from this image, so
+// this layer is C++.  It owns NO compute on reads: every per-read step goes through
+// libsavont_b200.so (include/savont_b200.h); what runs here is what savont also runs once per call on
+// the host: the equivalence-class histogram, the EM and the writers.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/savont_b200.h"
+
+namespace savont_host {
+
+// the Cli fields the path reads (reference src/cli.rs:45-187)
+struct Cli {
+    int kmer_size = 17;            // src/cli.rs:153-154
+    int c = 11;                    // src/cli.rs:83-84
+    int blockmer_length = 3;       // src/cli.rs:157-158
+    int minimum_base_quality = 25; // src/cli.rs:99-100
+    int band = 64;                 // b200: DP half band
+    int strand_mode = 0;
+    bool low_polymorphism = false; // src/alignment.rs:1730 -- not implemented by this path (throws)
+};
+
+// KmerGlobalInfo reduced to what the path uses: both alleles of every SNPmer, i.e. the u64 values of
+// reference src/kmer_comp.rs:41-48
+struct KmerGlobalInfo {
+    std::vector<uint64_t> snpmers;
+};
+
+// reference src/types.rs:162-190, fields used by Stage 7 / 7b and the writers
+struct ConsensusSequence {
+    std::vector<uint8_t> sequence;       // decompressed ASV sequence (ACGT)
+    size_t depth = 0;
+    size_t appended_depth = 0;
+    size_t id = 0;
+    long long chimera_score = 0;
+    size_t unambig_best_read_map_count = 0;
+    size_t ambig_read_map_count = 0;
+    size_t num_map_leq_10nm = 0;
+    std::vector<size_t> per_sample_depths;
+};
+
+// the reads of Stage 1.5 in twin_reads order (src/main.rs:538), kept as raw bases + Phred
+struct ReadSet {
+    const uint8_t *bases = nullptr;
+    const uint8_t *quals = nullptr;      // may be null
+    const uint64_t *offsets = nullptr;   // [n + 1]
+    const uint32_t *file_idx = nullptr;  // TwinRead.file_idx, may be null
+    size_t n = 0;
+};
+
+// sorted equivalence classes with counts (the reference's HashMap<EquivalenceClass, usize>,
+// src/alignment.rs:1517-1523,1915-1916, iterated here in lexicographic order)
+struct EqClasses {
+    std::vector<uint64_t> offsets{0};
+    std::vector<uint32_t> asv;
+    std::vector<uint64_t> counts;
+    uint64_t total_assigned = 0;
+    size_t size() const { return counts.size(); }
+};
+
+// per-read result of savont_b200_map_reads
+struct Assignments {
+    std::vector<uint8_t> status;
+    std::vector<int32_t> best_nm;
+    std::vector<uint64_t> class_offsets;
+    std::vector<uint32_t> class_asv;
+    std::vector<uint64_t> unambig, ambig, leq10, sample_singleton;
+    uint64_t totals[2] = {0, 0};
+    savont_b200_stats stats{};
+};
+
+class Mapper {   // RAII over savont_b200_ctx
+public:
+    Mapper(int device, const Cli &args, const KmerGlobalInfo &kmer_info);
+    ~Mapper();
+    Mapper(const Mapper &) = delete;
+    Mapper &operator=(const Mapper &) = delete;
+    void load_asvs(const std::vector<ConsensusSequence> &consensuses);
+    Assignments map_reads(const ReadSet &reads, int n_samples);
+    savont_b200_ctx *raw() { return ctx_; }
+    size_t n_asv() const { return n_asv_; }
+
+private:
+    savont_b200_ctx *ctx_ = nullptr;
+    size_t n_asv_ = 0;
+};
+
+// sample < 0: all reads; otherwise only reads with file_idx == sample (src/alignment.rs:2095-2096)
+EqClasses build_eq_classes(const Assignments &a, const uint32_t *file_idx, int sample);
+
+// reference src/alignment.rs:1957-2009: returns the iteration count; depths = round(ab * total)
+int run_em(size_t n_asv, const EqClasses &classes, std::vector<double> &abundances, std::vector<uint64_t> &depths);
+
+// reference src/alignment.rs:1723-1729 (Stage 7).  Updates depth and the three counters, drops ASVs
+// whose EM depth is 0 (:2031).  temp_dir receives final_asvs_for_em.fasta like the reference.
+void refine_asv_depths_with_em(const ReadSet &twin_reads, std::vector<ConsensusSequence> &consensuses,
+                               const KmerGlobalInfo &kmer_info, const Cli &args, const std::string &temp_dir, int device = 0);
+
+// reference src/alignment.rs:2044-2051 (Stage 7b): result[asv][sample]
+std::vector<std::vector<size_t>> compute_per_sample_depths(const ReadSet &twin_reads, size_t n_samples,
+                                                           const std::vector<ConsensusSequence> &consensuses,
+                                                           const KmerGlobalInfo &kmer_info, const Cli &args, int device = 0);
+
+// reference src/alignment.rs:830-860 and src/main.rs:381-400
+void write_consensus_fasta(const std::vector<ConsensusSequence> &consensuses, const std::string &path, const std::string &prefix);
+void write_feature_table(const std::vector<ConsensusSequence> &consensuses, const std::string &path,
+                         const std::vector<std::string> &sample_names);
+
+}  // namespace savont_host

@@ -1,0 +1,83 @@
+"""N>1 path on CPU: world_size-2 gloo run of the sharding / all-reduce / class-gather logic of
+savont_b200/dist.py, with the CPU oracle standing in for the per-rank mapper (the CUDA context needs a GPU)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+class OracleMapper:
+    def __init__(self, w):
+        from oracle import oracle as O
+        self.orc = O.Oracle(O.default_params(band=w.band), w.snpmers)
+        self.orc.load_asvs(w.asv_bases, w.asv_offsets)
+
+    def map_shard(self, bases, quals, offsets, file_idx, n_samples):
+        return self.orc.map_reads(bases, quals, offsets, file_idx=file_idx, n_samples=n_samples, n_threads=1)
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    from savont_b200 import dist as sd, synth
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    w = synth.Workload("pooled", n_roots=3, n_samples=2, sites_per_genus=4)
+    reads = w.reads(301)
+    out = sd.map_reads_sharded(OracleMapper(w), reads, w.n_asv, n_samples=2)
+    payload = dict(rank=rank, shard=out["shard"], counters={k: v.tolist() for k, v in out["counters"].items()},
+                   multi=None if out["multi_classes"] is None else {repr(k): v for k, v in out["multi_classes"].items()})
+    if rank == 0:
+        payload["depths"] = sd.depths_from_counts(out["counters"], out["multi_classes"], w.n_asv).tolist()
+        payload["depths_s1"] = sd.depths_from_counts(out["counters"], out["multi_classes"], w.n_asv, sample=1).tolist()
+    q.put(payload)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shard_bounds_cover_all_reads():
+    from savont_b200 import dist as sd
+    for n in (0, 1, 7, 100, 301):
+        for world in (1, 2, 3, 8):
+            b = [sd.shard_bounds(n, world, r) for r in range(world)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+            assert max(hi - lo for lo, hi in b) - min(hi - lo for lo, hi in b) <= 1
+
+
+def test_two_rank_gloo_matches_single_process():
+    pytest.importorskip("torch")
+    from oracle import oracle as O
+    from savont_b200 import api, synth
+    if not os.path.exists(api._HOST_PATH):
+        pytest.skip("libsavont_host.so not built")
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs: p.start()
+    outs = [q.get(timeout=240) for _ in range(world)]
+    for p in procs: p.join(timeout=60)
+    outs.sort(key=lambda d: d["rank"])
+    assert outs[0]["shard"] == (0, 151) and outs[1]["shard"] == (151, 301)
+    assert outs[0]["counters"] == outs[1]["counters"]                # every rank holds the reduced counters
+    # single-process truth
+    w = synth.Workload("pooled", n_roots=3, n_samples=2, sites_per_genus=4)
+    reads = w.reads(301)
+    orc = O.Oracle(O.default_params(band=w.band), w.snpmers); orc.load_asvs(w.asv_bases, w.asv_offsets)
+    full = orc.map_reads(reads["bases"], reads["quals"], reads["offsets"], file_idx=reads["file_idx"], n_samples=2)
+    c = outs[0]["counters"]
+    assert c["unambig"] == full["unambig"].tolist() and c["ambig"] == full["ambig"].tolist() and c["leq10"] == full["leq10"].tolist()
+    assert c["totals"] == full["totals"].tolist() and c["sample_singleton"] == full["sample_singleton"].tolist()
+    offs, flat, counts, total = api.eq_classes(full["status"], full["class_offsets"], full["class_asv"])
+    _, depths, _ = O.em(w.n_asv, offs, flat, counts, total)
+    assert outs[0]["depths"] == depths.tolist()
+    offs, flat, counts, total = api.eq_classes(full["status"], full["class_offsets"], full["class_asv"], reads["file_idx"], 1)
+    _, d1, _ = O.em(w.n_asv, offs, flat, counts, total)
+    assert outs[0]["depths_s1"] == d1.tolist()
+    assert outs[1]["multi"] is None and outs[0]["multi"] is not None

@@ -1,0 +1,138 @@
+"""Host layer (C++ libsavont_host.so through savont_b200/api.py): EM, writers on CPU; Stage 7 / 7b drivers on GPU."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+
+def _host_available():
+    from savont_b200 import api
+    return os.path.exists(api._HOST_PATH)
+
+
+def test_em_matches_oracle_em():
+    from savont_b200 import api
+    rng = np.random.default_rng(3)
+    A = 12
+    classes = {}
+    for _ in range(40):
+        size = int(rng.integers(1, 4))
+        key = tuple(sorted(rng.choice(A, size=size, replace=False).tolist()))
+        classes[key] = classes.get(key, 0) + int(rng.integers(1, 50))
+    keys = sorted(classes)
+    offs = np.zeros(len(keys) + 1, np.uint64); offs[1:] = np.cumsum([len(k) for k in keys])
+    flat = np.array([a for k in keys for a in k], np.uint32)
+    counts = np.array([classes[k] for k in keys], np.uint64)
+    total = int(counts.sum())
+    ab_h, dp_h, it_h = api.em(A, offs, flat, counts, total)
+    ab_o, dp_o, it_o = O.em(A, offs, flat, counts, total)
+    assert it_h == it_o
+    assert np.array_equal(dp_h, dp_o)
+    assert np.array_equal(ab_h.view(np.uint64), ab_o.view(np.uint64))      # same summation order -> same bits
+    assert int(dp_h.sum()) in range(total - A, total + A + 1)
+
+
+def test_writers_follow_reference_formats(tmp_path):
+    from savont_b200 import api
+    cons = [api.ConsensusSequence(b"NNACGTACGTNN", depth=7, id=3, unambig_best_read_map_count=5, ambig_read_map_count=2, num_map_leq_10nm=6),
+            api.ConsensusSequence(b"GGGTTTAAAC", depth=2, id=0)]
+    fa, tb = tmp_path / "final_asvs.fasta", tmp_path / "feature-table.tsv"
+    api.write_consensus_fasta(cons, fa, "final")
+    api.write_feature_table(cons, tb, ["s1"])
+    # src/alignment.rs:848-850 header; leading/trailing N trimmed (:842-843)
+    assert fa.read_text().splitlines() == [
+        ">final_consensus_0_depth_7 debug_id:3 chimera_score:0 unambiguous_read_assignments:5 ambig_read_assignments:2 num_align_leq_10_mismatches:6",
+        "ACGTACGT",
+        ">final_consensus_1_depth_2 debug_id:0 chimera_score:0 unambiguous_read_assignments:0 ambig_read_assignments:0 num_align_leq_10_mismatches:0",
+        "GGGTTTAAAC"]
+    # src/main.rs:388-392
+    assert tb.read_text().splitlines() == ["#OTU ID\ts1", "final_consensus_0_depth_7\t7", "final_consensus_1_depth_2\t2"]
+    for c, d in zip(cons, ([4, 3, 0], [0, 1, 1])):
+        c.per_sample_depths = d
+    api.write_consensus_fasta(cons, fa, "final")
+    api.write_feature_table(cons, tb, ["a", "b", "c"])
+    assert fa.read_text().splitlines()[0].startswith(">final_consensus_0_depth_4-3-0 debug_id:3")
+    # pooled: dash-joined depths in the id, one column per sample (src/main.rs:394-397)
+    assert tb.read_text().splitlines() == ["#OTU ID\ta\tb\tc", "final_consensus_0_depth_4-3-0\t4\t3\t0", "final_consensus_1_depth_0-1-1\t0\t1\t1"]
+
+
+def test_eq_classes_helper():
+    from savont_b200 import api
+    status = np.array([0, 1, 0, 0, 2, 0], np.uint8)
+    co = np.array([0, 1, 1, 3, 4, 4, 6], np.uint64)
+    ca = np.array([2, 0, 1, 2, 0, 1], np.uint32)
+    offs, flat, counts, total = api.eq_classes(status, co, ca)
+    assert total == 4 and offs.tolist() == [0, 2, 3] and flat.tolist() == [0, 1, 2] and counts.tolist() == [2, 2]
+    offs, flat, counts, total = api.eq_classes(status, co, ca, file_idx=np.array([0, 0, 1, 1, 1, 0]), sample=1)
+    assert total == 2 and counts.tolist() == [1, 1]
+
+
+def _oracle_depths(orc, reads, n_asv, n_samples=1, file_idx=None):
+    res = orc.map_reads(reads["bases"], reads["quals"], reads["offsets"], file_idx=file_idx, n_samples=n_samples)
+    from savont_b200 import api
+    out = []
+    for s in ([None] if file_idx is None else range(n_samples)):
+        offs, flat, counts, total = api.eq_classes(res["status"], res["class_offsets"], res["class_asv"], file_idx, s)
+        if total == 0:
+            out.append(np.zeros(n_asv, np.uint64)); continue
+        _, depths, _ = O.em(n_asv, offs, flat, counts, total)
+        out.append(depths)
+    return res, out
+
+
+@pytest.mark.gpu
+def test_refine_asv_depths_with_em_matches_oracle_pipeline(tmp_path):
+    from savont_b200 import api, synth
+    w = synth.Workload("ont16s", n_roots=5, sites_per_genus=6)
+    r = w.reads(3000)
+    seqs = [bytes(w.asv_bases[int(w.asv_offsets[a]):int(w.asv_offsets[a + 1])]) for a in range(w.n_asv)]
+    cons = [api.ConsensusSequence(s, depth=1, id=i) for i, s in enumerate(seqs)]
+    args = api.Cli(band=w.band)
+    api.refine_asv_depths_with_em(r, cons, w.snpmers, args, temp_dir=tmp_path)
+    orc = O.Oracle(O.default_params(band=w.band), w.snpmers); orc.load_asvs(w.asv_bases, w.asv_offsets)
+    res, (depths,) = _oracle_depths(orc, r, w.n_asv)
+    kept = [a for a in range(w.n_asv) if depths[a] > 0]
+    assert [c.id for c in cons] == kept                                   # zero-depth ASVs dropped (src/alignment.rs:2031)
+    assert [c.depth for c in cons] == [int(depths[a]) for a in kept]
+    assert [c.unambig_best_read_map_count for c in cons] == [int(res["unambig"][a]) for a in kept]
+    assert [c.ambig_read_map_count for c in cons] == [int(res["ambig"][a]) for a in kept]
+    assert [c.num_map_leq_10nm for c in cons] == [int(res["leq10"][a]) for a in kept]
+    assert (tmp_path / "final_asvs_for_em.fasta").read_text().count(">em_refinement_consensus_") == w.n_asv
+    assert sum(c.depth for c in cons) > 0.5 * 3000
+
+
+@pytest.mark.gpu
+def test_compute_per_sample_depths_matches_oracle_pipeline():
+    from savont_b200 import api, synth
+    w = synth.Workload("pooled", n_roots=4, n_samples=3)
+    r = w.reads(2500)
+    seqs = [bytes(w.asv_bases[int(w.asv_offsets[a]):int(w.asv_offsets[a + 1])]) for a in range(w.n_asv)]
+    cons = [api.ConsensusSequence(s, depth=1, id=i) for i, s in enumerate(seqs)]
+    got = api.compute_per_sample_depths(r, 3, cons, w.snpmers, api.Cli(band=w.band))
+    orc = O.Oracle(O.default_params(band=w.band), w.snpmers); orc.load_asvs(w.asv_bases, w.asv_offsets)
+    _, per = _oracle_depths(orc, r, w.n_asv, n_samples=3, file_idx=r["file_idx"])
+    want = np.stack(per, axis=1).astype(np.int64).tolist()
+    assert got == want
+
+
+@pytest.mark.gpu
+def test_python_mirrors_of_sketch_and_candidates():
+    from savont_b200 import _lib, api, synth
+    w = synth.Workload("ont16s", n_roots=3)
+    r = w.reads(50)
+    ctx = _lib.Context(0, _lib.default_params(band=w.band))
+    ctx.load_snpmers(w.snpmers); ctx.load_asvs(w.asv_bases, w.asv_offsets)
+    o = r["offsets"]
+    rd = bytes(r["bases"][int(o[0]):int(o[1])]); ql = bytes(r["quals"][int(o[0]):int(o[1])])
+    tw = api.get_twin_read_syncmer(ctx, rd, ql, "r0")
+    want = O.sketch_batch(O.default_params(band=w.band), w.snpmers, *O.concat([rd])[:1], np.frombuffer(ql, np.uint8), O.concat([rd])[1])
+    assert np.array_equal(tw["minimizer_kmers"], want["mini_kmer"]) and np.array_equal(tw["snpmer_positions"], want["snp_pos"])
+    assert tw["est_id"] == want["est_id"][0]
+    assert api.get_twin_read_syncmer(ctx, b"ACGT", None) is None           # len < k -> None (src/seeding.rs:339-341)
+    asv_sk = api.twin_reads_from_fasta(ctx, [bytes(w.asv_bases[int(w.asv_offsets[a]):int(w.asv_offsets[a + 1])]) for a in range(3)])
+    assert len(asv_sk["mini_offsets"]) == 4 and np.all(np.isnan(asv_sk["est_id"]))
+    c = api.find_compatible_candidates(ctx, r["bases"], r["quals"], r["offsets"])
+    assert len(c["status"]) == 50
+    ctx.close()
