@@ -1,7 +1,7 @@
 // align.cu -- K3: banded, both-ends-free unit-cost edit distance (NM), bit-parallel.
 //
 // Stands in for the minimap2 call of reference src/alignment.rs:1848-1863 (NM of read vs ASV) with
-// the north-star definition (SURVEY.md 8c "S2", restated in oracle/savont_oracle.c banded_align):
+// the north-star definition (SURVEY.md 8c "S2"):
 //   rows i = 0..n (ASV), columns j = 0..m (oriented read), cells |i-j| <= B,
 //   D[0][j] = D[i][0] = 0, unit costs, NM = min over last-row / last-column cells,
 //   tie -> largest i+j, then the last-row cell.
