@@ -52,7 +52,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -172,11 +172,11 @@ def run_b200(args, rank, world, local_rank):
 
     # ---------------- kernel-only arm: reads resident in HBM ----------------
     ctx.upload_reads(r["bases"], r["quals"], r["offsets"], file_idx=fidx, n_samples=w.n_samples)
+    sampler = ClockSampler(local_rank)
+    sampler.start()                       # runs through warm-up, the timed steps and the e2e steps (all under load)
     for _ in range(args.warmup):
         ctx.map_resident(); allreduce_counts()
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
     step_ms, stats = [], []
     for _ in range(args.steps):
         barrier()
@@ -187,7 +187,6 @@ def run_b200(args, rank, world, local_rank):
         e1.record(stream)
         barrier()
         step_ms.append(e0.elapsed_time(e1)); stats.append(st)
-    clocks = sampler.stop()
     dev_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(dev_ms, op=dist.ReduceOp.MAX)
@@ -209,6 +208,7 @@ def run_b200(args, rank, world, local_rank):
         barrier()
         e2e_ms.append(e0.elapsed_time(e1))
         e2e_stats = res["stats"]
+    clocks = sampler.stop()
     e2e_t = torch.tensor([sum(e2e_ms)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
@@ -246,12 +246,16 @@ def run_b200(args, rank, world, local_rank):
         "kernel_ms": {"sketch": sketch_ms, "filter": filter_ms, "align": align_ms, "assign": assign_ms},
         "pairs_per_step": pairs, "dp_cells_per_step": cells,
         "roofline": {"bound": "int32", "kernel": "align_nm_kernel", "achieved": gcups, "peak": peak_gcups, "unit": "GCUPS",
-                     "frac": gcups / peak_gcups if peak_gcups else None, "traffic": None,
+                     "frac": gcups / peak_gcups if peak_gcups else None,
+                     "traffic": _ncu_traffic("align_nm_kernel") if (n_reads == 1_000_000 and args.workload == "ont16s") else None,
+                     "algorithmic_bytes": pairs * (376 + 21),
                      "peak_how": f"148 SM x 64 INT32 ALU lanes x {sm_mhz:.0f} MHz (sampled) x 32 cells / {OPS_PER_WORD} ALU ops per "
                                  f"32-cell word, x {used_frac:.3f} (band {2 * w.band + 1} of {32 * nw} vector bits)"},
         "roofline_hbm": {"bound": "hbm", "kernel": "sketch_kernel", "achieved": sk_bytes / (sketch_ms / 1e3) / 1e9 if sketch_ms else None,
                          "peak": peaks["hbm_gbs"], "unit": "GB/s", "peak_source": peaks["source"],
-                         "frac": (sk_bytes / (sketch_ms / 1e3) / 1e9) / peaks["hbm_gbs"] if sketch_ms else None, "traffic": None},
+                         "frac": (sk_bytes / (sketch_ms / 1e3) / 1e9) / peaks["hbm_gbs"] if sketch_ms else None,
+                         "traffic": _ncu_traffic("sketch_kernel") if (n_reads == 1_000_000 and args.workload == "ont16s") else None,
+                         "algorithmic_bytes": sk_bytes},
         "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(e2e_stats["h2d_bytes"]),
                 "d2h_bytes_per_step": int(e2e_stats["d2h_bytes"]), "steps": e2e_steps, "ms_per_step": e2e_total_ms / e2e_steps,
                 "h2d_ms": e2e_stats["h2d_ms"], "d2h_ms": e2e_stats["d2h_ms"]},
@@ -279,8 +283,25 @@ def run_b200(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
 
 
-# INT32 ALU-pipe instructions per 32-cell word-column of align_nm_kernel<5> (counted in DESIGN.md from cuobjdump -sass)
-OPS_PER_WORD = 15.0
+# INT32 ALU-pipe instructions per 32-cell word-column of the banded Myers/Hyyro recurrence as formulated in
+# align.cu (2 SHF + 2 LOP3 for Eq, X, t, IADD3.X, D0, Ph, Mh, the re-alignment SHF, Pv', Mv').  The SASS
+# inner loop of align_nm_kernel<5> is 81 instructions per column = 16.2 per word including loop/char overhead.
+OPS_PER_WORD = 13.0
+
+
+def _ncu_traffic(kernel):
+    """dram bytes read+written per launch from the committed ncu --set full summary (1M-read launch), or None"""
+    path = os.path.join(ROOT, "profiles", f"r01_{kernel}_full.txt")
+    try:
+        tot = 0.0
+        for line in open(path):
+            f = line.split()
+            if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                mult = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(f[2], 1.0)
+                tot += float(f[1]) * mult
+        return tot or None
+    except Exception:
+        return None
 
 
 def main():

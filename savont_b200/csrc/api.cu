@@ -97,7 +97,9 @@ struct Batch {
     // assign
     DevBuf rstatus, best_nm, class_cnt, class_slot, class_off, class_out, scan_tmp;
     bool mapped = false;
+    PinBuf pin_offsets;
     void release() {
+        pin_offsets.release();
         DevBuf *all[] = {&bases, &quals, &offsets, &file_idx, &planes, &sk_status, &flatq, &mini_cnt, &mini_kmer, &mini_pos,
                          &snp_start, &snp_cnt, &snp_kmer, &snp_pos, &est_id, &spill_k, &spill_p, &ctrs, &cand_status, &pair_start, &pair_cnt,
                          &low_mm, &p_read, &p_asv, &p_mini, &p_strand, &nm, &asv_end, &read_end, &rstatus, &best_nm,
@@ -130,10 +132,12 @@ struct Context {
     // counters [unambig A | ambig A | leq10 A | assigned | filtered | singleton S*A]
     DevBuf d_counters; size_t counters_len = 0; int counters_samples = 0;
 
-    Batch work, resident, asvb;
+    Batch work, work2, resident, asvb;
     int resident_samples = 1;
-    PinBuf pin_offsets, pin_small, pin_out;
+    PinBuf pin_small, pin_out;
+    cudaStream_t copy_stream = nullptr;          // H2D of batch i+1 overlaps the kernels of batch i
     cudaEvent_t ev[8] = {nullptr};
+    cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_h0[2] = {nullptr, nullptr};
     savont_b200_stats last_stats;
 };
 
@@ -260,12 +264,13 @@ static int upload_snp_set(Context *c) {
 // batch staging
 // ------------------------------------------------------------------------------------------------
 static int batch_upload(Context *c, Batch &b, const uint8_t *bases, const uint8_t *quals, const uint64_t *offsets,
-                        const uint32_t *file_idx, size_t n, uint64_t *h2d_bytes) {
+                        const uint32_t *file_idx, size_t n, uint64_t *h2d_bytes, cudaStream_t st = nullptr) {
+    if (st == nullptr) st = c->stream;
     const uint64_t base0 = offsets[0];
     const uint64_t total = offsets[n] - base0;
     if (total >= (1ull << 32) - 64) return fail(SAVONT_B200_ERR_INVALID, "batch of %llu bases exceeds 4 Gi", (unsigned long long)total);
-    TRY(c->pin_offsets.ensure((n + 1) * sizeof(uint64_t)));
-    uint64_t *rel = c->pin_offsets.as<uint64_t>();
+    TRY(b.pin_offsets.ensure((n + 1) * sizeof(uint64_t)));
+    uint64_t *rel = b.pin_offsets.as<uint64_t>();
     uint32_t max_len = 0;
     for (size_t i = 0; i <= n; ++i) {
         if (i > 0 && offsets[i] < offsets[i - 1]) return fail(SAVONT_B200_ERR_INVALID, "offsets not monotonic at %zu", i);
@@ -276,17 +281,17 @@ static int batch_upload(Context *c, Batch &b, const uint8_t *bases, const uint8_
     b.has_quals = quals != nullptr; b.has_file_idx = file_idx != nullptr;
     TRY(b.bases.ensure(total + 64));
     TRY(b.offsets.ensure((n + 1) * sizeof(uint64_t)));
-    CK(cudaMemcpyAsync(b.offsets.p, rel, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
-    if (total) CK(cudaMemcpyAsync(b.bases.p, bases + base0, total, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(b.offsets.p, rel, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    if (total) CK(cudaMemcpyAsync(b.bases.p, bases + base0, total, cudaMemcpyHostToDevice, st));
     uint64_t bytes = (n + 1) * sizeof(uint64_t) + total;
     if (quals) {
         TRY(b.quals.ensure(total + 64));
-        if (total) CK(cudaMemcpyAsync(b.quals.p, quals + base0, total, cudaMemcpyHostToDevice, c->stream));
+        if (total) CK(cudaMemcpyAsync(b.quals.p, quals + base0, total, cudaMemcpyHostToDevice, st));
         bytes += total;
     }
     if (file_idx) {
         TRY(b.file_idx.ensure(n * sizeof(uint32_t) + 4));
-        if (n) CK(cudaMemcpyAsync(b.file_idx.p, file_idx, n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        if (n) CK(cudaMemcpyAsync(b.file_idx.p, file_idx, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
         bytes += n * sizeof(uint32_t);
     }
     if (h2d_bytes) *h2d_bytes += bytes;
@@ -700,7 +705,9 @@ int savont_b200_create(int device_id, savont_b200_ctx **out) {
     c->sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
+    CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     for (auto &ev : c->ev) CK(cudaEventCreate(&ev));
+    for (int i = 0; i < 2; ++i) { CK(cudaEventCreate(&c->ev_up[i])); CK(cudaEventCreate(&c->ev_h0[i])); }
     savont_b200_default_params(&c->params);
     c->dp = make_device_params(c->params);
     memset(&c->last_stats, 0, sizeof(c->last_stats));
@@ -715,12 +722,14 @@ int savont_b200_destroy(savont_b200_ctx *h) {
     Context *c = &h->c;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    c->work.release(); c->resident.release(); c->asvb.release();
+    c->work.release(); c->work2.release(); c->resident.release(); c->asvb.release();
     DevBuf *bufs[] = {&c->d_rank_table, &c->d_snp_keys, &c->d_snp_bloom, &c->d_phred, &c->d_idx_keys, &c->d_idx_vals, &c->d_idx_entries, &c->d_mset,
                       &c->d_mset_off, &c->d_asv_planes, &c->d_asv_plane_off, &c->d_asv_len, &c->d_counters};
     for (DevBuf *b : bufs) b->release();
-    c->pin_offsets.release(); c->pin_small.release(); c->pin_out.release();
+    c->pin_small.release(); c->pin_out.release();
     for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
+    for (int i = 0; i < 2; ++i) { if (c->ev_up[i]) cudaEventDestroy(c->ev_up[i]); if (c->ev_h0[i]) cudaEventDestroy(c->ev_h0[i]); }
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete h;
     return 0;
@@ -983,16 +992,33 @@ int savont_b200_map_reads(savont_b200_ctx *h, const uint8_t *bases, const uint8_
     CK(cudaEventRecord(c->ev[6], c->stream));
     class_offsets[0] = 0;
     uint64_t class_base = 0;
+    // batch boundaries
+    std::vector<size_t> cuts{0};
     for (size_t r0 = 0; r0 < n_reads;) {
         size_t r1 = std::min(n_reads, r0 + c->batch_reads);
         while (r1 > r0 + 1 && offsets[r1] - offsets[r0] > (3ull << 30)) r1 = r0 + (r1 - r0) / 2;
-        const size_t n = r1 - r0;
-        Batch &b = c->work;
-        CK(cudaEventRecord(c->ev[5], c->stream));
-        TRY(batch_upload(c, b, bases, quals, offsets + r0, file_idx ? file_idx + r0 : nullptr, n, &st.h2d_bytes));
-        CK(cudaEventRecord(c->ev[0], c->stream));
-        CK(cudaStreamSynchronize(c->stream));
-        st.h2d_ms += ev_ms(c->ev[5], c->ev[0]);
+        cuts.push_back(r1);
+        r0 = r1;
+    }
+    const size_t nb = cuts.size() - 1;
+    Batch *bufs[2] = {&c->work, &c->work2};
+    // double buffering: the H2D copies of batch i+1 run on the copy stream while batch i computes
+    auto upload = [&](size_t bi) -> int {
+        const int slot = (int)(bi & 1);
+        const size_t r0 = cuts[bi], n = cuts[bi + 1] - r0;
+        CK(cudaEventRecord(c->ev_h0[slot], c->copy_stream));
+        TRY(batch_upload(c, *bufs[slot], bases, quals, offsets + r0, file_idx ? file_idx + r0 : nullptr, n, &st.h2d_bytes, c->copy_stream));
+        CK(cudaEventRecord(c->ev_up[slot], c->copy_stream));
+        return 0;
+    };
+    CK(cudaStreamWaitEvent(c->copy_stream, c->ev[6], 0));   // order after earlier work on the caller's stream
+    if (nb) TRY(upload(0));
+    for (size_t bi = 0; bi < nb; ++bi) {
+        const int slot = (int)(bi & 1);
+        const size_t r0 = cuts[bi];
+        Batch &b = *bufs[slot];
+        if (bi + 1 < nb) TRY(upload(bi + 1));
+        CK(cudaStreamWaitEvent(c->stream, c->ev_up[slot], 0));
         TRY(run_path(c, b, n_samples, st));
         CK(cudaEventRecord(c->ev[5], c->stream));
         uint64_t n_cls = 0;
@@ -1000,9 +1026,9 @@ int savont_b200_map_reads(savont_b200_ctx *h, const uint8_t *bases, const uint8_
         CK(cudaEventRecord(c->ev[0], c->stream));
         CK(cudaStreamSynchronize(c->stream));
         st.d2h_ms += ev_ms(c->ev[5], c->ev[0]);
+        st.h2d_ms += ev_ms(c->ev_h0[slot], c->ev_up[slot]);
         class_base += n_cls;
         st.n_batches += 1;
-        r0 = r1;
     }
     TRY(read_counters(c, unambig, ambig, leq10, totals, sample_singleton, true));
     st.d2h_bytes += c->counters_len * 8;

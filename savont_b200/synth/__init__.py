@@ -48,6 +48,8 @@ def _L():
         L.synth_asv_bytes.restype = C.c_size_t; L.synth_asv_bytes.argtypes = [C.c_void_p]
         L.synth_get_asvs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.synth_snpmers.restype = C.c_size_t; L.synth_snpmers.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
+        L.synth_snpmers_from.restype = C.c_size_t
+        L.synth_snpmers_from.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t]
         L.synth_read_lengths.argtypes = [C.c_void_p, C.c_uint64, C.c_size_t, C.c_void_p]
         L.synth_reads.argtypes = [C.c_void_p, C.c_uint64, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
@@ -99,3 +101,13 @@ class Workload:
         L.synth_reads(self.h, first, n, offs.ctypes.data, bases.ctypes.data, quals.ctypes.data, ta.ctypes.data, ts.ctypes.data,
                       fi.ctypes.data)
         return dict(bases=bases[:total], quals=quals[:total], offsets=offs, truth_asv=ta, truth_strand=ts, file_idx=fi)
+
+
+def snpmers_from_sequences(bases, offsets, k=17):
+    """SNPmer set the way Stage 1 would call it from a set of ASV sequences (see synth.cpp header)"""
+    L = _L()
+    b = np.ascontiguousarray(bases, np.uint8); o = np.ascontiguousarray(offsets, np.uint64)
+    n = int(L.synth_snpmers_from(b.ctypes.data, o.ctypes.data, len(o) - 1, k, None, 0))
+    out = np.zeros(max(n, 1), np.uint64)
+    L.synth_snpmers_from(b.ctypes.data, o.ctypes.data, len(o) - 1, k, out.ctypes.data, n)
+    return out[:n]

@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cctype>
 #include <cstring>
 #include <map>
 #include <string>
@@ -190,13 +191,26 @@ void synth_get_asvs(void *h, uint8_t *bases, uint64_t *offsets) {
     for (size_t a = 0; a < S->asvs.size(); ++a) { memcpy(bases + off, S->asvs[a].data(), S->asvs[a].size()); off += S->asvs[a].size(); offsets[a + 1] = off; }
 }
 
+static size_t snpmers_of(const std::vector<std::string> &asvs, int k, uint64_t *out, size_t cap);
+
 // SNPmer set from the ASVs; returns the number written (or needed if cap too small)
-size_t synth_snpmers(void *h, int k, uint64_t *out, size_t cap) {
-    Synth *S = (Synth *)h;
+size_t synth_snpmers(void *h, int k, uint64_t *out, size_t cap) { return snpmers_of(((Synth *)h)->asvs, k, out, cap); }
+
+// same derivation for caller-supplied sequences (any non-ACGT base is read as A, like BYTE_TO_SEQ)
+size_t synth_snpmers_from(const uint8_t *bases, const uint64_t *offsets, size_t n, int k, uint64_t *out, size_t cap) {
+    std::vector<std::string> v(n);
+    for (size_t i = 0; i < n; ++i) {
+        v[i].assign((const char *)bases + offsets[i], (const char *)bases + offsets[i + 1]);
+        for (char &c : v[i]) { c = (char)toupper((unsigned char)c); if (c == 'U') c = 'T'; if (c != 'A' && c != 'C' && c != 'G' && c != 'T') c = 'A'; }
+    }
+    return snpmers_of(v, k, out, cap);
+}
+
+static size_t snpmers_of(const std::vector<std::string> &asvs, int k, uint64_t *out, size_t cap) {
     const uint64_t split_mask = ~(3ull << (k - 1));
     const uint64_t kmask = (1ull << (2 * k)) - 1;
     std::vector<uint64_t> all;   // canonical k-mers (one per ASV occurrence)
-    for (auto &s : S->asvs) {
+    for (auto &s : asvs) {
         uint64_t f = 0, r = 0;
         for (size_t i = 0; i < s.size(); ++i) {
             const uint64_t c = (uint64_t)code(s[i]);

@@ -1,0 +1,73 @@
+"""Config 1 of BASELINE.json (real ONT reads vs the zymo reference 16S copies): committed golden vectors
+(tests/golden/zymo_subset.npz, made by tests/golden/make_golden.py from the reference's own test data).
+CPU: the oracle still reproduces them.  GPU: the library reproduces them through the C ABI."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+G = os.path.join(os.path.dirname(__file__), "golden", "zymo_subset.npz")
+
+
+def _digest(*arrays):
+    h = hashlib.sha256()
+    for a in arrays:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+@pytest.fixture(scope="module")
+def g():
+    return np.load(G)
+
+
+def test_fixture_shape(g):
+    assert len(g["asv_offsets"]) - 1 == 63 and len(g["read_offsets"]) - 1 == 260
+    lens = (g["read_offsets"][1:] - g["read_offsets"][:-1]).astype(int)
+    assert lens.min() >= 1100 and lens.max() <= 2000                  # src/cli.rs:87-92
+    assert int(g["totals"][0]) == int((g["status"] == 0).sum()) == 249
+
+
+def test_oracle_reproduces_golden(g):
+    p = O.default_params(band=64)
+    sk = O.sketch_batch(p, g["snpmers"], g["read_bases"], g["read_quals"], g["read_offsets"])
+    assert _digest(sk["mini_pos"], sk["mini_kmer"], sk["mini_fwd"], sk["snp_pos"], sk["snp_kmer"]) == str(g["sk_digest"])
+    assert np.array_equal(sk["mini_offsets"], g["sk_mini_offsets"]) and np.array_equal(sk["est_id"], g["sk_est_id"])
+    orc = O.Oracle(p, g["snpmers"]); orc.load_asvs(g["asv_bases"], g["asv_offsets"])
+    res = orc.map_reads(g["read_bases"], g["read_quals"], g["read_offsets"])
+    for key in ("status", "best_nm", "class_offsets", "class_asv", "unambig", "ambig", "leq10", "totals"):
+        assert np.array_equal(res[key], g[key]), key
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_golden(g):
+    from savont_b200 import _lib
+    ctx = _lib.Context(0, _lib.default_params(band=64))
+    ctx.load_snpmers(g["snpmers"]); ctx.load_asvs(g["asv_bases"], g["asv_offsets"])
+    sk = ctx.sketch(g["read_bases"], g["read_quals"], g["read_offsets"])
+    assert _digest(sk["mini_pos"], sk["mini_kmer"], sk["mini_fwd"], sk["snp_pos"], sk["snp_kmer"]) == str(g["sk_digest"])
+    assert np.array_equal(sk["snp_offsets"], g["sk_snp_offsets"]) and np.array_equal(sk["est_id"], g["sk_est_id"])
+    ask = ctx.sketch(g["asv_bases"], None, g["asv_offsets"])
+    assert _digest(ask["mini_pos"], ask["mini_kmer"], ask["mini_fwd"], ask["snp_pos"], ask["snp_kmer"]) == str(g["asv_sk_digest"])
+    cand = ctx.find_candidates(g["read_bases"], g["read_quals"], g["read_offsets"])
+    for key in ("status", "offsets", "asv", "mm", "mini", "strand"):
+        assert np.array_equal(cand[key], g["cand_" + key]), key
+    res = ctx.map_reads(g["read_bases"], g["read_quals"], g["read_offsets"])
+    for key in ("status", "best_nm", "class_offsets", "class_asv", "unambig", "ambig", "leq10", "totals"):
+        assert np.array_equal(res[key], g[key]), key
+    # reverse-complementing every read must give the same assignments with the opposite strand
+    comp = np.zeros(256, np.uint8); comp[:] = ord("N")
+    for a, b in zip(b"ACGTacgt", b"TGCAtgca"):
+        comp[a] = b
+    o = g["read_offsets"].astype(np.int64)
+    rb = np.concatenate([comp[g["read_bases"][o[i]:o[i + 1]][::-1]] for i in range(len(o) - 1)])
+    rq = np.concatenate([g["read_quals"][o[i]:o[i + 1]][::-1] for i in range(len(o) - 1)])
+    rc = ctx.map_reads(rb, rq, g["read_offsets"])
+    crc = ctx.find_candidates(rb, rq, g["read_offsets"])
+    assert np.array_equal(crc["asv"], cand["asv"]) and np.array_equal(crc["strand"], 1 - cand["strand"])
+    for key in ("status", "best_nm", "class_offsets", "class_asv", "totals"):
+        assert np.array_equal(rc[key], g[key]), key
+    ctx.close()
