@@ -312,7 +312,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="ont16s")
     ap.add_argument("--reads", type=int, default=1_000_000, help="reads per GPU per step")
-    ap.add_argument("--batch-reads", type=int, default=262144)
+    ap.add_argument("--batch-reads", type=int, default=131072)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-reads", type=int, default=100_000, help="sample size of the CPU baseline / reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -32,6 +32,7 @@ struct AlignArgs {
     const uint32_t *pair_asv;
     const uint8_t *pair_strand;
     const uint32_t *n_pairs_dev;   // device-side pair count (may be null -> n_pairs_max)
+    const uint32_t *err;           // device error word (may be null): non-zero -> an upstream pool overflowed, do nothing
     uint32_t n_pairs_max;
     int32_t *nm, *asv_end, *read_end;
     // traceback mode
@@ -336,6 +337,7 @@ __device__ __forceinline__ void align_pair(const AlignArgs &a, uint32_t pi, uint
 
 template <int NW>
 __global__ void __launch_bounds__(128) align_nm_kernel(AlignArgs a) {
+    if (a.err && *a.err) return;
     const uint32_t n_pairs = a.n_pairs_dev ? min(*a.n_pairs_dev, a.n_pairs_max) : a.n_pairs_max;
     for (uint32_t pi = blockIdx.x * blockDim.x + threadIdx.x; pi < n_pairs; pi += gridDim.x * blockDim.x)
         align_pair<NW, false>(a, pi, 0);
@@ -369,10 +371,10 @@ static AlignArgs make_args(const SeqBatch &in, const uint2 *read_planes, const A
 
 void launch_align_nm(const SeqBatch &in, const uint2 *read_planes, const AsvIndex &ix, const uint32_t *pair_read,
                      const uint32_t *pair_asv, const uint8_t *pair_strand, const uint32_t *n_pairs_dev, uint32_t n_pairs_max,
-                     const AlignOut &out, const DeviceParams &p, int sm_count, cudaStream_t st) {
+                     const uint32_t *err, const AlignOut &out, const DeviceParams &p, int sm_count, cudaStream_t st) {
     if (n_pairs_max == 0) return;
     AlignArgs a = make_args(in, read_planes, ix, pair_read, pair_asv, pair_strand, out, p);
-    a.n_pairs_dev = n_pairs_dev; a.n_pairs_max = n_pairs_max;
+    a.n_pairs_dev = n_pairs_dev; a.n_pairs_max = n_pairs_max; a.err = err;
     uint32_t grid = (n_pairs_max + 127u) / 128u;
     const uint32_t cap = (uint32_t)sm_count * 16u;       // 16 CTAs x 128 threads = full occupancy per SM
     if (grid > cap) grid = cap;

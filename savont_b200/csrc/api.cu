@@ -114,7 +114,7 @@ struct Context {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     savont_b200_params params;
     DeviceParams dp;
-    size_t batch_reads = 262144;
+    size_t batch_reads = 131072;
 
     // tables
     DevBuf d_rank_table; bool use_rank_table = false;
@@ -263,6 +263,8 @@ static int upload_snp_set(Context *c) {
 // ------------------------------------------------------------------------------------------------
 // batch staging
 // ------------------------------------------------------------------------------------------------
+constexpr size_t kCtrBytes = 32;   // u32 snp pool counter, pair counter, error bits, spare; u64 dp_cells; pad
+
 static int batch_upload(Context *c, Batch &b, const uint8_t *bases, const uint8_t *quals, const uint64_t *offsets,
                         const uint32_t *file_idx, size_t n, uint64_t *h2d_bytes, cudaStream_t st = nullptr) {
     if (st == nullptr) st = c->stream;
@@ -341,32 +343,46 @@ static int stage_sketch(Context *c, Batch &b, bool with_pos) {
     if (with_pos) TRY(b.mini_pos.ensure(mini_slots * 4));
     TRY(b.snp_start.ensure((n + 1) * 4)); TRY(b.snp_cnt.ensure((n + 1) * 4));
     if (b.snp_cap == 0 || b.snp_cap < total / 8 + 4096) b.snp_cap = (uint32_t)std::min<uint64_t>(total / 8 + 4096, 0xfffffff0u);
-    TRY(b.ctrs.ensure(4 * sizeof(uint32_t)));
+    TRY(b.ctrs.ensure(kCtrBytes));
     {   // per-warp spill region for sequences with more than kSnpHitCap SNPmer hits
         const uint32_t grid = sketch_grid(b.n, b.max_len, c->use_rank_table, c->dp, snp_view(c), c->sm_count);
         b.spill_stride = b.max_len + 1;
         const size_t entries = (size_t)grid * kSketchWarps * b.spill_stride;
         TRY(b.spill_k.ensure(entries * 8)); TRY(b.spill_p.ensure(entries * 4));
     }
-    for (int attempt = 0; attempt < 3; ++attempt) {
-        TRY(b.snp_kmer.ensure((size_t)b.snp_cap * 8)); TRY(b.snp_pos.ensure((size_t)b.snp_cap * 4));
-        CK(cudaMemsetAsync(b.ctrs.p, 0, 4 * sizeof(uint32_t), c->stream));
-        launch_sketch(seq_view(b), sketch_view(b, with_pos), snp_view(c), c->use_rank_table ? c->d_rank_table.as<uint16_t>() : nullptr,
-                      c->dp, c->sm_count, c->stream);
-        CK(cudaGetLastError());
-        c->last_stats.kernel_launches += 1;
-        // the SNPmer pool is sized generously (1 entry per 8 bases); verify lazily with the pair pool check
-        uint32_t h[4];
-        CK(cudaMemcpyAsync(h, b.ctrs.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
-        if (h[2] & kErrSnpPool) {
-            if (attempt == 2) return fail(SAVONT_B200_ERR_OVERFLOW, "SNPmer pool overflow (%u needed)", h[0]);
-            b.snp_cap = h[0] + 1024;
-            continue;
-        }
-        break;
-    }
+    TRY(b.snp_kmer.ensure((size_t)b.snp_cap * 8)); TRY(b.snp_pos.ensure((size_t)b.snp_cap * 4));
+    CK(cudaMemsetAsync(b.ctrs.p, 0, kCtrBytes, c->stream));
+    launch_sketch(seq_view(b), sketch_view(b, with_pos), snp_view(c), c->use_rank_table ? c->d_rank_table.as<uint16_t>() : nullptr,
+                  c->dp, c->sm_count, c->stream);
+    CK(cudaGetLastError());
+    c->last_stats.kernel_launches += 1;
     return 0;
+}
+
+// Reads the batch counters after the stream drained.  Pool overflows are not errors: the kernels downstream of
+// an overflow do nothing (they test the error word), the pools are grown to the exact need and *retry is set.
+struct BatchCounters { uint32_t snp_used, n_pairs, err, spare; unsigned long long dp_cells; };
+static int check_batch(Context *c, Batch &b, BatchCounters *out, bool *retry) {
+    BatchCounters h;
+    CK(cudaMemcpyAsync(&h, b.ctrs.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    *retry = false;
+    if (h.err & kErrSnpPool) { b.snp_cap = h.snp_used + 1024; *retry = true; }
+    if (h.err & kErrPairPool) { b.pair_cap = h.n_pairs + 1024; *retry = true; }
+    if (h.err & ~(kErrSnpPool | kErrPairPool)) return fail(SAVONT_B200_ERR_OVERFLOW, "device error flags 0x%x", h.err);
+    *out = h;
+    return 0;
+}
+
+// sketch + error check, re-run with a larger SNPmer pool when it overflowed
+static int sketch_checked(Context *c, Batch &b, bool with_pos) {
+    for (int attempt = 0;; ++attempt) {
+        TRY(stage_sketch(c, b, with_pos));
+        BatchCounters h{}; bool retry = false;
+        TRY(check_batch(c, b, &h, &retry));
+        if (!retry) return 0;
+        if (attempt == 3) return fail(SAVONT_B200_ERR_OVERFLOW, "SNPmer pool sizing did not converge");
+    }
 }
 
 static AsvIndex index_view(const Context *c) {
@@ -400,42 +416,31 @@ static int ensure_pair_pool(Batch &b) {
     return 0;
 }
 
-// filter with pool-overflow retry; leaves the pair count in *n_pairs
-static int stage_filter(Context *c, Batch &b, int strand_mode, uint32_t *n_pairs) {
+// candidate filter (launch only; the pair count stays on the device)
+static int stage_filter(Context *c, Batch &b, int strand_mode) {
     const size_t n = b.n;
     if (n > 0 && (uint64_t)b.max_len / (uint64_t)c->dp.mini_spacing + 2 >= 32768u)
         return fail(SAVONT_B200_ERR_OVERFLOW, "read of %u bases is too long for the candidate filter", b.max_len);
     TRY(b.cand_status.ensure(n + 4)); TRY(b.pair_start.ensure((n + 1) * 4)); TRY(b.pair_cnt.ensure((n + 1) * 4));
     TRY(b.low_mm.ensure((n + 1) * 4));
     const uint32_t per = strand_mode == 1 ? 2u : 1u;
-    if (b.pair_cap < 4u * per * (uint32_t)n + 1024u) b.pair_cap = 4u * per * (uint32_t)n + 1024u;
+    if (b.pair_cap < 2u * per * (uint32_t)n + 1024u) b.pair_cap = 2u * per * (uint32_t)n + 1024u;
     DeviceParams dp = c->dp; dp.strand_mode = strand_mode;
-    for (int attempt = 0; attempt < 3; ++attempt) {
-        TRY(ensure_pair_pool(b));
-        CK(cudaMemsetAsync(b.ctrs.as<uint32_t>() + 1, 0, 2 * sizeof(uint32_t), c->stream));
-        launch_filter(seq_view(b), sketch_view(b, false), index_view(c), pool_view(b), filter_view(b), dp, c->sm_count, c->stream);
-        CK(cudaGetLastError());
-        c->last_stats.kernel_launches += 1;
-        uint32_t h[4];
-        CK(cudaMemcpyAsync(h, b.ctrs.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
-        if (h[2] & kErrPairPool) {
-            if (attempt == 2) return fail(SAVONT_B200_ERR_OVERFLOW, "candidate pair pool overflow (%u needed)", h[1]);
-            b.pair_cap = h[1] + 1024;
-            continue;
-        }
-        *n_pairs = h[1];
-        break;
-    }
+    TRY(ensure_pair_pool(b));
+    launch_filter(seq_view(b), sketch_view(b, false), index_view(c), pool_view(b), filter_view(b), dp, c->sm_count, c->stream);
+    CK(cudaGetLastError());
+    c->last_stats.kernel_launches += 1;
     return 0;
 }
 
-static int stage_align(Context *c, Batch &b, uint32_t n_pairs) {
+// n_pairs_dev: device-side pair count written by the filter (null: exactly n_pairs_max pairs)
+static int stage_align(Context *c, Batch &b, const uint32_t *n_pairs_dev, uint32_t n_pairs_max) {
     AlignOut ao{b.nm.as<int32_t>(), b.asv_end.as<int32_t>(), b.read_end.as<int32_t>()};
     launch_align_nm(seq_view(b), b.planes.as<uint2>(), index_view(c), b.p_read.as<uint32_t>(), b.p_asv.as<uint32_t>(),
-                    b.p_strand.as<uint8_t>(), nullptr, n_pairs, ao, c->dp, c->sm_count, c->stream);
+                    b.p_strand.as<uint8_t>(), n_pairs_dev, n_pairs_max, n_pairs_dev ? b.ctrs.as<uint32_t>() + 2 : nullptr, ao, c->dp,
+                    c->sm_count, c->stream);
     CK(cudaGetLastError());
-    if (n_pairs) c->last_stats.kernel_launches += 1;
+    if (n_pairs_max) c->last_stats.kernel_launches += 1;
     return 0;
 }
 
@@ -456,7 +461,8 @@ static int stage_assign(Context *c, Batch &b, int n_samples, int strand_mode) {
     TRY(b.class_off.ensure((n + 2) * 4)); TRY(b.class_out.ensure((size_t)b.pair_cap * 4 + 4));
     TRY(b.scan_tmp.ensure((n / 2048 + 4) * 4));
     launch_assign(filter_view(b), pool_view(b), b.nm.as<int32_t>(), b.has_file_idx ? b.file_idx.as<uint32_t>() : nullptr, (uint32_t)n,
-                  (uint32_t)c->n_asv, n_samples, strand_mode, b.rstatus.as<uint8_t>(), b.best_nm.as<int32_t>(),
+                  (uint32_t)c->n_asv, n_samples, strand_mode, c->d_asv_len.as<uint32_t>(), (uint32_t)(2 * c->dp.band + 1),
+                  reinterpret_cast<unsigned long long *>(b.ctrs.as<uint32_t>() + 4), b.rstatus.as<uint8_t>(), b.best_nm.as<int32_t>(),
                   b.class_cnt.as<uint32_t>(), b.class_slot.as<uint32_t>(), c->d_counters.as<unsigned long long>(), c->stream);
     launch_scan_u32(b.class_cnt.as<uint32_t>(), b.class_off.as<uint32_t>(), (uint32_t)n, b.scan_tmp.as<uint32_t>(), c->stream);
     launch_gather_u32(b.class_slot.as<uint32_t>(), b.pair_start.as<uint32_t>(), b.class_cnt.as<uint32_t>(), b.class_off.as<uint32_t>(),
@@ -479,7 +485,7 @@ static int build_asv_index(Context *c) {
     const int k = c->dp.k;
     Batch &b = c->asvb;
     TRY(batch_upload(c, b, c->asv_bases_h.data(), nullptr, c->asv_offsets_h.data(), nullptr, A, nullptr));
-    TRY(stage_sketch(c, b, true));
+    TRY(sketch_checked(c, b, true));
     // download the sketches
     const size_t mini_slots = (size_t)mini_slot_off(b.total_bases, A, (uint32_t)c->dp.mini_spacing) + 4;
     std::vector<uint8_t> st(A);
@@ -599,33 +605,32 @@ static int use_device(Context *c) {
 
 static float ev_ms(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
 
-// sketch -> filter -> align -> assign on a device-resident batch, timed with events on the stream
+// sketch -> filter -> align -> assign on a device-resident batch: four kernel groups enqueued back to back, ONE
+// host synchronisation at the end; per-group device times from CUDA events on the stream
 static int run_path(Context *c, Batch &b, int n_samples, savont_b200_stats &st) {
-    uint32_t n_pairs = 0;
-    CK(cudaEventRecord(c->ev[0], c->stream));
-    TRY(stage_sketch(c, b, false));
-    CK(cudaEventRecord(c->ev[1], c->stream));
-    TRY(stage_filter(c, b, c->dp.strand_mode, &n_pairs));
-    CK(cudaEventRecord(c->ev[2], c->stream));
-    TRY(stage_align(c, b, n_pairs));
-    CK(cudaEventRecord(c->ev[3], c->stream));
-    TRY(stage_assign(c, b, n_samples, c->dp.strand_mode));
-    CK(cudaEventRecord(c->ev[4], c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    BatchCounters h{};
+    for (int attempt = 0;; ++attempt) {
+        CK(cudaEventRecord(c->ev[0], c->stream));
+        TRY(stage_sketch(c, b, false));
+        CK(cudaEventRecord(c->ev[1], c->stream));
+        TRY(stage_filter(c, b, c->dp.strand_mode));
+        CK(cudaEventRecord(c->ev[2], c->stream));
+        TRY(stage_align(c, b, b.ctrs.as<uint32_t>() + 1, b.pair_cap));
+        CK(cudaEventRecord(c->ev[3], c->stream));
+        TRY(stage_assign(c, b, n_samples, c->dp.strand_mode));
+        CK(cudaEventRecord(c->ev[4], c->stream));
+        bool retry = false;
+        TRY(check_batch(c, b, &h, &retry));
+        if (!retry) break;
+        if (attempt == 3) return fail(SAVONT_B200_ERR_OVERFLOW, "pool sizing did not converge");
+    }
     st.sketch_ms += ev_ms(c->ev[0], c->ev[1]);
     st.filter_ms += ev_ms(c->ev[1], c->ev[2]);
     st.align_ms += ev_ms(c->ev[2], c->ev[3]);
     st.assign_ms += ev_ms(c->ev[3], c->ev[4]);
-    st.n_pairs += n_pairs;
+    st.n_pairs += h.n_pairs;
     st.n_reads += b.n; st.n_bases += b.total_bases;
-    // dp_cells = sum over pairs of L_asv * (2B+1): needs the pair ASVs; computed from a device-side copy of p_asv
-    if (n_pairs) {
-        std::vector<uint32_t> pa(n_pairs);
-        CK(cudaMemcpy(pa.data(), b.p_asv.p, (size_t)n_pairs * 4, cudaMemcpyDeviceToHost));
-        uint64_t cells = 0;
-        for (uint32_t a : pa) cells += (uint64_t)c->asv_len_h[a] * (uint64_t)(2 * c->dp.band + 1);
-        st.dp_cells += cells;
-    }
+    st.dp_cells += h.dp_cells;
     return 0;
 }
 
@@ -754,7 +759,7 @@ int savont_b200_set_params(savont_b200_ctx *h, const savont_b200_params *p) {
 
 int savont_b200_set_batch_reads(savont_b200_ctx *h, size_t n) {
     if (!h) return fail(SAVONT_B200_ERR_INVALID, "null context");
-    h->c.batch_reads = n ? n : 262144;
+    h->c.batch_reads = n ? n : 131072;
     return 0;
 }
 
@@ -805,7 +810,7 @@ int savont_b200_sketch(savont_b200_ctx *h, const uint8_t *bases, const uint8_t *
         const size_t n = r1 - r0;
         Batch &b = c->work;
         TRY(batch_upload(c, b, bases, quals, offsets + r0, nullptr, n, nullptr));
-        TRY(stage_sketch(c, b, true));
+        TRY(sketch_checked(c, b, true));
         // compact CSR on the device
         TRY(b.class_off.ensure((n + 2) * 4)); TRY(b.pair_start.ensure((n + 2) * 4)); TRY(b.scan_tmp.ensure((n / 2048 + 4) * 4));
         uint32_t *d_moff = b.class_off.as<uint32_t>(), *d_soff = b.pair_start.as<uint32_t>();
@@ -868,8 +873,15 @@ int savont_b200_find_candidates(savont_b200_ctx *h, const uint8_t *bases, const 
         Batch &b = c->work;
         uint32_t n_pairs = 0;
         TRY(batch_upload(c, b, bases, quals, offsets + r0, nullptr, n, nullptr));
-        TRY(stage_sketch(c, b, false));
-        TRY(stage_filter(c, b, 0, &n_pairs));
+        for (int attempt = 0;; ++attempt) {
+            TRY(stage_sketch(c, b, false));
+            TRY(stage_filter(c, b, 0));
+            BatchCounters h{}; bool retry = false;
+            TRY(check_batch(c, b, &h, &retry));
+            n_pairs = h.n_pairs;
+            if (!retry) break;
+            if (attempt == 3) return fail(SAVONT_B200_ERR_OVERFLOW, "pool sizing did not converge");
+        }
         if (base + n_pairs > cand_cap) return fail(SAVONT_B200_ERR_CAPACITY, "candidate capacity too small (need >= %zu)", base + n_pairs);
         TRY(b.class_off.ensure((n + 2) * 4)); TRY(b.scan_tmp.ensure((n / 2048 + 4) * 4));
         TRY(b.class_out.ensure(((size_t)n_pairs + 1) * 4)); TRY(b.class_slot.ensure(((size_t)n_pairs + 1) * 4));
@@ -922,7 +934,7 @@ int savont_b200_align_pairs(savont_b200_ctx *h, const uint8_t *bases, const uint
     }
     if (cigar_offsets) cigar_offsets[0] = 0;
     if (!want_cigar) {
-        TRY(stage_align(c, b, (uint32_t)n_pairs));
+        TRY(stage_align(c, b, nullptr, (uint32_t)n_pairs));
         if (n_pairs) {
             CK(cudaMemcpyAsync(nm, b.nm.p, n_pairs * 4, cudaMemcpyDeviceToHost, c->stream));
             CK(cudaMemcpyAsync(asv_end, b.asv_end.p, n_pairs * 4, cudaMemcpyDeviceToHost, c->stream));

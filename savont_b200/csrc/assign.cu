@@ -10,12 +10,17 @@
 namespace sb {
 
 __global__ void assign_kernel(FilterOut fo, PairPool pool, const int32_t *__restrict__ nm, const uint32_t *__restrict__ file_idx,
-                              uint32_t n_reads, uint32_t n_asv, int n_samples, int strand_mode, uint8_t *status,
-                              int32_t *best_nm, uint32_t *class_cnt, uint32_t *class_slot, unsigned long long *counters) {
+                              uint32_t n_reads, uint32_t n_asv, int n_samples, int strand_mode,
+                              const uint32_t *__restrict__ asv_len, uint32_t cells_per_row, unsigned long long *dp_cells,
+                              uint8_t *status, int32_t *best_nm, uint32_t *class_cnt, uint32_t *class_slot,
+                              unsigned long long *counters) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     bool assigned = false, filtered = false;
-    if (r < n_reads) {
+    unsigned long long cells = 0;                 // banded DP cells of this read's pairs: L_asv * (2B+1) each
+    const bool skip = *fo.err != 0u;              // a pool overflowed upstream: the host re-runs the batch
+    if (skip) { if (r < n_reads) class_cnt[r] = 0; }
+    else if (r < n_reads) {
         const uint8_t st = fo.cand_status[r];
         if (st != 0) {
             status[r] = st; best_nm[r] = 0x7fffffff; class_cnt[r] = 0;
@@ -24,6 +29,7 @@ __global__ void assign_kernel(FilterOut fo, PairPool pool, const int32_t *__rest
             const uint32_t start = fo.pair_start[r], cnt = fo.pair_cnt[r];
             const uint32_t per = (strand_mode == 1) ? 2u : 1u;
             const uint32_t ncand = cnt / per;
+            for (uint32_t c = 0; c < cnt; ++c) cells += (unsigned long long)asv_len[pool.asv[start + c]] * cells_per_row;
             int best = 0x7fffffff;
             for (uint32_t c = 0; c < ncand; ++c) {
                 int v = nm[start + c * per];
@@ -57,18 +63,22 @@ __global__ void assign_kernel(FilterOut fo, PairPool pool, const int32_t *__rest
     }
     const uint32_t na = __popc(__ballot_sync(0xffffffffu, assigned));
     const uint32_t nf = __popc(__ballot_sync(0xffffffffu, filtered));
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) cells += __shfl_xor_sync(0xffffffffu, cells, d);
     if (lane == 0) {
         if (na) atomicAdd(counters + 3ull * n_asv, (unsigned long long)na);
         if (nf) atomicAdd(counters + 3ull * n_asv + 1ull, (unsigned long long)nf);
+        if (cells) atomicAdd(dp_cells, cells);
     }
 }
 
 void launch_assign(const FilterOut &fo, const PairPool &pool, const int32_t *nm, const uint32_t *file_idx, uint32_t n_reads,
-                   uint32_t n_asv, int n_samples, int strand_mode, uint8_t *status, int32_t *best_nm, uint32_t *class_cnt,
-                   uint32_t *class_slot, unsigned long long *counters, cudaStream_t st) {
+                   uint32_t n_asv, int n_samples, int strand_mode, const uint32_t *asv_len, uint32_t cells_per_row,
+                   unsigned long long *dp_cells, uint8_t *status, int32_t *best_nm, uint32_t *class_cnt, uint32_t *class_slot,
+                   unsigned long long *counters, cudaStream_t st) {
     if (n_reads == 0) return;
-    assign_kernel<<<(n_reads + 255u) / 256u, 256, 0, st>>>(fo, pool, nm, file_idx, n_reads, n_asv, n_samples, strand_mode, status,
-                                                         best_nm, class_cnt, class_slot, counters);
+    assign_kernel<<<(n_reads + 255u) / 256u, 256, 0, st>>>(fo, pool, nm, file_idx, n_reads, n_asv, n_samples, strand_mode, asv_len,
+                                                         cells_per_row, dp_cells, status, best_nm, class_cnt, class_slot, counters);
 }
 
 // ---------------- exclusive scan (u32), three small kernels ----------------

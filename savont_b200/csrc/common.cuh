@@ -15,9 +15,7 @@ namespace sb {
 
 constexpr uint64_t kEmpty64 = ~0ull;
 constexpr uint64_t kFwdBit = 1ull << 63;
-constexpr int kSnpHitCap = 32;         // per-sequence SNPmer hits held in shared memory (more spill to global)
-constexpr int kSnpCandPerLane = 3;     // Bloom-positive k-mers a lane buffers per chunk for the exact probe (more resolve inline)
-constexpr int kSnpCandCap = 32 * kSnpCandPerLane;
+constexpr int kSnpHitCap = 64;         // per-sequence SNPmer hits held in shared memory (more spill to global)
 constexpr int kSketchWarps = 16;       // warps per CTA in the sketch kernel
 constexpr int kFilterWarps = 4;        // warps per CTA in the filter kernel
 
@@ -154,7 +152,7 @@ void launch_filter(const SeqBatch &in, const SketchOut &sk, const AsvIndex &ix, 
                    const DeviceParams &p, int sm_count, cudaStream_t st);
 void launch_align_nm(const SeqBatch &in, const uint2 *read_planes, const AsvIndex &ix, const uint32_t *pair_read,
                      const uint32_t *pair_asv, const uint8_t *pair_strand, const uint32_t *n_pairs_dev, uint32_t n_pairs_max,
-                     const AlignOut &out, const DeviceParams &p, int sm_count, cudaStream_t st);
+                     const uint32_t *err, const AlignOut &out, const DeviceParams &p, int sm_count, cudaStream_t st);
 // traceback variant for a sub-batch of n_pairs (all pointers pre-offset to the sub-batch): history workspace
 // hist[(col * 2*NW + w) * n_pairs + t]; cigar slots of `cigar_stride` ops per pair filled from the back
 // (the last cigar_cnt[t] entries of slot t are the ops in forward order).
@@ -167,6 +165,7 @@ int align_words_for_band(int band);
 size_t align_tb_hist_words(uint32_t n_pairs, uint32_t hist_cols, const DeviceParams &p);
 void launch_assign(const FilterOut &fo, const PairPool &pool, const int32_t *nm,
                    const uint32_t *file_idx, uint32_t n_reads, uint32_t n_asv, int n_samples, int strand_mode,
+                   const uint32_t *asv_len, uint32_t cells_per_row, unsigned long long *dp_cells,
                    uint8_t *status, int32_t *best_nm, uint32_t *class_cnt, uint32_t *class_slot,
                    unsigned long long *counters, cudaStream_t st);
 void launch_gather_cand(const PairPool &pool, const uint32_t *pair_start, const uint32_t *pair_cnt, const uint32_t *low_mm,

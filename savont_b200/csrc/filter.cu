@@ -45,6 +45,7 @@ filter_kernel(SeqBatch in, SketchOut sk, AsvIndex ix, PairPool pool, FilterOut o
     const uint32_t rshift = 64u - (uint32_t)__popc(rmask);
     const uint32_t clear_words = lay.acc_words + 2u * lay.bm_words + lay.sum_words;
     const int mid_shift = p.k - 1;
+    if (*out.err & kErrSnpPool) return;          // the sketch ran out of pool space: the host grows it and re-runs the batch
 
     for (uint32_t seq = blockIdx.x * kFilterWarps + warp; seq < in.n; seq += gridDim.x * kFilterWarps) {
         if (sk.status[seq] != 0) {

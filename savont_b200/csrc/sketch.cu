@@ -43,6 +43,11 @@ __device__ __forceinline__ uint64_t window64(const uint32_t *packed, uint32_t a)
     const uint32_t lo = __funnelshift_l(w2, w1, sh);
     return ((uint64_t)hi << 32) | lo;
 }
+// len (1..16) bases starting at base a, right-aligned, first base in the highest used pair
+__device__ __forceinline__ uint32_t extract32(const uint32_t *packed, uint32_t a, uint32_t len) {
+    const uint32_t w = a >> 4, sh = (a & 15u) * 2u;
+    return __funnelshift_l(packed[w + 1], packed[w], sh) >> (32u - 2u * len);
+}
 __device__ __forceinline__ uint64_t swap_pairs64(uint64_t r) {
     return ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1);
 }
@@ -132,8 +137,7 @@ struct SketchSmem {
     uint32_t max_t;          // chunk length per lane (positions)
     uint32_t mini_cap;       // minimizers a lane can emit per chunk: max_t / spacing + 2
     __host__ __device__ size_t per_warp() const {
-        const size_t b = (size_t)(kSnpHitCap + kSnpCandCap) * 12u + 16u + ring_bytes + (size_t)mini_cap * 32u * 8u +
-                         (size_t)packed_words * 4u;
+        const size_t b = (size_t)kSnpHitCap * 12u + 16u + ring_bytes + (size_t)mini_cap * 32u * 8u + (size_t)packed_words * 4u;
         return (b + 15u) & ~(size_t)15u;
     }
     __host__ __device__ size_t total() const { return 256u + (size_t)table_bytes + bloom_bytes + per_warp() * kSketchWarps; }
@@ -175,12 +179,10 @@ sketch_kernel(SeqBatch in, SketchOut out, SnpSet set, const uint16_t *__restrict
     }
     uint8_t *wbase = smem + 256 + lay.table_bytes + lay.bloom_bytes + (size_t)warp * lay.per_warp();
     uint64_t *hits_k = reinterpret_cast<uint64_t *>(wbase);
-    uint64_t *cand_k = hits_k + kSnpHitCap;                                         // Bloom-positive k-mers awaiting the exact probe
-    uint64_t *mbuf = cand_k + kSnpCandCap;                                          // [mini_cap][32]
+    uint64_t *mbuf = hits_k + kSnpHitCap;                                           // [mini_cap][32]
     rank_t *ring = reinterpret_cast<rank_t *>(mbuf + (size_t)lay.mini_cap * 32u);   // [c][32] (runtime-c path)
     uint32_t *hits_p = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(ring) + lay.ring_bytes);
-    uint32_t *cand_p = hits_p + kSnpHitCap;
-    uint32_t *hcnt = cand_p + kSnpCandCap;                                          // [0] hits
+    uint32_t *hcnt = hits_p + kSnpHitCap;                                           // [0] hits
     uint32_t *packed = hcnt + 4;
 
     const uint32_t mid_idx = (c - 1u) >> 1;      // (k - s) / 2, src/seeding.rs:528
@@ -207,7 +209,6 @@ sketch_kernel(SeqBatch in, SketchOut out, SnpSet set, const uint16_t *__restrict
         __syncwarp();
         const bool flat = pack_sequence(in, off, L, planes, packed, s_lut, lane);
         if (lane == 0) hcnt[0] = 0u;
-        uint32_t ccnt = 0;                      // Bloom-positive k-mers buffered by this lane
         __syncwarp();
 
         // exact SNPmer set probe + mid-base quality gate (src/seeding.rs:509-521) -> hit list
@@ -255,29 +256,25 @@ sketch_kernel(SeqBatch in, SketchOut out, SnpSet set, const uint16_t *__restrict
                 Rv = revcomp_top(x, km1_mask) << 2;
             }
             uint32_t bidx = qs + k - 1u;                                    // next base to push
-            uint32_t pw = packed[bidx >> 4] << (2u * (bidx & 15u));
+            uint32_t pw = K ? 0u : packed[bidx >> 4] << (2u * (bidx & 15u));
             uint32_t cnt = 0;                                               // minimizers buffered by this lane
+            uint64_t cmask = 0;                                             // bit j: step j was Bloom-positive
             rank_t win[CC];
 #pragma unroll
             for (int t = 0; t < CC; ++t) win[t] = 0;
 
-            // QUIRK: positions q < s-1 may occur (first block of the first segment).  CHECKS: the step may
-            // still be a warm-up step (q < p0) or the window may not be full yet (first block of a segment).
-            auto step = [&](auto quirk_tag, auto checks_tag, const uint32_t j, const int jj) {
-                constexpr bool QUIRK = decltype(quirk_tag)::value;
-                constexpr bool CHECKS = decltype(checks_tag)::value;
+            // one position.  `first` (warp-uniform): the step belongs to the first block of the segment, where
+            // warm-up steps (q < p0), a not-yet-full window and (segment 0) the warm-up quirk can occur.
+            // `e`: the base pushed by this step.  Returns whether the k-mer passed the SNPmer Bloom filter.
+            auto step = [&](const bool first, const uint32_t j, const int jj, const uint32_t e) -> bool {
                 const uint32_t q = qs + j;
-                const uint32_t e = pw >> 30;
-                pw <<= 2;
-                ++bidx;
-                if ((bidx & 15u) == 0u) pw = packed[bidx >> 4];
                 F = ((F << 2) | (uint64_t)e) & kmer_mask;
                 Rv = (Rv >> 2) | ((uint64_t)(3u - e) << rc_shift);
                 const bool fwd = (F & split_mask) < (Rv & split_mask);      // tie -> reverse (src/seeding.rs:429)
                 const uint64_t canon = fwd ? F : Rv;
                 // the s-mer ending at base q+k-1 is the tail of this k-mer ...
                 uint32_t f = (uint32_t)F & smask;
-                if (QUIRK && q + 1u < s) {
+                if (first && seg == 0u && q + 1u < s) {
                     // ... except for the reference's warm-up quirk (src/seeding.rs:392-397,413)
                     const uint32_t nt = q + 1u;
                     const uint32_t head = (uint32_t)(F >> (2u * (k - (s - nt))));
@@ -291,18 +288,16 @@ sketch_kernel(SeqBatch in, SketchOut out, SnpSet set, const uint16_t *__restrict
                     rk = (rank_t)mm_hash64((uint64_t)(f < r ? f : r));
                 }
                 if (K) win[jj] = rk; else ring[(j % c) * 32u + lane] = rk;
-                if (CHECKS && q < p0) return;
-                // ---- SNPmer membership: Bloom filter now, exact probe after the loop ----
+                if (first && q < p0) return false;                          // warm-up step: roll and rank only
+                // ---- SNPmer membership: Bloom filter now (branch-free), exact probe after the loop ----
+                bool bloom_hit = false;
                 if (set.keys != nullptr) {
                     const uint32_t h = bloom_hash32(canon);
                     const uint32_t bmask = (1u << (h & 31u)) | (1u << ((h >> 5) & 31u));
-                    if ((s_bloom[h >> set.bloom_shift] & bmask) == bmask) {
-                        if (ccnt < (uint32_t)kSnpCandPerLane) { cand_k[ccnt * 32u + lane] = canon; cand_p[ccnt * 32u + lane] = q; ++ccnt; }
-                        else resolve_snp(canon, q);
-                    }
+                    bloom_hit = (s_bloom[h >> set.bloom_shift] & bmask) == bmask;
                 }
                 // ---- open syncmer: strict minimum at the middle of the last c ranks ----
-                if (!CHECKS || j + 1u >= c) {
+                if (!first || j + 1u >= c) {
                     bool is_mini;
                     if (K) {
                         const int mslot = (jj + 1 + ((CC - 1) >> 1)) % CC;
@@ -325,29 +320,32 @@ sketch_kernel(SeqBatch in, SketchOut out, SnpSet set, const uint16_t *__restrict
                         ++cnt;
                     }
                 }
+                return bloom_hit;
             };
 
             if (K) {
-                // first block of CC steps: warm-up and window-fill checks (and the quirk in segment 0)
-                if (seg == 0u) {
-#pragma unroll
-                    for (int jj = 0; jj < CC; ++jj)
-                        if ((uint32_t)jj < ns) step(std::true_type{}, std::true_type{}, (uint32_t)jj, jj);
-                } else {
-#pragma unroll
-                    for (int jj = 0; jj < CC; ++jj)
-                        if ((uint32_t)jj < ns) step(std::false_type{}, std::true_type{}, (uint32_t)jj, jj);
-                }
-                for (uint32_t jb = (uint32_t)CC; jb < NS; jb += (uint32_t)CC) {
+                // blocks of CC steps: the CC bases of a block are fetched at once, the window slot of a step is static
+                for (uint32_t jb = 0; jb < NS; jb += (uint32_t)CC) {
+                    const uint32_t bb = extract32(packed, bidx, (uint32_t)CC);
+                    bidx += (uint32_t)CC;
+                    uint32_t cm = 0;
 #pragma unroll
                     for (int jj = 0; jj < CC; ++jj) {
                         const uint32_t j = jb + (uint32_t)jj;
-                        if (j < ns) step(std::false_type{}, std::false_type{}, j, jj);
+                        if (j < ns && step(jb == 0u, j, jj, (bb >> (2 * (CC - 1 - jj))) & 3u)) cm |= 1u << jj;
                     }
+                    cmask |= (uint64_t)cm << jb;
                 }
             } else {
-                for (uint32_t j = 0; j < NS; ++j)
-                    if (j < ns) step(std::true_type{}, std::true_type{}, j, 0);
+                for (uint32_t j = 0; j < NS; ++j) {
+                    if (j < ns) {
+                        const uint32_t e = pw >> 30;
+                        pw <<= 2;
+                        ++bidx;
+                        if ((bidx & 15u) == 0u) pw = packed[bidx >> 4];
+                        if (step(j < max(c, s), j, 0, e)) cmask |= 1ull << j;   // quirk region (q < s-1) may exceed c steps
+                    }
+                }
             }
             // ---- write the buffered minimizers lane-major (= position order) ----
             uint32_t incl = cnt;
@@ -361,9 +359,16 @@ sketch_kernel(SeqBatch in, SketchOut out, SnpSet set, const uint16_t *__restrict
                 if (mini_pos_out) mini_pos_out[o0 + i] = p0 + (uint32_t)((v >> 48) & 0x3fu);
             }
             n_mini += total;
-            // ---- exact probe of the Bloom-positive k-mers this lane buffered in the segment ----
-            for (uint32_t t = 0; t < ccnt; ++t) resolve_snp(cand_k[t * 32u + lane], cand_p[t * 32u + lane]);
-            ccnt = 0;
+            // ---- exact probe of this lane's Bloom-positive positions (k-mer re-extracted from the packed read) ----
+            while (cmask) {
+                const uint32_t j = (uint32_t)__ffsll((long long)cmask) - 1u;
+                cmask &= cmask - 1ull;
+                const uint32_t q = qs + j;
+                const uint64_t x = window64(packed, q);
+                const uint64_t kf = x >> (64u - 2u * k);
+                const uint64_t kr = revcomp_top(x, kmer_mask);
+                resolve_snp(((kf & split_mask) < (kr & split_mask)) ? kf : kr, q);
+            }
             __syncwarp();
         }
 
@@ -430,7 +435,7 @@ static SketchSmem sketch_layout(uint32_t max_len, bool use_table, const DevicePa
     lay.ring_bytes = fixed ? 0u : (uint32_t)((size_t)p.c * 32u * (use_table ? 4u : 8u));
     // chunk length: at most 64 positions per lane, and small enough that a lane emits <= 12 minimizers
     uint32_t max_t = 10u * (uint32_t)p.mini_spacing;
-    if (max_t > 64u) max_t = 64u;
+    if (max_t > 65u - (uint32_t)p.c) max_t = 65u - (uint32_t)p.c;       // T + c - 1 <= 64: one Bloom-mask bit per step
     lay.max_t = max_t;
     // the longest chunk any lane can get for this batch
     const uint32_t n_pos = max_len >= (uint32_t)p.k ? max_len - (uint32_t)p.k + 1u : 1u;
