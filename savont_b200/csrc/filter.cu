@@ -62,28 +62,40 @@ filter_kernel(SeqBatch in, SketchOut sk, AsvIndex ix, PairPool pool, FilterOut o
         const uint64_t mo = mini_slot_off(off, seq, (uint32_t)p.mini_spacing);
         const uint32_t nmini = sk.mini_cnt[seq];
         uint32_t nR = 0;
-        for (uint32_t t0 = 0; t0 < nmini; t0 += 32u) {
-            const uint32_t t = t0 + lane;
-            bool inserted = false;
-            if (t < nmini) {
-                const unsigned long long v = sk.mini_kmer[mo + t];
-                const unsigned long long key = v & ~kFwdBit;
-                uint32_t slot = hash_slot(key, rshift);
-                while (true) {
-                    const unsigned long long old = atomicCAS(&rset[slot], (unsigned long long)kEmpty64, v);
-                    if (old == kEmpty64) { inserted = true; break; }
-                    if ((old & ~kFwdBit) == key) {
-                        if (v & kFwdBit) atomicOr(&rset[slot], (unsigned long long)kFwdBit);
-                        break;
-                    }
-                    slot = (slot + 1u) & rmask;
-                }
+        for (uint32_t t0 = 0; t0 < nmini; t0 += 128u) {
+            // four independent loads per lane in flight before the (dependent) inserts
+            unsigned long long vv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t t = t0 + 32u * u + lane;
+                vv[u] = (t < nmini) ? sk.mini_kmer[mo + t] : kEmpty64;
             }
-            nR += __popc(__ballot_sync(0xffffffffu, inserted));
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned long long v = vv[u];
+                bool inserted = false;
+                if (v != kEmpty64) {
+                    const unsigned long long key = v & ~kFwdBit;
+                    uint32_t slot = hash_slot(key, rshift);
+                    while (true) {
+                        const unsigned long long old = atomicCAS(&rset[slot], (unsigned long long)kEmpty64, v);
+                        if (old == kEmpty64) { inserted = true; break; }
+                        if ((old & ~kFwdBit) == key) {
+                            if (v & kFwdBit) atomicOr(&rset[slot], (unsigned long long)kFwdBit);
+                            break;
+                        }
+                        slot = (slot + 1u) & rmask;
+                    }
+                }
+                nR += __popc(__ballot_sync(0xffffffffu, inserted));
+            }
         }
         __syncwarp();
 
         // ---- 2. SNPmer buckets -> per-ASV mismatch counters + candidate bitmap ----
+        // 32 SNPmers per round: every lane probes the splitmer table for its SNPmer, then the (SNPmer, bucket
+        // entry) pairs of the round are FLATTENED over the lanes (prefix sum of the bucket lengths + a 5-step
+        // search for the owner), so that all entry loads of a round are independent and in flight together.
         const uint32_t ns = sk.snp_cnt[seq], s0 = sk.snp_start[seq];
         for (uint32_t t0 = 0; t0 < ns; t0 += 32u) {
             const uint32_t t = t0 + lane;
@@ -100,15 +112,25 @@ filter_kernel(SeqBatch in, SketchOut sk, AsvIndex ix, PairPool pool, FilterOut o
                     slot = (slot + 1u) & ix.idx_mask;
                 }
             }
-            uint32_t active = __ballot_sync(0xffffffffu, blen > 0u);
-            while (active) {
-                const int src = __ffs(active) - 1;
-                active &= active - 1u;
-                const uint32_t bs = __shfl_sync(0xffffffffu, bstart, src);
-                const uint32_t bl = __shfl_sync(0xffffffffu, blen, src);
-                const uint32_t md = __shfl_sync(0xffffffffu, mid, src);
-                for (uint32_t e = lane; e < bl; e += 32u) {
-                    const uint32_t ent = __ldg(ix.idx_entries + bs + e);
+            uint32_t incl = blen;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += y; }
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            const uint32_t packed_owner = (bstart - (incl - blen));       // entry index = packed_owner(owner) + flat index
+            for (uint32_t f0 = 0; f0 < total; f0 += 32u) {
+                const uint32_t f = f0 + lane;
+                // owner = first lane whose inclusive prefix exceeds f
+                uint32_t lo = 0;
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1) {
+                    const uint32_t probe = __shfl_sync(0xffffffffu, incl, (int)(lo + step - 1u));
+                    if (probe <= f) lo += (uint32_t)step;
+                }
+                const uint32_t own = lo < 32u ? lo : 31u;
+                const uint32_t ebase = __shfl_sync(0xffffffffu, packed_owner, (int)own);
+                const uint32_t md = __shfl_sync(0xffffffffu, mid, (int)own);
+                if (f < total) {
+                    const uint32_t ent = __ldg(ix.idx_entries + (uint32_t)(ebase + f));   // 32-bit wrap-around sum
                     const uint32_t a = ent >> 2;
                     if ((ent & 3u) != md) atomicAdd(&acc[a >> 1], 1u << (16u * (a & 1u)));
                     const uint32_t w = a >> 5;

@@ -251,3 +251,47 @@ def test_errors_are_loud(ctx):
         ctx.align_pairs(rb, ro, [0], [5], [0])  # ASV index out of range
     with pytest.raises(_lib.SavontB200Error):
         ctx.map_reads(rb, None, ro, class_cap=None, n_samples=0)
+
+
+def test_map_reads_edge_cases(ctx):
+    """empty batch, only-too-short reads, no qualities, out-of-range sample ids"""
+    from savont_b200 import _lib
+    w = _make_workload("ont16s", n_roots=3)
+    gp, op = _params(_lib, band=w.band)
+    ctx.set_params(gp); ctx.load_snpmers(w.snpmers); ctx.load_asvs(w.asv_bases, w.asv_offsets)
+    orc = O.Oracle(op, w.snpmers); orc.load_asvs(w.asv_bases, w.asv_offsets)
+    # empty
+    e = ctx.map_reads(np.zeros(0, np.uint8), None, np.zeros(1, np.uint64))
+    assert len(e["status"]) == 0 and e["totals"].tolist() == [0, 0] and e["class_offsets"].tolist() == [0]
+    # only too-short reads
+    sb, so = O.concat([b"ACGT", b"", b"ACGTACGTACGTACGT"])
+    t = ctx.map_reads(sb, None, so)
+    assert t["status"].tolist() == [4, 4, 4] and t["totals"].tolist() == [0, 0]
+    # no qualities at all (FASTA reads): every SNPmer passes the gate (mid-base Q = 60)
+    r = w.reads(800)
+    assert_same(ctx.map_reads(r["bases"], None, r["offsets"]), orc.map_reads(r["bases"], None, r["offsets"]), MAP_KEYS, "no quals")
+    # file_idx beyond n_samples: counted in the per-ASV counters, not in the per-sample matrix
+    fidx = np.arange(800, dtype=np.uint32) % 5
+    got = ctx.map_reads(r["bases"], r["quals"], r["offsets"], file_idx=fidx, n_samples=3)
+    want = orc.map_reads(r["bases"], r["quals"], r["offsets"], file_idx=fidx, n_samples=3)
+    assert_same(got, want, MAP_KEYS, "sample ids out of range")
+    assert int(got["sample_singleton"].sum()) < int(got["unambig"].sum())
+    # lower-case and IUPAC bases follow BYTE_TO_SEQ
+    lb = r["bases"].copy(); lb[::7] |= 0x20; lb[5::501] = ord("R")
+    assert_same(ctx.map_reads(lb, r["quals"], r["offsets"]), orc.map_reads(lb, r["quals"], r["offsets"]), MAP_KEYS, "lower case / IUPAC")
+
+
+def test_many_candidates_trigger_pool_regrowth(ctx):
+    """near-identical ASVs: many kept candidates per read -> the pair pool overflows its first sizing and the batch is re-run"""
+    from savont_b200 import _lib
+    w = _make_workload("ont16s", n_roots=2, n_var=40, sites_per_genus=2)
+    r = w.reads(1500)
+    gp, op = _params(_lib, band=w.band)
+    ctx.set_params(gp); ctx.load_snpmers(w.snpmers); ctx.load_asvs(w.asv_bases, w.asv_offsets)
+    orc = O.Oracle(op, w.snpmers); orc.load_asvs(w.asv_bases, w.asv_offsets)
+    want = orc.map_reads(r["bases"], r["quals"], r["offsets"])
+    got = ctx.map_reads(r["bases"], r["quals"], r["offsets"], class_cap=64 * 1500)
+    assert_same(got, want, MAP_KEYS, "pool regrowth")
+    assert got["stats"]["n_pairs"] > 2 * 1500 + 1024          # more pairs than the first pool sizing
+    assert_same(ctx.find_candidates(r["bases"], r["quals"], r["offsets"], cap=64 * 1500),
+                orc.find_candidates(r["bases"], r["quals"], r["offsets"]), CAND_KEYS, "candidates with regrowth")
