@@ -42,6 +42,10 @@ typedef struct savont_b200_params {
     int32_t min_bq;             /* --minimum-base-quality; default 25 */
     int32_t band;               /* half band B of the DP: cells |i-j| <= B; default 64 */
     int32_t strand_mode;        /* 0: strand by minimizer seed vote; 1: align both strands, keep min NM */
+    int32_t candidate_mode;     /* 0: SNPmer-index candidates (refine_asv_depths_with_em, src/alignment.rs:1786-1843);
+                                   1: low-polymorphism mode (refine_asv_depths_with_minimap2, src/alignment.rs:1527-1719):
+                                      every ASV sharing minimizers with the read is a candidate, no SNPmer index */
+    int32_t reserved;
     double  ratio_thresh;       /* 0.0050  (src/alignment.rs:1829) */
     double  min_mini_frac_base; /* 0.950, raised to the k-th power (src/alignment.rs:1806) */
 } savont_b200_params;

@@ -20,13 +20,13 @@ STATUS_ASSIGNED, STATUS_NO_CANDIDATE, STATUS_RATIO_FILTERED, STATUS_NO_ALIGNMENT
 class Params(C.Structure):
     _fields_ = [
         ("k", C.c_int32), ("c", C.c_int32), ("l", C.c_int32), ("min_bq", C.c_int32),
-        ("band", C.c_int32), ("strand_mode", C.c_int32),
+        ("band", C.c_int32), ("strand_mode", C.c_int32), ("candidate_mode", C.c_int32), ("reserved", C.c_int32),
         ("ratio_thresh", C.c_double), ("min_mini_frac_base", C.c_double),
     ]
 
 
 def default_params(**kw) -> Params:
-    p = Params(17, 11, 3, 25, 64, 0, 0.005, 0.95)
+    p = Params(17, 11, 3, 25, 64, 0, 0, 0, 0.005, 0.95)
     for k, v in kw.items():
         setattr(p, k, v)
     return p

@@ -456,6 +456,15 @@ static int candidates_one(const so_ctx *c, const sketch_t *rd, uint32_t *hits, u
 
     const double min_frac = so_powi(c->p.min_mini_frac_base, k);          /* (0.950f64).powi(k) :1806 */
     cand_vec scores = {0, 0, 0};
+    if (c->p.candidate_mode == 1) {
+        /* low-polymorphism mode (refine_asv_depths_with_minimap2, src/alignment.rs:1527-1719): no SNPmer index;
+         * the reference maps the read against ALL ASVs with minimap2 and keeps hits with mapq > 0.  North-star
+         * restatement: every ASV sharing minimizers with the read and passing the same containment test is a
+         * candidate with 0 SNPmer mismatches (the mapq filter has no counterpart here). */
+        for (size_t ti = 0; ti < n_touched; ti++) { hits[touched[ti]] = 0; mism[touched[ti]] = 0; }
+        n_touched = 0;
+        for (uint32_t a = 0; a < (uint32_t)c->n_asv; a++) touched[n_touched++] = a;
+    }
     for (size_t ti = 0; ti < n_touched; ti++) {                            /* :1796-1814 */
         uint32_t a = touched[ti];
         const asv_t *A = &c->asvs[a];

@@ -39,6 +39,9 @@ typedef struct so_params {
     int32_t min_bq;       /* src/cli.rs:99-100   default 25 */
     int32_t band;         /* DP half band B (|i-j| <= B) */
     int32_t strand_mode;  /* 0 = orientation by minimizer seed vote, 1 = both strands, min NM */
+    int32_t candidate_mode; /* 0 = SNPmer index candidates (src/alignment.rs:1786-1843);
+                               1 = low-polymorphism mode: every ASV sharing minimizers (src/alignment.rs:1527-1719) */
+    int32_t reserved;
     double  ratio_thresh;        /* src/alignment.rs:1829 0.0050 */
     double  min_mini_frac_base;  /* src/alignment.rs:1806 0.950 (raised to k) */
 } so_params;

@@ -23,7 +23,7 @@ OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_OVERFLOW, ERR_NOMEM = 0, -1, -2, -3
 class Params(C.Structure):
     _fields_ = [
         ("k", C.c_int32), ("c", C.c_int32), ("l", C.c_int32), ("min_bq", C.c_int32),
-        ("band", C.c_int32), ("strand_mode", C.c_int32),
+        ("band", C.c_int32), ("strand_mode", C.c_int32), ("candidate_mode", C.c_int32), ("reserved", C.c_int32),
         ("ratio_thresh", C.c_double), ("min_mini_frac_base", C.c_double),
     ]
 

@@ -56,10 +56,11 @@ class Cli:
     minimum_base_quality: int = 25
     band: int = 64
     strand_mode: int = 0
+    low_polymorphism: bool = False     # src/alignment.rs:1730: refine_asv_depths_with_minimap2 instead of the SNPmer index
 
     def params(self) -> _lib.Params:
         return _lib.default_params(k=self.kmer_size, c=self.c, l=self.blockmer_length, min_bq=self.minimum_base_quality,
-                                   band=self.band, strand_mode=self.strand_mode)
+                                   band=self.band, strand_mode=self.strand_mode, candidate_mode=1 if self.low_polymorphism else 0)
 
 
 @dataclass

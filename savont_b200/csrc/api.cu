@@ -126,7 +126,8 @@ struct Context {
     std::vector<uint8_t> asv_bases_h; std::vector<uint64_t> asv_offsets_h;
     size_t n_asv = 0; bool index_dirty = true; uint32_t max_asv_len = 0;
     DevBuf d_idx_keys, d_idx_vals, d_idx_entries, d_mset, d_mset_off, d_asv_planes, d_asv_plane_off, d_asv_len;
-    uint32_t idx_mask = 0, idx_shift = 0;
+    DevBuf d_mx_keys, d_mx_vals, d_mx_entries;
+    uint32_t idx_mask = 0, idx_shift = 0, mx_mask = 0, mx_shift = 0;
     std::vector<uint32_t> asv_len_h;
 
     // counters [unambig A | ambig A | leq10 A | assigned | filtered | singleton S*A]
@@ -155,6 +156,7 @@ static int validate_params(const savont_b200_params &p) {
         return fail(SAVONT_B200_ERR_INVALID, "band=%d unsupported (0..%d)", p.band, align_supported_band_max());
     if (p.min_bq < 0 || p.min_bq > 93) return fail(SAVONT_B200_ERR_INVALID, "min_bq=%d out of range", p.min_bq);
     if (p.strand_mode != 0 && p.strand_mode != 1) return fail(SAVONT_B200_ERR_INVALID, "strand_mode must be 0 or 1");
+    if (p.candidate_mode != 0 && p.candidate_mode != 1) return fail(SAVONT_B200_ERR_INVALID, "candidate_mode must be 0 or 1");
     if (!(p.ratio_thresh >= 0.0) || !(p.min_mini_frac_base > 0.0)) return fail(SAVONT_B200_ERR_INVALID, "bad thresholds");
     return 0;
 }
@@ -175,7 +177,7 @@ static double powi_rt(double a, int b) {
 static DeviceParams make_device_params(const savont_b200_params &p) {
     DeviceParams d{};
     d.k = p.k; d.c = p.c; d.s = p.k - p.c + 1;
-    d.min_bq = p.min_bq; d.band = p.band; d.strand_mode = p.strand_mode;
+    d.min_bq = p.min_bq; d.band = p.band; d.strand_mode = p.strand_mode; d.candidate_mode = p.candidate_mode;
     d.asv_padl = p.band + 32;      // window of DP column j starts at padded bit 32 + (j-1), see align.cu
     d.mini_spacing = (p.c - 1) / 2 + 1;
     d.split_mask = ~(3ull << (p.k - 1));
@@ -390,6 +392,8 @@ static AsvIndex index_view(const Context *c) {
     ix.idx_keys = c->idx_mask ? c->d_idx_keys.as<uint64_t>() : nullptr;
     ix.idx_vals = c->d_idx_vals.as<uint2>(); ix.idx_mask = c->idx_mask; ix.idx_shift = c->idx_shift; ix.idx_entries = c->d_idx_entries.as<uint32_t>();
     ix.mset = c->d_mset.as<uint64_t>(); ix.mset_off = c->d_mset_off.as<uint32_t>();
+    ix.mx_keys = c->mx_mask ? c->d_mx_keys.as<uint64_t>() : nullptr; ix.mx_vals = c->d_mx_vals.as<uint2>();
+    ix.mx_mask = c->mx_mask; ix.mx_shift = c->mx_shift; ix.mx_entries = c->d_mx_entries.as<uint32_t>();
     ix.planes = c->d_asv_planes.as<uint2>(); ix.plane_off = c->d_asv_plane_off.as<uint32_t>(); ix.len = c->d_asv_len.as<uint32_t>();
     ix.n_asv = (uint32_t)c->n_asv;
     return ix;
@@ -519,6 +523,35 @@ static int build_asv_index(Context *c) {
             else mset.push_back(key | (f ? kFwdBit : 0));
         }
         mset_off[a + 1] = (uint32_t)mset.size();
+    }
+    // (1b) minimizer inverted index for the low-polymorphism mode: k-mer -> (asv << 1 | forward-any flag)
+    {
+        struct ME { uint64_t key; uint32_t ent; };
+        std::vector<ME> me; me.reserve(mset.size());
+        for (size_t a = 0; a < A; ++a)
+            for (uint32_t t = mset_off[a]; t < mset_off[a + 1]; ++t)
+                me.push_back({mset[t] & ~kFwdBit, (uint32_t)(a << 1) | (uint32_t)(mset[t] >> 63)});
+        std::sort(me.begin(), me.end(), [](const ME &x, const ME &y) { return x.key != y.key ? x.key < y.key : x.ent < y.ent; });
+        size_t nk = 0;
+        for (size_t i = 0; i < me.size(); ++i) if (i == 0 || me[i].key != me[i - 1].key) ++nk;
+        const uint32_t mcap = nk ? next_pow2_u32(4 * nk + 2) : 0;
+        const uint32_t mshift = mcap ? shift_for_cap(mcap) : 0;
+        std::vector<uint64_t> mkeys(mcap ? mcap : 1, kEmpty64);
+        std::vector<uint2> mvals(mcap ? mcap : 1, make_uint2(0, 0));
+        std::vector<uint32_t> ments(me.size() + 1);
+        for (size_t i = 0; i < me.size();) {
+            size_t j = i;
+            while (j < me.size() && me[j].key == me[i].key) { ments[j] = me[j].ent; ++j; }
+            uint32_t slot = hash_slot(me[i].key, mshift);
+            while (mkeys[slot] != kEmpty64) slot = (slot + 1) & (mcap - 1);
+            mkeys[slot] = me[i].key; mvals[slot] = make_uint2((uint32_t)i, (uint32_t)(j - i));
+            i = j;
+        }
+        c->mx_mask = mcap ? mcap - 1 : 0; c->mx_shift = mshift;
+        TRY(c->d_mx_keys.ensure(mkeys.size() * 8)); TRY(c->d_mx_vals.ensure(mvals.size() * 8)); TRY(c->d_mx_entries.ensure(ments.size() * 4));
+        CK(cudaMemcpy(c->d_mx_keys.p, mkeys.data(), mkeys.size() * 8, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->d_mx_vals.p, mvals.data(), mvals.size() * 8, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->d_mx_entries.p, ments.data(), ments.size() * 4, cudaMemcpyHostToDevice));
     }
     // (2) SNPmer inverted index from asv.snpmers_vec(): k-mers re-extracted from positions with
     //     kmer_from_position's canonical rule (tie -> forward), src/types.rs:622-663
@@ -688,7 +721,7 @@ const char *savont_b200_last_error(void) { return g_last_error.c_str(); }
 
 void savont_b200_default_params(savont_b200_params *p) {
     if (!p) return;
-    p->k = 17; p->c = 11; p->l = 3; p->min_bq = 25; p->band = 64; p->strand_mode = 0;
+    p->k = 17; p->c = 11; p->l = 3; p->min_bq = 25; p->band = 64; p->strand_mode = 0; p->candidate_mode = 0; p->reserved = 0;
     p->ratio_thresh = 0.0050; p->min_mini_frac_base = 0.950;
 }
 
@@ -728,7 +761,7 @@ int savont_b200_destroy(savont_b200_ctx *h) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     c->work.release(); c->work2.release(); c->resident.release(); c->asvb.release();
-    DevBuf *bufs[] = {&c->d_rank_table, &c->d_snp_keys, &c->d_snp_bloom, &c->d_phred, &c->d_idx_keys, &c->d_idx_vals, &c->d_idx_entries, &c->d_mset,
+    DevBuf *bufs[] = {&c->d_rank_table, &c->d_snp_keys, &c->d_snp_bloom, &c->d_phred, &c->d_mx_keys, &c->d_mx_vals, &c->d_mx_entries, &c->d_idx_keys, &c->d_idx_vals, &c->d_idx_entries, &c->d_mset,
                       &c->d_mset_off, &c->d_asv_planes, &c->d_asv_plane_off, &c->d_asv_len, &c->d_counters};
     for (DevBuf *b : bufs) b->release();
     c->pin_small.release(); c->pin_out.release();

@@ -29,7 +29,7 @@ enum : uint32_t {
 
 struct DeviceParams {
     int k, c, s;            // s = k - c + 1
-    int min_bq, band, strand_mode;
+    int min_bq, band, strand_mode, candidate_mode;
     int asv_padl;           // left padding (bits) of the ASV DP planes
     int mini_spacing;       // minimum distance between two open syncmers = (c-1)/2 + 1
     uint64_t split_mask;    // ~(3 << (k-1))
@@ -111,6 +111,11 @@ struct AsvIndex {
     // distinct minimizer sets per ASV (sorted; bit 63 = forward-any flag)
     const uint64_t *mset;
     const uint32_t *mset_off;    // [A+1]
+    // minimizer inverted index (candidate_mode 1): k-mer -> bucket of (asv << 1 | forward-any flag)
+    const uint64_t *mx_keys;
+    const uint2 *mx_vals;        // (start, len)
+    uint32_t mx_mask, mx_shift;
+    const uint32_t *mx_entries;
     // DP planes (left-padded by asv_padl zero bits)
     const uint2 *planes;
     const uint32_t *plane_off;   // [A] word offsets

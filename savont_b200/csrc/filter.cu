@@ -24,12 +24,17 @@ struct FilterSmem {
     uint32_t acc_words; // ceil(A/2)
     uint32_t bm_words;  // ceil(A/32)
     uint32_t sum_words; // ceil(bm_words/32)
+    uint32_t same_words; // low-polymorphism mode: ceil(A/2) same-orientation counters, else 0
     __host__ __device__ size_t per_warp() const {
-        size_t b = (size_t)rcap * 8u + ((size_t)acc_words + 2u * bm_words + sum_words) * 4u;
+        size_t b = (size_t)rcap * 8u + ((size_t)acc_words + 2u * bm_words + sum_words + same_words) * 4u;
         return (b + 15u) & ~(size_t)15u;
     }
 };
 
+// LOWPOLY = candidate_mode 1 (refine_asv_depths_with_minimap2, reference src/alignment.rs:1527-1719): no SNPmer index;
+// the read's distinct minimizers probe the minimizer inverted index, `acc` counts the shared minimizers per ASV and
+// `same` those with equal orientation flags; every ASV passing the containment test is kept (0 SNPmer mismatches).
+template <bool LOWPOLY>
 __global__ void __launch_bounds__(kFilterWarps * 32)
 filter_kernel(SeqBatch in, SketchOut sk, AsvIndex ix, PairPool pool, FilterOut out, DeviceParams p, FilterSmem lay) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -41,9 +46,10 @@ filter_kernel(SeqBatch in, SketchOut sk, AsvIndex ix, PairPool pool, FilterOut o
     uint32_t *bm1 = acc + lay.acc_words;
     uint32_t *bm2 = bm1 + lay.bm_words;
     uint32_t *sum1 = bm2 + lay.bm_words;
+    uint32_t *same = sum1 + lay.sum_words;
     const uint32_t rmask = lay.rcap - 1u;
     const uint32_t rshift = 64u - (uint32_t)__popc(rmask);
-    const uint32_t clear_words = lay.acc_words + 2u * lay.bm_words + lay.sum_words;
+    const uint32_t clear_words = lay.acc_words + 2u * lay.bm_words + lay.sum_words + lay.same_words;
     const int mid_shift = p.k - 1;
     if (*out.err & kErrSnpPool) return;          // the sketch ran out of pool space: the host grows it and re-runs the batch
 
@@ -92,6 +98,79 @@ filter_kernel(SeqBatch in, SketchOut sk, AsvIndex ix, PairPool pool, FilterOut o
         }
         __syncwarp();
 
+        uint32_t lowest = 0xffffffffu, n_low = 0;
+        bool any_scored = false;
+        if (LOWPOLY) {
+            // ---- 2'. every distinct read minimizer probes the minimizer inverted index (flattened bucket walk) ----
+            for (uint32_t s0 = 0; s0 < lay.rcap; s0 += 32u) {
+                const unsigned long long rv = rset[s0 + lane];
+                uint32_t bstart = 0, blen = 0, rf = 0;
+                if (rv != kEmpty64 && ix.mx_keys != nullptr) {
+                    const uint64_t key = rv & ~kFwdBit;
+                    rf = (uint32_t)(rv >> 63);
+                    uint32_t slot = hash_slot(key, ix.mx_shift);
+                    while (true) {
+                        const uint64_t kk = __ldg(ix.mx_keys + slot);
+                        if (kk == key) { const uint2 v = __ldg(ix.mx_vals + slot); bstart = v.x; blen = v.y; break; }
+                        if (kk == kEmpty64) break;
+                        slot = (slot + 1u) & ix.mx_mask;
+                    }
+                }
+                uint32_t incl = blen;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += y; }
+                const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+                const uint32_t packed_owner = (bstart - (incl - blen));
+                for (uint32_t f0 = 0; f0 < total; f0 += 32u) {
+                    const uint32_t f = f0 + lane;
+                    uint32_t lo = 0;
+#pragma unroll
+                    for (int step = 16; step > 0; step >>= 1) {
+                        const uint32_t probe = __shfl_sync(0xffffffffu, incl, (int)(lo + step - 1u));
+                        if (probe <= f) lo += (uint32_t)step;
+                    }
+                    const uint32_t own = lo < 32u ? lo : 31u;
+                    const uint32_t ebase = __shfl_sync(0xffffffffu, packed_owner, (int)own);
+                    const uint32_t of = __shfl_sync(0xffffffffu, rf, (int)own);
+                    if (f < total) {
+                        const uint32_t ent = __ldg(ix.mx_entries + (uint32_t)(ebase + f));
+                        const uint32_t a = ent >> 1;
+                        atomicAdd(&acc[a >> 1], 1u << (16u * (a & 1u)));
+                        if ((ent & 1u) == of) atomicAdd(&same[a >> 1], 1u << (16u * (a & 1u)));
+                        const uint32_t w = a >> 5;
+                        const uint32_t old = atomicOr(&bm1[w], 1u << (a & 31u));
+                        if (old == 0u) atomicOr(&sum1[w >> 5], 1u << (w & 31u));
+                    }
+                }
+            }
+            __syncwarp();
+            // ---- 3'. containment test per candidate, ascending ASV order; all survivors are kept ----
+            for (uint32_t w = lane; w < lay.bm_words; w += 32u) {
+                uint32_t bits = bm1[w], keep = 0;
+                while (bits) {
+                    const uint32_t bit = (uint32_t)(__ffs(bits) - 1);
+                    bits &= bits - 1u;
+                    const uint32_t a = w * 32u + bit;
+                    const uint32_t sh = 16u * (a & 1u);
+                    const uint32_t m = (acc[a >> 1] >> sh) & 0xffffu;
+                    const uint32_t sm = (same[a >> 1] >> sh) & 0xffffu;
+                    const uint32_t nA = __ldg(ix.mset_off + a + 1) - __ldg(ix.mset_off + a);
+                    const uint32_t mn = nR < nA ? nR : nA;
+                    if (m == 0u || (double)m / (double)mn < p.min_frac) continue;      // src/alignment.rs:1801-1808 analogue
+                    keep |= 1u << bit;
+                    const uint32_t stash = (m & 0x7fffu) | (((m - sm) > sm) ? 0x8000u : 0u);
+                    atomicAnd(&acc[a >> 1], ~(0xffffu << sh));
+                    atomicOr(&acc[a >> 1], stash << sh);
+                }
+                bm2[w] = keep;
+                n_low += __popc(keep);
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) n_low += __shfl_xor_sync(0xffffffffu, n_low, d);
+            any_scored = n_low > 0u;
+            lowest = 0u;
+            __syncwarp();
+        } else {
         // ---- 2. SNPmer buckets -> per-ASV mismatch counters + candidate bitmap ----
         // 32 SNPmers per round: every lane probes the splitmer table for its SNPmer, then the (SNPmer, bucket
         // entry) pairs of the round are FLATTENED over the lanes (prefix sum of the bucket lengths + a 5-step
@@ -146,8 +225,6 @@ filter_kernel(SeqBatch in, SketchOut sk, AsvIndex ix, PairPool pool, FilterOut o
         // tests are kept (src/alignment.rs:1829-1843), so the groups are visited in ascending
         // mismatch order and the walk stops at the first group with a passing candidate; every
         // group is visited (and any_scored is exact) only when nothing passes.
-        uint32_t lowest = 0xffffffffu, n_low = 0;
-        bool any_scored = false;
         uint32_t cur = 0;
         while (true) {
             // smallest mismatch count >= cur over all candidates (lanes stride over bitmap words)
@@ -224,6 +301,8 @@ filter_kernel(SeqBatch in, SketchOut sk, AsvIndex ix, PairPool pool, FilterOut o
         }
         __syncwarp();
 
+        }
+
         // ---- 4. emit the kept candidates ----
         uint8_t status = 0;
         uint32_t total = 0, start = 0;
@@ -291,15 +370,19 @@ void launch_filter(const SeqBatch &in, const SketchOut &sk, const AsvIndex &ix, 
     lay.bm_words = (ix.n_asv + 31u) / 32u;
     if (lay.bm_words == 0u) lay.bm_words = 1u;
     lay.sum_words = (lay.bm_words + 31u) / 32u;
+    const bool lowpoly = p.candidate_mode == 1;
+    lay.same_words = lowpoly ? lay.acc_words : 0u;
     const size_t smem = lay.per_warp() * kFilterWarps;
-    cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (lowpoly) cudaFuncSetAttribute(filter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    else cudaFuncSetAttribute(filter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int ctas_per_sm = (int)(220u * 1024u / (smem + 1024u));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
     if (ctas_per_sm > 12) ctas_per_sm = 12;
     uint32_t grid = (uint32_t)(sm_count * ctas_per_sm);
     const uint32_t need = (in.n + kFilterWarps - 1) / kFilterWarps;
     if (grid > need) grid = need;
-    filter_kernel<<<grid, kFilterWarps * 32, smem, st>>>(in, sk, ix, pool, out, p, lay);
+    if (lowpoly) filter_kernel<true><<<grid, kFilterWarps * 32, smem, st>>>(in, sk, ix, pool, out, p, lay);
+    else filter_kernel<false><<<grid, kFilterWarps * 32, smem, st>>>(in, sk, ix, pool, out, p, lay);
 }
 
 }  // namespace sb

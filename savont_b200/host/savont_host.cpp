@@ -18,13 +18,11 @@ namespace savont_host {
 static void ck(int rc, const char *what) { if (rc != 0) die(what); }
 
 Mapper::Mapper(int device, const Cli &args, const KmerGlobalInfo &kmer_info) {
-    if (args.low_polymorphism)
-        throw std::runtime_error("low-polymorphism mode (refine_asv_depths_with_minimap2, src/alignment.rs:1527) is not part of this path");
     ck(savont_b200_create(device, &ctx_), "savont_b200_create");
     savont_b200_params p;
     savont_b200_default_params(&p);
     p.k = args.kmer_size; p.c = args.c; p.l = args.blockmer_length; p.min_bq = args.minimum_base_quality;
-    p.band = args.band; p.strand_mode = args.strand_mode;
+    p.band = args.band; p.strand_mode = args.strand_mode; p.candidate_mode = args.low_polymorphism ? 1 : 0;
     ck(savont_b200_set_params(ctx_, &p), "savont_b200_set_params");
     ck(savont_b200_load_snpmers(ctx_, kmer_info.snpmers.data(), kmer_info.snpmers.size()), "savont_b200_load_snpmers");
 }
@@ -230,7 +228,7 @@ long long savont_host_refine(int device, const savont_b200_params *p, const uint
     try {
         savont_host::Cli args;
         args.kmer_size = p->k; args.c = p->c; args.blockmer_length = p->l; args.minimum_base_quality = p->min_bq;
-        args.band = p->band; args.strand_mode = p->strand_mode;
+        args.band = p->band; args.strand_mode = p->strand_mode; args.low_polymorphism = p->candidate_mode == 1;
         savont_host::KmerGlobalInfo ki; ki.snpmers.assign(snpmers, snpmers + n_snpmers);
         std::vector<savont_host::ConsensusSequence> cons(n_asv);
         for (size_t a = 0; a < n_asv; ++a) { cons[a].sequence.assign(asv_bases + asv_offsets[a], asv_bases + asv_offsets[a + 1]); cons[a].id = a; cons[a].depth = 1; }
@@ -252,7 +250,7 @@ int savont_host_per_sample(int device, const savont_b200_params *p, const uint64
     try {
         savont_host::Cli args;
         args.kmer_size = p->k; args.c = p->c; args.blockmer_length = p->l; args.minimum_base_quality = p->min_bq;
-        args.band = p->band; args.strand_mode = p->strand_mode;
+        args.band = p->band; args.strand_mode = p->strand_mode; args.low_polymorphism = p->candidate_mode == 1;
         savont_host::KmerGlobalInfo ki; ki.snpmers.assign(snpmers, snpmers + n_snpmers);
         std::vector<savont_host::ConsensusSequence> cons(n_asv);
         for (size_t a = 0; a < n_asv; ++a) { cons[a].sequence.assign(asv_bases + asv_offsets[a], asv_bases + asv_offsets[a + 1]); cons[a].id = a; }

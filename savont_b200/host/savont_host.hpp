@@ -23,7 +23,7 @@ struct Cli {
     int minimum_base_quality = 25; // src/cli.rs:99-100
     int band = 64;                 // b200: DP half band
     int strand_mode = 0;
-    bool low_polymorphism = false; // src/alignment.rs:1730 -- not implemented by this path (throws)
+    bool low_polymorphism = false; // src/alignment.rs:1730 -> candidate_mode 1 (every ASV sharing minimizers is a candidate)
 };
 
 // KmerGlobalInfo reduced to what the path uses: both alleles of every SNPmer, i.e. the u64 values of

@@ -295,3 +295,26 @@ def test_many_candidates_trigger_pool_regrowth(ctx):
     assert got["stats"]["n_pairs"] > 2 * 1500 + 1024          # more pairs than the first pool sizing
     assert_same(ctx.find_candidates(r["bases"], r["quals"], r["offsets"], cap=64 * 1500),
                 orc.find_candidates(r["bases"], r["quals"], r["offsets"]), CAND_KEYS, "candidates with regrowth")
+
+
+@pytest.mark.parametrize("with_snpmers", [True, False])
+def test_low_polymorphism_mode(ctx, with_snpmers):
+    """candidate_mode = 1 (refine_asv_depths_with_minimap2 analogue): all ASVs sharing minimizers are candidates;
+    works without any SNPmer (the case that auto-enables the mode in the reference, src/main.rs:543)"""
+    from savont_b200 import _lib
+    w = _make_workload("ont16s", n_roots=6, sites_per_genus=5)
+    r = w.reads(2500)
+    snp = w.snpmers if with_snpmers else np.zeros(0, np.uint64)
+    gp, op = _params(_lib, band=w.band, candidate_mode=1)
+    ctx.set_params(gp); ctx.load_snpmers(snp); ctx.load_asvs(w.asv_bases, w.asv_offsets)
+    orc = O.Oracle(op, snp); orc.load_asvs(w.asv_bases, w.asv_offsets)
+    assert_same(ctx.find_candidates(r["bases"], r["quals"], r["offsets"], cap=w.n_asv * 2500),
+                orc.find_candidates(r["bases"], r["quals"], r["offsets"]), CAND_KEYS, "low-poly candidates")
+    want = orc.map_reads(r["bases"], r["quals"], r["offsets"])
+    got = ctx.map_reads(r["bases"], r["quals"], r["offsets"], class_cap=w.n_asv * 2500)
+    assert_same(got, want, MAP_KEYS, "low-poly map_reads")
+    assert int(want["totals"][0]) == 2500                      # every read finds its genus by minimizers alone
+    co = want["class_offsets"].astype(np.int64)
+    hit = [r["truth_asv"][i] in want["class_asv"][co[i]:co[i + 1]] for i in range(2500)]
+    assert np.mean(hit) > 0.97
+    ctx.set_params(_lib.default_params())

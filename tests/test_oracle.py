@@ -196,3 +196,21 @@ def test_em_simple():
     assert abs(ab.sum() - 1.0) < 1e-9 and it > 1
     ab, depths, it = O.em(3, [0, 1, 2, 3], [0, 1, 2], [5, 3, 2], 10)
     assert depths.tolist() == [5, 3, 2]
+
+
+def test_low_polymorphism_mode_needs_no_snpmers():
+    """candidate_mode = 1: with an empty SNPmer set the default mode assigns nothing, the low-polymorphism mode
+    (src/alignment.rs:1527-1719 analogue) assigns every read to its genus by minimizers + NM"""
+    from savont_b200 import synth
+    w = synth.Workload("ont16s", n_roots=3, sites_per_genus=5)
+    r = w.reads(120)
+    for mode, expect_all in ((0, False), (1, True)):
+        orc = O.Oracle(O.default_params(band=w.band, candidate_mode=mode), [])
+        orc.load_asvs(w.asv_bases, w.asv_offsets)
+        res = orc.map_reads(r["bases"], r["quals"], r["offsets"])
+        if expect_all:
+            assert int(res["totals"][0]) == 120
+            co = res["class_offsets"].astype(int)
+            assert all(r["truth_asv"][i] // 10 == res["class_asv"][co[i]] // 10 for i in range(120))   # right genus
+        else:
+            assert int(res["totals"][0]) == 0 and np.all(res["status"] == O.STATUS_NO_CANDIDATE)
