@@ -147,6 +147,27 @@ int savont_b200_map_reads(savont_b200_ctx *ctx, const uint8_t *bases, const uint
                           uint64_t *unambig, uint64_t *ambig, uint64_t *leq10, uint64_t *totals,
                           uint64_t *sample_singleton, savont_b200_stats *stats);
 
+/* The same closure with the reads in the form the reference hands them to Stage 7 / 7b: `&[TwinRead]`
+ * (refine_asv_depths_with_em, src/alignment.rs:1723-1729; compute_per_sample_depths, :2044-2051).  Per read the
+ * shim passes three TwinRead fields (src/types.rs:386-412) without re-encoding them:
+ *   dna_seq       bio-seq Seq<Dna> raw words, 2 bits per base, base i in bits 2(i%32).. of word i/32 (first base in
+ *                 the LOW bits; A=0 C=1 G=2 T=3, src/types.rs:575-579), each read starting at a word boundary:
+ *                 words [dna_word_offsets[r], dna_word_offsets[r+1]) hold the lengths[r] bases of read r
+ *   snpmer_kmers  the quality-gated, de-duplicated SNPmers of the read (src/alignment.rs:1787, :1791), either as the
+ *                 Vec<Kmer48> bytes themselves (snpmer_kmer_bytes = 6, little endian, src/types.rs:104-134) or
+ *                 widened to u64 (snpmer_kmer_bytes = 8); read r owns [snpmer_offsets[r], snpmer_offsets[r+1])
+ *   file_idx      sample index (NULL: one sample)
+ * The read's minimizer k-mers are NOT passed: they are a pure function of dna_seq (get_twin_read_syncmer,
+ * src/seeding.rs:526-543) and are recomputed on the GPU together with their strand flags; qualities are not needed
+ * because they only gate SNPmers (src/seeding.rs:510-521), which arrive already gated.  Outputs as map_reads. */
+int savont_b200_map_twin_reads(savont_b200_ctx *ctx, const uint64_t *dna_words, const uint64_t *dna_word_offsets,
+                               const uint32_t *lengths, const void *snpmer_kmers, int snpmer_kmer_bytes,
+                               const uint64_t *snpmer_offsets, const uint32_t *file_idx, size_t n_reads, int n_samples,
+                               uint8_t *status, int32_t *best_nm, uint64_t *class_offsets, uint32_t *class_asv,
+                               size_t class_cap,
+                               uint64_t *unambig, uint64_t *ambig, uint64_t *leq10, uint64_t *totals,
+                               uint64_t *sample_singleton, savont_b200_stats *stats);
+
 /* Device-resident variant used for kernel-only measurement and by the multi-GPU host layer:
  * upload once, then map repeatedly without host<->device traffic of the inputs.
  * map_resident leaves the counters in the context's device counter vector
@@ -156,6 +177,9 @@ int savont_b200_map_reads(savont_b200_ctx *ctx, const uint8_t *bases, const uint
  * savont_b200_fetch_resident. */
 int savont_b200_upload_reads(savont_b200_ctx *ctx, const uint8_t *bases, const uint8_t *quals, const uint64_t *offsets,
                              const uint32_t *file_idx, size_t n_reads, int n_samples);
+int savont_b200_upload_twin_reads(savont_b200_ctx *ctx, const uint64_t *dna_words, const uint64_t *dna_word_offsets,
+                                  const uint32_t *lengths, const void *snpmer_kmers, int snpmer_kmer_bytes,
+                                  const uint64_t *snpmer_offsets, const uint32_t *file_idx, size_t n_reads, int n_samples);
 int savont_b200_map_resident(savont_b200_ctx *ctx, int zero_counters, savont_b200_stats *stats);
 int savont_b200_fetch_resident(savont_b200_ctx *ctx, uint8_t *status, int32_t *best_nm, uint64_t *class_offsets,
                                uint32_t *class_asv, size_t class_cap);

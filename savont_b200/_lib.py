@@ -245,6 +245,46 @@ class Context:
                                             _p(B["totals"], C.c_uint64), _p(B["sample_singleton"], C.c_uint64), C.byref(st)))
         return self._finish(B, n, n_samples, st)
 
+    # ---- whole path, reads handed over as TwinRead fields (src/types.rs:386-412) ----
+    @staticmethod
+    def _twin_args(twin):
+        w = np.ascontiguousarray(twin["dna_words"], dtype=np.uint64)
+        wo = np.ascontiguousarray(twin["dna_word_offsets"], dtype=np.uint64)
+        ln = np.ascontiguousarray(twin["lengths"], dtype=np.uint32)
+        so = np.ascontiguousarray(twin["snpmer_offsets"], dtype=np.uint64)
+        sk = twin["snpmer_kmers"]
+        if sk.dtype == np.uint8:            # Vec<Kmer48> bytes
+            sk = np.ascontiguousarray(sk); kb = 6
+            assert len(sk) == 6 * int(so[-1])
+        else:
+            sk = np.ascontiguousarray(sk, dtype=np.uint64); kb = 8
+        fi = twin.get("file_idx")
+        fi = None if fi is None else np.ascontiguousarray(fi, dtype=np.uint32)
+        return w, wo, ln, sk, kb, so, fi
+
+    def map_twin_reads(self, twin, n_samples=1, class_cap=None):
+        """twin: dict(dna_words u64, dna_word_offsets u64[n+1], lengths u32[n], snpmer_kmers u64 | u8 (Kmer48 bytes),
+        snpmer_offsets u64[n+1], file_idx u32[n] | None) -- see savont_b200/twin.py"""
+        w, wo, ln, sk, kb, so, fi = self._twin_args(twin)
+        n = len(ln)
+        class_cap = class_cap or max(8 * n + 1024, 16)
+        B = self._out_buffers(n, n_samples, class_cap)
+        st = Stats()
+        _check(self.L.savont_b200_map_twin_reads(self.h, _p(w, C.c_uint64), _p(wo, C.c_uint64), _p(ln, C.c_uint32),
+                                                 C.c_void_p(sk.ctypes.data), C.c_int(kb), _p(so, C.c_uint64), _p(fi, C.c_uint32),
+                                                 C.c_size_t(n), C.c_int(n_samples), _p(B["status"], C.c_uint8), _p(B["best_nm"], C.c_int32),
+                                                 _p(B["class_offsets"], C.c_uint64), _p(B["class_asv"], C.c_uint32), C.c_size_t(class_cap),
+                                                 _p(B["unambig"], C.c_uint64), _p(B["ambig"], C.c_uint64), _p(B["leq10"], C.c_uint64),
+                                                 _p(B["totals"], C.c_uint64), _p(B["sample_singleton"], C.c_uint64), C.byref(st)))
+        return self._finish(B, n, n_samples, st)
+
+    def upload_twin_reads(self, twin, n_samples=1):
+        w, wo, ln, sk, kb, so, fi = self._twin_args(twin)
+        _check(self.L.savont_b200_upload_twin_reads(self.h, _p(w, C.c_uint64), _p(wo, C.c_uint64), _p(ln, C.c_uint32),
+                                                    C.c_void_p(sk.ctypes.data), C.c_int(kb), _p(so, C.c_uint64), _p(fi, C.c_uint32),
+                                                    C.c_size_t(len(ln)), C.c_int(n_samples)))
+        self._resident = (len(ln), n_samples)
+
     def _finish(self, B, n, n_samples, st):
         A = self.n_asv
         t = int(B["class_offsets"][-1])

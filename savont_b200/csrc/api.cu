@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <functional>
 #include <vector>
 
 #include "../../include/savont_b200.h"
@@ -81,7 +82,10 @@ struct PinBuf {
 // device-resident inputs, intermediates and outputs of one batch of sequences
 struct Batch {
     DevBuf bases, quals, offsets, file_idx;
+    DevBuf dna_words, word_offsets, snp_raw, snp_dummy;   // TwinRead input: Seq<Dna> words; Kmer48 staging; scratch counters
     bool has_quals = false, has_file_idx = false;
+    bool twin = false;            // sequences are TwinRead.dna_seq words and the SNPmers come from the caller
+    bool force_generic = false;   // the fast sketch kernel overflowed one of its shared-memory lists on this batch
     uint32_t n = 0, max_len = 0;
     uint64_t total_bases = 0;
     // sketch
@@ -100,7 +104,7 @@ struct Batch {
     PinBuf pin_offsets;
     void release() {
         pin_offsets.release();
-        DevBuf *all[] = {&bases, &quals, &offsets, &file_idx, &planes, &sk_status, &flatq, &mini_cnt, &mini_kmer, &mini_pos,
+        DevBuf *all[] = {&dna_words, &word_offsets, &snp_raw, &snp_dummy, &bases, &quals, &offsets, &file_idx, &planes, &sk_status, &flatq, &mini_cnt, &mini_kmer, &mini_pos,
                          &snp_start, &snp_cnt, &snp_kmer, &snp_pos, &est_id, &spill_k, &spill_p, &ctrs, &cand_status, &pair_start, &pair_cnt,
                          &low_mm, &p_read, &p_asv, &p_mini, &p_strand, &nm, &asv_end, &read_end, &rstatus, &best_nm,
                          &class_cnt, &class_slot, &class_off, &class_out, &scan_tmp};
@@ -250,7 +254,9 @@ static int upload_snp_set(Context *c) {
         uint32_t slot = hash_slot(key, shift);
         while (keys[slot] != kEmpty64 && keys[slot] != key) slot = (slot + 1) & (cap - 1);
         keys[slot] = key;
-        const uint32_t h = bloom_hash32(key);                     // blocked: both bits in one word
+        // strand-symmetric Bloom key: k-mer + its reverse complement (the kernels probe F + Rv without choosing the
+        // canonical strand first); blocked: both bits in one word
+        const uint32_t h = bloom_hash32(key + revcomp_kmer_host(key, c->dp.k));
         bloom[h >> bshift] |= (1u << (h & 31)) | (1u << ((h >> 5) & 31));
     }
     TRY(c->d_snp_keys.ensure(cap * sizeof(uint64_t)));
@@ -283,6 +289,7 @@ static int batch_upload(Context *c, Batch &b, const uint8_t *bases, const uint8_
     }
     b.n = (uint32_t)n; b.total_bases = total; b.max_len = max_len; b.mapped = false;
     b.has_quals = quals != nullptr; b.has_file_idx = file_idx != nullptr;
+    b.twin = false; b.force_generic = false;
     TRY(b.bases.ensure(total + 64));
     TRY(b.offsets.ensure((n + 1) * sizeof(uint64_t)));
     CK(cudaMemcpyAsync(b.offsets.p, rel, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
@@ -302,6 +309,79 @@ static int batch_upload(Context *c, Batch &b, const uint8_t *bases, const uint8_
     return 0;
 }
 
+// TwinRead batch (savont_b200_map_twin_reads): Seq<Dna> words + the caller's SNPmer k-mers.  The per-read SNPmer
+// chunks (snp_start / snp_cnt / snp_kmer) are filled here instead of by the sketch kernel.
+struct TwinInput {
+    const uint64_t *dna_words, *word_offsets;
+    const uint32_t *lengths;
+    const void *snp_kmers; int kmer_bytes;
+    const uint64_t *snp_offsets;
+    const uint32_t *file_idx;
+};
+static int batch_upload_twin(Context *c, Batch &b, const TwinInput &in, size_t r0, size_t n, uint64_t *h2d_bytes,
+                             cudaStream_t st = nullptr) {
+    if (st == nullptr) st = c->stream;
+    TRY(b.pin_offsets.ensure((n + 1) * 16 + n * 8 + 64));
+    uint64_t *rel = b.pin_offsets.as<uint64_t>();
+    uint64_t *wrel = rel + (n + 1);
+    uint32_t *sstart = reinterpret_cast<uint32_t *>(wrel + (n + 1));
+    uint32_t *scnt = sstart + n;
+    const uint64_t w0 = in.word_offsets[r0], s0 = in.snp_offsets[r0];
+    uint64_t total = 0; uint32_t max_len = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const uint32_t len = in.lengths[r0 + i];
+        const uint64_t wa = in.word_offsets[r0 + i], wb = in.word_offsets[r0 + i + 1];
+        const uint64_t sa = in.snp_offsets[r0 + i], sb_ = in.snp_offsets[r0 + i + 1];
+        if (wb < wa || wb - wa < ((uint64_t)len + 31u) / 32u)
+            return fail(SAVONT_B200_ERR_INVALID, "read %zu: %llu words cannot hold %u bases", r0 + i, (unsigned long long)(wb - wa), len);
+        if (sb_ < sa || sb_ - s0 >= (1ull << 32)) return fail(SAVONT_B200_ERR_INVALID, "snpmer_offsets not monotonic / too large at read %zu", r0 + i);
+        rel[i] = total; wrel[i] = wa - w0;
+        sstart[i] = (uint32_t)(sa - s0); scnt[i] = (uint32_t)(sb_ - sa);
+        total += len;
+        if (len > max_len) max_len = len;
+    }
+    rel[n] = total; wrel[n] = in.word_offsets[r0 + n] - w0;
+    if (total >= (1ull << 32) - 64) return fail(SAVONT_B200_ERR_INVALID, "batch of %llu bases exceeds 4 Gi", (unsigned long long)total);
+    const uint64_t n_words = wrel[n], n_snp = in.snp_offsets[r0 + n] - s0;
+    b.n = (uint32_t)n; b.total_bases = total; b.max_len = max_len; b.mapped = false;
+    b.has_quals = false; b.has_file_idx = in.file_idx != nullptr;
+    b.twin = true; b.force_generic = false;
+    TRY(b.offsets.ensure((n + 1) * 8)); TRY(b.word_offsets.ensure((n + 1) * 8)); TRY(b.dna_words.ensure((n_words + 2) * 8));
+    TRY(b.snp_start.ensure((n + 1) * 4)); TRY(b.snp_cnt.ensure((n + 1) * 4)); TRY(b.snp_kmer.ensure((n_snp + 1) * 8));
+    CK(cudaMemcpyAsync(b.offsets.p, rel, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(b.word_offsets.p, wrel, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (n) CK(cudaMemcpyAsync(b.snp_start.p, sstart, n * 4, cudaMemcpyHostToDevice, st));
+    if (n) CK(cudaMemcpyAsync(b.snp_cnt.p, scnt, n * 4, cudaMemcpyHostToDevice, st));
+    if (n_words) CK(cudaMemcpyAsync(b.dna_words.p, in.dna_words + w0, n_words * 8, cudaMemcpyHostToDevice, st));
+    uint64_t bytes = (n + 1) * 16 + n * 8 + n_words * 8;
+    if (n_snp) {
+        if (in.kmer_bytes == 8) {
+            CK(cudaMemcpyAsync(b.snp_kmer.p, static_cast<const uint64_t *>(in.snp_kmers) + s0, n_snp * 8, cudaMemcpyHostToDevice, st));
+        } else {
+            TRY(b.snp_raw.ensure(n_snp * 6 + 16));
+            CK(cudaMemcpyAsync(b.snp_raw.p, static_cast<const uint8_t *>(in.snp_kmers) + s0 * 6, n_snp * 6, cudaMemcpyHostToDevice, st));
+            launch_widen_kmer48(b.snp_raw.as<uint8_t>(), b.snp_kmer.as<uint64_t>(), n_snp, st);
+            CK(cudaGetLastError());
+            c->last_stats.kernel_launches += 1;
+        }
+        bytes += n_snp * (uint64_t)in.kmer_bytes;
+    }
+    if (in.file_idx) {
+        TRY(b.file_idx.ensure(n * 4 + 4));
+        if (n) CK(cudaMemcpyAsync(b.file_idx.p, in.file_idx + r0, n * 4, cudaMemcpyHostToDevice, st));
+        bytes += n * 4;
+    }
+    if (h2d_bytes) *h2d_bytes += bytes;
+    return 0;
+}
+static int validate_twin(const TwinInput &in, size_t n) {
+    if (!in.word_offsets || !in.lengths || !in.snp_offsets) return fail(SAVONT_B200_ERR_INVALID, "null argument");
+    if (in.kmer_bytes != 6 && in.kmer_bytes != 8) return fail(SAVONT_B200_ERR_INVALID, "snpmer_kmer_bytes must be 6 (Kmer48) or 8 (u64)");
+    if (n && !in.dna_words && in.word_offsets[n] > in.word_offsets[0]) return fail(SAVONT_B200_ERR_INVALID, "dna_words is null");
+    if (n && !in.snp_kmers && in.snp_offsets[n] > in.snp_offsets[0]) return fail(SAVONT_B200_ERR_INVALID, "snpmer_kmers is null");
+    return 0;
+}
+
 static SnpSet snp_view(const Context *c) {
     SnpSet set{};
     if (c->snp_mask) {
@@ -313,10 +393,12 @@ static SnpSet snp_view(const Context *c) {
 
 static SeqBatch seq_view(const Batch &b) {
     SeqBatch v{};
-    v.bases = b.bases.as<uint8_t>();
+    v.bases = b.twin ? nullptr : b.bases.as<uint8_t>();
     v.quals = b.has_quals ? b.quals.as<uint8_t>() : nullptr;
     v.offsets = b.offsets.as<uint64_t>();
     v.n = b.n; v.max_len = b.max_len;
+    v.dna_words = b.twin ? b.dna_words.as<uint64_t>() : nullptr;
+    v.word_offsets = b.twin ? b.word_offsets.as<uint64_t>() : nullptr;
     return v;
 }
 
@@ -344,9 +426,36 @@ static int stage_sketch(Context *c, Batch &b, bool with_pos) {
     TRY(b.mini_cnt.ensure((n + 1) * 4)); TRY(b.mini_kmer.ensure(mini_slots * 8));
     if (with_pos) TRY(b.mini_pos.ensure(mini_slots * 4));
     TRY(b.snp_start.ensure((n + 1) * 4)); TRY(b.snp_cnt.ensure((n + 1) * 4));
-    if (b.snp_cap == 0 || b.snp_cap < total / 8 + 4096) b.snp_cap = (uint32_t)std::min<uint64_t>(total / 8 + 4096, 0xfffffff0u);
     TRY(b.ctrs.ensure(kCtrBytes));
-    {   // per-warp spill region for sequences with more than kSnpHitCap SNPmer hits
+    const uint16_t *rank = c->use_rank_table ? c->d_rank_table.as<uint16_t>() : nullptr;
+    const bool fast = !b.force_generic && sketch_fast_supported(b.max_len, c->dp, c->use_rank_table, snp_view(c));
+    if (b.twin) {
+        // the caller's SNPmers are already in the pool (batch_upload_twin); only planes + minimizers are computed
+        CK(cudaMemsetAsync(b.ctrs.p, 0, kCtrBytes, c->stream));
+        SketchOut so = sketch_view(b, with_pos);
+        if (fast) {
+            launch_sketch_fast(seq_view(b), so, SnpSet{}, rank, c->dp, c->sm_count, c->stream);
+            c->last_stats.kernel_launches += 1;
+        } else {
+            // generic parameters: unpack to one code byte per base and run the generic kernel without a SNPmer set;
+            // its (empty) SNPmer bookkeeping goes to scratch arrays
+            TRY(b.bases.ensure(total + 64)); TRY(b.snp_dummy.ensure((n + 1) * 8));
+            launch_unpack_twin(seq_view(b), b.bases.as<uint8_t>(), c->stream);
+            SeqBatch sv = seq_view(b); sv.bases = b.bases.as<uint8_t>(); sv.quals = nullptr; sv.dna_words = nullptr; sv.word_offsets = nullptr;
+            so.snp_start = b.snp_dummy.as<uint32_t>(); so.snp_cnt = b.snp_dummy.as<uint32_t>() + (n + 1);
+            const uint32_t grid = sketch_grid(b.n, b.max_len, c->use_rank_table, c->dp, SnpSet{}, c->sm_count);
+            b.spill_stride = b.max_len + 1;
+            const size_t entries = (size_t)grid * kSketchWarps * b.spill_stride;
+            TRY(b.spill_k.ensure(entries * 8)); TRY(b.spill_p.ensure(entries * 4));
+            so.spill_kmer = b.spill_k.as<uint64_t>(); so.spill_pos = b.spill_p.as<uint32_t>(); so.spill_stride = b.spill_stride;
+            launch_sketch(sv, so, SnpSet{}, rank, c->dp, c->sm_count, c->stream);
+            c->last_stats.kernel_launches += 2;
+        }
+        CK(cudaGetLastError());
+        return 0;
+    }
+    if (b.snp_cap == 0 || b.snp_cap < total / 8 + 4096) b.snp_cap = (uint32_t)std::min<uint64_t>(total / 8 + 4096, 0xfffffff0u);
+    if (!fast) {   // per-warp spill region for sequences with more than kSnpHitCap SNPmer hits
         const uint32_t grid = sketch_grid(b.n, b.max_len, c->use_rank_table, c->dp, snp_view(c), c->sm_count);
         b.spill_stride = b.max_len + 1;
         const size_t entries = (size_t)grid * kSketchWarps * b.spill_stride;
@@ -354,8 +463,8 @@ static int stage_sketch(Context *c, Batch &b, bool with_pos) {
     }
     TRY(b.snp_kmer.ensure((size_t)b.snp_cap * 8)); TRY(b.snp_pos.ensure((size_t)b.snp_cap * 4));
     CK(cudaMemsetAsync(b.ctrs.p, 0, kCtrBytes, c->stream));
-    launch_sketch(seq_view(b), sketch_view(b, with_pos), snp_view(c), c->use_rank_table ? c->d_rank_table.as<uint16_t>() : nullptr,
-                  c->dp, c->sm_count, c->stream);
+    if (fast) launch_sketch_fast(seq_view(b), sketch_view(b, with_pos), snp_view(c), rank, c->dp, c->sm_count, c->stream);
+    else launch_sketch(seq_view(b), sketch_view(b, with_pos), snp_view(c), rank, c->dp, c->sm_count, c->stream);
     CK(cudaGetLastError());
     c->last_stats.kernel_launches += 1;
     return 0;
@@ -371,6 +480,7 @@ static int check_batch(Context *c, Batch &b, BatchCounters *out, bool *retry) {
     *retry = false;
     if (h.err & kErrSnpPool) { b.snp_cap = h.snp_used + 1024; *retry = true; }
     if (h.err & kErrPairPool) { b.pair_cap = h.n_pairs + 1024; *retry = true; }
+    if ((h.err & kErrSnpHits) && !b.force_generic) { b.force_generic = true; *retry = true; h.err &= ~kErrSnpHits; }
     if (h.err & ~(kErrSnpPool | kErrPairPool)) return fail(SAVONT_B200_ERR_OVERFLOW, "device error flags 0x%x", h.err);
     *out = h;
     return 0;
@@ -1022,37 +1132,24 @@ int savont_b200_align_pairs(savont_b200_ctx *h, const uint8_t *bases, const uint
     return rc;
 }
 
-int savont_b200_map_reads(savont_b200_ctx *h, const uint8_t *bases, const uint8_t *quals, const uint64_t *offsets,
-                          const uint32_t *file_idx, size_t n_reads, int n_samples, uint8_t *status, int32_t *best_nm,
-                          uint64_t *class_offsets, uint32_t *class_asv, size_t class_cap, uint64_t *unambig, uint64_t *ambig,
-                          uint64_t *leq10, uint64_t *totals, uint64_t *sample_singleton, savont_b200_stats *stats) {
-    TRY(use_device(h ? &h->c : nullptr));
-    Context *c = &h->c;
-    TRY(ensure_index(c));
-    if (!offsets || !status || !best_nm || !class_offsets) return fail(SAVONT_B200_ERR_INVALID, "null argument");
-    if (n_samples < 1) return fail(SAVONT_B200_ERR_INVALID, "n_samples must be >= 1");
+// shared body of savont_b200_map_reads / savont_b200_map_twin_reads: double-buffered batches, the H2D copies of
+// batch i+1 run on the copy stream while batch i computes
+using UploadFn = std::function<int(Batch &, size_t, size_t, uint64_t *, cudaStream_t)>;
+static int map_batches(Context *c, const std::vector<size_t> &cuts, const UploadFn &upload_batch, int n_samples, uint8_t *status,
+                       int32_t *best_nm, uint64_t *class_offsets, uint32_t *class_asv, size_t class_cap, uint64_t *unambig,
+                       uint64_t *ambig, uint64_t *leq10, uint64_t *totals, uint64_t *sample_singleton, savont_b200_stats *stats) {
     savont_b200_stats st; memset(&st, 0, sizeof(st));
     memset(&c->last_stats, 0, sizeof(c->last_stats));
     TRY(ensure_counters(c, n_samples, true));
     CK(cudaEventRecord(c->ev[6], c->stream));
     class_offsets[0] = 0;
     uint64_t class_base = 0;
-    // batch boundaries
-    std::vector<size_t> cuts{0};
-    for (size_t r0 = 0; r0 < n_reads;) {
-        size_t r1 = std::min(n_reads, r0 + c->batch_reads);
-        while (r1 > r0 + 1 && offsets[r1] - offsets[r0] > (3ull << 30)) r1 = r0 + (r1 - r0) / 2;
-        cuts.push_back(r1);
-        r0 = r1;
-    }
     const size_t nb = cuts.size() - 1;
     Batch *bufs[2] = {&c->work, &c->work2};
-    // double buffering: the H2D copies of batch i+1 run on the copy stream while batch i computes
     auto upload = [&](size_t bi) -> int {
         const int slot = (int)(bi & 1);
-        const size_t r0 = cuts[bi], n = cuts[bi + 1] - r0;
         CK(cudaEventRecord(c->ev_h0[slot], c->copy_stream));
-        TRY(batch_upload(c, *bufs[slot], bases, quals, offsets + r0, file_idx ? file_idx + r0 : nullptr, n, &st.h2d_bytes, c->copy_stream));
+        TRY(upload_batch(*bufs[slot], cuts[bi], cuts[bi + 1] - cuts[bi], &st.h2d_bytes, c->copy_stream));
         CK(cudaEventRecord(c->ev_up[slot], c->copy_stream));
         return 0;
     };
@@ -1083,6 +1180,75 @@ int savont_b200_map_reads(savont_b200_ctx *h, const uint8_t *bases, const uint8_
     st.kernel_launches = c->last_stats.kernel_launches;
     c->last_stats = st;
     if (stats) *stats = st;
+    return 0;
+}
+
+int savont_b200_map_reads(savont_b200_ctx *h, const uint8_t *bases, const uint8_t *quals, const uint64_t *offsets,
+                          const uint32_t *file_idx, size_t n_reads, int n_samples, uint8_t *status, int32_t *best_nm,
+                          uint64_t *class_offsets, uint32_t *class_asv, size_t class_cap, uint64_t *unambig, uint64_t *ambig,
+                          uint64_t *leq10, uint64_t *totals, uint64_t *sample_singleton, savont_b200_stats *stats) {
+    TRY(use_device(h ? &h->c : nullptr));
+    Context *c = &h->c;
+    TRY(ensure_index(c));
+    if (!offsets || !status || !best_nm || !class_offsets) return fail(SAVONT_B200_ERR_INVALID, "null argument");
+    if (n_samples < 1) return fail(SAVONT_B200_ERR_INVALID, "n_samples must be >= 1");
+    std::vector<size_t> cuts{0};
+    for (size_t r0 = 0; r0 < n_reads;) {
+        size_t r1 = std::min(n_reads, r0 + c->batch_reads);
+        while (r1 > r0 + 1 && offsets[r1] - offsets[r0] > (3ull << 30)) r1 = r0 + (r1 - r0) / 2;
+        cuts.push_back(r1);
+        r0 = r1;
+    }
+    auto up = [&](Batch &b, size_t r0, size_t n, uint64_t *bytes, cudaStream_t st) -> int {
+        return batch_upload(c, b, bases, quals, offsets + r0, file_idx ? file_idx + r0 : nullptr, n, bytes, st);
+    };
+    return map_batches(c, cuts, up, n_samples, status, best_nm, class_offsets, class_asv, class_cap, unambig, ambig, leq10, totals,
+                       sample_singleton, stats);
+}
+
+static std::vector<size_t> twin_cuts(const Context *c, const TwinInput &in, size_t n_reads) {
+    std::vector<size_t> cuts{0};
+    for (size_t r0 = 0; r0 < n_reads;) {
+        size_t r1 = std::min(n_reads, r0 + c->batch_reads);
+        while (r1 > r0 + 1 && (in.word_offsets[r1] - in.word_offsets[r0]) * 32ull > (3ull << 30)) r1 = r0 + (r1 - r0) / 2;
+        cuts.push_back(r1);
+        r0 = r1;
+    }
+    return cuts;
+}
+
+int savont_b200_map_twin_reads(savont_b200_ctx *h, const uint64_t *dna_words, const uint64_t *dna_word_offsets,
+                               const uint32_t *lengths, const void *snpmer_kmers, int snpmer_kmer_bytes,
+                               const uint64_t *snpmer_offsets, const uint32_t *file_idx, size_t n_reads, int n_samples,
+                               uint8_t *status, int32_t *best_nm, uint64_t *class_offsets, uint32_t *class_asv, size_t class_cap,
+                               uint64_t *unambig, uint64_t *ambig, uint64_t *leq10, uint64_t *totals, uint64_t *sample_singleton,
+                               savont_b200_stats *stats) {
+    TRY(use_device(h ? &h->c : nullptr));
+    Context *c = &h->c;
+    TRY(ensure_index(c));
+    if (!status || !best_nm || !class_offsets) return fail(SAVONT_B200_ERR_INVALID, "null argument");
+    if (n_samples < 1) return fail(SAVONT_B200_ERR_INVALID, "n_samples must be >= 1");
+    const TwinInput in{dna_words, dna_word_offsets, lengths, snpmer_kmers, snpmer_kmer_bytes, snpmer_offsets, file_idx};
+    TRY(validate_twin(in, n_reads));
+    const std::vector<size_t> cuts = twin_cuts(c, in, n_reads);
+    auto up = [&](Batch &b, size_t r0, size_t n, uint64_t *bytes, cudaStream_t st) -> int {
+        return batch_upload_twin(c, b, in, r0, n, bytes, st);
+    };
+    return map_batches(c, cuts, up, n_samples, status, best_nm, class_offsets, class_asv, class_cap, unambig, ambig, leq10, totals,
+                       sample_singleton, stats);
+}
+
+int savont_b200_upload_twin_reads(savont_b200_ctx *h, const uint64_t *dna_words, const uint64_t *dna_word_offsets,
+                                  const uint32_t *lengths, const void *snpmer_kmers, int snpmer_kmer_bytes,
+                                  const uint64_t *snpmer_offsets, const uint32_t *file_idx, size_t n_reads, int n_samples) {
+    TRY(use_device(h ? &h->c : nullptr));
+    Context *c = &h->c;
+    if (n_samples < 1) return fail(SAVONT_B200_ERR_INVALID, "n_samples must be >= 1");
+    const TwinInput in{dna_words, dna_word_offsets, lengths, snpmer_kmers, snpmer_kmer_bytes, snpmer_offsets, file_idx};
+    TRY(validate_twin(in, n_reads));
+    TRY(batch_upload_twin(c, c->resident, in, 0, n_reads, nullptr));
+    CK(cudaStreamSynchronize(c->stream));
+    c->resident_samples = n_samples;
     return 0;
 }
 

@@ -71,6 +71,10 @@ struct SeqBatch {            // device view of a batch of sequences
     const uint64_t *offsets; // [n+1]
     uint32_t n;
     uint32_t max_len;
+    // TwinRead input (savont_b200_map_twin_reads): bases == nullptr, the sequences are the reference's 2-bit
+    // Seq<Dna> words (first base in the low bits), sequence r starting at word word_offsets[r]
+    const uint64_t *dna_words;
+    const uint64_t *word_offsets;
 };
 
 struct SketchOut {
@@ -149,6 +153,12 @@ struct AlignOut {
 // launchers (defined in the .cu files)
 void launch_sketch(const SeqBatch &in, const SketchOut &out, const SnpSet &set, const uint16_t *rank_table,
                    const DeviceParams &p, int sm_count, cudaStream_t st);
+// k = 17, c = 11 fast path (sketch_fast.cu); in.dna_words != nullptr selects the TwinRead input encoding
+bool sketch_fast_supported(uint32_t max_len, const DeviceParams &p, bool use_table, const SnpSet &set);
+void launch_sketch_fast(const SeqBatch &in, const SketchOut &out, const SnpSet &set, const uint16_t *rank_table,
+                        const DeviceParams &p, int sm_count, cudaStream_t st);
+void launch_unpack_twin(const SeqBatch &in, uint8_t *codes, cudaStream_t st);
+void launch_widen_kmer48(const uint8_t *src, uint64_t *dst, uint64_t n, cudaStream_t st);
 uint32_t sketch_grid(uint32_t n, uint32_t max_len, bool use_table, const DeviceParams &p, const SnpSet &set, int sm_count);
 void launch_est_id(const SeqBatch &in, const uint8_t *status, const uint8_t *flatq, const double *phred_table,
                    double *est_id, cudaStream_t st);

@@ -318,3 +318,78 @@ def test_low_polymorphism_mode(ctx, with_snpmers):
     hit = [r["truth_asv"][i] in want["class_asv"][co[i]:co[i + 1]] for i in range(2500)]
     assert np.mean(hit) > 0.97
     ctx.set_params(_lib.default_params())
+
+
+@pytest.mark.parametrize("name,kw,n,kmer48,k,c", [
+    ("ont16s", dict(n_roots=8), 4000, False, 17, 11),
+    ("ont16s", dict(n_roots=5, sites_per_genus=3), 2500, True, 17, 11),
+    ("operon", dict(n_roots=4), 500, True, 17, 11),
+    ("pooled", dict(n_roots=6, n_samples=4), 2500, False, 17, 11),
+    ("ont16s", dict(n_roots=6), 1500, True, 15, 9),               # generic-parameter path (unpack + generic sketch kernel)
+])
+def test_map_twin_reads(ctx, name, kw, n, kmer48, k, c):
+    """The TwinRead entry point (Seq<Dna> words + TwinRead.snpmer_kmers, what Stage 7 is handed by the reference,
+    src/alignment.rs:1723-1729) gives the same answer as the ASCII entry point and the oracle."""
+    from savont_b200 import _lib, twin
+    w = _make_workload(name, k=k, **kw)
+    r = w.reads(n)
+    bases = r["bases"].copy(); offs = r["offsets"]
+    bases[5::997] = ord("N")                                         # non-ACGT -> A in dna_seq (src/seeding.rs:604-626)
+    gp, op = _params(_lib, band=w.band, k=k, c=c)
+    ctx.set_params(gp); ctx.load_snpmers(w.snpmers); ctx.load_asvs(w.asv_bases, w.asv_offsets)
+    orc = O.Oracle(op, w.snpmers); orc.load_asvs(w.asv_bases, w.asv_offsets)
+    ns = w.n_samples
+    fidx = r["file_idx"] if ns > 1 else None
+    want = orc.map_reads(bases, r["quals"], offs, file_idx=fidx, n_samples=ns)
+    sk = O.sketch_batch(op, w.snpmers, bases, r["quals"], offs)      # what Stage 1.5 stored in the TwinReads
+    tw = twin.from_sketch(sk, offs, file_idx=fidx, kmer48=kmer48)
+    ctx.set_batch_reads(900)
+    try:
+        got = ctx.map_twin_reads(tw, n_samples=ns)
+    finally:
+        ctx.set_batch_reads(0)
+    assert_same(got, want, MAP_KEYS, f"map_twin_reads {name} k={k}")
+    assert got["stats"]["dp_cells"] == want["dp_cells"]
+    assert got["stats"]["h2d_bytes"] < 0.5 * len(bases)               # 2 bits per base + SNPmers instead of two bytes per base
+    ctx.upload_twin_reads(tw, n_samples=ns)
+    ctx.map_resident()
+    assert_same(ctx.fetch_resident(), want, MAP_KEYS, f"twin resident {name}")
+    ctx.set_params(_lib.default_params())
+
+
+def test_map_twin_reads_edge_cases(ctx):
+    from savont_b200 import _lib, twin
+    w = _make_workload("ont16s", n_roots=3)
+    gp, op = _params(_lib, band=w.band)
+    ctx.set_params(gp); ctx.load_snpmers(w.snpmers); ctx.load_asvs(w.asv_bases, w.asv_offsets)
+    orc = O.Oracle(op, w.snpmers); orc.load_asvs(w.asv_bases, w.asv_offsets)
+    # empty call
+    e = ctx.map_twin_reads(dict(dna_words=np.zeros(0, np.uint64), dna_word_offsets=np.zeros(1, np.uint64), lengths=np.zeros(0, np.uint32),
+                                snpmer_kmers=np.zeros(0, np.uint64), snpmer_offsets=np.zeros(1, np.uint64)))
+    assert len(e["status"]) == 0 and e["totals"].tolist() == [0, 0]
+    # reads of awkward lengths around the word size, too short reads, a read without SNPmers
+    r = w.reads(300)
+    seqs = [bytes(r["bases"][int(r["offsets"][i]):int(r["offsets"][i + 1])]) for i in range(300)]
+    quals = [bytes(r["quals"][int(r["offsets"][i]):int(r["offsets"][i + 1])]) for i in range(300)]
+    for i, cut in enumerate([0, 5, 16, 17, 31, 32, 33, 63, 64, 65, 95, 96, 97, 1023, 1024, 1025]):
+        seqs[i] = seqs[i][:cut]; quals[i] = quals[i][:cut]
+    bases, offs = O.concat(seqs); qcat, _ = O.concat(quals)
+    want = orc.map_reads(bases, qcat, offs)
+    sk = O.sketch_batch(op, w.snpmers, bases, qcat, offs)
+    got = ctx.map_twin_reads(twin.from_sketch(sk, offs, kmer48=True))
+    assert_same(got, want, MAP_KEYS, "twin ragged")
+    assert got["status"][0] == 4 and got["status"][2] == 4 and got["status"][3] != 4
+    # garbage beyond the last base inside the last word must be ignored
+    tw = twin.from_sketch(sk, offs)
+    words = tw["dna_words"].copy()
+    wo = tw["dna_word_offsets"].astype(np.int64); ln = tw["lengths"].astype(np.int64)
+    for i in range(300):
+        rem = int(ln[i] % 32)
+        if rem and ln[i] > 0:
+            words[wo[i + 1] - 1] |= np.uint64(((1 << 64) - 1) ^ ((1 << (2 * rem)) - 1))
+    tw["dna_words"] = words
+    assert_same(ctx.map_twin_reads(tw), want, MAP_KEYS, "twin with dirty tail bits")
+    # invalid arguments are loud
+    bad = dict(tw); bad["dna_word_offsets"] = tw["dna_word_offsets"].copy(); bad["dna_word_offsets"][5:] -= np.uint64(3)
+    with pytest.raises(_lib.SavontB200Error):
+        ctx.map_twin_reads(bad)
