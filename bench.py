@@ -12,6 +12,8 @@ library's device counter vector).
   value     whole-job reads/s with the reads already resident in HBM (kernel pipeline only)
   e2e       the same metric through savont_b200_map_reads with pinned HOST buffers
             (H2D of bases+quals+offsets and D2H of per-read results inside the timed region)
+  e2e_twin  the same through savont_b200_map_twin_reads: the reads as the reference's Stage 7 receives them
+            (&[TwinRead]: 2-bit dna_seq words + snpmer_kmers), 8x fewer H2D bytes
   roofline  the dominant kernel (banded DP): achieved GCUPS vs the INT32 ALU-pipe peak
   cpu_baseline / --impl reference: the CPU oracle (C port of the reference path; the Rust
             reference itself cannot be built here) on all host cores.
@@ -208,11 +210,40 @@ def run_b200(args, rank, world, local_rank):
         barrier()
         e2e_ms.append(e0.elapsed_time(e1))
         e2e_stats = res["stats"]
-    clocks = sampler.stop()
     e2e_t = torch.tensor([sum(e2e_ms)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_total_ms = float(e2e_t.item())
+
+    # ---------------- e2e arm 2: the reads as &[TwinRead] (what Stage 7 is handed by the reference) ----------------
+    # dna_seq words + snpmer_kmers (Vec<Kmer48>) in pinned host memory; prepared outside the timed region, as Stage 1.5
+    # prepares them in the reference
+    twin_line = None
+    if not args.no_twin:
+        from savont_b200 import twin
+        tw = twin.twin_reads_from_snpmers(ctx, r["bases"], r["quals"], r["offsets"], file_idx=fidx, kmer48=True, alloc=_lib.pinned_array)
+        res = ctx.map_twin_reads(tw, n_samples=w.n_samples)                                     # warm-up (allocations)
+        tw_ms, tw_stats = [], None
+        for _ in range(e2e_steps):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            res = ctx.map_twin_reads(tw, n_samples=w.n_samples)
+            allreduce_counts()
+            e1.record(stream)
+            barrier()
+            tw_ms.append(e0.elapsed_time(e1)); tw_stats = res["stats"]
+        tw_t = torch.tensor([sum(tw_ms)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tw_t, op=dist.ReduceOp.MAX)
+        same = all(np.array_equal(res[k], got[k]) for k in ("status", "best_nm", "class_offsets", "class_asv")) if world == 1 else None
+        twin_line = {"value": world * n_reads * e2e_steps / (float(tw_t.item()) / 1e3), "unit": "reads/s",
+                     "h2d_bytes_per_step": int(tw_stats["h2d_bytes"]), "d2h_bytes_per_step": int(tw_stats["d2h_bytes"]),
+                     "steps": e2e_steps, "ms_per_step": float(tw_t.item()) / e2e_steps, "h2d_ms": tw_stats["h2d_ms"],
+                     "kernel_ms": {"sketch": tw_stats["sketch_ms"], "filter": tw_stats["filter_ms"], "align": tw_stats["align_ms"]},
+                     "input": "TwinRead.dna_seq words + TwinRead.snpmer_kmers (Kmer48) through savont_b200_map_twin_reads",
+                     "same_result_as_ascii_entry": same}
+    clocks = sampler.stop()
 
     if rank != 0:
         return
@@ -259,6 +290,7 @@ def run_b200(args, rank, world, local_rank):
         "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(e2e_stats["h2d_bytes"]),
                 "d2h_bytes_per_step": int(e2e_stats["d2h_bytes"]), "steps": e2e_steps, "ms_per_step": e2e_total_ms / e2e_steps,
                 "h2d_ms": e2e_stats["h2d_ms"], "d2h_ms": e2e_stats["d2h_ms"]},
+        "e2e_twin": twin_line,
         "gpu_launches": int(sum(s["kernel_launches"] for s in stats)),
         "clocks": clocks,
         "assigned_frac": float(got["totals"][0]) / max(n_reads * (world if world > 1 else 1), 1),
@@ -316,6 +348,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-reads", type=int, default=100_000, help="sample size of the CPU baseline / reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-twin", action="store_true", help="skip the TwinRead-input e2e arm")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

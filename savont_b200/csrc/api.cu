@@ -137,12 +137,19 @@ struct Context {
     // counters [unambig A | ambig A | leq10 A | assigned | filtered | singleton S*A]
     DevBuf d_counters; size_t counters_len = 0; int counters_samples = 0;
 
-    Batch work, work2, resident, asvb;
+    Batch work, work2, work3, resident, asvb;
     int resident_samples = 1;
     PinBuf pin_small, pin_out;
     cudaStream_t copy_stream = nullptr;          // H2D of batch i+1 overlaps the kernels of batch i
+    cudaStream_t d2h_stream = nullptr;           // D2H of batch i-1's results overlaps the kernels of batch i
+    cudaEvent_t ev_d2h[2] = {nullptr, nullptr};
+    // map_reads / map_twin_reads run consecutive batches on two internal compute lanes, so the tail of batch i's DP
+    // kernel (a partial last wave) overlaps the sketch / filter kernels of batch i+1
+    cudaStream_t lane_stream[2] = {nullptr, nullptr};
+    cudaEvent_t lane_ev[2][5] = {{nullptr}};
+    cudaEvent_t *pev = nullptr;                  // the 5 stage events enqueue_path / finish_path use (ev or lane_ev[i])
     cudaEvent_t ev[8] = {nullptr};
-    cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_h0[2] = {nullptr, nullptr};
+    cudaEvent_t ev_up[3] = {nullptr, nullptr, nullptr}, ev_h0[3] = {nullptr, nullptr, nullptr};
     savont_b200_stats last_stats;
 };
 
@@ -748,51 +755,66 @@ static int use_device(Context *c) {
 
 static float ev_ms(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
 
-// sketch -> filter -> align -> assign on a device-resident batch: four kernel groups enqueued back to back, ONE
-// host synchronisation at the end; per-group device times from CUDA events on the stream
-static int run_path(Context *c, Batch &b, int n_samples, savont_b200_stats &st) {
+// sketch -> filter -> align -> assign on a device-resident batch: four kernel groups enqueued back to back; the ONE
+// host synchronisation happens in finish_path; per-group device times from CUDA events on the stream
+static int enqueue_path(Context *c, Batch &b, int n_samples) {
+    CK(cudaEventRecord(c->pev[0], c->stream));
+    TRY(stage_sketch(c, b, false));
+    CK(cudaEventRecord(c->pev[1], c->stream));
+    TRY(stage_filter(c, b, c->dp.strand_mode));
+    CK(cudaEventRecord(c->pev[2], c->stream));
+    TRY(stage_align(c, b, b.ctrs.as<uint32_t>() + 1, b.pair_cap));
+    CK(cudaEventRecord(c->pev[3], c->stream));
+    TRY(stage_assign(c, b, n_samples, c->dp.strand_mode));
+    CK(cudaEventRecord(c->pev[4], c->stream));
+    return 0;
+}
+// waits for the batch enqueued last, re-runs it with larger pools when one overflowed, accumulates the statistics
+static int finish_path(Context *c, Batch &b, int n_samples, savont_b200_stats &st) {
     BatchCounters h{};
     for (int attempt = 0;; ++attempt) {
-        CK(cudaEventRecord(c->ev[0], c->stream));
-        TRY(stage_sketch(c, b, false));
-        CK(cudaEventRecord(c->ev[1], c->stream));
-        TRY(stage_filter(c, b, c->dp.strand_mode));
-        CK(cudaEventRecord(c->ev[2], c->stream));
-        TRY(stage_align(c, b, b.ctrs.as<uint32_t>() + 1, b.pair_cap));
-        CK(cudaEventRecord(c->ev[3], c->stream));
-        TRY(stage_assign(c, b, n_samples, c->dp.strand_mode));
-        CK(cudaEventRecord(c->ev[4], c->stream));
         bool retry = false;
         TRY(check_batch(c, b, &h, &retry));
         if (!retry) break;
         if (attempt == 3) return fail(SAVONT_B200_ERR_OVERFLOW, "pool sizing did not converge");
+        TRY(enqueue_path(c, b, n_samples));
     }
-    st.sketch_ms += ev_ms(c->ev[0], c->ev[1]);
-    st.filter_ms += ev_ms(c->ev[1], c->ev[2]);
-    st.align_ms += ev_ms(c->ev[2], c->ev[3]);
-    st.assign_ms += ev_ms(c->ev[3], c->ev[4]);
+    st.sketch_ms += ev_ms(c->pev[0], c->pev[1]);
+    st.filter_ms += ev_ms(c->pev[1], c->pev[2]);
+    st.align_ms += ev_ms(c->pev[2], c->pev[3]);
+    st.assign_ms += ev_ms(c->pev[3], c->pev[4]);
     st.n_pairs += h.n_pairs;
     st.n_reads += b.n; st.n_bases += b.total_bases;
     st.dp_cells += h.dp_cells;
     return 0;
 }
+// runs the stage launchers / the batch check on one of the internal compute lanes instead of the caller's stream
+struct LaneGuard {
+    Context *c; cudaStream_t s0; cudaEvent_t *e0;
+    LaneGuard(Context *ctx, int lane) : c(ctx), s0(ctx->stream), e0(ctx->pev) { c->stream = c->lane_stream[lane]; c->pev = c->lane_ev[lane]; }
+    ~LaneGuard() { c->stream = s0; c->pev = e0; }
+};
+static int run_path(Context *c, Batch &b, int n_samples, savont_b200_stats &st) {
+    TRY(enqueue_path(c, b, n_samples));
+    return finish_path(c, b, n_samples, st);
+}
 
-static int fetch_batch(Context *c, Batch &b, uint8_t *status, int32_t *best_nm, uint64_t *class_offsets, uint64_t class_base,
-                       uint32_t *class_asv, size_t class_cap, uint64_t *n_class_out, uint64_t *d2h_bytes) {
-    const size_t n = b.n;
+// results of a finished batch of n reads -> caller memory, on stream `fs` (the batch's kernels must have completed)
+static int fetch_batch(Context *c, Batch &b, size_t n, cudaStream_t fs, uint8_t *status, int32_t *best_nm, uint64_t *class_offsets,
+                       uint64_t class_base, uint32_t *class_asv, size_t class_cap, uint64_t *n_class_out, uint64_t *d2h_bytes) {
     TRY(c->pin_small.ensure((n + 2) * 4));
     uint32_t *off = c->pin_small.as<uint32_t>();
-    CK(cudaMemcpyAsync(off, b.class_off.p, (n + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
-    if (n) CK(cudaMemcpyAsync(status, b.rstatus.p, n, cudaMemcpyDeviceToHost, c->stream));
-    if (n) CK(cudaMemcpyAsync(best_nm, b.best_nm.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpyAsync(off, b.class_off.p, (n + 1) * 4, cudaMemcpyDeviceToHost, fs));
+    if (n) CK(cudaMemcpyAsync(status, b.rstatus.p, n, cudaMemcpyDeviceToHost, fs));
+    if (n) CK(cudaMemcpyAsync(best_nm, b.best_nm.p, n * 4, cudaMemcpyDeviceToHost, fs));
+    CK(cudaStreamSynchronize(fs));
     const uint32_t total = off[n];
     if (class_base + total > class_cap)
         return fail(SAVONT_B200_ERR_CAPACITY, "class_asv capacity %zu too small (need >= %llu)", class_cap,
                     (unsigned long long)(class_base + total));
-    if (total) CK(cudaMemcpyAsync(class_asv + class_base, b.class_out.p, (size_t)total * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (total) CK(cudaMemcpyAsync(class_asv + class_base, b.class_out.p, (size_t)total * 4, cudaMemcpyDeviceToHost, fs));
     for (size_t i = 0; i <= n; ++i) class_offsets[i] = class_base + off[i];
-    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaStreamSynchronize(fs));
     *n_class_out = total;
     if (d2h_bytes) *d2h_bytes += (n + 1) * 4 + n * 5 + (uint64_t)total * 4;
     return 0;
@@ -854,8 +876,15 @@ int savont_b200_create(int device_id, savont_b200_ctx **out) {
     CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+    for (auto &ev : c->ev_d2h) CK(cudaEventCreate(&ev));
+    for (int i = 0; i < 2; ++i) {
+        CK(cudaStreamCreateWithFlags(&c->lane_stream[i], cudaStreamNonBlocking));
+        for (auto &ev : c->lane_ev[i]) CK(cudaEventCreate(&ev));
+    }
+    c->pev = c->ev;
     for (auto &ev : c->ev) CK(cudaEventCreate(&ev));
-    for (int i = 0; i < 2; ++i) { CK(cudaEventCreate(&c->ev_up[i])); CK(cudaEventCreate(&c->ev_h0[i])); }
+    for (int i = 0; i < 3; ++i) { CK(cudaEventCreate(&c->ev_up[i])); CK(cudaEventCreate(&c->ev_h0[i])); }
     savont_b200_default_params(&c->params);
     c->dp = make_device_params(c->params);
     memset(&c->last_stats, 0, sizeof(c->last_stats));
@@ -870,14 +899,20 @@ int savont_b200_destroy(savont_b200_ctx *h) {
     Context *c = &h->c;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    c->work.release(); c->work2.release(); c->resident.release(); c->asvb.release();
+    c->work.release(); c->work2.release(); c->work3.release(); c->resident.release(); c->asvb.release();
     DevBuf *bufs[] = {&c->d_rank_table, &c->d_snp_keys, &c->d_snp_bloom, &c->d_phred, &c->d_mx_keys, &c->d_mx_vals, &c->d_mx_entries, &c->d_idx_keys, &c->d_idx_vals, &c->d_idx_entries, &c->d_mset,
                       &c->d_mset_off, &c->d_asv_planes, &c->d_asv_plane_off, &c->d_asv_len, &c->d_counters};
     for (DevBuf *b : bufs) b->release();
     c->pin_small.release(); c->pin_out.release();
     for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
-    for (int i = 0; i < 2; ++i) { if (c->ev_up[i]) cudaEventDestroy(c->ev_up[i]); if (c->ev_h0[i]) cudaEventDestroy(c->ev_h0[i]); }
+    for (int i = 0; i < 3; ++i) { if (c->ev_up[i]) cudaEventDestroy(c->ev_up[i]); if (c->ev_h0[i]) cudaEventDestroy(c->ev_h0[i]); }
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    for (auto &ev : c->ev_d2h) if (ev) cudaEventDestroy(ev);
+    for (int i = 0; i < 2; ++i) {
+        for (auto &ev : c->lane_ev[i]) if (ev) cudaEventDestroy(ev);
+        if (c->lane_stream[i]) cudaStreamDestroy(c->lane_stream[i]);
+    }
+    if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete h;
     return 0;
@@ -1134,6 +1169,13 @@ int savont_b200_align_pairs(savont_b200_ctx *h, const uint8_t *bases, const uint
 
 // shared body of savont_b200_map_reads / savont_b200_map_twin_reads: double-buffered batches, the H2D copies of
 // batch i+1 run on the copy stream while batch i computes
+// the first batches are smaller (1/8, 1/4, 1/2 of batch_reads) so that the pipeline fills quickly: nothing overlaps
+// the upload of batch 0
+static size_t ramp_batch(const Context *c, size_t bi) {
+    const size_t full = c->batch_reads;
+    if (bi >= 3 || full < 8 * 4096) return full;
+    return full >> (3 - bi);
+}
 using UploadFn = std::function<int(Batch &, size_t, size_t, uint64_t *, cudaStream_t)>;
 static int map_batches(Context *c, const std::vector<size_t> &cuts, const UploadFn &upload_batch, int n_samples, uint8_t *status,
                        int32_t *best_nm, uint64_t *class_offsets, uint32_t *class_asv, size_t class_cap, uint64_t *unambig,
@@ -1145,33 +1187,53 @@ static int map_batches(Context *c, const std::vector<size_t> &cuts, const Upload
     class_offsets[0] = 0;
     uint64_t class_base = 0;
     const size_t nb = cuts.size() - 1;
-    Batch *bufs[2] = {&c->work, &c->work2};
+    // three batch slots, two compute lanes: batch bi lives in slot bi % 3 and runs on lane bi & 1.  While batch bi
+    // computes, batch bi-1 finishes on the other lane (the tail of its DP kernel overlaps bi's sketch / filter kernels) and
+    // has its results fetched on the D2H stream, and batch bi+1 is uploaded on the copy stream into the third slot.
+    Batch *bufs[3] = {&c->work, &c->work2, &c->work3};
     auto upload = [&](size_t bi) -> int {
-        const int slot = (int)(bi & 1);
+        const int slot = (int)(bi % 3);
         CK(cudaEventRecord(c->ev_h0[slot], c->copy_stream));
         TRY(upload_batch(*bufs[slot], cuts[bi], cuts[bi + 1] - cuts[bi], &st.h2d_bytes, c->copy_stream));
         CK(cudaEventRecord(c->ev_up[slot], c->copy_stream));
         return 0;
     };
     CK(cudaStreamWaitEvent(c->copy_stream, c->ev[6], 0));   // order after earlier work on the caller's stream
+    for (int l = 0; l < 2; ++l) CK(cudaStreamWaitEvent(c->lane_stream[l], c->ev[6], 0));
+    struct Pending { Batch *b; size_t n, r0; int slot, lane; bool live; } prev{nullptr, 0, 0, 0, 0, false};
+    auto finish_prev = [&]() -> int {
+        if (!prev.live) return 0;
+        {
+            LaneGuard g(c, prev.lane);
+            TRY(finish_path(c, *prev.b, n_samples, st));
+        }
+        st.h2d_ms += ev_ms(c->ev_h0[prev.slot], c->ev_up[prev.slot]);
+        uint64_t n_cls = 0;
+        CK(cudaEventRecord(c->ev_d2h[0], c->d2h_stream));
+        TRY(fetch_batch(c, *prev.b, prev.n, c->d2h_stream, status + prev.r0, best_nm + prev.r0, class_offsets + prev.r0, class_base,
+                        class_asv, class_cap, &n_cls, &st.d2h_bytes));
+        CK(cudaEventRecord(c->ev_d2h[1], c->d2h_stream));
+        CK(cudaEventSynchronize(c->ev_d2h[1]));
+        st.d2h_ms += ev_ms(c->ev_d2h[0], c->ev_d2h[1]);
+        class_base += n_cls;
+        prev.live = false;
+        return 0;
+    };
     if (nb) TRY(upload(0));
     for (size_t bi = 0; bi < nb; ++bi) {
-        const int slot = (int)(bi & 1);
-        const size_t r0 = cuts[bi];
+        const int slot = (int)(bi % 3), lane = (int)(bi & 1);
         Batch &b = *bufs[slot];
-        if (bi + 1 < nb) TRY(upload(bi + 1));
-        CK(cudaStreamWaitEvent(c->stream, c->ev_up[slot], 0));
-        TRY(run_path(c, b, n_samples, st));
-        CK(cudaEventRecord(c->ev[5], c->stream));
-        uint64_t n_cls = 0;
-        TRY(fetch_batch(c, b, status + r0, best_nm + r0, class_offsets + r0, class_base, class_asv, class_cap, &n_cls, &st.d2h_bytes));
-        CK(cudaEventRecord(c->ev[0], c->stream));
-        CK(cudaStreamSynchronize(c->stream));
-        st.d2h_ms += ev_ms(c->ev[5], c->ev[0]);
-        st.h2d_ms += ev_ms(c->ev_h0[slot], c->ev_up[slot]);
-        class_base += n_cls;
+        if (bi + 1 < nb) TRY(upload(bi + 1));       // slot (bi+1) % 3 held batch bi-2: finished and fetched
+        {
+            LaneGuard g(c, lane);
+            CK(cudaStreamWaitEvent(c->stream, c->ev_up[slot], 0));
+            TRY(enqueue_path(c, b, n_samples));
+        }
+        TRY(finish_prev());
+        prev = Pending{&b, cuts[bi + 1] - cuts[bi], cuts[bi], slot, lane, true};
         st.n_batches += 1;
     }
+    TRY(finish_prev());
     TRY(read_counters(c, unambig, ambig, leq10, totals, sample_singleton, true));
     st.d2h_bytes += c->counters_len * 8;
     CK(cudaEventRecord(c->ev[7], c->stream));
@@ -1194,7 +1256,7 @@ int savont_b200_map_reads(savont_b200_ctx *h, const uint8_t *bases, const uint8_
     if (n_samples < 1) return fail(SAVONT_B200_ERR_INVALID, "n_samples must be >= 1");
     std::vector<size_t> cuts{0};
     for (size_t r0 = 0; r0 < n_reads;) {
-        size_t r1 = std::min(n_reads, r0 + c->batch_reads);
+        size_t r1 = std::min(n_reads, r0 + ramp_batch(c, cuts.size() - 1));
         while (r1 > r0 + 1 && offsets[r1] - offsets[r0] > (3ull << 30)) r1 = r0 + (r1 - r0) / 2;
         cuts.push_back(r1);
         r0 = r1;
@@ -1209,7 +1271,7 @@ int savont_b200_map_reads(savont_b200_ctx *h, const uint8_t *bases, const uint8_
 static std::vector<size_t> twin_cuts(const Context *c, const TwinInput &in, size_t n_reads) {
     std::vector<size_t> cuts{0};
     for (size_t r0 = 0; r0 < n_reads;) {
-        size_t r1 = std::min(n_reads, r0 + c->batch_reads);
+        size_t r1 = std::min(n_reads, r0 + ramp_batch(c, cuts.size() - 1));
         while (r1 > r0 + 1 && (in.word_offsets[r1] - in.word_offsets[r0]) * 32ull > (3ull << 30)) r1 = r0 + (r1 - r0) / 2;
         cuts.push_back(r1);
         r0 = r1;
@@ -1290,7 +1352,7 @@ int savont_b200_fetch_resident(savont_b200_ctx *h, uint8_t *status, int32_t *bes
     if (!c->resident.mapped) return fail(SAVONT_B200_ERR_INVALID, "map_resident has not run");
     if (!status || !best_nm || !class_offsets) return fail(SAVONT_B200_ERR_INVALID, "null argument");
     uint64_t n_cls = 0;
-    return fetch_batch(c, c->resident, status, best_nm, class_offsets, 0, class_asv, class_cap, &n_cls, nullptr);
+    return fetch_batch(c, c->resident, c->resident.n, c->stream, status, best_nm, class_offsets, 0, class_asv, class_cap, &n_cls, nullptr);
 }
 
 int savont_b200_counts_dev(savont_b200_ctx *h, void **dev_ptr, size_t *n_u64) {

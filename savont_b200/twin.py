@@ -11,26 +11,30 @@ from __future__ import annotations
 import numpy as np
 
 
-def pack_dna_words(codes: np.ndarray, offsets: np.ndarray):
+def pack_dna_words(codes: np.ndarray, offsets: np.ndarray, chunk_reads: int = 32768):
     """2-bit codes (A0 C1 G2 T3, one per byte, concatenated) -> (words u64, word_offsets u64[n+1], lengths u32[n]).
     Base i of a read sits in bits 2(i%32).. of the read's word i/32 (first base in the LOW bits, src/types.rs:575-579);
-    every read starts at a word boundary."""
+    every read starts at a word boundary.  Works through the reads in chunks to bound the scatter's index memory."""
     offsets = np.asarray(offsets, np.int64)
     n = len(offsets) - 1
     lens = (offsets[1:] - offsets[:-1]).astype(np.int64)
     nwords = (lens + 31) // 32
     woffs = np.zeros(n + 1, np.int64)
     np.cumsum(nwords, out=woffs[1:])
-    total_words = int(woffs[-1])
-    padded = np.zeros(total_words * 32, np.uint8)
-    if n and int(lens.sum()):
-        shift = np.repeat(woffs[:-1] * 32 - (offsets[:-1] - offsets[0]), lens)
-        idx = np.arange(int(lens.sum()), dtype=np.int64) + shift
-        padded[idx] = np.asarray(codes[int(offsets[0]):int(offsets[-1])], np.uint8) & 3
-    # 4 bases -> one byte (little endian bit order), 8 bytes -> one little-endian u64
-    q = padded.reshape(-1, 4)
-    by = (q[:, 0] | (q[:, 1] << 2) | (q[:, 2] << 4) | (q[:, 3] << 6)).astype(np.uint8)
-    words = by.view("<u8").copy() if total_words else np.zeros(0, np.uint64)
+    words = np.zeros(int(woffs[-1]), np.uint64)
+    for r0 in range(0, n, chunk_reads):
+        r1 = min(n, r0 + chunk_reads)
+        nb = int(offsets[r1] - offsets[r0]); nw = int(woffs[r1] - woffs[r0])
+        if nb == 0:
+            continue
+        padded = np.zeros(nw * 32, np.uint8)
+        shift = np.repeat((woffs[r0:r1] - woffs[r0]) * 32 - (offsets[r0:r1] - offsets[r0]), lens[r0:r1])
+        idx = np.arange(nb, dtype=np.int64) + shift
+        padded[idx] = np.asarray(codes[int(offsets[r0]):int(offsets[r1])], np.uint8) & 3
+        # 4 bases -> one byte (little endian bit order), 8 bytes -> one little-endian u64
+        q = padded.reshape(-1, 4)
+        by = (q[:, 0] | (q[:, 1] << 2) | (q[:, 2] << 4) | (q[:, 3] << 6)).astype(np.uint8)
+        words[int(woffs[r0]):int(woffs[r1])] = by.view("<u8")
     return words, woffs.astype(np.uint64), lens.astype(np.uint32)
 
 
@@ -49,3 +53,31 @@ def from_sketch(sk: dict, offsets: np.ndarray, file_idx=None, kmer48: bool = Fal
                 snpmer_kmers=kmer48_bytes(sk_k) if kmer48 else sk_k,
                 snpmer_offsets=np.ascontiguousarray(sk["snp_offsets"], np.uint64),
                 file_idx=None if file_idx is None else np.ascontiguousarray(file_idx, np.uint32))
+
+
+def twin_reads_from_snpmers(ctx, bases, quals, offsets, file_idx=None, kmer48: bool = False, chunk_reads: int = 65536, alloc=None) -> dict:
+    """Read side of Stage 1.5 (kmer_comp::twin_reads_from_snpmers, src/kmer_comp.rs:68-258, the part Stage 7 consumes):
+    sketch the reads on the GPU (Context.sketch) and lay dna_seq / snpmer_kmers out as the TwinRead fields.
+    `alloc(nbytes)` may return a uint8 array (e.g. pinned memory) for the two big buffers."""
+    offsets = np.asarray(offsets, np.uint64)
+    n = len(offsets) - 1
+    words, woffs, lens, kmers = [], [np.zeros(1, np.uint64)], [], []
+    soffs = [np.zeros(1, np.uint64)]
+    wbase = sbase = 0
+    for r0 in range(0, n, chunk_reads):
+        r1 = min(n, r0 + chunk_reads)
+        o = offsets[r0:r1 + 1]
+        b0, b1 = int(o[0]), int(o[-1])
+        sk = ctx.sketch(bases[b0:b1], None if quals is None else quals[b0:b1], o - o[0])
+        w, wo, ln = pack_dna_words(sk["codes"], o - o[0])
+        words.append(w); woffs.append(wo[1:] + np.uint64(wbase)); lens.append(ln)
+        kmers.append(np.ascontiguousarray(sk["snp_kmer"], np.uint64)); soffs.append(sk["snp_offsets"][1:] + np.uint64(sbase))
+        wbase += int(wo[-1]); sbase += int(sk["snp_offsets"][-1])
+    cat = lambda xs, dt: np.concatenate(xs).astype(dt, copy=False) if xs else np.zeros(0, dt)
+    words = cat(words, np.uint64); kmers = cat(kmers, np.uint64)
+    kk = kmer48_bytes(kmers) if kmer48 else kmers
+    if alloc is not None:
+        pw = alloc(words.nbytes)[:words.nbytes].view(np.uint64); pw[:] = words; words = pw
+        pk = alloc(kk.nbytes)[:kk.nbytes].view(kk.dtype); pk[:] = kk; kk = pk
+    return dict(dna_words=words, dna_word_offsets=cat(woffs, np.uint64), lengths=cat(lens, np.uint32), snpmer_kmers=kk,
+                snpmer_offsets=cat(soffs, np.uint64), file_idx=None if file_idx is None else np.ascontiguousarray(file_idx, np.uint32))
