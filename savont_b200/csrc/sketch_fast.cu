@@ -40,7 +40,8 @@ struct FastSmem {
     uint32_t stage_bytes;    // per warp: aligned plane staging / position list / SNPmer dedup table (aliased)
     uint32_t hit_cap;        // per warp, power of two
     __host__ __device__ size_t per_warp() const { return (size_t)packed_words * 4u + stage_bytes + (size_t)hit_cap * 12u + 16u; }
-    __host__ __device__ size_t total() const { return 32768u + 2048u + bloom_bytes + per_warp() * kFastWarps; }
+    uint32_t warps;          // warps per CTA (32 unless long reads need more shared memory per warp)
+    __host__ __device__ size_t total() const { return 32768u + 2048u + bloom_bytes + per_warp() * warps; }
 };
 
 // 32 -> 16: keep the even bits of x
@@ -98,7 +99,7 @@ sketch_fast_kernel(SeqBatch in, SketchOut out, SnpSet set, const uint16_t *__res
     uint32_t *hits_p = reinterpret_cast<uint32_t *>(hits_k + lay.hit_cap);
     constexpr bool want_snp = (SRC == 0) && SNP;
 
-    for (uint32_t seq = blockIdx.x * kFastWarps + warp; seq < in.n; seq += gridDim.x * kFastWarps) {
+    for (uint32_t seq = blockIdx.x * lay.warps + warp; seq < in.n; seq += gridDim.x * lay.warps) {
         const uint64_t off = in.offsets[seq];
         const uint32_t L = (uint32_t)(in.offsets[seq + 1] - off);
         uint2 *planes = out.planes + plane_word_off(off, seq);
@@ -480,6 +481,10 @@ static FastSmem fast_layout(uint32_t max_len, const SnpSet &set) {
     if (stage < kFastListCap * 2u) stage = kFastListCap * 2u;
     if (stage < lay.hit_cap * 16u) stage = lay.hit_cap * 16u;
     lay.stage_bytes = (stage + 15u) & ~15u;
+    // one persistent CTA per SM: as many warps as the per-warp regions allow in 225 KB (32 for 16S reads, fewer for
+    // multi-kb operon reads)
+    lay.warps = kFastWarps;
+    while (lay.warps > 8u && lay.total() > 225u * 1024u) lay.warps -= 8u;
     return lay;
 }
 
@@ -496,17 +501,17 @@ void launch_sketch_fast(const SeqBatch &in, const SketchOut &out, const SnpSet &
     const FastSmem lay = fast_layout(in.max_len, set);
     const size_t smem = lay.total();
     uint32_t grid = (uint32_t)sm_count;
-    const uint32_t need = (in.n + kFastWarps - 1) / kFastWarps;
+    const uint32_t need = (in.n + lay.warps - 1) / lay.warps;
     if (grid > need) grid = need;
     if (in.dna_words != nullptr) {
         cudaFuncSetAttribute(sketch_fast_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        sketch_fast_kernel<1, false><<<grid, kFastWarps * 32, smem, st>>>(in, out, set, rank_table, p, lay);
+        sketch_fast_kernel<1, false><<<grid, lay.warps * 32, smem, st>>>(in, out, set, rank_table, p, lay);
     } else if (set.keys != nullptr) {
         cudaFuncSetAttribute(sketch_fast_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        sketch_fast_kernel<0, true><<<grid, kFastWarps * 32, smem, st>>>(in, out, set, rank_table, p, lay);
+        sketch_fast_kernel<0, true><<<grid, lay.warps * 32, smem, st>>>(in, out, set, rank_table, p, lay);
     } else {
         cudaFuncSetAttribute(sketch_fast_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        sketch_fast_kernel<0, false><<<grid, kFastWarps * 32, smem, st>>>(in, out, set, rank_table, p, lay);
+        sketch_fast_kernel<0, false><<<grid, lay.warps * 32, smem, st>>>(in, out, set, rank_table, p, lay);
     }
 }
 
