@@ -282,10 +282,10 @@ def run_b200(args, rank, world, local_rank):
                      "algorithmic_bytes": pairs * (376 + 21),
                      "peak_how": f"148 SM x 64 INT32 ALU lanes x {sm_mhz:.0f} MHz (sampled) x 32 cells / {OPS_PER_WORD} ALU ops per "
                                  f"32-cell word, x {used_frac:.3f} (band {2 * w.band + 1} of {32 * nw} vector bits)"},
-        "roofline_hbm": {"bound": "hbm", "kernel": "sketch_kernel", "achieved": sk_bytes / (sketch_ms / 1e3) / 1e9 if sketch_ms else None,
+        "roofline_hbm": {"bound": "hbm", "kernel": "sketch_fast_kernel", "achieved": sk_bytes / (sketch_ms / 1e3) / 1e9 if sketch_ms else None,
                          "peak": peaks["hbm_gbs"], "unit": "GB/s", "peak_source": peaks["source"],
                          "frac": (sk_bytes / (sketch_ms / 1e3) / 1e9) / peaks["hbm_gbs"] if sketch_ms else None,
-                         "traffic": _ncu_traffic("sketch_kernel") if (n_reads == 1_000_000 and args.workload == "ont16s") else None,
+                         "traffic": _ncu_traffic("sketch_fast_kernel") if (n_reads == 1_000_000 and args.workload == "ont16s") else None,
                          "algorithmic_bytes": sk_bytes},
         "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(e2e_stats["h2d_bytes"]),
                 "d2h_bytes_per_step": int(e2e_stats["d2h_bytes"]), "steps": e2e_steps, "ms_per_step": e2e_total_ms / e2e_steps,
@@ -315,15 +315,17 @@ def run_b200(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
 
 
-# INT32 ALU-pipe instructions per 32-cell word-column of the banded Myers/Hyyro recurrence as formulated in
-# align.cu (2 SHF + 2 LOP3 for Eq, X, t, IADD3.X, D0, Ph, Mh, the re-alignment SHF, Pv', Mv').  The SASS
-# inner loop of align_nm_kernel<5> is 81 instructions per column = 16.2 per word including loop/char overhead.
-OPS_PER_WORD = 13.0
+# INT32 ALU-pipe instructions per 32-cell word-column that the banded Myers/Hyyro recurrence as formulated in align.cu
+# cannot avoid (NW = 5 words): 2 LOP3 per word-aligned ASV word for the mismatch bits (2*(NW+1)/NW = 2.4), 1 SHF to align
+# them to the band, X, t, IADD3.X, D0, Ph, Mh, the re-alignment SHF, Pv', Mv' = 12.4.  The SASS inner loop of
+# align_nm_kernel<5> is 71 instructions per column (66 ALU-pipe, 4 IMAD, 1 BRA: `python tools/sass_loops.py`) = 13.2 ALU
+# per word including the per-column overhead (read-base broadcast, band-top score, loop counter).
+OPS_PER_WORD = 12.4
 
 
 def _ncu_traffic(kernel):
     """dram bytes read+written per launch from the committed ncu --set full summary (1M-read launch), or None"""
-    path = os.path.join(ROOT, "profiles", f"r01_{kernel}_full.txt")
+    path = os.path.join(ROOT, "profiles", f"r01c_{kernel}_full.txt")
     try:
         tot = 0.0
         for line in open(path):

@@ -132,21 +132,24 @@ struct Band {
 template <int NW, bool TB, bool TOP, bool LAST>
 __device__ __forceinline__ void dp_column(Band<NW, TB> &s, uint32_t (&TM)[NW], uint32_t clo, uint32_t chi, uint32_t sh, int j, int n,
                                           int B, uint32_t *hist_col, uint32_t hist_stride) {
-    uint32_t Eq[NW], X[NW], t[NW], sum[NW], D0[NW], Ph[NW], Mh[NW];
+    uint32_t Nr[NW + 1], X[NW], t[NW], sum[NW], D0[NW], Ph[NW], Mh[NW];
+    // MISmatch bits on the word-aligned window first (2 LOP3 per raw word), ONE funnel shift per band word afterwards;
+    // the complement is folded into the LOP3 that forms X = Eq | Mv
+#pragma unroll
+    for (int w = 0; w <= NW; ++w) Nr[w] = (s.Alo[w] ^ clo) | (s.Ahi[w] ^ chi);
 #pragma unroll
     for (int w = 0; w < NW; ++w) {
-        const uint32_t lo = __funnelshift_r(s.Alo[w], s.Alo[w + 1], sh);
-        const uint32_t hi = __funnelshift_r(s.Ahi[w], s.Ahi[w + 1], sh);
-        Eq[w] = ~((lo ^ clo) | (hi ^ chi));
-        if (TOP) Eq[w] |= TM[w];
-        X[w] = Eq[w] | s.Mv[w];
+        const uint32_t Ns = __funnelshift_r(Nr[w], Nr[w + 1], sh);
+        X[w] = TOP ? (~Ns | s.Mv[w] | TM[w]) : (~Ns | s.Mv[w]);
         t[w] = X[w] & s.Pv[w];
     }
     add_chain<NW>(t, s.Pv, sum);
 #pragma unroll
     for (int w = 0; w < NW; ++w) {
         D0[w] = (sum[w] ^ s.Pv[w]) | X[w];
-        Ph[w] = s.Mv[w] | ~(D0[w] | s.Pv[w]);
+        // Ph = Mv | ~(D0 | Pv) as ONE LOP3 on (Mv, D0, Pv): left to itself the compiler rebuilds D0 | Pv from
+        // (sum, Pv, X) with a second LOP3 per word
+        asm("lop3.b32 %0, %1, %2, %3, 0xF1;" : "=r"(Ph[w]) : "r"(s.Mv[w]), "r"(D0[w]), "r"(s.Pv[w]));
         Mh[w] = s.Pv[w] & D0[w];
     }
     s.T += (int)((~D0[0]) & 1u);
@@ -244,13 +247,22 @@ __device__ __forceinline__ void align_pair(const AlignArgs &a, uint32_t pi, uint
                     s.Alo[NW] = nv.x; s.Ahi[NW] = nv.y;
                 }
             }
+            // columns j..stop share the read word; the loop runs on the bit index alone.  cl / ch hold the bit-reversed
+            // read word shifted so that the current column's bit is the sign bit: the broadcast mask is one arithmetic
+            // shift and the advance is an add (IMAD on the FMA pipe), instead of a variable shift pair per plane.  (IMAD.HI as the
+            // sign broadcast was measured: it costs an ALU-pipe slot as well on B200, tools/pipe_bench.cu, so no gain.)
             const int stop = min(jend, j + 31 - (int)bit);
-            for (; j <= stop; ++j, ++bit) {
-                const uint32_t clo = (uint32_t)((int32_t)(cw_lo << (31u - bit)) >> 31);
-                const uint32_t chi = (uint32_t)((int32_t)(cw_hi << (31u - bit)) >> 31);
-                dp_column<NW, TB, TOP, LAST>(s, TM, clo, chi, bit, j, n, B,
-                                             TB ? hist + (size_t)(j - 1) * hist_col_stride : nullptr, a.hist_stride);
+            const uint32_t bit_end = bit + (uint32_t)(stop - j);
+            const int jbase = j - (int)bit;
+            uint32_t cl = __brev(cw_lo) << bit, ch = __brev(cw_hi) << bit;
+            for (; bit <= bit_end; ++bit) {
+                const uint32_t clo = (uint32_t)((int32_t)cl >> 31);
+                const uint32_t chi = (uint32_t)((int32_t)ch >> 31);
+                cl += cl; ch += ch;
+                dp_column<NW, TB, TOP, LAST>(s, TM, clo, chi, bit, jbase + (int)bit, n, B,
+                                             TB ? hist + (size_t)(jbase + (int)bit - 1) * hist_col_stride : nullptr, a.hist_stride);
             }
+            j = stop + 1;
         }
     };
     // phase 1: virtual rows (<= 0) inside the window; phase 2: interior; phase 3: last row inside the window
