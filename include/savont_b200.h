@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SAVONT_B200_ABI_VERSION 1
+#define SAVONT_B200_ABI_VERSION 2
 
 typedef struct savont_b200_ctx savont_b200_ctx;
 
@@ -56,8 +56,22 @@ enum {
     SAVONT_B200_READ_NO_CANDIDATE = 1,   /* asv_scores empty            src/alignment.rs:1817-1820 */
     SAVONT_B200_READ_RATIO_FILTERED = 2, /* nothing with ratio<=thresh  src/alignment.rs:1835-1838 */
     SAVONT_B200_READ_NO_ALIGNMENT = 3,   /* best_alns empty             src/alignment.rs:1921-1924 */
-    SAVONT_B200_READ_TOO_SHORT = 4       /* len < k: no TwinRead        src/seeding.rs:339-341 */
+    SAVONT_B200_READ_TOO_SHORT = 4,      /* len < k: no TwinRead        src/seeding.rs:339-341 */
+    /* only with a read filter (savont_b200_set_read_filter): the read never becomes a TwinRead and is counted
+     * neither as assigned nor as filtered */
+    SAVONT_B200_READ_LENGTH_FILTERED = 5, /* outside [min,max] length   src/kmer_comp.rs:117-120 */
+    SAVONT_B200_READ_REPETITIVE = 6,     /* #solid minimizers < len/c/20 src/kmer_comp.rs:185-188 */
+    SAVONT_B200_READ_LOW_QUALITY = 7     /* est_id < quality cutoff     src/kmer_comp.rs:248 */
 };
+
+/* The Cli fields / constants the read-side wrapper kmer_comp::twin_reads_from_snpmers reads (src/kmer_comp.rs:68-258). */
+typedef struct savont_b200_read_filter {
+    uint32_t min_read_length;        /* --min-read-length  (src/cli.rs:87-88, default 1100); 0 = off */
+    uint32_t max_read_length;        /* --max-read-length  (src/cli.rs:91-92, default 2000); 0 = no upper bound */
+    uint32_t max_kmer_count_in_read; /* MAX_KMER_COUNT_IN_READ = 500 (src/constants.rs) */
+    uint32_t reserved;
+    double   quality_value_cutoff;   /* --quality-value-cutoff (src/cli.rs:95-96, default 98.0); <= 0 = off */
+} savont_b200_read_filter;
 
 enum {
     SAVONT_B200_OK = 0,
@@ -96,6 +110,24 @@ int savont_b200_set_batch_reads(savont_b200_ctx *ctx, size_t max_reads_per_batch
 /* The SNPmer set: both alleles of every SNPmer, exactly the u64 values the reference inserts
  * at src/kmer_comp.rs:41-48 (`split_kmer | mid_base << (k-1)`). */
 int savont_b200_load_snpmers(savont_b200_ctx *ctx, const uint64_t *kmers, size_t n);
+
+/* The high-frequency k-mer set of Stage 1 (KmerGlobalInfo.high_freq_kmers, Kmer48 values widened to u64), read by the
+ * repetitive-read test of twin_reads_from_snpmers (src/kmer_comp.rs:163-188).  n = 0 clears it. */
+int savont_b200_load_high_freq_kmers(savont_b200_ctx *ctx, const uint64_t *kmers, size_t n);
+/* Switches the read tests of twin_reads_from_snpmers on (f != NULL) or off (NULL, the default: Stage 7 / 7b receive
+ * reads that already passed them).  With a filter set, savont_b200_map_reads / upload_reads + map_resident /
+ * find_candidates take raw FASTQ reads: a read failing a test gets status 5 / 6 / 7 and takes no part in the
+ * assignment.  The TwinRead entry points ignore the filter (TwinReads exist only for reads that passed). */
+int savont_b200_set_read_filter(savont_b200_ctx *ctx, const savont_b200_read_filter *f);
+/* Replaces the per-read part of kmer_comp::twin_reads_from_snpmers (src/kmer_comp.rs:68-258) for a batch of FASTQ
+ * reads, using the read filter and high-frequency set of the context (a filter must be set): status[i] in
+ * {0 kept, 4, 5, 6, 7}, est_id[i] (NaN = None), and the number of minimizer / SNPmer positions that
+ * retain_mini_indices / retain_snpmer_indices leave (src/types.rs:702-715; 0 for dropped reads).  The sort by read id
+ * (:233) and by est_id (src/main.rs:538) that defines the Stage-7 read order is host work on these outputs
+ * (savont_b200/host: twin_read_order). */
+int savont_b200_twin_reads_from_snpmers(savont_b200_ctx *ctx, const uint8_t *bases, const uint8_t *quals,
+                                        const uint64_t *offsets, size_t n_reads, uint8_t *status, double *est_id,
+                                        uint32_t *n_solid_mini, uint32_t *n_solid_snp);
 
 /* Replaces kmer_comp::twin_reads_from_fasta (src/kmer_comp.rs:39-66) + the SNPmer inverted
  * index build (src/alignment.rs:1754-1765): sketches the ASVs on the GPU (no qualities) and

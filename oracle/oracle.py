@@ -15,6 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libsavont_oracle.so")
 
 STATUS_ASSIGNED, STATUS_NO_CANDIDATE, STATUS_RATIO_FILTERED, STATUS_NO_ALIGNMENT, STATUS_TOO_SHORT = 0, 1, 2, 3, 4
+STATUS_LENGTH_FILTERED, STATUS_REPETITIVE, STATUS_LOW_QUALITY = 5, 6, 7
 
 
 class Params(C.Structure):
@@ -23,6 +24,17 @@ class Params(C.Structure):
         ("band", C.c_int32), ("strand_mode", C.c_int32), ("candidate_mode", C.c_int32), ("reserved", C.c_int32),
         ("ratio_thresh", C.c_double), ("min_mini_frac_base", C.c_double),
     ]
+
+
+class ReadFilter(C.Structure):
+    """a4 options (so_read_filter): the Cli fields / constants kmer_comp::twin_reads_from_snpmers reads"""
+    _fields_ = [("min_read_length", C.c_uint32), ("max_read_length", C.c_uint32), ("max_kmer_count_in_read", C.c_uint32),
+                ("reserved", C.c_uint32), ("quality_value_cutoff", C.c_double)]
+
+
+def read_filter(min_read_length=1100, max_read_length=2000, quality_value_cutoff=98.0, max_kmer_count_in_read=500) -> ReadFilter:
+    """defaults of src/cli.rs:87-96 and MAX_KMER_COUNT_IN_READ (src/constants.rs)"""
+    return ReadFilter(min_read_length, max_read_length, max_kmer_count_in_read, 0, quality_value_cutoff)
 
 
 def default_params(**kw) -> Params:
@@ -84,6 +96,8 @@ def lib():
         L.so_align_pairs.restype = C.c_int
         L.so_map_reads.restype = C.c_int
         L.so_em.restype = C.c_int
+        L.so_twin_reads_filter.restype = C.c_int
+        L.so_set_read_filter.restype = None
         _lib = L
     return _lib
 
@@ -135,7 +149,37 @@ def sketch_batch(params: Params, snpmers, bases, quals, offsets):
                 mini_fwd=mf[:nm], snp_offsets=so, snp_pos=spos[:ns], snp_kmer=sk[:ns], codes=codes[:total])
 
 
+def concat_ids(ids):
+    """list of str/bytes read ids -> (uint8 concatenation, uint64 offsets[n+1])"""
+    return concat([i.encode() if isinstance(i, str) else bytes(i) for i in ids])
+
+
+def twin_reads_filter(params: Params, rf: ReadFilter, snpmers, high_freq, bases, quals, offsets, ids=None):
+    """a4: kmer_comp::twin_reads_from_snpmers + the read order of src/main.rs:538 (so_twin_reads_filter)"""
+    L = lib()
+    snp = np.ascontiguousarray(snpmers, dtype=np.uint64)
+    hf = np.ascontiguousarray(high_freq if high_freq is not None else [], dtype=np.uint64)
+    bases = as_u8(bases)
+    quals = None if quals is None else as_u8(quals)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    n = len(offsets) - 1
+    idb, ido = (None, None) if ids is None else concat_ids(ids)
+    st = np.zeros(max(n, 1), np.uint8); est = np.zeros(max(n, 1), np.float64)
+    sm = np.zeros(max(n, 1), np.uint32); ss = np.zeros(max(n, 1), np.uint32); order = np.zeros(max(n, 1), np.uint32)
+    nk = C.c_size_t(0)
+    rc = L.so_twin_reads_filter(C.byref(params), C.byref(rf), _p(snp, C.c_uint64), C.c_size_t(len(snp)), _p(hf, C.c_uint64),
+                                C.c_size_t(len(hf)), _p(bases, C.c_uint8), _p(quals, C.c_uint8), _p(offsets, C.c_uint64), C.c_size_t(n),
+                                _p(idb, C.c_uint8), _p(ido, C.c_uint64), _p(st, C.c_uint8), _p(est, C.c_double),
+                                _p(sm, C.c_uint32), _p(ss, C.c_uint32), _p(order, C.c_uint32), C.byref(nk))
+    assert rc == 0, rc
+    return dict(status=st[:n], est_id=est[:n], n_solid_mini=sm[:n], n_solid_snp=ss[:n], order=order[:int(nk.value)])
+
+
 class Oracle:
+    def set_read_filter(self, rf: ReadFilter | None, high_freq=None):
+        hf = np.ascontiguousarray(high_freq if high_freq is not None else [], dtype=np.uint64)
+        self.L.so_set_read_filter(C.c_void_p(self.h), None if rf is None else C.byref(rf), _p(hf, C.c_uint64), C.c_size_t(len(hf)))
+
     def __init__(self, params: Params, snpmers):
         self.L = lib()
         self.params = params

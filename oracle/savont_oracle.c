@@ -320,6 +320,7 @@ struct so_ctx {
     u64map snpmer_set;
     asv_t *asvs; size_t n_asv;
     idx_entry *index; size_t n_index;                   /* sorted by splitmer */
+    int has_filter; so_read_filter rf; u64map high_freq; /* a4 tests inside so_map_reads */
 };
 
 so_ctx *so_create(const so_params *p, const uint64_t *snpmers, size_t n_snpmers) {
@@ -336,6 +337,7 @@ static void free_asvs(so_ctx *c) {
     c->asvs = NULL; c->index = NULL; c->n_asv = 0; c->n_index = 0;
 }
 void so_destroy(so_ctx *c) {
+    if (c && c->high_freq.cap) u64map_free(&c->high_freq);
     if (!c) return;
     free_asvs(c); u64map_free(&c->snpmer_set); free(c);
 }
@@ -650,6 +652,98 @@ int so_align_pairs(so_ctx *c, const uint8_t *bases, const uint64_t *offsets, siz
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* a4: kmer_comp::twin_reads_from_snpmers, src/kmer_comp.rs:68-258                      */
+/* ------------------------------------------------------------------------------------ */
+/* the tests a read goes through before it becomes a TwinRead; the quality cutoff (:248) is applied after the id sort in
+ * the reference but is a per-read predicate, so it is evaluated here as the last test */
+static int read_filter_one(const so_params *p, const so_read_filter *f, const u64map *high_freq, size_t len, const sketch_t *sk,
+                           uint32_t *n_solid_mini, uint32_t *n_solid_snp) {
+    *n_solid_mini = 0; *n_solid_snp = 0;
+    if (len < f->min_read_length || (f->max_read_length && len > f->max_read_length)) return SO_LENGTH_FILTERED;   /* :117-120 */
+    if (!sk->ok) return SO_TOO_SHORT;                                            /* :160-161 twin_read.is_some() */
+    u64map counter; u64map_init(&counter, sk->n_mini + 1);                       /* :163-166 kmer_counter_map */
+    for (size_t i = 0; i < sk->n_mini; i++) *u64map_slot(&counter, sk->mini_kmer[i], 1) += 1;
+    uint32_t solid = 0;
+    for (size_t i = 0; i < sk->n_mini; i++) {                                    /* :168-183 */
+        if (*u64map_slot(&counter, sk->mini_kmer[i], 0) > f->max_kmer_count_in_read) continue;
+        if (!(high_freq->cap && u64map_slot((u64map *)high_freq, sk->mini_kmer[i], 0))) solid++;   /* USE_SOLID_KMERS = false */
+    }
+    u64map_free(&counter);
+    if (solid < len / (size_t)p->c / 20) return SO_REPETITIVE;                   /* :185-188 */
+    uint32_t ssnp = 0;
+    for (size_t i = 0; i < sk->n_snp; i++)                                       /* :190-203 */
+        if (!(high_freq->cap && u64map_slot((u64map *)high_freq, sk->snp_kmer[i], 0))) ssnp++;
+    *n_solid_mini = solid; *n_solid_snp = ssnp;
+    if (f->quality_value_cutoff > 0.0 && !isnan(sk->est_id) && sk->est_id < f->quality_value_cutoff) return SO_LOW_QUALITY; /* :248 */
+    return 0;
+}
+
+typedef struct { const uint8_t *id; size_t id_len; double est; uint32_t idx; } order_t;
+static int cmp_order_id(const void *a, const void *b) {      /* String::cmp = byte-wise, shorter first on a common prefix */
+    const order_t *x = (const order_t *)a, *y = (const order_t *)b;
+    size_t m = x->id_len < y->id_len ? x->id_len : y->id_len;
+    int c = m ? memcmp(x->id, y->id, m) : 0;
+    if (c) return c;
+    if (x->id_len != y->id_len) return x->id_len < y->id_len ? -1 : 1;
+    return x->idx < y->idx ? -1 : (x->idx > y->idx);        /* stable */
+}
+static void merge_sort_est_desc(order_t *v, order_t *tmp, size_t n) {   /* stable, src/main.rs:538 */
+    if (n < 2) return;
+    size_t h = n / 2;
+    merge_sort_est_desc(v, tmp, h); merge_sort_est_desc(v + h, tmp, n - h);
+    size_t i = 0, j = h, o = 0;
+    while (i < h && j < n) tmp[o++] = (v[j].est > v[i].est) ? v[j++] : v[i++];   /* take right only if strictly larger */
+    while (i < h) tmp[o++] = v[i++];
+    while (j < n) tmp[o++] = v[j++];
+    memcpy(v, tmp, n * sizeof(order_t));
+}
+
+int so_twin_reads_filter(const so_params *p, const so_read_filter *f, const uint64_t *snpmers, size_t n_snpmers,
+                         const uint64_t *high_freq, size_t n_high_freq,
+                         const uint8_t *bases, const uint8_t *quals, const uint64_t *offsets, size_t n_reads,
+                         const uint8_t *ids, const uint64_t *id_offsets,
+                         uint8_t *status, double *est_id, uint32_t *n_solid_mini, uint32_t *n_solid_snp,
+                         uint32_t *order, size_t *n_kept) {
+    u64map set; u64map_init(&set, n_snpmers);
+    for (size_t i = 0; i < n_snpmers; i++) u64map_slot(&set, snpmers[i], 1);
+    u64map hf; memset(&hf, 0, sizeof(hf));
+    if (n_high_freq) { u64map_init(&hf, n_high_freq); for (size_t i = 0; i < n_high_freq; i++) u64map_slot(&hf, high_freq[i], 1); }
+    order_t *ord = (order_t *)malloc((n_reads + 1) * sizeof(order_t));
+    size_t nk = 0;
+    for (size_t r = 0; r < n_reads; r++) {
+        size_t off = offsets[r], len = offsets[r + 1] - off;
+        sketch_t sk; sketch_one(p, &set, bases + off, quals ? quals + off : NULL, len, &sk);
+        uint32_t sm = 0, ss = 0;
+        int st = read_filter_one(p, f, &hf, len, &sk, &sm, &ss);
+        status[r] = (uint8_t)st;
+        if (est_id) est_id[r] = sk.ok ? sk.est_id : NAN;
+        if (n_solid_mini) n_solid_mini[r] = sm;
+        if (n_solid_snp) n_solid_snp[r] = ss;
+        if (st == 0) {
+            ord[nk].idx = (uint32_t)r; ord[nk].est = isnan(sk.est_id) ? 100.0 : sk.est_id;   /* unwrap_or(100.0) */
+            ord[nk].id = ids ? ids + id_offsets[r] : NULL; ord[nk].id_len = ids ? (size_t)(id_offsets[r + 1] - id_offsets[r]) : 0;
+            nk++;
+        }
+        sketch_free(&sk);
+    }
+    if (ids) qsort(ord, nk, sizeof(order_t), cmp_order_id);                      /* :233 */
+    order_t *tmp = (order_t *)malloc((nk + 1) * sizeof(order_t));
+    merge_sort_est_desc(ord, tmp, nk);                                           /* src/main.rs:538 */
+    if (order) for (size_t i = 0; i < nk; i++) order[i] = ord[i].idx;
+    if (n_kept) *n_kept = nk;
+    free(tmp); free(ord); u64map_free(&set); if (hf.cap) u64map_free(&hf);
+    return 0;
+}
+
+void so_set_read_filter(so_ctx *c, const so_read_filter *f, const uint64_t *high_freq, size_t n_high_freq) {
+    if (c->high_freq.cap) { u64map_free(&c->high_freq); memset(&c->high_freq, 0, sizeof(c->high_freq)); }
+    c->has_filter = f != NULL;
+    if (!f) return;
+    c->rf = *f;
+    if (n_high_freq) { u64map_init(&c->high_freq, n_high_freq); for (size_t i = 0; i < n_high_freq; i++) u64map_slot(&c->high_freq, high_freq[i], 1); }
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* whole path, src/alignment.rs:1786-1925 (Stage 7b duplicate :2095-2171)               */
 /* ------------------------------------------------------------------------------------ */
 int so_map_reads(so_ctx *c, const uint8_t *bases, const uint8_t *quals, const uint64_t *offsets,
@@ -677,6 +771,11 @@ int so_map_reads(so_ctx *c, const uint8_t *bases, const uint8_t *quals, const ui
             size_t off = offsets[r], len = offsets[r + 1] - off;
             best_nm_out[r] = INT32_MAX;
             sketch_t sk; sketch_one(&c->p, &c->snpmer_set, bases + off, quals ? quals + off : NULL, len, &sk);
+            if (c->has_filter) {                       /* a4: the read must survive twin_reads_from_snpmers to reach Stage 7 */
+                uint32_t sm, ss;
+                int fs = read_filter_one(&c->p, &c->rf, &c->high_freq, len, &sk, &sm, &ss);
+                if (fs != 0) { status[r] = (uint8_t)fs; sketch_free(&sk); continue; }
+            }
             if (!sk.ok) { status[r] = SO_TOO_SHORT; sketch_free(&sk); continue; }
             int st = candidates_one(c, &sk, hits, mism, &kept);
             if (st != 0) { status[r] = (uint8_t)st; sketch_free(&sk); continue; }
@@ -733,7 +832,7 @@ int so_map_reads(so_ctx *c, const uint8_t *bases, const uint8_t *quals, const ui
                 if (best_nm_out[r] <= 10) for (uint32_t t = 0; t < cn; t++) leq10[cls[r][t]]++;
                 totals[0]++;
             }
-        } else if (status[r] != SO_TOO_SHORT) {
+        } else if (status[r] < SO_TOO_SHORT) {
             totals[1]++;
         }
         class_offsets[r + 1] = n;

@@ -52,8 +52,21 @@ enum {
     SO_NO_CANDIDATE = 1, /* asv_scores empty                    src/alignment.rs:1817-1820 */
     SO_RATIO_FILTERED = 2, /* no candidate with ratio <= thresh src/alignment.rs:1835-1838 */
     SO_NO_ALIGNMENT = 3, /* best_alns empty                     src/alignment.rs:1921-1924 */
-    SO_TOO_SHORT = 4   /* get_twin_read_syncmer returned None   src/seeding.rs:339-341 */
+    SO_TOO_SHORT = 4,  /* get_twin_read_syncmer returned None   src/seeding.rs:339-341 */
+    /* read-side wrapper twin_reads_from_snpmers (a4): the read never becomes a TwinRead */
+    SO_LENGTH_FILTERED = 5, /* len < min_read_length || len > max_read_length   src/kmer_comp.rs:117-120 */
+    SO_REPETITIVE = 6,      /* #solid minimizers < len / c / 20                 src/kmer_comp.rs:185-188 */
+    SO_LOW_QUALITY = 7      /* est_id < quality_value_cutoff                    src/kmer_comp.rs:248 */
 };
+
+/* a4 options: the Cli fields / constants twin_reads_from_snpmers reads */
+typedef struct so_read_filter {
+    uint32_t min_read_length;        /* src/cli.rs:87-88   default 1100; 0 = off */
+    uint32_t max_read_length;        /* src/cli.rs:91-92   default 2000; 0 = no upper bound */
+    uint32_t max_kmer_count_in_read; /* MAX_KMER_COUNT_IN_READ = 500, src/constants.rs */
+    uint32_t reserved;
+    double   quality_value_cutoff;   /* src/cli.rs:95-96   default 98.0; <= 0 = off */
+} so_read_filter;
 
 /* ---- primitives with known answers ------------------------------------------------ */
 uint8_t  so_encode_base(uint8_t b);                 /* src/types.rs:92-101 */
@@ -120,6 +133,25 @@ int so_map_reads(so_ctx *ctx, const uint8_t *bases, const uint8_t *quals, const 
                  uint8_t *status, int32_t *best_nm, uint64_t *class_offsets, uint32_t *class_asv, size_t class_cap,
                  uint64_t *unambig, uint64_t *ambig, uint64_t *leq10, uint64_t *totals, uint64_t *sample_singleton,
                  uint64_t *dp_cells, int n_threads);
+
+/* ---- a4: read-side wrapper kmer_comp::twin_reads_from_snpmers (src/kmer_comp.rs:68-258) and the read order of
+ * src/main.rs:538.  Per read, in the reference's order of tests: length filter (:117-120), sketch (None -> SO_TOO_SHORT),
+ * per-read minimizer multiplicities, "solid" = multiplicity <= max_kmer_count_in_read and not in high_freq (:163-183;
+ * USE_SOLID_KMERS = false, src/constants.rs), repetitive-read drop (:185-188), then after the id sort the quality cutoff
+ * (:248, only reads that have an est_id).  n_solid_mini / n_solid_snp = sizes of the position vectors that
+ * retain_mini_indices / retain_snpmer_indices leave (src/types.rs:702-715; the k-mer vectors are NOT pruned).
+ * ids: concatenated read ids with id_offsets[n+1] (may be NULL: order by input index).  order[0..*n_kept) = input indices
+ * of the kept reads in the reference's Stage-7 read order: sort by id (:233, byte-wise String order, stable), then stable
+ * sort by est_id descending with None as 100.0 (src/main.rs:538). */
+int so_twin_reads_filter(const so_params *p, const so_read_filter *f, const uint64_t *snpmers, size_t n_snpmers,
+                         const uint64_t *high_freq, size_t n_high_freq,
+                         const uint8_t *bases, const uint8_t *quals, const uint64_t *offsets, size_t n_reads,
+                         const uint8_t *ids, const uint64_t *id_offsets,
+                         uint8_t *status, double *est_id, uint32_t *n_solid_mini, uint32_t *n_solid_snp,
+                         uint32_t *order, size_t *n_kept);
+/* the same tests inside the whole path: reads that fail get their a4 status and are counted neither as assigned nor as
+ * filtered (they do not exist in Stage 7).  f == NULL switches the tests off. */
+void so_set_read_filter(so_ctx *ctx, const so_read_filter *f, const uint64_t *high_freq, size_t n_high_freq);
 
 /* ---- a13-a14: EM over equivalence classes (src/alignment.rs:1957-2038) ---------------
  * classes in CSR (cls_offsets[n_cls+1], cls_asv), counts[n_cls]; total_assigned;

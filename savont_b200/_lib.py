@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libsavont_b200.so")
 HEADER_PATH = os.path.join(_HERE, "..", "include", "savont_b200.h")
 
 READ_ASSIGNED, READ_NO_CANDIDATE, READ_RATIO_FILTERED, READ_NO_ALIGNMENT, READ_TOO_SHORT = 0, 1, 2, 3, 4
+READ_LENGTH_FILTERED, READ_REPETITIVE, READ_LOW_QUALITY = 5, 6, 7
 OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_OVERFLOW, ERR_NOMEM = 0, -1, -2, -3, -4, -5
 
 
@@ -26,6 +27,16 @@ class Params(C.Structure):
         ("band", C.c_int32), ("strand_mode", C.c_int32), ("candidate_mode", C.c_int32), ("reserved", C.c_int32),
         ("ratio_thresh", C.c_double), ("min_mini_frac_base", C.c_double),
     ]
+
+
+class ReadFilter(C.Structure):
+    """savont_b200_read_filter: the options of kmer_comp::twin_reads_from_snpmers (src/cli.rs:87-96, src/constants.rs)"""
+    _fields_ = [("min_read_length", C.c_uint32), ("max_read_length", C.c_uint32), ("max_kmer_count_in_read", C.c_uint32),
+                ("reserved", C.c_uint32), ("quality_value_cutoff", C.c_double)]
+
+
+def read_filter(min_read_length=1100, max_read_length=2000, quality_value_cutoff=98.0, max_kmer_count_in_read=500) -> ReadFilter:
+    return ReadFilter(min_read_length, max_read_length, max_kmer_count_in_read, 0, quality_value_cutoff)
 
 
 class Stats(C.Structure):
@@ -148,6 +159,25 @@ class Context:
     def load_snpmers(self, kmers):
         k = np.ascontiguousarray(kmers, dtype=np.uint64)
         _check(self.L.savont_b200_load_snpmers(self.h, _p(k, C.c_uint64), C.c_size_t(len(k))))
+
+    # ---- a4 ----
+    def load_high_freq_kmers(self, kmers):
+        k = np.ascontiguousarray(kmers if kmers is not None else [], dtype=np.uint64)
+        _check(self.L.savont_b200_load_high_freq_kmers(self.h, _p(k, C.c_uint64), C.c_size_t(len(k))))
+
+    def set_read_filter(self, rf: ReadFilter | None):
+        _check(self.L.savont_b200_set_read_filter(self.h, None if rf is None else C.byref(rf)))
+
+    def twin_reads_from_snpmers(self, bases, quals, offsets):
+        """per-read part of kmer_comp::twin_reads_from_snpmers: status (0 kept / 4 / 5 / 6 / 7), est_id, solid counts"""
+        b = _u8(bases); q = _u8(quals)
+        o = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(o) - 1
+        st = np.zeros(max(n, 1), np.uint8); est = np.zeros(max(n, 1), np.float64)
+        sm = np.zeros(max(n, 1), np.uint32); ss = np.zeros(max(n, 1), np.uint32)
+        _check(self.L.savont_b200_twin_reads_from_snpmers(self.h, _p(b, C.c_uint8), _p(q, C.c_uint8), _p(o, C.c_uint64), C.c_size_t(n),
+                                                          _p(st, C.c_uint8), _p(est, C.c_double), _p(sm, C.c_uint32), _p(ss, C.c_uint32)))
+        return dict(status=st[:n], est_id=est[:n], n_solid_mini=sm[:n], n_solid_snp=ss[:n])
 
     def load_asvs(self, bases, offsets):
         b = _u8(bases)

@@ -35,6 +35,7 @@ def host():
         H.savont_host_refine.restype = C.c_longlong
         H.savont_host_per_sample.restype = C.c_int
         H.savont_host_write_outputs.restype = C.c_int
+        H.savont_host_twin_read_order.restype = C.c_longlong
         _host = H
     return _host
 
@@ -57,6 +58,9 @@ class Cli:
     band: int = 64
     strand_mode: int = 0
     low_polymorphism: bool = False     # src/alignment.rs:1730: refine_asv_depths_with_minimap2 instead of the SNPmer index
+    min_read_length: int = 1100        # src/cli.rs:87-88
+    max_read_length: int = 2000        # src/cli.rs:91-92
+    quality_value_cutoff: float = 98.0  # src/cli.rs:95-96
 
     def params(self) -> _lib.Params:
         return _lib.default_params(k=self.kmer_size, c=self.c, l=self.blockmer_length, min_bq=self.minimum_base_quality,
@@ -99,6 +103,34 @@ def twin_reads_from_fasta(ctx: _lib.Context, seqs):
     """ASV sequences -> sketches (qualities None, no high-frequency pruning)"""
     b, o = _concat(seqs)
     return ctx.sketch(b, None, o, want_codes=False)
+
+
+def twin_reads_from_snpmers(ctx: _lib.Context, reads, args: Cli, high_freq_kmers=None):
+    """Stage 1.5, the part Stage 7 depends on (src/kmer_comp.rs:68-258 + src/main.rs:538): which FASTQ reads become
+    TwinReads and in which order.  reads: dict(bases, quals, offsets, ids [optional list of str/bytes]).
+    Returns dict(status, est_id, n_solid_mini, n_solid_snp, order, auto_low_polymorphism)."""
+    H = host()
+    ctx.load_high_freq_kmers(high_freq_kmers)
+    ctx.set_read_filter(_lib.read_filter(args.min_read_length, args.max_read_length, args.quality_value_cutoff))
+    try:
+        out = ctx.twin_reads_from_snpmers(reads["bases"], reads.get("quals"), reads["offsets"])
+    finally:
+        ctx.set_read_filter(None)
+    n = len(out["status"])
+    ids = reads.get("ids")
+    idb = ido = None
+    if ids is not None:
+        idb, ido = _concat([i.encode() if isinstance(i, str) else bytes(i) for i in ids])
+    order = np.zeros(max(n, 1), np.uint32)
+    st = np.ascontiguousarray(out["status"]); est = np.ascontiguousarray(out["est_id"])
+    nk = H.savont_host_twin_read_order(_p(st, C.c_uint8), _p(est, C.c_double), C.c_size_t(n), _p(idb, C.c_uint8), _p(ido, C.c_uint64),
+                                       _p(order, C.c_uint32))
+    if nk < 0:
+        _fail("twin_read_order")
+    out["order"] = order[:int(nk)]
+    kept = out["order"]
+    out["auto_low_polymorphism"] = bool(len(kept) and float((out["n_solid_snp"][kept] == 0).mean()) > 0.75)
+    return out
 
 
 def find_compatible_candidates(ctx: _lib.Context, bases, quals, offsets):

@@ -82,6 +82,7 @@ struct PinBuf {
 // device-resident inputs, intermediates and outputs of one batch of sequences
 struct Batch {
     DevBuf bases, quals, offsets, file_idx;
+    DevBuf solid_mini, solid_snp;                        // a4 outputs (savont_b200_twin_reads_from_snpmers)
     DevBuf dna_words, word_offsets, snp_raw, snp_dummy;   // TwinRead input: Seq<Dna> words; Kmer48 staging; scratch counters
     bool has_quals = false, has_file_idx = false;
     bool twin = false;            // sequences are TwinRead.dna_seq words and the SNPmers come from the caller
@@ -104,7 +105,7 @@ struct Batch {
     PinBuf pin_offsets;
     void release() {
         pin_offsets.release();
-        DevBuf *all[] = {&dna_words, &word_offsets, &snp_raw, &snp_dummy, &bases, &quals, &offsets, &file_idx, &planes, &sk_status, &flatq, &mini_cnt, &mini_kmer, &mini_pos,
+        DevBuf *all[] = {&solid_mini, &solid_snp, &dna_words, &word_offsets, &snp_raw, &snp_dummy, &bases, &quals, &offsets, &file_idx, &planes, &sk_status, &flatq, &mini_cnt, &mini_kmer, &mini_pos,
                          &snp_start, &snp_cnt, &snp_kmer, &snp_pos, &est_id, &spill_k, &spill_p, &ctrs, &cand_status, &pair_start, &pair_cnt,
                          &low_mm, &p_read, &p_asv, &p_mini, &p_strand, &nm, &asv_end, &read_end, &rstatus, &best_nm,
                          &class_cnt, &class_slot, &class_off, &class_out, &scan_tmp};
@@ -137,6 +138,8 @@ struct Context {
     // counters [unambig A | ambig A | leq10 A | assigned | filtered | singleton S*A]
     DevBuf d_counters; size_t counters_len = 0; int counters_samples = 0;
 
+    // a4 read filter (twin_reads_from_snpmers): options + high-frequency k-mer set
+    bool rf_on = false; ReadFilter rf{}; std::vector<uint64_t> h_hf; DevBuf d_hf_keys; uint32_t hf_mask = 0, hf_shift = 0;
     Batch work, work2, work3, resident, asvb;
     int resident_samples = 1;
     PinBuf pin_small, pin_out;
@@ -504,6 +507,26 @@ static int sketch_checked(Context *c, Batch &b, bool with_pos) {
     }
 }
 
+// a4: the read tests of twin_reads_from_snpmers on the sketches of an ASCII batch (no-op without a read filter; TwinRead
+// batches are reads that already passed)
+static int stage_prefilter(Context *c, Batch &b, bool want_counts) {
+    if (!c->rf_on || b.twin || b.n == 0) return 0;
+    const double *est = nullptr;
+    if (c->rf.use_cutoff && b.has_quals) {
+        TRY(b.est_id.ensure((b.n + 1) * 8));
+        launch_est_id(seq_view(b), b.sk_status.as<uint8_t>(), b.flatq.as<uint8_t>(), c->d_phred.as<double>(), b.est_id.as<double>(), c->stream);
+        est = b.est_id.as<double>();
+        c->last_stats.kernel_launches += 1;
+    }
+    if (want_counts) { TRY(b.solid_mini.ensure((b.n + 1) * 4)); TRY(b.solid_snp.ensure((b.n + 1) * 4)); }
+    HfSet hf{c->hf_mask ? c->d_hf_keys.as<uint64_t>() : nullptr, c->hf_mask, c->hf_shift};
+    launch_read_filter(seq_view(b), sketch_view(b, false), hf, est, c->rf, c->dp, want_counts ? b.solid_mini.as<uint32_t>() : nullptr,
+                       want_counts ? b.solid_snp.as<uint32_t>() : nullptr, c->sm_count, c->stream);
+    CK(cudaGetLastError());
+    c->last_stats.kernel_launches += 1;
+    return 0;
+}
+
 static AsvIndex index_view(const Context *c) {
     AsvIndex ix{};
     ix.idx_keys = c->idx_mask ? c->d_idx_keys.as<uint64_t>() : nullptr;
@@ -760,6 +783,7 @@ static float ev_ms(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapse
 static int enqueue_path(Context *c, Batch &b, int n_samples) {
     CK(cudaEventRecord(c->pev[0], c->stream));
     TRY(stage_sketch(c, b, false));
+    TRY(stage_prefilter(c, b, false));
     CK(cudaEventRecord(c->pev[1], c->stream));
     TRY(stage_filter(c, b, c->dp.strand_mode));
     CK(cudaEventRecord(c->pev[2], c->stream));
@@ -901,7 +925,7 @@ int savont_b200_destroy(savont_b200_ctx *h) {
     cudaStreamSynchronize(c->stream);
     c->work.release(); c->work2.release(); c->work3.release(); c->resident.release(); c->asvb.release();
     DevBuf *bufs[] = {&c->d_rank_table, &c->d_snp_keys, &c->d_snp_bloom, &c->d_phred, &c->d_mx_keys, &c->d_mx_vals, &c->d_mx_entries, &c->d_idx_keys, &c->d_idx_vals, &c->d_idx_entries, &c->d_mset,
-                      &c->d_mset_off, &c->d_asv_planes, &c->d_asv_plane_off, &c->d_asv_len, &c->d_counters};
+                      &c->d_mset_off, &c->d_asv_planes, &c->d_asv_plane_off, &c->d_asv_len, &c->d_counters, &c->d_hf_keys};
     for (DevBuf *b : bufs) b->release();
     c->pin_small.release(); c->pin_out.release();
     for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
@@ -952,6 +976,71 @@ int savont_b200_load_snpmers(savont_b200_ctx *h, const uint64_t *kmers, size_t n
         if (v == kEmpty64) return fail(SAVONT_B200_ERR_INVALID, "0xffffffffffffffff is not a valid k-mer");
     c->index_dirty = true;
     return upload_snp_set(c);
+}
+
+int savont_b200_load_high_freq_kmers(savont_b200_ctx *h, const uint64_t *kmers, size_t n) {
+    TRY(use_device(h ? &h->c : nullptr));
+    if (n && !kmers) return fail(SAVONT_B200_ERR_INVALID, "kmers is null");
+    Context *c = &h->c;
+    c->h_hf.assign(kmers, kmers + n);
+    std::sort(c->h_hf.begin(), c->h_hf.end());
+    c->h_hf.erase(std::unique(c->h_hf.begin(), c->h_hf.end()), c->h_hf.end());
+    for (uint64_t v : c->h_hf)
+        if (v == kEmpty64) return fail(SAVONT_B200_ERR_INVALID, "0xffffffffffffffff is not a valid k-mer");
+    if (c->h_hf.empty()) { c->hf_mask = 0; return 0; }
+    const uint32_t cap = next_pow2_u32(4 * c->h_hf.size() + 2);
+    const uint32_t shift = shift_for_cap(cap);
+    std::vector<uint64_t> keys(cap, kEmpty64);
+    for (uint64_t key : c->h_hf) {
+        uint32_t slot = hash_slot(key, shift);
+        while (keys[slot] != kEmpty64) slot = (slot + 1) & (cap - 1);
+        keys[slot] = key;
+    }
+    TRY(c->d_hf_keys.ensure((size_t)cap * 8));
+    CK(cudaMemcpyAsync(c->d_hf_keys.p, keys.data(), (size_t)cap * 8, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->hf_mask = cap - 1; c->hf_shift = shift;
+    return 0;
+}
+
+int savont_b200_set_read_filter(savont_b200_ctx *h, const savont_b200_read_filter *f) {
+    if (!h) return fail(SAVONT_B200_ERR_INVALID, "null context");
+    Context *c = &h->c;
+    if (!f) { c->rf_on = false; return 0; }
+    if (f->max_read_length && f->max_read_length < f->min_read_length)
+        return fail(SAVONT_B200_ERR_INVALID, "max_read_length %u < min_read_length %u", f->max_read_length, f->min_read_length);
+    if (f->quality_value_cutoff != f->quality_value_cutoff) return fail(SAVONT_B200_ERR_INVALID, "quality_value_cutoff is NaN");
+    c->rf.min_len = f->min_read_length; c->rf.max_len = f->max_read_length; c->rf.max_count = f->max_kmer_count_in_read;
+    c->rf.use_cutoff = f->quality_value_cutoff > 0.0 ? 1u : 0u; c->rf.cutoff = f->quality_value_cutoff;
+    c->rf_on = true;
+    return 0;
+}
+
+int savont_b200_twin_reads_from_snpmers(savont_b200_ctx *h, const uint8_t *bases, const uint8_t *quals, const uint64_t *offsets,
+                                        size_t n_reads, uint8_t *status, double *est_id, uint32_t *n_solid_mini,
+                                        uint32_t *n_solid_snp) {
+    TRY(use_device(h ? &h->c : nullptr));
+    Context *c = &h->c;
+    if (!offsets || !status) return fail(SAVONT_B200_ERR_INVALID, "null argument");
+    if (!c->rf_on) return fail(SAVONT_B200_ERR_INVALID, "no read filter set (call savont_b200_set_read_filter first)");
+    for (size_t r0 = 0; r0 < n_reads;) {
+        size_t r1 = std::min(n_reads, r0 + c->batch_reads);
+        while (r1 > r0 + 1 && offsets[r1] - offsets[r0] > (3ull << 30)) r1 = r0 + (r1 - r0) / 2;
+        const size_t n = r1 - r0;
+        Batch &b = c->work;
+        TRY(batch_upload(c, b, bases, quals, offsets + r0, nullptr, n, nullptr));
+        TRY(sketch_checked(c, b, false));
+        TRY(b.est_id.ensure((n + 1) * 8));
+        launch_est_id(seq_view(b), b.sk_status.as<uint8_t>(), b.flatq.as<uint8_t>(), c->d_phred.as<double>(), b.est_id.as<double>(), c->stream);
+        if (est_id) CK(cudaMemcpyAsync(est_id + r0, b.est_id.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
+        TRY(stage_prefilter(c, b, true));
+        CK(cudaMemcpyAsync(status + r0, b.sk_status.p, n, cudaMemcpyDeviceToHost, c->stream));
+        if (n_solid_mini) CK(cudaMemcpyAsync(n_solid_mini + r0, b.solid_mini.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+        if (n_solid_snp) CK(cudaMemcpyAsync(n_solid_snp + r0, b.solid_snp.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        r0 = r1;
+    }
+    return 0;
 }
 
 int savont_b200_load_asvs(savont_b200_ctx *h, const uint8_t *bases, const uint64_t *offsets, size_t n_asv) {
@@ -1053,6 +1142,7 @@ int savont_b200_find_candidates(savont_b200_ctx *h, const uint8_t *bases, const 
         TRY(batch_upload(c, b, bases, quals, offsets + r0, nullptr, n, nullptr));
         for (int attempt = 0;; ++attempt) {
             TRY(stage_sketch(c, b, false));
+            TRY(stage_prefilter(c, b, false));
             TRY(stage_filter(c, b, 0));
             BatchCounters h{}; bool retry = false;
             TRY(check_batch(c, b, &h, &retry));

@@ -24,7 +24,7 @@ __global__ void assign_kernel(FilterOut fo, PairPool pool, const int32_t *__rest
         const uint8_t st = fo.cand_status[r];
         if (st != 0) {
             status[r] = st; best_nm[r] = 0x7fffffff; class_cnt[r] = 0;
-            filtered = (st != 4);
+            filtered = (st < 4);                  // 4: no TwinRead (too short); 5-7: dropped by the read filter (a4)
         } else {
             const uint32_t start = fo.pair_start[r], cnt = fo.pair_cnt[r];
             const uint32_t per = (strand_mode == 1) ? 2u : 1u;

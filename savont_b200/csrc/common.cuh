@@ -150,7 +150,18 @@ struct AlignOut {
     int32_t *read_end;  // [pairs] or null
 };
 
+// a4 (twin_reads_from_snpmers) read tests, prefilter.cu
+struct HfSet { const uint64_t *keys; uint32_t mask, shift; };       // high-frequency k-mers, open addressing (hash_slot)
+struct ReadFilter {
+    uint32_t min_len, max_len;     // max_len 0 = no upper bound
+    uint32_t max_count;            // MAX_KMER_COUNT_IN_READ
+    uint32_t use_cutoff;
+    double cutoff;
+};
+
 // launchers (defined in the .cu files)
+void launch_read_filter(const SeqBatch &in, const SketchOut &sk, const HfSet &hf, const double *est_id, const ReadFilter &f,
+                        const DeviceParams &p, uint32_t *n_solid_mini, uint32_t *n_solid_snp, int sm_count, cudaStream_t st);
 void launch_sketch(const SeqBatch &in, const SketchOut &out, const SnpSet &set, const uint16_t *rank_table,
                    const DeviceParams &p, int sm_count, cudaStream_t st);
 // k = 17, c = 11 fast path (sketch_fast.cu); in.dna_words != nullptr selects the TwinRead input encoding

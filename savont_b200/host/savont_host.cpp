@@ -60,6 +60,49 @@ Assignments Mapper::map_reads(const ReadSet &r, int n_samples) {
     return a;
 }
 
+std::vector<uint32_t> twin_read_order(const std::vector<uint8_t> &status, const std::vector<double> &est_id,
+                                      const uint8_t *ids, const uint64_t *id_offsets) {
+    std::vector<uint32_t> order;
+    for (size_t i = 0; i < status.size(); ++i) if (status[i] == 0) order.push_back((uint32_t)i);
+    if (ids) {   // twin_reads.sort_by(|a, b| a.id.cmp(&b.id)): byte-wise String order, stable (src/kmer_comp.rs:233)
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
+            const size_t lx = id_offsets[x + 1] - id_offsets[x], ly = id_offsets[y + 1] - id_offsets[y];
+            const int c = std::memcmp(ids + id_offsets[x], ids + id_offsets[y], std::min(lx, ly));
+            return c != 0 ? c < 0 : lx < ly;
+        });
+    }
+    // sort_by(|a, b| b.est_id.unwrap_or(100.0).partial_cmp(&a.est_id.unwrap_or(100.0))): descending, stable (src/main.rs:538)
+    auto key = [&](uint32_t i) { return std::isnan(est_id[i]) ? 100.0 : est_id[i]; };
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return key(x) > key(y); });
+    return order;
+}
+
+TwinReadSelection twin_reads_from_snpmers(Mapper &mapper, const ReadSet &r, const std::vector<std::string> &ids,
+                                          const KmerGlobalInfo &kmer_info, const Cli &args) {
+    savont_b200_read_filter f{};
+    f.min_read_length = (uint32_t)args.min_read_length; f.max_read_length = (uint32_t)args.max_read_length;
+    f.max_kmer_count_in_read = 500;                       // MAX_KMER_COUNT_IN_READ, src/constants.rs
+    f.quality_value_cutoff = args.quality_value_cutoff;
+    ck(savont_b200_load_high_freq_kmers(mapper.raw(), kmer_info.high_freq_kmers.data(), kmer_info.high_freq_kmers.size()),
+       "savont_b200_load_high_freq_kmers");
+    ck(savont_b200_set_read_filter(mapper.raw(), &f), "savont_b200_set_read_filter");
+    TwinReadSelection s;
+    s.status.assign(r.n ? r.n : 1, 0); s.est_id.assign(r.n ? r.n : 1, 0.0);
+    s.n_solid_mini.assign(r.n ? r.n : 1, 0); s.n_solid_snp.assign(r.n ? r.n : 1, 0);
+    ck(savont_b200_twin_reads_from_snpmers(mapper.raw(), r.bases, r.quals, r.offsets, r.n, s.status.data(), s.est_id.data(),
+                                           s.n_solid_mini.data(), s.n_solid_snp.data()), "savont_b200_twin_reads_from_snpmers");
+    ck(savont_b200_set_read_filter(mapper.raw(), nullptr), "savont_b200_set_read_filter");   // Stage 7 takes the kept reads as they are
+    s.status.resize(r.n); s.est_id.resize(r.n); s.n_solid_mini.resize(r.n); s.n_solid_snp.resize(r.n);
+    std::vector<uint8_t> idbuf; std::vector<uint64_t> idoff{0};
+    for (const auto &id : ids) { idbuf.insert(idbuf.end(), id.begin(), id.end()); idoff.push_back(idbuf.size()); }
+    const bool have_ids = ids.size() == r.n && r.n > 0;
+    s.order = twin_read_order(s.status, s.est_id, have_ids ? idbuf.data() : nullptr, have_ids ? idoff.data() : nullptr);
+    size_t without = 0;
+    for (uint32_t i : s.order) if (s.n_solid_snp[i] == 0) ++without;      // tr.snpmers_vec().is_empty(), src/main.rs:539
+    s.auto_low_polymorphism = !s.order.empty() && (double)without / (double)s.order.size() > 0.75;
+    return s;
+}
+
 EqClasses build_eq_classes(const Assignments &a, const uint32_t *file_idx, int sample) {
     std::map<std::vector<uint32_t>, uint64_t> hist;
     uint64_t total = 0;
@@ -202,6 +245,17 @@ extern "C" {
 
 static thread_local std::string g_host_error;
 const char *savont_host_last_error(void) { return g_host_error.c_str(); }
+
+// Stage-7 read order of the kept reads (status == 0); returns the number of kept reads, or -1 on error
+long long savont_host_twin_read_order(const uint8_t *status, const double *est_id, size_t n, const uint8_t *ids,
+                                      const uint64_t *id_offsets, uint32_t *order) {
+    try {
+        std::vector<uint8_t> st(status, status + n); std::vector<double> est(est_id, est_id + n);
+        const std::vector<uint32_t> o = savont_host::twin_read_order(st, est, ids, id_offsets);
+        for (size_t i = 0; i < o.size(); ++i) order[i] = o[i];
+        return (long long)o.size();
+    } catch (const std::exception &e) { g_host_error = e.what(); return -1; }
+}
 
 // EM over CSR classes; returns iterations, or -1 on error
 int savont_host_em(size_t n_asv, const uint64_t *cls_offsets, const uint32_t *cls_asv, const uint64_t *counts, size_t n_cls,

@@ -24,12 +24,16 @@ struct Cli {
     int band = 64;                 // b200: DP half band
     int strand_mode = 0;
     bool low_polymorphism = false; // src/alignment.rs:1730 -> candidate_mode 1 (every ASV sharing minimizers is a candidate)
+    size_t min_read_length = 1100; // src/cli.rs:87-88
+    size_t max_read_length = 2000; // src/cli.rs:91-92
+    double quality_value_cutoff = 98.0; // src/cli.rs:95-96
 };
 
 // KmerGlobalInfo reduced to what the path uses: both alleles of every SNPmer, i.e. the u64 values of
 // reference src/kmer_comp.rs:41-48
 struct KmerGlobalInfo {
     std::vector<uint64_t> snpmers;
+    std::vector<uint64_t> high_freq_kmers;   // src/types.rs:801-824 (Kmer48 values), read by twin_reads_from_snpmers
 };
 
 // reference src/types.rs:162-190, fields used by Stage 7 / 7b and the writers
@@ -90,6 +94,23 @@ private:
     savont_b200_ctx *ctx_ = nullptr;
     size_t n_asv_ = 0;
 };
+
+// reference src/kmer_comp.rs:68-258 + src/main.rs:538 (Stage 1.5, the part Stage 7 depends on): which FASTQ reads become
+// TwinReads and in which order Stage 7 sees them.  The per-read tests run on the GPU
+// (savont_b200_twin_reads_from_snpmers); the sort by id (:233), the quality cutoff and the stable sort by est_id
+// descending (None = 100.0, src/main.rs:538) are done here.  ids[i] is the read id (FASTQ header up to the first space).
+struct TwinReadSelection {
+    std::vector<uint8_t> status;          // per input read: 0 kept, 4 / 5 / 6 / 7 (include/savont_b200.h)
+    std::vector<double> est_id;           // NaN = None
+    std::vector<uint32_t> n_solid_mini, n_solid_snp;
+    std::vector<uint32_t> order;          // input indices of the kept reads in Stage-7 order
+    bool auto_low_polymorphism = false;   // > 75 % of the kept reads without SNPmer positions (src/main.rs:539-543)
+};
+TwinReadSelection twin_reads_from_snpmers(Mapper &mapper, const ReadSet &reads, const std::vector<std::string> &ids,
+                                          const KmerGlobalInfo &kmer_info, const Cli &args);
+// order only (also used by the flat C wrapper): stable by id, then stable by est_id descending
+std::vector<uint32_t> twin_read_order(const std::vector<uint8_t> &status, const std::vector<double> &est_id,
+                                      const uint8_t *ids, const uint64_t *id_offsets);
 
 // sample < 0: all reads; otherwise only reads with file_idx == sample (src/alignment.rs:2095-2096)
 EqClasses build_eq_classes(const Assignments &a, const uint32_t *file_idx, int sample);

@@ -100,3 +100,30 @@ def banded_nm(a, r, B):
         if d < best[0] or (d == best[0] and i + j > best[1] + best[2]):
             best = (d, i, j)
     return best
+
+
+def twin_reads_filter(reads, quals, ids, k, c, min_bq, snpmer_set, high_freq, min_len, max_len, cutoff, max_count=500):
+    """Independent restatement of kmer_comp::twin_reads_from_snpmers (reference src/kmer_comp.rs:68-258) + the read order
+    of src/main.rs:538.  Returns (status list, kept indices in Stage-7 order)."""
+    from collections import Counter
+    status, kept = [], []
+    for idx, (sq, ql) in enumerate(zip(reads, quals)):
+        if len(sq) < min_len or (max_len and len(sq) > max_len):
+            status.append(5); continue
+        sk = sketch(sq, ql, k, c, min_bq, snpmer_set)
+        if sk is None:
+            status.append(4); continue
+        kmers = [m[1] for m in sk["mini"]]
+        cnt = Counter(kmers)
+        solid = sum(1 for x in kmers if cnt[x] <= max_count and x not in high_freq)
+        if solid < len(sq) // c // 20:
+            status.append(6); continue
+        status.append(0)
+        kept.append((idx, sk["est_id"]))
+    kept.sort(key=lambda t: (ids[t[0]].encode() if isinstance(ids[t[0]], str) else ids[t[0]]))       # stable
+    kept = [t for t in kept if t[1] is None or t[1] >= cutoff or cutoff <= 0]
+    dropped = set(i for i in range(len(reads)) if status[i] == 0) - set(t[0] for t in kept)
+    for i in dropped:
+        status[i] = 7
+    kept.sort(key=lambda t: -(t[1] if t[1] is not None else 100.0))                                    # stable, descending
+    return status, [t[0] for t in kept]

@@ -393,3 +393,73 @@ def test_map_twin_reads_edge_cases(ctx):
     bad = dict(tw); bad["dna_word_offsets"] = tw["dna_word_offsets"].copy(); bad["dna_word_offsets"][5:] -= np.uint64(3)
     with pytest.raises(_lib.SavontB200Error):
         ctx.map_twin_reads(bad)
+
+
+@pytest.mark.parametrize("k,c", [(17, 11), (15, 9)])
+def test_twin_reads_from_snpmers_ragged(ctx, k, c):
+    """a4 (kmer_comp::twin_reads_from_snpmers): per-read tests on the GPU, order on the host, vs the oracle"""
+    from savont_b200 import _lib, api
+    from tests.test_oracle import _a4_inputs
+    reads, quals, ids = _a4_inputs(31 + k, k)
+    snp = sorted(snpmer_set_from(reads, k))
+    gp, op = _params(_lib, k=k, c=c)
+    ctx.set_params(gp); ctx.load_snpmers(snp)
+    sk = O.sketch_batch(op, snp, *O.concat(reads)[:1], O.concat(quals)[0], O.concat(reads)[1])
+    mo = sk["mini_offsets"].astype(np.int64)
+    hf = sorted(set(int(x) for i in (4, 10, 16) for x in sk["mini_kmer"][mo[i]:mo[i + 1]]))
+    bases, offs = O.concat(reads); qcat, _ = O.concat(quals)
+    for (mn, mx, cut, maxc) in [(0, 0, 0.0, 500), (300, 640, 97.0, 500), (17, 0, 99.5, 3), (400, 500, 90.0, 1)]:
+        want = O.twin_reads_filter(op, O.read_filter(mn, mx, cut, maxc), snp, hf, bases, qcat, offs, ids)
+        ctx.load_high_freq_kmers(hf)
+        ctx.set_read_filter(_lib.read_filter(mn, mx, cut, maxc))
+        try:
+            got = ctx.twin_reads_from_snpmers(bases, qcat, offs)
+        finally:
+            ctx.set_read_filter(None)
+        assert_same(got, want, ["status", "est_id", "n_solid_mini", "n_solid_snp"], f"a4 k={k} {(mn, mx, cut, maxc)}")
+    # host layer: defaults of the Cli + the Stage-7 read order
+    args = api.Cli(kmer_size=k, c=c, min_read_length=300, max_read_length=900, quality_value_cutoff=97.0)
+    got = api.twin_reads_from_snpmers(ctx, dict(bases=bases, quals=qcat, offsets=offs, ids=ids), args, high_freq_kmers=hf)
+    want = O.twin_reads_filter(op, O.read_filter(300, 900, 97.0), snp, hf, bases, qcat, offs, ids)
+    assert_same(got, want, ["status", "order"], "a4 host order")
+    assert len(want["order"]) > 5 and set(want["status"].tolist()) >= {0, 5, 6, 7}
+    ctx.load_high_freq_kmers([])
+    ctx.set_params(_lib.default_params())
+    with pytest.raises(_lib.SavontB200Error):
+        ctx.twin_reads_from_snpmers(bases, qcat, offs)             # no filter set
+
+
+def test_map_reads_with_read_filter(ctx):
+    """FASTQ reads straight into Stage 7: reads failing the a4 tests get status 5 / 6 / 7 and take no part"""
+    from savont_b200 import _lib
+    w = _make_workload("ont16s", n_roots=6)
+    r = w.reads(3000)
+    quals = r["quals"].copy(); offs = r["offsets"]
+    for i in range(0, 3000, 17):                                     # low quality, not flat
+        quals[int(offs[i]):int(offs[i + 1])] = 33 + 9
+        quals[int(offs[i])] = 33 + 12
+    gp, op = _params(_lib, band=w.band)
+    ctx.set_params(gp); ctx.load_snpmers(w.snpmers); ctx.load_asvs(w.asv_bases, w.asv_offsets)
+    orc = O.Oracle(op, w.snpmers); orc.load_asvs(w.asv_bases, w.asv_offsets)
+    sk = O.sketch_batch(op, w.snpmers, r["bases"], quals, offs)
+    mo = sk["mini_offsets"].astype(np.int64)
+    genus0 = np.flatnonzero(r["truth_asv"] < 10)[:40]                # the reads of one genus lose (nearly) all minimizers
+    hf = sorted(set(int(x) for i in genus0 for x in sk["mini_kmer"][mo[i]:mo[i + 1]]))
+    rf_args = (1475, 1525, 98.0)
+    orc.set_read_filter(O.read_filter(*rf_args), hf)
+    want = orc.map_reads(r["bases"], quals, offs)
+    ctx.load_high_freq_kmers(hf); ctx.set_read_filter(_lib.read_filter(*rf_args))
+    try:
+        ctx.set_batch_reads(800)
+        got = ctx.map_reads(r["bases"], quals, offs)
+        ctx.set_batch_reads(0)
+        assert_same(got, want, MAP_KEYS, "map_reads with read filter")
+        assert set(want["status"].tolist()) >= {0, 5, 6, 7}
+        ctx.upload_reads(r["bases"], quals, offs); ctx.map_resident()
+        assert_same(ctx.fetch_resident(), want, MAP_KEYS, "map_resident with read filter")
+        cand = ctx.find_candidates(r["bases"], quals, offs)
+        assert np.array_equal(cand["status"][want["status"] >= 4], want["status"][want["status"] >= 4])
+    finally:
+        ctx.set_batch_reads(0); ctx.set_read_filter(None); ctx.load_high_freq_kmers([])
+    orc.set_read_filter(None)
+    assert_same(ctx.map_reads(r["bases"], quals, offs), orc.map_reads(r["bases"], quals, offs), MAP_KEYS, "filter off again")

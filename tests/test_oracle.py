@@ -214,3 +214,76 @@ def test_low_polymorphism_mode_needs_no_snpmers():
             assert all(r["truth_asv"][i] // 10 == res["class_asv"][co[i]] // 10 for i in range(120))   # right genus
         else:
             assert int(res["totals"][0]) == 0 and np.all(res["status"] == O.STATUS_NO_CANDIDATE)
+
+
+def _a4_inputs(seed=11, k=17):
+    """reads that trip every a4 test: too short / too long, below k, repetitive (tandem repeats and high-frequency
+    k-mers), low quality, flat quality (est_id None), duplicate ids"""
+    import random
+    from tests.util import rand_seq
+    rng = random.Random(seed)
+    reads, quals, ids = [], [], []
+    for t in range(60):
+        L = rng.choice([10, 16, 300, 420, 500, 640, 900])
+        sq = rand_seq(rng, L)
+        if t % 6 == 1 and L >= 300:
+            unit = rand_seq(rng, rng.choice([3, 7, 23]))
+            sq = (unit * (L // len(unit) + 1))[:L]                   # tandem repeat: few distinct minimizers
+        q = [33 + rng.choice([12, 20, 30, 40]) for _ in range(L)]
+        if t % 5 == 2:
+            q = [33 + rng.choice([8, 10, 14]) for _ in range(L)]     # est_id well below any sensible cutoff
+        if t % 7 == 3:
+            q = [33 + 30] * L                                        # flat: est_id None, never dropped by quality
+        reads.append(sq); quals.append(bytes(q)); ids.append(f"r{rng.randrange(40):03d}" if t % 9 else "r007")
+    return reads, quals, ids
+
+
+@pytest.mark.parametrize("k,c", [(17, 11), (15, 9)])
+def test_twin_reads_filter_matches_python_restatement(k, c):
+    from tests.util import snpmer_set_from
+    reads, quals, ids = _a4_inputs(11 + k, k)
+    snp = sorted(snpmer_set_from(reads, k))
+    p = O.default_params(k=k, c=c)
+    # high-frequency k-mers: every minimizer of three of the reads -> those reads lose all their solid minimizers
+    hf = set()
+    for i in (4, 10, 16):
+        sk = pyref.sketch(reads[i], quals[i], k, c, 25, set(snp))
+        if sk:
+            hf.update(m[1] for m in sk["mini"])
+    bases, offs = O.concat(reads); qcat, _ = O.concat(quals)
+    for (mn, mx, cut, maxc) in [(0, 0, 0.0, 500), (300, 640, 97.0, 500), (17, 0, 99.5, 3), (400, 500, 90.0, 1)]:
+        rf = O.read_filter(mn, mx, cut, maxc)
+        got = O.twin_reads_filter(p, rf, snp, sorted(hf), bases, qcat, offs, ids)
+        want_status, want_order = pyref.twin_reads_filter(reads, quals, ids, k, c, 25, set(snp), hf, mn, mx, cut, maxc)
+        assert got["status"].tolist() == want_status, (mn, mx, cut, maxc)
+        assert got["order"].tolist() == want_order, (mn, mx, cut, maxc)
+    # every status occurs in at least one of the settings above
+    rf = O.read_filter(300, 640, 97.0, 500)
+    st = O.twin_reads_filter(p, rf, snp, sorted(hf), bases, qcat, offs, ids)["status"]
+    assert set(st.tolist()) >= {0, 5, 6, 7}
+
+
+def test_map_reads_with_read_filter_skips_filtered_reads():
+    """reads failing a4 never reach Stage 7: not assigned, not counted as filtered"""
+    from savont_b200 import synth
+    w = synth.Workload("ont16s", n_roots=3)
+    r = w.reads(200)
+    quals = r["quals"].copy()
+    quals[int(r["offsets"][3]):int(r["offsets"][4])] = 33 + 9          # low quality read ...
+    quals[int(r["offsets"][3])] = 33 + 11                              # ... but not flat (flat qualities -> est_id None, src/seeding.rs:570-573)
+    p = O.default_params(band=w.band)
+    orc = O.Oracle(p, w.snpmers); orc.load_asvs(w.asv_bases, w.asv_offsets)
+    base = orc.map_reads(r["bases"], quals, r["offsets"])
+    rf = O.read_filter(1490, 1505, 98.0)
+    orc.set_read_filter(rf, [])
+    got = orc.map_reads(r["bases"], quals, r["offsets"])
+    flt = O.twin_reads_filter(p, rf, w.snpmers, [], r["bases"], quals, r["offsets"])
+    assert got["status"][3] == O.STATUS_LOW_QUALITY
+    drop = flt["status"] != 0
+    assert drop.any() and (~drop).any()
+    assert np.array_equal(got["status"][drop], flt["status"][drop])
+    assert np.array_equal(got["status"][~drop], base["status"][~drop])
+    assert int(got["totals"][0]) == int((got["status"] == 0).sum())
+    assert int(got["totals"][1]) == int(((got["status"] > 0) & (got["status"] < 4)).sum())
+    orc.set_read_filter(None)
+    assert np.array_equal(orc.map_reads(r["bases"], quals, r["offsets"])["status"], base["status"])
