@@ -36,6 +36,8 @@ def host():
         H.savont_host_per_sample.restype = C.c_int
         H.savont_host_write_outputs.restype = C.c_int
         H.savont_host_twin_read_order.restype = C.c_longlong
+        H.savont_host_refine_twin.restype = C.c_longlong
+        H.savont_host_per_sample_twin.restype = C.c_int
         _host = H
     return _host
 
@@ -166,21 +168,36 @@ def eq_classes(status, class_offsets, class_asv, file_idx=None, sample=None):
     return offs, flat, np.array([hist[k] for k in keys], np.uint64), int(len(sel))
 
 
+def _twin_ptrs(tw):
+    """TwinRead-field dict (savont_b200/twin.py) -> ctypes arguments of the *_twin host entry points"""
+    w, wo, ln, sk, kb, so, fi = _lib.Context._twin_args(tw)
+    keep = (w, wo, ln, sk, so, fi)
+    return keep, [_p(w, C.c_uint64), _p(wo, C.c_uint64), _p(ln, C.c_uint32), C.c_void_p(sk.ctypes.data), C.c_int(kb), _p(so, C.c_uint64)], fi, len(ln)
+
+
 def refine_asv_depths_with_em(twin_reads, consensuses, kmer_info, args: Cli, temp_dir=None, device=0):
-    """Stage 7.  twin_reads: dict(bases, quals, offsets); kmer_info: u64 SNPmer k-mers (both alleles);
-    consensuses: list[ConsensusSequence], updated and filtered in place like the reference."""
+    """Stage 7.  twin_reads: dict(bases, quals, offsets) (raw reads) or the TwinRead fields dict(dna_words, dna_word_offsets,
+    lengths, snpmer_kmers, snpmer_offsets) of savont_b200/twin.py (what the reference passes: &[TwinRead]);
+    kmer_info: u64 SNPmer k-mers (both alleles); consensuses: list[ConsensusSequence], updated and filtered in place like
+    the reference."""
     H = host()
     ab, ao = _concat([c.sequence for c in consensuses])
-    b = np.ascontiguousarray(twin_reads["bases"], np.uint8)
-    q = None if twin_reads.get("quals") is None else np.ascontiguousarray(twin_reads["quals"], np.uint8)
-    o = np.ascontiguousarray(twin_reads["offsets"], np.uint64)
     snp = np.ascontiguousarray(kmer_info, np.uint64)
     A = len(consensuses)
     out = [np.zeros(max(A, 1), np.uint64) for _ in range(5)]
     p = args.params()
-    n = H.savont_host_refine(C.c_int(device), C.byref(p), _p(snp, C.c_uint64), C.c_size_t(len(snp)), _p(ab, C.c_uint8), _p(ao, C.c_uint64),
-                             C.c_size_t(A), _p(b, C.c_uint8), _p(q, C.c_uint8), _p(o, C.c_uint64), C.c_size_t(len(o) - 1),
-                             None if temp_dir is None else str(temp_dir).encode(), *[_p(x, C.c_uint64) for x in out])
+    td = None if temp_dir is None else str(temp_dir).encode()
+    if "dna_words" in twin_reads:
+        keep, tp, _, n_reads = _twin_ptrs(twin_reads)
+        n = H.savont_host_refine_twin(C.c_int(device), C.byref(p), _p(snp, C.c_uint64), C.c_size_t(len(snp)), _p(ab, C.c_uint8),
+                                      _p(ao, C.c_uint64), C.c_size_t(A), *tp, C.c_size_t(n_reads), td, *[_p(x, C.c_uint64) for x in out])
+    else:
+        b = np.ascontiguousarray(twin_reads["bases"], np.uint8)
+        q = None if twin_reads.get("quals") is None else np.ascontiguousarray(twin_reads["quals"], np.uint8)
+        o = np.ascontiguousarray(twin_reads["offsets"], np.uint64)
+        n = H.savont_host_refine(C.c_int(device), C.byref(p), _p(snp, C.c_uint64), C.c_size_t(len(snp)), _p(ab, C.c_uint8), _p(ao, C.c_uint64),
+                                 C.c_size_t(A), _p(b, C.c_uint8), _p(q, C.c_uint8), _p(o, C.c_uint64), C.c_size_t(len(o) - 1),
+                                 td, *[_p(x, C.c_uint64) for x in out])
     if n < 0:
         _fail("refine_asv_depths_with_em")
     kept = []
@@ -193,20 +210,26 @@ def refine_asv_depths_with_em(twin_reads, consensuses, kmer_info, args: Cli, tem
 
 
 def compute_per_sample_depths(twin_reads, n_samples, consensuses, kmer_info, args: Cli, device=0):
-    """Stage 7b -> list[asv][sample]"""
+    """Stage 7b -> list[asv][sample]; twin_reads as in refine_asv_depths_with_em, with file_idx"""
     H = host()
     ab, ao = _concat([c.sequence for c in consensuses])
-    b = np.ascontiguousarray(twin_reads["bases"], np.uint8)
-    q = None if twin_reads.get("quals") is None else np.ascontiguousarray(twin_reads["quals"], np.uint8)
-    o = np.ascontiguousarray(twin_reads["offsets"], np.uint64)
-    fi = np.ascontiguousarray(twin_reads["file_idx"], np.uint32)
     snp = np.ascontiguousarray(kmer_info, np.uint64)
     A = len(consensuses)
     out = np.zeros(max(A * n_samples, 1), np.uint64)
     p = args.params()
-    rc = H.savont_host_per_sample(C.c_int(device), C.byref(p), _p(snp, C.c_uint64), C.c_size_t(len(snp)), _p(ab, C.c_uint8), _p(ao, C.c_uint64),
-                                  C.c_size_t(A), _p(b, C.c_uint8), _p(q, C.c_uint8), _p(o, C.c_uint64), _p(fi, C.c_uint32),
-                                  C.c_size_t(len(o) - 1), C.c_size_t(n_samples), _p(out, C.c_uint64))
+    if "dna_words" in twin_reads:
+        keep, tp, fi, n_reads = _twin_ptrs(twin_reads)
+        rc = H.savont_host_per_sample_twin(C.c_int(device), C.byref(p), _p(snp, C.c_uint64), C.c_size_t(len(snp)), _p(ab, C.c_uint8),
+                                           _p(ao, C.c_uint64), C.c_size_t(A), *tp, _p(fi, C.c_uint32), C.c_size_t(n_reads),
+                                           C.c_size_t(n_samples), _p(out, C.c_uint64))
+    else:
+        b = np.ascontiguousarray(twin_reads["bases"], np.uint8)
+        q = None if twin_reads.get("quals") is None else np.ascontiguousarray(twin_reads["quals"], np.uint8)
+        o = np.ascontiguousarray(twin_reads["offsets"], np.uint64)
+        fi = np.ascontiguousarray(twin_reads["file_idx"], np.uint32)
+        rc = H.savont_host_per_sample(C.c_int(device), C.byref(p), _p(snp, C.c_uint64), C.c_size_t(len(snp)), _p(ab, C.c_uint8), _p(ao, C.c_uint64),
+                                      C.c_size_t(A), _p(b, C.c_uint8), _p(q, C.c_uint8), _p(o, C.c_uint64), _p(fi, C.c_uint32),
+                                      C.c_size_t(len(o) - 1), C.c_size_t(n_samples), _p(out, C.c_uint64))
     if rc != 0:
         _fail("compute_per_sample_depths")
     return out[:A * n_samples].reshape(A, n_samples).astype(np.int64).tolist()

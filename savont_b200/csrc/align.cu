@@ -126,10 +126,13 @@ struct Band {
     const uint2 *ap;
     int T;                               // D at the band's top cell
     int bd, bi, bj;                      // best end cell so far
+    int dn;                              // D(n, j) of the last column whose last-row cell was evaluated
 };
 
-// one DP column.  TOP: rows <= 0 may be inside the window (j <= B).  LAST: j may be >= n-B.
-template <int NW, bool TB, bool TOP, bool LAST>
+// one DP column.  TOP: rows <= 0 may be inside the window (j <= B).  LAST: j may be >= n-B, the last-row cell (n, j) is
+// scored: 1 = from the band's top score and the vertical deltas (popcounts over the column), 2 = from the previous
+// column's D(n, j-1) and the horizontal delta bits of row n (needs a LAST column right before this one).
+template <int NW, bool TB, bool TOP, int LAST>
 __device__ __forceinline__ void dp_column(Band<NW, TB> &s, uint32_t (&TM)[NW], uint32_t clo, uint32_t chi, uint32_t sh, int j, int n,
                                           int B, uint32_t *hist_col, uint32_t hist_stride) {
     uint32_t Nr[NW + 1], X[NW], t[NW], sum[NW], D0[NW], Ph[NW], Mh[NW];
@@ -170,7 +173,7 @@ __device__ __forceinline__ void dp_column(Band<NW, TB> &s, uint32_t (&TM)[NW], u
 #pragma unroll
         for (int w = 0; w < NW; ++w) TM[w] = (w + 1 < NW) ? __funnelshift_r(TM[w], TM[w + 1], 1) : (TM[w] >> 1);
     }
-    if (LAST) {
+    if (LAST == 1) {
         if (j + B >= n) {                                   // row n is inside the window: bit b = n - j + B
             const int b = n - j + B;
             int d = s.T;
@@ -180,8 +183,19 @@ __device__ __forceinline__ void dp_column(Band<NW, TB> &s, uint32_t (&TM)[NW], u
                 const uint32_t msk = rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
                 d += __popc(s.Pv[w] & msk) - __popc(s.Mv[w] & msk);
             }
+            s.dn = d;
             if (d < s.bd || (d == s.bd && n + j > s.bi + s.bj)) { s.bd = d; s.bi = n; s.bj = j; }
         }
+    }
+    if (LAST == 2) {                                        // j > n - B here: D(n, j) = D(n, j-1) + Ph[b] - Mh[b]
+        const int b = n - j + B;
+        const int bw = b >> 5;
+        uint32_t ph = Ph[0], mh = Mh[0];
+#pragma unroll
+        for (int w = 1; w < NW; ++w) if (bw == w) { ph = Ph[w]; mh = Mh[w]; }
+        const int d = s.dn + (int)((ph >> (b & 31)) & 1u) - (int)((mh >> (b & 31)) & 1u);
+        s.dn = d;
+        if (d <= s.bd) { s.bd = d; s.bi = n; s.bj = j; }     // n + j grows with j: a tie goes to the later column
     }
 }
 
@@ -234,7 +248,7 @@ __device__ __forceinline__ void align_pair(const AlignArgs &a, uint32_t pi, uint
     // reload / register rotation is a real (rare) branch and the column body stays straight-line
     auto run_phase = [&](auto top_tag, auto last_tag, const int jend) {
         constexpr bool TOP = decltype(top_tag)::value;
-        constexpr bool LAST = decltype(last_tag)::value;
+        constexpr int LAST = decltype(last_tag)::value;
         while (j <= jend) {
             uint32_t bit = (uint32_t)(j - 1) & 31u;
             if (bit == 0u) {
@@ -265,10 +279,16 @@ __device__ __forceinline__ void align_pair(const AlignArgs &a, uint32_t pi, uint
             j = stop + 1;
         }
     };
-    // phase 1: virtual rows (<= 0) inside the window; phase 2: interior; phase 3: last row inside the window
-    run_phase(std::true_type{}, std::true_type{}, B < jmax ? B : jmax);
-    run_phase(std::false_type{}, std::false_type{}, (n - B - 1) < jmax ? (n - B - 1) : jmax);
-    run_phase(std::false_type{}, std::true_type{}, jmax);
+    // phase 1: virtual rows (<= 0) inside the window; phase 2: interior; phase 3: last row inside the window -- its first
+    // column scores the last-row cell from the column's vertical deltas, the following ones incrementally
+    using L0 = std::integral_constant<int, 0>; using L1 = std::integral_constant<int, 1>; using L2 = std::integral_constant<int, 2>;
+    run_phase(std::true_type{}, L1{}, B < jmax ? B : jmax);
+    run_phase(std::false_type{}, L0{}, (n - B - 1) < jmax ? (n - B - 1) : jmax);
+    if (TB) run_phase(std::false_type{}, L1{}, jmax);
+    else {
+        if (j <= jmax) run_phase(std::false_type{}, L1{}, j);
+        run_phase(std::false_type{}, L2{}, jmax);
+    }
 
     // row n may already be inside the window of column 0 (n <= B): cell (n, 0) = 0 is a last-row cell
     // (handled below together with the last column when m == 0; for m > 0 the oracle also considers it)

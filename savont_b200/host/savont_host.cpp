@@ -35,9 +35,10 @@ void Mapper::load_asvs(const std::vector<ConsensusSequence> &consensuses) {
     n_asv_ = consensuses.size();
 }
 
-Assignments Mapper::map_reads(const ReadSet &r, int n_samples) {
+// one call into the library with growing class capacity; `call(cap)` returns the library's status
+template <typename Call>
+static Assignments map_with(size_t n, size_t A, int n_samples, Call call) {
     Assignments a;
-    const size_t n = r.n, A = n_asv_;
     a.status.assign(n ? n : 1, 0); a.best_nm.assign(n ? n : 1, 0); a.class_offsets.assign(n + 1, 0);
     a.unambig.assign(A ? A : 1, 0); a.ambig.assign(A ? A : 1, 0); a.leq10.assign(A ? A : 1, 0);
     a.sample_singleton.assign(A * (size_t)n_samples + 1, 0);
@@ -47,9 +48,7 @@ Assignments Mapper::map_reads(const ReadSet &r, int n_samples) {
         std::fill(a.unambig.begin(), a.unambig.end(), 0); std::fill(a.ambig.begin(), a.ambig.end(), 0);
         std::fill(a.leq10.begin(), a.leq10.end(), 0); std::fill(a.sample_singleton.begin(), a.sample_singleton.end(), 0);
         a.totals[0] = a.totals[1] = 0;
-        const int rc = savont_b200_map_reads(ctx_, r.bases, r.quals, r.offsets, r.file_idx, n, n_samples, a.status.data(), a.best_nm.data(),
-                                             a.class_offsets.data(), a.class_asv.data(), cap, a.unambig.data(), a.ambig.data(), a.leq10.data(),
-                                             a.totals, a.sample_singleton.data(), &a.stats);
+        const int rc = call(a, cap);
         if (rc == SAVONT_B200_ERR_CAPACITY) { cap *= 4; continue; }
         ck(rc, "savont_b200_map_reads");
         break;
@@ -58,6 +57,23 @@ Assignments Mapper::map_reads(const ReadSet &r, int n_samples) {
     a.class_asv.resize(a.class_offsets[n]);
     a.unambig.resize(A); a.ambig.resize(A); a.leq10.resize(A); a.sample_singleton.resize(A * (size_t)n_samples);
     return a;
+}
+
+Assignments Mapper::map_reads(const ReadSet &r, int n_samples) {
+    return map_with(r.n, n_asv_, n_samples, [&](Assignments &a, size_t cap) {
+        return savont_b200_map_reads(ctx_, r.bases, r.quals, r.offsets, r.file_idx, r.n, n_samples, a.status.data(), a.best_nm.data(),
+                                     a.class_offsets.data(), a.class_asv.data(), cap, a.unambig.data(), a.ambig.data(), a.leq10.data(),
+                                     a.totals, a.sample_singleton.data(), &a.stats);
+    });
+}
+
+Assignments Mapper::map_reads(const TwinReadSet &r, int n_samples) {
+    return map_with(r.n, n_asv_, n_samples, [&](Assignments &a, size_t cap) {
+        return savont_b200_map_twin_reads(ctx_, r.dna_words, r.dna_word_offsets, r.lengths, r.snpmer_kmers, r.snpmer_kmer_bytes,
+                                          r.snpmer_offsets, r.file_idx, r.n, n_samples, a.status.data(), a.best_nm.data(),
+                                          a.class_offsets.data(), a.class_asv.data(), cap, a.unambig.data(), a.ambig.data(),
+                                          a.leq10.data(), a.totals, a.sample_singleton.data(), &a.stats);
+    });
 }
 
 std::vector<uint32_t> twin_read_order(const std::vector<uint8_t> &status, const std::vector<double> &est_id,
@@ -198,8 +214,9 @@ void write_feature_table(const std::vector<ConsensusSequence> &cons, const std::
     }
 }
 
-void refine_asv_depths_with_em(const ReadSet &twin_reads, std::vector<ConsensusSequence> &consensuses,
-                               const KmerGlobalInfo &kmer_info, const Cli &args, const std::string &temp_dir, int device) {
+template <typename Reads>
+static void refine_impl(const Reads &twin_reads, std::vector<ConsensusSequence> &consensuses,
+                        const KmerGlobalInfo &kmer_info, const Cli &args, const std::string &temp_dir, int device) {
     if (consensuses.empty()) return;                                        // :1734-1737
     if (!temp_dir.empty()) write_consensus_fasta(consensuses, temp_dir + "/final_asvs_for_em.fasta", "em_refinement");   // :1747-1749
     Mapper mapper(device, args, kmer_info);
@@ -219,9 +236,19 @@ void refine_asv_depths_with_em(const ReadSet &twin_reads, std::vector<ConsensusS
                       consensuses.end());                                  // :2031
 }
 
-std::vector<std::vector<size_t>> compute_per_sample_depths(const ReadSet &twin_reads, size_t n_samples,
-                                                           const std::vector<ConsensusSequence> &consensuses,
-                                                           const KmerGlobalInfo &kmer_info, const Cli &args, int device) {
+void refine_asv_depths_with_em(const ReadSet &twin_reads, std::vector<ConsensusSequence> &consensuses,
+                               const KmerGlobalInfo &kmer_info, const Cli &args, const std::string &temp_dir, int device) {
+    refine_impl(twin_reads, consensuses, kmer_info, args, temp_dir, device);
+}
+void refine_asv_depths_with_em(const TwinReadSet &twin_reads, std::vector<ConsensusSequence> &consensuses,
+                               const KmerGlobalInfo &kmer_info, const Cli &args, const std::string &temp_dir, int device) {
+    refine_impl(twin_reads, consensuses, kmer_info, args, temp_dir, device);
+}
+
+template <typename Reads>
+static std::vector<std::vector<size_t>> per_sample_impl(const Reads &twin_reads, size_t n_samples,
+                                                        const std::vector<ConsensusSequence> &consensuses,
+                                                        const KmerGlobalInfo &kmer_info, const Cli &args, int device) {
     const size_t n_asvs = consensuses.size();
     std::vector<std::vector<size_t>> result(n_asvs, std::vector<size_t>(n_samples, 0));
     if (n_asvs == 0 || n_samples == 0) return result;                       // :2055-2057
@@ -236,6 +263,16 @@ std::vector<std::vector<size_t>> compute_per_sample_depths(const ReadSet &twin_r
         for (size_t i = 0; i < n_asvs; ++i) result[i][s] = (size_t)depths[i];
     }
     return result;
+}
+std::vector<std::vector<size_t>> compute_per_sample_depths(const ReadSet &twin_reads, size_t n_samples,
+                                                           const std::vector<ConsensusSequence> &consensuses,
+                                                           const KmerGlobalInfo &kmer_info, const Cli &args, int device) {
+    return per_sample_impl(twin_reads, n_samples, consensuses, kmer_info, args, device);
+}
+std::vector<std::vector<size_t>> compute_per_sample_depths(const TwinReadSet &twin_reads, size_t n_samples,
+                                                           const std::vector<ConsensusSequence> &consensuses,
+                                                           const KmerGlobalInfo &kmer_info, const Cli &args, int device) {
+    return per_sample_impl(twin_reads, n_samples, consensuses, kmer_info, args, device);
 }
 
 }  // namespace savont_host
@@ -254,6 +291,56 @@ long long savont_host_twin_read_order(const uint8_t *status, const double *est_i
         const std::vector<uint32_t> o = savont_host::twin_read_order(st, est, ids, id_offsets);
         for (size_t i = 0; i < o.size(); ++i) order[i] = o[i];
         return (long long)o.size();
+    } catch (const std::exception &e) { g_host_error = e.what(); return -1; }
+}
+
+static savont_host::Cli cli_from(const savont_b200_params *p) {
+    savont_host::Cli args;
+    args.kmer_size = p->k; args.c = p->c; args.blockmer_length = p->l; args.minimum_base_quality = p->min_bq;
+    args.band = p->band; args.strand_mode = p->strand_mode; args.low_polymorphism = p->candidate_mode == 1;
+    return args;
+}
+static std::vector<savont_host::ConsensusSequence> cons_from(const uint8_t *asv_bases, const uint64_t *asv_offsets, size_t n_asv) {
+    std::vector<savont_host::ConsensusSequence> cons(n_asv);
+    for (size_t a = 0; a < n_asv; ++a) { cons[a].sequence.assign(asv_bases + asv_offsets[a], asv_bases + asv_offsets[a + 1]); cons[a].id = a; cons[a].depth = 1; }
+    return cons;
+}
+
+// Stage 7 / 7b with the reads as TwinRead fields (savont_host::TwinReadSet); same outputs as savont_host_refine /
+// savont_host_per_sample
+long long savont_host_refine_twin(int device, const savont_b200_params *p, const uint64_t *snpmers, size_t n_snpmers,
+                                  const uint8_t *asv_bases, const uint64_t *asv_offsets, size_t n_asv,
+                                  const uint64_t *dna_words, const uint64_t *dna_word_offsets, const uint32_t *lengths,
+                                  const void *snpmer_kmers, int snpmer_kmer_bytes, const uint64_t *snpmer_offsets, size_t n_reads,
+                                  const char *temp_dir, uint64_t *depth, uint64_t *unambig, uint64_t *ambig, uint64_t *leq10, uint64_t *orig_idx) {
+    try {
+        savont_host::KmerGlobalInfo ki; ki.snpmers.assign(snpmers, snpmers + n_snpmers);
+        auto cons = cons_from(asv_bases, asv_offsets, n_asv);
+        savont_host::TwinReadSet rs;
+        rs.dna_words = dna_words; rs.dna_word_offsets = dna_word_offsets; rs.lengths = lengths; rs.snpmer_kmers = snpmer_kmers;
+        rs.snpmer_kmer_bytes = snpmer_kmer_bytes; rs.snpmer_offsets = snpmer_offsets; rs.n = n_reads;
+        savont_host::refine_asv_depths_with_em(rs, cons, ki, cli_from(p), temp_dir ? temp_dir : "", device);
+        for (size_t i = 0; i < cons.size(); ++i) {
+            depth[i] = cons[i].depth; unambig[i] = cons[i].unambig_best_read_map_count; ambig[i] = cons[i].ambig_read_map_count;
+            leq10[i] = cons[i].num_map_leq_10nm; orig_idx[i] = cons[i].id;
+        }
+        return (long long)cons.size();
+    } catch (const std::exception &e) { g_host_error = e.what(); return -1; }
+}
+int savont_host_per_sample_twin(int device, const savont_b200_params *p, const uint64_t *snpmers, size_t n_snpmers,
+                                const uint8_t *asv_bases, const uint64_t *asv_offsets, size_t n_asv,
+                                const uint64_t *dna_words, const uint64_t *dna_word_offsets, const uint32_t *lengths,
+                                const void *snpmer_kmers, int snpmer_kmer_bytes, const uint64_t *snpmer_offsets,
+                                const uint32_t *file_idx, size_t n_reads, size_t n_samples, uint64_t *out) {
+    try {
+        savont_host::KmerGlobalInfo ki; ki.snpmers.assign(snpmers, snpmers + n_snpmers);
+        const auto cons = cons_from(asv_bases, asv_offsets, n_asv);
+        savont_host::TwinReadSet rs;
+        rs.dna_words = dna_words; rs.dna_word_offsets = dna_word_offsets; rs.lengths = lengths; rs.snpmer_kmers = snpmer_kmers;
+        rs.snpmer_kmer_bytes = snpmer_kmer_bytes; rs.snpmer_offsets = snpmer_offsets; rs.file_idx = file_idx; rs.n = n_reads;
+        const auto res = savont_host::compute_per_sample_depths(rs, n_samples, cons, ki, cli_from(p), device);
+        for (size_t a = 0; a < n_asv; ++a) for (size_t s_ = 0; s_ < n_samples; ++s_) out[a * n_samples + s_] = res[a][s_];
+        return 0;
     } catch (const std::exception &e) { g_host_error = e.what(); return -1; }
 }
 

@@ -58,6 +58,19 @@ struct ReadSet {
     size_t n = 0;
 };
 
+// the same reads as the reference hands them to Stage 7 / 7b: `&[TwinRead]` (src/types.rs:386-412), the three fields
+// the path reads, laid out back to back without re-encoding (include/savont_b200.h, savont_b200_map_twin_reads)
+struct TwinReadSet {
+    const uint64_t *dna_words = nullptr;        // TwinRead.dna_seq raw words (bio-seq Seq<Dna>), each read word aligned
+    const uint64_t *dna_word_offsets = nullptr; // [n + 1]
+    const uint32_t *lengths = nullptr;          // [n] bases per read
+    const void *snpmer_kmers = nullptr;         // TwinRead.snpmer_kmers: Kmer48 bytes (6) or u64 (8)
+    int snpmer_kmer_bytes = 6;
+    const uint64_t *snpmer_offsets = nullptr;   // [n + 1]
+    const uint32_t *file_idx = nullptr;         // TwinRead.file_idx, may be null
+    size_t n = 0;
+};
+
 // sorted equivalence classes with counts (the reference's HashMap<EquivalenceClass, usize>,
 // src/alignment.rs:1517-1523,1915-1916, iterated here in lexicographic order)
 struct EqClasses {
@@ -87,6 +100,7 @@ public:
     Mapper &operator=(const Mapper &) = delete;
     void load_asvs(const std::vector<ConsensusSequence> &consensuses);
     Assignments map_reads(const ReadSet &reads, int n_samples);
+    Assignments map_reads(const TwinReadSet &reads, int n_samples);
     savont_b200_ctx *raw() { return ctx_; }
     size_t n_asv() const { return n_asv_; }
 
@@ -122,9 +136,14 @@ int run_em(size_t n_asv, const EqClasses &classes, std::vector<double> &abundanc
 // whose EM depth is 0 (:2031).  temp_dir receives final_asvs_for_em.fasta like the reference.
 void refine_asv_depths_with_em(const ReadSet &twin_reads, std::vector<ConsensusSequence> &consensuses,
                                const KmerGlobalInfo &kmer_info, const Cli &args, const std::string &temp_dir, int device = 0);
+void refine_asv_depths_with_em(const TwinReadSet &twin_reads, std::vector<ConsensusSequence> &consensuses,
+                               const KmerGlobalInfo &kmer_info, const Cli &args, const std::string &temp_dir, int device = 0);
 
 // reference src/alignment.rs:2044-2051 (Stage 7b): result[asv][sample]
 std::vector<std::vector<size_t>> compute_per_sample_depths(const ReadSet &twin_reads, size_t n_samples,
+                                                           const std::vector<ConsensusSequence> &consensuses,
+                                                           const KmerGlobalInfo &kmer_info, const Cli &args, int device = 0);
+std::vector<std::vector<size_t>> compute_per_sample_depths(const TwinReadSet &twin_reads, size_t n_samples,
                                                            const std::vector<ConsensusSequence> &consensuses,
                                                            const KmerGlobalInfo &kmer_info, const Cli &args, int device = 0);
 

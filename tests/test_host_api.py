@@ -101,6 +101,13 @@ def test_refine_asv_depths_with_em_matches_oracle_pipeline(tmp_path):
     assert [c.num_map_leq_10nm for c in cons] == [int(res["leq10"][a]) for a in kept]
     assert (tmp_path / "final_asvs_for_em.fasta").read_text().count(">em_refinement_consensus_") == w.n_asv
     assert sum(c.depth for c in cons) > 0.5 * 3000
+    # the same Stage 7 with the reads handed over as TwinRead fields (&[TwinRead], src/alignment.rs:1723-1729)
+    from savont_b200 import twin
+    sk = O.sketch_batch(O.default_params(band=w.band), w.snpmers, r["bases"], r["quals"], r["offsets"])
+    cons2 = [api.ConsensusSequence(s, depth=1, id=i) for i, s in enumerate(seqs)]
+    api.refine_asv_depths_with_em(twin.from_sketch(sk, r["offsets"], kmer48=True), cons2, w.snpmers, args)
+    assert [(c.id, c.depth, c.unambig_best_read_map_count, c.ambig_read_map_count, c.num_map_leq_10nm) for c in cons2] == \
+           [(c.id, c.depth, c.unambig_best_read_map_count, c.ambig_read_map_count, c.num_map_leq_10nm) for c in cons]
 
 
 @pytest.mark.gpu
@@ -115,6 +122,10 @@ def test_compute_per_sample_depths_matches_oracle_pipeline():
     _, per = _oracle_depths(orc, r, w.n_asv, n_samples=3, file_idx=r["file_idx"])
     want = np.stack(per, axis=1).astype(np.int64).tolist()
     assert got == want
+    from savont_b200 import twin
+    sk = O.sketch_batch(O.default_params(band=w.band), w.snpmers, r["bases"], r["quals"], r["offsets"])
+    tw = twin.from_sketch(sk, r["offsets"], file_idx=r["file_idx"])
+    assert api.compute_per_sample_depths(tw, 3, cons, w.snpmers, api.Cli(band=w.band)) == want
 
 
 @pytest.mark.gpu
