@@ -129,6 +129,30 @@ int savont_b200_twin_reads_from_snpmers(savont_b200_ctx *ctx, const uint8_t *bas
                                         const uint64_t *offsets, size_t n_reads, uint8_t *status, double *est_id,
                                         uint32_t *n_solid_mini, uint32_t *n_solid_snp);
 
+/* ---- Stage 1 counting: replaces the counting of seq_parse::read_to_split_kmers
+ * (src/seq_parse.rs:12-83, bloom_filter_size == 0) over seeding::split_kmer_mid (src/seeding.rs:975-1068) for the reads
+ * of one call = all input files.  k and min_bq come from savont_b200_set_params.  rc[i] != 0 (rc may be NULL) marks a read
+ * whose id ends in the token "rc": it is reverse-complemented first (src/seq_parse.rs:361-369, src/utils.rs:51-65).
+ * Output: the (k-mer, [c0, c1]) entries that pass the reference's filter (:30-44; c[flag] with flag = 1 iff the forward
+ * strand is the canonical one), in UNSPECIFIED order (the reference's is hash-map order; get_snpmers_inplace_sort sorts
+ * them itself, src/kmer_comp.rs:483).  out_counts holds 2 u32 per entry.  *n_out = number of entries; when it exceeds
+ * out_cap the call fails with SAVONT_B200_ERR_CAPACITY and the message carries the required capacity.
+ * Unlike the reference's "Total SNPmers after bloom filter" the library cannot report the exact number of distinct
+ * k-mers (k-mers seen once are never stored); stats->first_seen is that number up to Bloom-filter false positives. */
+typedef struct savont_b200_kmer_stats {
+    double   pass1_ms, pass2_ms, compact_ms, h2d_ms, total_ms;   /* device times (CUDA events) */
+    uint64_t n_reads, n_bases;
+    uint64_t bloom_bytes, table_slots, table_used;               /* exact table: 16 B per slot */
+    uint64_t first_seen;                                         /* occurrences that found their Bloom bits clear */
+    uint64_t h2d_bytes, d2h_bytes, kernel_launches, table_regrows;
+} savont_b200_kmer_stats;
+int savont_b200_count_split_kmers(savont_b200_ctx *ctx, const uint8_t *bases, const uint8_t *quals, const uint64_t *offsets,
+                                  const uint8_t *rc, size_t n_reads, int single_strand, uint64_t *out_kmers,
+                                  uint32_t *out_counts, size_t out_cap, size_t *n_out, savont_b200_kmer_stats *stats);
+/* The same over the reads left in HBM by savont_b200_upload_reads (no rc flags): kernel-only measurement. */
+int savont_b200_count_split_kmers_resident(savont_b200_ctx *ctx, int single_strand, uint64_t *out_kmers, uint32_t *out_counts,
+                                           size_t out_cap, size_t *n_out, savont_b200_kmer_stats *stats);
+
 /* Replaces kmer_comp::twin_reads_from_fasta (src/kmer_comp.rs:39-66) + the SNPmer inverted
  * index build (src/alignment.rs:1754-1765): sketches the ASVs on the GPU (no qualities) and
  * builds the replicated device index.  ASV index = order given. */

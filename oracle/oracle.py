@@ -97,6 +97,8 @@ def lib():
         L.so_map_reads.restype = C.c_int
         L.so_em.restype = C.c_int
         L.so_twin_reads_filter.restype = C.c_int
+        L.so_count_split_kmers.restype = C.c_longlong
+        L.so_high_freq_kmers.restype = C.c_uint32
         L.so_set_read_filter.restype = None
         _lib = L
     return _lib
@@ -173,6 +175,34 @@ def twin_reads_filter(params: Params, rf: ReadFilter, snpmers, high_freq, bases,
                                 _p(sm, C.c_uint32), _p(ss, C.c_uint32), _p(order, C.c_uint32), C.byref(nk))
     assert rc == 0, rc
     return dict(status=st[:n], est_id=est[:n], n_solid_mini=sm[:n], n_solid_snp=ss[:n], order=order[:int(nk.value)])
+
+
+def count_split_kmers(bases, quals, offsets, rc=None, k=17, min_bq=25, single_strand=False, n_threads=0, cap=None):
+    """Stage 1 counting (so_count_split_kmers): -> dict(kmers u64 sorted, counts u32 [n,2], n_distinct)"""
+    L = lib()
+    bases = as_u8(bases); quals = None if quals is None else as_u8(quals)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    n = len(offsets) - 1
+    rcf = None if rc is None else np.ascontiguousarray(rc, dtype=np.uint8)
+    cap = cap or max(int(offsets[-1] - offsets[0]) // 2 + 16, 16)
+    km = np.zeros(cap, np.uint64); ct = np.zeros(2 * cap, np.uint32)
+    nd = C.c_uint64(0)
+    m = L.so_count_split_kmers(C.c_int(k), C.c_int(min_bq), C.c_int(1 if single_strand else 0), _p(bases, C.c_uint8), _p(quals, C.c_uint8),
+                               _p(offsets, C.c_uint64), _p(rcf, C.c_uint8), C.c_size_t(n), _p(km, C.c_uint64), _p(ct, C.c_uint32),
+                               C.c_size_t(cap), C.byref(nd), C.c_int(n_threads))
+    assert m >= 0, m
+    return dict(kmers=km[:m], counts=ct[:2 * m].reshape(m, 2), n_distinct=int(nd.value))
+
+
+def high_freq_kmers(kmers, counts):
+    """src/kmer_comp.rs:459-500 -> (high_freq_thresh, high-frequency k-mers in input order)"""
+    L = lib()
+    km = np.ascontiguousarray(kmers, np.uint64); ct = np.ascontiguousarray(counts, np.uint32).reshape(-1)
+    n = len(km)
+    assert n > 0
+    out = np.zeros(n, np.uint64); nh = C.c_size_t(0)
+    th = L.so_high_freq_kmers(_p(km, C.c_uint64), _p(ct, C.c_uint32), C.c_size_t(n), _p(out, C.c_uint64), C.byref(nh))
+    return int(th), out[:int(nh.value)]
 
 
 class Oracle:

@@ -844,6 +844,130 @@ int so_map_reads(so_ctx *c, const uint8_t *bases, const uint8_t *quals, const ui
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* Stage 1 counting: seeding::split_kmer_mid (src/seeding.rs:975-1068) +                 */
+/* seq_parse::read_to_split_kmers (src/seq_parse.rs:12-83, :315-497), bloom_filter_size 0 */
+/* ------------------------------------------------------------------------------------ */
+/* marked k-mers of one read: canonical k-mer | (forward is canonical) << 63; returns how many were written */
+static size_t split_kmer_mid(const uint8_t *string, const uint8_t *qualities, size_t len, int k, int minimum_bq, uint64_t *out) {
+    if (len < (size_t)k) return 0;                                           /* :982-984 */
+    size_t n = 0;
+    uint64_t rolling_kmer_f = 0, rolling_kmer_r = 0;
+    const int marker_reverse_shift_dist = 2 * (k - 1);
+    const uint64_t marker_mask = UINT64_MAX >> (64 - 2 * k);
+    const uint64_t marker_rev_mask = ~((uint64_t)3 << (2 * k - 2));
+    const uint64_t split_mask = ~((uint64_t)3 << (k - 1));
+    const int mid_k = k / 2;
+    int use_q = 0;                                                           /* :1004-1018 positions_to_skip */
+    if (qualities) for (size_t i = 1; i < len; i++) if (qualities[i] != qualities[0]) { use_q = 1; break; }
+    for (int i = 0; i < k - 1; i++) {                                        /* :1021-1028 */
+        uint64_t nuc_f = so_encode_base(string[i]), nuc_r = 3 - nuc_f;
+        rolling_kmer_f <<= 2; rolling_kmer_f |= nuc_f;
+        rolling_kmer_r >>= 2; rolling_kmer_r |= nuc_r << marker_reverse_shift_dist;
+    }
+    for (size_t i = (size_t)k - 1; i < len; i++) {                           /* :1030-1065 */
+        uint64_t nuc_f = so_encode_base(string[i]), nuc_r = 3 - nuc_f;
+        rolling_kmer_f <<= 2; rolling_kmer_f |= nuc_f; rolling_kmer_f &= marker_mask;
+        rolling_kmer_r >>= 2; rolling_kmer_r &= marker_rev_mask; rolling_kmer_r |= nuc_r << marker_reverse_shift_dist;
+        uint64_t split_f = rolling_kmer_f & split_mask, split_r = rolling_kmer_r & split_mask;
+        if (split_f == split_r) continue;                                    /* palindromic splitmer, :1044-1046 */
+        if (use_q) {
+            size_t mid_pos = i + 1 + (size_t)mid_k - (size_t)k;
+            if ((int)qualities[mid_pos] - 33 < minimum_bq) continue;         /* :1012, :1049-1051 */
+        }
+        int canonical_marker = split_f < split_r;
+        uint64_t canonical = canonical_marker ? rolling_kmer_f : rolling_kmer_r;
+        out[n++] = canonical | ((uint64_t)canonical_marker << 63);           /* :1063 */
+    }
+    return n;
+}
+
+static int cmp_marked(const void *a, const void *b) {
+    const uint64_t m = ~((uint64_t)1 << 63);
+    uint64_t x = *(const uint64_t *)a, y = *(const uint64_t *)b;
+    if ((x & m) != (y & m)) return (x & m) < (y & m) ? -1 : 1;
+    return (x >> 63) < (y >> 63) ? -1 : ((x >> 63) > (y >> 63));
+}
+
+long long so_count_split_kmers(int k, int min_bq, int single_strand, const uint8_t *bases, const uint8_t *quals,
+                               const uint64_t *offsets, const uint8_t *rc, size_t n_reads, uint64_t *out_kmers,
+                               uint32_t *out_counts, size_t cap, uint64_t *n_distinct, int n_threads) {
+    /* per-read output segments: at most len - k + 1 marked k-mers each */
+    uint64_t *seg = (uint64_t *)malloc((n_reads + 1) * sizeof(uint64_t));
+    seg[0] = 0;
+    for (size_t r = 0; r < n_reads; r++) {
+        size_t len = offsets[r + 1] - offsets[r];
+        seg[r + 1] = seg[r] + (len >= (size_t)k ? len - (size_t)k + 1 : 0);
+    }
+    uint64_t *all = (uint64_t *)malloc((seg[n_reads] + 1) * sizeof(uint64_t));
+    uint64_t *cnt = (uint64_t *)calloc(n_reads + 1, sizeof(uint64_t));
+#ifdef _OPENMP
+    if (n_threads > 0) omp_set_num_threads(n_threads);
+#else
+    (void)n_threads;
+#endif
+#pragma omp parallel for schedule(dynamic, 64)
+    for (long long rr = 0; rr < (long long)n_reads; rr++) {
+        size_t r = (size_t)rr, off = offsets[r], len = offsets[r + 1] - off;
+        const uint8_t *sq = bases + off, *ql = quals ? quals + off : NULL;
+        uint8_t *tmp = NULL;
+        if (rc && rc[r]) {                                                   /* src/seq_parse.rs:361-369 + utils::reverse_complement */
+            tmp = (uint8_t *)malloc(2 * len + 2);
+            for (size_t i = 0; i < len; i++) {
+                uint8_t b = sq[len - 1 - i], c;
+                switch (b) {                                                 /* src/utils.rs:51-65 reverse_complement */
+                    case 'A': case 'a': c = 'T'; break;
+                    case 'T': case 't': c = 'A'; break;
+                    case 'C': case 'c': c = 'G'; break;
+                    case 'G': case 'g': c = 'C'; break;
+                    default: c = 'N';                                        /* N, n and anything else (also U) */
+                }
+                tmp[i] = c;
+                if (ql) tmp[len + i] = ql[len - 1 - i];
+            }
+            sq = tmp; if (ql) ql = tmp + len;
+        }
+        cnt[r] = split_kmer_mid(sq, ql, len, k, min_bq, all + seg[r]);
+        free(tmp);
+    }
+    /* compact, sort by (k-mer, flag), run-length count: the FxHashMap<u64,[u32;2]> of :455-460 */
+    size_t n = 0;
+    for (size_t r = 0; r < n_reads; r++) { memmove(all + n, all + seg[r], cnt[r] * sizeof(uint64_t)); n += cnt[r]; }
+    qsort(all, n, sizeof(uint64_t), cmp_marked);
+    const uint64_t mask = ~((uint64_t)1 << 63);
+    long long n_out = 0; uint64_t distinct = 0; int rcode = 0;
+    for (size_t i = 0; i < n;) {
+        uint64_t kmer = all[i] & mask; uint32_t c[2] = {0, 0};
+        size_t j = i;
+        while (j < n && (all[j] & mask) == kmer) { c[all[j] >> 63]++; j++; }
+        distinct++;
+        int keep = single_strand ? (c[0] > 2) : (c[0] > 0 && c[1] > 0 && c[0] + c[1] > 2);   /* :30-44 */
+        if (keep) {
+            if ((size_t)n_out >= cap) { rcode = -1; break; }
+            out_kmers[n_out] = kmer; out_counts[2 * n_out] = c[0]; out_counts[2 * n_out + 1] = c[1]; n_out++;
+        }
+        i = j;
+    }
+    if (n_distinct) *n_distinct = distinct;
+    free(all); free(seg); free(cnt);
+    return rcode ? -1 : n_out;
+}
+
+static int cmp_u32(const void *a, const void *b) { uint32_t x = *(const uint32_t *)a, y = *(const uint32_t *)b; return x < y ? -1 : x > y; }
+uint32_t so_high_freq_kmers(const uint64_t *kmers, const uint32_t *counts, size_t n, uint64_t *hf_out, size_t *n_hf) {
+    uint32_t *kc = (uint32_t *)malloc((n + 1) * sizeof(uint32_t));                  /* src/kmer_comp.rs:463-466 */
+    for (size_t i = 0; i < n; i++) kc[i] = counts[2 * i] + counts[2 * i + 1];
+    qsort(kc, n, sizeof(uint32_t), cmp_u32);
+    uint32_t thresh = kc[n - (n / 100000) - 1];                                     /* :474 */
+    if (thresh < 100) thresh = 100;
+    free(kc);
+    size_t m = 0;
+    for (size_t i = 0; i < n; i++)
+        if (counts[2 * i] + counts[2 * i + 1] > thresh) { if (hf_out) hf_out[m] = kmers[i]; m++; }   /* :497-499 */
+    if (n_hf) *n_hf = m;
+    return thresh;
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* a13-a14: EM, src/alignment.rs:1957-2038                                              */
 /* ------------------------------------------------------------------------------------ */
 int so_em(size_t n_asv, const uint64_t *cls_offsets, const uint32_t *cls_asv, const uint64_t *counts, size_t n_cls,

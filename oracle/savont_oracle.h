@@ -153,6 +153,24 @@ int so_twin_reads_filter(const so_params *p, const so_read_filter *f, const uint
  * filtered (they do not exist in Stage 7).  f == NULL switches the tests off. */
 void so_set_read_filter(so_ctx *ctx, const so_read_filter *f, const uint64_t *high_freq, size_t n_high_freq);
 
+/* ---- Stage 1 counting (the integer part): seq_parse::read_to_split_kmers with
+ * bloom_filter_size == 0 (src/seq_parse.rs:12-83, :315-497) over seeding::split_kmer_mid (src/seeding.rs:975-1068).
+ * Every k-mer of every read whose splitmer is not palindromic (:1044-1046) and whose middle base has Phred >= min_bq
+ * (:1009-1018; only when the read's qualities are not all equal) is counted per canonical k-mer and per strand flag
+ * (counts[flag], flag = 1 iff the forward strand is the canonical one, :1053-1063; src/seq_parse.rs:455-460).
+ * rc[r] != 0 (may be NULL): the last whitespace-separated token of the read id is "rc" (src/seq_parse.rs:361-369): the
+ * read is reverse-complemented (and its qualities reversed) first.
+ * Output: the entries that pass the filter of src/seq_parse.rs:30-44 (both strands seen and more than 2 occurrences; with
+ * single_strand: counts[0] > 2), sorted by k-mer (the reference's order is hash-map order); out_counts = [c0, c1] per
+ * entry.  *n_distinct = number of distinct k-mers before the filter ("Total SNPmers after bloom filter", :27).
+ * Returns the number of entries, or -1 if cap is too small. */
+long long so_count_split_kmers(int k, int min_bq, int single_strand, const uint8_t *bases, const uint8_t *quals,
+                               const uint64_t *offsets, const uint8_t *rc, size_t n_reads, uint64_t *out_kmers,
+                               uint32_t *out_counts, size_t cap, uint64_t *n_distinct, int n_threads);
+/* src/kmer_comp.rs:459-500: high_freq_thresh = max(100, sorted(c0+c1)[len - len/100000 - 1]); the high-frequency set =
+ * k-mers with c0 + c1 > high_freq_thresh (the set a4 reads), in input order.  Returns the threshold; n must be > 0. */
+uint32_t so_high_freq_kmers(const uint64_t *kmers, const uint32_t *counts, size_t n, uint64_t *hf_out, size_t *n_hf);
+
 /* ---- a13-a14: EM over equivalence classes (src/alignment.rs:1957-2038) ---------------
  * classes in CSR (cls_offsets[n_cls+1], cls_asv), counts[n_cls]; total_assigned;
  * out: abundances[A] (f64), depths[A] = round(ab*total).  Classes are iterated in the

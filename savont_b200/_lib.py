@@ -51,6 +51,16 @@ class Stats(C.Structure):
         return {f: getattr(self, f) for f, _ in self._fields_}
 
 
+class KmerStats(C.Structure):
+    _fields_ = [("pass1_ms", C.c_double), ("pass2_ms", C.c_double), ("compact_ms", C.c_double), ("h2d_ms", C.c_double),
+                ("total_ms", C.c_double), ("n_reads", C.c_uint64), ("n_bases", C.c_uint64), ("bloom_bytes", C.c_uint64),
+                ("table_slots", C.c_uint64), ("table_used", C.c_uint64), ("first_seen", C.c_uint64), ("h2d_bytes", C.c_uint64),
+                ("d2h_bytes", C.c_uint64), ("kernel_launches", C.c_uint64), ("table_regrows", C.c_uint64)]
+
+    def as_dict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
 class SavontB200Error(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"libsavont_b200 error {code}: {msg}")
@@ -178,6 +188,40 @@ class Context:
         _check(self.L.savont_b200_twin_reads_from_snpmers(self.h, _p(b, C.c_uint8), _p(q, C.c_uint8), _p(o, C.c_uint64), C.c_size_t(n),
                                                           _p(st, C.c_uint8), _p(est, C.c_double), _p(sm, C.c_uint32), _p(ss, C.c_uint32)))
         return dict(status=st[:n], est_id=est[:n], n_solid_mini=sm[:n], n_solid_snp=ss[:n])
+
+    # ---- Stage 1 counting (K5) ----
+    def _kmer_out(self, call, cap, sort):
+        for _ in range(3):
+            km = np.zeros(max(cap, 1), np.uint64); ct = np.zeros(2 * max(cap, 1), np.uint32)
+            n = C.c_size_t(0); st = KmerStats()
+            rc = call(_p(km, C.c_uint64), _p(ct, C.c_uint32), C.c_size_t(cap), C.byref(n), C.byref(st))
+            if rc == ERR_CAPACITY and n.value > cap:
+                cap = int(n.value) + 16
+                continue
+            _check(rc)
+            break
+        m = int(n.value)
+        km = km[:m]; ct = ct[:2 * m].reshape(m, 2)
+        if sort:                                      # the library's order is unspecified (like the reference's hash maps)
+            o = np.argsort(km, kind="stable"); km = km[o]; ct = ct[o]
+        return dict(kmers=km, counts=ct, stats=st.as_dict())
+
+    def count_split_kmers(self, bases, quals, offsets, rc=None, single_strand=False, cap=None, sort=True):
+        """seq_parse::read_to_split_kmers (counting part): -> dict(kmers, counts [n, 2], stats)"""
+        b = _u8(bases); q = _u8(quals)
+        o = np.ascontiguousarray(offsets, dtype=np.uint64)
+        r = None if rc is None else np.ascontiguousarray(rc, dtype=np.uint8)
+        n = len(o) - 1
+        cap = cap or max(int(o[-1] - o[0]) // 64 + 4096, 4096)
+        call = lambda km, ct, cp, nn, st: self.L.savont_b200_count_split_kmers(
+            self.h, _p(b, C.c_uint8), _p(q, C.c_uint8), _p(o, C.c_uint64), _p(r, C.c_uint8), C.c_size_t(n),
+            C.c_int(1 if single_strand else 0), km, ct, cp, nn, st)
+        return self._kmer_out(call, cap, sort)
+
+    def count_split_kmers_resident(self, single_strand=False, cap=1 << 22, sort=True):
+        call = lambda km, ct, cp, nn, st: self.L.savont_b200_count_split_kmers_resident(
+            self.h, C.c_int(1 if single_strand else 0), km, ct, cp, nn, st)
+        return self._kmer_out(call, cap, sort)
 
     def load_asvs(self, bases, offsets):
         b = _u8(bases)

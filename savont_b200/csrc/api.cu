@@ -138,6 +138,11 @@ struct Context {
     // counters [unambig A | ambig A | leq10 A | assigned | filtered | singleton S*A]
     DevBuf d_counters; size_t counters_len = 0; int counters_samples = 0;
 
+    // K5 (Stage 1 split-k-mer counting): Bloom filter, exact table, counters, output staging, read chunks
+    DevBuf d_kc_bloom, d_kc_table, d_kc_ctr, d_kc_out_k, d_kc_out_c;
+    struct KcChunk { DevBuf bases, quals, offsets, rc; PinBuf pin; uint32_t n = 0, max_len = 0; uint64_t total = 0; bool has_quals = false, has_rc = false; };
+    std::vector<KcChunk> kc_chunks;
+    cudaEvent_t kc_ev_up[2] = {nullptr, nullptr}, kc_ev_done[2] = {nullptr, nullptr};
     // a4 read filter (twin_reads_from_snpmers): options + high-frequency k-mer set
     bool rf_on = false; ReadFilter rf{}; std::vector<uint64_t> h_hf; DevBuf d_hf_keys; uint32_t hf_mask = 0, hf_shift = 0;
     Batch work, work2, work3, resident, asvb;
@@ -863,6 +868,94 @@ static int read_counters(Context *c, uint64_t *unambig, uint64_t *ambig, uint64_
 
 }  // namespace sb
 
+
+// ------------------------------------------------------------------------------------------------
+// K5: Stage 1 split-k-mer counting (kmercount.cu)
+// ------------------------------------------------------------------------------------------------
+namespace sb {
+
+struct KcView { SeqBatch in; const uint8_t *rc; };
+// the two passes + compaction over device-resident chunk views; (re)sizes the Bloom filter and the table, grows the table
+// and starts over when it fills up.  `views(i, pass)` returns the i-th chunk after making sure it is on the device.
+template <typename GetView>
+static int kc_run(Context *c, size_t n_chunks, uint64_t total_bases, GetView view, int single_strand, uint64_t *out_kmers,
+                  uint32_t *out_counts, size_t out_cap, size_t *n_out, savont_b200_kmer_stats &st) {
+    // sizing: one Bloom word bit budget of 8 bits per k-mer occurrence (>= 16 bits per distinct k-mer), table slots =
+    // occurrences / 8 (k-mers seen at least twice are a small fraction of the occurrences), load <= 0.5
+    uint64_t bloom_words = 1ull << 14;
+    while (bloom_words * 4ull < total_bases && bloom_words < (1ull << 33)) bloom_words <<= 1;      // 32 bits per word
+    uint64_t slots = 1ull << 16;
+    while (slots * 8ull < total_bases && slots < (1ull << 31)) slots <<= 1;
+    TRY(c->d_kc_ctr.ensure(64));
+    TRY(c->d_kc_bloom.ensure(bloom_words * 4ull));
+    uint32_t ctr[4] = {0, 0, 0, 0};
+    for (int attempt = 0;; ++attempt) {
+        TRY(c->d_kc_table.ensure(slots * sizeof(KmerSlot)));
+        const uint32_t tshift = shift_for_cap((uint32_t)slots), tmask = (uint32_t)(slots - 1);
+        uint32_t bshift = 64; { uint64_t w = bloom_words; while (w > 1) { w >>= 1; --bshift; } }
+        CK(cudaEventRecord(c->ev[0], c->stream));
+        CK(cudaMemsetAsync(c->d_kc_ctr.p, 0, 64, c->stream));
+        CK(cudaMemsetAsync(c->d_kc_bloom.p, 0, bloom_words * 4ull, c->stream));
+        launch_kmer_table_clear(c->d_kc_table.as<KmerSlot>(), slots, c->stream);
+        st.kernel_launches += 1;
+        for (size_t i = 0; i < n_chunks; ++i) {
+            KcView v{};
+            TRY(view(i, 1, &v));
+            launch_kmer_pass(1, v.in, v.rc, c->dp.k, c->dp.min_bq, c->d_kc_bloom.as<uint32_t>(), bshift, c->d_kc_table.as<KmerSlot>(),
+                             tshift, tmask, c->d_kc_ctr.as<uint32_t>(), (uint32_t)(slots / 2), c->sm_count, c->stream);
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(c->kc_ev_done[i & 1], c->stream));
+            st.kernel_launches += 1;
+        }
+        CK(cudaEventRecord(c->ev[1], c->stream));
+        CK(cudaMemcpyAsync(ctr, c->d_kc_ctr.p, sizeof(ctr), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        st.pass1_ms += ev_ms(c->ev[0], c->ev[1]);
+        if (ctr[1] == 0) {
+            for (size_t i = 0; i < n_chunks; ++i) {
+                KcView v{};
+                TRY(view(i, 2, &v));
+                launch_kmer_pass(2, v.in, v.rc, c->dp.k, c->dp.min_bq, c->d_kc_bloom.as<uint32_t>(), bshift, c->d_kc_table.as<KmerSlot>(),
+                                 tshift, tmask, c->d_kc_ctr.as<uint32_t>(), (uint32_t)(slots / 2), c->sm_count, c->stream);
+                CK(cudaGetLastError());
+                CK(cudaEventRecord(c->kc_ev_done[i & 1], c->stream));
+                st.kernel_launches += 1;
+            }
+            CK(cudaEventRecord(c->ev[2], c->stream));
+            break;
+        }
+        if (attempt == 4 || slots >= (1ull << 31)) return fail(SAVONT_B200_ERR_OVERFLOW, "k-mer table sizing did not converge (%llu slots)", (unsigned long long)slots);
+        slots <<= 2; st.table_regrows += 1;
+    }
+    st.bloom_bytes = bloom_words * 4ull; st.table_slots = slots; st.table_used = ctr[0];
+    st.first_seen = (uint64_t)ctr[2] | ((uint64_t)ctr[3] << 32);
+    // compaction: at most table_used survivors
+    const uint32_t cap_dev = ctr[0] + 32u;
+    TRY(c->d_kc_out_k.ensure((size_t)cap_dev * 8)); TRY(c->d_kc_out_c.ensure((size_t)cap_dev * 8));
+    CK(cudaMemsetAsync(c->d_kc_ctr.as<uint32_t>() + 8, 0, 4, c->stream));
+    launch_kmer_compact(c->d_kc_table.as<KmerSlot>(), slots, single_strand, c->d_kc_out_k.as<uint64_t>(), c->d_kc_out_c.as<uint32_t>(),
+                        cap_dev, c->d_kc_ctr.as<uint32_t>() + 8, c->stream);
+    CK(cudaGetLastError());
+    st.kernel_launches += 1;
+    CK(cudaEventRecord(c->ev[3], c->stream));
+    uint32_t n_found = 0;
+    CK(cudaMemcpyAsync(&n_found, c->d_kc_ctr.as<uint32_t>() + 8, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    st.pass2_ms += ev_ms(c->ev[1], c->ev[2]);
+    st.compact_ms += ev_ms(c->ev[2], c->ev[3]);
+    if (n_out) *n_out = n_found;
+    if (n_found > out_cap) return fail(SAVONT_B200_ERR_CAPACITY, "k-mer output capacity %zu too small (need >= %u)", out_cap, n_found);
+    if (n_found) {
+        CK(cudaMemcpyAsync(out_kmers, c->d_kc_out_k.p, (size_t)n_found * 8, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(out_counts, c->d_kc_out_c.p, (size_t)n_found * 8, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    st.d2h_bytes += (uint64_t)n_found * 16 + 16;
+    return 0;
+}
+
+}  // namespace sb
+
 // ================================================================================================
 // extern "C"
 // ================================================================================================
@@ -902,6 +995,7 @@ int savont_b200_create(int device_id, savont_b200_ctx **out) {
     CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
     for (auto &ev : c->ev_d2h) CK(cudaEventCreate(&ev));
+    for (int i = 0; i < 2; ++i) { CK(cudaEventCreate(&c->kc_ev_up[i])); CK(cudaEventCreate(&c->kc_ev_done[i])); }
     for (int i = 0; i < 2; ++i) {
         CK(cudaStreamCreateWithFlags(&c->lane_stream[i], cudaStreamNonBlocking));
         for (auto &ev : c->lane_ev[i]) CK(cudaEventCreate(&ev));
@@ -932,6 +1026,10 @@ int savont_b200_destroy(savont_b200_ctx *h) {
     for (int i = 0; i < 3; ++i) { if (c->ev_up[i]) cudaEventDestroy(c->ev_up[i]); if (c->ev_h0[i]) cudaEventDestroy(c->ev_h0[i]); }
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     for (auto &ev : c->ev_d2h) if (ev) cudaEventDestroy(ev);
+    for (int i = 0; i < 2; ++i) { if (c->kc_ev_up[i]) cudaEventDestroy(c->kc_ev_up[i]); if (c->kc_ev_done[i]) cudaEventDestroy(c->kc_ev_done[i]); }
+    for (auto &ch : c->kc_chunks) { ch.bases.release(); ch.quals.release(); ch.offsets.release(); ch.rc.release(); ch.pin.release(); }
+    c->kc_chunks.clear();
+    c->d_kc_bloom.release(); c->d_kc_table.release(); c->d_kc_ctr.release(); c->d_kc_out_k.release(); c->d_kc_out_c.release();
     for (int i = 0; i < 2; ++i) {
         for (auto &ev : c->lane_ev[i]) if (ev) cudaEventDestroy(ev);
         if (c->lane_stream[i]) cudaStreamDestroy(c->lane_stream[i]);
@@ -1402,6 +1500,100 @@ int savont_b200_upload_twin_reads(savont_b200_ctx *h, const uint64_t *dna_words,
     CK(cudaStreamSynchronize(c->stream));
     c->resident_samples = n_samples;
     return 0;
+}
+
+int savont_b200_count_split_kmers(savont_b200_ctx *h, const uint8_t *bases, const uint8_t *quals, const uint64_t *offsets,
+                                  const uint8_t *rc, size_t n_reads, int single_strand, uint64_t *out_kmers,
+                                  uint32_t *out_counts, size_t out_cap, size_t *n_out, savont_b200_kmer_stats *stats) {
+    TRY(use_device(h ? &h->c : nullptr));
+    Context *c = &h->c;
+    if (!offsets || (n_reads && !bases) || (out_cap && (!out_kmers || !out_counts))) return fail(SAVONT_B200_ERR_INVALID, "null argument");
+    savont_b200_kmer_stats st; memset(&st, 0, sizeof(st));
+    CK(cudaEventRecord(c->ev[6], c->stream));
+    // chunks of at most 1 Gi bases / 4 Mi reads; every chunk keeps its own device buffers when the whole input fits in
+    // the device memory that is left beside the tables, otherwise two chunk buffers are re-filled in both passes
+    std::vector<size_t> cuts{0};
+    for (size_t r0 = 0; r0 < n_reads;) {
+        size_t r1 = std::min(n_reads, r0 + ((size_t)1 << 22));
+        while (r1 > r0 + 1 && offsets[r1] - offsets[r0] > (1ull << 30)) r1 = r0 + (r1 - r0) / 2;
+        cuts.push_back(r1); r0 = r1;
+    }
+    const size_t nch = cuts.size() - 1;
+    const uint64_t total = n_reads ? offsets[n_reads] - offsets[0] : 0;
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    const uint64_t need_resident = total * (quals ? 2ull : 1ull) + (uint64_t)n_reads * 9ull + total / 2ull + total * 2ull + (4ull << 30);
+    const bool resident = nch <= 2 || need_resident < (uint64_t)free_b;
+    const size_t nbuf = resident ? nch : 2;
+    if (c->kc_chunks.size() < nbuf) c->kc_chunks.resize(nbuf);
+    std::vector<char> uploaded(nbuf, 0);
+    CK(cudaStreamWaitEvent(c->copy_stream, c->ev[6], 0));
+    auto upload = [&](size_t i) -> int {
+        Context::KcChunk &ch = c->kc_chunks[i % nbuf];
+        const size_t r0 = cuts[i], n = cuts[i + 1] - r0;
+        const uint64_t base0 = offsets[r0], tot = offsets[r0 + n] - base0;
+        TRY(ch.pin.ensure((n + 1) * 8));
+        uint64_t *rel = ch.pin.as<uint64_t>();
+        uint32_t mx = 0;
+        for (size_t j = 0; j <= n; ++j) rel[j] = offsets[r0 + j] - base0;
+        for (size_t j = 0; j < n; ++j) { const uint64_t l = rel[j + 1] - rel[j]; if (l >= (1ull << 22)) return fail(SAVONT_B200_ERR_INVALID, "read %zu is too long", r0 + j); if (l > mx) mx = (uint32_t)l; }
+        ch.n = (uint32_t)n; ch.max_len = mx; ch.total = tot; ch.has_quals = quals != nullptr; ch.has_rc = rc != nullptr;
+        TRY(ch.bases.ensure(tot + 64)); TRY(ch.offsets.ensure((n + 1) * 8));
+        if (quals) TRY(ch.quals.ensure(tot + 64));
+        if (rc) TRY(ch.rc.ensure(n + 16));
+        // buffer reuse (non-resident mode): the kernel that last read this buffer must be done
+        CK(cudaStreamWaitEvent(c->copy_stream, c->kc_ev_done[i & 1], 0));
+        CK(cudaEventRecord(c->ev_h0[0], c->copy_stream));
+        CK(cudaMemcpyAsync(ch.offsets.p, rel, (n + 1) * 8, cudaMemcpyHostToDevice, c->copy_stream));
+        if (tot) CK(cudaMemcpyAsync(ch.bases.p, bases + base0, tot, cudaMemcpyHostToDevice, c->copy_stream));
+        if (quals && tot) CK(cudaMemcpyAsync(ch.quals.p, quals + base0, tot, cudaMemcpyHostToDevice, c->copy_stream));
+        if (rc && n) CK(cudaMemcpyAsync(ch.rc.p, rc + r0, n, cudaMemcpyHostToDevice, c->copy_stream));
+        CK(cudaEventRecord(c->kc_ev_up[i & 1], c->copy_stream));
+        st.h2d_bytes += (n + 1) * 8 + tot * (quals ? 2ull : 1ull) + (rc ? n : 0);
+        return 0;
+    };
+    auto view = [&](size_t i, int pass, KcView *v) -> int {
+        Context::KcChunk &ch = c->kc_chunks[i % nbuf];
+        if (pass == 1 || !resident) {
+            if (!(resident && uploaded[i % nbuf])) {
+                // non-resident: the pin buffer of this slot is rewritten, so the previous copy out of it must be complete
+                if (!resident) CK(cudaStreamSynchronize(c->copy_stream));
+                TRY(upload(i));
+                uploaded[i % nbuf] = 1;
+            }
+            CK(cudaStreamWaitEvent(c->stream, c->kc_ev_up[i & 1], 0));
+        }
+        v->in = SeqBatch{};
+        v->in.bases = ch.bases.as<uint8_t>(); v->in.quals = ch.has_quals ? ch.quals.as<uint8_t>() : nullptr;
+        v->in.offsets = ch.offsets.as<uint64_t>(); v->in.n = ch.n; v->in.max_len = ch.max_len;
+        v->rc = ch.has_rc ? ch.rc.as<uint8_t>() : nullptr;
+        return 0;
+    };
+    st.n_reads = n_reads; st.n_bases = total;
+    const int rcode = kc_run(c, nch, total, view, single_strand, out_kmers, out_counts, out_cap, n_out, st);
+    CK(cudaEventRecord(c->ev[7], c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    st.total_ms = ev_ms(c->ev[6], c->ev[7]);
+    if (stats) *stats = st;
+    return rcode;
+}
+
+int savont_b200_count_split_kmers_resident(savont_b200_ctx *h, int single_strand, uint64_t *out_kmers, uint32_t *out_counts,
+                                           size_t out_cap, size_t *n_out, savont_b200_kmer_stats *stats) {
+    TRY(use_device(h ? &h->c : nullptr));
+    Context *c = &h->c;
+    Batch &b = c->resident;
+    if (b.twin) return fail(SAVONT_B200_ERR_INVALID, "the resident reads are TwinReads: k-mer counting needs the FASTQ bytes");
+    savont_b200_kmer_stats st; memset(&st, 0, sizeof(st));
+    CK(cudaEventRecord(c->ev[6], c->stream));
+    auto view = [&](size_t, int, KcView *v) -> int { v->in = seq_view(b); v->rc = nullptr; return 0; };
+    st.n_reads = b.n; st.n_bases = b.total_bases;
+    const int rcode = kc_run(c, b.n ? 1 : 0, b.total_bases, view, single_strand, out_kmers, out_counts, out_cap, n_out, st);
+    CK(cudaEventRecord(c->ev[7], c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    st.total_ms = ev_ms(c->ev[6], c->ev[7]);
+    if (stats) *stats = st;
+    return rcode;
 }
 
 int savont_b200_upload_reads(savont_b200_ctx *h, const uint8_t *bases, const uint8_t *quals, const uint64_t *offsets,

@@ -127,3 +127,40 @@ def twin_reads_filter(reads, quals, ids, k, c, min_bq, snpmer_set, high_freq, mi
         status[i] = 7
     kept.sort(key=lambda t: -(t[1] if t[1] is not None else 100.0))                                    # stable, descending
     return status, [t[0] for t in kept]
+
+
+def split_kmer_counts(reads, quals, rc, k, min_bq, single_strand=False):
+    """Independent restatement of seeding::split_kmer_mid (reference src/seeding.rs:975-1068) +
+    seq_parse::read_to_split_kmers with bloom_filter_size == 0 (src/seq_parse.rs:12-83, :315-497).
+    Returns (sorted list of (kmer, c0, c1) passing the filter, number of distinct k-mers)."""
+    comp = {ord('A'): ord('T'), ord('a'): ord('T'), ord('T'): ord('A'), ord('t'): ord('A'), ord('C'): ord('G'), ord('c'): ord('G'),
+            ord('G'): ord('C'), ord('g'): ord('C')}
+    split_mask = M64 ^ (3 << (k - 1))
+    counts = {}
+    for sq, ql, r in zip(reads, quals, rc):
+        if r:                                          # id ends in "rc": utils::reverse_complement + reversed qualities
+            sq = bytes(comp.get(b, ord('N')) for b in reversed(sq))
+            ql = None if ql is None else bytes(reversed(ql))
+        L = len(sq)
+        if L < k:
+            continue
+        use_q = ql is not None and any(q != ql[0] for q in ql)
+        for p in range(L - k + 1):
+            f = 0
+            for b in sq[p:p + k]:
+                f = (f << 2) | enc(b)
+            rv = revcomp_kmer(f, k)
+            sf, sr = f & split_mask, rv & split_mask
+            if sf == sr:
+                continue
+            if use_q and ql[p + k // 2] - 33 < min_bq:
+                continue
+            fwd = sf < sr
+            c = counts.setdefault(f if fwd else rv, [0, 0])
+            c[1 if fwd else 0] += 1
+    out = []
+    for kmer in sorted(counts):
+        c0, c1 = counts[kmer]
+        if (c0 > 2) if single_strand else (c0 > 0 and c1 > 0 and c0 + c1 > 2):
+            out.append((kmer, c0, c1))
+    return out, len(counts)

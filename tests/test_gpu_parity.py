@@ -463,3 +463,51 @@ def test_map_reads_with_read_filter(ctx):
         ctx.set_batch_reads(0); ctx.set_read_filter(None); ctx.load_high_freq_kmers([])
     orc.set_read_filter(None)
     assert_same(ctx.map_reads(r["bases"], quals, offs), orc.map_reads(r["bases"], quals, offs), MAP_KEYS, "filter off again")
+
+
+KMER_KEYS = ["kmers", "counts"]
+
+
+@pytest.mark.parametrize("k,single", [(17, False), (17, True), (15, False), (21, False)])
+def test_count_split_kmers_ragged(ctx, k, single):
+    """K5 (Stage 1 counting, seq_parse::read_to_split_kmers): rc-tagged reads, N / lower case / U, palindromic splitmers,
+    flat and low qualities, reads shorter than k"""
+    from savont_b200 import _lib
+    from tests.test_oracle import _kmer_count_inputs
+    reads, quals, rc = _kmer_count_inputs(40 + k)
+    bases, offs = O.concat(reads); qcat, _ = O.concat(quals)
+    ctx.set_params(_lib.default_params(k=k, c=min(11, k - 2)))
+    for q in (qcat, None):
+        for r in (rc, None):
+            want = O.count_split_kmers(bases, q, offs, rc=r, k=k, min_bq=25, single_strand=single)
+            got = ctx.count_split_kmers(bases, q, offs, rc=r, single_strand=single)
+            assert_same(got, want, KMER_KEYS, f"count_split_kmers k={k} single={single} quals={q is not None} rc={r is not None}")
+            assert len(want["kmers"]) > 20
+    ctx.set_params(_lib.default_params(min_bq=30))                 # a different quality gate
+    if k == 17:
+        assert_same(ctx.count_split_kmers(bases, qcat, offs, rc=rc), O.count_split_kmers(bases, qcat, offs, rc=rc, k=17, min_bq=30),
+                    KMER_KEYS, "min_bq 30")
+    empty = ctx.count_split_kmers(np.zeros(0, np.uint8), None, np.zeros(1, np.uint64))
+    assert len(empty["kmers"]) == 0
+    ctx.set_params(_lib.default_params())
+
+
+def test_count_split_kmers_synthetic_reads(ctx):
+    """16S-like redundancy: the counts of 6000 reads, the output capacity regrowth, the resident variant and the
+    high-frequency rule on the result"""
+    from savont_b200 import _lib
+    w = _make_workload("ont16s", n_roots=6)
+    r = w.reads(6000)
+    rc = (np.arange(6000) % 7 == 0).astype(np.uint8)
+    ctx.set_params(_lib.default_params())
+    want = O.count_split_kmers(r["bases"], r["quals"], r["offsets"], rc=rc, n_threads=0)
+    got = ctx.count_split_kmers(r["bases"], r["quals"], r["offsets"], rc=rc, cap=1000)     # too small on purpose -> regrow
+    assert_same(got, want, KMER_KEYS, "synthetic reads")
+    assert len(want["kmers"]) > 50000
+    st = got["stats"]
+    assert st["table_used"] >= len(want["kmers"]) and st["table_used"] <= st["table_slots"] // 2
+    assert 0.98 * want["n_distinct"] <= st["first_seen"] <= want["n_distinct"]               # exact up to Bloom false positives
+    ctx.upload_reads(r["bases"], r["quals"], r["offsets"])
+    assert_same(ctx.count_split_kmers_resident(), O.count_split_kmers(r["bases"], r["quals"], r["offsets"]), KMER_KEYS, "resident")
+    th, hf = O.high_freq_kmers(want["kmers"], want["counts"])
+    assert th >= 100 and len(hf) < len(want["kmers"])

@@ -287,3 +287,57 @@ def test_map_reads_with_read_filter_skips_filtered_reads():
     assert int(got["totals"][1]) == int(((got["status"] > 0) & (got["status"] < 4)).sum())
     orc.set_read_filter(None)
     assert np.array_equal(orc.map_reads(r["bases"], quals, r["offsets"])["status"], base["status"])
+
+
+def _kmer_count_inputs(seed=5):
+    """a small read set with shared k-mers on both strands, rc-tagged reads, N / lower case / U bases, palindromic splitmers,
+    low and flat qualities, reads shorter than k"""
+    import random
+    from tests.util import mutate, rand_seq
+    rng = random.Random(seed)
+    roots = [rand_seq(rng, 120) for _ in range(3)]
+    roots[0] = roots[0][:40] + b"ACGTACGTACGTACGTACGTACGT" + roots[0][64:]          # palindromic stretches
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    reads, quals, rc = [], [], []
+    for t in range(70):
+        s = mutate(rng, roots[t % 3], rng.randrange(3), rng.randrange(2), rng.randrange(2))
+        if t % 2:
+            s = s.translate(comp)[::-1]
+        if t % 11 == 0:
+            s = s[:30] + b"N" + s[31:60] + b"u" + s[61:90].lower() + s[90:]
+        if t % 13 == 5:
+            s = s[:rng.randrange(0, 17)]
+        q = bytes(33 + rng.choice([10, 24, 25, 26, 35]) for _ in range(len(s)))
+        if t % 9 == 4:
+            q = bytes([33 + 12] * len(s))                                             # flat: no quality skip at all
+        reads.append(s); quals.append(q); rc.append(1 if t % 5 == 0 else 0)
+    return reads, quals, rc
+
+
+@pytest.mark.parametrize("k,single", [(17, False), (17, True), (15, False), (21, False)])
+def test_count_split_kmers_matches_python_restatement(k, single):
+    reads, quals, rc = _kmer_count_inputs(5 + k)
+    bases, offs = O.concat(reads); qcat, _ = O.concat(quals)
+    for q in (qcat, None):
+        got = O.count_split_kmers(bases, q, offs, rc=rc, k=k, min_bq=25, single_strand=single)
+        want, nd = pyref.split_kmer_counts(reads, quals if q is not None else [None] * len(reads), rc, k, 25, single)
+        assert got["n_distinct"] == nd
+        assert [(int(a), int(b[0]), int(b[1])) for a, b in zip(got["kmers"], got["counts"])] == want
+        assert len(want) > 20
+    # rc = None is all zeros; multi-threaded extraction gives the same answer
+    a = O.count_split_kmers(bases, qcat, offs, rc=None, k=k)
+    b = O.count_split_kmers(bases, qcat, offs, rc=np.zeros(len(reads), np.uint8), k=k, n_threads=3)
+    assert np.array_equal(a["kmers"], b["kmers"]) and np.array_equal(a["counts"], b["counts"])
+
+
+def test_high_freq_threshold_rule():
+    # src/kmer_comp.rs:474: sorted[len - len/100000 - 1].max(100); members are strictly above the threshold
+    km = np.arange(10, dtype=np.uint64) + 7
+    ct = np.array([[1, 2], [50, 60], [100, 1], [0, 100], [99, 1], [300, 1], [2, 2], [120, 0], [3, 3], [1, 1]], np.uint32)
+    th, hf = O.high_freq_kmers(km, ct)
+    assert th == 301 and len(hf) == 0                                                 # n < 100000: the maximum itself
+    n = 200001
+    km = np.arange(n, dtype=np.uint64); ct = np.zeros((n, 2), np.uint32); ct[:, 0] = np.arange(n) % 1000; ct[:, 1] = 1
+    th, hf = O.high_freq_kmers(km, ct)
+    s = np.sort(ct.sum(1)); assert th == max(100, int(s[n - n // 100000 - 1]))
+    assert np.array_equal(hf, km[ct.sum(1) > th])
