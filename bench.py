@@ -130,6 +130,83 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_kmercount(args, rank, world, local_rank):
+    """--path kmercount: Stage 1 split-k-mer counting (K5, seq_parse::read_to_split_kmers) of the same reads.  Not the
+    headline path; one JSON line with the same keys."""
+    import torch
+    from savont_b200 import _lib
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the b200 arm has no CPU fallback")
+    if world > 1:
+        if rank == 0:
+            print(json.dumps({"metric": "reads counted/sec (Stage 1 split k-mer counting)", "unavailable": "single-GPU path: the k-mer table is not sharded yet"}))
+        return
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    w = _workload(args)
+    n_reads = args.reads
+    ctx = _lib.Context(local_rank, _lib.default_params(band=w.band))
+    stream = torch.cuda.current_stream(dev)
+    ctx.set_stream(stream.cuda_stream)
+    r = w.reads(n_reads, alloc=_lib.pinned_array)
+    ctx.upload_reads(r["bases"], r["quals"], r["offsets"])
+    sampler = ClockSampler(local_rank); sampler.start()
+    cap = max(1 << 24, n_reads * 16)
+    for _ in range(args.warmup):
+        out = ctx.count_split_kmers_resident(sort=False, cap=cap)
+    torch.cuda.synchronize(dev)
+    ms, stats = [], []
+    for _ in range(args.steps):
+        out = ctx.count_split_kmers_resident(sort=False, cap=cap)
+        # kernel-only: table clear + counting + compaction (CUDA events inside the library, on this stream); the copy of the
+        # surviving entries to the host belongs to the e2e number below
+        ms.append(out["stats"]["count_ms"] + out["stats"]["compact_ms"]); stats.append(out["stats"])
+    e2e_ms = []
+    ctx.count_split_kmers(r["bases"], r["quals"], r["offsets"], sort=False, cap=cap)
+    for _ in range(max(1, min(args.steps, args.e2e_steps))):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        res = ctx.count_split_kmers(r["bases"], r["quals"], r["offsets"], sort=False, cap=cap)
+        e1.record(stream); torch.cuda.synchronize(dev)
+        e2e_ms.append(e0.elapsed_time(e1))
+    clocks = sampler.stop()
+    peaks = _peaks()
+    st = stats[-1]
+    kern_ms = float(np.mean([s["count_ms"] + s["compact_ms"] for s in stats]))
+    bases = st["n_bases"]
+    n_kmers = bases - 16 * n_reads
+    # algorithmic bytes: bases + qualities read once, one 16-byte table slot read and written per k-mer occurrence, the
+    # table cleared and scanned once
+    alg = 2 * bases + 2 * 16 * n_kmers + 2 * 16 * st["table_slots"]
+    line = {
+        "metric": "reads counted/sec (Stage 1 split k-mer counting)", "value": n_reads * args.steps / (sum(ms) / 1e3), "unit": "reads/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sum(ms) / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64 k-mers / u32 counts", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {w.cfg['desc']} (k-mer counting of the reads)", "reads_per_gpu_per_step": n_reads,
+                   "l2": "k-mer table (%.1f GB) larger than L2" % (16 * st["table_slots"] / 1e9)},
+        "kernel_ms": {"count": float(np.mean([s["count_ms"] for s in stats])), "compact": float(np.mean([s["compact_ms"] for s in stats]))},
+        "kmers_per_step": int(n_kmers), "entries_out": int(len(out["kmers"])), "n_distinct": int(st["n_distinct"]),
+        "roofline": {"bound": "hbm", "kernel": "kmer_count_kernel", "achieved": alg / (kern_ms / 1e3) / 1e9, "peak": peaks["hbm_gbs"],
+                     "unit": "GB/s", "peak_source": peaks["source"], "frac": alg / (kern_ms / 1e3) / 1e9 / peaks["hbm_gbs"],
+                     "traffic": None, "algorithmic_bytes": alg,
+                     "note": "random 32-byte sector accesses; the hot (true) k-mers stay in L2, error k-mers pay a DRAM round trip "
+                             "(profiles/r01c_kmer_count_kernel_full.txt)"},
+        "e2e": {"value": n_reads * len(e2e_ms) / (sum(e2e_ms) / 1e3), "unit": "reads/s", "h2d_bytes_per_step": int(res["stats"]["h2d_bytes"]),
+                "d2h_bytes_per_step": int(res["stats"]["d2h_bytes"]), "ms_per_step": sum(e2e_ms) / len(e2e_ms)},
+        "gpu_launches": int(sum(s["kernel_launches"] for s in stats)), "clocks": clocks,
+    }
+    if not args.no_cpu_baseline:
+        from oracle import oracle as O
+        cores = os.cpu_count() or 1
+        ns = min(args.cpu_reads // 4, n_reads)
+        t0 = time.perf_counter()
+        want = O.count_split_kmers(r["bases"], r["quals"], r["offsets"][: ns + 1], n_threads=cores)
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": ns / dt, "unit": "reads/s", "cores": cores, "kind": "port",
+                                "sample": f"first {ns} reads: extraction on all cores, sort + run-length count on one (oracle/savont_oracle.c)"}
+    print(json.dumps(line), flush=True)
+
+
 def run_b200(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -351,6 +428,8 @@ def main():
     ap.add_argument("--cpu-reads", type=int, default=100_000, help="sample size of the CPU baseline / reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-twin", action="store_true", help="skip the TwinRead-input e2e arm")
+    ap.add_argument("--path", default="assign", choices=["assign", "kmercount"],
+                    help="assign: the headline read-vs-ASV path; kmercount: Stage 1 split-k-mer counting (K5)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -361,6 +440,8 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.path == "kmercount":
+        run_kmercount(args, rank, world, local_rank)
     else:
         run_b200(args, rank, world, local_rank)
         try:

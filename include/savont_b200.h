@@ -137,13 +137,12 @@ int savont_b200_twin_reads_from_snpmers(savont_b200_ctx *ctx, const uint8_t *bas
  * strand is the canonical one), in UNSPECIFIED order (the reference's is hash-map order; get_snpmers_inplace_sort sorts
  * them itself, src/kmer_comp.rs:483).  out_counts holds 2 u32 per entry.  *n_out = number of entries; when it exceeds
  * out_cap the call fails with SAVONT_B200_ERR_CAPACITY and the message carries the required capacity.
- * Unlike the reference's "Total SNPmers after bloom filter" the library cannot report the exact number of distinct
- * k-mers (k-mers seen once are never stored); stats->first_seen is that number up to Bloom-filter false positives. */
+ * stats->n_distinct is the reference's "Total SNPmers after bloom filter" (the number of distinct k-mers before the
+ * filter, src/seq_parse.rs:26-28). */
 typedef struct savont_b200_kmer_stats {
-    double   pass1_ms, pass2_ms, compact_ms, h2d_ms, total_ms;   /* device times (CUDA events) */
+    double   count_ms, compact_ms, h2d_ms, total_ms;             /* device times (CUDA events) */
     uint64_t n_reads, n_bases;
-    uint64_t bloom_bytes, table_slots, table_used;               /* exact table: 16 B per slot */
-    uint64_t first_seen;                                         /* occurrences that found their Bloom bits clear */
+    uint64_t table_slots, n_distinct;                            /* exact table: 16 B per slot */
     uint64_t h2d_bytes, d2h_bytes, kernel_launches, table_regrows;
 } savont_b200_kmer_stats;
 int savont_b200_count_split_kmers(savont_b200_ctx *ctx, const uint8_t *bases, const uint8_t *quals, const uint64_t *offsets,

@@ -36,6 +36,7 @@ def host():
         H.savont_host_per_sample.restype = C.c_int
         H.savont_host_write_outputs.restype = C.c_int
         H.savont_host_twin_read_order.restype = C.c_longlong
+        H.savont_host_high_freq_kmers.restype = C.c_longlong
         H.savont_host_refine_twin.restype = C.c_longlong
         H.savont_host_per_sample_twin.restype = C.c_int
         _host = H
@@ -105,6 +106,28 @@ def twin_reads_from_fasta(ctx: _lib.Context, seqs):
     """ASV sequences -> sketches (qualities None, no high-frequency pruning)"""
     b, o = _concat(seqs)
     return ctx.sketch(b, None, o, want_codes=False)
+
+
+def read_to_split_kmers(ctx: _lib.Context, reads, single_strand=False):
+    """Stage 1 counting (src/seq_parse.rs:12-83, bloom_filter_size 0): reads = dict(bases, quals, offsets, ids [optional]);
+    a read whose id ends in the token "rc" is reverse-complemented first (:361-369).
+    -> dict(kmers, counts [n, 2], n_distinct), sorted by k-mer"""
+    rc = None
+    if reads.get("ids") is not None:
+        rc = np.array([1 if (i.decode() if isinstance(i, (bytes, bytearray)) else i).split()[-1:] == ["rc"] else 0 for i in reads["ids"]], np.uint8)
+    out = ctx.count_split_kmers(reads["bases"], reads.get("quals"), reads["offsets"], rc=rc, single_strand=single_strand)
+    return dict(kmers=out["kmers"], counts=out["counts"], n_distinct=out["stats"]["n_distinct"])
+
+
+def high_freq_kmers(kmers, counts):
+    """src/kmer_comp.rs:459-500 -> (high_freq_thresh, high-frequency k-mers)"""
+    H = host()
+    km = np.ascontiguousarray(kmers, np.uint64); ct = np.ascontiguousarray(counts, np.uint32).reshape(-1)
+    out = np.zeros(max(len(km), 1), np.uint64); nh = C.c_size_t(0)
+    th = H.savont_host_high_freq_kmers(_p(km, C.c_uint64), _p(ct, C.c_uint32), C.c_size_t(len(km)), _p(out, C.c_uint64), C.byref(nh))
+    if th < 0:
+        _fail("high_freq_kmers")
+    return int(th), out[:int(nh.value)]
 
 
 def twin_reads_from_snpmers(ctx: _lib.Context, reads, args: Cli, high_freq_kmers=None):

@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <functional>
@@ -880,29 +881,24 @@ struct KcView { SeqBatch in; const uint8_t *rc; };
 template <typename GetView>
 static int kc_run(Context *c, size_t n_chunks, uint64_t total_bases, GetView view, int single_strand, uint64_t *out_kmers,
                   uint32_t *out_counts, size_t out_cap, size_t *n_out, savont_b200_kmer_stats &st) {
-    // sizing: one Bloom word bit budget of 8 bits per k-mer occurrence (>= 16 bits per distinct k-mer), table slots =
-    // occurrences / 8 (k-mers seen at least twice are a small fraction of the occurrences), load <= 0.5
-    uint64_t bloom_words = 1ull << 14;
-    while (bloom_words * 4ull < total_bases && bloom_words < (1ull << 33)) bloom_words <<= 1;      // 32 bits per word
+    // sizing: slots = occurrences / 8 rounded up to a power of two (load <= 0.5 is enforced: the table is regrown x4 and the
+    // pass re-run when more than half of the slots fill up)
     uint64_t slots = 1ull << 16;
     while (slots * 8ull < total_bases && slots < (1ull << 31)) slots <<= 1;
     TRY(c->d_kc_ctr.ensure(64));
-    TRY(c->d_kc_bloom.ensure(bloom_words * 4ull));
     uint32_t ctr[4] = {0, 0, 0, 0};
     for (int attempt = 0;; ++attempt) {
         TRY(c->d_kc_table.ensure(slots * sizeof(KmerSlot)));
         const uint32_t tshift = shift_for_cap((uint32_t)slots), tmask = (uint32_t)(slots - 1);
-        uint32_t bshift = 64; { uint64_t w = bloom_words; while (w > 1) { w >>= 1; --bshift; } }
         CK(cudaEventRecord(c->ev[0], c->stream));
         CK(cudaMemsetAsync(c->d_kc_ctr.p, 0, 64, c->stream));
-        CK(cudaMemsetAsync(c->d_kc_bloom.p, 0, bloom_words * 4ull, c->stream));
         launch_kmer_table_clear(c->d_kc_table.as<KmerSlot>(), slots, c->stream);
         st.kernel_launches += 1;
         for (size_t i = 0; i < n_chunks; ++i) {
             KcView v{};
             TRY(view(i, 1, &v));
-            launch_kmer_pass(1, v.in, v.rc, c->dp.k, c->dp.min_bq, c->d_kc_bloom.as<uint32_t>(), bshift, c->d_kc_table.as<KmerSlot>(),
-                             tshift, tmask, c->d_kc_ctr.as<uint32_t>(), (uint32_t)(slots / 2), c->sm_count, c->stream);
+            launch_kmer_count(v.in, v.rc, c->dp.k, c->dp.min_bq, c->d_kc_table.as<KmerSlot>(), tshift, tmask, c->d_kc_ctr.as<uint32_t>(),
+                              (uint32_t)(slots / 2), c->sm_count, c->stream);
             CK(cudaGetLastError());
             CK(cudaEventRecord(c->kc_ev_done[i & 1], c->stream));
             st.kernel_launches += 1;
@@ -910,25 +906,14 @@ static int kc_run(Context *c, size_t n_chunks, uint64_t total_bases, GetView vie
         CK(cudaEventRecord(c->ev[1], c->stream));
         CK(cudaMemcpyAsync(ctr, c->d_kc_ctr.p, sizeof(ctr), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
-        st.pass1_ms += ev_ms(c->ev[0], c->ev[1]);
-        if (ctr[1] == 0) {
-            for (size_t i = 0; i < n_chunks; ++i) {
-                KcView v{};
-                TRY(view(i, 2, &v));
-                launch_kmer_pass(2, v.in, v.rc, c->dp.k, c->dp.min_bq, c->d_kc_bloom.as<uint32_t>(), bshift, c->d_kc_table.as<KmerSlot>(),
-                                 tshift, tmask, c->d_kc_ctr.as<uint32_t>(), (uint32_t)(slots / 2), c->sm_count, c->stream);
-                CK(cudaGetLastError());
-                CK(cudaEventRecord(c->kc_ev_done[i & 1], c->stream));
-                st.kernel_launches += 1;
-            }
-            CK(cudaEventRecord(c->ev[2], c->stream));
-            break;
-        }
-        if (attempt == 4 || slots >= (1ull << 31)) return fail(SAVONT_B200_ERR_OVERFLOW, "k-mer table sizing did not converge (%llu slots)", (unsigned long long)slots);
+        st.count_ms += ev_ms(c->ev[0], c->ev[1]);
+        if (ctr[1] == 0) break;
+        if (attempt == 4 || slots >= (1ull << 31))
+            return fail(SAVONT_B200_ERR_OVERFLOW, "k-mer table sizing did not converge (%llu slots): split the call", (unsigned long long)slots);
         slots <<= 2; st.table_regrows += 1;
     }
-    st.bloom_bytes = bloom_words * 4ull; st.table_slots = slots; st.table_used = ctr[0];
-    st.first_seen = (uint64_t)ctr[2] | ((uint64_t)ctr[3] << 32);
+    st.table_slots = slots; st.n_distinct = ctr[0];
+    CK(cudaEventRecord(c->ev[2], c->stream));
     // compaction: at most table_used survivors
     const uint32_t cap_dev = ctr[0] + 32u;
     TRY(c->d_kc_out_k.ensure((size_t)cap_dev * 8)); TRY(c->d_kc_out_c.ensure((size_t)cap_dev * 8));
@@ -941,7 +926,6 @@ static int kc_run(Context *c, size_t n_chunks, uint64_t total_bases, GetView vie
     uint32_t n_found = 0;
     CK(cudaMemcpyAsync(&n_found, c->d_kc_ctr.as<uint32_t>() + 8, 4, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    st.pass2_ms += ev_ms(c->ev[1], c->ev[2]);
     st.compact_ms += ev_ms(c->ev[2], c->ev[3]);
     if (n_out) *n_out = n_found;
     if (n_found > out_cap) return fail(SAVONT_B200_ERR_CAPACITY, "k-mer output capacity %zu too small (need >= %u)", out_cap, n_found);
@@ -1510,12 +1494,12 @@ int savont_b200_count_split_kmers(savont_b200_ctx *h, const uint8_t *bases, cons
     if (!offsets || (n_reads && !bases) || (out_cap && (!out_kmers || !out_counts))) return fail(SAVONT_B200_ERR_INVALID, "null argument");
     savont_b200_kmer_stats st; memset(&st, 0, sizeof(st));
     CK(cudaEventRecord(c->ev[6], c->stream));
-    // chunks of at most 1 Gi bases / 4 Mi reads; every chunk keeps its own device buffers when the whole input fits in
+    // chunks of at most 256 Mi bases / 4 Mi reads (the upload of chunk i+1 overlaps the counting of chunk i); every chunk keeps its own device buffers when the whole input fits in
     // the device memory that is left beside the tables, otherwise two chunk buffers are re-filled in both passes
     std::vector<size_t> cuts{0};
     for (size_t r0 = 0; r0 < n_reads;) {
         size_t r1 = std::min(n_reads, r0 + ((size_t)1 << 22));
-        while (r1 > r0 + 1 && offsets[r1] - offsets[r0] > (1ull << 30)) r1 = r0 + (r1 - r0) / 2;
+        while (r1 > r0 + 1 && offsets[r1] - offsets[r0] > (1ull << 28)) r1 = r0 + (r1 - r0) / 2;
         cuts.push_back(r1); r0 = r1;
     }
     const size_t nch = cuts.size() - 1;

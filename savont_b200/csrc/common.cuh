@@ -152,9 +152,8 @@ struct AlignOut {
 
 // K5 (Stage 1 split-k-mer counting, kmercount.cu): one slot of the exact table
 struct KmerSlot { unsigned long long key; uint32_t c0, c1; };     // key = kEmpty64 when free; c[flag], flag 1 = forward canonical
-void launch_kmer_pass(int pass, const SeqBatch &in, const uint8_t *rc, int k, int min_bq, uint32_t *bloom, uint32_t bloom_shift,
-                      KmerSlot *table, uint32_t tshift, uint32_t tmask, uint32_t *ctr, uint32_t fill_limit, int sm_count,
-                      cudaStream_t st);
+void launch_kmer_count(const SeqBatch &in, const uint8_t *rc, int k, int min_bq, KmerSlot *table, uint32_t tshift, uint32_t tmask,
+                       uint32_t *ctr, uint32_t fill_limit, int sm_count, cudaStream_t st);
 void launch_kmer_table_clear(KmerSlot *table, uint64_t n, cudaStream_t st);
 void launch_kmer_compact(const KmerSlot *table, uint64_t n_slots, int single_strand, uint64_t *out_kmers, uint32_t *out_counts,
                          uint32_t out_cap, uint32_t *out_n, cudaStream_t st);

@@ -3,17 +3,18 @@
 // (src/seeding.rs:975-1068).
 //
 // The reference counts every k-mer of every read in sharded FxHashMap<u64, [u32; 2]> and afterwards keeps the entries
-// seen on both strands more than twice (src/seq_parse.rs:30-44).  A 16S read set is extremely redundant (a few 10^5
-// true k-mers carry ~70 % of all occurrences, the rest are sequencing-error k-mers seen once), so the counting is done
-// without sorting or storing the 1.5 G k-mer occurrences of 1 M reads:
-//   pass 1  every occurrence sets two bits of a blocked Bloom filter (one 32-bit word per k-mer, in HBM; the hot words
-//           stay in L2).  An occurrence that finds its bits already set (= the k-mer was seen before, or a false
-//           positive) makes sure the k-mer has a slot in an exact open-addressing table (key, c0, c1: 16 B).
-//   pass 2  every occurrence looks its k-mer up in the (now read-only) key column and, if present, bumps c[flag].
-//   compact the table is scanned, the reference's filter applied, survivors appended to the output.
-// Exactness: a k-mer with >= 2 occurrences is in the table after pass 1 (Bloom filters have no false negatives, and of
-// two racing first occurrences at least one sees the other's bits); pass 2 counts ALL its occurrences; k-mers seen once
-// cannot pass the filter (it needs > 2 occurrences); false positives only add slots whose exact counts fail the filter.
+// seen on both strands more than twice (src/seq_parse.rs:30-44).  Here ONE pass over the reads counts every occurrence
+// in one open-addressing table in HBM (16-byte slots: key, c0, c1; two slots per 32-byte sector), sized from the number
+// of occurrences (load <= 0.5, regrown x4 and re-run otherwise): per occurrence one key probe and one atomicAdd into the
+// same sector.  A 16S read set is extremely redundant -- 1 M ONT reads hold 1.48 G occurrences of 48 M distinct k-mers,
+// two thirds of the occurrences belong to < 1 M true k-mers -- so the hot sectors stay in L2 and only the error k-mers
+// pay a DRAM round trip.  (A first version with a Bloom filter in front of the table and a second counting pass touched
+// two structures per occurrence and took twice as long.)  Measured on 1 M reads: extraction alone 5.5 ms, + key probes
+// 42.7 ms, + count atomics 81.7 ms: the kernel is bound by the rate of scattered 32-byte L2 / DRAM operations
+// (~40 G/s for loads as well as for reductions; 41.7 GB of DRAM reads = one 64-byte burst per error k-mer occurrence),
+// not by issue slots or memory-level parallelism (4 probes in flight per lane change nothing).  Partitioning the k-mers
+// by hash first, so that every partition is counted in shared memory, is the round-2 design.
+// A final scan applies the reference's filter and appends the survivors to the output.
 // Reads whose id ends in "rc" are reverse-complemented first exactly like utils::reverse_complement does it
 // (src/utils.rs:51-65: anything but ACGT/acgt becomes N, which encodes as A).
 #include "common.cuh"
@@ -22,23 +23,21 @@
 namespace sb {
 
 constexpr int kKcWarps = 16;
+constexpr int kKcUnroll = 4;
 constexpr uint64_t kKcMul2 = 0xD6E8FEB86659FD93ull;
 
 struct KcArgs {
     SeqBatch in;
     const uint8_t *rc;        // per read, may be null
     int k, min_bq;
-    uint32_t *bloom; uint32_t bloom_shift;          // word index = (kmer * kFibMul) >> bloom_shift
     KmerSlot *table; uint32_t tshift, tmask;        // slot = (kmer * kKcMul2) >> tshift
-    uint32_t *ctr;                                  // [0] slots in use, [1] error bits, [2..3] u64 first sightings
+    uint32_t *ctr;                                  // [0] slots in use (= distinct k-mers), [1] error bits
     uint32_t fill_limit;
     uint32_t packed_words;                          // per warp
 };
 
-// PASS 1: Bloom + slot reservation.  PASS 2: exact per-strand counts.
-template <int PASS>
-__global__ void __launch_bounds__(kKcWarps * 32)
-kmer_pass_kernel(KcArgs a) {
+__global__ void __launch_bounds__(kKcWarps * 32, 2)
+kmer_count_kernel(KcArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint8_t *s_lut = smem;                           // [0..255] forward codes, [256..511] codes of the reverse complement
@@ -54,7 +53,6 @@ kmer_pass_kernel(KcArgs a) {
     const uint32_t K = (uint32_t)a.k;
     const uint64_t kmer_mask = (K == 32u) ? ~0ull : ((1ull << (2u * K)) - 1ull);
     const uint64_t split_mask = ~(3ull << (K - 1u));
-    unsigned long long first_seen = 0;
 
     for (uint32_t seq = blockIdx.x * kKcWarps + warp; seq < a.in.n; seq += gridDim.x * kKcWarps) {
         const uint64_t off = a.in.offsets[seq];
@@ -91,61 +89,60 @@ kmer_pass_kernel(KcArgs a) {
             }
         }
         __syncwarp();
-        // ---- one k-mer per lane and step ----
+        // ---- kKcUnroll k-mers per lane and step: all key probes of a step are issued before the first one is
+        //      consumed (the kernel is bound by the latency of these random L2 / DRAM accesses, not by issue slots) ----
         const uint32_t n_pos = L - K + 1u;
-        for (uint32_t p = lane; p < n_pos; p += 32u) {
-            const uint64_t x = window64(packed, p);
-            const uint64_t kf = x >> (64u - 2u * K);
-            const uint64_t kr = revcomp_top(x, kmer_mask);
-            const uint64_t sf = kf & split_mask, sr = kr & split_mask;
-            if (sf == sr) continue;                                           // palindromic splitmer, :1044-1046
-            if (use_q) {
-                const uint32_t mid = p + (K >> 1);                            // in processing orientation
-                const int q = (int)qp[rc ? L - 1u - mid : mid] - 33;
-                if (q < a.min_bq) continue;                                   // :1012
+        for (uint32_t p0 = 0; p0 < n_pos; p0 += 32u * kKcUnroll) {
+            unsigned long long canon[kKcUnroll], found[kKcUnroll];
+            uint32_t slot[kKcUnroll];
+            bool valid[kKcUnroll], fwd[kKcUnroll];
+            int q[kKcUnroll];
+#pragma unroll
+            for (int u = 0; u < kKcUnroll; ++u) {                             // middle-base qualities first (global loads)
+                const uint32_t p = p0 + 32u * u + lane;
+                q[u] = 1000;
+                if (use_q && p < n_pos) { const uint32_t mid = p + (K >> 1); q[u] = (int)qp[rc ? L - 1u - mid : mid] - 33; }
             }
-            const bool fwd = sf < sr;                                         // :1053
-            const unsigned long long canon = fwd ? kf : kr;
-            uint32_t slot = (uint32_t)((canon * kKcMul2) >> a.tshift);
-            if (PASS == 1) {
-                const uint64_t h = canon * kFibMul;
-                uint32_t *wp = a.bloom + (h >> a.bloom_shift);
-                const uint32_t m = (1u << ((uint32_t)(h >> 20) & 31u)) | (1u << ((uint32_t)(h >> 26) & 31u));
-                bool seen = (__ldcg(wp) & m) == m;                            // hot k-mers: a plain L2 read
-                if (!seen) {
-                    seen = (atomicOr(wp, m) & m) == m;
-                    if (!seen) ++first_seen;
+#pragma unroll
+            for (int u = 0; u < kKcUnroll; ++u) {
+                const uint32_t p = p0 + 32u * u + lane;
+                valid[u] = false; fwd[u] = false; canon[u] = 0; slot[u] = 0;
+                if (p < n_pos) {
+                    const uint64_t x = window64(packed, p);
+                    const uint64_t kf = x >> (64u - 2u * K);
+                    const uint64_t kr = revcomp_top(x, kmer_mask);
+                    const uint64_t sf = kf & split_mask, sr = kr & split_mask;
+                    fwd[u] = sf < sr;                                         // :1053
+                    canon[u] = fwd[u] ? kf : kr;
+                    valid[u] = (sf != sr) && (q[u] >= a.min_bq);              // palindromic splitmer :1044-1046; quality :1012
+                    slot[u] = (uint32_t)((canon[u] * kKcMul2) >> a.tshift);
                 }
-                if (seen) {
-                    for (uint32_t probes = 0;; ++probes) {
-                        const unsigned long long v = __ldcg(&a.table[slot].key);
-                        if (v == canon) break;
-                        if (v == kEmpty64) {
-                            const unsigned long long old = atomicCAS(&a.table[slot].key, (unsigned long long)kEmpty64, canon);
-                            if (old == kEmpty64) {
-                                if (atomicAdd(a.ctr, 1u) >= a.fill_limit) atomicOr(a.ctr + 1, 1u);
-                                break;
-                            }
-                            if (old == canon) break;
+            }
+#pragma unroll
+            for (int u = 0; u < kKcUnroll; ++u) found[u] = valid[u] ? __ldcg(&a.table[slot[u]].key) : 0ull;
+#pragma unroll
+            for (int u = 0; u < kKcUnroll; ++u) {
+                if (!valid[u]) continue;
+                uint32_t sl = slot[u];
+                unsigned long long v = found[u];
+                uint32_t *cnt = nullptr;
+                for (uint32_t probes = 0;; ++probes) {
+                    if (v == canon[u]) { cnt = fwd[u] ? &a.table[sl].c1 : &a.table[sl].c0; break; }
+                    if (v == kEmpty64) {
+                        const unsigned long long old = atomicCAS(&a.table[sl].key, (unsigned long long)kEmpty64, canon[u]);
+                        if (old == kEmpty64) {
+                            if (atomicAdd(a.ctr, 1u) >= a.fill_limit) atomicOr(a.ctr + 1, 1u);  // the host regrows and re-runs
+                            cnt = fwd[u] ? &a.table[sl].c1 : &a.table[sl].c0; break;
                         }
-                        if (probes > 2048u) { atomicOr(a.ctr + 1, 1u); break; }
-                        slot = (slot + 1u) & a.tmask;
+                        if (old == canon[u]) { cnt = fwd[u] ? &a.table[sl].c1 : &a.table[sl].c0; break; }
                     }
+                    if (probes > 4096u) { atomicOr(a.ctr + 1, 1u); break; }
+                    sl = (sl + 1u) & a.tmask;
+                    v = __ldcg(&a.table[sl].key);
                 }
-            } else {
-                for (uint32_t probes = 0; probes <= 2049u; ++probes) {
-                    const unsigned long long v = __ldg(&a.table[slot].key);   // read-only in this pass
-                    if (v == canon) { atomicAdd(fwd ? &a.table[slot].c1 : &a.table[slot].c0, 1u); break; }
-                    if (v == kEmpty64) break;
-                    slot = (slot + 1u) & a.tmask;
-                }
+                if (cnt != nullptr) atomicAdd(cnt, 1u);                       // src/seq_parse.rs:455-460
             }
         }
-    }
-    if (PASS == 1) {
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) first_seen += __shfl_xor_sync(0xffffffffu, first_seen, d);
-        if (lane == 0 && first_seen) atomicAdd(reinterpret_cast<unsigned long long *>(a.ctr + 2), first_seen);
     }
 }
 
@@ -180,12 +177,11 @@ __global__ void kmer_compact_kernel(const KmerSlot *table, uint64_t n_slots, int
     }
 }
 
-void launch_kmer_pass(int pass, const SeqBatch &in, const uint8_t *rc, int k, int min_bq, uint32_t *bloom, uint32_t bloom_shift,
-                      KmerSlot *table, uint32_t tshift, uint32_t tmask, uint32_t *ctr, uint32_t fill_limit, int sm_count,
-                      cudaStream_t st) {
+void launch_kmer_count(const SeqBatch &in, const uint8_t *rc, int k, int min_bq, KmerSlot *table, uint32_t tshift, uint32_t tmask,
+                       uint32_t *ctr, uint32_t fill_limit, int sm_count, cudaStream_t st) {
     if (in.n == 0) return;
     KcArgs a{};
-    a.in = in; a.rc = rc; a.k = k; a.min_bq = min_bq; a.bloom = bloom; a.bloom_shift = bloom_shift;
+    a.in = in; a.rc = rc; a.k = k; a.min_bq = min_bq;
     a.table = table; a.tshift = tshift; a.tmask = tmask; a.ctr = ctr; a.fill_limit = fill_limit;
     a.packed_words = ((in.max_len + 15u) >> 4) + 4u;
     const size_t smem = 512u + (size_t)a.packed_words * 4u * kKcWarps;
@@ -195,13 +191,8 @@ void launch_kmer_pass(int pass, const SeqBatch &in, const uint8_t *rc, int k, in
     uint32_t grid = (uint32_t)(sm_count * ctas);
     const uint32_t need = (in.n + kKcWarps - 1) / kKcWarps;
     if (grid > need) grid = need;
-    if (pass == 1) {
-        cudaFuncSetAttribute(kmer_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kmer_pass_kernel<1><<<grid, kKcWarps * 32, smem, st>>>(a);
-    } else {
-        cudaFuncSetAttribute(kmer_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kmer_pass_kernel<2><<<grid, kKcWarps * 32, smem, st>>>(a);
-    }
+    cudaFuncSetAttribute(kmer_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kmer_count_kernel<<<grid, kKcWarps * 32, smem, st>>>(a);
 }
 
 void launch_kmer_table_clear(KmerSlot *table, uint64_t n, cudaStream_t st) {

@@ -119,6 +119,36 @@ TwinReadSelection twin_reads_from_snpmers(Mapper &mapper, const ReadSet &r, cons
     return s;
 }
 
+SplitKmerCounts read_to_split_kmers(Mapper &mapper, const ReadSet &r, const uint8_t *rc, bool single_strand) {
+    SplitKmerCounts out;
+    size_t cap = (size_t)((r.n ? r.offsets[r.n] - r.offsets[0] : 0) / 64) + 4096, n = 0;
+    savont_b200_kmer_stats st{};
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        out.kmers.assign(cap, 0); out.counts.assign(2 * cap, 0);
+        const int rcode = savont_b200_count_split_kmers(mapper.raw(), r.bases, r.quals, r.offsets, rc, r.n, single_strand ? 1 : 0,
+                                                        out.kmers.data(), out.counts.data(), cap, &n, &st);
+        if (rcode == SAVONT_B200_ERR_CAPACITY && n > cap) { cap = n + 16; continue; }
+        ck(rcode, "savont_b200_count_split_kmers");
+        break;
+    }
+    out.kmers.resize(n); out.counts.resize(2 * n); out.n_distinct = st.n_distinct;
+    return out;
+}
+
+uint32_t high_freq_kmers(const SplitKmerCounts &c, std::vector<uint64_t> &high_freq) {
+    high_freq.clear();
+    const size_t n = c.kmers.size();
+    if (n == 0) throw std::runtime_error("No k-mers found");              // the reference exits here, src/kmer_comp.rs:469-472
+    std::vector<uint32_t> kc(n);
+    for (size_t i = 0; i < n; ++i) kc[i] = c.counts[2 * i] + c.counts[2 * i + 1];
+    const size_t idx = n - (n / 100000) - 1;                               // :474
+    std::nth_element(kc.begin(), kc.begin() + idx, kc.end());
+    const uint32_t thresh = std::max<uint32_t>(kc[idx], 100u);
+    for (size_t i = 0; i < n; ++i)
+        if (c.counts[2 * i] + c.counts[2 * i + 1] > thresh) high_freq.push_back(c.kmers[i]);     // :497-499
+    return thresh;
+}
+
 EqClasses build_eq_classes(const Assignments &a, const uint32_t *file_idx, int sample) {
     std::map<std::vector<uint32_t>, uint64_t> hist;
     uint64_t total = 0;
@@ -282,6 +312,19 @@ extern "C" {
 
 static thread_local std::string g_host_error;
 const char *savont_host_last_error(void) { return g_host_error.c_str(); }
+
+// high-frequency rule on (k-mer, [c0, c1]) entries: returns the threshold (or -1), *n_hf entries written to hf_out
+long long savont_host_high_freq_kmers(const uint64_t *kmers, const uint32_t *counts, size_t n, uint64_t *hf_out, size_t *n_hf) {
+    try {
+        savont_host::SplitKmerCounts c;
+        c.kmers.assign(kmers, kmers + n); c.counts.assign(counts, counts + 2 * n);
+        std::vector<uint64_t> hf;
+        const uint32_t th = savont_host::high_freq_kmers(c, hf);
+        for (size_t i = 0; i < hf.size(); ++i) hf_out[i] = hf[i];
+        *n_hf = hf.size();
+        return (long long)th;
+    } catch (const std::exception &e) { g_host_error = e.what(); return -1; }
+}
 
 // Stage-7 read order of the kept reads (status == 0); returns the number of kept reads, or -1 on error
 long long savont_host_twin_read_order(const uint8_t *status, const double *est_id, size_t n, const uint8_t *ids,

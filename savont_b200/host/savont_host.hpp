@@ -126,6 +126,18 @@ TwinReadSelection twin_reads_from_snpmers(Mapper &mapper, const ReadSet &reads, 
 std::vector<uint32_t> twin_read_order(const std::vector<uint8_t> &status, const std::vector<double> &est_id,
                                       const uint8_t *ids, const uint64_t *id_offsets);
 
+// reference src/seq_parse.rs:12-83 (Stage 1 counting, bloom_filter_size == 0): the filtered (k-mer, [c0, c1]) vector that
+// get_snpmers_inplace_sort consumes.  rc[i] != 0 marks a read whose id ends in the token "rc" (:361-369); rc may be null.
+struct SplitKmerCounts {
+    std::vector<uint64_t> kmers;
+    std::vector<uint32_t> counts;        // 2 per k-mer
+    uint64_t n_distinct = 0;             // "Total SNPmers after bloom filter", :26-28
+};
+SplitKmerCounts read_to_split_kmers(Mapper &mapper, const ReadSet &reads, const uint8_t *rc, bool single_strand);
+// reference src/kmer_comp.rs:459-500: high_freq_thresh = max(100, sorted(c0 + c1)[len - len/100000 - 1]); returns it and
+// fills the high-frequency k-mers (c0 + c1 > thresh), the set twin_reads_from_snpmers reads
+uint32_t high_freq_kmers(const SplitKmerCounts &counts, std::vector<uint64_t> &high_freq);
+
 // sample < 0: all reads; otherwise only reads with file_idx == sample (src/alignment.rs:2095-2096)
 EqClasses build_eq_classes(const Assignments &a, const uint32_t *file_idx, int sample);
 

@@ -58,6 +58,20 @@ def test_writers_follow_reference_formats(tmp_path):
     assert tb.read_text().splitlines() == ["#OTU ID\ta\tb\tc", "final_consensus_0_depth_4-3-0\t4\t3\t0", "final_consensus_1_depth_0-1-1\t0\t1\t1"]
 
 
+def test_high_freq_kmers_matches_oracle():
+    from savont_b200 import api
+    rng = np.random.default_rng(9)
+    for n in (1, 7, 99999, 100000, 250003):
+        km = rng.permutation(n).astype(np.uint64) + 5
+        ct = rng.integers(0, 400, size=(n, 2)).astype(np.uint32)
+        ct[rng.integers(0, n, size=max(n // 50, 1))] += 5000
+        th, hf = api.high_freq_kmers(km, ct)
+        th_o, hf_o = O.high_freq_kmers(km, ct)
+        assert th == th_o and np.array_equal(hf, hf_o)
+    with pytest.raises(RuntimeError):
+        api.high_freq_kmers(np.zeros(0, np.uint64), np.zeros((0, 2), np.uint32))
+
+
 def test_eq_classes_helper():
     from savont_b200 import api
     status = np.array([0, 1, 0, 0, 2, 0], np.uint8)
@@ -126,6 +140,35 @@ def test_compute_per_sample_depths_matches_oracle_pipeline():
     sk = O.sketch_batch(O.default_params(band=w.band), w.snpmers, r["bases"], r["quals"], r["offsets"])
     tw = twin.from_sketch(sk, r["offsets"], file_idx=r["file_idx"])
     assert api.compute_per_sample_depths(tw, 3, cons, w.snpmers, api.Cli(band=w.band)) == want
+
+
+@pytest.mark.gpu
+def test_stage1_counting_feeds_the_read_filter():
+    """Stage 1 counting -> high-frequency set -> Stage 1.5 read tests, GPU + host layer vs the oracle chain"""
+    from savont_b200 import _lib, api, synth
+    w = synth.Workload("ont16s", n_roots=4)
+    r = w.reads(3000)
+    ids = [f"read_{i:05d}" + (" rc" if i % 3 == 0 else " fw") for i in range(3000)]
+    ctx = _lib.Context(0, _lib.default_params(band=w.band))
+    ctx.load_snpmers(w.snpmers)
+    got = api.read_to_split_kmers(ctx, dict(bases=r["bases"], quals=r["quals"], offsets=r["offsets"], ids=ids))
+    rc = np.array([1 if i % 3 == 0 else 0 for i in range(3000)], np.uint8)
+    want = O.count_split_kmers(r["bases"], r["quals"], r["offsets"], rc=rc)
+    assert np.array_equal(got["kmers"], want["kmers"]) and np.array_equal(got["counts"], want["counts"])
+    assert got["n_distinct"] == want["n_distinct"]
+    th, hf = api.high_freq_kmers(got["kmers"], got["counts"])
+    th_o, hf_o = O.high_freq_kmers(want["kmers"], want["counts"])
+    assert th == th_o and np.array_equal(hf, hf_o)
+    # lower the bar so that the set is not empty on this small sample, then run the read tests with it
+    hf = got["kmers"][got["counts"].sum(1) > np.quantile(got["counts"].sum(1), 0.97)]
+    args = api.Cli(band=w.band, min_read_length=1400, max_read_length=1600)
+    sel = api.twin_reads_from_snpmers(ctx, dict(bases=r["bases"], quals=r["quals"], offsets=r["offsets"], ids=[i.split()[0] for i in ids]), args,
+                                      high_freq_kmers=hf)
+    ref = O.twin_reads_filter(O.default_params(band=w.band), O.read_filter(1400, 1600, 98.0), w.snpmers, hf, r["bases"], r["quals"], r["offsets"],
+                              [i.split()[0] for i in ids])
+    assert np.array_equal(sel["status"], ref["status"]) and np.array_equal(sel["order"], ref["order"])
+    assert np.array_equal(sel["n_solid_mini"], ref["n_solid_mini"])
+    ctx.close()
 
 
 @pytest.mark.gpu
