@@ -140,10 +140,12 @@ int savont_b200_twin_reads_from_snpmers(savont_b200_ctx *ctx, const uint8_t *bas
  * stats->n_distinct is the reference's "Total SNPmers after bloom filter" (the number of distinct k-mers before the
  * filter, src/seq_parse.rs:26-28). */
 typedef struct savont_b200_kmer_stats {
-    double   count_ms, compact_ms, h2d_ms, total_ms;             /* device times (CUDA events) */
+    double   count_ms, compact_ms, h2d_ms, total_ms;             /* device times (CUDA events); count_ms = all counting kernels */
+    double   hist_ms, scatter_ms;                                /* partitioned algorithm: the first two of its three steps */
     uint64_t n_reads, n_bases;
-    uint64_t table_slots, n_distinct;                            /* exact table: 16 B per slot */
+    uint64_t table_slots, n_distinct;                            /* global table (16 B per slot); distinct k-mers before the filter */
     uint64_t h2d_bytes, d2h_bytes, kernel_launches, table_regrows;
+    uint64_t partitions, spilled_distinct;                       /* partitioned algorithm (0 partitions = single-table algorithm) */
 } savont_b200_kmer_stats;
 int savont_b200_count_split_kmers(savont_b200_ctx *ctx, const uint8_t *bases, const uint8_t *quals, const uint64_t *offsets,
                                   const uint8_t *rc, size_t n_reads, int single_strand, uint64_t *out_kmers,

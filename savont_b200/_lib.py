@@ -53,8 +53,10 @@ class Stats(C.Structure):
 
 class KmerStats(C.Structure):
     _fields_ = [("count_ms", C.c_double), ("compact_ms", C.c_double), ("h2d_ms", C.c_double), ("total_ms", C.c_double),
+                ("hist_ms", C.c_double), ("scatter_ms", C.c_double),
                 ("n_reads", C.c_uint64), ("n_bases", C.c_uint64), ("table_slots", C.c_uint64), ("n_distinct", C.c_uint64),
-                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("kernel_launches", C.c_uint64), ("table_regrows", C.c_uint64)]
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("kernel_launches", C.c_uint64), ("table_regrows", C.c_uint64),
+                ("partitions", C.c_uint64), ("spilled_distinct", C.c_uint64)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}

@@ -140,9 +140,11 @@ struct Context {
     DevBuf d_counters; size_t counters_len = 0; int counters_samples = 0;
 
     // K5 (Stage 1 split-k-mer counting): Bloom filter, exact table, counters, output staging, read chunks
-    DevBuf d_kc_bloom, d_kc_table, d_kc_ctr, d_kc_out_k, d_kc_out_c;
+    DevBuf d_kc_bloom, d_kc_table, d_kc_ctr, d_kc_out_k, d_kc_out_c, d_kp_small, d_kp_entries;
     struct KcChunk { DevBuf bases, quals, offsets, rc; PinBuf pin; uint32_t n = 0, max_len = 0; uint64_t total = 0; bool has_quals = false, has_rc = false; };
     std::vector<KcChunk> kc_chunks;
+    bool kc_partitioned = true;                          // SAVONT_B200_KC_PARTITIONED=0 forces the single-table algorithm
+    uint32_t kc_smem_limit = 0;                          // SAVONT_B200_KC_SMEM_LIMIT: distinct k-mers per shared-memory round (tests)
     cudaEvent_t kc_ev_up[2] = {nullptr, nullptr}, kc_ev_done[2] = {nullptr, nullptr};
     // a4 read filter (twin_reads_from_snpmers): options + high-frequency k-mer set
     bool rf_on = false; ReadFilter rf{}; std::vector<uint64_t> h_hf; DevBuf d_hf_keys; uint32_t hf_mask = 0, hf_shift = 0;
@@ -876,6 +878,101 @@ static int read_counters(Context *c, uint64_t *unambig, uint64_t *ambig, uint64_
 namespace sb {
 
 struct KcView { SeqBatch in; const uint8_t *rc; };
+
+static uint64_t mod_inverse_pow2(uint64_t a, uint64_t mask) {        // a odd: a^-1 mod 2^64 by Newton iteration, then masked
+    uint64_t x = a;                                                   // correct to 3 bits
+    for (int i = 0; i < 6; ++i) x *= 2 - a * x;
+    return x & mask;
+}
+
+// Partitioned counting (kmercount.cu): histogram -> scatter -> per-partition shared-memory counting.  Returns 1 when the
+// spill table overflowed (the caller falls back to the single-table algorithm), 0 on success, < 0 on error.
+template <typename GetView>
+static int kc_run_part(Context *c, size_t n_chunks, uint64_t total_bases, GetView view, int single_strand, uint64_t *out_kmers,
+                       uint32_t *out_counts, size_t out_cap, size_t *n_out, savont_b200_kmer_stats &st) {
+    const int k = c->dp.k, pbits = kKmerPartBits, rem_bits = 2 * k - pbits;
+    const uint32_t P = 1u << pbits;
+    KmerPartPlan pl{};
+    pl.kmask = (1ull << (2 * k)) - 1ull;
+    pl.mul = (kFibMul | 1ull) & pl.kmask; pl.inv = mod_inverse_pow2(pl.mul, pl.kmask);
+    pl.pbits = pbits; pl.rem_bits = rem_bits; pl.single_strand = single_strand;
+    pl.smem_fill_limit = c->kc_smem_limit;
+    // small device block: hist[P] | cursor[P] | part_off[P + 1] (u64) | ctr[16] | out_n | queue | n_distinct (u64)
+    const size_t small_bytes = (size_t)P * 8 + (size_t)(P + 1) * 8 + 256;
+    TRY(c->d_kp_small.ensure(small_bytes));
+    uint8_t *sm = c->d_kp_small.as<uint8_t>();
+    pl.hist = reinterpret_cast<uint32_t *>(sm); pl.cursor = pl.hist + P;
+    unsigned long long *d_off = reinterpret_cast<unsigned long long *>(sm + (size_t)P * 8);
+    pl.part_off = d_off;
+    uint32_t *tail = reinterpret_cast<uint32_t *>(sm + (size_t)P * 8 + (size_t)(P + 1) * 8);
+    pl.ctr = tail; pl.out_n = tail + 16; pl.queue = tail + 17; pl.n_distinct = reinterpret_cast<unsigned long long *>(tail + 18);
+    // spill table
+    const uint64_t slots = 1ull << 22;
+    TRY(c->d_kc_table.ensure(slots * sizeof(KmerSlot)));
+    pl.table = c->d_kc_table.as<KmerSlot>(); pl.tshift = shift_for_cap((uint32_t)slots); pl.tmask = (uint32_t)(slots - 1);
+    pl.fill_limit = (uint32_t)(slots / 2);
+    CK(cudaEventRecord(c->ev[0], c->stream));
+    CK(cudaMemsetAsync(sm, 0, small_bytes, c->stream));
+    launch_kmer_table_clear(pl.table, slots, c->stream);
+    for (size_t i = 0; i < n_chunks; ++i) {
+        KcView v{};
+        TRY(view(i, 1, &v));
+        launch_kmer_hist(pl, v.in, v.rc, k, c->dp.min_bq, c->sm_count, c->stream);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(c->kc_ev_done[i & 1], c->stream));
+        st.kernel_launches += 1;
+    }
+    CK(cudaEventRecord(c->ev[1], c->stream));
+    std::vector<uint32_t> hist(P);
+    CK(cudaMemcpyAsync(hist.data(), pl.hist, (size_t)P * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    std::vector<unsigned long long> off(P + 1, 0);
+    for (uint32_t i = 0; i < P; ++i) off[i + 1] = off[i] + hist[i];
+    const uint64_t total = off[P];
+    TRY(c->d_kp_entries.ensure((total + 64) * 4));
+    pl.entries = c->d_kp_entries.as<uint32_t>();
+    CK(cudaMemcpyAsync(d_off, off.data(), (size_t)(P + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    for (size_t i = 0; i < n_chunks; ++i) {
+        KcView v{};
+        TRY(view(i, 2, &v));
+        launch_kmer_scatter(pl, v.in, v.rc, k, c->dp.min_bq, c->sm_count, c->stream);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(c->kc_ev_done[i & 1], c->stream));
+        st.kernel_launches += 1;
+    }
+    CK(cudaEventRecord(c->ev[2], c->stream));
+    // every survivor has more than two occurrences
+    const uint64_t cap64 = std::min<uint64_t>((uint64_t)out_cap, total / 3 + 32);
+    const uint32_t cap_dev = (uint32_t)std::min<uint64_t>(cap64, 0xfffffff0ull);
+    TRY(c->d_kc_out_k.ensure((size_t)cap_dev * 8 + 64)); TRY(c->d_kc_out_c.ensure((size_t)cap_dev * 8 + 64));
+    pl.out_kmers = c->d_kc_out_k.as<uint64_t>(); pl.out_counts = c->d_kc_out_c.as<uint32_t>(); pl.out_cap = cap_dev;
+    launch_kmer_count_part(pl, c->sm_count, c->stream);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ev[3], c->stream));
+    launch_kmer_compact(pl.table, slots, single_strand, pl.out_kmers, pl.out_counts, cap_dev, pl.out_n, c->stream);
+    CK(cudaGetLastError());
+    st.kernel_launches += 3;
+    CK(cudaEventRecord(c->ev[4], c->stream));
+    uint32_t t[20];
+    CK(cudaMemcpyAsync(t, tail, sizeof(t), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    st.hist_ms += ev_ms(c->ev[0], c->ev[1]); st.scatter_ms += ev_ms(c->ev[1], c->ev[2]);
+    st.count_ms += ev_ms(c->ev[0], c->ev[3]); st.compact_ms += ev_ms(c->ev[3], c->ev[4]);
+    if (t[1] != 0) return 1;                                          // spill table overflow: not a 16S-like input
+    const uint32_t n_found = t[16];
+    unsigned long long nd = 0; memcpy(&nd, t + 18, 8);
+    st.table_slots = slots; st.n_distinct = nd + t[0]; st.partitions = P; st.spilled_distinct = t[0];
+    if (n_out) *n_out = n_found;
+    if (n_found > out_cap) return fail(SAVONT_B200_ERR_CAPACITY, "k-mer output capacity %zu too small (need >= %u)", out_cap, n_found);
+    if (n_found) {
+        CK(cudaMemcpyAsync(out_kmers, pl.out_kmers, (size_t)n_found * 8, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(out_counts, pl.out_counts, (size_t)n_found * 8, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    st.d2h_bytes += (uint64_t)n_found * 16 + 16;
+    return 0;
+}
+
 // the two passes + compaction over device-resident chunk views; (re)sizes the Bloom filter and the table, grows the table
 // and starts over when it fills up.  `views(i, pass)` returns the i-th chunk after making sure it is on the device.
 template <typename GetView>
@@ -985,6 +1082,8 @@ int savont_b200_create(int device_id, savont_b200_ctx **out) {
         for (auto &ev : c->lane_ev[i]) CK(cudaEventCreate(&ev));
     }
     c->pev = c->ev;
+    if (const char *e = getenv("SAVONT_B200_KC_PARTITIONED")) c->kc_partitioned = atoi(e) != 0;
+    if (const char *e = getenv("SAVONT_B200_KC_SMEM_LIMIT")) c->kc_smem_limit = (uint32_t)atoi(e);
     for (auto &ev : c->ev) CK(cudaEventCreate(&ev));
     for (int i = 0; i < 3; ++i) { CK(cudaEventCreate(&c->ev_up[i])); CK(cudaEventCreate(&c->ev_h0[i])); }
     savont_b200_default_params(&c->params);
@@ -1013,7 +1112,7 @@ int savont_b200_destroy(savont_b200_ctx *h) {
     for (int i = 0; i < 2; ++i) { if (c->kc_ev_up[i]) cudaEventDestroy(c->kc_ev_up[i]); if (c->kc_ev_done[i]) cudaEventDestroy(c->kc_ev_done[i]); }
     for (auto &ch : c->kc_chunks) { ch.bases.release(); ch.quals.release(); ch.offsets.release(); ch.rc.release(); ch.pin.release(); }
     c->kc_chunks.clear();
-    c->d_kc_bloom.release(); c->d_kc_table.release(); c->d_kc_ctr.release(); c->d_kc_out_k.release(); c->d_kc_out_c.release();
+    c->d_kc_bloom.release(); c->d_kc_table.release(); c->d_kc_ctr.release(); c->d_kc_out_k.release(); c->d_kc_out_c.release(); c->d_kp_small.release(); c->d_kp_entries.release();
     for (int i = 0; i < 2; ++i) {
         for (auto &ev : c->lane_ev[i]) if (ev) cudaEventDestroy(ev);
         if (c->lane_stream[i]) cudaStreamDestroy(c->lane_stream[i]);
@@ -1554,7 +1653,15 @@ int savont_b200_count_split_kmers(savont_b200_ctx *h, const uint8_t *bases, cons
         return 0;
     };
     st.n_reads = n_reads; st.n_bases = total;
-    const int rcode = kc_run(c, nch, total, view, single_strand, out_kmers, out_counts, out_cap, n_out, st);
+    uint32_t max_len_all = 0;
+    for (size_t r = 0; r < n_reads; ++r) { const uint64_t l = offsets[r + 1] - offsets[r]; if (l > max_len_all) max_len_all = (uint32_t)std::min<uint64_t>(l, 0xffffffffu); }
+    int rcode = 1;
+    if (c->kc_partitioned && kmer_part_supported(c->dp.k, max_len_all))
+        rcode = kc_run_part(c, nch, total, view, single_strand, out_kmers, out_counts, out_cap, n_out, st);
+    if (rcode == 1) {                                                 // unsupported k, or too many distinct k-mers for the partitions
+        std::fill(uploaded.begin(), uploaded.end(), 0);
+        rcode = kc_run(c, nch, total, view, single_strand, out_kmers, out_counts, out_cap, n_out, st);
+    }
     CK(cudaEventRecord(c->ev[7], c->stream));
     CK(cudaStreamSynchronize(c->stream));
     st.total_ms = ev_ms(c->ev[6], c->ev[7]);
@@ -1572,7 +1679,10 @@ int savont_b200_count_split_kmers_resident(savont_b200_ctx *h, int single_strand
     CK(cudaEventRecord(c->ev[6], c->stream));
     auto view = [&](size_t, int, KcView *v) -> int { v->in = seq_view(b); v->rc = nullptr; return 0; };
     st.n_reads = b.n; st.n_bases = b.total_bases;
-    const int rcode = kc_run(c, b.n ? 1 : 0, b.total_bases, view, single_strand, out_kmers, out_counts, out_cap, n_out, st);
+    int rcode = 1;
+    if (c->kc_partitioned && kmer_part_supported(c->dp.k, b.max_len))
+        rcode = kc_run_part(c, b.n ? 1 : 0, b.total_bases, view, single_strand, out_kmers, out_counts, out_cap, n_out, st);
+    if (rcode == 1) rcode = kc_run(c, b.n ? 1 : 0, b.total_bases, view, single_strand, out_kmers, out_counts, out_cap, n_out, st);
     CK(cudaEventRecord(c->ev[7], c->stream));
     CK(cudaStreamSynchronize(c->stream));
     st.total_ms = ev_ms(c->ev[6], c->ev[7]);

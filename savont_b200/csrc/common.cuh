@@ -155,6 +155,20 @@ struct KmerSlot { unsigned long long key; uint32_t c0, c1; };     // key = kEmpt
 void launch_kmer_count(const SeqBatch &in, const uint8_t *rc, int k, int min_bq, KmerSlot *table, uint32_t tshift, uint32_t tmask,
                        uint32_t *ctr, uint32_t fill_limit, int sm_count, cudaStream_t st);
 void launch_kmer_table_clear(KmerSlot *table, uint64_t n, cudaStream_t st);
+// partitioned counting (k <= 21): histogram -> scatter of 32-bit entries -> per-partition shared-memory counting
+constexpr int kKmerPartBits = 13;              // 8192 partitions
+struct KmerPartPlan {
+    uint64_t mul, inv, kmask; int pbits, rem_bits;
+    uint32_t *hist; uint32_t *cursor; uint32_t *entries; const unsigned long long *part_off;
+    KmerSlot *table; uint32_t tshift, tmask; uint32_t *ctr; uint32_t fill_limit;       // spill table
+    int single_strand; uint64_t *out_kmers; uint32_t *out_counts; uint32_t out_cap; uint32_t *out_n;
+    unsigned long long *n_distinct; uint32_t *queue;
+    uint32_t smem_fill_limit;                // 0 = default
+};
+bool kmer_part_supported(int k, uint32_t max_len);
+void launch_kmer_hist(const KmerPartPlan &pl, const SeqBatch &in, const uint8_t *rc, int k, int min_bq, int sm_count, cudaStream_t st);
+void launch_kmer_scatter(const KmerPartPlan &pl, const SeqBatch &in, const uint8_t *rc, int k, int min_bq, int sm_count, cudaStream_t st);
+void launch_kmer_count_part(const KmerPartPlan &pl, int sm_count, cudaStream_t st);
 void launch_kmer_compact(const KmerSlot *table, uint64_t n_slots, int single_strand, uint64_t *out_kmers, uint32_t *out_counts,
                          uint32_t out_cap, uint32_t *out_n, cudaStream_t st);
 

@@ -146,6 +146,350 @@ kmer_count_kernel(KcArgs a) {
     }
 }
 
+// =================================================================================================
+// Partitioned counting (k <= 21): sequential traffic instead of one scattered sector operation per occurrence.
+//   1. kmer_hist_kernel     every occurrence -> histogram over P = 2^pbits partitions (top bits of h = kmer * M mod 2^2k,
+//                           M odd: a bijection on the k-mer space, so partition + remainder identify the k-mer)
+//   2. host                 exclusive scan of the histogram = partition offsets
+//   3. kmer_scatter_kernel  every occurrence again -> 32-bit entry (remainder | flag << 31) appended to its partition;
+//                           a CTA reserves the space of a whole tile of reads per partition with ONE global atomic
+//   4. kmer_count_part_kernel  one CTA per partition: the partition's k-mers are counted in a shared-memory table
+//                           (16 K slots of 12 B), in R rounds over a slice of the remainders when the partition is large;
+//                           survivors of the reference's filter are reconstructed (h * M^-1) and appended to the output.
+//                           k-mers that find the shared table full are counted in the global table instead (spill).
+// =================================================================================================
+constexpr int kKpTileReads = 4;              // reads per warp and tile in the scatter kernel
+constexpr uint32_t kKpSlots = 16384;         // shared-memory table slots of the counting kernel
+constexpr uint32_t kKpFillLimit = 11000;     // distinct k-mers per round before spilling
+
+struct KpArgs {
+    KcArgs kc;                               // reads, k, min_bq, the global (spill) table, counters
+    uint64_t mul, inv, kmask;                // h = (kmer * mul) & kmask; kmer = (h * inv) & kmask
+    int pbits, rem_bits;                     // partition = h >> rem_bits; entry = (h & rem_mask) | flag << 31
+    uint32_t *hist;                          // [P] occurrences per partition
+    uint32_t *cursor;                        // [P] next free entry of the partition, relative to part_off (scatter)
+    uint32_t *entries;                       // all partitions back to back
+    const unsigned long long *part_off;      // [P + 1]
+    int single_strand;
+    uint64_t *out_kmers; uint32_t *out_counts; uint32_t out_cap;
+    uint32_t *out_n;                         // survivors written
+    unsigned long long *n_distinct;          // distinct k-mers counted in shared memory
+    uint32_t *queue;                         // partition work queue
+    uint32_t packed_words;
+    uint32_t smem_fill_limit;               // distinct k-mers per round before the round goes to the global table
+};
+
+// one warp: pack `seq` into `packed` (processing orientation) and report whether the quality skip is active
+__device__ __forceinline__ bool kp_pack_read(const KcArgs &a, const uint8_t *s_lut, uint32_t *packed, uint32_t seq, int lane,
+                                             uint32_t &L, bool &rc, const uint8_t *&qp) {
+    const uint64_t off = a.in.offsets[seq];
+    L = (uint32_t)(a.in.offsets[seq + 1] - off);
+    rc = a.rc != nullptr && a.rc[seq] != 0;
+    const uint8_t *bp = a.in.bases + off;
+    qp = a.in.quals ? a.in.quals + off : nullptr;
+    const uint32_t nwords = (L + 15u) >> 4;
+    for (uint32_t w = lane; w < nwords + 3u; w += 32u) {
+        uint32_t pk = 0;
+        if (w < nwords) {
+#pragma unroll 4
+            for (uint32_t t = 0; t < 16u; ++t) {
+                const uint32_t i = 16u * w + t;
+                uint32_t c = 0;
+                if (i < L) c = rc ? s_lut[256u + bp[L - 1u - i]] : s_lut[bp[i]];
+                pk |= c << (30u - 2u * t);
+            }
+        }
+        packed[w] = pk;
+    }
+    bool use_q = false;
+    if (qp != nullptr && L > 0u) {
+        const uint8_t q0 = qp[0];
+        for (uint32_t i0 = 0; i0 < L && !use_q; i0 += 128u) {
+            bool d = false;
+#pragma unroll
+            for (uint32_t u = 0; u < 4u; ++u) { const uint32_t i = i0 + 32u * u + lane; if (i < L && qp[i] != q0) d = true; }
+            use_q = __any_sync(0xffffffffu, d);
+        }
+    }
+    __syncwarp();
+    return use_q;
+}
+
+// the occurrence at position p of a packed read: false = skipped (palindromic splitmer / low middle-base quality)
+__device__ __forceinline__ bool kp_occurrence(const uint32_t *packed, uint32_t p, uint32_t K, uint64_t kmer_mask, uint64_t split_mask,
+                                              bool use_q, const uint8_t *qp, bool rc, uint32_t L, int min_bq, uint64_t &canon, bool &fwd) {
+    const uint64_t x = window64(packed, p);
+    const uint64_t kf = x >> (64u - 2u * K);
+    const uint64_t kr = revcomp_top(x, kmer_mask);
+    const uint64_t sf = kf & split_mask, sr = kr & split_mask;
+    if (sf == sr) return false;
+    if (use_q) {
+        const uint32_t mid = p + (K >> 1);
+        if ((int)qp[rc ? L - 1u - mid : mid] - 33 < min_bq) return false;
+    }
+    fwd = sf < sr;
+    canon = fwd ? kf : kr;
+    return true;
+}
+
+__device__ __forceinline__ void kp_lut(uint8_t *s_lut) {
+    for (uint32_t i = threadIdx.x; i < 256u; i += blockDim.x) {
+        const uint32_t c = enc_base(i);
+        const uint32_t u = i & 0xDFu;
+        const bool acgt = (u == 'A' || u == 'C' || u == 'G' || u == 'T');
+        s_lut[i] = (uint8_t)c;
+        s_lut[256 + i] = (uint8_t)(acgt ? 3u - c : 0u);
+    }
+}
+
+// count one occurrence in the global table (spill path of the partitioned kernels; same protocol as kmer_count_kernel)
+__device__ __forceinline__ void kc_global_count(const KcArgs &a, unsigned long long canon, bool fwd) {
+    uint32_t sl = (uint32_t)((canon * kKcMul2) >> a.tshift);
+    for (uint32_t probes = 0;; ++probes) {
+        const unsigned long long v = __ldcg(&a.table[sl].key);
+        bool mine = v == canon;
+        if (!mine && v == kEmpty64) {
+            const unsigned long long old = atomicCAS(&a.table[sl].key, (unsigned long long)kEmpty64, canon);
+            if (old == kEmpty64) { if (atomicAdd(a.ctr, 1u) >= a.fill_limit) atomicOr(a.ctr + 1, 1u); mine = true; }
+            else mine = old == canon;
+        }
+        if (mine) { atomicAdd(fwd ? &a.table[sl].c1 : &a.table[sl].c0, 1u); return; }
+        if (probes > 4096u) { atomicOr(a.ctr + 1, 1u); return; }
+        sl = (sl + 1u) & a.tmask;
+    }
+}
+
+__global__ void __launch_bounds__(kKcWarps * 32)
+kmer_hist_kernel(KpArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t *s_lut = smem;
+    uint32_t *s_hist = reinterpret_cast<uint32_t *>(smem + 512);
+    const uint32_t P = 1u << a.pbits;
+    uint32_t *packed = s_hist + P + (size_t)warp * a.packed_words;
+    kp_lut(s_lut);
+    for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) s_hist[i] = 0u;
+    __syncthreads();
+    const uint32_t K = (uint32_t)a.kc.k;
+    const uint64_t kmer_mask = (1ull << (2u * K)) - 1ull, split_mask = ~(3ull << (K - 1u));
+    for (uint32_t seq = blockIdx.x * kKcWarps + warp; seq < a.kc.in.n; seq += gridDim.x * kKcWarps) {
+        uint32_t L; bool rc; const uint8_t *qp;
+        __syncwarp();
+        const bool use_q = kp_pack_read(a.kc, s_lut, packed, seq, lane, L, rc, qp);
+        if (L < K) continue;
+        for (uint32_t p = lane; p < L - K + 1u; p += 32u) {
+            uint64_t canon; bool fwd;
+            if (!kp_occurrence(packed, p, K, kmer_mask, split_mask, use_q, qp, rc, L, a.kc.min_bq, canon, fwd)) continue;
+            const uint64_t h = (canon * a.mul) & a.kmask;
+            atomicAdd(&s_hist[(uint32_t)(h >> a.rem_bits)], 1u);
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) if (s_hist[i]) atomicAdd(&a.hist[i], s_hist[i]);
+}
+
+__global__ void __launch_bounds__(kKcWarps * 32)
+kmer_scatter_kernel(KpArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t *s_lut = smem;
+    const uint32_t P = 1u << a.pbits;
+    uint32_t *s_base = reinterpret_cast<uint32_t *>(smem + 512);
+    uint32_t *s_hist = s_base + P;
+    uint32_t *packed = s_hist + P + (size_t)warp * a.packed_words * kKpTileReads;
+    kp_lut(s_lut);
+    for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) s_hist[i] = 0u;
+    __syncthreads();
+    const uint32_t K = (uint32_t)a.kc.k;
+    const uint64_t kmer_mask = (1ull << (2u * K)) - 1ull, split_mask = ~(3ull << (K - 1u));
+    const uint64_t rem_mask = (1ull << a.rem_bits) - 1ull;
+    const uint32_t tile = kKcWarps * kKpTileReads;
+    const uint32_t n_tiles = (a.kc.in.n + tile - 1u) / tile;
+    for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        uint32_t Ls[kKpTileReads]; bool rcs[kKpTileReads], uqs[kKpTileReads]; const uint8_t *qps[kKpTileReads];
+        // phase A: pack this warp's reads, count the tile's occurrences per partition
+#pragma unroll
+        for (int j = 0; j < kKpTileReads; ++j) {
+            const uint32_t seq = t * tile + (uint32_t)warp * kKpTileReads + (uint32_t)j;
+            Ls[j] = 0; rcs[j] = false; uqs[j] = false; qps[j] = nullptr;
+            if (seq >= a.kc.in.n) continue;
+            uint32_t *pk = packed + (size_t)j * a.packed_words;
+            uqs[j] = kp_pack_read(a.kc, s_lut, pk, seq, lane, Ls[j], rcs[j], qps[j]);
+            if (Ls[j] < K) { Ls[j] = 0; continue; }
+            for (uint32_t p = lane; p < Ls[j] - K + 1u; p += 32u) {
+                uint64_t canon; bool fwd;
+                if (!kp_occurrence(pk, p, K, kmer_mask, split_mask, uqs[j], qps[j], rcs[j], Ls[j], a.kc.min_bq, canon, fwd)) continue;
+                const uint64_t h = (canon * a.mul) & a.kmask;
+                atomicAdd(&s_hist[(uint32_t)(h >> a.rem_bits)], 1u);
+            }
+        }
+        __syncthreads();
+        // one global reservation per non-empty partition
+        for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {
+            const uint32_t c = s_hist[i];
+            if (c) s_base[i] = atomicAdd(&a.cursor[i], c);
+            s_hist[i] = 0u;
+        }
+        __syncthreads();
+        // phase B: the same occurrences again, now written to their reserved places
+#pragma unroll
+        for (int j = 0; j < kKpTileReads; ++j) {
+            if (Ls[j] == 0u) continue;
+            const uint32_t *pk = packed + (size_t)j * a.packed_words;
+            for (uint32_t p = lane; p < Ls[j] - K + 1u; p += 32u) {
+                uint64_t canon; bool fwd;
+                if (!kp_occurrence(pk, p, K, kmer_mask, split_mask, uqs[j], qps[j], rcs[j], Ls[j], a.kc.min_bq, canon, fwd)) continue;
+                const uint64_t h = (canon * a.mul) & a.kmask;
+                const uint32_t bin = (uint32_t)(h >> a.rem_bits);
+                const uint32_t r = atomicAdd(&s_hist[bin], 1u);
+                a.entries[__ldg(a.part_off + bin) + s_base[bin] + r] = (uint32_t)(h & rem_mask) | (fwd ? 0x80000000u : 0u);
+            }
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) s_hist[i] = 0u;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(1024, 1)
+kmer_count_part_kernel(KpArgs a) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint32_t *s_key = reinterpret_cast<uint32_t *>(smem);                 // remainder or 0xffffffff
+    uint32_t *s_cnt = s_key + kKpSlots;                                   // [slot][2]
+    __shared__ uint32_t s_fill, s_part, s_over;
+    const uint32_t P = 1u << a.pbits;
+    const int lane = threadIdx.x & 31;
+    unsigned long long distinct = 0;
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_part = atomicAdd(a.queue, 1u);
+        __syncthreads();
+        const uint32_t part = s_part;
+        if (part >= P) break;
+        const unsigned long long e0 = a.part_off[part], n = a.part_off[part + 1] - e0;
+        if (n == 0) continue;
+        // rounds: a slice of the remainders per round so that the distinct k-mers of a round fit the table (assumes >= 32
+        // occurrences per distinct k-mer; whatever does not fit spills into the global table)
+        uint32_t R = 1;
+        while (R < 64u && (unsigned long long)R * kKpFillLimit * 32ull < n) R <<= 1;
+        for (uint32_t r = 0; r < R; ++r) {
+            for (uint32_t i = threadIdx.x; i < kKpSlots; i += blockDim.x) { s_key[i] = 0xffffffffu; s_cnt[2 * i] = 0u; s_cnt[2 * i + 1] = 0u; }
+            if (threadIdx.x == 0) { s_fill = 0u; s_over = 0u; }
+            __syncthreads();
+            volatile uint32_t *vkey = s_key;
+            for (unsigned long long i = threadIdx.x; i < n; i += blockDim.x) {
+                if (*(volatile uint32_t *)&s_over) break;
+                const uint32_t e = __ldg(a.entries + e0 + i);
+                const uint32_t key = e & 0x7fffffffu, flag = e >> 31;
+                if ((key & (R - 1u)) != r) continue;
+                uint32_t slot = (key * 0x9E3779B1u) >> 18;                // 14 bits
+                for (uint32_t probes = 0; probes < kKpSlots; ++probes) {
+                    const uint32_t v = vkey[slot];
+                    bool mine = v == key;
+                    if (!mine && v == 0xffffffffu) {
+                        const uint32_t old = atomicCAS(&s_key[slot], 0xffffffffu, key);
+                        if (old == 0xffffffffu) { if (atomicAdd(&s_fill, 1u) >= a.smem_fill_limit) s_over = 1u; mine = true; }
+                        else mine = old == key;
+                    }
+                    if (mine) { atomicAdd(&s_cnt[2u * slot + flag], 1u); break; }
+                    slot = (slot + 1u) & (kKpSlots - 1u);
+                }
+            }
+            __syncthreads();
+            if (s_over) {
+                // more distinct k-mers than the table holds: this round is counted in the global table instead (exact: the
+                // shared-memory counts of the round are dropped as a whole)
+                for (unsigned long long i = threadIdx.x; i < n; i += blockDim.x) {
+                    const uint32_t e = __ldg(a.entries + e0 + i);
+                    const uint32_t key = e & 0x7fffffffu;
+                    if ((key & (R - 1u)) != r) continue;
+                    const unsigned long long h = ((unsigned long long)part << a.rem_bits) | key;
+                    kc_global_count(a.kc, (h * a.inv) & a.kmask, (e >> 31) != 0u);
+                }
+                __syncthreads();
+                continue;
+            }
+            // survivors of the reference's filter (src/seq_parse.rs:30-44)
+            for (uint32_t i0 = 0; i0 < kKpSlots; i0 += blockDim.x) {
+                const uint32_t i = i0 + threadIdx.x;
+                const uint32_t key = s_key[i], c0 = s_cnt[2 * i], c1 = s_cnt[2 * i + 1];
+                const bool used = key != 0xffffffffu;
+                const bool keep = used && (a.single_strand ? (c0 > 2u) : (c0 > 0u && c1 > 0u && c0 + c1 > 2u));
+                if (used) ++distinct;
+                const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+                if (bal) {
+                    uint32_t base = 0;
+                    if (lane == 0) base = atomicAdd(a.out_n, (uint32_t)__popc(bal));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (keep) {
+                        const uint32_t o = base + (uint32_t)__popc(bal & ((1u << lane) - 1u));
+                        if (o < a.out_cap) {
+                            const unsigned long long h = ((unsigned long long)part << a.rem_bits) | key;
+                            a.out_kmers[o] = (h * a.inv) & a.kmask; a.out_counts[2u * o] = c0; a.out_counts[2u * o + 1u] = c1;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) distinct += __shfl_xor_sync(0xffffffffu, distinct, d);
+    if (lane == 0 && distinct) atomicAdd(a.n_distinct, distinct);
+}
+
+static KpArgs kp_args(const KmerPartPlan &pl, const SeqBatch &in, const uint8_t *rc, int k, int min_bq) {
+    KpArgs a{};
+    a.kc.in = in; a.kc.rc = rc; a.kc.k = k; a.kc.min_bq = min_bq;
+    a.kc.table = pl.table; a.kc.tshift = pl.tshift; a.kc.tmask = pl.tmask; a.kc.ctr = pl.ctr; a.kc.fill_limit = pl.fill_limit;
+    a.mul = pl.mul; a.inv = pl.inv; a.kmask = pl.kmask; a.pbits = pl.pbits; a.rem_bits = pl.rem_bits;
+    a.hist = pl.hist; a.cursor = pl.cursor; a.entries = pl.entries; a.part_off = pl.part_off;
+    a.single_strand = pl.single_strand; a.out_kmers = pl.out_kmers; a.out_counts = pl.out_counts; a.out_cap = pl.out_cap;
+    a.out_n = pl.out_n; a.n_distinct = pl.n_distinct; a.queue = pl.queue;
+    a.packed_words = ((in.max_len + 15u) >> 4) + 4u;
+    a.smem_fill_limit = pl.smem_fill_limit ? pl.smem_fill_limit : kKpFillLimit;
+    return a;
+}
+
+bool kmer_part_supported(int k, uint32_t max_len) { return 2 * k - kKmerPartBits + 1 <= 32 && 2 * k > kKmerPartBits && max_len < 60000u; }
+
+void launch_kmer_hist(const KmerPartPlan &pl, const SeqBatch &in, const uint8_t *rc, int k, int min_bq, int sm_count, cudaStream_t st) {
+    if (in.n == 0) return;
+    KpArgs a = kp_args(pl, in, rc, k, min_bq);
+    const size_t smem = 512u + (4u << a.pbits) + (size_t)a.packed_words * 4u * kKcWarps;
+    int ctas = (int)(200u * 1024u / (smem + 1024u));
+    if (ctas < 1) ctas = 1;
+    if (ctas > 4) ctas = 4;
+    uint32_t grid = (uint32_t)(sm_count * ctas);
+    const uint32_t need = (in.n + kKcWarps - 1) / kKcWarps;
+    if (grid > need) grid = need;
+    cudaFuncSetAttribute(kmer_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kmer_hist_kernel<<<grid, kKcWarps * 32, smem, st>>>(a);
+}
+
+void launch_kmer_scatter(const KmerPartPlan &pl, const SeqBatch &in, const uint8_t *rc, int k, int min_bq, int sm_count, cudaStream_t st) {
+    if (in.n == 0) return;
+    KpArgs a = kp_args(pl, in, rc, k, min_bq);
+    const size_t smem = 512u + (8u << a.pbits) + (size_t)a.packed_words * 4u * kKcWarps * kKpTileReads;
+    int ctas = (int)(220u * 1024u / (smem + 1024u));
+    if (ctas < 1) ctas = 1;
+    if (ctas > 4) ctas = 4;
+    uint32_t grid = (uint32_t)(sm_count * ctas);
+    const uint32_t tile = kKcWarps * kKpTileReads;
+    const uint32_t need = (in.n + tile - 1) / tile;
+    if (grid > need) grid = need;
+    cudaFuncSetAttribute(kmer_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kmer_scatter_kernel<<<grid, kKcWarps * 32, smem, st>>>(a);
+}
+
+void launch_kmer_count_part(const KmerPartPlan &pl, int sm_count, cudaStream_t st) {
+    KpArgs a = kp_args(pl, SeqBatch{}, nullptr, 17, 0);
+    const size_t smem = (size_t)kKpSlots * 12u;
+    cudaFuncSetAttribute(kmer_count_part_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kmer_count_part_kernel<<<sm_count, 1024, smem, st>>>(a);
+}
+
+
 __global__ void kmer_table_clear_kernel(KmerSlot *table, uint64_t n) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         KmerSlot s; s.key = kEmpty64; s.c0 = 0u; s.c1 = 0u;

@@ -505,8 +505,44 @@ def test_count_split_kmers_synthetic_reads(ctx):
     assert_same(got, want, KMER_KEYS, "synthetic reads")
     assert len(want["kmers"]) > 50000
     st = got["stats"]
-    assert st["n_distinct"] == want["n_distinct"] and st["n_distinct"] <= st["table_slots"] // 2
+    assert st["n_distinct"] == want["n_distinct"] and st["partitions"] == 8192 and st["spilled_distinct"] == 0
     ctx.upload_reads(r["bases"], r["quals"], r["offsets"])
     assert_same(ctx.count_split_kmers_resident(), O.count_split_kmers(r["bases"], r["quals"], r["offsets"]), KMER_KEYS, "resident")
     th, hf = O.high_freq_kmers(want["kmers"], want["counts"])
     assert th >= 100 and len(hf) < len(want["kmers"])
+
+
+@pytest.mark.parametrize("env,expect", [({"SAVONT_B200_KC_PARTITIONED": "0"}, "single"), ({"SAVONT_B200_KC_SMEM_LIMIT": "40"}, "spill")])
+def test_count_split_kmers_other_algorithms(env, expect):
+    """the single-table algorithm (also the fallback for k > 21) and the spill path of the partitioned one (shared-memory
+    rounds that overflow are counted in the global table) give the same answer"""
+    import os
+    from savont_b200 import _lib
+    w = _make_workload("ont16s", n_roots=5)
+    r = w.reads(4000)
+    rc = (np.arange(4000) % 4 == 1).astype(np.uint8)
+    want = O.count_split_kmers(r["bases"], r["quals"], r["offsets"], rc=rc)
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        c2 = _lib.Context(0)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    try:
+        got = c2.count_split_kmers(r["bases"], r["quals"], r["offsets"], rc=rc)
+        assert_same(got, want, KMER_KEYS, expect)
+        assert got["stats"]["n_distinct"] == want["n_distinct"]
+        if expect == "single":
+            assert got["stats"]["partitions"] == 0
+        else:
+            assert got["stats"]["partitions"] == 8192 and got["stats"]["spilled_distinct"] > 1000
+        c2.set_params(_lib.default_params(k=23, c=11))                 # k = 23: 46-bit k-mers do not fit the 32-bit entries
+        got = c2.count_split_kmers(r["bases"], r["quals"], r["offsets"], rc=rc)
+        assert_same(got, O.count_split_kmers(r["bases"], r["quals"], r["offsets"], rc=rc, k=23), KMER_KEYS, "k=23")
+        assert got["stats"]["partitions"] == 0
+    finally:
+        c2.close()
