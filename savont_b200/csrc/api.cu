@@ -140,7 +140,7 @@ struct Context {
     DevBuf d_counters; size_t counters_len = 0; int counters_samples = 0;
 
     // K5 (Stage 1 split-k-mer counting): Bloom filter, exact table, counters, output staging, read chunks
-    DevBuf d_kc_bloom, d_kc_table, d_kc_ctr, d_kc_out_k, d_kc_out_c, d_kp_small, d_kp_entries;
+    DevBuf d_kc_bloom, d_kc_table, d_kc_ctr, d_kc_out_k, d_kc_out_c, d_kp_small, d_kp_entries, d_kp_entries1;
     struct KcChunk { DevBuf bases, quals, offsets, rc; PinBuf pin; uint32_t n = 0, max_len = 0; uint64_t total = 0; bool has_quals = false, has_rc = false; };
     std::vector<KcChunk> kc_chunks;
     bool kc_partitioned = true;                          // SAVONT_B200_KC_PARTITIONED=0 forces the single-table algorithm
@@ -898,7 +898,7 @@ static int kc_run_part(Context *c, size_t n_chunks, uint64_t total_bases, GetVie
     pl.pbits = pbits; pl.rem_bits = rem_bits; pl.single_strand = single_strand;
     pl.smem_fill_limit = c->kc_smem_limit;
     // small device block: hist[P] | cursor[P] | part_off[P + 1] (u64) | ctr[16] | out_n | queue | n_distinct (u64)
-    const size_t small_bytes = (size_t)P * 8 + (size_t)(P + 1) * 8 + 256;
+    const size_t small_bytes = (size_t)P * 8 + (size_t)(P + 1) * 8 + 256 + 128 * 4 + 132 * 4;
     TRY(c->d_kp_small.ensure(small_bytes));
     uint8_t *sm = c->d_kp_small.as<uint8_t>();
     pl.hist = reinterpret_cast<uint32_t *>(sm); pl.cursor = pl.hist + P;
@@ -906,6 +906,7 @@ static int kc_run_part(Context *c, size_t n_chunks, uint64_t total_bases, GetVie
     pl.part_off = d_off;
     uint32_t *tail = reinterpret_cast<uint32_t *>(sm + (size_t)P * 8 + (size_t)(P + 1) * 8);
     pl.ctr = tail; pl.out_n = tail + 16; pl.queue = tail + 17; pl.n_distinct = reinterpret_cast<unsigned long long *>(tail + 18);
+    uint32_t *cursor1 = tail + 64, *d_tile_start = tail + 64 + 128;
     // spill table
     const uint64_t slots = 1ull << 22;
     TRY(c->d_kc_table.ensure(slots * sizeof(KmerSlot)));
@@ -932,12 +933,33 @@ static int kc_run_part(Context *c, size_t n_chunks, uint64_t total_bases, GetVie
     TRY(c->d_kp_entries.ensure((total + 64) * 4));
     pl.entries = c->d_kp_entries.as<uint32_t>();
     CK(cudaMemcpyAsync(d_off, off.data(), (size_t)(P + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    uint32_t max_len_all = 0;
+    for (size_t i = 0; i < n_chunks; ++i) { KcView v{}; TRY(view(i, 0, &v)); if (v.in.max_len > max_len_all) max_len_all = v.in.max_len; }
+    const bool two_level = kmer_part_two_level(k, max_len_all);
+    std::vector<uint32_t> tile_start(132, 0);
+    if (two_level) {
+        // level 1 (from the reads, 128 bins) into entries1, level 2 (tiles of entries1) into the final partitions
+        const int sub = pbits - kmer_scatter1_bits();
+        const uint32_t P1 = 1u << kmer_scatter1_bits(), tile2 = kmer_scatter2_tile();
+        for (uint32_t b1 = 0; b1 < P1; ++b1) {
+            const unsigned long long nb = off[(size_t)(b1 + 1) << sub] - off[(size_t)b1 << sub];
+            tile_start[b1 + 1] = tile_start[b1] + (uint32_t)((nb + tile2 - 1) / tile2);
+        }
+        TRY(c->d_kp_entries1.ensure((total + 64) * 4));
+        CK(cudaMemcpyAsync(d_tile_start, tile_start.data(), 132 * 4, cudaMemcpyHostToDevice, c->stream));
+    }
     for (size_t i = 0; i < n_chunks; ++i) {
         KcView v{};
         TRY(view(i, 2, &v));
-        launch_kmer_scatter(pl, v.in, v.rc, k, c->dp.min_bq, c->sm_count, c->stream);
+        if (two_level) launch_kmer_scatter1(pl, c->d_kp_entries1.as<uint32_t>(), cursor1, v.in, v.rc, k, c->dp.min_bq, c->sm_count, c->stream);
+        else launch_kmer_scatter(pl, v.in, v.rc, k, c->dp.min_bq, c->sm_count, c->stream);
         CK(cudaGetLastError());
         CK(cudaEventRecord(c->kc_ev_done[i & 1], c->stream));
+        st.kernel_launches += 1;
+    }
+    if (two_level) {
+        launch_kmer_scatter2(pl, c->d_kp_entries1.as<uint32_t>(), d_tile_start, tile_start[1u << kmer_scatter1_bits()], k, c->sm_count, c->stream);
+        CK(cudaGetLastError());
         st.kernel_launches += 1;
     }
     CK(cudaEventRecord(c->ev[2], c->stream));
@@ -1112,7 +1134,7 @@ int savont_b200_destroy(savont_b200_ctx *h) {
     for (int i = 0; i < 2; ++i) { if (c->kc_ev_up[i]) cudaEventDestroy(c->kc_ev_up[i]); if (c->kc_ev_done[i]) cudaEventDestroy(c->kc_ev_done[i]); }
     for (auto &ch : c->kc_chunks) { ch.bases.release(); ch.quals.release(); ch.offsets.release(); ch.rc.release(); ch.pin.release(); }
     c->kc_chunks.clear();
-    c->d_kc_bloom.release(); c->d_kc_table.release(); c->d_kc_ctr.release(); c->d_kc_out_k.release(); c->d_kc_out_c.release(); c->d_kp_small.release(); c->d_kp_entries.release();
+    c->d_kc_bloom.release(); c->d_kc_table.release(); c->d_kc_ctr.release(); c->d_kc_out_k.release(); c->d_kc_out_c.release(); c->d_kp_small.release(); c->d_kp_entries.release(); c->d_kp_entries1.release();
     for (int i = 0; i < 2; ++i) {
         for (auto &ev : c->lane_ev[i]) if (ev) cudaEventDestroy(ev);
         if (c->lane_stream[i]) cudaStreamDestroy(c->lane_stream[i]);
@@ -1637,6 +1659,13 @@ int savont_b200_count_split_kmers(savont_b200_ctx *h, const uint8_t *bases, cons
     };
     auto view = [&](size_t i, int pass, KcView *v) -> int {
         Context::KcChunk &ch = c->kc_chunks[i % nbuf];
+        if (pass == 0) {                                              // metadata only (max_len of the chunk)
+            v->in = SeqBatch{}; v->rc = nullptr;
+            uint32_t mx = 0;
+            for (size_t r = cuts[i]; r < cuts[i + 1]; ++r) { const uint64_t l = offsets[r + 1] - offsets[r]; if (l > mx) mx = (uint32_t)std::min<uint64_t>(l, 0xffffffffu); }
+            v->in.max_len = mx;
+            return 0;
+        }
         if (pass == 1 || !resident) {
             if (!(resident && uploaded[i % nbuf])) {
                 // non-resident: the pin buffer of this slot is rewritten, so the previous copy out of it must be complete

@@ -169,6 +169,14 @@ bool kmer_part_supported(int k, uint32_t max_len);
 void launch_kmer_hist(const KmerPartPlan &pl, const SeqBatch &in, const uint8_t *rc, int k, int min_bq, int sm_count, cudaStream_t st);
 void launch_kmer_scatter(const KmerPartPlan &pl, const SeqBatch &in, const uint8_t *rc, int k, int min_bq, int sm_count, cudaStream_t st);
 void launch_kmer_count_part(const KmerPartPlan &pl, int sm_count, cudaStream_t st);
+// two-level scatter with coalesced writes (2k <= 38): level 1 from the reads into 128 bins, level 2 into the partitions
+bool kmer_part_two_level(int k, uint32_t max_len);
+uint32_t kmer_scatter2_tile();
+int kmer_scatter1_bits();
+void launch_kmer_scatter1(const KmerPartPlan &pl, uint32_t *entries1, uint32_t *cursor1, const SeqBatch &in, const uint8_t *rc, int k,
+                          int min_bq, int sm_count, cudaStream_t st);
+void launch_kmer_scatter2(const KmerPartPlan &pl, const uint32_t *entries1, const uint32_t *tile_start, uint32_t n_tiles2, int k,
+                          int sm_count, cudaStream_t st);
 void launch_kmer_compact(const KmerSlot *table, uint64_t n_slots, int single_strand, uint64_t *out_kmers, uint32_t *out_counts,
                          uint32_t out_cap, uint32_t *out_n, cudaStream_t st);
 

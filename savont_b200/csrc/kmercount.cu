@@ -3,18 +3,18 @@
 // (src/seeding.rs:975-1068).
 //
 // The reference counts every k-mer of every read in sharded FxHashMap<u64, [u32; 2]> and afterwards keeps the entries
-// seen on both strands more than twice (src/seq_parse.rs:30-44).  Here ONE pass over the reads counts every occurrence
-// in one open-addressing table in HBM (16-byte slots: key, c0, c1; two slots per 32-byte sector), sized from the number
-// of occurrences (load <= 0.5, regrown x4 and re-run otherwise): per occurrence one key probe and one atomicAdd into the
-// same sector.  A 16S read set is extremely redundant -- 1 M ONT reads hold 1.48 G occurrences of 48 M distinct k-mers,
-// two thirds of the occurrences belong to < 1 M true k-mers -- so the hot sectors stay in L2 and only the error k-mers
-// pay a DRAM round trip.  (A first version with a Bloom filter in front of the table and a second counting pass touched
-// two structures per occurrence and took twice as long.)  Measured on 1 M reads: extraction alone 5.5 ms, + key probes
-// 42.7 ms, + count atomics 81.7 ms: the kernel is bound by the rate of scattered 32-byte L2 / DRAM operations
-// (~40 G/s for loads as well as for reductions; 41.7 GB of DRAM reads = one 64-byte burst per error k-mer occurrence),
-// not by issue slots or memory-level parallelism (4 probes in flight per lane change nothing).  Partitioning the k-mers
-// by hash first, so that every partition is counted in shared memory, is the round-2 design.
-// A final scan applies the reference's filter and appends the survivors to the output.
+// seen on both strands more than twice (src/seq_parse.rs:30-44).  1 M ONT 16S reads hold 1.48 G k-mer occurrences of
+// 48 M distinct k-mers.  Two algorithms, both exact:
+//   partitioned (k <= 21, the default)   histogram of the occurrences over 8192 hash partitions -> scatter of 32-bit
+//       entries into the partitions (two levels with a shared-memory sort per tile, so that global writes are coalesced
+//       runs; one level of direct stores for k = 21) -> one CTA per partition counts in a shared-memory table and emits
+//       the survivors.  Sequential traffic only: 32 ms per 1 M reads (hist 5.8, scatter 18.5, count 7.9).
+//   single table (k = 23, or when a partition holds more distinct k-mers than the spill table takes)   one pass, one
+//       open-addressing table in HBM (16-byte slots), per occurrence one key probe + one atomicAdd in the same sector:
+//       83 ms per 1 M reads.  Measured: extraction alone 5.5 ms, + probes 42.7 ms, + count atomics 81.7 ms -- scattered
+//       32-byte sector operations run at ~40 G/s on B200 whatever their kind (load, reduction, store), far below what the
+//       issue slots (7 % busy) or DRAM (8 %) could take; 4 probes in flight per lane change nothing.  That is why the
+//       partitioned algorithm exists.
 // Reads whose id ends in "rc" are reverse-complemented first exactly like utils::reverse_complement does it
 // (src/utils.rs:51-65: anything but ACGT/acgt becomes N, which encodes as A).
 #include "common.cuh"
@@ -351,6 +351,161 @@ kmer_scatter_kernel(KpArgs a) {
     }
 }
 
+// ---- two-level scatter (2k - 7 + 1 <= 32): both levels sort a tile by bin in shared memory first, so that the global
+// writes are runs of consecutive entries (coalesced) and a tile costs one global atomic per bin.  The direct scatter above
+// issues one 4-byte store per occurrence to 8192 different places: scattered sector operations run at ~40 G/s on B200
+// whatever their kind (load, reduction, store), which made it the slowest step. ----
+constexpr int kKp1Bits = 7;                  // level 1: 128 bins (the top bits of h)
+constexpr uint32_t kKp1TileCap = 24576;      // entries per level-1 tile (16 reads of up to 1536 k-mers)
+constexpr uint32_t kKp2Tile = 12288;         // entries per level-2 tile
+
+struct Kp2Args {
+    KpArgs p;
+    uint32_t *entries1;                      // level-1 output: (h & rem1_mask) | flag << 31, 128 bins back to back
+    uint32_t *cursor1;                       // [128] relative
+    const uint32_t *tile_start;              // [129] first level-2 tile of every level-1 bin
+    uint32_t n_tiles2, tile_reads;
+};
+
+__global__ void __launch_bounds__(kKcWarps * 32)
+kmer_scatter1_kernel(Kp2Args b) {
+    const KpArgs &a = b.p;
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr uint32_t P1 = 1u << kKp1Bits;
+    uint8_t *s_lut = smem;
+    uint32_t *s_hist = reinterpret_cast<uint32_t *>(smem + 512);           // counts, then fill cursors
+    uint32_t *s_off = s_hist + P1;                                         // [P1 + 1]
+    uint32_t *s_gbase = s_off + P1 + 1;
+    uint32_t *sorted = s_gbase + P1;
+    uint32_t *packed = sorted + kKp1TileCap + (size_t)warp * a.packed_words;
+    kp_lut(s_lut);
+    for (uint32_t i = threadIdx.x; i < P1; i += blockDim.x) s_hist[i] = 0u;
+    __syncthreads();
+    const uint32_t K = (uint32_t)a.kc.k;
+    const uint64_t kmer_mask = (1ull << (2u * K)) - 1ull, split_mask = ~(3ull << (K - 1u));
+    const int rem1_bits = 2 * a.kc.k - kKp1Bits;
+    const uint64_t rem1_mask = (1ull << rem1_bits) - 1ull;
+    const int sub_bits = a.pbits - kKp1Bits;
+    const uint32_t tile = b.tile_reads;
+    const uint32_t n_tiles = (a.kc.in.n + tile - 1u) / tile;
+    for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const uint32_t seq = t * tile + (uint32_t)warp;
+        uint32_t L = 0; bool rc = false, use_q = false; const uint8_t *qp = nullptr;
+        const bool have = (uint32_t)warp < tile && seq < a.kc.in.n;
+        if (have) {
+            use_q = kp_pack_read(a.kc, s_lut, packed, seq, lane, L, rc, qp);
+            if (L < K) L = 0;
+        }
+        if (L) {
+            for (uint32_t p = lane; p < L - K + 1u; p += 32u) {
+                uint64_t canon; bool fwd;
+                if (!kp_occurrence(packed, p, K, kmer_mask, split_mask, use_q, qp, rc, L, a.kc.min_bq, canon, fwd)) continue;
+                const uint64_t h = (canon * a.mul) & a.kmask;
+                atomicAdd(&s_hist[(uint32_t)(h >> rem1_bits)], 1u);
+            }
+        }
+        __syncthreads();
+        if (warp == 0) {                                   // exclusive scan of 128 counts + one global reservation per bin
+            uint32_t c[4], sum = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { c[j] = s_hist[4 * lane + j]; sum += c[j]; }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += y; }
+            uint32_t run = incl - sum;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t bin = 4u * lane + j;
+                s_off[bin] = run; run += c[j];
+                s_gbase[bin] = c[j] ? atomicAdd(&b.cursor1[bin], c[j]) : 0u;
+                s_hist[bin] = 0u;
+            }
+            if (lane == 31) s_off[P1] = run;
+        }
+        __syncthreads();
+        if (L) {
+            for (uint32_t p = lane; p < L - K + 1u; p += 32u) {
+                uint64_t canon; bool fwd;
+                if (!kp_occurrence(packed, p, K, kmer_mask, split_mask, use_q, qp, rc, L, a.kc.min_bq, canon, fwd)) continue;
+                const uint64_t h = (canon * a.mul) & a.kmask;
+                const uint32_t bin = (uint32_t)(h >> rem1_bits);
+                const uint32_t pos = s_off[bin] + atomicAdd(&s_hist[bin], 1u);
+                sorted[pos] = (uint32_t)(h & rem1_mask) | (fwd ? 0x80000000u : 0u);
+            }
+        }
+        __syncthreads();
+        for (uint32_t bin = warp; bin < P1; bin += kKcWarps) {             // coalesced runs
+            const uint32_t s0 = s_off[bin], cnt = s_off[bin + 1] - s0;
+            uint32_t *dst = b.entries1 + __ldg(a.part_off + ((size_t)bin << sub_bits)) + s_gbase[bin];
+            for (uint32_t i = lane; i < cnt; i += 32u) dst[i] = sorted[s0 + i];
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < P1; i += blockDim.x) s_hist[i] = 0u;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(512)
+kmer_scatter2_kernel(Kp2Args b) {
+    const KpArgs &a = b.p;
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr uint32_t P1 = 1u << kKp1Bits;
+    const int sub_bits = a.pbits - kKp1Bits;
+    const uint32_t P2 = 1u << sub_bits;                                    // <= 64
+    uint32_t *s_hist = reinterpret_cast<uint32_t *>(smem);
+    uint32_t *s_off = s_hist + 64;
+    uint32_t *s_gbase = s_off + 65;
+    uint32_t *sorted = s_gbase + 64;
+    const uint32_t rem_mask = (uint32_t)((1ull << a.rem_bits) - 1ull);
+    for (uint32_t t = blockIdx.x; t < b.n_tiles2; t += gridDim.x) {
+        uint32_t lo = 0, hi = P1;                                          // level-1 bin of this tile
+        while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(b.tile_start + mid) <= t) lo = mid; else hi = mid; }
+        const uint32_t bin1 = lo;
+        const unsigned long long b0 = __ldg(a.part_off + ((size_t)bin1 << sub_bits));
+        const unsigned long long nb = __ldg(a.part_off + ((size_t)(bin1 + 1) << sub_bits)) - b0;
+        const unsigned long long start = (unsigned long long)(t - __ldg(b.tile_start + bin1)) * kKp2Tile;
+        const uint32_t cnt = (uint32_t)min((unsigned long long)kKp2Tile, nb - start);
+        const uint32_t *src = b.entries1 + b0 + start;
+        if (threadIdx.x < 64) s_hist[threadIdx.x] = 0u;
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x)
+            atomicAdd(&s_hist[((__ldg(src + i) & 0x7fffffffu) >> a.rem_bits) & (P2 - 1u)], 1u);
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t c[2], sum = 0;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) { c[j] = s_hist[2 * lane + j]; sum += c[j]; }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += y; }
+            uint32_t run = incl - sum;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const uint32_t s = 2u * lane + j;
+                s_off[s] = run; run += c[j];
+                s_gbase[s] = (c[j] && s < P2) ? atomicAdd(&a.cursor[((size_t)bin1 << sub_bits) + s], c[j]) : 0u;
+                s_hist[s] = 0u;
+            }
+            if (lane == 31) s_off[64] = run;
+        }
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+            const uint32_t e = __ldg(src + i);
+            const uint32_t s = ((e & 0x7fffffffu) >> a.rem_bits) & (P2 - 1u);
+            sorted[s_off[s] + atomicAdd(&s_hist[s], 1u)] = (e & rem_mask) | (e & 0x80000000u);
+        }
+        __syncthreads();
+        for (uint32_t s = warp; s < P2; s += 16u) {
+            const uint32_t s0 = s_off[s], c = s_off[s + 1] - s0;
+            uint32_t *dst = a.entries + __ldg(a.part_off + ((size_t)bin1 << sub_bits) + s) + s_gbase[s];
+            for (uint32_t i = lane; i < c; i += 32u) dst[i] = sorted[s0 + i];
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(1024, 1)
 kmer_count_part_kernel(KpArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -480,6 +635,44 @@ void launch_kmer_scatter(const KmerPartPlan &pl, const SeqBatch &in, const uint8
     if (grid > need) grid = need;
     cudaFuncSetAttribute(kmer_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kmer_scatter_kernel<<<grid, kKcWarps * 32, smem, st>>>(a);
+}
+
+bool kmer_part_two_level(int k, uint32_t max_len) {
+    return 2 * k - kKp1Bits + 1 <= 32 && max_len >= 1u && kKp1TileCap / max_len >= 1u && kKmerPartBits - kKp1Bits <= 6;
+}
+
+void launch_kmer_scatter1(const KmerPartPlan &pl, uint32_t *entries1, uint32_t *cursor1, const SeqBatch &in, const uint8_t *rc, int k,
+                          int min_bq, int sm_count, cudaStream_t st) {
+    if (in.n == 0) return;
+    Kp2Args b{};
+    b.p = kp_args(pl, in, rc, k, min_bq);
+    b.entries1 = entries1; b.cursor1 = cursor1;
+    b.tile_reads = kKp1TileCap / (in.max_len ? in.max_len : 1u);
+    if (b.tile_reads > (uint32_t)kKcWarps) b.tile_reads = kKcWarps;
+    const size_t smem = 512u + (size_t)(3u * (1u << kKp1Bits) + 1u) * 4u + (size_t)kKp1TileCap * 4u + (size_t)b.p.packed_words * 4u * kKcWarps;
+    int ctas = (int)(220u * 1024u / (smem + 1024u));
+    if (ctas < 1) ctas = 1;
+    uint32_t grid = (uint32_t)(sm_count * ctas);
+    const uint32_t need = (in.n + b.tile_reads - 1) / b.tile_reads;
+    if (grid > need) grid = need;
+    cudaFuncSetAttribute(kmer_scatter1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kmer_scatter1_kernel<<<grid, kKcWarps * 32, smem, st>>>(b);
+}
+
+uint32_t kmer_scatter2_tile() { return kKp2Tile; }
+int kmer_scatter1_bits() { return kKp1Bits; }
+
+void launch_kmer_scatter2(const KmerPartPlan &pl, const uint32_t *entries1, const uint32_t *tile_start, uint32_t n_tiles2, int k,
+                          int sm_count, cudaStream_t st) {
+    if (n_tiles2 == 0) return;
+    Kp2Args b{};
+    b.p = kp_args(pl, SeqBatch{}, nullptr, k, 0);
+    b.entries1 = const_cast<uint32_t *>(entries1); b.tile_start = tile_start; b.n_tiles2 = n_tiles2;
+    const size_t smem = (size_t)(64 + 65 + 64) * 4u + (size_t)kKp2Tile * 4u;
+    uint32_t grid = (uint32_t)sm_count * 4u;
+    if (grid > n_tiles2) grid = n_tiles2;
+    cudaFuncSetAttribute(kmer_scatter2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kmer_scatter2_kernel<<<grid, 512, smem, st>>>(b);
 }
 
 void launch_kmer_count_part(const KmerPartPlan &pl, int sm_count, cudaStream_t st) {
