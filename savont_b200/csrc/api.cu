@@ -139,8 +139,8 @@ struct Context {
     // counters [unambig A | ambig A | leq10 A | assigned | filtered | singleton S*A]
     DevBuf d_counters; size_t counters_len = 0; int counters_samples = 0;
 
-    // K5 (Stage 1 split-k-mer counting): Bloom filter, exact table, counters, output staging, read chunks
-    DevBuf d_kc_bloom, d_kc_table, d_kc_ctr, d_kc_out_k, d_kc_out_c, d_kp_small, d_kp_entries, d_kp_entries1;
+    // K5 (Stage 1 split-k-mer counting): global table, counters, output staging, partition entries, read chunks
+    DevBuf d_kc_table, d_kc_ctr, d_kc_out_k, d_kc_out_c, d_kp_small, d_kp_entries, d_kp_entries1;
     struct KcChunk { DevBuf bases, quals, offsets, rc; PinBuf pin; uint32_t n = 0, max_len = 0; uint64_t total = 0; bool has_quals = false, has_rc = false; };
     std::vector<KcChunk> kc_chunks;
     bool kc_partitioned = true;                          // SAVONT_B200_KC_PARTITIONED=0 forces the single-table algorithm
@@ -1134,7 +1134,7 @@ int savont_b200_destroy(savont_b200_ctx *h) {
     for (int i = 0; i < 2; ++i) { if (c->kc_ev_up[i]) cudaEventDestroy(c->kc_ev_up[i]); if (c->kc_ev_done[i]) cudaEventDestroy(c->kc_ev_done[i]); }
     for (auto &ch : c->kc_chunks) { ch.bases.release(); ch.quals.release(); ch.offsets.release(); ch.rc.release(); ch.pin.release(); }
     c->kc_chunks.clear();
-    c->d_kc_bloom.release(); c->d_kc_table.release(); c->d_kc_ctr.release(); c->d_kc_out_k.release(); c->d_kc_out_c.release(); c->d_kp_small.release(); c->d_kp_entries.release(); c->d_kp_entries1.release();
+    c->d_kc_table.release(); c->d_kc_ctr.release(); c->d_kc_out_k.release(); c->d_kc_out_c.release(); c->d_kp_small.release(); c->d_kp_entries.release(); c->d_kp_entries1.release();
     for (int i = 0; i < 2; ++i) {
         for (auto &ev : c->lane_ev[i]) if (ev) cudaEventDestroy(ev);
         if (c->lane_stream[i]) cudaStreamDestroy(c->lane_stream[i]);

@@ -606,7 +606,13 @@ static KpArgs kp_args(const KmerPartPlan &pl, const SeqBatch &in, const uint8_t 
     return a;
 }
 
-bool kmer_part_supported(int k, uint32_t max_len) { return 2 * k - kKmerPartBits + 1 <= 32 && 2 * k > kKmerPartBits && max_len < 60000u; }
+bool kmer_part_two_level(int k, uint32_t max_len);
+// 32-bit entries need 2k - 13 + 1 <= 32; the scatter kernels keep whole reads in shared memory: up to 24576 bases with
+// the two-level scatter (k <= 19), up to 9000 with the one-level scatter (k = 21)
+bool kmer_part_supported(int k, uint32_t max_len) {
+    if (!(2 * k - kKmerPartBits + 1 <= 32 && 2 * k > kKmerPartBits)) return false;
+    return kmer_part_two_level(k, max_len) || max_len <= 9000u;
+}
 
 void launch_kmer_hist(const KmerPartPlan &pl, const SeqBatch &in, const uint8_t *rc, int k, int min_bq, int sm_count, cudaStream_t st) {
     if (in.n == 0) return;
@@ -638,7 +644,7 @@ void launch_kmer_scatter(const KmerPartPlan &pl, const SeqBatch &in, const uint8
 }
 
 bool kmer_part_two_level(int k, uint32_t max_len) {
-    return 2 * k - kKp1Bits + 1 <= 32 && max_len >= 1u && kKp1TileCap / max_len >= 1u && kKmerPartBits - kKp1Bits <= 6;
+    return 2 * k - kKp1Bits + 1 <= 32 && max_len >= 1u && max_len <= 24000u && kKmerPartBits - kKp1Bits <= 6;
 }
 
 void launch_kmer_scatter1(const KmerPartPlan &pl, uint32_t *entries1, uint32_t *cursor1, const SeqBatch &in, const uint8_t *rc, int k,

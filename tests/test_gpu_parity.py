@@ -546,3 +546,23 @@ def test_count_split_kmers_other_algorithms(env, expect):
         assert got["stats"]["partitions"] == 0
     finally:
         c2.close()
+
+
+def test_count_split_kmers_long_reads(ctx):
+    """reads that fill a level-1 tile on their own, and reads longer than the partitioned kernels support (single table)"""
+    from savont_b200 import _lib
+    rng = random.Random(77)
+    root = rand_seq(rng, 30000)
+    ctx.set_params(_lib.default_params())
+    for L, expect_parts in ((20000, 8192), (26000, 0)):
+        base = (root * 3)[:L]
+        reads = [mutate(rng, base, 40, 10, 10) for _ in range(6)] + [rand_seq(rng, 400), b"ACGT"]
+        comp = bytes.maketrans(b"ACGT", b"TGCA")
+        reads[1] = reads[1].translate(comp)[::-1]; reads[3] = reads[3].translate(comp)[::-1]
+        quals = [bytes(33 + rng.choice([20, 30, 40]) for _ in range(len(s))) for s in reads]
+        bases, offs = O.concat(reads); qcat, _ = O.concat(quals)
+        want = O.count_split_kmers(bases, qcat, offs)
+        got = ctx.count_split_kmers(bases, qcat, offs)
+        assert_same(got, want, KMER_KEYS, f"long reads {L}")
+        assert got["stats"]["partitions"] == expect_parts and got["stats"]["n_distinct"] == want["n_distinct"]
+        assert len(want["kmers"]) > 10000
