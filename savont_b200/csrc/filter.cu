@@ -292,6 +292,7 @@ filter_kernel(SeqBatch in, SketchOut sk, AsvIndex ix, PairPool pool, FilterOut o
                                 const uint32_t sh = 16u * (a & 1u);
                                 acc[a >> 1] = (acc[a >> 1] & ~(0xffffu << sh)) | (stash << sh);
                             }
+                            __syncwarp();          // the next candidate's counter may share this 32-bit word (warp-uniform branch)
                         }
                     }
                 }

@@ -71,3 +71,55 @@ def test_gpu_reproduces_golden(g):
     for key in ("status", "best_nm", "class_offsets", "class_asv", "totals"):
         assert np.array_equal(rc[key], g[key]), key
     ctx.close()
+
+
+# ---- the two stages in front of Stage 7 on the same real reads (tests/golden/zymo_stage1.npz, make_golden_stage1.py) ----
+G1 = os.path.join(os.path.dirname(__file__), "golden", "zymo_stage1.npz")
+
+
+@pytest.fixture(scope="module")
+def g1():
+    return np.load(G1)
+
+
+def _ids(g1):
+    o = g1["id_offsets"].astype(np.int64)
+    return [bytes(g1["id_bytes"][o[i]:o[i + 1]]).decode() for i in range(len(o) - 1)]
+
+
+def test_stage1_fixture_shape(g1):
+    ids = _ids(g1)
+    assert len(ids) == 400 and int(g1["rc"].sum()) == 205
+    assert all((i.split()[-1] == "rc") == bool(r) for i, r in zip(ids, g1["rc"]))     # src/seq_parse.rs:361-369
+    assert set(g1["flt_status"].tolist()) == {0, 5, 7}
+
+
+def test_oracle_reproduces_stage1_golden(g1):
+    kc = O.count_split_kmers(g1["read_bases"], g1["read_quals"], g1["read_offsets"], rc=g1["rc"])
+    assert len(kc["kmers"]) == int(g1["kc_n"]) and kc["n_distinct"] == int(g1["kc_n_distinct"])
+    assert _digest(kc["kmers"], kc["counts"]) == str(g1["kc_digest"])
+    th, hf = O.high_freq_kmers(kc["kmers"], kc["counts"])
+    assert th == int(g1["hf_thresh"]) and len(hf) == int(g1["hf_n"])
+    flt = O.twin_reads_filter(O.default_params(band=64), O.read_filter(1100, 2000, 98.0), g1["snpmers"], g1["hf_set"],
+                              g1["read_bases"], g1["read_quals"], g1["read_offsets"], _ids(g1))
+    for key in ("status", "order", "est_id", "n_solid_mini", "n_solid_snp"):
+        assert np.array_equal(flt[key], g1["flt_" + {"n_solid_mini": "solid_mini", "n_solid_snp": "solid_snp"}.get(key, key)]), key
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_stage1_golden(g1):
+    from savont_b200 import _lib, api
+    ctx = _lib.Context(0, _lib.default_params(band=64))
+    ctx.load_snpmers(g1["snpmers"])
+    reads = dict(bases=g1["read_bases"], quals=g1["read_quals"], offsets=g1["read_offsets"], ids=_ids(g1))
+    kc = api.read_to_split_kmers(ctx, reads)                                         # rc flags from the ids
+    assert len(kc["kmers"]) == int(g1["kc_n"]) and kc["n_distinct"] == int(g1["kc_n_distinct"])
+    assert _digest(kc["kmers"], kc["counts"]) == str(g1["kc_digest"])
+    assert np.array_equal(kc["kmers"][:16], g1["kc_head"]) and np.array_equal(kc["counts"][:16], g1["kc_head_counts"])
+    th, hf = api.high_freq_kmers(kc["kmers"], kc["counts"])
+    assert th == int(g1["hf_thresh"]) and len(hf) == int(g1["hf_n"])
+    sel = api.twin_reads_from_snpmers(ctx, reads, api.Cli(band=64), high_freq_kmers=g1["hf_set"])    # Cli defaults 1100 / 2000 / 98.0
+    assert np.array_equal(sel["status"], g1["flt_status"]) and np.array_equal(sel["order"], g1["flt_order"])
+    assert np.array_equal(sel["est_id"].view(np.uint64), g1["flt_est_id"].view(np.uint64))
+    assert np.array_equal(sel["n_solid_mini"], g1["flt_solid_mini"]) and np.array_equal(sel["n_solid_snp"], g1["flt_solid_snp"])
+    ctx.close()
