@@ -209,6 +209,25 @@ def run_kmercount(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
 
 
+def _bind_to_gpu_numa_node(gpu_index):
+    """pin this rank (and therefore the pinned host buffers it first-touches) to the CPU cores next to its GPU, so that
+    eight ranks do not pull their H2D traffic across the socket interconnect"""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def run_b200(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -220,6 +239,7 @@ def run_b200(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=dev)
+    numa = _bind_to_gpu_numa_node(local_rank) if world > 1 else None
 
     w = _workload(args)
     n_reads = args.reads
@@ -373,6 +393,7 @@ def run_b200(args, rank, world, local_rank):
         "gpu_launches": int(sum(s["kernel_launches"] for s in stats)),
         "clocks": clocks,
         "assigned_frac": float(got["totals"][0]) / max(n_reads * (world if world > 1 else 1), 1),
+        "host_cores_per_rank": numa,
         "gen_s": t_gen,
     }
     if not args.no_cpu_baseline and world == 1:

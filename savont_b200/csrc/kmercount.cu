@@ -532,22 +532,32 @@ kmer_count_part_kernel(KpArgs a) {
             if (threadIdx.x == 0) { s_fill = 0u; s_over = 0u; }
             __syncthreads();
             volatile uint32_t *vkey = s_key;
-            for (unsigned long long i = threadIdx.x; i < n; i += blockDim.x) {
+            // four independent entry loads per thread in flight (the kernel is bound by the latency of these streaming loads)
+            for (unsigned long long i = threadIdx.x; i < n; i += 4ull * blockDim.x) {
                 if (*(volatile uint32_t *)&s_over) break;
-                const uint32_t e = __ldg(a.entries + e0 + i);
-                const uint32_t key = e & 0x7fffffffu, flag = e >> 31;
-                if ((key & (R - 1u)) != r) continue;
-                uint32_t slot = (key * 0x9E3779B1u) >> 18;                // 14 bits
-                for (uint32_t probes = 0; probes < kKpSlots; ++probes) {
-                    const uint32_t v = vkey[slot];
-                    bool mine = v == key;
-                    if (!mine && v == 0xffffffffu) {
-                        const uint32_t old = atomicCAS(&s_key[slot], 0xffffffffu, key);
-                        if (old == 0xffffffffu) { if (atomicAdd(&s_fill, 1u) >= a.smem_fill_limit) s_over = 1u; mine = true; }
-                        else mine = old == key;
+                uint32_t ev[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const unsigned long long j = i + (unsigned long long)u * blockDim.x;
+                    ev[u] = j < n ? __ldg(a.entries + e0 + j) : 0xffffffffu;       // no entry has all remainder bits set
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t e = ev[u];
+                    const uint32_t key = e & 0x7fffffffu, flag = e >> 31;
+                    if (e == 0xffffffffu || (key & (R - 1u)) != r) continue;
+                    uint32_t slot = (key * 0x9E3779B1u) >> 18;                // 14 bits
+                    for (uint32_t probes = 0; probes < kKpSlots; ++probes) {
+                        const uint32_t v = vkey[slot];
+                        bool mine = v == key;
+                        if (!mine && v == 0xffffffffu) {
+                            const uint32_t old = atomicCAS(&s_key[slot], 0xffffffffu, key);
+                            if (old == 0xffffffffu) { if (atomicAdd(&s_fill, 1u) >= a.smem_fill_limit) s_over = 1u; mine = true; }
+                            else mine = old == key;
+                        }
+                        if (mine) { atomicAdd(&s_cnt[2u * slot + flag], 1u); break; }
+                        slot = (slot + 1u) & (kKpSlots - 1u);
                     }
-                    if (mine) { atomicAdd(&s_cnt[2u * slot + flag], 1u); break; }
-                    slot = (slot + 1u) & (kKpSlots - 1u);
                 }
             }
             __syncthreads();
