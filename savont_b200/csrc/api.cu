@@ -579,9 +579,9 @@ static int stage_filter(Context *c, Batch &b, int strand_mode) {
     if (b.pair_cap < 2u * per * (uint32_t)n + 1024u) b.pair_cap = 2u * per * (uint32_t)n + 1024u;
     DeviceParams dp = c->dp; dp.strand_mode = strand_mode;
     TRY(ensure_pair_pool(b));
-    launch_filter(seq_view(b), sketch_view(b, false), index_view(c), pool_view(b), filter_view(b), dp, c->sm_count, c->stream);
+    c->last_stats.kernel_launches += (uint64_t)launch_filter(seq_view(b), sketch_view(b, false), index_view(c), pool_view(b), filter_view(b), dp,
+                                                             c->sm_count, c->stream);
     CK(cudaGetLastError());
-    c->last_stats.kernel_launches += 1;
     return 0;
 }
 

@@ -204,8 +204,8 @@ uint32_t sketch_grid(uint32_t n, uint32_t max_len, bool use_table, const DeviceP
 void launch_est_id(const SeqBatch &in, const uint8_t *status, const uint8_t *flatq, const double *phred_table,
                    double *est_id, cudaStream_t st);
 void launch_codes(const uint8_t *bases, uint8_t *codes, uint64_t total, cudaStream_t st);
-void launch_filter(const SeqBatch &in, const SketchOut &sk, const AsvIndex &ix, const PairPool &pool, const FilterOut &out,
-                   const DeviceParams &p, int sm_count, cudaStream_t st);
+int launch_filter(const SeqBatch &in, const SketchOut &sk, const AsvIndex &ix, const PairPool &pool, const FilterOut &out,
+                  const DeviceParams &p, int sm_count, cudaStream_t st);   // returns the number of kernels launched
 void launch_align_nm(const SeqBatch &in, const uint2 *read_planes, const AsvIndex &ix, const uint32_t *pair_read,
                      const uint32_t *pair_asv, const uint8_t *pair_strand, const uint32_t *n_pairs_dev, uint32_t n_pairs_max,
                      const uint32_t *err, const AlignOut &out, const DeviceParams &p, int sm_count, cudaStream_t st);

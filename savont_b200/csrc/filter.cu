@@ -15,6 +15,8 @@
 //      (src/alignment.rs:1805-1811, :1829);
 //   4. candidates with ratio <= threshold and the minimum SNPmer mismatch count are emitted, in
 //      ASV order, into a chunk of the pair pool (one atomic bump per read).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace sb {
@@ -36,7 +38,7 @@ struct FilterSmem {
 // `same` those with equal orientation flags; every ASV passing the containment test is kept (0 SNPmer mismatches).
 template <bool LOWPOLY>
 __global__ void __launch_bounds__(kFilterWarps * 32)
-filter_kernel(SeqBatch in, SketchOut sk, AsvIndex ix, PairPool pool, FilterOut out, DeviceParams p, FilterSmem lay) {
+filter_kernel(SeqBatch in, SketchOut sk, AsvIndex ix, PairPool pool, FilterOut out, DeviceParams p, FilterSmem lay, int redo_only) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -54,6 +56,7 @@ filter_kernel(SeqBatch in, SketchOut sk, AsvIndex ix, PairPool pool, FilterOut o
     if (*out.err & kErrSnpPool) return;          // the sketch ran out of pool space: the host grows it and re-runs the batch
 
     for (uint32_t seq = blockIdx.x * kFilterWarps + warp; seq < in.n; seq += gridDim.x * kFilterWarps) {
+        if (redo_only && out.cand_status[seq] != 0xFE) continue;       // second launch after filter_compact_kernel (kCandRedo)
         if (sk.status[seq] != 0) {
             if (lane == 0) { out.cand_status[seq] = sk.status[seq]; out.pair_start[seq] = 0; out.pair_cnt[seq] = 0; out.low_mm[seq] = 0; }
             continue;
@@ -358,11 +361,269 @@ filter_kernel(SeqBatch in, SketchOut sk, AsvIndex ix, PairPool pool, FilterOut o
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Compact variant for large ASV sets (candidate_mode 0): the dense kernel above keeps one 16-bit mismatch counter per
+// ASV and two bitmaps per warp in shared memory -- 10.6 KB per warp at 5000 ASVs, which cuts the occupancy to 18 % and
+// makes every read clear and scan structures sized by A.  A read only ever meets the ASVs of its SNPmer buckets (tens),
+// so this kernel counts mismatches in a small per-warp hash table (asv -> mismatches).  A read that meets more distinct
+// ASVs than the table holds is marked kCandRedo and handled afterwards by the dense kernel (redo_only = 1).
+// Same results: candidates are evaluated group by group in ascending mismatch order, the kept ones are emitted in
+// ascending ASV order.
+// ------------------------------------------------------------------------------------------------
+constexpr uint8_t kCandRedo = 0xFE;
+constexpr uint32_t kCompactEmpty = 0xffffffffu;
+
+struct CompactSmem {
+    uint32_t rcap;       // read set capacity (power of two)
+    uint32_t ccap;       // candidate table capacity (power of two)
+    uint32_t climit;     // distinct candidates before the read is handed to the dense kernel
+    __host__ __device__ size_t per_warp() const { return ((size_t)rcap * 8u + (size_t)ccap * 16u + 15u) & ~(size_t)15u; }
+};
+
+__global__ void __launch_bounds__(kFilterWarps * 32)
+filter_compact_kernel(SeqBatch in, SketchOut sk, AsvIndex ix, PairPool pool, FilterOut out, DeviceParams p, CompactSmem lay) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint8_t *wbase = smem + (size_t)warp * lay.per_warp();
+    unsigned long long *rset = reinterpret_cast<unsigned long long *>(wbase);
+    uint32_t *ckey = reinterpret_cast<uint32_t *>(wbase + (size_t)lay.rcap * 8u);   // asv id or kCompactEmpty
+    uint32_t *cval = ckey + lay.ccap;                                               // SNPmer mismatches
+    uint32_t *clist = cval + lay.ccap;                                              // occupied slots, then kept slots
+    uint32_t *cstash = clist + lay.ccap;                                            // (m | strand << 15) of kept candidates
+    const uint32_t rmask = lay.rcap - 1u, cmask = lay.ccap - 1u;
+    const uint32_t rshift = 64u - (uint32_t)__popc(rmask);
+    const int mid_shift = p.k - 1;
+    if (*out.err & kErrSnpPool) return;
+
+    for (uint32_t seq = blockIdx.x * kFilterWarps + warp; seq < in.n; seq += gridDim.x * kFilterWarps) {
+        if (sk.status[seq] != 0) {
+            if (lane == 0) { out.cand_status[seq] = sk.status[seq]; out.pair_start[seq] = 0; out.pair_cnt[seq] = 0; out.low_mm[seq] = 0; }
+            continue;
+        }
+        for (uint32_t i = lane; i < lay.rcap; i += 32u) rset[i] = kEmpty64;
+        for (uint32_t i = lane; i < lay.ccap; i += 32u) { ckey[i] = kCompactEmpty; cval[i] = 0u; }
+        __syncwarp();
+
+        // ---- 1. read minimizer set (as in the dense kernel) ----
+        const uint64_t off = in.offsets[seq];
+        const uint64_t mo = mini_slot_off(off, seq, (uint32_t)p.mini_spacing);
+        const uint32_t nmini = sk.mini_cnt[seq];
+        uint32_t nR = 0;
+        for (uint32_t t0 = 0; t0 < nmini; t0 += 128u) {
+            unsigned long long vv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t t = t0 + 32u * u + lane;
+                vv[u] = (t < nmini) ? sk.mini_kmer[mo + t] : kEmpty64;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned long long v = vv[u];
+                bool inserted = false;
+                if (v != kEmpty64) {
+                    const unsigned long long key = v & ~kFwdBit;
+                    uint32_t slot = hash_slot(key, rshift);
+                    while (true) {
+                        const unsigned long long old = atomicCAS(&rset[slot], (unsigned long long)kEmpty64, v);
+                        if (old == kEmpty64) { inserted = true; break; }
+                        if ((old & ~kFwdBit) == key) {
+                            if (v & kFwdBit) atomicOr(&rset[slot], (unsigned long long)kFwdBit);
+                            break;
+                        }
+                        slot = (slot + 1u) & rmask;
+                    }
+                }
+                nR += __popc(__ballot_sync(0xffffffffu, inserted));
+            }
+        }
+        __syncwarp();
+
+        // ---- 2. SNPmer buckets -> candidate table (asv -> mismatches) ----
+        uint32_t n_distinct = 0;
+        bool overflow = false;
+        const uint32_t ns = sk.snp_cnt[seq], s0 = sk.snp_start[seq];
+        for (uint32_t t0 = 0; t0 < ns && !overflow; t0 += 32u) {
+            const uint32_t t = t0 + lane;
+            uint32_t bstart = 0, blen = 0, mid = 0;
+            if (t < ns && ix.idx_keys != nullptr) {
+                const uint64_t q = sk.snp_kmer[s0 + t];
+                const uint64_t sp = q & p.split_mask;
+                mid = (uint32_t)(q >> mid_shift) & 3u;
+                uint32_t slot = hash_slot(sp, ix.idx_shift);
+                while (true) {
+                    const uint64_t key = __ldg(ix.idx_keys + slot);
+                    if (key == sp) { const uint2 v = __ldg(ix.idx_vals + slot); bstart = v.x; blen = v.y; break; }
+                    if (key == kEmpty64) break;
+                    slot = (slot + 1u) & ix.idx_mask;
+                }
+            }
+            uint32_t incl = blen;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += y; }
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            const uint32_t packed_owner = (bstart - (incl - blen));
+            for (uint32_t f0 = 0; f0 < total; f0 += 32u) {
+                const uint32_t f = f0 + lane;
+                uint32_t lo = 0;
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1) {
+                    const uint32_t probe = __shfl_sync(0xffffffffu, incl, (int)(lo + step - 1u));
+                    if (probe <= f) lo += (uint32_t)step;
+                }
+                const uint32_t own = lo < 32u ? lo : 31u;
+                const uint32_t ebase = __shfl_sync(0xffffffffu, packed_owner, (int)own);
+                const uint32_t md = __shfl_sync(0xffffffffu, mid, (int)own);
+                bool fresh = false;
+                if (f < total) {
+                    const uint32_t ent = __ldg(ix.idx_entries + (uint32_t)(ebase + f));
+                    const uint32_t a = ent >> 2;
+                    uint32_t slot = (a * 0x9E3779B1u) >> (32u - (uint32_t)__popc(cmask));
+                    for (uint32_t probes = 0; probes < lay.ccap; ++probes) {
+                        const uint32_t v = *(volatile uint32_t *)&ckey[slot];
+                        bool mine = v == a;
+                        if (!mine && v == kCompactEmpty) {
+                            const uint32_t old = atomicCAS(&ckey[slot], kCompactEmpty, a);
+                            if (old == kCompactEmpty) { fresh = true; mine = true; }
+                            else mine = old == a;
+                        }
+                        if (mine) { if ((ent & 3u) != md) atomicAdd(&cval[slot], 1u); break; }
+                        slot = (slot + 1u) & cmask;
+                    }
+                }
+                n_distinct += __popc(__ballot_sync(0xffffffffu, fresh));
+                if (n_distinct > lay.climit) { overflow = true; break; }       // warp-uniform
+            }
+        }
+        __syncwarp();
+        if (overflow) {                                                         // too many distinct candidate ASVs: dense kernel
+            if (lane == 0) { out.cand_status[seq] = kCandRedo; out.pair_start[seq] = 0; out.pair_cnt[seq] = 0; out.low_mm[seq] = 0; }
+            continue;
+        }
+        // occupied slots -> clist (any order)
+        uint32_t n_c = 0;
+        for (uint32_t i0 = 0; i0 < lay.ccap; i0 += 32u) {
+            const bool occ = ckey[i0 + lane] != kCompactEmpty;
+            const uint32_t bal = __ballot_sync(0xffffffffu, occ);
+            if (occ) clist[n_c + (uint32_t)__popc(bal & lt_mask)] = i0 + lane;
+            n_c += (uint32_t)__popc(bal);
+        }
+        __syncwarp();
+
+        // ---- 3. evaluate candidates, lowest SNPmer mismatch count first (src/alignment.rs:1829-1843) ----
+        uint32_t lowest = 0xffffffffu, n_low = 0, cur = 0;
+        bool any_scored = false;
+        while (true) {
+            uint32_t round_min = 0xffffffffu;
+            for (uint32_t i = lane; i < n_c; i += 32u) {
+                const uint32_t mm = cval[clist[i]];
+                if (mm >= cur && mm < round_min) round_min = mm;
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                const uint32_t y = __shfl_xor_sync(0xffffffffu, round_min, d);
+                round_min = y < round_min ? y : round_min;
+            }
+            if (round_min == 0xffffffffu) break;
+            for (uint32_t ci = 0; ci < n_c; ++ci) {
+                const uint32_t slot = clist[ci];
+                const uint32_t mm = cval[slot];
+                if (mm != round_min) continue;
+                const uint32_t a = ckey[slot];
+                const uint32_t m0 = __ldg(ix.mset_off + a);
+                const uint32_t nA = __ldg(ix.mset_off + a + 1) - m0;
+                uint32_t m = 0, same = 0;
+                for (uint32_t t0 = 0; t0 < nA; t0 += 32u) {
+                    const uint32_t t = t0 + lane;
+                    bool found = false, sm = false;
+                    if (t < nA) {
+                        const uint64_t v = __ldg(ix.mset + m0 + t);
+                        const uint64_t key = v & ~kFwdBit;
+                        uint32_t sl = hash_slot(key, rshift);
+                        while (true) {
+                            const uint64_t r = rset[sl];
+                            if (r == kEmpty64) break;
+                            if ((r & ~kFwdBit) == key) { found = true; sm = ((r ^ v) >> 63) == 0ull; break; }
+                            sl = (sl + 1u) & rmask;
+                        }
+                    }
+                    m += __popc(__ballot_sync(0xffffffffu, found));
+                    same += __popc(__ballot_sync(0xffffffffu, found && sm));
+                }
+                if (m == 0u) continue;                                        // src/alignment.rs:1801-1803
+                const uint32_t mn = nR < nA ? nR : nA;
+                if ((double)m / (double)mn < p.min_frac) continue;            // :1805-1808
+                any_scored = true;
+                const double ratio = (double)mm / (double)m / (double)p.c;    // :1811
+                if (ratio <= p.ratio_thresh) {                                // :1829-1833
+                    if (lane == 0) {
+                        const uint32_t opp = m - same;
+                        cstash[n_low] = (m & 0x7fffu) | ((opp > same) ? 0x8000u : 0u);
+                        cval[slot] = 0x80000000u | n_low;                     // kept marker (mm of a kept ASV = lowest)
+                    }
+                    ++n_low;
+                    __syncwarp();
+                }
+            }
+            if (n_low) { lowest = round_min; break; }
+            cur = round_min + 1u;
+        }
+        __syncwarp();
+
+        // ---- 4. emit the kept candidates in ascending ASV order ----
+        uint8_t status = 0;
+        uint32_t total = 0, start = 0;
+        if (!any_scored) status = 1;
+        else if (n_low == 0u) status = 2;
+        else {
+            const uint32_t per = (p.strand_mode == 1) ? 2u : 1u;
+            total = n_low * per;
+            if (lane == 0) start = atomicAdd(pool.counter, total);
+            start = __shfl_sync(0xffffffffu, start, 0);
+            if ((uint64_t)start + total > pool.cap) {
+                if (lane == 0) atomicOr(out.err, kErrPairPool);
+                total = 0;
+            } else {
+                for (uint32_t i = lane; i < n_c; i += 32u) {
+                    const uint32_t slot = clist[i];
+                    const uint32_t v = cval[slot];
+                    if (!(v & 0x80000000u)) continue;
+                    const uint32_t a = ckey[slot];
+                    uint32_t rank = 0;                                        // kept ASVs with a smaller id
+                    for (uint32_t j = 0; j < n_c; ++j) {
+                        const uint32_t sj = clist[j];
+                        if ((cval[sj] & 0x80000000u) && ckey[sj] < a) ++rank;
+                    }
+                    const uint32_t stash = cstash[v & 0x7fffffffu];
+                    const uint32_t o = start + rank * per;
+                    if (per == 1u) {
+                        pool.read[o] = seq; pool.asv[o] = a; pool.mini[o] = stash & 0x7fffu; pool.strand[o] = (uint8_t)(stash >> 15);
+                    } else {
+                        pool.read[o] = seq; pool.asv[o] = a; pool.mini[o] = stash & 0x7fffu; pool.strand[o] = 0;
+                        pool.read[o + 1] = seq; pool.asv[o + 1] = a; pool.mini[o + 1] = stash & 0x7fffu; pool.strand[o + 1] = 1;
+                    }
+                }
+            }
+        }
+        if (lane == 0) {
+            out.cand_status[seq] = status;
+            out.pair_start[seq] = start;
+            out.pair_cnt[seq] = total;
+            out.low_mm[seq] = (status == 0) ? lowest : 0u;
+        }
+        __syncwarp();
+    }
+}
+
 static uint32_t next_pow2(uint32_t x) { uint32_t p = 1; while (p < x) p <<= 1; return p; }
 
-void launch_filter(const SeqBatch &in, const SketchOut &sk, const AsvIndex &ix, const PairPool &pool, const FilterOut &out,
-                   const DeviceParams &p, int sm_count, cudaStream_t st) {
-    if (in.n == 0) return;
+static uint32_t env_u32(const char *name, uint32_t dflt) {
+    const char *e = getenv(name);
+    return (e && atoi(e) > 0) ? (uint32_t)atoi(e) : dflt;
+}
+
+static void launch_filter_dense(const SeqBatch &in, const SketchOut &sk, const AsvIndex &ix, const PairPool &pool, const FilterOut &out,
+                                const DeviceParams &p, int sm_count, int redo_only, cudaStream_t st) {
     FilterSmem lay;
     const uint32_t max_mini = in.max_len / (uint32_t)p.mini_spacing + 2u;
     lay.rcap = next_pow2(2u * max_mini + 2u);
@@ -382,8 +643,38 @@ void launch_filter(const SeqBatch &in, const SketchOut &sk, const AsvIndex &ix, 
     uint32_t grid = (uint32_t)(sm_count * ctas_per_sm);
     const uint32_t need = (in.n + kFilterWarps - 1) / kFilterWarps;
     if (grid > need) grid = need;
-    if (lowpoly) filter_kernel<true><<<grid, kFilterWarps * 32, smem, st>>>(in, sk, ix, pool, out, p, lay);
-    else filter_kernel<false><<<grid, kFilterWarps * 32, smem, st>>>(in, sk, ix, pool, out, p, lay);
+    if (lowpoly) filter_kernel<true><<<grid, kFilterWarps * 32, smem, st>>>(in, sk, ix, pool, out, p, lay, redo_only);
+    else filter_kernel<false><<<grid, kFilterWarps * 32, smem, st>>>(in, sk, ix, pool, out, p, lay, redo_only);
+}
+
+// Large ASV sets go through the compact kernel first and the dense kernel picks up the reads it could not hold
+// (SAVONT_B200_FILTER_COMPACT_MIN_ASV / _LIMIT override the switch-over point and the table size: tests).
+int launch_filter(const SeqBatch &in, const SketchOut &sk, const AsvIndex &ix, const PairPool &pool, const FilterOut &out,
+                  const DeviceParams &p, int sm_count, cudaStream_t st) {
+    if (in.n == 0) return 0;
+    static const uint32_t min_asv = env_u32("SAVONT_B200_FILTER_COMPACT_MIN_ASV", 1024u);
+    static const uint32_t climit = env_u32("SAVONT_B200_FILTER_COMPACT_LIMIT", 96u);
+    if (p.candidate_mode == 1 || ix.n_asv < min_asv) {
+        launch_filter_dense(in, sk, ix, pool, out, p, sm_count, 0, st);
+        return 1;
+    }
+    CompactSmem lay;
+    const uint32_t max_mini = in.max_len / (uint32_t)p.mini_spacing + 2u;
+    lay.rcap = next_pow2(2u * max_mini + 2u);
+    if (lay.rcap < 64u) lay.rcap = 64u;
+    lay.climit = climit;
+    lay.ccap = next_pow2(2u * climit + 64u);
+    const size_t smem = lay.per_warp() * kFilterWarps;
+    cudaFuncSetAttribute(filter_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int ctas_per_sm = (int)(220u * 1024u / (smem + 1024u));
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    if (ctas_per_sm > 12) ctas_per_sm = 12;
+    uint32_t grid = (uint32_t)(sm_count * ctas_per_sm);
+    const uint32_t need = (in.n + kFilterWarps - 1) / kFilterWarps;
+    if (grid > need) grid = need;
+    filter_compact_kernel<<<grid, kFilterWarps * 32, smem, st>>>(in, sk, ix, pool, out, p, lay);
+    launch_filter_dense(in, sk, ix, pool, out, p, sm_count, 1, st);
+    return 2;
 }
 
 }  // namespace sb

@@ -566,3 +566,27 @@ def test_count_split_kmers_long_reads(ctx):
         assert_same(got, want, KMER_KEYS, f"long reads {L}")
         assert got["stats"]["partitions"] == expect_parts and got["stats"]["n_distinct"] == want["n_distinct"]
         assert len(want["kmers"]) > 10000
+
+
+def test_candidates_large_asv_set(ctx):
+    """more than 1024 ASVs: the compact candidate table of the filter (dense kernel only for reads that overflow it)"""
+    from savont_b200 import _lib
+    w = _make_workload("pooled", n_roots=130, n_samples=3)            # 1300 ASVs
+    r = w.reads(2500)
+    gp, op = _params(_lib, band=w.band)
+    ctx.set_params(gp); ctx.load_snpmers(w.snpmers); ctx.load_asvs(w.asv_bases, w.asv_offsets)
+    orc = O.Oracle(op, w.snpmers); orc.load_asvs(w.asv_bases, w.asv_offsets)
+    assert w.n_asv > 1024
+    assert_same(ctx.find_candidates(r["bases"], r["quals"], r["offsets"]), orc.find_candidates(r["bases"], r["quals"], r["offsets"]),
+                CAND_KEYS, "candidates A=1300")
+    want = orc.map_reads(r["bases"], r["quals"], r["offsets"], file_idx=r["file_idx"], n_samples=3)
+    got = ctx.map_reads(r["bases"], r["quals"], r["offsets"], file_idx=r["file_idx"], n_samples=3)
+    assert_same(got, want, MAP_KEYS, "map_reads A=1300")
+    assert got["stats"]["kernel_launches"] >= 9                       # sketch, compact filter + dense redo, align, assign x5
+    gp2, op2 = _params(_lib, band=w.band, strand_mode=1)
+    ctx.set_params(gp2); ctx.load_asvs(w.asv_bases, w.asv_offsets)
+    orc2 = O.Oracle(op2, w.snpmers); orc2.load_asvs(w.asv_bases, w.asv_offsets)
+    assert_same(ctx.map_reads(r["bases"][:int(r["offsets"][600])], r["quals"][:int(r["offsets"][600])], r["offsets"][:601]),
+                orc2.map_reads(r["bases"][:int(r["offsets"][600])], r["quals"][:int(r["offsets"][600])], r["offsets"][:601]), MAP_KEYS,
+                "A=1300 both strands")
+    ctx.set_params(_lib.default_params())
