@@ -653,7 +653,7 @@ int launch_filter(const SeqBatch &in, const SketchOut &sk, const AsvIndex &ix, c
                   const DeviceParams &p, int sm_count, cudaStream_t st) {
     if (in.n == 0) return 0;
     static const uint32_t min_asv = env_u32("SAVONT_B200_FILTER_COMPACT_MIN_ASV", 1024u);
-    static const uint32_t climit = env_u32("SAVONT_B200_FILTER_COMPACT_LIMIT", 96u);
+    static const uint32_t climit = env_u32("SAVONT_B200_FILTER_COMPACT_LIMIT", 48u);
     if (p.candidate_mode == 1 || ix.n_asv < min_asv) {
         launch_filter_dense(in, sk, ix, pool, out, p, sm_count, 0, st);
         return 1;
@@ -663,7 +663,7 @@ int launch_filter(const SeqBatch &in, const SketchOut &sk, const AsvIndex &ix, c
     lay.rcap = next_pow2(2u * max_mini + 2u);
     if (lay.rcap < 64u) lay.rcap = 64u;
     lay.climit = climit;
-    lay.ccap = next_pow2(2u * climit + 64u);
+    lay.ccap = next_pow2(2u * climit + 32u);        // one flattened step can add 32 entries before the limit is checked
     const size_t smem = lay.per_warp() * kFilterWarps;
     cudaFuncSetAttribute(filter_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int ctas_per_sm = (int)(220u * 1024u / (smem + 1024u));
