@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsavont_b200.so")
-SOURCES = ["sketch.cu", "sketch_fast.cu", "prefilter.cu", "kmercount.cu", "filter.cu", "align.cu", "assign.cu", "api.cu"]
+SOURCES = ["sketch.cu", "sketch_fast.cu", "prefilter.cu", "kmercount.cu", "filter.cu", "align.cu", "assign.cu", "api.cu", "api_kmer.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall"]
 
@@ -39,7 +39,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     os.makedirs(LIB_DIR, exist_ok=True)
     nvcc = _nvcc()
-    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "sketch_dev.cuh"), os.path.join(HERE, "..", "include", "savont_b200.h")]
+    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "sketch_dev.cuh"), os.path.join(CSRC, "api_internal.cuh"), os.path.join(HERE, "..", "include", "savont_b200.h")]
     env = dict(os.environ)
     # the image exports CC/CXX pointing at a gcc without a full install; let nvcc find /usr/bin/g++
     ccbin = shutil.which("g++") or "/usr/bin/g++"

@@ -1,0 +1,173 @@
+// api_internal.cuh -- types and helpers shared by the host-side translation units of libsavont_b200.so
+// (api.cu: the read-vs-ASV path; api_kmer.cu: Stage 1 split-k-mer counting).  Not part of the ABI.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <string>
+#include <vector>
+
+#include "../../include/savont_b200.h"
+#include "common.cuh"
+
+namespace sb {
+
+
+std::string &last_error_ref();          // thread-local message behind savont_b200_last_error()
+
+inline int fail(int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    last_error_ref() = buf;
+    return code;
+}
+
+#define CK(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e__ = (call);                                                                             \
+        if (e__ != cudaSuccess)                                                                               \
+            return fail(SAVONT_B200_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,            \
+                        cudaGetErrorString(e__));                                                             \
+    } while (0)
+#define TRY(call)                    \
+    do {                             \
+        int rc__ = (call);           \
+        if (rc__ != 0) return rc__;  \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            return fail(SAVONT_B200_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e != cudaSuccess) { p = nullptr; return fail(SAVONT_B200_ERR_NOMEM, "cudaMallocHost(%zu) failed", want); }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+// device-resident inputs, intermediates and outputs of one batch of sequences
+struct Batch {
+    DevBuf bases, quals, offsets, file_idx;
+    DevBuf solid_mini, solid_snp;                        // a4 outputs (savont_b200_twin_reads_from_snpmers)
+    DevBuf dna_words, word_offsets, snp_raw, snp_dummy;   // TwinRead input: Seq<Dna> words; Kmer48 staging; scratch counters
+    bool has_quals = false, has_file_idx = false;
+    bool twin = false;            // sequences are TwinRead.dna_seq words and the SNPmers come from the caller
+    bool force_generic = false;   // the fast sketch kernel overflowed one of its shared-memory lists on this batch
+    uint32_t n = 0, max_len = 0;
+    uint64_t total_bases = 0;
+    // sketch
+    DevBuf planes, sk_status, flatq, mini_cnt, mini_kmer, mini_pos, snp_start, snp_cnt, snp_kmer, snp_pos, est_id;
+    DevBuf spill_k, spill_p; uint32_t spill_stride = 0;
+    uint32_t snp_cap = 0;
+    DevBuf ctrs;   // u32[4]: snp pool counter, pair counter, error bits, spare
+    // filter
+    DevBuf cand_status, pair_start, pair_cnt, low_mm, p_read, p_asv, p_mini, p_strand;
+    uint32_t pair_cap = 0;
+    // align
+    DevBuf nm, asv_end, read_end;
+    // assign
+    DevBuf rstatus, best_nm, class_cnt, class_slot, class_off, class_out, scan_tmp;
+    bool mapped = false;
+    PinBuf pin_offsets;
+    void release() {
+        pin_offsets.release();
+        DevBuf *all[] = {&solid_mini, &solid_snp, &dna_words, &word_offsets, &snp_raw, &snp_dummy, &bases, &quals, &offsets, &file_idx, &planes, &sk_status, &flatq, &mini_cnt, &mini_kmer, &mini_pos,
+                         &snp_start, &snp_cnt, &snp_kmer, &snp_pos, &est_id, &spill_k, &spill_p, &ctrs, &cand_status, &pair_start, &pair_cnt,
+                         &low_mm, &p_read, &p_asv, &p_mini, &p_strand, &nm, &asv_end, &read_end, &rstatus, &best_nm,
+                         &class_cnt, &class_slot, &class_off, &class_out, &scan_tmp};
+        for (DevBuf *b : all) b->release();
+    }
+};
+
+struct Context {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    savont_b200_params params;
+    DeviceParams dp;
+    size_t batch_reads = 131072;
+
+    // tables
+    DevBuf d_rank_table; bool use_rank_table = false;
+    DevBuf d_snp_keys, d_snp_bloom; uint32_t snp_mask = 0, snp_shift = 0, bloom_shift = 0, bloom_words = 0;
+    std::vector<uint64_t> h_snpmers;
+    DevBuf d_phred;
+
+    // ASVs (replicated index)
+    std::vector<uint8_t> asv_bases_h; std::vector<uint64_t> asv_offsets_h;
+    size_t n_asv = 0; bool index_dirty = true; uint32_t max_asv_len = 0;
+    DevBuf d_idx_keys, d_idx_vals, d_idx_entries, d_mset, d_mset_off, d_asv_planes, d_asv_plane_off, d_asv_len;
+    DevBuf d_mx_keys, d_mx_vals, d_mx_entries;
+    uint32_t idx_mask = 0, idx_shift = 0, mx_mask = 0, mx_shift = 0;
+    std::vector<uint32_t> asv_len_h;
+
+    // counters [unambig A | ambig A | leq10 A | assigned | filtered | singleton S*A]
+    DevBuf d_counters; size_t counters_len = 0; int counters_samples = 0;
+
+    // K5 (Stage 1 split-k-mer counting): global table, counters, output staging, partition entries, read chunks
+    DevBuf d_kc_table, d_kc_ctr, d_kc_out_k, d_kc_out_c, d_kp_small, d_kp_entries, d_kp_entries1;
+    struct KcChunk { DevBuf bases, quals, offsets, rc; PinBuf pin; uint32_t n = 0, max_len = 0; uint64_t total = 0; bool has_quals = false, has_rc = false; };
+    std::vector<KcChunk> kc_chunks;
+    bool kc_partitioned = true;                          // SAVONT_B200_KC_PARTITIONED=0 forces the single-table algorithm
+    uint32_t kc_smem_limit = 0;                          // SAVONT_B200_KC_SMEM_LIMIT: distinct k-mers per shared-memory round (tests)
+    cudaEvent_t kc_ev_up[2] = {nullptr, nullptr}, kc_ev_done[2] = {nullptr, nullptr};
+    // a4 read filter (twin_reads_from_snpmers): options + high-frequency k-mer set
+    bool rf_on = false; ReadFilter rf{}; std::vector<uint64_t> h_hf; DevBuf d_hf_keys; uint32_t hf_mask = 0, hf_shift = 0;
+    Batch work, work2, work3, resident, asvb;
+    int resident_samples = 1;
+    PinBuf pin_small, pin_out;
+    cudaStream_t copy_stream = nullptr;          // H2D of batch i+1 overlaps the kernels of batch i
+    cudaStream_t d2h_stream = nullptr;           // D2H of batch i-1's results overlaps the kernels of batch i
+    cudaEvent_t ev_d2h[2] = {nullptr, nullptr};
+    // map_reads / map_twin_reads run consecutive batches on two internal compute lanes, so the tail of batch i's DP
+    // kernel (a partial last wave) overlaps the sketch / filter kernels of batch i+1
+    cudaStream_t lane_stream[2] = {nullptr, nullptr};
+    cudaEvent_t lane_ev[2][5] = {{nullptr}};
+    cudaEvent_t *pev = nullptr;                  // the 5 stage events enqueue_path / finish_path use (ev or lane_ev[i])
+    cudaEvent_t ev[8] = {nullptr};
+    cudaEvent_t ev_up[3] = {nullptr, nullptr, nullptr}, ev_h0[3] = {nullptr, nullptr, nullptr};
+    savont_b200_stats last_stats;
+};
+
+struct Context;
+inline uint32_t next_pow2_u32(uint64_t x) { uint32_t p = 2; while ((uint64_t)p < x) p <<= 1; return p; }
+inline uint32_t shift_for_cap(uint32_t cap) { uint32_t b = 0; while ((1u << b) < cap) ++b; return 64u - b; }
+inline float ev_ms(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
+int use_device(Context *c);
+SeqBatch seq_view(const Batch &b);
+
+}  // namespace sb
+
+struct savont_b200_ctx { sb::Context c; };
