@@ -191,9 +191,12 @@ class Context:
         return dict(status=st[:n], est_id=est[:n], n_solid_mini=sm[:n], n_solid_snp=ss[:n])
 
     # ---- Stage 1 counting (K5) ----
-    def _kmer_out(self, call, cap, sort):
+    def _kmer_out(self, call, cap, sort, out=None):
         for _ in range(3):
-            km = np.zeros(max(cap, 1), np.uint64); ct = np.zeros(2 * max(cap, 1), np.uint32)
+            if out is not None and len(out[0]) >= cap and len(out[1]) >= 2 * cap:
+                km, ct = out        # caller's buffers (e.g. page-locked: the D2H of the survivors then runs at PCIe speed)
+            else:
+                km = np.zeros(max(cap, 1), np.uint64); ct = np.zeros(2 * max(cap, 1), np.uint32)
             n = C.c_size_t(0); st = KmerStats()
             rc = call(_p(km, C.c_uint64), _p(ct, C.c_uint32), C.c_size_t(cap), C.byref(n), C.byref(st))
             if rc == ERR_CAPACITY and n.value > cap:
@@ -207,7 +210,7 @@ class Context:
             o = np.argsort(km, kind="stable"); km = km[o]; ct = ct[o]
         return dict(kmers=km, counts=ct, stats=st.as_dict())
 
-    def count_split_kmers(self, bases, quals, offsets, rc=None, single_strand=False, cap=None, sort=True):
+    def count_split_kmers(self, bases, quals, offsets, rc=None, single_strand=False, cap=None, sort=True, out=None):
         """seq_parse::read_to_split_kmers (counting part): -> dict(kmers, counts [n, 2], stats)"""
         b = _u8(bases); q = _u8(quals)
         o = np.ascontiguousarray(offsets, dtype=np.uint64)
@@ -217,7 +220,7 @@ class Context:
         call = lambda km, ct, cp, nn, st: self.L.savont_b200_count_split_kmers(
             self.h, _p(b, C.c_uint8), _p(q, C.c_uint8), _p(o, C.c_uint64), _p(r, C.c_uint8), C.c_size_t(n),
             C.c_int(1 if single_strand else 0), km, ct, cp, nn, st)
-        return self._kmer_out(call, cap, sort)
+        return self._kmer_out(call, cap, sort, out)
 
     def count_split_kmers_resident(self, single_strand=False, cap=1 << 22, sort=True):
         call = lambda km, ct, cp, nn, st: self.L.savont_b200_count_split_kmers_resident(

@@ -210,7 +210,8 @@ int savont_b200_count_split_kmers(savont_b200_ctx *h, const uint8_t *bases, cons
     const uint64_t total = n_reads ? offsets[n_reads] - offsets[0] : 0;
     size_t free_b = 0, total_b = 0;
     CK(cudaMemGetInfo(&free_b, &total_b));
-    const uint64_t need_resident = total * (quals ? 2ull : 1ull) + (uint64_t)n_reads * 9ull + total / 2ull + total * 2ull + (4ull << 30);
+    // the reads (1 or 2 bytes per base) stay on the device next to the partition entries (2 x 4 bytes per k-mer occurrence)
+    const uint64_t need_resident = total * (quals ? 2ull : 1ull) + (uint64_t)n_reads * 9ull + total * 8ull + (4ull << 30);
     const bool resident = nch <= 2 || need_resident < (uint64_t)free_b;
     const size_t nbuf = resident ? nch : 2;
     if (c->kc_chunks.size() < nbuf) c->kc_chunks.resize(nbuf);
