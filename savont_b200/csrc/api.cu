@@ -119,7 +119,7 @@ static int upload_snp_set(Context *c) {
         keys[slot] = key;
         // strand-symmetric Bloom key: k-mer + its reverse complement (the kernels probe F + Rv without choosing the
         // canonical strand first); blocked: both bits in one word
-        const uint32_t h = bloom_hash32(key + revcomp_kmer_host(key, c->dp.k));
+        const uint32_t h = bloom_hash32_sym((uint32_t)key, (uint32_t)revcomp_kmer_host(key, c->dp.k));
         bloom[h >> bshift] |= (1u << (h & 31)) | (1u << ((h >> 5) & 31));
     }
     TRY(c->d_snp_keys.ensure(cap * sizeof(uint64_t)));

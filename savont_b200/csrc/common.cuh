@@ -41,10 +41,10 @@ struct DeviceParams {
 // TOP log2(cap) bits of key * 2^64/phi (shift = 64 - log2(cap), cap >= 2).
 constexpr uint64_t kFibMul = 0x9E3779B97F4A7C15ull;
 __host__ __device__ __forceinline__ uint32_t hash_slot(uint64_t key, uint32_t shift) { return (uint32_t)((key * kFibMul) >> shift); }
-// 32-bit hash for the SNPmer Bloom filter: word = h >> (32 - log2(words)), bits h & 31 and (h >> 5) & 31
-__host__ __device__ __forceinline__ uint32_t bloom_hash32(uint64_t key) {
-    return ((uint32_t)key ^ ((uint32_t)(key >> 32) * 0x85EBCA6Bu)) * 0x9E3779B1u;
-}
+// 32-bit hash for the SNPmer Bloom filter, strand symmetric: the key is the sum of the low words of the k-mer and of its
+// reverse complement (the sketch kernels probe it without choosing the canonical strand first).
+// word = h >> (32 - log2(words)), bits h & 31 and (h >> 5) & 31
+__host__ __device__ __forceinline__ uint32_t bloom_hash32_sym(uint32_t lo_fwd, uint32_t lo_rev) { return (lo_fwd + lo_rev) * 0x9E3779B1u; }
 
 // src/seeding.rs:18-28
 __host__ __device__ __forceinline__ uint64_t mm_hash64(uint64_t key) {
@@ -100,7 +100,7 @@ struct SnpSet {              // open addressing, kEmpty64 = empty
     const uint64_t *keys;    // null when the set is empty
     uint32_t mask;           // cap-1
     uint32_t shift;          // 64 - log2(cap)
-    const uint32_t *bloom;   // blocked two-bit Bloom filter keyed by bloom_hash32 (staged in shared memory)
+    const uint32_t *bloom;   // blocked two-bit Bloom filter keyed by bloom_hash32_sym (staged in shared memory)
     uint32_t bloom_shift;    // 32 - log2(bloom words)
     uint32_t bloom_words;
 };

@@ -255,7 +255,7 @@ sketch_kernel(SeqBatch in, SketchOut out, SnpSet set, const uint16_t *__restrict
                 // ---- SNPmer membership: Bloom filter now (branch-free), exact probe after the loop ----
                 bool bloom_hit = false;
                 if (set.keys != nullptr) {
-                    const uint32_t h = bloom_hash32(F + Rv);            // strand symmetric key (shared with sketch_fast.cu)
+                    const uint32_t h = bloom_hash32_sym((uint32_t)F, (uint32_t)Rv);   // strand symmetric key (shared with sketch_fast.cu)
                     const uint32_t bmask = (1u << (h & 31u)) | (1u << ((h >> 5) & 31u));
                     bloom_hit = (s_bloom[h >> set.bloom_shift] & bmask) == bmask;
                 }

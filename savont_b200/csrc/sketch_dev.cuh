@@ -13,6 +13,15 @@ __device__ __forceinline__ uint32_t enc_base(uint32_t b) {
     return code;
 }
 
+// a * b + c as IMAD: the sketch kernels are bound by the INT32 ALU pipe (LOP3 / SHF / IADD3), IMAD issues beside it on the
+// FMA pipe at the same rate (tools/pipe_bench.cu), so shift-and-merge steps whose bit fields cannot overlap are written as
+// multiply-adds
+__device__ __forceinline__ uint32_t mad_lo(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
 // 64 bits of the packed sequence starting at base a (base a in the top bit pair)
 __device__ __forceinline__ uint64_t window64(const uint32_t *packed, uint32_t a) {
     const uint32_t w = a >> 4, sh = (a & 15u) * 2u;

@@ -125,8 +125,8 @@ sketch_fast_kernel(SeqBatch in, SketchOut out, SnpSet set, const uint16_t *__res
                 for (int t = 0; t < 16; ++t) {
                     const uint32_t byte = (xs[t >> 2] >> (8 * (t & 3))) & 0xffu;
                     const uint2 e = s_lut[byte];
-                    pk |= e.x << (30 - 2 * t);
-                    pl |= e.y << t;
+                    pk = mad_lo(e.x, 1u << (30 - 2 * t), pk);                 // disjoint bit fields: OR as multiply-add
+                    pl = mad_lo(e.y, 1u << t, pl);
                 }
                 // bases outside [0, L) (before the misaligned start, after the end) are zero
                 const int first = (int)mis - (int)(ch * 16u);               // chunk positions < first are invalid
@@ -236,7 +236,7 @@ sketch_fast_kernel(SeqBatch in, SketchOut out, SnpSet set, const uint16_t *__res
 
             // ---- registers after bases p0..p0+15; ranks of the s-mers starting at p0..p0+9 ----
             const uint64_t x0 = window64(packed, pb + p0);
-            uint32_t Flo = (uint32_t)(x0 >> 32), Fhi = 0u;
+            uint32_t Flo = (uint32_t)(x0 >> 32);
             uint32_t Rlo, Rhi;
             { const uint32_t rc = revcomp16(Flo); Rlo = rc << 2; Rhi = rc >> 30; }
             uint32_t win[C];
@@ -254,18 +254,17 @@ sketch_fast_kernel(SeqBatch in, SketchOut out, SnpSet set, const uint16_t *__res
 #pragma unroll
                 for (int jj = 0; jj < (int)C; ++jj) {
                     const uint32_t e = (bb >> (30 - 2 * jj)) & 3u;
-                    Fhi = Flo >> 30;
-                    Flo = (Flo << 2) | e;
+                    Flo = mad_lo(Flo, 4u, e);                                  // (Flo << 2) | e
                     Rlo = __funnelshift_r(Rlo, Rhi, 2);
                     Rhi = e ^ 3u;
                     win[(jj + (int)C - 1) % (int)C] = s_rank[Flo & 0x3fffu];
                     if (want_snp) {
-                        // Bloom probe on F + revcomp(F) (identical for both strands)
-                        const uint32_t klo = Flo + Rlo;
-                        const uint32_t khi = Fhi + Rhi + (klo < Flo ? 1u : 0u);
-                        const uint32_t h = (klo ^ (khi * 0x85EBCA6Bu)) * 0x9E3779B1u;
+                        // Bloom probe on low(F) + low(revcomp(F)) (identical for both strands); the funnel shifts take
+                        // their shift amount modulo 32, so the two bit indices need no masking
+                        const uint32_t h = bloom_hash32_sym(Flo, Rlo);
                         const uint32_t w = s_bloom[h >> set.bloom_shift];
-                        cmb |= ((w >> (h & 31u)) & (w >> ((h >> 5) & 31u)) & 1u) << jj;
+                        const uint32_t hit = __funnelshift_r(w, 0u, h) & __funnelshift_r(w, 0u, h >> 5) & 1u;
+                        cmb = mad_lo(hit, 1u << jj, cmb);
                     }
                     // open syncmer: strict minimum at the middle of the 11 ranks (src/seeding.rs:526-543)
                     constexpr int CI = (int)C;
