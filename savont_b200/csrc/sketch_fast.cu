@@ -272,7 +272,7 @@ sketch_fast_kernel(SeqBatch in, SketchOut out, SnpSet set, const uint16_t *__res
                     uint32_t others = 0xffffffffu;
 #pragma unroll
                     for (int t = 0; t < CI; ++t) if (t != ms) others = min(others, win[t]);
-                    mmb |= (win[ms] < others ? 1u : 0u) << jj;
+                    if (win[ms] < others) mmb |= 1u << jj;
                 }
                 cm |= (uint64_t)cmb << (C * b);
                 mm |= (uint64_t)mmb << (C * b);
