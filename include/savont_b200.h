@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SAVONT_B200_ABI_VERSION 2
+#define SAVONT_B200_ABI_VERSION 3
 
 typedef struct savont_b200_ctx savont_b200_ctx;
 
@@ -240,6 +240,16 @@ int savont_b200_upload_twin_reads(savont_b200_ctx *ctx, const uint64_t *dna_word
 int savont_b200_map_resident(savont_b200_ctx *ctx, int zero_counters, savont_b200_stats *stats);
 int savont_b200_fetch_resident(savont_b200_ctx *ctx, uint8_t *status, int32_t *best_nm, uint64_t *class_offsets,
                                uint32_t *class_asv, size_t class_cap);
+/* Best-hit alignment record of every read of the resident batch (after savont_b200_map_resident): what the reference's
+ * Stage 7 holds in the minimap2 Mapping of the best ASV (src/alignment.rs:1858-1867: `map(asv_seq)` against the read's
+ * index, first mapping, stable sort by NM).  best_asv = first member of the read's class (lowest ASV index), strand = the
+ * orientation it was aligned in, coordinates in DP orientation as in savont_b200_align_pairs, identity =
+ * 1 - nm / (asv_end - asv_start) with the ASV as the query (the reference's formula, src/chimera.rs:443-451; 0 for an
+ * empty span), CIGAR BAM-encoded in CSR (cigar_offsets[n+1]).  Unassigned reads: best_asv = UINT32_MAX, strand = 0xff,
+ * coordinates -1, identity NaN, empty CIGAR.  All per-read arrays have n_reads entries. */
+int savont_b200_best_hits_resident(savont_b200_ctx *ctx, uint32_t *best_asv, uint8_t *strand, int32_t *asv_start,
+                                   int32_t *asv_end, int32_t *read_start, int32_t *read_end, double *identity,
+                                   uint64_t *cigar_offsets, uint32_t *cigar, size_t cigar_cap);
 int savont_b200_counts_dev(savont_b200_ctx *ctx, void **dev_ptr, size_t *n_u64);
 int savont_b200_read_counts(savont_b200_ctx *ctx, uint64_t *unambig, uint64_t *ambig, uint64_t *leq10, uint64_t *totals,
                             uint64_t *sample_singleton);

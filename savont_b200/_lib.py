@@ -394,6 +394,24 @@ class Context:
                                               _p(B["totals"], C.c_uint64), _p(B["sample_singleton"], C.c_uint64)))
         return self._finish(B, n, n_samples, Stats())
 
+    def best_hits_resident(self, cigar_cap=None):
+        """best-hit alignment record (ASV, strand, coordinates, identity, CIGAR) per read of the resident batch"""
+        n, _ = self._resident
+        m = max(n, 1)
+        out = dict(best_asv=np.zeros(m, np.uint32), strand=np.zeros(m, np.uint8), asv_start=np.zeros(m, np.int32),
+                   asv_end=np.zeros(m, np.int32), read_start=np.zeros(m, np.int32), read_end=np.zeros(m, np.int32),
+                   identity=np.zeros(m, np.float64))
+        co = np.zeros(n + 1, np.uint64)
+        cg = np.zeros(cigar_cap or max(64 * n, 1024), np.uint32)
+        _check(self.L.savont_b200_best_hits_resident(self.h, _p(out["best_asv"], C.c_uint32), _p(out["strand"], C.c_uint8),
+                                                     _p(out["asv_start"], C.c_int32), _p(out["asv_end"], C.c_int32),
+                                                     _p(out["read_start"], C.c_int32), _p(out["read_end"], C.c_int32),
+                                                     _p(out["identity"], C.c_double), _p(co, C.c_uint64), _p(cg, C.c_uint32),
+                                                     C.c_size_t(len(cg))))
+        out = {k: v[:n] for k, v in out.items()}
+        out.update(cigar_offsets=co, cigar=cg[:int(co[-1])])
+        return out
+
     def counts_dev(self):
         """(device pointer, length in u64) of [unambig|ambig|leq10|assigned|filtered|singleton S*A]"""
         ptr = C.c_void_p(); n = C.c_size_t()

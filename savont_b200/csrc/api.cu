@@ -725,6 +725,67 @@ static int read_counters(Context *c, uint64_t *unambig, uint64_t *ambig, uint64_
 using namespace sb;
 
 
+namespace sb {
+// Traceback (align_tb_kernel) of explicit device-resident pairs against the batch's read planes, in sub-batches bounded by
+// a 1 GiB history workspace; the CIGAR slots are compacted on the device (scan of the op counts + warp-per-pair copy) so that
+// only the ops cross PCIe.  cigar_offsets[0] must be set by the caller (base of this call's ops in `cigar`).
+static int traceback_pairs(Context *c, Batch &b, const uint32_t *d_pr, const uint32_t *d_pa, const uint8_t *d_ps, size_t n_pairs,
+                           int32_t *nm, int32_t *asv_end, int32_t *read_end, int32_t *asv_start, int32_t *read_start,
+                           uint64_t *cigar_offsets, uint32_t *cigar, size_t cigar_cap) {
+    const uint32_t hist_cols = std::max<uint32_t>(b.max_len, 1u);
+    const uint32_t cigar_stride = b.max_len + c->max_asv_len + 2;
+    const size_t per_pair_words = align_tb_hist_words(1, hist_cols, c->dp);
+    size_t sub = std::max<size_t>(128, ((size_t)1 << 28) / std::max<size_t>(per_pair_words, 1));
+    sub = std::min<size_t>(sub, 1u << 16);
+    DevBuf d_hist, d_slots, d_cnt, d_off, d_tmp, d_ops, d_out;
+    auto cleanup = [&]() { d_hist.release(); d_slots.release(); d_cnt.release(); d_off.release(); d_tmp.release(); d_ops.release(); d_out.release(); };
+    uint64_t cig_base = cigar_offsets[0];
+    std::vector<uint32_t> h_off;
+    std::vector<int32_t> h_out;
+    int rc = 0;
+    for (size_t p0 = 0; p0 < n_pairs && rc == 0; p0 += sub) {
+        const uint32_t np = (uint32_t)std::min(sub, n_pairs - p0);
+        if ((rc = d_hist.ensure(align_tb_hist_words(np, hist_cols, c->dp) * 4)) != 0) break;
+        if ((rc = d_slots.ensure((size_t)np * cigar_stride * 4)) != 0) break;
+        if ((rc = d_ops.ensure((size_t)np * cigar_stride * 4)) != 0) break;
+        if ((rc = d_cnt.ensure((size_t)np * 4)) != 0) break;
+        if ((rc = d_off.ensure(((size_t)np + 1) * 4)) != 0) break;
+        if ((rc = d_tmp.ensure(((size_t)np / 2048 + 4) * 4)) != 0) break;
+        if ((rc = d_out.ensure((size_t)np * 5 * 4)) != 0) break;
+        int32_t *o = d_out.as<int32_t>();
+        AlignOut ao{o, o + np, o + 2 * (size_t)np};
+        launch_align_tb(seq_view(b), b.planes.as<uint2>(), index_view(c), d_pr + p0, d_pa + p0, d_ps + p0, np, d_hist.as<uint32_t>(), ao,
+                        o + 3 * (size_t)np, o + 4 * (size_t)np, d_slots.as<uint32_t>(), cigar_stride, d_cnt.as<uint32_t>(), c->dp, c->stream);
+        launch_scan_u32(d_cnt.as<uint32_t>(), d_off.as<uint32_t>(), np, d_tmp.as<uint32_t>(), c->stream);
+        launch_cigar_compact(d_slots.as<uint32_t>(), cigar_stride, d_cnt.as<uint32_t>(), d_off.as<uint32_t>(), np, d_ops.as<uint32_t>(),
+                             c->stream);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { rc = fail(SAVONT_B200_ERR_CUDA, "align_tb launch: %s", cudaGetErrorString(e)); break; }
+        c->last_stats.kernel_launches += 5;
+        h_off.resize((size_t)np + 1); h_out.resize((size_t)np * 5);
+        cudaMemcpyAsync(h_off.data(), d_off.p, ((size_t)np + 1) * 4, cudaMemcpyDeviceToHost, c->stream);
+        cudaMemcpyAsync(h_out.data(), d_out.p, (size_t)np * 5 * 4, cudaMemcpyDeviceToHost, c->stream);
+        e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) { rc = fail(SAVONT_B200_ERR_CUDA, "align_tb: %s", cudaGetErrorString(e)); break; }
+        const uint32_t total = h_off[np];
+        if (cig_base + total > cigar_cap) { rc = fail(SAVONT_B200_ERR_CAPACITY, "cigar capacity %zu too small", cigar_cap); break; }
+        if (total) cudaMemcpyAsync(cigar + cig_base, d_ops.p, (size_t)total * 4, cudaMemcpyDeviceToHost, c->stream);
+        memcpy(nm + p0, h_out.data(), (size_t)np * 4);
+        memcpy(asv_end + p0, h_out.data() + np, (size_t)np * 4);
+        memcpy(read_end + p0, h_out.data() + 2 * (size_t)np, (size_t)np * 4);
+        memcpy(asv_start + p0, h_out.data() + 3 * (size_t)np, (size_t)np * 4);
+        memcpy(read_start + p0, h_out.data() + 4 * (size_t)np, (size_t)np * 4);
+        for (uint32_t t = 0; t < np; ++t) cigar_offsets[p0 + t + 1] = cig_base + h_off[t + 1];
+        e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) { rc = fail(SAVONT_B200_ERR_CUDA, "align_tb copy: %s", cudaGetErrorString(e)); break; }
+        cig_base += total;
+    }
+    cleanup();
+    return rc;
+}
+
+}  // namespace sb
+
 extern "C" {
 
 int savont_b200_abi_version(void) { return SAVONT_B200_ABI_VERSION; }
@@ -1073,50 +1134,8 @@ int savont_b200_align_pairs(savont_b200_ctx *h, const uint8_t *bases, const uint
         CK(cudaStreamSynchronize(c->stream));
         return 0;
     }
-    // traceback path, in sub-batches bounded by a 1 GiB history workspace
-    const uint32_t hist_cols = std::max<uint32_t>(b.max_len, 1u);
-    const uint32_t cigar_stride = b.max_len + c->max_asv_len + 2;
-    const size_t per_pair_words = align_tb_hist_words(1, hist_cols, c->dp);
-    size_t sub = std::max<size_t>(128, ((size_t)1 << 28) / std::max<size_t>(per_pair_words, 1));
-    sub = std::min<size_t>(sub, 1u << 16);
-    DevBuf d_hist, d_cigar, d_cnt, d_as, d_rs;
-    auto cleanup = [&]() { d_hist.release(); d_cigar.release(); d_cnt.release(); d_as.release(); d_rs.release(); };
-    size_t cig_base = 0;
-    std::vector<uint32_t> h_cnt, h_cig;
-    int rc = 0;
-    for (size_t p0 = 0; p0 < n_pairs && rc == 0; p0 += sub) {
-        const uint32_t np = (uint32_t)std::min(sub, n_pairs - p0);
-        if ((rc = d_hist.ensure(align_tb_hist_words(np, hist_cols, c->dp) * 4)) != 0) break;
-        if ((rc = d_cigar.ensure((size_t)np * cigar_stride * 4)) != 0) break;
-        if ((rc = d_cnt.ensure((size_t)np * 4)) != 0) break;
-        if ((rc = d_as.ensure((size_t)np * 4)) != 0) break;
-        if ((rc = d_rs.ensure((size_t)np * 4)) != 0) break;
-        AlignOut ao{b.nm.as<int32_t>() + p0, b.asv_end.as<int32_t>() + p0, b.read_end.as<int32_t>() + p0};
-        launch_align_tb(seq_view(b), b.planes.as<uint2>(), index_view(c), b.p_read.as<uint32_t>() + p0, b.p_asv.as<uint32_t>() + p0,
-                        b.p_strand.as<uint8_t>() + p0, np, d_hist.as<uint32_t>(), ao, d_as.as<int32_t>(), d_rs.as<int32_t>(),
-                        d_cigar.as<uint32_t>(), cigar_stride, d_cnt.as<uint32_t>(), c->dp, c->stream);
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) { rc = fail(SAVONT_B200_ERR_CUDA, "align_tb launch: %s", cudaGetErrorString(e)); break; }
-        h_cnt.resize(np); h_cig.resize((size_t)np * cigar_stride);
-        cudaMemcpyAsync(h_cnt.data(), d_cnt.p, (size_t)np * 4, cudaMemcpyDeviceToHost, c->stream);
-        cudaMemcpyAsync(h_cig.data(), d_cigar.p, (size_t)np * cigar_stride * 4, cudaMemcpyDeviceToHost, c->stream);
-        cudaMemcpyAsync(nm + p0, ao.nm, (size_t)np * 4, cudaMemcpyDeviceToHost, c->stream);
-        cudaMemcpyAsync(asv_end + p0, ao.asv_end, (size_t)np * 4, cudaMemcpyDeviceToHost, c->stream);
-        cudaMemcpyAsync(read_end + p0, ao.read_end, (size_t)np * 4, cudaMemcpyDeviceToHost, c->stream);
-        cudaMemcpyAsync(asv_start + p0, d_as.p, (size_t)np * 4, cudaMemcpyDeviceToHost, c->stream);
-        cudaMemcpyAsync(read_start + p0, d_rs.p, (size_t)np * 4, cudaMemcpyDeviceToHost, c->stream);
-        e = cudaStreamSynchronize(c->stream);
-        if (e != cudaSuccess) { rc = fail(SAVONT_B200_ERR_CUDA, "align_tb: %s", cudaGetErrorString(e)); break; }
-        for (uint32_t t = 0; t < np; ++t) {
-            const uint32_t cnt = h_cnt[t];
-            if (cig_base + cnt > cigar_cap) { rc = fail(SAVONT_B200_ERR_CAPACITY, "cigar capacity too small"); break; }
-            if (cnt) memcpy(cigar + cig_base, h_cig.data() + (size_t)t * cigar_stride + (cigar_stride - cnt), (size_t)cnt * 4);
-            cig_base += cnt;
-            cigar_offsets[p0 + t + 1] = cig_base;
-        }
-    }
-    cleanup();
-    return rc;
+    return traceback_pairs(c, b, b.p_read.as<uint32_t>(), b.p_asv.as<uint32_t>(), b.p_strand.as<uint8_t>(), n_pairs, nm, asv_end,
+                           read_end, asv_start, read_start, cigar_offsets, cigar, cigar_cap);
 }
 
 // shared body of savont_b200_map_reads / savont_b200_map_twin_reads: double-buffered batches, the H2D copies of
@@ -1305,6 +1324,59 @@ int savont_b200_fetch_resident(savont_b200_ctx *h, uint8_t *status, int32_t *bes
     if (!status || !best_nm || !class_offsets) return fail(SAVONT_B200_ERR_INVALID, "null argument");
     uint64_t n_cls = 0;
     return fetch_batch(c, c->resident, c->resident.n, c->stream, status, best_nm, class_offsets, 0, class_asv, class_cap, &n_cls, nullptr);
+}
+
+int savont_b200_best_hits_resident(savont_b200_ctx *h, uint32_t *best_asv, uint8_t *strand, int32_t *asv_start, int32_t *asv_end,
+                                   int32_t *read_start, int32_t *read_end, double *identity, uint64_t *cigar_offsets,
+                                   uint32_t *cigar, size_t cigar_cap) {
+    TRY(use_device(h ? &h->c : nullptr));
+    Context *c = &h->c;
+    Batch &b = c->resident;
+    if (!b.mapped) return fail(SAVONT_B200_ERR_INVALID, "map_resident has not run");
+    if (!best_asv || !strand || !asv_start || !asv_end || !read_start || !read_end || !identity || !cigar_offsets)
+        return fail(SAVONT_B200_ERR_INVALID, "null argument");
+    const size_t n = b.n;
+    cigar_offsets[0] = 0;
+    if (n == 0) return 0;
+    DevBuf d_flag, d_off, d_tmp, d_basv, d_bstr, d_pr, d_pa, d_ps;
+    auto cleanup = [&]() { DevBuf *all[] = {&d_flag, &d_off, &d_tmp, &d_basv, &d_bstr, &d_pr, &d_pa, &d_ps}; for (DevBuf *x : all) x->release(); };
+    int rc = 0;
+    if ((rc = d_flag.ensure(n * 4)) || (rc = d_off.ensure((n + 1) * 4)) || (rc = d_tmp.ensure((n / 2048 + 4) * 4)) ||
+        (rc = d_basv.ensure(n * 4)) || (rc = d_bstr.ensure(n + 4)) || (rc = d_pr.ensure(n * 4)) || (rc = d_pa.ensure(n * 4)) ||
+        (rc = d_ps.ensure(n + 4))) { cleanup(); return rc; }
+    launch_best_pairs(filter_view(b), pool_view(b), b.nm.as<int32_t>(), b.rstatus.as<uint8_t>(), b.best_nm.as<int32_t>(), (uint32_t)n,
+                      c->dp.strand_mode, d_flag.as<uint32_t>(), d_off.as<uint32_t>(), d_tmp.as<uint32_t>(), d_basv.as<uint32_t>(),
+                      d_bstr.as<uint8_t>(), d_pr.as<uint32_t>(), d_pa.as<uint32_t>(), d_ps.as<uint8_t>(), c->stream);
+    c->last_stats.kernel_launches += 5;
+    std::vector<uint32_t> off(n + 1);
+    cudaMemcpyAsync(off.data(), d_off.p, (n + 1) * 4, cudaMemcpyDeviceToHost, c->stream);
+    cudaMemcpyAsync(best_asv, d_basv.p, n * 4, cudaMemcpyDeviceToHost, c->stream);
+    cudaMemcpyAsync(strand, d_bstr.p, n, cudaMemcpyDeviceToHost, c->stream);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) { cleanup(); return fail(SAVONT_B200_ERR_CUDA, "best_pairs: %s", cudaGetErrorString(e)); }
+    const size_t np = off[n];
+    std::vector<int32_t> v(np * 5);
+    std::vector<uint64_t> coff(np + 1, 0);
+    if (np) {
+        rc = traceback_pairs(c, b, d_pr.as<uint32_t>(), d_pa.as<uint32_t>(), d_ps.as<uint8_t>(), np, v.data(), v.data() + np,
+                             v.data() + 2 * np, v.data() + 3 * np, v.data() + 4 * np, coff.data(), cigar, cigar_cap);
+        if (rc) { cleanup(); return rc; }
+    }
+    for (size_t r = 0; r < n; ++r) {
+        if (off[r + 1] == off[r]) {
+            asv_start[r] = asv_end[r] = read_start[r] = read_end[r] = -1;
+            identity[r] = std::nan("");
+        } else {
+            const size_t t = off[r];
+            asv_end[r] = v[np + t]; read_end[r] = v[2 * np + t]; asv_start[r] = v[3 * np + t]; read_start[r] = v[4 * np + t];
+            // the reference's identity with the ASV as the query: 1 - nm / (query_end - query_start), src/chimera.rs:444-452
+            const double span = (double)(asv_end[r] - asv_start[r]);
+            identity[r] = span > 0.0 ? 1.0 - (double)v[t] / span : 0.0;
+        }
+        cigar_offsets[r + 1] = coff[off[r + 1]];
+    }
+    cleanup();
+    return 0;
 }
 
 int savont_b200_counts_dev(savont_b200_ctx *h, void **dev_ptr, size_t *n_u64) {

@@ -161,6 +161,64 @@ void launch_gather_u32(const uint32_t *src, const uint32_t *src_start, const uin
     gather_u32_kernel<<<(n + 255u) / 256u, 256, 0, st>>>(src, src_start, cnt, dst_off, dst, n);
 }
 
+// Best hit of every assigned read as an explicit (read, ASV, strand) pair for the traceback kernel: the first member of the
+// class (lowest ASV index; the reference's stable sort by NM keeps candidate order, src/alignment.rs:1865-1867) and, when
+// both strands were aligned, the strand with the smaller NM (tie -> forward).  flag[r] = 1 iff the read has a best hit.
+__global__ void best_pair_kernel(FilterOut fo, PairPool pool, const int32_t *__restrict__ nm, const uint8_t *__restrict__ status,
+                                 const int32_t *__restrict__ best_nm, uint32_t n_reads, int strand_mode, uint32_t *flag,
+                                 uint32_t *best_asv, uint8_t *best_strand) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    uint32_t a = 0xffffffffu; uint8_t s = 0xffu;
+    if (status[r] == 0) {
+        const uint32_t start = fo.pair_start[r], cnt = fo.pair_cnt[r];
+        const uint32_t per = (strand_mode == 1) ? 2u : 1u;
+        const int best = best_nm[r];
+        for (uint32_t c = 0; c < cnt / per; ++c) {
+            const uint32_t i0 = start + c * per;
+            int v = nm[i0]; uint32_t pick = i0;
+            if (per == 2u) { const int v2 = nm[i0 + 1]; if (v2 < v) { v = v2; pick = i0 + 1; } }
+            if (v == best) { a = pool.asv[pick]; s = pool.strand[pick]; break; }
+        }
+    }
+    flag[r] = a != 0xffffffffu ? 1u : 0u;
+    best_asv[r] = a; best_strand[r] = s;
+}
+__global__ void best_pair_scatter_kernel(const uint32_t *__restrict__ flag, const uint32_t *__restrict__ off,
+                                         const uint32_t *__restrict__ best_asv, const uint8_t *__restrict__ best_strand,
+                                         uint32_t n_reads, uint32_t *p_read, uint32_t *p_asv, uint8_t *p_strand) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads || !flag[r]) return;
+    const uint32_t d = off[r];
+    p_read[d] = r; p_asv[d] = best_asv[r]; p_strand[d] = best_strand[r];
+}
+// off needs n_reads + 1 words (off[n_reads] = number of pairs), tmp as launch_scan_u32
+void launch_best_pairs(const FilterOut &fo, const PairPool &pool, const int32_t *nm, const uint8_t *status, const int32_t *best_nm,
+                       uint32_t n_reads, int strand_mode, uint32_t *flag, uint32_t *off, uint32_t *tmp, uint32_t *best_asv,
+                       uint8_t *best_strand, uint32_t *p_read, uint32_t *p_asv, uint8_t *p_strand, cudaStream_t st) {
+    if (n_reads == 0) { cudaMemsetAsync(off, 0, sizeof(uint32_t), st); return; }
+    const uint32_t g = (n_reads + 255u) / 256u;
+    best_pair_kernel<<<g, 256, 0, st>>>(fo, pool, nm, status, best_nm, n_reads, strand_mode, flag, best_asv, best_strand);
+    launch_scan_u32(flag, off, n_reads, tmp, st);
+    best_pair_scatter_kernel<<<g, 256, 0, st>>>(flag, off, best_asv, best_strand, n_reads, p_read, p_asv, p_strand);
+}
+
+// CIGAR slots (filled from the back by the traceback kernel) -> one compact run per pair; a warp per pair
+__global__ void cigar_compact_kernel(const uint32_t *__restrict__ slots, uint32_t stride, const uint32_t *__restrict__ cnt,
+                                     const uint32_t *__restrict__ off, uint32_t n_pairs, uint32_t *__restrict__ dst) {
+    const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (t >= n_pairs) return;
+    const uint32_t c = cnt[t];
+    const uint32_t *src = slots + (size_t)t * stride + (stride - c);
+    uint32_t *d = dst + off[t];
+    for (uint32_t i = lane; i < c; i += 32) d[i] = src[i];
+}
+void launch_cigar_compact(const uint32_t *slots, uint32_t stride, const uint32_t *cnt, const uint32_t *off, uint32_t n_pairs,
+                          uint32_t *dst, cudaStream_t st) {
+    if (n_pairs == 0) return;
+    cigar_compact_kernel<<<(n_pairs + 7u) / 8u, 256, 0, st>>>(slots, stride, cnt, off, n_pairs, dst);
+}
+
 // gather for find_candidates: per read copy asv / mini / strand of its pair chunk
 __global__ void gather_cand_kernel(PairPool pool, const uint32_t *pair_start, const uint32_t *pair_cnt, const uint32_t *low_mm,
                                    const uint32_t *dst_off, uint32_t *asv, uint32_t *mm, uint32_t *mini, uint8_t *strand,

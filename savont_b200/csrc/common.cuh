@@ -224,6 +224,11 @@ void launch_assign(const FilterOut &fo, const PairPool &pool, const int32_t *nm,
                    const uint32_t *asv_len, uint32_t cells_per_row, unsigned long long *dp_cells,
                    uint8_t *status, int32_t *best_nm, uint32_t *class_cnt, uint32_t *class_slot,
                    unsigned long long *counters, cudaStream_t st);
+void launch_best_pairs(const FilterOut &fo, const PairPool &pool, const int32_t *nm, const uint8_t *status, const int32_t *best_nm,
+                       uint32_t n_reads, int strand_mode, uint32_t *flag, uint32_t *off, uint32_t *tmp, uint32_t *best_asv,
+                       uint8_t *best_strand, uint32_t *p_read, uint32_t *p_asv, uint8_t *p_strand, cudaStream_t st);
+void launch_cigar_compact(const uint32_t *slots, uint32_t stride, const uint32_t *cnt, const uint32_t *off, uint32_t n_pairs,
+                          uint32_t *dst, cudaStream_t st);
 void launch_gather_cand(const PairPool &pool, const uint32_t *pair_start, const uint32_t *pair_cnt, const uint32_t *low_mm,
                         const uint32_t *dst_off, uint32_t *asv, uint32_t *mm, uint32_t *mini, uint8_t *strand, uint32_t n,
                         cudaStream_t st);

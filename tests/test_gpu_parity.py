@@ -179,6 +179,60 @@ def test_map_reads_both_strands_mode(ctx):
     assert got["stats"]["dp_cells"] == want["dp_cells"]
 
 
+@pytest.mark.parametrize("strand_mode", [0, 1])
+def test_best_hit_alignment_records(ctx, strand_mode):
+    """per read: best-hit ASV, strand, coordinates, identity and CIGAR (north star) = the oracle's traceback of the pair
+    (read, first ASV of the oracle's class, strand by seed vote / smaller NM)"""
+    from savont_b200 import _lib
+    w = _make_workload("ont16s", n_roots=5, sites_per_genus=4)
+    r = w.reads(1200)
+    bases = r["bases"].copy(); offs = r["offsets"]
+    bases[int(offs[3]):int(offs[4])] = ord("N")                       # an unassigned read in the middle
+    gp, op = _params(_lib, band=w.band, strand_mode=strand_mode)
+    ctx.set_params(gp); ctx.load_snpmers(w.snpmers); ctx.load_asvs(w.asv_bases, w.asv_offsets)
+    orc = O.Oracle(op, w.snpmers); orc.load_asvs(w.asv_bases, w.asv_offsets)
+    want = orc.map_reads(bases, r["quals"], offs)
+    cand = orc.find_candidates(bases, r["quals"], offs)
+    n = len(offs) - 1
+    co = want["class_offsets"].astype(np.int64)
+    reads = np.flatnonzero(want["status"] == 0)
+    assert 0 < len(reads) < n
+    asv = want["class_asv"][co[reads]]
+    if strand_mode == 0:
+        cofs = cand["offsets"].astype(np.int64)
+        strand = np.array([cand["strand"][cofs[rd]:cofs[rd + 1]][list(cand["asv"][cofs[rd]:cofs[rd + 1]]).index(a)]
+                           for rd, a in zip(reads, asv)], np.uint8)
+    else:
+        f = orc.align_pairs(bases, offs, reads, asv, np.zeros(len(reads), np.uint8))["nm"]
+        v = orc.align_pairs(bases, offs, reads, asv, np.ones(len(reads), np.uint8))["nm"]
+        strand = (v < f).astype(np.uint8)
+    ref = orc.align_pairs(bases, offs, reads, asv, strand, want_cigar=True)
+    assert np.array_equal(ref["nm"], want["best_nm"][reads])
+    ctx.upload_reads(bases, r["quals"], offs)
+    ctx.map_resident()
+    assert_same(ctx.fetch_resident(), want, MAP_KEYS, "map_resident")
+    got = ctx.best_hits_resident()
+    hit = got["best_asv"] != 0xffffffff
+    assert np.array_equal(np.flatnonzero(hit), reads)
+    assert np.array_equal(got["best_asv"][reads], asv) and np.array_equal(got["strand"][reads], strand)
+    assert np.all(got["strand"][~hit] == 0xff) and np.all(np.isnan(got["identity"][~hit])) and np.all(got["asv_start"][~hit] == -1)
+    for key in ("asv_start", "asv_end", "read_start", "read_end"):
+        assert np.array_equal(got[key][reads], ref[key]), key
+    gco = got["cigar_offsets"].astype(np.int64); rco = ref["cigar_offsets"].astype(np.int64)
+    assert np.array_equal((gco[1:] - gco[:-1])[reads], rco[1:] - rco[:-1]) and np.all((gco[1:] - gco[:-1])[~hit] == 0)
+    assert np.array_equal(got["cigar"], ref["cigar"])
+    span = (ref["asv_end"] - ref["asv_start"]).astype(np.float64)
+    assert np.array_equal(got["identity"][reads], 1.0 - ref["nm"].astype(np.float64) / span)
+    # CIGAR consistency: M + D spans the ASV interval, M + I the read interval; the ops are run-length maximal
+    ops = got["cigar"] & 15; lens = (got["cigar"] >> 4).astype(np.int64)
+    owner = np.repeat(np.arange(n), gco[1:] - gco[:-1])
+    asv_span = np.bincount(owner, weights=lens * (ops != 1), minlength=n).astype(np.int64)
+    read_span = np.bincount(owner, weights=lens * (ops != 2), minlength=n).astype(np.int64)
+    assert np.array_equal(asv_span[reads], got["asv_end"][reads] - got["asv_start"][reads])
+    assert np.array_equal(read_span[reads], got["read_end"][reads] - got["read_start"][reads])
+    assert ops.max() <= 2 and np.all((ops[1:] != ops[:-1]) | (owner[1:] != owner[:-1]))
+
+
 def test_map_reads_pooled_samples_and_degenerate_reads(ctx):
     from savont_b200 import _lib
     w = _make_workload("pooled", n_roots=6, n_samples=5)
