@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SAVONT_B200_ABI_VERSION 3
+#define SAVONT_B200_ABI_VERSION 4
 
 typedef struct savont_b200_ctx savont_b200_ctx;
 
@@ -253,6 +253,33 @@ int savont_b200_best_hits_resident(savont_b200_ctx *ctx, uint32_t *best_asv, uin
 int savont_b200_counts_dev(savont_b200_ctx *ctx, void **dev_ptr, size_t *n_u64);
 int savont_b200_read_counts(savont_b200_ctx *ctx, uint64_t *unambig, uint64_t *ambig, uint64_t *leq10, uint64_t *totals,
                             uint64_t *sample_singleton);
+
+/* ---- Stage 4 pileups: replaces alignment::generate_consensus_pileups, src/alignment.rs:415-641,
+ * called from src/main.rs Stage 4 with the clusters' consensus sequences.  Reads arrive in cluster order
+ * (`cluster[0..min(len, MAX_SEQS_CONSENSUS = 250)]`, src/alignment.rs:446-450, src/constants.rs:60), read_cons[r] = index
+ * of the read's consensus, non-decreasing; read_bases = the upper-case ACGT the reference decodes from TwinRead.dna_seq
+ * (:452-454), read_quals = the per-base qualities it expands from qual_seq (:456-478; NULL = 33 everywhere).  Each read
+ * is homopolymer-compressed when use_hpc != 0 (utils::homopolymer_compress_with_quality, src/utils.rs:135-184; run
+ * lengths cap at 255, quality = minimum of the run) and aligned to its (already compressed) consensus with the banded
+ * both-ends-free edit-distance DP of this library on both strands (band = params.band; smaller NM wins, tie -> forward)
+ * in place of minimap2 `map_ont` (:439-444,483): parity of the alignments with minimap2 is unpinned.  The CIGAR walk of
+ * :524-569 then fills one column per consensus position.
+ * Output: columns in CSR over the concatenated consensus positions -- pos_offsets[total_pos + 1], entries in the
+ * reference's push order (read order, then CIGAR order); ref_hp_length[total_pos] = median run length of the column's
+ * Base entries (:589-622; 1 when the column has none); read_strand[n_reads] 0/1 (0xff: read not aligned: empty read or
+ * consensus), read_nm[n_reads] (-1 likewise).  SAVONT_B200_ERR_CAPACITY if entry_cap is too small (the sum over
+ * the reads of read length + consensus length is always enough). */
+typedef struct savont_b200_pileup_entry {
+    uint32_t read;        /* index of the read in this call */
+    uint8_t  kind;        /* 0 = Base, 1 = Deletion, 2 = Insertion (PileupBase, src/alignment.rs:17-26) */
+    uint8_t  n;           /* bases carried: 1, 0, 1..MAX_INSERTION_LENGTH (= 2, src/constants.rs:3) */
+    uint8_t  base[2], qual[2], hp[2];   /* ASCII base, quality, homopolymer run length */
+} savont_b200_pileup_entry;
+int savont_b200_consensus_pileups(savont_b200_ctx *ctx, int use_hpc, const uint8_t *cons_bases, const uint64_t *cons_offsets,
+                                  size_t n_cons, const uint8_t *read_bases, const uint8_t *read_quals,
+                                  const uint64_t *read_offsets, const uint32_t *read_cons, size_t n_reads,
+                                  uint64_t *pos_offsets, savont_b200_pileup_entry *entries, size_t entry_cap,
+                                  uint64_t *n_entries, uint8_t *ref_hp_length, uint8_t *read_strand, int32_t *read_nm);
 
 /* Pinned host memory helpers (inputs placed here are copied without a staging pass). */
 int savont_b200_host_alloc(size_t bytes, void **out);

@@ -98,6 +98,7 @@ def lib():
         L.so_em.restype = C.c_int
         L.so_twin_reads_filter.restype = C.c_int
         L.so_count_split_kmers.restype = C.c_longlong
+        L.so_consensus_pileups.restype = C.c_longlong
         L.so_high_freq_kmers.restype = C.c_uint32
         L.so_set_read_filter.restype = None
         _lib = L
@@ -203,6 +204,31 @@ def high_freq_kmers(kmers, counts):
     out = np.zeros(n, np.uint64); nh = C.c_size_t(0)
     th = L.so_high_freq_kmers(_p(km, C.c_uint64), _p(ct, C.c_uint32), C.c_size_t(n), _p(out, C.c_uint64), C.byref(nh))
     return int(th), out[:int(nh.value)]
+
+
+PILEUP_ENTRY = np.dtype([("read", np.uint32), ("kind", np.uint8), ("n", np.uint8), ("base", np.uint8, 2), ("qual", np.uint8, 2),
+                         ("hp", np.uint8, 2)])      # so_pileup_entry / savont_b200_pileup_entry, 12 bytes
+assert PILEUP_ENTRY.itemsize == 12
+
+
+def consensus_pileups(cons_bases, cons_offsets, read_bases, read_quals, read_offsets, read_cons, band=64, use_hpc=True, cap=None):
+    """Stage 4 pileups (so_consensus_pileups) -> dict(pos_offsets, entries (PILEUP_ENTRY), ref_hp_length, read_strand, read_nm)"""
+    L = lib()
+    cb = as_u8(cons_bases); co = np.ascontiguousarray(cons_offsets, dtype=np.uint64)
+    rb = as_u8(read_bases); rq = None if read_quals is None else as_u8(read_quals)
+    ro = np.ascontiguousarray(read_offsets, dtype=np.uint64)
+    rc_ = np.ascontiguousarray(read_cons, dtype=np.uint32)
+    n = len(ro) - 1
+    npos = int(co[-1] - co[0])
+    cap = cap or int((ro[-1] - ro[0]) + sum(int(co[ci + 1] - co[ci]) for ci in rc_) + npos + 64)
+    po = np.zeros(npos + 1, np.uint64); ent = np.zeros(cap, PILEUP_ENTRY)
+    hp = np.zeros(max(npos, 1), np.uint8); st = np.zeros(max(n, 1), np.uint8); nm = np.zeros(max(n, 1), np.int32)
+    m = L.so_consensus_pileups(C.c_int(band), C.c_int(1 if use_hpc else 0), _p(cb, C.c_uint8), _p(co, C.c_uint64), C.c_size_t(len(co) - 1),
+                               _p(rb, C.c_uint8), _p(rq, C.c_uint8), _p(ro, C.c_uint64), _p(rc_, C.c_uint32), C.c_size_t(n),
+                               _p(po, C.c_uint64), C.c_void_p(ent.ctypes.data), C.c_size_t(cap), _p(hp, C.c_uint8), _p(st, C.c_uint8),
+                               _p(nm, C.c_int32))
+    assert m >= 0, m
+    return dict(pos_offsets=po, entries=ent[:m], ref_hp_length=hp[:npos], read_strand=st[:n], read_nm=nm[:n])
 
 
 class Oracle:

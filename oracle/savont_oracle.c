@@ -652,6 +652,139 @@ int so_align_pairs(so_ctx *c, const uint8_t *bases, const uint64_t *offsets, siz
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* Stage 4 pileups, alignment::generate_consensus_pileups          */
+/* (src/alignment.rs:415-641) over utils::homopolymer_compress_with_quality              */
+/* (src/utils.rs:135-184).  The minimap2 `map_ont` call of :439-483 is replaced by the   */
+/* north-star DP above on both strands (smaller NM wins, tie -> forward): parity of the  */
+/* alignments with minimap2 is UNPINNED, everything around them is restated line by line.*/
+/* ------------------------------------------------------------------------------------ */
+/* src/utils.rs:135-184 on 2-bit codes (the reference compares the upper-case ACGT characters decoded from the TwinRead's
+ * 2-bit dna_seq, src/alignment.rs:452-454); returns the compressed length */
+static size_t hpc_with_quality(const uint8_t *codes, const uint8_t *quals, size_t len, int do_hpc, uint8_t *hc, uint8_t *hq,
+                               uint8_t *hl) {
+    if (len == 0) return 0;
+    if (!do_hpc) {
+        for (size_t i = 0; i < len; i++) { hc[i] = codes[i]; hq[i] = quals[i]; hl[i] = 1; }
+        return len;
+    }
+    size_t n = 0;
+    uint8_t cur = codes[0], cur_len = 1, cur_min = quals[0];
+    for (size_t i = 1; i < len; i++) {
+        if (codes[i] == cur && cur_len < 255) { cur_len++; if (quals[i] < cur_min) cur_min = quals[i]; }
+        else { hc[n] = cur; hq[n] = cur_min; hl[n] = cur_len; n++; cur = codes[i]; cur_len = 1; cur_min = quals[i]; }
+    }
+    hc[n] = cur; hq[n] = cur_min; hl[n] = cur_len; n++;
+    return n;
+}
+
+typedef struct { so_pileup_entry *v; size_t n, cap; } pile_col;
+static void col_push(pile_col *c, so_pileup_entry e) {
+    if (c->n == c->cap) { c->cap = c->cap ? c->cap * 2 : 8; c->v = (so_pileup_entry *)realloc(c->v, c->cap * sizeof(so_pileup_entry)); }
+    c->v[c->n++] = e;
+}
+
+long long so_consensus_pileups(int band, int use_hpc, const uint8_t *cons_bases, const uint64_t *cons_offsets, size_t n_cons,
+                               const uint8_t *read_bases, const uint8_t *read_quals, const uint64_t *read_offsets,
+                               const uint32_t *read_cons, size_t n_reads, uint64_t *pos_offsets, so_pileup_entry *entries,
+                               size_t entry_cap, uint8_t *ref_hp_length, uint8_t *read_strand, int32_t *read_nm) {
+    static const char ACGT[4] = {'A', 'C', 'G', 'T'};
+    const size_t total_pos = (size_t)(cons_offsets[n_cons] - cons_offsets[0]);
+    pile_col *cols = (pile_col *)calloc(total_pos ? total_pos : 1, sizeof(pile_col));
+    for (size_t r = 0; r < n_reads; r++) {                                    /* :447-450, reads in cluster order */
+        read_strand[r] = 0xff; read_nm[r] = -1;
+        const uint32_t ci = read_cons[r];
+        if (ci >= n_cons) { free(cols); return -3; }
+        const size_t coff = (size_t)(cons_offsets[ci] - cons_offsets[0]), clen = (size_t)(cons_offsets[ci + 1] - cons_offsets[ci]);
+        const size_t off = read_offsets[r], len = read_offsets[r + 1] - off;
+        uint8_t *codes = (uint8_t *)malloc(len + 1), *q = (uint8_t *)malloc(len + 1);
+        for (size_t t = 0; t < len; t++) { codes[t] = so_encode_base(read_bases[off + t]); q[t] = read_quals ? read_quals[off + t] : 33; }
+        uint8_t *hc = (uint8_t *)malloc(len + 1), *hq = (uint8_t *)malloc(len + 1), *hl = (uint8_t *)malloc(len + 1);
+        const size_t hn = hpc_with_quality(codes, q, len, use_hpc, hc, hq, hl);             /* :481 */
+        if (hn > 0 && clen > 0) {              /* minimap2 returns Err for an empty sequence: the read is skipped (:486) */
+            uint8_t *ccodes = (uint8_t *)malloc(clen);
+            for (size_t t = 0; t < clen; t++) ccodes[t] = so_encode_base(cons_bases[cons_offsets[ci] + t]);
+            aln_t al[2]; memset(al, 0, sizeof(al));
+            uint8_t *ori[2];
+            for (int sd = 0; sd < 2; sd++) {
+                ori[sd] = oriented_codes(hc, hn, sd);
+                banded_align(ccodes, (int)clen, ori[sd], (int)hn, band, 1, &al[sd]);
+            }
+            const int sd = al[1].nm < al[0].nm ? 1 : 0;
+            read_strand[r] = (uint8_t)sd; read_nm[r] = al[sd].nm;
+            /* :497-521: the read in alignment orientation; qualities and run lengths reversed with it */
+            const uint8_t *fseq = ori[sd];
+            uint8_t *fq = (uint8_t *)malloc(hn), *fl = (uint8_t *)malloc(hn);
+            for (size_t t = 0; t < hn; t++) { fq[t] = sd ? hq[hn - 1 - t] : hq[t]; fl[t] = sd ? hl[hn - 1 - t] : hl[t]; }
+            const size_t qs = (size_t)al[sd].read_start, qe = (size_t)al[sd].read_end;
+            const size_t mlen = qe - qs;                                               /* mapped_seq = final_seq[qs..qe] */
+            size_t ref_pos = (size_t)al[sd].asv_start, query_pos = 0;                  /* :524-525 */
+            for (size_t t = 0; t < al[sd].n_cigar; t++) {
+                const size_t ln = al[sd].cigar[t] >> 4; const int op = (int)(al[sd].cigar[t] & 15u);
+                if (op == 0) {                                                          /* :531-543 */
+                    for (size_t j = 0; j < ln; j++)
+                        if (ref_pos + j < clen && query_pos + j < mlen) {
+                            so_pileup_entry e; memset(&e, 0, sizeof(e));
+                            e.read = (uint32_t)r; e.kind = 0; e.n = 1;
+                            e.base[0] = (uint8_t)ACGT[fseq[qs + query_pos + j]]; e.qual[0] = fq[qs + query_pos + j]; e.hp[0] = fl[qs + query_pos + j];
+                            col_push(&cols[coff + ref_pos + j], e);
+                        }
+                    ref_pos += ln; query_pos += ln;
+                } else if (op == 1) {                                                   /* :544-557, MAX_INSERTION_LENGTH = 2 */
+                    if (ref_pos > 0 && ref_pos - 1 < clen && query_pos + ln <= mlen) {
+                        so_pileup_entry e; memset(&e, 0, sizeof(e));
+                        e.read = (uint32_t)r; e.kind = 2; e.n = (uint8_t)(ln < 2 ? ln : 2);
+                        for (size_t j = 0; j < e.n; j++) {
+                            e.base[j] = (uint8_t)ACGT[fseq[qs + query_pos + j]]; e.qual[j] = fq[qs + query_pos + j]; e.hp[j] = fl[qs + query_pos + j];
+                        }
+                        col_push(&cols[coff + ref_pos - 1], e);
+                    }
+                    query_pos += ln;
+                } else {                                                                /* :558-566 */
+                    for (size_t j = 0; j < ln; j++)
+                        if (ref_pos + j < clen) {
+                            so_pileup_entry e; memset(&e, 0, sizeof(e));
+                            e.read = (uint32_t)r; e.kind = 1;
+                            col_push(&cols[coff + ref_pos + j], e);
+                        }
+                    ref_pos += ln;
+                }
+            }
+            for (int t = 0; t < 2; t++) { free(al[t].cigar); free(ori[t]); }
+            free(fq); free(fl); free(ccodes);
+        }
+        free(codes); free(q); free(hc); free(hq); free(hl);
+    }
+    /* flatten + the median run length per position (:589-622: sorted hp lengths of the Base entries, even count ->
+     * (s[mid-1] + s[mid]) / 2 in u16, no bases -> 1) */
+    size_t ne = 0; long long rc = 0;
+    pos_offsets[0] = 0;
+    for (size_t p = 0; p < total_pos; p++) {
+        uint32_t hist[256]; memset(hist, 0, sizeof(hist));
+        size_t nb = 0;
+        for (size_t t = 0; t < cols[p].n; t++) {
+            if (rc == 0) { if (ne < entry_cap) entries[ne] = cols[p].v[t]; else rc = -1; }
+            ne++;
+            if (cols[p].v[t].kind == 0) { hist[cols[p].v[t].hp[0]]++; nb++; }
+        }
+        pos_offsets[p + 1] = ne;
+        if (nb == 0) ref_hp_length[p] = 1;
+        else {
+            const size_t mid = nb / 2;
+            int lo = -1, hi = -1; size_t acc = 0;                    /* sorted[mid-1], sorted[mid] */
+            for (int v = 0; v < 256; v++) {
+                acc += hist[v];
+                if (lo < 0 && mid >= 1 && acc >= mid) lo = v;       /* index mid-1 is covered once acc >= mid */
+                if (hi < 0 && acc >= mid + 1) { hi = v; break; }
+            }
+            ref_hp_length[p] = (nb % 2 == 0) ? (uint8_t)(((uint16_t)lo + (uint16_t)hi) / 2) : (uint8_t)hi;
+        }
+        free(cols[p].v);
+    }
+    free(cols);
+    return rc ? rc : (long long)ne;
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* a4: kmer_comp::twin_reads_from_snpmers, src/kmer_comp.rs:68-258                      */
 /* ------------------------------------------------------------------------------------ */
 /* the tests a read goes through before it becomes a TwinRead; the quality cutoff (:248) is applied after the id sort in

@@ -171,6 +171,26 @@ long long so_count_split_kmers(int k, int min_bq, int single_strand, const uint8
  * k-mers with c0 + c1 > high_freq_thresh (the set a4 reads), in input order.  Returns the threshold; n must be > 0. */
 uint32_t so_high_freq_kmers(const uint64_t *kmers, const uint32_t *counts, size_t n, uint64_t *hf_out, size_t *n_hf);
 
+/* ---- Stage 4 pileups, alignment::generate_consensus_pileups (src/alignment.rs:415-641).
+ * Reads arrive in cluster order, at most MAX_SEQS_CONSENSUS = 250 per consensus (src/constants.rs:60), read_cons[r] = the
+ * consensus of read r (non-decreasing); read_quals = the per-base qualities the reference expands from qual_seq
+ * (:456-478; NULL = 33 everywhere).  Each read is homopolymer-compressed (src/utils.rs:135-184) and aligned to its
+ * consensus (already compressed) with the north-star DP on both strands (replaces minimap2 `map_ont`: parity unpinned);
+ * the CIGAR walk of :524-569 fills one column per consensus position.  Output: columns in CSR (pos_offsets over the
+ * concatenated consensus positions), entries in push order (read order, then CIGAR order); ref_hp_length = the median
+ * run length of :589-622 (1 when no base is aligned); read_strand 0/1 (0xff: not aligned), read_nm.
+ * Returns the number of entries, or -1 if entry_cap is too small. */
+typedef struct so_pileup_entry {
+    uint32_t read;       /* index of the read in the call */
+    uint8_t kind;        /* 0 = Base, 1 = Deletion, 2 = Insertion (src/alignment.rs:17-26) */
+    uint8_t n;           /* bases carried: 1, 0, 1..MAX_INSERTION_LENGTH (= 2, src/constants.rs:3) */
+    uint8_t base[2], qual[2], hp[2];
+} so_pileup_entry;
+long long so_consensus_pileups(int band, int use_hpc, const uint8_t *cons_bases, const uint64_t *cons_offsets, size_t n_cons,
+                               const uint8_t *read_bases, const uint8_t *read_quals, const uint64_t *read_offsets,
+                               const uint32_t *read_cons, size_t n_reads, uint64_t *pos_offsets, so_pileup_entry *entries,
+                               size_t entry_cap, uint8_t *ref_hp_length, uint8_t *read_strand, int32_t *read_nm);
+
 /* ---- a13-a14: EM over equivalence classes (src/alignment.rs:1957-2038) ---------------
  * classes in CSR (cls_offsets[n_cls+1], cls_asv), counts[n_cls]; total_assigned;
  * out: abundances[A] (f64), depths[A] = round(ab*total).  Classes are iterated in the

@@ -136,8 +136,8 @@ static int upload_snp_set(Context *c) {
 // ------------------------------------------------------------------------------------------------
 constexpr size_t kCtrBytes = 32;   // u32 snp pool counter, pair counter, error bits, spare; u64 dp_cells; pad
 
-static int batch_upload(Context *c, Batch &b, const uint8_t *bases, const uint8_t *quals, const uint64_t *offsets,
-                        const uint32_t *file_idx, size_t n, uint64_t *h2d_bytes, cudaStream_t st = nullptr) {
+int batch_upload(Context *c, Batch &b, const uint8_t *bases, const uint8_t *quals, const uint64_t *offsets,
+                 const uint32_t *file_idx, size_t n, uint64_t *h2d_bytes, cudaStream_t st) {
     if (st == nullptr) st = c->stream;
     const uint64_t base0 = offsets[0];
     const uint64_t total = offsets[n] - base0;
@@ -473,6 +473,33 @@ static int stage_assign(Context *c, Batch &b, int n_samples, int strand_mode) {
 // ------------------------------------------------------------------------------------------------
 // ASV index (reference src/kmer_comp.rs:39-66 + src/alignment.rs:1754-1765)
 // ------------------------------------------------------------------------------------------------
+// DP planes of the sequences the reads are aligned against (ASVs; consensus sequences in the pileup path): per sequence
+// padl zero bits, then the bases (bit i + padl of plane word (i + padl) / 32), then >= 32 * (NW + 4) zero bits
+void build_dp_planes(const DeviceParams &dp, const uint8_t *bases, const uint64_t *offsets, size_t A, std::vector<uint2> &planes,
+                     std::vector<uint32_t> &plane_off, std::vector<uint32_t> &lens, uint32_t *max_len) {
+    const int nw = align_words_for_band(dp.band);
+    const uint32_t padl = (uint32_t)dp.asv_padl;
+    plane_off.assign(A, 0); lens.assign(A, 0);
+    size_t words = 0;
+    *max_len = 0;
+    for (size_t a = 0; a < A; ++a) {
+        const uint32_t len = (uint32_t)(offsets[a + 1] - offsets[a]);
+        lens[a] = len; plane_off[a] = (uint32_t)words;
+        words += (padl + len) / 32 + (size_t)nw + 6;
+        if (len > *max_len) *max_len = len;
+    }
+    planes.assign(words + 8, make_uint2(0, 0));
+    for (size_t a = 0; a < A; ++a) {
+        const uint8_t *sq = bases + offsets[a];
+        uint2 *pw = planes.data() + plane_off[a];
+        for (uint32_t i = 0; i < lens[a]; ++i) {
+            const uint32_t code = enc_host(sq[i]), bit = i + padl;
+            if (code & 1) pw[bit >> 5].x |= 1u << (bit & 31);
+            if (code & 2) pw[bit >> 5].y |= 1u << (bit & 31);
+        }
+    }
+}
+
 static int build_asv_index(Context *c) {
     const size_t A = c->asv_offsets_h.empty() ? 0 : c->asv_offsets_h.size() - 1;
     c->n_asv = A;
@@ -579,28 +606,10 @@ static int build_asv_index(Context *c) {
         i = j;
     }
     c->idx_mask = cap ? cap - 1 : 0; c->idx_shift = ishift;
-    // (3) DP planes: padl zero bits, then the bases, then >= 32*(NW+4) zero bits
-    const int nw = align_words_for_band(c->dp.band);
-    const uint32_t padl = (uint32_t)c->dp.asv_padl;
-    std::vector<uint32_t> plane_off(A), lens(A);
-    size_t words = 0;
-    c->max_asv_len = 0;
-    for (size_t a = 0; a < A; ++a) {
-        const uint32_t len = (uint32_t)(c->asv_offsets_h[a + 1] - c->asv_offsets_h[a]);
-        lens[a] = len; plane_off[a] = (uint32_t)words;
-        words += (padl + len) / 32 + (size_t)nw + 6;
-        if (len > c->max_asv_len) c->max_asv_len = len;
-    }
-    std::vector<uint2> planes(words + 8, make_uint2(0, 0));
-    for (size_t a = 0; a < A; ++a) {
-        const uint8_t *sq = c->asv_bases_h.data() + c->asv_offsets_h[a];
-        uint2 *pw = planes.data() + plane_off[a];
-        for (uint32_t i = 0; i < lens[a]; ++i) {
-            const uint32_t code = enc_host(sq[i]), bit = i + padl;
-            if (code & 1) pw[bit >> 5].x |= 1u << (bit & 31);
-            if (code & 2) pw[bit >> 5].y |= 1u << (bit & 31);
-        }
-    }
+    // (3) DP planes
+    std::vector<uint32_t> plane_off, lens;
+    std::vector<uint2> planes;
+    build_dp_planes(c->dp, c->asv_bases_h.data(), c->asv_offsets_h.data(), A, planes, plane_off, lens, &c->max_asv_len);
     c->asv_len_h = lens;
     // upload
     TRY(c->d_mset.ensure((mset.size() + 1) * 8)); TRY(c->d_mset_off.ensure((A + 1) * 4));
@@ -729,11 +738,11 @@ namespace sb {
 // Traceback (align_tb_kernel) of explicit device-resident pairs against the batch's read planes, in sub-batches bounded by
 // a 1 GiB history workspace; the CIGAR slots are compacted on the device (scan of the op counts + warp-per-pair copy) so that
 // only the ops cross PCIe.  cigar_offsets[0] must be set by the caller (base of this call's ops in `cigar`).
-static int traceback_pairs(Context *c, Batch &b, const uint32_t *d_pr, const uint32_t *d_pa, const uint8_t *d_ps, size_t n_pairs,
-                           int32_t *nm, int32_t *asv_end, int32_t *read_end, int32_t *asv_start, int32_t *read_start,
-                           uint64_t *cigar_offsets, uint32_t *cigar, size_t cigar_cap) {
+int traceback_pairs(Context *c, Batch &b, const AsvIndex &ix, uint32_t max_ref_len, const uint32_t *d_pr, const uint32_t *d_pa,
+                    const uint8_t *d_ps, size_t n_pairs, int32_t *nm, int32_t *asv_end, int32_t *read_end, int32_t *asv_start,
+                    int32_t *read_start, uint64_t *cigar_offsets, uint32_t *cigar, size_t cigar_cap, std::vector<uint32_t> *cigar_vec) {
     const uint32_t hist_cols = std::max<uint32_t>(b.max_len, 1u);
-    const uint32_t cigar_stride = b.max_len + c->max_asv_len + 2;
+    const uint32_t cigar_stride = b.max_len + max_ref_len + 2;
     const size_t per_pair_words = align_tb_hist_words(1, hist_cols, c->dp);
     size_t sub = std::max<size_t>(128, ((size_t)1 << 28) / std::max<size_t>(per_pair_words, 1));
     sub = std::min<size_t>(sub, 1u << 16);
@@ -754,7 +763,7 @@ static int traceback_pairs(Context *c, Batch &b, const uint32_t *d_pr, const uin
         if ((rc = d_out.ensure((size_t)np * 5 * 4)) != 0) break;
         int32_t *o = d_out.as<int32_t>();
         AlignOut ao{o, o + np, o + 2 * (size_t)np};
-        launch_align_tb(seq_view(b), b.planes.as<uint2>(), index_view(c), d_pr + p0, d_pa + p0, d_ps + p0, np, d_hist.as<uint32_t>(), ao,
+        launch_align_tb(seq_view(b), b.planes.as<uint2>(), ix, d_pr + p0, d_pa + p0, d_ps + p0, np, d_hist.as<uint32_t>(), ao,
                         o + 3 * (size_t)np, o + 4 * (size_t)np, d_slots.as<uint32_t>(), cigar_stride, d_cnt.as<uint32_t>(), c->dp, c->stream);
         launch_scan_u32(d_cnt.as<uint32_t>(), d_off.as<uint32_t>(), np, d_tmp.as<uint32_t>(), c->stream);
         launch_cigar_compact(d_slots.as<uint32_t>(), cigar_stride, d_cnt.as<uint32_t>(), d_off.as<uint32_t>(), np, d_ops.as<uint32_t>(),
@@ -768,7 +777,8 @@ static int traceback_pairs(Context *c, Batch &b, const uint32_t *d_pr, const uin
         e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) { rc = fail(SAVONT_B200_ERR_CUDA, "align_tb: %s", cudaGetErrorString(e)); break; }
         const uint32_t total = h_off[np];
-        if (cig_base + total > cigar_cap) { rc = fail(SAVONT_B200_ERR_CAPACITY, "cigar capacity %zu too small", cigar_cap); break; }
+        if (cigar_vec) { cigar_vec->resize(cig_base + total + 1); cigar = cigar_vec->data(); }   // growable destination
+        else if (cig_base + total > cigar_cap) { rc = fail(SAVONT_B200_ERR_CAPACITY, "cigar capacity %zu too small", cigar_cap); break; }
         if (total) cudaMemcpyAsync(cigar + cig_base, d_ops.p, (size_t)total * 4, cudaMemcpyDeviceToHost, c->stream);
         memcpy(nm + p0, h_out.data(), (size_t)np * 4);
         memcpy(asv_end + p0, h_out.data() + np, (size_t)np * 4);
@@ -1134,8 +1144,8 @@ int savont_b200_align_pairs(savont_b200_ctx *h, const uint8_t *bases, const uint
         CK(cudaStreamSynchronize(c->stream));
         return 0;
     }
-    return traceback_pairs(c, b, b.p_read.as<uint32_t>(), b.p_asv.as<uint32_t>(), b.p_strand.as<uint8_t>(), n_pairs, nm, asv_end,
-                           read_end, asv_start, read_start, cigar_offsets, cigar, cigar_cap);
+    return traceback_pairs(c, b, index_view(c), c->max_asv_len, b.p_read.as<uint32_t>(), b.p_asv.as<uint32_t>(), b.p_strand.as<uint8_t>(),
+                           n_pairs, nm, asv_end, read_end, asv_start, read_start, cigar_offsets, cigar, cigar_cap);
 }
 
 // shared body of savont_b200_map_reads / savont_b200_map_twin_reads: double-buffered batches, the H2D copies of
@@ -1358,7 +1368,7 @@ int savont_b200_best_hits_resident(savont_b200_ctx *h, uint32_t *best_asv, uint8
     std::vector<int32_t> v(np * 5);
     std::vector<uint64_t> coff(np + 1, 0);
     if (np) {
-        rc = traceback_pairs(c, b, d_pr.as<uint32_t>(), d_pa.as<uint32_t>(), d_ps.as<uint8_t>(), np, v.data(), v.data() + np,
+        rc = traceback_pairs(c, b, index_view(c), c->max_asv_len, d_pr.as<uint32_t>(), d_pa.as<uint32_t>(), d_ps.as<uint8_t>(), np, v.data(), v.data() + np,
                              v.data() + 2 * np, v.data() + 3 * np, v.data() + 4 * np, coff.data(), cigar, cigar_cap);
         if (rc) { cleanup(); return rc; }
     }

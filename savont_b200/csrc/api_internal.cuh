@@ -166,6 +166,15 @@ inline uint32_t next_pow2_u32(uint64_t x) { uint32_t p = 2; while ((uint64_t)p <
 inline uint32_t shift_for_cap(uint32_t cap) { uint32_t b = 0; while ((1u << b) < cap) ++b; return 64u - b; }
 inline float ev_ms(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
 int use_device(Context *c);
+// api.cu helpers shared with api_pileup.cu
+int batch_upload(Context *c, Batch &b, const uint8_t *bases, const uint8_t *quals, const uint64_t *offsets, const uint32_t *file_idx,
+                 size_t n, uint64_t *h2d_bytes, cudaStream_t st = nullptr);
+void build_dp_planes(const DeviceParams &dp, const uint8_t *bases, const uint64_t *offsets, size_t A, std::vector<uint2> &planes,
+                     std::vector<uint32_t> &plane_off, std::vector<uint32_t> &lens, uint32_t *max_len);
+int traceback_pairs(Context *c, Batch &b, const AsvIndex &ix, uint32_t max_ref_len, const uint32_t *d_pr, const uint32_t *d_pa,
+                    const uint8_t *d_ps, size_t n_pairs, int32_t *nm, int32_t *asv_end, int32_t *read_end, int32_t *asv_start,
+                    int32_t *read_start, uint64_t *cigar_offsets, uint32_t *cigar, size_t cigar_cap,
+                    std::vector<uint32_t> *cigar_vec = nullptr);
 SeqBatch seq_view(const Batch &b);
 
 }  // namespace sb

@@ -241,4 +241,42 @@ void launch_gather_sketch(const SeqBatch &in, const SketchOut &sk, const uint32_
                           const DeviceParams &p, cudaStream_t st);
 void launch_pack_planes(const SeqBatch &in, uint2 *planes, cudaStream_t st);
 
+// ---- Stage 4 pileups (pileup.cu) ----
+struct PileupEntry {         // == savont_b200_pileup_entry (include/savont_b200.h), 12 bytes
+    uint32_t read;
+    uint8_t kind;            // 0 Base, 1 Deletion, 2 Insertion
+    uint8_t n;
+    uint8_t base[2], qual[2], hp[2];
+};
+struct PileupArgs {
+    // aligned reads t = 0..n_aln (cluster order): read index in the batch, consensus (batch-local), strand, alignment
+    uint32_t n_aln;
+    const uint32_t *aln_read, *aln_cons;
+    const uint8_t *strand;
+    const int32_t *cons_start, *read_start, *read_end;
+    const uint32_t *cigar_off;       // [n_aln + 1]
+    const uint32_t *cigar;
+    const uint64_t *row_off;         // [n_aln] first cell of the read's row in cnt / excl (row length = its consensus length)
+    // compressed reads
+    const uint64_t *hpc_offsets;     // [n_reads + 1]
+    const uint8_t *hc, *hq, *hl;
+    // consensus sequences of the batch
+    const uint32_t *cons_len, *cons_pos_off, *cons_aln_off;   // [n_cons], [n_cons + 1] first position, [n_cons + 1] first aligned read
+    const uint32_t *pos_cons;        // [n_pos] consensus of a global position
+    uint32_t n_pos;
+    uint32_t read_base;              // index of the batch's first read in the call (entries carry call-wide read indices)
+    uint8_t *cnt; uint16_t *excl;
+    uint32_t *col_total;             // [n_pos]
+    const uint32_t *pos_off;         // [n_pos + 1] exclusive scan of col_total
+    PileupEntry *entries;
+};
+void launch_hpc_count(const SeqBatch &in, int do_hpc, uint32_t *cnt, cudaStream_t st);
+void launch_hpc_write(const SeqBatch &in, int do_hpc, const uint32_t *out_off, uint8_t *hc, uint8_t *hq, uint8_t *hl, cudaStream_t st);
+void launch_pick_strand(const int32_t *nm2, const uint32_t *pr2, const uint32_t *pa2, uint32_t n, uint32_t *pr, uint32_t *pa,
+                        uint8_t *ps, cudaStream_t st);
+void launch_pileup_count(const PileupArgs &a, cudaStream_t st);
+void launch_pileup_rank(const PileupArgs &a, cudaStream_t st);
+void launch_pileup_emit(const PileupArgs &a, cudaStream_t st);
+void launch_pileup_median(const PileupArgs &a, uint8_t *ref_hp, cudaStream_t st);
+
 }  // namespace sb

@@ -164,3 +164,69 @@ def split_kmer_counts(reads, quals, rc, k, min_bq, single_strand=False):
         if (c0 > 2) if single_strand else (c0 > 0 and c1 > 0 and c0 + c1 > 2):
             out.append((kmer, c0, c1))
     return out, len(counts)
+
+
+def hpc_with_quality(seq: bytes, qual: bytes, do_hpc=True):
+    """utils::homopolymer_compress_with_quality (src/utils.rs:135-184) on the upper-case ACGT decoded from 2-bit codes"""
+    codes = [enc(b) for b in seq]
+    if not codes:
+        return [], [], []
+    if not do_hpc:
+        return codes, list(qual), [1] * len(codes)
+    hc, hq, hl = [], [], []
+    cur, ln, mq = codes[0], 1, qual[0]
+    for c_, q in zip(codes[1:], qual[1:]):
+        if c_ == cur and ln < 255:
+            ln += 1; mq = min(mq, q)
+        else:
+            hc.append(cur); hq.append(mq); hl.append(ln)
+            cur, ln, mq = c_, 1, q
+    hc.append(cur); hq.append(mq); hl.append(ln)
+    return hc, hq, hl
+
+
+def pileup_columns(cons_lens, reads, aln):
+    """CIGAR walk + median run length of generate_consensus_pileups (src/alignment.rs:524-622).
+    reads[r] = (cons index, hc, hq, hl) compressed read; aln[r] = None or (strand, cons_start, read_start, read_end, cigar ops
+    [(len, op)]).  Returns (columns[cons][pos] = list of (read, kind, bases, quals, hps), ref_hp[cons][pos])."""
+    cols = [[[] for _ in range(n)] for n in cons_lens]
+    for r, (ci, hc, hq, hl) in enumerate(reads):
+        if aln[r] is None:
+            continue
+        sd, cs, qs, qe, cig = aln[r]
+        if sd:
+            fs = [3 - x for x in reversed(hc)]; fq = list(reversed(hq)); fl = list(reversed(hl))
+        else:
+            fs, fq, fl = hc, hq, hl
+        ms, mq, ml = fs[qs:qe], fq[qs:qe], fl[qs:qe]
+        ref, qp = cs, 0
+        col = cols[ci]
+        for ln, op in cig:
+            if op == 0:
+                for j in range(ln):
+                    if ref + j < len(col) and qp + j < len(ms):
+                        col[ref + j].append((r, 0, [b"ACGT"[ms[qp + j]]], [mq[qp + j]], [ml[qp + j]]))
+                ref += ln; qp += ln
+            elif op == 1:
+                if ref > 0 and ref - 1 < len(col) and qp + ln <= len(ms):
+                    m = min(ln, 2)
+                    col[ref - 1].append((r, 2, [b"ACGT"[x] for x in ms[qp:qp + m]], mq[qp:qp + m], ml[qp:qp + m]))
+                qp += ln
+            else:
+                for j in range(ln):
+                    if ref + j < len(col):
+                        col[ref + j].append((r, 1, [], [], []))
+                ref += ln
+    hp = []
+    for col in cols:
+        out = []
+        for entries in col:
+            v = sorted(e[4][0] for e in entries if e[1] == 0)
+            if not v:
+                out.append(1)
+            elif len(v) % 2 == 0:
+                out.append((v[len(v) // 2 - 1] + v[len(v) // 2]) // 2)
+            else:
+                out.append(v[len(v) // 2])
+        hp.append(out)
+    return cols, hp

@@ -644,3 +644,63 @@ def test_candidates_large_asv_set(ctx):
                 orc2.map_reads(r["bases"][:int(r["offsets"][600])], r["quals"][:int(r["offsets"][600])], r["offsets"][:601]), MAP_KEYS,
                 "A=1300 both strands")
     ctx.set_params(_lib.default_params())
+
+
+PILEUP_KEYS = ["pos_offsets", "ref_hp_length", "read_strand", "read_nm"]
+
+
+def _assert_pileups(got, want, what):
+    assert_same(got, want, PILEUP_KEYS, what)
+    assert got["entries"].tobytes() == want["entries"].tobytes(), f"{what}: entries differ"
+
+
+@pytest.mark.parametrize("use_hpc,band,long_runs", [(True, 16, True), (False, 40, False), (True, 3, False), (True, 64, False)])
+def test_consensus_pileups_ragged_clusters(ctx, use_hpc, band, long_runs):
+    """Stage 4 pileups: empty reads / consensus, consensus without reads, N bases, runs beyond 255, both strands"""
+    from savont_b200 import _lib
+    from tests.util import pileup_case
+    gp, _ = _params(_lib, band=band)
+    ctx.set_params(gp)
+    cons, reads, quals, rcons = pileup_case(5200 + band, n_cons=7, reads_per=15, long_runs=long_runs)
+    cb, co = O.concat(cons); rb, ro = O.concat(reads); qb, _ = O.concat(quals)
+    want = O.consensus_pileups(cb, co, rb, qb, ro, rcons, band=band, use_hpc=use_hpc)
+    got = ctx.consensus_pileups(cb, co, rb, qb, ro, rcons, use_hpc=use_hpc)
+    _assert_pileups(got, want, f"pileups hpc={use_hpc} band={band}")
+    assert len(got["entries"]) > 500
+    # without qualities (quality 33 everywhere), no reads at all, no consensus at all
+    _assert_pileups(ctx.consensus_pileups(cb, co, rb, None, ro, rcons, use_hpc=use_hpc),
+                    O.consensus_pileups(cb, co, rb, None, ro, rcons, band=band, use_hpc=use_hpc), "pileups without qualities")
+    e = ctx.consensus_pileups(cb, co, b"", None, [0], [], use_hpc=use_hpc)
+    assert len(e["entries"]) == 0 and np.all(e["ref_hp_length"] == 1) and np.all(e["pos_offsets"] == 0)
+    e = ctx.consensus_pileups(b"", [0], b"", None, [0], [], use_hpc=use_hpc)
+    assert len(e["entries"]) == 0 and len(e["pos_offsets"]) == 1
+    # a too small entry buffer is an error, not a truncation
+    with pytest.raises(_lib.SavontB200Error):
+        ctx.consensus_pileups(cb, co, rb, qb, ro, rcons, use_hpc=use_hpc, cap=len(got["entries"]) - 1)
+
+
+def test_consensus_pileups_full_clusters(ctx):
+    """16S-sized clusters: 250 reads (MAX_SEQS_CONSENSUS) of ~1500 bp at 2% errors per consensus, band 64"""
+    from savont_b200 import _lib, synth
+    w = synth.Workload("ont16s", n_roots=2)
+    n_cons, per = 6, 250
+    gp, _ = _params(_lib, band=64)
+    ctx.set_params(gp)
+    rng = np.random.default_rng(7)
+    asv = [bytes(w.asv_bases[int(w.asv_offsets[a]):int(w.asv_offsets[a + 1])]) for a in range(n_cons)]
+    from tests import pyref
+    cons = [bytes(b"ACGT"[x] for x in pyref.hpc_with_quality(s, bytes(len(s)))[0]) for s in asv]
+    r = w.reads(4000)
+    reads, quals, rcons = [], [], []
+    for a in range(n_cons):
+        idx = np.flatnonzero(r["truth_asv"] % n_cons == a)[:per]
+        for i in idx:
+            o0, o1 = int(r["offsets"][i]), int(r["offsets"][i + 1])
+            # reads drawn from other ASVs of the same genus: realistic mismatches against this consensus
+            reads.append(bytes(r["bases"][o0:o1])); quals.append(bytes(r["quals"][o0:o1])); rcons.append(a)
+    cb, co = O.concat(cons); rb, ro = O.concat(reads); qb, _ = O.concat(quals)
+    want = O.consensus_pileups(cb, co, rb, qb, ro, rcons, band=64, use_hpc=True)
+    got = ctx.consensus_pileups(cb, co, rb, qb, ro, rcons, use_hpc=True)
+    _assert_pileups(got, want, "full clusters")
+    assert len(got["entries"]) > 0.5 * len(reads) * 1000
+    del rng

@@ -341,3 +341,47 @@ def test_high_freq_threshold_rule():
     th, hf = O.high_freq_kmers(km, ct)
     s = np.sort(ct.sum(1)); assert th == max(100, int(s[n - n // 100000 - 1]))
     assert np.array_equal(hf, km[ct.sum(1) > th])
+
+
+@pytest.mark.parametrize("use_hpc,band", [(True, 16), (False, 40), (True, 3)])
+def test_consensus_pileups_match_python_restatement(use_hpc, band):
+    """so_consensus_pileups vs tests/pyref.py (compression, strand choice over the oracle's DP, CIGAR walk, median)"""
+    from tests.util import pileup_case
+    cons, reads, quals, rcons = pileup_case(4100 + band, long_runs=use_hpc)
+    cb, co = O.concat(cons); rb, ro = O.concat(reads); qb, _ = O.concat(quals)
+    got = O.consensus_pileups(cb, co, rb, qb, ro, rcons, band=band, use_hpc=use_hpc)
+    # independent walk; the alignments themselves come from so_align_pairs on the compressed reads
+    comp = [pyref.hpc_with_quality(r, q, use_hpc) for r, q in zip(reads, quals)]
+    hreads = [bytes(b"ACGT"[x] for x in hc) for hc, _, _ in comp]
+    orc = O.Oracle(O.default_params(band=band), [])
+    ab, ao = O.concat([c_ or b"A" * 30 for c_ in cons])     # the ASV loader rejects empty sequences; never paired below
+    orc.load_asvs(ab, ao)
+    keep = [r for r in range(len(reads)) if len(hreads[r]) and len(cons[rcons[r]])]
+    pr = np.repeat(np.array(keep, np.uint32), 2); pa = np.array([rcons[r] for r in pr], np.uint32); ps = np.tile(np.array([0, 1], np.uint8), len(keep))
+    hb, ho = O.concat(hreads)
+    al = orc.align_pairs(hb, ho, pr, pa, ps, want_cigar=True)
+    aln = [None] * len(reads)
+    for t, r in enumerate(keep):
+        sd = 1 if al["nm"][2 * t + 1] < al["nm"][2 * t] else 0
+        i = 2 * t + sd
+        cig = [(int(e) >> 4, int(e) & 15) for e in al["cigar"][int(al["cigar_offsets"][i]):int(al["cigar_offsets"][i + 1])]]
+        aln[r] = (sd, int(al["asv_start"][i]), int(al["read_start"][i]), int(al["read_end"][i]), cig)
+        assert got["read_strand"][r] == sd and got["read_nm"][r] == al["nm"][i]
+    for r in range(len(reads)):
+        if aln[r] is None:
+            assert got["read_strand"][r] == 0xff and got["read_nm"][r] == -1
+    cols, hp = pyref.pileup_columns([len(c_) for c_ in cons], [(rcons[r],) + comp[r] for r in range(len(reads))], aln)
+    flat = [e for c_ in cols for col in c_ for e in col]
+    assert len(flat) == len(got["entries"]) and len(flat) > 100
+    pos = 0; k = 0
+    for c_ in cols:
+        for col in c_:
+            assert int(got["pos_offsets"][pos + 1]) - int(got["pos_offsets"][pos]) == len(col)
+            for (r, kind, bs, qs, hs) in col:
+                e = got["entries"][k]; k += 1
+                assert (int(e["read"]), int(e["kind"]), int(e["n"])) == (r, kind, len(bs))
+                assert list(e["base"][:len(bs)]) == bs and list(e["qual"][:len(bs)]) == list(qs) and list(e["hp"][:len(bs)]) == list(hs)
+            pos += 1
+    assert list(got["ref_hp_length"]) == [x for h in hp for x in h]
+    if use_hpc:
+        assert max(max(h) for h in hp if h) > 1

@@ -74,3 +74,38 @@ def assert_same(a, b, keys, ctx=""):
                 idx = np.flatnonzero(x != y)
                 bad = (idx[:8], x[idx[:8]], y[idx[:8]])
             raise AssertionError(f"{ctx}: mismatch in '{key}': shapes {x.shape} vs {y.shape}; first diffs {bad}")
+
+
+def pileup_case(seed, n_cons=5, reads_per=12, cons_len=(60, 200), long_runs=False):
+    """clusters for the Stage 4 pileups: homopolymer-compressed consensus sequences and raw reads (with homopolymer runs put
+    back, errors, both strands, N bases, clipped / extended ends, empty reads) in cluster order"""
+    rng = random.Random(seed)
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    cons, reads, quals, rcons = [], [], [], []
+    for ci in range(n_cons):
+        L = rng.randrange(*cons_len) if ci != 2 else 0          # one empty consensus
+        s = bytearray()
+        while len(s) < L:
+            b = rng.choice(b"ACGT")
+            if not s or s[-1] != b:
+                s.append(b)
+        cons.append(bytes(s))
+        for t in range(reads_per if ci != 3 else 0):            # one consensus without reads
+            raw = bytearray()
+            for b in s:
+                run = rng.choice([1, 1, 1, 2, 3, 5]) if not (long_runs and rng.random() < 0.01) else rng.choice([254, 255, 256, 300, 520])
+                raw += bytes([b]) * run
+            rd = mutate(rng, bytes(raw), rng.randrange(4), rng.randrange(3), rng.randrange(3)) if raw else b""
+            if t % 5 == 1 and len(rd) > 20:
+                rd = rd[rng.randrange(1, 9):]
+            if t % 5 == 2 and len(rd) > 20:
+                rd = rd[:-rng.randrange(1, 9)] + rand_seq(rng, 4)
+            if t % 7 == 3 and len(rd) > 10:
+                i = rng.randrange(len(rd)); rd = rd[:i] + b"N" + rd[i + 1:]
+            if t % 2:
+                rd = rd.translate(comp)[::-1]
+            if t == 6:
+                rd = b""
+            reads.append(rd); rcons.append(ci)
+            quals.append(bytes(33 + rng.choice([3, 10, 20, 30, 40]) for _ in range(len(rd))))
+    return cons, reads, quals, rcons
