@@ -210,6 +210,123 @@ def run_kmercount(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
 
 
+def _pileup_clusters(w, n_cons, per, gen_reads):
+    """Stage 4 input shaped like the reference's: per consensus (the homopolymer-compressed ASV) the first `per` reads of its
+    cluster (reads drawn from that ASV), in cluster order"""
+    r = w.reads(gen_reads)
+    order = np.argsort(r["truth_asv"], kind="stable")
+    ta = r["truth_asv"][order]
+    keep = np.zeros(len(order), bool)
+    start = np.searchsorted(ta, np.arange(n_cons)); stop = np.searchsorted(ta, np.arange(n_cons) + 1)
+    for a in range(n_cons):
+        keep[start[a]:min(stop[a], start[a] + per)] = True
+    sel = order[keep]
+    lens = (r["offsets"][1:] - r["offsets"][:-1]).astype(np.int64)
+    ro = np.zeros(len(sel) + 1, np.uint64); ro[1:] = np.cumsum(lens[sel])
+    idx = np.concatenate([np.arange(int(r["offsets"][i]), int(r["offsets"][i + 1])) for i in sel]) if len(sel) else np.zeros(0, np.int64)
+    rb, rq = r["bases"][idx], r["quals"][idx]
+    cons = []
+    for a in range(n_cons):
+        sq = np.asarray(w.asv_bases[int(w.asv_offsets[a]):int(w.asv_offsets[a + 1])])
+        cons.append(sq[np.concatenate([[True], sq[1:] != sq[:-1]])].tobytes())
+    cb = np.frombuffer(b"".join(cons), np.uint8); co = np.zeros(n_cons + 1, np.uint64); co[1:] = np.cumsum([len(c_) for c_ in cons])
+    return cb, co, rb, rq, ro, ta[keep].astype(np.uint32)
+
+
+def run_pileup(args, rank, world, local_rank):
+    """--path pileup: Stage 4 pileups (alignment::generate_consensus_pileups) through savont_b200_consensus_pileups.  Not the
+    headline path; one JSON line with the same keys.  The call takes host buffers, so every number here is end to end."""
+    import torch
+    from savont_b200 import _lib
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the b200 arm has no CPU fallback")
+    if world > 1:
+        if rank == 0:
+            print(json.dumps({"metric": "reads piled up/sec (Stage 4 pileups)", "unavailable": "clusters are independent: run one process per GPU on disjoint clusters"}))
+        return
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    w = _workload(args)
+    ctx = _lib.Context(local_rank, _lib.default_params(band=w.band))
+    stream = torch.cuda.current_stream(dev)
+    ctx.set_stream(stream.cuda_stream)
+    cb, co, rb, rq, ro, rc = _pileup_clusters(w, w.n_asv, 250, args.reads)
+    n_reads = len(rc)
+
+    def pinned(x):
+        y = _lib.pinned_array(max(x.nbytes, 1))[:x.nbytes].view(x.dtype); y[:] = x
+        return y
+    rb, rq, cb = pinned(rb), pinned(rq), pinned(cb)                  # page-locked inputs and entry buffer, as in the headline path
+    cap = int(ro[-1]) + int((co[1:] - co[:-1])[rc].sum()) + 64
+    ent_buf = _lib.pinned_array(12 * cap).view(_lib.PILEUP_ENTRY)
+    sampler = ClockSampler(local_rank); sampler.start()
+    for _ in range(args.warmup):
+        out = ctx.consensus_pileups(cb, co, rb, rq, ro, rc, entries_out=ent_buf)
+    torch.cuda.synchronize(dev)
+    ms, stats = [], []
+    for _ in range(args.steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        out = ctx.consensus_pileups(cb, co, rb, rq, ro, rc, entries_out=ent_buf)
+        e1.record(stream); torch.cuda.synchronize(dev)
+        ms.append(e0.elapsed_time(e1)); stats.append(out["stats"])
+    clocks = sampler.stop()
+    peaks = _peaks()
+    st = stats[-1]
+    km = {k: float(np.mean([s_[k] for s_ in stats])) for k in ("sketch_ms", "align_ms", "filter_ms", "assign_ms")}
+    # dominant stage: traceback.  Algorithmic bytes of align_tb_kernel: the per-column history (2 * NW words per column and
+    # pair, written once, read back along the traceback path only -> counted once) + the CIGAR slots' ops
+    nw = {16: 2, 32: 3, 64: 5, 192: 13}.get(w.band, 5)
+    aligned = int((out["read_strand"] != 0xff).sum())
+    lut = np.zeros(256, np.uint8); lut[[ord(x) for x in "CcGgTtUu"]] = [1, 1, 2, 2, 3, 3, 3, 3]
+    codes = lut[rb]
+    run_start = np.ones(len(codes), bool); run_start[1:] = codes[1:] != codes[:-1]; run_start[ro[:-1][ro[:-1] < len(codes)].astype(np.int64)] = True
+    hcols = int(run_start.sum())                       # columns of the DP = compressed read bases (all reads are aligned here)
+    alg = hcols * 2 * nw * 4
+    val = n_reads * args.steps / (sum(ms) / 1e3)
+    line = {
+        "metric": "reads piled up/sec (Stage 4 pileups)", "value": val, "unit": "reads/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sum(ms) / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32 (bit-parallel INT32 DP) / u8 columns", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {w.n_asv} homopolymer-compressed consensus sequences x <= 250 reads of their clusters "
+                               f"({n_reads} reads, {int(ro[-1])} bases), band {w.band}",
+                   "l2": "every step re-uploads the reads from host memory (H2D inside the timed region)"},
+        "stage_ms": {"upload+compress+pack": km["sketch_ms"], "nm_both_strands": km["align_ms"], "traceback": km["filter_ms"],
+                     "columns": km["assign_ms"], "host": sum(ms) / args.steps - sum(km.values())},
+        "entries_per_step": int(len(out["entries"])), "reads_aligned": aligned,
+        "gcups": st["dp_cells"] / (km["align_ms"] / 1e3) / 1e9 if km["align_ms"] > 0 else None,
+        "roofline": {"bound": "hbm", "kernel": "align_tb_kernel (traceback history)", "achieved": alg / (km["filter_ms"] / 1e3) / 1e9,
+                     "peak": peaks["hbm_gbs"], "unit": "GB/s", "peak_source": peaks["source"],
+                     "frac": alg / (km["filter_ms"] / 1e3) / 1e9 / peaks["hbm_gbs"], "traffic": None, "algorithmic_bytes": alg,
+                     "note": "stage time includes CIGAR compaction and the D2H copies of the sub-batches"},
+        "e2e": {"value": val, "unit": "reads/s", "h2d_bytes_per_step": int(st["h2d_bytes"]), "d2h_bytes_per_step": int(st["d2h_bytes"]),
+                "ms_per_step": sum(ms) / args.steps},
+        "gpu_launches": int(sum(s_["kernel_launches"] for s_ in stats)), "clocks": clocks,
+    }
+    if not args.no_cpu_baseline:
+        from concurrent.futures import ThreadPoolExecutor
+        from oracle import oracle as O
+        cores = os.cpu_count() or 1
+        nc = min(w.n_asv, max(cores, 2 * cores))
+        r_end = np.searchsorted(rc, np.arange(nc + 1))
+
+        def one(a):
+            i0, i1 = int(r_end[a]), int(r_end[a + 1])
+            b0, b1 = int(ro[i0]), int(ro[i1])
+            return O.consensus_pileups(cb[int(co[a]):int(co[a + 1])], [0, int(co[a + 1] - co[a])], rb[b0:b1], rq[b0:b1], ro[i0:i1 + 1] - ro[i0],
+                                       np.zeros(i1 - i0, np.uint32), band=w.band)
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(cores) as ex:
+            parts = list(ex.map(one, range(nc)))
+        dt = time.perf_counter() - t0
+        ns = int(r_end[nc])
+        same = all(np.array_equal(parts[a]["read_nm"], out["read_nm"][int(r_end[a]):int(r_end[a + 1])]) for a in range(nc))
+        line["cpu_baseline"] = {"value": ns / dt, "unit": "reads/s", "cores": cores, "kind": "port",
+                                "sample": f"first {nc} clusters ({ns} reads), one cluster per thread like the reference's par_iter over consensuses "
+                                          "(oracle/savont_oracle.c)", "gpu_matches_oracle_on_sample": bool(same)}
+    print(json.dumps(line), flush=True)
+
+
 def _bind_to_gpu_numa_node(gpu_index):
     """pin this rank (and therefore the pinned host buffers it first-touches) to the CPU cores next to its GPU, so that
     eight ranks do not pull their H2D traffic across the socket interconnect"""
@@ -452,7 +569,7 @@ def main():
     ap.add_argument("--cpu-reads", type=int, default=100_000, help="sample size of the CPU baseline / reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-twin", action="store_true", help="skip the TwinRead-input e2e arm")
-    ap.add_argument("--path", default="assign", choices=["assign", "kmercount"],
+    ap.add_argument("--path", default="assign", choices=["assign", "kmercount", "pileup"],
                     help="assign: the headline read-vs-ASV path; kmercount: Stage 1 split-k-mer counting (K5)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -466,6 +583,8 @@ def main():
         run_reference(args, rank, world)
     elif args.path == "kmercount":
         run_kmercount(args, rank, world, local_rank)
+    elif args.path == "pileup":
+        run_pileup(args, rank, world, local_rank)
     else:
         run_b200(args, rank, world, local_rank)
         try:

@@ -268,7 +268,10 @@ int savont_b200_read_counts(savont_b200_ctx *ctx, uint64_t *unambig, uint64_t *a
  * reference's push order (read order, then CIGAR order); ref_hp_length[total_pos] = median run length of the column's
  * Base entries (:589-622; 1 when the column has none); read_strand[n_reads] 0/1 (0xff: read not aligned: empty read or
  * consensus), read_nm[n_reads] (-1 likewise).  SAVONT_B200_ERR_CAPACITY if entry_cap is too small (the sum over
- * the reads of read length + consensus length is always enough). */
+ * the reads of read length + consensus length is always enough).
+ * stats (device time per stage, summed over the internal chunks): sketch_ms = upload + compression + plane packing,
+ * align_ms = the both-strand NM kernel, filter_ms = traceback + CIGAR compaction + their copies, assign_ms = the column
+ * kernels; n_pairs / dp_cells count both strands. */
 typedef struct savont_b200_pileup_entry {
     uint32_t read;        /* index of the read in this call */
     uint8_t  kind;        /* 0 = Base, 1 = Deletion, 2 = Insertion (PileupBase, src/alignment.rs:17-26) */
@@ -279,7 +282,8 @@ int savont_b200_consensus_pileups(savont_b200_ctx *ctx, int use_hpc, const uint8
                                   size_t n_cons, const uint8_t *read_bases, const uint8_t *read_quals,
                                   const uint64_t *read_offsets, const uint32_t *read_cons, size_t n_reads,
                                   uint64_t *pos_offsets, savont_b200_pileup_entry *entries, size_t entry_cap,
-                                  uint64_t *n_entries, uint8_t *ref_hp_length, uint8_t *read_strand, int32_t *read_nm);
+                                  uint64_t *n_entries, uint8_t *ref_hp_length, uint8_t *read_strand, int32_t *read_nm,
+                                  savont_b200_stats *stats /* may be NULL */);
 
 /* Pinned host memory helpers (inputs placed here are copied without a staging pass). */
 int savont_b200_host_alloc(size_t bytes, void **out);

@@ -418,9 +418,11 @@ class Context:
         out.update(cigar_offsets=co, cigar=cg[:int(co[-1])])
         return out
 
-    def consensus_pileups(self, cons_bases, cons_offsets, read_bases, read_quals, read_offsets, read_cons, use_hpc=True, cap=None):
+    def consensus_pileups(self, cons_bases, cons_offsets, read_bases, read_quals, read_offsets, read_cons, use_hpc=True, cap=None,
+                          entries_out=None):
         """Stage 4 pileups (generate_consensus_pileups, src/alignment.rs:415-641) -> dict(pos_offsets, entries
-        (PILEUP_ENTRY records), ref_hp_length, read_strand, read_nm)"""
+        (PILEUP_ENTRY records), ref_hp_length, read_strand, read_nm).  entries_out: caller-provided PILEUP_ENTRY array
+        (e.g. a view of pinned_array memory), its length is the capacity"""
         cb = _u8(cons_bases); co = np.ascontiguousarray(cons_offsets, dtype=np.uint64)
         rb = _u8(read_bases); rq = None if read_quals is None else _u8(read_quals)
         ro = np.ascontiguousarray(read_offsets, dtype=np.uint64)
@@ -428,14 +430,20 @@ class Context:
         n = len(ro) - 1
         npos = int(co[-1] - co[0])
         cap = cap if cap is not None else int((ro[-1] - ro[0]) + (co[1:] - co[:-1])[rc].sum() + 64)
-        po = np.zeros(npos + 1, np.uint64); ent = np.zeros(max(cap, 1), PILEUP_ENTRY)
+        if entries_out is not None:
+            ent, cap = entries_out, len(entries_out)
+        else:
+            ent = np.zeros(max(cap, 1), PILEUP_ENTRY)
+        po = np.zeros(npos + 1, np.uint64)
         hp = np.zeros(max(npos, 1), np.uint8); st = np.zeros(max(n, 1), np.uint8); nm = np.zeros(max(n, 1), np.int32)
-        ne = C.c_uint64(0)
+        ne = C.c_uint64(0); stt = Stats()
         _check(self.L.savont_b200_consensus_pileups(self.h, C.c_int(1 if use_hpc else 0), _p(cb, C.c_uint8), _p(co, C.c_uint64),
                                                     C.c_size_t(len(co) - 1), _p(rb, C.c_uint8), _p(rq, C.c_uint8), _p(ro, C.c_uint64),
                                                     _p(rc, C.c_uint32), C.c_size_t(n), _p(po, C.c_uint64), C.c_void_p(ent.ctypes.data),
-                                                    C.c_size_t(cap), C.byref(ne), _p(hp, C.c_uint8), _p(st, C.c_uint8), _p(nm, C.c_int32)))
-        return dict(pos_offsets=po, entries=ent[:int(ne.value)], ref_hp_length=hp[:npos], read_strand=st[:n], read_nm=nm[:n])
+                                                    C.c_size_t(cap), C.byref(ne), _p(hp, C.c_uint8), _p(st, C.c_uint8), _p(nm, C.c_int32),
+                                                    C.byref(stt)))
+        return dict(pos_offsets=po, entries=ent[:int(ne.value)], ref_hp_length=hp[:npos], read_strand=st[:n], read_nm=nm[:n],
+                    stats=stt.as_dict())
 
     def counts_dev(self):
         """(device pointer, length in u64) of [unambig|ambig|leq10|assigned|filtered|singleton S*A]"""

@@ -746,8 +746,9 @@ int traceback_pairs(Context *c, Batch &b, const AsvIndex &ix, uint32_t max_ref_l
     const size_t per_pair_words = align_tb_hist_words(1, hist_cols, c->dp);
     size_t sub = std::max<size_t>(128, ((size_t)1 << 28) / std::max<size_t>(per_pair_words, 1));
     sub = std::min<size_t>(sub, 1u << 16);
-    DevBuf d_hist, d_slots, d_cnt, d_off, d_tmp, d_ops, d_out;
-    auto cleanup = [&]() { d_hist.release(); d_slots.release(); d_cnt.release(); d_off.release(); d_tmp.release(); d_ops.release(); d_out.release(); };
+    DevBuf &d_hist = c->tb_ws[0], &d_slots = c->tb_ws[1], &d_cnt = c->tb_ws[2], &d_off = c->tb_ws[3], &d_tmp = c->tb_ws[4],
+           &d_ops = c->tb_ws[5], &d_out = c->tb_ws[6];
+    auto cleanup = [&]() {};                     // the workspace stays with the context (released by savont_b200_destroy)
     uint64_t cig_base = cigar_offsets[0];
     std::vector<uint32_t> h_off;
     std::vector<int32_t> h_out;
@@ -856,7 +857,9 @@ int savont_b200_destroy(savont_b200_ctx *h) {
     DevBuf *bufs[] = {&c->d_rank_table, &c->d_snp_keys, &c->d_snp_bloom, &c->d_phred, &c->d_mx_keys, &c->d_mx_vals, &c->d_mx_entries, &c->d_idx_keys, &c->d_idx_vals, &c->d_idx_entries, &c->d_mset,
                       &c->d_mset_off, &c->d_asv_planes, &c->d_asv_plane_off, &c->d_asv_len, &c->d_counters, &c->d_hf_keys};
     for (DevBuf *b : bufs) b->release();
-    c->pin_small.release(); c->pin_out.release();
+    c->pin_small.release(); c->pin_out.release(); c->tb_pin.release();
+    for (DevBuf &b : c->tb_ws) b.release();
+    for (DevBuf &b : c->pileup_ws) b.release();
     for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
     for (int i = 0; i < 3; ++i) { if (c->ev_up[i]) cudaEventDestroy(c->ev_up[i]); if (c->ev_h0[i]) cudaEventDestroy(c->ev_h0[i]); }
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);

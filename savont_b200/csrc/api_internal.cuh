@@ -159,6 +159,9 @@ struct Context {
     cudaEvent_t ev[8] = {nullptr};
     cudaEvent_t ev_up[3] = {nullptr, nullptr, nullptr}, ev_h0[3] = {nullptr, nullptr, nullptr};
     savont_b200_stats last_stats;
+    // traceback workspace (history, CIGAR slots, compacted ops, ...) and the Stage 4 pileup scratch: kept between calls
+    DevBuf tb_ws[7]; PinBuf tb_pin;
+    DevBuf pileup_ws[40];
 };
 
 struct Context;

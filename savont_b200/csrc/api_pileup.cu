@@ -10,18 +10,18 @@ namespace sb {
 
 namespace {
 
+// device scratch of the call, kept in Context::pileup_ws between calls
 struct PileupScratch {
-    DevBuf hcnt, hoff32, scan_tmp, hc, hq, hl;
-    DevBuf cplanes, cplane_off, clen;
-    DevBuf pr2, pa2, ps2, nm2, ae2, re2, pr, pa, ps;
-    DevBuf cstart, rstart, rend, cig_off, cig, row_off, cons_pos_off, cons_aln_off, pos_cons, cnt, excl, col_total, pos_off,
-        entries, ref_hp;
-    void release() {
-        DevBuf *all[] = {&hcnt, &hoff32, &scan_tmp, &hc, &hq, &hl, &cplanes, &cplane_off, &clen, &pr2, &pa2, &ps2, &nm2, &ae2, &re2, &pr,
-                         &pa, &ps, &cstart, &rstart, &rend, &cig_off, &cig, &row_off, &cons_pos_off, &cons_aln_off, &pos_cons, &cnt, &excl,
-                         &col_total, &pos_off, &entries, &ref_hp};
-        for (DevBuf *b : all) b->release();
-    }
+    DevBuf &hcnt, &hoff32, &scan_tmp, &hc, &hq, &hl;
+    DevBuf &cplanes, &cplane_off, &clen;
+    DevBuf &pr2, &pa2, &ps2, &nm2, &ae2, &re2, &pr, &pa, &ps;
+    DevBuf &cstart, &rstart, &rend, &cig_off, &cig, &row_off, &cons_pos_off, &cons_aln_off, &pos_cons, &cnt, &excl, &col_total, &pos_off,
+        &entries, &ref_hp, &entries2;
+    explicit PileupScratch(DevBuf *w)
+        : hcnt(w[0]), hoff32(w[1]), scan_tmp(w[2]), hc(w[3]), hq(w[4]), hl(w[5]), cplanes(w[6]), cplane_off(w[7]), clen(w[8]), pr2(w[9]),
+          pa2(w[10]), ps2(w[11]), nm2(w[12]), ae2(w[13]), re2(w[14]), pr(w[15]), pa(w[16]), ps(w[17]), cstart(w[18]), rstart(w[19]),
+          rend(w[20]), cig_off(w[21]), cig(w[22]), row_off(w[23]), cons_pos_off(w[24]), cons_aln_off(w[25]), pos_cons(w[26]), cnt(w[27]),
+          excl(w[28]), col_total(w[29]), pos_off(w[30]), entries(w[31]), ref_hp(w[32]), entries2(w[33]) {}
 };
 
 template <typename T>
@@ -32,11 +32,12 @@ int up(DevBuf &d, const std::vector<T> &v, cudaStream_t st) {
 }
 
 // one chunk: consensus sequences [c0, c1), reads [r0, r1) (exactly the reads whose read_cons lies in the chunk)
-int pileup_chunk(Context *c, PileupScratch &s, int use_hpc, const uint8_t *cons_bases, const uint64_t *cons_offsets, size_t c0, size_t c1,
+int pileup_chunk(Context *c, PileupScratch &s, size_t chunk, int use_hpc, const uint8_t *cons_bases, const uint64_t *cons_offsets, size_t c0, size_t c1,
                  const uint8_t *read_bases, const uint8_t *read_quals, const uint64_t *read_offsets, const uint32_t *read_cons, size_t r0,
                  size_t r1, uint64_t *pos_offsets, savont_b200_pileup_entry *entries, size_t entry_cap, uint64_t *n_entries,
                  uint8_t *ref_hp_length, uint8_t *read_strand, int32_t *read_nm) {
     cudaStream_t st = c->stream;
+    cudaEvent_t *ev = c->ev;       // 0 start, 1 reads compressed + packed, 2 both-strand NM, 3 traceback, 4 columns
     const size_t n = r1 - r0, nc = c1 - c0;
     const uint64_t pos0 = cons_offsets[c0] - cons_offsets[0];
     const size_t n_pos = (size_t)(cons_offsets[c1] - cons_offsets[c0]);
@@ -49,6 +50,7 @@ int pileup_chunk(Context *c, PileupScratch &s, int use_hpc, const uint8_t *cons_
 
     // ---- reads: upload, homopolymer compression (src/utils.rs:135-184) ----
     Batch &rb = c->work, &hb = c->work2;
+    CK(cudaEventRecord(ev[0], st));
     TRY(batch_upload(c, rb, read_bases, read_quals, read_offsets + r0, nullptr, n, &c->last_stats.h2d_bytes));
     TRY(s.hcnt.ensure((n + 1) * 4)); TRY(s.hoff32.ensure((n + 2) * 4)); TRY(s.scan_tmp.ensure((n / 2048 + 4) * 4));
     launch_hpc_count(seq_view(rb), use_hpc, s.hcnt.as<uint32_t>(), st);
@@ -74,6 +76,7 @@ int pileup_chunk(Context *c, PileupScratch &s, int use_hpc, const uint8_t *cons_
     TRY(hb.planes.ensure(((size_t)plane_word_off(htotal, n) + 4) * sizeof(uint2)));
     launch_pack_planes(seq_view(hb), hb.planes.as<uint2>(), st);
     c->last_stats.kernel_launches += 1;
+    c->last_stats.n_reads += n; c->last_stats.n_bases += rb.total_bases;
 
     // ---- consensus sequences: DP planes ----
     std::vector<uint2> planes; std::vector<uint32_t> plane_off, clen;
@@ -99,12 +102,16 @@ int pileup_chunk(Context *c, PileupScratch &s, int use_hpc, const uint8_t *cons_
     TRY(s.nm2.ensure((size_t)n_aln * 8)); TRY(s.ae2.ensure((size_t)n_aln * 8)); TRY(s.re2.ensure((size_t)n_aln * 8));
     TRY(s.pr.ensure((size_t)n_aln * 4)); TRY(s.pa.ensure((size_t)n_aln * 4)); TRY(s.ps.ensure((size_t)n_aln + 4));
     AlignOut ao{s.nm2.as<int32_t>(), s.ae2.as<int32_t>(), s.re2.as<int32_t>()};
+    CK(cudaEventRecord(ev[1], st));
     launch_align_nm(seq_view(hb), hb.planes.as<uint2>(), ix, s.pr2.as<uint32_t>(), s.pa2.as<uint32_t>(), s.ps2.as<uint8_t>(), nullptr,
                     2u * n_aln, nullptr, ao, c->dp, c->sm_count, st);
     launch_pick_strand(s.nm2.as<int32_t>(), s.pr2.as<uint32_t>(), s.pa2.as<uint32_t>(), n_aln, s.pr.as<uint32_t>(), s.pa.as<uint32_t>(),
                        s.ps.as<uint8_t>(), st);
     CK(cudaGetLastError());
+    CK(cudaEventRecord(ev[2], st));
     c->last_stats.kernel_launches += 2;
+    c->last_stats.n_pairs += 2ull * n_aln;
+    for (uint32_t t = 0; t < n_aln; ++t) c->last_stats.dp_cells += 2ull * clen[pa2[2 * t]] * (2ull * (uint64_t)c->dp.band + 1ull);
     std::vector<uint8_t> strand(n_aln);
     CK(cudaMemcpyAsync(strand.data(), s.ps.p, n_aln, cudaMemcpyDeviceToHost, st));
 
@@ -116,6 +123,7 @@ int pileup_chunk(Context *c, PileupScratch &s, int use_hpc, const uint8_t *cons_
                         v.data() + n_aln, v.data() + 2 * (size_t)n_aln, v.data() + 3 * (size_t)n_aln, v.data() + 4 * (size_t)n_aln,
                         coff.data(), nullptr, 0, &cigar));
     if (coff[n_aln] >= (1ull << 32)) return fail(SAVONT_B200_ERR_OVERFLOW, "CIGAR ops of one chunk exceed 4 Gi");
+    CK(cudaEventRecord(ev[3], st));
     for (uint32_t t = 0; t < n_aln; ++t) { read_strand[r0 + pr2[2 * t]] = strand[t]; read_nm[r0 + pr2[2 * t]] = v[t]; }
 
     // ---- columns ----
@@ -159,17 +167,26 @@ int pileup_chunk(Context *c, PileupScratch &s, int use_hpc, const uint8_t *cons_
     if (*n_entries + ne > entry_cap)
         return fail(SAVONT_B200_ERR_CAPACITY, "pileup entry capacity %zu too small (need >= %llu)", entry_cap,
                     (unsigned long long)(*n_entries + ne));
-    TRY(s.entries.ensure(ne * sizeof(PileupEntry) + 16));
-    a.entries = s.entries.as<PileupEntry>();
+    // two entry buffers: the copy of chunk i to the host (d2h_stream) runs under the kernels of chunk i + 1
+    DevBuf &dent = (chunk & 1) ? s.entries2 : s.entries;
+    cudaEvent_t ev_free = c->ev_d2h[chunk & 1];               // recorded after the previous copy out of this buffer
+    if (chunk >= 2) CK(cudaEventSynchronize(ev_free));
+    TRY(dent.ensure(ne * sizeof(PileupEntry) + 16));
+    a.entries = dent.as<PileupEntry>();
     launch_pileup_emit(a, st);
     launch_pileup_median(a, s.ref_hp.as<uint8_t>(), st);
     CK(cudaGetLastError());
+    CK(cudaEventRecord(ev[4], st));
     c->last_stats.kernel_launches += 7;
-    if (ne) CK(cudaMemcpyAsync(entries + *n_entries, s.entries.p, ne * sizeof(PileupEntry), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(ref_hp_length + pos0, s.ref_hp.p, n_pos, cudaMemcpyDeviceToHost, st));
     for (size_t p = 0; p < n_pos; ++p) pos_offsets[pos0 + p + 1] = *n_entries + pos_off[p + 1];
     CK(cudaStreamSynchronize(st));
+    if (ne) CK(cudaMemcpyAsync(entries + *n_entries, dent.p, ne * sizeof(PileupEntry), cudaMemcpyDeviceToHost, c->d2h_stream));
+    CK(cudaEventRecord(ev_free, c->d2h_stream));
     c->last_stats.d2h_bytes += ne * sizeof(PileupEntry) + n_pos;
+    c->last_stats.sketch_ms += ev_ms(ev[0], ev[1]); c->last_stats.align_ms += ev_ms(ev[1], ev[2]);
+    c->last_stats.filter_ms += ev_ms(ev[2], ev[3]); c->last_stats.assign_ms += ev_ms(ev[3], ev[4]);
+    c->last_stats.n_batches += 1;
     *n_entries += ne;
     return 0;
 }
@@ -184,7 +201,8 @@ extern "C" int savont_b200_consensus_pileups(savont_b200_ctx *h, int use_hpc, co
                                              size_t n_cons, const uint8_t *read_bases, const uint8_t *read_quals,
                                              const uint64_t *read_offsets, const uint32_t *read_cons, size_t n_reads,
                                              uint64_t *pos_offsets, savont_b200_pileup_entry *entries, size_t entry_cap,
-                                             uint64_t *n_entries, uint8_t *ref_hp_length, uint8_t *read_strand, int32_t *read_nm) {
+                                             uint64_t *n_entries, uint8_t *ref_hp_length, uint8_t *read_strand, int32_t *read_nm,
+                                             savont_b200_stats *stats) {
     static_assert(sizeof(savont_b200_pileup_entry) == sizeof(PileupEntry) && sizeof(PileupEntry) == 12, "pileup entry layout");
     TRY(use_device(h ? &h->c : nullptr));
     Context *c = &h->c;
@@ -201,13 +219,14 @@ extern "C" int savont_b200_consensus_pileups(savont_b200_ctx *h, int use_hpc, co
     }
     c->last_stats = savont_b200_stats{};
     *n_entries = 0; pos_offsets[0] = 0;
-    // chunks of consecutive consensus sequences: <= 2^27 (read, position) cells of column workspace, <= 65536 reads
+    // chunks of consecutive consensus sequences: <= 2^27 (read, position) cells of column workspace, <= 32768 reads
     // (a single consensus beyond these bounds forms a chunk of its own)
     constexpr uint64_t kMaxCells = 1ull << 27;
-    constexpr size_t kMaxReads = 65536;
-    PileupScratch s;
+    size_t kMaxReads = 32768;
+    if (const char *e = getenv("SAVONT_B200_PILEUP_CHUNK_READS")) kMaxReads = std::max<size_t>(1, strtoull(e, nullptr, 10));   // tests
+    PileupScratch s(c->pileup_ws);
     int rc = 0;
-    size_t c0 = 0, r0 = 0;
+    size_t c0 = 0, r0 = 0, chunk = 0;
     while (c0 < n_cons && rc == 0) {
         size_t c1 = c0, r1 = r0;
         uint64_t cells = 0;
@@ -220,10 +239,15 @@ extern "C" int savont_b200_consensus_pileups(savont_b200_ctx *h, int use_hpc, co
             cells += add; r1 = re; ++c1;
         }
         if (rc) break;
-        rc = pileup_chunk(c, s, use_hpc, cons_bases, cons_offsets, c0, c1, read_bases, read_quals, read_offsets, read_cons, r0, r1,
+        rc = pileup_chunk(c, s, chunk++, use_hpc, cons_bases, cons_offsets, c0, c1, read_bases, read_quals, read_offsets, read_cons, r0, r1,
                           pos_offsets, entries, entry_cap, n_entries, ref_hp_length, read_strand, read_nm);
         c0 = c1; r0 = r1;
     }
-    s.release();
+    {   // the last copies of the entries
+        cudaError_t e = cudaStreamSynchronize(c->d2h_stream);
+        if (e != cudaSuccess && rc == 0) rc = fail(SAVONT_B200_ERR_CUDA, "pileup entries copy: %s", cudaGetErrorString(e));
+    }
+    c->last_stats.total_ms = c->last_stats.sketch_ms + c->last_stats.align_ms + c->last_stats.filter_ms + c->last_stats.assign_ms;
+    if (stats) *stats = c->last_stats;
     return rc;
 }

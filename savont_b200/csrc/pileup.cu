@@ -6,10 +6,10 @@
 // (:524-569); the median run length of the aligned bases becomes the column's ref_hp_length (:589-622).
 //
 // Columns are built without atomics and in the reference's push order (read order, then CIGAR order):
-//   count    thread per read: CIGAR walk -> cnt[read row][position] (0..2 entries)
+//   count    warp per read: CIGAR walk -> cnt[read row][position] (0..2 entries)
 //   rank     thread per consensus position: running sum of cnt over the reads of the consensus -> excl (u16), column total
 //   (scan of the column totals -> pos_offsets)
-//   emit     thread per read: second CIGAR walk, entry index = pos_offsets[position] + excl + (insertion after a base ? 1 : 0)
+//   emit     warp per read: second CIGAR walk, entry index = pos_offsets[position] + excl + (insertion after a base ? 1 : 0)
 //   median   warp per position: 256-bin histogram of the run lengths of the Base entries in shared memory
 #include "common.cuh"
 #include "sketch_dev.cuh"
@@ -104,10 +104,12 @@ void launch_pick_strand(const int32_t *nm2, const uint32_t *pr2, const uint32_t 
 }
 
 // ---------------- CIGAR walk (src/alignment.rs:524-569) ----------------
+// Warp per aligned read: the ops are taken in order (warp-uniform), the lanes share the positions of a match / deletion run.
 // EMIT = false: cnt[row + position]++ per entry; EMIT = true: write the entries.
 template <bool EMIT>
 __global__ void pileup_walk_kernel(PileupArgs a) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31u;
     if (t >= a.n_aln) return;
     const uint32_t r = a.aln_read[t];
     const uint32_t ci = a.aln_cons[t];
@@ -129,7 +131,7 @@ __global__ void pileup_walk_kernel(PileupArgs a) {
     for (uint32_t k = c0; k < c1; ++k) {
         const uint32_t ln = a.cigar[k] >> 4, op = a.cigar[k] & 15u;
         if (op == 0u) {
-            for (uint32_t j = 0; j < ln; ++j) {
+            for (uint32_t j = lane; j < ln; j += 32u) {
                 if (ref_pos + j < clen && query_pos + j < mlen) {
                     if (!EMIT) a.cnt[row + ref_pos + j] += 1;
                     else {
@@ -141,7 +143,7 @@ __global__ void pileup_walk_kernel(PileupArgs a) {
             }
             ref_pos += ln; query_pos += ln;
         } else if (op == 1u) {
-            if (ref_pos > 0 && ref_pos - 1 < clen && query_pos + ln <= mlen) {
+            if (lane == 0u && ref_pos > 0 && ref_pos - 1 < clen && query_pos + ln <= mlen) {
                 if (!EMIT) a.cnt[row + ref_pos - 1] += 1;
                 else {
                     PileupEntry e{}; e.read = r + a.read_base; e.kind = 2; e.n = (uint8_t)min(ln, 2u);
@@ -152,7 +154,7 @@ __global__ void pileup_walk_kernel(PileupArgs a) {
             }
             query_pos += ln;
         } else {
-            for (uint32_t j = 0; j < ln; ++j) {
+            for (uint32_t j = lane; j < ln; j += 32u) {
                 if (ref_pos + j < clen) {
                     if (!EMIT) a.cnt[row + ref_pos + j] += 1;
                     else {
@@ -163,6 +165,7 @@ __global__ void pileup_walk_kernel(PileupArgs a) {
             }
             ref_pos += ln;
         }
+        if (!EMIT) __syncwarp();      // the insertion count lands on a cell another lane has just written
     }
 }
 
@@ -216,13 +219,13 @@ __global__ void pileup_median_kernel(PileupArgs a, uint8_t *ref_hp) {
 }
 
 void launch_pileup_count(const PileupArgs &a, cudaStream_t st) {
-    if (a.n_aln) pileup_walk_kernel<false><<<(a.n_aln + 127u) / 128u, 128, 0, st>>>(a);
+    if (a.n_aln) pileup_walk_kernel<false><<<(a.n_aln + 7u) / 8u, 256, 0, st>>>(a);
 }
 void launch_pileup_rank(const PileupArgs &a, cudaStream_t st) {
     if (a.n_pos) pileup_rank_kernel<<<(a.n_pos + 255u) / 256u, 256, 0, st>>>(a);
 }
 void launch_pileup_emit(const PileupArgs &a, cudaStream_t st) {
-    if (a.n_aln) pileup_walk_kernel<true><<<(a.n_aln + 127u) / 128u, 128, 0, st>>>(a);
+    if (a.n_aln) pileup_walk_kernel<true><<<(a.n_aln + 7u) / 8u, 256, 0, st>>>(a);
 }
 void launch_pileup_median(const PileupArgs &a, uint8_t *ref_hp, cudaStream_t st) {
     if (a.n_pos) pileup_median_kernel<<<(a.n_pos + 7u) / 8u, 256, 0, st>>>(a, ref_hp);

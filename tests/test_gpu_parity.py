@@ -679,6 +679,21 @@ def test_consensus_pileups_ragged_clusters(ctx, use_hpc, band, long_runs):
         ctx.consensus_pileups(cb, co, rb, qb, ro, rcons, use_hpc=use_hpc, cap=len(got["entries"]) - 1)
 
 
+def test_consensus_pileups_many_chunks(ctx, monkeypatch):
+    """chunks of <= 20 reads: the double-buffered entry copies and the call-wide read / entry indices"""
+    from savont_b200 import _lib
+    from tests.util import pileup_case
+    gp, _ = _params(_lib, band=24)
+    ctx.set_params(gp)
+    cons, reads, quals, rcons = pileup_case(77, n_cons=9, reads_per=11)
+    cb, co = O.concat(cons); rb, ro = O.concat(reads); qb, _ = O.concat(quals)
+    want = O.consensus_pileups(cb, co, rb, qb, ro, rcons, band=24, use_hpc=True)
+    monkeypatch.setenv("SAVONT_B200_PILEUP_CHUNK_READS", "20")
+    got = ctx.consensus_pileups(cb, co, rb, qb, ro, rcons, use_hpc=True)
+    assert got["stats"]["n_batches"] >= 4
+    _assert_pileups(got, want, "pileups in chunks")
+
+
 def test_consensus_pileups_full_clusters(ctx):
     """16S-sized clusters: 250 reads (MAX_SEQS_CONSENSUS) of ~1500 bp at 2% errors per consensus, band 64"""
     from savont_b200 import _lib, synth
