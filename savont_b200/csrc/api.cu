@@ -736,7 +736,7 @@ using namespace sb;
 
 namespace sb {
 // Traceback (align_tb_kernel) of explicit device-resident pairs against the batch's read planes, in sub-batches bounded by
-// a 1 GiB history workspace; the CIGAR slots are compacted on the device (scan of the op counts + warp-per-pair copy) so that
+// a 4 GiB history workspace; the CIGAR slots are compacted on the device (scan of the op counts + warp-per-pair copy) so that
 // only the ops cross PCIe.  cigar_offsets[0] must be set by the caller (base of this call's ops in `cigar`).
 int traceback_pairs(Context *c, Batch &b, const AsvIndex &ix, uint32_t max_ref_len, const uint32_t *d_pr, const uint32_t *d_pa,
                     const uint8_t *d_ps, size_t n_pairs, int32_t *nm, int32_t *asv_end, int32_t *read_end, int32_t *asv_start,
@@ -744,8 +744,8 @@ int traceback_pairs(Context *c, Batch &b, const AsvIndex &ix, uint32_t max_ref_l
     const uint32_t hist_cols = std::max<uint32_t>(b.max_len, 1u);
     const uint32_t cigar_stride = b.max_len + max_ref_len + 2;
     const size_t per_pair_words = align_tb_hist_words(1, hist_cols, c->dp);
-    size_t sub = std::max<size_t>(128, ((size_t)1 << 28) / std::max<size_t>(per_pair_words, 1));
-    sub = std::min<size_t>(sub, 1u << 16);
+    size_t sub = std::max<size_t>(128, ((size_t)1 << 30) / std::max<size_t>(per_pair_words, 1));
+    sub = std::min<size_t>(sub, 1u << 17);
     DevBuf &d_hist = c->tb_ws[0], &d_slots = c->tb_ws[1], &d_cnt = c->tb_ws[2], &d_off = c->tb_ws[3], &d_tmp = c->tb_ws[4],
            &d_ops = c->tb_ws[5], &d_out = c->tb_ws[6];
     auto cleanup = [&]() {};                     // the workspace stays with the context (released by savont_b200_destroy)

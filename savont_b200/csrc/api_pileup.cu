@@ -181,7 +181,20 @@ int pileup_chunk(Context *c, PileupScratch &s, size_t chunk, int use_hpc, const 
     CK(cudaMemcpyAsync(ref_hp_length + pos0, s.ref_hp.p, n_pos, cudaMemcpyDeviceToHost, st));
     for (size_t p = 0; p < n_pos; ++p) pos_offsets[pos0 + p + 1] = *n_entries + pos_off[p + 1];
     CK(cudaStreamSynchronize(st));
-    if (ne) CK(cudaMemcpyAsync(entries + *n_entries, dent.p, ne * sizeof(PileupEntry), cudaMemcpyDeviceToHost, c->d2h_stream));
+    if (ne) {
+        // page-locked destination: SM copy (see copy_to_host_kernel); pageable: the copy engine's staged path
+        cudaPointerAttributes at{};
+        const bool pinned = cudaPointerGetAttributes(&at, entries) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer != nullptr;
+        if (!pinned) cudaGetLastError();
+        if (pinned) {
+            launch_copy_to_host(dent.p, reinterpret_cast<uint8_t *>(at.devicePointer) + *n_entries * sizeof(PileupEntry), ne * sizeof(PileupEntry),
+                                c->d2h_stream);
+            CK(cudaGetLastError());
+            c->last_stats.kernel_launches += 1;
+        } else {
+            CK(cudaMemcpyAsync(entries + *n_entries, dent.p, ne * sizeof(PileupEntry), cudaMemcpyDeviceToHost, c->d2h_stream));
+        }
+    }
     CK(cudaEventRecord(ev_free, c->d2h_stream));
     c->last_stats.d2h_bytes += ne * sizeof(PileupEntry) + n_pos;
     c->last_stats.sketch_ms += ev_ms(ev[0], ev[1]); c->last_stats.align_ms += ev_ms(ev[1], ev[2]);

@@ -274,6 +274,7 @@ void launch_hpc_count(const SeqBatch &in, int do_hpc, uint32_t *cnt, cudaStream_
 void launch_hpc_write(const SeqBatch &in, int do_hpc, const uint32_t *out_off, uint8_t *hc, uint8_t *hq, uint8_t *hl, cudaStream_t st);
 void launch_pick_strand(const int32_t *nm2, const uint32_t *pr2, const uint32_t *pa2, uint32_t n, uint32_t *pr, uint32_t *pa,
                         uint8_t *ps, cudaStream_t st);
+void launch_copy_to_host(const void *src_dev, void *dst_host, uint64_t bytes, cudaStream_t st);
 void launch_pileup_count(const PileupArgs &a, cudaStream_t st);
 void launch_pileup_rank(const PileupArgs &a, cudaStream_t st);
 void launch_pileup_emit(const PileupArgs &a, cudaStream_t st);

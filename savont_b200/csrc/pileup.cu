@@ -218,6 +218,25 @@ __global__ void pileup_median_kernel(PileupArgs a, uint8_t *ref_hp) {
     }
 }
 
+// Device -> page-locked host copy done by a few CTAs instead of the copy engine: the entry stream of a chunk (hundreds of MB)
+// must not sit in the DMA queue in front of the small result copies the next chunk's host logic waits for.  Warps store
+// 128-byte aligned runs of the destination (dst is only 4-byte aligned).
+__global__ void copy_to_host_kernel(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst, uint64_t n_words, uint32_t pad) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_words + pad; g += 4 * stride) {
+        uint32_t v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const uint64_t w = g + u * stride; v[u] = (w >= pad && w < n_words + pad) ? src[w - pad] : 0u; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const uint64_t w = g + u * stride; if (w >= pad && w < n_words + pad) dst[w - pad] = v[u]; }
+    }
+}
+void launch_copy_to_host(const void *src_dev, void *dst_host, uint64_t bytes, cudaStream_t st) {   // bytes % 4 == 0, both 4-byte aligned
+    if (bytes == 0) return;
+    const uint32_t pad = (uint32_t)((reinterpret_cast<uintptr_t>(dst_host) & 127u) >> 2);
+    copy_to_host_kernel<<<32, 512, 0, st>>>(reinterpret_cast<const uint32_t *>(src_dev), reinterpret_cast<uint32_t *>(dst_host), bytes / 4, pad);
+}
+
 void launch_pileup_count(const PileupArgs &a, cudaStream_t st) {
     if (a.n_aln) pileup_walk_kernel<false><<<(a.n_aln + 7u) / 8u, 256, 0, st>>>(a);
 }
