@@ -231,6 +231,29 @@ def consensus_pileups(cons_bases, cons_offsets, read_bases, read_quals, read_off
     return dict(pos_offsets=po, entries=ent[:m], ref_hp_length=hp[:npos], read_strand=st[:n], read_nm=nm[:n])
 
 
+def lsh_signatures(kmers, offsets):
+    """so_lsh_signatures -> (sig [n, 20] u64, valid [n] u8)"""
+    L = lib()
+    km = np.ascontiguousarray(kmers, dtype=np.uint64); off = np.ascontiguousarray(offsets, dtype=np.uint64)
+    n = len(off) - 1
+    sig = np.zeros((max(n, 1), 20), np.uint64); valid = np.zeros(max(n, 1), np.uint8)
+    rc = L.so_lsh_signatures(_p(km, C.c_uint64), _p(off, C.c_uint64), C.c_size_t(n), _p(sig, C.c_uint64), _p(valid, C.c_uint8))
+    assert rc == 0
+    return sig[:n], valid[:n]
+
+
+def cluster_reads_by_kmers(kmers, offsets, k=17, threshold=0.95):
+    """so_cluster_reads_by_kmers -> rep_of [n] u32"""
+    L = lib()
+    km = np.ascontiguousarray(kmers, dtype=np.uint64); off = np.ascontiguousarray(offsets, dtype=np.uint64)
+    n = len(off) - 1
+    rep = np.zeros(max(n, 1), np.uint32); nr = C.c_uint64(0)
+    rc = L.so_cluster_reads_by_kmers(C.c_int(k), C.c_double(threshold), _p(km, C.c_uint64), _p(off, C.c_uint64), C.c_size_t(n),
+                                     _p(rep, C.c_uint32), C.byref(nr))
+    assert rc == 0
+    return rep[:n]
+
+
 class Oracle:
     def set_read_filter(self, rf: ReadFilter | None, high_freq=None):
         hf = np.ascontiguousarray(high_freq if high_freq is not None else [], dtype=np.uint64)

@@ -785,6 +785,138 @@ long long so_consensus_pileups(int band, int use_hpc, const uint8_t *cons_bases,
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* SURVEY.md 8(f) row 3, Stage 2: TwinRead::compute_lsh_signatures (src/types.rs:719-747) */
+/* and asv_cluster::cluster_reads_by_kmers (src/asv_cluster.rs:72-249, bucketed branch).  */
+/* FxHasher64 is the fxhash crate 0.2.1 (Cargo.lock:503-505; not under /root/reference):  */
+/* write_u64(w): hash = (rotl(hash, 5) ^ w) * 0x517cc1b727220a95, finish() = hash.        */
+/* ------------------------------------------------------------------------------------ */
+#define SO_LSH_NUM_TABLES 20            /* src/constants.rs:67 */
+#define SO_LSH_BUCKET_SIZE 3            /* src/constants.rs:68 */
+static uint64_t fx_write_u64(uint64_t h, uint64_t w) { return (((h << 5) | (h >> 59)) ^ w) * 0x517cc1b727220a95ull; }
+
+typedef struct { uint64_t hash, kmer; size_t idx; } lsh_item;
+static int cmp_lsh_item(const void *a, const void *b) {          /* sort_by_key(hash) is stable: ties keep input order */
+    const lsh_item *x = (const lsh_item *)a, *y = (const lsh_item *)b;
+    if (x->hash != y->hash) return x->hash < y->hash ? -1 : 1;
+    return x->idx < y->idx ? -1 : x->idx > y->idx;
+}
+
+int so_lsh_signatures(const uint64_t *kmers, const uint64_t *offsets, size_t n_reads, uint64_t *sig, uint8_t *valid) {
+    for (size_t r = 0; r < n_reads; r++) {
+        const uint64_t *km = kmers + offsets[r];
+        const size_t n = (size_t)(offsets[r + 1] - offsets[r]);
+        valid[r] = n >= SO_LSH_BUCKET_SIZE;                                              /* :728-730 */
+        lsh_item *it = (lsh_item *)malloc((n ? n : 1) * sizeof(lsh_item));
+        for (int t = 0; t < SO_LSH_NUM_TABLES; t++) {
+            sig[r * SO_LSH_NUM_TABLES + t] = 0;
+            if (!valid[r]) continue;
+            for (size_t i = 0; i < n; i++) { it[i].hash = fx_write_u64(fx_write_u64(0, (uint64_t)t), km[i]); it[i].kmer = km[i]; it[i].idx = i; }
+            qsort(it, n, sizeof(lsh_item), cmp_lsh_item);                                /* :741 */
+            uint64_t sg = 0;
+            for (int i = 0; i < SO_LSH_BUCKET_SIZE; i++) sg ^= it[i].kmer * (uint64_t)(i + 1);   /* :743-745 */
+            sig[r * SO_LSH_NUM_TABLES + t] = sg;
+        }
+        free(it);
+    }
+    return 0;
+}
+
+typedef struct { uint32_t *v; size_t n, cap; } u32vec;
+static void u32vec_push(u32vec *a, uint32_t x) {
+    if (a->n == a->cap) { a->cap = a->cap ? a->cap * 2 : 4; a->v = (uint32_t *)realloc(a->v, a->cap * sizeof(uint32_t)); }
+    a->v[a->n++] = x;
+}
+typedef struct { uint32_t id, hits; } lsh_cand;
+static int cmp_lsh_cand(const void *a, const void *b) {          /* (b.1, b.0).cmp(&(a.1, a.0)): hits desc, then id desc */
+    const lsh_cand *x = (const lsh_cand *)a, *y = (const lsh_cand *)b;
+    if (x->hits != y->hits) return x->hits > y->hits ? -1 : 1;
+    return x->id > y->id ? -1 : x->id < y->id;
+}
+
+int so_cluster_reads_by_kmers(int k, double threshold, const uint64_t *kmers, const uint64_t *offsets, size_t n_reads, uint32_t *rep_of,
+                              uint64_t *n_reps_out) {
+    const size_t top_n_candidates = 10;                                                  /* :85 */
+    uint64_t *sig = (uint64_t *)malloc((n_reads ? n_reads : 1) * SO_LSH_NUM_TABLES * sizeof(uint64_t));
+    uint8_t *valid = (uint8_t *)malloc(n_reads ? n_reads : 1);
+    so_lsh_signatures(kmers, offsets, n_reads, sig, valid);
+    /* sorted distinct k-mers per read (the reference's HashSet of the query / Vec::contains on the representative) */
+    uint64_t *dk = (uint64_t *)malloc((size_t)(offsets[n_reads] ? offsets[n_reads] : 1) * sizeof(uint64_t));
+    uint32_t *nd = (uint32_t *)malloc((n_reads ? n_reads : 1) * sizeof(uint32_t));
+    for (size_t r = 0; r < n_reads; r++) {
+        const size_t n = (size_t)(offsets[r + 1] - offsets[r]);
+        uint64_t *d = dk + offsets[r];
+        memcpy(d, kmers + offsets[r], n * sizeof(uint64_t));
+        qsort(d, n, sizeof(uint64_t), cmp_u64);
+        size_t m = 0;
+        for (size_t i = 0; i < n; i++) if (i == 0 || d[i] != d[i - 1]) d[m++] = d[i];
+        nd[r] = (uint32_t)m;
+    }
+    u64map tab[SO_LSH_NUM_TABLES];                         /* signature -> index into lists (+1) */
+    u32vec *lists = NULL; size_t n_lists = 0, cap_lists = 0;
+    for (int t = 0; t < SO_LSH_NUM_TABLES; t++) u64map_init(&tab[t], 1024);
+    uint8_t *hits = (uint8_t *)calloc(n_reads ? n_reads : 1, 1);
+    lsh_cand *cand = (lsh_cand *)malloc((n_reads ? n_reads : 1) * sizeof(lsh_cand));
+    uint64_t n_reps = 0;
+    for (size_t i = 0; i < n_reads; i++) {                                               /* :100 */
+        size_t nc = 0;
+        if (valid[i])
+            for (int t = 0; t < SO_LSH_NUM_TABLES; t++) {                                /* query_read_against_bucket_index :299-337 */
+                const uint32_t *slot = u64map_slot(&tab[t], sig[i * SO_LSH_NUM_TABLES + t], 0);
+                if (!slot) continue;
+                const u32vec *l = &lists[*slot - 1];
+                for (size_t q = 0; q < l->n; q++) { if (hits[l->v[q]]++ == 0) cand[nc++].id = l->v[q]; }
+            }
+        long best = -1;
+        if (nc) {
+            for (size_t q = 0; q < nc; q++) { cand[q].hits = hits[cand[q].id]; hits[cand[q].id] = 0; }
+            qsort(cand, nc, sizeof(lsh_cand), cmp_lsh_cand);                             /* :111 */
+            const uint32_t max_hits = cand[0].hits;
+            double best_similarity = 0.0;
+            size_t checked = 0;
+            for (size_t q = 0; q < nc; q++) {                                            /* :118-125 */
+                if (!(cand[q].hits == max_hits || checked < top_n_candidates)) break;
+                checked++;
+                const uint32_t c = cand[q].id;
+                size_t count = 0;                                                        /* :133-141 */
+                for (uint32_t a = 0; a < nd[i]; a++)
+                    if (bsearch(&dk[offsets[i] + a], dk + offsets[c], nd[c], sizeof(uint64_t), cmp_u64)) count++;
+                const size_t rep_len = (size_t)(offsets[c + 1] - offsets[c]);
+                const size_t den = nd[i] > rep_len ? nd[i] : rep_len;
+                const double ratio = (double)count / (double)den;                        /* :143 */
+                const double similarity = pow(ratio, 1.0 / (double)k);                   /* :144 */
+                if (similarity > best_similarity) { best_similarity = similarity; best = (long)c; }
+            }
+            if (!(best_similarity > threshold)) best = -1;                               /* :152-156 */
+        }
+        if (best >= 0) rep_of[i] = (uint32_t)best;
+        else {                                                                           /* :178-187 */
+            if (valid[i])
+                for (int t = 0; t < SO_LSH_NUM_TABLES; t++) {
+                    if (tab[t].n * 2 + 2 >= tab[t].cap) {                                /* grow */
+                        u64map g; u64map_init(&g, tab[t].cap);
+                        for (size_t q = 0; q < tab[t].cap; q++)
+                            if (tab[t].keys[q] != UINT64_MAX) *u64map_slot(&g, tab[t].keys[q], 1) = tab[t].vals[q];
+                        u64map_free(&tab[t]); tab[t] = g;
+                    }
+                    uint32_t *slot = u64map_slot(&tab[t], sig[i * SO_LSH_NUM_TABLES + t], 1);
+                    if (*slot == 0) {
+                        if (n_lists == cap_lists) { cap_lists = cap_lists ? cap_lists * 2 : 1024; lists = (u32vec *)realloc(lists, cap_lists * sizeof(u32vec)); }
+                        memset(&lists[n_lists], 0, sizeof(u32vec));
+                        *slot = (uint32_t)(++n_lists);
+                    }
+                    u32vec_push(&lists[*slot - 1], (uint32_t)i);
+                }
+            rep_of[i] = (uint32_t)i; n_reps++;
+        }
+    }
+    for (size_t q = 0; q < n_lists; q++) free(lists[q].v);
+    for (int t = 0; t < SO_LSH_NUM_TABLES; t++) u64map_free(&tab[t]);
+    free(lists); free(hits); free(cand); free(sig); free(valid); free(dk); free(nd);
+    if (n_reps_out) *n_reps_out = n_reps;
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* a4: kmer_comp::twin_reads_from_snpmers, src/kmer_comp.rs:68-258                      */
 /* ------------------------------------------------------------------------------------ */
 /* the tests a read goes through before it becomes a TwinRead; the quality cutoff (:248) is applied after the id sort in

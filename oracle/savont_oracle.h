@@ -191,6 +191,16 @@ long long so_consensus_pileups(int band, int use_hpc, const uint8_t *cons_bases,
                                const uint32_t *read_cons, size_t n_reads, uint64_t *pos_offsets, so_pileup_entry *entries,
                                size_t entry_cap, uint8_t *ref_hp_length, uint8_t *read_strand, int32_t *read_nm);
 
+/* ---- SURVEY.md 8(f) row 3 (Stage 2): LSH signatures and greedy k-mer clustering.
+ * Input: the reads' minimizer k-mers (TwinRead::minimizer_kmers(), duplicates kept, in position order) in CSR.
+ * so_lsh_signatures: TwinRead::compute_lsh_signatures, src/types.rs:719-747: sig[r*20 + t], valid[r] = 0 for reads with fewer
+ *   than LSH_BUCKET_SIZE = 3 minimizers (all their signatures are None).
+ * so_cluster_reads_by_kmers: asv_cluster::cluster_reads_by_kmers, src/asv_cluster.rs:72-190 (use_bucketed = true):
+ *   rep_of[r] = the representative read r was assigned to (r itself if it became a representative). */
+int so_lsh_signatures(const uint64_t *kmers, const uint64_t *offsets, size_t n_reads, uint64_t *sig, uint8_t *valid);
+int so_cluster_reads_by_kmers(int k, double threshold, const uint64_t *kmers, const uint64_t *offsets, size_t n_reads, uint32_t *rep_of,
+                              uint64_t *n_reps);
+
 /* ---- a13-a14: EM over equivalence classes (src/alignment.rs:1957-2038) ---------------
  * classes in CSR (cls_offsets[n_cls+1], cls_asv), counts[n_cls]; total_assigned;
  * out: abundances[A] (f64), depths[A] = round(ab*total).  Classes are iterated in the

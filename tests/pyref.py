@@ -230,3 +230,71 @@ def pileup_columns(cons_lens, reads, aln):
                 out.append(v[len(v) // 2])
         hp.append(out)
     return cols, hp
+
+
+_M64 = (1 << 64) - 1
+
+
+def fx_hash2(seed, kmer):
+    """FxHasher64 (fxhash 0.2.1): write_u64(seed); write_u64(kmer); finish()"""
+    h = 0
+    for w in (seed, kmer):
+        h = ((((h << 5) | (h >> 59)) & _M64) ^ w) * 0x517cc1b727220a95 & _M64
+    return h
+
+
+def lsh_signatures(minis, n_tables=20, bucket=3):
+    """TwinRead::compute_lsh_signatures (src/types.rs:719-747) -> list of 20 Option<u64>"""
+    out = []
+    for t in range(n_tables):
+        if len(minis) < bucket:
+            out.append(None); continue
+        hashed = sorted(((fx_hash2(t, km), km) for km in minis), key=lambda x: x[0])      # stable, by hash only
+        sg = 0
+        for i in range(bucket):
+            sg ^= (hashed[i][1] * (i + 1)) & _M64
+        out.append(sg)
+    return out
+
+
+def cluster_reads_by_kmers(reads_minis, k=17, threshold=0.95, top_n=10):
+    """asv_cluster::cluster_reads_by_kmers (src/asv_cluster.rs:72-190, bucketed branch) -> rep_of"""
+    sigs = [lsh_signatures(m) for m in reads_minis]
+    tables = [dict() for _ in range(20)]
+    rep_of = []
+    for i, minis in enumerate(reads_minis):
+        hits = {}
+        for t in range(20):
+            sg = sigs[i][t]
+            if sg is not None:
+                for c in tables[t].get(sg, ()):
+                    hits[c] = hits.get(c, 0) + 1
+        best = None
+        if hits:
+            cands = sorted(hits.items(), key=lambda x: (x[1], x[0]), reverse=True)
+            max_hits = cands[0][1]
+            check = []
+            for c, h in cands:
+                if h == max_hits or len(check) < top_n:
+                    check.append(c)
+                else:
+                    break
+            best_sim = 0.0
+            rset = set(minis)
+            for c in check:
+                rep = reads_minis[c]
+                count = sum(1 for km in rset if km in rep)
+                ratio = count / max(len(rset), len(rep))
+                sim = ratio ** (1.0 / k)
+                if sim > best_sim:
+                    best_sim, best = sim, c
+            if not best_sim > threshold:
+                best = None
+        if best is None:
+            for t in range(20):
+                if sigs[i][t] is not None:
+                    tables[t].setdefault(sigs[i][t], []).append(i)
+            rep_of.append(i)
+        else:
+            rep_of.append(best)
+    return rep_of

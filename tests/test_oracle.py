@@ -385,3 +385,31 @@ def test_consensus_pileups_match_python_restatement(use_hpc, band):
     assert list(got["ref_hp_length"]) == [x for h in hp for x in h]
     if use_hpc:
         assert max(max(h) for h in hp if h) > 1
+
+
+def test_fx_hash_known_answers():
+    """FxHasher64 (fxhash 0.2.1) from its published definition: hash = (rotl(hash, 5) ^ word) * 0x517cc1b727220a95"""
+    K = 0x517cc1b727220a95
+    assert pyref.fx_hash2(0, 0) == 0
+    assert pyref.fx_hash2(0, 1) == K
+    assert pyref.fx_hash2(1, 0) == (((K << 5) | (K >> 59)) & (2 ** 64 - 1)) * K % 2 ** 64
+    sig = pyref.lsh_signatures([5, 9, 5, 1 << 40, 77])
+    assert len(sig) == 20 and all(s is not None for s in sig) and pyref.lsh_signatures([1, 2]) == [None] * 20
+
+
+@pytest.mark.parametrize("seed,err", [(1, 0.02), (2, 0.005), (3, 0.04)])
+def test_lsh_and_kmer_clustering_match_python_restatement(seed, err):
+    from tests.util import clustering_case
+    km, off, _ = clustering_case(600 + seed, n_reads=260, err=err)
+    minis = [[int(x) for x in km[int(off[i]):int(off[i + 1])]] for i in range(len(off) - 1)]
+    sig, valid = O.lsh_signatures(km, off)
+    for i, m in enumerate(minis):
+        want = pyref.lsh_signatures(m)
+        assert bool(valid[i]) == (want[0] is not None)
+        if valid[i]:
+            assert [int(x) for x in sig[i]] == want
+    rep = O.cluster_reads_by_kmers(km, off)
+    want = pyref.cluster_reads_by_kmers(minis)
+    assert [int(x) for x in rep] == want
+    n_rep = sum(1 for i, r in enumerate(want) if r == i)
+    assert 6 <= n_rep < len(want) and any(len(m) != len(set(m)) for m in minis) and any(len(m) < 3 for m in minis)

@@ -109,3 +109,26 @@ def pileup_case(seed, n_cons=5, reads_per=12, cons_len=(60, 200), long_runs=Fals
             reads.append(rd); rcons.append(ci)
             quals.append(bytes(33 + rng.choice([3, 10, 20, 30, 40]) for _ in range(len(rd))))
     return cons, reads, quals, rcons
+
+
+def clustering_case(seed, n_species=6, n_reads=300, length=700, err=0.02, k=17, c=11):
+    """minimizer lists (CSR) of reads drawn from a few related 'species' + degenerate reads (no / few / duplicated minimizers)"""
+    from oracle import oracle as O
+    rng = random.Random(seed)
+    roots = [rand_seq(rng, length) for _ in range(max(1, n_species // 2))]
+    species = [roots[s % len(roots)] if s < len(roots) else mutate(rng, roots[s % len(roots)], 12, 2, 2) for s in range(n_species)]
+    reads = []
+    for i in range(n_reads):
+        s = species[rng.randrange(n_species)]
+        ne = int(len(s) * err * rng.choice([0.2, 1, 1, 2]))
+        rd = mutate(rng, s, ne // 2, ne // 4, ne // 4)
+        if i % 37 == 5:
+            rd = rd[:rng.choice([5, 17, 27, 30, 40])]            # too short for any / for three minimizers
+        if i % 41 == 7:
+            rd = reads[-1]                                        # identical to the previous read
+        if i % 43 == 9:
+            rd = rd[:200] + rd[:200] + rd[:200]                   # repeated k-mers: duplicates in the minimizer list
+        reads.append(rd)
+    b, o = O.concat(reads)
+    sk = O.sketch_batch(O.default_params(k=k, c=c), [], b, None, o)
+    return np.asarray(sk["mini_kmer"], np.uint64), np.asarray(sk["mini_offsets"], np.uint64), reads
