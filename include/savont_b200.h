@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SAVONT_B200_ABI_VERSION 4
+#define SAVONT_B200_ABI_VERSION 5
 
 typedef struct savont_b200_ctx savont_b200_ctx;
 
@@ -284,6 +284,23 @@ int savont_b200_consensus_pileups(savont_b200_ctx *ctx, int use_hpc, const uint8
                                   uint64_t *pos_offsets, savont_b200_pileup_entry *entries, size_t entry_cap,
                                   uint64_t *n_entries, uint8_t *ref_hp_length, uint8_t *read_strand, int32_t *read_nm,
                                   savont_b200_stats *stats /* may be NULL */);
+
+/* ---- Stage 2 greedy k-mer clustering.  Input of both calls: the reads' minimizer k-mers in CSR,
+ * exactly TwinRead::minimizer_kmers() (src/types.rs: duplicates kept, position order; Kmer48 widened to u64), reads in the
+ * order of `twin_reads` (Stage 1.5 output order, src/main.rs:538).
+ * savont_b200_lsh_signatures replaces TwinRead::compute_lsh_signatures (src/types.rs:719-747; FxHasher64 of the fxhash crate
+ *   0.2.1): sig[r * 20 + t] for the LSH_NUM_TABLES = 20 tables, valid[r] = 0 when the read has fewer than LSH_BUCKET_SIZE = 3
+ *   minimizers (all its signatures are None).
+ * savont_b200_cluster_reads_by_kmers replaces the greedy loop of asv_cluster::cluster_reads_by_kmers
+ *   (src/asv_cluster.rs:72-190, use_bucketed = true; k = params.k, threshold = args.primary_clustering_threshold, default 0.95):
+ *   rep_of[r] = the representative read r was assigned to, r itself when it became a representative.  The cluster list of
+ *   :192-210 (group by representative, sort by size then first member, drop clusters below min_cluster_size) is host work on
+ *   rep_of.  The result is identical to the sequential loop.  stats: sketch_ms = upload + signatures + sorted minimizer sets,
+ *   filter_ms = bucket query kernels, align_ms = in-block pair kernels, n_batches = blocks. */
+int savont_b200_lsh_signatures(savont_b200_ctx *ctx, const uint64_t *kmers, const uint64_t *offsets, size_t n_reads, uint64_t *sig,
+                               uint8_t *valid);
+int savont_b200_cluster_reads_by_kmers(savont_b200_ctx *ctx, const uint64_t *kmers, const uint64_t *offsets, size_t n_reads,
+                                       double threshold, uint32_t *rep_of, uint64_t *n_reps, savont_b200_stats *stats /* may be NULL */);
 
 /* Pinned host memory helpers (inputs placed here are copied without a staging pass). */
 int savont_b200_host_alloc(size_t bytes, void **out);

@@ -802,6 +802,7 @@ static int cmp_lsh_item(const void *a, const void *b) {          /* sort_by_key(
 }
 
 int so_lsh_signatures(const uint64_t *kmers, const uint64_t *offsets, size_t n_reads, uint64_t *sig, uint8_t *valid) {
+#pragma omp parallel for schedule(dynamic, 64)
     for (size_t r = 0; r < n_reads; r++) {
         const uint64_t *km = kmers + offsets[r];
         const size_t n = (size_t)(offsets[r + 1] - offsets[r]);
@@ -842,6 +843,7 @@ int so_cluster_reads_by_kmers(int k, double threshold, const uint64_t *kmers, co
     /* sorted distinct k-mers per read (the reference's HashSet of the query / Vec::contains on the representative) */
     uint64_t *dk = (uint64_t *)malloc((size_t)(offsets[n_reads] ? offsets[n_reads] : 1) * sizeof(uint64_t));
     uint32_t *nd = (uint32_t *)malloc((n_reads ? n_reads : 1) * sizeof(uint32_t));
+#pragma omp parallel for schedule(dynamic, 64)
     for (size_t r = 0; r < n_reads; r++) {
         const size_t n = (size_t)(offsets[r + 1] - offsets[r]);
         uint64_t *d = dk + offsets[r];

@@ -445,6 +445,24 @@ class Context:
         return dict(pos_offsets=po, entries=ent[:int(ne.value)], ref_hp_length=hp[:npos], read_strand=st[:n], read_nm=nm[:n],
                     stats=stt.as_dict())
 
+    def lsh_signatures(self, kmers, offsets):
+        """TwinRead::compute_lsh_signatures (src/types.rs:719-747) -> (sig [n, 20] u64, valid [n] u8)"""
+        km = np.ascontiguousarray(kmers, dtype=np.uint64); off = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(off) - 1
+        sig = np.zeros((max(n, 1), 20), np.uint64); valid = np.zeros(max(n, 1), np.uint8)
+        _check(self.L.savont_b200_lsh_signatures(self.h, _p(km, C.c_uint64), _p(off, C.c_uint64), C.c_size_t(n), _p(sig, C.c_uint64),
+                                                 _p(valid, C.c_uint8)))
+        return sig[:n], valid[:n]
+
+    def cluster_reads_by_kmers(self, kmers, offsets, threshold=0.95):
+        """greedy loop of asv_cluster::cluster_reads_by_kmers (src/asv_cluster.rs:72-190) -> dict(rep_of, n_reps, stats)"""
+        km = np.ascontiguousarray(kmers, dtype=np.uint64); off = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(off) - 1
+        rep = np.zeros(max(n, 1), np.uint32); nr = C.c_uint64(0); stt = Stats()
+        _check(self.L.savont_b200_cluster_reads_by_kmers(self.h, _p(km, C.c_uint64), _p(off, C.c_uint64), C.c_size_t(n),
+                                                         C.c_double(threshold), _p(rep, C.c_uint32), C.byref(nr), C.byref(stt)))
+        return dict(rep_of=rep[:n], n_reps=int(nr.value), stats=stt.as_dict())
+
     def counts_dev(self):
         """(device pointer, length in u64) of [unambig|ambig|leq10|assigned|filtered|singleton S*A]"""
         ptr = C.c_void_p(); n = C.c_size_t()

@@ -860,6 +860,8 @@ int savont_b200_destroy(savont_b200_ctx *h) {
     c->pin_small.release(); c->pin_out.release(); c->tb_pin.release();
     for (DevBuf &b : c->tb_ws) b.release();
     for (DevBuf &b : c->pileup_ws) b.release();
+    for (DevBuf &b : c->cluster_ws) b.release();
+    for (PinBuf &b : c->cluster_pin) b.release();
     for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
     for (int i = 0; i < 3; ++i) { if (c->ev_up[i]) cudaEventDestroy(c->ev_up[i]); if (c->ev_h0[i]) cudaEventDestroy(c->ev_h0[i]); }
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);

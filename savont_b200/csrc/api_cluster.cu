@@ -1,0 +1,306 @@
+// api_cluster.cu -- host side of savont_b200_lsh_signatures / savont_b200_cluster_reads_by_kmers.
+//
+// Stands in for asv_cluster::cluster_reads_by_kmers (reference src/asv_cluster.rs:72-190, bucketed branch).  The reference is
+// a sequential greedy loop: read i is compared with the representatives created by reads < i and either joins the best one
+// or becomes a representative itself.  Here the reads go through in blocks:
+//   1. rep_query_kernel compares every read of the block with the representatives known BEFORE the block (bucket hits,
+//      candidate window, containment counts of the window);
+//   2. the reads that find no match there are the block's potential representatives; pair_stats_kernel gives hits and
+//      containment of every (read, earlier potential representative) pair of the block;
+//   3. the host walks the block in read order and merges, per read, the pre-block candidates with the representatives that were
+//      actually created earlier in the block -- the reference's order (hits, id descending; in-block representatives have the
+//      larger ids), window (max-hits group + first 10) and "first strictly greater similarity" rule.  A read that becomes a
+//      representative although it had a pre-block match (its match was pushed out of the first 10 by in-block representatives) is
+//      not among the pairs of step 2: its pairs are computed on demand.
+// The result is identical to the sequential loop; block sizes follow the rate of new representatives.
+#include <map>
+
+#include "api_internal.cuh"
+
+namespace sb {
+
+namespace {
+
+struct Cand { uint32_t id, hits, cnt, den; };
+inline bool ratio_gt(const Cand &a, const Cand &b) { return (uint64_t)a.cnt * b.den > (uint64_t)b.cnt * a.den; }   // a.cnt/a.den > b.cnt/b.den
+
+struct ThresholdTest {       // similarity = ratio.powf(1/k) > threshold (src/asv_cluster.rs:143-152), pow only near the boundary
+    double threshold, inv_k, t_pow;
+    ThresholdTest(double thr, int k) : threshold(thr), inv_k(1.0 / (double)k), t_pow(thr > 0 ? std::pow(thr, (double)k) : 0.0) {}
+    bool pass(uint32_t cnt, uint32_t den) const {
+        if (cnt == 0) return false;                          // similarity 0.0 is never > best_similarity = 0.0
+        const double ratio = (double)cnt / (double)den;
+        if (threshold > 0) {
+            if (ratio > t_pow * (1.0 + 1e-9)) return true;
+            if (ratio < t_pow * (1.0 - 1e-9)) return false;
+        }
+        return std::pow(ratio, inv_k) > threshold;
+    }
+};
+
+template <typename T>
+int up(DevBuf &d, const T *v, size_t n, cudaStream_t st) {
+    TRY(d.ensure(n * sizeof(T) + 16));
+    if (n) CK(cudaMemcpyAsync(d.p, v, n * sizeof(T), cudaMemcpyHostToDevice, st));
+    return 0;
+}
+
+struct ClusterDev {
+    DevBuf &kmers, &offsets, &dk, &nd, &sig, &valid, &tsig, &trep, &toff, &res, &pi, &pj, &ph, &pc;
+    explicit ClusterDev(DevBuf *w)
+        : kmers(w[0]), offsets(w[1]), dk(w[2]), nd(w[3]), sig(w[4]), valid(w[5]), tsig(w[6]), trep(w[7]), toff(w[8]), res(w[9]), pi(w[10]),
+          pj(w[11]), ph(w[12]), pc(w[13]) {}
+};
+
+// upload + signatures + sorted distinct lists; host copies of nd / sig / valid when asked for
+int cluster_prepare(Context *c, ClusterDev &d, const uint64_t *kmers, const uint64_t *offsets, size_t n, std::vector<uint64_t> &rel,
+                    std::vector<uint32_t> *nd_h, std::vector<uint64_t> *sig_h, std::vector<uint8_t> *valid_h) {
+    cudaStream_t st = c->stream;
+    const uint64_t base0 = offsets[0], total = offsets[n] - base0;
+    rel.resize(n + 1);
+    for (size_t i = 0; i <= n; ++i) {
+        if (i && offsets[i] < offsets[i - 1]) return fail(SAVONT_B200_ERR_INVALID, "offsets not monotonic at %zu", i);
+        rel[i] = offsets[i] - base0;
+    }
+    TRY(up(d.kmers, kmers + base0, total, st)); TRY(up(d.offsets, rel.data(), n + 1, st));
+    TRY(d.dk.ensure(total * 8 + 16)); TRY(d.nd.ensure(n * 4 + 16)); TRY(d.sig.ensure(n * kLshTables * 8 + 16)); TRY(d.valid.ensure(n + 16));
+    launch_lsh_sig(d.kmers.as<uint64_t>(), d.offsets.as<uint64_t>(), (uint32_t)n, d.sig.as<uint64_t>(), d.valid.as<uint8_t>(), st);
+    c->last_stats.kernel_launches += 1;
+    c->last_stats.h2d_bytes += total * 8 + (n + 1) * 8;
+    if (sig_h) {
+        sig_h->resize(n * kLshTables); valid_h->resize(n);
+        if (n) {
+            CK(cudaMemcpyAsync(sig_h->data(), d.sig.p, n * kLshTables * 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(valid_h->data(), d.valid.p, n, cudaMemcpyDeviceToHost, st));
+        }
+        c->last_stats.d2h_bytes += n * kLshTables * 8 + n;
+    }
+    if (nd_h) {
+        launch_sort_dedup(d.kmers.as<uint64_t>(), d.offsets.as<uint64_t>(), (uint32_t)n, d.dk.as<uint64_t>(), d.nd.as<uint32_t>(), c->sm_count, st);
+        c->last_stats.kernel_launches += 1;
+        nd_h->resize(n);
+        if (n) CK(cudaMemcpyAsync(nd_h->data(), d.nd.p, n * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        // reads with more minimizers than the shared-memory sort holds: sorted on the host
+        std::vector<uint64_t> tmp;
+        for (size_t r = 0; r < n; ++r) {
+            if ((*nd_h)[r] != 0xffffffffu) continue;
+            tmp.assign(kmers + offsets[r], kmers + offsets[r + 1]);
+            std::sort(tmp.begin(), tmp.end());
+            tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+            (*nd_h)[r] = (uint32_t)tmp.size();
+            CK(cudaMemcpy(d.dk.as<uint64_t>() + rel[r], tmp.data(), tmp.size() * 8, cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(d.nd.as<uint32_t>() + r, &(*nd_h)[r], 4, cudaMemcpyHostToDevice));
+        }
+    }
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+}  // namespace sb
+
+using namespace sb;
+
+extern "C" int savont_b200_lsh_signatures(savont_b200_ctx *h, const uint64_t *kmers, const uint64_t *offsets, size_t n_reads, uint64_t *sig,
+                                          uint8_t *valid) {
+    TRY(use_device(h ? &h->c : nullptr));
+    Context *c = &h->c;
+    if (!offsets || (n_reads && (!sig || !valid))) return fail(SAVONT_B200_ERR_INVALID, "null argument");
+    if (n_reads >= 0xfffffff0ull) return fail(SAVONT_B200_ERR_INVALID, "too many reads");
+    if (offsets[n_reads] > offsets[0] && !kmers) return fail(SAVONT_B200_ERR_INVALID, "null argument");
+    c->last_stats = savont_b200_stats{};
+    ClusterDev d(c->cluster_ws);
+    std::vector<uint64_t> rel, sig_h; std::vector<uint8_t> valid_h;
+    TRY(cluster_prepare(c, d, kmers, offsets, n_reads, rel, nullptr, &sig_h, &valid_h));
+    if (n_reads) { memcpy(sig, sig_h.data(), n_reads * kLshTables * 8); memcpy(valid, valid_h.data(), n_reads); }
+    return 0;
+}
+
+extern "C" int savont_b200_cluster_reads_by_kmers(savont_b200_ctx *h, const uint64_t *kmers, const uint64_t *offsets, size_t n_reads,
+                                                  double threshold, uint32_t *rep_of, uint64_t *n_reps_out, savont_b200_stats *stats) {
+    TRY(use_device(h ? &h->c : nullptr));
+    Context *c = &h->c;
+    if (!offsets || (n_reads && !rep_of)) return fail(SAVONT_B200_ERR_INVALID, "null argument");
+    if (n_reads >= 0xfffffff0ull) return fail(SAVONT_B200_ERR_INVALID, "too many reads");
+    if (offsets[n_reads] > offsets[0] && !kmers) return fail(SAVONT_B200_ERR_INVALID, "null argument");
+    c->last_stats = savont_b200_stats{};
+    cudaStream_t st = c->stream;
+    const size_t n = n_reads;
+    ClusterDev d(c->cluster_ws);
+    std::vector<uint64_t> rel, sig; std::vector<uint8_t> valid; std::vector<uint32_t> nd;
+    CK(cudaEventRecord(c->ev[0], st));
+    TRY(cluster_prepare(c, d, kmers, offsets, n, rel, &nd, &sig, &valid));
+    CK(cudaEventRecord(c->ev[1], st));
+    const ThresholdTest thr(threshold, c->params.k);
+    auto tot_of = [&](uint32_t r) { return (uint32_t)(rel[r + 1] - rel[r]); };
+
+    // bucket tables on the host: per table (signature, representative) sorted; flat copies go to the device per block
+    std::vector<std::pair<uint64_t, uint32_t>> tab[kLshTables];
+    std::vector<uint64_t> flat_sig; std::vector<uint32_t> flat_rep; uint32_t toff[kLshTables + 1] = {0};
+    bool tables_dirty = true;
+    uint64_t n_reps = 0;
+    size_t block = 256;
+    if (const char *e = getenv("SAVONT_B200_CLUSTER_BLOCK")) block = std::max<size_t>(1, strtoull(e, nullptr, 10));   // tests
+    const bool fixed_block = getenv("SAVONT_B200_CLUSTER_BLOCK") != nullptr;
+    constexpr size_t kMaxBlock = 16384, kMinBlock = 256, kTargetNew = 96, kMaxPairs = 1u << 24;
+    std::vector<ClusterResult> res;
+    std::vector<uint32_t> p0, before, pair_i, pair_j, pcnt; std::vector<uint64_t> pair_start; std::vector<uint8_t> phits;
+    std::vector<Cand> inblk, order;
+    double query_ms = 0, pair_ms = 0;
+
+    for (size_t b0 = 0; b0 < n;) {
+        size_t b1 = std::min(n, b0 + block);
+        // ---- 1. the block against the representatives known so far ----
+        if (tables_dirty) {
+            size_t e = 0;
+            for (int t = 0; t < kLshTables; ++t) e += tab[t].size();
+            flat_sig.resize(e); flat_rep.resize(e);
+            e = 0;
+            for (int t = 0; t < kLshTables; ++t) {
+                toff[t] = (uint32_t)e;
+                for (const auto &x : tab[t]) { flat_sig[e] = x.first; flat_rep[e] = x.second; ++e; }
+            }
+            toff[kLshTables] = (uint32_t)e;
+            TRY(up(d.tsig, flat_sig.data(), e, st)); TRY(up(d.trep, flat_rep.data(), e, st)); TRY(up(d.toff, toff, (size_t)kLshTables + 1, st));
+            c->last_stats.h2d_bytes += e * 12;
+            tables_dirty = false;
+        }
+        const uint32_t nb = (uint32_t)(b1 - b0);
+        TRY(d.res.ensure((size_t)nb * sizeof(ClusterResult)));
+        ClusterQuery q{};
+        q.offsets = d.offsets.as<uint64_t>(); q.dk = d.dk.as<uint64_t>(); q.nd = d.nd.as<uint32_t>(); q.sig = d.sig.as<uint64_t>();
+        q.valid = d.valid.as<uint8_t>(); q.table_sig = d.tsig.as<uint64_t>(); q.table_rep = d.trep.as<uint32_t>();
+        q.table_off = d.toff.as<uint32_t>(); q.first = (uint32_t)b0; q.n_block = nb; q.out = d.res.as<ClusterResult>();
+        CK(cudaEventRecord(c->ev[2], st));
+        launch_rep_query(q, st);
+        CK(cudaEventRecord(c->ev[3], st));
+        res.resize(nb);
+        CK(cudaMemcpyAsync(res.data(), d.res.p, (size_t)nb * sizeof(ClusterResult), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        query_ms += ev_ms(c->ev[2], c->ev[3]);
+        c->last_stats.kernel_launches += 1; c->last_stats.d2h_bytes += (size_t)nb * sizeof(ClusterResult);
+
+        // ---- 2. potential representatives of the block and their pairs ----
+        p0.clear(); before.assign(nb, 0); pair_start.assign((size_t)nb + 1, 0);
+        for (uint32_t li = 0; li < nb; ++li) {
+            before[li] = (uint32_t)p0.size();
+            pair_start[li + 1] = pair_start[li] + before[li];
+            if (pair_start[li + 1] > kMaxPairs && li > 0) { b1 = b0 + li; break; }          // bounded pair workspace: cut the block here
+            const ClusterResult &r = res[li];
+            const bool match = r.best_rep != 0xffffffffu && thr.pass(r.best_cnt, r.best_den);
+            if (!match) p0.push_back((uint32_t)(b0 + li));
+        }
+        const uint32_t nbk = (uint32_t)(b1 - b0);
+        const size_t n_pairs = (size_t)pair_start[nbk];
+        pair_i.resize(n_pairs); pair_j.resize(n_pairs); phits.resize(n_pairs); pcnt.resize(n_pairs);
+        for (uint32_t li = 0; li < nbk; ++li)
+            for (uint32_t pidx = 0; pidx < before[li]; ++pidx) { pair_i[pair_start[li] + pidx] = (uint32_t)(b0 + li); pair_j[pair_start[li] + pidx] = p0[pidx]; }
+        if (n_pairs) {
+            TRY(up(d.pi, pair_i.data(), n_pairs, st)); TRY(up(d.pj, pair_j.data(), n_pairs, st));
+            TRY(d.ph.ensure(n_pairs + 16)); TRY(d.pc.ensure(n_pairs * 4 + 16));
+            CK(cudaEventRecord(c->ev[2], st));
+            launch_pair_stats(q, d.pi.as<uint32_t>(), d.pj.as<uint32_t>(), (uint32_t)n_pairs, d.ph.as<uint8_t>(), d.pc.as<uint32_t>(), st);
+            CK(cudaEventRecord(c->ev[3], st));
+            CK(cudaMemcpyAsync(phits.data(), d.ph.p, n_pairs, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(pcnt.data(), d.pc.p, n_pairs * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            CK(cudaGetLastError());
+            pair_ms += ev_ms(c->ev[2], c->ev[3]);
+            c->last_stats.kernel_launches += 1; c->last_stats.n_pairs += n_pairs;
+            c->last_stats.h2d_bytes += n_pairs * 8; c->last_stats.d2h_bytes += n_pairs * 5;
+        }
+
+        // ---- 3. the block in read order ----
+        struct NewRep { uint32_t id; int32_t pidx; };                                   // pidx < 0: not a potential representative (extra)
+        std::vector<NewRep> newreps;
+        std::map<uint32_t, std::pair<std::vector<uint8_t>, std::vector<uint32_t>>> extra;   // rep id -> stats of the reads behind it
+        size_t p0_pos = 0;
+        for (uint32_t li = 0; li < nbk; ++li) {
+            const uint32_t i = (uint32_t)(b0 + li);
+            const ClusterResult &r = res[li];
+            const bool in_p0 = p0_pos < p0.size() && p0[p0_pos] == i;
+            const int32_t my_pidx = in_p0 ? (int32_t)p0_pos : -1;
+            if (in_p0) ++p0_pos;
+            // representatives created earlier in this block that share a bucket with the read
+            inblk.clear();
+            uint32_t newmax = r.n_cand ? r.max_hits : 0u;
+            for (const NewRep &nr : newreps) {
+                uint32_t hh, cc;
+                if (nr.pidx >= 0) { const size_t at = pair_start[li] + (size_t)nr.pidx; hh = phits[at]; cc = pcnt[at]; }
+                else { const auto &ex = extra[nr.id]; const size_t at = i - nr.id - 1; hh = ex.first[at]; cc = ex.second[at]; }
+                if (hh) { inblk.push_back(Cand{nr.id, hh, cc, std::max(nd[i], tot_of(nr.id))}); newmax = std::max(newmax, hh); }
+            }
+            bool have = false; Cand best{0, 0, 0, 1};
+            if (inblk.empty()) {
+                if (r.best_rep != 0xffffffffu) { best = Cand{r.best_rep, r.best_hits, r.best_cnt, r.best_den}; have = true; }
+            } else {
+                // merged order: hits descending, id descending (in-block ids are larger than every pre-block id)
+                std::sort(inblk.begin(), inblk.end(), [](const Cand &a, const Cand &b) { return a.hits != b.hits ? a.hits > b.hits : a.id > b.id; });
+                order.clear();
+                for (size_t x = 0; x < inblk.size(); ++x) {
+                    uint32_t ahead = (uint32_t)x;                                       // in-block candidates in front of it
+                    for (uint32_t hh = inblk[x].hits + 1; hh <= (uint32_t)kLshTables; ++hh) ahead += r.n_cand ? r.cnt_h[hh] : 0u;
+                    if (inblk[x].hits == newmax || ahead < (uint32_t)kClusterTopN) order.push_back(inblk[x]);
+                }
+                const uint32_t n_top = std::min<uint32_t>(r.n_cand, (uint32_t)kClusterTopN);
+                for (uint32_t qx = 0; qx < n_top; ++qx) {
+                    const uint32_t hq = r.top_hits[qx];
+                    uint32_t ahead = qx;
+                    for (const Cand &e : inblk) if (e.hits >= hq) ++ahead;
+                    if (hq == newmax || ahead < (uint32_t)kClusterTopN)
+                        order.push_back(Cand{r.top_rep[qx], hq, r.top_cnt[qx], std::max(nd[i], r.top_tot[qx])});
+                }
+                // a max-hits group larger than the list: its best member stands for the members the list does not hold
+                if (r.n_cand && r.n_max > (uint32_t)kClusterTopN && newmax == r.max_hits && r.best_rep != 0xffffffffu)
+                    order.push_back(Cand{r.best_rep, r.best_hits, r.best_cnt, r.best_den});
+                std::stable_sort(order.begin(), order.end(), [](const Cand &a, const Cand &b) { return a.hits != b.hits ? a.hits > b.hits : a.id > b.id; });
+                for (const Cand &e : order)
+                    if (e.cnt > 0 && (!have || ratio_gt(e, best))) { best = e; have = true; }   // first strictly greater similarity
+            }
+            if (have && thr.pass(best.cnt, best.den)) { rep_of[i] = best.id; continue; }
+            // new representative (src/asv_cluster.rs:178-187)
+            rep_of[i] = i; ++n_reps;
+            if (valid[i]) {
+                for (int t = 0; t < kLshTables; ++t) {
+                    const std::pair<uint64_t, uint32_t> e(sig[(size_t)i * kLshTables + t], i);
+                    tab[t].insert(std::upper_bound(tab[t].begin(), tab[t].end(), e), e);
+                }
+                tables_dirty = true;
+                if (my_pidx < 0 && li + 1 < nbk) {
+                    // not among the potential representatives: hits / containment of the reads behind it, on demand
+                    const uint32_t m = nbk - li - 1;
+                    std::vector<uint32_t> xi(m), xj(m, i);
+                    for (uint32_t x = 0; x < m; ++x) xi[x] = i + 1 + x;
+                    auto &ex = extra[i];
+                    ex.first.resize(m); ex.second.resize(m);
+                    TRY(up(d.pi, xi.data(), m, st)); TRY(up(d.pj, xj.data(), m, st));
+                    TRY(d.ph.ensure(m + 16)); TRY(d.pc.ensure((size_t)m * 4 + 16));
+                    launch_pair_stats(q, d.pi.as<uint32_t>(), d.pj.as<uint32_t>(), m, d.ph.as<uint8_t>(), d.pc.as<uint32_t>(), st);
+                    CK(cudaMemcpyAsync(ex.first.data(), d.ph.p, m, cudaMemcpyDeviceToHost, st));
+                    CK(cudaMemcpyAsync(ex.second.data(), d.pc.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+                    CK(cudaStreamSynchronize(st));
+                    CK(cudaGetLastError());
+                    c->last_stats.kernel_launches += 1; c->last_stats.n_pairs += m;
+                }
+                newreps.push_back(NewRep{i, my_pidx});
+            }
+        }
+        // next block size: about kTargetNew new representatives per block
+        if (!fixed_block) {
+            const double rate = std::max<double>((double)newreps.size(), 0.5) / (double)nbk;
+            block = (size_t)std::min<double>((double)kMaxBlock, std::max<double>((double)kMinBlock, (double)kTargetNew / rate));
+        }
+        c->last_stats.n_batches += 1;
+        b0 = b1;
+    }
+    if (n_reps_out) *n_reps_out = n_reps;
+    c->last_stats.n_reads = n; c->last_stats.n_bases = rel[n];
+    c->last_stats.sketch_ms = ev_ms(c->ev[0], c->ev[1]); c->last_stats.filter_ms = query_ms; c->last_stats.align_ms = pair_ms;
+    c->last_stats.total_ms = c->last_stats.sketch_ms + query_ms + pair_ms;
+    if (stats) *stats = c->last_stats;
+    return 0;
+}

@@ -162,6 +162,7 @@ struct Context {
     // traceback workspace (history, CIGAR slots, compacted ops, ...) and the Stage 4 pileup scratch: kept between calls
     DevBuf tb_ws[7]; PinBuf tb_pin;
     DevBuf pileup_ws[40];
+    DevBuf cluster_ws[16]; PinBuf cluster_pin[4];
 };
 
 struct Context;

@@ -280,4 +280,35 @@ void launch_pileup_rank(const PileupArgs &a, cudaStream_t st);
 void launch_pileup_emit(const PileupArgs &a, cudaStream_t st);
 void launch_pileup_median(const PileupArgs &a, uint8_t *ref_hp, cudaStream_t st);
 
+// ---- Stage 2 greedy k-mer clustering (cluster.cu) ----
+constexpr int kLshTables = 20;        // LSH_NUM_TABLES, reference src/constants.rs:67
+constexpr int kLshBucket = 3;         // LSH_BUCKET_SIZE, src/constants.rs:68
+constexpr int kClusterTopN = 10;      // top_n_candidates, src/asv_cluster.rs:85
+struct ClusterResult {                // per read of a block: its candidates among the representatives known before the block
+    uint32_t n_cand, max_hits, n_max;                     // representatives with >= 1 bucket hit; maximum hits; how many reach it
+    uint32_t best_rep, best_hits, best_cnt, best_den;     // best containment of the window (max-hits group + first kClusterTopN); UINT32_MAX: none
+    uint32_t cnt_h[kLshTables + 1];                       // representatives per hit count
+    uint32_t top_rep[kClusterTopN], top_cnt[kClusterTopN], top_tot[kClusterTopN];   // first kClusterTopN by (hits, id) descending
+    uint8_t top_hits[kClusterTopN]; uint8_t pad[2];
+};
+struct ClusterQuery {
+    const uint64_t *offsets;          // [n + 1] minimizer CSR
+    const uint64_t *dk;               // sorted distinct minimizers per read (same offsets)
+    const uint32_t *nd;               // [n] number of distinct minimizers
+    const uint64_t *sig;              // [n * kLshTables]
+    const uint8_t *valid;             // [n]
+    const uint64_t *table_sig;        // the kLshTables bucket tables, each sorted by (signature, representative)
+    const uint32_t *table_rep;
+    const uint32_t *table_off;        // [kLshTables + 1]
+    uint32_t first, n_block;          // reads [first, first + n_block)
+    ClusterResult *out;               // [n_block]
+};
+void launch_lsh_sig(const uint64_t *kmers, const uint64_t *offsets, uint32_t n_reads, uint64_t *sig, uint8_t *valid, cudaStream_t st);
+void launch_sort_dedup(const uint64_t *kmers, const uint64_t *offsets, uint32_t n_reads, uint64_t *dk, uint32_t *nd, int sm_count,
+                       cudaStream_t st);
+uint32_t cluster_sort_max();
+void launch_rep_query(const ClusterQuery &q, cudaStream_t st);
+void launch_pair_stats(const ClusterQuery &q, const uint32_t *pair_i, const uint32_t *pair_j, uint32_t n_pairs, uint8_t *hits, uint32_t *cnt,
+                       cudaStream_t st);
+
 }  // namespace sb

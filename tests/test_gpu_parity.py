@@ -719,3 +719,52 @@ def test_consensus_pileups_full_clusters(ctx):
     _assert_pileups(got, want, "full clusters")
     assert len(got["entries"]) > 0.5 * len(reads) * 1000
     del rng
+
+
+@pytest.mark.parametrize("seed,err,n,block", [(11, 0.02, 400, None), (12, 0.005, 400, "7"), (13, 0.04, 500, "64"), (14, 0.02, 300, "1")])
+def test_lsh_signatures_and_kmer_clustering(ctx, monkeypatch, seed, err, n, block):
+    """Stage 2: LSH signatures and the greedy k-mer clustering against the sequential oracle, with block sizes that force
+    in-block representatives (block=None: the adaptive default)"""
+    from savont_b200 import _lib
+    from tests.util import clustering_case
+    gp, _ = _params(_lib)
+    ctx.set_params(gp)
+    km, off, _ = clustering_case(800 + seed, n_reads=n, err=err)
+    sig, valid = ctx.lsh_signatures(km, off)
+    wsig, wvalid = O.lsh_signatures(km, off)
+    assert np.array_equal(valid, wvalid) and np.array_equal(sig[valid == 1], wsig[wvalid == 1])
+    if block:
+        monkeypatch.setenv("SAVONT_B200_CLUSTER_BLOCK", block)
+    got = ctx.cluster_reads_by_kmers(km, off)
+    want = O.cluster_reads_by_kmers(km, off)
+    assert np.array_equal(got["rep_of"], want), np.flatnonzero(got["rep_of"] != want)[:10]
+    n_rep = int((want == np.arange(len(want))).sum())
+    assert got["n_reps"] == n_rep and 5 < n_rep < n
+    # another threshold, empty input, reads without minimizers only
+    for thr in (0.9, 0.99):
+        assert np.array_equal(ctx.cluster_reads_by_kmers(km, off, threshold=thr)["rep_of"], O.cluster_reads_by_kmers(km, off, threshold=thr))
+    e = ctx.cluster_reads_by_kmers(np.zeros(0, np.uint64), [0])
+    assert len(e["rep_of"]) == 0 and e["n_reps"] == 0
+    e = ctx.cluster_reads_by_kmers(np.array([5, 6], np.uint64), [0, 0, 2, 2])
+    assert list(e["rep_of"]) == [0, 1, 2]
+
+
+def test_kmer_clustering_large_groups(ctx, monkeypatch):
+    """many near-identical reads: max-hits groups beyond the first 10 candidates, thousands of bucket entries per read"""
+    from savont_b200 import _lib, synth
+    gp, op = _params(_lib)
+    ctx.set_params(gp)
+    w = synth.Workload("ont16s", n_roots=3)
+    r = w.reads(6000)
+    sk = ctx.sketch(r["bases"], r["quals"], r["offsets"], want_codes=False)
+    km, off = np.asarray(sk["mini_kmer"], np.uint64), np.asarray(sk["mini_offsets"], np.uint64)
+    want = O.cluster_reads_by_kmers(km, off, threshold=0.97)       # a high threshold: many representatives per species
+    n_rep = int((want == np.arange(len(want))).sum())
+    assert n_rep > 300
+    got = ctx.cluster_reads_by_kmers(km, off, threshold=0.97)
+    assert np.array_equal(got["rep_of"], want), np.flatnonzero(got["rep_of"] != want)[:10]
+    monkeypatch.setenv("SAVONT_B200_CLUSTER_BLOCK", "1500")
+    got = ctx.cluster_reads_by_kmers(km, off, threshold=0.97)
+    assert np.array_equal(got["rep_of"], want), np.flatnonzero(got["rep_of"] != want)[:10]
+    got = ctx.cluster_reads_by_kmers(km, off)
+    assert np.array_equal(got["rep_of"], O.cluster_reads_by_kmers(km, off))
