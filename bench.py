@@ -327,6 +327,86 @@ def run_pileup(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
 
 
+def run_cluster(args, rank, world, local_rank):
+    """--path cluster: Stage 2 greedy k-mer clustering (asv_cluster::cluster_reads_by_kmers) through
+    savont_b200_cluster_reads_by_kmers.  Not the headline path; one JSON line with the same keys.  The call takes host buffers (the
+    reads' minimizer k-mers), so every number here is end to end."""
+    import torch
+    from savont_b200 import _lib
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the b200 arm has no CPU fallback")
+    if world > 1:
+        if rank == 0:
+            print(json.dumps({"metric": "reads clustered/sec (Stage 2 greedy k-mer clustering)", "unavailable": "sequential greedy order: single GPU"}))
+        return
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    w = _workload(args)
+    ctx = _lib.Context(local_rank, _lib.default_params(band=w.band))
+    stream = torch.cuda.current_stream(dev)
+    ctx.set_stream(stream.cuda_stream)
+    n_reads = args.reads
+    r = w.reads(n_reads)
+    ctx.load_snpmers(w.snpmers)
+    kms, offs = [], [np.zeros(1, np.uint64)]
+    for b0 in range(0, n_reads, 200_000):                          # TwinRead::minimizer_kmers() of the reads, from the sketch kernel
+        b1 = min(n_reads, b0 + 200_000)
+        sk = ctx.sketch(r["bases"], r["quals"], r["offsets"][b0:b1 + 1], want_codes=False)
+        kms.append(np.asarray(sk["mini_kmer"], np.uint64)); offs.append(np.asarray(sk["mini_offsets"][1:], np.uint64) + offs[-1][-1])
+    km = _lib.pinned_array(8 * sum(len(x) for x in kms)).view(np.uint64); km[:] = np.concatenate(kms)
+    off = np.concatenate(offs)
+    del kms, offs, r
+    sampler = ClockSampler(local_rank); sampler.start()
+    for _ in range(args.warmup):
+        out = ctx.cluster_reads_by_kmers(km, off)
+    torch.cuda.synchronize(dev)
+    ms, stats = [], []
+    for _ in range(args.steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        out = ctx.cluster_reads_by_kmers(km, off)
+        e1.record(stream); torch.cuda.synchronize(dev)
+        ms.append(e0.elapsed_time(e1)); stats.append(out["stats"])
+    clocks = sampler.stop()
+    peaks = _peaks()
+    st = stats[-1]
+    km_ms = {k: float(np.mean([s_[k] for s_ in stats])) for k in ("sketch_ms", "filter_ms", "align_ms")}
+    val = n_reads * args.steps / (sum(ms) / 1e3)
+    # dominant kernel: rep_query_kernel (20-way merge of the read's buckets by representative id, two passes).  Algorithmic bytes:
+    # every bucket entry (4 B) is read twice + the per-read result record
+    alg = 2 * 4 * int(st["dp_cells"]) + 248 * n_reads
+    line = {
+        "metric": "reads clustered/sec (Stage 2 greedy k-mer clustering)", "value": val, "unit": "reads/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sum(ms) / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64 k-mers / u32 counts, f64 threshold on the host", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {w.cfg['desc']} (minimizer k-mers of the reads: {len(km)} k-mers)",
+                   "threshold": 0.95, "l2": "every step re-uploads the k-mers from host memory (H2D inside the timed region)"},
+        "stage_ms": {"upload+signatures+sorted_sets": km_ms["sketch_ms"], "bucket_query": km_ms["filter_ms"], "in_block_pairs": km_ms["align_ms"],
+                     "host": sum(ms) / args.steps - sum(km_ms.values())},
+        "n_reps": int(out["n_reps"]), "blocks": int(st["n_batches"]), "in_block_pairs": int(st["n_pairs"]), "bucket_entries": int(st["dp_cells"]),
+        "roofline": {"bound": "hbm", "kernel": "rep_query_kernel", "achieved": alg / (km_ms["filter_ms"] / 1e3) / 1e9, "peak": peaks["hbm_gbs"],
+                     "unit": "GB/s", "peak_source": peaks["source"], "frac": alg / (km_ms["filter_ms"] / 1e3) / 1e9 / peaks["hbm_gbs"],
+                     "traffic": None, "algorithmic_bytes": alg,
+                     "note": "latency bound, not bandwidth bound: a warp walks ~hundreds of bucket entries serially (REDUX min over the 20 list "
+                             "heads per step) and a block holds only as many reads as the sequential greedy order allows (see DESIGN.md K7)"},
+        "e2e": {"value": val, "unit": "reads/s", "h2d_bytes_per_step": int(st["h2d_bytes"]), "d2h_bytes_per_step": int(st["d2h_bytes"]),
+                "ms_per_step": sum(ms) / args.steps},
+        "gpu_launches": int(sum(s_["kernel_launches"] for s_ in stats)), "clocks": clocks,
+    }
+    if not args.no_cpu_baseline:
+        from oracle import oracle as O
+        cores = os.cpu_count() or 1
+        ns = min(args.cpu_reads // 2, n_reads)
+        t0 = time.perf_counter()
+        want = O.cluster_reads_by_kmers(km[:int(off[ns])], off[:ns + 1])
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": ns / dt, "unit": "reads/s", "cores": cores, "kind": "port",
+                                "sample": f"first {ns} reads (signatures and sorted sets on all cores, the greedy loop on one, like the reference; the cost "
+                                          "per read grows with the number of representatives, so a prefix flatters the CPU)",
+                                "gpu_matches_oracle_on_sample": bool(np.array_equal(want, out["rep_of"][:ns]))}
+    print(json.dumps(line), flush=True)
+
+
 def _bind_to_gpu_numa_node(gpu_index):
     """pin this rank (and therefore the pinned host buffers it first-touches) to the CPU cores next to its GPU, so that
     eight ranks do not pull their H2D traffic across the socket interconnect"""
@@ -569,7 +649,7 @@ def main():
     ap.add_argument("--cpu-reads", type=int, default=100_000, help="sample size of the CPU baseline / reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-twin", action="store_true", help="skip the TwinRead-input e2e arm")
-    ap.add_argument("--path", default="assign", choices=["assign", "kmercount", "pileup"],
+    ap.add_argument("--path", default="assign", choices=["assign", "kmercount", "pileup", "cluster"],
                     help="assign: the headline read-vs-ASV path; kmercount: Stage 1 split-k-mer counting (K5)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -585,6 +665,8 @@ def main():
         run_kmercount(args, rank, world, local_rank)
     elif args.path == "pileup":
         run_pileup(args, rank, world, local_rank)
+    elif args.path == "cluster":
+        run_cluster(args, rank, world, local_rank)
     else:
         run_b200(args, rank, world, local_rank)
         try:

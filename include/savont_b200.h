@@ -296,7 +296,8 @@ int savont_b200_consensus_pileups(savont_b200_ctx *ctx, int use_hpc, const uint8
  *   rep_of[r] = the representative read r was assigned to, r itself when it became a representative.  The cluster list of
  *   :192-210 (group by representative, sort by size then first member, drop clusters below min_cluster_size) is host work on
  *   rep_of.  The result is identical to the sequential loop.  stats: sketch_ms = upload + signatures + sorted minimizer sets,
- *   filter_ms = bucket query kernels, align_ms = in-block pair kernels, n_batches = blocks. */
+ *   filter_ms = bucket query kernels, align_ms = in-block pair kernels, n_batches = blocks, n_pairs = in-block pairs,
+ *   dp_cells = bucket entries the query kernels walked (each twice). */
 int savont_b200_lsh_signatures(savont_b200_ctx *ctx, const uint64_t *kmers, const uint64_t *offsets, size_t n_reads, uint64_t *sig,
                                uint8_t *valid);
 int savont_b200_cluster_reads_by_kmers(savont_b200_ctx *ctx, const uint64_t *kmers, const uint64_t *offsets, size_t n_reads,

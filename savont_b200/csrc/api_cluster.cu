@@ -13,6 +13,7 @@
 //      representative although it had a pre-block match (its match was pushed out of the first 10 by in-block representatives) is
 //      not among the pairs of step 2: its pairs are computed on demand.
 // The result is identical to the sequential loop; block sizes follow the rate of new representatives.
+#include <chrono>
 #include <map>
 
 #include "api_internal.cuh"
@@ -46,10 +47,10 @@ int up(DevBuf &d, const T *v, size_t n, cudaStream_t st) {
 }
 
 struct ClusterDev {
-    DevBuf &kmers, &offsets, &dk, &nd, &sig, &valid, &tsig, &trep, &toff, &res, &pi, &pj, &ph, &pc;
+    DevBuf &kmers, &offsets, &dk, &nd, &sig, &valid, &tsig, &trep, &toff, &res, &pi, &pj, &ph, &pc, &dsig, &drep;
     explicit ClusterDev(DevBuf *w)
         : kmers(w[0]), offsets(w[1]), dk(w[2]), nd(w[3]), sig(w[4]), valid(w[5]), tsig(w[6]), trep(w[7]), toff(w[8]), res(w[9]), pi(w[10]),
-          pj(w[11]), ph(w[12]), pc(w[13]) {}
+          pj(w[11]), ph(w[12]), pc(w[13]), dsig(w[14]), drep(w[15]) {}
 };
 
 // upload + signatures + sorted distinct lists; host copies of nd / sig / valid when asked for
@@ -137,86 +138,122 @@ extern "C" int savont_b200_cluster_reads_by_kmers(savont_b200_ctx *h, const uint
     const ThresholdTest thr(threshold, c->params.k);
     auto tot_of = [&](uint32_t r) { return (uint32_t)(rel[r + 1] - rel[r]); };
 
-    // bucket tables on the host: per table (signature, representative) sorted; flat copies go to the device per block
-    std::vector<std::pair<uint64_t, uint32_t>> tab[kLshTables];
-    std::vector<uint64_t> flat_sig; std::vector<uint32_t> flat_rep; uint32_t toff[kLshTables + 1] = {0};
+    // bucket tables on the host, two levels: `tab` (main, rebuilt when the delta has grown to a quarter of it) and `dlt` (the
+    // representatives created since, all with larger ids); per table (signature, representative) sorted.  Flat copies go to
+    // the device: the delta after every block that created representatives, the main level only when rebuilt.
+    typedef std::pair<uint64_t, uint32_t> Ent;
+    std::vector<Ent> tab[kLshTables], dlt[kLshTables], fresh[kLshTables], merged;
+    std::vector<uint64_t> flat_sig; std::vector<uint32_t> flat_rep;
+    uint32_t toff[2 * (kLshTables + 1)] = {0};             // main offsets, then delta offsets (one device array)
+    size_t n_main = 0, n_delta = 0;
+    auto flatten = [&](std::vector<Ent> *lvl, uint32_t *off, DevBuf &dsg, DevBuf &drp) -> int {
+        size_t e = 0;
+        for (int t = 0; t < kLshTables; ++t) e += lvl[t].size();
+        flat_sig.resize(e); flat_rep.resize(e);
+        e = 0;
+        for (int t = 0; t < kLshTables; ++t) {
+            off[t] = (uint32_t)e;
+            for (const Ent &x : lvl[t]) { flat_sig[e] = x.first; flat_rep[e] = x.second; ++e; }
+        }
+        off[kLshTables] = (uint32_t)e;
+        TRY(up(dsg, flat_sig.data(), e, st)); TRY(up(drp, flat_rep.data(), e, st));
+        CK(cudaStreamSynchronize(st));                     // flat_* are reused for the other level
+        c->last_stats.h2d_bytes += e * 12;
+        return 0;
+    };
+    bool main_dirty = true;
     bool tables_dirty = true;
     uint64_t n_reps = 0;
     size_t block = 256;
     if (const char *e = getenv("SAVONT_B200_CLUSTER_BLOCK")) block = std::max<size_t>(1, strtoull(e, nullptr, 10));   // tests
     const bool fixed_block = getenv("SAVONT_B200_CLUSTER_BLOCK") != nullptr;
-    constexpr size_t kMaxBlock = 16384, kMinBlock = 256, kTargetNew = 96, kMaxPairs = 1u << 24;
-    std::vector<ClusterResult> res;
-    std::vector<uint32_t> p0, before, pair_i, pair_j, pcnt; std::vector<uint64_t> pair_start; std::vector<uint8_t> phits;
+    constexpr size_t kMaxBlock = 16384, kMinBlock = 256, kMaxPairs = 1u << 24;
+    size_t kTargetNew = 160;
+    if (const char *e = getenv("SAVONT_B200_CLUSTER_TARGET")) kTargetNew = std::max<size_t>(1, strtoull(e, nullptr, 10));   // tuning
+    struct PairHit { uint32_t pidx, hits, cnt; };
+    std::vector<uint32_t> p0, before, pair_start, hit_off, hit_fill; std::vector<PairHit> hit_list; std::vector<uint8_t> p0_rep;
     std::vector<Cand> inblk, order;
     double query_ms = 0, pair_ms = 0;
+    // host-side wall clock per phase (SAVONT_B200_CLUSTER_TRACE=1 prints it)
+    double tw[8] = {0}; auto tnow = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double tl = tnow(); auto lap = [&](int k) { const double x = tnow(); tw[k] += x - tl; tl = x; };
 
     for (size_t b0 = 0; b0 < n;) {
         size_t b1 = std::min(n, b0 + block);
         // ---- 1. the block against the representatives known so far ----
         if (tables_dirty) {
-            size_t e = 0;
-            for (int t = 0; t < kLshTables; ++t) e += tab[t].size();
-            flat_sig.resize(e); flat_rep.resize(e);
-            e = 0;
-            for (int t = 0; t < kLshTables; ++t) {
-                toff[t] = (uint32_t)e;
-                for (const auto &x : tab[t]) { flat_sig[e] = x.first; flat_rep[e] = x.second; ++e; }
-            }
-            toff[kLshTables] = (uint32_t)e;
-            TRY(up(d.tsig, flat_sig.data(), e, st)); TRY(up(d.trep, flat_rep.data(), e, st)); TRY(up(d.toff, toff, (size_t)kLshTables + 1, st));
-            c->last_stats.h2d_bytes += e * 12;
+            if (main_dirty) { TRY(flatten(tab, toff, d.tsig, d.trep)); main_dirty = false; }
+            TRY(flatten(dlt, toff + kLshTables + 1, d.dsig, d.drep));
+            TRY(up(d.toff, toff, (size_t)2 * (kLshTables + 1), st));
             tables_dirty = false;
         }
+        lap(0);
         const uint32_t nb = (uint32_t)(b1 - b0);
         TRY(d.res.ensure((size_t)nb * sizeof(ClusterResult)));
         ClusterQuery q{};
         q.offsets = d.offsets.as<uint64_t>(); q.dk = d.dk.as<uint64_t>(); q.nd = d.nd.as<uint32_t>(); q.sig = d.sig.as<uint64_t>();
         q.valid = d.valid.as<uint8_t>(); q.table_sig = d.tsig.as<uint64_t>(); q.table_rep = d.trep.as<uint32_t>();
-        q.table_off = d.toff.as<uint32_t>(); q.first = (uint32_t)b0; q.n_block = nb; q.out = d.res.as<ClusterResult>();
+        q.table_off = d.toff.as<uint32_t>();
+        q.delta_sig = d.dsig.as<uint64_t>(); q.delta_rep = d.drep.as<uint32_t>(); q.delta_off = d.toff.as<uint32_t>() + kLshTables + 1;
+        q.first = (uint32_t)b0; q.n_block = nb; q.out = d.res.as<ClusterResult>();
         CK(cudaEventRecord(c->ev[2], st));
         launch_rep_query(q, st);
         CK(cudaEventRecord(c->ev[3], st));
-        res.resize(nb);
-        CK(cudaMemcpyAsync(res.data(), d.res.p, (size_t)nb * sizeof(ClusterResult), cudaMemcpyDeviceToHost, st));
+        TRY(c->cluster_pin[0].ensure((size_t)nb * sizeof(ClusterResult)));
+        const ClusterResult *res = c->cluster_pin[0].as<ClusterResult>();
+        CK(cudaMemcpyAsync(c->cluster_pin[0].p, d.res.p, (size_t)nb * sizeof(ClusterResult), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         CK(cudaGetLastError());
         query_ms += ev_ms(c->ev[2], c->ev[3]);
         c->last_stats.kernel_launches += 1; c->last_stats.d2h_bytes += (size_t)nb * sizeof(ClusterResult);
 
+        lap(1);
         // ---- 2. potential representatives of the block and their pairs ----
         p0.clear(); before.assign(nb, 0); pair_start.assign((size_t)nb + 1, 0);
         for (uint32_t li = 0; li < nb; ++li) {
             before[li] = (uint32_t)p0.size();
+            if ((size_t)pair_start[li] + before[li] > kMaxPairs && li > 0) { b1 = b0 + li; break; }   // bounded pair workspace: cut the block here
             pair_start[li + 1] = pair_start[li] + before[li];
-            if (pair_start[li + 1] > kMaxPairs && li > 0) { b1 = b0 + li; break; }          // bounded pair workspace: cut the block here
             const ClusterResult &r = res[li];
+            c->last_stats.dp_cells += r.n_entries;
             const bool match = r.best_rep != 0xffffffffu && thr.pass(r.best_cnt, r.best_den);
             if (!match) p0.push_back((uint32_t)(b0 + li));
         }
         const uint32_t nbk = (uint32_t)(b1 - b0);
         const size_t n_pairs = (size_t)pair_start[nbk];
-        pair_i.resize(n_pairs); pair_j.resize(n_pairs); phits.resize(n_pairs); pcnt.resize(n_pairs);
-        for (uint32_t li = 0; li < nbk; ++li)
-            for (uint32_t pidx = 0; pidx < before[li]; ++pidx) { pair_i[pair_start[li] + pidx] = (uint32_t)(b0 + li); pair_j[pair_start[li] + pidx] = p0[pidx]; }
+        lap(2);
+        // pairs sharing a bucket, bucketed by read: hit_off[li] .. hit_off[li + 1] into hit_list (pidx, hits, count)
+        hit_off.assign((size_t)nbk + 1, 0); hit_list.clear();
         if (n_pairs) {
-            TRY(up(d.pi, pair_i.data(), n_pairs, st)); TRY(up(d.pj, pair_j.data(), n_pairs, st));
-            TRY(d.ph.ensure(n_pairs + 16)); TRY(d.pc.ensure(n_pairs * 4 + 16));
+            q.n_block = nbk;
+            TRY(up(d.pi, pair_start.data(), (size_t)nbk + 1, st)); TRY(up(d.pj, p0.data(), p0.size(), st));
+            TRY(d.ph.ensure(n_pairs * sizeof(uint4) + 16)); TRY(d.pc.ensure(16));
+            CK(cudaMemsetAsync(d.pc.p, 0, 4, st));
             CK(cudaEventRecord(c->ev[2], st));
-            launch_pair_stats(q, d.pi.as<uint32_t>(), d.pj.as<uint32_t>(), (uint32_t)n_pairs, d.ph.as<uint8_t>(), d.pc.as<uint32_t>(), st);
+            launch_block_pair_stats(q, d.pi.as<uint32_t>(), d.pj.as<uint32_t>(), (uint32_t)n_pairs, d.ph.as<uint4>(), d.pc.as<uint32_t>(), st);
             CK(cudaEventRecord(c->ev[3], st));
-            CK(cudaMemcpyAsync(phits.data(), d.ph.p, n_pairs, cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(pcnt.data(), d.pc.p, n_pairs * 4, cudaMemcpyDeviceToHost, st));
+            uint32_t n_hit = 0;
+            CK(cudaMemcpyAsync(&n_hit, d.pc.p, 4, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             CK(cudaGetLastError());
+            TRY(c->cluster_pin[1].ensure((size_t)n_hit * sizeof(uint4) + 16));
+            if (n_hit) CK(cudaMemcpyAsync(c->cluster_pin[1].p, d.ph.p, (size_t)n_hit * sizeof(uint4), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            const uint4 *raw = c->cluster_pin[1].as<uint4>();
+            for (uint32_t x = 0; x < n_hit; ++x) hit_off[raw[x].x + 1]++;
+            for (uint32_t li = 0; li < nbk; ++li) hit_off[li + 1] += hit_off[li];
+            hit_list.resize(n_hit); hit_fill.assign(hit_off.begin(), hit_off.end() - 1);
+            for (uint32_t x = 0; x < n_hit; ++x) hit_list[hit_fill[raw[x].x]++] = PairHit{raw[x].y, raw[x].z, raw[x].w};
             pair_ms += ev_ms(c->ev[2], c->ev[3]);
             c->last_stats.kernel_launches += 1; c->last_stats.n_pairs += n_pairs;
-            c->last_stats.h2d_bytes += n_pairs * 8; c->last_stats.d2h_bytes += n_pairs * 5;
+            c->last_stats.h2d_bytes += ((size_t)nbk + 1 + p0.size()) * 4; c->last_stats.d2h_bytes += (size_t)n_hit * sizeof(uint4);
         }
+        p0_rep.assign(p0.size(), 0);
+        lap(3);
 
         // ---- 3. the block in read order ----
-        struct NewRep { uint32_t id; int32_t pidx; };                                   // pidx < 0: not a potential representative (extra)
-        std::vector<NewRep> newreps;
+        size_t n_new = 0;
+        std::vector<uint32_t> extra_reps;                                               // representatives outside p0
         std::map<uint32_t, std::pair<std::vector<uint8_t>, std::vector<uint32_t>>> extra;   // rep id -> stats of the reads behind it
         size_t p0_pos = 0;
         for (uint32_t li = 0; li < nbk; ++li) {
@@ -228,11 +265,15 @@ extern "C" int savont_b200_cluster_reads_by_kmers(savont_b200_ctx *h, const uint
             // representatives created earlier in this block that share a bucket with the read
             inblk.clear();
             uint32_t newmax = r.n_cand ? r.max_hits : 0u;
-            for (const NewRep &nr : newreps) {
-                uint32_t hh, cc;
-                if (nr.pidx >= 0) { const size_t at = pair_start[li] + (size_t)nr.pidx; hh = phits[at]; cc = pcnt[at]; }
-                else { const auto &ex = extra[nr.id]; const size_t at = i - nr.id - 1; hh = ex.first[at]; cc = ex.second[at]; }
-                if (hh) { inblk.push_back(Cand{nr.id, hh, cc, std::max(nd[i], tot_of(nr.id))}); newmax = std::max(newmax, hh); }
+            for (uint32_t x = hit_off[li]; x < hit_off[li + 1]; ++x) {                 // potential representatives that became one
+                const PairHit &ph = hit_list[x];
+                if (!p0_rep[ph.pidx]) continue;
+                const uint32_t j = p0[ph.pidx];
+                inblk.push_back(Cand{j, ph.hits, ph.cnt, std::max(nd[i], tot_of(j))}); newmax = std::max(newmax, ph.hits);
+            }
+            for (const uint32_t xr : extra_reps) {                                      // the rare other ones
+                const auto &ex = extra[xr]; const size_t at = i - xr - 1;
+                if (ex.first[at]) { inblk.push_back(Cand{xr, ex.first[at], ex.second[at], std::max(nd[i], tot_of(xr))}); newmax = std::max<uint32_t>(newmax, ex.first[at]); }
             }
             bool have = false; Cand best{0, 0, 0, 1};
             if (inblk.empty()) {
@@ -265,12 +306,10 @@ extern "C" int savont_b200_cluster_reads_by_kmers(savont_b200_ctx *h, const uint
             // new representative (src/asv_cluster.rs:178-187)
             rep_of[i] = i; ++n_reps;
             if (valid[i]) {
-                for (int t = 0; t < kLshTables; ++t) {
-                    const std::pair<uint64_t, uint32_t> e(sig[(size_t)i * kLshTables + t], i);
-                    tab[t].insert(std::upper_bound(tab[t].begin(), tab[t].end(), e), e);
-                }
+                for (int t = 0; t < kLshTables; ++t) fresh[t].push_back(Ent(sig[(size_t)i * kLshTables + t], i));
                 tables_dirty = true;
                 if (my_pidx < 0 && li + 1 < nbk) {
+                    lap(4);
                     // not among the potential representatives: hits / containment of the reads behind it, on demand
                     const uint32_t m = nbk - li - 1;
                     std::vector<uint32_t> xi(m), xj(m, i);
@@ -285,18 +324,43 @@ extern "C" int savont_b200_cluster_reads_by_kmers(savont_b200_ctx *h, const uint
                     CK(cudaStreamSynchronize(st));
                     CK(cudaGetLastError());
                     c->last_stats.kernel_launches += 1; c->last_stats.n_pairs += m;
+                    lap(5);
                 }
-                newreps.push_back(NewRep{i, my_pidx});
+                if (my_pidx >= 0) p0_rep[my_pidx] = 1; else extra_reps.push_back(i);
+                ++n_new;
+            }
+        }
+        lap(4);
+        // the block's representatives join the delta level; the delta is folded into the main level when it reaches a quarter of it
+        if (n_new) {
+            for (int t = 0; t < kLshTables; ++t) {
+                std::sort(fresh[t].begin(), fresh[t].end());
+                merged.resize(dlt[t].size() + fresh[t].size());
+                std::merge(dlt[t].begin(), dlt[t].end(), fresh[t].begin(), fresh[t].end(), merged.begin());
+                dlt[t].swap(merged); fresh[t].clear();
+            }
+            n_delta += n_new;
+            if (n_delta > 1024 && n_delta * 4 > n_main) {
+                for (int t = 0; t < kLshTables; ++t) {
+                    merged.resize(tab[t].size() + dlt[t].size());
+                    std::merge(tab[t].begin(), tab[t].end(), dlt[t].begin(), dlt[t].end(), merged.begin());
+                    tab[t].swap(merged); dlt[t].clear();
+                }
+                n_main += n_delta; n_delta = 0; main_dirty = true;
             }
         }
         // next block size: about kTargetNew new representatives per block
         if (!fixed_block) {
-            const double rate = std::max<double>((double)newreps.size(), 0.5) / (double)nbk;
+            const double rate = std::max<double>((double)n_new, 0.5) / (double)nbk;
             block = (size_t)std::min<double>((double)kMaxBlock, std::max<double>((double)kMinBlock, (double)kTargetNew / rate));
         }
         c->last_stats.n_batches += 1;
         b0 = b1;
+        lap(6);
     }
+    if (getenv("SAVONT_B200_CLUSTER_TRACE"))
+        fprintf(stderr, "cluster host ms: tables %.1f query %.1f p0 %.1f pairs %.1f resolve %.1f fallback %.1f merge %.1f\n", tw[0], tw[1], tw[2],
+                tw[3], tw[4], tw[5], tw[6]);
     if (n_reps_out) *n_reps_out = n_reps;
     c->last_stats.n_reads = n; c->last_stats.n_bases = rel[n];
     c->last_stats.sketch_ms = ev_ms(c->ev[0], c->ev[1]); c->last_stats.filter_ms = query_ms; c->last_stats.align_ms = pair_ms;

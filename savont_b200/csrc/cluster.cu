@@ -142,6 +142,13 @@ __device__ __forceinline__ uint32_t intersect_count(const uint64_t *__restrict__
 }
 
 // ---------------- bucket query + candidate window + containment counts ----------------
+__device__ __forceinline__ void equal_range_u64(const uint64_t *__restrict__ v, uint32_t t0, uint32_t t1, uint64_t key, uint32_t &lo, uint32_t &hi) {
+    uint32_t a = t0, b = t1;
+    while (a < b) { const uint32_t mid = (a + b) >> 1; if (__ldg(v + mid) < key) a = mid + 1; else b = mid; }
+    lo = a; b = t1;
+    while (a < b) { const uint32_t mid = (a + b) >> 1; if (__ldg(v + mid) <= key) a = mid + 1; else b = mid; }
+    hi = a;
+}
 __global__ void rep_query_kernel(ClusterQuery q) {
     const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31u;
@@ -151,28 +158,29 @@ __global__ void rep_query_kernel(ClusterQuery q) {
     res.best_rep = 0xffffffffu;
     const uint64_t off = q.offsets[r];
     const uint32_t ndr = q.nd[r];
-    // equal range of the read's signature in table `lane`
-    uint32_t lo = 0, hi = 0;
+    // equal ranges of the read's signature in table `lane` of the main and of the delta level; the lane's bucket is the main
+    // range followed by the delta range (ascending representative ids)
+    uint32_t lo = 0, hi = 0, lo2 = 0, hi2 = 0;
     if (lane < (uint32_t)kLshTables && q.valid[r]) {
         const uint64_t sg = q.sig[(uint64_t)r * kLshTables + lane];
-        const uint32_t t0 = q.table_off[lane], t1 = q.table_off[lane + 1];
-        uint32_t a = t0, b = t1;
-        while (a < b) { const uint32_t mid = (a + b) >> 1; if (__ldg(q.table_sig + mid) < sg) a = mid + 1; else b = mid; }
-        lo = a; b = t1;
-        while (a < b) { const uint32_t mid = (a + b) >> 1; if (__ldg(q.table_sig + mid) <= sg) a = mid + 1; else b = mid; }
-        hi = a;
+        equal_range_u64(q.table_sig, q.table_off[lane], q.table_off[lane + 1], sg, lo, hi);
+        equal_range_u64(q.delta_sig, q.delta_off[lane], q.delta_off[lane + 1], sg, lo2, hi2);
     }
+    auto head = [&](uint32_t p, uint32_t p2) -> uint32_t {
+        return p < hi ? __ldg(q.table_rep + p) : (p2 < hi2 ? __ldg(q.delta_rep + p2) : 0xffffffffu);
+    };
+    res.n_entries = __reduce_add_sync(0xffffffffu, (hi - lo) + (hi2 - lo2));
     // pass 1: histogram of the hit counts (lane h holds the number of representatives with h hits)
     uint32_t cnt_h = 0;
     {
-        uint32_t p = lo;
-        uint32_t cur = p < hi ? __ldg(q.table_rep + p) : 0xffffffffu;
+        uint32_t p = lo, p2 = lo2;
+        uint32_t cur = head(p, p2);
         while (true) {
             const uint32_t m = __reduce_min_sync(0xffffffffu, cur);
             if (m == 0xffffffffu) break;
             const uint32_t h = __popc(__ballot_sync(0xffffffffu, cur == m));
             if (lane == h) cnt_h++;
-            if (cur == m) { ++p; cur = p < hi ? __ldg(q.table_rep + p) : 0xffffffffu; }
+            if (cur == m) { if (p < hi) ++p; else ++p2; cur = head(p, p2); }
         }
     }
     const uint32_t nz = __ballot_sync(0xffffffffu, cnt_h != 0);
@@ -192,8 +200,8 @@ __global__ void rep_query_kernel(ClusterQuery q) {
         // pass 2
         uint32_t seen = 0;
         uint32_t b_rep = 0xffffffffu, b_hits = 0, b_cnt = 0, b_den = 1;
-        uint32_t p = lo;
-        uint32_t cur = p < hi ? __ldg(q.table_rep + p) : 0xffffffffu;
+        uint32_t p = lo, p2 = lo2;
+        uint32_t cur = head(p, p2);
         while (true) {
             const uint32_t m = __reduce_min_sync(0xffffffffu, cur);
             if (m == 0xffffffffu) break;
@@ -220,7 +228,7 @@ __global__ void rep_query_kernel(ClusterQuery q) {
                     }
                 }
             }
-            if (cur == m) { ++p; cur = p < hi ? __ldg(q.table_rep + p) : 0xffffffffu; }
+            if (cur == m) { if (p < hi) ++p; else ++p2; cur = head(p, p2); }
         }
         res.n_cand = total; res.max_hits = max_hits; res.n_max = __shfl_sync(0xffffffffu, cnt_h, max_hits);
         res.best_rep = b_rep; res.best_hits = b_hits; res.best_cnt = b_cnt; res.best_den = b_den;
@@ -248,6 +256,29 @@ __global__ void pair_stats_kernel(ClusterQuery q, const uint32_t *__restrict__ p
     uint32_t c = 0;
     if (h) c = intersect_count(q.dk + q.offsets[i], q.nd[i], q.dk + q.offsets[j], q.nd[j], lane);
     if (lane == 0) { hits_out[w] = (uint8_t)h; cnt_out[w] = c; }
+}
+// Only the pairs that share a bucket matter to the host: they are appended to `out` (any order) as
+// (read index in the block, index into p0, hits, containment count).
+__global__ void block_pair_stats_kernel(ClusterQuery q, const uint32_t *__restrict__ pair_start, const uint32_t *__restrict__ p0, uint32_t n_pairs,
+                                        uint4 *__restrict__ out, uint32_t *__restrict__ out_n) {
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31u;
+    if (w >= n_pairs) return;
+    uint32_t a = 0, b = q.n_block;                       // li = the last read with pair_start[li] <= w
+    while (a < b) { const uint32_t mid = (a + b) >> 1; if (__ldg(pair_start + mid + 1) <= w) a = mid + 1; else b = mid; }
+    const uint32_t pidx = w - __ldg(pair_start + a);
+    const uint32_t i = q.first + a, j = __ldg(p0 + pidx);
+    bool eq = false;
+    if (lane < (uint32_t)kLshTables && q.valid[i] && q.valid[j])
+        eq = q.sig[(uint64_t)i * kLshTables + lane] == q.sig[(uint64_t)j * kLshTables + lane];
+    const uint32_t h = __popc(__ballot_sync(0xffffffffu, eq));
+    if (h == 0u) return;
+    const uint32_t c = intersect_count(q.dk + q.offsets[i], q.nd[i], q.dk + q.offsets[j], q.nd[j], lane);
+    if (lane == 0) out[atomicAdd(out_n, 1u)] = make_uint4(a, pidx, h, c);
+}
+void launch_block_pair_stats(const ClusterQuery &q, const uint32_t *pair_start, const uint32_t *p0, uint32_t n_pairs, uint4 *out,
+                             uint32_t *out_n, cudaStream_t st) {
+    if (n_pairs) block_pair_stats_kernel<<<(n_pairs + 7u) / 8u, 256, 0, st>>>(q, pair_start, p0, n_pairs, out, out_n);
 }
 void launch_pair_stats(const ClusterQuery &q, const uint32_t *pair_i, const uint32_t *pair_j, uint32_t n_pairs, uint8_t *hits, uint32_t *cnt,
                        cudaStream_t st) {

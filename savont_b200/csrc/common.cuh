@@ -290,6 +290,7 @@ struct ClusterResult {                // per read of a block: its candidates amo
     uint32_t cnt_h[kLshTables + 1];                       // representatives per hit count
     uint32_t top_rep[kClusterTopN], top_cnt[kClusterTopN], top_tot[kClusterTopN];   // first kClusterTopN by (hits, id) descending
     uint8_t top_hits[kClusterTopN]; uint8_t pad[2];
+    uint32_t n_entries;                                   // bucket entries of the read's 20 buckets (each is walked twice)
 };
 struct ClusterQuery {
     const uint64_t *offsets;          // [n + 1] minimizer CSR
@@ -300,6 +301,9 @@ struct ClusterQuery {
     const uint64_t *table_sig;        // the kLshTables bucket tables, each sorted by (signature, representative)
     const uint32_t *table_rep;
     const uint32_t *table_off;        // [kLshTables + 1]
+    const uint64_t *delta_sig;        // second level: the representatives created since the main tables were last rebuilt (all
+    const uint32_t *delta_rep;        // their ids are larger than every id of the main tables), same layout
+    const uint32_t *delta_off;        // [kLshTables + 1]
     uint32_t first, n_block;          // reads [first, first + n_block)
     ClusterResult *out;               // [n_block]
 };
@@ -310,5 +314,9 @@ uint32_t cluster_sort_max();
 void launch_rep_query(const ClusterQuery &q, cudaStream_t st);
 void launch_pair_stats(const ClusterQuery &q, const uint32_t *pair_i, const uint32_t *pair_j, uint32_t n_pairs, uint8_t *hits, uint32_t *cnt,
                        cudaStream_t st);
+// pairs (read first + li, p0[pidx]) for pidx < pair_start[li + 1] - pair_start[li]; those sharing a bucket are appended to out as
+// (li, pidx, hits, containment count), out_n = their number (zeroed by the caller)
+void launch_block_pair_stats(const ClusterQuery &q, const uint32_t *pair_start, const uint32_t *p0, uint32_t n_pairs, uint4 *out,
+                             uint32_t *out_n, cudaStream_t st);
 
 }  // namespace sb
