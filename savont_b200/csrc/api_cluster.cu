@@ -362,6 +362,7 @@ extern "C" int savont_b200_cluster_reads_by_kmers(savont_b200_ctx *h, const uint
         fprintf(stderr, "cluster host ms: tables %.1f query %.1f p0 %.1f pairs %.1f resolve %.1f fallback %.1f merge %.1f\n", tw[0], tw[1], tw[2],
                 tw[3], tw[4], tw[5], tw[6]);
     if (n_reps_out) *n_reps_out = n_reps;
+    CK(cudaStreamSynchronize(st));                 // ev[1] when there was no block
     c->last_stats.n_reads = n; c->last_stats.n_bases = rel[n];
     c->last_stats.sketch_ms = ev_ms(c->ev[0], c->ev[1]); c->last_stats.filter_ms = query_ms; c->last_stats.align_ms = pair_ms;
     c->last_stats.total_ms = c->last_stats.sketch_ms + query_ms + pair_ms;
