@@ -60,6 +60,7 @@ int pileup_chunk(Context *c, PileupScratch &s, size_t chunk, int use_hpc, const 
     CK(cudaStreamSynchronize(st));
     const uint64_t htotal = hoff32[n];
     TRY(s.hc.ensure(htotal + 64)); TRY(s.hq.ensure(htotal + 64)); TRY(s.hl.ensure(htotal + 64));
+    CK(cudaMemsetAsync(s.hc.as<uint8_t>() + htotal, 0, 64, st));       // the plane packing reads whole words past the last base
     launch_hpc_write(seq_view(rb), use_hpc, s.hoff32.as<uint32_t>(), s.hc.as<uint8_t>(), s.hq.as<uint8_t>(), s.hl.as<uint8_t>(), st);
     c->last_stats.kernel_launches += 5;
     // the compressed reads as a batch of their own (device-resident bases)
