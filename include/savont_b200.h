@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SAVONT_B200_ABI_VERSION 5
+#define SAVONT_B200_ABI_VERSION 6
 
 typedef struct savont_b200_ctx savont_b200_ctx;
 
@@ -302,6 +302,31 @@ int savont_b200_lsh_signatures(savont_b200_ctx *ctx, const uint64_t *kmers, cons
                                uint8_t *valid);
 int savont_b200_cluster_reads_by_kmers(savont_b200_ctx *ctx, const uint64_t *kmers, const uint64_t *offsets, size_t n_reads,
                                        double threshold, uint32_t *rep_of, uint64_t *n_reps, savont_b200_stats *stats /* may be NULL */);
+
+/* ---- Sharded Stage 1 counting over several GPUs (one context and one process per GPU; reads left in HBM by
+ * savont_b200_upload_reads, each rank its own shard).  Partition p of the P = savont_b200_kmer_shard_partitions() hash
+ * partitions belongs to rank p * n_ranks / P.  Per call of the multi-GPU count (savont_b200/dist.py: count_split_kmers_sharded):
+ *   1. savont_b200_kmer_shard_hist      hist[P] = this rank's occurrences per partition            -> all-gather of the histograms
+ *   2. savont_b200_kmer_shard_alloc     entry buffer (4 B per occurrence) of the partitions this rank owns; the other ranks map
+ *                                       it with savont_b200_ipc_export / _ipc_open (cudaIpc*, NVLink peer memory)
+ *   3. savont_b200_kmer_shard_scatter   scatters this rank's reads; the level-2 scatter kernel writes the run of partition p
+ *                                       straight into peer_entries[owner(p)] + dst_off[p] (dst_off[p] = start of the partition
+ *                                       in the owner's buffer + the occurrences of the lower ranks): the exchange step is the
+ *                                       kernel's own store, there is no separate all-to-all.  Returns after the stream has
+ *                                       drained; the caller barriers.
+ *   4. savont_b200_kmer_shard_count     counts the owned partitions (part_off[P + 1]: offsets in the own buffer, empty ranges
+ *                                       for partitions of other ranks); output as savont_b200_count_split_kmers, restricted
+ *                                       to the k-mers of the owned partitions.
+ * Needs the two-level partitioned algorithm (k <= 19, reads <= 24000 bases). */
+int savont_b200_kmer_shard_partitions(void);
+int savont_b200_kmer_shard_hist(savont_b200_ctx *ctx, uint32_t *hist);
+int savont_b200_kmer_shard_alloc(savont_b200_ctx *ctx, uint64_t n_entries, void **dev_ptr);
+int savont_b200_ipc_export(savont_b200_ctx *ctx, const void *dev_ptr, void *handle64 /* 64 bytes */);
+int savont_b200_ipc_open(savont_b200_ctx *ctx, const void *handle64, void **dev_ptr);
+int savont_b200_ipc_close(savont_b200_ctx *ctx, void *dev_ptr);
+int savont_b200_kmer_shard_scatter(savont_b200_ctx *ctx, int n_ranks, void *const *peer_entries, const uint64_t *dst_off);
+int savont_b200_kmer_shard_count(savont_b200_ctx *ctx, const uint64_t *part_off, int single_strand, uint64_t *out_kmers,
+                                 uint32_t *out_counts, size_t out_cap, size_t *n_out, savont_b200_kmer_stats *stats);
 
 /* Pinned host memory helpers (inputs placed here are copied without a staging pass). */
 int savont_b200_host_alloc(size_t bytes, void **out);

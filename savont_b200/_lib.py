@@ -463,6 +463,43 @@ class Context:
                                                          C.c_double(threshold), _p(rep, C.c_uint32), C.byref(nr), C.byref(stt)))
         return dict(rep_of=rep[:n], n_reps=int(nr.value), stats=stt.as_dict())
 
+    # ---- sharded Stage 1 counting (one context per GPU; savont_b200/dist.py drives the phases) ----
+    def kmer_shard_hist(self):
+        P = self.L.savont_b200_kmer_shard_partitions()
+        hist = np.zeros(P, np.uint32)
+        _check(self.L.savont_b200_kmer_shard_hist(self.h, _p(hist, C.c_uint32)))
+        return hist
+
+    def kmer_shard_alloc(self, n_entries: int) -> int:
+        ptr = C.c_void_p()
+        _check(self.L.savont_b200_kmer_shard_alloc(self.h, C.c_uint64(int(n_entries)), C.byref(ptr)))
+        return int(ptr.value)
+
+    def ipc_export(self, dev_ptr: int) -> bytes:
+        buf = (C.c_uint8 * 64)()
+        _check(self.L.savont_b200_ipc_export(self.h, C.c_void_p(dev_ptr), buf))
+        return bytes(buf)
+
+    def ipc_open(self, handle: bytes) -> int:
+        ptr = C.c_void_p(); buf = (C.c_uint8 * 64).from_buffer_copy(handle)
+        _check(self.L.savont_b200_ipc_open(self.h, buf, C.byref(ptr)))
+        return int(ptr.value)
+
+    def ipc_close(self, dev_ptr: int):
+        _check(self.L.savont_b200_ipc_close(self.h, C.c_void_p(dev_ptr)))
+
+    def kmer_shard_scatter(self, peer_entries, dst_off):
+        n = len(peer_entries)
+        arr = (C.c_void_p * n)(*[C.c_void_p(int(x)) for x in peer_entries])
+        do = np.ascontiguousarray(dst_off, dtype=np.uint64)
+        _check(self.L.savont_b200_kmer_shard_scatter(self.h, C.c_int(n), arr, _p(do, C.c_uint64)))
+
+    def kmer_shard_count(self, part_off, single_strand=False, cap=1 << 22, sort=True):
+        po = np.ascontiguousarray(part_off, dtype=np.uint64)
+        call = lambda km, ct, cp, nn, st: self.L.savont_b200_kmer_shard_count(
+            self.h, _p(po, C.c_uint64), C.c_int(1 if single_strand else 0), km, ct, cp, nn, st)
+        return self._kmer_out(call, cap, sort)
+
     def counts_dev(self):
         """(device pointer, length in u64) of [unambig|ambig|leq10|assigned|filtered|singleton S*A]"""
         ptr = C.c_void_p(); n = C.c_size_t()

@@ -861,6 +861,7 @@ int savont_b200_destroy(savont_b200_ctx *h) {
     for (DevBuf &b : c->tb_ws) b.release();
     for (DevBuf &b : c->pileup_ws) b.release();
     for (DevBuf &b : c->cluster_ws) b.release();
+    c->d_ks_entries.release(); c->d_ks_dstptr.release(); c->d_ks_partoff.release();
     for (PinBuf &b : c->cluster_pin) b.release();
     for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
     for (int i = 0; i < 3; ++i) { if (c->ev_up[i]) cudaEventDestroy(c->ev_up[i]); if (c->ev_h0[i]) cudaEventDestroy(c->ev_h0[i]); }

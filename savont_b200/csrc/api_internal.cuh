@@ -163,6 +163,12 @@ struct Context {
     DevBuf tb_ws[7]; PinBuf tb_pin;
     DevBuf pileup_ws[40];
     DevBuf cluster_ws[16]; PinBuf cluster_pin[4];
+    // sharded k-mer counting (savont_b200_kmer_shard_*): state between the phases
+    struct KmerShard {
+        bool active = false; KmerPartPlan pl{}; std::vector<unsigned long long> off_local; uint32_t *cursor1 = nullptr, *d_tile_start = nullptr,
+             *tail = nullptr; uint64_t slots = 0; int n_ranks = 0;
+    } ks;
+    DevBuf d_ks_entries, d_ks_dstptr, d_ks_partoff;
 };
 
 struct Context;

@@ -184,6 +184,195 @@ static int kc_run(Context *c, size_t n_chunks, uint64_t total_bases, GetView vie
     return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Sharded counting over several GPUs (one context per GPU, one process per GPU): every rank histograms and scatters ITS reads;
+// partition p belongs to rank p * n_ranks / P, and the level-2 scatter kernel writes each rank's run of partition p straight into
+// the owner's entry buffer (peer memory over NVLink, cudaIpc-mapped by the caller) at the offset the all-gathered histograms
+// give it.  After a barrier every owner counts its partitions.  The host-side index arithmetic lives with the caller
+// (savont_b200/dist.py: kmer_shard_layout) because it needs all ranks' histograms.
+// ------------------------------------------------------------------------------------------------
+static int ks_check(Context *c) {
+    Batch &b = c->resident;
+    if (b.twin) return fail(SAVONT_B200_ERR_INVALID, "the resident reads are TwinReads: k-mer counting needs the FASTQ bytes");
+    if (!(kmer_part_supported(c->dp.k, b.max_len) && kmer_part_two_level(c->dp.k, std::max(b.max_len, 1u))))
+        return fail(SAVONT_B200_ERR_INVALID, "sharded k-mer counting needs the two-level partitioned algorithm (k <= 19, reads <= 24000 bases)");
+    return 0;
+}
+
+}  // namespace sb
+
+using namespace sb;
+
+extern "C" {
+
+int savont_b200_kmer_shard_partitions(void) { return 1 << kKmerPartBits; }
+
+int savont_b200_kmer_shard_hist(savont_b200_ctx *h, uint32_t *hist) {
+    TRY(use_device(h ? &h->c : nullptr));
+    Context *c = &h->c;
+    if (!hist) return fail(SAVONT_B200_ERR_INVALID, "null argument");
+    TRY(ks_check(c));
+    Batch &b = c->resident;
+    Context::KmerShard &ks = c->ks;
+    ks = Context::KmerShard{};
+    const int k = c->dp.k, pbits = kKmerPartBits, rem_bits = 2 * k - pbits;
+    const uint32_t P = 1u << pbits;
+    KmerPartPlan &pl = ks.pl;
+    pl.kmask = (1ull << (2 * k)) - 1ull;
+    pl.mul = (kFibMul | 1ull) & pl.kmask; pl.inv = mod_inverse_pow2(pl.mul, pl.kmask);
+    pl.pbits = pbits; pl.rem_bits = rem_bits; pl.smem_fill_limit = c->kc_smem_limit;
+    const size_t small_bytes = (size_t)P * 8 + (size_t)(P + 1) * 8 + 256 + 128 * 4 + 132 * 4;      // as in kc_run_part
+    TRY(c->d_kp_small.ensure(small_bytes));
+    uint8_t *sm = c->d_kp_small.as<uint8_t>();
+    pl.hist = reinterpret_cast<uint32_t *>(sm); pl.cursor = pl.hist + P;
+    unsigned long long *d_off = reinterpret_cast<unsigned long long *>(sm + (size_t)P * 8);
+    pl.part_off = d_off;
+    uint32_t *tail = reinterpret_cast<uint32_t *>(sm + (size_t)P * 8 + (size_t)(P + 1) * 8);
+    pl.ctr = tail; pl.out_n = tail + 16; pl.queue = tail + 17; pl.n_distinct = reinterpret_cast<unsigned long long *>(tail + 18);
+    ks.tail = tail; ks.cursor1 = tail + 64; ks.d_tile_start = tail + 64 + 128;
+    ks.slots = 1ull << 22;
+    TRY(c->d_kc_table.ensure(ks.slots * sizeof(KmerSlot)));
+    pl.table = c->d_kc_table.as<KmerSlot>(); pl.tshift = shift_for_cap((uint32_t)ks.slots); pl.tmask = (uint32_t)(ks.slots - 1);
+    pl.fill_limit = (uint32_t)(ks.slots / 2);
+    CK(cudaEventRecord(c->ev[0], c->stream));
+    CK(cudaMemsetAsync(sm, 0, small_bytes, c->stream));
+    launch_kmer_table_clear(pl.table, ks.slots, c->stream);
+    if (b.n) launch_kmer_hist(pl, seq_view(b), nullptr, k, c->dp.min_bq, c->sm_count, c->stream);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ev[1], c->stream));
+    CK(cudaMemcpyAsync(hist, pl.hist, (size_t)P * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    ks.off_local.assign(P + 1, 0);
+    for (uint32_t i = 0; i < P; ++i) ks.off_local[i + 1] = ks.off_local[i] + hist[i];
+    CK(cudaMemcpyAsync(d_off, ks.off_local.data(), (size_t)(P + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    TRY(c->d_kp_entries1.ensure((ks.off_local[P] + 64) * 4));
+    ks.active = true;
+    return 0;
+}
+
+int savont_b200_kmer_shard_alloc(savont_b200_ctx *h, uint64_t n_entries, void **dev_ptr) {
+    TRY(use_device(h ? &h->c : nullptr));
+    Context *c = &h->c;
+    if (!dev_ptr) return fail(SAVONT_B200_ERR_INVALID, "null argument");
+    TRY(c->d_ks_entries.ensure((n_entries + 64) * 4));
+    *dev_ptr = c->d_ks_entries.p;
+    return 0;
+}
+
+int savont_b200_ipc_export(savont_b200_ctx *h, const void *dev_ptr, void *handle64) {
+    TRY(use_device(h ? &h->c : nullptr));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t");
+    if (!dev_ptr || !handle64) return fail(SAVONT_B200_ERR_INVALID, "null argument");
+    cudaIpcMemHandle_t hd;
+    CK(cudaIpcGetMemHandle(&hd, const_cast<void *>(dev_ptr)));
+    memcpy(handle64, &hd, 64);
+    return 0;
+}
+int savont_b200_ipc_open(savont_b200_ctx *h, const void *handle64, void **dev_ptr) {
+    TRY(use_device(h ? &h->c : nullptr));
+    if (!dev_ptr || !handle64) return fail(SAVONT_B200_ERR_INVALID, "null argument");
+    cudaIpcMemHandle_t hd; memcpy(&hd, handle64, 64);
+    CK(cudaIpcOpenMemHandle(dev_ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+int savont_b200_ipc_close(savont_b200_ctx *h, void *dev_ptr) {
+    TRY(use_device(h ? &h->c : nullptr));
+    if (dev_ptr) CK(cudaIpcCloseMemHandle(dev_ptr));
+    return 0;
+}
+
+int savont_b200_kmer_shard_scatter(savont_b200_ctx *h, int n_ranks, void *const *peer_entries, const uint64_t *dst_off) {
+    TRY(use_device(h ? &h->c : nullptr));
+    Context *c = &h->c;
+    Context::KmerShard &ks = c->ks;
+    if (!ks.active) return fail(SAVONT_B200_ERR_INVALID, "savont_b200_kmer_shard_hist has not been called");
+    if (n_ranks < 1 || !peer_entries || !dst_off) return fail(SAVONT_B200_ERR_INVALID, "bad argument");
+    Batch &b = c->resident;
+    KmerPartPlan &pl = ks.pl;
+    const int k = c->dp.k;
+    const uint32_t P = 1u << kKmerPartBits;
+    ks.n_ranks = n_ranks;
+    std::vector<uint32_t *> dst(P);
+    for (uint32_t p = 0; p < P; ++p) {
+        const int owner = (int)(((uint64_t)p * (uint64_t)n_ranks) >> kKmerPartBits);
+        if (!peer_entries[owner]) return fail(SAVONT_B200_ERR_INVALID, "null entry buffer of rank %d", owner);
+        dst[p] = reinterpret_cast<uint32_t *>(peer_entries[owner]) + dst_off[p];
+    }
+    TRY(c->d_ks_dstptr.ensure((size_t)P * sizeof(uint32_t *)));
+    CK(cudaMemcpyAsync(c->d_ks_dstptr.p, dst.data(), (size_t)P * sizeof(uint32_t *), cudaMemcpyHostToDevice, c->stream));
+    pl.dst_ptr = c->d_ks_dstptr.as<uint32_t *>();
+    pl.entries = nullptr;
+    const int sub = kKmerPartBits - kmer_scatter1_bits();
+    const uint32_t P1 = 1u << kmer_scatter1_bits(), tile2 = kmer_scatter2_tile();
+    std::vector<uint32_t> tile_start(132, 0);
+    for (uint32_t b1 = 0; b1 < P1; ++b1) {
+        const unsigned long long nb = ks.off_local[(size_t)(b1 + 1) << sub] - ks.off_local[(size_t)b1 << sub];
+        tile_start[b1 + 1] = tile_start[b1] + (uint32_t)((nb + tile2 - 1) / tile2);
+    }
+    CK(cudaMemcpyAsync(ks.d_tile_start, tile_start.data(), 132 * 4, cudaMemcpyHostToDevice, c->stream));
+    if (b.n) launch_kmer_scatter1(pl, c->d_kp_entries1.as<uint32_t>(), ks.cursor1, seq_view(b), nullptr, k, c->dp.min_bq, c->sm_count, c->stream);
+    launch_kmer_scatter2(pl, c->d_kp_entries1.as<uint32_t>(), ks.d_tile_start, tile_start[P1], k, c->sm_count, c->stream);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ev[2], c->stream));
+    CK(cudaStreamSynchronize(c->stream));          // the caller's barrier comes next: the peers' buffers are complete after it
+    return 0;
+}
+
+int savont_b200_kmer_shard_count(savont_b200_ctx *h, const uint64_t *part_off, int single_strand, uint64_t *out_kmers, uint32_t *out_counts,
+                                 size_t out_cap, size_t *n_out, savont_b200_kmer_stats *stats) {
+    TRY(use_device(h ? &h->c : nullptr));
+    Context *c = &h->c;
+    Context::KmerShard &ks = c->ks;
+    if (!ks.active || ks.n_ranks == 0) return fail(SAVONT_B200_ERR_INVALID, "savont_b200_kmer_shard_scatter has not been called");
+    if (!part_off || (out_cap && (!out_kmers || !out_counts))) return fail(SAVONT_B200_ERR_INVALID, "null argument");
+    KmerPartPlan &pl = ks.pl;
+    const uint32_t P = 1u << kKmerPartBits;
+    const uint64_t total = part_off[P];
+    if ((total + 64) * 4 > c->d_ks_entries.cap) return fail(SAVONT_B200_ERR_INVALID, "part_off exceeds the allocated entry buffer");
+    savont_b200_kmer_stats st; memset(&st, 0, sizeof(st));
+    st.n_reads = c->resident.n; st.n_bases = c->resident.total_bases;
+    TRY(c->d_ks_partoff.ensure((size_t)(P + 1) * 8));
+    CK(cudaMemcpyAsync(c->d_ks_partoff.p, part_off, (size_t)(P + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    pl.part_off = c->d_ks_partoff.as<unsigned long long>(); pl.entries = c->d_ks_entries.as<uint32_t>(); pl.dst_ptr = nullptr;
+    pl.single_strand = single_strand;
+    const uint64_t cap64 = std::min<uint64_t>((uint64_t)out_cap, total / 3 + 32);
+    const uint32_t cap_dev = (uint32_t)std::min<uint64_t>(cap64, 0xfffffff0ull);
+    TRY(c->d_kc_out_k.ensure((size_t)cap_dev * 8 + 64)); TRY(c->d_kc_out_c.ensure((size_t)cap_dev * 8 + 64));
+    pl.out_kmers = c->d_kc_out_k.as<uint64_t>(); pl.out_counts = c->d_kc_out_c.as<uint32_t>(); pl.out_cap = cap_dev;
+    CK(cudaEventRecord(c->ev[5], c->stream));
+    launch_kmer_count_part(pl, c->sm_count, c->stream);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ev[3], c->stream));
+    launch_kmer_compact(pl.table, ks.slots, single_strand, pl.out_kmers, pl.out_counts, cap_dev, pl.out_n, c->stream);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ev[4], c->stream));
+    uint32_t t[20];
+    CK(cudaMemcpyAsync(t, ks.tail, sizeof(t), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    st.hist_ms = ev_ms(c->ev[0], c->ev[1]); st.scatter_ms = ev_ms(c->ev[1], c->ev[2]);      // scatter_ms includes the caller's all-gather
+    st.count_ms = st.hist_ms + st.scatter_ms + ev_ms(c->ev[5], c->ev[3]); st.compact_ms = ev_ms(c->ev[3], c->ev[4]);
+    st.total_ms = st.count_ms + st.compact_ms;
+    st.kernel_launches = 6; st.partitions = P; st.table_slots = ks.slots;
+    ks.active = false;
+    if (t[1] != 0) return fail(SAVONT_B200_ERR_OVERFLOW, "spill table overflow in sharded k-mer counting");
+    const uint32_t n_found = t[16];
+    unsigned long long nd = 0; memcpy(&nd, t + 18, 8);
+    st.n_distinct = nd + t[0]; st.spilled_distinct = t[0];
+    if (n_out) *n_out = n_found;
+    if (stats) *stats = st;
+    if (n_found > out_cap) return fail(SAVONT_B200_ERR_CAPACITY, "k-mer output capacity %zu too small (need >= %u)", out_cap, n_found);
+    if (n_found) {
+        CK(cudaMemcpyAsync(out_kmers, pl.out_kmers, (size_t)n_found * 8, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(out_counts, pl.out_counts, (size_t)n_found * 8, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+}  // extern "C"
+
+namespace sb {
 }  // namespace sb
 
 using namespace sb;

@@ -164,6 +164,7 @@ struct KmerPartPlan {
     int single_strand; uint64_t *out_kmers; uint32_t *out_counts; uint32_t out_cap; uint32_t *out_n;
     unsigned long long *n_distinct; uint32_t *queue;
     uint32_t smem_fill_limit;                // 0 = default
+    uint32_t *const *dst_ptr;                // sharded counting (scatter level 2): per-partition destination, null = local
 };
 bool kmer_part_supported(int k, uint32_t max_len);
 void launch_kmer_hist(const KmerPartPlan &pl, const SeqBatch &in, const uint8_t *rc, int k, int min_bq, int sm_count, cudaStream_t st);

@@ -170,6 +170,8 @@ struct KpArgs {
     uint32_t *cursor;                        // [P] next free entry of the partition, relative to part_off (scatter)
     uint32_t *entries;                       // all partitions back to back
     const unsigned long long *part_off;      // [P + 1]
+    uint32_t *const *dst_ptr;                // sharded counting: [P] where this rank's entries of a partition go (a peer's HBM
+                                             // through NVLink, or local); null = entries + part_off
     int single_strand;
     uint64_t *out_kmers; uint32_t *out_counts; uint32_t out_cap;
     uint32_t *out_n;                         // survivors written
@@ -499,7 +501,10 @@ kmer_scatter2_kernel(Kp2Args b) {
         __syncthreads();
         for (uint32_t s = warp; s < P2; s += 16u) {
             const uint32_t s0 = s_off[s], c = s_off[s + 1] - s0;
-            uint32_t *dst = a.entries + __ldg(a.part_off + ((size_t)bin1 << sub_bits) + s) + s_gbase[s];
+            // the final partition: local, or (sharded counting) the owning GPU's buffer -- the runs are written straight into
+            // peer memory, so the exchange step of the multi-GPU algorithm is this store
+            const size_t part = ((size_t)bin1 << sub_bits) + s;
+            uint32_t *dst = (a.dst_ptr ? a.dst_ptr[part] : a.entries + __ldg(a.part_off + part)) + s_gbase[s];
             for (uint32_t i = lane; i < c; i += 32u) dst[i] = sorted[s0 + i];
         }
         __syncthreads();
@@ -608,7 +613,7 @@ static KpArgs kp_args(const KmerPartPlan &pl, const SeqBatch &in, const uint8_t 
     a.kc.in = in; a.kc.rc = rc; a.kc.k = k; a.kc.min_bq = min_bq;
     a.kc.table = pl.table; a.kc.tshift = pl.tshift; a.kc.tmask = pl.tmask; a.kc.ctr = pl.ctr; a.kc.fill_limit = pl.fill_limit;
     a.mul = pl.mul; a.inv = pl.inv; a.kmask = pl.kmask; a.pbits = pl.pbits; a.rem_bits = pl.rem_bits;
-    a.hist = pl.hist; a.cursor = pl.cursor; a.entries = pl.entries; a.part_off = pl.part_off;
+    a.hist = pl.hist; a.cursor = pl.cursor; a.entries = pl.entries; a.part_off = pl.part_off; a.dst_ptr = pl.dst_ptr;
     a.single_strand = pl.single_strand; a.out_kmers = pl.out_kmers; a.out_counts = pl.out_counts; a.out_cap = pl.out_cap;
     a.out_n = pl.out_n; a.n_distinct = pl.n_distinct; a.queue = pl.queue;
     a.packed_words = ((in.max_len + 15u) >> 4) + 4u;

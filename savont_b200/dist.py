@@ -125,3 +125,86 @@ def depths_from_counts(counters, multi_classes, n_asv, sample=None):
     counts = np.array([classes[k] for k in keys], np.uint64)
     _, depths, _ = api.em(n_asv, offs, flat, counts, int(counts.sum()))
     return depths
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Sharded Stage 1 k-mer counting (K5 over several GPUs).  Every rank counts the occurrences of ITS reads per hash partition;
+# partition p belongs to rank p * world // P; the scatter kernel of every rank writes its run of partition p directly into the
+# owner's entry buffer through NVLink peer memory (savont_b200_kmer_shard_scatter), so the only collectives are one all-gather
+# of the P-entry histograms and one of the 64-byte IPC handles, plus a barrier between scatter and count.
+# ---------------------------------------------------------------------------------------------------------
+def kmer_shard_layout(hists: np.ndarray):
+    """hists [world, P] occurrences per rank and partition -> (owner [P], part_off [world, P + 1], dst_off [world, P]):
+    part_off[o] = offsets of the partitions inside owner o's entry buffer (empty ranges for partitions it does not own),
+    dst_off[r][p] = where rank r's run of partition p starts inside the owner's buffer (ranks in order inside a partition)"""
+    H = np.asarray(hists, np.uint64)
+    world, P = H.shape
+    owner = (np.arange(P, dtype=np.uint64) * np.uint64(world) // np.uint64(P)).astype(np.int64)
+    tot = H.sum(axis=0)
+    part_off = np.zeros((world, P + 1), np.uint64)
+    for o in range(world):
+        part_off[o, 1:] = np.cumsum(np.where(owner == o, tot, 0).astype(np.uint64))
+    before = np.cumsum(H, axis=0) - H                                   # occurrences of the lower ranks
+    start = part_off[owner, np.arange(P)]                               # start of p inside its owner's buffer
+    dst_off = (start[None, :] + before).astype(np.uint64)
+    return owner, part_off, dst_off
+
+
+class KmerShardPeers:
+    """the peers' entry buffers, cudaIpc-mapped; re-opened only when a peer re-allocated its buffer"""
+
+    def __init__(self, ctx):
+        self.ctx, self.handles, self.ptrs = ctx, {}, {}
+
+    def update(self, rank, handles, own_ptr):
+        out = []
+        for r, hd in enumerate(handles):
+            if r == rank:
+                out.append(own_ptr); continue
+            if self.handles.get(r) != hd:
+                if r in self.ptrs:
+                    self.ctx.ipc_close(self.ptrs[r])
+                self.ptrs[r] = self.ctx.ipc_open(hd); self.handles[r] = hd
+            out.append(self.ptrs[r])
+        return out
+
+    def close(self):
+        for p in self.ptrs.values():
+            self.ctx.ipc_close(p)
+        self.handles, self.ptrs = {}, {}
+
+
+def count_split_kmers_sharded(ctx, peers: KmerShardPeers | None = None, single_strand=False, cap=1 << 24, sort=False, group=None):
+    """K5 over the ranks of `group`; the reads of this rank are resident (ctx.upload_reads).  Returns this rank's shard of the
+    result (the k-mers of the partitions it owns) as ctx.count_split_kmers does."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    dev = torch.device("cuda", ctx.device)
+    hist = ctx.kmer_shard_hist()
+    if world > 1:
+        t = torch.from_numpy(hist.astype(np.int64)).to(dev)
+        g = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(g, t, group=group)
+        H = torch.stack(g).cpu().numpy().astype(np.uint64)
+    else:
+        H = hist[None, :].astype(np.uint64)
+    owner, part_off, dst_off = kmer_shard_layout(H)
+    own_ptr = ctx.kmer_shard_alloc(int(part_off[rank, -1]))
+    if world > 1:
+        hd = torch.frombuffer(bytearray(ctx.ipc_export(own_ptr)), dtype=torch.uint8).to(dev)
+        gh = [torch.empty_like(hd) for _ in range(world)]
+        dist.all_gather(gh, hd, group=group)                 # also orders this step's allocation before any peer's scatter
+        handles = [bytes(x.cpu().numpy().tobytes()) for x in gh]
+        own_peers = peers or KmerShardPeers(ctx)
+        ptrs = own_peers.update(rank, handles, own_ptr)
+    else:
+        own_peers, ptrs = None, [own_ptr]
+    ctx.kmer_shard_scatter(ptrs, dst_off[rank])
+    if world > 1:
+        dist.barrier(group=group)                            # every rank's runs have landed in the owners' buffers
+    out = ctx.kmer_shard_count(part_off[rank], single_strand=single_strand, cap=cap, sort=sort)
+    if world > 1:
+        dist.barrier(group=group)                            # nobody re-allocates or overwrites a buffer a peer still counts from
+        if peers is None:
+            own_peers.close()
+    return out

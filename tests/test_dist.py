@@ -81,3 +81,28 @@ def test_two_rank_gloo_matches_single_process():
     _, d1, _ = O.em(w.n_asv, offs, flat, counts, total)
     assert outs[0]["depths_s1"] == d1.tolist()
     assert outs[1]["multi"] is None and outs[0]["multi"] is not None
+
+
+def test_kmer_shard_layout_is_a_partition_of_the_owner_buffers():
+    """index arithmetic of the sharded k-mer counting: every (rank, partition) run lands in its owner's buffer, runs are
+    disjoint, ordered by rank inside a partition, and together cover the buffer exactly"""
+    from savont_b200 import dist as sd
+    rng = np.random.default_rng(5)
+    for world in (1, 2, 3, 8):
+        P = 8192
+        H = rng.integers(0, 50, size=(world, P)).astype(np.uint64)
+        H[:, rng.integers(0, P, 300)] = 0
+        owner, part_off, dst_off = sd.kmer_shard_layout(H)
+        assert owner.min() == 0 and owner.max() == world - 1 and np.all(np.diff(owner) >= 0)
+        assert np.all(np.bincount(owner, minlength=world) >= P // world)
+        for o in range(world):
+            own = owner == o
+            assert part_off[o, -1] == H[:, own].sum()
+            assert np.all((part_off[o, 1:] - part_off[o, :-1])[~own] == 0)
+            filled = np.zeros(int(part_off[o, -1]), np.int32)
+            for r in range(world):
+                for p in np.flatnonzero(own & (H[r] > 0)):
+                    a = int(dst_off[r, p]); b = a + int(H[r, p])
+                    assert int(part_off[o, p]) <= a and b <= int(part_off[o, p + 1])
+                    filled[a:b] += 1
+            assert np.all(filled == 1)

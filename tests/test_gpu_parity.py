@@ -768,3 +768,37 @@ def test_kmer_clustering_large_groups(ctx, monkeypatch):
     assert np.array_equal(got["rep_of"], want), np.flatnonzero(got["rep_of"] != want)[:10]
     got = ctx.cluster_reads_by_kmers(km, off)
     assert np.array_equal(got["rep_of"], O.cluster_reads_by_kmers(km, off))
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_count_split_kmers_sharded_ranks_on_one_gpu(world):
+    """the multi-GPU k-mer counting with its ranks emulated by `world` contexts on one device: the peers' entry buffers are plain
+    device pointers here (cudaIpc-mapped under torchrun); the union of the shards must be the single-GPU / oracle result"""
+    from savont_b200 import _lib, dist as sd, synth
+    w = synth.Workload("ont16s", n_roots=3)
+    r = w.reads(3000)
+    ctxs = [_lib.Context(0, _lib.default_params(band=w.band)) for _ in range(world)]
+    try:
+        for rk, c in enumerate(ctxs):
+            lo, hi = sd.shard_bounds(3000, world, rk)
+            sh = sd.slice_reads(r, lo, hi)
+            c.upload_reads(sh["bases"], sh["quals"], sh["offsets"])
+        H = np.stack([c.kmer_shard_hist() for c in ctxs]).astype(np.uint64)
+        owner, part_off, dst_off = sd.kmer_shard_layout(H)
+        ptrs = [c.kmer_shard_alloc(int(part_off[rk, -1])) for rk, c in enumerate(ctxs)]
+        for rk, c in enumerate(ctxs):
+            c.kmer_shard_scatter(ptrs, dst_off[rk])
+        outs = [c.kmer_shard_count(part_off[rk], cap=1 << 20) for rk, c in enumerate(ctxs)]
+        km = np.concatenate([o["kmers"] for o in outs]); ct = np.concatenate([o["counts"] for o in outs])
+        o = np.argsort(km, kind="stable"); km, ct = km[o], ct[o]
+        want = O.count_split_kmers(r["bases"], r["quals"], r["offsets"])
+        assert len(want["kmers"]) > 1000
+        assert np.array_equal(km, want["kmers"]) and np.array_equal(ct, want["counts"])
+        if world > 1:
+            assert all(len(o_["kmers"]) > 0 for o_ in outs)            # every rank owns part of the result
+        # the phases must be called in order
+        with pytest.raises(_lib.SavontB200Error):
+            ctxs[0].kmer_shard_count(part_off[0])
+    finally:
+        for c in ctxs:
+            c.close()
