@@ -130,6 +130,91 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_kmercount_sharded(args, rank, world, local_rank):
+    """--path kmercount --gpus N: every rank counts its own shard of reads; partition p of the 8192 hash partitions belongs to rank
+    p * N / 8192 and the scatter kernel writes the runs straight into the owner's buffer over NVLink (savont_b200/dist.py:
+    count_split_kmers_sharded).  Weak scaling: --reads per GPU."""
+    import torch
+    import torch.distributed as dist
+    from savont_b200 import _lib, dist as sd
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist.init_process_group("nccl", device_id=dev)
+    _bind_to_gpu_numa_node(local_rank)
+    w = _workload(args)
+    n_reads = args.reads
+    ctx = _lib.Context(local_rank, _lib.default_params(band=w.band))
+    stream = torch.cuda.current_stream(dev)
+    ctx.set_stream(stream.cuda_stream)
+    r = w.reads(n_reads, first=rank * n_reads, alloc=_lib.pinned_array)
+    ctx.upload_reads(r["bases"], r["quals"], r["offsets"])
+    peers = sd.KmerShardPeers(ctx)
+    cap = max(1 << 24, n_reads * 16)
+
+    def barrier():
+        dist.barrier(); torch.cuda.synchronize(dev)
+
+    sampler = ClockSampler(local_rank); sampler.start()
+    for _ in range(args.warmup):
+        out = sd.count_split_kmers_sharded(ctx, peers, cap=cap, sort=False, fetch=False)
+    barrier()
+    ms, stats = [], []
+    for _ in range(args.steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        out = sd.count_split_kmers_sharded(ctx, peers, cap=cap, sort=False, fetch=False)   # kernel-only, like the single-GPU line:
+        e1.record(stream)                                                                  # the survivors stay on the device
+        barrier()
+        ms.append(e0.elapsed_time(e1)); stats.append(out["stats"])
+    e2e_ms = []
+    out_bufs = None
+    for _ in range(max(1, min(args.steps, args.e2e_steps))):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        ctx.upload_reads(r["bases"], r["quals"], r["offsets"])
+        res = sd.count_split_kmers_sharded(ctx, peers, cap=cap, sort=False)
+        e1.record(stream)
+        barrier()
+        e2e_ms.append(e0.elapsed_time(e1))
+    clocks = sampler.stop()
+    t = torch.tensor([sum(ms), sum(e2e_ms), float(len(res["kmers"]))], dtype=torch.float64, device=dev)
+    tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    tsum = t.clone(); dist.all_reduce(tsum)
+    peers.close()
+    if rank == 0:
+        peaks = _peaks()
+        st = stats[-1]
+        total_ms, e2e_total = float(tmax[0]), float(tmax[1])
+        bases = st["n_bases"]; n_kmers = bases - 16 * n_reads
+        kern_ms = float(np.mean([s_["hist_ms"] + (s_["count_ms"] - s_["hist_ms"] - s_["scatter_ms"]) + s_["compact_ms"] for s_ in stats]))
+        alg = 2 * 2 * bases + 4 * 4 * n_kmers + 16 * len(res["kmers"])          # per GPU, as in the single-GPU line
+        line = {
+            "metric": "reads counted/sec (Stage 1 split k-mer counting)", "value": world * n_reads * args.steps / (total_ms / 1e3), "unit": "reads/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64 k-mers / u32 counts", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {w.cfg['desc']} (k-mer counting of the reads)", "reads_per_gpu_per_step": n_reads,
+                       "parallelism": f"reads sharded x{world}; hash partitions owned by rank p*{world}/8192; scatter into peer HBM over NVLink",
+                       "l2": "inputs and partition entries larger than L2"},
+            "stage_ms_rank0": {"hist": float(np.mean([s_["hist_ms"] for s_ in stats])),
+                               "scatter+allgather+peer stores": float(np.mean([s_["scatter_ms"] for s_ in stats])),
+                               "count": float(np.mean([s_["count_ms"] - s_["hist_ms"] - s_["scatter_ms"] for s_ in stats])),
+                               "compact": float(np.mean([s_["compact_ms"] for s_ in stats]))},
+            "survivors_total": int(tsum[2]),
+            "roofline": {"bound": "hbm", "kernel": "kmer_hist + kmer_scatter1/2 + kmer_count_part (per GPU)",
+                         "achieved": alg / (total_ms / args.steps / 1e3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s", "peak_source": peaks["source"],
+                         "frac": alg / (total_ms / args.steps / 1e3) / 1e9 / peaks["hbm_gbs"], "traffic": None, "algorithmic_bytes": alg,
+                         "note": "whole step per GPU incl. the two small all-gathers and two barriers"},
+            "e2e": {"value": world * n_reads * len(e2e_ms) / (e2e_total / 1e3), "unit": "reads/s", "h2d_bytes_per_step": int(2 * bases + 8 * (n_reads + 1)),
+                    "d2h_bytes_per_step": int(16 * len(res["kmers"])), "ms_per_step": e2e_total / len(e2e_ms)},
+            "gpu_launches": int(sum(s_["kernel_launches"] for s_ in stats)), "clocks": clocks, "kernel_ms_rank0": kern_ms,
+        }
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def run_kmercount(args, rank, world, local_rank):
     """--path kmercount: Stage 1 split-k-mer counting (K5, seq_parse::read_to_split_kmers) of the same reads.  Not the
     headline path; one JSON line with the same keys."""
@@ -138,9 +223,7 @@ def run_kmercount(args, rank, world, local_rank):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the b200 arm has no CPU fallback")
     if world > 1:
-        if rank == 0:
-            print(json.dumps({"metric": "reads counted/sec (Stage 1 split k-mer counting)", "unavailable": "single-GPU path: the k-mer table is not sharded yet"}))
-        return
+        return run_kmercount_sharded(args, rank, world, local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     w = _workload(args)

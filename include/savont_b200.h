@@ -316,11 +316,11 @@ int savont_b200_cluster_reads_by_kmers(savont_b200_ctx *ctx, const uint64_t *kme
  *                                       drained; the caller barriers.
  *   4. savont_b200_kmer_shard_count     counts the owned partitions (part_off[P + 1]: offsets in the own buffer, empty ranges
  *                                       for partitions of other ranks); output as savont_b200_count_split_kmers, restricted
- *                                       to the k-mers of the owned partitions.
+ *                                       to the k-mers of the owned partitions (out_kmers = out_counts = NULL: count only).
  * Needs the two-level partitioned algorithm (k <= 19, reads <= 24000 bases). */
 int savont_b200_kmer_shard_partitions(void);
 int savont_b200_kmer_shard_hist(savont_b200_ctx *ctx, uint32_t *hist);
-int savont_b200_kmer_shard_alloc(savont_b200_ctx *ctx, uint64_t n_entries, void **dev_ptr);
+int savont_b200_kmer_shard_alloc(savont_b200_ctx *ctx, uint64_t n_entries, void **dev_ptr, uint64_t *capacity /* entries, may be NULL */);
 int savont_b200_ipc_export(savont_b200_ctx *ctx, const void *dev_ptr, void *handle64 /* 64 bytes */);
 int savont_b200_ipc_open(savont_b200_ctx *ctx, const void *handle64, void **dev_ptr);
 int savont_b200_ipc_close(savont_b200_ctx *ctx, void *dev_ptr);

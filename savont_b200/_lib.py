@@ -470,10 +470,10 @@ class Context:
         _check(self.L.savont_b200_kmer_shard_hist(self.h, _p(hist, C.c_uint32)))
         return hist
 
-    def kmer_shard_alloc(self, n_entries: int) -> int:
-        ptr = C.c_void_p()
-        _check(self.L.savont_b200_kmer_shard_alloc(self.h, C.c_uint64(int(n_entries)), C.byref(ptr)))
-        return int(ptr.value)
+    def kmer_shard_alloc(self, n_entries: int, with_capacity=False):
+        ptr = C.c_void_p(); cap = C.c_uint64(0)
+        _check(self.L.savont_b200_kmer_shard_alloc(self.h, C.c_uint64(int(n_entries)), C.byref(ptr), C.byref(cap)))
+        return (int(ptr.value), int(cap.value)) if with_capacity else int(ptr.value)
 
     def ipc_export(self, dev_ptr: int) -> bytes:
         buf = (C.c_uint8 * 64)()
@@ -494,8 +494,13 @@ class Context:
         do = np.ascontiguousarray(dst_off, dtype=np.uint64)
         _check(self.L.savont_b200_kmer_shard_scatter(self.h, C.c_int(n), arr, _p(do, C.c_uint64)))
 
-    def kmer_shard_count(self, part_off, single_strand=False, cap=1 << 22, sort=True):
+    def kmer_shard_count(self, part_off, single_strand=False, cap=1 << 22, sort=True, fetch=True):
         po = np.ascontiguousarray(part_off, dtype=np.uint64)
+        if not fetch:                                   # count only: the number of survivors and the stage times
+            n = C.c_size_t(0); st = KmerStats()
+            _check(self.L.savont_b200_kmer_shard_count(self.h, _p(po, C.c_uint64), C.c_int(1 if single_strand else 0), None, None,
+                                                       C.c_size_t(0), C.byref(n), C.byref(st)))
+            return dict(n=int(n.value), stats=st.as_dict())
         call = lambda km, ct, cp, nn, st: self.L.savont_b200_kmer_shard_count(
             self.h, _p(po, C.c_uint64), C.c_int(1 if single_strand else 0), km, ct, cp, nn, st)
         return self._kmer_out(call, cap, sort)

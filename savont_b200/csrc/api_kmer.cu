@@ -251,12 +251,13 @@ int savont_b200_kmer_shard_hist(savont_b200_ctx *h, uint32_t *hist) {
     return 0;
 }
 
-int savont_b200_kmer_shard_alloc(savont_b200_ctx *h, uint64_t n_entries, void **dev_ptr) {
+int savont_b200_kmer_shard_alloc(savont_b200_ctx *h, uint64_t n_entries, void **dev_ptr, uint64_t *capacity) {
     TRY(use_device(h ? &h->c : nullptr));
     Context *c = &h->c;
     if (!dev_ptr) return fail(SAVONT_B200_ERR_INVALID, "null argument");
     TRY(c->d_ks_entries.ensure((n_entries + 64) * 4));
     *dev_ptr = c->d_ks_entries.p;
+    if (capacity) *capacity = c->d_ks_entries.cap / 4 - 64;
     return 0;
 }
 
@@ -325,7 +326,9 @@ int savont_b200_kmer_shard_count(savont_b200_ctx *h, const uint64_t *part_off, i
     Context *c = &h->c;
     Context::KmerShard &ks = c->ks;
     if (!ks.active || ks.n_ranks == 0) return fail(SAVONT_B200_ERR_INVALID, "savont_b200_kmer_shard_scatter has not been called");
-    if (!part_off || (out_cap && (!out_kmers || !out_counts))) return fail(SAVONT_B200_ERR_INVALID, "null argument");
+    if (!part_off || ((out_kmers == nullptr) != (out_counts == nullptr))) return fail(SAVONT_B200_ERR_INVALID, "null argument");
+    const bool fetch = out_kmers != nullptr;            // NULL outputs: count only (n_out, stats); the survivors stay on the device
+    if (!fetch) out_cap = (size_t)1 << 32;
     KmerPartPlan &pl = ks.pl;
     const uint32_t P = 1u << kKmerPartBits;
     const uint64_t total = part_off[P];
@@ -362,7 +365,7 @@ int savont_b200_kmer_shard_count(savont_b200_ctx *h, const uint64_t *part_off, i
     if (n_out) *n_out = n_found;
     if (stats) *stats = st;
     if (n_found > out_cap) return fail(SAVONT_B200_ERR_CAPACITY, "k-mer output capacity %zu too small (need >= %u)", out_cap, n_found);
-    if (n_found) {
+    if (n_found && fetch) {
         CK(cudaMemcpyAsync(out_kmers, pl.out_kmers, (size_t)n_found * 8, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaMemcpyAsync(out_counts, pl.out_counts, (size_t)n_found * 8, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));

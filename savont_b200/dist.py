@@ -168,43 +168,61 @@ class KmerShardPeers:
             out.append(self.ptrs[r])
         return out
 
+    def drop(self, r):
+        if r in self.ptrs:
+            self.ctx.ipc_close(self.ptrs.pop(r)); self.handles.pop(r, None)
+
     def close(self):
         for p in self.ptrs.values():
             self.ctx.ipc_close(p)
         self.handles, self.ptrs = {}, {}
 
 
-def count_split_kmers_sharded(ctx, peers: KmerShardPeers | None = None, single_strand=False, cap=1 << 24, sort=False, group=None):
+def count_split_kmers_sharded(ctx, peers: KmerShardPeers | None = None, single_strand=False, cap=1 << 24, sort=False, group=None,
+                              fetch=True):
     """K5 over the ranks of `group`; the reads of this rank are resident (ctx.upload_reads).  Returns this rank's shard of the
-    result (the k-mers of the partitions it owns) as ctx.count_split_kmers does."""
+    result (the k-mers of the partitions it owns) as ctx.count_split_kmers does (fetch=False: only their number and the times).
+    Collectives per call: ONE all-gather of [histogram | buffer capacity | IPC handle] (a second one only when some rank had to
+    grow its buffer, i.e. on the first call), a barrier after the scatter and one after the count."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     dev = torch.device("cuda", ctx.device)
     hist = ctx.kmer_shard_hist()
-    if world > 1:
-        t = torch.from_numpy(hist.astype(np.int64)).to(dev)
-        g = [torch.empty_like(t) for _ in range(world)]
-        dist.all_gather(g, t, group=group)
-        H = torch.stack(g).cpu().numpy().astype(np.uint64)
-    else:
-        H = hist[None, :].astype(np.uint64)
-    owner, part_off, dst_off = kmer_shard_layout(H)
-    own_ptr = ctx.kmer_shard_alloc(int(part_off[rank, -1]))
-    if world > 1:
-        hd = torch.frombuffer(bytearray(ctx.ipc_export(own_ptr)), dtype=torch.uint8).to(dev)
-        gh = [torch.empty_like(hd) for _ in range(world)]
-        dist.all_gather(gh, hd, group=group)                 # also orders this step's allocation before any peer's scatter
-        handles = [bytes(x.cpu().numpy().tobytes()) for x in gh]
-        own_peers = peers or KmerShardPeers(ctx)
-        ptrs = own_peers.update(rank, handles, own_ptr)
-    else:
-        own_peers, ptrs = None, [own_ptr]
+    P = len(hist)
+    if world == 1:
+        owner, part_off, dst_off = kmer_shard_layout(hist[None, :])
+        own_ptr = ctx.kmer_shard_alloc(int(part_off[0, -1]))
+        ctx.kmer_shard_scatter([own_ptr], dst_off[0])
+        return ctx.kmer_shard_count(part_off[0], single_strand=single_strand, cap=cap, sort=sort, fetch=fetch)
+    own_peers = peers or KmerShardPeers(ctx)
+
+    def exchange(own_ptr, own_cap):
+        payload = np.zeros(P + 9, np.int64)
+        payload[:P] = hist; payload[P] = own_cap
+        payload[P + 1:] = np.frombuffer(ctx.ipc_export(own_ptr), np.int64)
+        t = torch.from_numpy(payload).to(dev)
+        g = torch.empty((world, P + 9), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(g, t, group=group)
+        return g.cpu().numpy()
+    own_ptr, own_cap = ctx.kmer_shard_alloc(0, with_capacity=True)          # the buffer of the previous call, if any
+    G = exchange(own_ptr, own_cap)
+    owner, part_off, dst_off = kmer_shard_layout(G[:, :P].astype(np.uint64))
+    need = part_off[:, -1].astype(np.int64)
+    grow = need > G[:, P]
+    if np.any(grow):                                                        # somebody has to grow: everybody sees it
+        for r in np.flatnonzero(grow):                                      # unmap a buffer before its owner frees it
+            if r != rank:
+                own_peers.drop(int(r))
+        dist.barrier(group=group)
+        if grow[rank]:
+            own_ptr, own_cap = ctx.kmer_shard_alloc(int(need[rank] + need[rank] // 8), with_capacity=True)
+        G = exchange(own_ptr, own_cap)
+    handles = [G[r, P + 1:].tobytes() for r in range(world)]
+    ptrs = own_peers.update(rank, handles, own_ptr)
     ctx.kmer_shard_scatter(ptrs, dst_off[rank])
-    if world > 1:
-        dist.barrier(group=group)                            # every rank's runs have landed in the owners' buffers
-    out = ctx.kmer_shard_count(part_off[rank], single_strand=single_strand, cap=cap, sort=sort)
-    if world > 1:
-        dist.barrier(group=group)                            # nobody re-allocates or overwrites a buffer a peer still counts from
-        if peers is None:
-            own_peers.close()
+    dist.barrier(group=group)                                # every rank's runs have landed in the owners' buffers
+    out = ctx.kmer_shard_count(part_off[rank], single_strand=single_strand, cap=cap, sort=sort, fetch=fetch)
+    dist.barrier(group=group)                                # nobody overwrites a buffer a peer still counts from
+    if peers is None:
+        own_peers.close()
     return out
