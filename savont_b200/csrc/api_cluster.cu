@@ -69,12 +69,14 @@ int cluster_prepare(Context *c, ClusterDev &d, const uint64_t *kmers, const uint
     c->last_stats.kernel_launches += 1;
     c->last_stats.h2d_bytes += total * 8 + (n + 1) * 8;
     if (sig_h) {
-        sig_h->resize(n * kLshTables); valid_h->resize(n);
-        if (n) {
-            CK(cudaMemcpyAsync(sig_h->data(), d.sig.p, n * kLshTables * 8, cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(valid_h->data(), d.valid.p, n, cudaMemcpyDeviceToHost, st));
-        }
-        c->last_stats.d2h_bytes += n * kLshTables * 8 + n;
+        sig_h->resize(n * kLshTables);
+        if (n) CK(cudaMemcpyAsync(sig_h->data(), d.sig.p, n * kLshTables * 8, cudaMemcpyDeviceToHost, st));
+        c->last_stats.d2h_bytes += n * kLshTables * 8;
+    }
+    if (valid_h) {
+        valid_h->resize(n);
+        if (n) CK(cudaMemcpyAsync(valid_h->data(), d.valid.p, n, cudaMemcpyDeviceToHost, st));
+        c->last_stats.d2h_bytes += n;
     }
     if (nd_h) {
         launch_sort_dedup(d.kmers.as<uint64_t>(), d.offsets.as<uint64_t>(), (uint32_t)n, d.dk.as<uint64_t>(), d.nd.as<uint32_t>(), c->sm_count, st);
@@ -131,9 +133,9 @@ extern "C" int savont_b200_cluster_reads_by_kmers(savont_b200_ctx *h, const uint
     cudaStream_t st = c->stream;
     const size_t n = n_reads;
     ClusterDev d(c->cluster_ws);
-    std::vector<uint64_t> rel, sig; std::vector<uint8_t> valid; std::vector<uint32_t> nd;
+    std::vector<uint64_t> rel; std::vector<uint8_t> valid; std::vector<uint32_t> nd;
     CK(cudaEventRecord(c->ev[0], st));
-    TRY(cluster_prepare(c, d, kmers, offsets, n, rel, &nd, &sig, &valid));
+    TRY(cluster_prepare(c, d, kmers, offsets, n, rel, &nd, nullptr, &valid));
     CK(cudaEventRecord(c->ev[1], st));
     const ThresholdTest thr(threshold, c->params.k);
     auto tot_of = [&](uint32_t r) { return (uint32_t)(rel[r + 1] - rel[r]); };
@@ -173,6 +175,7 @@ extern "C" int savont_b200_cluster_reads_by_kmers(savont_b200_ctx *h, const uint
     struct PairHit { uint32_t pidx, hits, cnt; };
     std::vector<uint32_t> p0, before, pair_start, hit_off, hit_fill; std::vector<PairHit> hit_list; std::vector<uint8_t> p0_rep;
     std::vector<Cand> inblk, order;
+    std::vector<uint32_t> new_ids; std::vector<uint64_t> new_sig;
     double query_ms = 0, pair_ms = 0;
     // host-side wall clock per phase (SAVONT_B200_CLUSTER_TRACE=1 prints it)
     double tw[8] = {0}; auto tnow = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -306,7 +309,7 @@ extern "C" int savont_b200_cluster_reads_by_kmers(savont_b200_ctx *h, const uint
             // new representative (src/asv_cluster.rs:178-187)
             rep_of[i] = i; ++n_reps;
             if (valid[i]) {
-                for (int t = 0; t < kLshTables; ++t) fresh[t].push_back(Ent(sig[(size_t)i * kLshTables + t], i));
+                new_ids.push_back(i);
                 tables_dirty = true;
                 if (my_pidx < 0 && li + 1 < nbk) {
                     lap(4);
@@ -333,6 +336,18 @@ extern "C" int savont_b200_cluster_reads_by_kmers(savont_b200_ctx *h, const uint
         lap(4);
         // the block's representatives join the delta level; the delta is folded into the main level when it reaches a quarter of it
         if (n_new) {
+            // their signatures (the only ones the host ever needs) come from the device
+            const uint32_t nn = (uint32_t)new_ids.size();
+            TRY(up(d.pi, new_ids.data(), nn, st)); TRY(d.ph.ensure((size_t)nn * kLshTables * 8 + 16));
+            launch_gather_sig(d.sig.as<uint64_t>(), d.pi.as<uint32_t>(), nn, d.ph.as<uint64_t>(), st);
+            new_sig.resize((size_t)nn * kLshTables);
+            CK(cudaMemcpyAsync(new_sig.data(), d.ph.p, (size_t)nn * kLshTables * 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            CK(cudaGetLastError());
+            c->last_stats.kernel_launches += 1; c->last_stats.d2h_bytes += (size_t)nn * kLshTables * 8;
+            for (uint32_t x = 0; x < nn; ++x)
+                for (int t = 0; t < kLshTables; ++t) fresh[t].push_back(Ent(new_sig[(size_t)x * kLshTables + t], new_ids[x]));
+            new_ids.clear();
             for (int t = 0; t < kLshTables; ++t) {
                 std::sort(fresh[t].begin(), fresh[t].end());
                 merged.resize(dlt[t].size() + fresh[t].size());

@@ -69,6 +69,15 @@ void launch_lsh_sig(const uint64_t *kmers, const uint64_t *offsets, uint32_t n_r
     if (n_reads) lsh_sig_kernel<<<(n_reads + 7u) / 8u, 256, 0, st>>>(kmers, offsets, n_reads, sig, valid);
 }
 
+// signatures of a few reads (the representatives a block created), for the host's bucket tables
+__global__ void gather_sig_kernel(const uint64_t *__restrict__ sig, const uint32_t *__restrict__ ids, uint32_t n, uint64_t *__restrict__ out) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n * (uint32_t)kLshTables) out[t] = sig[(uint64_t)ids[t / kLshTables] * kLshTables + t % kLshTables];
+}
+void launch_gather_sig(const uint64_t *sig, const uint32_t *ids, uint32_t n, uint64_t *out, cudaStream_t st) {
+    if (n) gather_sig_kernel<<<(n * kLshTables + 255u) / 256u, 256, 0, st>>>(sig, ids, n, out);
+}
+
 // ---------------- sorted distinct minimizers per read ----------------
 // reads with more than kSortMax minimizers are left to the host (nd[r] = UINT32_MAX marks them)
 constexpr uint32_t kSortMax = 2048;

@@ -312,6 +312,7 @@ void launch_lsh_sig(const uint64_t *kmers, const uint64_t *offsets, uint32_t n_r
 void launch_sort_dedup(const uint64_t *kmers, const uint64_t *offsets, uint32_t n_reads, uint64_t *dk, uint32_t *nd, int sm_count,
                        cudaStream_t st);
 uint32_t cluster_sort_max();
+void launch_gather_sig(const uint64_t *sig, const uint32_t *ids, uint32_t n, uint64_t *out, cudaStream_t st);
 void launch_rep_query(const ClusterQuery &q, cudaStream_t st);
 void launch_pair_stats(const ClusterQuery &q, const uint32_t *pair_i, const uint32_t *pair_j, uint32_t n_pairs, uint8_t *hits, uint32_t *cnt,
                        cudaStream_t st);
