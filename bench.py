@@ -10,10 +10,12 @@ index replicated, one all-reduce of the per-ASV count vector per step (NCCL, in 
 library's device counter vector).
 
   value     whole-job reads/s with the reads already resident in HBM (kernel pipeline only)
-  e2e       the same metric through savont_b200_map_reads with pinned HOST buffers
-            (H2D of bases+quals+offsets and D2H of per-read results inside the timed region)
-  e2e_twin  the same through savont_b200_map_twin_reads: the reads as the reference's Stage 7 receives them
-            (&[TwinRead]: 2-bit dna_seq words + snpmer_kmers), 8x fewer H2D bytes
+  e2e       the same metric through the drop-in call of the reference's Stage 7 seam, savont_b200_map_twin_reads:
+            `refine_asv_depths_with_em(twin_reads: &[TwinRead], ..)` hands over TwinReads, so the HOST buffers are the
+            2-bit dna_seq words + snpmer_kmers of the reads, in pinned memory (H2D of them and D2H of the per-read results
+            inside the timed region).  With --no-twin: the FASTQ-byte call below.
+  e2e_fastq the same through savont_b200_map_reads: ASCII bases + Phred bytes (the form the reference arm / CPU oracle
+            is fed with), 5.5x more H2D bytes -> PCIe bound
   roofline  the dominant kernel (banded DP): achieved GCUPS vs the INT32 ALU-pipe peak
   cpu_baseline / --impl reference: the CPU oracle (C port of the reference path; the Rust
             reference itself cannot be built here) on all host cores.
@@ -621,12 +623,17 @@ def run_b200(args, rank, world, local_rank):
                      "h2d_bytes_per_step": int(tw_stats["h2d_bytes"]), "d2h_bytes_per_step": int(tw_stats["d2h_bytes"]),
                      "steps": e2e_steps, "ms_per_step": float(tw_t.item()) / e2e_steps, "h2d_ms": tw_stats["h2d_ms"],
                      "kernel_ms": {"sketch": tw_stats["sketch_ms"], "filter": tw_stats["filter_ms"], "align": tw_stats["align_ms"]},
-                     "input": "TwinRead.dna_seq words + TwinRead.snpmer_kmers (Kmer48) through savont_b200_map_twin_reads",
+                     "input": "&[TwinRead] as the reference's Stage 7 receives them: TwinRead.dna_seq words + TwinRead.snpmer_kmers (Kmer48) "
+                              "through savont_b200_map_twin_reads",
                      "same_result_as_ascii_entry": same}
     clocks = sampler.stop()
 
     if rank != 0:
         return
+    fastq_line = {"value": world * n_reads * e2e_steps / (e2e_total_ms / 1e3), "unit": "reads/s", "h2d_bytes_per_step": int(e2e_stats["h2d_bytes"]),
+                  "d2h_bytes_per_step": int(e2e_stats["d2h_bytes"]), "steps": e2e_steps, "ms_per_step": e2e_total_ms / e2e_steps,
+                  "h2d_ms": e2e_stats["h2d_ms"], "d2h_ms": e2e_stats["d2h_ms"],
+                  "input": "FASTQ bytes (ASCII bases + Phred) through savont_b200_map_reads"}
     peaks = _peaks()
     K = args.steps
     value = world * n_reads * K / (total_ms / 1e3)
@@ -667,10 +674,8 @@ def run_b200(args, rank, world, local_rank):
                          "frac": (sk_bytes / (sketch_ms / 1e3) / 1e9) / peaks["hbm_gbs"] if sketch_ms else None,
                          "traffic": _ncu_traffic("sketch_fast_kernel") if (n_reads == 1_000_000 and args.workload == "ont16s") else None,
                          "algorithmic_bytes": sk_bytes},
-        "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(e2e_stats["h2d_bytes"]),
-                "d2h_bytes_per_step": int(e2e_stats["d2h_bytes"]), "steps": e2e_steps, "ms_per_step": e2e_total_ms / e2e_steps,
-                "h2d_ms": e2e_stats["h2d_ms"], "d2h_ms": e2e_stats["d2h_ms"]},
-        "e2e_twin": twin_line,
+        "e2e": twin_line if twin_line is not None else fastq_line,
+        "e2e_fastq": fastq_line,
         "gpu_launches": int(sum(s["kernel_launches"] for s in stats)),
         "clocks": clocks,
         "assigned_frac": float(got["totals"][0]) / max(n_reads * (world if world > 1 else 1), 1),
