@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SAVONT_B200_ABI_VERSION 6
+#define SAVONT_B200_ABI_VERSION 7
 
 typedef struct savont_b200_ctx savont_b200_ctx;
 
@@ -327,6 +327,20 @@ int savont_b200_ipc_close(savont_b200_ctx *ctx, void *dev_ptr);
 int savont_b200_kmer_shard_scatter(savont_b200_ctx *ctx, int n_ranks, void *const *peer_entries, const uint64_t *dst_off);
 int savont_b200_kmer_shard_count(savont_b200_ctx *ctx, const uint64_t *part_off, int single_strand, uint64_t *out_kmers,
                                  uint32_t *out_counts, size_t out_cap, size_t *n_out, savont_b200_kmer_stats *stats);
+
+/* ---- Stage 3 reclustering: reads -- or consensus lists -- against the clusters' consensus SNPmers.
+ * cons_kmers / cons_offsets: per cluster the ConsensusSnpmer k-mers (`cs.kmer`; a later entry with the same splitmer replaces an
+ * earlier one, as HashMap::insert at src/asv_cluster.rs:1031-1034); read_kmers / read_offsets: per read the k-mers of
+ * TwinRead::snpmers_vec() (:1049).  Replaces the candidate loop of asv_cluster::reassign_reads_to_best_cluster (:1052-1098, SNPmer
+ * markers): best_cons[r] = the first cluster with the fewest mismatches, then the most matches (UINT32_MAX without clusters),
+ * best_mismatches / best_matches = its score.  matrix (optional, [n_reads][n_cons][2] u16) = (matches, mismatches) of every pair:
+ * with consensus lists as "reads" this is compare_consensus_snpmers (:968-994) for all cluster pairs of a reclustering round.
+ * k = params.k.  Limits: 51200 clusters, 65535 markers per read.  stats: filter_ms = the comparison kernel(s), h2d_ms = index +
+ * markers upload, n_pairs = n_reads * n_cons. */
+int savont_b200_snpmer_compare(savont_b200_ctx *ctx, const uint64_t *cons_kmers, const uint64_t *cons_offsets, size_t n_cons,
+                               const uint64_t *read_kmers, const uint64_t *read_offsets, size_t n_reads, uint32_t *best_cons,
+                               uint32_t *best_mismatches, uint32_t *best_matches, uint16_t *matrix /* may be NULL */,
+                               savont_b200_stats *stats /* may be NULL */);
 
 /* Pinned host memory helpers (inputs placed here are copied without a staging pass). */
 int savont_b200_host_alloc(size_t bytes, void **out);

@@ -254,6 +254,23 @@ def cluster_reads_by_kmers(kmers, offsets, k=17, threshold=0.95):
     return rep[:n]
 
 
+def snpmer_compare(cons_kmers, cons_offsets, read_kmers, read_offsets, k=17, want_matrix=False):
+    """so_snpmer_compare -> dict(best_cons, best_mismatches, best_matches[, matrix [n_reads, n_cons, 2]])"""
+    L = lib()
+    ck = np.ascontiguousarray(cons_kmers, dtype=np.uint64); co = np.ascontiguousarray(cons_offsets, dtype=np.uint64)
+    rk = np.ascontiguousarray(read_kmers, dtype=np.uint64); ro = np.ascontiguousarray(read_offsets, dtype=np.uint64)
+    nc, n = len(co) - 1, len(ro) - 1
+    bc = np.zeros(max(n, 1), np.uint32); bmm = np.zeros(max(n, 1), np.uint32); bm = np.zeros(max(n, 1), np.uint32)
+    mat = np.zeros((max(n, 1), max(nc, 1), 2), np.uint16) if want_matrix else None
+    rc = L.so_snpmer_compare(C.c_int(k), _p(ck, C.c_uint64), _p(co, C.c_uint64), C.c_size_t(nc), _p(rk, C.c_uint64), _p(ro, C.c_uint64),
+                             C.c_size_t(n), _p(bc, C.c_uint32), _p(bmm, C.c_uint32), _p(bm, C.c_uint32), _p(mat, C.c_uint16))
+    assert rc == 0
+    out = dict(best_cons=bc[:n], best_mismatches=bmm[:n], best_matches=bm[:n])
+    if want_matrix:
+        out["matrix"] = mat[:n, :nc]
+    return out
+
+
 class Oracle:
     def set_read_filter(self, rf: ReadFilter | None, high_freq=None):
         hf = np.ascontiguousarray(high_freq if high_freq is not None else [], dtype=np.uint64)

@@ -919,6 +919,43 @@ int so_cluster_reads_by_kmers(int k, double threshold, const uint64_t *kmers, co
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* SURVEY.md 8(f) row 3, Stage 3 reclustering: the read-vs-consensus SNPmer comparison of */
+/* asv_cluster::reassign_reads_to_best_cluster (src/asv_cluster.rs:1007-1131, SNPmer       */
+/* markers) and compare_consensus_snpmers (:968-994).  The consensus lists (built by        */
+/* build_consensus_snpmers, :840-893, whose ties follow hash-map iteration order) are input.*/
+/* ------------------------------------------------------------------------------------ */
+int so_snpmer_compare(int k, const uint64_t *cons_kmers, const uint64_t *cons_offsets, size_t n_cons, const uint64_t *read_kmers,
+                      const uint64_t *read_offsets, size_t n_reads, uint32_t *best_cons, uint32_t *best_mismatches, uint32_t *best_matches,
+                      uint16_t *matrix) {
+    const uint64_t mask = so_split_mask(k);
+    /* splitmer_to_consensus_kmers[c]: insert(cs.splitmer, cs.kmer), a later entry of the same splitmer replaces an earlier (:1027-1037) */
+    u64map *maps = (u64map *)malloc((n_cons ? n_cons : 1) * sizeof(u64map));
+    for (size_t c = 0; c < n_cons; c++) {
+        const size_t n = (size_t)(cons_offsets[c + 1] - cons_offsets[c]);
+        u64map_init(&maps[c], n);
+        for (size_t i = 0; i < n; i++) *u64map_slot(&maps[c], cons_kmers[cons_offsets[c] + i] & mask, 1) = (uint32_t)(i + 1);
+    }
+#pragma omp parallel for schedule(dynamic, 16)
+    for (size_t r = 0; r < n_reads; r++) {
+        size_t best = 0; uint64_t b_mm = UINT64_MAX, b_m = 0;                       /* best_score = (usize::MAX, 0), :1055 */
+        for (size_t c = 0; c < n_cons; c++) {
+            uint32_t m = 0, mm = 0;
+            for (uint64_t i = read_offsets[r]; i < read_offsets[r + 1]; i++) {         /* :1064-1084 */
+                const uint32_t *slot = u64map_slot(&maps[c], read_kmers[i] & mask, 0);
+                if (slot) { if (cons_kmers[cons_offsets[c] + *slot - 1] == read_kmers[i]) m++; else mm++; }
+            }
+            if (matrix) { matrix[(r * n_cons + c) * 2] = (uint16_t)(m > 65535 ? 65535 : m); matrix[(r * n_cons + c) * 2 + 1] = (uint16_t)(mm > 65535 ? 65535 : mm); }
+            if (mm < b_mm || (mm == b_mm && m > b_m)) { b_mm = mm; b_m = m; best = c; }   /* :1087-1091 */
+        }
+        best_cons[r] = n_cons ? (uint32_t)best : UINT32_MAX;
+        best_mismatches[r] = n_cons ? (uint32_t)b_mm : 0; best_matches[r] = (uint32_t)b_m;
+    }
+    for (size_t c = 0; c < n_cons; c++) u64map_free(&maps[c]);
+    free(maps);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* a4: kmer_comp::twin_reads_from_snpmers, src/kmer_comp.rs:68-258                      */
 /* ------------------------------------------------------------------------------------ */
 /* the tests a read goes through before it becomes a TwinRead; the quality cutoff (:248) is applied after the id sort in

@@ -201,6 +201,16 @@ int so_lsh_signatures(const uint64_t *kmers, const uint64_t *offsets, size_t n_r
 int so_cluster_reads_by_kmers(int k, double threshold, const uint64_t *kmers, const uint64_t *offsets, size_t n_reads, uint32_t *rep_of,
                               uint64_t *n_reps);
 
+/* ---- SURVEY.md 8(f) row 3 (Stage 3 reclustering): reads (or consensus lists) against cluster consensus SNPmers.
+ * cons_kmers / cons_offsets: per cluster the ConsensusSnpmer k-mers (splitmer = kmer & split_mask); read_kmers / read_offsets:
+ * per read the k-mers of TwinRead::snpmers_vec().  Per read: best_cons = the first cluster with the fewest mismatches, then the
+ * most matches (reassign_reads_to_best_cluster, src/asv_cluster.rs:1052-1098; UINT32_MAX without clusters), its mismatches and
+ * matches; matrix (optional) [n_reads][n_cons][2] = (matches, mismatches) of every pair, saturated at 65535
+ * (compare_consensus_snpmers, :968-994, when the "reads" are consensus lists). */
+int so_snpmer_compare(int k, const uint64_t *cons_kmers, const uint64_t *cons_offsets, size_t n_cons, const uint64_t *read_kmers,
+                      const uint64_t *read_offsets, size_t n_reads, uint32_t *best_cons, uint32_t *best_mismatches, uint32_t *best_matches,
+                      uint16_t *matrix);
+
 /* ---- a13-a14: EM over equivalence classes (src/alignment.rs:1957-2038) ---------------
  * classes in CSR (cls_offsets[n_cls+1], cls_asv), counts[n_cls]; total_assigned;
  * out: abundances[A] (f64), depths[A] = round(ab*total).  Classes are iterated in the

@@ -505,6 +505,23 @@ class Context:
             self.h, _p(po, C.c_uint64), C.c_int(1 if single_strand else 0), km, ct, cp, nn, st)
         return self._kmer_out(call, cap, sort)
 
+    def snpmer_compare(self, cons_kmers, cons_offsets, read_kmers, read_offsets, want_matrix=False):
+        """reassign_reads_to_best_cluster / compare_consensus_snpmers (src/asv_cluster.rs:968-1098) ->
+        dict(best_cons, best_mismatches, best_matches[, matrix [n_reads, n_cons, 2]], stats)"""
+        ck = np.ascontiguousarray(cons_kmers, dtype=np.uint64); co = np.ascontiguousarray(cons_offsets, dtype=np.uint64)
+        rk = np.ascontiguousarray(read_kmers, dtype=np.uint64); ro = np.ascontiguousarray(read_offsets, dtype=np.uint64)
+        nc, n = len(co) - 1, len(ro) - 1
+        bc = np.zeros(max(n, 1), np.uint32); bmm = np.zeros(max(n, 1), np.uint32); bm = np.zeros(max(n, 1), np.uint32)
+        mat = np.zeros((max(n, 1), max(nc, 1), 2), np.uint16) if want_matrix else None
+        stt = Stats()
+        _check(self.L.savont_b200_snpmer_compare(self.h, _p(ck, C.c_uint64), _p(co, C.c_uint64), C.c_size_t(nc), _p(rk, C.c_uint64),
+                                                 _p(ro, C.c_uint64), C.c_size_t(n), _p(bc, C.c_uint32), _p(bmm, C.c_uint32),
+                                                 _p(bm, C.c_uint32), _p(mat, C.c_uint16), C.byref(stt)))
+        out = dict(best_cons=bc[:n], best_mismatches=bmm[:n], best_matches=bm[:n], stats=stt.as_dict())
+        if want_matrix:
+            out["matrix"] = mat[:n, :nc]
+        return out
+
     def counts_dev(self):
         """(device pointer, length in u64) of [unambig|ambig|leq10|assigned|filtered|singleton S*A]"""
         ptr = C.c_void_p(); n = C.c_size_t()

@@ -321,4 +321,18 @@ void launch_pair_stats(const ClusterQuery &q, const uint32_t *pair_i, const uint
 void launch_block_pair_stats(const ClusterQuery &q, const uint32_t *pair_start, const uint32_t *p0, uint32_t n_pairs, uint4 *out,
                              uint32_t *out_n, cudaStream_t st);
 
+// ---- Stage 3 reclustering: reads against the clusters' consensus SNPmers (reassign.cu) ----
+struct SnpCompareArgs {
+    int k;
+    // inverted index over all clusters: splitmer -> bucket of (cluster << 2 | middle base), as AsvIndex::idx_*
+    const uint64_t *idx_keys; const uint2 *idx_vals; uint32_t idx_mask, idx_shift; const uint32_t *idx_entries;
+    uint32_t n_cons;
+    const uint64_t *read_kmers; const uint64_t *read_offsets; uint32_t n_reads;
+    uint32_t *best_cons, *best_mismatches, *best_matches;
+    uint32_t *matrix;            // optional: rows of n_cons words, matches | mismatches << 16
+    uint32_t first_row;
+};
+// reads [first, first + n) of the arrays in `a` (matrix = the rows of exactly these reads); returns 1 if n_cons is too large
+int launch_snpmer_compare(const SnpCompareArgs &a, uint32_t first, uint32_t n, int sm_count, cudaStream_t st);
+
 }  // namespace sb

@@ -298,3 +298,32 @@ def cluster_reads_by_kmers(reads_minis, k=17, threshold=0.95, top_n=10):
         else:
             rep_of.append(best)
     return rep_of
+
+
+def reassign_reads(cons, reads, k=17):
+    """reassign_reads_to_best_cluster (src/asv_cluster.rs:1052-1098, SNPmer markers) + the (matches, mismatches) matrix of
+    compare_consensus_snpmers (:968-994): cons / reads = lists of k-mer lists -> (best cluster, mismatches, matches, matrix)"""
+    mask = _M64 ^ (3 << (k - 1))
+    maps = []
+    for c in cons:
+        m = {}
+        for km in c:
+            m[km & mask] = km
+        maps.append(m)
+    out, mat = [], []
+    for rd in reads:
+        best, score, row = None, (1 << 64, 0), []
+        for ci, m in enumerate(maps):
+            ma = mm = 0
+            for km in rd:
+                ck = m.get(km & mask)
+                if ck is not None:
+                    if ck == km:
+                        ma += 1
+                    else:
+                        mm += 1
+            row.append((ma, mm))
+            if mm < score[0] or (mm == score[0] and ma > score[1]):
+                score, best = (mm, ma), ci
+        out.append((best, score[0], score[1])); mat.append(row)
+    return out, mat

@@ -802,3 +802,48 @@ def test_count_split_kmers_sharded_ranks_on_one_gpu(world):
     finally:
         for c in ctxs:
             c.close()
+
+
+SNPCMP_KEYS = ["best_cons", "best_mismatches", "best_matches"]
+
+
+@pytest.mark.parametrize("seed,k", [(1, 17), (2, 17), (3, 15), (4, 21)])
+def test_snpmer_compare_small_cases(ctx, seed, k):
+    """Stage 3 reclustering: reads and consensus lists against cluster consensus SNPmers (empty reads / lists, unknown sites,
+    duplicated splitmers, identical lists)"""
+    from savont_b200 import _lib
+    from tests.util import csr_u64, reassign_case
+    gp, _ = _params(_lib, k=k, c=k - 6)
+    ctx.set_params(gp)
+    cons, reads = reassign_case(90 + seed, k=k)
+    ck, co = csr_u64(cons); rk, ro = csr_u64(reads)
+    want = O.snpmer_compare(ck, co, rk, ro, k=k, want_matrix=True)
+    got = ctx.snpmer_compare(ck, co, rk, ro, want_matrix=True)
+    assert_same(got, want, SNPCMP_KEYS + ["matrix"], f"snpmer compare k={k}")
+    assert_same(ctx.snpmer_compare(ck, co, rk, ro), want, SNPCMP_KEYS, "without matrix")
+    # consensus lists against each other, no clusters, no reads
+    assert_same(ctx.snpmer_compare(ck, co, ck, co, want_matrix=True), O.snpmer_compare(ck, co, ck, co, k=k, want_matrix=True),
+                SNPCMP_KEYS + ["matrix"], "consensus vs consensus")
+    e = ctx.snpmer_compare(np.zeros(0, np.uint64), [0], rk, ro)
+    assert np.all(e["best_cons"] == 0xffffffff)
+    assert len(ctx.snpmer_compare(ck, co, np.zeros(0, np.uint64), [0])["best_cons"]) == 0
+
+
+def test_snpmer_compare_16s_clusters(ctx):
+    """500 'clusters' (the ASVs' SNPmers as consensus lists) against the SNPmers of 20 k ONT reads"""
+    from savont_b200 import _lib, synth
+    w = synth.Workload("ont16s")
+    gp, _ = _params(_lib)
+    ctx.set_params(gp); ctx.load_snpmers(w.snpmers)
+    sa = ctx.sketch(w.asv_bases, None, w.asv_offsets, want_codes=False)
+    r = w.reads(20000)
+    sr = ctx.sketch(r["bases"], r["quals"], r["offsets"], want_codes=False)
+    ck, co = np.asarray(sa["snp_kmer"], np.uint64), np.asarray(sa["snp_offsets"], np.uint64)
+    rk, ro = np.asarray(sr["snp_kmer"], np.uint64), np.asarray(sr["snp_offsets"], np.uint64)
+    want = O.snpmer_compare(ck, co, rk[:int(ro[3000])], ro[:3001], want_matrix=True)
+    got = ctx.snpmer_compare(ck, co, rk, ro)
+    assert_same({k_: got[k_][:3000] for k_ in SNPCMP_KEYS}, want, SNPCMP_KEYS, "16S clusters")
+    gm = ctx.snpmer_compare(ck, co, rk[:int(ro[3000])], ro[:3001], want_matrix=True)
+    assert_same(gm, want, SNPCMP_KEYS + ["matrix"], "16S clusters, matrix")
+    # most reads are reassigned to an ASV of their own genus with several matching SNPmers
+    assert float((got["best_matches"] > 2).mean()) > 0.8

@@ -413,3 +413,18 @@ def test_lsh_and_kmer_clustering_match_python_restatement(seed, err):
     assert [int(x) for x in rep] == want
     n_rep = sum(1 for i, r in enumerate(want) if r == i)
     assert 6 <= n_rep < len(want) and any(len(m) != len(set(m)) for m in minis) and any(len(m) < 3 for m in minis)
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_snpmer_compare_matches_python_restatement(seed):
+    from tests.util import csr_u64, reassign_case
+    cons, reads = reassign_case(70 + seed)
+    ck, co = csr_u64(cons); rk, ro = csr_u64(reads)
+    got = O.snpmer_compare(ck, co, rk, ro, want_matrix=True)
+    want, mat = pyref.reassign_reads(cons, reads)
+    assert [(int(a), int(b), int(c_)) for a, b, c_ in zip(got["best_cons"], got["best_mismatches"], got["best_matches"])] == want
+    assert got["matrix"].tolist() == [[list(x) for x in row] for row in mat]
+    assert len(set(int(x) for x in got["best_cons"])) > 5 and int(got["best_mismatches"].max()) == 0 and int(got["matrix"][:, :, 1].max()) > 0
+    # consensus lists against each other (compare_consensus_snpmers): the diagonal has no mismatches
+    cc = O.snpmer_compare(ck, co, ck, co, want_matrix=True)["matrix"]
+    assert all(int(cc[i, i, 1]) == 0 or i == 5 for i in range(len(cons)))

@@ -132,3 +132,46 @@ def clustering_case(seed, n_species=6, n_reads=300, length=700, err=0.02, k=17, 
     b, o = O.concat(reads)
     sk = O.sketch_batch(O.default_params(k=k, c=c), [], b, None, o)
     return np.asarray(sk["mini_kmer"], np.uint64), np.asarray(sk["mini_offsets"], np.uint64), reads
+
+
+def reassign_case(seed, n_cons=12, n_sites=60, n_reads=150, k=17):
+    """cluster consensus SNPmer lists over a shared set of SNP sites (splitmers) and reads carrying subsets of the sites with a
+    few allele flips; some sites unknown to every consensus, empty reads / consensus lists, duplicated splitmers in a list"""
+    rng = random.Random(seed)
+    mask = ((1 << 64) - 1) ^ (3 << (k - 1))
+    sites = []
+    while len(sites) < n_sites:
+        s = rng.getrandbits(2 * k) & mask
+        if s not in sites:
+            sites.append(s)
+    def km(site, allele):
+        return site | (allele << (k - 1))
+    cons_alleles = [[rng.randrange(4) if rng.random() < 0.8 else None for _ in sites] for _ in range(n_cons)]
+    cons = [[km(s, a) for s, a in zip(sites, al) if a is not None] for al in cons_alleles]
+    cons[3] = []                                                   # a cluster without consensus SNPmers
+    cons[5] = cons[5] + [km(sites[0], 1), km(sites[0], 2)]         # duplicated splitmer: the last entry wins (HashMap::insert)
+    cons[7] = list(cons[6])                                        # identical lists: the lower index wins ties
+    reads = []
+    for r in range(n_reads):
+        src = cons_alleles[rng.randrange(n_cons)]
+        rd = []
+        for s, a in zip(sites, src):
+            if rng.random() < 0.5:
+                al = a if a is not None else rng.randrange(4)
+                if rng.random() < 0.05:
+                    al = (al + 1) & 3
+                rd.append(km(s, al))
+        if r % 17 == 3:
+            rd = []
+        if r % 19 == 4:
+            rd = [rng.getrandbits(2 * k) for _ in range(8)]        # sites nobody knows
+        rng.shuffle(rd)
+        reads.append(rd)
+    return cons, reads
+
+
+def csr_u64(lists):
+    off = np.zeros(len(lists) + 1, np.uint64)
+    off[1:] = np.cumsum([len(x) for x in lists])
+    flat = np.array([v for x in lists for v in x], np.uint64)
+    return flat, off
