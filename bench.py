@@ -492,6 +492,84 @@ def run_cluster(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
 
 
+def run_reassign(args, rank, world, local_rank):
+    """--path reassign: the read-vs-consensus SNPmer comparison of Stage 3 reclustering (asv_cluster::reassign_reads_to_best_cluster)
+    through savont_b200_snpmer_compare.  Not the headline path; one JSON line with the same keys.  Host buffers in, so end to end."""
+    import torch
+    from savont_b200 import _lib
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the b200 arm has no CPU fallback")
+    if world > 1:
+        if rank == 0:
+            print(json.dumps({"metric": "reads reassigned/sec (Stage 3 reclustering)", "unavailable": "reads are independent: shard them, one process per GPU"}))
+        return
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    w = _workload(args)
+    ctx = _lib.Context(local_rank, _lib.default_params(band=w.band))
+    stream = torch.cuda.current_stream(dev)
+    ctx.set_stream(stream.cuda_stream)
+    ctx.load_snpmers(w.snpmers)
+    n_reads = args.reads
+    r = w.reads(n_reads)
+    sa = ctx.sketch(w.asv_bases, None, w.asv_offsets, want_codes=False)          # the clusters' consensus SNPmers: those of the ASVs
+    ck, co = np.asarray(sa["snp_kmer"], np.uint64), np.asarray(sa["snp_offsets"], np.uint64)
+    kms, offs = [], [np.zeros(1, np.uint64)]
+    for b0 in range(0, n_reads, 200_000):
+        b1 = min(n_reads, b0 + 200_000)
+        sk = ctx.sketch(r["bases"], r["quals"], r["offsets"][b0:b1 + 1], want_codes=False)
+        kms.append(np.asarray(sk["snp_kmer"], np.uint64)); offs.append(np.asarray(sk["snp_offsets"][1:], np.uint64) + offs[-1][-1])
+    rk = _lib.pinned_array(8 * max(1, sum(len(x) for x in kms))).view(np.uint64)[:sum(len(x) for x in kms)]; rk[:] = np.concatenate(kms)
+    ro = np.concatenate(offs)
+    del kms, offs, r
+    sampler = ClockSampler(local_rank); sampler.start()
+    for _ in range(args.warmup):
+        out = ctx.snpmer_compare(ck, co, rk, ro)
+    torch.cuda.synchronize(dev)
+    ms, stats = [], []
+    for _ in range(args.steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        out = ctx.snpmer_compare(ck, co, rk, ro)
+        e1.record(stream); torch.cuda.synchronize(dev)
+        ms.append(e0.elapsed_time(e1)); stats.append(out["stats"])
+    clocks = sampler.stop()
+    peaks = _peaks()
+    st = stats[-1]
+    kern = float(np.mean([s_["filter_ms"] for s_ in stats]))
+    val = n_reads * args.steps / (sum(ms) / 1e3)
+    # algorithmic bytes of the kernel: the markers (8 B) + per read the three result words; the index is L2 resident
+    alg = 8 * len(rk) + 12 * n_reads
+    line = {
+        "metric": "reads reassigned/sec (Stage 3 reclustering, read-vs-consensus SNPmer comparison)", "value": val, "unit": "reads/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sum(ms) / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64 k-mers / u16 counts", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {w.cfg['desc']}: SNPmers of the reads ({len(rk)}) against {len(co) - 1} cluster consensus lists "
+                               f"({len(ck)} consensus SNPmers)", "l2": "every step re-uploads the markers from host memory"},
+        "stage_ms": {"index+upload": float(np.mean([s_["h2d_ms"] for s_ in stats])), "compare_kernel": kern, "host": sum(ms) / args.steps - float(np.mean([s_["total_ms"] for s_ in stats]))},
+        "pair_comparisons_per_step": int(st["n_pairs"]),
+        "roofline": {"bound": "hbm", "kernel": "snpmer_compare_kernel", "achieved": alg / (kern / 1e3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "peak_source": peaks["source"], "frac": alg / (kern / 1e3) / 1e9 / peaks["hbm_gbs"], "traffic": None, "algorithmic_bytes": alg,
+                     "note": "bound by shared-memory work, not HBM: per read a dense row of one word per cluster is cleared, updated by atomics "
+                             "and reduced"},
+        "e2e": {"value": val, "unit": "reads/s", "h2d_bytes_per_step": int(st["h2d_bytes"]), "d2h_bytes_per_step": int(st["d2h_bytes"]),
+                "ms_per_step": sum(ms) / args.steps},
+        "gpu_launches": int(sum(s_["kernel_launches"] for s_ in stats)), "clocks": clocks,
+    }
+    if not args.no_cpu_baseline:
+        from oracle import oracle as O
+        cores = os.cpu_count() or 1
+        ns = min(args.cpu_reads // 5, n_reads)
+        t0 = time.perf_counter()
+        want = O.snpmer_compare(ck, co, rk[:int(ro[ns])], ro[:ns + 1])
+        dt = time.perf_counter() - t0
+        same = all(np.array_equal(want[k_], out[k_][:ns]) for k_ in ("best_cons", "best_mismatches", "best_matches"))
+        line["cpu_baseline"] = {"value": ns / dt, "unit": "reads/s", "cores": cores, "kind": "port",
+                                "sample": f"first {ns} reads, OpenMP over reads, one hash map per cluster probed with every marker like the reference "
+                                          "(oracle/savont_oracle.c)", "gpu_matches_oracle_on_sample": bool(same)}
+    print(json.dumps(line), flush=True)
+
+
 def _bind_to_gpu_numa_node(gpu_index):
     """pin this rank (and therefore the pinned host buffers it first-touches) to the CPU cores next to its GPU, so that
     eight ranks do not pull their H2D traffic across the socket interconnect"""
@@ -737,7 +815,7 @@ def main():
     ap.add_argument("--cpu-reads", type=int, default=100_000, help="sample size of the CPU baseline / reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-twin", action="store_true", help="skip the TwinRead-input e2e arm")
-    ap.add_argument("--path", default="assign", choices=["assign", "kmercount", "pileup", "cluster"],
+    ap.add_argument("--path", default="assign", choices=["assign", "kmercount", "pileup", "cluster", "reassign"],
                     help="assign: the headline read-vs-ASV path; kmercount: Stage 1 split-k-mer counting (K5)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -755,6 +833,8 @@ def main():
         run_pileup(args, rank, world, local_rank)
     elif args.path == "cluster":
         run_cluster(args, rank, world, local_rank)
+    elif args.path == "reassign":
+        run_reassign(args, rank, world, local_rank)
     else:
         run_b200(args, rank, world, local_rank)
         try:
