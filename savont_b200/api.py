@@ -281,3 +281,71 @@ def write_consensus_fasta(consensuses, output_path, prefix):
 
 def write_feature_table(consensuses, path, sample_names):
     _write(consensuses, None, "final", path, sample_names)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Stage 2 / 3 / 4 neighbours of the path: host halves of the reference functions
+# ---------------------------------------------------------------------------------------------------------
+def clusters_from_assignment(rep_of, min_cluster_size: int = 1):
+    """the tail of cluster_reads_by_kmers (src/asv_cluster.rs:192-210): group by representative, order by size descending,
+    members ascending, drop clusters below min_cluster_size.  Equal sizes: the reference orders by `a.first()` of a member list
+    filled in std::HashMap iteration order (random per process); here by the smallest member (= the representative)."""
+    rep_of = np.asarray(rep_of, np.int64)
+    order = np.argsort(rep_of, kind="stable")
+    reps, start = np.unique(rep_of[order], return_index=True)
+    groups = np.split(order, start[1:]) if len(order) else []
+    clusters = [np.sort(g) for g in groups]
+    clusters.sort(key=lambda c: (-len(c), int(c[0])))
+    return [c for c in clusters if len(c) >= min_cluster_size]
+
+
+def cluster_reads_by_kmers(ctx: _lib.Context, minimizer_kmers, minimizer_offsets, min_cluster_size: int = 1, threshold: float = 0.95):
+    """asv_cluster::cluster_reads_by_kmers (src/asv_cluster.rs:72-249) on `TwinRead::minimizer_kmers()` in CSR"""
+    out = ctx.cluster_reads_by_kmers(minimizer_kmers, minimizer_offsets, threshold=threshold)
+    return clusters_from_assignment(out["rep_of"], min_cluster_size)
+
+
+def clusters_from_reassignment(clusters, best_cons, min_cluster_size: int = 1):
+    """the tail of reassign_reads_to_best_cluster (src/asv_cluster.rs:1040-1131): reads listed cluster by cluster (`clusters`),
+    best_cons[i] = new cluster of the i-th listed read -> (new clusters: members ascending, empty / small ones dropped,
+    number of reads that changed cluster)"""
+    flat = np.concatenate([np.asarray(c, np.int64) for c in clusters]) if clusters else np.zeros(0, np.int64)
+    old = np.concatenate([np.full(len(c), i, np.int64) for i, c in enumerate(clusters)]) if clusters else np.zeros(0, np.int64)
+    best = np.asarray(best_cons, np.int64)
+    new = [np.sort(flat[best == i]) for i in range(len(clusters))]
+    return [c for c in new if len(c) and len(c) >= min_cluster_size], int((best != old).sum())
+
+
+def reassign_reads_to_best_cluster(ctx: _lib.Context, clusters, cons_kmers, cons_offsets, snpmer_kmers, snpmer_offsets, min_cluster_size=1):
+    """asv_cluster::reassign_reads_to_best_cluster (src/asv_cluster.rs:1007-1131, SNPmer markers): `cons_*` = the ConsensusSnpmer
+    k-mers of the current clusters, `snpmer_*` = snpmers_vec() k-mers of ALL reads (CSR indexed by read id)"""
+    so = np.asarray(snpmer_offsets, np.uint64); sk = np.asarray(snpmer_kmers, np.uint64)
+    ids = np.concatenate([np.asarray(c, np.int64) for c in clusters]) if clusters else np.zeros(0, np.int64)
+    lens = (so[ids + 1] - so[ids]).astype(np.int64)
+    ro = np.zeros(len(ids) + 1, np.uint64); ro[1:] = np.cumsum(lens)
+    rk = np.concatenate([sk[int(so[i]):int(so[i + 1])] for i in ids]) if len(ids) else np.zeros(0, np.uint64)
+    out = ctx.snpmer_compare(cons_kmers, cons_offsets, rk, ro)
+    return clusters_from_reassignment(clusters, out["best_cons"], min_cluster_size)
+
+
+def pileups_from_columns(res, cons_offsets):
+    """savont_b200_consensus_pileups output -> the reference's Vec<Vec<Pileup>> shape: per consensus a list of columns
+    dict(ref_hp_length, bases=[("Base", base, qual, hp) | ("Deletion",) | ("Insertion", [(base, qual, hp), ..])]) (src/alignment.rs:17-60)"""
+    co = np.asarray(cons_offsets, np.int64) - int(cons_offsets[0])
+    po, ent, hp = res["pos_offsets"], res["entries"], res["ref_hp_length"]
+    out = []
+    for ci in range(len(co) - 1):
+        cols = []
+        for p in range(int(co[ci]), int(co[ci + 1])):
+            col = []
+            for e in ent[int(po[p]):int(po[p + 1])]:
+                kind = int(e["kind"])
+                if kind == 0:
+                    col.append(("Base", chr(e["base"][0]), int(e["qual"][0]), int(e["hp"][0])))
+                elif kind == 1:
+                    col.append(("Deletion",))
+                else:
+                    col.append(("Insertion", [(chr(e["base"][j]), int(e["qual"][j]), int(e["hp"][j])) for j in range(int(e["n"]))]))
+            cols.append(dict(ref_hp_length=int(hp[p]), bases=col))
+        out.append(cols)
+    return out

@@ -190,3 +190,39 @@ def test_python_mirrors_of_sketch_and_candidates():
     c = api.find_compatible_candidates(ctx, r["bases"], r["quals"], r["offsets"])
     assert len(c["status"]) == 50
     ctx.close()
+
+
+def test_cluster_lists_from_assignments():
+    """host halves of cluster_reads_by_kmers (:192-210) and reassign_reads_to_best_cluster (:1040-1131) on oracle outputs"""
+    from savont_b200 import api
+    from tests.util import clustering_case, csr_u64, reassign_case
+    km, off, _ = clustering_case(31, n_reads=200)
+    rep = O.cluster_reads_by_kmers(km, off)
+    cl = api.clusters_from_assignment(rep, 1)
+    assert sorted(int(x) for c in cl for x in c) == list(range(200))
+    assert all(len(a) >= len(b) for a, b in zip(cl, cl[1:]))
+    assert all(np.all(np.diff(c) > 0) and int(rep[c[0]]) == int(c[0]) and np.all(rep[c] == c[0]) for c in cl)
+    big = api.clusters_from_assignment(rep, 5)
+    assert big and all(len(c) >= 5 for c in big) and len(big) < len(cl)
+    # reassignment: reads listed cluster by cluster
+    cons, reads = reassign_case(5, n_cons=8, n_reads=60)
+    ck, co = csr_u64(cons); rk, ro = csr_u64(reads)
+    clusters = [np.arange(i * 10, (i + 1) * 10) for i in range(6)] + [np.zeros(0, np.int64)] * 2
+    best = O.snpmer_compare(ck, co, rk, ro)["best_cons"]
+    new, moved = api.clusters_from_reassignment(clusters, best, 1)
+    assert sorted(int(x) for c in new for x in c) == list(range(60)) and moved == int((best != np.repeat(np.arange(6), 10)).sum()) and moved > 0
+    assert all(np.all(best[c] == best[c[0]]) for c in new)
+
+
+def test_pileups_from_columns_shape():
+    from savont_b200 import api
+    from tests.util import pileup_case
+    cons, reads, quals, rcons = pileup_case(9, n_cons=4, reads_per=6)
+    cb, co = O.concat(cons); rb, ro = O.concat(reads); qb, _ = O.concat(quals)
+    res = O.consensus_pileups(cb, co, rb, qb, ro, rcons, band=16)
+    pl = api.pileups_from_columns(res, co)
+    assert [len(p) for p in pl] == [len(c) for c in cons]
+    assert sum(len(col["bases"]) for p in pl for col in p) == len(res["entries"])
+    kinds = {b[0] for p in pl for col in p for b in col["bases"]}
+    assert kinds == {"Base", "Deletion", "Insertion"}
+    assert all(1 <= len(b[1]) <= 2 for p in pl for col in p for b in col["bases"] if b[0] == "Insertion")
