@@ -14,7 +14,6 @@
 //      not among the pairs of step 2: its pairs are computed on demand.
 // The result is identical to the sequential loop; block sizes follow the rate of new representatives.
 #include <chrono>
-#include <map>
 
 #include "api_internal.cuh"
 
@@ -256,8 +255,8 @@ extern "C" int savont_b200_cluster_reads_by_kmers(savont_b200_ctx *h, const uint
 
         // ---- 3. the block in read order ----
         size_t n_new = 0;
-        std::vector<uint32_t> extra_reps;                                               // representatives outside p0
-        std::map<uint32_t, std::pair<std::vector<uint8_t>, std::vector<uint32_t>>> extra;   // rep id -> stats of the reads behind it
+        struct Extra { uint32_t id; std::vector<uint8_t> hits; std::vector<uint32_t> cnt; };   // a representative outside p0 and the
+        std::vector<Extra> extras;                                                              // stats of the reads behind it
         size_t p0_pos = 0;
         for (uint32_t li = 0; li < nbk; ++li) {
             const uint32_t i = (uint32_t)(b0 + li);
@@ -274,9 +273,9 @@ extern "C" int savont_b200_cluster_reads_by_kmers(savont_b200_ctx *h, const uint
                 const uint32_t j = p0[ph.pidx];
                 inblk.push_back(Cand{j, ph.hits, ph.cnt, std::max(nd[i], tot_of(j))}); newmax = std::max(newmax, ph.hits);
             }
-            for (const uint32_t xr : extra_reps) {                                      // the rare other ones
-                const auto &ex = extra[xr]; const size_t at = i - xr - 1;
-                if (ex.first[at]) { inblk.push_back(Cand{xr, ex.first[at], ex.second[at], std::max(nd[i], tot_of(xr))}); newmax = std::max<uint32_t>(newmax, ex.first[at]); }
+            for (const Extra &ex : extras) {                                            // the rare other ones
+                const size_t at = i - ex.id - 1;
+                if (ex.hits[at]) { inblk.push_back(Cand{ex.id, ex.hits[at], ex.cnt[at], std::max(nd[i], tot_of(ex.id))}); newmax = std::max<uint32_t>(newmax, ex.hits[at]); }
             }
             bool have = false; Cand best{0, 0, 0, 1};
             if (inblk.empty()) {
@@ -317,19 +316,19 @@ extern "C" int savont_b200_cluster_reads_by_kmers(savont_b200_ctx *h, const uint
                     const uint32_t m = nbk - li - 1;
                     std::vector<uint32_t> xi(m), xj(m, i);
                     for (uint32_t x = 0; x < m; ++x) xi[x] = i + 1 + x;
-                    auto &ex = extra[i];
-                    ex.first.resize(m); ex.second.resize(m);
+                    extras.push_back(Extra{i, std::vector<uint8_t>(m), std::vector<uint32_t>(m)});
+                    Extra &ex = extras.back();
                     TRY(up(d.pi, xi.data(), m, st)); TRY(up(d.pj, xj.data(), m, st));
                     TRY(d.ph.ensure(m + 16)); TRY(d.pc.ensure((size_t)m * 4 + 16));
                     launch_pair_stats(q, d.pi.as<uint32_t>(), d.pj.as<uint32_t>(), m, d.ph.as<uint8_t>(), d.pc.as<uint32_t>(), st);
-                    CK(cudaMemcpyAsync(ex.first.data(), d.ph.p, m, cudaMemcpyDeviceToHost, st));
-                    CK(cudaMemcpyAsync(ex.second.data(), d.pc.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+                    CK(cudaMemcpyAsync(ex.hits.data(), d.ph.p, m, cudaMemcpyDeviceToHost, st));
+                    CK(cudaMemcpyAsync(ex.cnt.data(), d.pc.p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
                     CK(cudaStreamSynchronize(st));
                     CK(cudaGetLastError());
                     c->last_stats.kernel_launches += 1; c->last_stats.n_pairs += m;
                     lap(5);
                 }
-                if (my_pidx >= 0) p0_rep[my_pidx] = 1; else extra_reps.push_back(i);
+                if (my_pidx >= 0) p0_rep[my_pidx] = 1;
                 ++n_new;
             }
         }
