@@ -1162,8 +1162,9 @@ int savont_b200_align_pairs(savont_b200_ctx *h, const uint8_t *bases, const uint
 // synchronisations -- and left out)
 static size_t ramp_batch(const Context *c, size_t bi, size_t /*remaining*/) {
     const size_t full = c->batch_reads;
-    if (bi >= 3 || full < 8 * 4096) return full;
-    return full >> (3 - bi);
+    static const int steps = [] { const char *e = getenv("SAVONT_B200_RAMP"); return e ? std::max(0, std::min(5, atoi(e))) : 3; }();   // tuning
+    if (bi >= (size_t)steps || full < 8 * 4096) return full;
+    return full >> (steps - bi);
 }
 using UploadFn = std::function<int(Batch &, size_t, size_t, uint64_t *, cudaStream_t)>;
 static int map_batches(Context *c, const std::vector<size_t> &cuts, const UploadFn &upload_batch, int n_samples, uint8_t *status,
