@@ -186,7 +186,8 @@ def count_split_kmers_sharded(ctx, peers: KmerShardPeers | None = None, single_s
     grow its buffer, i.e. on the first call), a barrier after the scatter and one after the count."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
-    dev = torch.device("cuda", ctx.device)
+    # NCCL moves device tensors; the CPU-only tests drive the same code over gloo with a stub context
+    dev = torch.device("cuda", ctx.device) if dist.is_initialized() and dist.get_backend(group) == "nccl" else torch.device("cpu")
     hist = ctx.kmer_shard_hist()
     P = len(hist)
     if world == 1:
@@ -201,9 +202,9 @@ def count_split_kmers_sharded(ctx, peers: KmerShardPeers | None = None, single_s
         payload[:P] = hist; payload[P] = own_cap
         payload[P + 1:] = np.frombuffer(ctx.ipc_export(own_ptr), np.int64)
         t = torch.from_numpy(payload).to(dev)
-        g = torch.empty((world, P + 9), dtype=torch.int64, device=dev)
+        g = torch.empty(world * (P + 9), dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(g, t, group=group)
-        return g.cpu().numpy()
+        return g.cpu().numpy().reshape(world, P + 9)
     own_ptr, own_cap = ctx.kmer_shard_alloc(0, with_capacity=True)          # the buffer of the previous call, if any
     G = exchange(own_ptr, own_cap)
     owner, part_off, dst_off = kmer_shard_layout(G[:, :P].astype(np.uint64))

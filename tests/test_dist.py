@@ -106,3 +106,87 @@ def test_kmer_shard_layout_is_a_partition_of_the_owner_buffers():
                     assert int(part_off[o, p]) <= a and b <= int(part_off[o, p + 1])
                     filled[a:b] += 1
             assert np.all(filled == 1)
+
+
+class StubShardCtx:
+    """stands in for the CUDA context in count_split_kmers_sharded: 'device buffers' are ids in a table shared through the
+    handles, the scatter / count phases only record what they were given"""
+    P = 64
+
+    def __init__(self, rank, hists):
+        self.rank, self.hists, self.step, self.cap, self.gen, self.device = rank, hists, 0, 0, 0, 0
+        self.log = []
+
+    def kmer_shard_hist(self):
+        return self.hists[self.step].astype(np.uint32)
+
+    def kmer_shard_alloc(self, n, with_capacity=False):
+        if n > self.cap:
+            self.cap = int(n); self.gen += 1
+            self.log.append(("alloc", self.step, int(n)))
+        ptr = 1000 * (self.rank + 1) + self.gen
+        return (ptr, self.cap) if with_capacity else ptr
+
+    def ipc_export(self, ptr):
+        return int(ptr).to_bytes(8, "little") * 8
+
+    def ipc_open(self, handle):
+        self.log.append(("open", self.step, int.from_bytes(handle[:8], "little")))
+        return int.from_bytes(handle[:8], "little")
+
+    def ipc_close(self, ptr):
+        self.log.append(("close", self.step, int(ptr)))
+
+    def kmer_shard_scatter(self, ptrs, dst_off):
+        self.log.append(("scatter", self.step, [int(x) for x in ptrs], np.asarray(dst_off).tolist()))
+
+    def kmer_shard_count(self, part_off, single_strand=False, cap=0, sort=False, fetch=True):
+        self.log.append(("count", self.step, np.asarray(part_off).tolist()))
+        self.step += 1
+        return dict(n=0)
+
+
+def _shard_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from savont_b200 import dist as sd
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(100 + rank)
+    hists = [rng.integers(0, 20, StubShardCtx.P), rng.integers(0, 20, StubShardCtx.P), rng.integers(50, 90, StubShardCtx.P)]   # step 2 grows
+    ctx = StubShardCtx(rank, hists)
+    peers = sd.KmerShardPeers(ctx)
+    for _ in range(3):
+        sd.count_split_kmers_sharded(ctx, peers, fetch=False)
+    peers.close()
+    q.put(dict(rank=rank, hists=[h.tolist() for h in hists], log=ctx.log))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_kmer_counting_driver_two_ranks_gloo():
+    """count_split_kmers_sharded over gloo with stub contexts: every rank derives the same layout from the all-gathered histograms,
+    peers are re-mapped only when a buffer grew, and a mapping is closed before its owner re-allocates"""
+    from savont_b200 import dist as sd
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_shard_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs: p.start()
+    outs = sorted([q.get(timeout=240) for _ in range(world)], key=lambda d: d["rank"])
+    for p in procs: p.join(timeout=60)
+    for step in range(3):
+        H = np.array([outs[r]["hists"][step] for r in range(world)], np.uint64)
+        owner, part_off, dst_off = sd.kmer_shard_layout(H)
+        for r in range(world):
+            sc = [e for e in outs[r]["log"] if e[0] == "scatter" and e[1] == step][0]
+            ct = [e for e in outs[r]["log"] if e[0] == "count" and e[1] == step][0]
+            assert sc[3] == dst_off[r].tolist() and ct[2] == part_off[r].tolist()
+            peer = 1 - r
+            assert sc[2][r] // 1000 == r + 1 and sc[2][peer] // 1000 == peer + 1      # own buffer, the peer's mapped buffer
+    for r in range(world):
+        log = outs[r]["log"]
+        opens = [e for e in log if e[0] == "open"]; closes = [e for e in log if e[0] == "close"]; allocs = [e for e in log if e[0] == "alloc"]
+        assert [e[1] for e in opens] == [0, 2] and [e[1] for e in allocs] == [0, 2]     # mapped at the first call and after the growth only
+        assert len(closes) == 2 and closes[0][1] == 2                                    # old mapping closed in step 2 (before the re-allocation) ...
+        assert log.index(closes[0]) < log.index(allocs[1]) and closes[0][2] == opens[0][2]
+        assert closes[1][2] == opens[1][2]                                               # ... and the new one by peers.close()
