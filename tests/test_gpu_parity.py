@@ -847,3 +847,21 @@ def test_snpmer_compare_16s_clusters(ctx):
     assert_same(gm, want, SNPCMP_KEYS + ["matrix"], "16S clusters, matrix")
     # most reads are reassigned to an ASV of their own genus with several matching SNPmers
     assert float((got["best_matches"] > 2).mean()) > 0.8
+
+
+def test_count_split_kmers_sharded_processes_on_one_gpu():
+    """the real multi-process driver (savont_b200/dist.py: one process per rank, cudaIpc-mapped peer buffers, buffer growth between
+    calls) with both ranks on this GPU and gloo collectives; tools/shard_check.py compares the union of the shards with the
+    single-GPU count and exits non-zero on a mismatch"""
+    import os
+    import socket
+    import subprocess
+    import sys
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SHARD_CHECK_BACKEND="gloo")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), os.path.join(root, "tools", "shard_check.py"), "8000"],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "world=2" in r.stdout and " OK" in r.stdout

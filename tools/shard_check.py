@@ -1,5 +1,6 @@
 """torchrun --nproc-per-node N tools/shard_check.py [n_reads]: the sharded Stage 1 k-mer counting on N GPUs (cudaIpc peer buffers,
-one process per GPU) against the single-GPU count of the same reads (rank 0)."""
+one process per GPU) against the single-GPU count of the same reads (rank 0).  SHARD_CHECK_BACKEND=gloo runs the N processes on
+GPU 0 with gloo collectives (a one-GPU box is enough)."""
 import os
 import sys
 
@@ -15,8 +16,13 @@ from savont_b200 import _lib, dist as sd, synth  # noqa: E402
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 40000
     rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(lr)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    if os.environ.get("SHARD_CHECK_BACKEND") == "gloo":     # all ranks on GPU 0 (cudaIpc between processes on one device), gloo collectives
+        lr = 0
+        torch.cuda.set_device(0)
+        dist.init_process_group("gloo")
+    else:
+        torch.cuda.set_device(lr)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
     w = synth.Workload("ont16s", n_roots=5)
     r = w.reads(n)
     lo, hi = sd.shard_bounds(n, world, rank)
