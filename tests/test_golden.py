@@ -123,3 +123,39 @@ def test_gpu_reproduces_stage1_golden(g1):
     assert np.array_equal(sel["est_id"].view(np.uint64), g1["flt_est_id"].view(np.uint64))
     assert np.array_equal(sel["n_solid_mini"], g1["flt_solid_mini"]) and np.array_equal(sel["n_solid_snp"], g1["flt_solid_snp"])
     ctx.close()
+
+
+# ---- the neighbouring stages on the same reads (tests/golden/zymo_stages.npz, made by tests/golden/make_golden_stages.py) ----
+GS = os.path.join(os.path.dirname(__file__), "golden", "zymo_stages.npz")
+STAGE_KEYS = ("lsh_digest", "rep_of", "best_cons", "best_mismatches", "best_matches", "pile_digest", "pile_read_nm", "pile_n_entries")
+
+
+def _stages_module():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_stages", os.path.join(os.path.dirname(__file__), "golden", "make_golden_stages.py"))
+    m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    return m
+
+
+def test_oracle_reproduces_golden_stages(g):
+    gs = np.load(GS)
+    m = _stages_module()
+    out = m.outputs(g, O.lsh_signatures, O.cluster_reads_by_kmers, O.snpmer_compare,
+                    lambda cb, co, rb, rq, ro, rc: O.consensus_pileups(cb, co, rb, rq, ro, rc, band=64, use_hpc=True))
+    for key in STAGE_KEYS:
+        assert np.array_equal(out[key], gs[key]), key
+    rep = gs["rep_of"]
+    assert 10 < int((rep == np.arange(len(rep))).sum()) < 100 and int(gs["pile_n_entries"]) > 200000
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_golden_stages(g):
+    from savont_b200 import _lib
+    gs = np.load(GS)
+    m = _stages_module()
+    ctx = _lib.Context(0, _lib.default_params(band=64))
+    out = m.outputs(g, ctx.lsh_signatures, lambda km, off: ctx.cluster_reads_by_kmers(km, off)["rep_of"], ctx.snpmer_compare,
+                    lambda cb, co, rb, rq, ro, rc: ctx.consensus_pileups(cb, co, rb, rq, ro, rc, use_hpc=True))
+    for key in STAGE_KEYS:
+        assert np.array_equal(out[key], gs[key]), key
+    ctx.close()
