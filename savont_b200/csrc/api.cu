@@ -740,7 +740,8 @@ namespace sb {
 // only the ops cross PCIe.  cigar_offsets[0] must be set by the caller (base of this call's ops in `cigar`).
 int traceback_pairs(Context *c, Batch &b, const AsvIndex &ix, uint32_t max_ref_len, const uint32_t *d_pr, const uint32_t *d_pa,
                     const uint8_t *d_ps, size_t n_pairs, int32_t *nm, int32_t *asv_end, int32_t *read_end, int32_t *asv_start,
-                    int32_t *read_start, uint64_t *cigar_offsets, uint32_t *cigar, size_t cigar_cap, std::vector<uint32_t> *cigar_vec) {
+                    int32_t *read_start, uint64_t *cigar_offsets, uint32_t *cigar, size_t cigar_cap, std::vector<uint32_t> *cigar_vec,
+                    TbDevice *dev) {
     const uint32_t hist_cols = std::max<uint32_t>(b.max_len, 1u);
     const uint32_t cigar_stride = b.max_len + max_ref_len + 2;
     const size_t per_pair_words = align_tb_hist_words(1, hist_cols, c->dp);
@@ -778,9 +779,12 @@ int traceback_pairs(Context *c, Batch &b, const AsvIndex &ix, uint32_t max_ref_l
         e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) { rc = fail(SAVONT_B200_ERR_CUDA, "align_tb: %s", cudaGetErrorString(e)); break; }
         const uint32_t total = h_off[np];
-        if (cigar_vec) { cigar_vec->resize(cig_base + total + 1); cigar = cigar_vec->data(); }   // growable destination
+        const bool keep_on_device = dev && p0 == 0 && np == n_pairs;       // the caller consumes the ops on the device
+        if (dev) *dev = keep_on_device ? TbDevice{true, d_ops.as<uint32_t>(), d_off.as<uint32_t>(), d_out.as<int32_t>(), np} : TbDevice{};
+        if (keep_on_device) { /* no copy of the ops */ }
+        else if (cigar_vec) { cigar_vec->resize(cig_base + total + 1); cigar = cigar_vec->data(); }   // growable destination
         else if (cig_base + total > cigar_cap) { rc = fail(SAVONT_B200_ERR_CAPACITY, "cigar capacity %zu too small", cigar_cap); break; }
-        if (total) cudaMemcpyAsync(cigar + cig_base, d_ops.p, (size_t)total * 4, cudaMemcpyDeviceToHost, c->stream);
+        if (total && !keep_on_device) cudaMemcpyAsync(cigar + cig_base, d_ops.p, (size_t)total * 4, cudaMemcpyDeviceToHost, c->stream);
         memcpy(nm + p0, h_out.data(), (size_t)np * 4);
         memcpy(asv_end + p0, h_out.data() + np, (size_t)np * 4);
         memcpy(read_end + p0, h_out.data() + 2 * (size_t)np, (size_t)np * 4);

@@ -181,10 +181,13 @@ int batch_upload(Context *c, Batch &b, const uint8_t *bases, const uint8_t *qual
                  size_t n, uint64_t *h2d_bytes, cudaStream_t st = nullptr);
 void build_dp_planes(const DeviceParams &dp, const uint8_t *bases, const uint64_t *offsets, size_t A, std::vector<uint2> &planes,
                      std::vector<uint32_t> &plane_off, std::vector<uint32_t> &lens, uint32_t *max_len);
+// device-resident result of a traceback that fitted one sub-batch (valid): compacted ops + offsets, and the five int32 arrays
+// nm | asv_end | read_end | asv_start | read_start of n pairs each; they live in Context::tb_ws until the next traceback
+struct TbDevice { bool valid = false; const uint32_t *ops = nullptr; const uint32_t *off = nullptr; const int32_t *out = nullptr; uint32_t n = 0; };
 int traceback_pairs(Context *c, Batch &b, const AsvIndex &ix, uint32_t max_ref_len, const uint32_t *d_pr, const uint32_t *d_pa,
                     const uint8_t *d_ps, size_t n_pairs, int32_t *nm, int32_t *asv_end, int32_t *read_end, int32_t *asv_start,
                     int32_t *read_start, uint64_t *cigar_offsets, uint32_t *cigar, size_t cigar_cap,
-                    std::vector<uint32_t> *cigar_vec = nullptr);
+                    std::vector<uint32_t> *cigar_vec = nullptr, TbDevice *dev = nullptr);
 SeqBatch seq_view(const Batch &b);
 
 }  // namespace sb

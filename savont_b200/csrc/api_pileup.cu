@@ -120,9 +120,11 @@ int pileup_chunk(Context *c, PileupScratch &s, size_t chunk, int use_hpc, const 
     std::vector<int32_t> v((size_t)n_aln * 5);
     std::vector<uint64_t> coff((size_t)n_aln + 1, 0);
     std::vector<uint32_t> cigar;
+    TbDevice tb;                                      // one sub-batch (the usual case): the ops never leave the device
+    const bool host_cigar = getenv("SAVONT_B200_PILEUP_HOST_CIGAR") != nullptr;   // tests: the path of a traceback in several sub-batches
     TRY(traceback_pairs(c, hb, ix, max_clen, s.pr.as<uint32_t>(), s.pa.as<uint32_t>(), s.ps.as<uint8_t>(), n_aln, v.data(),
                         v.data() + n_aln, v.data() + 2 * (size_t)n_aln, v.data() + 3 * (size_t)n_aln, v.data() + 4 * (size_t)n_aln,
-                        coff.data(), nullptr, 0, &cigar));
+                        coff.data(), nullptr, 0, &cigar, host_cigar ? nullptr : &tb));
     if (coff[n_aln] >= (1ull << 32)) return fail(SAVONT_B200_ERR_OVERFLOW, "CIGAR ops of one chunk exceed 4 Gi");
     CK(cudaEventRecord(ev[3], st));
     for (uint32_t t = 0; t < n_aln; ++t) { read_strand[r0 + pr2[2 * t]] = strand[t]; read_nm[r0 + pr2[2 * t]] = v[t]; }
@@ -139,12 +141,12 @@ int pileup_chunk(Context *c, PileupScratch &s, size_t chunk, int use_hpc, const 
         for (uint64_t p = crel[i]; p < crel[i + 1]; ++p) pos_cons[p] = (uint32_t)i;
     }
     cons_pos_off[nc] = (uint32_t)crel[nc];
-    cigar.resize(coff[n_aln]);
-    TRY(up(s.cig_off, cig_off32, st)); TRY(up(s.cig, cigar, st)); TRY(up(s.row_off, row_off, st));
+    if (!tb.valid) { cigar.resize(coff[n_aln]); TRY(up(s.cig_off, cig_off32, st)); TRY(up(s.cig, cigar, st)); }
+    TRY(up(s.row_off, row_off, st));
     TRY(up(s.cons_pos_off, cons_pos_off, st)); TRY(up(s.cons_aln_off, cons_aln_off, st)); TRY(up(s.pos_cons, pos_cons, st));
     std::vector<int32_t> cs(v.begin() + 3 * (size_t)n_aln, v.begin() + 4 * (size_t)n_aln), rs(v.begin() + 4 * (size_t)n_aln, v.end()),
         re(v.begin() + 2 * (size_t)n_aln, v.begin() + 3 * (size_t)n_aln);
-    TRY(up(s.cstart, cs, st)); TRY(up(s.rstart, rs, st)); TRY(up(s.rend, re, st));
+    if (!tb.valid) { TRY(up(s.cstart, cs, st)); TRY(up(s.rstart, rs, st)); TRY(up(s.rend, re, st)); }
     TRY(s.cnt.ensure(rows + 16)); TRY(s.excl.ensure(rows * 2 + 16));
     TRY(s.col_total.ensure((n_pos + 1) * 4)); TRY(s.pos_off.ensure((n_pos + 2) * 4)); TRY(s.scan_tmp.ensure((n_pos / 2048 + 4) * 4));
     TRY(s.ref_hp.ensure(n_pos + 16));
@@ -153,6 +155,10 @@ int pileup_chunk(Context *c, PileupScratch &s, size_t chunk, int use_hpc, const 
     a.n_aln = n_aln; a.aln_read = s.pr.as<uint32_t>(); a.aln_cons = s.pa.as<uint32_t>(); a.strand = s.ps.as<uint8_t>();
     a.cons_start = s.cstart.as<int32_t>(); a.read_start = s.rstart.as<int32_t>(); a.read_end = s.rend.as<int32_t>();
     a.cigar_off = s.cig_off.as<uint32_t>(); a.cigar = s.cig.as<uint32_t>(); a.row_off = s.row_off.as<uint64_t>();
+    if (tb.valid) {
+        a.cons_start = tb.out + 3 * (size_t)n_aln; a.read_start = tb.out + 4 * (size_t)n_aln; a.read_end = tb.out + 2 * (size_t)n_aln;
+        a.cigar_off = tb.off; a.cigar = tb.ops;
+    }
     a.hpc_offsets = hb.offsets.as<uint64_t>(); a.hc = hb.bases.as<uint8_t>(); a.hq = s.hq.as<uint8_t>(); a.hl = s.hl.as<uint8_t>();
     a.cons_len = s.clen.as<uint32_t>(); a.cons_pos_off = s.cons_pos_off.as<uint32_t>(); a.cons_aln_off = s.cons_aln_off.as<uint32_t>();
     a.pos_cons = s.pos_cons.as<uint32_t>(); a.n_pos = (uint32_t)n_pos; a.read_base = (uint32_t)r0;

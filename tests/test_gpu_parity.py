@@ -692,6 +692,8 @@ def test_consensus_pileups_many_chunks(ctx, monkeypatch):
     got = ctx.consensus_pileups(cb, co, rb, qb, ro, rcons, use_hpc=True)
     assert got["stats"]["n_batches"] >= 4
     _assert_pileups(got, want, "pileups in chunks")
+    monkeypatch.setenv("SAVONT_B200_PILEUP_HOST_CIGAR", "1")      # CIGARs through the host, as when a traceback needs several sub-batches
+    _assert_pileups(ctx.consensus_pileups(cb, co, rb, qb, ro, rcons, use_hpc=True), want, "pileups, CIGARs through the host")
 
 
 def test_consensus_pileups_full_clusters(ctx):
