@@ -4,6 +4,8 @@
 // sequences (bounded device workspace): upload the chunk's reads, homopolymer-compress them on the device (pileup.cu),
 // align every compressed read to its consensus on both strands (align_nm_kernel), keep the better strand, trace it back
 // (align_tb_kernel + device CIGAR compaction), walk the CIGARs into columns and take the per-column median run length.
+#include <chrono>
+
 #include "api_internal.cuh"
 
 namespace sb {
@@ -50,8 +52,12 @@ int pileup_chunk(Context *c, PileupScratch &s, size_t chunk, int use_hpc, const 
 
     // ---- reads: upload, homopolymer compression (src/utils.rs:135-184) ----
     Batch &rb = c->work, &hb = c->work2;
+    static const bool trace = getenv("SAVONT_B200_PILEUP_TRACE") != nullptr;        // host wall clock of the first stage's steps
+    auto tnow = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double tl = tnow(), tw[6] = {0}; auto lap = [&](int k) { if (trace) { CK(cudaStreamSynchronize(st)); const double x = tnow(); tw[k] += x - tl; tl = x; } return 0; };
     CK(cudaEventRecord(ev[0], st));
     TRY(batch_upload(c, rb, read_bases, read_quals, read_offsets + r0, nullptr, n, &c->last_stats.h2d_bytes));
+    TRY(lap(0));
     TRY(s.hcnt.ensure((n + 1) * 4)); TRY(s.hoff32.ensure((n + 2) * 4)); TRY(s.scan_tmp.ensure((n / 2048 + 4) * 4));
     launch_hpc_count(seq_view(rb), use_hpc, s.hcnt.as<uint32_t>(), st);
     launch_scan_u32(s.hcnt.as<uint32_t>(), s.hoff32.as<uint32_t>(), (uint32_t)n, s.scan_tmp.as<uint32_t>(), st);
@@ -59,6 +65,7 @@ int pileup_chunk(Context *c, PileupScratch &s, size_t chunk, int use_hpc, const 
     CK(cudaMemcpyAsync(hoff32.data(), s.hoff32.p, (n + 1) * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     const uint64_t htotal = hoff32[n];
+    TRY(lap(1));
     TRY(s.hc.ensure(htotal + 64)); TRY(s.hq.ensure(htotal + 64)); TRY(s.hl.ensure(htotal + 64));
     CK(cudaMemsetAsync(s.hc.as<uint8_t>() + htotal, 0, 64, st));       // the plane packing reads whole words past the last base
     launch_hpc_write(seq_view(rb), use_hpc, s.hoff32.as<uint32_t>(), s.hc.as<uint8_t>(), s.hq.as<uint8_t>(), s.hl.as<uint8_t>(), st);
@@ -78,6 +85,7 @@ int pileup_chunk(Context *c, PileupScratch &s, size_t chunk, int use_hpc, const 
     launch_pack_planes(seq_view(hb), hb.planes.as<uint2>(), st);
     c->last_stats.kernel_launches += 1;
     c->last_stats.n_reads += n; c->last_stats.n_bases += rb.total_bases;
+    TRY(lap(2));
 
     // ---- consensus sequences: DP planes ----
     std::vector<uint2> planes; std::vector<uint32_t> plane_off, clen;
@@ -103,6 +111,8 @@ int pileup_chunk(Context *c, PileupScratch &s, size_t chunk, int use_hpc, const 
     TRY(s.nm2.ensure((size_t)n_aln * 8)); TRY(s.ae2.ensure((size_t)n_aln * 8)); TRY(s.re2.ensure((size_t)n_aln * 8));
     TRY(s.pr.ensure((size_t)n_aln * 4)); TRY(s.pa.ensure((size_t)n_aln * 4)); TRY(s.ps.ensure((size_t)n_aln + 4));
     AlignOut ao{s.nm2.as<int32_t>(), s.ae2.as<int32_t>(), s.re2.as<int32_t>()};
+    TRY(lap(3));
+    if (trace) fprintf(stderr, "pileup chunk %zu host ms: upload %.2f count+scan %.2f write+pack %.2f planes+pairs %.2f\n", chunk, tw[0], tw[1], tw[2], tw[3]);
     CK(cudaEventRecord(ev[1], st));
     launch_align_nm(seq_view(hb), hb.planes.as<uint2>(), ix, s.pr2.as<uint32_t>(), s.pa2.as<uint32_t>(), s.ps2.as<uint8_t>(), nullptr,
                     2u * n_aln, nullptr, ao, c->dp, c->sm_count, st);

@@ -11,6 +11,9 @@
 //   (scan of the column totals -> pos_offsets)
 //   emit     warp per read: second CIGAR walk, entry index = pos_offsets[position] + excl + (insertion after a base ? 1 : 0)
 //   median   warp per position: 256-bin histogram of the run lengths of the Base entries in shared memory
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.cuh"
 #include "sketch_dev.cuh"
 
@@ -234,7 +237,8 @@ __global__ void copy_to_host_kernel(const uint32_t *__restrict__ src, uint32_t *
 void launch_copy_to_host(const void *src_dev, void *dst_host, uint64_t bytes, cudaStream_t st) {   // bytes % 4 == 0, both 4-byte aligned
     if (bytes == 0) return;
     const uint32_t pad = (uint32_t)((reinterpret_cast<uintptr_t>(dst_host) & 127u) >> 2);
-    copy_to_host_kernel<<<32, 512, 0, st>>>(reinterpret_cast<const uint32_t *>(src_dev), reinterpret_cast<uint32_t *>(dst_host), bytes / 4, pad);
+    static const int ctas = [] { const char *e = getenv("SAVONT_B200_COPY_CTAS"); return e ? std::max(1, atoi(e)) : 16; }();   // tuning: 4 / 8 / 16 / 32 CTAs -> 40.5 / 39.8 / 37.6 / 39.7 ms per call; more CTAs finish the copy sooner but slow the next chunk's kernels
+    copy_to_host_kernel<<<ctas, 512, 0, st>>>(reinterpret_cast<const uint32_t *>(src_dev), reinterpret_cast<uint32_t *>(dst_host), bytes / 4, pad);
 }
 
 void launch_pileup_count(const PileupArgs &a, cudaStream_t st) {
