@@ -305,6 +305,106 @@ std::vector<std::vector<size_t>> compute_per_sample_depths(const TwinReadSet &tw
     return per_sample_impl(twin_reads, n_samples, consensuses, kmer_info, args, device);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// the neighbouring stages: cluster lists, reassignment, pileups
+// ------------------------------------------------------------------------------------------------
+std::vector<std::vector<size_t>> clusters_from_assignment(const uint32_t *rep_of, size_t n, size_t min_cluster_size) {
+    std::vector<std::vector<size_t>> by_rep(n);
+    for (size_t i = 0; i < n; ++i) {
+        if (rep_of[i] >= n) die("clusters_from_assignment: representative out of range");
+        by_rep[rep_of[i]].push_back(i);                       // ascending read ids
+    }
+    std::vector<std::vector<size_t>> out;
+    for (auto &c : by_rep) if (!c.empty()) out.push_back(std::move(c));
+    std::stable_sort(out.begin(), out.end(), [](const std::vector<size_t> &a, const std::vector<size_t> &b) {
+        return a.size() != b.size() ? a.size() > b.size() : a.front() < b.front();
+    });
+    out.erase(std::remove_if(out.begin(), out.end(), [&](const std::vector<size_t> &c) { return c.size() < min_cluster_size; }), out.end());
+    return out;
+}
+
+std::vector<std::vector<size_t>> cluster_reads_by_kmers(Mapper &mapper, const uint64_t *kmers, const uint64_t *offsets, size_t n,
+                                                        double threshold, size_t min_cluster_size) {
+    std::vector<uint32_t> rep(n ? n : 1);
+    uint64_t n_reps = 0;
+    ck(savont_b200_cluster_reads_by_kmers(mapper.raw(), kmers, offsets, n, threshold, rep.data(), &n_reps, nullptr), "cluster_reads_by_kmers");
+    return clusters_from_assignment(rep.data(), n, min_cluster_size);
+}
+
+std::pair<std::vector<std::vector<size_t>>, size_t> clusters_from_reassignment(const std::vector<std::vector<size_t>> &clusters,
+                                                                                const uint32_t *best_cons, size_t min_cluster_size) {
+    std::vector<std::vector<size_t>> fresh(clusters.size());
+    size_t moved = 0, at = 0;
+    for (size_t ci = 0; ci < clusters.size(); ++ci)
+        for (size_t read : clusters[ci]) {
+            const uint32_t b = best_cons[at++];
+            if (b >= clusters.size()) die("clusters_from_reassignment: cluster out of range");
+            fresh[b].push_back(read);
+            if (b != ci) ++moved;
+        }
+    std::vector<std::vector<size_t>> out;
+    for (auto &c : fresh) {
+        if (c.empty() || c.size() < min_cluster_size) continue;
+        std::sort(c.begin(), c.end());
+        out.push_back(std::move(c));
+    }
+    return {out, moved};
+}
+
+std::pair<std::vector<std::vector<size_t>>, size_t> reassign_reads_to_best_cluster(
+    Mapper &mapper, const std::vector<std::vector<size_t>> &clusters, const uint64_t *cons_kmers, const uint64_t *cons_offsets,
+    const uint64_t *snp_kmers, const uint64_t *snp_offsets, size_t min_cluster_size) {
+    std::vector<uint64_t> rk, ro{0};
+    for (const auto &c : clusters)
+        for (size_t read : c) {
+            rk.insert(rk.end(), snp_kmers + snp_offsets[read], snp_kmers + snp_offsets[read + 1]);
+            ro.push_back(rk.size());
+        }
+    const size_t n = ro.size() - 1;
+    std::vector<uint32_t> best(n ? n : 1), mm(n ? n : 1), ma(n ? n : 1);
+    ck(savont_b200_snpmer_compare(mapper.raw(), cons_kmers, cons_offsets, clusters.size(), rk.data(), ro.data(), n, best.data(), mm.data(),
+                                  ma.data(), nullptr, nullptr), "snpmer_compare");
+    return clusters_from_reassignment(clusters, best.data(), min_cluster_size);
+}
+
+std::vector<std::vector<Pileup>> generate_consensus_pileups(Mapper &mapper, const std::vector<ConsensusSequence> &consensuses,
+                                                            const ReadSet &reads, const uint32_t *read_cons, bool use_hpc) {
+    std::vector<uint8_t> cb; std::vector<uint64_t> co{0};
+    for (const auto &c : consensuses) { cb.insert(cb.end(), c.sequence.begin(), c.sequence.end()); co.push_back(cb.size()); }
+    size_t cap = 64;
+    for (size_t r = 0; r < reads.n; ++r) {
+        if (read_cons[r] >= consensuses.size()) die("generate_consensus_pileups: consensus out of range");
+        cap += (size_t)(reads.offsets[r + 1] - reads.offsets[r]) + consensuses[read_cons[r]].sequence.size();
+    }
+    std::vector<savont_b200_pileup_entry> ent(cap);
+    std::vector<uint64_t> po(cb.size() + 1);
+    std::vector<uint8_t> hp(cb.size() ? cb.size() : 1), strand(reads.n ? reads.n : 1);
+    std::vector<int32_t> nm(reads.n ? reads.n : 1);
+    uint64_t n_ent = 0;
+    ck(savont_b200_consensus_pileups(mapper.raw(), use_hpc ? 1 : 0, cb.data(), co.data(), consensuses.size(), reads.bases, reads.quals,
+                                     reads.offsets, read_cons, reads.n, po.data(), ent.data(), cap, &n_ent, hp.data(), strand.data(), nm.data(),
+                                     nullptr), "consensus_pileups");
+    std::vector<std::vector<Pileup>> out(consensuses.size());
+    for (size_t ci = 0; ci < consensuses.size(); ++ci) {
+        const size_t len = consensuses[ci].sequence.size();
+        out[ci].resize(len);
+        for (size_t p = 0; p < len; ++p) {
+            Pileup &col = out[ci][p];
+            const size_t g = co[ci] + p;
+            col.position = p; col.ref_base = consensuses[ci].sequence[p]; col.ref_hp_length = hp[g];
+            col.bases.reserve(po[g + 1] - po[g]);
+            for (uint64_t e = po[g]; e < po[g + 1]; ++e) {
+                PileupBase b{};
+                b.kind = ent[e].kind; b.n = ent[e].n;
+                for (int j = 0; j < 2; ++j) { b.base[j] = ent[e].base[j]; b.qual[j] = ent[e].qual[j]; b.hp[j] = ent[e].hp[j]; }
+                col.bases.push_back(b);
+            }
+        }
+    }
+    return out;
+}
+
 }  // namespace savont_host
 
 // ---- flat C wrappers so that the Python tests / host layer can drive this library with ctypes ----
@@ -312,6 +412,29 @@ extern "C" {
 
 static thread_local std::string g_host_error;
 const char *savont_host_last_error(void) { return g_host_error.c_str(); }
+
+// cluster lists from an assignment vector (host half of cluster_reads_by_kmers): CSR out, returns the number of clusters or -1
+long long savont_host_clusters_from_assignment(const uint32_t *rep_of, size_t n, size_t min_cluster_size, uint64_t *offsets, uint64_t *members) {
+    try {
+        const auto cl = savont_host::clusters_from_assignment(rep_of, n, min_cluster_size);
+        size_t at = 0; offsets[0] = 0;
+        for (size_t c = 0; c < cl.size(); ++c) { for (size_t r : cl[c]) members[at++] = r; offsets[c + 1] = at; }
+        return (long long)cl.size();
+    } catch (const std::exception &e) { g_host_error = e.what(); return -1; }
+}
+// host half of reassign_reads_to_best_cluster: clusters in CSR in, CSR out; returns the number of new clusters or -1; *moved = reassignments
+long long savont_host_clusters_from_reassignment(const uint64_t *cl_offsets, const uint64_t *cl_members, size_t n_clusters, const uint32_t *best_cons,
+                                                 size_t min_cluster_size, uint64_t *offsets, uint64_t *members, uint64_t *moved) {
+    try {
+        std::vector<std::vector<size_t>> cl(n_clusters);
+        for (size_t c = 0; c < n_clusters; ++c) cl[c].assign(cl_members + cl_offsets[c], cl_members + cl_offsets[c + 1]);
+        const auto res = savont_host::clusters_from_reassignment(cl, best_cons, min_cluster_size);
+        size_t at = 0; offsets[0] = 0;
+        for (size_t c = 0; c < res.first.size(); ++c) { for (size_t r : res.first[c]) members[at++] = r; offsets[c + 1] = at; }
+        *moved = res.second;
+        return (long long)res.first.size();
+    } catch (const std::exception &e) { g_host_error = e.what(); return -1; }
+}
 
 // high-frequency rule on (k-mer, [c0, c1]) entries: returns the threshold (or -1), *n_hf entries written to hf_out
 long long savont_host_high_freq_kmers(const uint64_t *kmers, const uint32_t *counts, size_t n, uint64_t *hf_out, size_t *n_hf) {

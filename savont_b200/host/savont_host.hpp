@@ -9,6 +9,7 @@
 #include <cstdint>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/savont_b200.h"
@@ -163,5 +164,28 @@ std::vector<std::vector<size_t>> compute_per_sample_depths(const TwinReadSet &tw
 void write_consensus_fasta(const std::vector<ConsensusSequence> &consensuses, const std::string &path, const std::string &prefix);
 void write_feature_table(const std::vector<ConsensusSequence> &consensuses, const std::string &path,
                          const std::vector<std::string> &sample_names);
+
+// ---- the neighbouring stages: host halves around the device calls ----
+// reference src/asv_cluster.rs:72-249 (cluster_reads_by_kmers): the greedy loop runs on the GPU
+// (savont_b200_cluster_reads_by_kmers on TwinRead::minimizer_kmers() in CSR), the cluster lists of :192-210 are built here:
+// grouped by representative, members ascending, larger clusters first (equal sizes: by the smallest member -- the reference
+// orders them by `a.first()` of a list filled in std::HashMap iteration order), clusters below min_cluster_size dropped.
+std::vector<std::vector<size_t>> clusters_from_assignment(const uint32_t *rep_of, size_t n_reads, size_t min_cluster_size);
+std::vector<std::vector<size_t>> cluster_reads_by_kmers(Mapper &mapper, const uint64_t *minimizer_kmers, const uint64_t *minimizer_offsets,
+                                                        size_t n_reads, double primary_clustering_threshold, size_t min_cluster_size);
+// reference src/asv_cluster.rs:1007-1131 (reassign_reads_to_best_cluster, SNPmer markers): `cons_*` = the ConsensusSnpmer k-mers
+// of the current clusters, `snpmer_*` = snpmers_vec() k-mers of all reads in CSR by read id.  Returns the new clusters (members
+// ascending, empty and small ones dropped) and the number of reads that changed cluster.
+std::pair<std::vector<std::vector<size_t>>, size_t> clusters_from_reassignment(const std::vector<std::vector<size_t>> &clusters,
+                                                                                const uint32_t *best_cons, size_t min_cluster_size);
+std::pair<std::vector<std::vector<size_t>>, size_t> reassign_reads_to_best_cluster(
+    Mapper &mapper, const std::vector<std::vector<size_t>> &clusters, const uint64_t *cons_kmers, const uint64_t *cons_offsets,
+    const uint64_t *snpmer_kmers, const uint64_t *snpmer_offsets, size_t min_cluster_size);
+// reference src/alignment.rs:17-60: one column of a consensus pileup
+struct PileupBase { uint8_t kind; uint8_t n; uint8_t base[2], qual[2], hp[2]; };   // kind 0 Base, 1 Deletion, 2 Insertion (n bases)
+struct Pileup { size_t position = 0; uint8_t ref_base = 0; uint8_t ref_hp_length = 1; std::vector<PileupBase> bases; };
+// reference src/alignment.rs:415-641 (generate_consensus_pileups): reads in cluster order (read_cons non-decreasing)
+std::vector<std::vector<Pileup>> generate_consensus_pileups(Mapper &mapper, const std::vector<ConsensusSequence> &consensuses,
+                                                            const ReadSet &reads, const uint32_t *read_cons, bool use_hpc);
 
 }  // namespace savont_host

@@ -226,3 +226,40 @@ def test_pileups_from_columns_shape():
     kinds = {b[0] for p in pl for col in p for b in col["bases"]}
     assert kinds == {"Base", "Deletion", "Insertion"}
     assert all(1 <= len(b[1]) <= 2 for p in pl for col in p for b in col["bases"] if b[0] == "Insertion")
+
+
+def test_cpp_host_cluster_lists_match_python():
+    """savont_host::clusters_from_assignment / clusters_from_reassignment (C++) against the Python halves in api.py"""
+    import ctypes as C
+    from savont_b200 import api
+    from tests.util import clustering_case, csr_u64, reassign_case
+    if not _host_available():
+        pytest.skip("libsavont_host.so not built")
+    H = api.host()
+    H.savont_host_clusters_from_assignment.restype = C.c_longlong
+    H.savont_host_clusters_from_reassignment.restype = C.c_longlong
+    u64p, u32p = C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)
+    km, off, _ = clustering_case(33, n_reads=220)
+    rep = np.ascontiguousarray(O.cluster_reads_by_kmers(km, off), np.uint32)
+    for min_size in (1, 3):
+        offs = np.zeros(len(rep) + 1, np.uint64); mem = np.zeros(len(rep), np.uint64)
+        nc = H.savont_host_clusters_from_assignment(rep.ctypes.data_as(u32p), C.c_size_t(len(rep)), C.c_size_t(min_size),
+                                                    offs.ctypes.data_as(u64p), mem.ctypes.data_as(u64p))
+        want = api.clusters_from_assignment(rep, min_size)
+        assert nc == len(want) and nc > 3
+        assert all(np.array_equal(mem[int(offs[c]):int(offs[c + 1])], want[c]) for c in range(nc))
+    # an out-of-range representative is an error, not a crash
+    bad = rep.copy(); bad[5] = 10 ** 6
+    assert H.savont_host_clusters_from_assignment(bad.ctypes.data_as(u32p), C.c_size_t(len(bad)), C.c_size_t(1), offs.ctypes.data_as(u64p),
+                                                  mem.ctypes.data_as(u64p)) == -1
+    cons, reads = reassign_case(6, n_cons=8, n_reads=64)
+    ck, co = csr_u64(cons); rk, ro = csr_u64(reads)
+    clusters = [np.arange(i * 8, (i + 1) * 8) for i in range(8)]
+    best = np.ascontiguousarray(O.snpmer_compare(ck, co, rk, ro)["best_cons"], np.uint32)
+    cl_off = np.arange(0, 65, 8, dtype=np.uint64); cl_mem = np.arange(64, dtype=np.uint64)
+    offs = np.zeros(9, np.uint64); mem = np.zeros(64, np.uint64); moved = C.c_uint64(0)
+    nc = H.savont_host_clusters_from_reassignment(cl_off.ctypes.data_as(u64p), cl_mem.ctypes.data_as(u64p), C.c_size_t(8), best.ctypes.data_as(u32p),
+                                                  C.c_size_t(2), offs.ctypes.data_as(u64p), mem.ctypes.data_as(u64p), C.byref(moved))
+    want, want_moved = api.clusters_from_reassignment(clusters, best, 2)
+    assert nc == len(want) and int(moved.value) == want_moved
+    assert all(np.array_equal(mem[int(offs[c]):int(offs[c + 1])], want[c]) for c in range(nc))
