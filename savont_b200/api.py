@@ -64,6 +64,9 @@ class Cli:
     min_read_length: int = 1100        # src/cli.rs:87-88
     max_read_length: int = 2000        # src/cli.rs:91-92
     quality_value_cutoff: float = 98.0  # src/cli.rs:95-96
+    primary_clustering_threshold: float = 0.95   # src/cli.rs:185-186 (Stage 2)
+    min_cluster_size: int = 12          # src/cli.rs (Stage 2 / 3 size filter; --hifi lowers it, src/main.rs:470-473)
+    use_hpc: bool = True                # homopolymer compression in Stage 4 (src/alignment.rs:481)
 
     def params(self) -> _lib.Params:
         return _lib.default_params(k=self.kmer_size, c=self.c, l=self.blockmer_length, min_bq=self.minimum_base_quality,
@@ -349,3 +352,18 @@ def pileups_from_columns(res, cons_offsets):
             cols.append(dict(ref_hp_length=int(hp[p]), bases=col))
         out.append(cols)
     return out
+
+
+def generate_consensus_pileups(ctx: _lib.Context, consensus_seqs, clusters, read_seqs, read_quals, args: Cli):
+    """alignment::generate_consensus_pileups (src/alignment.rs:415-641): consensus_seqs[i] = the (compressed) consensus of cluster i,
+    clusters[i] = its read ids (the first MAX_SEQS_CONSENSUS = 250 are used, :446-450), read_seqs / read_quals = per read id the
+    bases decoded from dna_seq and the per-base qualities.  Returns the reference's Vec<Vec<Pileup>> shape (pileups_from_columns)."""
+    MAX_SEQS_CONSENSUS = 250                                  # src/constants.rs:60
+    cb, co = _concat(consensus_seqs)
+    ids = [int(r) for c in clusters for r in list(c)[:MAX_SEQS_CONSENSUS]]
+    rcons = np.array([i for i, c in enumerate(clusters) for _ in list(c)[:MAX_SEQS_CONSENSUS]], np.uint32)
+    rb, ro = _concat([read_seqs[r] for r in ids])
+    rq = None if read_quals is None else _concat([read_quals[r] for r in ids])[0]
+    ctx.set_params(args.params())
+    res = ctx.consensus_pileups(cb, co, rb, rq, ro, rcons, use_hpc=args.use_hpc)
+    return pileups_from_columns(res, co)

@@ -263,3 +263,31 @@ def test_cpp_host_cluster_lists_match_python():
     want, want_moved = api.clusters_from_reassignment(clusters, best, 2)
     assert nc == len(want) and int(moved.value) == want_moved
     assert all(np.array_equal(mem[int(offs[c]):int(offs[c + 1])], want[c]) for c in range(nc))
+
+
+@pytest.mark.gpu
+def test_python_mirrors_of_stage_2_3_4():
+    """api.cluster_reads_by_kmers / reassign_reads_to_best_cluster / generate_consensus_pileups (reference signatures) on the GPU
+    against the same host halves fed with the oracle's device-side results"""
+    from savont_b200 import _lib, api
+    from tests.util import clustering_case, csr_u64, pileup_case, reassign_case
+    ctx = _lib.Context(0, _lib.default_params())
+    km, off, _ = clustering_case(41, n_reads=180)
+    got = api.cluster_reads_by_kmers(ctx, km, off, min_cluster_size=2)
+    want = api.clusters_from_assignment(O.cluster_reads_by_kmers(km, off), 2)
+    assert len(got) == len(want) and all(np.array_equal(a, b) for a, b in zip(got, want))
+    cons, reads = reassign_case(8, n_cons=8, n_reads=64)
+    ck, co = csr_u64(cons); sk, so = csr_u64(reads)
+    clusters = [np.arange(i * 8, (i + 1) * 8)[::-1] for i in range(8)]            # read ids in any order inside a cluster
+    got, moved = api.reassign_reads_to_best_cluster(ctx, clusters, ck, co, sk, so, min_cluster_size=1)
+    listed = [reads[int(r)] for c in clusters for r in c]
+    want, want_moved = api.clusters_from_reassignment(clusters, O.snpmer_compare(ck, co, *csr_u64(listed))["best_cons"], 1)
+    assert moved == want_moved and len(got) == len(want) and all(np.array_equal(a, b) for a, b in zip(got, want))
+    pcons, preads, pquals, prcons = pileup_case(12, n_cons=4, reads_per=5)
+    cl = [[r for r in range(len(preads)) if prcons[r] == i] for i in range(4)]
+    args = api.Cli(); args.band = 16
+    pl = api.generate_consensus_pileups(ctx, pcons, cl, preads, pquals, args)
+    cb, cof = O.concat(pcons); rb, ro = O.concat(preads); qb, _ = O.concat(pquals)
+    want_pl = api.pileups_from_columns(O.consensus_pileups(cb, cof, rb, qb, ro, prcons, band=16), cof)
+    assert pl == want_pl and sum(len(col["bases"]) for p in pl for col in p) > 100
+    ctx.close()
