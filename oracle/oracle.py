@@ -271,6 +271,18 @@ def snpmer_compare(cons_kmers, cons_offsets, read_kmers, read_offsets, k=17, wan
     return out
 
 
+def cluster_reads_by_snpmers(snp_kmers, snp_offsets, cluster, k=17, iterative_above=1000):
+    """so_cluster_reads_by_snpmers for one k-mer cluster -> rep_of (u32 per read id; UINT32_MAX outside the cluster)"""
+    L = lib()
+    sk = np.ascontiguousarray(snp_kmers, dtype=np.uint64); so = np.ascontiguousarray(snp_offsets, dtype=np.uint64)
+    cl = np.ascontiguousarray(cluster, dtype=np.uint32)
+    rep = np.full(max(len(so) - 1, 1), 0xffffffff, np.uint32)
+    rc = L.so_cluster_reads_by_snpmers(C.c_int(k), _p(sk, C.c_uint64), _p(so, C.c_uint64), _p(cl, C.c_uint32), C.c_size_t(len(cl)),
+                                       C.c_uint32(iterative_above), _p(rep, C.c_uint32))
+    assert rc == 0
+    return rep[:len(so) - 1]
+
+
 class Oracle:
     def set_read_filter(self, rf: ReadFilter | None, high_freq=None):
         hf = np.ascontiguousarray(high_freq if high_freq is not None else [], dtype=np.uint64)

@@ -956,6 +956,92 @@ int so_snpmer_compare(int k, const uint64_t *cons_kmers, const uint64_t *cons_of
 }
 
 /* ------------------------------------------------------------------------------------ */
+/* Stage 3 greedy loop, asv_cluster::cluster_reads_by_snpmers (src/asv_cluster.rs:561-700) */
+/* for one k-mer cluster -- restated ahead of a device implementation (no product code    */
+/* calls this yet).  Indexed branch (:467-510, blockmers off): candidates with 0          */
+/* mismatches and > 0 matches, ordered by (-matches, cluster size, read id).  Above 1000   */
+/* representatives the reference switches to rayon find_any (:413-464), whose choice is    */
+/* not deterministic; this restatement takes the FIRST compatible representative in        */
+/* creation order there (what find_first would return).                                    */
+/* ------------------------------------------------------------------------------------ */
+int so_cluster_reads_by_snpmers(int k, const uint64_t *snp_kmers, const uint64_t *snp_offsets, const uint32_t *cluster, size_t n,
+                                uint32_t iterative_above, uint32_t *rep_of) {
+    const uint64_t mask = so_split_mask(k);
+    /* index: splitmer -> list of (rep slot, kmer), src/asv_cluster.rs:340-353 */
+    u64map idx; u64map_init(&idx, 1024);
+    typedef struct { uint32_t *rep; uint64_t *kmer; size_t n, cap; } bucket_t;
+    bucket_t *buckets = NULL; size_t n_buckets = 0, cap_buckets = 0;
+    uint32_t *reps = (uint32_t *)malloc((n ? n : 1) * sizeof(uint32_t));          /* representative read ids in creation order */
+    uint32_t *rep_size = (uint32_t *)calloc(n ? n : 1, sizeof(uint32_t));
+    uint32_t *m = (uint32_t *)calloc(n ? n : 1, sizeof(uint32_t)), *mm = (uint32_t *)calloc(n ? n : 1, sizeof(uint32_t));
+    uint32_t *touched = (uint32_t *)malloc((n ? n : 1) * sizeof(uint32_t));
+    size_t n_reps = 0;
+    for (size_t ci = 0; ci < n; ci++) {
+        const uint32_t read = cluster[ci];
+        const uint64_t *q = snp_kmers + snp_offsets[read];
+        const size_t nq = (size_t)(snp_offsets[read + 1] - snp_offsets[read]);
+        long best = -1;
+        if (n_reps > iterative_above) {                                           /* :616-632 */
+            for (size_t r = 0; r < n_reps && best < 0; r++) {
+                const uint32_t rid = reps[r];
+                uint32_t ma = 0, mi = 0;
+                for (uint64_t i = snp_offsets[rid]; i < snp_offsets[rid + 1]; i++)   /* rep SNPmers against the read's map (later entries win) */
+                    for (size_t j = nq; j-- > 0;)
+                        if ((q[j] & mask) == (snp_kmers[i] & mask)) { if (q[j] == snp_kmers[i]) ma++; else mi++; break; }
+                if (mi == 0 && ma > 0) best = (long)r;
+            }
+        } else {                                                                  /* find_compatible_candidates + :483-509 */
+            size_t nt = 0;
+            for (size_t j = 0; j < nq; j++) {
+                const uint32_t *slot = u64map_slot(&idx, q[j] & mask, 0);
+                if (!slot) continue;
+                const bucket_t *b = &buckets[*slot - 1];
+                for (size_t e = 0; e < b->n; e++) {
+                    const uint32_t r = b->rep[e];
+                    if (m[r] == 0 && mm[r] == 0) touched[nt++] = r;
+                    if (b->kmer[e] == q[j]) m[r]++; else mm[r]++;
+                }
+            }
+            for (size_t t = 0; t < nt; t++) {
+                const uint32_t r = touched[t];
+                if (mm[r] == 0 && m[r] > 0) {
+                    if (best < 0) best = (long)r;
+                    else {
+                        const uint32_t b = (uint32_t)best;     /* sort key (-matches, size, read id) */
+                        if (m[r] > m[b] || (m[r] == m[b] && (rep_size[r] < rep_size[b] || (rep_size[r] == rep_size[b] && reps[r] < reps[b])))) best = (long)r;
+                    }
+                }
+            }
+            for (size_t t = 0; t < nt; t++) { m[touched[t]] = 0; mm[touched[t]] = 0; }
+        }
+        if (best >= 0) { rep_of[read] = reps[best]; rep_size[best]++; }           /* :386-394 */
+        else {                                                                    /* :397-410 */
+            const uint32_t r = (uint32_t)n_reps;
+            reps[n_reps++] = read; rep_size[r] = 1; rep_of[read] = read;
+            for (size_t j = 0; j < nq; j++) {
+                if (idx.n * 2 + 2 >= idx.cap) {
+                    u64map g; u64map_init(&g, idx.cap);
+                    for (size_t x = 0; x < idx.cap; x++) if (idx.keys[x] != UINT64_MAX) *u64map_slot(&g, idx.keys[x], 1) = idx.vals[x];
+                    u64map_free(&idx); idx = g;
+                }
+                uint32_t *slot = u64map_slot(&idx, q[j] & mask, 1);
+                if (*slot == 0) {
+                    if (n_buckets == cap_buckets) { cap_buckets = cap_buckets ? cap_buckets * 2 : 256; buckets = (bucket_t *)realloc(buckets, cap_buckets * sizeof(bucket_t)); }
+                    memset(&buckets[n_buckets], 0, sizeof(bucket_t));
+                    *slot = (uint32_t)(++n_buckets);
+                }
+                bucket_t *b = &buckets[*slot - 1];
+                if (b->n == b->cap) { b->cap = b->cap ? b->cap * 2 : 4; b->rep = (uint32_t *)realloc(b->rep, b->cap * 4); b->kmer = (uint64_t *)realloc(b->kmer, b->cap * 8); }
+                b->rep[b->n] = r; b->kmer[b->n] = q[j]; b->n++;
+            }
+        }
+    }
+    for (size_t x = 0; x < n_buckets; x++) { free(buckets[x].rep); free(buckets[x].kmer); }
+    free(buckets); u64map_free(&idx); free(reps); free(rep_size); free(m); free(mm); free(touched);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------ */
 /* a4: kmer_comp::twin_reads_from_snpmers, src/kmer_comp.rs:68-258                      */
 /* ------------------------------------------------------------------------------------ */
 /* the tests a read goes through before it becomes a TwinRead; the quality cutoff (:248) is applied after the id sort in

@@ -211,6 +211,14 @@ int so_snpmer_compare(int k, const uint64_t *cons_kmers, const uint64_t *cons_of
                       const uint64_t *read_offsets, size_t n_reads, uint32_t *best_cons, uint32_t *best_mismatches, uint32_t *best_matches,
                       uint16_t *matrix);
 
+/* ---- Stage 3 greedy loop for ONE k-mer cluster (asv_cluster::cluster_reads_by_snpmers, src/asv_cluster.rs:561-700; restated ahead of
+ * a device implementation).  snp_kmers / snp_offsets: snpmer_kmers() of all reads in CSR by read id; cluster[n]: the read ids of the
+ * k-mer cluster in order; rep_of[read] (only the cluster's reads are written) = the SNPmer-cluster representative.  iterative_above:
+ * the representative count above which the reference switches to its parallel search (1000, :613); there the first compatible
+ * representative in creation order is taken (the reference's find_any is not deterministic). */
+int so_cluster_reads_by_snpmers(int k, const uint64_t *snp_kmers, const uint64_t *snp_offsets, const uint32_t *cluster, size_t n,
+                                uint32_t iterative_above, uint32_t *rep_of);
+
 /* ---- a13-a14: EM over equivalence classes (src/alignment.rs:1957-2038) ---------------
  * classes in CSR (cls_offsets[n_cls+1], cls_asv), counts[n_cls]; total_assigned;
  * out: abundances[A] (f64), depths[A] = round(ab*total).  Classes are iterated in the

@@ -327,3 +327,45 @@ def reassign_reads(cons, reads, k=17):
                 score, best = (mm, ma), ci
         out.append((best, score[0], score[1])); mat.append(row)
     return out, mat
+
+
+def cluster_reads_by_snpmers(read_snpmers, cluster, k=17, iterative_above=1000):
+    """the greedy loop of asv_cluster::cluster_reads_by_snpmers for one k-mer cluster (src/asv_cluster.rs:561-700, blockmers off);
+    above `iterative_above` representatives the first compatible one in creation order (the reference's find_any is not
+    deterministic) -> {read: representative}"""
+    mask = _M64 ^ (3 << (k - 1))
+    index, reps, size, out = {}, [], {}, {}
+    for read in cluster:
+        q = read_snpmers[read]
+        best = None
+        if len(reps) > iterative_above:
+            qmap = {}
+            for km in q:
+                qmap[km & mask] = km
+            for rep in reps:
+                ma = mi = 0
+                for km in read_snpmers[rep]:
+                    hit = qmap.get(km & mask)
+                    if hit is not None:
+                        if hit == km:
+                            ma += 1
+                        else:
+                            mi += 1
+                if mi == 0 and ma > 0:
+                    best = rep; break
+        else:
+            stats = {}
+            for km in q:
+                for rep, rk in index.get(km & mask, ()):
+                    s = stats.setdefault(rep, [0, 0])
+                    s[0 if rk == km else 1] += 1
+            cands = sorted((-s[0], size[rep], rep) for rep, s in stats.items() if s[1] == 0 and s[0] > 0)
+            if cands:
+                best = cands[0][2]
+        if best is not None:
+            out[read] = best; size[best] += 1
+        else:
+            reps.append(read); size[read] = 1; out[read] = read
+            for km in q:
+                index.setdefault(km & mask, []).append((read, km))
+    return out

@@ -428,3 +428,20 @@ def test_snpmer_compare_matches_python_restatement(seed):
     # consensus lists against each other (compare_consensus_snpmers): the diagonal has no mismatches
     cc = O.snpmer_compare(ck, co, ck, co, want_matrix=True)["matrix"]
     assert all(int(cc[i, i, 1]) == 0 or i == 5 for i in range(len(cons)))
+
+
+@pytest.mark.parametrize("seed,iter_above", [(1, 1000), (2, 1000), (3, 4)])
+def test_snpmer_greedy_clustering_matches_python_restatement(seed, iter_above):
+    """Stage 3 greedy loop (oracle only so far): C vs Python, indexed branch and the branch above `iterative_above` representatives"""
+    from tests.util import csr_u64, reassign_case
+    _, reads = reassign_case(300 + seed, n_cons=10, n_sites=40, n_reads=220)
+    rng = random.Random(seed)
+    cluster = [r for r in range(len(reads)) if r % 9 != 4]
+    rng.shuffle(cluster)                                             # any order inside the cluster; reads outside stay untouched
+    sk, so = csr_u64(reads)
+    got = O.cluster_reads_by_snpmers(sk, so, cluster, iterative_above=iter_above)
+    want = pyref.cluster_reads_by_snpmers(reads, cluster, iterative_above=iter_above)
+    assert {r: int(got[r]) for r in cluster} == want
+    assert all(int(got[r]) == 0xffffffff for r in range(len(reads)) if r not in want)
+    n_rep = sum(1 for r, p in want.items() if r == p)
+    assert 8 <= n_rep < len(cluster)
