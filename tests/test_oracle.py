@@ -445,3 +445,37 @@ def test_snpmer_greedy_clustering_matches_python_restatement(seed, iter_above):
     assert all(int(got[r]) == 0xffffffff for r in range(len(reads)) if r not in want)
     n_rep = sum(1 for r, p in want.items() if r == p)
     assert 8 <= n_rep < len(cluster)
+
+
+def test_fuzz_stage2_stage3_restatements_agree():
+    """random small inputs with many ties (few distinct k-mers, equal bucket hits, equal containment ratios, duplicated splitmers): the C
+    oracle and the Python restatement of Stage 2 clustering, the SNPmer comparison and the Stage 3 greedy loop must agree"""
+    from hypothesis import given, settings, strategies as st
+    from tests.util import csr_u64
+    pool = [((i * 0x9E3779B97F4A7C15) >> 20) & ((1 << 34) - 1) for i in range(1, 25)]
+    lists = st.lists(st.lists(st.sampled_from(pool), min_size=0, max_size=10), min_size=1, max_size=30)
+
+    @settings(max_examples=60, deadline=None, derandomize=True)
+    @given(lists, st.sampled_from([0.3, 0.8, 0.95]))
+    def stage2(minis, thr):
+        km, off = csr_u64(minis)
+        assert [int(x) for x in O.cluster_reads_by_kmers(km, off, threshold=thr)] == pyref.cluster_reads_by_kmers(minis, threshold=thr)
+
+    @settings(max_examples=60, deadline=None, derandomize=True)
+    @given(lists, lists)
+    def compare(cons, reads):
+        ck, co = csr_u64(cons); rk, ro = csr_u64(reads)
+        got = O.snpmer_compare(ck, co, rk, ro, want_matrix=True)
+        want, mat = pyref.reassign_reads(cons, reads)
+        assert [(int(a), int(b), int(c_)) for a, b, c_ in zip(got["best_cons"], got["best_mismatches"], got["best_matches"])] == want
+        assert got["matrix"].tolist() == [[list(x) for x in row] for row in mat]
+
+    @settings(max_examples=60, deadline=None, derandomize=True)
+    @given(lists, st.sampled_from([1000, 2]))
+    def stage3(reads, it):
+        sk, so = csr_u64(reads)
+        cluster = list(range(len(reads)))
+        got = O.cluster_reads_by_snpmers(sk, so, cluster, iterative_above=it)
+        assert {r: int(got[r]) for r in cluster} == pyref.cluster_reads_by_snpmers(reads, cluster, iterative_above=it)
+
+    stage2(); compare(); stage3()
