@@ -479,3 +479,48 @@ def test_fuzz_stage2_stage3_restatements_agree():
         assert {r: int(got[r]) for r in cluster} == pyref.cluster_reads_by_snpmers(reads, cluster, iterative_above=it)
 
     stage2(); compare(); stage3()
+
+
+def test_fuzz_pileup_walk_restatements_agree():
+    """tiny consensus / read pairs, related or not (alignments that start with an insertion, end in a deletion, clip either end):
+    strand choice / NM of so_consensus_pileups against the full-matrix DP of tests/pyref.py, provenance of every entry, the median"""
+    from hypothesis import given, settings, strategies as st
+    seqs = st.text(alphabet="ACGT", min_size=1, max_size=24).map(lambda s_: s_.encode())
+
+    @settings(max_examples=80, deadline=None, derandomize=True)
+    @given(st.lists(seqs, min_size=1, max_size=3), st.lists(st.tuples(seqs, st.integers(0, 2)), min_size=1, max_size=8), st.sampled_from([2, 5, 30]),
+           st.booleans())
+    def run(cons, reads_c, band, use_hpc):
+        reads = [r for r, _ in reads_c]
+        rcons = sorted(c_ % len(cons) for _, c_ in reads_c)
+        quals = [bytes(33 + (7 * i + j) % 40 for j in range(len(r))) for i, r in enumerate(reads)]
+        cb, co = O.concat(cons); rb, ro = O.concat(reads); qb, _ = O.concat(quals)
+        got = O.consensus_pileups(cb, co, rb, qb, ro, rcons, band=band, use_hpc=use_hpc)
+        comp = [pyref.hpc_with_quality(r, q, use_hpc) for r, q in zip(reads, quals)]
+        hreads = [bytes(b"ACGT"[x] for x in hc) for hc, _, _ in comp]
+        for r in range(len(reads)):                                   # strand choice and NM against the full-matrix DP of pyref
+            a = [pyref.enc(b) for b in cons[rcons[r]]]
+            best = None
+            for sd in (0, 1):
+                rd = [pyref.enc(b) for b in hreads[r]]
+                if sd:
+                    rd = [3 - x for x in reversed(rd)]
+                nm, ie, je = pyref.banded_nm(a, rd, band)
+                if best is None or nm < best[0]:
+                    best = (nm, sd)
+            assert int(got["read_nm"][r]) == best[0] and int(got["read_strand"][r]) == best[1]
+        # entries: every Base entry's column base / quality / run length must come from the compressed read in its orientation
+        po, ent = got["pos_offsets"], got["entries"]
+        assert int(po[-1]) == len(ent) and np.all(np.diff(po.astype(np.int64)) >= 0)
+        for e in ent:
+            r = int(e["read"]); hc, hq, hl = comp[r]
+            sd = int(got["read_strand"][r])
+            alphabet = [b"ACGT"[3 - x] if sd else b"ACGT"[x] for x in hc]
+            for j in range(int(e["n"])):
+                assert int(e["base"][j]) in alphabet and int(e["qual"][j]) in hq and int(e["hp"][j]) in hl
+        hp = got["ref_hp_length"]
+        for p in range(len(hp)):
+            v = sorted(int(e["hp"][0]) for e in ent[int(po[p]):int(po[p + 1])] if int(e["kind"]) == 0)
+            want = 1 if not v else ((v[len(v) // 2 - 1] + v[len(v) // 2]) // 2 if len(v) % 2 == 0 else v[len(v) // 2])
+            assert int(hp[p]) == want
+    run()
