@@ -16,9 +16,11 @@
 // The score of the band's top cell is tracked from bit 0 of D0; last-row cells are read with
 // popcounts of the vertical deltas, last-column cells by a walk over the final column.
 // No tensor cores: this is integer DP, ~14 INT32 ops per 32 cells.
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
+#include "align_addchain.cuh"
 
 namespace sb {
 
@@ -45,60 +47,7 @@ struct AlignArgs {
     int band, padl;
 };
 
-// s = a + b (+ carry chain across NW words) in ONE asm statement so nothing can clobber CC.
-template <int NW>
-__device__ __forceinline__ void add_chain(const uint32_t (&a)[NW], const uint32_t (&b)[NW], uint32_t (&s)[NW]);
-
-template <>
-__device__ __forceinline__ void add_chain<1>(const uint32_t (&a)[1], const uint32_t (&b)[1], uint32_t (&s)[1]) { s[0] = a[0] + b[0]; }
-template <>
-__device__ __forceinline__ void add_chain<2>(const uint32_t (&a)[2], const uint32_t (&b)[2], uint32_t (&s)[2]) {
-    asm("add.cc.u32 %0, %2, %4;\n\taddc.u32 %1, %3, %5;" : "=r"(s[0]), "=r"(s[1]) : "r"(a[0]), "r"(a[1]), "r"(b[0]), "r"(b[1]));
-}
-template <>
-__device__ __forceinline__ void add_chain<3>(const uint32_t (&a)[3], const uint32_t (&b)[3], uint32_t (&s)[3]) {
-    asm("add.cc.u32 %0, %3, %6;\n\taddc.cc.u32 %1, %4, %7;\n\taddc.u32 %2, %5, %8;"
-        : "=r"(s[0]), "=r"(s[1]), "=r"(s[2])
-        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(b[0]), "r"(b[1]), "r"(b[2]));
-}
-template <>
-__device__ __forceinline__ void add_chain<5>(const uint32_t (&a)[5], const uint32_t (&b)[5], uint32_t (&s)[5]) {
-    asm("add.cc.u32 %0, %5, %10;\n\taddc.cc.u32 %1, %6, %11;\n\taddc.cc.u32 %2, %7, %12;\n\taddc.cc.u32 %3, %8, %13;\n\t"
-        "addc.u32 %4, %9, %14;"
-        : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4])
-        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]));
-}
-template <>
-__device__ __forceinline__ void add_chain<7>(const uint32_t (&a)[7], const uint32_t (&b)[7], uint32_t (&s)[7]) {
-    asm("add.cc.u32 %0, %7, %14;\n\taddc.cc.u32 %1, %8, %15;\n\taddc.cc.u32 %2, %9, %16;\n\taddc.cc.u32 %3, %10, %17;\n\t"
-        "addc.cc.u32 %4, %11, %18;\n\taddc.cc.u32 %5, %12, %19;\n\taddc.u32 %6, %13, %20;"
-        : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(s[5]), "=r"(s[6])
-        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]),
-          "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]));
-}
-template <>
-__device__ __forceinline__ void add_chain<9>(const uint32_t (&a)[9], const uint32_t (&b)[9], uint32_t (&s)[9]) {
-    asm("add.cc.u32 %0, %9, %18;\n\taddc.cc.u32 %1, %10, %19;\n\taddc.cc.u32 %2, %11, %20;\n\taddc.cc.u32 %3, %12, %21;\n\t"
-        "addc.cc.u32 %4, %13, %22;\n\taddc.cc.u32 %5, %14, %23;\n\taddc.cc.u32 %6, %15, %24;\n\taddc.cc.u32 %7, %16, %25;\n\t"
-        "addc.u32 %8, %17, %26;"
-        : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(s[5]), "=r"(s[6]), "=r"(s[7]), "=r"(s[8])
-        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(a[8]),
-          "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]), "r"(b[8]));
-}
-template <>
-__device__ __forceinline__ void add_chain<13>(const uint32_t (&a)[13], const uint32_t (&b)[13], uint32_t (&s)[13]) {
-    asm("add.cc.u32 %0, %13, %26;\n\taddc.cc.u32 %1, %14, %27;\n\taddc.cc.u32 %2, %15, %28;\n\taddc.cc.u32 %3, %16, %29;\n\t"
-        "addc.cc.u32 %4, %17, %30;\n\taddc.cc.u32 %5, %18, %31;\n\taddc.cc.u32 %6, %19, %32;\n\taddc.cc.u32 %7, %20, %33;\n\t"
-        "addc.cc.u32 %8, %21, %34;\n\taddc.cc.u32 %9, %22, %35;\n\taddc.cc.u32 %10, %23, %36;\n\taddc.cc.u32 %11, %24, %37;\n\t"
-        "addc.u32 %12, %25, %38;"
-        : "=r"(s[0]), "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(s[5]), "=r"(s[6]), "=r"(s[7]), "=r"(s[8]),
-          "=r"(s[9]), "=r"(s[10]), "=r"(s[11]), "=r"(s[12])
-        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]), "r"(a[8]), "r"(a[9]),
-          "r"(a[10]), "r"(a[11]), "r"(a[12]),
-          "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]), "r"(b[8]), "r"(b[9]),
-          "r"(b[10]), "r"(b[11]), "r"(b[12]));
-}
-
+// s = a + b (+ carry chain across NW words) in ONE asm statement so nothing can clobber CC: align_addchain.cuh (generated)
 // 32 bases [32t, 32t+32) of the oriented read as (low plane, high plane)
 __device__ __forceinline__ uint2 read_word(const uint2 *rp, uint32_t m, uint32_t t, bool rev) {
     if (!rev) return rp[t];
@@ -117,24 +66,34 @@ __device__ __forceinline__ uint2 read_word(const uint2 *rp, uint32_t m, uint32_t
     return make_uint2(~__brev(lo), ~__brev(hi));        // reverse + complement (3 - code)
 }
 
-template <int NW, bool TB>
+// TAIL: the band has exactly W = 32 * NW + 1 cells (B a multiple of 16: 2B + 1 = 129 for the default band 64).  Bits
+// 0 .. 32NW-1 live in NW words; of the last cell (bit 32NW, row j + B) only the diagonal delta D0 is ever needed -- its vertical
+// delta Mv is always 0 (masked after the diagonal shift), its Pv / Ph / Mh feed nothing but themselves, and no score is read at
+// or below it -- and D0 = Eq | carry-out of the word chain.  So the bottom cell costs one shift, one carry read-back and one OR
+// per column instead of a whole extra word (ten logic ops): 4 words instead of 5 for band 64, 2 instead of 3 for band 32.
+template <int NW, bool TB, bool TAIL>
 struct Band {
     uint32_t Pv[NW], Mv[NW];
     uint32_t Alo[NW + 1], Ahi[NW + 1];   // ASV window planes, word aligned; view = funnel shift by sh
-    uint32_t vm2[NW];                    // bits < W-1 (mask for Mv after the diagonal shift)
+    uint32_t vm2[TAIL ? 1 : NW];         // bits < W-1 (mask for Mv after the diagonal shift); all ones with TAIL
     uint32_t aw;                         // next ASV plane word to load
     const uint2 *ap;
-    int T;                               // D at the band's top cell
+    int T;                               // D at the band's top cell, up to the columns folded so far
+    uint32_t tacc;                       // bit 0 of D0 of the columns since the last fold, newest on top; unfilled bits are ones
     int bd, bi, bj;                      // best end cell so far
     int dn;                              // D(n, j) of the last column whose last-row cell was evaluated
+    // D at the band's top cell grows by 1 - (bit 0 of D0) per column
+    __device__ __forceinline__ int top() const { return T + __popc(~tacc); }
+    __device__ __forceinline__ void fold() { T += __popc(~tacc); tacc = 0xffffffffu; }
 };
 
 // one DP column.  TOP: rows <= 0 may be inside the window (j <= B).  LAST: j may be >= n-B, the last-row cell (n, j) is
 // scored: 1 = from the band's top score and the vertical deltas (popcounts over the column), 2 = from the previous
 // column's D(n, j-1) and the horizontal delta bits of row n (needs a LAST column right before this one).
-template <int NW, bool TB, bool TOP, int LAST>
-__device__ __forceinline__ void dp_column(Band<NW, TB> &s, uint32_t (&TM)[NW], uint32_t clo, uint32_t chi, uint32_t sh, int j, int n,
-                                          int B, uint32_t *hist_col, uint32_t hist_stride) {
+// et (TAIL): match bit of the bottom cell in the sign bit.
+template <int NW, bool TB, bool TOP, int LAST, bool TAIL>
+__device__ __forceinline__ void dp_column(Band<NW, TB, TAIL> &s, uint32_t (&TM)[NW], uint32_t clo, uint32_t chi, uint32_t sh, uint32_t et,
+                                          int j, int n, int B, uint32_t *hist_col, uint32_t hist_stride) {
     uint32_t Nr[NW + 1], X[NW], t[NW], sum[NW], D0[NW], Ph[NW], Mh[NW];
     // MISmatch bits on the word-aligned window first (2 LOP3 per raw word), ONE funnel shift per band word afterwards;
     // the complement is folded into the LOP3 that forms X = Eq | Mv
@@ -146,7 +105,12 @@ __device__ __forceinline__ void dp_column(Band<NW, TB> &s, uint32_t (&TM)[NW], u
         X[w] = TOP ? (~Ns | s.Mv[w] | TM[w]) : (~Ns | s.Mv[w]);
         t[w] = X[w] & s.Pv[w];
     }
-    add_chain<NW>(t, s.Pv, sum);
+    uint32_t d0t = 0u;
+    if (TAIL) {
+        add_chain_co<NW>(t, s.Pv, sum, et >> 31, d0t);      // D0 of the bottom cell = match | carry out (only bit 0 is used)
+    } else {
+        add_chain<NW>(t, s.Pv, sum);
+    }
 #pragma unroll
     for (int w = 0; w < NW; ++w) {
         D0[w] = (sum[w] ^ s.Pv[w]) | X[w];
@@ -155,12 +119,13 @@ __device__ __forceinline__ void dp_column(Band<NW, TB> &s, uint32_t (&TM)[NW], u
         asm("lop3.b32 %0, %1, %2, %3, 0xF1;" : "=r"(Ph[w]) : "r"(s.Mv[w]), "r"(D0[w]), "r"(s.Pv[w]));
         Mh[w] = s.Pv[w] & D0[w];
     }
-    s.T += (int)((~D0[0]) & 1u);
+    // collects bit 0 of D0 (one funnel shift; a mask + add per column otherwise): folded by popcount once per run of <= 32 columns
+    s.tacc = __funnelshift_r(s.tacc, D0[0], 1);
 #pragma unroll
     for (int w = 0; w < NW; ++w) {
-        const uint32_t Xs = (w + 1 < NW) ? __funnelshift_r(D0[w], D0[w + 1], 1) : (D0[w] >> 1);
+        const uint32_t Xs = (w + 1 < NW) ? __funnelshift_r(D0[w], D0[w + 1], 1) : (TAIL ? __funnelshift_r(D0[w], d0t, 1) : (D0[w] >> 1));
         s.Pv[w] = Mh[w] | ~(Xs | Ph[w]);
-        s.Mv[w] = Ph[w] & Xs & s.vm2[w];
+        s.Mv[w] = TAIL ? (Ph[w] & Xs) : (Ph[w] & Xs & s.vm2[w]);
     }
     if (TB) {
 #pragma unroll
@@ -176,7 +141,7 @@ __device__ __forceinline__ void dp_column(Band<NW, TB> &s, uint32_t (&TM)[NW], u
     if (LAST == 1) {
         if (j + B >= n) {                                   // row n is inside the window: bit b = n - j + B
             const int b = n - j + B;
-            int d = s.T;
+            int d = s.top();
 #pragma unroll
             for (int w = 0; w < NW; ++w) {
                 const int rem = b - 32 * w;                 // number of delta bits of this word below b
@@ -199,8 +164,9 @@ __device__ __forceinline__ void dp_column(Band<NW, TB> &s, uint32_t (&TM)[NW], u
     }
 }
 
-template <int NW, bool TB>
+template <int NW, bool TB, bool TAIL>
 __device__ __forceinline__ void align_pair(const AlignArgs &a, uint32_t pi, uint32_t tslot) {
+    static_assert(!(TB && TAIL), "the traceback history stores whole words: no tail-bit variant");
     const uint32_t r = a.pair_read[pi], asv = a.pair_asv[pi];
     const bool rev = a.pair_strand[pi] != 0;
     const uint64_t roff = a.read_offsets[r];
@@ -210,18 +176,21 @@ __device__ __forceinline__ void align_pair(const AlignArgs &a, uint32_t pi, uint
     const uint2 *rp = a.read_planes + plane_word_off(roff, r);
     const int jmax = m < n + B ? m : n + B;
 
-    Band<NW, TB> s;
+    Band<NW, TB, TAIL> s;
     s.ap = a.asv_planes + a.asv_plane_off[asv];
-    s.T = 0; s.bd = 1 << 29; s.bi = -1; s.bj = -1;
+    s.T = 0; s.tacc = 0xffffffffu; s.bd = 1 << 29; s.bi = -1; s.bj = -1;
     uint32_t TM[NW];
 #pragma unroll
     for (int w = 0; w < NW; ++w) {
         s.Pv[w] = 0u; s.Mv[w] = 0u;
-        const int remW = (W - 1) - 32 * w;                  // bits of this word below W-1
-        s.vm2[w] = remW >= 32 ? 0xffffffffu : (remW <= 0 ? 0u : ((1u << remW) - 1u));
+        if (!TAIL) {
+            const int remW = (W - 1) - 32 * w;              // bits of this word below W-1
+            s.vm2[w] = remW >= 32 ? 0xffffffffu : (remW <= 0 ? 0u : ((1u << remW) - 1u));
+        }
         const int remT = B - 32 * w;                        // column 1: rows <= 0 are bits 0..B-1
         TM[w] = remT >= 32 ? 0xffffffffu : (remT <= 0 ? 0u : ((1u << remT) - 1u));
     }
+    if (TAIL) s.vm2[0] = 0xffffffffu;
     // The planes are left-padded by padl = B + 32 zero bits, so the window of column j starts at padded
     // bit 32 + (j - 1): its offset inside the register window equals the read's bit index (j-1) & 31,
     // and both the ASV window and the read word advance at the same 32-column boundaries.
@@ -265,16 +234,29 @@ __device__ __forceinline__ void align_pair(const AlignArgs &a, uint32_t pi, uint
             // read word shifted so that the current column's bit is the sign bit: the broadcast mask is one arithmetic
             // shift and the advance is an add (IMAD on the FMA pipe), instead of a variable shift pair per plane.  (IMAD.HI as the
             // sign broadcast was measured: it costs an ALU-pipe slot as well on B200, tools/pipe_bench.cu, so no gain.)
+            // TAIL: the bottom cell of column j is window bit 32NW + bit, i.e. bit `bit` of the last raw word -- the same bit
+            // index as the read base -- so its match bits for the whole run are one word, walked like the read word.
             const int stop = min(jend, j + 31 - (int)bit);
             const uint32_t bit_end = bit + (uint32_t)(stop - j);
             const int jbase = j - (int)bit;
             uint32_t cl = __brev(cw_lo) << bit, ch = __brev(cw_hi) << bit;
-            for (; bit <= bit_end; ++bit) {
+            uint32_t el = TAIL ? (__brev(~((s.Alo[NW] ^ cw_lo) | (s.Ahi[NW] ^ cw_hi))) << bit) : 0u;
+            s.fold();
+            auto column = [&](const uint32_t sh) {
                 const uint32_t clo = (uint32_t)((int32_t)cl >> 31);
                 const uint32_t chi = (uint32_t)((int32_t)ch >> 31);
+                const uint32_t et = el;
                 cl += cl; ch += ch;
-                dp_column<NW, TB, TOP, LAST>(s, TM, clo, chi, bit, jbase + (int)bit, n, B,
-                                             TB ? hist + (size_t)(jbase + (int)bit - 1) * hist_col_stride : nullptr, a.hist_stride);
+                if (TAIL) el += el;
+                dp_column<NW, TB, TOP, LAST, TAIL>(s, TM, clo, chi, sh, et, jbase + (int)sh, n, B,
+                                                   TB ? hist + (size_t)(jbase + (int)sh - 1) * hist_col_stride : nullptr, a.hist_stride);
+            };
+            if (!TB && !TOP && LAST == 0 && bit == 0u && bit_end == 31u) {
+                // a whole 32-column block of the interior: fixed trip count, the loop counter amortised over 8 columns
+#pragma unroll 8
+                for (uint32_t sh = 0; sh < 32u; ++sh) column(sh);
+            } else {
+                for (; bit <= bit_end; ++bit) column(bit);
             }
             j = stop + 1;
         }
@@ -289,7 +271,6 @@ __device__ __forceinline__ void align_pair(const AlignArgs &a, uint32_t pi, uint
         if (j <= jmax) run_phase(std::false_type{}, L1{}, j);
         run_phase(std::false_type{}, L2{}, jmax);
     }
-
     // row n may already be inside the window of column 0 (n <= B): cell (n, 0) = 0 is a last-row cell
     // (handled below together with the last column when m == 0; for m > 0 the oracle also considers it)
     if (n <= B) {
@@ -298,7 +279,7 @@ __device__ __forceinline__ void align_pair(const AlignArgs &a, uint32_t pi, uint
     }
     // last-column cells (only if column m was reached)
     if (jmax == m) {
-        int d = s.T;                                        // b = 0: row m - B
+        int d = s.top();                                    // b = 0: row m - B
         const int bmin = B - m > 0 ? B - m : 0;
         const int bmax = (n - m + B) < 2 * B ? (n - m + B) : 2 * B;
         if (bmin == 0 && bmax >= 0) {
@@ -367,18 +348,18 @@ __device__ __forceinline__ void align_pair(const AlignArgs &a, uint32_t pi, uint
     }
 }
 
-template <int NW>
+template <int NW, bool TAIL>
 __global__ void __launch_bounds__(128) align_nm_kernel(AlignArgs a) {
     if (a.err && *a.err) return;
     const uint32_t n_pairs = a.n_pairs_dev ? min(*a.n_pairs_dev, a.n_pairs_max) : a.n_pairs_max;
     for (uint32_t pi = blockIdx.x * blockDim.x + threadIdx.x; pi < n_pairs; pi += gridDim.x * blockDim.x)
-        align_pair<NW, false>(a, pi, 0);
+        align_pair<NW, false, TAIL>(a, pi, 0);
 }
 template <int NW>
 __global__ void __launch_bounds__(128) align_tb_kernel(AlignArgs a) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= a.n_pairs_max) return;
-    align_pair<NW, true>(a, t, t);
+    align_pair<NW, true, false>(a, t, t);
 }
 
 static int pick_nw(int band) {
@@ -387,8 +368,20 @@ static int pick_nw(int band) {
     for (int v : avail) if (v >= need) return v;
     return -1;
 }
+// bands with 2B + 1 = 32q + 1 cells: q words + the tail bit (0 = no such variant); SAVONT_B200_DP_TAIL=0 forces the
+// whole-word kernels (tests compare the two)
+static int pick_nw_tail(int band) {
+    static const bool off = [] { const char *e = getenv("SAVONT_B200_DP_TAIL"); return e && atoi(e) == 0; }();
+    if (off || band < 16 || band % 16 != 0) return 0;
+    const int q = band / 16;
+    const int avail[] = {1, 2, 3, 4, 6, 8, 12};
+    for (int v : avail) if (v == q) return v;
+    return 0;
+}
 int align_supported_band_max() { return (13 * 32 - 1) / 2; }
 int align_words_for_band(int band) { return pick_nw(band); }
+// vector bits the NM kernel computes per column for this band (the roofline's denominator): 32q + 1 with the tail variant
+int align_bits_for_band(int band) { const int q = pick_nw_tail(band); return q ? 32 * q + 1 : 32 * pick_nw(band); }
 
 static AlignArgs make_args(const SeqBatch &in, const uint2 *read_planes, const AsvIndex &ix, const uint32_t *pair_read,
                            const uint32_t *pair_asv, const uint8_t *pair_strand, const AlignOut &out, const DeviceParams &p) {
@@ -410,14 +403,24 @@ void launch_align_nm(const SeqBatch &in, const uint2 *read_planes, const AsvInde
     uint32_t grid = (n_pairs_max + 127u) / 128u;
     const uint32_t cap = (uint32_t)sm_count * 16u;       // 16 CTAs x 128 threads = full occupancy per SM
     if (grid > cap) grid = cap;
+    switch (pick_nw_tail(p.band)) {
+        case 1: align_nm_kernel<1, true><<<grid, 128, 0, st>>>(a); return;
+        case 2: align_nm_kernel<2, true><<<grid, 128, 0, st>>>(a); return;
+        case 3: align_nm_kernel<3, true><<<grid, 128, 0, st>>>(a); return;
+        case 4: align_nm_kernel<4, true><<<grid, 128, 0, st>>>(a); return;
+        case 6: align_nm_kernel<6, true><<<grid, 128, 0, st>>>(a); return;
+        case 8: align_nm_kernel<8, true><<<grid, 128, 0, st>>>(a); return;
+        case 12: align_nm_kernel<12, true><<<grid, 128, 0, st>>>(a); return;
+        default: break;
+    }
     switch (pick_nw(p.band)) {
-        case 1: align_nm_kernel<1><<<grid, 128, 0, st>>>(a); break;
-        case 2: align_nm_kernel<2><<<grid, 128, 0, st>>>(a); break;
-        case 3: align_nm_kernel<3><<<grid, 128, 0, st>>>(a); break;
-        case 5: align_nm_kernel<5><<<grid, 128, 0, st>>>(a); break;
-        case 7: align_nm_kernel<7><<<grid, 128, 0, st>>>(a); break;
-        case 9: align_nm_kernel<9><<<grid, 128, 0, st>>>(a); break;
-        case 13: align_nm_kernel<13><<<grid, 128, 0, st>>>(a); break;
+        case 1: align_nm_kernel<1, false><<<grid, 128, 0, st>>>(a); break;
+        case 2: align_nm_kernel<2, false><<<grid, 128, 0, st>>>(a); break;
+        case 3: align_nm_kernel<3, false><<<grid, 128, 0, st>>>(a); break;
+        case 5: align_nm_kernel<5, false><<<grid, 128, 0, st>>>(a); break;
+        case 7: align_nm_kernel<7, false><<<grid, 128, 0, st>>>(a); break;
+        case 9: align_nm_kernel<9, false><<<grid, 128, 0, st>>>(a); break;
+        case 13: align_nm_kernel<13, false><<<grid, 128, 0, st>>>(a); break;
         default: break;
     }
 }

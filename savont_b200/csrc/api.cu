@@ -245,6 +245,15 @@ static int validate_twin(const TwinInput &in, size_t n) {
     return 0;
 }
 
+// sample ids index the S x A singleton matrix on the device: reject anything outside [0, n_samples)
+static int validate_file_idx(const uint32_t *file_idx, size_t n, int n_samples) {
+    if (!file_idx) return 0;
+    for (size_t i = 0; i < n; ++i)
+        if (file_idx[i] >= (uint32_t)n_samples)
+            return fail(SAVONT_B200_ERR_INVALID, "file_idx[%zu] = %u is not below n_samples = %d", i, file_idx[i], n_samples);
+    return 0;
+}
+
 static SnpSet snp_view(const Context *c) {
     SnpSet set{};
     if (c->snp_mask) {
@@ -803,6 +812,8 @@ int traceback_pairs(Context *c, Batch &b, const AsvIndex &ix, uint32_t max_ref_l
 
 extern "C" {
 
+static int ctx_init(savont_b200_ctx *h, int device_id);
+
 int savont_b200_abi_version(void) { return SAVONT_B200_ABI_VERSION; }
 const char *savont_b200_last_error(void) { return last_error_ref().c_str(); }
 
@@ -823,6 +834,13 @@ int savont_b200_create(int device_id, savont_b200_ctx **out) {
     if (device_id < 0 || device_id >= n_dev) return fail(SAVONT_B200_ERR_INVALID, "device %d out of range (0..%d)", device_id, n_dev - 1);
     CK(cudaSetDevice(device_id));
     savont_b200_ctx *h = new savont_b200_ctx();
+    const int rc_init = ctx_init(h, device_id);
+    if (rc_init != 0) { savont_b200_destroy(h); return rc_init; }      // releases whatever was created before the failure
+    *out = h;
+    return 0;
+}
+
+static int ctx_init(savont_b200_ctx *h, int device_id) {
     Context *c = &h->c;
     c->device = device_id;
     cudaDeviceProp prop;
@@ -846,17 +864,16 @@ int savont_b200_create(int device_id, savont_b200_ctx **out) {
     savont_b200_default_params(&c->params);
     c->dp = make_device_params(c->params);
     memset(&c->last_stats, 0, sizeof(c->last_stats));
-    int rc = build_tables(c);
-    if (rc != 0) { delete h; return rc; }
-    *out = h;
-    return 0;
+    return build_tables(c);
 }
 
 int savont_b200_destroy(savont_b200_ctx *h) {
     if (!h) return 0;
     Context *c = &h->c;
     cudaSetDevice(c->device);
+    // c->stream may be the caller's (savont_b200_set_stream); the lanes / copy streams may still hold work of a failed call
     cudaStreamSynchronize(c->stream);
+    for (cudaStream_t s : {c->own_stream, c->lane_stream[0], c->lane_stream[1], c->copy_stream, c->d2h_stream}) if (s) cudaStreamSynchronize(s);
     c->work.release(); c->work2.release(); c->work3.release(); c->resident.release(); c->asvb.release();
     DevBuf *bufs[] = {&c->d_rank_table, &c->d_snp_keys, &c->d_snp_bloom, &c->d_phred, &c->d_mx_keys, &c->d_mx_vals, &c->d_mx_entries, &c->d_idx_keys, &c->d_idx_vals, &c->d_idx_entries, &c->d_mset,
                       &c->d_mset_off, &c->d_asv_planes, &c->d_asv_plane_off, &c->d_asv_len, &c->d_counters, &c->d_hf_keys};
@@ -896,10 +913,15 @@ int savont_b200_set_params(savont_b200_ctx *h, const savont_b200_params *p) {
     if (!p) return fail(SAVONT_B200_ERR_INVALID, "params is null");
     TRY(validate_params(*p));
     Context *c = &h->c;
+    const int old_k = c->dp.k;
     c->params = *p;
     c->dp = make_device_params(*p);
     c->index_dirty = true;
-    return build_tables(c);
+    TRY(build_tables(c));
+    // the SNPmer Bloom filter is keyed by the k-mer and its reverse complement, i.e. by k: rebuild it from the host copy when k
+    // changed after savont_b200_load_snpmers
+    if (c->dp.k != old_k && !c->h_snpmers.empty()) TRY(upload_snp_set(c));
+    return 0;
 }
 
 int savont_b200_set_batch_reads(savont_b200_ctx *h, size_t n) {
@@ -1248,6 +1270,7 @@ int savont_b200_map_reads(savont_b200_ctx *h, const uint8_t *bases, const uint8_
     TRY(ensure_index(c));
     if (!offsets || !status || !best_nm || !class_offsets) return fail(SAVONT_B200_ERR_INVALID, "null argument");
     if (n_samples < 1) return fail(SAVONT_B200_ERR_INVALID, "n_samples must be >= 1");
+    TRY(validate_file_idx(file_idx, n_reads, n_samples));
     std::vector<size_t> cuts{0};
     for (size_t r0 = 0; r0 < n_reads;) {
         size_t r1 = std::min(n_reads, r0 + ramp_batch(c, cuts.size() - 1, n_reads - r0));
@@ -1286,6 +1309,7 @@ int savont_b200_map_twin_reads(savont_b200_ctx *h, const uint64_t *dna_words, co
     if (n_samples < 1) return fail(SAVONT_B200_ERR_INVALID, "n_samples must be >= 1");
     const TwinInput in{dna_words, dna_word_offsets, lengths, snpmer_kmers, snpmer_kmer_bytes, snpmer_offsets, file_idx};
     TRY(validate_twin(in, n_reads));
+    TRY(validate_file_idx(file_idx, n_reads, n_samples));
     const std::vector<size_t> cuts = twin_cuts(c, in, n_reads);
     auto up = [&](Batch &b, size_t r0, size_t n, uint64_t *bytes, cudaStream_t st) -> int {
         return batch_upload_twin(c, b, in, r0, n, bytes, st);
@@ -1302,6 +1326,7 @@ int savont_b200_upload_twin_reads(savont_b200_ctx *h, const uint64_t *dna_words,
     if (n_samples < 1) return fail(SAVONT_B200_ERR_INVALID, "n_samples must be >= 1");
     const TwinInput in{dna_words, dna_word_offsets, lengths, snpmer_kmers, snpmer_kmer_bytes, snpmer_offsets, file_idx};
     TRY(validate_twin(in, n_reads));
+    TRY(validate_file_idx(file_idx, n_reads, n_samples));
     TRY(batch_upload_twin(c, c->resident, in, 0, n_reads, nullptr));
     CK(cudaStreamSynchronize(c->stream));
     c->resident_samples = n_samples;
@@ -1314,6 +1339,7 @@ int savont_b200_upload_reads(savont_b200_ctx *h, const uint8_t *bases, const uin
     Context *c = &h->c;
     if (!offsets || (n_reads && !bases)) return fail(SAVONT_B200_ERR_INVALID, "null argument");
     if (n_samples < 1) return fail(SAVONT_B200_ERR_INVALID, "n_samples must be >= 1");
+    TRY(validate_file_idx(file_idx, n_reads, n_samples));
     TRY(batch_upload(c, c->resident, bases, quals, offsets, file_idx, n_reads, nullptr));
     CK(cudaStreamSynchronize(c->stream));
     c->resident_samples = n_samples;

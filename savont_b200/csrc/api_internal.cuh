@@ -166,7 +166,7 @@ struct Context {
     // sharded k-mer counting (savont_b200_kmer_shard_*): state between the phases
     struct KmerShard {
         bool active = false; KmerPartPlan pl{}; std::vector<unsigned long long> off_local; uint32_t *cursor1 = nullptr, *d_tile_start = nullptr,
-             *tail = nullptr; uint64_t slots = 0; int n_ranks = 0;
+             *tail = nullptr; uint64_t slots = 0; int n_ranks = 0; int count_runs = 0;
     } ks;
     DevBuf d_ks_entries, d_ks_dstptr, d_ks_partoff;
 };

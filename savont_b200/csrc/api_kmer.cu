@@ -343,6 +343,12 @@ int savont_b200_kmer_shard_count(savont_b200_ctx *h, const uint64_t *part_off, i
     const uint32_t cap_dev = (uint32_t)std::min<uint64_t>(cap64, 0xfffffff0ull);
     TRY(c->d_kc_out_k.ensure((size_t)cap_dev * 8 + 64)); TRY(c->d_kc_out_c.ensure((size_t)cap_dev * 8 + 64));
     pl.out_kmers = c->d_kc_out_k.as<uint64_t>(); pl.out_counts = c->d_kc_out_c.as<uint32_t>(); pl.out_cap = cap_dev;
+    if (ks.count_runs++ > 0) {
+        // a repeated call after ERR_CAPACITY: the entries are intact, the spill table, the counters and the output cursor are
+        // not -- reset them so that nothing is counted twice
+        CK(cudaMemsetAsync(ks.tail, 0, 64 * 4, c->stream));
+        launch_kmer_table_clear(pl.table, ks.slots, c->stream);
+    }
     CK(cudaEventRecord(c->ev[5], c->stream));
     launch_kmer_count_part(pl, c->sm_count, c->stream);
     CK(cudaGetLastError());
@@ -357,14 +363,15 @@ int savont_b200_kmer_shard_count(savont_b200_ctx *h, const uint64_t *part_off, i
     st.count_ms = st.hist_ms + st.scatter_ms + ev_ms(c->ev[5], c->ev[3]); st.compact_ms = ev_ms(c->ev[3], c->ev[4]);
     st.total_ms = st.count_ms + st.compact_ms;
     st.kernel_launches = 6; st.partitions = P; st.table_slots = ks.slots;
-    ks.active = false;
-    if (t[1] != 0) return fail(SAVONT_B200_ERR_OVERFLOW, "spill table overflow in sharded k-mer counting");
+    if (t[1] != 0) { ks.active = false; return fail(SAVONT_B200_ERR_OVERFLOW, "spill table overflow in sharded k-mer counting"); }
     const uint32_t n_found = t[16];
     unsigned long long nd = 0; memcpy(&nd, t + 18, 8);
     st.n_distinct = nd + t[0]; st.spilled_distinct = t[0];
     if (n_out) *n_out = n_found;
     if (stats) *stats = st;
+    // too small an output: the shard stays active (entries in place), the caller repeats the call with >= *n_out slots
     if (n_found > out_cap) return fail(SAVONT_B200_ERR_CAPACITY, "k-mer output capacity %zu too small (need >= %u)", out_cap, n_found);
+    ks.active = false;
     if (n_found && fetch) {
         CK(cudaMemcpyAsync(out_kmers, pl.out_kmers, (size_t)n_found * 8, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaMemcpyAsync(out_counts, pl.out_counts, (size_t)n_found * 8, cudaMemcpyDeviceToHost, c->stream));

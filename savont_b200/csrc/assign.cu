@@ -52,7 +52,7 @@ __global__ void assign_kernel(FilterOut fo, PairPool pool, const int32_t *__rest
                     const uint32_t a = class_slot[start];
                     atomicAdd(unambig + a, 1ull);
                     const uint32_t s = file_idx ? file_idx[r] : 0u;
-                    if ((int)s < n_samples) atomicAdd(single + (size_t)s * n_asv + a, 1ull);
+                    if (s < (uint32_t)n_samples) atomicAdd(single + (size_t)s * n_asv + a, 1ull);
                 } else {
                     for (uint32_t t = 0; t < kcls; ++t) atomicAdd(ambig + class_slot[start + t], 1ull);
                 }

@@ -219,6 +219,7 @@ void launch_align_tb(const SeqBatch &in, const uint2 *read_planes, const AsvInde
                      uint32_t *cigar, uint32_t cigar_stride, uint32_t *cigar_cnt, const DeviceParams &p, cudaStream_t st);
 int align_supported_band_max();
 int align_words_for_band(int band);
+int align_bits_for_band(int band);
 size_t align_tb_hist_words(uint32_t n_pairs, uint32_t hist_cols, const DeviceParams &p);
 void launch_assign(const FilterOut &fo, const PairPool &pool, const int32_t *nm,
                    const uint32_t *file_idx, uint32_t n_reads, uint32_t n_asv, int n_samples, int strand_mode,

@@ -43,6 +43,22 @@ def test_sketch_ragged_inputs(ctx, k, c):
         assert_same(got, want, SKETCH_KEYS, f"sketch k={k} c={c} quals={'y' if q is not None else 'n'}")
 
 
+def test_set_params_after_load_snpmers(ctx):
+    """the SNPmer Bloom filter is keyed by k: changing k after load_snpmers must rebuild it (no silently dropped SNPmers)"""
+    from savont_b200 import _lib
+    k, c = 19, 6
+    seqs, quals = weird_sequences(100 + k, k)
+    snp = sorted(snpmer_set_from(seqs, k))
+    assert len(snp) > 0
+    ctx.set_params(_lib.default_params())          # k = 17
+    ctx.load_snpmers(snp)                          # keys of a k = 19 run
+    gp, op = _params(_lib, k=k, c=c)
+    ctx.set_params(gp)
+    bases, offs = O.concat(seqs)
+    qcat, _ = O.concat(quals)
+    assert_same(ctx.sketch(bases, qcat, offs), O.sketch_batch(op, snp, bases, qcat, offs), SKETCH_KEYS, "set_params after load_snpmers")
+
+
 def test_sketch_empty_and_no_snpmers(ctx):
     from savont_b200 import _lib
     gp, op = _params(_lib)
@@ -93,7 +109,8 @@ def _dp_cases(seed, band):
     return asvs, reads, pr, pa, ps
 
 
-@pytest.mark.parametrize("band", [0, 1, 3, 8, 15, 16, 31, 33, 47, 64, 79, 100, 143, 192, 207])
+# bands with 2B + 1 = 32q + 1 (16, 32, 48, 64, 96, 128, 192) run the q-word + tail-bit kernels, the others whole words
+@pytest.mark.parametrize("band", [0, 1, 3, 8, 15, 16, 31, 32, 33, 47, 48, 64, 79, 96, 100, 128, 143, 192, 207])
 def test_align_pairs_nm_and_cigar(ctx, band):
     from savont_b200 import _lib
     asvs, reads, pr, pa, ps = _dp_cases(900 + band, band)
@@ -790,7 +807,9 @@ def test_count_split_kmers_sharded_ranks_on_one_gpu(world):
         ptrs = [c.kmer_shard_alloc(int(part_off[rk, -1])) for rk, c in enumerate(ctxs)]
         for rk, c in enumerate(ctxs):
             c.kmer_shard_scatter(ptrs, dst_off[rk])
-        outs = [c.kmer_shard_count(part_off[rk], cap=1 << 20) for rk, c in enumerate(ctxs)]
+        # rank 0 starts with far too small an output: ERR_CAPACITY must leave the shard recoverable (second call with the size the
+        # first one reported, nothing counted twice)
+        outs = [c.kmer_shard_count(part_off[rk], cap=(64 if rk == 0 else 1 << 20)) for rk, c in enumerate(ctxs)]
         km = np.concatenate([o["kmers"] for o in outs]); ct = np.concatenate([o["counts"] for o in outs])
         o = np.argsort(km, kind="stable"); km, ct = km[o], ct[o]
         want = O.count_split_kmers(r["bases"], r["quals"], r["offsets"])
