@@ -237,6 +237,10 @@ int savont_b200_upload_reads(savont_b200_ctx *ctx, const uint8_t *bases, const u
 int savont_b200_upload_twin_reads(savont_b200_ctx *ctx, const uint64_t *dna_words, const uint64_t *dna_word_offsets,
                                   const uint32_t *lengths, const void *snpmer_kmers, int snpmer_kmer_bytes,
                                   const uint64_t *snpmer_offsets, const uint32_t *file_idx, size_t n_reads, int n_samples);
+/* The resident reads are processed as n_parts parts pipelined over two internal streams, so that the sketch / filter kernels
+ * of one part share the SMs with the DP kernel of the previous one (same results for every n_parts).  0 = automatic (8 parts
+ * from 262144 reads on, else 1); takes effect at the next upload. */
+int savont_b200_set_resident_parts(savont_b200_ctx *ctx, int n_parts);
 int savont_b200_map_resident(savont_b200_ctx *ctx, int zero_counters, savont_b200_stats *stats);
 int savont_b200_fetch_resident(savont_b200_ctx *ctx, uint8_t *status, int32_t *best_nm, uint64_t *class_offsets,
                                uint32_t *class_asv, size_t class_cap);

@@ -21,7 +21,7 @@ STATUS_LENGTH_FILTERED, STATUS_REPETITIVE, STATUS_LOW_QUALITY = 5, 6, 7
 class Params(C.Structure):
     _fields_ = [
         ("k", C.c_int32), ("c", C.c_int32), ("l", C.c_int32), ("min_bq", C.c_int32),
-        ("band", C.c_int32), ("strand_mode", C.c_int32), ("candidate_mode", C.c_int32), ("reserved", C.c_int32),
+        ("band", C.c_int32), ("strand_mode", C.c_int32), ("candidate_mode", C.c_int32), ("nm_mode", C.c_int32),
         ("ratio_thresh", C.c_double), ("min_mini_frac_base", C.c_double),
     ]
 

@@ -615,6 +615,94 @@ static void banded_align(const uint8_t *a, int n, const uint8_t *r, int m, int B
 #undef INBAND
 }
 
+/* ------------------------------------------------------------------------------------ */
+/* NM under OTHER definitions -- a sensitivity study of a11, not the product's definition */
+/* (so_params.nm_mode; tests/test_nm_semantics.py, tools/nm_semantics.py).   */
+/*   mode 1  the S2 recurrence above with a four times wider band (4B).  Without any band */
+/*           S2 degenerates: a corner alignment of one base pair scores 0, so the band --  */
+/*           every alignment covers >= min(n, m) - B columns -- is part of the definition. */
+/*   mode 2  "minimap2-like": the best LOCAL alignment under the scoring of the presets   */
+/*           the reference uses (lr:hq / map-ont: match +2, mismatch -4, dual affine gaps */
+/*           min(4 + 2l, 24 + l); SURVEY.md 8c / Appendix D -- values from upstream       */
+/*           documentation, not checkable here) by Gotoh DP over the full matrix;         */
+/*           NM = mismatches + gap bases on the traceback of the best cell (the first one */
+/*           in row-major order; traceback preference diagonal, then the short-gap        */
+/*           states, then the long-gap states).  minimap2 itself chains exact 19-mer      */
+/*           anchors and fills between / beyond them with the same scoring (z-drop 400),  */
+/*           which for >= 97 % identical 16S pairs is this optimum up to tie-breaking;    */
+/*           a candidate "has no alignment" when the score is below min_dp_max = 80.      */
+/* ------------------------------------------------------------------------------------ */
+static int affine_local_nm(const uint8_t *a, int n, const uint8_t *r, int m, int32_t *nm_out, int32_t *score_out) {
+    const int MA = 2, MI = 4, Q1 = 4, E1 = 2, Q2 = 24, E2 = 1, NEG = -(1 << 28);
+    uint8_t *tb = (uint8_t *)malloc((size_t)(n + 1) * (size_t)(m + 1));
+    int32_t *H = (int32_t *)malloc((size_t)(m + 1) * sizeof(int32_t));
+    int32_t *F1 = (int32_t *)malloc((size_t)(m + 1) * sizeof(int32_t)), *F2 = (int32_t *)malloc((size_t)(m + 1) * sizeof(int32_t));
+    for (int j = 0; j <= m; j++) { H[j] = 0; F1[j] = NEG; F2[j] = NEG; tb[j] = 0; }
+    int32_t best = 0; int bi = 0, bj = 0;
+    for (int i = 1; i <= n; i++) {
+        uint8_t *row = tb + (size_t)i * (size_t)(m + 1);
+        int32_t diag = H[0], e1 = NEG, e2 = NEG;
+        H[0] = 0; row[0] = 0;
+        for (int j = 1; j <= m; j++) {
+            uint8_t fl = 0;
+            /* E: gap consuming read bases (insertion w.r.t. the ASV), along the row */
+            int32_t o = H[j - 1] - Q1 - E1, x = e1 - E1;
+            if (x > o) { e1 = x; fl |= 8; } else e1 = o;
+            o = H[j - 1] - Q2 - E2; x = e2 - E2;
+            if (x > o) { e2 = x; fl |= 32; } else e2 = o;
+            /* F: gap consuming ASV bases (deletion), along the column; H[j] still holds row i-1 */
+            o = H[j] - Q1 - E1; x = F1[j] - E1;
+            int32_t f1, f2;
+            if (x > o) { f1 = x; fl |= 16; } else f1 = o;
+            o = H[j] - Q2 - E2; x = F2[j] - E2;
+            if (x > o) { f2 = x; fl |= 64; } else f2 = o;
+            F1[j] = f1; F2[j] = f2;
+            int32_t h = diag + (a[i - 1] == r[j - 1] ? MA : -MI);
+            uint8_t src = 1;
+            if (e1 > h) { h = e1; src = 2; }
+            if (f1 > h) { h = f1; src = 3; }
+            if (e2 > h) { h = e2; src = 4; }
+            if (f2 > h) { h = f2; src = 5; }
+            if (h <= 0) { h = 0; src = 0; }
+            diag = H[j]; H[j] = h;
+            row[j] = (uint8_t)(fl | src);
+            if (h > best) { best = h; bi = i; bj = j; }
+        }
+    }
+    int32_t nm = 0;
+    {
+        int i = bi, j = bj, state = 0;                       /* 0 = H, 2..5 = inside a gap of that kind */
+        while (i > 0 && j > 0) {
+            const uint8_t t = tb[(size_t)i * (size_t)(m + 1) + (size_t)j];
+            if (state == 0) {
+                const int src = t & 7;
+                if (src == 0) break;
+                if (src == 1) { nm += a[i - 1] != r[j - 1]; i--; j--; }
+                else state = src;
+            } else if (state == 2) { nm++; const int ext = t & 8;  j--; if (!ext) state = 0; }
+            else if (state == 3)   { nm++; const int ext = t & 16; i--; if (!ext) state = 0; }
+            else if (state == 4)   { nm++; const int ext = t & 32; j--; if (!ext) state = 0; }
+            else                   { nm++; const int ext = t & 64; i--; if (!ext) state = 0; }
+        }
+    }
+    free(tb); free(H); free(F1); free(F2);
+    *nm_out = nm; *score_out = best;
+    return best >= 80;
+}
+
+/* NM of one oriented pair under so_params.nm_mode; returns 0 when the candidate has no alignment (mode 2 only) */
+static int nm_by_mode(const so_params *p, const uint8_t *a, int n, const uint8_t *r, int m, int32_t *nm) {
+    if (p->nm_mode == 2) { int32_t sc; return affine_local_nm(a, n, r, m, nm, &sc); }
+    aln_t al; memset(&al, 0, sizeof(al));
+    banded_align(a, n, r, m, p->nm_mode == 1 ? 4 * p->band : p->band, 0, &al);
+    *nm = al.nm;
+    return 1;
+}
+
+int so_nm_pair(const so_params *p, const uint8_t *asv_codes, int n, const uint8_t *read_codes, int m, int32_t *nm) {
+    return nm_by_mode(p, asv_codes, n, read_codes, m, nm);
+}
+
 static uint8_t *oriented_codes(const uint8_t *codes, size_t len, int strand) {
     uint8_t *o = (uint8_t *)malloc(len ? len : 1);
     if (!strand) memcpy(o, codes, len);
@@ -1175,16 +1263,18 @@ int so_map_reads(so_ctx *c, const uint8_t *bases, const uint8_t *quals, const ui
             uint8_t *fw = oriented_codes(sk.codes, len, 0), *rv = oriented_codes(sk.codes, len, 1);
             for (size_t i = 0; i < kept.n; i++) {
                 const asv_t *Av = &c->asvs[kept.v[i].asv];
-                aln_t al; memset(&al, 0, sizeof(al));
                 if (c->p.strand_mode == 1) {
-                    aln_t al2; memset(&al2, 0, sizeof(al2));
-                    banded_align(Av->codes, (int)Av->len, fw, (int)len, c->p.band, 0, &al);
-                    banded_align(Av->codes, (int)Av->len, rv, (int)len, c->p.band, 0, &al2);
-                    nms[i] = al2.nm < al.nm ? al2.nm : al.nm;
+                    int32_t n1 = INT32_MAX, n2 = INT32_MAX;
+                    const int ok1 = nm_by_mode(&c->p, Av->codes, (int)Av->len, fw, (int)len, &n1);
+                    const int ok2 = nm_by_mode(&c->p, Av->codes, (int)Av->len, rv, (int)len, &n2);
+                    if (!ok1) n1 = INT32_MAX;
+                    if (!ok2) n2 = INT32_MAX;
+                    nms[i] = n2 < n1 ? n2 : n1;
                     cells_total += 2ull * Av->len * (uint64_t)(2 * c->p.band + 1);
                 } else {
-                    banded_align(Av->codes, (int)Av->len, kept.v[i].strand ? rv : fw, (int)len, c->p.band, 0, &al);
-                    nms[i] = al.nm;
+                    int32_t n1 = INT32_MAX;
+                    if (!nm_by_mode(&c->p, Av->codes, (int)Av->len, kept.v[i].strand ? rv : fw, (int)len, &n1)) n1 = INT32_MAX;
+                    nms[i] = n1;
                     cells_total += (uint64_t)Av->len * (uint64_t)(2 * c->p.band + 1);
                 }
             }
@@ -1194,7 +1284,7 @@ int so_map_reads(so_ctx *c, const uint8_t *bases, const uint8_t *quals, const ui
             for (size_t i = 0; i < kept.n; i++) if (nms[i] < best) best = nms[i];
             size_t cn = 0;
             cls[r] = (uint32_t *)malloc((kept.n + 1) * sizeof(uint32_t));
-            for (size_t i = 0; i < kept.n; i++) if (nms[i] == best) cls[r][cn++] = kept.v[i].asv;
+            for (size_t i = 0; i < kept.n; i++) if (nms[i] == best && best != INT32_MAX) cls[r][cn++] = kept.v[i].asv;
             cls_n[r] = (uint32_t)cn;
             free(nms);
             if (cn == 0) { status[r] = SO_NO_ALIGNMENT; free(cls[r]); cls[r] = NULL; }

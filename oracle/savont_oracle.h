@@ -41,7 +41,8 @@ typedef struct so_params {
     int32_t strand_mode;  /* 0 = orientation by minimizer seed vote, 1 = both strands, min NM */
     int32_t candidate_mode; /* 0 = SNPmer index candidates (src/alignment.rs:1786-1843);
                                1 = low-polymorphism mode: every ASV sharing minimizers (src/alignment.rs:1527-1719) */
-    int32_t reserved;
+    int32_t nm_mode;      /* 0 = the product's NM definition (banded S2).  ORACLE ONLY, sensitivity study of a11:
+                             1 = S2 with band 4B, 2 = local dual-affine alignment with minimap2's lr:hq scoring */
     double  ratio_thresh;        /* src/alignment.rs:1829 0.0050 */
     double  min_mini_frac_base;  /* src/alignment.rs:1806 0.950 (raised to k) */
 } so_params;
@@ -128,6 +129,9 @@ int so_align_pairs(so_ctx *ctx, const uint8_t *bases, const uint64_t *offsets, s
  * sample_singleton: [n_samples*A] counts of singleton classes per (sample, asv) (may be NULL).
  * n_threads: OpenMP threads (<=0: all).
  */
+/* NM of one oriented pair of 2-bit code strings under p->nm_mode; returns 0 when the pair has no alignment (mode 2) */
+int so_nm_pair(const so_params *p, const uint8_t *asv_codes, int n, const uint8_t *read_codes, int m, int32_t *nm);
+
 int so_map_reads(so_ctx *ctx, const uint8_t *bases, const uint8_t *quals, const uint64_t *offsets,
                  const uint32_t *file_idx, size_t n_reads, int n_samples,
                  uint8_t *status, int32_t *best_nm, uint64_t *class_offsets, uint32_t *class_asv, size_t class_cap,

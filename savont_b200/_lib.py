@@ -385,6 +385,9 @@ class Context:
                                                C.c_size_t(len(o) - 1), C.c_int(n_samples)))
         self._resident = (len(o) - 1, n_samples)
 
+    def set_resident_parts(self, n_parts):
+        _check(self.L.savont_b200_set_resident_parts(self.h, C.c_int(int(n_parts))))
+
     def map_resident(self, zero_counters=True):
         st = Stats()
         _check(self.L.savont_b200_map_resident(self.h, C.c_int(1 if zero_counters else 0), C.byref(st)))

@@ -401,7 +401,10 @@ void launch_align_nm(const SeqBatch &in, const uint2 *read_planes, const AsvInde
     AlignArgs a = make_args(in, read_planes, ix, pair_read, pair_asv, pair_strand, out, p);
     a.n_pairs_dev = n_pairs_dev; a.n_pairs_max = n_pairs_max; a.err = err;
     uint32_t grid = (n_pairs_max + 127u) / 128u;
-    const uint32_t cap = (uint32_t)sm_count * 16u;       // 16 CTAs x 128 threads = full occupancy per SM
+    // CTAs per SM: 8 x 128 threads x 64 registers fill an SM's register file; SAVONT_B200_DP_CTAS = 4..6 leaves room for the
+    // sketch / filter kernels of the next part of the pipeline (api.cu map_resident)
+    static const uint32_t per_sm = [] { const char *e = getenv("SAVONT_B200_DP_CTAS"); const int v = e ? atoi(e) : 0; return (v >= 1 && v <= 32) ? (uint32_t)v : 8u; }();
+    const uint32_t cap = (uint32_t)sm_count * per_sm;
     if (grid > cap) grid = cap;
     switch (pick_nw_tail(p.band)) {
         case 1: align_nm_kernel<1, true><<<grid, 128, 0, st>>>(a); return;

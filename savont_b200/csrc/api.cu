@@ -96,7 +96,26 @@ static int build_tables(Context *c) {
     for (int b = 0; b < 256; ++b) { const double q = (double)(b - 33); ph[b] = pow(10.0, -q / 10.0); }
     TRY(c->d_phred.ensure(256 * sizeof(double)));
     CK(cudaMemcpyAsync(c->d_phred.p, ph.data(), 256 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    // integer thresholds of the filter's two f64 tests, in the reference's operation order (both are monotonic in the count)
+    std::vector<uint16_t> th(2 * kThreshTable, 0);
+    for (uint32_t mn = 1; mn < kThreshTable; ++mn) {
+        uint32_t lo = 0, hi = mn + 1;                       // smallest m in [0, mn + 1] with !(m / mn < min_frac); mn + 1 = none
+        while (lo < hi) { const uint32_t mid = (lo + hi) / 2; if ((double)mid / (double)mn < c->dp.min_frac) lo = mid + 1; else hi = mid; }
+        th[mn] = (uint16_t)std::min<uint32_t>(lo, 0xffffu);
+    }
+    th[0] = 0xffffu;
+    for (uint32_t m = 1; m < kThreshTable; ++m) {
+        uint32_t lo = 0, hi = 0xffffu;                      // largest mm in [0, 65535] with (mm / m) / c <= ratio_thresh; the test holds for mm = 0 iff 0 <= thresh
+        if (!((double)0 / (double)m / (double)c->dp.c <= c->dp.ratio_thresh)) { th[kThreshTable + m] = 0; continue; }
+        while (lo < hi) { const uint32_t mid = (lo + hi + 1) / 2; if ((double)mid / (double)m / (double)c->dp.c <= c->dp.ratio_thresh) lo = mid; else hi = mid - 1; }
+        th[kThreshTable + m] = (uint16_t)lo;
+    }
+    c->thresh_mm0_fails = !(0.0 <= c->dp.ratio_thresh);
+    TRY(c->d_thresh.ensure(th.size() * 2));
+    CK(cudaMemcpyAsync(c->d_thresh.p, th.data(), th.size() * 2, cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    c->dp.frac_min = c->d_thresh.as<uint16_t>(); c->dp.mm_max = c->d_thresh.as<uint16_t>() + kThreshTable;
+    c->dp.thresh_n = c->thresh_mm0_fails ? 0u : kThreshTable;      // a negative ratio threshold (nothing passes): keep the f64 path
     return 0;
 }
 
@@ -134,7 +153,7 @@ static int upload_snp_set(Context *c) {
 // ------------------------------------------------------------------------------------------------
 // batch staging
 // ------------------------------------------------------------------------------------------------
-constexpr size_t kCtrBytes = 32;   // u32 snp pool counter, pair counter, error bits, spare; u64 dp_cells; pad
+constexpr size_t kCtrBytes = 32;   // u32 snp pool counter, pair counter, error bits, sketch work counter; u64 dp_cells; u32 filter work counters [2]
 
 int batch_upload(Context *c, Batch &b, const uint8_t *bases, const uint8_t *quals, const uint64_t *offsets,
                  const uint32_t *file_idx, size_t n, uint64_t *h2d_bytes, cudaStream_t st) {
@@ -254,6 +273,62 @@ static int validate_file_idx(const uint32_t *file_idx, size_t n, int n_samples) 
     return 0;
 }
 
+// Cuts the resident reads (c->resident, uploaded by batch_upload / batch_upload_twin whose host-side offset arrays are still in
+// its pin_offsets) into parts: views of the resident input buffers plus part-relative offset arrays.
+static int resident_part_count(const Context *c, size_t n) {
+    if (c->resident_parts_req > 0) return c->resident_parts_req;
+    static const int env = [] { const char *e = getenv("SAVONT_B200_RESIDENT_PARTS"); return e ? atoi(e) : 0; }();
+    if (env > 0) return env;
+    return n >= 262144 ? 8 : 1;
+}
+static int build_resident_parts(Context *c) {
+    Batch &R = c->resident;
+    for (Batch &pb : c->res_parts) pb.release();
+    c->res_parts.clear(); c->res_cuts.clear();
+    const size_t n = R.n;
+    size_t P = (size_t)resident_part_count(c, n);
+    const size_t min_reads = c->resident_parts_req > 0 ? 8 : 1024;      // per part; an explicit request may cut small inputs (tests)
+    if (P > n / min_reads) P = n / min_reads;
+    if (P <= 1) return 0;
+    const uint64_t *rel = R.pin_offsets.as<uint64_t>();
+    const uint64_t *wrel = rel + (n + 1);                              // twin only
+    c->res_parts.resize(P);
+    c->res_cuts.assign(P + 1, 0);
+    for (size_t q = 0; q <= P; ++q) c->res_cuts[q] = n * q / P;
+    std::vector<uint64_t> tmp;
+    for (size_t q = 0; q < P; ++q) {
+        Batch &pb = c->res_parts[q];
+        const size_t r0 = c->res_cuts[q], cnt = c->res_cuts[q + 1] - r0;
+        pb.n = (uint32_t)cnt; pb.twin = R.twin; pb.has_quals = R.has_quals; pb.has_file_idx = R.has_file_idx;
+        pb.force_generic = false; pb.mapped = false;
+        pb.total_bases = rel[r0 + cnt] - rel[r0];
+        uint32_t mx = 0;
+        tmp.resize((cnt + 1) * (R.twin ? 2 : 1));
+        for (size_t i = 0; i <= cnt; ++i) {
+            tmp[i] = rel[r0 + i] - rel[r0];
+            if (i > 0) { const uint64_t len = tmp[i] - tmp[i - 1]; if (len > mx) mx = (uint32_t)len; }
+        }
+        pb.max_len = mx;
+        TRY(pb.offsets.ensure((cnt + 1) * 8));
+        CK(cudaMemcpyAsync(pb.offsets.p, tmp.data(), (cnt + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+        if (R.twin) {
+            for (size_t i = 0; i <= cnt; ++i) tmp[cnt + 1 + i] = wrel[r0 + i] - wrel[r0];
+            TRY(pb.word_offsets.ensure((cnt + 1) * 8));
+            CK(cudaMemcpyAsync(pb.word_offsets.p, tmp.data() + cnt + 1, (cnt + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+            pb.dna_words.borrow(R.dna_words.as<uint64_t>() + wrel[r0], (size_t)(wrel[r0 + cnt] - wrel[r0] + 2) * 8);
+            pb.snp_start.borrow(R.snp_start.as<uint32_t>() + r0, (cnt + 1) * 4);
+            pb.snp_cnt.borrow(R.snp_cnt.as<uint32_t>() + r0, (cnt + 1) * 4);
+            pb.snp_kmer.borrow(R.snp_kmer.p, R.snp_kmer.cap);
+        } else {
+            pb.bases.borrow(R.bases.as<uint8_t>() + rel[r0], (size_t)pb.total_bases + 64);
+            if (R.has_quals) pb.quals.borrow(R.quals.as<uint8_t>() + rel[r0], (size_t)pb.total_bases + 64);
+        }
+        if (R.has_file_idx) pb.file_idx.borrow(R.file_idx.as<uint32_t>() + r0, cnt * 4 + 4);
+        CK(cudaStreamSynchronize(c->stream));                          // tmp is reused
+    }
+    return 0;
+}
+
 static SnpSet snp_view(const Context *c) {
     SnpSet set{};
     if (c->snp_mask) {
@@ -285,6 +360,7 @@ static SketchOut sketch_view(const Batch &b, bool with_pos) {
     o.snp_pool_ctr = b.ctrs.as<uint32_t>(); o.snp_pool_cap = b.snp_cap;
     o.spill_kmer = b.spill_k.as<uint64_t>(); o.spill_pos = b.spill_p.as<uint32_t>(); o.spill_stride = b.spill_stride;
     o.err = b.ctrs.as<uint32_t>() + 2;
+    o.work_ctr = b.ctrs.as<uint32_t>() + 3;
     return o;
 }
 
@@ -410,7 +486,7 @@ static PairPool pool_view(const Batch &b) {
 static FilterOut filter_view(const Batch &b) {
     FilterOut f{};
     f.cand_status = b.cand_status.as<uint8_t>(); f.pair_start = b.pair_start.as<uint32_t>(); f.pair_cnt = b.pair_cnt.as<uint32_t>();
-    f.low_mm = b.low_mm.as<uint32_t>(); f.err = b.ctrs.as<uint32_t>() + 2;
+    f.low_mm = b.low_mm.as<uint32_t>(); f.err = b.ctrs.as<uint32_t>() + 2; f.work_ctr = b.ctrs.as<uint32_t>() + 6;
     return f;
 }
 
@@ -874,8 +950,9 @@ int savont_b200_destroy(savont_b200_ctx *h) {
     // c->stream may be the caller's (savont_b200_set_stream); the lanes / copy streams may still hold work of a failed call
     cudaStreamSynchronize(c->stream);
     for (cudaStream_t s : {c->own_stream, c->lane_stream[0], c->lane_stream[1], c->copy_stream, c->d2h_stream}) if (s) cudaStreamSynchronize(s);
+    for (Batch &pb : c->res_parts) pb.release();
     c->work.release(); c->work2.release(); c->work3.release(); c->resident.release(); c->asvb.release();
-    DevBuf *bufs[] = {&c->d_rank_table, &c->d_snp_keys, &c->d_snp_bloom, &c->d_phred, &c->d_mx_keys, &c->d_mx_vals, &c->d_mx_entries, &c->d_idx_keys, &c->d_idx_vals, &c->d_idx_entries, &c->d_mset,
+    DevBuf *bufs[] = {&c->d_rank_table, &c->d_snp_keys, &c->d_snp_bloom, &c->d_phred, &c->d_thresh, &c->d_mx_keys, &c->d_mx_vals, &c->d_mx_entries, &c->d_idx_keys, &c->d_idx_vals, &c->d_idx_entries, &c->d_mset,
                       &c->d_mset_off, &c->d_asv_planes, &c->d_asv_plane_off, &c->d_asv_len, &c->d_counters, &c->d_hf_keys};
     for (DevBuf *b : bufs) b->release();
     c->pin_small.release(); c->pin_out.release(); c->tb_pin.release();
@@ -1330,7 +1407,7 @@ int savont_b200_upload_twin_reads(savont_b200_ctx *h, const uint64_t *dna_words,
     TRY(batch_upload_twin(c, c->resident, in, 0, n_reads, nullptr));
     CK(cudaStreamSynchronize(c->stream));
     c->resident_samples = n_samples;
-    return 0;
+    return build_resident_parts(c);
 }
 
 int savont_b200_upload_reads(savont_b200_ctx *h, const uint8_t *bases, const uint8_t *quals, const uint64_t *offsets,
@@ -1343,6 +1420,13 @@ int savont_b200_upload_reads(savont_b200_ctx *h, const uint8_t *bases, const uin
     TRY(batch_upload(c, c->resident, bases, quals, offsets, file_idx, n_reads, nullptr));
     CK(cudaStreamSynchronize(c->stream));
     c->resident_samples = n_samples;
+    return build_resident_parts(c);
+}
+
+int savont_b200_set_resident_parts(savont_b200_ctx *h, int n_parts) {
+    if (!h) return fail(SAVONT_B200_ERR_INVALID, "null context");
+    if (n_parts < 0 || n_parts > 4096) return fail(SAVONT_B200_ERR_INVALID, "n_parts must be in 0..4096");
+    h->c.resident_parts_req = n_parts;
     return 0;
 }
 
@@ -1354,11 +1438,27 @@ int savont_b200_map_resident(savont_b200_ctx *h, int zero_counters, savont_b200_
     memset(&c->last_stats, 0, sizeof(c->last_stats));
     TRY(ensure_counters(c, c->resident_samples, zero_counters != 0));
     CK(cudaEventRecord(c->ev[6], c->stream));
-    TRY(run_path(c, c->resident, c->resident_samples, st));
+    if (c->res_parts.size() <= 1) {
+        TRY(run_path(c, c->resident, c->resident_samples, st));
+        st.n_batches = 1;
+    } else {
+        // part i runs on lane i & 1: its sketch / filter kernels are enqueued while the DP kernel of part i-1 still runs on the other
+        // lane (the DP grid leaves room on every SM, launch_align_nm); one host synchronisation per part, behind the enqueue of
+        // the next one
+        for (int l = 0; l < 2; ++l) CK(cudaStreamWaitEvent(c->lane_stream[l], c->ev[6], 0));
+        int prev = -1;
+        for (size_t i = 0; i < c->res_parts.size(); ++i) {
+            { LaneGuard g(c, (int)(i & 1)); TRY(enqueue_path(c, c->res_parts[i], c->resident_samples)); }
+            if (prev >= 0) { LaneGuard g(c, prev & 1); TRY(finish_path(c, c->res_parts[(size_t)prev], c->resident_samples, st)); }
+            prev = (int)i;
+        }
+        { LaneGuard g(c, prev & 1); TRY(finish_path(c, c->res_parts[(size_t)prev], c->resident_samples, st)); }
+        st.n_batches = c->res_parts.size();
+        c->resident.mapped = true;
+    }
     CK(cudaEventRecord(c->ev[7], c->stream));
     CK(cudaStreamSynchronize(c->stream));
     st.total_ms = ev_ms(c->ev[6], c->ev[7]);
-    st.n_batches = 1;
     st.kernel_launches = c->last_stats.kernel_launches;
     c->last_stats = st;
     if (stats) *stats = st;
@@ -1372,20 +1472,24 @@ int savont_b200_fetch_resident(savont_b200_ctx *h, uint8_t *status, int32_t *bes
     if (!c->resident.mapped) return fail(SAVONT_B200_ERR_INVALID, "map_resident has not run");
     if (!status || !best_nm || !class_offsets) return fail(SAVONT_B200_ERR_INVALID, "null argument");
     uint64_t n_cls = 0;
-    return fetch_batch(c, c->resident, c->resident.n, c->stream, status, best_nm, class_offsets, 0, class_asv, class_cap, &n_cls, nullptr);
+    if (c->res_parts.size() <= 1)
+        return fetch_batch(c, c->resident, c->resident.n, c->stream, status, best_nm, class_offsets, 0, class_asv, class_cap, &n_cls, nullptr);
+    uint64_t base = 0;
+    class_offsets[0] = 0;
+    for (size_t q = 0; q < c->res_parts.size(); ++q) {
+        const size_t r0 = c->res_cuts[q];
+        TRY(fetch_batch(c, c->res_parts[q], c->res_parts[q].n, c->stream, status + r0, best_nm + r0, class_offsets + r0, base, class_asv,
+                        class_cap, &n_cls, nullptr));
+        base += n_cls;
+    }
+    return 0;
 }
 
-int savont_b200_best_hits_resident(savont_b200_ctx *h, uint32_t *best_asv, uint8_t *strand, int32_t *asv_start, int32_t *asv_end,
-                                   int32_t *read_start, int32_t *read_end, double *identity, uint64_t *cigar_offsets,
-                                   uint32_t *cigar, size_t cigar_cap) {
-    TRY(use_device(h ? &h->c : nullptr));
-    Context *c = &h->c;
-    Batch &b = c->resident;
-    if (!b.mapped) return fail(SAVONT_B200_ERR_INVALID, "map_resident has not run");
-    if (!best_asv || !strand || !asv_start || !asv_end || !read_start || !read_end || !identity || !cigar_offsets)
-        return fail(SAVONT_B200_ERR_INVALID, "null argument");
+// best hit of every read of one mapped batch + its traceback; the CIGAR ops are appended to `cigar` behind *cig_base
+static int best_hits_batch(Context *c, Batch &b, uint32_t *best_asv, uint8_t *strand, int32_t *asv_start, int32_t *asv_end,
+                           int32_t *read_start, int32_t *read_end, double *identity, uint64_t *cigar_offsets /* [n + 1], [0] set */,
+                           uint32_t *cigar, size_t cigar_cap) {
     const size_t n = b.n;
-    cigar_offsets[0] = 0;
     if (n == 0) return 0;
     DevBuf d_flag, d_off, d_tmp, d_basv, d_bstr, d_pr, d_pa, d_ps;
     auto cleanup = [&]() { DevBuf *all[] = {&d_flag, &d_off, &d_tmp, &d_basv, &d_bstr, &d_pr, &d_pa, &d_ps}; for (DevBuf *x : all) x->release(); };
@@ -1406,6 +1510,7 @@ int savont_b200_best_hits_resident(savont_b200_ctx *h, uint32_t *best_asv, uint8
     const size_t np = off[n];
     std::vector<int32_t> v(np * 5);
     std::vector<uint64_t> coff(np + 1, 0);
+    coff[0] = cigar_offsets[0];
     if (np) {
         rc = traceback_pairs(c, b, index_view(c), c->max_asv_len, d_pr.as<uint32_t>(), d_pa.as<uint32_t>(), d_ps.as<uint8_t>(), np, v.data(), v.data() + np,
                              v.data() + 2 * np, v.data() + 3 * np, v.data() + 4 * np, coff.data(), cigar, cigar_cap);
@@ -1425,6 +1530,25 @@ int savont_b200_best_hits_resident(savont_b200_ctx *h, uint32_t *best_asv, uint8
         cigar_offsets[r + 1] = coff[off[r + 1]];
     }
     cleanup();
+    return 0;
+}
+
+int savont_b200_best_hits_resident(savont_b200_ctx *h, uint32_t *best_asv, uint8_t *strand, int32_t *asv_start, int32_t *asv_end,
+                                   int32_t *read_start, int32_t *read_end, double *identity, uint64_t *cigar_offsets,
+                                   uint32_t *cigar, size_t cigar_cap) {
+    TRY(use_device(h ? &h->c : nullptr));
+    Context *c = &h->c;
+    if (!c->resident.mapped) return fail(SAVONT_B200_ERR_INVALID, "map_resident has not run");
+    if (!best_asv || !strand || !asv_start || !asv_end || !read_start || !read_end || !identity || !cigar_offsets)
+        return fail(SAVONT_B200_ERR_INVALID, "null argument");
+    cigar_offsets[0] = 0;
+    if (c->res_parts.size() <= 1)
+        return best_hits_batch(c, c->resident, best_asv, strand, asv_start, asv_end, read_start, read_end, identity, cigar_offsets, cigar, cigar_cap);
+    for (size_t q = 0; q < c->res_parts.size(); ++q) {
+        const size_t r0 = c->res_cuts[q];
+        TRY(best_hits_batch(c, c->res_parts[q], best_asv + r0, strand + r0, asv_start + r0, asv_end + r0, read_start + r0, read_end + r0,
+                            identity + r0, cigar_offsets + r0, cigar, cigar_cap));
+    }
     return 0;
 }
 

@@ -45,8 +45,11 @@ inline int fail(int code, const char *fmt, ...) {
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
+    bool borrowed = false;        // a view into another buffer (parts of the resident reads): never freed, never grown
+    void borrow(void *ptr, size_t bytes) { release(); p = ptr; cap = bytes; borrowed = true; }
     int ensure(size_t bytes) {
         if (bytes <= cap) return 0;
+        if (borrowed) return fail(SAVONT_B200_ERR_INVALID, "internal: a borrowed device buffer of %zu bytes cannot grow to %zu", cap, bytes);
         if (p) { cudaFree(p); p = nullptr; cap = 0; }
         size_t want = bytes + bytes / 8 + 256;
         cudaError_t e = cudaMalloc(&p, want);
@@ -57,7 +60,7 @@ struct DevBuf {
         cap = want;
         return 0;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release() { if (p && !borrowed) cudaFree(p); p = nullptr; cap = 0; borrowed = false; }
     template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
@@ -123,7 +126,7 @@ struct Context {
     DevBuf d_rank_table; bool use_rank_table = false;
     DevBuf d_snp_keys, d_snp_bloom; uint32_t snp_mask = 0, snp_shift = 0, bloom_shift = 0, bloom_words = 0;
     std::vector<uint64_t> h_snpmers;
-    DevBuf d_phred;
+    DevBuf d_phred, d_thresh; bool thresh_mm0_fails = false;
 
     // ASVs (replicated index)
     std::vector<uint8_t> asv_bases_h; std::vector<uint64_t> asv_offsets_h;
@@ -147,6 +150,9 @@ struct Context {
     bool rf_on = false; ReadFilter rf{}; std::vector<uint64_t> h_hf; DevBuf d_hf_keys; uint32_t hf_mask = 0, hf_shift = 0;
     Batch work, work2, work3, resident, asvb;
     int resident_samples = 1;
+    // map_resident pipeline: the resident reads cut into parts (views of the resident inputs with their own intermediates) that
+    // run on the two compute lanes, so that the sketch / filter kernels of part i+1 share the SMs with the DP kernel of part i
+    std::vector<Batch> res_parts; std::vector<size_t> res_cuts; int resident_parts_req = 0;
     PinBuf pin_small, pin_out;
     cudaStream_t copy_stream = nullptr;          // H2D of batch i+1 overlaps the kernels of batch i
     cudaStream_t d2h_stream = nullptr;           // D2H of batch i-1's results overlaps the kernels of batch i

@@ -35,7 +35,13 @@ struct DeviceParams {
     uint64_t split_mask;    // ~(3 << (k-1))
     uint64_t kmer_mask;     // low 2k bits
     double ratio_thresh, min_frac;
+    // the two f64 tests of the candidate filter (src/alignment.rs:1805-1811, :1829) as integer thresholds, tabulated on the host
+    // with the very divisions the reference performs: frac_min[mn] = smallest m with m / mn >= min_frac (mn = min(|R|, |A|)),
+    // mm_max[m] = largest SNPmer mismatch count with (mm / m) / c <= ratio_thresh; valid for arguments < thresh_n
+    const uint16_t *frac_min, *mm_max;
+    uint32_t thresh_n;
 };
+constexpr uint32_t kThreshTable = 4096;
 
 // Fibonacci hashing shared by host-built and device-probed open-addressing tables: the slot is the
 // TOP log2(cap) bits of key * 2^64/phi (shift = 64 - log2(cap), cap >= 2).
@@ -94,6 +100,7 @@ struct SketchOut {
     uint32_t *spill_pos;
     uint32_t spill_stride;   // entries per warp (>= max_len)
     uint32_t *err;           // [1] error bits
+    uint32_t *work_ctr;      // [1] next sequence to sketch (dynamic distribution over however many CTAs are resident), zeroed per launch
 };
 
 struct SnpSet {              // open addressing, kEmpty64 = empty
@@ -142,6 +149,7 @@ struct FilterOut {
     uint32_t *pair_cnt;    // [n]
     uint32_t *low_mm;      // [n] SNPmer mismatches of the kept candidates
     uint32_t *err;
+    uint32_t *work_ctr;    // [2] next read of the first / second filter launch (zeroed with the batch counters)
 };
 
 struct AlignOut {

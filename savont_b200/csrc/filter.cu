@@ -21,6 +21,17 @@
 
 namespace sb {
 
+// the reference's two f64 tests on integer counts (src/alignment.rs:1805-1811, :1829): looked up in the host-built threshold tables
+// when the arguments are in range, evaluated in f64 in the reference's operation order otherwise
+__device__ __forceinline__ bool frac_too_low(const DeviceParams &p, uint32_t m, uint32_t mn) {
+    if (mn < p.thresh_n) return m < (uint32_t)__ldg(p.frac_min + mn);
+    return (double)m / (double)mn < p.min_frac;
+}
+__device__ __forceinline__ bool ratio_passes(const DeviceParams &p, uint32_t mm, uint32_t m) {
+    if (m < p.thresh_n) return mm <= (uint32_t)__ldg(p.mm_max + m);
+    return (double)mm / (double)m / (double)p.c <= p.ratio_thresh;
+}
+
 struct FilterSmem {
     uint32_t rcap;      // read set capacity (power of two)
     uint32_t acc_words; // ceil(A/2)
@@ -55,7 +66,12 @@ filter_kernel(SeqBatch in, SketchOut sk, AsvIndex ix, PairPool pool, FilterOut o
     const int mid_shift = p.k - 1;
     if (*out.err & kErrSnpPool) return;          // the sketch ran out of pool space: the host grows it and re-runs the batch
 
-    for (uint32_t seq = blockIdx.x * kFilterWarps + warp; seq < in.n; seq += gridDim.x * kFilterWarps) {
+    uint32_t *work = out.work_ctr + (redo_only ? 1 : 0);
+    while (true) {                                                     // reads are handed out dynamically (see sketch_fast.cu)
+        uint32_t seq = 0;
+        if (lane == 0) seq = atomicAdd(work, 1u);
+        seq = __shfl_sync(0xffffffffu, seq, 0);
+        if (seq >= in.n) break;
         if (redo_only && out.cand_status[seq] != 0xFE) continue;       // second launch after filter_compact_kernel (kCandRedo)
         if (sk.status[seq] != 0) {
             if (lane == 0) { out.cand_status[seq] = sk.status[seq]; out.pair_start[seq] = 0; out.pair_cnt[seq] = 0; out.low_mm[seq] = 0; }
@@ -159,7 +175,7 @@ filter_kernel(SeqBatch in, SketchOut sk, AsvIndex ix, PairPool pool, FilterOut o
                     const uint32_t sm = (same[a >> 1] >> sh) & 0xffffu;
                     const uint32_t nA = __ldg(ix.mset_off + a + 1) - __ldg(ix.mset_off + a);
                     const uint32_t mn = nR < nA ? nR : nA;
-                    if (m == 0u || (double)m / (double)mn < p.min_frac) continue;      // src/alignment.rs:1801-1808 analogue
+                    if (m == 0u || frac_too_low(p, m, mn)) continue;                   // src/alignment.rs:1801-1808 analogue
                     keep |= 1u << bit;
                     const uint32_t stash = (m & 0x7fffu) | (((m - sm) > sm) ? 0x8000u : 0u);
                     atomicAnd(&acc[a >> 1], ~(0xffffu << sh));
@@ -282,10 +298,9 @@ filter_kernel(SeqBatch in, SketchOut sk, AsvIndex ix, PairPool pool, FilterOut o
                         }
                         if (m == 0u) continue;                                        // src/alignment.rs:1801-1803
                         const uint32_t mn = nR < nA ? nR : nA;
-                        if ((double)m / (double)mn < p.min_frac) continue;            // :1805-1808
+                        if (frac_too_low(p, m, mn)) continue;                         // :1805-1808
                         any_scored = true;
-                        const double ratio = (double)mm / (double)m / (double)p.c;    // :1811
-                        if (ratio <= p.ratio_thresh) {                                // :1829-1833
+                        if (ratio_passes(p, mm, m)) {                                 // :1811, :1829-1833
                             ++n_low;
                             if (lane == 0) {
                                 bm2[w] |= 1u << bit;
@@ -396,7 +411,11 @@ filter_compact_kernel(SeqBatch in, SketchOut sk, AsvIndex ix, PairPool pool, Fil
     const int mid_shift = p.k - 1;
     if (*out.err & kErrSnpPool) return;
 
-    for (uint32_t seq = blockIdx.x * kFilterWarps + warp; seq < in.n; seq += gridDim.x * kFilterWarps) {
+    while (true) {
+        uint32_t seq = 0;
+        if (lane == 0) seq = atomicAdd(out.work_ctr, 1u);
+        seq = __shfl_sync(0xffffffffu, seq, 0);
+        if (seq >= in.n) break;
         if (sk.status[seq] != 0) {
             if (lane == 0) { out.cand_status[seq] = sk.status[seq]; out.pair_start[seq] = 0; out.pair_cnt[seq] = 0; out.low_mm[seq] = 0; }
             continue;
@@ -552,10 +571,9 @@ filter_compact_kernel(SeqBatch in, SketchOut sk, AsvIndex ix, PairPool pool, Fil
                 }
                 if (m == 0u) continue;                                        // src/alignment.rs:1801-1803
                 const uint32_t mn = nR < nA ? nR : nA;
-                if ((double)m / (double)mn < p.min_frac) continue;            // :1805-1808
+                if (frac_too_low(p, m, mn)) continue;                         // :1805-1808
                 any_scored = true;
-                const double ratio = (double)mm / (double)m / (double)p.c;    // :1811
-                if (ratio <= p.ratio_thresh) {                                // :1829-1833
+                if (ratio_passes(p, mm, m)) {                                 // :1811, :1829-1833
                     if (lane == 0) {
                         const uint32_t opp = m - same;
                         cstash[n_low] = (m & 0x7fffu) | ((opp > same) ? 0x8000u : 0u);

@@ -24,6 +24,9 @@
 //            (src/seeding.rs:550-568) is counted in a small shared-memory hash table.
 // Anything that does not fit the shared-memory budgets (more SNPmer hits / Bloom positives than the per-warp
 // lists hold) raises kErrSnpHits and the host re-runs the batch with the generic kernel.
+#include <cstdlib>
+#include <type_traits>
+
 #include "common.cuh"
 #include "sketch_dev.cuh"
 
@@ -99,7 +102,13 @@ sketch_fast_kernel(SeqBatch in, SketchOut out, SnpSet set, const uint16_t *__res
     uint32_t *hits_p = reinterpret_cast<uint32_t *>(hits_k + lay.hit_cap);
     constexpr bool want_snp = (SRC == 0) && SNP;
 
-    for (uint32_t seq = blockIdx.x * lay.warps + warp; seq < in.n; seq += gridDim.x * lay.warps) {
+    // sequences are handed out dynamically: the kernel makes progress at full efficiency with however many of its CTAs are
+    // resident (it shares the SMs with the DP kernel of the previous part, api.cu map_resident)
+    while (true) {
+        uint32_t seq = 0;
+        if (lane == 0) seq = atomicAdd(out.work_ctr, 1u);
+        seq = __shfl_sync(0xffffffffu, seq, 0);
+        if (seq >= in.n) break;
         const uint64_t off = in.offsets[seq];
         const uint32_t L = (uint32_t)(in.offsets[seq + 1] - off);
         uint2 *planes = out.planes + plane_word_off(off, seq);
@@ -246,13 +255,17 @@ sketch_fast_kernel(SeqBatch in, SketchOut out, SnpSet set, const uint16_t *__res
 
             uint64_t cm = 0, mm = 0;
             uint32_t bidx = pb + p0 + K - 1u;
-            const uint32_t nblk = (T + C - 1u) / C;
-            for (uint32_t b = 0; b < nblk; ++b) {
+            // one block = C consecutive positions (the register window rotates with the unrolled step index).  The last block of
+            // a chunk is usually partial (T = 47 positions = 4 blocks + 3 steps for 1.5 kb reads): it leaves the unrolled body early
+            // instead of computing up to C - 1 positions nobody reads
+            auto block = [&](auto partial_tag, const uint32_t b, const uint32_t steps) {
+                constexpr bool PARTIAL = decltype(partial_tag)::value;
                 const uint32_t bb = extract32(packed, bidx, C) << (32u - 2u * C);      // the block's bases, first one on top
                 bidx += C;
                 uint32_t cmb = 0, mmb = 0;
 #pragma unroll
                 for (int jj = 0; jj < (int)C; ++jj) {
+                    if (PARTIAL && (uint32_t)jj >= steps) break;
                     const uint32_t e = (bb >> (30 - 2 * jj)) & 3u;
                     Flo = mad_lo(Flo, 4u, e);                                  // (Flo << 2) | e
                     Rlo = __funnelshift_r(Rlo, Rhi, 2);
@@ -276,7 +289,10 @@ sketch_fast_kernel(SeqBatch in, SketchOut out, SnpSet set, const uint16_t *__res
                 }
                 cm |= (uint64_t)cmb << (C * b);
                 mm |= (uint64_t)mmb << (C * b);
-            }
+            };
+            const uint32_t full_blocks = T / C, rest = T - full_blocks * C;
+            for (uint32_t b = 0; b < full_blocks; ++b) block(std::false_type{}, b, C);
+            if (rest) block(std::true_type{}, full_blocks, rest);
             const uint64_t valid = ns >= 64u ? ~0ull : ((1ull << ns) - 1ull);
             mm &= valid; cm &= valid;
 
@@ -482,8 +498,10 @@ static FastSmem fast_layout(uint32_t max_len, const SnpSet &set) {
     lay.stage_bytes = (stage + 15u) & ~15u;
     // one persistent CTA per SM: as many warps as the per-warp regions allow in 225 KB (32 for 16S reads, fewer for
     // multi-kb operon reads)
-    lay.warps = kFastWarps;
-    while (lay.warps > 8u && lay.total() > 225u * 1024u) lay.warps -= 8u;
+    static const uint32_t want = [] { const char *e = getenv("SAVONT_B200_SKETCH_WARPS"); const int v = e ? atoi(e) : 0;
+                                      return (v == 8 || v == 16 || v == 24 || v == 32) ? (uint32_t)v : 16u; }();
+    lay.warps = want;
+    while (lay.warps > 8u && lay.total() > 225u * 1024u / (kFastWarps / lay.warps)) lay.warps -= 8u;
     return lay;
 }
 
@@ -499,7 +517,11 @@ void launch_sketch_fast(const SeqBatch &in, const SketchOut &out, const SnpSet &
     if (in.n == 0) return;
     const FastSmem lay = fast_layout(in.max_len, set);
     const size_t smem = lay.total();
-    uint32_t grid = (uint32_t)sm_count;
+    // as many CTAs per SM as 32 warps and the shared memory allow (two 16-warp CTAs by default: when the DP kernel holds half of
+    // an SM's registers one of them still fits)
+    uint32_t per_sm = kFastWarps / lay.warps;
+    while (per_sm > 1u && per_sm * smem > 225u * 1024u) --per_sm;
+    uint32_t grid = (uint32_t)sm_count * per_sm;
     const uint32_t need = (in.n + lay.warps - 1) / lay.warps;
     if (grid > need) grid = need;
     if (in.dna_words != nullptr) {

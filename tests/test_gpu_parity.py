@@ -248,6 +248,20 @@ def test_best_hit_alignment_records(ctx, strand_mode):
     assert np.array_equal(asv_span[reads], got["asv_end"][reads] - got["asv_start"][reads])
     assert np.array_equal(read_span[reads], got["read_end"][reads] - got["read_start"][reads])
     assert ops.max() <= 2 and np.all((ops[1:] != ops[:-1]) | (owner[1:] != owner[:-1]))
+    # the same through the parts pipeline (the resident reads cut into 5 parts on two streams): identical results
+    ctx.set_resident_parts(5)
+    try:
+        ctx.upload_reads(bases, r["quals"], offs)
+        st = ctx.map_resident()
+        assert st["n_batches"] == 5
+        assert_same(ctx.fetch_resident(), want, MAP_KEYS, "map_resident in 5 parts")
+        got5 = ctx.best_hits_resident()
+        for key in ("best_asv", "strand", "asv_start", "asv_end", "read_start", "read_end", "cigar_offsets", "cigar"):
+            assert np.array_equal(got5[key], got[key]), key
+        assert np.array_equal(np.isnan(got5["identity"]), np.isnan(got["identity"]))
+        assert np.array_equal(got5["identity"][reads], got["identity"][reads])
+    finally:
+        ctx.set_resident_parts(0)
 
 
 def test_map_reads_pooled_samples_and_degenerate_reads(ctx):
@@ -341,12 +355,17 @@ def test_map_reads_edge_cases(ctx):
     # no qualities at all (FASTA reads): every SNPmer passes the gate (mid-base Q = 60)
     r = w.reads(800)
     assert_same(ctx.map_reads(r["bases"], None, r["offsets"]), orc.map_reads(r["bases"], None, r["offsets"]), MAP_KEYS, "no quals")
-    # file_idx beyond n_samples: counted in the per-ASV counters, not in the per-sample matrix
+    # file_idx beyond n_samples is rejected (it would index outside the S x A matrix); inside the range: per-sample counts
     fidx = np.arange(800, dtype=np.uint32) % 5
-    got = ctx.map_reads(r["bases"], r["quals"], r["offsets"], file_idx=fidx, n_samples=3)
-    want = orc.map_reads(r["bases"], r["quals"], r["offsets"], file_idx=fidx, n_samples=3)
-    assert_same(got, want, MAP_KEYS, "sample ids out of range")
-    assert int(got["sample_singleton"].sum()) < int(got["unambig"].sum())
+    with pytest.raises(_lib.SavontB200Error):
+        ctx.map_reads(r["bases"], r["quals"], r["offsets"], file_idx=fidx, n_samples=3)
+    bad = fidx.copy(); bad[17] = 0x80000001
+    with pytest.raises(_lib.SavontB200Error):
+        ctx.map_reads(r["bases"], r["quals"], r["offsets"], file_idx=bad, n_samples=5)
+    got = ctx.map_reads(r["bases"], r["quals"], r["offsets"], file_idx=fidx, n_samples=5)
+    want = orc.map_reads(r["bases"], r["quals"], r["offsets"], file_idx=fidx, n_samples=5)
+    assert_same(got, want, MAP_KEYS, "five samples")
+    assert int(got["sample_singleton"].sum()) == int(got["unambig"].sum())
     # lower-case and IUPAC bases follow BYTE_TO_SEQ
     lb = r["bases"].copy(); lb[::7] |= 0x20; lb[5::501] = ord("R")
     assert_same(ctx.map_reads(lb, r["quals"], r["offsets"]), orc.map_reads(lb, r["quals"], r["offsets"]), MAP_KEYS, "lower case / IUPAC")
@@ -425,6 +444,13 @@ def test_map_twin_reads(ctx, name, kw, n, kmer48, k, c):
     ctx.upload_twin_reads(tw, n_samples=ns)
     ctx.map_resident()
     assert_same(ctx.fetch_resident(), want, MAP_KEYS, f"twin resident {name}")
+    ctx.set_resident_parts(3)
+    try:
+        ctx.upload_twin_reads(tw, n_samples=ns)
+        assert ctx.map_resident()["n_batches"] == 3
+        assert_same(ctx.fetch_resident(), want, MAP_KEYS, f"twin resident in 3 parts {name}")
+    finally:
+        ctx.set_resident_parts(0)
     ctx.set_params(_lib.default_params())
 
 
