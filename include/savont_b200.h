@@ -14,7 +14,13 @@
  *   - there is NO CPU fallback: without a usable CUDA device every call fails with
  *     SAVONT_B200_ERR_CUDA.
  *   - one context = one GPU; use one context per device (one process per GPU under
- *     torch.distributed / NCCL, or one thread per context).
+ *     torch.distributed / NCCL), or the multi-GPU handle savont_b200_create_multi, which owns a
+ *     context per device inside one process.
+ *   - call order: savont_b200_set_params first, then load_snpmers / load_asvs (changing k later
+ *     rebuilds the SNPmer set's Bloom filter and the ASV index from the host copies).
+ *   - NM, best_nm, leq10 and every CIGAR follow the banded edit distance of DESIGN.md section 3,
+ *     NOT minimap2's local affine NM that the reference reads (src/alignment.rs:1848-1863);
+ *     DESIGN.md section 2 quantifies the difference in classes and depths.
  *   - sequences are concatenated ASCII (`bases`, and Phred+33 `quals` or NULL) with
  *     `offsets[n+1]`; k-mers are u64 in the reference's encoding (A=0 C=1 G=2 T=3, first base
  *     in the highest used bit pair, canonical-by-splitmer; low 48 bits == Kmer48).
@@ -29,7 +35,7 @@
 extern "C" {
 #endif
 
-#define SAVONT_B200_ABI_VERSION 7
+#define SAVONT_B200_ABI_VERSION 8
 
 typedef struct savont_b200_ctx savont_b200_ctx;
 
@@ -91,6 +97,7 @@ typedef struct savont_b200_stats {
     uint64_t h2d_bytes, d2h_bytes;
     uint64_t kernel_launches;
     uint64_t n_batches;
+    double   gather_ms;                                 /* host time spent gathering per-read buffers (the *_ptrs entry points) */
 } savont_b200_stats;
 
 int         savont_b200_abi_version(void);
@@ -238,8 +245,8 @@ int savont_b200_upload_twin_reads(savont_b200_ctx *ctx, const uint64_t *dna_word
                                   const uint32_t *lengths, const void *snpmer_kmers, int snpmer_kmer_bytes,
                                   const uint64_t *snpmer_offsets, const uint32_t *file_idx, size_t n_reads, int n_samples);
 /* The resident reads are processed as n_parts parts pipelined over two internal streams, so that the sketch / filter kernels
- * of one part share the SMs with the DP kernel of the previous one (same results for every n_parts).  0 = automatic (8 parts
- * from 262144 reads on, else 1); takes effect at the next upload. */
+ * of one part share the SMs with the DP kernel of the previous one (same results for every n_parts).  0 = default (one part:
+ * measured on B200, 4-16 parts were never faster than one pass); takes effect at the next upload. */
 int savont_b200_set_resident_parts(savont_b200_ctx *ctx, int n_parts);
 int savont_b200_map_resident(savont_b200_ctx *ctx, int zero_counters, savont_b200_stats *stats);
 int savont_b200_fetch_resident(savont_b200_ctx *ctx, uint8_t *status, int32_t *best_nm, uint64_t *class_offsets,
@@ -345,6 +352,56 @@ int savont_b200_snpmer_compare(savont_b200_ctx *ctx, const uint64_t *cons_kmers,
                                const uint64_t *read_kmers, const uint64_t *read_offsets, size_t n_reads, uint32_t *best_cons,
                                uint32_t *best_mismatches, uint32_t *best_matches, uint16_t *matrix /* may be NULL */,
                                savont_b200_stats *stats /* may be NULL */);
+
+/* The same closure from a Vec<TwinRead> as it lies in the reference's memory: an array of structs whose dna_seq and snpmer_kmers
+ * are separate heap allocations (src/types.rs:386-412).  One pointer per read: dna_ptrs[r] -> the ceil(lengths[r] / 32) Seq<Dna>
+ * words of read r, snpmer_ptrs[r] -> its snpmer_counts[r] k-mers (snpmer_kmer_bytes = 6: the Vec<Kmer48> bytes, 8: u64).  Per
+ * internal batch the library gathers the buffers with host threads (savont_b200_set_host_threads, 0 = all cores up to 32) into
+ * page-locked staging and uploads from there; the gather of batch i+1 runs under the kernels of batch i.  stats->gather_ms = the
+ * host time of the gathers.  Outputs as map_reads. */
+int savont_b200_set_host_threads(savont_b200_ctx *ctx, int n_threads);
+int savont_b200_map_twin_read_ptrs(savont_b200_ctx *ctx, const uint64_t *const *dna_ptrs, const uint32_t *lengths,
+                                   const void *const *snpmer_ptrs, const uint32_t *snpmer_counts, int snpmer_kmer_bytes,
+                                   const uint32_t *file_idx, size_t n_reads, int n_samples, uint8_t *status, int32_t *best_nm,
+                                   uint64_t *class_offsets, uint32_t *class_asv, size_t class_cap, uint64_t *unambig,
+                                   uint64_t *ambig, uint64_t *leq10, uint64_t *totals, uint64_t *sample_singleton,
+                                   savont_b200_stats *stats);
+
+/* ---- One process, several GPUs.  `savont asv` is a single process whose rayon pool walks the reads
+ * (src/alignment.rs:1786, src/main.rs:476-480): the drop-in for it on a multi-GPU box is ONE handle.  It owns a context per device
+ * (device_ids may repeat a device: several contexts on one GPU), replicates parameters / SNPmer set / ASV index, shards the reads
+ * of a call into contiguous ranges in read order (src/main.rs:538), runs every shard from its own host thread, sums the counter
+ * vectors [unambig | ambig | leq10 | assigned | filtered | singleton S x A] across the devices and returns the per-read results
+ * concatenated in read order -- the same outputs as the single-context calls.  The sum is the path's only collective:
+ * savont_b200_multi_set_allreduce(0) (default) = one kernel on the first device that reads and rewrites all devices' vectors through
+ * peer memory (NVLink), (1) = ncclAllReduce (libnccl.so.2 is loaded on demand).  A failing device reports its code and message. */
+typedef struct savont_b200_multi savont_b200_multi;
+int savont_b200_create_multi(const int *device_ids, int n_dev, savont_b200_multi **out);
+int savont_b200_multi_destroy(savont_b200_multi *m);
+int savont_b200_multi_num_devices(savont_b200_multi *m, int *n_dev);
+int savont_b200_multi_ctx(savont_b200_multi *m, int i, savont_b200_ctx **ctx);       /* the i-th device's context (borrowed) */
+int savont_b200_multi_set_allreduce(savont_b200_multi *m, int mode);
+int savont_b200_multi_set_host_threads(savont_b200_multi *m, int n_threads);         /* gather threads over all devices; 0 = all cores */
+int savont_b200_multi_set_params(savont_b200_multi *m, const savont_b200_params *p);
+int savont_b200_multi_set_batch_reads(savont_b200_multi *m, size_t max_reads_per_batch);
+int savont_b200_multi_load_snpmers(savont_b200_multi *m, const uint64_t *kmers, size_t n);
+int savont_b200_multi_load_asvs(savont_b200_multi *m, const uint8_t *bases, const uint64_t *offsets, size_t n_asv);
+int savont_b200_multi_map_reads(savont_b200_multi *m, const uint8_t *bases, const uint8_t *quals, const uint64_t *offsets,
+                                const uint32_t *file_idx, size_t n_reads, int n_samples, uint8_t *status, int32_t *best_nm,
+                                uint64_t *class_offsets, uint32_t *class_asv, size_t class_cap, uint64_t *unambig, uint64_t *ambig,
+                                uint64_t *leq10, uint64_t *totals, uint64_t *sample_singleton, savont_b200_stats *stats);
+int savont_b200_multi_map_twin_reads(savont_b200_multi *m, const uint64_t *dna_words, const uint64_t *dna_word_offsets,
+                                     const uint32_t *lengths, const void *snpmer_kmers, int snpmer_kmer_bytes,
+                                     const uint64_t *snpmer_offsets, const uint32_t *file_idx, size_t n_reads, int n_samples,
+                                     uint8_t *status, int32_t *best_nm, uint64_t *class_offsets, uint32_t *class_asv, size_t class_cap,
+                                     uint64_t *unambig, uint64_t *ambig, uint64_t *leq10, uint64_t *totals, uint64_t *sample_singleton,
+                                     savont_b200_stats *stats);
+int savont_b200_multi_map_twin_read_ptrs(savont_b200_multi *m, const uint64_t *const *dna_ptrs, const uint32_t *lengths,
+                                         const void *const *snpmer_ptrs, const uint32_t *snpmer_counts, int snpmer_kmer_bytes,
+                                         const uint32_t *file_idx, size_t n_reads, int n_samples, uint8_t *status, int32_t *best_nm,
+                                         uint64_t *class_offsets, uint32_t *class_asv, size_t class_cap, uint64_t *unambig,
+                                         uint64_t *ambig, uint64_t *leq10, uint64_t *totals, uint64_t *sample_singleton,
+                                         savont_b200_stats *stats);
 
 /* Pinned host memory helpers (inputs placed here are copied without a staging pass). */
 int savont_b200_host_alloc(size_t bytes, void **out);

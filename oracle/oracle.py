@@ -101,6 +101,8 @@ def lib():
         L.so_consensus_pileups.restype = C.c_longlong
         L.so_high_freq_kmers.restype = C.c_uint32
         L.so_set_read_filter.restype = None
+        L.so_nm_pair.restype = C.c_int
+        L.so_nm_pair.argtypes = [C.POINTER(Params), C.POINTER(C.c_uint8), C.c_int, C.POINTER(C.c_uint8), C.c_int, C.POINTER(C.c_int32)]
         _lib = L
     return _lib
 
@@ -118,6 +120,16 @@ def concat(seqs):
         offs[1:] = np.cumsum([len(s) for s in seqs], dtype=np.uint64)
     buf = np.frombuffer(b"".join(bytes(s) for s in seqs), dtype=np.uint8).copy() if len(seqs) else np.zeros(0, np.uint8)
     return buf, offs
+
+
+def nm_pair(params: Params, asv: bytes, read: bytes):
+    """NM of one pair (both given in alignment orientation, ASCII) under params.nm_mode -> (has_alignment, nm); a11 sensitivity study"""
+    L = lib()
+    a = np.array([L.so_encode_base(b) for b in bytes(asv)], np.uint8)
+    r = np.array([L.so_encode_base(b) for b in bytes(read)], np.uint8)
+    nm = C.c_int32(0)
+    ok = L.so_nm_pair(C.byref(params), _p(a, C.c_uint8), C.c_int(len(a)), _p(r, C.c_uint8), C.c_int(len(r)), C.byref(nm))
+    return bool(ok), int(nm.value)
 
 
 def mm_hash64(x: int) -> int:

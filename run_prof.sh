@@ -1,7 +1,7 @@
 set -x
 mkdir -p gpurun_out
-python -m pytest tests -x -q -m gpu 2>&1 | tail -8 > gpurun_out/r02a_tests.log
-python bench.py --steps 5 --warmup 3 > gpurun_out/r02a_ont16s_1gpu.json 2> gpurun_out/r02a_ont16s_1gpu.err
-SAVONT_B200_DP_TAIL=0 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-twin > gpurun_out/r02a_ont16s_notail.json 2>/dev/null
-python bench.py --workload hifi16s --steps 5 --warmup 3 --no-cpu-baseline --no-twin > gpurun_out/r02a_hifi16s_1gpu.json 2>/dev/null
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/r02a_smi.txt
+ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_r02c.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-twin --e2e-steps 1 > gpurun_out/b_ncu_c.log 2>&1
+for k in sketch_fast_kernel filter_kernel align_nm_kernel; do
+ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 1 -f -o gpurun_out/prof_r02c_$k python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-twin --e2e-steps 1 > gpurun_out/ncu_c_$k.log 2>&1
+done
+ls -la gpurun_out/*.ncu-rep

@@ -45,6 +45,7 @@ class Stats(C.Structure):
         ("h2d_ms", C.c_double), ("d2h_ms", C.c_double), ("total_ms", C.c_double),
         ("n_reads", C.c_uint64), ("n_bases", C.c_uint64), ("n_pairs", C.c_uint64), ("dp_cells", C.c_uint64),
         ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("kernel_launches", C.c_uint64), ("n_batches", C.c_uint64),
+        ("gather_ms", C.c_double),
     ]
 
     def as_dict(self):
@@ -135,6 +136,14 @@ def pinned_array(nbytes: int) -> np.ndarray:
     _check(lib().savont_b200_host_alloc(C.c_size_t(max(nbytes, 1)), C.byref(ptr)))
     buf = (C.c_uint8 * max(nbytes, 1)).from_address(ptr.value)
     return np.frombuffer(buf, dtype=np.uint8, count=nbytes)
+
+
+def _heap_args(heap):
+    dp = np.ascontiguousarray(heap["dna_ptrs"], dtype=np.uint64); sp = np.ascontiguousarray(heap["snpmer_ptrs"], dtype=np.uint64)
+    ln = np.ascontiguousarray(heap["lengths"], dtype=np.uint32); sc = np.ascontiguousarray(heap["snpmer_counts"], dtype=np.uint32)
+    fi = heap.get("file_idx")
+    fi = None if fi is None else np.ascontiguousarray(fi, dtype=np.uint32)
+    return dp, ln, sp, sc, int(heap["kmer_bytes"]), fi
 
 
 class Context:
@@ -362,6 +371,25 @@ class Context:
                                                  _p(B["totals"], C.c_uint64), _p(B["sample_singleton"], C.c_uint64), C.byref(st)))
         return self._finish(B, n, n_samples, st)
 
+    def set_host_threads(self, n):
+        _check(self.L.savont_b200_set_host_threads(self.h, C.c_int(int(n))))
+
+    def map_twin_read_ptrs(self, heap, n_samples=1, class_cap=None):
+        """heap: dict(dna_ptrs u64[n], lengths u32[n], snpmer_ptrs u64[n], snpmer_counts u32[n], kmer_bytes, file_idx | None) --
+        one pointer per read into caller-owned host memory (savont_b200/twin.py: scatter_to_heap)"""
+        dp, ln, sp, sc, kb, fi = _heap_args(heap)
+        n = len(ln)
+        class_cap = class_cap or max(8 * n + 1024, 16)
+        B = self._out_buffers(n, n_samples, class_cap)
+        st = Stats()
+        _check(self.L.savont_b200_map_twin_read_ptrs(self.h, C.c_void_p(dp.ctypes.data), _p(ln, C.c_uint32), C.c_void_p(sp.ctypes.data),
+                                                     _p(sc, C.c_uint32), C.c_int(kb), _p(fi, C.c_uint32), C.c_size_t(n), C.c_int(n_samples),
+                                                     _p(B["status"], C.c_uint8), _p(B["best_nm"], C.c_int32), _p(B["class_offsets"], C.c_uint64),
+                                                     _p(B["class_asv"], C.c_uint32), C.c_size_t(class_cap), _p(B["unambig"], C.c_uint64),
+                                                     _p(B["ambig"], C.c_uint64), _p(B["leq10"], C.c_uint64), _p(B["totals"], C.c_uint64),
+                                                     _p(B["sample_singleton"], C.c_uint64), C.byref(st)))
+        return self._finish(B, n, n_samples, st)
+
     def upload_twin_reads(self, twin, n_samples=1):
         w, wo, ln, sk, kb, so, fi = self._twin_args(twin)
         _check(self.L.savont_b200_upload_twin_reads(self.h, _p(w, C.c_uint64), _p(wo, C.c_uint64), _p(ln, C.c_uint32),
@@ -530,3 +558,91 @@ class Context:
         ptr = C.c_void_p(); n = C.c_size_t()
         _check(self.L.savont_b200_counts_dev(self.h, C.byref(ptr), C.byref(n)))
         return int(ptr.value), int(n.value)
+
+
+class MultiContext:
+    """One process, several GPUs (savont_b200_create_multi): a context per device, reads sharded in read order, counters summed
+    across the devices, results concatenated.  Same call order and result dictionaries as Context."""
+
+    def __init__(self, devices, params: Params | None = None, allreduce: str = "peer"):
+        self.L = lib()
+        self.devices = [int(d) for d in devices]
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        h = C.c_void_p()
+        _check(self.L.savont_b200_create_multi(arr, C.c_int(len(self.devices)), C.byref(h)))
+        self.h = h
+        self.n_asv = 0
+        if params is not None:
+            self.set_params(params)
+        if allreduce != "peer":
+            self.set_allreduce(allreduce)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.savont_b200_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_params(self, p: Params):
+        _check(self.L.savont_b200_multi_set_params(self.h, C.byref(p)))
+
+    def set_allreduce(self, mode):
+        _check(self.L.savont_b200_multi_set_allreduce(self.h, C.c_int({"peer": 0, "nccl": 1}[mode])))
+
+    def set_host_threads(self, n):
+        _check(self.L.savont_b200_multi_set_host_threads(self.h, C.c_int(int(n))))
+
+    def set_batch_reads(self, n):
+        _check(self.L.savont_b200_multi_set_batch_reads(self.h, C.c_size_t(n)))
+
+    def load_snpmers(self, kmers):
+        k = np.ascontiguousarray(kmers, dtype=np.uint64)
+        _check(self.L.savont_b200_multi_load_snpmers(self.h, _p(k, C.c_uint64), C.c_size_t(len(k))))
+
+    def load_asvs(self, bases, offsets):
+        b = _u8(bases); o = np.ascontiguousarray(offsets, dtype=np.uint64)
+        _check(self.L.savont_b200_multi_load_asvs(self.h, _p(b, C.c_uint8), _p(o, C.c_uint64), C.c_size_t(len(o) - 1)))
+        self.n_asv = len(o) - 1
+
+    _out_buffers = Context._out_buffers
+    _finish = Context._finish
+
+    def _outs(self, B, class_cap, st):
+        return (_p(B["status"], C.c_uint8), _p(B["best_nm"], C.c_int32), _p(B["class_offsets"], C.c_uint64), _p(B["class_asv"], C.c_uint32),
+                C.c_size_t(class_cap), _p(B["unambig"], C.c_uint64), _p(B["ambig"], C.c_uint64), _p(B["leq10"], C.c_uint64),
+                _p(B["totals"], C.c_uint64), _p(B["sample_singleton"], C.c_uint64), C.byref(st))
+
+    def map_reads(self, bases, quals, offsets, file_idx=None, n_samples=1, class_cap=None):
+        b = _u8(bases); q = _u8(quals); o = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(o) - 1
+        fi = None if file_idx is None else np.ascontiguousarray(file_idx, dtype=np.uint32)
+        class_cap = class_cap or max(8 * n + 1024, 16)
+        B = self._out_buffers(n, n_samples, class_cap); st = Stats()
+        _check(self.L.savont_b200_multi_map_reads(self.h, _p(b, C.c_uint8), _p(q, C.c_uint8), _p(o, C.c_uint64), _p(fi, C.c_uint32),
+                                                  C.c_size_t(n), C.c_int(n_samples), *self._outs(B, class_cap, st)))
+        return self._finish(B, n, n_samples, st)
+
+    def map_twin_reads(self, twin, n_samples=1, class_cap=None):
+        w, wo, ln, sk, kb, so, fi = Context._twin_args(twin)
+        n = len(ln)
+        class_cap = class_cap or max(8 * n + 1024, 16)
+        B = self._out_buffers(n, n_samples, class_cap); st = Stats()
+        _check(self.L.savont_b200_multi_map_twin_reads(self.h, _p(w, C.c_uint64), _p(wo, C.c_uint64), _p(ln, C.c_uint32),
+                                                       C.c_void_p(sk.ctypes.data), C.c_int(kb), _p(so, C.c_uint64), _p(fi, C.c_uint32),
+                                                       C.c_size_t(n), C.c_int(n_samples), *self._outs(B, class_cap, st)))
+        return self._finish(B, n, n_samples, st)
+
+    def map_twin_read_ptrs(self, heap, n_samples=1, class_cap=None):
+        dp, ln, sp, sc, kb, fi = _heap_args(heap)
+        n = len(ln)
+        class_cap = class_cap or max(8 * n + 1024, 16)
+        B = self._out_buffers(n, n_samples, class_cap); st = Stats()
+        _check(self.L.savont_b200_multi_map_twin_read_ptrs(self.h, C.c_void_p(dp.ctypes.data), _p(ln, C.c_uint32), C.c_void_p(sp.ctypes.data),
+                                                           _p(sc, C.c_uint32), C.c_int(kb), _p(fi, C.c_uint32), C.c_size_t(n),
+                                                           C.c_int(n_samples), *self._outs(B, class_cap, st)))
+        return self._finish(B, n, n_samples, st)

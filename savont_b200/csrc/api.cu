@@ -5,6 +5,10 @@
 // align.cu, assign.cu; Stage 1 k-mer counting: kmercount.cu with its host side in api_kmer.cu).  The host only orchestrates: stages buffers, builds the (small, once per call)
 // replicated ASV index from the GPU-produced ASV sketches, and sums counters.  There is no CPU
 // fallback: without a device every entry point fails with SAVONT_B200_ERR_CUDA.
+#include <atomic>
+#include <chrono>
+#include <thread>
+
 #include "api_internal.cuh"
 
 namespace sb {
@@ -279,7 +283,8 @@ static int resident_part_count(const Context *c, size_t n) {
     if (c->resident_parts_req > 0) return c->resident_parts_req;
     static const int env = [] { const char *e = getenv("SAVONT_B200_RESIDENT_PARTS"); return e ? atoi(e) : 0; }();
     if (env > 0) return env;
-    return n >= 262144 ? 8 : 1;
+    (void)n;
+    return 1;     // measured on B200 (profiles/r02b_parts_sweep.txt): 4-16 parts never beat one pass -- every kernel of the path is issue bound
 }
 static int build_resident_parts(Context *c) {
     Batch &R = c->resident;
@@ -1316,12 +1321,14 @@ static int map_batches(Context *c, const std::vector<size_t> &cuts, const Upload
     for (size_t bi = 0; bi < nb; ++bi) {
         const int slot = (int)(bi % 3), lane = (int)(bi & 1);
         Batch &b = *bufs[slot];
-        if (bi + 1 < nb) TRY(upload(bi + 1));       // slot (bi+1) % 3 held batch bi-2: finished and fetched
         {
             LaneGuard g(c, lane);
             CK(cudaStreamWaitEvent(c->stream, c->ev_up[slot], 0));
             TRY(enqueue_path(c, b, n_samples));
         }
+        // batch bi's kernels are queued: now stage batch bi+1 (slot (bi+1) % 3 held batch bi-2: finished and fetched).  With the
+        // pointer entry point this includes the host-side gather of the reads' heap buffers, which so runs under bi's kernels
+        if (bi + 1 < nb) TRY(upload(bi + 1));
         TRY(finish_prev());
         prev = Pending{&b, cuts[bi + 1] - cuts[bi], cuts[bi], slot, lane, true};
         st.n_batches += 1;
@@ -1393,6 +1400,93 @@ int savont_b200_map_twin_reads(savont_b200_ctx *h, const uint64_t *dna_words, co
     };
     return map_batches(c, cuts, up, n_samples, status, best_nm, class_offsets, class_asv, class_cap, unambig, ambig, leq10, totals,
                        sample_singleton, stats);
+}
+
+// ---- TwinReads as they really lie in the reference's memory: a Vec<TwinRead> is an array of structs whose dna_seq / snpmer_kmers
+// are separate heap allocations (src/types.rs:386-412).  The caller passes one pointer per read; per batch the library gathers the
+// buffers with host threads into page-locked staging (three slots, one per batch in flight) and uploads from there, so the gather of
+// batch i+1 runs while batch i computes.
+struct PtrInput {
+    const uint64_t *const *dna_ptrs; const uint32_t *lengths; const void *const *snp_ptrs; const uint32_t *snp_counts; int kmer_bytes;
+    const uint32_t *file_idx;
+};
+static int gather_batch(Context *c, int slot, const PtrInput &in, size_t r0, size_t n, TwinInput *out, double *gather_ms) {
+    const auto t0 = std::chrono::steady_clock::now();
+    std::vector<uint64_t> &woff = c->gather_woff[slot], &soff = c->gather_soff[slot];
+    woff.resize(n + 1); soff.resize(n + 1);
+    woff[0] = 0; soff[0] = 0;
+    for (size_t i = 0; i < n; ++i) {
+        woff[i + 1] = woff[i] + ((uint64_t)in.lengths[r0 + i] + 31u) / 32u;
+        soff[i + 1] = soff[i] + in.snp_counts[r0 + i];
+    }
+    TRY(c->gather_words[slot].ensure((woff[n] + 2) * 8));
+    TRY(c->gather_snp[slot].ensure(soff[n] * (size_t)in.kmer_bytes + 16));
+    uint64_t *dw = c->gather_words[slot].as<uint64_t>();
+    uint8_t *ds = c->gather_snp[slot].as<uint8_t>();
+    const size_t kb = (size_t)in.kmer_bytes;
+    int T = c->host_threads > 0 ? c->host_threads : (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
+    if ((size_t)T > n / 2048 + 1) T = (int)(n / 2048 + 1);
+    std::atomic<int> bad{0};
+    auto work = [&](int t) {
+        const size_t a = n * (size_t)t / (size_t)T, b = n * (size_t)(t + 1) / (size_t)T;
+        for (size_t i = a; i < b; ++i) {
+            const uint64_t nw = woff[i + 1] - woff[i], ns = soff[i + 1] - soff[i];
+            if ((nw && !in.dna_ptrs[r0 + i]) || (ns && !in.snp_ptrs[r0 + i])) { bad.store(1); continue; }
+            if (nw) memcpy(dw + woff[i], in.dna_ptrs[r0 + i], nw * 8);
+            if (ns) memcpy(ds + soff[i] * kb, in.snp_ptrs[r0 + i], ns * kb);
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th) x.join();
+    if (bad.load()) return fail(SAVONT_B200_ERR_INVALID, "null read buffer in batch starting at read %zu", r0);
+    *out = TwinInput{dw, woff.data(), in.lengths + r0, ds, in.kmer_bytes, soff.data(), in.file_idx ? in.file_idx + r0 : nullptr};
+    *gather_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return 0;
+}
+
+int savont_b200_set_host_threads(savont_b200_ctx *h, int n_threads) {
+    if (!h) return fail(SAVONT_B200_ERR_INVALID, "null context");
+    if (n_threads < 0 || n_threads > 1024) return fail(SAVONT_B200_ERR_INVALID, "n_threads must be in 0..1024");
+    h->c.host_threads = n_threads;
+    return 0;
+}
+
+int savont_b200_map_twin_read_ptrs(savont_b200_ctx *h, const uint64_t *const *dna_ptrs, const uint32_t *lengths,
+                                   const void *const *snpmer_ptrs, const uint32_t *snpmer_counts, int snpmer_kmer_bytes,
+                                   const uint32_t *file_idx, size_t n_reads, int n_samples, uint8_t *status, int32_t *best_nm,
+                                   uint64_t *class_offsets, uint32_t *class_asv, size_t class_cap, uint64_t *unambig, uint64_t *ambig,
+                                   uint64_t *leq10, uint64_t *totals, uint64_t *sample_singleton, savont_b200_stats *stats) {
+    TRY(use_device(h ? &h->c : nullptr));
+    Context *c = &h->c;
+    TRY(ensure_index(c));
+    if (!status || !best_nm || !class_offsets) return fail(SAVONT_B200_ERR_INVALID, "null argument");
+    if (n_reads && (!dna_ptrs || !lengths || !snpmer_ptrs || !snpmer_counts)) return fail(SAVONT_B200_ERR_INVALID, "null argument");
+    if (snpmer_kmer_bytes != 6 && snpmer_kmer_bytes != 8) return fail(SAVONT_B200_ERR_INVALID, "snpmer_kmer_bytes must be 6 (Kmer48) or 8 (u64)");
+    if (n_samples < 1) return fail(SAVONT_B200_ERR_INVALID, "n_samples must be >= 1");
+    TRY(validate_file_idx(file_idx, n_reads, n_samples));
+    const PtrInput in{dna_ptrs, lengths, snpmer_ptrs, snpmer_counts, snpmer_kmer_bytes, file_idx};
+    std::vector<size_t> cuts{0};
+    for (size_t r0 = 0; r0 < n_reads;) {
+        size_t r1 = std::min(n_reads, r0 + ramp_batch(c, cuts.size() - 1, n_reads - r0));
+        uint64_t bases = 0;
+        for (size_t r = r0; r < r1; ++r) { bases += lengths[r]; if (bases > (3ull << 30)) { r1 = std::max(r, r0 + 1); break; } }
+        cuts.push_back(r1);
+        r0 = r1;
+    }
+    double gather_ms = 0.0;
+    auto up = [&](Batch &b, size_t r0, size_t n, uint64_t *bytes, cudaStream_t st) -> int {
+        const int slot = &b == &c->work ? 0 : (&b == &c->work2 ? 1 : 2);
+        TwinInput ti{};
+        TRY(gather_batch(c, slot, in, r0, n, &ti, &gather_ms));
+        return batch_upload_twin(c, b, ti, 0, n, bytes, st);
+    };
+    const int rc = map_batches(c, cuts, up, n_samples, status, best_nm, class_offsets, class_asv, class_cap, unambig, ambig, leq10, totals,
+                               sample_singleton, stats);
+    c->last_stats.gather_ms = gather_ms;
+    if (stats) stats->gather_ms = gather_ms;
+    return rc;
 }
 
 int savont_b200_upload_twin_reads(savont_b200_ctx *h, const uint64_t *dna_words, const uint64_t *dna_word_offsets,

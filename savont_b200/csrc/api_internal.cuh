@@ -154,6 +154,8 @@ struct Context {
     // run on the two compute lanes, so that the sketch / filter kernels of part i+1 share the SMs with the DP kernel of part i
     std::vector<Batch> res_parts; std::vector<size_t> res_cuts; int resident_parts_req = 0;
     PinBuf pin_small, pin_out;
+    // savont_b200_map_twin_read_ptrs: page-locked staging of the gathered reads, one slot per batch in flight
+    PinBuf gather_words[3], gather_snp[3]; std::vector<uint64_t> gather_woff[3], gather_soff[3]; int host_threads = 0;
     cudaStream_t copy_stream = nullptr;          // H2D of batch i+1 overlaps the kernels of batch i
     cudaStream_t d2h_stream = nullptr;           // D2H of batch i-1's results overlaps the kernels of batch i
     cudaEvent_t ev_d2h[2] = {nullptr, nullptr};

@@ -32,6 +32,12 @@ __device__ __forceinline__ bool ratio_passes(const DeviceParams &p, uint32_t mm,
     return (double)mm / (double)m / (double)p.c <= p.ratio_thresh;
 }
 
+// slot of a k-mer in the per-read minimizer set (shared memory, capacity 2^bits): a 32-bit multiplicative hash -- the set is
+// private to the kernel, so insert and probe only have to agree with each other
+__device__ __forceinline__ uint32_t rset_slot(uint64_t key, uint32_t shift32) {
+    return (((uint32_t)key ^ ((uint32_t)(key >> 32) * 0x85EBCA6Bu)) * 0x9E3779B1u) >> shift32;
+}
+
 struct FilterSmem {
     uint32_t rcap;      // read set capacity (power of two)
     uint32_t acc_words; // ceil(A/2)
@@ -61,7 +67,7 @@ filter_kernel(SeqBatch in, SketchOut sk, AsvIndex ix, PairPool pool, FilterOut o
     uint32_t *sum1 = bm2 + lay.bm_words;
     uint32_t *same = sum1 + lay.sum_words;
     const uint32_t rmask = lay.rcap - 1u;
-    const uint32_t rshift = 64u - (uint32_t)__popc(rmask);
+    const uint32_t rshift = 32u - (uint32_t)__popc(rmask);
     const uint32_t clear_words = lay.acc_words + 2u * lay.bm_words + lay.sum_words + lay.same_words;
     const int mid_shift = p.k - 1;
     if (*out.err & kErrSnpPool) return;          // the sketch ran out of pool space: the host grows it and re-runs the batch
@@ -101,7 +107,7 @@ filter_kernel(SeqBatch in, SketchOut sk, AsvIndex ix, PairPool pool, FilterOut o
                 bool inserted = false;
                 if (v != kEmpty64) {
                     const unsigned long long key = v & ~kFwdBit;
-                    uint32_t slot = hash_slot(key, rshift);
+                    uint32_t slot = rset_slot(key, rshift);
                     while (true) {
                         const unsigned long long old = atomicCAS(&rset[slot], (unsigned long long)kEmpty64, v);
                         if (old == kEmpty64) { inserted = true; break; }
@@ -210,6 +216,25 @@ filter_kernel(SeqBatch in, SketchOut sk, AsvIndex ix, PairPool pool, FilterOut o
                     slot = (slot + 1u) & ix.idx_mask;
                 }
             }
+            // short buckets (the common case: a site is variable in one group of related ASVs): every lane walks the bucket of
+            // its own SNPmer, four entry loads in flight; long buckets (conserved sites) are flattened over the lanes below
+            if (__reduce_max_sync(0xffffffffu, blen) <= 24u) {
+                for (uint32_t i0 = 0; i0 < blen; i0 += 4u) {
+                    uint32_t ent[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) ent[u] = (i0 + u < blen) ? __ldg(ix.idx_entries + bstart + i0 + u) : 0xffffffffu;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (ent[u] == 0xffffffffu) continue;
+                        const uint32_t a = ent[u] >> 2;
+                        if ((ent[u] & 3u) != mid) atomicAdd(&acc[a >> 1], 1u << (16u * (a & 1u)));
+                        const uint32_t w = a >> 5;
+                        const uint32_t old = atomicOr(&bm1[w], 1u << (a & 31u));
+                        if (old == 0u) atomicOr(&sum1[w >> 5], 1u << (w & 31u));
+                    }
+                }
+                continue;
+            }
             uint32_t incl = blen;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += y; }
@@ -244,24 +269,25 @@ filter_kernel(SeqBatch in, SketchOut sk, AsvIndex ix, PairPool pool, FilterOut o
         // tests are kept (src/alignment.rs:1829-1843), so the groups are visited in ascending
         // mismatch order and the walk stops at the first group with a passing candidate; every
         // group is visited (and any_scored is exact) only when nothing passes.
+        // The candidate bitmap is walked word by word (the summary bitmap names the non-empty words; related ASVs sit in one or two of
+        // them), lane b looking at ASV 32w + b: one shared-memory read per lane and word, no per-lane bit loops.
+        auto word_mm = [&](const uint32_t w, const uint32_t bits) -> uint32_t {          // this lane's candidate of word w: its mismatches
+            const uint32_t a = w * 32u + (uint32_t)lane;
+            return ((bits >> lane) & 1u) ? ((acc[a >> 1] >> (16u * (a & 1u))) & 0xffffu) : 0xffffffffu;
+        };
         uint32_t cur = 0;
         while (true) {
-            // smallest mismatch count >= cur over all candidates (lanes stride over bitmap words)
-            uint32_t round_min = 0xffffffffu;
-            for (uint32_t w = lane; w < lay.bm_words; w += 32u) {
-                uint32_t bits = bm1[w];
-                while (bits) {
-                    const uint32_t a = w * 32u + (uint32_t)(__ffs(bits) - 1);
-                    bits &= bits - 1u;
-                    const uint32_t mm = (acc[a >> 1] >> (16u * (a & 1u))) & 0xffffu;
+            uint32_t round_min = 0xffffffffu;                                             // smallest mismatch count >= cur
+            for (uint32_t sw = 0; sw < lay.sum_words; ++sw) {
+                uint32_t sbits = sum1[sw];
+                while (sbits) {
+                    const uint32_t w = sw * 32u + (uint32_t)(__ffs(sbits) - 1);
+                    sbits &= sbits - 1u;
+                    const uint32_t mm = word_mm(w, bm1[w]);
                     if (mm >= cur && mm < round_min) round_min = mm;
                 }
             }
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) {
-                const uint32_t y = __shfl_xor_sync(0xffffffffu, round_min, d);
-                round_min = y < round_min ? y : round_min;
-            }
+            round_min = __reduce_min_sync(0xffffffffu, round_min);
             if (round_min == 0xffffffffu) break;
             // visit the candidates of this group in ascending ASV order
             for (uint32_t sw = 0; sw < lay.sum_words; ++sw) {
@@ -269,13 +295,12 @@ filter_kernel(SeqBatch in, SketchOut sk, AsvIndex ix, PairPool pool, FilterOut o
                 while (sbits) {
                     const uint32_t w = sw * 32u + (uint32_t)(__ffs(sbits) - 1);
                     sbits &= sbits - 1u;
-                    uint32_t bits = bm1[w];
-                    while (bits) {
-                        const uint32_t bit = (uint32_t)(__ffs(bits) - 1);
-                        bits &= bits - 1u;
+                    uint32_t grp = __ballot_sync(0xffffffffu, word_mm(w, bm1[w]) == round_min);
+                    while (grp) {
+                        const uint32_t bit = (uint32_t)(__ffs(grp) - 1);
+                        grp &= grp - 1u;
                         const uint32_t a = w * 32u + bit;
-                        const uint32_t mm = (acc[a >> 1] >> (16u * (a & 1u))) & 0xffffu;
-                        if (mm != round_min) continue;
+                        const uint32_t mm = round_min;
                         const uint32_t m0 = __ldg(ix.mset_off + a);
                         const uint32_t nA = __ldg(ix.mset_off + a + 1) - m0;
                         uint32_t m = 0, same = 0;
@@ -285,7 +310,7 @@ filter_kernel(SeqBatch in, SketchOut sk, AsvIndex ix, PairPool pool, FilterOut o
                             if (t < nA) {
                                 const uint64_t v = __ldg(ix.mset + m0 + t);
                                 const uint64_t key = v & ~kFwdBit;
-                                uint32_t slot = hash_slot(key, rshift);
+                                uint32_t slot = rset_slot(key, rshift);
                                 while (true) {
                                     const uint64_t r = rset[slot];
                                     if (r == kEmpty64) break;
@@ -407,7 +432,7 @@ filter_compact_kernel(SeqBatch in, SketchOut sk, AsvIndex ix, PairPool pool, Fil
     uint32_t *clist = cval + lay.ccap;                                              // occupied slots, then kept slots
     uint32_t *cstash = clist + lay.ccap;                                            // (m | strand << 15) of kept candidates
     const uint32_t rmask = lay.rcap - 1u, cmask = lay.ccap - 1u;
-    const uint32_t rshift = 64u - (uint32_t)__popc(rmask);
+    const uint32_t rshift = 32u - (uint32_t)__popc(rmask);
     const int mid_shift = p.k - 1;
     if (*out.err & kErrSnpPool) return;
 
@@ -442,7 +467,7 @@ filter_compact_kernel(SeqBatch in, SketchOut sk, AsvIndex ix, PairPool pool, Fil
                 bool inserted = false;
                 if (v != kEmpty64) {
                     const unsigned long long key = v & ~kFwdBit;
-                    uint32_t slot = hash_slot(key, rshift);
+                    uint32_t slot = rset_slot(key, rshift);
                     while (true) {
                         const unsigned long long old = atomicCAS(&rset[slot], (unsigned long long)kEmpty64, v);
                         if (old == kEmpty64) { inserted = true; break; }
@@ -558,7 +583,7 @@ filter_compact_kernel(SeqBatch in, SketchOut sk, AsvIndex ix, PairPool pool, Fil
                     if (t < nA) {
                         const uint64_t v = __ldg(ix.mset + m0 + t);
                         const uint64_t key = v & ~kFwdBit;
-                        uint32_t sl = hash_slot(key, rshift);
+                        uint32_t sl = rset_slot(key, rshift);
                         while (true) {
                             const uint64_t r = rset[sl];
                             if (r == kEmpty64) break;

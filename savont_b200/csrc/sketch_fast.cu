@@ -252,6 +252,16 @@ sketch_fast_kernel(SeqBatch in, SketchOut out, SnpSet set, const uint16_t *__res
 #pragma unroll
             for (int t = 0; t < (int)C - 1; ++t) win[t] = s_rank[(uint32_t)(x0 >> (64 - 2 * (t + (int)S))) & 0x3fffu];
             win[C - 1] = 0u;
+            // sliding minima for the open-syncmer test: m3[i] = min(rank i..i+2), m5[i] = min(rank i..i+4), both indexed modulo C like
+            // `win`.  The k-mer whose middle s-mer is q is a syncmer iff rank q < min(m5[q-5], m5[q+1]): per position two 3-input
+            // minima extend m3 / m5 and one 2-input minimum + compare decide, instead of a 10-input minimum over the window.
+            uint32_t m3[C], m5[C];
+#pragma unroll
+            for (int t = 0; t < (int)C; ++t) { m3[t] = 0u; m5[t] = 0u; }
+#pragma unroll
+            for (int t = 0; t + 2 < (int)C - 1; ++t) m3[t] = min(min(win[t], win[t + 1]), win[t + 2]);
+#pragma unroll
+            for (int t = 0; t + 4 < (int)C - 1; ++t) m5[t] = min(min(m3[t], win[t + 3]), win[t + 4]);
 
             uint64_t cm = 0, mm = 0;
             uint32_t bidx = pb + p0 + K - 1u;
@@ -279,13 +289,14 @@ sketch_fast_kernel(SeqBatch in, SketchOut out, SnpSet set, const uint16_t *__res
                         const uint32_t hit = __funnelshift_r(w, 0u, h) & __funnelshift_r(w, 0u, h >> 5) & 1u;
                         cmb = mad_lo(hit, 1u << jj, cmb);
                     }
-                    // open syncmer: strict minimum at the middle of the 11 ranks (src/seeding.rs:526-543)
+                    // open syncmer: strict minimum at the middle of the 11 ranks (src/seeding.rs:526-543); tau = index of the newest rank
                     constexpr int CI = (int)C;
-                    const int ms = (jj + (CI - 1) / 2) % CI;
-                    uint32_t others = 0xffffffffu;
-#pragma unroll
-                    for (int t = 0; t < CI; ++t) if (t != ms) others = min(others, win[t]);
-                    if (win[ms] < others) mmb |= 1u << jj;
+                    static_assert(CI == 11, "the sliding minima below are laid out for c = 11 (windows of 5 on either side of the middle)");
+                    const int tau = (jj + CI - 1) % CI;
+                    m3[(tau + CI - 2) % CI] = min(min(win[(tau + CI - 2) % CI], win[(tau + CI - 1) % CI]), win[tau]);
+                    m5[(tau + CI - 4) % CI] = min(min(m3[(tau + CI - 4) % CI], win[(tau + CI - 1) % CI]), win[tau]);
+                    const uint32_t others = min(m5[(tau + CI - 10) % CI], m5[(tau + CI - 4) % CI]);
+                    if (win[(tau + CI - 5) % CI] < others) mmb |= 1u << jj;
                 }
                 cm |= (uint64_t)cmb << (C * b);
                 mm |= (uint64_t)mmb << (C * b);

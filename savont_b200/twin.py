@@ -81,3 +81,46 @@ def twin_reads_from_snpmers(ctx, bases, quals, offsets, file_idx=None, kmer48: b
         pk = alloc(kk.nbytes)[:kk.nbytes].view(kk.dtype); pk[:] = kk; kk = pk
     return dict(dna_words=words, dna_word_offsets=cat(woffs, np.uint64), lengths=cat(lens, np.uint32), snpmer_kmers=kk,
                 snpmer_offsets=cat(soffs, np.uint64), file_idx=None if file_idx is None else np.ascontiguousarray(file_idx, np.uint32))
+
+
+def scatter_to_heap(twin: dict, seed: int = 1) -> dict:
+    """Emulates a Vec<TwinRead> in the reference's memory: every read's dna_seq words and snpmer_kmers in its OWN block of ordinary
+    (pageable) host memory, blocks in shuffled order with allocator-like gaps, and one pointer per read -- the argument of
+    Context.map_twin_read_ptrs / savont_b200_map_twin_read_ptrs.  The returned dict keeps the arenas alive."""
+    rng = np.random.default_rng(seed)
+    wo = np.asarray(twin["dna_word_offsets"], np.int64); so = np.asarray(twin["snpmer_offsets"], np.int64)
+    n = len(wo) - 1
+    nw = wo[1:] - wo[:-1]; ns = so[1:] - so[:-1]
+    sk = twin["snpmer_kmers"]
+    kb = 6 if sk.dtype == np.uint8 else 8
+    order = rng.permutation(n)
+
+    def place(sizes_bytes, align):
+        # block i of the shuffled order starts behind block i-1 plus a malloc-like header / padding of 16..64 bytes
+        gaps = rng.integers(16, 65, size=n).astype(np.int64)
+        sz = sizes_bytes[order]
+        start_sh = np.zeros(n, np.int64)
+        step = (sz + gaps + align - 1) // align * align
+        np.cumsum(step[:-1], out=start_sh[1:])
+        start = np.zeros(n, np.int64); start[order] = start_sh
+        return start, int(start_sh[-1] + step[-1]) if n else 0
+
+    wstart, wtot = place(nw * 8, 16)
+    sstart, stot = place(ns * kb, 2)
+    warena = np.zeros(max(wtot, 16), np.uint8); sarena = np.zeros(max(stot, 16), np.uint8)
+    words = np.ascontiguousarray(twin["dna_words"], np.uint64).view(np.uint8)
+    skb = np.ascontiguousarray(sk).view(np.uint8)
+    # scatter (vectorised through flat byte indices, in chunks to bound the index memory)
+    for r0 in range(0, n, 65536):
+        r1 = min(n, r0 + 65536)
+        for arena, src, off, cnt, unit, dst in ((warena, words, wo, nw, 8, wstart), (sarena, skb, so, ns, kb, sstart)):
+            c = cnt[r0:r1] * unit
+            tot = int(c.sum())
+            if tot == 0:
+                continue
+            rel = np.arange(tot, dtype=np.int64) - np.repeat(np.cumsum(c) - c, c)
+            arena[np.repeat(dst[r0:r1], c) + rel] = src[int(off[r0]) * unit:int(off[r1]) * unit]
+    fi = twin.get("file_idx")
+    return dict(dna_ptrs=(warena.ctypes.data + wstart).astype(np.uint64), snpmer_ptrs=(sarena.ctypes.data + sstart).astype(np.uint64),
+                lengths=np.ascontiguousarray(twin["lengths"], np.uint32), snpmer_counts=ns.astype(np.uint32), kmer_bytes=kb,
+                file_idx=None if fi is None else np.ascontiguousarray(fi, np.uint32), _arenas=(warena, sarena))

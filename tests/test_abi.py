@@ -33,7 +33,7 @@ def test_default_params_and_struct_layout():
     p = _lib.default_params()
     assert (p.k, p.c, p.l, p.min_bq, p.band, p.strand_mode) == (17, 11, 3, 25, 64, 0)
     assert p.ratio_thresh == 0.005 and p.min_mini_frac_base == 0.95
-    assert C.sizeof(_lib.Params) == 48 and C.sizeof(_lib.Stats) == 15 * 8
+    assert C.sizeof(_lib.Params) == 48 and C.sizeof(_lib.Stats) == 16 * 8
     assert p.candidate_mode == 0
 
 

@@ -441,6 +441,15 @@ def test_map_twin_reads(ctx, name, kw, n, kmer48, k, c):
     assert_same(got, want, MAP_KEYS, f"map_twin_reads {name} k={k}")
     assert got["stats"]["dp_cells"] == want["dp_cells"]
     assert got["stats"]["h2d_bytes"] < 0.5 * len(bases)               # 2 bits per base + SNPmers instead of two bytes per base
+    # the same reads as a Vec<TwinRead> lies in memory: one heap block per read and field, gathered by the library
+    heap = twin.scatter_to_heap(tw, seed=n)
+    ctx.set_batch_reads(700); ctx.set_host_threads(3)
+    try:
+        got_p = ctx.map_twin_read_ptrs(heap, n_samples=ns)
+    finally:
+        ctx.set_batch_reads(0); ctx.set_host_threads(0)
+    assert_same(got_p, want, MAP_KEYS, f"map_twin_read_ptrs {name} k={k}")
+    assert got_p["stats"]["gather_ms"] > 0.0
     ctx.upload_twin_reads(tw, n_samples=ns)
     ctx.map_resident()
     assert_same(ctx.fetch_resident(), want, MAP_KEYS, f"twin resident {name}")
@@ -912,3 +921,45 @@ def test_count_split_kmers_sharded_processes_on_one_gpu():
                        env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "world=2" in r.stdout and " OK" in r.stdout
+
+
+@pytest.mark.parametrize("n_ctx,allreduce", [(1, "peer"), (3, "peer"), (2, "nccl")])
+def test_multi_handle_matches_single_context_and_oracle(n_ctx, allreduce):
+    """savont_b200_create_multi: one process, a context per device (here: per entry of the device list -- on a one-GPU box several
+    contexts share device 0; with >= n_ctx GPUs they are distinct devices), reads sharded in read order, counter vectors summed by
+    the peer-memory kernel or NCCL, results concatenated: every entry point must reproduce the oracle for the WHOLE read set"""
+    import torch
+    from savont_b200 import _lib, twin
+    n_gpu = torch.cuda.device_count()
+    devs = list(range(n_ctx)) if n_gpu >= n_ctx else [0] * n_ctx
+    if allreduce == "nccl" and len(set(devs)) < n_ctx:
+        pytest.skip("the NCCL all-reduce needs distinct devices")
+    w = _make_workload("pooled", n_roots=5, n_samples=3)
+    r = w.reads(2600)
+    gp, op = _params(_lib, band=w.band)
+    orc = O.Oracle(op, w.snpmers); orc.load_asvs(w.asv_bases, w.asv_offsets)
+    want = orc.map_reads(r["bases"], r["quals"], r["offsets"], file_idx=r["file_idx"], n_samples=3)
+    m = _lib.MultiContext(devs, gp, allreduce=allreduce)
+    try:
+        m.load_snpmers(w.snpmers); m.load_asvs(w.asv_bases, w.asv_offsets)
+        m.set_batch_reads(500)
+        got = m.map_reads(r["bases"], r["quals"], r["offsets"], file_idx=r["file_idx"], n_samples=3)
+        assert_same(got, want, MAP_KEYS, f"multi map_reads x{n_ctx}")
+        assert got["stats"]["n_reads"] == 2600 and got["stats"]["n_batches"] >= n_ctx
+        sk = O.sketch_batch(op, w.snpmers, r["bases"], r["quals"], r["offsets"])
+        tw = twin.from_sketch(sk, r["offsets"], file_idx=r["file_idx"], kmer48=True)
+        assert_same(m.map_twin_reads(tw, n_samples=3), want, MAP_KEYS, f"multi map_twin_reads x{n_ctx}")
+        m.set_host_threads(4)
+        assert_same(m.map_twin_read_ptrs(twin.scatter_to_heap(tw), n_samples=3), want, MAP_KEYS, f"multi map_twin_read_ptrs x{n_ctx}")
+        # fewer reads than devices, and none at all
+        few = {k_: (v[:2] if k_ in ("lengths", "file_idx") else v) for k_, v in tw.items()}
+        few["dna_word_offsets"] = tw["dna_word_offsets"][:3]; few["snpmer_offsets"] = tw["snpmer_offsets"][:3]
+        g2 = m.map_twin_reads(few, n_samples=3)
+        assert np.array_equal(g2["status"], want["status"][:2]) and np.array_equal(g2["best_nm"], want["best_nm"][:2])
+        e = m.map_reads(np.zeros(0, np.uint8), None, np.zeros(1, np.uint64))
+        assert len(e["status"]) == 0 and e["totals"].tolist() == [0, 0]
+        # an error on one device surfaces with its message
+        with pytest.raises(_lib.SavontB200Error):
+            m.map_reads(r["bases"], r["quals"], r["offsets"], file_idx=np.full(2600, 7, np.uint32), n_samples=3)
+    finally:
+        m.close()

@@ -1,0 +1,104 @@
+"""a11 sensitivity study: how much do equivalence classes and depths move when NM is defined differently?
+
+The reference's NM is minimap2 `lr:hq` `alignment.nm` (src/alignment.rs:1848-1863), which cannot be built here; the product uses
+the banded both-ends-free edit distance of DESIGN.md section 3.  The oracle can also compute NM with a four times wider band and
+as the NM of the best local dual-affine alignment under lr:hq's scoring (oracle/savont_oracle.c: affine_local_nm).  These tests
+pin the local-alignment code on hand-checkable pairs and re-measure the divergence on the committed zymo subset and a synthetic
+sample; tools/nm_semantics.py produced tests/golden/nm_semantics.json (all zymo reads, 100 k config-2 reads) the same way."""
+import json
+import os
+import random
+
+import numpy as np
+
+from oracle import oracle as O
+from tests.util import rand_seq
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _classes(res):
+    off = res["class_offsets"]
+    return [tuple(res["class_asv"][int(off[i]):int(off[i + 1])]) for i in range(len(off) - 1)]
+
+
+def test_affine_local_nm_known_answers():
+    rng = random.Random(7)
+    p = O.default_params(nm_mode=2)
+    a = rand_seq(rng, 300)
+    assert O.nm_pair(p, a, a) == (True, 0)
+    # one substitution in the middle: match 2 / mismatch -4 -> the alignment runs through it
+    b = bytearray(a); b[150] = ord("A") if a[150] != ord("A") else ord("C")
+    assert O.nm_pair(p, a, bytes(b)) == (True, 1)
+    # a 3-base deletion / insertion: one gap of 3 bases
+    assert O.nm_pair(p, a, a[:100] + a[103:]) == (True, 3)
+    assert O.nm_pair(p, a[:100] + a[103:], a) == (True, 3)
+    # a 40-base gap is still cheaper than restarting (24 + 40 = 64 < 2 * 100 matches gained): the long-gap state takes it
+    assert O.nm_pair(p, a, a[:100] + a[140:]) == (True, 40)
+    # unrelated flanks are clipped for free (local alignment): NM counts nothing outside the aligned core
+    junk1, junk2 = rand_seq(rng, 60), rand_seq(rng, 45)
+    ok, nm = O.nm_pair(p, a, junk1 + a + junk2)
+    assert ok and nm <= 2
+    # ... which is exactly where the banded both-ends-free definition differs: leading bases are free, trailing ones within the band too
+    ok0, nm0 = O.nm_pair(O.default_params(nm_mode=0, band=64), a, junk1 + a + junk2)
+    assert ok0 and nm0 <= 2
+    # a mismatch 2 bases from the end is clipped by the local alignment (-4 + 2 * 2 = 0 gain) but charged by the edit distance
+    c = bytearray(a); c[-3] = ord("A") if a[-3] != ord("A") else ord("C")
+    assert O.nm_pair(p, a, bytes(c)) == (True, 0)
+    assert O.nm_pair(O.default_params(nm_mode=0), a, bytes(c)) == (True, 1)
+    # too little in common: no alignment (score below min_dp_max)
+    assert O.nm_pair(p, rand_seq(rng, 30), rand_seq(rng, 30))[0] is False
+
+
+def test_wide_band_equals_product_definition_on_clean_pairs():
+    rng = random.Random(11)
+    a = rand_seq(rng, 400)
+    b = bytearray(a); b[77] ^= 2; del b[200:203]
+    for mode in (0, 1):
+        assert O.nm_pair(O.default_params(nm_mode=mode, band=32), a, bytes(b)) == (True, 4)
+
+
+def _divergence(asv_b, asv_o, rb, rq, ro, snp, band):
+    out = {}
+    for mode in (0, 1, 2):
+        orc = O.Oracle(O.default_params(band=band, nm_mode=mode), snp)
+        orc.load_asvs(asv_b, asv_o)
+        out[mode] = orc.map_reads(rb, rq, ro)
+        orc.close()
+    base = out[0]; c0 = _classes(base)
+    rows = {}
+    for mode in (1, 2):
+        r = out[mode]
+        assert np.array_equal(r["status"], base["status"])            # which reads are assigned does not depend on the NM definition here
+        ok = np.flatnonzero(base["status"] == 0)
+        cm = _classes(r)
+        rows[mode] = dict(class_changed=sum(1 for i in ok if cm[i] != c0[i]), n=len(ok),
+                          nm_changed=int(np.sum(r["best_nm"][ok] != base["best_nm"][ok])))
+    return rows
+
+
+def test_class_divergence_on_zymo_subset():
+    z = np.load(os.path.join(ROOT, "tests", "golden", "zymo_subset.npz"))
+    rows = _divergence(z["asv_bases"], z["asv_offsets"], z["read_bases"], z["read_quals"], z["read_offsets"], z["snpmers"], 64)
+    # measured: 5 of 249 assigned reads change class under the affine-local NM (2 %); the bound leaves room for tie-order changes only
+    assert rows[2]["n"] == 249 and rows[2]["class_changed"] <= 8
+    assert rows[1]["class_changed"] <= 8
+    assert rows[2]["nm_changed"] > 0                                  # the definitions do differ on real reads (clipped ends)
+
+
+def test_class_divergence_on_synthetic_reads():
+    from savont_b200 import synth
+    w = synth.Workload("ont16s")
+    r = w.reads(150)
+    rows = _divergence(w.asv_bases, w.asv_offsets, r["bases"], r["quals"], r["offsets"], w.snpmers, w.band)
+    assert rows[1] == dict(class_changed=0, n=150, nm_changed=0)
+    assert rows[2]["class_changed"] == 0
+
+
+def test_committed_study_is_consistent():
+    d = json.load(open(os.path.join(ROOT, "tests", "golden", "nm_semantics.json")))
+    assert [x["n_reads"] for x in d] == [884, 100000]
+    zy, syn = d
+    assert zy["modes"]["2"]["class_changed_reads"] == 13 and zy["modes"]["2"]["max_abs_depth_change"] == 2
+    assert syn["modes"]["2"]["class_changed_reads"] == 0 and syn["modes"]["2"]["asvs_with_changed_depth"] == 0
+    assert syn["modes"]["1"]["best_nm_changed_reads"] == 0
