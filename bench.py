@@ -600,6 +600,8 @@ def run_b200(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=dev)
+    # a CPU-side group: the ranks that sit out the single-process leg wait on it without keeping a kernel spinning on their GPU
+    gloo = dist.new_group(backend="gloo") if world > 1 else None
     numa = _bind_to_gpu_numa_node(local_rank) if world > 1 else None
 
     w = _workload(args)
@@ -676,35 +678,122 @@ def run_b200(args, rank, world, local_rank):
     e2e_total_ms = float(e2e_t.item())
 
     # ---------------- e2e arm 2: the reads as &[TwinRead] (what Stage 7 is handed by the reference) ----------------
-    # dna_seq words + snpmer_kmers (Vec<Kmer48>) in pinned host memory; prepared outside the timed region, as Stage 1.5
-    # prepares them in the reference
-    twin_line = None
+    # (a) `e2e` (headline): a Vec<TwinRead> as it lies in the reference's memory -- every read's dna_seq words and snpmer_kmers in
+    #     their own block of ordinary pageable host memory (twin.scatter_to_heap), one pointer per read -- through
+    #     savont_b200_map_twin_read_ptrs: the library's host threads gather the blocks into page-locked staging INSIDE the timed
+    #     region, batch i+1 under the kernels of batch i.
+    # (b) `e2e_twin_contiguous`: the same fields already concatenated in pinned memory (savont_b200_map_twin_reads), i.e. without
+    #     the gather -- the figure round 1 reported as e2e.
+    twin_line = ptr_line = None
+    sample_check = None
     if not args.no_twin:
         from savont_b200 import twin
         tw = twin.twin_reads_from_snpmers(ctx, r["bases"], r["quals"], r["offsets"], file_idx=fidx, kmer48=True, alloc=_lib.pinned_array)
-        res = ctx.map_twin_reads(tw, n_samples=w.n_samples)                                     # warm-up (allocations)
-        tw_ms, tw_stats = [], None
-        for _ in range(e2e_steps):
-            barrier()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            res = ctx.map_twin_reads(tw, n_samples=w.n_samples)
-            allreduce_counts()
-            e1.record(stream)
-            barrier()
-            tw_ms.append(e0.elapsed_time(e1)); tw_stats = res["stats"]
-        tw_t = torch.tensor([sum(tw_ms)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tw_t, op=dist.ReduceOp.MAX)
-        same = all(np.array_equal(res[k], got[k]) for k in ("status", "best_nm", "class_offsets", "class_asv")) if world == 1 else None
-        twin_line = {"value": world * n_reads * e2e_steps / (float(tw_t.item()) / 1e3), "unit": "reads/s",
-                     "h2d_bytes_per_step": int(tw_stats["h2d_bytes"]), "d2h_bytes_per_step": int(tw_stats["d2h_bytes"]),
-                     "steps": e2e_steps, "ms_per_step": float(tw_t.item()) / e2e_steps, "h2d_ms": tw_stats["h2d_ms"],
-                     "kernel_ms": {"sketch": tw_stats["sketch_ms"], "filter": tw_stats["filter_ms"], "align": tw_stats["align_ms"]},
-                     "input": "&[TwinRead] as the reference's Stage 7 receives them: TwinRead.dna_seq words + TwinRead.snpmer_kmers (Kmer48) "
-                              "through savont_b200_map_twin_reads",
-                     "same_result_as_ascii_entry": same}
+        heap = twin.scatter_to_heap(tw, seed=1 + rank)
+
+        def timed(call):
+            res = call()                                                                        # warm-up (allocations)
+            ms, stats_ = [], None
+            for _ in range(e2e_steps):
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                res = call()
+                allreduce_counts()
+                e1.record(stream)
+                barrier()
+                ms.append(e0.elapsed_time(e1)); stats_ = res["stats"]
+            t = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return res, float(t.item()), stats_
+
+        def line_of(res, tot_ms, st_, what):
+            same = all(np.array_equal(res[k], got[k]) for k in ("status", "best_nm", "class_offsets", "class_asv"))
+            return {"value": world * n_reads * e2e_steps / (tot_ms / 1e3), "unit": "reads/s",
+                    "h2d_bytes_per_step": int(st_["h2d_bytes"]), "d2h_bytes_per_step": int(st_["d2h_bytes"]),
+                    "steps": e2e_steps, "ms_per_step": tot_ms / e2e_steps, "h2d_ms": st_["h2d_ms"], "gather_ms": st_["gather_ms"],
+                    "kernel_ms": {"sketch": st_["sketch_ms"], "filter": st_["filter_ms"], "align": st_["align_ms"]},
+                    "input": what, "same_result_as_ascii_entry": bool(same)}
+
+        res, tot, st_ = timed(lambda: ctx.map_twin_reads(tw, n_samples=w.n_samples))
+        twin_line = line_of(res, tot, st_, "TwinRead.dna_seq words + TwinRead.snpmer_kmers (Kmer48) already concatenated in pinned host memory, "
+                                            "savont_b200_map_twin_reads")
+        res, tot, st_ = timed(lambda: ctx.map_twin_read_ptrs(heap, n_samples=w.n_samples))
+        ptr_line = line_of(res, tot, st_, "&[TwinRead] as it lies in the reference's memory: one pageable heap block per read for dna_seq and for "
+                                          "snpmer_kmers, one pointer per read, savont_b200_map_twin_read_ptrs (host-thread gather into pinned "
+                                          "staging inside the timed region)")
+        ptr_line["host_threads"] = os.cpu_count()
+
     clocks = sampler.stop()
+
+    # ---------------- correctness legs (untimed) ----------------
+    # N = 1: the first `cpu_reads` reads once more through the C ABI, every output and counter against the oracle (below).
+    # N > 1: every rank maps the first cpu_reads / N reads of ITS shard and the counter vectors are all-reduced over NCCL; rank 0
+    # then maps the concatenation of those samples on its one GPU (and through the oracle): the reduced vector must be identical.
+    multi_check = None
+    ns_s = min(args.cpu_reads // max(world, 1), n_reads)
+    sub_got = ctx.map_reads(r["bases"], r["quals"], r["offsets"][: ns_s + 1], file_idx=None if fidx is None else fidx[:ns_s], n_samples=w.n_samples)
+    if world > 1:
+        ptr_c, n_c = ctx.counts_dev()
+        vec = torch.as_tensor(CountsView(ptr_c, n_c), device=dev)
+        local = vec.clone()
+        dist.all_reduce(vec)
+        gathered = [torch.zeros_like(local) for _ in range(world)]
+        dist.all_gather(gathered, local)
+        reduced = vec.cpu().numpy().astype(np.uint64)
+        sum_of_ranks = sum(g.cpu().numpy().astype(np.uint64) for g in gathered)
+        if rank == 0:
+            parts = [w.reads(ns_s, first=q * n_reads) for q in range(world)]
+            cat = {k: np.concatenate([p_[k] for p_ in parts]) for k in ("bases", "quals")}
+            offs = np.zeros(world * ns_s + 1, np.uint64); base = 0; pos = 1
+            for p_ in parts:
+                o = p_["offsets"].astype(np.uint64)
+                offs[pos:pos + ns_s] = o[1:] + np.uint64(base); base += int(o[-1]); pos += ns_s
+            fcat = np.concatenate([p_["file_idx"] for p_ in parts]) if fidx is not None else None
+            one = ctx.map_reads(cat["bases"], cat["quals"], offs, file_idx=fcat, n_samples=w.n_samples)
+            A = w.n_asv
+            single_vec = np.concatenate([one["unambig"], one["ambig"], one["leq10"], one["totals"], one["sample_singleton"].reshape(-1)]).astype(np.uint64)
+            multi_check = {"reads_per_rank": ns_s, "allreduce_equals_sum_of_ranks": bool(np.array_equal(reduced, sum_of_ranks)),
+                           "multi_gpu_matches_single": bool(np.array_equal(reduced, single_vec)), "counter_vector_len": int(len(reduced)),
+                           "assigned": int(reduced[3 * A])}
+            if not args.no_cpu_baseline:
+                from oracle import oracle as O
+                orc = O.Oracle(O.default_params(band=w.band), w.snpmers); orc.load_asvs(w.asv_bases, w.asv_offsets)
+                want = orc.map_reads(cat["bases"], cat["quals"], offs, file_idx=fcat, n_samples=w.n_samples, n_threads=os.cpu_count() or 1)
+                ovec = np.concatenate([want["unambig"], want["ambig"], want["leq10"], want["totals"], want["sample_singleton"].reshape(-1)]).astype(np.uint64)
+                multi_check["multi_gpu_matches_oracle"] = bool(np.array_equal(reduced, ovec))
+    # ---------------- one process, all N GPUs (savont_b200_create_multi): `savont asv` is a single process ----------------
+    # rank 0 alone drives every GPU of the box through the multi-GPU handle while the other ranks wait on the CPU-side group.
+    # Every device's shard is the rank-0 shard again (N pointer lists into one 1M-read heap arena): N x the work, known counters.
+    sp_line = None
+    if world > 1 and not args.no_twin and not args.no_single_process:
+        ctx.close()
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=gloo)
+        if rank == 0:
+            m = _lib.MultiContext(list(range(world)), _lib.default_params(band=w.band))
+            m.load_snpmers(w.snpmers); m.load_asvs(w.asv_bases, w.asv_offsets); m.set_batch_reads(args.batch_reads)
+            big = dict(dna_ptrs=np.tile(heap["dna_ptrs"], world), snpmer_ptrs=np.tile(heap["snpmer_ptrs"], world),
+                       lengths=np.tile(heap["lengths"], world), snpmer_counts=np.tile(heap["snpmer_counts"], world), kmer_bytes=heap["kmer_bytes"],
+                       file_idx=None if heap["file_idx"] is None else np.tile(heap["file_idx"], world))
+            m.map_twin_read_ptrs(big, n_samples=w.n_samples)                                   # warm-up (allocations)
+            walls, st_ = [], None
+            for _ in range(e2e_steps):
+                t0 = time.perf_counter()
+                resm = m.map_twin_read_ptrs(big, n_samples=w.n_samples)                        # returns after every device finished
+                walls.append(time.perf_counter() - t0); st_ = resm["stats"]
+            ok = bool(np.array_equal(resm["totals"], world * res["totals"]) and np.array_equal(resm["unambig"], world * res["unambig"])
+                      and np.array_equal(resm["status"][:n_reads], res["status"]) and np.array_equal(resm["status"][-n_reads:], res["status"]))
+            sp_line = {"value": world * n_reads * e2e_steps / sum(walls), "unit": "reads/s", "ms_per_step": 1e3 * sum(walls) / e2e_steps,
+                       "timing": "host wall clock around the synchronous call (it contains host work: pointer gather, result concatenation)",
+                       "device_ms_max": st_["total_ms"], "gather_ms_max": st_["gather_ms"], "h2d_ms_max": st_["h2d_ms"],
+                       "h2d_bytes_per_step": int(st_["h2d_bytes"]), "d2h_bytes_per_step": int(st_["d2h_bytes"]), "steps": e2e_steps,
+                       "n_gpus": world, "host_threads": os.cpu_count(), "allreduce": "peer-memory kernel on device 0",
+                       "input": f"one process, savont_b200_multi_map_twin_read_ptrs over {world} GPUs; every device's shard = the rank-0 shard "
+                                "(pointer lists into one heap arena)", "counters_equal_n_times_single": ok}
+            m.close()
+        dist.barrier(group=gloo)
 
     if rank != 0:
         return
@@ -725,10 +814,8 @@ def run_b200(args, rank, world, local_rank):
     # INT32 roofline of the DP kernel: ALU pipe = 16 lanes/clk/SMSP x 4 SMSP x SMs; OPS_PER_WORD INT32 ALU
     # instructions per 32-cell word-column counted from the kernel's SASS (DESIGN.md "K3")
     sm_mhz = clocks.get("sm_mhz") or peaks["sm_max_mhz"]
-    nw = {64: 5, 32: 3, 192: 13}.get(w.band, (2 * w.band + 1 + 31) // 32)
-    used_frac = (2 * w.band + 1) / (32.0 * nw)
     alu_ops = 148 * 4 * 16 * sm_mhz * 1e6
-    peak_gcups = alu_ops * 32.0 * used_frac / OPS_PER_WORD / 1e9
+    peak_gcups = alu_ops * 32.0 / OPS_PER_WORD / 1e9          # no discount for vector bits the kernel computes beyond the band
     # HBM view of the sketch kernel (algorithmic bytes: bases + quals in, planes + sketch out)
     sk_bytes = bases * 2 + bases / 4 + 12.0 * (stats[-1]["n_reads"] * (bases / max(stats[-1]["n_reads"], 1) / 11.0 + 25))
     line = {
@@ -743,16 +830,20 @@ def run_b200(args, rank, world, local_rank):
         "pairs_per_step": pairs, "dp_cells_per_step": cells,
         "roofline": {"bound": "int32", "kernel": "align_nm_kernel", "achieved": gcups, "peak": peak_gcups, "unit": "GCUPS",
                      "frac": gcups / peak_gcups if peak_gcups else None,
-                     "traffic": _ncu_traffic("align_nm_kernel") if (n_reads == 1_000_000 and args.workload == "ont16s") else None,
+                     "traffic": _ncu_traffic("align_nm_kernel", align_ms) if (n_reads == 1_000_000 and args.workload == "ont16s") else None,
+                     "traffic_source": _ncu_traffic_note("align_nm_kernel", align_ms),
                      "algorithmic_bytes": pairs * (376 + 21),
-                     "peak_how": f"148 SM x 64 INT32 ALU lanes x {sm_mhz:.0f} MHz (sampled) x 32 cells / {OPS_PER_WORD} ALU ops per "
-                                 f"32-cell word, x {used_frac:.3f} (band {2 * w.band + 1} of {32 * nw} vector bits)"},
+                     "peak_how": f"148 SM x 64 INT32 ALU lanes x {sm_mhz:.0f} MHz (sampled) x 32 cells / {OPS_PER_WORD} ALU-pipe instructions "
+                                 f"per 32 band cells (the recurrence's minimum, DESIGN.md K3; the kernel issues {KERNEL_OPS_PER_COLUMN} per "
+                                 f"{2 * 64 + 1}-cell column at band 64); lane rate measured by tools/pipe_bench.cu (profiles/r02_pipe_bench.txt)"},
         "roofline_hbm": {"bound": "hbm", "kernel": "sketch_fast_kernel", "achieved": sk_bytes / (sketch_ms / 1e3) / 1e9 if sketch_ms else None,
                          "peak": peaks["hbm_gbs"], "unit": "GB/s", "peak_source": peaks["source"],
                          "frac": (sk_bytes / (sketch_ms / 1e3) / 1e9) / peaks["hbm_gbs"] if sketch_ms else None,
-                         "traffic": _ncu_traffic("sketch_fast_kernel") if (n_reads == 1_000_000 and args.workload == "ont16s") else None,
+                         "traffic": _ncu_traffic("sketch_fast_kernel", sketch_ms) if (n_reads == 1_000_000 and args.workload == "ont16s") else None,
                          "algorithmic_bytes": sk_bytes},
-        "e2e": twin_line if twin_line is not None else fastq_line,
+        "e2e": ptr_line if ptr_line is not None else fastq_line,
+        "e2e_twin_contiguous": twin_line,
+        "e2e_single_process": sp_line,
         "e2e_fastq": fastq_line,
         "gpu_launches": int(sum(s["kernel_launches"] for s in stats)),
         "clocks": clocks,
@@ -772,10 +863,18 @@ def run_b200(args, rank, world, local_rank):
         want = orc.map_reads(sub["bases"], sub["quals"], offs, file_idx=None if fidx is None else fidx[:ns], n_samples=w.n_samples,
                              n_threads=cores)
         dt = time.perf_counter() - t0
-        same = bool(np.array_equal(want["status"], got["status"][:ns]) and np.array_equal(want["best_nm"], got["best_nm"][:ns]))
+        keys = ("status", "best_nm", "class_offsets", "class_asv", "unambig", "ambig", "leq10", "totals", "sample_singleton")
+        same = bool(ns == ns_s and all(np.array_equal(np.asarray(want[k]), np.asarray(sub_got[k])) for k in keys))
+        same_resident = bool(np.array_equal(want["status"], got["status"][:ns]) and np.array_equal(want["best_nm"], got["best_nm"][:ns])
+                             and np.array_equal(want["class_offsets"], got["class_offsets"][:ns + 1])
+                             and np.array_equal(want["class_asv"], got["class_asv"][:int(got["class_offsets"][ns])]))
         line["cpu_baseline"] = {"value": ns / dt, "unit": "reads/s", "cores": cores, "kind": "port",
                                 "sample": f"first {ns} reads of the same workload, OpenMP over reads (oracle/savont_oracle.c)",
-                                "gpu_matches_oracle_on_sample": same}
+                                "gpu_matches_oracle_on_sample": bool(same and same_resident),
+                                "compared": "status, best_nm, class_offsets, class_asv of the timed resident pass; the same plus unambig / ambig / "
+                                            "leq10 / totals / per-sample singleton counters of a separate C-ABI call on the sample"}
+    if multi_check is not None:
+        line["multi_gpu_check"] = multi_check
     print(json.dumps(line), flush=True)
 
 
@@ -787,19 +886,43 @@ def run_b200(args, rank, world, local_rank):
 OPS_PER_WORD = 12.4
 
 
-def _ncu_traffic(kernel):
-    """dram bytes read+written per launch from the committed ncu --set full summary (1M-read launch), or None"""
-    path = os.path.join(ROOT, "profiles", f"r01c_{kernel}_full.txt")
+KERNEL_OPS_PER_COLUMN = 55.9     # ALU-pipe instructions per column in the SASS interior loop of align_nm_kernel<4, true> (tools/sass_loops.py)
+PROFILE_TAG = "r02c"             # profiles/<tag>_<kernel>_full.txt: ncu --set full summaries of THIS round's kernels (profiles/refresh.py)
+
+
+def _ncu_profile(kernel):
+    """(dram bytes read + written, kernel duration in ms) of the committed ncu --set full summary of a 1M-read launch, or None"""
+    path = os.path.join(ROOT, "profiles", f"{PROFILE_TAG}_{kernel}_full.txt")
     try:
-        tot = 0.0
+        tot, dur = 0.0, None
         for line in open(path):
             f = line.split()
             if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                 mult = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}.get(f[2], 1.0)
                 tot += float(f[1]) * mult
-        return tot or None
+            if len(f) >= 3 and f[0] == "gpu__time_duration.sum":
+                dur = float(f[1]) * {"ms": 1.0, "us": 1e-3, "s": 1e3, "ns": 1e-6}.get(f[2], 1.0)
+        return (tot or None), dur
     except Exception:
+        return None, None
+
+
+def _ncu_traffic(kernel, measured_ms):
+    """DRAM traffic per launch from the committed capture -- only if that capture is of the kernel as it runs now: its recorded
+    duration must be within 10 % of this run's CUDA-event time, otherwise the profile is stale and the traffic is not reported"""
+    tot, dur = _ncu_profile(kernel)
+    if tot is None or dur is None or not measured_ms or abs(dur - measured_ms) > 0.10 * measured_ms:
         return None
+    return tot
+
+
+def _ncu_traffic_note(kernel, measured_ms):
+    tot, dur = _ncu_profile(kernel)
+    if tot is None:
+        return f"no profile profiles/{PROFILE_TAG}_{kernel}_full.txt"
+    ok = dur is not None and measured_ms and abs(dur - measured_ms) <= 0.10 * measured_ms
+    return (f"profiles/{PROFILE_TAG}_{kernel}_full.txt (ncu --set full, one launch of the same 1M-read step: {dur:.3f} ms there, {measured_ms:.3f} ms here"
+            + ("" if ok else "; MORE THAN 10 % APART: profile is stale, traffic withheld") + ")")
 
 
 def main():
@@ -814,7 +937,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-reads", type=int, default=100_000, help="sample size of the CPU baseline / reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-twin", action="store_true", help="skip the TwinRead-input e2e arm")
+    ap.add_argument("--no-twin", action="store_true", help="skip the TwinRead-input e2e arms")
+    ap.add_argument("--no-single-process", action="store_true", help="N > 1: skip the leg in which rank 0 drives all GPUs through the multi-GPU handle")
     ap.add_argument("--path", default="assign", choices=["assign", "kmercount", "pileup", "cluster", "reassign"],
                     help="assign: the headline read-vs-ASV path; kmercount: Stage 1 split-k-mer counting (K5)")
     args = ap.parse_args()
