@@ -353,6 +353,21 @@ int savont_b200_snpmer_compare(savont_b200_ctx *ctx, const uint64_t *cons_kmers,
                                uint32_t *best_mismatches, uint32_t *best_matches, uint16_t *matrix /* may be NULL */,
                                savont_b200_stats *stats /* may be NULL */);
 
+/* Stage 3 greedy SNPmer clustering inside the k-mer clusters: the per-cluster loop of asv_cluster::cluster_reads_by_snpmers
+ * (src/asv_cluster.rs:561-700, blockmers off).  snp_kmers / snp_offsets: per read the k-mers of TwinRead::snpmer_kmers() (distinct
+ * splitmers within a read, at most 512); cluster_reads / cluster_offsets: the k-mer clusters of Stage 2 as read ids in processing
+ * order.  The reads of a cluster are visited in order: a read joins the representative it is compatible with (no mismatch, >= 1
+ * match) that has the most matches, then the smallest cluster, then the smallest read id (:483-509), else it becomes a
+ * representative.  Once a cluster has more than iterative_above representatives (the reference: 1000, :610) the reference asks
+ * rayon for ANY compatible representative (:413-464, not deterministic); here, as in the oracle, the first one in creation order
+ * wins.  rep_of[r] = the representative's read id (r itself for representatives, UINT32_MAX for reads in no cluster);
+ * *n_representatives (may be NULL) = their number.  The grouping / size filter / ordering of the resulting clusters (:660-690) is
+ * host work (savont_host::snpmer_clusters).  stats: filter_ms = the kernel, h2d_ms = the upload. */
+int savont_b200_cluster_reads_by_snpmers(savont_b200_ctx *ctx, const uint64_t *snp_kmers, const uint64_t *snp_offsets, size_t n_reads,
+                                         const uint32_t *cluster_reads, const uint64_t *cluster_offsets, size_t n_clusters,
+                                         uint32_t iterative_above, uint32_t *rep_of, uint64_t *n_representatives /* may be NULL */,
+                                         savont_b200_stats *stats /* may be NULL */);
+
 /* The same closure from a Vec<TwinRead> as it lies in the reference's memory: an array of structs whose dna_seq and snpmer_kmers
  * are separate heap allocations (src/types.rs:386-412).  One pointer per read: dna_ptrs[r] -> the ceil(lengths[r] / 32) Seq<Dna>
  * words of read r, snpmer_ptrs[r] -> its snpmer_counts[r] k-mers (snpmer_kmer_bytes = 6: the Vec<Kmer48> bytes, 8: u64).  Per

@@ -553,6 +553,17 @@ class Context:
             out["matrix"] = mat[:n, :nc]
         return out
 
+    def cluster_reads_by_snpmers(self, snp_kmers, snp_offsets, cluster_reads, cluster_offsets, iterative_above=1000):
+        """per-cluster loop of asv_cluster::cluster_reads_by_snpmers (src/asv_cluster.rs:561-700) -> dict(rep_of, n_representatives, stats)"""
+        km = np.ascontiguousarray(snp_kmers, dtype=np.uint64); so = np.ascontiguousarray(snp_offsets, dtype=np.uint64)
+        cr = np.ascontiguousarray(cluster_reads, dtype=np.uint32); co = np.ascontiguousarray(cluster_offsets, dtype=np.uint64)
+        n, nc = len(so) - 1, len(co) - 1
+        rep = np.zeros(max(n, 1), np.uint32); nr = C.c_uint64(0); st = Stats()
+        _check(self.L.savont_b200_cluster_reads_by_snpmers(self.h, _p(km, C.c_uint64), _p(so, C.c_uint64), C.c_size_t(n), _p(cr, C.c_uint32),
+                                                           _p(co, C.c_uint64), C.c_size_t(nc), C.c_uint32(int(iterative_above)),
+                                                           _p(rep, C.c_uint32), C.byref(nr), C.byref(st)))
+        return dict(rep_of=rep[:n], n_representatives=int(nr.value), stats=st.as_dict())
+
     def counts_dev(self):
         """(device pointer, length in u64) of [unambig|ambig|leq10|assigned|filtered|singleton S*A]"""
         ptr = C.c_void_p(); n = C.c_size_t()

@@ -308,6 +308,37 @@ def cluster_reads_by_kmers(ctx: _lib.Context, minimizer_kmers, minimizer_offsets
     return clusters_from_assignment(out["rep_of"], min_cluster_size)
 
 
+def snpmer_clusters_from_assignment(kmer_clusters, rep_of, min_cluster_size: int = 1):
+    """the tail of the per-cluster loop of cluster_reads_by_snpmers (src/asv_cluster.rs:660-690): per k-mer cluster its SNPmer
+    clusters -- grouped by representative, members ascending, larger first (equal sizes: smaller first member), small ones dropped"""
+    rep_of = np.asarray(rep_of, np.int64)
+    out = []
+    for kc in kmer_clusters:
+        kc = np.asarray(kc, np.int64)
+        local = clusters_from_assignment_subset(kc, rep_of[kc])
+        out.append([c for c in local if len(c) >= min_cluster_size])
+    return out
+
+
+def clusters_from_assignment_subset(reads, reps):
+    order = np.lexsort((reads, reps))
+    reads, reps = reads[order], reps[order]
+    cuts = np.flatnonzero(np.diff(reps)) + 1 if len(reps) else np.zeros(0, np.int64)
+    groups = np.split(reads, cuts) if len(reads) else []
+    groups.sort(key=lambda c: (-len(c), int(c[0])))
+    return groups
+
+
+def cluster_reads_by_snpmers(ctx: _lib.Context, snpmer_kmers, snpmer_offsets, kmer_clusters, min_cluster_size: int = 1, iterative_above: int = 1000):
+    """asv_cluster::cluster_reads_by_snpmers up to the reclustering rounds (src/asv_cluster.rs:561-700) on `TwinRead::snpmer_kmers()` in
+    CSR and the k-mer clusters of Stage 2 -> per k-mer cluster the list of its SNPmer clusters"""
+    cr = np.concatenate([np.asarray(c, np.uint32) for c in kmer_clusters]) if len(kmer_clusters) else np.zeros(0, np.uint32)
+    co = np.zeros(len(kmer_clusters) + 1, np.uint64)
+    co[1:] = np.cumsum([len(c) for c in kmer_clusters])
+    out = ctx.cluster_reads_by_snpmers(snpmer_kmers, snpmer_offsets, cr, co, iterative_above=iterative_above)
+    return snpmer_clusters_from_assignment(kmer_clusters, out["rep_of"], min_cluster_size)
+
+
 def clusters_from_reassignment(clusters, best_cons, min_cluster_size: int = 1):
     """the tail of reassign_reads_to_best_cluster (src/asv_cluster.rs:1040-1131): reads listed cluster by cluster (`clusters`),
     best_cons[i] = new cluster of the i-th listed read -> (new clusters: members ascending, empty / small ones dropped,

@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsavont_b200.so")
-SOURCES = ["sketch.cu", "sketch_fast.cu", "prefilter.cu", "kmercount.cu", "filter.cu", "align.cu", "assign.cu", "pileup.cu", "cluster.cu", "reassign.cu", "api.cu", "api_kmer.cu", "api_pileup.cu", "api_cluster.cu", "api_reassign.cu", "api_multi.cu"]
+SOURCES = ["sketch.cu", "sketch_fast.cu", "prefilter.cu", "kmercount.cu", "filter.cu", "align.cu", "assign.cu", "pileup.cu", "cluster.cu", "reassign.cu", "snpcluster.cu", "api.cu", "api_kmer.cu", "api_pileup.cu", "api_cluster.cu", "api_reassign.cu", "api_multi.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall"]
 

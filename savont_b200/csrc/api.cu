@@ -1427,19 +1427,32 @@ static int gather_batch(Context *c, int slot, const PtrInput &in, size_t r0, siz
     int T = c->host_threads > 0 ? c->host_threads : (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
     if ((size_t)T > n / 2048 + 1) T = (int)(n / 2048 + 1);
     std::atomic<int> bad{0};
-    auto work = [&](int t) {
-        const size_t a = n * (size_t)t / (size_t)T, b = n * (size_t)(t + 1) / (size_t)T;
-        for (size_t i = a; i < b; ++i) {
-            const uint64_t nw = woff[i + 1] - woff[i], ns = soff[i + 1] - soff[i];
-            if ((nw && !in.dna_ptrs[r0 + i]) || (ns && !in.snp_ptrs[r0 + i])) { bad.store(1); continue; }
-            if (nw) memcpy(dw + woff[i], in.dna_ptrs[r0 + i], nw * 8);
-            if (ns) memcpy(ds + soff[i] * kb, in.snp_ptrs[r0 + i], ns * kb);
+    // chunks of 512 reads handed out dynamically; the blocks of read i + 8 are prefetched while read i is copied (the blocks are
+    // scattered over the heap: without the prefetch every copy starts with a DRAM miss)
+    const size_t chunk = 512, n_chunks = (n + chunk - 1) / chunk;
+    std::atomic<size_t> next_chunk{0};
+    const std::function<void(int)> work = [&](int) {
+        constexpr size_t D = 8;
+        while (true) {
+            const size_t ch = next_chunk.fetch_add(1);
+            if (ch >= n_chunks) break;
+            const size_t a = ch * chunk, b = std::min(n, a + chunk);
+            for (size_t i = a; i < b; ++i) {
+                if (i + D < b) {
+                    const char *pw = reinterpret_cast<const char *>(in.dna_ptrs[r0 + i + D]);
+                    const char *ps = reinterpret_cast<const char *>(in.snp_ptrs[r0 + i + D]);
+                    const size_t bw = (size_t)(woff[i + D + 1] - woff[i + D]) * 8, bs = (size_t)(soff[i + D + 1] - soff[i + D]) * kb;
+                    if (pw) for (size_t o = 0; o < bw; o += 64) __builtin_prefetch(pw + o, 0, 0);
+                    if (ps) for (size_t o = 0; o < bs; o += 64) __builtin_prefetch(ps + o, 0, 0);
+                }
+                const uint64_t nw = woff[i + 1] - woff[i], ns = soff[i + 1] - soff[i];
+                if ((nw && !in.dna_ptrs[r0 + i]) || (ns && !in.snp_ptrs[r0 + i])) { bad.store(1); continue; }
+                if (nw) memcpy(dw + woff[i], in.dna_ptrs[r0 + i], nw * 8);
+                if (ns) memcpy(ds + soff[i] * kb, in.snp_ptrs[r0 + i], ns * kb);
+            }
         }
     };
-    std::vector<std::thread> th;
-    for (int t = 1; t < T; ++t) th.emplace_back(work, t);
-    work(0);
-    for (auto &x : th) x.join();
+    c->pool.run(T, work);
     if (bad.load()) return fail(SAVONT_B200_ERR_INVALID, "null read buffer in batch starting at read %zu", r0);
     *out = TwinInput{dw, woff.data(), in.lengths + r0, ds, in.kmer_bytes, soff.data(), in.file_idx ? in.file_idx + r0 : nullptr};
     *gather_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();

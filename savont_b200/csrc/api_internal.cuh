@@ -7,7 +7,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <functional>
+#include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -41,6 +44,53 @@ inline int fail(int code, const char *fmt, ...) {
         int rc__ = (call);           \
         if (rc__ != 0) return rc__;  \
     } while (0)
+
+// A small persistent pool of host threads (the gather of the *_ptrs entry points runs on it once per batch: creating threads per
+// batch costs more than the gather of a small batch).  run(n, f) executes f(0..n-1), f(0) on the caller, and returns when all are done.
+class HostPool {
+public:
+    ~HostPool() { stop(); }
+    void run(int n, const std::function<void(int)> &f) {
+        if (n <= 1) { if (n == 1) f(0); return; }
+        while ((int)th_.size() < n - 1) th_.emplace_back([this] { loop(); });
+        std::unique_lock<std::mutex> lk(mu_);
+        fn_ = &f; n_ = n; next_ = 0; pending_ = n; ++gen_;
+        cv_.notify_all();
+        while (next_ < n_) {                         // the caller takes indices too
+            const int idx = next_++;
+            lk.unlock(); f(idx); lk.lock();
+            --pending_;
+        }
+        done_.wait(lk, [&] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+    void stop() {
+        { std::unique_lock<std::mutex> lk(mu_); quit_ = true; }
+        cv_.notify_all();
+        for (auto &t : th_) t.join();
+        th_.clear(); quit_ = false;
+    }
+private:
+    void loop() {
+        uint64_t seen = 0;
+        std::unique_lock<std::mutex> lk(mu_);
+        while (true) {
+            cv_.wait(lk, [&] { return quit_ || gen_ != seen; });
+            if (quit_) return;
+            seen = gen_;
+            while (next_ < n_) {
+                const int idx = next_++;
+                const std::function<void(int)> *f = fn_;
+                lk.unlock(); (*f)(idx); lk.lock();
+                if (--pending_ == 0) done_.notify_all();
+            }
+        }
+    }
+    std::vector<std::thread> th_;
+    std::mutex mu_; std::condition_variable cv_, done_;
+    const std::function<void(int)> *fn_ = nullptr;
+    int n_ = 0, next_ = 0, pending_ = 0; uint64_t gen_ = 0; bool quit_ = false;
+};
 
 struct DevBuf {
     void *p = nullptr;
@@ -155,7 +205,7 @@ struct Context {
     std::vector<Batch> res_parts; std::vector<size_t> res_cuts; int resident_parts_req = 0;
     PinBuf pin_small, pin_out;
     // savont_b200_map_twin_read_ptrs: page-locked staging of the gathered reads, one slot per batch in flight
-    PinBuf gather_words[3], gather_snp[3]; std::vector<uint64_t> gather_woff[3], gather_soff[3]; int host_threads = 0;
+    PinBuf gather_words[3], gather_snp[3]; std::vector<uint64_t> gather_woff[3], gather_soff[3]; int host_threads = 0; HostPool pool;
     cudaStream_t copy_stream = nullptr;          // H2D of batch i+1 overlaps the kernels of batch i
     cudaStream_t d2h_stream = nullptr;           // D2H of batch i-1's results overlaps the kernels of batch i
     cudaEvent_t ev_d2h[2] = {nullptr, nullptr};

@@ -98,3 +98,77 @@ extern "C" int savont_b200_snpmer_compare(savont_b200_ctx *h, const uint64_t *co
     if (stats) *stats = c->last_stats;
     return 0;
 }
+
+// ---- Stage 3 greedy SNPmer clustering (snpcluster.cu) ----
+extern "C" int savont_b200_cluster_reads_by_snpmers(savont_b200_ctx *h, const uint64_t *snp_kmers, const uint64_t *snp_offsets, size_t n_reads,
+                                                    const uint32_t *cluster_reads, const uint64_t *cluster_offsets, size_t n_clusters,
+                                                    uint32_t iterative_above, uint32_t *rep_of, uint64_t *n_representatives,
+                                                    savont_b200_stats *stats) {
+    TRY(use_device(h ? &h->c : nullptr));
+    Context *c = &h->c;
+    if (!snp_offsets || !cluster_offsets || (n_reads && !rep_of)) return fail(SAVONT_B200_ERR_INVALID, "null argument");
+    if (n_reads >= 0xfffffff0ull || n_clusters >= 0xfffffff0ull) return fail(SAVONT_B200_ERR_INVALID, "too many reads / clusters");
+    const uint64_t m0 = snp_offsets[0], n_mark = snp_offsets[n_reads] - m0;
+    const uint64_t c0 = cluster_offsets[0], n_memb = cluster_offsets[n_clusters] - c0;
+    if ((n_mark && !snp_kmers) || (n_memb && !cluster_reads)) return fail(SAVONT_B200_ERR_INVALID, "null argument");
+    std::vector<uint64_t> rel(n_reads + 1), crel(n_clusters + 1);
+    for (size_t r = 0; r <= n_reads; ++r) {
+        if (r && snp_offsets[r] < snp_offsets[r - 1]) return fail(SAVONT_B200_ERR_INVALID, "snp_offsets not monotonic at %zu", r);
+        rel[r] = snp_offsets[r] - m0;
+    }
+    for (size_t q = 0; q <= n_clusters; ++q) {
+        if (q && cluster_offsets[q] < cluster_offsets[q - 1]) return fail(SAVONT_B200_ERR_INVALID, "cluster_offsets not monotonic at %zu", q);
+        crel[q] = cluster_offsets[q] - c0;
+    }
+    std::vector<uint8_t> seen(n_reads, 0);
+    for (uint64_t i = 0; i < n_memb; ++i) {
+        const uint32_t r = cluster_reads[c0 + i];
+        if (r >= n_reads) return fail(SAVONT_B200_ERR_INVALID, "cluster member %u out of range", r);
+        if (seen[r]) return fail(SAVONT_B200_ERR_INVALID, "read %u is a member of two clusters", r);
+        seen[r] = 1;
+    }
+    // largest cluster first: the reads of a cluster are a serial chain, so the long chains must start early
+    std::vector<uint32_t> order(n_clusters);
+    for (size_t q = 0; q < n_clusters; ++q) order[q] = (uint32_t)q;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return crel[x + 1] - crel[x] > crel[y + 1] - crel[y]; });
+    c->last_stats = savont_b200_stats{};
+    cudaStream_t st = c->stream;
+    DevBuf *w = c->cluster_ws;
+    CK(cudaEventRecord(c->ev[0], st));
+    TRY(w[0].ensure(n_mark * 8 + 16)); TRY(w[1].ensure((n_reads + 1) * 8)); TRY(w[2].ensure(n_memb * 4 + 16)); TRY(w[3].ensure((n_clusters + 1) * 8));
+    TRY(w[4].ensure(n_clusters * 4 + 16)); TRY(w[5].ensure(n_memb * 4 + 16)); TRY(w[6].ensure(n_memb * 4 + 16)); TRY(w[7].ensure(n_reads * 4 + 16));
+    TRY(w[8].ensure(64));
+    if (n_mark) CK(cudaMemcpyAsync(w[0].p, snp_kmers + m0, n_mark * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(w[1].p, rel.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (n_memb) CK(cudaMemcpyAsync(w[2].p, cluster_reads + c0, n_memb * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(w[3].p, crel.data(), (n_clusters + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (n_clusters) CK(cudaMemcpyAsync(w[4].p, order.data(), n_clusters * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(w[7].p, 0xff, n_reads * 4 + 16, st));                         // reads outside every cluster: UINT32_MAX
+    CK(cudaMemsetAsync(w[8].p, 0, 64, st));
+    c->last_stats.h2d_bytes = n_mark * 8 + (n_reads + 1) * 8 + n_memb * 4 + (n_clusters + 1) * 8 + n_clusters * 4;
+    SnpClusterArgs a{};
+    a.k = c->params.k; a.snp_kmers = w[0].as<uint64_t>(); a.snp_offsets = w[1].as<uint64_t>();
+    a.cluster_reads = w[2].as<uint32_t>(); a.cluster_offsets = w[3].as<uint64_t>(); a.order = w[4].as<uint32_t>();
+    a.n_clusters = (uint32_t)n_clusters; a.iterative_above = iterative_above;
+    a.reps = w[5].as<uint32_t>(); a.rep_size = w[6].as<uint32_t>(); a.rep_of = w[7].as<uint32_t>();
+    a.work_ctr = w[8].as<uint32_t>(); a.err = w[8].as<uint32_t>() + 1; a.total_reps = reinterpret_cast<unsigned long long *>(w[8].as<uint32_t>() + 2);
+    CK(cudaEventRecord(c->ev[1], st));
+    launch_snp_cluster(a, c->sm_count, st);
+    CK(cudaGetLastError());
+    if (n_clusters) c->last_stats.kernel_launches += 1;
+    CK(cudaEventRecord(c->ev[2], st));
+    uint32_t tail[4] = {0, 0, 0, 0};
+    CK(cudaMemcpyAsync(tail, w[8].p, sizeof(tail), cudaMemcpyDeviceToHost, st));
+    if (n_reads) CK(cudaMemcpyAsync(rep_of, w[7].p, n_reads * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (tail[1] & 1u) return fail(SAVONT_B200_ERR_OVERFLOW, "a read has more than 512 SNPmers");
+    if (tail[1] & 2u) return fail(SAVONT_B200_ERR_INVALID, "a read carries two SNPmers with the same splitmer (TwinRead.snpmer_kmers never does, src/seeding.rs:550-568)");
+    unsigned long long nr = 0; memcpy(&nr, tail + 2, 8);
+    if (n_representatives) *n_representatives = nr;
+    c->last_stats.d2h_bytes = n_reads * 4;
+    c->last_stats.n_reads = n_memb; c->last_stats.n_pairs = nr;
+    c->last_stats.h2d_ms = ev_ms(c->ev[0], c->ev[1]); c->last_stats.filter_ms = ev_ms(c->ev[1], c->ev[2]);
+    c->last_stats.total_ms = ev_ms(c->ev[0], c->ev[2]);
+    if (stats) *stats = c->last_stats;
+    return 0;
+}

@@ -344,4 +344,18 @@ struct SnpCompareArgs {
 // reads [first, first + n) of the arrays in `a` (matrix = the rows of exactly these reads); returns 1 if n_cons is too large
 int launch_snpmer_compare(const SnpCompareArgs &a, uint32_t first, uint32_t n, int sm_count, cudaStream_t st);
 
+
+// ---- Stage 3 greedy SNPmer clustering inside the k-mer clusters (snpcluster.cu) ----
+struct SnpClusterArgs {
+    int k;
+    const uint64_t *snp_kmers; const uint64_t *snp_offsets;                 // all reads' SNPmer lists (CSR)
+    const uint32_t *cluster_reads; const uint64_t *cluster_offsets;         // the k-mer clusters: read ids in processing order (CSR)
+    const uint32_t *order;                                                  // cluster indices, largest cluster first
+    uint32_t n_clusters, iterative_above;
+    uint32_t *reps, *rep_size;                                              // workspace, one slot per clustered read (segment = cluster)
+    uint32_t *rep_of;                                                       // [n_reads] out: representative read id
+    uint32_t *work_ctr, *err; unsigned long long *total_reps;
+};
+void launch_snp_cluster(const SnpClusterArgs &a, int sm_count, cudaStream_t st);
+
 }  // namespace sb

@@ -332,6 +332,43 @@ std::vector<std::vector<size_t>> cluster_reads_by_kmers(Mapper &mapper, const ui
     return clusters_from_assignment(rep.data(), n, min_cluster_size);
 }
 
+std::vector<std::vector<std::vector<size_t>>> snpmer_clusters_from_assignment(const std::vector<std::vector<size_t>> &kmer_clusters,
+                                                                              const uint32_t *rep_of, size_t min_cluster_size) {
+    std::vector<std::vector<std::vector<size_t>>> out(kmer_clusters.size());
+    for (size_t kc = 0; kc < kmer_clusters.size(); ++kc) {
+        std::vector<std::pair<uint32_t, size_t>> pairs;                 // (representative, read)
+        pairs.reserve(kmer_clusters[kc].size());
+        for (size_t read : kmer_clusters[kc]) pairs.push_back({rep_of[read], read});
+        std::sort(pairs.begin(), pairs.end());
+        std::vector<std::vector<size_t>> local;
+        for (size_t i = 0; i < pairs.size();) {
+            size_t j = i;
+            std::vector<size_t> c;
+            while (j < pairs.size() && pairs[j].first == pairs[i].first) c.push_back(pairs[j++].second);   // ascending (:681)
+            local.push_back(std::move(c));
+            i = j;
+        }
+        std::stable_sort(local.begin(), local.end(), [](const std::vector<size_t> &a, const std::vector<size_t> &b) {
+            return a.size() != b.size() ? a.size() > b.size() : a.front() < b.front();                       // :683-684
+        });
+        local.erase(std::remove_if(local.begin(), local.end(), [&](const std::vector<size_t> &c) { return c.size() < min_cluster_size; }),
+                    local.end());                                                                            // :688
+        out[kc] = std::move(local);
+    }
+    return out;
+}
+
+std::vector<std::vector<std::vector<size_t>>> cluster_reads_by_snpmers(Mapper &mapper, const uint64_t *snp_kmers, const uint64_t *snp_offsets,
+                                                                       size_t n_reads, const std::vector<std::vector<size_t>> &kmer_clusters,
+                                                                       size_t min_cluster_size, uint32_t iterative_above) {
+    std::vector<uint32_t> members; std::vector<uint64_t> offs{0};
+    for (const auto &c : kmer_clusters) { for (size_t r : c) members.push_back((uint32_t)r); offs.push_back(members.size()); }
+    std::vector<uint32_t> rep(n_reads ? n_reads : 1);
+    ck(savont_b200_cluster_reads_by_snpmers(mapper.raw(), snp_kmers, snp_offsets, n_reads, members.data(), offs.data(), kmer_clusters.size(),
+                                            iterative_above, rep.data(), nullptr, nullptr), "cluster_reads_by_snpmers");
+    return snpmer_clusters_from_assignment(kmer_clusters, rep.data(), min_cluster_size);
+}
+
 std::pair<std::vector<std::vector<size_t>>, size_t> clusters_from_reassignment(const std::vector<std::vector<size_t>> &clusters,
                                                                                 const uint32_t *best_cons, size_t min_cluster_size) {
     std::vector<std::vector<size_t>> fresh(clusters.size());
@@ -420,6 +457,20 @@ long long savont_host_clusters_from_assignment(const uint32_t *rep_of, size_t n,
         size_t at = 0; offsets[0] = 0;
         for (size_t c = 0; c < cl.size(); ++c) { for (size_t r : cl[c]) members[at++] = r; offsets[c + 1] = at; }
         return (long long)cl.size();
+    } catch (const std::exception &e) { g_host_error = e.what(); return -1; }
+}
+// host half of cluster_reads_by_snpmers: k-mer clusters in CSR + rep_of in; the SNPmer clusters of all k-mer clusters out, flattened in
+// k-mer cluster order (CSR) with kc_of[c] = k-mer cluster of SNPmer cluster c; returns their number or -1
+long long savont_host_snpmer_clusters_from_assignment(const uint64_t *kc_offsets, const uint32_t *kc_members, size_t n_kc, const uint32_t *rep_of,
+                                                      size_t min_cluster_size, uint64_t *offsets, uint64_t *members, uint32_t *kc_of) {
+    try {
+        std::vector<std::vector<size_t>> kcs(n_kc);
+        for (size_t c = 0; c < n_kc; ++c) kcs[c].assign(kc_members + kc_offsets[c], kc_members + kc_offsets[c + 1]);
+        const auto res = savont_host::snpmer_clusters_from_assignment(kcs, rep_of, min_cluster_size);
+        size_t at = 0, nc = 0; offsets[0] = 0;
+        for (size_t kc = 0; kc < res.size(); ++kc)
+            for (const auto &c : res[kc]) { for (size_t r : c) members[at++] = r; kc_of[nc] = (uint32_t)kc; offsets[++nc] = at; }
+        return (long long)nc;
     } catch (const std::exception &e) { g_host_error = e.what(); return -1; }
 }
 // host half of reassign_reads_to_best_cluster: clusters in CSR in, CSR out; returns the number of new clusters or -1; *moved = reassignments

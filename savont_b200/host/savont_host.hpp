@@ -173,6 +173,15 @@ void write_feature_table(const std::vector<ConsensusSequence> &consensuses, cons
 std::vector<std::vector<size_t>> clusters_from_assignment(const uint32_t *rep_of, size_t n_reads, size_t min_cluster_size);
 std::vector<std::vector<size_t>> cluster_reads_by_kmers(Mapper &mapper, const uint64_t *minimizer_kmers, const uint64_t *minimizer_offsets,
                                                         size_t n_reads, double primary_clustering_threshold, size_t min_cluster_size);
+// reference src/asv_cluster.rs:561-700 (cluster_reads_by_snpmers, per-cluster loop; blockmers off): the greedy loop of every
+// k-mer cluster runs on the GPU (savont_b200_cluster_reads_by_snpmers), the lists of :660-690 are built here -- per k-mer cluster
+// its SNPmer clusters: members ascending, larger first (equal sizes: smaller first member), clusters below min_cluster_size dropped.
+std::vector<std::vector<std::vector<size_t>>> snpmer_clusters_from_assignment(const std::vector<std::vector<size_t>> &kmer_clusters,
+                                                                              const uint32_t *rep_of, size_t min_cluster_size);
+std::vector<std::vector<std::vector<size_t>>> cluster_reads_by_snpmers(Mapper &mapper, const uint64_t *snpmer_kmers,
+                                                                       const uint64_t *snpmer_offsets, size_t n_reads,
+                                                                       const std::vector<std::vector<size_t>> &kmer_clusters,
+                                                                       size_t min_cluster_size, uint32_t iterative_above = 1000);
 // reference src/asv_cluster.rs:1007-1131 (reassign_reads_to_best_cluster, SNPmer markers): `cons_*` = the ConsensusSnpmer k-mers
 // of the current clusters, `snpmer_*` = snpmers_vec() k-mers of all reads in CSR by read id.  Returns the new clusters (members
 // ascending, empty and small ones dropped) and the number of reads that changed cluster.

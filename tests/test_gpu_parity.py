@@ -954,6 +954,7 @@ def test_multi_handle_matches_single_context_and_oracle(n_ctx, allreduce):
         # fewer reads than devices, and none at all
         few = {k_: (v[:2] if k_ in ("lengths", "file_idx") else v) for k_, v in tw.items()}
         few["dna_word_offsets"] = tw["dna_word_offsets"][:3]; few["snpmer_offsets"] = tw["snpmer_offsets"][:3]
+        few["snpmer_kmers"] = tw["snpmer_kmers"][:6 * int(tw["snpmer_offsets"][2])]
         g2 = m.map_twin_reads(few, n_samples=3)
         assert np.array_equal(g2["status"], want["status"][:2]) and np.array_equal(g2["best_nm"], want["best_nm"][:2])
         e = m.map_reads(np.zeros(0, np.uint8), None, np.zeros(1, np.uint64))
@@ -963,3 +964,63 @@ def test_multi_handle_matches_single_context_and_oracle(n_ctx, allreduce):
             m.map_reads(r["bases"], r["quals"], r["offsets"], file_idx=np.full(2600, 7, np.uint32), n_samples=3)
     finally:
         m.close()
+
+
+def _stage3_case(seed, n_reads, n_clusters, n_sites, dup_frac=0.3):
+    """reads = SNPmer lists over a few biallelic sites per k-mer cluster: haplotypes + random allele flips / drop-outs, many exact
+    duplicates (ties in matches and cluster sizes), reads without SNPmers, reads outside every cluster"""
+    rng = np.random.default_rng(seed)
+    k = 17
+    mid = k // 2
+    lists, members = [], [[] for _ in range(n_clusters)]
+    site_sp = rng.integers(0, 1 << 30, size=(n_clusters, n_sites)).astype(np.uint64)
+    def kmer(sp, allele):
+        lo = int(sp) & ((1 << (2 * mid)) - 1); hi = int(sp) >> (2 * mid)
+        return (hi << (2 * mid + 2)) | (int(allele) << (2 * mid)) | lo
+    haps = rng.integers(0, 2, size=(n_clusters, 6, n_sites))
+    for r in range(n_reads):
+        c = int(rng.integers(0, n_clusters + 1))
+        if lists and rng.random() < dup_frac:
+            lists.append(list(lists[int(rng.integers(0, len(lists)))]))
+        else:
+            cc = min(c, n_clusters - 1)
+            h = haps[cc, int(rng.integers(0, 6))].copy()
+            flip = rng.random(n_sites) < 0.05
+            keep = rng.random(n_sites) < 0.8
+            alle = np.where(flip, 2 + h, h)                                    # a third / fourth allele now and then
+            lists.append([kmer(site_sp[cc, s], alle[s]) for s in range(n_sites) if keep[s]] if rng.random() > 0.03 else [])
+        if c < n_clusters:
+            members[c].append(r)
+    for m_ in members:
+        rng.shuffle(m_)
+    offs = np.zeros(n_reads + 1, np.uint64); offs[1:] = np.cumsum([len(x) for x in lists])
+    km = np.array([v for x in lists for v in x], np.uint64)
+    coffs = np.zeros(n_clusters + 1, np.uint64); coffs[1:] = np.cumsum([len(m_) for m_ in members])
+    cr = np.array([v for m_ in members for v in m_], np.uint32)
+    return km, offs, cr, coffs
+
+
+@pytest.mark.parametrize("seed,n_reads,n_clusters,n_sites,above", [(1, 3000, 7, 12, 1000), (2, 6000, 3, 20, 40), (3, 500, 40, 5, 1000), (4, 2500, 1, 30, 5)])
+def test_stage3_greedy_snpmer_clustering(ctx, seed, n_reads, n_clusters, n_sites, above):
+    """savont_b200_cluster_reads_by_snpmers (one CTA per k-mer cluster, reads in sequence) == the oracle's restatement of
+    asv_cluster::cluster_reads_by_snpmers, cluster by cluster, in the indexed branch and beyond `above` representatives"""
+    from savont_b200 import _lib
+    ctx.set_params(_lib.default_params())
+    km, offs, cr, coffs = _stage3_case(seed, n_reads, n_clusters, n_sites)
+    got = ctx.cluster_reads_by_snpmers(km, offs, cr, coffs, iterative_above=above)
+    want = np.full(n_reads, 0xffffffff, np.uint32)
+    for c in range(n_clusters):
+        mem = cr[int(coffs[c]):int(coffs[c + 1])]
+        w_ = O.cluster_reads_by_snpmers(km, offs, mem, iterative_above=above)
+        want[mem] = w_[mem]
+    assert np.array_equal(got["rep_of"], want)
+    reps = np.flatnonzero(got["rep_of"] == np.arange(n_reads))
+    assert got["n_representatives"] == len(reps) and len(reps) > n_clusters
+    # no clusters / empty clusters
+    e = ctx.cluster_reads_by_snpmers(km, offs, np.zeros(0, np.uint32), np.zeros(1, np.uint64))
+    assert np.all(e["rep_of"] == 0xffffffff) and e["n_representatives"] == 0
+    # a read with two SNPmers on one splitmer is rejected
+    bad = km.copy(); first = int(np.flatnonzero((offs[1:] - offs[:-1]) >= 2)[0]); bad[int(offs[first]) + 1] = bad[int(offs[first])] ^ np.uint64(1 << 16)
+    if first in set(cr.tolist()):
+        with pytest.raises(_lib.SavontB200Error):
+            ctx.cluster_reads_by_snpmers(bad, offs, cr, coffs)

@@ -291,3 +291,35 @@ def test_python_mirrors_of_stage_2_3_4():
     want_pl = api.pileups_from_columns(O.consensus_pileups(cb, cof, rb, qb, ro, prcons, band=16), cof)
     assert pl == want_pl and sum(len(col["bases"]) for p in pl for col in p) > 100
     ctx.close()
+
+
+def test_snpmer_cluster_lists_cpp_matches_python():
+    """savont_host::snpmer_clusters_from_assignment (C++) == api.snpmer_clusters_from_assignment (Python) on the oracle's Stage 3
+    assignment; the lists partition every k-mer cluster and put the representative's cluster members in ascending order"""
+    import ctypes as C
+    from savont_b200 import api, build
+    from tests.test_gpu_parity import _stage3_case
+    km, offs, cr, coffs = _stage3_case(11, 1500, 5, 10)
+    kcs = [cr[int(coffs[c]):int(coffs[c + 1])].astype(np.int64) for c in range(5)]
+    rep = np.full(1500, 0xffffffff, np.uint32)
+    for mem in kcs:
+        w_ = O.cluster_reads_by_snpmers(km, offs, mem.astype(np.uint32))
+        rep[mem] = w_[mem]
+    H = C.CDLL(build.build_host())
+    H.savont_host_snpmer_clusters_from_assignment.restype = C.c_longlong
+    u32p, u64p = C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
+    for min_size in (1, 3):
+        want = api.snpmer_clusters_from_assignment(kcs, rep, min_size)
+        o = np.zeros(len(cr) + 1, np.uint64); mbuf = np.zeros(max(len(cr), 1), np.uint64); kc_of = np.zeros(max(len(cr), 1), np.uint32)
+        nc = H.savont_host_snpmer_clusters_from_assignment(coffs.ctypes.data_as(u64p), cr.ctypes.data_as(u32p), C.c_size_t(5), rep.ctypes.data_as(u32p),
+                                                           C.c_size_t(min_size), o.ctypes.data_as(u64p), mbuf.ctypes.data_as(u64p), kc_of.ctypes.data_as(u32p))
+        flat = [c for kc in want for c in kc]
+        assert nc == len(flat) and nc > 5
+        for i, c in enumerate(flat):
+            assert np.array_equal(mbuf[int(o[i]):int(o[i + 1])].astype(np.int64), c)
+        assert [int(x) for x in kc_of[:nc]] == [i for i, kc in enumerate(want) for _ in kc]
+        if min_size == 1:
+            for kc, local in zip(kcs, want):
+                assert sorted(int(x) for c in local for x in c) == sorted(int(x) for x in kc)
+                assert all(len(a) >= len(b) for a, b in zip(local, local[1:])) and all(np.all(np.diff(c) > 0) for c in local)
+                assert all(np.all(rep[c] == rep[c[0]]) for c in local)
