@@ -7,6 +7,8 @@
 // fallback: without a device every entry point fails with SAVONT_B200_ERR_CUDA.
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
 #include <thread>
 
 #include "api_internal.cuh"
@@ -941,7 +943,7 @@ static int ctx_init(savont_b200_ctx *h, int device_id) {
     if (const char *e = getenv("SAVONT_B200_KC_PARTITIONED")) c->kc_partitioned = atoi(e) != 0;
     if (const char *e = getenv("SAVONT_B200_KC_SMEM_LIMIT")) c->kc_smem_limit = (uint32_t)atoi(e);
     for (auto &ev : c->ev) CK(cudaEventCreate(&ev));
-    for (int i = 0; i < 3; ++i) { CK(cudaEventCreate(&c->ev_up[i])); CK(cudaEventCreate(&c->ev_h0[i])); }
+    for (int i = 0; i < 4; ++i) { CK(cudaEventCreate(&c->ev_up[i])); CK(cudaEventCreate(&c->ev_h0[i])); }
     savont_b200_default_params(&c->params);
     c->dp = make_device_params(c->params);
     memset(&c->last_stats, 0, sizeof(c->last_stats));
@@ -956,18 +958,20 @@ int savont_b200_destroy(savont_b200_ctx *h) {
     cudaStreamSynchronize(c->stream);
     for (cudaStream_t s : {c->own_stream, c->lane_stream[0], c->lane_stream[1], c->copy_stream, c->d2h_stream}) if (s) cudaStreamSynchronize(s);
     for (Batch &pb : c->res_parts) pb.release();
-    c->work.release(); c->work2.release(); c->work3.release(); c->resident.release(); c->asvb.release();
+    c->work.release(); c->work2.release(); c->work3.release(); c->work4.release(); c->resident.release(); c->asvb.release();
     DevBuf *bufs[] = {&c->d_rank_table, &c->d_snp_keys, &c->d_snp_bloom, &c->d_phred, &c->d_thresh, &c->d_mx_keys, &c->d_mx_vals, &c->d_mx_entries, &c->d_idx_keys, &c->d_idx_vals, &c->d_idx_entries, &c->d_mset,
                       &c->d_mset_off, &c->d_asv_planes, &c->d_asv_plane_off, &c->d_asv_len, &c->d_counters, &c->d_hf_keys};
     for (DevBuf *b : bufs) b->release();
     c->pin_small.release(); c->pin_out.release(); c->tb_pin.release();
+    for (int i = 0; i < 4; ++i) { c->gather_words[i].release(); c->gather_snp[i].release(); }
+    c->pool.stop();
     for (DevBuf &b : c->tb_ws) b.release();
     for (DevBuf &b : c->pileup_ws) b.release();
     for (DevBuf &b : c->cluster_ws) b.release();
     c->d_ks_entries.release(); c->d_ks_dstptr.release(); c->d_ks_partoff.release();
     for (PinBuf &b : c->cluster_pin) b.release();
     for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
-    for (int i = 0; i < 3; ++i) { if (c->ev_up[i]) cudaEventDestroy(c->ev_up[i]); if (c->ev_h0[i]) cudaEventDestroy(c->ev_h0[i]); }
+    for (int i = 0; i < 4; ++i) { if (c->ev_up[i]) cudaEventDestroy(c->ev_up[i]); if (c->ev_h0[i]) cudaEventDestroy(c->ev_h0[i]); }
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     for (auto &ev : c->ev_d2h) if (ev) cudaEventDestroy(ev);
     for (int i = 0; i < 2; ++i) { if (c->kc_ev_up[i]) cudaEventDestroy(c->kc_ev_up[i]); if (c->kc_ev_done[i]) cudaEventDestroy(c->kc_ev_done[i]); }
@@ -1277,7 +1281,8 @@ static size_t ramp_batch(const Context *c, size_t bi, size_t /*remaining*/) {
 using UploadFn = std::function<int(Batch &, size_t, size_t, uint64_t *, cudaStream_t)>;
 static int map_batches(Context *c, const std::vector<size_t> &cuts, const UploadFn &upload_batch, int n_samples, uint8_t *status,
                        int32_t *best_nm, uint64_t *class_offsets, uint32_t *class_asv, size_t class_cap, uint64_t *unambig,
-                       uint64_t *ambig, uint64_t *leq10, uint64_t *totals, uint64_t *sample_singleton, savont_b200_stats *stats) {
+                       uint64_t *ambig, uint64_t *leq10, uint64_t *totals, uint64_t *sample_singleton, savont_b200_stats *stats,
+                       const std::function<void(size_t)> &on_finished = nullptr) {
     savont_b200_stats st; memset(&st, 0, sizeof(st));
     memset(&c->last_stats, 0, sizeof(c->last_stats));
     TRY(ensure_counters(c, n_samples, true));
@@ -1285,12 +1290,15 @@ static int map_batches(Context *c, const std::vector<size_t> &cuts, const Upload
     class_offsets[0] = 0;
     uint64_t class_base = 0;
     const size_t nb = cuts.size() - 1;
-    // three batch slots, two compute lanes: batch bi lives in slot bi % 3 and runs on lane bi & 1.  While batch bi
+    // four batch slots, two compute lanes: batch bi lives in slot bi % 4 and runs on lane bi & 1.  While batch bi
     // computes, batch bi-1 finishes on the other lane (the tail of its DP kernel overlaps bi's sketch / filter kernels) and
-    // has its results fetched on the D2H stream, and batch bi+1 is uploaded on the copy stream into the third slot.
-    Batch *bufs[3] = {&c->work, &c->work2, &c->work3};
+    // has its results fetched on the D2H stream, and batches bi+1, bi+2 are uploaded on the copy stream: the upload runs two
+    // batches ahead of the kernels, because with TwinRead input a batch's H2D time equals its kernel time (PCIe bound) and a
+    // one-batch lead left bubbles in both chains.
+    constexpr int kSlots = 4;
+    Batch *bufs[kSlots] = {&c->work, &c->work2, &c->work3, &c->work4};
     auto upload = [&](size_t bi) -> int {
-        const int slot = (int)(bi % 3);
+        const int slot = (int)(bi % kSlots);
         CK(cudaEventRecord(c->ev_h0[slot], c->copy_stream));
         TRY(upload_batch(*bufs[slot], cuts[bi], cuts[bi + 1] - cuts[bi], &st.h2d_bytes, c->copy_stream));
         CK(cudaEventRecord(c->ev_up[slot], c->copy_stream));
@@ -1298,7 +1306,7 @@ static int map_batches(Context *c, const std::vector<size_t> &cuts, const Upload
     };
     CK(cudaStreamWaitEvent(c->copy_stream, c->ev[6], 0));   // order after earlier work on the caller's stream
     for (int l = 0; l < 2; ++l) CK(cudaStreamWaitEvent(c->lane_stream[l], c->ev[6], 0));
-    struct Pending { Batch *b; size_t n, r0; int slot, lane; bool live; } prev{nullptr, 0, 0, 0, 0, false};
+    struct Pending { Batch *b; size_t n, r0, bi; int slot, lane; bool live; } prev{nullptr, 0, 0, 0, 0, 0, false};
     auto finish_prev = [&]() -> int {
         if (!prev.live) return 0;
         {
@@ -1315,22 +1323,24 @@ static int map_batches(Context *c, const std::vector<size_t> &cuts, const Upload
         st.d2h_ms += ev_ms(c->ev_d2h[0], c->ev_d2h[1]);
         class_base += n_cls;
         prev.live = false;
+        if (on_finished) on_finished(prev.bi);
         return 0;
     };
     if (nb) TRY(upload(0));
+    if (nb > 1) TRY(upload(1));
     for (size_t bi = 0; bi < nb; ++bi) {
-        const int slot = (int)(bi % 3), lane = (int)(bi & 1);
+        const int slot = (int)(bi % kSlots), lane = (int)(bi & 1);
         Batch &b = *bufs[slot];
         {
             LaneGuard g(c, lane);
             CK(cudaStreamWaitEvent(c->stream, c->ev_up[slot], 0));
             TRY(enqueue_path(c, b, n_samples));
         }
-        // batch bi's kernels are queued: now stage batch bi+1 (slot (bi+1) % 3 held batch bi-2: finished and fetched).  With the
+        // batch bi's kernels are queued: now stage batch bi+2 (its slot held batch bi-2: finished and fetched).  With the
         // pointer entry point this includes the host-side gather of the reads' heap buffers, which so runs under bi's kernels
-        if (bi + 1 < nb) TRY(upload(bi + 1));
+        if (bi + 2 < nb) TRY(upload(bi + 2));
         TRY(finish_prev());
-        prev = Pending{&b, cuts[bi + 1] - cuts[bi], cuts[bi], slot, lane, true};
+        prev = Pending{&b, cuts[bi + 1] - cuts[bi], cuts[bi], bi, slot, lane, true};
         st.n_batches += 1;
     }
     TRY(finish_prev());
@@ -1488,15 +1498,54 @@ int savont_b200_map_twin_read_ptrs(savont_b200_ctx *h, const uint64_t *const *dn
         cuts.push_back(r1);
         r0 = r1;
     }
+    // A producer thread gathers batch after batch into the four staging slots (its copies run on the context's host pool) and runs
+    // ahead of the consumer, which uploads a batch as soon as it is gathered; a slot is handed back when its batch has finished.
     double gather_ms = 0.0;
-    auto up = [&](Batch &b, size_t r0, size_t n, uint64_t *bytes, cudaStream_t st) -> int {
-        const int slot = &b == &c->work ? 0 : (&b == &c->work2 ? 1 : 2);
-        TwinInput ti{};
-        TRY(gather_batch(c, slot, in, r0, n, &ti, &gather_ms));
-        return batch_upload_twin(c, b, ti, 0, n, bytes, st);
+    struct Pipe {
+        std::mutex mu; std::condition_variable cv;
+        size_t gathered = 0, released = 0; int rc = 0; std::string err; bool abort = false;
+    } pipe;
+    const size_t nb = cuts.size() - 1;
+    std::vector<TwinInput> staged(4);
+    std::thread producer([&]() {
+        cudaSetDevice(c->device);                            // the staging buffers are page-locked through this device's context
+        for (size_t b = 0; b < nb; ++b) {
+            {
+                std::unique_lock<std::mutex> lk(pipe.mu);
+                pipe.cv.wait(lk, [&] { return pipe.abort || b < pipe.released + 4; });
+                if (pipe.abort) return;
+            }
+            TwinInput ti{};
+            const int rc = gather_batch(c, (int)(b % 4), in, cuts[b], cuts[b + 1] - cuts[b], &ti, &gather_ms);
+            std::unique_lock<std::mutex> lk(pipe.mu);
+            if (rc != 0) { pipe.rc = rc; pipe.err = savont_b200_last_error(); pipe.cv.notify_all(); return; }
+            staged[b % 4] = ti; pipe.gathered = b + 1;
+            pipe.cv.notify_all();
+        }
+    });
+    size_t next_up = 0;                    // batches are uploaded in order
+    auto up = [&](Batch &b, size_t /*r0*/, size_t n, uint64_t *bytes, cudaStream_t st) -> int {
+        const size_t bi = next_up++;
+        {
+            std::unique_lock<std::mutex> lk(pipe.mu);
+            pipe.cv.wait(lk, [&] { return pipe.rc != 0 || pipe.gathered > bi; });
+            if (pipe.rc != 0) return fail(pipe.rc, "%s", pipe.err.c_str());
+        }
+        return batch_upload_twin(c, b, staged[bi % 4], 0, n, bytes, st);
+    };
+    auto on_finished = [&](size_t bi) {
+        std::unique_lock<std::mutex> lk(pipe.mu);
+        pipe.released = bi + 1;
+        pipe.cv.notify_all();
     };
     const int rc = map_batches(c, cuts, up, n_samples, status, best_nm, class_offsets, class_asv, class_cap, unambig, ambig, leq10, totals,
-                               sample_singleton, stats);
+                               sample_singleton, stats, on_finished);
+    {
+        std::unique_lock<std::mutex> lk(pipe.mu);
+        pipe.abort = true;
+        pipe.cv.notify_all();
+    }
+    producer.join();
     c->last_stats.gather_ms = gather_ms;
     if (stats) stats->gather_ms = gather_ms;
     return rc;

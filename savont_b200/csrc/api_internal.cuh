@@ -198,14 +198,14 @@ struct Context {
     cudaEvent_t kc_ev_up[2] = {nullptr, nullptr}, kc_ev_done[2] = {nullptr, nullptr};
     // a4 read filter (twin_reads_from_snpmers): options + high-frequency k-mer set
     bool rf_on = false; ReadFilter rf{}; std::vector<uint64_t> h_hf; DevBuf d_hf_keys; uint32_t hf_mask = 0, hf_shift = 0;
-    Batch work, work2, work3, resident, asvb;
+    Batch work, work2, work3, work4, resident, asvb;
     int resident_samples = 1;
     // map_resident pipeline: the resident reads cut into parts (views of the resident inputs with their own intermediates) that
     // run on the two compute lanes, so that the sketch / filter kernels of part i+1 share the SMs with the DP kernel of part i
     std::vector<Batch> res_parts; std::vector<size_t> res_cuts; int resident_parts_req = 0;
     PinBuf pin_small, pin_out;
     // savont_b200_map_twin_read_ptrs: page-locked staging of the gathered reads, one slot per batch in flight
-    PinBuf gather_words[3], gather_snp[3]; std::vector<uint64_t> gather_woff[3], gather_soff[3]; int host_threads = 0; HostPool pool;
+    PinBuf gather_words[4], gather_snp[4]; std::vector<uint64_t> gather_woff[4], gather_soff[4]; int host_threads = 0; HostPool pool;
     cudaStream_t copy_stream = nullptr;          // H2D of batch i+1 overlaps the kernels of batch i
     cudaStream_t d2h_stream = nullptr;           // D2H of batch i-1's results overlaps the kernels of batch i
     cudaEvent_t ev_d2h[2] = {nullptr, nullptr};
@@ -215,7 +215,7 @@ struct Context {
     cudaEvent_t lane_ev[2][5] = {{nullptr}};
     cudaEvent_t *pev = nullptr;                  // the 5 stage events enqueue_path / finish_path use (ev or lane_ev[i])
     cudaEvent_t ev[8] = {nullptr};
-    cudaEvent_t ev_up[3] = {nullptr, nullptr, nullptr}, ev_h0[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_up[4] = {nullptr, nullptr, nullptr, nullptr}, ev_h0[4] = {nullptr, nullptr, nullptr, nullptr};
     savont_b200_stats last_stats;
     // traceback workspace (history, CIGAR slots, compacted ops, ...) and the Stage 4 pileup scratch: kept between calls
     DevBuf tb_ws[7]; PinBuf tb_pin;
