@@ -1024,3 +1024,31 @@ def test_stage3_greedy_snpmer_clustering(ctx, seed, n_reads, n_clusters, n_sites
     if first in set(cr.tolist()):
         with pytest.raises(_lib.SavontB200Error):
             ctx.cluster_reads_by_snpmers(bad, offs, cr, coffs)
+
+
+@pytest.mark.parametrize("name,n,ns", [("operon", 5000, 1), ("pooled", 6000, 20)])
+def test_named_configs_at_full_asv_sets(ctx, name, n, ns):
+    """configs 4 and 5 of BASELINE.json at their full ASV sets (2000 ASVs / 4.5 kb reads / band 192; 5000 ASVs / 20 samples): the
+    whole path (FASTQ entry, resident pass and TwinRead pointer entry) against the oracle -- the shapes bench.py --total-reads streams"""
+    from savont_b200 import _lib, twin
+    w = _make_workload(name)
+    assert w.n_asv == (2000 if name == "operon" else 5000) and w.n_samples == ns
+    r = w.reads(n)
+    fidx = r["file_idx"] if ns > 1 else None
+    gp, op = _params(_lib, band=w.band)
+    ctx.set_params(gp); ctx.load_snpmers(w.snpmers); ctx.load_asvs(w.asv_bases, w.asv_offsets)
+    orc = O.Oracle(op, w.snpmers); orc.load_asvs(w.asv_bases, w.asv_offsets)
+    want = orc.map_reads(r["bases"], r["quals"], r["offsets"], file_idx=fidx, n_samples=ns)
+    assert int(want["totals"][0]) > 0.8 * n
+    ctx.set_batch_reads(1500)
+    try:
+        assert_same(ctx.map_reads(r["bases"], r["quals"], r["offsets"], file_idx=fidx, n_samples=ns), want, MAP_KEYS, f"map_reads {name}")
+        sk = O.sketch_batch(op, w.snpmers, r["bases"], r["quals"], r["offsets"])
+        heap = twin.scatter_to_heap(twin.from_sketch(sk, r["offsets"], file_idx=fidx, kmer48=True))
+        assert_same(ctx.map_twin_read_ptrs(heap, n_samples=ns), want, MAP_KEYS, f"map_twin_read_ptrs {name}")
+    finally:
+        ctx.set_batch_reads(0)
+    ctx.upload_reads(r["bases"], r["quals"], r["offsets"], file_idx=fidx, n_samples=ns)
+    ctx.map_resident()
+    assert_same(ctx.fetch_resident(), want, MAP_KEYS, f"map_resident {name}")
+    ctx.set_params(_lib.default_params())
