@@ -11,6 +11,8 @@
 #include <mutex>
 #include <thread>
 
+#include <emmintrin.h>
+
 #include "api_internal.cuh"
 
 namespace sb {
@@ -206,11 +208,14 @@ struct TwinInput {
     const uint64_t *snp_offsets;
     const uint32_t *file_idx;
 };
-static int batch_upload_twin(Context *c, Batch &b, const TwinInput &in, size_t r0, size_t n, uint64_t *h2d_bytes,
-                             cudaStream_t st = nullptr) {
-    if (st == nullptr) st = c->stream;
-    TRY(b.pin_offsets.ensure((n + 1) * 16 + n * 8 + 64));
-    uint64_t *rel = b.pin_offsets.as<uint64_t>();
+// Host half of a TwinRead batch: the per-read offset arrays relative to the batch (page-locked, `meta`), sizes and checks.
+struct TwinPrep {
+    uint64_t *rel = nullptr, *wrel = nullptr; uint32_t *sstart = nullptr, *scnt = nullptr;
+    uint64_t total = 0, n_words = 0, n_snp = 0, w0 = 0, s0 = 0; uint32_t max_len = 0; size_t n = 0;
+};
+static int prepare_twin(const TwinInput &in, size_t r0, size_t n, PinBuf &meta, TwinPrep *p) {
+    TRY(meta.ensure((n + 1) * 16 + n * 8 + 64));
+    uint64_t *rel = meta.as<uint64_t>();
     uint64_t *wrel = rel + (n + 1);
     uint32_t *sstart = reinterpret_cast<uint32_t *>(wrel + (n + 1));
     uint32_t *scnt = sstart + n;
@@ -230,29 +235,35 @@ static int batch_upload_twin(Context *c, Batch &b, const TwinInput &in, size_t r
     }
     rel[n] = total; wrel[n] = in.word_offsets[r0 + n] - w0;
     if (total >= (1ull << 32) - 64) return fail(SAVONT_B200_ERR_INVALID, "batch of %llu bases exceeds 4 Gi", (unsigned long long)total);
-    const uint64_t n_words = wrel[n], n_snp = in.snp_offsets[r0 + n] - s0;
-    b.n = (uint32_t)n; b.total_bases = total; b.max_len = max_len; b.mapped = false;
+    p->rel = rel; p->wrel = wrel; p->sstart = sstart; p->scnt = scnt;
+    p->total = total; p->n_words = wrel[n]; p->n_snp = in.snp_offsets[r0 + n] - s0; p->w0 = w0; p->s0 = s0; p->max_len = max_len; p->n = n;
+    return 0;
+}
+// Device half: sizes the batch's buffers and enqueues the copies on `st`
+static int issue_twin(Context *c, Batch &b, const TwinInput &in, size_t r0, const TwinPrep &p, uint64_t *h2d_bytes, cudaStream_t st) {
+    const size_t n = p.n;
+    b.n = (uint32_t)n; b.total_bases = p.total; b.max_len = p.max_len; b.mapped = false;
     b.has_quals = false; b.has_file_idx = in.file_idx != nullptr;
     b.twin = true; b.force_generic = false;
-    TRY(b.offsets.ensure((n + 1) * 8)); TRY(b.word_offsets.ensure((n + 1) * 8)); TRY(b.dna_words.ensure((n_words + 2) * 8));
-    TRY(b.snp_start.ensure((n + 1) * 4)); TRY(b.snp_cnt.ensure((n + 1) * 4)); TRY(b.snp_kmer.ensure((n_snp + 1) * 8));
-    CK(cudaMemcpyAsync(b.offsets.p, rel, (n + 1) * 8, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(b.word_offsets.p, wrel, (n + 1) * 8, cudaMemcpyHostToDevice, st));
-    if (n) CK(cudaMemcpyAsync(b.snp_start.p, sstart, n * 4, cudaMemcpyHostToDevice, st));
-    if (n) CK(cudaMemcpyAsync(b.snp_cnt.p, scnt, n * 4, cudaMemcpyHostToDevice, st));
-    if (n_words) CK(cudaMemcpyAsync(b.dna_words.p, in.dna_words + w0, n_words * 8, cudaMemcpyHostToDevice, st));
-    uint64_t bytes = (n + 1) * 16 + n * 8 + n_words * 8;
-    if (n_snp) {
+    TRY(b.offsets.ensure((n + 1) * 8)); TRY(b.word_offsets.ensure((n + 1) * 8)); TRY(b.dna_words.ensure((p.n_words + 2) * 8));
+    TRY(b.snp_start.ensure((n + 1) * 4)); TRY(b.snp_cnt.ensure((n + 1) * 4)); TRY(b.snp_kmer.ensure((p.n_snp + 1) * 8));
+    CK(cudaMemcpyAsync(b.offsets.p, p.rel, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(b.word_offsets.p, p.wrel, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (n) CK(cudaMemcpyAsync(b.snp_start.p, p.sstart, n * 4, cudaMemcpyHostToDevice, st));
+    if (n) CK(cudaMemcpyAsync(b.snp_cnt.p, p.scnt, n * 4, cudaMemcpyHostToDevice, st));
+    if (p.n_words) CK(cudaMemcpyAsync(b.dna_words.p, in.dna_words + p.w0, p.n_words * 8, cudaMemcpyHostToDevice, st));
+    uint64_t bytes = (n + 1) * 16 + n * 8 + p.n_words * 8;
+    if (p.n_snp) {
         if (in.kmer_bytes == 8) {
-            CK(cudaMemcpyAsync(b.snp_kmer.p, static_cast<const uint64_t *>(in.snp_kmers) + s0, n_snp * 8, cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(b.snp_kmer.p, static_cast<const uint64_t *>(in.snp_kmers) + p.s0, p.n_snp * 8, cudaMemcpyHostToDevice, st));
         } else {
-            TRY(b.snp_raw.ensure(n_snp * 6 + 16));
-            CK(cudaMemcpyAsync(b.snp_raw.p, static_cast<const uint8_t *>(in.snp_kmers) + s0 * 6, n_snp * 6, cudaMemcpyHostToDevice, st));
-            launch_widen_kmer48(b.snp_raw.as<uint8_t>(), b.snp_kmer.as<uint64_t>(), n_snp, st);
+            TRY(b.snp_raw.ensure(p.n_snp * 6 + 16));
+            CK(cudaMemcpyAsync(b.snp_raw.p, static_cast<const uint8_t *>(in.snp_kmers) + p.s0 * 6, p.n_snp * 6, cudaMemcpyHostToDevice, st));
+            launch_widen_kmer48(b.snp_raw.as<uint8_t>(), b.snp_kmer.as<uint64_t>(), p.n_snp, st);
             CK(cudaGetLastError());
             c->last_stats.kernel_launches += 1;
         }
-        bytes += n_snp * (uint64_t)in.kmer_bytes;
+        bytes += p.n_snp * (uint64_t)in.kmer_bytes;
     }
     if (in.file_idx) {
         TRY(b.file_idx.ensure(n * 4 + 4));
@@ -261,6 +272,13 @@ static int batch_upload_twin(Context *c, Batch &b, const TwinInput &in, size_t r
     }
     if (h2d_bytes) *h2d_bytes += bytes;
     return 0;
+}
+static int batch_upload_twin(Context *c, Batch &b, const TwinInput &in, size_t r0, size_t n, uint64_t *h2d_bytes,
+                             cudaStream_t st = nullptr) {
+    if (st == nullptr) st = c->stream;
+    TwinPrep p;
+    TRY(prepare_twin(in, r0, n, b.pin_offsets, &p));
+    return issue_twin(c, b, in, r0, p, h2d_bytes, st);
 }
 static int validate_twin(const TwinInput &in, size_t n) {
     if (!in.word_offsets || !in.lengths || !in.snp_offsets) return fail(SAVONT_B200_ERR_INVALID, "null argument");
@@ -963,7 +981,7 @@ int savont_b200_destroy(savont_b200_ctx *h) {
                       &c->d_mset_off, &c->d_asv_planes, &c->d_asv_plane_off, &c->d_asv_len, &c->d_counters, &c->d_hf_keys};
     for (DevBuf *b : bufs) b->release();
     c->pin_small.release(); c->pin_out.release(); c->tb_pin.release();
-    for (int i = 0; i < 4; ++i) { c->gather_words[i].release(); c->gather_snp[i].release(); }
+    for (int i = 0; i < 8; ++i) { c->gather_words[i].release(); c->gather_snp[i].release(); c->gather_meta[i].release(); }
     c->pool.stop();
     for (DevBuf &b : c->tb_ws) b.release();
     for (DevBuf &b : c->pileup_ws) b.release();
@@ -1279,12 +1297,18 @@ static size_t ramp_batch(const Context *c, size_t bi, size_t /*remaining*/) {
     return full >> (steps - bi);
 }
 using UploadFn = std::function<int(Batch &, size_t, size_t, uint64_t *, cudaStream_t)>;
+// SAVONT_B200_TRACE=1: per-batch host timeline of the e2e pipeline on stderr (ms since the call started)
+static bool trace_on() { static const bool on = [] { const char *e = getenv("SAVONT_B200_TRACE"); return e && atoi(e) != 0; }(); return on; }
+static std::chrono::steady_clock::time_point g_trace_t0;
+static double trace_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - g_trace_t0).count(); }
+#define TRACE(...) do { if (trace_on()) { fprintf(stderr, "[trace %8.3f] ", trace_ms()); fprintf(stderr, __VA_ARGS__); fputc('\n', stderr); } } while (0)
 static int map_batches(Context *c, const std::vector<size_t> &cuts, const UploadFn &upload_batch, int n_samples, uint8_t *status,
                        int32_t *best_nm, uint64_t *class_offsets, uint32_t *class_asv, size_t class_cap, uint64_t *unambig,
                        uint64_t *ambig, uint64_t *leq10, uint64_t *totals, uint64_t *sample_singleton, savont_b200_stats *stats,
                        const std::function<void(size_t)> &on_finished = nullptr) {
     savont_b200_stats st; memset(&st, 0, sizeof(st));
     memset(&c->last_stats, 0, sizeof(c->last_stats));
+    if (trace_on()) g_trace_t0 = std::chrono::steady_clock::now();
     TRY(ensure_counters(c, n_samples, true));
     CK(cudaEventRecord(c->ev[6], c->stream));
     class_offsets[0] = 0;
@@ -1299,9 +1323,11 @@ static int map_batches(Context *c, const std::vector<size_t> &cuts, const Upload
     Batch *bufs[kSlots] = {&c->work, &c->work2, &c->work3, &c->work4};
     auto upload = [&](size_t bi) -> int {
         const int slot = (int)(bi % kSlots);
+        TRACE("upload(%zu) begin", bi);
         CK(cudaEventRecord(c->ev_h0[slot], c->copy_stream));
         TRY(upload_batch(*bufs[slot], cuts[bi], cuts[bi + 1] - cuts[bi], &st.h2d_bytes, c->copy_stream));
         CK(cudaEventRecord(c->ev_up[slot], c->copy_stream));
+        TRACE("upload(%zu) issued", bi);
         return 0;
     };
     CK(cudaStreamWaitEvent(c->copy_stream, c->ev[6], 0));   // order after earlier work on the caller's stream
@@ -1309,10 +1335,13 @@ static int map_batches(Context *c, const std::vector<size_t> &cuts, const Upload
     struct Pending { Batch *b; size_t n, r0, bi; int slot, lane; bool live; } prev{nullptr, 0, 0, 0, 0, 0, false};
     auto finish_prev = [&]() -> int {
         if (!prev.live) return 0;
+        TRACE("finish(%zu) wait", prev.bi);
         {
             LaneGuard g(c, prev.lane);
             TRY(finish_path(c, *prev.b, n_samples, st));
         }
+        TRACE("finish(%zu) kernels done: h2d %.3f ms, kernels %.3f ms (device)", prev.bi, ev_ms(c->ev_h0[prev.slot], c->ev_up[prev.slot]),
+              ev_ms(c->lane_ev[prev.lane][0], c->lane_ev[prev.lane][4]));
         st.h2d_ms += ev_ms(c->ev_h0[prev.slot], c->ev_up[prev.slot]);
         uint64_t n_cls = 0;
         CK(cudaEventRecord(c->ev_d2h[0], c->d2h_stream));
@@ -1323,6 +1352,7 @@ static int map_batches(Context *c, const std::vector<size_t> &cuts, const Upload
         st.d2h_ms += ev_ms(c->ev_d2h[0], c->ev_d2h[1]);
         class_base += n_cls;
         prev.live = false;
+        TRACE("finish(%zu) fetched", prev.bi);
         if (on_finished) on_finished(prev.bi);
         return 0;
     };
@@ -1336,6 +1366,7 @@ static int map_batches(Context *c, const std::vector<size_t> &cuts, const Upload
             CK(cudaStreamWaitEvent(c->stream, c->ev_up[slot], 0));
             TRY(enqueue_path(c, b, n_samples));
         }
+        TRACE("enqueue(%zu) done", bi);
         // batch bi's kernels are queued: now stage batch bi+2 (its slot held batch bi-2: finished and fetched).  With the
         // pointer entry point this includes the host-side gather of the reads' heap buffers, which so runs under bi's kernels
         if (bi + 2 < nb) TRY(upload(bi + 2));
@@ -1420,7 +1451,7 @@ struct PtrInput {
     const uint64_t *const *dna_ptrs; const uint32_t *lengths; const void *const *snp_ptrs; const uint32_t *snp_counts; int kmer_bytes;
     const uint32_t *file_idx;
 };
-static int gather_batch(Context *c, int slot, const PtrInput &in, size_t r0, size_t n, TwinInput *out, double *gather_ms) {
+static int gather_batch(Context *c, int slot, const PtrInput &in, size_t r0, size_t n, TwinInput *out, TwinPrep *prep, double *gather_ms) {
     const auto t0 = std::chrono::steady_clock::now();
     std::vector<uint64_t> &woff = c->gather_woff[slot], &soff = c->gather_soff[slot];
     woff.resize(n + 1); soff.resize(n + 1);
@@ -1457,14 +1488,22 @@ static int gather_batch(Context *c, int slot, const PtrInput &in, size_t r0, siz
                 }
                 const uint64_t nw = woff[i + 1] - woff[i], ns = soff[i + 1] - soff[i];
                 if ((nw && !in.dna_ptrs[r0 + i]) || (ns && !in.snp_ptrs[r0 + i])) { bad.store(1); continue; }
-                if (nw) memcpy(dw + woff[i], in.dna_ptrs[r0 + i], nw * 8);
+                // the staging buffer is read next by the DMA engine, not by a core: non-temporal stores keep it out of the caches
+                // and spare the read-for-ownership of every destination line
+                if (nw) {
+                    const long long *src = reinterpret_cast<const long long *>(in.dna_ptrs[r0 + i]);
+                    long long *dst = reinterpret_cast<long long *>(dw + woff[i]);
+                    for (uint64_t q = 0; q < nw; ++q) _mm_stream_si64(dst + q, src[q]);
+                }
                 if (ns) memcpy(ds + soff[i] * kb, in.snp_ptrs[r0 + i], ns * kb);
             }
+            _mm_sfence();
         }
     };
     c->pool.run(T, work);
     if (bad.load()) return fail(SAVONT_B200_ERR_INVALID, "null read buffer in batch starting at read %zu", r0);
     *out = TwinInput{dw, woff.data(), in.lengths + r0, ds, in.kmer_bytes, soff.data(), in.file_idx ? in.file_idx + r0 : nullptr};
+    TRY(prepare_twin(*out, 0, n, c->gather_meta[slot], prep));
     *gather_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return 0;
 }
@@ -1506,32 +1545,35 @@ int savont_b200_map_twin_read_ptrs(savont_b200_ctx *h, const uint64_t *const *dn
         size_t gathered = 0, released = 0; int rc = 0; std::string err; bool abort = false;
     } pipe;
     const size_t nb = cuts.size() - 1;
-    std::vector<TwinInput> staged(4);
+    constexpr size_t kRing = 8;            // staging slots: the producer may run four batches ahead of the four the pipeline holds
+    std::vector<TwinInput> staged(kRing); std::vector<TwinPrep> preps(kRing);
     std::thread producer([&]() {
         cudaSetDevice(c->device);                            // the staging buffers are page-locked through this device's context
         for (size_t b = 0; b < nb; ++b) {
             {
                 std::unique_lock<std::mutex> lk(pipe.mu);
-                pipe.cv.wait(lk, [&] { return pipe.abort || b < pipe.released + 4; });
+                pipe.cv.wait(lk, [&] { return pipe.abort || b < pipe.released + kRing; });
                 if (pipe.abort) return;
             }
-            TwinInput ti{};
-            const int rc = gather_batch(c, (int)(b % 4), in, cuts[b], cuts[b + 1] - cuts[b], &ti, &gather_ms);
+            TwinInput ti{}; TwinPrep tp{};
+            TRACE("gather(%zu) begin (%zu reads)", b, cuts[b + 1] - cuts[b]);
+            const int rc = gather_batch(c, (int)(b % kRing), in, cuts[b], cuts[b + 1] - cuts[b], &ti, &tp, &gather_ms);
+            TRACE("gather(%zu) end", b);
             std::unique_lock<std::mutex> lk(pipe.mu);
             if (rc != 0) { pipe.rc = rc; pipe.err = savont_b200_last_error(); pipe.cv.notify_all(); return; }
-            staged[b % 4] = ti; pipe.gathered = b + 1;
+            staged[b % kRing] = ti; preps[b % kRing] = tp; pipe.gathered = b + 1;
             pipe.cv.notify_all();
         }
     });
     size_t next_up = 0;                    // batches are uploaded in order
-    auto up = [&](Batch &b, size_t /*r0*/, size_t n, uint64_t *bytes, cudaStream_t st) -> int {
+    auto up = [&](Batch &b, size_t /*r0*/, size_t /*n*/, uint64_t *bytes, cudaStream_t st) -> int {
         const size_t bi = next_up++;
         {
             std::unique_lock<std::mutex> lk(pipe.mu);
             pipe.cv.wait(lk, [&] { return pipe.rc != 0 || pipe.gathered > bi; });
             if (pipe.rc != 0) return fail(pipe.rc, "%s", pipe.err.c_str());
         }
-        return batch_upload_twin(c, b, staged[bi % 4], 0, n, bytes, st);
+        return issue_twin(c, b, staged[bi % kRing], 0, preps[bi % kRing], bytes, st);
     };
     auto on_finished = [&](size_t bi) {
         std::unique_lock<std::mutex> lk(pipe.mu);
