@@ -1472,17 +1472,21 @@ static int gather_batch(Context *c, int slot, const PtrInput &in, size_t r0, siz
     // scattered over the heap: without the prefetch every copy starts with a DRAM miss)
     const size_t chunk = 512, n_chunks = (n + chunk - 1) / chunk;
     std::atomic<size_t> next_chunk{0};
+    // tuning knobs (measured on the B200 hosts, tools/trace_e2e.py): prefetch distance in reads, prefetch every line of a block or
+    // only its first, non-temporal stores for the words
+    auto env_int = [](const char *name, int dflt) { const char *e = getenv(name); return e ? atoi(e) : dflt; };
+    const size_t D = (size_t)std::max(0, env_int("SAVONT_B200_GATHER_PF", 8));
+    const bool pf_all = env_int("SAVONT_B200_GATHER_PF_ALL", 1) != 0, nt = env_int("SAVONT_B200_GATHER_NT", 1) != 0;
     const std::function<void(int)> work = [&](int) {
-        constexpr size_t D = 8;
         while (true) {
             const size_t ch = next_chunk.fetch_add(1);
             if (ch >= n_chunks) break;
             const size_t a = ch * chunk, b = std::min(n, a + chunk);
             for (size_t i = a; i < b; ++i) {
-                if (i + D < b) {
+                if (D && i + D < b) {
                     const char *pw = reinterpret_cast<const char *>(in.dna_ptrs[r0 + i + D]);
                     const char *ps = reinterpret_cast<const char *>(in.snp_ptrs[r0 + i + D]);
-                    const size_t bw = (size_t)(woff[i + D + 1] - woff[i + D]) * 8, bs = (size_t)(soff[i + D + 1] - soff[i + D]) * kb;
+                    const size_t bw = pf_all ? (size_t)(woff[i + D + 1] - woff[i + D]) * 8 : 1, bs = pf_all ? (size_t)(soff[i + D + 1] - soff[i + D]) * kb : 1;
                     if (pw) for (size_t o = 0; o < bw; o += 64) __builtin_prefetch(pw + o, 0, 0);
                     if (ps) for (size_t o = 0; o < bs; o += 64) __builtin_prefetch(ps + o, 0, 0);
                 }
@@ -1490,11 +1494,11 @@ static int gather_batch(Context *c, int slot, const PtrInput &in, size_t r0, siz
                 if ((nw && !in.dna_ptrs[r0 + i]) || (ns && !in.snp_ptrs[r0 + i])) { bad.store(1); continue; }
                 // the staging buffer is read next by the DMA engine, not by a core: non-temporal stores keep it out of the caches
                 // and spare the read-for-ownership of every destination line
-                if (nw) {
+                if (nw && nt) {
                     const long long *src = reinterpret_cast<const long long *>(in.dna_ptrs[r0 + i]);
                     long long *dst = reinterpret_cast<long long *>(dw + woff[i]);
                     for (uint64_t q = 0; q < nw; ++q) _mm_stream_si64(dst + q, src[q]);
-                }
+                } else if (nw) memcpy(dw + woff[i], in.dna_ptrs[r0 + i], nw * 8);
                 if (ns) memcpy(ds + soff[i] * kb, in.snp_ptrs[r0 + i], ns * kb);
             }
             _mm_sfence();
