@@ -492,6 +492,89 @@ def run_cluster(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
 
 
+def run_snpcluster(args, rank, world, local_rank):
+    """--path snpcluster: the greedy SNPmer clustering of Stage 3 inside the k-mer clusters (asv_cluster::cluster_reads_by_snpmers)
+    through savont_b200_cluster_reads_by_snpmers.  The k-mer clusters of the synthetic workload are its genera (what Stage 2 separates:
+    the roots are unrelated sequences), the reads of a cluster in read order.  Host buffers in, so end to end."""
+    import torch
+    from savont_b200 import _lib
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the b200 arm has no CPU fallback")
+    if world > 1:
+        if rank == 0:
+            print(json.dumps({"metric": "reads clustered/sec (Stage 3 greedy SNPmer clustering)", "unavailable": "k-mer clusters are independent: shard them, one process per GPU"}))
+        return
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    w = _workload(args)
+    ctx = _lib.Context(local_rank, _lib.default_params(band=w.band))
+    stream = torch.cuda.current_stream(dev)
+    ctx.set_stream(stream.cuda_stream)
+    ctx.load_snpmers(w.snpmers)
+    n_reads = args.reads
+    r = w.reads(n_reads)
+    kms, offs = [], [np.zeros(1, np.uint64)]
+    for b0 in range(0, n_reads, 200_000):
+        b1 = min(n_reads, b0 + 200_000)
+        sk = ctx.sketch(r["bases"], r["quals"], r["offsets"][b0:b1 + 1], want_codes=False)
+        kms.append(np.asarray(sk["snp_kmer"], np.uint64)); offs.append(np.asarray(sk["snp_offsets"][1:], np.uint64) + offs[-1][-1])
+    rk = np.concatenate(kms); ro = np.concatenate(offs)
+    n_var = w.cfg["n_var"]
+    genus = (r["truth_asv"] // n_var).astype(np.int64)
+    order = np.argsort(genus, kind="stable").astype(np.uint32)                    # cluster by cluster, read order inside
+    sizes = np.bincount(genus, minlength=w.n_asv // n_var)
+    co = np.zeros(len(sizes) + 1, np.uint64); co[1:] = np.cumsum(sizes)
+    del kms, offs
+    sampler = ClockSampler(local_rank); sampler.start()
+    for _ in range(max(1, args.warmup)):
+        out = ctx.cluster_reads_by_snpmers(rk, ro, order, co)
+    torch.cuda.synchronize(dev)
+    ms, stats = [], []
+    for _ in range(args.steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        out = ctx.cluster_reads_by_snpmers(rk, ro, order, co)
+        e1.record(stream); torch.cuda.synchronize(dev)
+        ms.append(e0.elapsed_time(e1)); stats.append(out["stats"])
+    clocks = sampler.stop()
+    kern = float(np.mean([s_["filter_ms"] for s_ in stats]))
+    val = n_reads * args.steps / (sum(ms) / 1e3)
+    peaks = _peaks()
+    alg = 8 * len(rk) + 8 * n_reads
+    line = {
+        "metric": "reads clustered/sec (Stage 3 greedy SNPmer clustering inside the k-mer clusters)", "value": val, "unit": "reads/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": max(1, args.warmup), "ms_per_step": sum(ms) / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64 k-mers / u32 counts", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {w.cfg['desc']}: {n_reads} reads ({len(rk)} SNPmers) in {len(sizes)} k-mer clusters (largest "
+                               f"{int(sizes.max())} reads), {out['n_representatives']} representatives", "l2": "every step re-uploads the SNPmer lists from host memory"},
+        "stage_ms": {"upload": float(np.mean([s_["h2d_ms"] for s_ in stats])), "cluster_kernel": kern},
+        "n_representatives": int(out["n_representatives"]),
+        "roofline": {"bound": "hbm", "kernel": "snp_cluster_kernel", "achieved": alg / (kern / 1e3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "peak_source": peaks["source"], "frac": alg / (kern / 1e3) / 1e9 / peaks["hbm_gbs"], "traffic": None, "algorithmic_bytes": alg,
+                     "note": "a latency-bound serial chain per k-mer cluster (one CTA walks the cluster's reads in order), not an HBM stream: the "
+                             "kernel time is the longest chain"},
+        "e2e": {"value": val, "unit": "reads/s", "h2d_bytes_per_step": int(stats[-1]["h2d_bytes"]), "d2h_bytes_per_step": int(stats[-1]["d2h_bytes"]),
+                "ms_per_step": sum(ms) / args.steps},
+        "gpu_launches": int(sum(s_["kernel_launches"] for s_ in stats)), "clocks": clocks,
+    }
+    if not args.no_cpu_baseline:
+        from concurrent.futures import ThreadPoolExecutor
+        from oracle import oracle as O
+        cores = os.cpu_count() or 1
+        t0 = time.perf_counter()
+        def one(c):                                                               # the reference walks the k-mer clusters in a par_iter
+            mem = order[int(co[c]):int(co[c + 1])]
+            return mem, O.cluster_reads_by_snpmers(rk, ro, mem)
+        with ThreadPoolExecutor(max_workers=cores) as ex:
+            res = list(ex.map(one, range(len(sizes))))
+        dt = time.perf_counter() - t0
+        same = all(np.array_equal(out["rep_of"][mem], w_[mem]) for mem, w_ in res)
+        line["cpu_baseline"] = {"value": n_reads / dt, "unit": "reads/s", "cores": cores, "kind": "port",
+                                "sample": f"all {n_reads} reads, one thread per k-mer cluster like the reference's par_iter (oracle/savont_oracle.c)",
+                                "gpu_matches_oracle_on_sample": bool(same)}
+    print(json.dumps(line), flush=True)
+
+
 def run_reassign(args, rank, world, local_rank):
     """--path reassign: the read-vs-consensus SNPmer comparison of Stage 3 reclustering (asv_cluster::reassign_reads_to_best_cluster)
     through savont_b200_snpmer_compare.  Not the headline path; one JSON line with the same keys.  Host buffers in, so end to end."""
@@ -795,7 +878,7 @@ def run_b200(args, rank, world, local_rank):
     #     region, batch i+1 under the kernels of batch i.
     # (b) `e2e_twin_contiguous`: the same fields already concatenated in pinned memory (savont_b200_map_twin_reads), i.e. without
     #     the gather -- the figure round 1 reported as e2e.
-    twin_line = ptr_line = None
+    twin_line = ptr_line = twin_resident = None
     sample_check = None
     if not args.no_twin:
         from savont_b200 import twin
@@ -830,11 +913,33 @@ def run_b200(args, rank, world, local_rank):
         res, tot, st_ = timed(lambda: ctx.map_twin_reads(tw, n_samples=w.n_samples))
         twin_line = line_of(res, tot, st_, "TwinRead.dna_seq words + TwinRead.snpmer_kmers (Kmer48) already concatenated in pinned host memory, "
                                             "savont_b200_map_twin_reads")
+        gather_threads = max(1, (os.cpu_count() or 1) // world)                                 # the ranks share the host's cores
+        ctx.set_host_threads(gather_threads)
         res, tot, st_ = timed(lambda: ctx.map_twin_read_ptrs(heap, n_samples=w.n_samples))
         ptr_line = line_of(res, tot, st_, "&[TwinRead] as it lies in the reference's memory: one pageable heap block per read for dna_seq and for "
                                           "snpmer_kmers, one pointer per read, savont_b200_map_twin_read_ptrs (host-thread gather into pinned "
                                           "staging inside the timed region)")
-        ptr_line["host_threads"] = os.cpu_count()
+        ptr_line["host_threads"] = gather_threads
+        # the kernel pipeline once more with the TwinReads RESIDENT (what Stage 7 is handed; the sketch then has no SNPmer detection, no
+        # quality gate and 2-bit input): informational, `value` stays the FASTQ-resident form that round 1 reported
+        ctx.upload_twin_reads(tw, n_samples=w.n_samples)
+        for _ in range(2):
+            ctx.map_resident()
+        tr_ms, tr_st = [], None
+        for _ in range(args.steps):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream); tr_st = ctx.map_resident(); allreduce_counts(); e1.record(stream)
+            barrier()
+            tr_ms.append(e0.elapsed_time(e1))
+        t = torch.tensor([sum(tr_ms)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gtw = ctx.fetch_resident()
+        twin_resident = {"value": world * n_reads * args.steps / (float(t.item()) / 1e3), "unit": "reads/s", "ms_per_step": float(t.item()) / args.steps,
+                         "kernel_ms": {"sketch": tr_st["sketch_ms"], "filter": tr_st["filter_ms"], "align": tr_st["align_ms"], "assign": tr_st["assign_ms"]},
+                         "same_result_as_ascii_entry": bool(all(np.array_equal(gtw[k], got[k]) for k in ("status", "best_nm", "class_offsets", "class_asv"))),
+                         "input": "TwinRead fields resident in HBM (savont_b200_upload_twin_reads + savont_b200_map_resident)"}
 
     clocks = sampler.stop()
 
@@ -954,6 +1059,7 @@ def run_b200(args, rank, world, local_rank):
                          "algorithmic_bytes": sk_bytes},
         "e2e": ptr_line if ptr_line is not None else fastq_line,
         "e2e_twin_contiguous": twin_line,
+        "value_twin_resident": twin_resident,
         "e2e_single_process": sp_line,
         "e2e_fastq": fastq_line,
         "gpu_launches": int(sum(s["kernel_launches"] for s in stats)),
@@ -1051,7 +1157,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-twin", action="store_true", help="skip the TwinRead-input e2e arms")
     ap.add_argument("--no-single-process", action="store_true", help="N > 1: skip the leg in which rank 0 drives all GPUs through the multi-GPU handle")
-    ap.add_argument("--path", default="assign", choices=["assign", "kmercount", "pileup", "cluster", "reassign"],
+    ap.add_argument("--path", default="assign", choices=["assign", "kmercount", "pileup", "cluster", "reassign", "snpcluster"],
                     help="assign: the headline read-vs-ASV path; kmercount: Stage 1 split-k-mer counting (K5)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -1071,6 +1177,8 @@ def main():
         run_cluster(args, rank, world, local_rank)
     elif args.path == "reassign":
         run_reassign(args, rank, world, local_rank)
+    elif args.path == "snpcluster":
+        run_snpcluster(args, rank, world, local_rank)
     elif args.total_reads > args.reads:
         run_streamed(args, rank, world, local_rank)
     else:

@@ -18,7 +18,31 @@ def run(label):
         st = res["stats"]
         if best is None or st["total_ms"] < best[1]["total_ms"]: best = (dt, st)
     print(label, "wall ms", round(best[0] * 1e3, 2), {k: round(v, 2) if isinstance(v, float) else v for k, v in best[1].items() if k in ("gather_ms", "h2d_ms", "total_ms", "n_batches")}, flush=True)
-if len(sys.argv) > 1 and sys.argv[1] == "sweep":
+if len(sys.argv) > 1 and sys.argv[1] == "threads":
+    for thr in (16, 32, 64, 128):
+        ctx.set_host_threads(thr); run(f"threads {thr}")
+    # the same heap in 2 MB pages (transparent huge pages requested for the arenas)
+    import ctypes, mmap
+    libc = ctypes.CDLL(None)
+    def huge_copy(a):
+        n = (a.nbytes + (2 << 20) - 1) // (2 << 20) * (2 << 20)
+        m = mmap.mmap(-1, n + (2 << 20))
+        buf = np.frombuffer(m, dtype=np.uint8)
+        off = (-buf.ctypes.data) % (2 << 20)
+        libc.madvise(ctypes.c_void_p(buf.ctypes.data + off), ctypes.c_size_t(n), 14)      # MADV_HUGEPAGE
+        out = buf[off:off + a.nbytes]; out[:] = a
+        return out, m
+    wa, sa = heap["_arenas"]
+    w2, m1 = huge_copy(wa); s2, m2 = huge_copy(sa)
+    heap2 = dict(heap)
+    heap2["dna_ptrs"] = (heap["dna_ptrs"].astype(np.int64) - wa.ctypes.data + w2.ctypes.data).astype(np.uint64)
+    heap2["snpmer_ptrs"] = (heap["snpmer_ptrs"].astype(np.int64) - sa.ctypes.data + s2.ctypes.data).astype(np.uint64)
+    heap_small = heap; heap = heap2
+    for thr in (16, 32):
+        ctx.set_host_threads(thr); run(f"hugepage arenas, threads {thr}")
+    print(open("/sys/kernel/mm/transparent_hugepage/enabled").read().strip(), flush=True)
+    heap = heap_small
+elif len(sys.argv) > 1 and sys.argv[1] == "sweep":
     for pf, pf_all, nt in [(8, 1, 1), (8, 1, 0), (0, 1, 1), (4, 1, 1), (16, 1, 1), (32, 1, 1), (16, 0, 1), (32, 0, 1), (16, 0, 0)]:
         os.environ["SAVONT_B200_GATHER_PF"] = str(pf); os.environ["SAVONT_B200_GATHER_PF_ALL"] = str(pf_all); os.environ["SAVONT_B200_GATHER_NT"] = str(nt)
         run(f"pf={pf} all={pf_all} nt={nt}")
