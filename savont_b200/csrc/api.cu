@@ -1453,61 +1453,93 @@ struct PtrInput {
 };
 static int gather_batch(Context *c, int slot, const PtrInput &in, size_t r0, size_t n, TwinInput *out, TwinPrep *prep, double *gather_ms) {
     const auto t0 = std::chrono::steady_clock::now();
-    std::vector<uint64_t> &woff = c->gather_woff[slot], &soff = c->gather_soff[slot];
-    woff.resize(n + 1); soff.resize(n + 1);
-    woff[0] = 0; soff[0] = 0;
-    for (size_t i = 0; i < n; ++i) {
-        woff[i + 1] = woff[i] + ((uint64_t)in.lengths[r0 + i] + 31u) / 32u;
-        soff[i + 1] = soff[i] + in.snp_counts[r0 + i];
-    }
-    TRY(c->gather_words[slot].ensure((woff[n] + 2) * 8));
-    TRY(c->gather_snp[slot].ensure(soff[n] * (size_t)in.kmer_bytes + 16));
-    uint64_t *dw = c->gather_words[slot].as<uint64_t>();
-    uint8_t *ds = c->gather_snp[slot].as<uint8_t>();
     const size_t kb = (size_t)in.kmer_bytes;
     int T = c->host_threads > 0 ? c->host_threads : (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
     if ((size_t)T > n / 2048 + 1) T = (int)(n / 2048 + 1);
-    std::atomic<int> bad{0};
-    // chunks of 512 reads handed out dynamically; the blocks of read i + 8 are prefetched while read i is copied (the blocks are
-    // scattered over the heap: without the prefetch every copy starts with a DRAM miss)
+    // The batch's offset arrays (what batch_upload_twin would compute) are built by the same threads that copy: pass A sums words /
+    // SNPmers / bases per chunk of 512 reads, a serial scan over the (few hundred) chunks places the chunks, pass B fills the per-read
+    // arrays of a chunk and copies its blocks.  Nothing per read runs on one thread.
     const size_t chunk = 512, n_chunks = (n + chunk - 1) / chunk;
+    std::vector<uint64_t> cw(n_chunks + 1, 0), cs(n_chunks + 1, 0), cl(n_chunks + 1, 0);
+    std::vector<uint32_t> cmax(n_chunks, 0);
     std::atomic<size_t> next_chunk{0};
-    // tuning knobs (measured on the B200 hosts, tools/trace_e2e.py): prefetch distance in reads, prefetch every line of a block or
-    // only its first, non-temporal stores for the words
-    auto env_int = [](const char *name, int dflt) { const char *e = getenv(name); return e ? atoi(e) : dflt; };
-    const size_t D = (size_t)std::max(0, env_int("SAVONT_B200_GATHER_PF", 8));
-    const bool pf_all = env_int("SAVONT_B200_GATHER_PF_ALL", 1) != 0, nt = env_int("SAVONT_B200_GATHER_NT", 1) != 0;
-    const std::function<void(int)> work = [&](int) {
+    const std::function<void(int)> pass_a = [&](int) {
         while (true) {
             const size_t ch = next_chunk.fetch_add(1);
             if (ch >= n_chunks) break;
             const size_t a = ch * chunk, b = std::min(n, a + chunk);
+            uint64_t w = 0, sn = 0, l = 0; uint32_t mx = 0;
             for (size_t i = a; i < b; ++i) {
+                const uint32_t len = in.lengths[r0 + i];
+                w += ((uint64_t)len + 31u) / 32u; sn += in.snp_counts[r0 + i]; l += len;
+                if (len > mx) mx = len;
+            }
+            cw[ch + 1] = w; cs[ch + 1] = sn; cl[ch + 1] = l; cmax[ch] = mx;
+        }
+    };
+    c->pool.run(T, pass_a);
+    uint32_t max_len = 0;
+    for (size_t ch = 0; ch < n_chunks; ++ch) { cw[ch + 1] += cw[ch]; cs[ch + 1] += cs[ch]; cl[ch + 1] += cl[ch]; if (cmax[ch] > max_len) max_len = cmax[ch]; }
+    const uint64_t n_words = cw[n_chunks], n_snp = cs[n_chunks], total = cl[n_chunks];
+    if (total >= (1ull << 32) - 64) return fail(SAVONT_B200_ERR_INVALID, "batch of %llu bases exceeds 4 Gi", (unsigned long long)total);
+    if (n_snp >= (1ull << 32)) return fail(SAVONT_B200_ERR_INVALID, "batch of %llu SNPmers is too large", (unsigned long long)n_snp);
+    TRY(c->gather_words[slot].ensure((n_words + 2) * 8));
+    TRY(c->gather_snp[slot].ensure(n_snp * kb + 16));
+    TRY(c->gather_meta[slot].ensure((n + 1) * 16 + n * 8 + 64));
+    uint64_t *dw = c->gather_words[slot].as<uint64_t>();
+    uint8_t *ds = c->gather_snp[slot].as<uint8_t>();
+    uint64_t *rel = c->gather_meta[slot].as<uint64_t>();
+    uint64_t *wrel = rel + (n + 1);
+    uint32_t *sstart = reinterpret_cast<uint32_t *>(wrel + (n + 1));
+    uint32_t *scnt = sstart + n;
+    rel[n] = total; wrel[n] = n_words;
+    std::atomic<int> bad{0};
+    // tuning knobs (measured on the B200 hosts, tools/trace_e2e.py, profiles/r02i_gather_sweep.txt): prefetch distance in reads,
+    // prefetch every line of a block or only its first, non-temporal stores for the words
+    auto env_int = [](const char *name, int dflt) { const char *e = getenv(name); return e ? atoi(e) : dflt; };
+    const size_t D = (size_t)std::max(0, env_int("SAVONT_B200_GATHER_PF", 8));
+    const bool pf_all = env_int("SAVONT_B200_GATHER_PF_ALL", 1) != 0, nt = env_int("SAVONT_B200_GATHER_NT", 1) != 0;
+    next_chunk.store(0);
+    const std::function<void(int)> pass_b = [&](int) {
+        while (true) {
+            const size_t ch = next_chunk.fetch_add(1);
+            if (ch >= n_chunks) break;
+            const size_t a = ch * chunk, b = std::min(n, a + chunk);
+            uint64_t w = cw[ch], sn = cs[ch], l = cl[ch];
+            for (size_t i = a; i < b; ++i) {
+                // the blocks of read i + D are prefetched while read i is copied (they are scattered over the heap: without the
+                // prefetch every copy starts with a DRAM miss)
                 if (D && i + D < b) {
                     const char *pw = reinterpret_cast<const char *>(in.dna_ptrs[r0 + i + D]);
                     const char *ps = reinterpret_cast<const char *>(in.snp_ptrs[r0 + i + D]);
-                    const size_t bw = pf_all ? (size_t)(woff[i + D + 1] - woff[i + D]) * 8 : 1, bs = pf_all ? (size_t)(soff[i + D + 1] - soff[i + D]) * kb : 1;
+                    const size_t bw = pf_all ? (((size_t)in.lengths[r0 + i + D] + 31u) / 32u) * 8 : 1, bs = pf_all ? (size_t)in.snp_counts[r0 + i + D] * kb : 1;
                     if (pw) for (size_t o = 0; o < bw; o += 64) __builtin_prefetch(pw + o, 0, 0);
                     if (ps) for (size_t o = 0; o < bs; o += 64) __builtin_prefetch(ps + o, 0, 0);
                 }
-                const uint64_t nw = woff[i + 1] - woff[i], ns = soff[i + 1] - soff[i];
-                if ((nw && !in.dna_ptrs[r0 + i]) || (ns && !in.snp_ptrs[r0 + i])) { bad.store(1); continue; }
-                // the staging buffer is read next by the DMA engine, not by a core: non-temporal stores keep it out of the caches
-                // and spare the read-for-ownership of every destination line
-                if (nw && nt) {
-                    const long long *src = reinterpret_cast<const long long *>(in.dna_ptrs[r0 + i]);
-                    long long *dst = reinterpret_cast<long long *>(dw + woff[i]);
-                    for (uint64_t q = 0; q < nw; ++q) _mm_stream_si64(dst + q, src[q]);
-                } else if (nw) memcpy(dw + woff[i], in.dna_ptrs[r0 + i], nw * 8);
-                if (ns) memcpy(ds + soff[i] * kb, in.snp_ptrs[r0 + i], ns * kb);
+                const uint32_t len = in.lengths[r0 + i];
+                const uint64_t nw = ((uint64_t)len + 31u) / 32u, ns = in.snp_counts[r0 + i];
+                rel[i] = l; wrel[i] = w; sstart[i] = (uint32_t)sn; scnt[i] = (uint32_t)ns;
+                if ((nw && !in.dna_ptrs[r0 + i]) || (ns && !in.snp_ptrs[r0 + i])) bad.store(1);
+                else {
+                    // the staging buffer is read next by the DMA engine, not by a core: non-temporal stores keep it out of the
+                    // caches and spare the read-for-ownership of every destination line
+                    if (nw && nt) {
+                        const long long *src = reinterpret_cast<const long long *>(in.dna_ptrs[r0 + i]);
+                        long long *dst = reinterpret_cast<long long *>(dw + w);
+                        for (uint64_t q = 0; q < nw; ++q) _mm_stream_si64(dst + q, src[q]);
+                    } else if (nw) memcpy(dw + w, in.dna_ptrs[r0 + i], nw * 8);
+                    if (ns) memcpy(ds + sn * kb, in.snp_ptrs[r0 + i], ns * kb);
+                }
+                w += nw; sn += ns; l += len;
             }
             _mm_sfence();
         }
     };
-    c->pool.run(T, work);
+    c->pool.run(T, pass_b);
     if (bad.load()) return fail(SAVONT_B200_ERR_INVALID, "null read buffer in batch starting at read %zu", r0);
-    *out = TwinInput{dw, woff.data(), in.lengths + r0, ds, in.kmer_bytes, soff.data(), in.file_idx ? in.file_idx + r0 : nullptr};
-    TRY(prepare_twin(*out, 0, n, c->gather_meta[slot], prep));
+    *out = TwinInput{dw, nullptr, in.lengths + r0, ds, in.kmer_bytes, nullptr, in.file_idx ? in.file_idx + r0 : nullptr};
+    prep->rel = rel; prep->wrel = wrel; prep->sstart = sstart; prep->scnt = scnt;
+    prep->total = total; prep->n_words = n_words; prep->n_snp = n_snp; prep->w0 = 0; prep->s0 = 0; prep->max_len = max_len; prep->n = n;
     *gather_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return 0;
 }

@@ -205,7 +205,7 @@ struct Context {
     std::vector<Batch> res_parts; std::vector<size_t> res_cuts; int resident_parts_req = 0;
     PinBuf pin_small, pin_out;
     // savont_b200_map_twin_read_ptrs: page-locked staging of the gathered reads, one slot per batch in flight
-    PinBuf gather_words[8], gather_snp[8], gather_meta[8]; std::vector<uint64_t> gather_woff[8], gather_soff[8]; int host_threads = 0; HostPool pool;
+    PinBuf gather_words[8], gather_snp[8], gather_meta[8]; int host_threads = 0; HostPool pool;
     cudaStream_t copy_stream = nullptr;          // H2D of batch i+1 overlaps the kernels of batch i
     cudaStream_t d2h_stream = nullptr;           // D2H of batch i-1's results overlaps the kernels of batch i
     cudaEvent_t ev_d2h[2] = {nullptr, nullptr};

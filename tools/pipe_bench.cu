@@ -28,7 +28,9 @@ __global__ void __launch_bounds__(256) bench(uint32_t *out, uint32_t a, uint32_t
                 if (MODE == 7) { if ((i & 3) == 0) asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(a), "r"(b));
                                  else asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(x[i]) : "r"(a), "r"(b)); }
                 if (MODE == 8) asm volatile("mul.wide.u32 %0, %1, %2;" : "+l"(*reinterpret_cast<unsigned long long *>(&x[i & 6])) : "r"(x[i]), "r"(a));
-                if (MODE == 9) asm volatile("vmin.u32.u32.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(a));
+                if (MODE == 9) asm volatile("min.u32 %0, %0, %1;" : "+r"(x[i]) : "r"(x[(i + 1) & 7]));
+                if (MODE == 11) asm volatile("{ .reg .u32 t; min.u32 t, %0, %1; min.u32 %0, t, %2; }" : "+r"(x[i]) : "r"(x[(i + 1) & 7]), "r"(x[(i + 2) & 7]));
+                if (MODE == 12) asm volatile("{ .reg .pred p; setp.lt.u32 p, %0, %1; selp.u32 %0, %0, %1, p; }" : "+r"(x[i]) : "r"(x[(i + 1) & 7]));
                 if (MODE == 10) { if (i & 1) asm volatile("shf.r.wrap.b32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(a), "r"(b));
                                   else asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[i]) : "r"(a), "r"(b)); }
             }
@@ -69,7 +71,9 @@ int main() {
     run<6>("LOP3 : IMAD.HI 1:1", d, p.multiProcessorCount, khz);
     run<7>("LOP3 : IMAD.HI 3:1", d, p.multiProcessorCount, khz);
     run<8>("IMAD.WIDE (mul.wide)", d, p.multiProcessorCount, khz);
-    run<9>("VIMNMX (min)", d, p.multiProcessorCount, khz);
+    run<9>("VIMNMX (min.u32)", d, p.multiProcessorCount, khz);
+    run<11>("VIMNMX3 (min of 3), per op", d, p.multiProcessorCount, khz);
+    run<12>("ISETP + SEL (min by select)", d, p.multiProcessorCount, khz);
     run<10>("SHF : IMAD 1:1", d, p.multiProcessorCount, khz);
     return 0;
 }
