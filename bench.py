@@ -885,6 +885,9 @@ def run_b200(args, rank, world, local_rank):
         tw = twin.twin_reads_from_snpmers(ctx, r["bases"], r["quals"], r["offsets"], file_idx=fidx, kmer48=True, alloc=_lib.pinned_array)
         heap = twin.scatter_to_heap(tw, seed=1 + rank)
 
+        ctx.reuse_outputs = True            # the caller's output arrays are allocated once and reused, like its input buffers
+        twin_cap = 2 * n_reads + 1024       # class_asv capacity: the library reports ERR_CAPACITY if a read set ever needs more
+
         def timed(call):
             res = call()                                                                        # warm-up (allocations)
             ms, stats_ = [], None
@@ -910,16 +913,18 @@ def run_b200(args, rank, world, local_rank):
                     "kernel_ms": {"sketch": st_["sketch_ms"], "filter": st_["filter_ms"], "align": st_["align_ms"]},
                     "input": what, "same_result_as_ascii_entry": bool(same)}
 
-        res, tot, st_ = timed(lambda: ctx.map_twin_reads(tw, n_samples=w.n_samples))
+        res, tot, st_ = timed(lambda: ctx.map_twin_reads(tw, n_samples=w.n_samples, class_cap=twin_cap))
         twin_line = line_of(res, tot, st_, "TwinRead.dna_seq words + TwinRead.snpmer_kmers (Kmer48) already concatenated in pinned host memory, "
                                             "savont_b200_map_twin_reads")
         gather_threads = max(1, (os.cpu_count() or 1) // world)                                 # the ranks share the host's cores
         ctx.set_host_threads(gather_threads)
-        res, tot, st_ = timed(lambda: ctx.map_twin_read_ptrs(heap, n_samples=w.n_samples))
+        res, tot, st_ = timed(lambda: ctx.map_twin_read_ptrs(heap, n_samples=w.n_samples, class_cap=twin_cap))
         ptr_line = line_of(res, tot, st_, "&[TwinRead] as it lies in the reference's memory: one pageable heap block per read for dna_seq and for "
                                           "snpmer_kmers, one pointer per read, savont_b200_map_twin_read_ptrs (host-thread gather into pinned "
                                           "staging inside the timed region)")
         ptr_line["host_threads"] = gather_threads
+        res = {k: (np.array(v) if isinstance(v, np.ndarray) else v) for k, v in res.items()}   # detach from the reused output arrays
+        ctx.reuse_outputs = False
         # the kernel pipeline once more with the TwinReads RESIDENT (what Stage 7 is handed; the sketch then has no SNPmer detection, no
         # quality gate and 2-bit input): informational, `value` stays the FASTQ-resident form that round 1 reported
         ctx.upload_twin_reads(tw, n_samples=w.n_samples)

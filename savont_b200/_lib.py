@@ -316,8 +316,26 @@ class Context:
         return out
 
     # ---- whole path ----
+    # reuse_outputs = True: the output arrays of the map_* calls are kept and handed out again for calls of the same shape (a caller that
+    # maps batch after batch into the same Vecs); the arrays of a result are then only valid until the next call
+    reuse_outputs = False
+
     def _out_buffers(self, n, n_samples, class_cap):
         A = self.n_asv
+        if self.reuse_outputs:
+            key = (n, n_samples, class_cap, A)
+            cache = self.__dict__.setdefault("_out_cache", {})
+            if key not in cache:
+                cache.clear()
+                self.reuse_outputs = False
+                try:
+                    cache[key] = self._out_buffers(n, n_samples, class_cap)
+                finally:
+                    self.reuse_outputs = True
+            B = cache[key]
+            for k in ("unambig", "ambig", "leq10", "totals", "sample_singleton"):      # the library ADDS into the counter arrays
+                B[k][:] = 0
+            return B
         return dict(status=np.zeros(max(n, 1), np.uint8), best_nm=np.zeros(max(n, 1), np.int32),
                     class_offsets=np.zeros(n + 1, np.uint64), class_asv=np.zeros(max(class_cap, 1), np.uint32),
                     unambig=np.zeros(max(A, 1), np.uint64), ambig=np.zeros(max(A, 1), np.uint64), leq10=np.zeros(max(A, 1), np.uint64),

@@ -135,7 +135,7 @@ extern "C" int savont_b200_cluster_reads_by_snpmers(savont_b200_ctx *h, const ui
     cudaStream_t st = c->stream;
     DevBuf *w = c->cluster_ws;
     CK(cudaEventRecord(c->ev[0], st));
-    TRY(w[0].ensure(n_mark * 8 + 16)); TRY(w[1].ensure((n_reads + 1) * 8)); TRY(w[2].ensure(n_memb * 4 + 16)); TRY(w[3].ensure((n_clusters + 1) * 8));
+    TRY(w[0].ensure(n_mark * 8 + 16)); TRY(w[1].ensure((n_reads + 1) * 8)); TRY(w[2].ensure(n_memb * 4 + 1024)); TRY(w[3].ensure((n_clusters + 1) * 8));
     TRY(w[4].ensure(n_clusters * 4 + 16)); TRY(w[5].ensure(n_memb * 4 + 16)); TRY(w[6].ensure(n_memb * 4 + 16)); TRY(w[7].ensure(n_reads * 4 + 16));
     TRY(w[8].ensure(64));
     if (n_mark) CK(cudaMemcpyAsync(w[0].p, snp_kmers + m0, n_mark * 8, cudaMemcpyHostToDevice, st));
@@ -153,6 +153,17 @@ extern "C" int savont_b200_cluster_reads_by_snpmers(savont_b200_ctx *h, const ui
     a.reps = w[5].as<uint32_t>(); a.rep_size = w[6].as<uint32_t>(); a.rep_of = w[7].as<uint32_t>();
     a.work_ctr = w[8].as<uint32_t>(); a.err = w[8].as<uint32_t>() + 1; a.total_reps = reinterpret_cast<unsigned long long *>(w[8].as<uint32_t>() + 2);
     CK(cudaEventRecord(c->ev[1], st));
+    // cluster-major copy of the lists (count -> scan -> gather): the cluster kernel then streams consecutive memory
+    if (n_mark >= (1ull << 32)) return fail(SAVONT_B200_ERR_OVERFLOW, "more than 4 Gi SNPmers in one call");
+    TRY(w[9].ensure(n_memb * 4 + 16)); TRY(w[10].ensure((n_memb + 2) * 4 + 256)); TRY(w[11].ensure((n_memb / 2048 + 4) * 4)); TRY(w[12].ensure(n_mark * 8 + 4096 + 16));
+    if (n_memb) {
+        launch_snp_cluster_count(a, (uint32_t)n_memb, w[9].as<uint32_t>(), st);
+        launch_scan_u32(w[9].as<uint32_t>(), w[10].as<uint32_t>(), (uint32_t)n_memb, w[11].as<uint32_t>(), st);
+        a.poff = w[10].as<uint32_t>();
+        launch_snp_cluster_gather(a, (uint32_t)n_memb, w[12].as<unsigned long long>(), st);
+        a.pkmers = w[12].as<unsigned long long>();
+        c->last_stats.kernel_launches += 5;
+    }
     launch_snp_cluster(a, c->sm_count, st);
     CK(cudaGetLastError());
     if (n_clusters) c->last_stats.kernel_launches += 1;

@@ -352,10 +352,13 @@ struct SnpClusterArgs {
     const uint32_t *cluster_reads; const uint64_t *cluster_offsets;         // the k-mer clusters: read ids in processing order (CSR)
     const uint32_t *order;                                                  // cluster indices, largest cluster first
     uint32_t n_clusters, iterative_above;
-    uint32_t *reps, *rep_size;                                              // workspace, one slot per clustered read (segment = cluster)
+    const uint32_t *poff; const unsigned long long *pkmers;                 // cluster-major copy of the lists: position p of the concatenated clusters
+    uint32_t *reps, *rep_size;                                              // workspace, one slot per clustered read (segment = cluster); reps = positions
     uint32_t *rep_of;                                                       // [n_reads] out: representative read id
     uint32_t *work_ctr, *err; unsigned long long *total_reps;
 };
 void launch_snp_cluster(const SnpClusterArgs &a, int sm_count, cudaStream_t st);
+void launch_snp_cluster_count(const SnpClusterArgs &a, uint32_t n_memb, uint32_t *cnt, cudaStream_t st);
+void launch_snp_cluster_gather(const SnpClusterArgs &a, uint32_t n_memb, unsigned long long *dst, cudaStream_t st);
 
 }  // namespace sb

@@ -15,6 +15,8 @@
 // the reference's inverted index turned around: the index answers "which representatives share this SNPmer", the walk answers the
 // same question per representative, and with the splitmers of a read being distinct (src/seeding.rs:550-568 keeps only SNPmers
 // whose splitmer occurs once) both count exactly the same (matches, mismatches).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace sb {
@@ -54,8 +56,13 @@ snp_cluster_kernel(SnpClusterArgs a) {
         uint32_t n_reps = 0;                                     // every thread keeps the same copy (the winner is computed by all)
         for (uint64_t pos = c0; pos < c1; ++pos) {
             const uint32_t read = a.cluster_reads[pos];
-            const uint64_t q0 = a.snp_offsets[read], q1 = a.snp_offsets[read + 1];
-            const uint32_t nq = (uint32_t)(q1 - q0);
+            const uint32_t q0 = a.poff[pos], q1 = a.poff[pos + 1];              // cluster-major copy: consecutive reads, consecutive lists
+            const uint32_t nq = q1 - q0;
+            // the lists of the next reads are pulled into L2 while this one is processed (no hardware prefetcher on the GPU; the
+            // chain is latency bound, so a DRAM miss per read would be most of its time)
+            if (tid == 0) asm volatile("prefetch.global.L2 [%0];" :: "l"(a.pkmers + q0 + 512));
+            if (tid == 32) asm volatile("prefetch.global.L2 [%0];" :: "l"(a.poff + pos + 64));
+            if (tid == 64) asm volatile("prefetch.global.L2 [%0];" :: "l"(a.cluster_reads + pos + 64));
             // ---- the read's SNPmers -> map (splitmer -> k-mer); every inserting thread remembers its slots and empties them again
             //      after the scoring, so the map is never cleared as a whole ----
             uint32_t my_slot[2] = {0xffffffffu, 0xffffffffu};
@@ -65,7 +72,7 @@ snp_cluster_kernel(SnpClusterArgs a) {
                 for (int u = 0; u < 2; ++u) {
                     const uint32_t i = tid + u * kSnpClusterThreads;
                     if (i >= nq) break;
-                    const unsigned long long km = a.snp_kmers[q0 + i];
+                    const unsigned long long km = a.pkmers[q0 + i];
                     const unsigned long long sp = km & mask;
                     uint32_t slot = (uint32_t)((sp * kFibMul) >> 54) & (kSnpClusterMap - 1u);
                     while (true) {
@@ -82,14 +89,14 @@ snp_cluster_kernel(SnpClusterArgs a) {
             SnpClusterCand best{0u, 0u, 0u, 0u};
             if (nq > 0u && nq <= kSnpClusterMap / 2u) {
                 for (uint32_t r = warp; r < n_reps; r += kWarps) {
-                    const uint32_t rid = reps[r];
-                    const uint64_t e0 = a.snp_offsets[rid], e1 = a.snp_offsets[rid + 1];
+                    const uint32_t rpos = reps[r];                           // position of the representative in the cluster-major arrays
+                    const uint32_t e0 = a.poff[rpos], e1 = a.poff[rpos + 1];
                     uint32_t m = 0, mm = 0;
-                    for (uint64_t eb = e0; eb < e1 && mm == 0u; eb += 32u) {
-                        const uint64_t e = eb + lane;
+                    for (uint32_t eb = e0; eb < e1 && mm == 0u; eb += 32u) {
+                        const uint32_t e = eb + lane;
                         bool hit = false, eq = false;
                         if (e < e1) {
-                            const unsigned long long km = a.snp_kmers[e];
+                            const unsigned long long km = a.pkmers[e];
                             const unsigned long long sp = km & mask;
                             uint32_t slot = (uint32_t)((sp * kFibMul) >> 54) & (kSnpClusterMap - 1u);
                             while (true) {
@@ -103,7 +110,7 @@ snp_cluster_kernel(SnpClusterArgs a) {
                         mm += (uint32_t)__popc(__ballot_sync(0xffffffffu, hit && !eq));
                     }
                     if (mm == 0u && m > 0u) {
-                        const SnpClusterCand cnd{m, rep_size[r], rid, r};
+                        const SnpClusterCand cnd{m, rep_size[r], a.cluster_reads[rpos], r};
                         if (snpcluster_better(cnd, best, iterative)) best = cnd;
                     }
                 }
@@ -116,7 +123,7 @@ snp_cluster_kernel(SnpClusterArgs a) {
             for (int i = 1; i < kWarps; ++i) { const SnpClusterCand o = warp_best[i]; if (snpcluster_better(o, w, iterative)) w = o; }
             if (tid == 0) {
                 if (w.m > 0u) { a.rep_of[read] = w.rid; rep_size[w.r] += 1u; }                        // src/asv_cluster.rs:386-394
-                else { reps[n_reps] = read; rep_size[n_reps] = 1u; a.rep_of[read] = read; }           // :397-410
+                else { reps[n_reps] = (uint32_t)pos; rep_size[n_reps] = 1u; a.rep_of[read] = read; }  // :397-410
             }
             if (w.m == 0u) ++n_reps;
 #pragma unroll
@@ -125,6 +132,32 @@ snp_cluster_kernel(SnpClusterArgs a) {
         }
         if (tid == 0) atomicAdd(a.total_reps, (unsigned long long)n_reps);
     }
+}
+
+// cluster-major copy of the SNPmer lists: position p of the concatenated clusters gets the list of read cluster_reads[p]
+__global__ void snp_cluster_count_kernel(SnpClusterArgs a, uint32_t n_memb, uint32_t *cnt) {
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n_memb; p += gridDim.x * blockDim.x) {
+        const uint32_t read = a.cluster_reads[p];
+        cnt[p] = (uint32_t)(a.snp_offsets[read + 1] - a.snp_offsets[read]);
+    }
+}
+__global__ void snp_cluster_gather_kernel(SnpClusterArgs a, uint32_t n_memb, unsigned long long *dst) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; p < n_memb; p += warps) {
+        const uint32_t read = a.cluster_reads[p];
+        const uint64_t s0 = a.snp_offsets[read];
+        const uint32_t n = a.poff[p + 1] - a.poff[p], d0 = a.poff[p];
+        for (uint32_t i = lane; i < n; i += 32u) dst[d0 + i] = a.snp_kmers[s0 + i];
+    }
+}
+void launch_snp_cluster_count(const SnpClusterArgs &a, uint32_t n_memb, uint32_t *cnt, cudaStream_t st) {
+    if (n_memb == 0) return;
+    snp_cluster_count_kernel<<<std::min<uint32_t>((n_memb + 255u) / 256u, 148u * 8u), 256, 0, st>>>(a, n_memb, cnt);
+}
+void launch_snp_cluster_gather(const SnpClusterArgs &a, uint32_t n_memb, unsigned long long *dst, cudaStream_t st) {
+    if (n_memb == 0) return;
+    snp_cluster_gather_kernel<<<std::min<uint32_t>((n_memb + 7u) / 8u, 148u * 16u), 256, 0, st>>>(a, n_memb, dst);
 }
 
 void launch_snp_cluster(const SnpClusterArgs &a, int sm_count, cudaStream_t st) {

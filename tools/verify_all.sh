@@ -12,13 +12,13 @@ python -m pytest tests -x -q -m gpu
 python -c "import __graft_entry__ as g; g.smoke()"
 python bench.py --impl reference --steps 2 --warmup 1 | tail -1 > "gpurun_out/${tag}_reference_1gpu.json"
 python bench.py --steps 5 --warmup 3 | tail -1 > "gpurun_out/${tag}_ont16s_1gpu.json"
-for p in kmercount cluster reassign pileup; do
+for p in kmercount cluster reassign snpcluster pileup; do
   python bench.py --path "$p" --steps 3 --warmup 3 | tail -1 > "gpurun_out/${tag}_${p}_1gpu.json"
 done
 python - "$tag" <<'PY'
 import json, sys
 tag = sys.argv[1]
-for name in ("reference", "ont16s", "kmercount", "cluster", "reassign", "pileup"):
+for name in ("reference", "ont16s", "kmercount", "cluster", "reassign", "snpcluster", "pileup"):
     d = json.loads(open(f"gpurun_out/{tag}_{name}_1gpu.json").read())
     e2e = (d.get("e2e") or {}).get("value")
     print(f"{name:10s} value {d['value']:.4g} {d['unit']}  e2e {e2e:.4g}  roofline.frac {(d.get('roofline') or {}).get('frac')}")
