@@ -11,7 +11,9 @@
 // reads of a cluster strictly in sequence.  Per read the CTA puts the read's SNPmers into a shared-memory map (splitmer -> k-mer)
 // and every WARP scores one representative against it, the lanes taking that representative's own SNPmers (the lists are the
 // input CSR: nothing is copied, and the hot ones stay in L1 / L2); every thread then picks the winner of the 8 per-warp candidates
-// by the same lexicographic rule.  Three block barriers per read; the map is emptied slot by slot by the threads that filled it.  This is
+// by the same lexicographic rule.  The lists and sizes of the first 64 representatives live in shared memory, the read's map is double
+// buffered and emptied slot by slot by the threads that filled it, the next read's list is loaded one read ahead: two block barriers
+// and no global-memory round trip on the critical path per read.  This is
 // the reference's inverted index turned around: the index answers "which representatives share this SNPmer", the walk answers the
 // same question per representative, and with the splitmers of a read being distinct (src/seeding.rs:550-568 keeps only SNPmers
 // whose splitmer occurs once) both count exactly the same (matches, mismatches).
@@ -35,15 +37,20 @@ __device__ __forceinline__ bool snpcluster_better(const SnpClusterCand &a, const
     return a.rid < b.rid;
 }
 
+constexpr uint32_t kSnpCacheReps = 64;             // representatives whose SNPmer list and size live in shared memory
+constexpr uint32_t kSnpCacheLen = 32;              // ... if the list has at most this many SNPmers
+
 __global__ void __launch_bounds__(kSnpClusterThreads)
 snp_cluster_kernel(SnpClusterArgs a) {
-    __shared__ unsigned long long qmap[kSnpClusterMap];
+    __shared__ unsigned long long qmap[2][kSnpClusterMap];                 // the read's SNPmers, double buffered (even / odd reads)
+    __shared__ unsigned long long rep_km[kSnpCacheReps][kSnpCacheLen];
+    __shared__ uint32_t rep_n[kSnpCacheReps], rep_sz[kSnpCacheReps], rep_rid[kSnpCacheReps];
     __shared__ SnpClusterCand warp_best[kSnpClusterThreads / 32];
     __shared__ uint32_t s_next;
     constexpr int kWarps = kSnpClusterThreads / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint64_t mask = ~(3ull << (a.k - 1));
-    for (uint32_t i = tid; i < kSnpClusterMap; i += kSnpClusterThreads) qmap[i] = kEmpty64;
+    for (uint32_t i = tid; i < 2u * kSnpClusterMap; i += kSnpClusterThreads) (&qmap[0][0])[i] = kEmpty64;
     while (true) {
         __syncthreads();
         if (tid == 0) s_next = atomicAdd(a.work_ctr, 1u);
@@ -54,55 +61,68 @@ snp_cluster_kernel(SnpClusterArgs a) {
         const uint64_t c0 = a.cluster_offsets[ci], c1 = a.cluster_offsets[ci + 1];
         uint32_t *reps = a.reps + c0, *rep_size = a.rep_size + c0;
         uint32_t n_reps = 0;                                     // every thread keeps the same copy (the winner is computed by all)
+        // the SNPmers of the read about to be processed, one or two per thread, loaded one read ahead
+        uint32_t q0 = 0, nq = 0;
+        unsigned long long km[2] = {0ull, 0ull};
+        auto load_read = [&](const uint64_t pos) {
+            q0 = a.poff[pos]; nq = a.poff[pos + 1] - q0;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) { const uint32_t i = tid + u * kSnpClusterThreads; if (i < nq && nq <= kSnpClusterMap / 2u) km[u] = a.pkmers[q0 + i]; }
+        };
+        if (c0 < c1) load_read(c0);
         for (uint64_t pos = c0; pos < c1; ++pos) {
+            unsigned long long (&qm)[kSnpClusterMap] = qmap[pos & 1];
             const uint32_t read = a.cluster_reads[pos];
-            const uint32_t q0 = a.poff[pos], q1 = a.poff[pos + 1];              // cluster-major copy: consecutive reads, consecutive lists
-            const uint32_t nq = q1 - q0;
-            // the lists of the next reads are pulled into L2 while this one is processed (no hardware prefetcher on the GPU; the
-            // chain is latency bound, so a DRAM miss per read would be most of its time)
-            if (tid == 0) asm volatile("prefetch.global.L2 [%0];" :: "l"(a.pkmers + q0 + 512));
-            if (tid == 32) asm volatile("prefetch.global.L2 [%0];" :: "l"(a.poff + pos + 64));
-            if (tid == 64) asm volatile("prefetch.global.L2 [%0];" :: "l"(a.cluster_reads + pos + 64));
-            // ---- the read's SNPmers -> map (splitmer -> k-mer); every inserting thread remembers its slots and empties them again
-            //      after the scoring, so the map is never cleared as a whole ----
+            const uint32_t nq_cur = nq;
+            const unsigned long long km_cur[2] = {km[0], km[1]};
+            // ---- 1. the read's SNPmers -> map (splitmer -> k-mer); every inserting thread remembers its slots and empties them again
+            //         after the scoring, so a map is never cleared as a whole ----
             uint32_t my_slot[2] = {0xffffffffu, 0xffffffffu};
-            if (nq > kSnpClusterMap / 2u) { if (tid == 0) atomicOr(a.err, 1u); }
+            if (nq_cur > kSnpClusterMap / 2u) { if (tid == 0) atomicOr(a.err, 1u); }
             else {
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     const uint32_t i = tid + u * kSnpClusterThreads;
-                    if (i >= nq) break;
-                    const unsigned long long km = a.pkmers[q0 + i];
-                    const unsigned long long sp = km & mask;
+                    if (i >= nq_cur) break;
+                    const unsigned long long sp = km_cur[u] & mask;
                     uint32_t slot = (uint32_t)((sp * kFibMul) >> 54) & (kSnpClusterMap - 1u);
                     while (true) {
-                        const unsigned long long old = atomicCAS(&qmap[slot], (unsigned long long)kEmpty64, km);
+                        const unsigned long long old = atomicCAS(&qm[slot], (unsigned long long)kEmpty64, km_cur[u]);
                         if (old == kEmpty64) { my_slot[u] = slot; break; }
                         if ((old & mask) == sp) { atomicOr(a.err, 2u); break; }      // the splitmers of a read must be distinct
                         slot = (slot + 1u) & (kSnpClusterMap - 1u);
                     }
                 }
             }
+            // the next read's list is requested now and consumed in the next iteration (the chain is latency bound); further ahead
+            // the lists are pulled into L2
+            if (pos + 1 < c1) load_read(pos + 1);
+            if (tid == 0) asm volatile("prefetch.global.L2 [%0];" :: "l"(a.pkmers + q0 + 512));
+            if (tid == 32) asm volatile("prefetch.global.L2 [%0];" :: "l"(a.poff + pos + 64));
+            if (tid == 64) asm volatile("prefetch.global.L2 [%0];" :: "l"(a.cluster_reads + pos + 64));
             __syncthreads();
-            // ---- one WARP per representative (r = warp, warp + 8, ...): the lanes take the representative's SNPmers ----
+            // ---- 2. one WARP per representative (r = warp, warp + 8, ...): the lanes take the representative's SNPmers, from shared
+            //         memory for the first 64 representatives, from the cluster-major lists otherwise ----
             const bool iterative = n_reps > a.iterative_above;
             SnpClusterCand best{0u, 0u, 0u, 0u};
-            if (nq > 0u && nq <= kSnpClusterMap / 2u) {
+            if (nq_cur > 0u && nq_cur <= kSnpClusterMap / 2u) {
                 for (uint32_t r = warp; r < n_reps; r += kWarps) {
-                    const uint32_t rpos = reps[r];                           // position of the representative in the cluster-major arrays
-                    const uint32_t e0 = a.poff[rpos], e1 = a.poff[rpos + 1];
+                    const bool cached = r < kSnpCacheReps && rep_n[r] != 0xffffffffu;
+                    uint32_t e0 = 0, e1 = 0, rpos = 0;
+                    if (cached) e1 = rep_n[r];
+                    else { rpos = reps[r]; e0 = a.poff[rpos]; e1 = a.poff[rpos + 1]; }
                     uint32_t m = 0, mm = 0;
                     for (uint32_t eb = e0; eb < e1 && mm == 0u; eb += 32u) {
                         const uint32_t e = eb + lane;
                         bool hit = false, eq = false;
                         if (e < e1) {
-                            const unsigned long long km = a.pkmers[e];
-                            const unsigned long long sp = km & mask;
+                            const unsigned long long k2 = cached ? rep_km[r][e] : a.pkmers[e];
+                            const unsigned long long sp = k2 & mask;
                             uint32_t slot = (uint32_t)((sp * kFibMul) >> 54) & (kSnpClusterMap - 1u);
                             while (true) {
-                                const unsigned long long v = qmap[slot];
+                                const unsigned long long v = qm[slot];
                                 if (v == kEmpty64) break;
-                                if ((v & mask) == sp) { hit = true; eq = v == km; break; }
+                                if ((v & mask) == sp) { hit = true; eq = v == k2; break; }
                                 slot = (slot + 1u) & (kSnpClusterMap - 1u);
                             }
                         }
@@ -110,25 +130,31 @@ snp_cluster_kernel(SnpClusterArgs a) {
                         mm += (uint32_t)__popc(__ballot_sync(0xffffffffu, hit && !eq));
                     }
                     if (mm == 0u && m > 0u) {
-                        const SnpClusterCand cnd{m, rep_size[r], a.cluster_reads[rpos], r};
+                        const SnpClusterCand cnd{m, r < kSnpCacheReps ? rep_sz[r] : rep_size[r], r < kSnpCacheReps ? rep_rid[r] : a.cluster_reads[reps[r]], r};
                         if (snpcluster_better(cnd, best, iterative)) best = cnd;
                     }
                 }
             }
             if (lane == 0) warp_best[warp] = best;
             __syncthreads();
-            // ---- the winner, computed by every thread from the 8 per-warp candidates ----
+            // ---- 3. the winner, computed by every thread from the 8 per-warp candidates; bookkeeping; the map is emptied.  No barrier
+            //         behind this: the next read uses the other map, and everything written here is read after its first barrier ----
             SnpClusterCand w = warp_best[0];
 #pragma unroll
             for (int i = 1; i < kWarps; ++i) { const SnpClusterCand o = warp_best[i]; if (snpcluster_better(o, w, iterative)) w = o; }
-            if (tid == 0) {
-                if (w.m > 0u) { a.rep_of[read] = w.rid; rep_size[w.r] += 1u; }                        // src/asv_cluster.rs:386-394
-                else { reps[n_reps] = (uint32_t)pos; rep_size[n_reps] = 1u; a.rep_of[read] = read; }  // :397-410
+            if (w.m > 0u) {                                                                            // src/asv_cluster.rs:386-394
+                if (tid == 0) { a.rep_of[read] = w.rid; if (w.r < kSnpCacheReps) rep_sz[w.r] += 1u; else rep_size[w.r] += 1u; }
+            } else {                                                                                   // :397-410
+                if (tid == 0) {
+                    reps[n_reps] = (uint32_t)pos; a.rep_of[read] = read;
+                    if (n_reps < kSnpCacheReps) { rep_sz[n_reps] = 1u; rep_rid[n_reps] = read; rep_n[n_reps] = nq_cur <= kSnpCacheLen ? nq_cur : 0xffffffffu; }
+                    else rep_size[n_reps] = 1u;
+                }
+                if (n_reps < kSnpCacheReps && nq_cur <= kSnpCacheLen && (uint32_t)tid < nq_cur) rep_km[n_reps][tid] = km_cur[0];
+                ++n_reps;
             }
-            if (w.m == 0u) ++n_reps;
 #pragma unroll
-            for (int u = 0; u < 2; ++u) if (my_slot[u] != 0xffffffffu) qmap[my_slot[u]] = kEmpty64;
-            __syncthreads();
+            for (int u = 0; u < 2; ++u) if (my_slot[u] != 0xffffffffu) qm[my_slot[u]] = kEmpty64;
         }
         if (tid == 0) atomicAdd(a.total_reps, (unsigned long long)n_reps);
     }

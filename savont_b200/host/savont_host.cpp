@@ -17,21 +17,38 @@ namespace savont_host {
 }
 static void ck(int rc, const char *what) { if (rc != 0) die(what); }
 
-Mapper::Mapper(int device, const Cli &args, const KmerGlobalInfo &kmer_info) {
-    ck(savont_b200_create(device, &ctx_), "savont_b200_create");
+static savont_b200_params params_of(const Cli &args) {
     savont_b200_params p;
     savont_b200_default_params(&p);
     p.k = args.kmer_size; p.c = args.c; p.l = args.blockmer_length; p.min_bq = args.minimum_base_quality;
     p.band = args.band; p.strand_mode = args.strand_mode; p.candidate_mode = args.low_polymorphism ? 1 : 0;
+    return p;
+}
+Mapper::Mapper(int device, const Cli &args, const KmerGlobalInfo &kmer_info) {
+    ck(savont_b200_create(device, &ctx_), "savont_b200_create");
+    const savont_b200_params p = params_of(args);
     ck(savont_b200_set_params(ctx_, &p), "savont_b200_set_params");
     ck(savont_b200_load_snpmers(ctx_, kmer_info.snpmers.data(), kmer_info.snpmers.size()), "savont_b200_load_snpmers");
 }
-Mapper::~Mapper() { if (ctx_) savont_b200_destroy(ctx_); }
+Mapper::Mapper(const std::vector<int> &devices, const Cli &args, const KmerGlobalInfo &kmer_info) {
+    if (devices.empty()) throw std::runtime_error("Mapper: empty device list");
+    ck(savont_b200_create_multi(devices.data(), (int)devices.size(), &multi_), "savont_b200_create_multi");
+    n_dev_ = (int)devices.size();
+    const savont_b200_params p = params_of(args);
+    ck(savont_b200_multi_set_params(multi_, &p), "savont_b200_multi_set_params");
+    ck(savont_b200_multi_load_snpmers(multi_, kmer_info.snpmers.data(), kmer_info.snpmers.size()), "savont_b200_multi_load_snpmers");
+    ck(savont_b200_multi_ctx(multi_, 0, &ctx_), "savont_b200_multi_ctx");
+}
+Mapper::~Mapper() {
+    if (multi_) savont_b200_multi_destroy(multi_);         // owns the per-device contexts, ctx_ included
+    else if (ctx_) savont_b200_destroy(ctx_);
+}
 
 void Mapper::load_asvs(const std::vector<ConsensusSequence> &consensuses) {
     std::vector<uint8_t> bases; std::vector<uint64_t> off{0};
     for (const auto &c : consensuses) { bases.insert(bases.end(), c.sequence.begin(), c.sequence.end()); off.push_back(bases.size()); }
-    ck(savont_b200_load_asvs(ctx_, bases.data(), off.data(), consensuses.size()), "savont_b200_load_asvs");
+    if (multi_) ck(savont_b200_multi_load_asvs(multi_, bases.data(), off.data(), consensuses.size()), "savont_b200_multi_load_asvs");
+    else ck(savont_b200_load_asvs(ctx_, bases.data(), off.data(), consensuses.size()), "savont_b200_load_asvs");
     n_asv_ = consensuses.size();
 }
 
@@ -61,6 +78,10 @@ static Assignments map_with(size_t n, size_t A, int n_samples, Call call) {
 
 Assignments Mapper::map_reads(const ReadSet &r, int n_samples) {
     return map_with(r.n, n_asv_, n_samples, [&](Assignments &a, size_t cap) {
+        if (multi_)
+            return savont_b200_multi_map_reads(multi_, r.bases, r.quals, r.offsets, r.file_idx, r.n, n_samples, a.status.data(), a.best_nm.data(),
+                                               a.class_offsets.data(), a.class_asv.data(), cap, a.unambig.data(), a.ambig.data(),
+                                               a.leq10.data(), a.totals, a.sample_singleton.data(), &a.stats);
         return savont_b200_map_reads(ctx_, r.bases, r.quals, r.offsets, r.file_idx, r.n, n_samples, a.status.data(), a.best_nm.data(),
                                      a.class_offsets.data(), a.class_asv.data(), cap, a.unambig.data(), a.ambig.data(), a.leq10.data(),
                                      a.totals, a.sample_singleton.data(), &a.stats);
@@ -69,10 +90,28 @@ Assignments Mapper::map_reads(const ReadSet &r, int n_samples) {
 
 Assignments Mapper::map_reads(const TwinReadSet &r, int n_samples) {
     return map_with(r.n, n_asv_, n_samples, [&](Assignments &a, size_t cap) {
+        if (multi_)
+            return savont_b200_multi_map_twin_reads(multi_, r.dna_words, r.dna_word_offsets, r.lengths, r.snpmer_kmers, r.snpmer_kmer_bytes,
+                                                    r.snpmer_offsets, r.file_idx, r.n, n_samples, a.status.data(), a.best_nm.data(),
+                                                    a.class_offsets.data(), a.class_asv.data(), cap, a.unambig.data(), a.ambig.data(),
+                                                    a.leq10.data(), a.totals, a.sample_singleton.data(), &a.stats);
         return savont_b200_map_twin_reads(ctx_, r.dna_words, r.dna_word_offsets, r.lengths, r.snpmer_kmers, r.snpmer_kmer_bytes,
                                           r.snpmer_offsets, r.file_idx, r.n, n_samples, a.status.data(), a.best_nm.data(),
                                           a.class_offsets.data(), a.class_asv.data(), cap, a.unambig.data(), a.ambig.data(),
                                           a.leq10.data(), a.totals, a.sample_singleton.data(), &a.stats);
+    });
+}
+
+Assignments Mapper::map_reads(const TwinReadPtrs &r, int n_samples) {
+    return map_with(r.n, n_asv_, n_samples, [&](Assignments &a, size_t cap) {
+        if (multi_)
+            return savont_b200_multi_map_twin_read_ptrs(multi_, r.dna_ptrs, r.lengths, r.snpmer_ptrs, r.snpmer_counts, r.snpmer_kmer_bytes,
+                                                        r.file_idx, r.n, n_samples, a.status.data(), a.best_nm.data(), a.class_offsets.data(),
+                                                        a.class_asv.data(), cap, a.unambig.data(), a.ambig.data(), a.leq10.data(), a.totals,
+                                                        a.sample_singleton.data(), &a.stats);
+        return savont_b200_map_twin_read_ptrs(ctx_, r.dna_ptrs, r.lengths, r.snpmer_ptrs, r.snpmer_counts, r.snpmer_kmer_bytes, r.file_idx, r.n,
+                                              n_samples, a.status.data(), a.best_nm.data(), a.class_offsets.data(), a.class_asv.data(), cap,
+                                              a.unambig.data(), a.ambig.data(), a.leq10.data(), a.totals, a.sample_singleton.data(), &a.stats);
     });
 }
 

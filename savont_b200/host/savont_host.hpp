@@ -93,20 +93,38 @@ struct Assignments {
     savont_b200_stats stats{};
 };
 
-class Mapper {   // RAII over savont_b200_ctx
+// a Vec<TwinRead> as it lies in the reference's memory: one pointer per read into its dna_seq words and its snpmer_kmers
+// (include/savont_b200.h, savont_b200_map_twin_read_ptrs); the library gathers the blocks itself
+struct TwinReadPtrs {
+    const uint64_t *const *dna_ptrs = nullptr;   // [n] -> ceil(lengths[r] / 32) Seq<Dna> words
+    const uint32_t *lengths = nullptr;           // [n]
+    const void *const *snpmer_ptrs = nullptr;    // [n] -> snpmer_counts[r] k-mers
+    const uint32_t *snpmer_counts = nullptr;     // [n]
+    int snpmer_kmer_bytes = 6;
+    const uint32_t *file_idx = nullptr;
+    size_t n = 0;
+};
+
+class Mapper {   // RAII over savont_b200_ctx (one GPU) or savont_b200_multi (one process, several GPUs)
 public:
     Mapper(int device, const Cli &args, const KmerGlobalInfo &kmer_info);
+    // `savont asv` is one process: all GPUs of the box behind one Mapper (reads sharded in read order, counters summed over NVLink)
+    Mapper(const std::vector<int> &devices, const Cli &args, const KmerGlobalInfo &kmer_info);
     ~Mapper();
     Mapper(const Mapper &) = delete;
     Mapper &operator=(const Mapper &) = delete;
     void load_asvs(const std::vector<ConsensusSequence> &consensuses);
     Assignments map_reads(const ReadSet &reads, int n_samples);
     Assignments map_reads(const TwinReadSet &reads, int n_samples);
-    savont_b200_ctx *raw() { return ctx_; }
+    Assignments map_reads(const TwinReadPtrs &reads, int n_samples);
+    savont_b200_ctx *raw() { return ctx_; }          // the (first) device's context: the single-GPU entry points of the other stages
     size_t n_asv() const { return n_asv_; }
+    int n_devices() const { return n_dev_; }
 
 private:
     savont_b200_ctx *ctx_ = nullptr;
+    savont_b200_multi *multi_ = nullptr;
+    int n_dev_ = 1;
     size_t n_asv_ = 0;
 };
 
