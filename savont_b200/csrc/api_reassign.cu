@@ -164,9 +164,17 @@ extern "C" int savont_b200_cluster_reads_by_snpmers(savont_b200_ctx *h, const ui
         a.pkmers = w[12].as<unsigned long long>();
         c->last_stats.kernel_launches += 5;
     }
+    const bool prof = getenv("SAVONT_B200_SNPCLUSTER_PROF") != nullptr;
+    if (prof) { TRY(w[13].ensure(64)); CK(cudaMemsetAsync(w[13].p, 0, 64, st)); a.prof = w[13].as<unsigned long long>(); }
     launch_snp_cluster(a, c->sm_count, st);
     CK(cudaGetLastError());
     if (n_clusters) c->last_stats.kernel_launches += 1;
+    if (prof) {
+        unsigned long long hp[8];
+        CK(cudaMemcpyAsync(hp, w[13].p, 64, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
+        fprintf(stderr, "[snpcluster prof] largest cluster: %llu reads, %llu reps; cycles per read: insert+loads %.0f, barrier A %.0f, scoring %.0f, barrier B %.0f, "
+                        "winner+clear %.0f\n", hp[5], hp[6], (double)hp[0] / hp[5], (double)hp[1] / hp[5], (double)hp[2] / hp[5], (double)hp[3] / hp[5], (double)hp[4] / hp[5]);
+    }
     CK(cudaEventRecord(c->ev[2], st));
     uint32_t tail[4] = {0, 0, 0, 0};
     CK(cudaMemcpyAsync(tail, w[8].p, sizeof(tail), cudaMemcpyDeviceToHost, st));

@@ -70,7 +70,9 @@ snp_cluster_kernel(SnpClusterArgs a) {
             for (int u = 0; u < 2; ++u) { const uint32_t i = tid + u * kSnpClusterThreads; if (i < nq && nq <= kSnpClusterMap / 2u) km[u] = a.pkmers[q0 + i]; }
         };
         if (c0 < c1) load_read(c0);
+        long long tprof[5] = {0, 0, 0, 0, 0};
         for (uint64_t pos = c0; pos < c1; ++pos) {
+            const long long tp0 = a.prof ? clock64() : 0;
             unsigned long long (&qm)[kSnpClusterMap] = qmap[pos & 1];
             const uint32_t read = a.cluster_reads[pos];
             const uint32_t nq_cur = nq;
@@ -100,7 +102,9 @@ snp_cluster_kernel(SnpClusterArgs a) {
             if (tid == 0) asm volatile("prefetch.global.L2 [%0];" :: "l"(a.pkmers + q0 + 512));
             if (tid == 32) asm volatile("prefetch.global.L2 [%0];" :: "l"(a.poff + pos + 64));
             if (tid == 64) asm volatile("prefetch.global.L2 [%0];" :: "l"(a.cluster_reads + pos + 64));
+            const long long tp1 = a.prof ? clock64() : 0;
             __syncthreads();
+            const long long tp2 = a.prof ? clock64() : 0;
             // ---- 2. one WARP per representative (r = warp, warp + 8, ...): the lanes take the representative's SNPmers, from shared
             //         memory for the first 64 representatives, from the cluster-major lists otherwise ----
             const bool iterative = n_reps > a.iterative_above;
@@ -136,7 +140,9 @@ snp_cluster_kernel(SnpClusterArgs a) {
                 }
             }
             if (lane == 0) warp_best[warp] = best;
+            const long long tp3 = a.prof ? clock64() : 0;
             __syncthreads();
+            const long long tp4 = a.prof ? clock64() : 0;
             // ---- 3. the winner, computed by every thread from the 8 per-warp candidates; bookkeeping; the map is emptied.  No barrier
             //         behind this: the next read uses the other map, and everything written here is read after its first barrier ----
             SnpClusterCand w = warp_best[0];
@@ -155,7 +161,9 @@ snp_cluster_kernel(SnpClusterArgs a) {
             }
 #pragma unroll
             for (int u = 0; u < 2; ++u) if (my_slot[u] != 0xffffffffu) qm[my_slot[u]] = kEmpty64;
+            if (a.prof) { const long long tp5 = clock64(); tprof[0] += tp1 - tp0; tprof[1] += tp2 - tp1; tprof[2] += tp3 - tp2; tprof[3] += tp4 - tp3; tprof[4] += tp5 - tp4; }
         }
+        if (a.prof && tid == 0 && oi == 0) { for (int i = 0; i < 5; ++i) a.prof[i] = (unsigned long long)tprof[i]; a.prof[5] = c1 - c0; a.prof[6] = n_reps; }
         if (tid == 0) atomicAdd(a.total_reps, (unsigned long long)n_reps);
     }
 }
