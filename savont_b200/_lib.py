@@ -638,6 +638,7 @@ class MultiContext:
         _check(self.L.savont_b200_multi_load_asvs(self.h, _p(b, C.c_uint8), _p(o, C.c_uint64), C.c_size_t(len(o) - 1)))
         self.n_asv = len(o) - 1
 
+    reuse_outputs = False
     _out_buffers = Context._out_buffers
     _finish = Context._finish
 

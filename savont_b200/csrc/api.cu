@@ -495,7 +495,6 @@ static AsvIndex index_view(const Context *c) {
     ix.idx_keys = c->idx_mask ? c->d_idx_keys.as<uint64_t>() : nullptr;
     ix.idx_vals = c->d_idx_vals.as<uint2>(); ix.idx_mask = c->idx_mask; ix.idx_shift = c->idx_shift; ix.idx_entries = c->d_idx_entries.as<uint32_t>();
     ix.mset = c->d_mset.as<uint64_t>(); ix.mset_off = c->d_mset_off.as<uint32_t>();
-    ix.mtab = c->d_mtab.as<uint64_t>(); ix.mtab_off = c->d_mtab_off.as<uint32_t>(); ix.mtab_fwd = c->d_mtab_fwd.as<uint32_t>();
     ix.mx_keys = c->mx_mask ? c->d_mx_keys.as<uint64_t>() : nullptr; ix.mx_vals = c->d_mx_vals.as<uint2>();
     ix.mx_mask = c->mx_mask; ix.mx_shift = c->mx_shift; ix.mx_entries = c->d_mx_entries.as<uint32_t>();
     ix.planes = c->d_asv_planes.as<uint2>(); ix.plane_off = c->d_asv_plane_off.as<uint32_t>(); ix.len = c->d_asv_len.as<uint32_t>();
@@ -655,25 +654,6 @@ static int build_asv_index(Context *c) {
         }
         mset_off[a + 1] = (uint32_t)mset.size();
     }
-    // (1a) the same sets as per-ASV open-addressing tables + forward-flag bitmaps (filter.cu fast path)
-    std::vector<uint64_t> mtab; std::vector<uint32_t> mtab_off(A + 1, 0), mtab_fwd;
-    for (size_t a = 0; a < A; ++a) {
-        const uint32_t nA = mset_off[a + 1] - mset_off[a];
-        uint32_t cap = 32; while (cap < 2u * nA) cap <<= 1;
-        const uint32_t shift = 32u - (uint32_t)__builtin_ctz(cap);
-        const size_t base = mtab.size();
-        mtab.resize(base + cap, kEmpty64);
-        mtab_fwd.resize((base + cap) / 32, 0u);
-        for (uint32_t t = mset_off[a]; t < mset_off[a + 1]; ++t) {
-            const uint64_t key = mset[t] & ~kFwdBit;
-            uint32_t slot = rset_slot(key, shift);
-            while (mtab[base + slot] != kEmpty64) slot = (slot + 1u) & (cap - 1u);
-            mtab[base + slot] = mset[t];
-            if (mset[t] & kFwdBit) mtab_fwd[(base + slot) >> 5] |= 1u << ((base + slot) & 31u);
-        }
-        mtab_off[a + 1] = (uint32_t)(base + cap);
-        if (base + cap >= (1ull << 32)) return fail(SAVONT_B200_ERR_OVERFLOW, "ASV minimizer tables exceed 4 Gi slots");
-    }
     // (1b) minimizer inverted index for the low-polymorphism mode: k-mer -> (asv << 1 | forward-any flag)
     {
         struct ME { uint64_t key; uint32_t ent; };
@@ -745,10 +725,6 @@ static int build_asv_index(Context *c) {
     TRY(c->d_mset.ensure((mset.size() + 1) * 8)); TRY(c->d_mset_off.ensure((A + 1) * 4));
     TRY(c->d_idx_keys.ensure(keys.size() * 8)); TRY(c->d_idx_vals.ensure(vals.size() * 8)); TRY(c->d_idx_entries.ensure(entries.size() * 4));
     TRY(c->d_asv_planes.ensure(planes.size() * 8)); TRY(c->d_asv_plane_off.ensure(A * 4)); TRY(c->d_asv_len.ensure(A * 4));
-    TRY(c->d_mtab.ensure((mtab.size() + 1) * 8)); TRY(c->d_mtab_off.ensure((A + 1) * 4)); TRY(c->d_mtab_fwd.ensure((mtab_fwd.size() + 1) * 4));
-    if (!mtab.empty()) CK(cudaMemcpy(c->d_mtab.p, mtab.data(), mtab.size() * 8, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(c->d_mtab_off.p, mtab_off.data(), (A + 1) * 4, cudaMemcpyHostToDevice));
-    if (!mtab_fwd.empty()) CK(cudaMemcpy(c->d_mtab_fwd.p, mtab_fwd.data(), mtab_fwd.size() * 4, cudaMemcpyHostToDevice));
     if (!mset.empty()) CK(cudaMemcpy(c->d_mset.p, mset.data(), mset.size() * 8, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->d_mset_off.p, mset_off.data(), (A + 1) * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->d_idx_keys.p, keys.data(), keys.size() * 8, cudaMemcpyHostToDevice));
@@ -1001,7 +977,7 @@ int savont_b200_destroy(savont_b200_ctx *h) {
     for (cudaStream_t s : {c->own_stream, c->lane_stream[0], c->lane_stream[1], c->copy_stream, c->d2h_stream}) if (s) cudaStreamSynchronize(s);
     for (Batch &pb : c->res_parts) pb.release();
     c->work.release(); c->work2.release(); c->work3.release(); c->work4.release(); c->resident.release(); c->asvb.release();
-    DevBuf *bufs[] = {&c->d_rank_table, &c->d_snp_keys, &c->d_snp_bloom, &c->d_phred, &c->d_thresh, &c->d_mx_keys, &c->d_mx_vals, &c->d_mx_entries, &c->d_idx_keys, &c->d_idx_vals, &c->d_idx_entries, &c->d_mset, &c->d_mtab, &c->d_mtab_off, &c->d_mtab_fwd,
+    DevBuf *bufs[] = {&c->d_rank_table, &c->d_snp_keys, &c->d_snp_bloom, &c->d_phred, &c->d_thresh, &c->d_mx_keys, &c->d_mx_vals, &c->d_mx_entries, &c->d_idx_keys, &c->d_idx_vals, &c->d_idx_entries, &c->d_mset,
                       &c->d_mset_off, &c->d_asv_planes, &c->d_asv_plane_off, &c->d_asv_len, &c->d_counters, &c->d_hf_keys};
     for (DevBuf *b : bufs) b->release();
     c->pin_small.release(); c->pin_out.release(); c->tb_pin.release();

@@ -183,7 +183,6 @@ struct Context {
     size_t n_asv = 0; bool index_dirty = true; uint32_t max_asv_len = 0;
     DevBuf d_idx_keys, d_idx_vals, d_idx_entries, d_mset, d_mset_off, d_asv_planes, d_asv_plane_off, d_asv_len;
     DevBuf d_mx_keys, d_mx_vals, d_mx_entries;
-    DevBuf d_mtab, d_mtab_off, d_mtab_fwd;       // per-ASV minimizer tables (filter fast path)
     uint32_t idx_mask = 0, idx_shift = 0, mx_mask = 0, mx_shift = 0;
     std::vector<uint32_t> asv_len_h;
 

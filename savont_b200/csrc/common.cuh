@@ -52,12 +52,6 @@ __host__ __device__ __forceinline__ uint32_t hash_slot(uint64_t key, uint32_t sh
 // word = h >> (32 - log2(words)), bits h & 31 and (h >> 5) & 31
 __host__ __device__ __forceinline__ uint32_t bloom_hash32_sym(uint32_t lo_fwd, uint32_t lo_rev) { return (lo_fwd + lo_rev) * 0x9E3779B1u; }
 
-// slot of a k-mer in a small set of minimizers (the per-read set in shared memory, the per-ASV tables in HBM): 32-bit multiplicative
-// hash, capacity 2^(32 - shift32)
-__host__ __device__ __forceinline__ uint32_t rset_slot(uint64_t key, uint32_t shift32) {
-    return (((uint32_t)key ^ ((uint32_t)(key >> 32) * 0x85EBCA6Bu)) * 0x9E3779B1u) >> shift32;
-}
-
 // src/seeding.rs:18-28
 __host__ __device__ __forceinline__ uint64_t mm_hash64(uint64_t key) {
     key = (~key) + (key << 21);
@@ -128,11 +122,6 @@ struct AsvIndex {
     // distinct minimizer sets per ASV (sorted; bit 63 = forward-any flag)
     const uint64_t *mset;
     const uint32_t *mset_off;    // [A+1]
-    // the same sets as open-addressing tables (slot = rset_slot, capacity a power of two >= 2 |A|, kEmpty64 = free), so that a
-    // read's minimizers can be counted against ONE candidate without building the read's own set first (filter.cu)
-    const uint64_t *mtab;
-    const uint32_t *mtab_off;    // [A+1] first slot of the ASV's table
-    const uint32_t *mtab_fwd;    // forward-any flags of the table slots as a bitmap (word mtab_off[a] / 32 + ...)
     // minimizer inverted index (candidate_mode 1): k-mer -> bucket of (asv << 1 | forward-any flag)
     const uint64_t *mx_keys;
     const uint2 *mx_vals;        // (start, len)

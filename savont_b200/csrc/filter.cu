@@ -32,44 +32,10 @@ __device__ __forceinline__ bool ratio_passes(const DeviceParams &p, uint32_t mm,
     return (double)mm / (double)m / (double)p.c <= p.ratio_thresh;
 }
 
-// m = |set(read minimizers) n set(minimizers of ASV a)| and the orientation vote, counted against the ASV's prebuilt table (AsvIndex::mtab):
-// every read minimizer probes the table; a hit sets a bit per table slot, so a k-mer that occurs twice in the read counts once and the
-// forward flags of its occurrences are OR-ed -- the set semantics of src/alignment.rs:1788,1798-1800 without building the read's own set.
-// seen / rfw: per-warp bitmaps of kTabWords words.
-constexpr uint32_t kTabSlotsMax = 2048, kTabWords = kTabSlotsMax / 32;
-__device__ __forceinline__ void count_against_table(const AsvIndex &ix, uint32_t a, const uint64_t *minis, uint32_t nmini, uint32_t *seen,
-                                                    uint32_t *rfw, int lane, uint32_t &m, uint32_t &same) {
-    const uint32_t t0 = __ldg(ix.mtab_off + a), cap = __ldg(ix.mtab_off + a + 1) - t0, cmask = cap - 1u;
-    const uint32_t shift = (uint32_t)__clz(cap) + 1u, nw = cap >> 5;
-    for (uint32_t w = lane; w < nw; w += 32u) { seen[w] = 0u; rfw[w] = 0u; }
-    __syncwarp();
-    for (uint32_t i0 = 0; i0 < nmini; i0 += 32u) {
-        const uint32_t i = i0 + lane;
-        if (i < nmini) {
-            const uint64_t v = minis[i], key = v & ~kFwdBit;
-            uint32_t slot = rset_slot(key, shift);
-            while (true) {
-                const uint64_t e = __ldg(ix.mtab + t0 + slot);
-                if (e == kEmpty64) break;
-                if ((e & ~kFwdBit) == key) {
-                    atomicOr(&seen[slot >> 5], 1u << (slot & 31u));
-                    if (v >> 63) atomicOr(&rfw[slot >> 5], 1u << (slot & 31u));
-                    break;
-                }
-                slot = (slot + 1u) & cmask;
-            }
-        }
-    }
-    __syncwarp();
-    uint32_t cm = 0, cs = 0;
-    for (uint32_t w = lane; w < nw; w += 32u) {
-        const uint32_t sn = seen[w];
-        cm += (uint32_t)__popc(sn);
-        cs += (uint32_t)__popc(sn & ~(rfw[w] ^ __ldg(ix.mtab_fwd + (t0 >> 5) + w)));
-    }
-    m = __reduce_add_sync(0xffffffffu, cm);
-    same = __reduce_add_sync(0xffffffffu, cs);
-    __syncwarp();
+// slot of a k-mer in the per-read minimizer set (shared memory, capacity 2^bits): a 32-bit multiplicative hash -- the set is
+// private to the kernel, so insert and probe only have to agree with each other
+__device__ __forceinline__ uint32_t rset_slot(uint64_t key, uint32_t shift32) {
+    return (((uint32_t)key ^ ((uint32_t)(key >> 32) * 0x85EBCA6Bu)) * 0x9E3779B1u) >> shift32;
 }
 
 struct FilterSmem {
@@ -79,7 +45,7 @@ struct FilterSmem {
     uint32_t sum_words; // ceil(bm_words/32)
     uint32_t same_words; // low-polymorphism mode: ceil(A/2) same-orientation counters, else 0
     __host__ __device__ size_t per_warp() const {
-        size_t b = (size_t)rcap * 8u + ((size_t)acc_words + 2u * bm_words + sum_words + same_words + 2u * kTabWords) * 4u;
+        size_t b = (size_t)rcap * 8u + ((size_t)acc_words + 2u * bm_words + sum_words + same_words) * 4u;
         return (b + 15u) & ~(size_t)15u;
     }
 };
@@ -100,7 +66,6 @@ filter_kernel(SeqBatch in, SketchOut sk, AsvIndex ix, PairPool pool, FilterOut o
     uint32_t *bm2 = bm1 + lay.bm_words;
     uint32_t *sum1 = bm2 + lay.bm_words;
     uint32_t *same = sum1 + lay.sum_words;
-    uint32_t *tseen = same + lay.same_words, *trfw = tseen + kTabWords;
     const uint32_t rmask = lay.rcap - 1u;
     const uint32_t rshift = 32u - (uint32_t)__popc(rmask);
     const uint32_t clear_words = lay.acc_words + 2u * lay.bm_words + lay.sum_words + lay.same_words;
@@ -119,52 +84,44 @@ filter_kernel(SeqBatch in, SketchOut sk, AsvIndex ix, PairPool pool, FilterOut o
             continue;
         }
         // ---- clear per-read state ----
+        for (uint32_t i = lane; i < lay.rcap; i += 32u) rset[i] = kEmpty64;
         for (uint32_t i = lane; i < clear_words; i += 32u) acc[i] = 0u;
         __syncwarp();
 
-        // ---- 1. read minimizer set: built only when needed (low-polymorphism mode; a candidate whose table is too large for the
-        //         bitmaps; a candidate that fails the containment test with |R| bounded by the raw minimizer count) ----
+        // ---- 1. read minimizer set ----
         const uint64_t off = in.offsets[seq];
         const uint64_t mo = mini_slot_off(off, seq, (uint32_t)p.mini_spacing);
         const uint32_t nmini = sk.mini_cnt[seq];
         uint32_t nR = 0;
-        bool rset_built = false;
-        auto ensure_rset = [&]() {
-            if (rset_built) return;
-            rset_built = true;
-            for (uint32_t i = lane; i < lay.rcap; i += 32u) rset[i] = kEmpty64;
-            __syncwarp();
-            for (uint32_t t0 = 0; t0 < nmini; t0 += 128u) {
-                // four independent loads per lane in flight before the (dependent) inserts
-                unsigned long long vv[4];
+        for (uint32_t t0 = 0; t0 < nmini; t0 += 128u) {
+            // four independent loads per lane in flight before the (dependent) inserts
+            unsigned long long vv[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const uint32_t t = t0 + 32u * u + lane;
-                    vv[u] = (t < nmini) ? sk.mini_kmer[mo + t] : kEmpty64;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const unsigned long long v = vv[u];
-                    bool inserted = false;
-                    if (v != kEmpty64) {
-                        const unsigned long long key = v & ~kFwdBit;
-                        uint32_t slot = rset_slot(key, rshift);
-                        while (true) {
-                            const unsigned long long old = atomicCAS(&rset[slot], (unsigned long long)kEmpty64, v);
-                            if (old == kEmpty64) { inserted = true; break; }
-                            if ((old & ~kFwdBit) == key) {
-                                if (v & kFwdBit) atomicOr(&rset[slot], (unsigned long long)kFwdBit);
-                                break;
-                            }
-                            slot = (slot + 1u) & rmask;
-                        }
-                    }
-                    nR += __popc(__ballot_sync(0xffffffffu, inserted));
-                }
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t t = t0 + 32u * u + lane;
+                vv[u] = (t < nmini) ? sk.mini_kmer[mo + t] : kEmpty64;
             }
-            __syncwarp();
-        };
-        if (LOWPOLY) ensure_rset();
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned long long v = vv[u];
+                bool inserted = false;
+                if (v != kEmpty64) {
+                    const unsigned long long key = v & ~kFwdBit;
+                    uint32_t slot = rset_slot(key, rshift);
+                    while (true) {
+                        const unsigned long long old = atomicCAS(&rset[slot], (unsigned long long)kEmpty64, v);
+                        if (old == kEmpty64) { inserted = true; break; }
+                        if ((old & ~kFwdBit) == key) {
+                            if (v & kFwdBit) atomicOr(&rset[slot], (unsigned long long)kFwdBit);
+                            break;
+                        }
+                        slot = (slot + 1u) & rmask;
+                    }
+                }
+                nR += __popc(__ballot_sync(0xffffffffu, inserted));
+            }
+        }
+        __syncwarp();
 
         uint32_t lowest = 0xffffffffu, n_low = 0;
         bool any_scored = false;
@@ -347,36 +304,26 @@ filter_kernel(SeqBatch in, SketchOut sk, AsvIndex ix, PairPool pool, FilterOut o
                         const uint32_t m0 = __ldg(ix.mset_off + a);
                         const uint32_t nA = __ldg(ix.mset_off + a + 1) - m0;
                         uint32_t m = 0, same = 0;
-                        if (__ldg(ix.mtab_off + a + 1) - __ldg(ix.mtab_off + a) <= kTabSlotsMax) {
-                            count_against_table(ix, a, sk.mini_kmer + mo, nmini, tseen, trfw, lane, m, same);
-                        } else {
-                            ensure_rset();
-                            for (uint32_t t0 = 0; t0 < nA; t0 += 32u) {
-                                const uint32_t t = t0 + lane;
-                                bool found = false, sm = false;
-                                if (t < nA) {
-                                    const uint64_t v = __ldg(ix.mset + m0 + t);
-                                    const uint64_t key = v & ~kFwdBit;
-                                    uint32_t slot = rset_slot(key, rshift);
-                                    while (true) {
-                                        const uint64_t r = rset[slot];
-                                        if (r == kEmpty64) break;
-                                        if ((r & ~kFwdBit) == key) { found = true; sm = ((r ^ v) >> 63) == 0ull; break; }
-                                        slot = (slot + 1u) & rmask;
-                                    }
+                        for (uint32_t t0 = 0; t0 < nA; t0 += 32u) {
+                            const uint32_t t = t0 + lane;
+                            bool found = false, sm = false;
+                            if (t < nA) {
+                                const uint64_t v = __ldg(ix.mset + m0 + t);
+                                const uint64_t key = v & ~kFwdBit;
+                                uint32_t slot = rset_slot(key, rshift);
+                                while (true) {
+                                    const uint64_t r = rset[slot];
+                                    if (r == kEmpty64) break;
+                                    if ((r & ~kFwdBit) == key) { found = true; sm = ((r ^ v) >> 63) == 0ull; break; }
+                                    slot = (slot + 1u) & rmask;
                                 }
-                                m += __popc(__ballot_sync(0xffffffffu, found));
-                                same += __popc(__ballot_sync(0xffffffffu, found && sm));
                             }
+                            m += __popc(__ballot_sync(0xffffffffu, found));
+                            same += __popc(__ballot_sync(0xffffffffu, found && sm));
                         }
                         if (m == 0u) continue;                                        // src/alignment.rs:1801-1803
-                        // :1805-1808 with mn = min(|R|, |A|).  |R| <= the raw minimizer count and m / mn falls as mn grows, so a pass with
-                        // that bound is a pass; only a failure needs the exact |R|, i.e. the read's set
-                        if (frac_too_low(p, m, rset_built ? (nR < nA ? nR : nA) : (nmini < nA ? nmini : nA))) {
-                            if (rset_built) continue;
-                            ensure_rset();
-                            if (frac_too_low(p, m, nR < nA ? nR : nA)) continue;
-                        }
+                        const uint32_t mn = nR < nA ? nR : nA;
+                        if (frac_too_low(p, m, mn)) continue;                         // :1805-1808
                         any_scored = true;
                         if (ratio_passes(p, mm, m)) {                                 // :1811, :1829-1833
                             ++n_low;
@@ -470,7 +417,7 @@ struct CompactSmem {
     uint32_t rcap;       // read set capacity (power of two)
     uint32_t ccap;       // candidate table capacity (power of two)
     uint32_t climit;     // distinct candidates before the read is handed to the dense kernel
-    __host__ __device__ size_t per_warp() const { return ((size_t)rcap * 8u + (size_t)ccap * 16u + 2u * kTabWords * 4u + 15u) & ~(size_t)15u; }
+    __host__ __device__ size_t per_warp() const { return ((size_t)rcap * 8u + (size_t)ccap * 16u + 15u) & ~(size_t)15u; }
 };
 
 __global__ void __launch_bounds__(kFilterWarps * 32)
@@ -484,7 +431,6 @@ filter_compact_kernel(SeqBatch in, SketchOut sk, AsvIndex ix, PairPool pool, Fil
     uint32_t *cval = ckey + lay.ccap;                                               // SNPmer mismatches
     uint32_t *clist = cval + lay.ccap;                                              // occupied slots, then kept slots
     uint32_t *cstash = clist + lay.ccap;                                            // (m | strand << 15) of kept candidates
-    uint32_t *tseen = cstash + lay.ccap, *trfw = tseen + kTabWords;                 // count_against_table bitmaps
     const uint32_t rmask = lay.rcap - 1u, cmask = lay.ccap - 1u;
     const uint32_t rshift = 32u - (uint32_t)__popc(rmask);
     const int mid_shift = p.k - 1;
@@ -499,49 +445,43 @@ filter_compact_kernel(SeqBatch in, SketchOut sk, AsvIndex ix, PairPool pool, Fil
             if (lane == 0) { out.cand_status[seq] = sk.status[seq]; out.pair_start[seq] = 0; out.pair_cnt[seq] = 0; out.low_mm[seq] = 0; }
             continue;
         }
+        for (uint32_t i = lane; i < lay.rcap; i += 32u) rset[i] = kEmpty64;
         for (uint32_t i = lane; i < lay.ccap; i += 32u) { ckey[i] = kCompactEmpty; cval[i] = 0u; }
         __syncwarp();
 
-        // ---- 1. read minimizer set, built only when a candidate needs it (as in the dense kernel) ----
+        // ---- 1. read minimizer set (as in the dense kernel) ----
         const uint64_t off = in.offsets[seq];
         const uint64_t mo = mini_slot_off(off, seq, (uint32_t)p.mini_spacing);
         const uint32_t nmini = sk.mini_cnt[seq];
         uint32_t nR = 0;
-        bool rset_built = false;
-        auto ensure_rset = [&]() {
-            if (rset_built) return;
-            rset_built = true;
-            for (uint32_t i = lane; i < lay.rcap; i += 32u) rset[i] = kEmpty64;
-            __syncwarp();
-            for (uint32_t t0 = 0; t0 < nmini; t0 += 128u) {
-                unsigned long long vv[4];
+        for (uint32_t t0 = 0; t0 < nmini; t0 += 128u) {
+            unsigned long long vv[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const uint32_t t = t0 + 32u * u + lane;
-                    vv[u] = (t < nmini) ? sk.mini_kmer[mo + t] : kEmpty64;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const unsigned long long v = vv[u];
-                    bool inserted = false;
-                    if (v != kEmpty64) {
-                        const unsigned long long key = v & ~kFwdBit;
-                        uint32_t slot = rset_slot(key, rshift);
-                        while (true) {
-                            const unsigned long long old = atomicCAS(&rset[slot], (unsigned long long)kEmpty64, v);
-                            if (old == kEmpty64) { inserted = true; break; }
-                            if ((old & ~kFwdBit) == key) {
-                                if (v & kFwdBit) atomicOr(&rset[slot], (unsigned long long)kFwdBit);
-                                break;
-                            }
-                            slot = (slot + 1u) & rmask;
-                        }
-                    }
-                    nR += __popc(__ballot_sync(0xffffffffu, inserted));
-                }
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t t = t0 + 32u * u + lane;
+                vv[u] = (t < nmini) ? sk.mini_kmer[mo + t] : kEmpty64;
             }
-            __syncwarp();
-        };
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const unsigned long long v = vv[u];
+                bool inserted = false;
+                if (v != kEmpty64) {
+                    const unsigned long long key = v & ~kFwdBit;
+                    uint32_t slot = rset_slot(key, rshift);
+                    while (true) {
+                        const unsigned long long old = atomicCAS(&rset[slot], (unsigned long long)kEmpty64, v);
+                        if (old == kEmpty64) { inserted = true; break; }
+                        if ((old & ~kFwdBit) == key) {
+                            if (v & kFwdBit) atomicOr(&rset[slot], (unsigned long long)kFwdBit);
+                            break;
+                        }
+                        slot = (slot + 1u) & rmask;
+                    }
+                }
+                nR += __popc(__ballot_sync(0xffffffffu, inserted));
+            }
+        }
+        __syncwarp();
 
         // ---- 2. SNPmer buckets -> candidate table (asv -> mismatches) ----
         uint32_t n_distinct = 0;
@@ -637,34 +577,26 @@ filter_compact_kernel(SeqBatch in, SketchOut sk, AsvIndex ix, PairPool pool, Fil
                 const uint32_t m0 = __ldg(ix.mset_off + a);
                 const uint32_t nA = __ldg(ix.mset_off + a + 1) - m0;
                 uint32_t m = 0, same = 0;
-                if (__ldg(ix.mtab_off + a + 1) - __ldg(ix.mtab_off + a) <= kTabSlotsMax) {
-                    count_against_table(ix, a, sk.mini_kmer + mo, nmini, tseen, trfw, lane, m, same);
-                } else {
-                    ensure_rset();
-                    for (uint32_t t0 = 0; t0 < nA; t0 += 32u) {
-                        const uint32_t t = t0 + lane;
-                        bool found = false, sm = false;
-                        if (t < nA) {
-                            const uint64_t v = __ldg(ix.mset + m0 + t);
-                            const uint64_t key = v & ~kFwdBit;
-                            uint32_t sl = rset_slot(key, rshift);
-                            while (true) {
-                                const uint64_t r = rset[sl];
-                                if (r == kEmpty64) break;
-                                if ((r & ~kFwdBit) == key) { found = true; sm = ((r ^ v) >> 63) == 0ull; break; }
-                                sl = (sl + 1u) & rmask;
-                            }
+                for (uint32_t t0 = 0; t0 < nA; t0 += 32u) {
+                    const uint32_t t = t0 + lane;
+                    bool found = false, sm = false;
+                    if (t < nA) {
+                        const uint64_t v = __ldg(ix.mset + m0 + t);
+                        const uint64_t key = v & ~kFwdBit;
+                        uint32_t sl = rset_slot(key, rshift);
+                        while (true) {
+                            const uint64_t r = rset[sl];
+                            if (r == kEmpty64) break;
+                            if ((r & ~kFwdBit) == key) { found = true; sm = ((r ^ v) >> 63) == 0ull; break; }
+                            sl = (sl + 1u) & rmask;
                         }
-                        m += __popc(__ballot_sync(0xffffffffu, found));
-                        same += __popc(__ballot_sync(0xffffffffu, found && sm));
                     }
+                    m += __popc(__ballot_sync(0xffffffffu, found));
+                    same += __popc(__ballot_sync(0xffffffffu, found && sm));
                 }
                 if (m == 0u) continue;                                        // src/alignment.rs:1801-1803
-                if (frac_too_low(p, m, rset_built ? (nR < nA ? nR : nA) : (nmini < nA ? nmini : nA))) {    // :1805-1808, see the dense kernel
-                    if (rset_built) continue;
-                    ensure_rset();
-                    if (frac_too_low(p, m, nR < nA ? nR : nA)) continue;
-                }
+                const uint32_t mn = nR < nA ? nR : nA;
+                if (frac_too_low(p, m, mn)) continue;                         // :1805-1808
                 any_scored = true;
                 if (ratio_passes(p, mm, m)) {                                 // :1811, :1829-1833
                     if (lane == 0) {
