@@ -99,6 +99,36 @@ extern "C" int savont_b200_snpmer_compare(savont_b200_ctx *h, const uint64_t *co
     return 0;
 }
 
+// Pageable host memory -> device through a ring of pinned chunks that the host pool fills (a cudaMemcpyAsync straight from pageable
+// memory is staged by the driver on one thread, ~11 GB/s measured here; the pool reaches the PCIe rate).  Ordered on `st` like a copy.
+static int upload_staged(Context *c, void *dst, const void *src, size_t bytes, cudaStream_t st) {
+    constexpr size_t kChunk = 8u << 20;
+    constexpr int kRing = 3;
+    if (bytes < 2 * kChunk) { if (bytes) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st)); return 0; }
+    TRY(c->cluster_pin[2].ensure(kRing * kChunk));
+    cudaEvent_t ev[kRing];
+    for (auto &e : ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    const int T = c->host_threads > 0 ? c->host_threads : (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+    int rc = 0;
+    size_t i = 0;
+    for (size_t off = 0; off < bytes && rc == 0; off += kChunk, ++i) {
+        const size_t len = std::min(kChunk, bytes - off);
+        char *pin = c->cluster_pin[2].as<char>() + (i % kRing) * kChunk;
+        if (i >= (size_t)kRing && cudaEventSynchronize(ev[i % kRing]) != cudaSuccess) { rc = fail(SAVONT_B200_ERR_CUDA, "staged upload: event wait failed"); break; }
+        const size_t per = (len + T - 1) / T;
+        c->pool.run(T, [&](int t) {
+            const size_t a0 = std::min(len, (size_t)t * per), a1 = std::min(len, a0 + per);
+            if (a1 > a0) memcpy(pin + a0, (const char *)src + off + a0, a1 - a0);
+        });
+        if (cudaMemcpyAsync((char *)dst + off, pin, len, cudaMemcpyHostToDevice, st) != cudaSuccess || cudaEventRecord(ev[i % kRing], st) != cudaSuccess)
+            rc = fail(SAVONT_B200_ERR_CUDA, "staged upload: copy failed");
+    }
+    // the ring is reused by the next call: its last copies must have left the pinned chunks
+    for (int r = 0; r < kRing && (size_t)r < i; ++r) cudaEventSynchronize(ev[r]);
+    for (auto &e : ev) cudaEventDestroy(e);
+    return rc;
+}
+
 // ---- Stage 3 greedy SNPmer clustering (snpcluster.cu) ----
 extern "C" int savont_b200_cluster_reads_by_snpmers(savont_b200_ctx *h, const uint64_t *snp_kmers, const uint64_t *snp_offsets, size_t n_reads,
                                                     const uint32_t *cluster_reads, const uint64_t *cluster_offsets, size_t n_clusters,
@@ -138,7 +168,7 @@ extern "C" int savont_b200_cluster_reads_by_snpmers(savont_b200_ctx *h, const ui
     TRY(w[0].ensure(n_mark * 8 + 16)); TRY(w[1].ensure((n_reads + 1) * 8)); TRY(w[2].ensure(n_memb * 4 + 1024)); TRY(w[3].ensure((n_clusters + 1) * 8));
     TRY(w[4].ensure(n_clusters * 4 + 16)); TRY(w[5].ensure(n_memb * 4 + 16)); TRY(w[6].ensure(n_memb * 4 + 16)); TRY(w[7].ensure(n_reads * 4 + 16));
     TRY(w[8].ensure(64));
-    if (n_mark) CK(cudaMemcpyAsync(w[0].p, snp_kmers + m0, n_mark * 8, cudaMemcpyHostToDevice, st));
+    TRY(upload_staged(c, w[0].p, snp_kmers + m0, n_mark * 8, st));
     CK(cudaMemcpyAsync(w[1].p, rel.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
     if (n_memb) CK(cudaMemcpyAsync(w[2].p, cluster_reads + c0, n_memb * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(w[3].p, crel.data(), (n_clusters + 1) * 8, cudaMemcpyHostToDevice, st));
@@ -164,23 +194,59 @@ extern "C" int savont_b200_cluster_reads_by_snpmers(savont_b200_ctx *h, const ui
         a.pkmers = w[12].as<unsigned long long>();
         c->last_stats.kernel_launches += 5;
     }
+    // tiles of the round kernels (a tile never spans two clusters), the ring of next representatives, the per-position state
+    std::vector<uint32_t> tiles;
+    for (size_t q = 0; q < n_clusters; ++q)
+        for (uint64_t p0 = crel[q]; p0 < crel[q + 1]; p0 += kSnpTile) { tiles.push_back((uint32_t)q); tiles.push_back((uint32_t)p0); }
+    const uint32_t n_tiles = (uint32_t)(tiles.size() / 2);
+    TRY(w[13].ensure(3 * n_clusters * 4 + 16)); TRY(w[14].ensure(tiles.size() * 4 + 16)); TRY(w[15].ensure((2 + kSnpTies) * n_memb * 4 + n_memb + 64));
+    std::vector<uint32_t> tl(tiles.size());
+    for (uint32_t t = 0; t < n_tiles; ++t) { tl[t] = tiles[2 * t]; tl[n_tiles + t] = tiles[2 * t + 1]; }
+    if (n_tiles) CK(cudaMemcpyAsync(w[14].p, tl.data(), tl.size() * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(w[13].p, 0xff, 3 * n_clusters * 4 + 16, st));                   // no representative known; last_round = -1
+    a.n_memb = (uint32_t)n_memb; a.n_tiles = n_tiles;
+    a.tile_cl = w[14].as<uint32_t>(); a.tile_p0 = w[14].as<uint32_t>() + n_tiles;
+    a.next3 = w[13].as<uint32_t>(); a.last_round = reinterpret_cast<int *>(w[13].as<uint32_t>() + 3 * n_clusters);
+    a.st_mt = w[15].as<uint32_t>(); a.st_first = a.st_mt + n_memb; a.st_tie = a.st_first + n_memb;
+    a.is_rep = reinterpret_cast<uint8_t *>(a.st_tie + (size_t)kSnpTies * n_memb);
     const bool prof = getenv("SAVONT_B200_SNPCLUSTER_PROF") != nullptr;
-    if (prof) { TRY(w[13].ensure(64)); CK(cudaMemsetAsync(w[13].p, 0, 64, st)); a.prof = w[13].as<unsigned long long>(); }
-    launch_snp_cluster(a, c->sm_count, st);
-    CK(cudaGetLastError());
-    if (n_clusters) c->last_stats.kernel_launches += 1;
-    if (prof) {
-        unsigned long long hp[8];
-        CK(cudaMemcpyAsync(hp, w[13].p, 64, cudaMemcpyDeviceToHost, st)); CK(cudaStreamSynchronize(st));
-        fprintf(stderr, "[snpcluster prof] largest cluster: %llu reads, %llu reps; cycles per read: insert+loads %.0f, barrier A %.0f, scoring %.0f, barrier B %.0f, "
-                        "winner+clear %.0f\n", hp[5], hp[6], (double)hp[0] / hp[5], (double)hp[1] / hp[5], (double)hp[2] / hp[5], (double)hp[3] / hp[5], (double)hp[4] / hp[5]);
+    cudaEvent_t pe[3];
+    a.prof = prof ? 1 : 0;
+    if (prof) { for (auto &e : pe) CK(cudaEventCreate(&e)); CK(cudaEventRecord(pe[0], st)); }
+    launch_snp_init(a, st);
+    // rounds in batches: the number of rounds is the largest number of (non-empty) representatives of a cluster, known only to the device;
+    // a round without any representative left is a no-op, so overshooting costs launches only
+    uint32_t rounds = 0, batch = 8;
+    while (n_tiles) {
+        for (uint32_t j = 0; j < batch; ++j) launch_snp_round(a, rounds + j, st);
+        rounds += batch;
+        int last = -1;
+        CK(cudaMemcpyAsync(&last, a.last_round, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (last < (int)rounds - 1) break;
+        if (batch < 64) batch *= 2;
     }
+    if (prof) CK(cudaEventRecord(pe[1], st));
+    launch_snp_resolve(a, c->sm_count, st);
+    CK(cudaGetLastError());
+    if (prof) {
+        CK(cudaEventRecord(pe[2], st)); CK(cudaStreamSynchronize(st));
+        uint32_t cnt[16];
+        CK(cudaMemcpy(cnt, w[8].p, 64, cudaMemcpyDeviceToHost));
+        { unsigned long long pr[4]; memcpy(pr, cnt + 8, 32); fprintf(stderr, "[snpcluster prof] largest cluster %llu reads: head %llu cycles, body %llu cycles, 3+-way ties %llu\n", pr[3], pr[0], pr[1], pr[2]); }
+        fprintf(stderr, "[snpcluster prof] %u tiles, %u rounds launched: init + rounds %.3f ms, resolve %.3f ms; tied reads %u, re-scored reads %u\n", n_tiles, rounds,
+                ev_ms(pe[0], pe[1]), ev_ms(pe[1], pe[2]), cnt[4], cnt[5]);
+        for (auto &e : pe) cudaEventDestroy(e);
+    }
+    if (n_clusters) c->last_stats.kernel_launches += 2 + rounds;
+    c->last_stats.n_batches = rounds;
     CK(cudaEventRecord(c->ev[2], st));
     uint32_t tail[4] = {0, 0, 0, 0};
     CK(cudaMemcpyAsync(tail, w[8].p, sizeof(tail), cudaMemcpyDeviceToHost, st));
     if (n_reads) CK(cudaMemcpyAsync(rep_of, w[7].p, n_reads * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (tail[1] & 1u) return fail(SAVONT_B200_ERR_OVERFLOW, "a read has more than 512 SNPmers");
+    if (tail[1] & 4u) return fail(SAVONT_B200_ERR_CUDA, "internal: a read without a compatible representative was not promoted");
     if (tail[1] & 2u) return fail(SAVONT_B200_ERR_INVALID, "a read carries two SNPmers with the same splitmer (TwinRead.snpmer_kmers never does, src/seeding.rs:550-568)");
     unsigned long long nr = 0; memcpy(&nr, tail + 2, 8);
     if (n_representatives) *n_representatives = nr;

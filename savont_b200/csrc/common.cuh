@@ -346,19 +346,27 @@ int launch_snpmer_compare(const SnpCompareArgs &a, uint32_t first, uint32_t n, i
 
 
 // ---- Stage 3 greedy SNPmer clustering inside the k-mer clusters (snpcluster.cu) ----
+constexpr uint32_t kSnpTile = 512;                 // positions per tile of the round kernels (a tile never spans two clusters)
+constexpr uint32_t kSnpTies = 6;                   // tied representatives kept per read
 struct SnpClusterArgs {
     int k;
     const uint64_t *snp_kmers; const uint64_t *snp_offsets;                 // all reads' SNPmer lists (CSR)
     const uint32_t *cluster_reads; const uint64_t *cluster_offsets;         // the k-mer clusters: read ids in processing order (CSR)
     const uint32_t *order;                                                  // cluster indices, largest cluster first
-    uint32_t n_clusters, iterative_above;
+    uint32_t n_clusters, iterative_above, n_memb, n_tiles;
     const uint32_t *poff; const unsigned long long *pkmers;                 // cluster-major copy of the lists: position p of the concatenated clusters
-    uint32_t *reps, *rep_size;                                              // workspace, one slot per clustered read (segment = cluster); reps = positions
+    const uint32_t *tile_cl, *tile_p0;                                      // tiles: cluster, first position
+    uint32_t *next3;                                                        // [3][n_clusters]: the representative of round j at [j % 3]
+    uint32_t *st_mt, *st_first, *st_tie;                                    // per position: best matches | ties << 16; first compatible rep; [kSnpTies][n_memb] tied reps
+    uint8_t *is_rep;                                                        // per position
+    uint32_t *reps, *rep_size;                                              // per cluster segment: representative positions in creation order; per position: size
     uint32_t *rep_of;                                                       // [n_reads] out: representative read id
-    uint32_t *work_ctr, *err; unsigned long long *total_reps;
-    unsigned long long *prof;                                               // SAVONT_B200_SNPCLUSTER_PROF=1: phase cycle sums of the largest cluster
+    uint32_t *work_ctr, *err; unsigned long long *total_reps; int *last_round;
+    int prof;                                                               // SAVONT_B200_SNPCLUSTER_PROF: statistics of the resolve kernel
 };
-void launch_snp_cluster(const SnpClusterArgs &a, int sm_count, cudaStream_t st);
+void launch_snp_init(const SnpClusterArgs &a, cudaStream_t st);
+void launch_snp_round(const SnpClusterArgs &a, uint32_t j, cudaStream_t st);
+void launch_snp_resolve(const SnpClusterArgs &a, int sm_count, cudaStream_t st);
 void launch_snp_cluster_count(const SnpClusterArgs &a, uint32_t n_memb, uint32_t *cnt, cudaStream_t st);
 void launch_snp_cluster_gather(const SnpClusterArgs &a, uint32_t n_memb, unsigned long long *dst, cudaStream_t st);
 

@@ -1000,7 +1000,8 @@ def _stage3_case(seed, n_reads, n_clusters, n_sites, dup_frac=0.3):
     return km, offs, cr, coffs
 
 
-@pytest.mark.parametrize("seed,n_reads,n_clusters,n_sites,above", [(1, 3000, 7, 12, 1000), (2, 6000, 3, 20, 40), (3, 500, 40, 5, 1000), (4, 2500, 1, 30, 5)])
+@pytest.mark.parametrize("seed,n_reads,n_clusters,n_sites,above", [(1, 3000, 7, 12, 1000), (2, 6000, 3, 20, 40), (3, 500, 40, 5, 1000), (4, 2500, 1, 30, 5),
+                                                               (5, 3000, 2, 80, 1000), (6, 20000, 3, 3, 1000)])
 def test_stage3_greedy_snpmer_clustering(ctx, seed, n_reads, n_clusters, n_sites, above):
     """savont_b200_cluster_reads_by_snpmers (one CTA per k-mer cluster, reads in sequence) == the oracle's restatement of
     asv_cluster::cluster_reads_by_snpmers, cluster by cluster, in the indexed branch and beyond `above` representatives"""
@@ -1024,6 +1025,37 @@ def test_stage3_greedy_snpmer_clustering(ctx, seed, n_reads, n_clusters, n_sites
     if first in set(cr.tolist()):
         with pytest.raises(_lib.SavontB200Error):
             ctx.cluster_reads_by_snpmers(bad, offs, cr, coffs)
+
+
+def test_stage3_many_tied_representatives(ctx):
+    """16 mutually incompatible representatives that all contain one shared SNPmer; reads carrying only that SNPmer tie on all of
+    them (more than the per-read state holds: the warp re-scores the read), the live cluster sizes and then the read ids decide"""
+    from savont_b200 import _lib
+    ctx.set_params(_lib.default_params())
+    rng = np.random.default_rng(7)
+    k = 17; mid = k // 2
+    def kmer(sp, allele):
+        lo = int(sp) & ((1 << (2 * mid)) - 1); hi = int(sp) >> (2 * mid)
+        return (hi << (2 * mid + 2)) | (int(allele) << (2 * mid)) | lo
+    s0, s1, s2, s3 = (int(x) for x in rng.integers(0, 1 << 30, 4))
+    lists = [[kmer(s0, 0), kmer(s1, x), kmer(s2, y)] for x in range(4) for y in range(4)]
+    for _ in range(3000):
+        u = rng.random()
+        if u < 0.5: lists.append([kmer(s0, 0)])                                               # ties on all 16
+        elif u < 0.7: lists.append([kmer(s0, 0), kmer(s1, int(rng.integers(0, 4)))])          # ties on 4
+        elif u < 0.8: lists.append([kmer(s1, int(rng.integers(0, 4))), kmer(s2, int(rng.integers(0, 4))), kmer(s3, 1)])
+        elif u < 0.9: lists.append([kmer(s0, 0), kmer(s1, int(rng.integers(0, 4))), kmer(s2, int(rng.integers(0, 4)))])
+        else: lists.append([kmer(s0, 1)] if rng.random() < 0.5 else [])
+    n = len(lists)
+    offs = np.zeros(n + 1, np.uint64); offs[1:] = np.cumsum([len(x) for x in lists])
+    km = np.array([v for x in lists for v in x], np.uint64)
+    mem = np.concatenate([np.arange(16), 16 + rng.permutation(n - 16)]).astype(np.uint32)
+    coffs = np.array([0, n], np.uint64)
+    for above in (1000, 10):
+        got = ctx.cluster_reads_by_snpmers(km, offs, mem, coffs, iterative_above=above)
+        want = O.cluster_reads_by_snpmers(km, offs, mem, iterative_above=above)
+        assert np.array_equal(got["rep_of"], want)
+    assert len(np.unique(want)) >= 17
 
 
 @pytest.mark.parametrize("name,n,ns", [("operon", 5000, 1), ("pooled", 6000, 20)])
