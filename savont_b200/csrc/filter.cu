@@ -50,6 +50,57 @@ struct FilterSmem {
     }
 };
 
+// A candidate ASV's distinct minimizers streamed through the read's set: m = shared ones, same = of those, with the read's orientation
+// flag.  128 entries per step, the four loads of a lane issued before the first probe (the ASV lists sit in L2: one latency per
+// step instead of one per 32 entries); the counts stay in the lanes and are summed once.
+__device__ __forceinline__ void count_shared_minimizers(const uint64_t *__restrict__ list, const uint32_t nA, const unsigned long long *rset,
+                                                        const uint32_t rshift, const uint32_t rmask, const int lane, uint32_t &m, uint32_t &same) {
+    uint32_t acc = 0;                                        // found in the low half, same orientation in the high half
+    for (uint32_t t0 = 0; t0 < nA; t0 += 128u) {
+        uint64_t vv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const uint32_t t = t0 + 32u * u + lane; vv[u] = t < nA ? __ldg(list + t) : kEmpty64; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint64_t v = vv[u];
+            if (v == kEmpty64) continue;
+            const uint64_t key = v & ~kFwdBit;
+            uint32_t slot = rset_slot(key, rshift);
+            while (true) {
+                const uint64_t r = rset[slot];
+                if (r == kEmpty64) break;
+                if ((r & ~kFwdBit) == key) { acc += 1u + ((((r ^ v) >> 63) == 0ull) ? 0x10000u : 0u); break; }
+                slot = (slot + 1u) & rmask;
+            }
+        }
+    }
+    acc = __reduce_add_sync(0xffffffffu, acc);
+    m = acc & 0xffffu; same = acc >> 16;
+}
+
+// What a warp needs to know about a read before it touches the read's lists.  The kernels fetch it for the NEXT read while the
+// current one is processed, and pull that read's minimizer / SNPmer lists towards L2 half-way through (the sketches were written
+// by the previous kernel and come from HBM: the filter is bound by such latencies, profiles/r02s_filter_kernel_full.txt).
+struct ReadMeta { uint64_t off; uint32_t status, nmini, ns, s0; };
+template <bool SNP>
+__device__ __forceinline__ ReadMeta load_read_meta(const SeqBatch &in, const SketchOut &sk, const uint32_t seq) {
+    ReadMeta m;
+    m.status = sk.status[seq]; m.off = in.offsets[seq]; m.nmini = sk.mini_cnt[seq];
+    m.ns = SNP ? sk.snp_cnt[seq] : 0u; m.s0 = SNP ? sk.snp_start[seq] : 0u;
+    return m;
+}
+template <bool SNP>
+__device__ __forceinline__ void prefetch_read_lists(const SketchOut &sk, const DeviceParams &p, const ReadMeta &m, const uint32_t seq, const int lane) {
+    if (m.status != 0u) return;
+    if (lane < 16) {
+        const char *a = reinterpret_cast<const char *>(sk.mini_kmer + mini_slot_off(m.off, seq, (uint32_t)p.mini_spacing));
+        if ((uint32_t)lane * 128u < m.nmini * 8u + 127u) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + lane * 128));
+    } else if (SNP) {
+        const char *b = reinterpret_cast<const char *>(sk.snp_kmer + m.s0);
+        if ((uint32_t)(lane - 16) * 128u < m.ns * 8u + 127u) asm volatile("prefetch.global.L2 [%0];" ::"l"(b + (lane - 16) * 128));
+    }
+}
+
 // LOWPOLY = candidate_mode 1 (refine_asv_depths_with_minimap2, reference src/alignment.rs:1527-1719): no SNPmer index;
 // the read's distinct minimizers probe the minimizer inverted index, `acc` counts the shared minimizers per ASV and
 // `same` those with equal orientation flags; every ASV passing the containment test is kept (0 SNPmer mismatches).
@@ -73,14 +124,21 @@ filter_kernel(SeqBatch in, SketchOut sk, AsvIndex ix, PairPool pool, FilterOut o
     if (*out.err & kErrSnpPool) return;          // the sketch ran out of pool space: the host grows it and re-runs the batch
 
     uint32_t *work = out.work_ctr + (redo_only ? 1 : 0);
+    uint32_t seq_n = 0;
+    if (lane == 0) seq_n = atomicAdd(work, 1u);
+    seq_n = __shfl_sync(0xffffffffu, seq_n, 0);
+    ReadMeta meta_n{};
+    if (seq_n < in.n) meta_n = load_read_meta<!LOWPOLY>(in, sk, seq_n);
     while (true) {                                                     // reads are handed out dynamically (see sketch_fast.cu)
-        uint32_t seq = 0;
-        if (lane == 0) seq = atomicAdd(work, 1u);
-        seq = __shfl_sync(0xffffffffu, seq, 0);
+        const uint32_t seq = seq_n;
+        const ReadMeta me = meta_n;
         if (seq >= in.n) break;
+        if (lane == 0) seq_n = atomicAdd(work, 1u);
+        seq_n = __shfl_sync(0xffffffffu, seq_n, 0);
+        if (seq_n < in.n) meta_n = load_read_meta<!LOWPOLY>(in, sk, seq_n);      // in flight while this read is processed
         if (redo_only && out.cand_status[seq] != 0xFE) continue;       // second launch after filter_compact_kernel (kCandRedo)
-        if (sk.status[seq] != 0) {
-            if (lane == 0) { out.cand_status[seq] = sk.status[seq]; out.pair_start[seq] = 0; out.pair_cnt[seq] = 0; out.low_mm[seq] = 0; }
+        if (me.status != 0u) {
+            if (lane == 0) { out.cand_status[seq] = (uint8_t)me.status; out.pair_start[seq] = 0; out.pair_cnt[seq] = 0; out.low_mm[seq] = 0; }
             continue;
         }
         // ---- clear per-read state ----
@@ -89,9 +147,9 @@ filter_kernel(SeqBatch in, SketchOut sk, AsvIndex ix, PairPool pool, FilterOut o
         __syncwarp();
 
         // ---- 1. read minimizer set ----
-        const uint64_t off = in.offsets[seq];
+        const uint64_t off = me.off;
         const uint64_t mo = mini_slot_off(off, seq, (uint32_t)p.mini_spacing);
-        const uint32_t nmini = sk.mini_cnt[seq];
+        const uint32_t nmini = me.nmini;
         uint32_t nR = 0;
         for (uint32_t t0 = 0; t0 < nmini; t0 += 128u) {
             // four independent loads per lane in flight before the (dependent) inserts
@@ -122,6 +180,7 @@ filter_kernel(SeqBatch in, SketchOut sk, AsvIndex ix, PairPool pool, FilterOut o
             }
         }
         __syncwarp();
+        if (!redo_only && seq_n < in.n) prefetch_read_lists<!LOWPOLY>(sk, p, meta_n, seq_n, lane);
 
         uint32_t lowest = 0xffffffffu, n_low = 0;
         bool any_scored = false;
@@ -200,7 +259,7 @@ filter_kernel(SeqBatch in, SketchOut sk, AsvIndex ix, PairPool pool, FilterOut o
         // 32 SNPmers per round: every lane probes the splitmer table for its SNPmer, then the (SNPmer, bucket
         // entry) pairs of the round are FLATTENED over the lanes (prefix sum of the bucket lengths + a 5-step
         // search for the owner), so that all entry loads of a round are independent and in flight together.
-        const uint32_t ns = sk.snp_cnt[seq], s0 = sk.snp_start[seq];
+        const uint32_t ns = me.ns, s0 = me.s0;
         for (uint32_t t0 = 0; t0 < ns; t0 += 32u) {
             const uint32_t t = t0 + lane;
             uint32_t bstart = 0, blen = 0, mid = 0;
@@ -304,23 +363,7 @@ filter_kernel(SeqBatch in, SketchOut sk, AsvIndex ix, PairPool pool, FilterOut o
                         const uint32_t m0 = __ldg(ix.mset_off + a);
                         const uint32_t nA = __ldg(ix.mset_off + a + 1) - m0;
                         uint32_t m = 0, same = 0;
-                        for (uint32_t t0 = 0; t0 < nA; t0 += 32u) {
-                            const uint32_t t = t0 + lane;
-                            bool found = false, sm = false;
-                            if (t < nA) {
-                                const uint64_t v = __ldg(ix.mset + m0 + t);
-                                const uint64_t key = v & ~kFwdBit;
-                                uint32_t slot = rset_slot(key, rshift);
-                                while (true) {
-                                    const uint64_t r = rset[slot];
-                                    if (r == kEmpty64) break;
-                                    if ((r & ~kFwdBit) == key) { found = true; sm = ((r ^ v) >> 63) == 0ull; break; }
-                                    slot = (slot + 1u) & rmask;
-                                }
-                            }
-                            m += __popc(__ballot_sync(0xffffffffu, found));
-                            same += __popc(__ballot_sync(0xffffffffu, found && sm));
-                        }
+                        count_shared_minimizers(ix.mset + m0, nA, rset, rshift, rmask, lane, m, same);
                         if (m == 0u) continue;                                        // src/alignment.rs:1801-1803
                         const uint32_t mn = nR < nA ? nR : nA;
                         if (frac_too_low(p, m, mn)) continue;                         // :1805-1808
@@ -577,23 +620,7 @@ filter_compact_kernel(SeqBatch in, SketchOut sk, AsvIndex ix, PairPool pool, Fil
                 const uint32_t m0 = __ldg(ix.mset_off + a);
                 const uint32_t nA = __ldg(ix.mset_off + a + 1) - m0;
                 uint32_t m = 0, same = 0;
-                for (uint32_t t0 = 0; t0 < nA; t0 += 32u) {
-                    const uint32_t t = t0 + lane;
-                    bool found = false, sm = false;
-                    if (t < nA) {
-                        const uint64_t v = __ldg(ix.mset + m0 + t);
-                        const uint64_t key = v & ~kFwdBit;
-                        uint32_t sl = rset_slot(key, rshift);
-                        while (true) {
-                            const uint64_t r = rset[sl];
-                            if (r == kEmpty64) break;
-                            if ((r & ~kFwdBit) == key) { found = true; sm = ((r ^ v) >> 63) == 0ull; break; }
-                            sl = (sl + 1u) & rmask;
-                        }
-                    }
-                    m += __popc(__ballot_sync(0xffffffffu, found));
-                    same += __popc(__ballot_sync(0xffffffffu, found && sm));
-                }
+                count_shared_minimizers(ix.mset + m0, nA, rset, rshift, rmask, lane, m, same);
                 if (m == 0u) continue;                                        // src/alignment.rs:1801-1803
                 const uint32_t mn = nR < nA ? nR : nA;
                 if (frac_too_low(p, m, mn)) continue;                         // :1805-1808
@@ -669,7 +696,7 @@ static void launch_filter_dense(const SeqBatch &in, const SketchOut &sk, const A
                                 const DeviceParams &p, int sm_count, int redo_only, cudaStream_t st) {
     FilterSmem lay;
     const uint32_t max_mini = in.max_len / (uint32_t)p.mini_spacing + 2u;
-    lay.rcap = next_pow2(2u * max_mini + 2u);
+    lay.rcap = next_pow2(2u * max_mini + 2u);       // load factor <= 0.5: a 256-slot set for 1.5 kb reads (48 instead of 40 warps per SM) measured 12 % slower
     if (lay.rcap < 64u) lay.rcap = 64u;
     lay.acc_words = (ix.n_asv + 1u) / 2u + 1u;
     lay.bm_words = (ix.n_asv + 31u) / 32u;
@@ -703,7 +730,7 @@ int launch_filter(const SeqBatch &in, const SketchOut &sk, const AsvIndex &ix, c
     }
     CompactSmem lay;
     const uint32_t max_mini = in.max_len / (uint32_t)p.mini_spacing + 2u;
-    lay.rcap = next_pow2(2u * max_mini + 2u);
+    lay.rcap = next_pow2(2u * max_mini + 2u);       // load factor <= 0.5: a 256-slot set for 1.5 kb reads (48 instead of 40 warps per SM) measured 12 % slower
     if (lay.rcap < 64u) lay.rcap = 64u;
     lay.climit = climit;
     lay.ccap = next_pow2(2u * climit + 32u);        // one flattened step can add 32 entries before the limit is checked
