@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define SAVONT_B200_ABI_VERSION 8
+#define SAVONT_B200_ABI_VERSION 9
 
 typedef struct savont_b200_ctx savont_b200_ctx;
 
@@ -135,6 +135,14 @@ int savont_b200_set_read_filter(savont_b200_ctx *ctx, const savont_b200_read_fil
 int savont_b200_twin_reads_from_snpmers(savont_b200_ctx *ctx, const uint8_t *bases, const uint8_t *quals,
                                         const uint64_t *offsets, size_t n_reads, uint8_t *status, double *est_id,
                                         uint32_t *n_solid_mini, uint32_t *n_solid_snp);
+/* TwinRead.qual_seq of a batch of FASTQ reads (seeding::get_twin_read_syncmer, src/seeding.rs:578-602): the minimum quality byte of
+ * every QUALITY_SEQ_BIN = 4 bases (src/constants.rs:48; the last bin may be shorter), rounded by QualCompact3::try_from_bits
+ * (src/types.rs:437-459: bytes 0..34 -> code 0, 35..37 -> 1, ..., >= 77 -> 15), packed as bio-seq stores a Seq<QualCompact3>: 4 bits per
+ * bin, bin i of a read in bits 4(i % 16).. of the read's word i / 16, unused bits zero, every read word aligned.  Outputs:
+ * word_offsets[n_reads + 1] (in words, starting at 0) and the words themselves; SAVONT_B200_ERR_CAPACITY (message = words needed)
+ * when words_cap is too small.  Stage 4 expands these codes back to qualities (src/alignment.rs:456-478: code * 3 + 33 per bin). */
+int savont_b200_qual_seq(savont_b200_ctx *ctx, const uint8_t *quals, const uint64_t *offsets, size_t n_reads,
+                         uint64_t *word_offsets, uint64_t *qual_words, size_t words_cap);
 
 /* ---- Stage 1 counting: replaces the counting of seq_parse::read_to_split_kmers
  * (src/seq_parse.rs:12-83, bloom_filter_size == 0) over seeding::split_kmer_mid (src/seeding.rs:975-1068) for the reads

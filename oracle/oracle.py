@@ -393,6 +393,33 @@ class Oracle:
                     leq10=le[:A], totals=tot, sample_singleton=ss[:A * n_samples].reshape(n_samples, A), dp_cells=int(cells.value))
 
 
+def qual_seq(quals, offsets):
+    """TwinRead.qual_seq of a batch of reads (seeding::get_twin_read_syncmer, reference src/seeding.rs:578-602): minimum quality byte of
+    every QUALITY_SEQ_BIN = 4 bases (src/constants.rs:48), rounded by QualCompact3::try_from_bits (src/types.rs:437-459), packed as a
+    bio-seq Seq of a 4-bit codec (bin i of a read in bits 4(i % 16).. of the read's word i / 16).  -> (words u64, word_offsets u64[n+1])"""
+    q = as_u8(quals); o = np.asarray(offsets, np.int64)
+    n = len(o) - 1
+    lens = o[1:] - o[:-1]
+    bins = (lens + 3) // 4
+    nwords = (bins + 15) // 16
+    wo = np.zeros(n + 1, np.uint64); wo[1:] = np.cumsum(nwords)
+    words = np.zeros(int(wo[-1]), np.uint64)
+    # src/types.rs:441-458: 0..=34 -> 0, 35..=37 -> 1, ... 74..=76 -> 14, everything above -> 15
+    table = np.array([0 if b <= 34 else min(15, (b - 35) // 3 + 1) for b in range(256)], np.uint64)
+    for r in range(n):
+        L = int(lens[r])
+        if L == 0:
+            continue
+        x = q[int(o[r]):int(o[r + 1])]
+        pad = np.full(int(bins[r]) * 4, 255, np.uint8); pad[:L] = x
+        mn = pad.reshape(-1, 4).min(axis=1)                                    # :585-599, the last bin may hold fewer than 4
+        codes = table[mn]
+        cp = np.zeros(int(nwords[r]) * 16, np.uint64); cp[:len(codes)] = codes
+        sh = (np.arange(16, dtype=np.uint64) * np.uint64(4))
+        words[int(wo[r]):int(wo[r + 1])] = np.bitwise_or.reduce(cp.reshape(-1, 16) << sh, axis=1)
+    return words, wo
+
+
 def em(n_asv, cls_offsets, cls_asv, counts, total_assigned):
     L = lib()
     co = np.ascontiguousarray(cls_offsets, dtype=np.uint64)

@@ -205,6 +205,17 @@ class Context:
                                                           _p(st, C.c_uint8), _p(est, C.c_double), _p(sm, C.c_uint32), _p(ss, C.c_uint32)))
         return dict(status=st[:n], est_id=est[:n], n_solid_mini=sm[:n], n_solid_snp=ss[:n])
 
+    def qual_seq(self, quals, offsets):
+        """TwinRead.qual_seq (Seq<QualCompact3>) of a batch of reads: (words u64, word_offsets u64[n+1])"""
+        q = _u8(quals); o = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(o) - 1
+        lens = (o[1:] - o[:-1]).astype(np.int64)
+        cap = int((((lens + 3) // 4 + 15) // 16).sum())
+        wo = np.zeros(n + 1, np.uint64); words = np.zeros(max(cap, 1), np.uint64)
+        _check(self.L.savont_b200_qual_seq(self.h, _p(q, C.c_uint8), _p(o, C.c_uint64), C.c_size_t(n), _p(wo, C.c_uint64),
+                                           _p(words, C.c_uint64), C.c_size_t(cap)))
+        return words[:cap], wo
+
     # ---- Stage 1 counting (K5) ----
     def _kmer_out(self, call, cap, sort, out=None):
         for _ in range(3):

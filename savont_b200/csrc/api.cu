@@ -1112,6 +1112,40 @@ int savont_b200_twin_reads_from_snpmers(savont_b200_ctx *h, const uint8_t *bases
     return 0;
 }
 
+int savont_b200_qual_seq(savont_b200_ctx *h, const uint8_t *quals, const uint64_t *offsets, size_t n_reads, uint64_t *word_offsets,
+                         uint64_t *qual_words, size_t words_cap) {
+    TRY(use_device(h ? &h->c : nullptr));
+    Context *c = &h->c;
+    if (!offsets || !word_offsets || (n_reads && !quals)) return fail(SAVONT_B200_ERR_INVALID, "null argument");
+    word_offsets[0] = 0;
+    for (size_t r = 0; r < n_reads; ++r) {
+        if (offsets[r + 1] < offsets[r]) return fail(SAVONT_B200_ERR_INVALID, "offsets not monotonic at %zu", r + 1);
+        const uint64_t bins = (offsets[r + 1] - offsets[r] + 3u) / 4u;               // QUALITY_SEQ_BIN = 4 (src/constants.rs:48)
+        word_offsets[r + 1] = word_offsets[r] + (bins + 15u) / 16u;
+    }
+    if (word_offsets[n_reads] > words_cap) return fail(SAVONT_B200_ERR_CAPACITY, "qual_words holds %zu words, %llu needed", words_cap, (unsigned long long)word_offsets[n_reads]);
+    if (word_offsets[n_reads] && !qual_words) return fail(SAVONT_B200_ERR_INVALID, "null argument");
+    DevBuf *w = c->cluster_ws;                                                         // the clustering scratch is free between calls
+    cudaStream_t st = c->stream;
+    for (size_t r0 = 0; r0 < n_reads;) {
+        size_t r1 = std::min(n_reads, r0 + (size_t)(1u << 20));
+        while (r1 > r0 + 1 && offsets[r1] - offsets[r0] > (1ull << 30)) r1 = r0 + (r1 - r0) / 2;
+        const size_t n = r1 - r0;
+        const uint64_t nbytes = offsets[r1] - offsets[r0], nwords = word_offsets[r1] - word_offsets[r0];
+        std::vector<uint64_t> rel(2 * (n + 1));
+        for (size_t i = 0; i <= n; ++i) { rel[i] = offsets[r0 + i] - offsets[r0]; rel[n + 1 + i] = word_offsets[r0 + i] - word_offsets[r0]; }
+        TRY(w[0].ensure(nbytes + 16)); TRY(w[1].ensure(rel.size() * 8)); TRY(w[2].ensure(nwords * 8 + 16));
+        if (nbytes) CK(cudaMemcpyAsync(w[0].p, quals + offsets[r0], nbytes, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(w[1].p, rel.data(), rel.size() * 8, cudaMemcpyHostToDevice, st));
+        launch_qual_seq(w[0].as<uint8_t>(), w[1].as<uint64_t>(), w[1].as<uint64_t>() + n + 1, (uint32_t)n, w[2].as<uint64_t>(), c->sm_count, st);
+        CK(cudaGetLastError());
+        if (nwords) CK(cudaMemcpyAsync(qual_words + word_offsets[r0], w[2].p, nwords * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        r0 = r1;
+    }
+    return 0;
+}
+
 int savont_b200_load_asvs(savont_b200_ctx *h, const uint8_t *bases, const uint64_t *offsets, size_t n_asv) {
     TRY(use_device(h ? &h->c : nullptr));
     if (n_asv && (!bases || !offsets)) return fail(SAVONT_B200_ERR_INVALID, "null ASV input");

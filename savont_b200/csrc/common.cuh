@@ -210,6 +210,7 @@ void launch_sketch_fast(const SeqBatch &in, const SketchOut &out, const SnpSet &
 void launch_unpack_twin(const SeqBatch &in, uint8_t *codes, cudaStream_t st);
 void launch_widen_kmer48(const uint8_t *src, uint64_t *dst, uint64_t n, cudaStream_t st);
 uint32_t sketch_grid(uint32_t n, uint32_t max_len, bool use_table, const DeviceParams &p, const SnpSet &set, int sm_count);
+void launch_qual_seq(const uint8_t *quals, const uint64_t *offsets, const uint64_t *word_offsets, uint32_t n, uint64_t *words, int sm_count, cudaStream_t st);
 void launch_est_id(const SeqBatch &in, const uint8_t *status, const uint8_t *flatq, const double *phred_table,
                    double *est_id, cudaStream_t st);
 void launch_codes(const uint8_t *bases, uint8_t *codes, uint64_t total, cudaStream_t st);

@@ -9,6 +9,8 @@
 //   quality cutoff                      est_id is Some and < quality_value_cutoff            :248      -> status 7
 // n_solid_mini / n_solid_snp are the sizes retain_mini_indices / retain_snpmer_indices leave in the POSITION vectors
 // (src/types.rs:702-715; the k-mer vectors Stage 7 reads are not pruned).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace sb {
@@ -97,6 +99,40 @@ void launch_read_filter(const SeqBatch &in, const SketchOut &sk, const HfSet &hf
     const uint32_t need = (in.n + kPrefilterWarps - 1) / kPrefilterWarps;
     if (grid > need) grid = need;
     read_filter_kernel<<<grid, kPrefilterWarps * 32, smem, st>>>(in, sk, hf, est_id, f, p, rcap, n_solid_mini, n_solid_snp);
+}
+
+// TwinRead.qual_seq (seeding::get_twin_read_syncmer, reference src/seeding.rs:578-602): the minimum quality BYTE of every QUALITY_SEQ_BIN = 4
+// bases (src/constants.rs:48), rounded by QualCompact3::try_from_bits (src/types.rs:437-459: 0..=34 -> 0, then one code per 3, 15 from 77 on
+// = clamp((byte - 32) / 3, 0, 15)), packed like bio-seq stores a Seq of a 4-bit codec: bin i in bits 4(i % 16).. of the read's word i / 16.
+// One warp per read, a lane per bin (the byte loads of a warp cover 128 consecutive bytes), 8 lanes -> one 32-bit half word.
+__global__ void __launch_bounds__(256) qual_seq_kernel(const uint8_t *__restrict__ quals, const uint64_t *__restrict__ offsets,
+                                                       const uint64_t *__restrict__ word_offsets, uint32_t n, uint32_t *__restrict__ half_words) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
+        const uint64_t off = offsets[r];
+        const uint32_t L = (uint32_t)(offsets[r + 1] - off), nb = (L + 3u) >> 2;
+        const uint64_t h0 = 2ull * word_offsets[r];
+        const uint32_t nh = (uint32_t)(2ull * (word_offsets[r + 1] - word_offsets[r]));
+        for (uint32_t b0 = 0; b0 < nh * 8u; b0 += 32u) {
+            const uint32_t b = b0 + (uint32_t)lane;
+            uint32_t code = 0;
+            if (b < nb) {
+                uint32_t mn = 255u;
+#pragma unroll
+                for (uint32_t t = 0; t < 4u; ++t) { const uint32_t i = 4u * b + t; if (i < L) mn = min(mn, (uint32_t)__ldg(quals + off + i)); }
+                code = mn < 32u ? 0u : min(15u, (mn - 32u) / 3u);
+            }
+            uint32_t v = code << (4u * ((uint32_t)lane & 7u));
+            v |= __shfl_xor_sync(0xffffffffu, v, 1); v |= __shfl_xor_sync(0xffffffffu, v, 2); v |= __shfl_xor_sync(0xffffffffu, v, 4);
+            if ((lane & 7) == 0 && (b >> 3) < nh) half_words[h0 + (b >> 3)] = v;
+        }
+    }
+}
+void launch_qual_seq(const uint8_t *quals, const uint64_t *offsets, const uint64_t *word_offsets, uint32_t n, uint64_t *words, int sm_count, cudaStream_t st) {
+    if (n == 0) return;
+    const uint32_t need = (n + 7u) / 8u;
+    qual_seq_kernel<<<std::min<uint32_t>(need, (uint32_t)sm_count * 8u), 256, 0, st>>>(quals, offsets, word_offsets, n, reinterpret_cast<uint32_t *>(words));
 }
 
 }  // namespace sb

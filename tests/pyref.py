@@ -369,3 +369,26 @@ def cluster_reads_by_snpmers(read_snpmers, cluster, k=17, iterative_above=1000):
             for km in q:
                 index.setdefault(km & mask, []).append((read, km))
     return out
+
+
+def qual_seq(qual: bytes):
+    """TwinRead.qual_seq of one read, element by element (reference src/seeding.rs:578-602 + QualCompact3::try_from_bits src/types.rs:437-459)
+    -> list of 4-bit codes, one per bin of 4 bases"""
+    binned, counter, mn = [], 0, 255
+    for b in qual:
+        if counter == 4:
+            binned.append(mn); counter = 0; mn = 255
+        counter += 1
+        if b < mn:
+            mn = b
+    if counter != 0:
+        binned.append(mn)
+    ranges = [(0, 34)] + [(35 + 3 * i, 37 + 3 * i) for i in range(14)]
+    out = []
+    for v in binned:
+        code = 15
+        for c, (lo, hi) in enumerate(ranges):
+            if lo <= v <= hi:
+                code = c; break
+        out.append(code)
+    return out

@@ -1084,3 +1084,20 @@ def test_named_configs_at_full_asv_sets(ctx, name, n, ns):
     ctx.map_resident()
     assert_same(ctx.fetch_resident(), want, MAP_KEYS, f"map_resident {name}")
     ctx.set_params(_lib.default_params())
+
+
+def test_qual_seq(ctx):
+    """savont_b200_qual_seq == oracle.qual_seq: bins of 4, QualCompact3 rounding, word-aligned reads, empty reads, capacity error"""
+    from savont_b200 import _lib
+    rng = np.random.default_rng(9)
+    lens = np.concatenate([np.arange(0, 140), rng.integers(1000, 1700, 400)])
+    flat = rng.integers(0, 127, size=int(lens.sum()), dtype=np.uint8)
+    offs = np.zeros(len(lens) + 1, np.uint64); offs[1:] = np.cumsum(lens)
+    want_w, want_o = O.qual_seq(flat, offs)
+    got_w, got_o = ctx.qual_seq(flat, offs)
+    assert np.array_equal(got_o, want_o) and np.array_equal(got_w, want_w)
+    import ctypes as C
+    wo = np.zeros(len(lens) + 1, np.uint64); small = np.zeros(4, np.uint64)
+    rc = ctx.L.savont_b200_qual_seq(ctx.h, _lib._p(flat, C.c_uint8), _lib._p(offs, C.c_uint64), C.c_size_t(len(lens)), _lib._p(wo, C.c_uint64),
+                                    _lib._p(small, C.c_uint64), C.c_size_t(4))
+    assert rc == _lib.ERR_CAPACITY

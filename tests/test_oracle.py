@@ -524,3 +524,23 @@ def test_fuzz_pileup_walk_restatements_agree():
             want = 1 if not v else ((v[len(v) // 2 - 1] + v[len(v) // 2]) // 2 if len(v) % 2 == 0 else v[len(v) // 2])
             assert int(hp[p]) == want
     run()
+
+
+def test_qual_seq_matches_elementwise_restatement():
+    """oracle.qual_seq (numpy) == the loop of get_twin_read_syncmer + QualCompact3::try_from_bits, incl. partial last bins, one-base
+    reads, bytes below '!' and above 'N' + 33"""
+    from tests import pyref
+    rng = np.random.default_rng(5)
+    quals = [bytes(rng.integers(0, 127, size=int(L), dtype=np.uint8)) for L in list(range(1, 70)) + [128, 129, 1500, 1503]]
+    quals.append(bytes([33] * 64)); quals.append(bytes([126] * 65)); quals.append(bytes([34, 35, 37, 38, 76, 77, 78, 32]))
+    flat = np.frombuffer(b"".join(quals), np.uint8)
+    offs = np.zeros(len(quals) + 1, np.uint64); offs[1:] = np.cumsum([len(x) for x in quals])
+    words, wo = O.qual_seq(flat, offs)
+    for r, qs in enumerate(quals):
+        want = pyref.qual_seq(qs)
+        w = words[int(wo[r]):int(wo[r + 1])]
+        assert len(w) == (len(want) + 15) // 16
+        got = [int((int(w[i // 16]) >> (4 * (i % 16))) & 15) for i in range(len(want))]
+        assert got == want
+        tail = int(w[-1]) >> (4 * ((len(want) - 1) % 16 + 1)) if len(want) % 16 else 0
+        assert tail == 0
