@@ -88,13 +88,50 @@ def study(name, asv_b, asv_o, rb, rq, ro, snp, band, threads):
     return out
 
 
+def lowpoly_study(name, asv_b, asv_o, rb, rq, ro, snp, band, threads):
+    """candidate_mode = 1 (refine_asv_depths_with_minimap2, src/alignment.rs:1527-1719).  The reference keeps minimap2's hits with
+    mapq > 0 (:1579-1581) -- in practice the primary hit of a read that has a clearly better target than any other -- and DROPS a read
+    whose best targets cannot be told apart (mapq 0).  The product keeps the minimum-NM ties as a class.  The two agree on every read
+    with a unique best ASV; this counts the others and what dropping them would do to the depths (an upper bound of the divergence)."""
+    n_asv = len(asv_o) - 1
+    out = {"dataset": name, "n_reads": int(len(ro) - 1), "n_asv": int(n_asv), "band": band, "modes": {}}
+    for mode in (0, 2):
+        p = O.default_params(band=band, nm_mode=mode, candidate_mode=1)
+        orc = O.Oracle(p, snp); orc.load_asvs(asv_b, asv_o)
+        res = orc.map_reads(rb, rq, ro, n_threads=threads)
+        cl = classes(res)
+        dep = depths(res, n_asv)
+        tied = [i for i, c in enumerate(cl) if len(c) > 1]
+        # the same result with the tied reads dropped (what mapq > 0 does to them)
+        keep = dict(res)
+        off = res["class_offsets"]; flat = []; noff = np.zeros(len(cl) + 1, np.uint64)
+        for i, c in enumerate(cl):
+            if len(c) == 1:
+                flat.extend(c)
+            noff[i + 1] = len(flat)
+        keep["class_offsets"] = noff; keep["class_asv"] = np.array(flat, np.uint32)
+        keep["totals"] = np.array([int(res["totals"][0]) - len(tied), int(res["totals"][1]) + len(tied)], np.uint64)
+        dep2 = depths(keep, n_asv)
+        row = {"definition": MODES[mode], "assigned": int(res["totals"][0]), "reads_with_tied_best_asvs": len(tied),
+               "tied_frac_of_assigned": len(tied) / max(int(res["totals"][0]), 1),
+               "asvs_with_changed_depth_if_ties_dropped": int(np.sum(dep != dep2)),
+               "max_abs_depth_change_if_ties_dropped": int(np.max(np.abs(dep - dep2))) if n_asv else 0,
+               "sum_abs_depth_change_if_ties_dropped": int(np.sum(np.abs(dep - dep2))), "sum_depth": int(np.sum(dep))}
+        out["modes"][str(mode)] = row
+        print("low-polymorphism mode,", name, row, flush=True)
+        orc.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--zymo-all", action="store_true")
     ap.add_argument("--synthetic", type=int, default=2000)
     ap.add_argument("--threads", type=int, default=os.cpu_count() or 1)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--lowpoly", action="store_true", help="the candidate_mode = 1 study (ties vs the reference's mapq > 0 rule) instead of the NM study")
     a = ap.parse_args()
+    fn = lowpoly_study if a.lowpoly else study
     results = []
     from savont_b200 import synth
     if a.zymo_all:
@@ -105,15 +142,15 @@ def main():
         ab, ao = O.concat(asvs)
         rb, ro = O.concat([r[0] for r in reads]); rq, _ = O.concat([r[1] for r in reads])
         snp = synth.snpmers_from_sequences(ab, ao, 17)
-        results.append(study("zymo: all reads of ont_zymo_1000 in [1100, 2000] vs the 63 zymo reference copies", ab, ao, rb, rq, ro, snp, 64, a.threads))
+        results.append(fn("zymo: all reads of ont_zymo_1000 in [1100, 2000] vs the 63 zymo reference copies", ab, ao, rb, rq, ro, snp, 64, a.threads))
     else:
         z = np.load(os.path.join(ROOT, "tests", "golden", "zymo_subset.npz"))
-        results.append(study("zymo subset: 260 reads (tests/golden/zymo_subset.npz) vs the 63 zymo reference copies", z["asv_bases"], z["asv_offsets"],
+        results.append(fn("zymo subset: 260 reads (tests/golden/zymo_subset.npz) vs the 63 zymo reference copies", z["asv_bases"], z["asv_offsets"],
                              z["read_bases"], z["read_quals"], z["read_offsets"], z["snpmers"], 64, a.threads))
     if a.synthetic > 0:
         w = synth.Workload("ont16s")
         r = w.reads(a.synthetic)
-        results.append(study(f"config 2 (ont16s): first {a.synthetic} synthetic reads vs 500 ASVs", w.asv_bases, w.asv_offsets, r["bases"], r["quals"],
+        results.append(fn(f"config 2 (ont16s): first {a.synthetic} synthetic reads vs 500 ASVs", w.asv_bases, w.asv_offsets, r["bases"], r["quals"],
                              r["offsets"], w.snpmers, w.band, a.threads))
     if a.out:
         json.dump(results, open(a.out, "w"), indent=1)
