@@ -269,6 +269,14 @@ int savont_b200_fetch_resident(savont_b200_ctx *ctx, uint8_t *status, int32_t *b
 int savont_b200_best_hits_resident(savont_b200_ctx *ctx, uint32_t *best_asv, uint8_t *strand, int32_t *asv_start,
                                    int32_t *asv_end, int32_t *read_start, int32_t *read_end, double *identity,
                                    uint64_t *cigar_offsets, uint32_t *cigar, size_t cigar_cap);
+/* The rows the reference writes to temp/read_to_asv_mappings.tsv for every read of the resident batch (after savont_b200_map_resident;
+ * src/alignment.rs:1866, :1875-1887): the read's aligned candidates stable-sorted by NM, the first max_rows_per_read of them (the
+ * reference: 5), each with the ASV index, its NM and the read's SNPmer mismatch count against the kept candidates (all kept candidates
+ * share it, :1839-1843).  Candidates with equal NM come in ascending ASV index (the reference: hash-map order, :1794).  Reads that were
+ * not aligned have no rows.  CSR: row_offsets[n_reads + 1]; SAVONT_B200_ERR_CAPACITY when row_cap is too small (n_reads *
+ * max_rows_per_read always suffices).  The text itself is host work: savont_host::write_read_to_asv_mappings. */
+int savont_b200_mapping_rows_resident(savont_b200_ctx *ctx, uint32_t max_rows_per_read, uint64_t *row_offsets, uint32_t *row_asv,
+                                      int32_t *row_nm, uint32_t *row_snp_mismatches, size_t row_cap);
 int savont_b200_counts_dev(savont_b200_ctx *ctx, void **dev_ptr, size_t *n_u64);
 int savont_b200_read_counts(savont_b200_ctx *ctx, uint64_t *unambig, uint64_t *ambig, uint64_t *leq10, uint64_t *totals,
                             uint64_t *sample_singleton);

@@ -1,4 +1,3 @@
 set -x
 mkdir -p gpurun_out
-SAVONT_B200_FILTER_TIGHT=1 timeout 600 python bench.py --steps 5 --warmup 3 --no-twin --no-cpu-baseline > gpurun_out/r02u_tight.json 2> gpurun_out/r02u.err
-timeout 600 python bench.py --steps 5 --warmup 3 --no-twin --no-cpu-baseline > gpurun_out/r02u_base.json 2>> gpurun_out/r02u.err
+timeout 900 python -m pytest tests -x -q -m gpu -k "mapping_rows or qual_seq or best_hits or resident" 2>&1 | tail -15 > gpurun_out/r02w_tests.log

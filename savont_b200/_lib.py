@@ -478,6 +478,16 @@ class Context:
         out.update(cigar_offsets=co, cigar=cg[:int(co[-1])])
         return out
 
+    def mapping_rows_resident(self, max_rows=5):
+        """rows of temp/read_to_asv_mappings.tsv per read of the resident batch: dict(row_offsets, asv, nm, snp_mismatches)"""
+        n, _ = self._resident
+        cap = max(n * max_rows, 1)
+        ro = np.zeros(n + 1, np.uint64); ra = np.zeros(cap, np.uint32); rn = np.zeros(cap, np.int32); rm = np.zeros(cap, np.uint32)
+        _check(self.L.savont_b200_mapping_rows_resident(self.h, C.c_uint32(max_rows), _p(ro, C.c_uint64), _p(ra, C.c_uint32), _p(rn, C.c_int32),
+                                                        _p(rm, C.c_uint32), C.c_size_t(cap)))
+        t = int(ro[-1])
+        return dict(row_offsets=ro, asv=ra[:t], nm=rn[:t], snp_mismatches=rm[:t])
+
     def consensus_pileups(self, cons_bases, cons_offsets, read_bases, read_quals, read_offsets, read_cons, use_hpc=True, cap=None,
                           entries_out=None):
         """Stage 4 pileups (generate_consensus_pileups, src/alignment.rs:415-641) -> dict(pos_offsets, entries

@@ -286,6 +286,16 @@ def write_feature_table(consensuses, path, sample_names):
     _write(consensuses, None, "final", path, sample_names)
 
 
+def write_read_to_asv_mappings(path, read_ids, consensus_ids, rows):
+    """temp/read_to_asv_mappings.tsv (src/alignment.rs:1766-1768, :1875-1887) from Context.mapping_rows_resident():
+    "{read id}\tdebug_id:{consensus id}\t{SNPmer mismatches}\t{NM}" per row, reads in index order"""
+    ro = rows["row_offsets"]
+    with open(path, "w") as f:
+        for r, rid in enumerate(read_ids):
+            for i in range(int(ro[r]), int(ro[r + 1])):
+                f.write(f"{rid}\tdebug_id:{consensus_ids[int(rows['asv'][i])]}\t{int(rows['snp_mismatches'][i])}\t{int(rows['nm'][i])}\n")
+
+
 # ---------------------------------------------------------------------------------------------------------
 # Stage 2 / 3 / 4 neighbours of the path (SURVEY.md 8f): host halves of the reference functions
 # ---------------------------------------------------------------------------------------------------------

@@ -1753,6 +1753,64 @@ int savont_b200_fetch_resident(savont_b200_ctx *h, uint8_t *status, int32_t *bes
     return 0;
 }
 
+// The rows of temp/read_to_asv_mappings.tsv for one mapped batch (src/alignment.rs:1866, :1875-1887): a read's aligned candidates,
+// stable-sorted by NM, the first max_rows of them.  Small per-pair arrays come to the host and are grouped there.
+static int mapping_rows_batch(Context *c, Batch &b, uint32_t max_rows, uint64_t *row_offsets /* [n + 1], [0] set */, uint32_t *row_asv,
+                              int32_t *row_nm, uint32_t *row_mm, size_t row_cap) {
+    const size_t n = b.n;
+    if (n == 0) return 0;
+    std::vector<uint32_t> start(n), cnt(n), low(n);
+    std::vector<uint8_t> st(n);
+    CK(cudaMemcpyAsync(start.data(), b.pair_start.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(cnt.data(), b.pair_cnt.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(low.data(), b.low_mm.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(st.data(), b.cand_status.p, n, cudaMemcpyDeviceToHost, c->stream));
+    uint32_t np = 0;
+    CK(cudaMemcpyAsync(&np, b.ctrs.as<uint32_t>() + 1, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    std::vector<uint32_t> pasv(np);
+    std::vector<int32_t> pnm(np);
+    if (np) {
+        CK(cudaMemcpyAsync(pasv.data(), b.p_asv.p, (size_t)np * 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(pnm.data(), b.nm.p, (size_t)np * 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    const uint32_t per = c->dp.strand_mode == 1 ? 2u : 1u;
+    std::vector<std::pair<int32_t, uint32_t>> rows;
+    uint64_t o = row_offsets[0];
+    for (size_t r = 0; r < n; ++r) {
+        rows.clear();
+        if (st[r] == 0) {
+            if ((uint64_t)start[r] + cnt[r] > np) return fail(SAVONT_B200_ERR_CUDA, "internal: pair chunk of read %zu outside the pool", r);
+            for (uint32_t q = 0; q < cnt[r] / per; ++q) {
+                int32_t v = pnm[start[r] + q * per];
+                if (per == 2u) v = std::min(v, pnm[start[r] + q * per + 1]);
+                rows.emplace_back(v, pasv[start[r] + q * per]);
+            }
+            std::stable_sort(rows.begin(), rows.end(), [](const std::pair<int32_t, uint32_t> &x, const std::pair<int32_t, uint32_t> &y) { return x.first < y.first; });
+        }
+        const size_t k = std::min<size_t>(rows.size(), max_rows);
+        if (o + k > row_cap) return fail(SAVONT_B200_ERR_CAPACITY, "mapping rows: capacity %zu too small (at read %zu)", row_cap, r);
+        for (size_t i = 0; i < k; ++i) { row_asv[o + i] = rows[i].second; row_nm[o + i] = rows[i].first; row_mm[o + i] = low[r]; }
+        o += k;
+        row_offsets[r + 1] = o;
+    }
+    return 0;
+}
+
+int savont_b200_mapping_rows_resident(savont_b200_ctx *h, uint32_t max_rows_per_read, uint64_t *row_offsets, uint32_t *row_asv, int32_t *row_nm,
+                                      uint32_t *row_snp_mismatches, size_t row_cap) {
+    TRY(use_device(h ? &h->c : nullptr));
+    Context *c = &h->c;
+    if (!c->resident.mapped) return fail(SAVONT_B200_ERR_INVALID, "map_resident has not run");
+    if (!row_offsets || (row_cap && (!row_asv || !row_nm || !row_snp_mismatches))) return fail(SAVONT_B200_ERR_INVALID, "null argument");
+    row_offsets[0] = 0;
+    if (c->res_parts.size() <= 1) return mapping_rows_batch(c, c->resident, max_rows_per_read, row_offsets, row_asv, row_nm, row_snp_mismatches, row_cap);
+    for (size_t q = 0; q < c->res_parts.size(); ++q)
+        TRY(mapping_rows_batch(c, c->res_parts[q], max_rows_per_read, row_offsets + c->res_cuts[q], row_asv, row_nm, row_snp_mismatches, row_cap));
+    return 0;
+}
+
 // best hit of every read of one mapped batch + its traceback; the CIGAR ops are appended to `cigar` behind *cig_base
 static int best_hits_batch(Context *c, Batch &b, uint32_t *best_asv, uint8_t *strand, int32_t *asv_start, int32_t *asv_end,
                            int32_t *read_start, int32_t *read_end, double *identity, uint64_t *cigar_offsets /* [n + 1], [0] set */,

@@ -283,6 +283,15 @@ void write_feature_table(const std::vector<ConsensusSequence> &cons, const std::
     }
 }
 
+void write_read_to_asv_mappings(const std::string &path, const std::vector<std::string> &read_ids, const std::vector<size_t> &consensus_ids,
+                                const uint64_t *row_offsets, const uint32_t *row_asv, const int32_t *row_nm, const uint32_t *row_snp_mismatches) {
+    std::ofstream f(path);
+    if (!f) throw std::runtime_error("cannot create " + path);
+    for (size_t r = 0; r < read_ids.size(); ++r)
+        for (uint64_t i = row_offsets[r]; i < row_offsets[r + 1]; ++i)
+            f << read_ids[r] << "\tdebug_id:" << consensus_ids.at(row_asv[i]) << "\t" << row_snp_mismatches[i] << "\t" << row_nm[i] << "\n";
+}
+
 template <typename Reads>
 static void refine_impl(const Reads &twin_reads, std::vector<ConsensusSequence> &consensuses,
                         const KmerGlobalInfo &kmer_info, const Cli &args, const std::string &temp_dir, int device) {
@@ -510,6 +519,18 @@ long long savont_host_snpmer_clusters_from_assignment(const uint64_t *kc_offsets
         for (size_t kc = 0; kc < res.size(); ++kc)
             for (const auto &c : res[kc]) { for (size_t r : c) members[at++] = r; kc_of[nc] = (uint32_t)kc; offsets[++nc] = at; }
         return (long long)nc;
+    } catch (const std::exception &e) { g_host_error = e.what(); return -1; }
+}
+// temp/read_to_asv_mappings.tsv: read ids joined by '\n'; returns 0 or -1
+int savont_host_write_read_to_asv_mappings(const char *path, const char *read_ids_nl, size_t n_reads, const uint64_t *consensus_ids, size_t n_cons,
+                                           const uint64_t *row_offsets, const uint32_t *row_asv, const int32_t *row_nm, const uint32_t *row_mm) {
+    try {
+        std::vector<std::string> ids; ids.reserve(n_reads);
+        const char *p = read_ids_nl;
+        for (size_t r = 0; r < n_reads; ++r) { const char *e = strchr(p, '\n'); if (!e) e = p + strlen(p); ids.emplace_back(p, e); p = *e ? e + 1 : e; }
+        std::vector<size_t> cons(consensus_ids, consensus_ids + n_cons);
+        savont_host::write_read_to_asv_mappings(path, ids, cons, row_offsets, row_asv, row_nm, row_mm);
+        return 0;
     } catch (const std::exception &e) { g_host_error = e.what(); return -1; }
 }
 // host half of reassign_reads_to_best_cluster: clusters in CSR in, CSR out; returns the number of new clusters or -1; *moved = reassignments

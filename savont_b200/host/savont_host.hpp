@@ -182,6 +182,11 @@ std::vector<std::vector<size_t>> compute_per_sample_depths(const TwinReadSet &tw
 void write_consensus_fasta(const std::vector<ConsensusSequence> &consensuses, const std::string &path, const std::string &prefix);
 void write_feature_table(const std::vector<ConsensusSequence> &consensuses, const std::string &path,
                          const std::vector<std::string> &sample_names);
+// reference src/alignment.rs:1766-1768, :1875-1887 (temp/read_to_asv_mappings.tsv): one line per row of
+// savont_b200_mapping_rows_resident, "{read id}\tdebug_id:{consensus id}\t{SNPmer mismatches}\t{NM}" (the reference's variable
+// names for the last two columns are swapped, the columns are these), reads in index order (the reference: rayon completion order)
+void write_read_to_asv_mappings(const std::string &path, const std::vector<std::string> &read_ids, const std::vector<size_t> &consensus_ids,
+                                const uint64_t *row_offsets, const uint32_t *row_asv, const int32_t *row_nm, const uint32_t *row_snp_mismatches);
 
 // ---- the neighbouring stages: host halves around the device calls ----
 // reference src/asv_cluster.rs:72-249 (cluster_reads_by_kmers): the greedy loop runs on the GPU

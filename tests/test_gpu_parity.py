@@ -1101,3 +1101,58 @@ def test_qual_seq(ctx):
     rc = ctx.L.savont_b200_qual_seq(ctx.h, _lib._p(flat, C.c_uint8), _lib._p(offs, C.c_uint64), C.c_size_t(len(lens)), _lib._p(wo, C.c_uint64),
                                     _lib._p(small, C.c_uint64), C.c_size_t(4))
     assert rc == _lib.ERR_CAPACITY
+
+
+@pytest.mark.parametrize("strand_mode", [0, 1])
+def test_mapping_rows_resident(ctx, strand_mode, tmp_path):
+    """a12's debug rows (temp/read_to_asv_mappings.tsv, src/alignment.rs:1866, :1875-1887): per read its aligned candidates stable-sorted
+    by NM, at most 5, with the SNPmer mismatch count -- composed from the oracle's candidates + pair alignments; near-identical variants
+    so that reads have several candidates; also through the 4-part resident pipeline, and the text writer"""
+    from savont_b200 import _lib, api
+    w = _make_workload("ont16s", n_roots=5, sites_per_genus=3)
+    r = w.reads(1500)
+    bases = r["bases"].copy(); offs = r["offsets"]
+    bases[int(offs[7]):int(offs[8])] = ord("N")
+    gp, op = _params(_lib, band=w.band, strand_mode=strand_mode)
+    ctx.set_params(gp); ctx.load_snpmers(w.snpmers); ctx.load_asvs(w.asv_bases, w.asv_offsets)
+    orc = O.Oracle(op, w.snpmers); orc.load_asvs(w.asv_bases, w.asv_offsets)
+    cand = orc.find_candidates(bases, r["quals"], offs)
+    cofs = cand["offsets"].astype(np.int64)
+    n = len(offs) - 1
+    pr = np.repeat(np.arange(n, dtype=np.uint32), cofs[1:] - cofs[:-1])
+    if strand_mode == 0:
+        nm = orc.align_pairs(bases, offs, pr, cand["asv"], cand["strand"])["nm"]
+    else:
+        f = orc.align_pairs(bases, offs, pr, cand["asv"], np.zeros(len(pr), np.uint8))["nm"]
+        v = orc.align_pairs(bases, offs, pr, cand["asv"], np.ones(len(pr), np.uint8))["nm"]
+        nm = np.minimum(f, v)
+    want_off = [0]; want_asv = []; want_nm = []; want_mm = []
+    for rd in range(n):
+        rows = sorted(range(cofs[rd], cofs[rd + 1]), key=lambda i: int(nm[i]))[:5]        # sorted() is stable; candidates ascend by ASV
+        want_asv += [int(cand["asv"][i]) for i in rows]; want_nm += [int(nm[i]) for i in rows]; want_mm += [int(cand["mm"][i]) for i in rows]
+        want_off.append(len(want_asv))
+    assert max(np.diff(want_off)) >= 2 and min(np.diff(want_off)) == 0
+    for parts in (1, 4):
+        ctx.set_resident_parts(parts)
+        try:
+            ctx.upload_reads(bases, r["quals"], offs)
+            ctx.map_resident()
+            got = ctx.mapping_rows_resident()
+        finally:
+            ctx.set_resident_parts(1)
+        assert np.array_equal(got["row_offsets"], np.array(want_off, np.uint64))
+        assert got["asv"].tolist() == want_asv and got["nm"].tolist() == want_nm and got["snp_mismatches"].tolist() == want_mm
+    one = ctx.mapping_rows_resident(max_rows=1)
+    res = ctx.fetch_resident()
+    assigned = res["status"] == 0
+    assert np.array_equal((one["row_offsets"][1:] - one["row_offsets"][:-1]) == 1, assigned)
+    assert np.array_equal(one["nm"], res["best_nm"][assigned])                    # the first row is a best hit
+    ids = [f"read{i} rc" if i % 3 == 0 else f"read{i}" for i in range(n)]
+    cons_ids = [1000 + a for a in range(w.n_asv)]
+    path = tmp_path / "read_to_asv_mappings.tsv"
+    api.write_read_to_asv_mappings(path, ids, cons_ids, got)
+    lines = open(path).read().splitlines()
+    assert len(lines) == len(want_asv)
+    first = int(np.flatnonzero(np.diff(want_off) > 0)[0])
+    assert lines[0] == f"{ids[first]}\tdebug_id:{1000 + want_asv[0]}\t{want_mm[0]}\t{want_nm[0]}"
+    ctx.set_params(_lib.default_params())

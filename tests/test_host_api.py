@@ -323,3 +323,27 @@ def test_snpmer_cluster_lists_cpp_matches_python():
                 assert sorted(int(x) for c in local for x in c) == sorted(int(x) for x in kc)
                 assert all(len(a) >= len(b) for a, b in zip(local, local[1:])) and all(np.all(np.diff(c) > 0) for c in local)
                 assert all(np.all(rep[c] == rep[c[0]]) for c in local)
+
+
+def test_read_to_asv_mappings_writer_cpp_matches_python(tmp_path):
+    """temp/read_to_asv_mappings.tsv (src/alignment.rs:1875-1887): "{read id}\tdebug_id:{consensus id}\t{SNPmer mismatches}\t{NM}",
+    C++ writer == Python writer, reads without rows skipped"""
+    import ctypes as C
+    from savont_b200 import api
+    H = api.host()
+    rows = dict(row_offsets=np.array([0, 2, 2, 3, 8], np.uint64), asv=np.array([3, 1, 0, 4, 2, 3, 1, 0], np.uint32),
+                nm=np.array([4, 9, 0, 7, 7, 8, 12, 40], np.int32), snp_mismatches=np.array([0, 0, 2, 1, 1, 1, 1, 1], np.uint32))
+    ids = ["r0 rc", "r1", "r2", "some/longer id"]
+    cons = [10, 11, 12, 13, 99]
+    p1 = tmp_path / "py.tsv"; p2 = tmp_path / "cpp.tsv"
+    api.write_read_to_asv_mappings(p1, ids, cons, rows)
+    H.savont_host_write_read_to_asv_mappings.restype = C.c_int
+    ca = np.array(cons, np.uint64)
+    rc = H.savont_host_write_read_to_asv_mappings(str(p2).encode(), "\n".join(ids).encode(), C.c_size_t(len(ids)),
+                                                  ca.ctypes.data_as(C.POINTER(C.c_uint64)), C.c_size_t(len(cons)),
+                                                  rows["row_offsets"].ctypes.data_as(C.POINTER(C.c_uint64)), rows["asv"].ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                  rows["nm"].ctypes.data_as(C.POINTER(C.c_int32)), rows["snp_mismatches"].ctypes.data_as(C.POINTER(C.c_uint32)))
+    assert rc == 0
+    txt = open(p1).read()
+    assert txt == open(p2).read()
+    assert txt.splitlines()[0] == "r0 rc\tdebug_id:13\t0\t4" and txt.splitlines()[2] == "r2\tdebug_id:10\t2\t0" and len(txt.splitlines()) == 8
