@@ -42,6 +42,44 @@ if len(sys.argv) > 1 and sys.argv[1] == "threads":
         ctx.set_host_threads(thr); run(f"hugepage arenas, threads {thr}")
     print(open("/sys/kernel/mm/transparent_hugepage/enabled").read().strip(), flush=True)
     heap = heap_small
+elif len(sys.argv) > 1 and sys.argv[1] == "multi":
+    # one process driving 2 GPUs: where does the gather time go compared with one context per process?
+    import threading
+    cores = os.cpu_count() or 1
+    half = max(1, cores // 2)
+    ctx.set_host_threads(half); run(f"one context, {half} threads")
+    def copy_heap(h):
+        wa, sa = h["_arenas"]
+        w2 = wa.copy(); s2 = sa.copy()
+        o = dict(h)
+        o["dna_ptrs"] = (h["dna_ptrs"].astype(np.int64) - wa.ctypes.data + w2.ctypes.data).astype(np.uint64)
+        o["snpmer_ptrs"] = (h["snpmer_ptrs"].astype(np.int64) - sa.ctypes.data + s2.ctypes.data).astype(np.uint64)
+        o["_arenas"] = (w2, s2)
+        return o
+    heapB = copy_heap(heap)
+    ctx1 = _lib.Context(1, _lib.default_params(band=w.band))
+    ctx1.load_snpmers(w.snpmers); ctx1.load_asvs(w.asv_bases, w.asv_offsets); ctx1.set_host_threads(half)
+    for hb, label in ((heap, "same heap"), (heapB, "own heap")):
+        ctx1.map_twin_read_ptrs(hb)
+        out = [None, None]
+        def go(i, cx, hh):
+            t0 = time.perf_counter(); res = cx.map_twin_read_ptrs(hh); out[i] = (time.perf_counter() - t0, res["stats"])
+        for _ in range(2):
+            th = [threading.Thread(target=go, args=(0, ctx, heap)), threading.Thread(target=go, args=(1, ctx1, hb))]
+            t0 = time.perf_counter(); [t.start() for t in th]; [t.join() for t in th]; dt = time.perf_counter() - t0
+        print(f"two contexts from two threads ({label}): wall ms", round(dt * 1e3, 2), [(round(o[0] * 1e3, 2), round(o[1]["gather_ms"], 2), round(o[1]["total_ms"], 2)) for o in out], flush=True)
+    ctx1.close()
+    m = _lib.MultiContext([0, 1], _lib.default_params(band=w.band))
+    m.load_snpmers(w.snpmers); m.load_asvs(w.asv_bases, w.asv_offsets)
+    for hb, label in ((heap, "same heap"), (heapB, "own heap")):
+        big = {k: np.concatenate([heap[k], hb[k]]) for k in ("dna_ptrs", "snpmer_ptrs", "lengths", "snpmer_counts")}
+        big["kmer_bytes"] = heap["kmer_bytes"]; big["file_idx"] = None
+        for thr in (0, cores, 2 * cores):
+            m.set_host_threads(thr)
+            m.map_twin_read_ptrs(big)
+            t0 = time.perf_counter(); res = m.map_twin_read_ptrs(big); dt = time.perf_counter() - t0
+            print(f"MultiContext 2 devices ({label}), host threads {thr}: wall ms", round(dt * 1e3, 2), "gather_ms", round(res["stats"]["gather_ms"], 2), "total_ms", round(res["stats"]["total_ms"], 2), flush=True)
+    m.close()
 elif len(sys.argv) > 1 and sys.argv[1] == "sweep":
     for pf, pf_all, nt in [(8, 1, 1), (8, 1, 0), (0, 1, 1), (4, 1, 1), (16, 1, 1), (32, 1, 1), (16, 0, 1), (32, 0, 1), (16, 0, 0)]:
         os.environ["SAVONT_B200_GATHER_PF"] = str(pf); os.environ["SAVONT_B200_GATHER_PF_ALL"] = str(pf_all); os.environ["SAVONT_B200_GATHER_NT"] = str(nt)
