@@ -1,4 +1,16 @@
+# The ncu evidence of a round, on one B200 (gpurun -- 'bash run_prof.sh'); then, back in the container:
+#   python profiles/refresh.py r02s r02s      (launch list + per-kernel summaries -> profiles/)
+# and set PROFILE_TAG in bench.py to the same tag: bench.py takes roofline.traffic from these summaries only while the capture's
+# kernel duration is within 10 % of the run's CUDA-event time.  Numbers printed under ncu are never bench values.
 set -x
+TAG=${TAG:-r02s}
 mkdir -p gpurun_out
-nproc > gpurun_out/r02x_multi.txt
-timeout 900 python tools/trace_e2e.py multi >> gpurun_out/r02x_multi.txt 2> gpurun_out/r02x_multi.err
+B="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-twin"
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv $B > gpurun_out/${TAG}_launch_run.log 2>&1
+for k in sketch_fast_kernel filter_kernel align_nm_kernel; do
+  ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 1 -f -o gpurun_out/prof_${TAG}_$k $B > gpurun_out/${TAG}_ncu_$k.log 2>&1
+done
+S="python bench.py --path snpcluster --steps 1 --warmup 1 --no-cpu-baseline"
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${TAG}_snpcluster.csv $S > gpurun_out/${TAG}_snp_launch_run.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:snp_round_kernel -s 30 -c 1 -f -o gpurun_out/prof_${TAG}_snp_round_kernel $S > gpurun_out/${TAG}_ncu_snp_round.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:snp_resolve_kernel -s 1 -c 1 -f -o gpurun_out/prof_${TAG}_snp_resolve_kernel $S > gpurun_out/${TAG}_ncu_snp_resolve.log 2>&1
