@@ -208,7 +208,6 @@ extern "C" int savont_b200_cluster_reads_by_snpmers(savont_b200_ctx *h, const ui
     a.tile_cl = w[14].as<uint32_t>(); a.tile_p0 = w[14].as<uint32_t>() + n_tiles;
     a.next3 = w[13].as<uint32_t>(); a.last_round = reinterpret_cast<int *>(w[13].as<uint32_t>() + 3 * n_clusters);
     a.st_mt = w[15].as<uint32_t>(); a.st_first = a.st_mt + n_memb; a.st_tie = a.st_first + n_memb;
-    a.is_rep = reinterpret_cast<uint8_t *>(a.st_tie + (size_t)kSnpTies * n_memb);
     const bool prof = getenv("SAVONT_B200_SNPCLUSTER_PROF") != nullptr;
     cudaEvent_t pe[3];
     a.prof = prof ? 1 : 0;

@@ -358,8 +358,7 @@ struct SnpClusterArgs {
     const uint32_t *poff; const unsigned long long *pkmers;                 // cluster-major copy of the lists: position p of the concatenated clusters
     const uint32_t *tile_cl, *tile_p0;                                      // tiles: cluster, first position
     uint32_t *next3;                                                        // [3][n_clusters]: the representative of round j at [j % 3]
-    uint32_t *st_mt, *st_first, *st_tie;                                    // per position: best matches | ties << 16; first compatible rep; [kSnpTies][n_memb] tied reps
-    uint8_t *is_rep;                                                        // per position
+    uint32_t *st_mt, *st_first, *st_tie;                                    // per position: best matches | ties << 16 | representative kind << 30; first compatible rep; [kSnpTies][n_memb] tied reps
     uint32_t *reps, *rep_size;                                              // per cluster segment: representative positions in creation order; per position: size
     uint32_t *rep_of;                                                       // [n_reads] out: representative read id
     uint32_t *work_ctr, *err; unsigned long long *total_reps; int *last_round;

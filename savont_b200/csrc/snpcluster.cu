@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(kSnpThreads) snp_init_kernel(SnpClusterArgs a)
     uint32_t mn = kSnpInf;
     for (uint32_t p = p0 + tid; p < p1; p += kSnpThreads) {
         const uint32_t nq = a.poff[p + 1] - a.poff[p];
-        a.st_mt[p] = 0u; a.st_first[p] = kSnpInf; a.is_rep[p] = nq == 0u ? 1 : 0;
+        a.st_mt[p] = nq == 0u ? (1u << 30) : 0u; a.st_first[p] = kSnpInf;      // bits 30-31 of st_mt: 1 = representative without SNPmers, 2 = with
         if (nq > kSnpMapMax / 2u) atomicOr(a.err, 1u);
         else if (nq > 0u && mn == kSnpInf) mn = p;
     }
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(kSnpThreads) snp_round_kernel(SnpClusterArgs a
     const uint32_t rp = a.next3[(j % 3u) * nc + cl];
     if (p0 == c0 && tid == 0) {                                    // the cluster's first tile keeps the three-deep ring of "next representative"
         a.next3[((j + 2u) % 3u) * nc + cl] = kSnpInf;
-        if (rp != kSnpInf) { a.is_rep[rp] = 2; a.reps[c0 + j] = rp; atomicMax(a.last_round, (int)j); }     // the cluster's j-th representative with SNPmers
+        if (rp != kSnpInf) { atomicOr(&a.st_mt[rp], 2u << 30); a.reps[c0 + j] = rp; atomicMax(a.last_round, (int)j); }     // the cluster's j-th representative with SNPmers
     }
     if (rp == kSnpInf || p1 <= rp + 1u) return;
     const unsigned long long mask = ~(3ull << (a.k - 1));
@@ -123,12 +123,12 @@ __global__ void __launch_bounds__(kSnpThreads) snp_round_kernel(SnpClusterArgs a
         acc += __shfl_xor_sync(kFull, acc, 1); acc += __shfl_xor_sync(kFull, acc, 2); acc += __shfl_xor_sync(kFull, acc, 4);
         if (valid && gl == 0u && nq > 0u) {
             const uint32_t m = acc & 0xffffu, mm = acc >> 16, mt = a.st_mt[p];
-            uint32_t bm = mt & 0xffffu, nt = mt >> 16;
+            uint32_t bm = mt & 0xffffu, nt = (mt >> 16) & 0xffu;
             if (mm == 0u && m > 0u) {
                 if (bm == 0u) a.st_first[p] = j;
                 if (m > bm) { bm = m; nt = 1u; a.st_tie[p] = j; }
                 else if (m == bm) { if (nt < kSnpTies) a.st_tie[(size_t)nt * a.n_memb + p] = j; nt = min(nt + 1u, kSnpTies + 1u); }
-                a.st_mt[p] = bm | (nt << 16);
+                a.st_mt[p] = bm | (nt << 16) | (mt & 0xc0000000u);
             } else if (bm == 0u && mn == kSnpInf) mn = p;          // still homeless; a thread's positions increase
         }
     }
@@ -142,12 +142,18 @@ __global__ void __launch_bounds__(kSnpThreads) snp_round_kernel(SnpClusterArgs a
 // representatives with SNPmers (= the round that scored them); sizes and read ids of the first kSnpSizeCache live in shared memory.
 constexpr int kSnpResolveWarps = 4;
 constexpr uint32_t kSnpSizeCache = 512;
+constexpr uint32_t kSnpAhead = 4;                  // steps of read state in flight per warp (cp.async groups)
+constexpr uint32_t kSnpResolveWarpBytes = kSnpMapMax * 8u + 2u * kSnpSizeCache * 4u + kSnpAhead * 5u * 32u * 4u;
+__device__ __forceinline__ void cp_async4(uint32_t *smem_dst, const uint32_t *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
 __global__ void __launch_bounds__(kSnpResolveWarps * 32) snp_resolve_kernel(SnpClusterArgs a) {
-    __shared__ unsigned long long qmap[kSnpResolveWarps][kSnpMapMax];
-    __shared__ uint32_t s_size[kSnpResolveWarps][kSnpSizeCache], s_rid[kSnpResolveWarps][kSnpSizeCache];
+    extern __shared__ __align__(16) uint8_t resolve_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned long long *qm = qmap[warp];
-    uint32_t *ssz = s_size[warp], *srid = s_rid[warp];
+    uint8_t *wb = resolve_smem + (size_t)warp * kSnpResolveWarpBytes;
+    unsigned long long *qm = reinterpret_cast<unsigned long long *>(wb);                      // the slow path's read map
+    uint32_t *ssz = reinterpret_cast<uint32_t *>(wb + kSnpMapMax * 8u), *srid = ssz + kSnpSizeCache;
+    uint32_t *ring = srid + kSnpSizeCache;                                                     // [kSnpAhead][5 fields][32 lanes]
     const unsigned long long mask = ~(3ull << (a.k - 1));
     const uint32_t lt = (1u << lane) - 1u;
     while (true) {
@@ -163,23 +169,38 @@ __global__ void __launch_bounds__(kSnpResolveWarps * 32) snp_resolve_kernel(SnpC
         auto size_inc = [&](const uint32_t w) { if (w < kSnpSizeCache) atomicAdd(&ssz[w], 1u); else atomicAdd(&gsize[w], 1u); };
         auto rid_get = [&](const uint32_t w) -> uint32_t { return w < kSnpSizeCache ? srid[w] : a.cluster_reads[reps[w]]; };
         uint32_t n_reps = 0, n_ne = 0;
-        // the state of the next 32 reads is requested one step ahead
-        uint32_t isr_n = 0, mt_n = 0, first_n = kSnpInf, read_n = 0, tie0_n = kSnpInf, tie1_n = kSnpInf;
-        auto load = [&](const uint32_t p) {
-            if (p < c1) { isr_n = a.is_rep[p]; mt_n = a.st_mt[p]; first_n = a.st_first[p]; read_n = a.cluster_reads[p]; tie0_n = a.st_tie[p]; tie1_n = a.st_tie[(size_t)a.n_memb + p]; }
+        // The state of the reads is requested kSnpAhead steps ahead with cp.async into a shared-memory ring, one commit group per step.
+        // (Register prefetching does not work here: a consumer waits on a scoreboard that the loads issued since share, so the loop ran
+        // at the speed of the memory latency whatever the lead -- measured with 1 and 3 steps of lead.)  A lane reads back only what it
+        // copied itself, so the ring needs no barrier.
+        uint32_t step = 0;
+        auto issue = [&](const uint32_t stage, const uint32_t pb) {
+            const uint32_t p = pb + (uint32_t)lane;
+            uint32_t *dst = ring + stage * 160u + (uint32_t)lane;
+            if (p < c1) {
+                cp_async4(dst, a.st_mt + p); cp_async4(dst + 32, a.st_first + p); cp_async4(dst + 64, a.cluster_reads + p);
+                cp_async4(dst + 96, a.st_tie + p); cp_async4(dst + 128, a.st_tie + (size_t)a.n_memb + p);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
         };
-        load(c0 + lane);
+        for (uint32_t i = 0; i < kSnpAhead; ++i) issue(i, c0 + 32u * i);
         long long tpa = 0, tpb = 0, tpc = 0, tpn3 = 0;
         for (uint32_t base = c0; base < c1; base += 32u) {
             const long long t0 = a.prof ? clock64() : 0;
             const uint32_t p = base + lane;
             const bool valid = p < c1;
-            const uint32_t isr = isr_n, mt = mt_n, first = first_n, read = read_n, tie0 = tie0_n, tie1 = tie1_n;
-            load(p + 32u);
+            asm volatile("cp.async.wait_group %0;" ::"n"(kSnpAhead - 1) : "memory");
+            const uint32_t stage = step % kSnpAhead;
+            const uint32_t *src = ring + stage * 160u + (uint32_t)lane;
+            uint32_t mt = 0, first = kSnpInf, read = 0, tie0 = kSnpInf, tie1 = kSnpInf;
+            if (valid) { mt = src[0]; first = src[32]; read = src[64]; tie0 = src[96]; tie1 = src[128]; }
+            const uint32_t isr = mt >> 30;
+            issue(stage, base + 32u * kSnpAhead);
+            ++step;
             const uint32_t rep_mask = __ballot_sync(kFull, valid && isr != 0u), ne_mask = __ballot_sync(kFull, valid && isr == 2u);
             const uint32_t my_nreps = n_reps + (uint32_t)__popc(rep_mask & lt);          // representatives created before this read
             const uint32_t my_ne = n_ne + (uint32_t)__popc(ne_mask & lt);                // ... of those, with SNPmers
-            const uint32_t nt = mt >> 16;
+            const uint32_t nt = (mt >> 16) & 0xffu;
             bool need = false;
             uint32_t winner = kSnpInf;
             if (valid) {
@@ -275,6 +296,7 @@ __global__ void __launch_bounds__(kSnpResolveWarps * 32) snp_resolve_kernel(SnpC
             tpa += t1 - t0; tpb += t2 - t1;
         }
         if (a.prof && oi == 0 && lane == 0) { unsigned long long *pr = reinterpret_cast<unsigned long long *>(a.work_ctr + 8); pr[0] = tpa; pr[1] = tpb; pr[2] = tpn3; pr[3] = c1 - c0; }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         if (lane == 0) atomicAdd(a.total_reps, (unsigned long long)n_reps);
     }
 }
@@ -325,7 +347,9 @@ void launch_snp_round(const SnpClusterArgs &a, uint32_t j, cudaStream_t st) {
 void launch_snp_resolve(const SnpClusterArgs &a, int sm_count, cudaStream_t st) {
     if (a.n_clusters == 0) return;
     const uint32_t want = (a.n_clusters + kSnpResolveWarps - 1u) / kSnpResolveWarps;
-    snp_resolve_kernel<<<std::min<uint32_t>(want, (uint32_t)sm_count * 4u), kSnpResolveWarps * 32, 0, st>>>(a);
+    const size_t smem = (size_t)kSnpResolveWarps * kSnpResolveWarpBytes;
+    cudaFuncSetAttribute(snp_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    snp_resolve_kernel<<<std::min<uint32_t>(want, (uint32_t)sm_count * 3u), kSnpResolveWarps * 32, smem, st>>>(a);
 }
 
 }  // namespace sb
