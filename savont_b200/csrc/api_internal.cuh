@@ -221,6 +221,7 @@ struct Context {
     DevBuf tb_ws[7]; PinBuf tb_pin;
     DevBuf pileup_ws[40];
     DevBuf cluster_ws[16]; PinBuf cluster_pin[4];
+    PinBuf stage_pin;                 // upload_host: ring of pinned chunks for pageable sources
     // sharded k-mer counting (savont_b200_kmer_shard_*): state between the phases
     struct KmerShard {
         bool active = false; KmerPartPlan pl{}; std::vector<unsigned long long> off_local; uint32_t *cursor1 = nullptr, *d_tile_start = nullptr,
@@ -235,6 +236,7 @@ inline uint32_t shift_for_cap(uint32_t cap) { uint32_t b = 0; while ((1u << b) <
 inline float ev_ms(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
 int use_device(Context *c);
 // api.cu helpers shared with api_pileup.cu
+int upload_host(Context *c, void *dst, const void *src, size_t bytes, cudaStream_t st);
 int batch_upload(Context *c, Batch &b, const uint8_t *bases, const uint8_t *quals, const uint64_t *offsets, const uint32_t *file_idx,
                  size_t n, uint64_t *h2d_bytes, cudaStream_t st = nullptr);
 void build_dp_planes(const DeviceParams &dp, const uint8_t *bases, const uint64_t *offsets, size_t A, std::vector<uint2> &planes,

@@ -99,36 +99,6 @@ extern "C" int savont_b200_snpmer_compare(savont_b200_ctx *h, const uint64_t *co
     return 0;
 }
 
-// Pageable host memory -> device through a ring of pinned chunks that the host pool fills (a cudaMemcpyAsync straight from pageable
-// memory is staged by the driver on one thread, ~11 GB/s measured here; the pool reaches the PCIe rate).  Ordered on `st` like a copy.
-static int upload_staged(Context *c, void *dst, const void *src, size_t bytes, cudaStream_t st) {
-    constexpr size_t kChunk = 8u << 20;
-    constexpr int kRing = 3;
-    if (bytes < 2 * kChunk) { if (bytes) CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st)); return 0; }
-    TRY(c->cluster_pin[2].ensure(kRing * kChunk));
-    cudaEvent_t ev[kRing];
-    for (auto &e : ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    const int T = c->host_threads > 0 ? c->host_threads : (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
-    int rc = 0;
-    size_t i = 0;
-    for (size_t off = 0; off < bytes && rc == 0; off += kChunk, ++i) {
-        const size_t len = std::min(kChunk, bytes - off);
-        char *pin = c->cluster_pin[2].as<char>() + (i % kRing) * kChunk;
-        if (i >= (size_t)kRing && cudaEventSynchronize(ev[i % kRing]) != cudaSuccess) { rc = fail(SAVONT_B200_ERR_CUDA, "staged upload: event wait failed"); break; }
-        const size_t per = (len + T - 1) / T;
-        c->pool.run(T, [&](int t) {
-            const size_t a0 = std::min(len, (size_t)t * per), a1 = std::min(len, a0 + per);
-            if (a1 > a0) memcpy(pin + a0, (const char *)src + off + a0, a1 - a0);
-        });
-        if (cudaMemcpyAsync((char *)dst + off, pin, len, cudaMemcpyHostToDevice, st) != cudaSuccess || cudaEventRecord(ev[i % kRing], st) != cudaSuccess)
-            rc = fail(SAVONT_B200_ERR_CUDA, "staged upload: copy failed");
-    }
-    // the ring is reused by the next call: its last copies must have left the pinned chunks
-    for (int r = 0; r < kRing && (size_t)r < i; ++r) cudaEventSynchronize(ev[r]);
-    for (auto &e : ev) cudaEventDestroy(e);
-    return rc;
-}
-
 // ---- Stage 3 greedy SNPmer clustering (snpcluster.cu) ----
 extern "C" int savont_b200_cluster_reads_by_snpmers(savont_b200_ctx *h, const uint64_t *snp_kmers, const uint64_t *snp_offsets, size_t n_reads,
                                                     const uint32_t *cluster_reads, const uint64_t *cluster_offsets, size_t n_clusters,
@@ -168,7 +138,7 @@ extern "C" int savont_b200_cluster_reads_by_snpmers(savont_b200_ctx *h, const ui
     TRY(w[0].ensure(n_mark * 8 + 16)); TRY(w[1].ensure((n_reads + 1) * 8)); TRY(w[2].ensure(n_memb * 4 + 1024)); TRY(w[3].ensure((n_clusters + 1) * 8));
     TRY(w[4].ensure(n_clusters * 4 + 16)); TRY(w[5].ensure(n_memb * 4 + 16)); TRY(w[6].ensure(n_memb * 4 + 16)); TRY(w[7].ensure(n_reads * 4 + 16));
     TRY(w[8].ensure(64));
-    TRY(upload_staged(c, w[0].p, snp_kmers + m0, n_mark * 8, st));
+    TRY(upload_host(c, w[0].p, snp_kmers + m0, n_mark * 8, st));
     CK(cudaMemcpyAsync(w[1].p, rel.data(), (n_reads + 1) * 8, cudaMemcpyHostToDevice, st));
     if (n_memb) CK(cudaMemcpyAsync(w[2].p, cluster_reads + c0, n_memb * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(w[3].p, crel.data(), (n_clusters + 1) * 8, cudaMemcpyHostToDevice, st));

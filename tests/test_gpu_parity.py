@@ -1156,3 +1156,26 @@ def test_mapping_rows_resident(ctx, strand_mode, tmp_path):
     first = int(np.flatnonzero(np.diff(want_off) > 0)[0])
     assert lines[0] == f"{ids[first]}\tdebug_id:{1000 + want_asv[0]}\t{want_mm[0]}\t{want_nm[0]}"
     ctx.set_params(_lib.default_params())
+
+
+def test_map_reads_from_pageable_memory_uses_the_staging_ring(ctx):
+    """batch_upload sends page-locked sources straight to the DMA engine and pageable ones (>= 16 MB) through the ring of pinned chunks
+    filled by the host pool (upload_host): same results either way, for every batch of the call"""
+    from savont_b200 import _lib
+    w = _make_workload("ont16s", n_roots=6)
+    n = 24000
+    r = w.reads(n)                                                   # numpy arrays: pageable, ~36 MB of bases and of qualities
+    assert r["bases"].nbytes > 2 * (16 << 20)
+    ctx.set_params(_lib.default_params(band=w.band)); ctx.load_snpmers(w.snpmers); ctx.load_asvs(w.asv_bases, w.asv_offsets)
+    got = ctx.map_reads(r["bases"], r["quals"], r["offsets"])
+    pb = _lib.pinned_array(r["bases"].nbytes); pb[:] = r["bases"]
+    pq = _lib.pinned_array(r["quals"].nbytes); pq[:] = r["quals"]
+    ref = ctx.map_reads(pb, pq, r["offsets"])
+    assert_same(got, ref, MAP_KEYS, "pageable vs page-locked input")
+    assert int(got["totals"][0]) > 0.8 * n
+    _, op = _params(_lib, band=w.band)
+    orc = O.Oracle(op, w.snpmers); orc.load_asvs(w.asv_bases, w.asv_offsets)
+    m = 1500
+    want = orc.map_reads(r["bases"][:int(r["offsets"][m])], r["quals"][:int(r["offsets"][m])], r["offsets"][:m + 1])
+    assert np.array_equal(got["status"][:m], want["status"]) and np.array_equal(got["best_nm"][:m], want["best_nm"])
+    ctx.set_params(_lib.default_params())
