@@ -289,14 +289,14 @@ static int issue_twin(Context *c, Batch &b, const TwinInput &in, size_t r0, cons
     CK(cudaMemcpyAsync(b.word_offsets.p, p.wrel, (n + 1) * 8, cudaMemcpyHostToDevice, st));
     if (n) CK(cudaMemcpyAsync(b.snp_start.p, p.sstart, n * 4, cudaMemcpyHostToDevice, st));
     if (n) CK(cudaMemcpyAsync(b.snp_cnt.p, p.scnt, n * 4, cudaMemcpyHostToDevice, st));
-    if (p.n_words) CK(cudaMemcpyAsync(b.dna_words.p, in.dna_words + p.w0, p.n_words * 8, cudaMemcpyHostToDevice, st));
+    TRY(upload_host(c, b.dna_words.p, in.dna_words + p.w0, p.n_words * 8, st));      // pageable sources: through the pinned ring
     uint64_t bytes = (n + 1) * 16 + n * 8 + p.n_words * 8;
     if (p.n_snp) {
         if (in.kmer_bytes == 8) {
-            CK(cudaMemcpyAsync(b.snp_kmer.p, static_cast<const uint64_t *>(in.snp_kmers) + p.s0, p.n_snp * 8, cudaMemcpyHostToDevice, st));
+            TRY(upload_host(c, b.snp_kmer.p, static_cast<const uint64_t *>(in.snp_kmers) + p.s0, p.n_snp * 8, st));
         } else {
             TRY(b.snp_raw.ensure(p.n_snp * 6 + 16));
-            CK(cudaMemcpyAsync(b.snp_raw.p, static_cast<const uint8_t *>(in.snp_kmers) + p.s0 * 6, p.n_snp * 6, cudaMemcpyHostToDevice, st));
+            TRY(upload_host(c, b.snp_raw.p, static_cast<const uint8_t *>(in.snp_kmers) + p.s0 * 6, p.n_snp * 6, st));
             launch_widen_kmer48(b.snp_raw.as<uint8_t>(), b.snp_kmer.as<uint64_t>(), p.n_snp, st);
             CK(cudaGetLastError());
             c->last_stats.kernel_launches += 1;

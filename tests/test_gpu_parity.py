@@ -1163,8 +1163,8 @@ def test_map_reads_from_pageable_memory_uses_the_staging_ring(ctx):
     filled by the host pool (upload_host): same results either way, for every batch of the call"""
     from savont_b200 import _lib
     w = _make_workload("ont16s", n_roots=6)
-    n = 24000
-    r = w.reads(n)                                                   # numpy arrays: pageable, ~36 MB of bases and of qualities
+    n = 50000
+    r = w.reads(n)                                                   # numpy arrays: pageable, ~75 MB of bases and of qualities
     assert r["bases"].nbytes > 2 * (16 << 20)
     ctx.set_params(_lib.default_params(band=w.band)); ctx.load_snpmers(w.snpmers); ctx.load_asvs(w.asv_bases, w.asv_offsets)
     got = ctx.map_reads(r["bases"], r["quals"], r["offsets"])
@@ -1173,6 +1173,11 @@ def test_map_reads_from_pageable_memory_uses_the_staging_ring(ctx):
     ref = ctx.map_reads(pb, pq, r["offsets"])
     assert_same(got, ref, MAP_KEYS, "pageable vs page-locked input")
     assert int(got["totals"][0]) > 0.8 * n
+    # the TwinRead fields from pageable memory (dna words of the one batch: 19 MB)
+    from savont_b200 import twin
+    tw = twin.twin_reads_from_snpmers(ctx, r["bases"], r["quals"], r["offsets"], kmer48=True)
+    assert tw["dna_words"].nbytes > (16 << 20)
+    assert_same(ctx.map_twin_reads(tw), ref, MAP_KEYS, "TwinRead fields from pageable memory")
     _, op = _params(_lib, band=w.band)
     orc = O.Oracle(op, w.snpmers); orc.load_asvs(w.asv_bases, w.asv_offsets)
     m = 1500
