@@ -306,35 +306,72 @@ __device__ __forceinline__ void align_pair(const AlignArgs &a, uint32_t pi, uint
 
     if (TB) {
         // ---- traceback over the stored D0 / Pv' vectors; preference diagonal > D (ASV) > I (read) ----
+        // The walk is a serial chain per pair with a history word per step.  The words of the next kTbAhead columns are fetched
+        // with cp.async into a per-thread ring in shared memory (round 2; round 1 loaded them on demand: one L2 / HBM latency per
+        // step).  A column's D0 / Pv word index is predicted from the row offset at issue time; when the walk drifts over a word
+        // boundary before it gets there, the word is loaded directly.  The plane words of ASV and read are kept in registers.
+        constexpr int kTbAhead = 4;
+        __shared__ uint32_t tb_ring[3 * kTbAhead][128];
+        const int tx = threadIdx.x;
         const uint2 *app = a.asv_planes + a.asv_plane_off[asv];
         int i = s.bi, jj = s.bj;
         uint32_t *cg = a.cigar + (size_t)tslot * a.cigar_stride;
         uint32_t pos = a.cigar_stride;           // fill from the back
         uint32_t cur_op = 3u, cur_len = 0u;
+        auto issue = [&](const int c, const int bpred) {
+            if (c >= 0) {
+                int wd = bpred >> 5, wp = (bpred - 1) >> 5;
+                wd = wd < 0 ? 0 : (wd > NW - 1 ? NW - 1 : wd); wp = wp < 0 ? 0 : (wp > NW - 1 ? NW - 1 : wp);
+                const uint32_t *hcol = hist + (size_t)c * hist_col_stride;
+                const int st3 = 3 * (c & (kTbAhead - 1));
+                cp_async4(&tb_ring[st3][tx], hcol + (size_t)wd * a.hist_stride);
+                cp_async4(&tb_ring[st3 + 1][tx], hcol + (size_t)(NW + wp) * a.hist_stride);
+                tb_ring[st3 + 2][tx] = (uint32_t)wd | ((uint32_t)wp << 8);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        int c = jj - 1;
+#pragma unroll
+        for (int k = 0; k < kTbAhead; ++k) issue(c - k, i - jj + B);
+        bool fresh = true;
+        uint32_t d0w = 0u, pvw = 0u; int wdt = -1, wpt = -1;
+        uint2 av = make_uint2(0u, 0u), rv = make_uint2(0u, 0u); uint32_t avw = 0xffffffffu, rvw = 0xffffffffu;
         while (i > 0 && jj > 0) {
             const int b = i - jj + B;
+            if (fresh) {
+                asm volatile("cp.async.wait_group %0;" ::"n"(kTbAhead - 1) : "memory");
+                const int st3 = 3 * (c & (kTbAhead - 1));
+                d0w = tb_ring[st3][tx]; pvw = tb_ring[st3 + 1][tx];
+                const uint32_t tag = tb_ring[st3 + 2][tx];
+                wdt = (int)(tag & 0xffu); wpt = (int)(tag >> 8);
+                fresh = false;
+            }
             const uint32_t *hc = hist + (size_t)(jj - 1) * hist_col_stride;
-            const uint32_t d0 = (hc[(size_t)(b >> 5) * a.hist_stride] >> (b & 31)) & 1u;
+            if ((b >> 5) != wdt) { wdt = b >> 5; d0w = hc[(size_t)wdt * a.hist_stride]; }
+            const uint32_t d0 = (d0w >> (b & 31)) & 1u;
             // bases: ASV row i -> base i-1 at padded bit i-1+padl; read column jj -> oriented base jj-1
             const uint32_t abit = (uint32_t)(i - 1 + a.padl);
-            const uint2 av = app[abit >> 5];
+            if ((abit >> 5) != avw) { avw = abit >> 5; av = app[avw]; }
             const uint32_t ac = ((av.x >> (abit & 31u)) & 1u) | (((av.y >> (abit & 31u)) & 1u) << 1);
-            uint32_t rc;
-            if (!rev) {
-                const uint32_t rb = (uint32_t)(jj - 1);
-                const uint2 rv = rp[rb >> 5];
-                rc = ((rv.x >> (rb & 31u)) & 1u) | (((rv.y >> (rb & 31u)) & 1u) << 1);
-            } else {
-                const uint32_t rb = (uint32_t)(m - jj);
-                const uint2 rv = rp[rb >> 5];
-                rc = 3u - (((rv.x >> (rb & 31u)) & 1u) | (((rv.y >> (rb & 31u)) & 1u) << 1));
-            }
+            const uint32_t rb = rev ? (uint32_t)(m - jj) : (uint32_t)(jj - 1);
+            if ((rb >> 5) != rvw) { rvw = rb >> 5; rv = rp[rvw]; }
+            uint32_t rc = ((rv.x >> (rb & 31u)) & 1u) | (((rv.y >> (rb & 31u)) & 1u) << 1);
+            if (rev) rc = 3u - rc;
             uint32_t op;
-            if (ac == rc || d0 == 0u) { op = 0u; --i; --jj; }
+            bool advance = false;
+            if (ac == rc || d0 == 0u) { op = 0u; --i; --jj; advance = true; }
             else {
                 uint32_t pvb = 0u;
-                if (b >= 1) pvb = (hc[(size_t)(NW + ((b - 1) >> 5)) * a.hist_stride] >> ((b - 1) & 31)) & 1u;
-                if (pvb) { op = 2u; --i; } else { op = 1u; --jj; }
+                if (b >= 1) {
+                    const int wp = (b - 1) >> 5;
+                    if (wp != wpt) { wpt = wp; pvw = hc[(size_t)(NW + wp) * a.hist_stride]; }
+                    pvb = (pvw >> ((b - 1) & 31)) & 1u;
+                }
+                if (pvb) { op = 2u; --i; } else { op = 1u; --jj; advance = true; }
+            }
+            if (advance) {                      // column c is done: its stage takes column c - kTbAhead, predicted from the new row offset
+                issue(c - kTbAhead, i - jj + B);
+                --c; fresh = true;
             }
             if (op == cur_op) ++cur_len;
             else {
@@ -342,6 +379,7 @@ __device__ __forceinline__ void align_pair(const AlignArgs &a, uint32_t pi, uint
                 cur_op = op; cur_len = 1u;
             }
         }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         if (cur_len && pos > 0) cg[--pos] = (cur_len << 4) | cur_op;
         a.asv_start[pi] = i; a.read_start[pi] = jj;
         a.cigar_cnt[pi] = a.cigar_stride - pos;

@@ -46,6 +46,13 @@ constexpr uint32_t kThreshTable = 4096;
 // Fibonacci hashing shared by host-built and device-probed open-addressing tables: the slot is the
 // TOP log2(cap) bits of key * 2^64/phi (shift = 64 - log2(cap), cap >= 2).
 constexpr uint64_t kFibMul = 0x9E3779B97F4A7C15ull;
+#ifdef __CUDACC__
+// 4-byte asynchronous copy global -> shared (LDGSTS): no destination register, hence no scoreboard for a later consumer to wait on --
+// the way to prefetch along a serial chain inside one thread (cp.async.commit_group / wait_group N order the copies)
+__device__ __forceinline__ void cp_async4(uint32_t *smem_dst, const uint32_t *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+#endif
 __host__ __device__ __forceinline__ uint32_t hash_slot(uint64_t key, uint32_t shift) { return (uint32_t)((key * kFibMul) >> shift); }
 // 32-bit hash for the SNPmer Bloom filter, strand symmetric: the key is the sum of the low words of the k-mer and of its
 // reverse complement (the sketch kernels probe it without choosing the canonical strand first).

@@ -144,9 +144,6 @@ constexpr int kSnpResolveWarps = 4;
 constexpr uint32_t kSnpSizeCache = 512;
 constexpr uint32_t kSnpAhead = 4;                  // steps of read state in flight per warp (cp.async groups)
 constexpr uint32_t kSnpResolveWarpBytes = kSnpMapMax * 8u + 2u * kSnpSizeCache * 4u + kSnpAhead * 5u * 32u * 4u;
-__device__ __forceinline__ void cp_async4(uint32_t *smem_dst, const uint32_t *gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
 __global__ void __launch_bounds__(kSnpResolveWarps * 32) snp_resolve_kernel(SnpClusterArgs a) {
     extern __shared__ __align__(16) uint8_t resolve_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
