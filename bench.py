@@ -852,6 +852,27 @@ def run_b200(args, rank, world, local_rank):
     total_ms = float(dev_ms.item())
     got = ctx.fetch_resident()
 
+    # ---------------- the same pass WITH the alignment record of every read (strand, coordinates, identity, CIGAR) ----------------
+    # north_star names identity / CIGAR per read; Stage 7 itself consumes only NM (src/alignment.rs:1862), so the headline pass leaves the
+    # traceback out.  This arm adds savont_b200_best_hits_resident: a second, history-keeping DP pass over the best pair of every read and
+    # the walk, the records fetched to host memory.  One pass, rank 0, host wall clock.
+    cigar_line = None
+    if rank == 0 and not args.no_cigar:
+        cig_buf = _lib.pinned_array(4 * (48 * n_reads + 1024)).view(np.uint32)          # the caller's CIGAR buffer, page-locked
+        ctx.map_resident()
+        ctx.best_hits_resident(cigar_out=cig_buf)                                        # warm-up (workspaces)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        ctx.map_resident()
+        bh = ctx.best_hits_resident(cigar_out=cig_buf)
+        dt = time.perf_counter() - t0
+        hit = bh["best_asv"] != 0xffffffff
+        cigar_line = {"value": n_reads / dt, "unit": "reads/s", "ms_per_step": 1e3 * dt, "reads_with_record": int(hit.sum()),
+                      "cigar_ops": int(len(bh["cigar"])), "mean_identity": float(np.nanmean(bh["identity"])) if hit.any() else None,
+                      "what": "map_resident + best_hits_resident on the resident reads of one GPU: NM pass, then a history-keeping DP pass "
+                              "(2 bits per band cell) + walk for the best pair of every read; records copied to host arrays, CIGARs to a page-locked buffer"}
+        del bh
+
     # ---------------- e2e arm: host buffers through the C ABI ----------------
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     ctx.map_reads(r["bases"], r["quals"], r["offsets"], file_idx=fidx, n_samples=w.n_samples)   # warm-up (allocations)
@@ -1075,6 +1096,7 @@ def run_b200(args, rank, world, local_rank):
         "e2e": ptr_line if ptr_line is not None else fastq_line,
         "e2e_twin_contiguous": twin_line,
         "value_twin_resident": twin_resident,
+        "value_with_cigar": cigar_line,
         "e2e_single_process": sp_line,
         "e2e_fastq": fastq_line,
         "gpu_launches": int(sum(s["kernel_launches"] for s in stats)),
@@ -1171,6 +1193,7 @@ def main():
     ap.add_argument("--cpu-reads", type=int, default=100_000, help="sample size of the CPU baseline / reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-twin", action="store_true", help="skip the TwinRead-input e2e arms")
+    ap.add_argument("--no-cigar", action="store_true", help="skip the arm that also fetches strand / coordinates / identity / CIGAR of every read")
     ap.add_argument("--no-single-process", action="store_true", help="N > 1: skip the leg in which rank 0 drives all GPUs through the multi-GPU handle")
     ap.add_argument("--path", default="assign", choices=["assign", "kmercount", "pileup", "cluster", "reassign", "snpcluster"],
                     help="assign: the headline read-vs-ASV path; kmercount: Stage 1 split-k-mer counting (K5)")

@@ -5,7 +5,7 @@
 set -x
 TAG=${TAG:-r02s}
 mkdir -p gpurun_out
-B="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-twin"
+B="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-twin --no-cigar"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv $B > gpurun_out/${TAG}_launch_run.log 2>&1
 for k in sketch_fast_kernel filter_kernel align_nm_kernel; do
   ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 1 -f -o gpurun_out/prof_${TAG}_$k $B > gpurun_out/${TAG}_ncu_$k.log 2>&1

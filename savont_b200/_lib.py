@@ -460,15 +460,16 @@ class Context:
                                               _p(B["totals"], C.c_uint64), _p(B["sample_singleton"], C.c_uint64)))
         return self._finish(B, n, n_samples, Stats())
 
-    def best_hits_resident(self, cigar_cap=None):
-        """best-hit alignment record (ASV, strand, coordinates, identity, CIGAR) per read of the resident batch"""
+    def best_hits_resident(self, cigar_cap=None, cigar_out=None):
+        """best-hit alignment record (ASV, strand, coordinates, identity, CIGAR) per read of the resident batch.  cigar_out: a caller's
+        uint32 array for the CIGAR ops (e.g. a view of pinned_array memory; its length is the capacity)"""
         n, _ = self._resident
         m = max(n, 1)
         out = dict(best_asv=np.zeros(m, np.uint32), strand=np.zeros(m, np.uint8), asv_start=np.zeros(m, np.int32),
                    asv_end=np.zeros(m, np.int32), read_start=np.zeros(m, np.int32), read_end=np.zeros(m, np.int32),
                    identity=np.zeros(m, np.float64))
         co = np.zeros(n + 1, np.uint64)
-        cg = np.zeros(cigar_cap or max(64 * n, 1024), np.uint32)
+        cg = cigar_out if cigar_out is not None else np.empty(cigar_cap or max(64 * n, 1024), np.uint32)
         _check(self.L.savont_b200_best_hits_resident(self.h, _p(out["best_asv"], C.c_uint32), _p(out["strand"], C.c_uint8),
                                                      _p(out["asv_start"], C.c_int32), _p(out["asv_end"], C.c_int32),
                                                      _p(out["read_start"], C.c_int32), _p(out["read_end"], C.c_int32),
