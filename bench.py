@@ -869,8 +869,8 @@ def run_b200(args, rank, world, local_rank):
         hit = bh["best_asv"] != 0xffffffff
         cigar_line = {"value": n_reads / dt, "unit": "reads/s", "ms_per_step": 1e3 * dt, "reads_with_record": int(hit.sum()),
                       "cigar_ops": int(len(bh["cigar"])), "mean_identity": float(np.nanmean(bh["identity"])) if hit.any() else None,
-                      "what": "map_resident + best_hits_resident on the resident reads of one GPU: NM pass, then a history-keeping DP pass "
-                              "(2 bits per band cell) + walk for the best pair of every read; records copied to host arrays, CIGARs to a page-locked buffer"}
+                      "what": "map_resident + best_hits_resident on the resident reads of one GPU: NM pass, then a checkpointing DP pass "
+                              "+ block-wise recomputation and walk for the best pair of every read; records copied to host arrays, CIGARs to a page-locked buffer"}
         del bh
 
     # ---------------- e2e arm: host buffers through the C ABI ----------------

@@ -38,7 +38,7 @@ struct AlignArgs {
     uint32_t n_pairs_max;
     int32_t *nm, *asv_end, *read_end;
     // traceback mode
-    uint32_t *hist;                // [(col*2*NW + w) * hist_stride + t]
+    uint32_t *hist;                // checkpoints: [(block*2*NW + w) * hist_stride + t], block = 32 columns; Pv words then Mv words
     uint32_t hist_stride;
     int32_t *asv_start, *read_start;
     uint32_t *cigar;               // [pair * cigar_stride + ...] filled from the back
@@ -91,8 +91,8 @@ struct Band {
 // scored: 1 = from the band's top score and the vertical deltas (popcounts over the column), 2 = from the previous
 // column's D(n, j-1) and the horizontal delta bits of row n (needs a LAST column right before this one).
 // et (TAIL): match bit of the bottom cell in the sign bit.
-template <int NW, bool TB, bool TOP, int LAST, bool TAIL>
-__device__ __forceinline__ void dp_column(Band<NW, TB, TAIL> &s, uint32_t (&TM)[NW], uint32_t clo, uint32_t chi, uint32_t sh, uint32_t et,
+template <int NW, bool TB, bool TOP, int LAST, bool TAIL, bool BTB>
+__device__ __forceinline__ void dp_column(Band<NW, BTB, TAIL> &s, uint32_t (&TM)[NW], uint32_t clo, uint32_t chi, uint32_t sh, uint32_t et,
                                           int j, int n, int B, uint32_t *hist_col, uint32_t hist_stride) {
     uint32_t Nr[NW + 1], X[NW], t[NW], sum[NW], D0[NW], Ph[NW], Mh[NW];
     // MISmatch bits on the word-aligned window first (2 LOP3 per raw word), ONE funnel shift per band word afterwards;
@@ -229,6 +229,11 @@ __device__ __forceinline__ void align_pair(const AlignArgs &a, uint32_t pi, uint
                     const uint2 nv = s.ap[s.aw++];
                     s.Alo[NW] = nv.x; s.Ahi[NW] = nv.y;
                 }
+                if (TB) {                                   // checkpoint: the vertical deltas in front of column j = 32 * block + 1
+                    uint32_t *ck = hist + (size_t)((uint32_t)(j - 1) >> 5) * hist_col_stride;
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) { ck[(size_t)w * a.hist_stride] = s.Pv[w]; ck[(size_t)(NW + w) * a.hist_stride] = s.Mv[w]; }
+                }
             }
             // columns j..stop share the read word; the loop runs on the bit index alone.  cl / ch hold the bit-reversed
             // read word shifted so that the current column's bit is the sign bit: the broadcast mask is one arithmetic
@@ -248,8 +253,7 @@ __device__ __forceinline__ void align_pair(const AlignArgs &a, uint32_t pi, uint
                 const uint32_t et = el;
                 cl += cl; ch += ch;
                 if (TAIL) el += el;
-                dp_column<NW, TB, TOP, LAST, TAIL>(s, TM, clo, chi, sh, et, jbase + (int)sh, n, B,
-                                                   TB ? hist + (size_t)(jbase + (int)sh - 1) * hist_col_stride : nullptr, a.hist_stride);
+                dp_column<NW, false, TOP, LAST, TAIL>(s, TM, clo, chi, sh, et, jbase + (int)sh, n, B, nullptr, 0u);
             };
             if (!TB && !TOP && LAST == 0 && bit == 0u && bit_end == 31u) {
                 // a whole 32-column block of the interior: fixed trip count, the loop counter amortised over 8 columns
@@ -304,82 +308,70 @@ __device__ __forceinline__ void align_pair(const AlignArgs &a, uint32_t pi, uint
     a.nm[pi] = s.bd;
     if (a.asv_end) { a.asv_end[pi] = s.bi; a.read_end[pi] = s.bj; }
 
-    if (TB) {
-        // ---- traceback over the stored D0 / Pv' vectors; preference diagonal > D (ASV) > I (read) ----
-        // The walk is a serial chain per pair with a history word per step.  The words of the next kTbAhead columns are fetched
-        // with cp.async into a per-thread ring in shared memory (round 2; round 1 loaded them on demand: one L2 / HBM latency per
-        // step).  A column's D0 / Pv word index is predicted from the row offset at issue time; when the walk drifts over a word
-        // boundary before it gets there, the word is loaded directly.  The plane words of ASV and read are kept in registers.
-        constexpr int kTbAhead = 4;
-        __shared__ uint32_t tb_ring[3 * kTbAhead][128];
-        const int tx = threadIdx.x;
+    if constexpr (TB) {
+        // ---- traceback; preference diagonal > D (ASV) > I (read) ----
+        // The forward pass kept only a checkpoint of the vertical deltas every 32 columns (2 NW words: 1.9 KB per 1.5 kb pair at band
+        // 64; round 1 stored D0 / Pv' of EVERY column, 60 KB per pair, and streamed it through HBM twice).  The walk goes back block by
+        // block: the block's columns up to the current one are recomputed from the checkpoint into a per-thread buffer in local memory
+        // (32 columns x 2 NW words, L1 / L2 resident), then walked.  One more forward pass in total, no history traffic to HBM.
+        uint32_t hb[32 * 2 * NW];
         const uint2 *app = a.asv_planes + a.asv_plane_off[asv];
         int i = s.bi, jj = s.bj;
         uint32_t *cg = a.cigar + (size_t)tslot * a.cigar_stride;
         uint32_t pos = a.cigar_stride;           // fill from the back
         uint32_t cur_op = 3u, cur_len = 0u;
-        auto issue = [&](const int c, const int bpred) {
-            if (c >= 0) {
-                int wd = bpred >> 5, wp = (bpred - 1) >> 5;
-                wd = wd < 0 ? 0 : (wd > NW - 1 ? NW - 1 : wd); wp = wp < 0 ? 0 : (wp > NW - 1 ? NW - 1 : wp);
-                const uint32_t *hcol = hist + (size_t)c * hist_col_stride;
-                const int st3 = 3 * (c & (kTbAhead - 1));
-                cp_async4(&tb_ring[st3][tx], hcol + (size_t)wd * a.hist_stride);
-                cp_async4(&tb_ring[st3 + 1][tx], hcol + (size_t)(NW + wp) * a.hist_stride);
-                tb_ring[st3 + 2][tx] = (uint32_t)wd | ((uint32_t)wp << 8);
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        };
-        int c = jj - 1;
-#pragma unroll
-        for (int k = 0; k < kTbAhead; ++k) issue(c - k, i - jj + B);
-        bool fresh = true;
-        uint32_t d0w = 0u, pvw = 0u; int wdt = -1, wpt = -1;
         uint2 av = make_uint2(0u, 0u), rv = make_uint2(0u, 0u); uint32_t avw = 0xffffffffu, rvw = 0xffffffffu;
+        // Outer loop = one block, inner loop = the walk inside it: the lanes of a warp leave the inner loop at different times and
+        // reconverge behind it, so the recomputation (the expensive part, identical instructions for every lane) runs in lockstep.
+        // It always covers the block's 32 columns -- those behind the current one, or behind the read's end, are computed but never read.
         while (i > 0 && jj > 0) {
-            const int b = i - jj + B;
-            if (fresh) {
-                asm volatile("cp.async.wait_group %0;" ::"n"(kTbAhead - 1) : "memory");
-                const int st3 = 3 * (c & (kTbAhead - 1));
-                d0w = tb_ring[st3][tx]; pvw = tb_ring[st3 + 1][tx];
-                const uint32_t tag = tb_ring[st3 + 2][tx];
-                wdt = (int)(tag & 0xffu); wpt = (int)(tag >> 8);
-                fresh = false;
-            }
-            const uint32_t *hc = hist + (size_t)(jj - 1) * hist_col_stride;
-            if ((b >> 5) != wdt) { wdt = b >> 5; d0w = hc[(size_t)wdt * a.hist_stride]; }
-            const uint32_t d0 = (d0w >> (b & 31)) & 1u;
-            // bases: ASV row i -> base i-1 at padded bit i-1+padl; read column jj -> oriented base jj-1
-            const uint32_t abit = (uint32_t)(i - 1 + a.padl);
-            if ((abit >> 5) != avw) { avw = abit >> 5; av = app[avw]; }
-            const uint32_t ac = ((av.x >> (abit & 31u)) & 1u) | (((av.y >> (abit & 31u)) & 1u) << 1);
-            const uint32_t rb = rev ? (uint32_t)(m - jj) : (uint32_t)(jj - 1);
-            if ((rb >> 5) != rvw) { rvw = rb >> 5; rv = rp[rvw]; }
-            uint32_t rc = ((rv.x >> (rb & 31u)) & 1u) | (((rv.y >> (rb & 31u)) & 1u) << 1);
-            if (rev) rc = 3u - rc;
-            uint32_t op;
-            bool advance = false;
-            if (ac == rc || d0 == 0u) { op = 0u; --i; --jj; advance = true; }
-            else {
-                uint32_t pvb = 0u;
-                if (b >= 1) {
-                    const int wp = (b - 1) >> 5;
-                    if (wp != wpt) { wpt = wp; pvw = hc[(size_t)(NW + wp) * a.hist_stride]; }
-                    pvb = (pvw >> ((b - 1) & 31)) & 1u;
+            const int k = (jj - 1) >> 5;
+            {
+                const uint32_t *ck = hist + (size_t)k * hist_col_stride;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) { s.Pv[w] = ck[(size_t)w * a.hist_stride]; s.Mv[w] = ck[(size_t)(NW + w) * a.hist_stride]; }
+#pragma unroll
+                for (int w = 0; w <= NW; ++w) { const uint2 v = app[k + 1 + w]; s.Alo[w] = v.x; s.Ahi[w] = v.y; }
+#pragma unroll
+                for (int w = 0; w < NW; ++w) {               // the virtual-row mask of column 1 moved down by 32 k rows
+                    const int remT = B - 32 * (w + k);
+                    TM[w] = remT >= 32 ? 0xffffffffu : (remT <= 0 ? 0u : ((1u << remT) - 1u));
                 }
-                if (pvb) { op = 2u; --i; } else { op = 1u; --jj; advance = true; }
+                const uint2 cwv = read_word(rp, (uint32_t)m, (uint32_t)k, rev);
+                for (int sh = 0; sh < 32; ++sh) {
+                    const uint32_t clo = 0u - ((cwv.x >> sh) & 1u), chi = 0u - ((cwv.y >> sh) & 1u);
+                    const int jc = 32 * k + 1 + sh;
+                    if (jc <= B) dp_column<NW, true, true, 0, false>(s, TM, clo, chi, (uint32_t)sh, 0u, jc, n, B, hb + sh * 2 * NW, 1u);
+                    else dp_column<NW, true, false, 0, false>(s, TM, clo, chi, (uint32_t)sh, 0u, jc, n, B, hb + sh * 2 * NW, 1u);
+                }
             }
-            if (advance) {                      // column c is done: its stage takes column c - kTbAhead, predicted from the new row offset
-                issue(c - kTbAhead, i - jj + B);
-                --c; fresh = true;
-            }
-            if (op == cur_op) ++cur_len;
-            else {
-                if (cur_len && pos > 0) cg[--pos] = (cur_len << 4) | cur_op;
-                cur_op = op; cur_len = 1u;
+            while (i > 0 && jj > 32 * k) {
+                const int c = jj - 1;
+                const int b = i - jj + B;
+                const uint32_t *hc = hb + (c & 31) * 2 * NW;
+                const uint32_t d0 = (hc[b >> 5] >> (b & 31)) & 1u;
+                // bases: ASV row i -> base i-1 at padded bit i-1+padl; read column jj -> oriented base jj-1
+                const uint32_t abit = (uint32_t)(i - 1 + a.padl);
+                if ((abit >> 5) != avw) { avw = abit >> 5; av = app[avw]; }
+                const uint32_t ac = ((av.x >> (abit & 31u)) & 1u) | (((av.y >> (abit & 31u)) & 1u) << 1);
+                const uint32_t rb = rev ? (uint32_t)(m - jj) : (uint32_t)(jj - 1);
+                if ((rb >> 5) != rvw) { rvw = rb >> 5; rv = rp[rvw]; }
+                uint32_t rc = ((rv.x >> (rb & 31u)) & 1u) | (((rv.y >> (rb & 31u)) & 1u) << 1);
+                if (rev) rc = 3u - rc;
+                uint32_t op;
+                if (ac == rc || d0 == 0u) { op = 0u; --i; --jj; }
+                else {
+                    uint32_t pvb = 0u;
+                    if (b >= 1) pvb = (hc[NW + ((b - 1) >> 5)] >> ((b - 1) & 31)) & 1u;
+                    if (pvb) { op = 2u; --i; } else { op = 1u; --jj; }
+                }
+                if (op == cur_op) ++cur_len;
+                else {
+                    if (cur_len && pos > 0) cg[--pos] = (cur_len << 4) | cur_op;
+                    cur_op = op; cur_len = 1u;
+                }
             }
         }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
         if (cur_len && pos > 0) cg[--pos] = (cur_len << 4) | cur_op;
         a.asv_start[pi] = i; a.read_start[pi] = jj;
         a.cigar_cnt[pi] = a.cigar_stride - pos;
@@ -468,7 +460,7 @@ void launch_align_nm(const SeqBatch &in, const uint2 *read_planes, const AsvInde
 
 size_t align_tb_hist_words(uint32_t n_pairs, uint32_t hist_cols, const DeviceParams &p) {
     const int nw = pick_nw(p.band);
-    return (size_t)n_pairs * hist_cols * 2u * (size_t)(nw > 0 ? nw : 1);
+    return (size_t)n_pairs * ((hist_cols + 31u) / 32u + 1u) * 2u * (size_t)(nw > 0 ? nw : 1);      // one checkpoint per 32 columns
 }
 
 void launch_align_tb(const SeqBatch &in, const uint2 *read_planes, const AsvIndex &ix, const uint32_t *pair_read,
