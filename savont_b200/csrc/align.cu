@@ -321,10 +321,49 @@ __device__ __forceinline__ void align_pair(const AlignArgs &a, uint32_t pi, uint
         uint32_t pos = a.cigar_stride;           // fill from the back
         uint32_t cur_op = 3u, cur_len = 0u;
         uint2 av = make_uint2(0u, 0u), rv = make_uint2(0u, 0u); uint32_t avw = 0xffffffffu, rvw = 0xffffffffu;
+        auto emit = [&](const uint32_t op, const uint32_t len) {
+            if (op == cur_op) cur_len += len;
+            else {
+                if (cur_len && pos > 0) cg[--pos] = (cur_len << 4) | cur_op;
+                cur_op = op; cur_len = len;
+            }
+        };
+        // A cell whose bases match is left along the diagonal whatever the DP says (the preference order), so runs of matches are
+        // taken 32 bases at a time from the bit planes alone: window bit 31 - t = base (i - 1 - t) of the ASV / oriented base
+        // (jj - 1 - t) of the read.  Only the cells where the bases differ need the DP's deltas.
+        auto skip_matches = [&]() {
+            while (i > 0 && jj > 0) {
+                const uint32_t lo = (uint32_t)(i - 1 + a.padl) - 31u;                    // padl >= 32: never negative
+                const uint2 a0 = app[lo >> 5], a1 = app[(lo >> 5) + 1];
+                const uint32_t wax = __funnelshift_r(a0.x, a1.x, lo & 31u), way = __funnelshift_r(a0.y, a1.y, lo & 31u);
+                uint32_t wrx, wry;
+                if (!rev) {
+                    const int r0 = jj - 32;                                             // bits r0 .. jj - 1 of the forward read
+                    if (r0 >= 0) {
+                        const uint2 b0 = rp[(uint32_t)r0 >> 5], b1 = rp[((uint32_t)r0 >> 5) + 1];
+                        wrx = __funnelshift_r(b0.x, b1.x, (uint32_t)r0 & 31u); wry = __funnelshift_r(b0.y, b1.y, (uint32_t)r0 & 31u);
+                    } else { const uint2 b0 = rp[0]; wrx = b0.x << (uint32_t)(-r0); wry = b0.y << (uint32_t)(-r0); }
+                } else {
+                    const uint32_t f0 = (uint32_t)(m - jj);                             // oriented base jj - 1 - t = complement of forward base f0 + t
+                    const uint2 b0 = rp[f0 >> 5], b1 = rp[(f0 >> 5) + 1];
+                    wrx = ~__brev(__funnelshift_r(b0.x, b1.x, f0 & 31u)); wry = ~__brev(__funnelshift_r(b0.y, b1.y, f0 & 31u));
+                }
+                const uint32_t mism = (wax ^ wrx) | (way ^ wry);
+                uint32_t run = (uint32_t)__clz((int)mism);                              // 32 when the whole window matches
+                run = min(run, min((uint32_t)i, (uint32_t)jj));
+                if (run == 0u) break;
+                i -= (int)run; jj -= (int)run;
+                emit(0u, run);
+                if (run < 32u) break;                                                   // stopped at a mismatch (or at a sequence start)
+            }
+        };
         // Outer loop = one block, inner loop = the walk inside it: the lanes of a warp leave the inner loop at different times and
         // reconverge behind it, so the recomputation (the expensive part, identical instructions for every lane) runs in lockstep.
         // It always covers the block's 32 columns -- those behind the current one, or behind the read's end, are computed but never read.
-        while (i > 0 && jj > 0) {
+        // Blocks that the walk crosses inside a run of matches are never recomputed.
+        while (true) {
+            skip_matches();
+            if (!(i > 0 && jj > 0)) break;
             const int k = (jj - 1) >> 5;
             {
                 const uint32_t *ck = hist + (size_t)k * hist_col_stride;
@@ -365,11 +404,8 @@ __device__ __forceinline__ void align_pair(const AlignArgs &a, uint32_t pi, uint
                     if (b >= 1) pvb = (hc[NW + ((b - 1) >> 5)] >> ((b - 1) & 31)) & 1u;
                     if (pvb) { op = 2u; --i; } else { op = 1u; --jj; }
                 }
-                if (op == cur_op) ++cur_len;
-                else {
-                    if (cur_len && pos > 0) cg[--pos] = (cur_len << 4) | cur_op;
-                    cur_op = op; cur_len = 1u;
-                }
+                emit(op, 1u);
+                skip_matches();                                  // the cells behind an edit mostly match again: the run may leave the block
             }
         }
         if (cur_len && pos > 0) cg[--pos] = (cur_len << 4) | cur_op;

@@ -902,7 +902,11 @@ int traceback_pairs(Context *c, Batch &b, const AsvIndex &ix, uint32_t max_ref_l
     std::vector<uint32_t> h_off;
     std::vector<int32_t> h_out;
     int rc = 0;
+    static const bool tb_trace = getenv("SAVONT_B200_TRACE") != nullptr;
+    auto tnow = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_kern = 0, t_copy = 0, t_host = 0;
     for (size_t p0 = 0; p0 < n_pairs && rc == 0; p0 += sub) {
+        const double ta = tnow();
         const uint32_t np = (uint32_t)std::min(sub, n_pairs - p0);
         if ((rc = d_hist.ensure(align_tb_hist_words(np, hist_cols, c->dp) * 4)) != 0) break;
         if ((rc = d_slots.ensure((size_t)np * cigar_stride * 4)) != 0) break;
@@ -926,6 +930,7 @@ int traceback_pairs(Context *c, Batch &b, const AsvIndex &ix, uint32_t max_ref_l
         cudaMemcpyAsync(h_out.data(), d_out.p, (size_t)np * 5 * 4, cudaMemcpyDeviceToHost, c->stream);
         e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) { rc = fail(SAVONT_B200_ERR_CUDA, "align_tb: %s", cudaGetErrorString(e)); break; }
+        const double tb_ = tnow();
         const uint32_t total = h_off[np];
         const bool keep_on_device = dev && p0 == 0 && np == n_pairs;       // the caller consumes the ops on the device
         if (dev) *dev = keep_on_device ? TbDevice{true, d_ops.as<uint32_t>(), d_off.as<uint32_t>(), d_out.as<int32_t>(), np} : TbDevice{};
@@ -939,10 +944,14 @@ int traceback_pairs(Context *c, Batch &b, const AsvIndex &ix, uint32_t max_ref_l
         memcpy(asv_start + p0, h_out.data() + 3 * (size_t)np, (size_t)np * 4);
         memcpy(read_start + p0, h_out.data() + 4 * (size_t)np, (size_t)np * 4);
         for (uint32_t t = 0; t < np; ++t) cigar_offsets[p0 + t + 1] = cig_base + h_off[t + 1];
+        const double tc = tnow();
         e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) { rc = fail(SAVONT_B200_ERR_CUDA, "align_tb copy: %s", cudaGetErrorString(e)); break; }
         cig_base += total;
+        const double td = tnow();
+        t_kern += tb_ - ta; t_host += tc - tb_; t_copy += td - tc;
     }
+    if (tb_trace) fprintf(stderr, "[trace] traceback_pairs: %zu pairs in sub-batches of %zu: kernels + record copy %.2f ms, host %.2f ms, CIGAR copy wait %.2f ms\n", n_pairs, sub, t_kern, t_host, t_copy);
     cleanup();
     return rc;
 }
@@ -1027,6 +1036,7 @@ int savont_b200_destroy(savont_b200_ctx *h) {
     c->d_ks_entries.release(); c->d_ks_dstptr.release(); c->d_ks_partoff.release();
     for (PinBuf &b : c->cluster_pin) b.release();
     c->stage_pin.release();
+    for (DevBuf &b : c->bh_ws) b.release();
     for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
     for (int i = 0; i < 4; ++i) { if (c->ev_up[i]) cudaEventDestroy(c->ev_up[i]); if (c->ev_h0[i]) cudaEventDestroy(c->ev_h0[i]); }
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -1856,25 +1866,30 @@ static int best_hits_batch(Context *c, Batch &b, uint32_t *best_asv, uint8_t *st
                            uint32_t *cigar, size_t cigar_cap) {
     const size_t n = b.n;
     if (n == 0) return 0;
-    DevBuf d_flag, d_off, d_tmp, d_basv, d_bstr, d_pr, d_pa, d_ps;
-    auto cleanup = [&]() { DevBuf *all[] = {&d_flag, &d_off, &d_tmp, &d_basv, &d_bstr, &d_pr, &d_pa, &d_ps}; for (DevBuf *x : all) x->release(); };
+    DevBuf &d_flag = c->bh_ws[0], &d_off = c->bh_ws[1], &d_tmp = c->bh_ws[2], &d_basv = c->bh_ws[3], &d_bstr = c->bh_ws[4], &d_pr = c->bh_ws[5],
+           &d_pa = c->bh_ws[6], &d_ps = c->bh_ws[7];
+    auto cleanup = [&]() {};                     // the workspace stays with the context (released by savont_b200_destroy)
     int rc = 0;
     if ((rc = d_flag.ensure(n * 4)) || (rc = d_off.ensure((n + 1) * 4)) || (rc = d_tmp.ensure((n / 2048 + 4) * 4)) ||
         (rc = d_basv.ensure(n * 4)) || (rc = d_bstr.ensure(n + 4)) || (rc = d_pr.ensure(n * 4)) || (rc = d_pa.ensure(n * 4)) ||
         (rc = d_ps.ensure(n + 4))) { cleanup(); return rc; }
+    const auto bh_t0 = std::chrono::steady_clock::now();
     launch_best_pairs(filter_view(b), pool_view(b), b.nm.as<int32_t>(), b.rstatus.as<uint8_t>(), b.best_nm.as<int32_t>(), (uint32_t)n,
                       c->dp.strand_mode, d_flag.as<uint32_t>(), d_off.as<uint32_t>(), d_tmp.as<uint32_t>(), d_basv.as<uint32_t>(),
                       d_bstr.as<uint8_t>(), d_pr.as<uint32_t>(), d_pa.as<uint32_t>(), d_ps.as<uint8_t>(), c->stream);
     c->last_stats.kernel_launches += 5;
-    std::vector<uint32_t> off(n + 1);
+    std::vector<uint32_t> &off = c->bh_off;
+    if (off.size() < n + 1) off.resize(n + 1);
     cudaMemcpyAsync(off.data(), d_off.p, (n + 1) * 4, cudaMemcpyDeviceToHost, c->stream);
     cudaMemcpyAsync(best_asv, d_basv.p, n * 4, cudaMemcpyDeviceToHost, c->stream);
     cudaMemcpyAsync(strand, d_bstr.p, n, cudaMemcpyDeviceToHost, c->stream);
     cudaError_t e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) { cleanup(); return fail(SAVONT_B200_ERR_CUDA, "best_pairs: %s", cudaGetErrorString(e)); }
     const size_t np = off[n];
-    std::vector<int32_t> v(np * 5);
-    std::vector<uint64_t> coff(np + 1, 0);
+    std::vector<int32_t> &v = c->bh_rec;
+    std::vector<uint64_t> &coff = c->bh_coff;
+    if (v.size() < np * 5) v.resize(np * 5);
+    if (coff.size() < np + 1) coff.resize(np + 1);
     coff[0] = cigar_offsets[0];
     if (np) {
         rc = traceback_pairs(c, b, index_view(c), c->max_asv_len, d_pr.as<uint32_t>(), d_pa.as<uint32_t>(), d_ps.as<uint8_t>(), np, v.data(), v.data() + np,
@@ -1895,6 +1910,7 @@ static int best_hits_batch(Context *c, Batch &b, uint32_t *best_asv, uint8_t *st
         cigar_offsets[r + 1] = coff[off[r + 1]];
     }
     cleanup();
+    if (getenv("SAVONT_B200_TRACE")) fprintf(stderr, "[trace] best_hits_batch: %zu reads, %.2f ms in all\n", n, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - bh_t0).count());
     return 0;
 }
 

@@ -219,6 +219,8 @@ struct Context {
     savont_b200_stats last_stats;
     // traceback workspace (history, CIGAR slots, compacted ops, ...) and the Stage 4 pileup scratch: kept between calls
     DevBuf tb_ws[7]; PinBuf tb_pin;
+    DevBuf bh_ws[8];                  // best_hits_batch: flags / offsets / best pairs (kept between calls: cudaMalloc + cudaFree cost more than the kernels)
+    std::vector<uint32_t> bh_off; std::vector<int32_t> bh_rec; std::vector<uint64_t> bh_coff;
     DevBuf pileup_ws[40];
     DevBuf cluster_ws[16]; PinBuf cluster_pin[4];
     PinBuf stage_pin;                 // upload_host: ring of pinned chunks for pageable sources
