@@ -133,6 +133,7 @@ __device__ __forceinline__ void dp_column(Band<NW, BTB, TAIL> &s, uint32_t (&TM)
             hist_col[(size_t)w * hist_stride] = D0[w];
             hist_col[(size_t)(NW + w) * hist_stride] = s.Pv[w];
         }
+        if (TAIL) hist_col[(size_t)(2 * NW) * hist_stride] = d0t;       // D0 of the bottom cell (bit 0)
     }
     if (TOP) {
 #pragma unroll
@@ -166,7 +167,6 @@ __device__ __forceinline__ void dp_column(Band<NW, BTB, TAIL> &s, uint32_t (&TM)
 
 template <int NW, bool TB, bool TAIL>
 __device__ __forceinline__ void align_pair(const AlignArgs &a, uint32_t pi, uint32_t tslot) {
-    static_assert(!(TB && TAIL), "the traceback history stores whole words: no tail-bit variant");
     const uint32_t r = a.pair_read[pi], asv = a.pair_asv[pi];
     const bool rev = a.pair_strand[pi] != 0;
     const uint64_t roff = a.read_offsets[r];
@@ -270,11 +270,8 @@ __device__ __forceinline__ void align_pair(const AlignArgs &a, uint32_t pi, uint
     using L0 = std::integral_constant<int, 0>; using L1 = std::integral_constant<int, 1>; using L2 = std::integral_constant<int, 2>;
     run_phase(std::true_type{}, L1{}, B < jmax ? B : jmax);
     run_phase(std::false_type{}, L0{}, (n - B - 1) < jmax ? (n - B - 1) : jmax);
-    if (TB) run_phase(std::false_type{}, L1{}, jmax);
-    else {
-        if (j <= jmax) run_phase(std::false_type{}, L1{}, j);
-        run_phase(std::false_type{}, L2{}, jmax);
-    }
+    if (j <= jmax) run_phase(std::false_type{}, L1{}, j);
+    run_phase(std::false_type{}, L2{}, jmax);
     // row n may already be inside the window of column 0 (n <= B): cell (n, 0) = 0 is a last-row cell
     // (handled below together with the last column when m == 0; for m > 0 the oracle also considers it)
     if (n <= B) {
@@ -314,7 +311,8 @@ __device__ __forceinline__ void align_pair(const AlignArgs &a, uint32_t pi, uint
         // 64; round 1 stored D0 / Pv' of EVERY column, 60 KB per pair, and streamed it through HBM twice).  The walk goes back block by
         // block: the block's columns up to the current one are recomputed from the checkpoint into a per-thread buffer in local memory
         // (32 columns x 2 NW words, L1 / L2 resident), then walked.  One more forward pass in total, no history traffic to HBM.
-        uint32_t hb[32 * 2 * NW];
+        constexpr int HW = 2 * NW + (TAIL ? 1 : 0);          // words per recomputed column: D0, Pv' (+ the bottom cell's D0)
+        uint32_t hb[32 * HW];
         const uint2 *app = a.asv_planes + a.asv_plane_off[asv];
         int i = s.bi, jj = s.bj;
         uint32_t *cg = a.cigar + (size_t)tslot * a.cigar_stride;
@@ -377,18 +375,20 @@ __device__ __forceinline__ void align_pair(const AlignArgs &a, uint32_t pi, uint
                     TM[w] = remT >= 32 ? 0xffffffffu : (remT <= 0 ? 0u : ((1u << remT) - 1u));
                 }
                 const uint2 cwv = read_word(rp, (uint32_t)m, (uint32_t)k, rev);
+                const uint32_t elw = TAIL ? ~((s.Alo[NW] ^ cwv.x) | (s.Ahi[NW] ^ cwv.y)) : 0u;      // match bits of the bottom cells of the block's columns
                 for (int sh = 0; sh < 32; ++sh) {
                     const uint32_t clo = 0u - ((cwv.x >> sh) & 1u), chi = 0u - ((cwv.y >> sh) & 1u);
+                    const uint32_t et = (elw >> sh) << 31;
                     const int jc = 32 * k + 1 + sh;
-                    if (jc <= B) dp_column<NW, true, true, 0, false>(s, TM, clo, chi, (uint32_t)sh, 0u, jc, n, B, hb + sh * 2 * NW, 1u);
-                    else dp_column<NW, true, false, 0, false>(s, TM, clo, chi, (uint32_t)sh, 0u, jc, n, B, hb + sh * 2 * NW, 1u);
+                    if (jc <= B) dp_column<NW, true, true, 0, TAIL>(s, TM, clo, chi, (uint32_t)sh, et, jc, n, B, hb + sh * HW, 1u);
+                    else dp_column<NW, true, false, 0, TAIL>(s, TM, clo, chi, (uint32_t)sh, et, jc, n, B, hb + sh * HW, 1u);
                 }
             }
             while (i > 0 && jj > 32 * k) {
                 const int c = jj - 1;
                 const int b = i - jj + B;
-                const uint32_t *hc = hb + (c & 31) * 2 * NW;
-                const uint32_t d0 = (hc[b >> 5] >> (b & 31)) & 1u;
+                const uint32_t *hc = hb + (c & 31) * HW;
+                const uint32_t d0 = (TAIL && (b >> 5) == NW) ? (hc[2 * NW] & 1u) : ((hc[b >> 5] >> (b & 31)) & 1u);
                 // bases: ASV row i -> base i-1 at padded bit i-1+padl; read column jj -> oriented base jj-1
                 const uint32_t abit = (uint32_t)(i - 1 + a.padl);
                 if ((abit >> 5) != avw) { avw = abit >> 5; av = app[avw]; }
@@ -421,11 +421,11 @@ __global__ void __launch_bounds__(128) align_nm_kernel(AlignArgs a) {
     for (uint32_t pi = blockIdx.x * blockDim.x + threadIdx.x; pi < n_pairs; pi += gridDim.x * blockDim.x)
         align_pair<NW, false, TAIL>(a, pi, 0);
 }
-template <int NW>
+template <int NW, bool TAIL>
 __global__ void __launch_bounds__(128) align_tb_kernel(AlignArgs a) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= a.n_pairs_max) return;
-    align_pair<NW, true, false>(a, t, t);
+    align_pair<NW, true, TAIL>(a, t, t);
 }
 
 static int pick_nw(int band) {
@@ -495,7 +495,7 @@ void launch_align_nm(const SeqBatch &in, const uint2 *read_planes, const AsvInde
 }
 
 size_t align_tb_hist_words(uint32_t n_pairs, uint32_t hist_cols, const DeviceParams &p) {
-    const int nw = pick_nw(p.band);
+    const int nw = pick_nw_tail(p.band) ? pick_nw_tail(p.band) : pick_nw(p.band);
     return (size_t)n_pairs * ((hist_cols + 31u) / 32u + 1u) * 2u * (size_t)(nw > 0 ? nw : 1);      // one checkpoint per 32 columns
 }
 
@@ -510,14 +510,24 @@ void launch_align_tb(const SeqBatch &in, const uint2 *read_planes, const AsvInde
     a.asv_start = asv_start; a.read_start = read_start;
     a.cigar = cigar; a.cigar_stride = cigar_stride; a.cigar_cnt = cigar_cnt;
     const uint32_t grid = (n_pairs + 127u) / 128u;
+    switch (pick_nw_tail(p.band)) {                      // bands of 32 q + 1 cells: q words + the tail bit, as in the NM pass
+        case 1: align_tb_kernel<1, true><<<grid, 128, 0, st>>>(a); return;
+        case 2: align_tb_kernel<2, true><<<grid, 128, 0, st>>>(a); return;
+        case 3: align_tb_kernel<3, true><<<grid, 128, 0, st>>>(a); return;
+        case 4: align_tb_kernel<4, true><<<grid, 128, 0, st>>>(a); return;
+        case 6: align_tb_kernel<6, true><<<grid, 128, 0, st>>>(a); return;
+        case 8: align_tb_kernel<8, true><<<grid, 128, 0, st>>>(a); return;
+        case 12: align_tb_kernel<12, true><<<grid, 128, 0, st>>>(a); return;
+        default: break;
+    }
     switch (pick_nw(p.band)) {
-        case 1: align_tb_kernel<1><<<grid, 128, 0, st>>>(a); break;
-        case 2: align_tb_kernel<2><<<grid, 128, 0, st>>>(a); break;
-        case 3: align_tb_kernel<3><<<grid, 128, 0, st>>>(a); break;
-        case 5: align_tb_kernel<5><<<grid, 128, 0, st>>>(a); break;
-        case 7: align_tb_kernel<7><<<grid, 128, 0, st>>>(a); break;
-        case 9: align_tb_kernel<9><<<grid, 128, 0, st>>>(a); break;
-        case 13: align_tb_kernel<13><<<grid, 128, 0, st>>>(a); break;
+        case 1: align_tb_kernel<1, false><<<grid, 128, 0, st>>>(a); break;
+        case 2: align_tb_kernel<2, false><<<grid, 128, 0, st>>>(a); break;
+        case 3: align_tb_kernel<3, false><<<grid, 128, 0, st>>>(a); break;
+        case 5: align_tb_kernel<5, false><<<grid, 128, 0, st>>>(a); break;
+        case 7: align_tb_kernel<7, false><<<grid, 128, 0, st>>>(a); break;
+        case 9: align_tb_kernel<9, false><<<grid, 128, 0, st>>>(a); break;
+        case 13: align_tb_kernel<13, false><<<grid, 128, 0, st>>>(a); break;
         default: break;
     }
 }
