@@ -34,7 +34,7 @@ int up(DevBuf &d, const std::vector<T> &v, cudaStream_t st) {
 }
 
 // one chunk: consensus sequences [c0, c1), reads [r0, r1) (exactly the reads whose read_cons lies in the chunk)
-int pileup_chunk(Context *c, PileupScratch &s, size_t chunk, int use_hpc, const uint8_t *cons_bases, const uint64_t *cons_offsets, size_t c0, size_t c1,
+int pileup_chunk(Context *c, PileupScratch &s, Batch &rb, size_t chunk, int use_hpc, const uint8_t *cons_bases, const uint64_t *cons_offsets, size_t c0, size_t c1,
                  const uint8_t *read_bases, const uint8_t *read_quals, const uint64_t *read_offsets, const uint32_t *read_cons, size_t r0,
                  size_t r1, uint64_t *pos_offsets, savont_b200_pileup_entry *entries, size_t entry_cap, uint64_t *n_entries,
                  uint8_t *ref_hp_length, uint8_t *read_strand, int32_t *read_nm) {
@@ -51,12 +51,12 @@ int pileup_chunk(Context *c, PileupScratch &s, size_t chunk, int use_hpc, const 
     if (n_pos >= (1ull << 31)) return fail(SAVONT_B200_ERR_INVALID, "consensus chunk too long");
 
     // ---- reads: upload, homopolymer compression (src/utils.rs:135-184) ----
-    Batch &rb = c->work, &hb = c->work2;
+    Batch &hb = c->work2;                    // rb: the chunk's raw reads, uploaded by the caller on the copy stream (one chunk ahead)
     static const bool trace = getenv("SAVONT_B200_PILEUP_TRACE") != nullptr;        // host wall clock of the first stage's steps
     auto tnow = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     double tl = tnow(), tw[6] = {0}; auto lap = [&](int k) { if (trace) { CK(cudaStreamSynchronize(st)); const double x = tnow(); tw[k] += x - tl; tl = x; } return 0; };
     CK(cudaEventRecord(ev[0], st));
-    TRY(batch_upload(c, rb, read_bases, read_quals, read_offsets + r0, nullptr, n, &c->last_stats.h2d_bytes));
+    (void)read_bases; (void)read_quals; (void)read_offsets;
     TRY(lap(0));
     TRY(s.hcnt.ensure((n + 1) * 4)); TRY(s.hoff32.ensure((n + 2) * 4)); TRY(s.scan_tmp.ensure((n / 2048 + 4) * 4));
     launch_hpc_count(seq_view(rb), use_hpc, s.hcnt.as<uint32_t>(), st);
@@ -256,23 +256,45 @@ extern "C" int savont_b200_consensus_pileups(savont_b200_ctx *h, int use_hpc, co
     if (const char *e = getenv("SAVONT_B200_PILEUP_CHUNK_READS")) kMaxReads = std::max<size_t>(1, strtoull(e, nullptr, 10));   // tests
     PileupScratch s(c->pileup_ws);
     int rc = 0;
-    size_t c0 = 0, r0 = 0, chunk = 0;
-    while (c0 < n_cons && rc == 0) {
-        size_t c1 = c0, r1 = r0;
-        uint64_t cells = 0;
-        while (c1 < n_cons) {
-            size_t re = r1;
-            while (re < n_reads && read_cons[re] == c1) ++re;
-            if (re - r1 > 32767) { rc = fail(SAVONT_B200_ERR_INVALID, "consensus %zu: %zu reads (at most 32767 per consensus)", c1, re - r1); break; }
-            const uint64_t add = (uint64_t)(re - r1) * (cons_offsets[c1 + 1] - cons_offsets[c1]);
-            if (c1 > c0 && (cells + add > kMaxCells || re - r0 > kMaxReads)) break;
-            cells += add; r1 = re; ++c1;
+    struct Chunk { size_t c0, c1, r0, r1; };
+    std::vector<Chunk> chunks;
+    {
+        size_t c0 = 0, r0 = 0;
+        while (c0 < n_cons && rc == 0) {
+            size_t c1 = c0, r1 = r0;
+            uint64_t cells = 0;
+            while (c1 < n_cons) {
+                size_t re = r1;
+                while (re < n_reads && read_cons[re] == c1) ++re;
+                if (re - r1 > 32767) { rc = fail(SAVONT_B200_ERR_INVALID, "consensus %zu: %zu reads (at most 32767 per consensus)", c1, re - r1); break; }
+                const uint64_t add = (uint64_t)(re - r1) * (cons_offsets[c1 + 1] - cons_offsets[c1]);
+                if (c1 > c0 && (cells + add > kMaxCells || re - r0 > kMaxReads)) break;
+                cells += add; r1 = re; ++c1;
+            }
+            if (rc) break;
+            chunks.push_back(Chunk{c0, c1, r0, r1});
+            c0 = c1; r0 = r1;
         }
-        if (rc) break;
-        rc = pileup_chunk(c, s, chunk++, use_hpc, cons_bases, cons_offsets, c0, c1, read_bases, read_quals, read_offsets, read_cons, r0, r1,
-                          pos_offsets, entries, entry_cap, n_entries, ref_hp_length, read_strand, read_nm);
-        c0 = c1; r0 = r1;
     }
+    // The raw reads of chunk i + 1 are uploaded (copy stream, second buffer) while chunk i is processed: a chunk's steps are separated
+    // by host synchronisations (sizes come back from the device), so without this the link idles during the kernels and vice versa.
+    Batch *raw[2] = {&c->work, &c->work3};
+    auto upload = [&](size_t ci) -> int {
+        const Chunk &k = chunks[ci];
+        if (k.r1 > k.r0) TRY(batch_upload(c, *raw[ci & 1], read_bases, read_quals, read_offsets + k.r0, nullptr, k.r1 - k.r0, &c->last_stats.h2d_bytes, c->copy_stream));
+        CK(cudaEventRecord(c->ev_up[ci & 1], c->copy_stream));
+        return 0;
+    };
+    if (rc == 0 && !chunks.empty()) rc = upload(0);
+    for (size_t ci = 0; ci < chunks.size() && rc == 0; ++ci) {
+        const Chunk &k = chunks[ci];
+        // chunk ci - 1 (the previous user of the other buffer) has returned: its kernels on the raw reads are complete
+        if (ci + 1 < chunks.size()) { rc = upload(ci + 1); if (rc) break; }
+        if (cudaStreamWaitEvent(c->stream, c->ev_up[ci & 1], 0) != cudaSuccess) { rc = fail(SAVONT_B200_ERR_CUDA, "pileup: wait for the upload failed"); break; }
+        rc = pileup_chunk(c, s, *raw[ci & 1], ci, use_hpc, cons_bases, cons_offsets, k.c0, k.c1, read_bases, read_quals, read_offsets, read_cons, k.r0, k.r1,
+                          pos_offsets, entries, entry_cap, n_entries, ref_hp_length, read_strand, read_nm);
+    }
+    if (rc) cudaStreamSynchronize(c->copy_stream);          // an upload may still be in flight
     {   // the last copies of the entries
         cudaError_t e = cudaStreamSynchronize(c->d2h_stream);
         if (e != cudaSuccess && rc == 0) rc = fail(SAVONT_B200_ERR_CUDA, "pileup entries copy: %s", cudaGetErrorString(e));
