@@ -1141,7 +1141,7 @@ OPS_PER_WORD = 12.4
 
 
 KERNEL_OPS_PER_COLUMN = 55.9     # ALU-pipe instructions per column in the SASS interior loop of align_nm_kernel<4, true> (tools/sass_loops.py)
-PROFILE_TAG = "r02s"             # profiles/<tag>_<kernel>_full.txt: ncu --set full summaries of THIS round's kernels (profiles/refresh.py)
+PROFILE_TAG = "r02t"             # profiles/<tag>_<kernel>_full.txt: ncu --set full summaries of THIS round's kernels (profiles/refresh.py)
 
 
 def _ncu_profile(kernel):

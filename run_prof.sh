@@ -1,9 +1,9 @@
 # The ncu evidence of a round, on one B200 (gpurun -- 'bash run_prof.sh'); then, back in the container:
-#   python profiles/refresh.py r02s r02s      (launch list + per-kernel summaries -> profiles/)
+#   python profiles/refresh.py r02t r02t      (launch list + per-kernel summaries -> profiles/)
 # and set PROFILE_TAG in bench.py to the same tag: bench.py takes roofline.traffic from these summaries only while the capture's
 # kernel duration is within 10 % of the run's CUDA-event time.  Numbers printed under ncu are never bench values.
 set -x
-TAG=${TAG:-r02s}
+TAG=${TAG:-r02t}
 mkdir -p gpurun_out
 B="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-twin --no-cigar"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv $B > gpurun_out/${TAG}_launch_run.log 2>&1
