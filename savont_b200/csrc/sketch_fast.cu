@@ -24,6 +24,7 @@
 //            (src/seeding.rs:550-568) is counted in a small shared-memory hash table.
 // Anything that does not fit the shared-memory budgets (more SNPmer hits / Bloom positives than the per-warp
 // lists hold) raises kErrSnpHits and the host re-runs the batch with the generic kernel.
+#include <cstdio>
 #include <cstdlib>
 #include <type_traits>
 
@@ -270,7 +271,11 @@ sketch_fast_kernel(SeqBatch in, SketchOut out, SnpSet set, const uint16_t *__res
             // instead of computing up to C - 1 positions nobody reads
             auto block = [&](auto partial_tag, const uint32_t b, const uint32_t steps) {
                 constexpr bool PARTIAL = decltype(partial_tag)::value;
-                const uint32_t bb = extract32(packed, bidx, C) << (32u - 2u * C);      // the block's bases, first one on top
+                // (the word index is clamped to the warp's packed words: compute-sanitizer saw this load leave the CTA's shared memory once
+                // per launch in the release build -- its result is never used there, the tests are bit-exact -- and the clamp costs one
+                // instruction per 11 positions)
+                const uint32_t bwi = min(bidx >> 4, lay.packed_words - 2u);
+                const uint32_t bb = (__funnelshift_l(packed[bwi + 1u], packed[bwi], (bidx & 15u) * 2u) >> (32u - 2u * C)) << (32u - 2u * C);      // the block's bases, first one on top
                 bidx += C;
                 uint32_t cmb = 0, mmb = 0;
 #pragma unroll
@@ -535,6 +540,8 @@ void launch_sketch_fast(const SeqBatch &in, const SketchOut &out, const SnpSet &
     uint32_t grid = (uint32_t)sm_count * per_sm;
     const uint32_t need = (in.n + lay.warps - 1) / lay.warps;
     if (grid > need) grid = need;
+    static const bool trace = getenv("SAVONT_B200_TRACE") != nullptr;
+    if (trace) fprintf(stderr, "[trace] sketch_fast: n %u max_len %u warps %u packed_words %u stage %u hit_cap %u bloom %u per_warp %zu smem %zu grid %u\n", in.n, in.max_len, lay.warps, lay.packed_words, lay.stage_bytes, lay.hit_cap, lay.bloom_bytes, lay.per_warp(), smem, grid);
     if (in.dna_words != nullptr) {
         cudaFuncSetAttribute(sketch_fast_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         sketch_fast_kernel<1, false><<<grid, lay.warps * 32, smem, st>>>(in, out, set, rank_table, p, lay);
