@@ -54,3 +54,16 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "savont_oracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
+
+
+def test_integration_md_names_every_entry_point():
+    """INTEGRATION.md is where a maintainer looks for the binding of an entry point: every function declared in include/savont_b200.h
+    is named there (the kmer_shard family by its shorthand)"""
+    import os
+    from savont_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    text = text.replace("`savont_b200_kmer_shard_hist` / `_partitions` / `_alloc` / `_scatter` / `_count`",
+                        " ".join("savont_b200_kmer_shard_" + x for x in ("hist", "partitions", "alloc", "scatter", "count")))
+    missing = [sym for sym in _lib.declared_symbols() if sym not in text]
+    assert not missing, missing
