@@ -9,16 +9,25 @@ ASVs by default).  N>1 (under torchrun): reads are sharded, R reads per rank (we
 index replicated, one all-reduce of the per-ASV count vector per step (NCCL, in place on the
 library's device counter vector).
 
-  value     whole-job reads/s with the reads already resident in HBM (kernel pipeline only)
-  e2e       the same metric through the drop-in call of the reference's Stage 7 seam, savont_b200_map_twin_reads:
-            `refine_asv_depths_with_em(twin_reads: &[TwinRead], ..)` hands over TwinReads, so the HOST buffers are the
-            2-bit dna_seq words + snpmer_kmers of the reads, in pinned memory (H2D of them and D2H of the per-read results
-            inside the timed region).  With --no-twin: the FASTQ-byte call below.
+  value     whole-job reads/s with the reads (FASTQ bytes) already resident in HBM (kernel pipeline only)
+  e2e       the same metric through the drop-in call of the reference's Stage 7 seam: `refine_asv_depths_with_em(twin_reads:
+            &[TwinRead], ..)` hands over TwinReads as they lie in the reference's memory -- one pageable heap block per read for
+            dna_seq and for snpmer_kmers, one pointer per read -- through savont_b200_map_twin_read_ptrs: the library's host threads
+            gather the blocks into page-locked staging INSIDE the timed region, as are the H2D of them and the D2H of the per-read
+            results.  With --no-twin: the FASTQ-byte call below.
+  e2e_twin_contiguous   the TwinRead fields already concatenated in pinned memory (savont_b200_map_twin_reads): no gather
   e2e_fastq the same through savont_b200_map_reads: ASCII bases + Phred bytes (the form the reference arm / CPU oracle
             is fed with), 5.5x more H2D bytes -> PCIe bound
-  roofline  the dominant kernel (banded DP): achieved GCUPS vs the INT32 ALU-pipe peak
+  value_twin_resident   `value` with the TwinRead fields resident instead of FASTQ bytes (no ASCII encode, no SNPmer detection)
+  value_with_cigar      the resident pass followed by savont_b200_best_hits_resident: strand, coordinates, identity and CIGAR of
+            every read's best hit fetched as well (rank 0, one pass, host wall clock; --no-cigar skips it)
+  e2e_single_process    N > 1: rank 0 alone drives all N GPUs through savont_b200_create_multi (the other ranks idle)
+  multi_gpu_check       N > 1: all-reduced counters == sum over ranks == one GPU over the concatenated samples == oracle
+  roofline  the dominant kernel (banded DP): achieved GCUPS vs the INT32 ALU-pipe peak; traffic from the committed ncu capture
+            of the same kernel (profiles/<PROFILE_TAG>_*_full.txt) while its duration is within 10 % of this run's
   cpu_baseline / --impl reference: the CPU oracle (C port of the reference path; the Rust
             reference itself cannot be built here) on all host cores.
+  --path kmercount | cluster | reassign | snpcluster | pileup: the neighbouring stages (one JSON line each, same keys)
 """
 from __future__ import annotations
 
